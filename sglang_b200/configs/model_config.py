@@ -1,0 +1,176 @@
+"""ModelConfig: architecture description + built-in presets (no network: presets stand in for HF hub configs).
+
+Parity: reference ``python/sglang/srt/configs/model_config.py`` (arch detection, context length, head dims).
+``model_path`` may be ``dummy:<preset>`` (random-init weights of that architecture, reference
+``DummyModelLoader`` ``model_loader/loader.py:1602``) or a local directory with an HF ``config.json``.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+
+@dataclass
+class ModelConfig:
+    architecture: str = "LlamaForCausalLM"
+    hidden_size: int = 4096
+    intermediate_size: int = 14336
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    num_key_value_heads: int = 8
+    head_dim: Optional[int] = None
+    vocab_size: int = 128256
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    rope_scaling: Optional[Dict[str, Any]] = None
+    max_position_embeddings: int = 8192
+    tie_word_embeddings: bool = False
+    attention_bias: bool = False
+    mlp_bias: bool = False
+    hidden_act: str = "silu"
+    qk_norm: bool = False
+    sliding_window: Optional[int] = None
+    attn_logit_softcapping: float = 0.0
+    final_logit_softcapping: float = 0.0
+    rope_is_neox: bool = True
+    partial_rotary_factor: float = 1.0
+    # MoE
+    num_local_experts: int = 0
+    num_experts_per_tok: int = 0
+    moe_intermediate_size: Optional[int] = None
+    norm_topk_prob: bool = True
+    # multimodal (LLaVA-style)
+    vision: Optional[Dict[str, Any]] = None
+    image_token_id: Optional[int] = None
+    # special tokens
+    bos_token_id: int = 1
+    eos_token_id: Any = 2
+    pad_token_id: int = 0
+    dtype: str = "bfloat16"
+    name: str = ""
+
+    def __post_init__(self) -> None:
+        if self.head_dim is None:
+            self.head_dim = self.hidden_size // self.num_attention_heads
+        if self.moe_intermediate_size is None:
+            self.moe_intermediate_size = self.intermediate_size
+
+    @property
+    def eos_token_ids(self) -> List[int]:
+        e = self.eos_token_id
+        return list(e) if isinstance(e, (list, tuple)) else [int(e)]
+
+    @property
+    def is_moe(self) -> bool:
+        return self.num_local_experts > 0
+
+    @property
+    def is_multimodal(self) -> bool:
+        return self.vision is not None
+
+    def num_params(self) -> int:
+        h, i, L, V = self.hidden_size, self.intermediate_size, self.num_hidden_layers, self.vocab_size
+        qkv = h * (self.num_attention_heads + 2 * self.num_key_value_heads) * self.head_dim
+        o = self.num_attention_heads * self.head_dim * h
+        mlp = 3 * h * (self.moe_intermediate_size if self.is_moe else i) * (self.num_local_experts if self.is_moe else 1)
+        emb = V * h * (1 if self.tie_word_embeddings else 2)
+        return L * (qkv + o + mlp + 2 * h) + emb + h
+
+
+_LLAMA3_ROPE = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                "original_max_position_embeddings": 8192}
+_CLIP_L_336 = {"hidden_size": 1024, "intermediate_size": 4096, "num_hidden_layers": 24, "num_attention_heads": 16,
+               "image_size": 336, "patch_size": 14, "select_layer": -2, "projector_hidden_act": "gelu"}
+
+PRESETS: Dict[str, Dict[str, Any]] = {
+    # ---- tiny CPU-test models
+    "tiny-llama": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                       vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
+    "tiny-llama-gpu": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                           num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
+    "tiny-mixtral": dict(architecture="MixtralForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                         num_local_experts=4, num_experts_per_tok=2, rope_theta=10000.0, dtype="float32"),
+    "tiny-mixtral-gpu": dict(architecture="MixtralForCausalLM", hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                             num_attention_heads=4, num_key_value_heads=2, head_dim=128, vocab_size=2048,
+                             max_position_embeddings=2048, num_local_experts=8, num_experts_per_tok=2, rope_theta=10000.0),
+    "tiny-qwen2": dict(architecture="Qwen2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                       attention_bias=True, rope_theta=10000.0, dtype="float32"),
+    "tiny-qwen3": dict(architecture="Qwen3ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, head_dim=32, vocab_size=512, max_position_embeddings=512,
+                       qk_norm=True, rope_theta=10000.0, dtype="float32"),
+    "tiny-gemma": dict(architecture="GemmaForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=1, head_dim=32, vocab_size=512, max_position_embeddings=512,
+                       hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True, rope_theta=10000.0, dtype="float32"),
+    "tiny-llava": dict(architecture="LlavaForConditionalGeneration", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=1024,
+                       rope_theta=10000.0, dtype="float32", image_token_id=500,
+                       vision={"hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 2, "num_attention_heads": 2,
+                               "image_size": 28, "patch_size": 14, "select_layer": -2, "projector_hidden_act": "gelu"}),
+    # ---- real architectures (random-init offline)
+    "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                       num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, rope_theta=500000.0,
+                       bos_token_id=128000, eos_token_id=[128001, 128009]),
+    "llama-3.1-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                         num_key_value_heads=8, vocab_size=128256, max_position_embeddings=131072, rope_theta=500000.0,
+                         rope_scaling=_LLAMA3_ROPE, bos_token_id=128000, eos_token_id=[128001, 128008, 128009]),
+    "llama-3-70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64,
+                        num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, rope_theta=500000.0,
+                        bos_token_id=128000, eos_token_id=[128001, 128009]),
+    "llama-2-7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+                       num_key_value_heads=32, vocab_size=32000, max_position_embeddings=4096, rope_theta=10000.0),
+    "mixtral-8x7b": dict(architecture="MixtralForCausalLM", hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                         num_attention_heads=32, num_key_value_heads=8, vocab_size=32000, max_position_embeddings=32768,
+                         rope_theta=1000000.0, num_local_experts=8, num_experts_per_tok=2),
+    "qwen2-7b": dict(architecture="Qwen2ForCausalLM", hidden_size=3584, intermediate_size=18944, num_hidden_layers=28,
+                     num_attention_heads=28, num_key_value_heads=4, vocab_size=152064, max_position_embeddings=32768,
+                     rope_theta=1000000.0, attention_bias=True, rms_norm_eps=1e-6, eos_token_id=[151643, 151645]),
+    "qwen3-8b": dict(architecture="Qwen3ForCausalLM", hidden_size=4096, intermediate_size=12288, num_hidden_layers=36,
+                     num_attention_heads=32, num_key_value_heads=8, head_dim=128, vocab_size=151936,
+                     max_position_embeddings=40960, rope_theta=1000000.0, qk_norm=True, rms_norm_eps=1e-6,
+                     eos_token_id=[151643, 151645]),
+    "gemma-2b": dict(architecture="GemmaForCausalLM", hidden_size=2048, intermediate_size=16384, num_hidden_layers=18,
+                     num_attention_heads=8, num_key_value_heads=1, head_dim=256, vocab_size=256000,
+                     max_position_embeddings=8192, hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True,
+                     rope_theta=10000.0, rms_norm_eps=1e-6),
+    "llava-1.5-7b": dict(architecture="LlavaForConditionalGeneration", hidden_size=4096, intermediate_size=11008,
+                         num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=32, vocab_size=32064,
+                         max_position_embeddings=4096, rope_theta=10000.0, image_token_id=32000, vision=_CLIP_L_336),
+}
+
+_HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM"}
+
+
+def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = None, context_length: Optional[int] = None) -> ModelConfig:
+    overrides = dict(overrides or {})
+    if model_path.startswith("dummy:"):
+        name = model_path.split(":", 1)[1]
+        if name not in PRESETS:
+            raise ValueError(f"unknown preset {name!r}; available: {sorted(PRESETS)}")
+        kw = {**PRESETS[name], **overrides, "name": name}
+    else:
+        cfg_file = os.path.join(model_path, "config.json")
+        if not os.path.exists(cfg_file):
+            raise FileNotFoundError(f"{cfg_file} not found (offline box: use dummy:<preset> or a local HF directory)")
+        with open(cfg_file) as f:
+            hf = json.load(f)
+        text = hf.get("text_config", hf)
+        fields = {f.name for f in dataclasses.fields(ModelConfig)}
+        kw = {k: v for k, v in text.items() if k in fields}
+        arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
+        kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
+        if "vision_config" in hf:
+            kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
+                            "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
+            kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))
+        kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype", "bfloat16"), "bfloat16")
+        kw["name"] = os.path.basename(model_path.rstrip("/"))
+        kw.update(overrides)
+    cfg = ModelConfig(**kw)
+    if context_length is not None:
+        cfg.max_position_embeddings = min(cfg.max_position_embeddings, context_length) if context_length > 0 else cfg.max_position_embeddings
+    return cfg

@@ -1,0 +1,221 @@
+// torch.ops.sglb.* — thin adapters from at::Tensor to the raw-pointer kernel API (kernels/api.h).
+// Loaded with torch.ops.load_library(sglang_b200/_C.so).  Every adapter bumps a launch counter so bench.py can
+// report how many of OUR kernels ran inside the timed region (CUDA-graph replays are accounted in Python).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include <atomic>
+
+#include "kernels/api.h"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+inline void count(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+#define CHECK_CUDA(t) TORCH_CHECK((t).is_cuda(), #t " must be a CUDA tensor")
+#define CHECK_BF16(t) TORCH_CHECK((t).scalar_type() == at::kBFloat16, #t " must be bfloat16")
+#define CHECK_I32(t) TORCH_CHECK((t).scalar_type() == at::kInt, #t " must be int32")
+#define CHECK_LAST_CONTIG(t) TORCH_CHECK((t).stride(-1) == 1, #t " must be contiguous in the last dim")
+template <typename T>
+const T* opt_ptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<T>() : nullptr; }
+template <typename T>
+T* opt_mptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<T>() : nullptr; }
+
+int64_t launch_count() { return g_launches.load(); }
+void reset_launch_count() { g_launches.store(0); }
+
+void rmsnorm(at::Tensor x, c10::optional<at::Tensor> residual, const at::Tensor& w, at::Tensor out, double eps, bool gemma) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_BF16(w); CHECK_BF16(out); CHECK_LAST_CONTIG(x); CHECK_LAST_CONTIG(out);
+  TORCH_CHECK(x.dim() == 2 && out.dim() == 2);
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->is_contiguous()); }
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::rmsnorm(x.data_ptr(), residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), out.data_ptr(),
+                (int)x.size(0), (int)x.size(1), (int)x.stride(0), (int)out.stride(0), (float)eps, gemma, cur_stream());
+  count();
+}
+
+void act_and_mul(const at::Tensor& x, at::Tensor out, int64_t act) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_BF16(out); CHECK_LAST_CONTIG(x); TORCH_CHECK(out.is_contiguous());
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::act_and_mul(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)out.size(1), (int)x.stride(0), (int)act, cur_stream());
+  count();
+}
+
+void rope_kv_write(at::Tensor q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& positions,
+                   const at::Tensor& cos_sin, at::Tensor k_cache, at::Tensor v_cache, const at::Tensor& out_loc, bool neox,
+                   double k_scale, double v_scale) {
+  CHECK_CUDA(q); CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_I32(positions); CHECK_I32(out_loc);
+  TORCH_CHECK(q.dim() == 3 && k.dim() == 3 && v.dim() == 3, "q/k/v must be [T, H, D]");
+  TORCH_CHECK(cos_sin.scalar_type() == at::kFloat && cos_sin.is_contiguous());
+  TORCH_CHECK(q.stride(2) == 1 && q.stride(1) == q.size(2) && k.stride(1) == k.size(2) && v.stride(1) == v.size(2));
+  const bool fp8 = k_cache.scalar_type() == at::kFloat8_e4m3fn;
+  TORCH_CHECK(fp8 || k_cache.scalar_type() == at::kBFloat16, "kv cache must be bf16 or fp8_e4m3");
+  TORCH_CHECK(k_cache.is_contiguous() && v_cache.is_contiguous());
+  c10::cuda::CUDAGuard g(q.device());
+  sglb::rope_kv_write(q.data_ptr(), k.data_ptr(), v.data_ptr(), positions.data_ptr<int>(), cos_sin.data_ptr<float>(),
+                      k_cache.data_ptr(), v_cache.data_ptr(), out_loc.data_ptr<int>(), (int)q.size(0), (int)q.size(1),
+                      (int)k.size(1), (int)q.size(2), (int)cos_sin.size(1), (int)q.stride(0), (int)k.stride(0),
+                      (int)v.stride(0), neox, fp8, (float)k_scale, (float)v_scale, cur_stream());
+  count();
+}
+
+void apply_pt_delta(at::Tensor page_table, const at::Tensor& rows, const at::Tensor& cols, const at::Tensor& vals,
+                    c10::optional<at::Tensor> n, int64_t n_max) {
+  CHECK_CUDA(page_table); CHECK_I32(page_table); CHECK_I32(rows); CHECK_I32(cols); CHECK_I32(vals);
+  if (n_max <= 0) return;
+  c10::cuda::CUDAGuard g(page_table.device());
+  sglb::apply_pt_delta(page_table.data_ptr<int>(), (int)page_table.stride(0), rows.data_ptr<int>(), cols.data_ptr<int>(),
+                       vals.data_ptr<int>(), opt_ptr<int>(n), (int)n_max, cur_stream());
+  count();
+}
+
+void embedding(const at::Tensor& weight, const at::Tensor& ids, c10::optional<at::Tensor> gather_idx, at::Tensor out,
+               int64_t vocab_start) {
+  CHECK_CUDA(weight); CHECK_BF16(weight); CHECK_I32(ids); CHECK_BF16(out);
+  TORCH_CHECK(weight.is_contiguous() && out.is_contiguous());
+  c10::cuda::CUDAGuard g(weight.device());
+  sglb::embedding(weight.data_ptr(), ids.data_ptr<int>(), opt_ptr<int>(gather_idx), out.data_ptr(), (int)out.size(0),
+                  (int)weight.size(1), (int)weight.size(0), (int)vocab_start, cur_stream());
+  count();
+}
+
+void gather_rows(const at::Tensor& x, const at::Tensor& idx, at::Tensor out) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_I32(idx); CHECK_LAST_CONTIG(x); TORCH_CHECK(out.is_contiguous());
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::gather_rows(x.data_ptr(), idx.data_ptr<int>(), out.data_ptr(), (int)idx.size(0), (int)x.size(1), (int)x.stride(0),
+                    cur_stream());
+  count();
+}
+
+// impl: 0 = tcgen05, 1 = SIMT reference
+void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& v_cache, at::Tensor out,
+              c10::optional<at::Tensor> lse, c10::optional<at::Tensor> part_o, c10::optional<at::Tensor> part_lse,
+              const at::Tensor& page_table, const at::Tensor& req_slots, const at::Tensor& seq_lens,
+              c10::optional<at::Tensor> cu_q, c10::optional<at::Tensor> tok2req, int64_t max_q_len, int64_t page_size,
+              int64_t num_splits, double scale, bool causal, int64_t window, double logit_cap, double k_scale,
+              double v_scale, int64_t impl) {
+  CHECK_CUDA(q); CHECK_BF16(q); CHECK_BF16(out); CHECK_I32(page_table); CHECK_I32(req_slots); CHECK_I32(seq_lens);
+  TORCH_CHECK(q.dim() == 3 && q.stride(2) == 1 && q.stride(1) == q.size(2), "q must be [T, Hq, D] with packed heads");
+  TORCH_CHECK(out.is_contiguous() && k_cache.is_contiguous() && v_cache.is_contiguous());
+  TORCH_CHECK(k_cache.dim() == 3, "k_cache must be [slots, Hkv, D]");
+  const int T = (int)q.size(0), Hq = (int)q.size(1), D = (int)q.size(2), Hkv = (int)k_cache.size(1);
+  const int B = (int)req_slots.size(0);
+  const bool fp8 = k_cache.scalar_type() == at::kFloat8_e4m3fn;
+  c10::cuda::CUDAGuard g(q.device());
+  if (impl == 0) {
+    TORCH_CHECK(!fp8, "tcgen05 attention: fp8 KV cache not yet supported (use impl=1)");
+    if (num_splits > 1) TORCH_CHECK(part_o.has_value() && part_lse.has_value(), "split-KV needs workspaces");
+    sglb::attn_fwd_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),
+                      opt_mptr<float>(part_o), opt_mptr<float>(part_lse), page_table.data_ptr<int>(),
+                      (int)page_table.stride(0), req_slots.data_ptr<int>(), seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), B, T,
+                      (int)q.stride(0), (int)max_q_len, Hq, Hkv, D, (int)k_cache.size(0), (int)page_size, (int)num_splits,
+                      (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, cur_stream());
+    count(num_splits > 1 ? 2 : 1);
+  } else {
+    sglb::attn_fwd_simt(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),
+                        page_table.data_ptr<int>(), (int)page_table.stride(0), req_slots.data_ptr<int>(),
+                        seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), opt_ptr<int>(tok2req), T, (int)q.stride(0), Hq, Hkv, D,
+                        (int)page_size, (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, fp8, (float)k_scale,
+                        (float)v_scale, cur_stream());
+    count();
+  }
+}
+
+// out[M, N(/2 for silu_mul)] = a[M, K] @ w[N, K]^T (+bias | silu*mul)
+void gemm(const at::Tensor& a, const at::Tensor& w, at::Tensor out, c10::optional<at::Tensor> bias, int64_t epilogue,
+          int64_t bn) {
+  CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_BF16(out); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w); CHECK_LAST_CONTIG(out);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && out.dim() == 2 && a.size(1) == w.size(1));
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(out.data_ptr()) & 15) == 0, "gemm operands must be 16-byte aligned");
+  c10::cuda::CUDAGuard g(a.device());
+  sglb::gemm_bf16_tc(a.data_ptr(), w.data_ptr(), out.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr,
+                     (int)a.size(0), (int)w.size(0), (int)a.size(1), (int)a.stride(0), (int)w.stride(0), (int)out.stride(0),
+                     (int)epilogue, (int)bn, num_sms(), cur_stream());
+  count();
+}
+int64_t gemm_pick_bn(int64_t M, int64_t N, int64_t K) { return sglb::gemm_pick_bn((int)M, (int)N, (int)K, num_sms()); }
+
+void sample(const at::Tensor& logits, const at::Tensor& temperature, const at::Tensor& top_k, const at::Tensor& top_p,
+            const at::Tensor& min_p, c10::optional<at::Tensor> seeds, c10::optional<at::Tensor> out_slots,
+            c10::optional<at::Tensor> next_token_buf, at::Tensor out_tokens, c10::optional<at::Tensor> out_logprobs,
+            int64_t global_seed, c10::optional<at::Tensor> step_ptr, int64_t step) {
+  CHECK_CUDA(logits); CHECK_LAST_CONTIG(logits); CHECK_I32(top_k); CHECK_I32(out_tokens);
+  TORCH_CHECK(logits.dim() == 2);
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(bf16 || logits.scalar_type() == at::kFloat, "logits must be bf16 or fp32");
+  c10::cuda::CUDAGuard g(logits.device());
+  sglb::sample(logits.data_ptr(), bf16, (int)logits.size(0), (int)logits.size(1), (int)logits.stride(0),
+               temperature.data_ptr<float>(), top_k.data_ptr<int>(), top_p.data_ptr<float>(), min_p.data_ptr<float>(),
+               seeds.has_value() ? (const long long*)seeds->data_ptr<int64_t>() : nullptr, opt_ptr<int>(out_slots),
+               opt_mptr<int>(next_token_buf), out_tokens.data_ptr<int>(), opt_mptr<float>(out_logprobs),
+               (unsigned long long)global_seed, step_ptr.has_value() ? (const long long*)step_ptr->data_ptr<int64_t>() : nullptr,
+               (long long)step, cur_stream());
+  count();
+}
+
+void apply_token_bitmask(at::Tensor logits, const at::Tensor& bitmask, c10::optional<at::Tensor> row_idx) {
+  CHECK_CUDA(logits); CHECK_I32(bitmask); TORCH_CHECK(bitmask.is_contiguous() && logits.dim() == 2);
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  c10::cuda::CUDAGuard g(logits.device());
+  sglb::apply_token_bitmask(logits.data_ptr(), bf16, bitmask.data_ptr<int>(), opt_ptr<int>(row_idx), (int)bitmask.size(0),
+                            (int)logits.size(1), (int)logits.stride(0), cur_stream());
+  count();
+}
+
+void apply_penalties(at::Tensor logits, const at::Tensor& counts, c10::optional<at::Tensor> prompt_mask, const at::Tensor& freq,
+                     const at::Tensor& pres, const at::Tensor& rep) {
+  CHECK_CUDA(logits); TORCH_CHECK(logits.scalar_type() == at::kFloat && logits.dim() == 2); CHECK_I32(counts);
+  c10::cuda::CUDAGuard g(logits.device());
+  sglb::apply_penalties(logits.data_ptr<float>(), counts.data_ptr<int>(),
+                        prompt_mask.has_value() ? prompt_mask->data_ptr<uint8_t>() : nullptr, freq.data_ptr<float>(),
+                        pres.data_ptr<float>(), rep.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1),
+                        (int)logits.stride(0), cur_stream());
+  count();
+}
+
+void bump_counts(at::Tensor counts, const at::Tensor& tokens) {
+  CHECK_CUDA(counts); CHECK_I32(counts); CHECK_I32(tokens);
+  c10::cuda::CUDAGuard g(counts.device());
+  sglb::bump_counts(counts.data_ptr<int>(), tokens.data_ptr<int>(), (int)tokens.size(0), (int)counts.size(1), cur_stream());
+  count();
+}
+
+}  // namespace
+
+TORCH_LIBRARY(sglb, m) {
+  m.def("launch_count() -> int", &launch_count);
+  m.def("reset_launch_count() -> ()", &reset_launch_count);
+  m.def("gemm_pick_bn(int M, int N, int K) -> int", &gemm_pick_bn);
+  m.def("rmsnorm(Tensor(a!) x, Tensor(b!)? residual, Tensor w, Tensor(c!) out, float eps, bool gemma) -> ()", &rmsnorm);
+  m.def("act_and_mul(Tensor x, Tensor(a!) out, int act) -> ()", &act_and_mul);
+  m.def("rope_kv_write(Tensor(a!) q, Tensor k, Tensor v, Tensor positions, Tensor cos_sin, Tensor(b!) k_cache, "
+        "Tensor(c!) v_cache, Tensor out_loc, bool neox, float k_scale, float v_scale) -> ()", &rope_kv_write);
+  m.def("apply_pt_delta(Tensor(a!) page_table, Tensor rows, Tensor cols, Tensor vals, Tensor? n, int n_max) -> ()", &apply_pt_delta);
+  m.def("embedding(Tensor weight, Tensor ids, Tensor? gather_idx, Tensor(a!) out, int vocab_start) -> ()", &embedding);
+  m.def("gather_rows(Tensor x, Tensor idx, Tensor(a!) out) -> ()", &gather_rows);
+  m.def("attn_fwd(Tensor q, Tensor k_cache, Tensor v_cache, Tensor(a!) out, Tensor(b!)? lse, Tensor(c!)? part_o, "
+        "Tensor(d!)? part_lse, Tensor page_table, Tensor req_slots, Tensor seq_lens, Tensor? cu_q, Tensor? tok2req, "
+        "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
+        "float k_scale, float v_scale, int impl) -> ()", &attn_fwd);
+  m.def("gemm(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int bn) -> ()", &gemm);
+  m.def("sample(Tensor logits, Tensor temperature, Tensor top_k, Tensor top_p, Tensor min_p, Tensor? seeds, "
+        "Tensor? out_slots, Tensor(a!)? next_token_buf, Tensor(b!) out_tokens, Tensor(c!)? out_logprobs, int global_seed, "
+        "Tensor? step_ptr, int step) -> ()", &sample);
+  m.def("apply_token_bitmask(Tensor(a!) logits, Tensor bitmask, Tensor? row_idx) -> ()", &apply_token_bitmask);
+  m.def("apply_penalties(Tensor(a!) logits, Tensor counts, Tensor? prompt_mask, Tensor freq, Tensor pres, Tensor rep) -> ()",
+        &apply_penalties);
+  m.def("bump_counts(Tensor(a!) counts, Tensor tokens) -> ()", &bump_counts);
+}

@@ -1,0 +1,48 @@
+// Host launch API of the sm_100a kernels (raw pointers + stream; no torch dependency so the .cu files
+// compile in seconds).  binding.cpp adapts these to torch.ops.sglb.*
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sglb {
+
+// elementwise.cu
+void rmsnorm(void* x, void* residual, const void* w, void* out, int T, int H, int x_stride, int out_stride, float eps,
+             bool gemma, cudaStream_t stream);
+void act_and_mul(const void* x, void* out, int T, int I, int x_stride, int act, cudaStream_t stream);
+void rope_kv_write(void* q, const void* k, const void* v, const int* positions, const float* cos_sin, void* k_cache,
+                   void* v_cache, const int* out_loc, int T, int Hq, int Hkv, int D, int rot, int q_stride, int k_stride,
+                   int v_stride, bool neox, bool fp8_cache, float k_scale, float v_scale, cudaStream_t stream);
+void apply_pt_delta(int* page_table, int stride, const int* rows, const int* cols, const int* vals, const int* n_ptr,
+                    int n_max, cudaStream_t stream);
+void embedding(const void* weight, const int* ids, const int* gather_idx, void* out, int T, int H, int vocab, int vocab_start,
+               cudaStream_t stream);
+void gather_rows(const void* x, const int* idx, void* out, int n, int H, int x_stride, cudaStream_t stream);
+void attn_fwd_simt(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, const int* page_table,
+                   int pt_stride, const int* req_slots, const int* seq_lens, const int* cu_q, const int* tok2req, int T,
+                   int q_stride, int Hq, int Hkv, int D, int page_size, float scale, int causal, int window, float logit_cap,
+                   bool fp8_cache, float k_scale, float v_scale, cudaStream_t stream);
+
+// attention_tc.cu
+void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o,
+                 float* part_lse, const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens,
+                 const int* cu_q, int B, int T, int q_stride, int max_q_len, int Hq, int Hkv, int D, int num_slots,
+                 int page_size, int num_splits, float scale, int causal, int window, float logit_cap, cudaStream_t stream);
+
+// gemm_tc.cu
+void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc,
+                  int epilogue, int bn, int num_sms, cudaStream_t stream);
+int gemm_pick_bn(int M, int N, int K, int num_sms);
+
+// sampling.cu
+void sample(const void* logits, bool bf16, int B, int V, int stride, const float* temperature, const int* top_k,
+            const float* top_p, const float* min_p, const long long* seeds, const int* out_slots, int* next_token_buf,
+            int* out_tokens, float* out_logprobs, unsigned long long global_seed, const long long* step_ptr, long long step,
+            cudaStream_t stream);
+void apply_token_bitmask(void* logits, bool bf16, const int* bitmask, const int* row_idx, int n_rows, int V, int stride,
+                         cudaStream_t stream);
+void apply_penalties(float* logits, const int* counts, const unsigned char* prompt_mask, const float* freq, const float* pres,
+                     const float* rep, int B, int V, int stride, cudaStream_t stream);
+void bump_counts(int* counts, const int* tokens, int B, int V, cudaStream_t stream);
+
+}  // namespace sglb

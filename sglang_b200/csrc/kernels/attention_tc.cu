@@ -1,0 +1,401 @@
+// Paged RadixAttention forward for sm_100a: ONE tcgen05/TMEM kernel family for ragged prefill (extend)
+// and decode, reading K/V only through the page table with TMA page gathers.
+//
+//   grid  = (q tiles, kv_heads * kv_splits, requests)        block = 192 threads
+//   warp 0    : TMA producer — Q tile once, then K/V tiles page by page (page table -> TMA coords)
+//   warp 1    : MMA issuer   — S = Q K^T (SS, K-major) into TMEM, O += P V (TS: P from TMEM, V MN-major)
+//   warps 2-5 : softmax      — tcgen05.ld S, online softmax with lazy O rescale, P (bf16) back to TMEM,
+//                              final normalise + store (or fp32 partial + LSE for split-KV)
+//   Q rows pack GQA: row r of the 128-row tile = (token r / G, head r % G) so one KV tile serves all
+//   G query heads of its KV head (decode: G valid rows, only one softmax warp does work).
+//
+// Stands in for the reference's trtllm-gen / FA4 attention (python/sglang/srt/layers/attention/
+// trtllm_mha_backend.py:1113,1470; kernels/ops/attention/flash_attn/cute/flash_fwd_sm100.py) and the Triton
+// extend/decode kernels (kernels/ops/attention/extend_attention.py:305, decode_attention.py:472).
+#include <math.h>
+
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace sglb {
+
+constexpr int ATT_D = 128;          // head dim
+constexpr int ATT_KT = 128;         // kv tile
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 32 KB (Q, K or V tile)
+constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
+constexpr int ATT_SMEM = 5 * ATT_TILE_BYTES + 1024 + 256;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units; lazy rescale (FA4-style)
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  float* part_o;      // [splits, T, Hq, D]
+  float* part_lse;    // [splits, T, Hq]
+  float* lse;         // optional [T, Hq]
+  const int* page_table;
+  const int* req_slots;
+  const int* seq_lens;
+  const int* cu_q;    // nullptr => decode (one query token per request)
+  int pt_stride, Hq, Hkv, G, page_size, num_splits, T;
+  float scale_log2, logit_cap;
+  int causal, window;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const int b = blockIdx.z;
+  const int kvh = blockIdx.y / p.num_splits;
+  const int split = blockIdx.y % p.num_splits;
+  const int G = p.G;
+  const int TQ = 128 / G;
+  const int q_start = p.cu_q ? p.cu_q[b] : b;
+  const int q_len = p.cu_q ? (p.cu_q[b + 1] - q_start) : 1;
+  const int seq_len = p.seq_lens[b];
+  const int prefix = seq_len - q_len;
+  const int t0 = blockIdx.x * TQ;
+  if (t0 >= q_len) return;
+  const int t_hi = min(t0 + TQ, q_len);                       // tokens [t0, t_hi) of this request
+  const int kv_hi = p.causal ? min(seq_len, prefix + t_hi) : seq_len;
+  int kv_lo = 0;
+  if (p.window > 0) kv_lo = max(0, prefix + t0 - p.window + 1);
+  const int tile_lo_all = kv_lo / ATT_KT;
+  const int tile_hi_all = (kv_hi + ATT_KT - 1) / ATT_KT;
+  const int per_split = (tile_hi_all - tile_lo_all + p.num_splits - 1) / p.num_splits;
+  const int tile_begin = tile_lo_all + split * per_split;
+  const int tile_end = min(tile_hi_all, tile_begin + per_split);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (tile_begin >= tile_end) {
+    // empty split: publish a neutral partial so the merge kernel can ignore it
+    if (p.num_splits > 1 && warp >= 2) {
+      const int r = ((warp & 3) << 5) + lane;
+      const int tok = t0 + r / G;
+      if (tok < q_len) {
+        const size_t row = ((size_t)split * p.T + q_start + tok) * p.Hq + kvh * G + (r % G);
+        p.part_lse[row] = -INFINITY;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* dst = reinterpret_cast<float4*>(p.part_o + row * ATT_D);
+        for (int i = 0; i < ATT_D / 4; ++i) dst[i] = z;
+      }
+    }
+    return;
+  }
+  const int n_tiles = tile_end - tile_begin;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;       // 2 stages
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;   // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* o_done = bars + 13;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
+    }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S0 = tmem_base;          // S buffers: cols [0,128) and [128,256); P aliases cols [0,64) of each
+  const uint32_t tmem_O = tmem_base + 256;     // O: cols [256,384)
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ producer
+    mbar_expect_tx(q_full, ATT_TILE_BYTES);
+    tma_load_4d(sQ, &tmQ, q_full, 0, 0, kvh, q_start + t0);
+    tma_load_4d(sQ + ATT_HALF_BYTES, &tmQ, q_full, 64, 0, kvh, q_start + t0);
+    const int ps = p.page_size;
+    const int pages_per_tile = ATT_KT / ps;
+    const int* pt = p.page_table + (size_t)p.req_slots[b] * p.pt_stride;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int pg0 = (tile_begin + j) * pages_per_tile;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+      for (int i = 0; i < pages_per_tile; ++i) {
+        const int page = pt[min(pg0 + i, p.pt_stride - 1)];
+        uint8_t* dst = sK + st * ATT_TILE_BYTES + i * ps * 128;
+        tma_load_3d(dst, &tmK, &k_full[st], 0, kvh, page * ps);
+        tma_load_3d(dst + ATT_HALF_BYTES, &tmK, &k_full[st], 64, kvh, page * ps);
+      }
+      mbar_wait(&v_empty[st], ph ^ 1);
+      mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+      for (int i = 0; i < pages_per_tile; ++i) {
+        const int page = pt[min(pg0 + i, p.pt_stride - 1)];
+        uint8_t* dst = sV + st * ATT_TILE_BYTES + i * ps * 128;
+        tma_load_3d(dst, &tmV, &v_full[st], 0, kvh, page * ps);
+        tma_load_3d(dst + ATT_HALF_BYTES, &tmV, &v_full[st], 64, kvh, page * ps);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, 128, ATT_KT, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc(UMMA_BF16, UMMA_BF16, 128, ATT_D, 0, 1);   // B (V) is MN-major
+    const uint32_t q_addr = smem_u32(sQ);
+    auto issue_S = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k) {
+        const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
+        umma_f16_ss(tmem_S0 + st * 128, make_smem_desc_sw128(q_addr + off, 0, 1024),
+                    make_smem_desc_sw128(k_addr + off, 0, 1024), idesc_s, k != 0);
+      }
+      umma_commit(&k_empty[st]);
+      umma_commit(&s_full[st]);
+    };
+    mbar_wait(q_full, 0);
+    issue_S(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      if (j + 1 < n_tiles) issue_S(j + 1);
+      mbar_wait(&p_full[st], ph);
+      mbar_wait(&v_full[st], ph);
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < ATT_KT / 16; ++k) {
+        // A = P (bf16 pairs in TMEM: 16 K-elements = 8 columns), B = V rows [16k, 16k+16) (MN-major)
+        umma_f16_ts(tmem_O, tmem_S0 + st * 128 + k * 8, make_smem_desc_sw128(v_addr + k * 2048, ATT_HALF_BYTES, 1024),
+                    idesc_o, (j | k) != 0);
+      }
+      umma_commit(&v_empty[st]);
+      umma_commit(o_done);
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ softmax + epilogue
+    const int q = warp & 3;                       // TMEM lane quadrant
+    const int r = (q << 5) + lane;                // row in the 128-row tile
+    const int tok = t0 + r / G;                   // token index inside this request's queries
+    const bool row_valid = tok < q_len;
+    const bool warp_valid = (t0 + (q << 5) / G) < q_len;
+    const int q_pos = prefix + tok;               // absolute position of this query token
+    const uint32_t lane_addr = (uint32_t)(q << 5) << 16;
+    float m_i = -INFINITY, l_i = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      if (warp_valid) {
+        const uint32_t s_addr = tmem_S0 + lane_addr + st * 128;
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr[c]);
+        tmem_ld_wait();
+        const int kv0 = (tile_begin + j) * ATT_KT;
+        const bool need_mask = (kv0 + ATT_KT > kv_hi) || (p.causal && kv0 + ATT_KT - 1 > prefix + t0) ||
+                               (p.window > 0 && kv0 < prefix + t_hi - p.window);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = __uint_as_float(sr[c][i]) * p.scale_log2;
+            if (p.logit_cap > 0.f) {
+              // s is in log2 units: cap * tanh(x / cap) with x = s * ln2
+              const float x = s * 0.6931471805599453f;
+              s = p.logit_cap * tanhf(x / p.logit_cap) * 1.4426950408889634f;
+            }
+            if (need_mask) {
+              const int kv = kv0 + c * 32 + i;
+              bool ok = kv < seq_len;
+              if (p.causal) ok = ok && (kv <= q_pos);
+              if (p.window > 0) ok = ok && (kv > q_pos - p.window);
+              if (!ok) s = -INFINITY;
+            }
+            sr[c][i] = __float_as_uint(s);
+            mx = fmaxf(mx, s);
+          }
+        }
+        const float m_new = fmaxf(m_i, mx);
+        const bool first = (j == 0);
+        const bool need = (!first) && (m_new > m_i + ATT_RESCALE_THRESHOLD);
+        float m_use = m_i;
+        if (first) {
+          m_use = m_new;
+        } else if (__any_sync(0xffffffffu, need)) {
+          // lazy rescale of the O row in TMEM (warp-collective): wait for PV(j-1), scale, write back
+          const float f = (m_new == -INFINITY) ? 1.f : exp2f(m_i - m_new);
+          mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t orow[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * f);
+            tmem_st_32x32b_x32(tmem_O + lane_addr + c * 32, orow);
+          }
+          tmem_st_wait();
+          l_i *= f;
+          m_use = m_new;
+        }
+        m_i = m_use;
+        const float m_sub = (m_i == -INFINITY) ? 0.f : m_i;
+        float psum = 0.f;
+        const uint32_t p_addr = tmem_S0 + lane_addr + st * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = exp2f(__uint_as_float(sr[c][i]) - m_sub);
+            const float p1 = exp2f(__uint_as_float(sr[c][i + 1]) - m_sub);
+            psum += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x32b_x16(p_addr + c * 16, pk);
+        }
+        l_i += psum;
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[st]);
+    }
+
+    // ---- epilogue: wait for the last PV, normalise, store
+    mbar_wait(o_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    if (warp_valid) {
+      const float inv_l = (l_i > 0.f) ? 1.f / l_i : 0.f;
+      const float lse = (l_i > 0.f) ? (m_i + log2f(l_i)) * 0.6931471805599453f : -INFINITY;
+      const int g = r % G;
+      const size_t out_row = ((size_t)(q_start + tok)) * p.Hq + kvh * G + g;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t orow[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, orow);
+        tmem_ld_wait();
+        if (row_valid) {
+          if (p.num_splits == 1) {
+            __nv_bfloat16* dst = p.out + out_row * ATT_D + c * 32;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              U4 o;
+              o.x = pack_bf16(__uint_as_float(orow[v * 8 + 0]) * inv_l, __uint_as_float(orow[v * 8 + 1]) * inv_l);
+              o.y = pack_bf16(__uint_as_float(orow[v * 8 + 2]) * inv_l, __uint_as_float(orow[v * 8 + 3]) * inv_l);
+              o.z = pack_bf16(__uint_as_float(orow[v * 8 + 4]) * inv_l, __uint_as_float(orow[v * 8 + 5]) * inv_l);
+              o.w = pack_bf16(__uint_as_float(orow[v * 8 + 6]) * inv_l, __uint_as_float(orow[v * 8 + 7]) * inv_l);
+              st128(dst + v * 8, o);
+            }
+          } else {
+            float* dst = p.part_o + (((size_t)split * p.T + q_start + tok) * p.Hq + kvh * G + g) * ATT_D + c * 32;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 o = make_float4(__uint_as_float(orow[v * 4 + 0]) * inv_l, __uint_as_float(orow[v * 4 + 1]) * inv_l,
+                                     __uint_as_float(orow[v * 4 + 2]) * inv_l, __uint_as_float(orow[v * 4 + 3]) * inv_l);
+              *reinterpret_cast<float4*>(dst + v * 4) = o;
+            }
+          }
+        }
+      }
+      if (row_valid) {
+        if (p.num_splits == 1) {
+          if (p.lse) p.lse[out_row] = lse;
+        } else {
+          p.part_lse[((size_t)split * p.T + q_start + tok) * p.Hq + kvh * G + g] = lse;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// merge split-KV partials: one warp per (token, head) row
+__global__ void attn_merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int rows,
+                                         int num_splits) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float m = -INFINITY;
+  for (int s = 0; s < num_splits; ++s) m = fmaxf(m, part_lse[(size_t)s * rows + row]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f;
+  for (int s = 0; s < num_splits; ++s) {
+    const float l = part_lse[(size_t)s * rows + row];
+    const float w = (l == -INFINITY) ? 0.f : __expf(l - m);
+    wsum += w;
+    const float4 v = *reinterpret_cast<const float4*>(part_o + ((size_t)s * rows + row) * ATT_D + lane * 4);
+    acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
+  }
+  const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+  uint2 o;
+  o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+  o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<uint2*>(out + (size_t)row * ATT_D + lane * 4) = o;
+  if (lse_out && lane == 0) lse_out[row] = wsum > 0.f ? m + __logf(wsum) : -INFINITY;
+}
+
+void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o,
+                 float* part_lse, const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens,
+                 const int* cu_q, int B, int T, int q_stride, int max_q_len, int Hq, int Hkv, int D, int num_slots, int page_size,
+                 int num_splits, float scale, int causal, int window, float logit_cap, cudaStream_t stream) {
+  if (D != ATT_D) throw std::runtime_error("sglb attn_tc: head_dim must be 128");
+  const int G = Hq / Hkv;
+  if (G < 1 || G > 128 || (128 % G) != 0) throw std::runtime_error("sglb attn_tc: GQA group must divide 128");
+  if (page_size < 8 || page_size > 128 || (page_size & (page_size - 1))) throw std::runtime_error("sglb attn_tc: page_size must be 8..128 (pow2)");
+  const int TQ = 128 / G;
+  // Q viewed as [T][Hkv][G][D]
+  uint64_t dq[4] = {(uint64_t)D, (uint64_t)G, (uint64_t)Hkv, (uint64_t)T};
+  uint64_t sq[3] = {(uint64_t)D * 2, (uint64_t)G * D * 2, (uint64_t)q_stride * 2};
+  uint32_t bq[4] = {64, (uint32_t)G, 1, (uint32_t)TQ};
+  CUtensorMap tmQ = make_tmap(q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t dk[3] = {(uint64_t)D, (uint64_t)Hkv, (uint64_t)num_slots};
+  uint64_t sk[2] = {(uint64_t)D * 2, (uint64_t)Hkv * D * 2};
+  uint32_t bk[3] = {64, 1, (uint32_t)page_size};
+  CUtensorMap tmK = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
+  AttnParams p;
+  p.out = (__nv_bfloat16*)out; p.part_o = part_o; p.part_lse = part_lse; p.lse = lse;
+  p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens; p.cu_q = cu_q;
+  p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.T = T;
+  p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.causal = causal; p.window = window;
+  static bool configured = false;
+  if (!configured) {
+    SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  dim3 grid((max_q_len + TQ - 1) / TQ, Hkv * num_splits, B);
+  attn_fwd_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+  if (num_splits > 1) {
+    const int rows = T * Hq;
+    attn_merge_splits_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(part_o, part_lse, (__nv_bfloat16*)out, lse, rows, num_splits);
+    SGLB_CUDA_CHECK(cudaGetLastError());
+  }
+}
+
+}  // namespace sglb

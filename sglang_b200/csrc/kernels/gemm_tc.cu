@@ -1,0 +1,237 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:   C[M,N] = A[M,K] * W[N,K]^T  (+ epilogue)
+//
+//   warp 0      : TMA producer  (A and W tiles, 128-B swizzle, multi-stage mbarrier ring)
+//   warp 1      : MMA issuer    (one thread; tcgen05.mma cta_group::1 kind::f16, fp32 accum in TMEM)
+//   warp 2      : TMEM allocator (2 accumulator buffers so tile i's epilogue overlaps tile i+1's mainloop)
+//   warps 4..7  : epilogue      (tcgen05.ld -> bias / SiLU*mul -> bf16 -> 128-bit global stores)
+//
+// Stands in for the reference's cuBLASLt / CuTe-DSL bf16 GEMM (python/sglang/srt/layers/quantization/
+// unquant.py:72-169, kernels/ops/gemm/cutedsl_bf16_gemm.py) and its separate silu_and_mul kernel
+// (kernels/aot/csrc/elementwise/activation.cu:98) when EPI_SILU_MUL is fused.
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace sglb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+enum GemmEpilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_SILU_MUL = 2 };
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool A_FP8>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int ldc) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+        tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, GEMM_BM, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES), 0, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // +32 B per K=16 step inside the 128-B swizzled row (start-address field is in 16-B units)
+          umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (EPI == EPI_SILU_MUL) {
+          // columns [0,16) = gate, [16,32) = up of the same 16 intermediate features
+          if (row < M && col0 < N) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float g0 = __uint_as_float(r[2 * i]), g1 = __uint_as_float(r[2 * i + 1]);
+              float u0 = __uint_as_float(r[16 + 2 * i]), u1 = __uint_as_float(r[16 + 2 * i + 1]);
+              float a0 = g0 / (1.f + __expf(-g0)) * u0;
+              float a1 = g1 / (1.f + __expf(-g1)) * u1;
+              o[i] = pack_bf16(a0, a1);
+            }
+            __nv_bfloat16* dst = C + (size_t)row * ldc + (col0 >> 1);
+            st128(dst, U4{o[0], o[1], o[2], o[3]});
+            st128(dst + 8, U4{o[4], o[5], o[6], o[7]});
+          }
+        } else {
+          if (row < M) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int col = col0 + v * 8;
+              if (col < N) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]);
+                if (EPI == EPI_BIAS) {
+                  U4 b = ldg128(bias + col);
+                  f[0] += bf16_lo(b.x); f[1] += bf16_hi(b.x); f[2] += bf16_lo(b.y); f[3] += bf16_hi(b.y);
+                  f[4] += bf16_lo(b.z); f[5] += bf16_hi(b.z); f[6] += bf16_lo(b.w); f[7] += bf16_hi(b.w);
+                }
+                st128(C + (size_t)row * ldc + col,
+                      U4{pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])});
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int EPI>
+static void launch_gemm(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw,
+                        int ldc, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sAs[1] = {(uint64_t)lda * 2};
+  uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sBs[1] = {(uint64_t)ldw * 2};
+  uint32_t bA[2] = {GEMM_BK, GEMM_BM}, bB[2] = {GEMM_BK, (uint32_t)BN};
+  CUtensorMap tmA = make_tmap(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, sAs, bA, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmB = make_tmap(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, sBs, bB, CU_TENSOR_MAP_SWIZZLE_128B);
+  auto kern = gemm_tc_kernel<BN, EPI, false>;
+  static bool configured = false;
+  if (!configured) {
+    SGLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
+  const int grid = min(m_tiles * n_tiles, num_sms);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, (__nv_bfloat16*)C, (const __nv_bfloat16*)bias, M, N, K, ldc);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+}
+
+template <int EPI>
+static void dispatch_bn(int bn, const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda,
+                        int ldw, int ldc, int num_sms, cudaStream_t stream) {
+  switch (bn) {
+    case 32: launch_gemm<32, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case 64: launch_gemm<64, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case 128: launch_gemm<128, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case 256: launch_gemm<256, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    default: throw std::runtime_error("sglb gemm: unsupported BN");
+  }
+}
+
+// Heuristic tile-N: enough CTAs to keep HBM busy when weight-bandwidth bound (small M), wide tiles when
+// compute bound (large M).  `bn <= 0` selects automatically.
+int gemm_pick_bn(int M, int N, int K, int num_sms) {
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  if (m_tiles >= 8) return (N % 256 == 0) ? 256 : 128;
+  int best = 128;
+  for (int bn : {256, 128, 64, 32}) {
+    if (N % bn) continue;
+    best = bn;
+    if (m_tiles * (N / bn) >= num_sms) break;
+  }
+  return best;
+}
+
+void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw,
+                  int ldc, int epilogue, int bn, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return;
+  if (K % 8 || N % 8 || lda % 8 || ldw % 8) throw std::runtime_error("sglb gemm: K, N, lda, ldw must be multiples of 8");
+  if (bn <= 0) bn = gemm_pick_bn(M, N, K, num_sms);
+  switch (epilogue) {
+    case EPI_NONE: dispatch_bn<EPI_NONE>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case EPI_BIAS: dispatch_bn<EPI_BIAS>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case EPI_SILU_MUL: dispatch_bn<EPI_SILU_MUL>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    default: throw std::runtime_error("sglb gemm: bad epilogue");
+  }
+}
+
+}  // namespace sglb

@@ -1,0 +1,123 @@
+// pybind11 module `sglb_rt`: host-side C++ runtime (radix tree, page allocator, n-gram corpus, page hashing).
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <stdexcept>
+
+#include "ngram_corpus.h"
+#include "radix_tree.h"
+
+namespace py = pybind11;
+using namespace sglb_rt;
+using i32arr = py::array_t<int32_t, py::array::c_style | py::array::forcecast>;
+
+static py::array_t<int32_t> to_np(const std::vector<int32_t>& v) {
+  py::array_t<int32_t> a((py::ssize_t)v.size());
+  if (!v.empty()) std::memcpy(a.mutable_data(), v.data(), v.size() * sizeof(int32_t));
+  return a;
+}
+
+// ---------------------------------------------------------------- LIFO page allocator (page 0 reserved)
+class PageAllocator {
+ public:
+  explicit PageAllocator(int64_t num_pages) : n_(num_pages) { clear(); }
+  void clear() {
+    free_.clear();
+    free_.reserve(n_);
+    for (int64_t p = n_ - 1; p >= 1; --p) free_.push_back((int32_t)p);
+    is_free_.assign(n_, 1);
+    is_free_[0] = 0;
+  }
+  int64_t available() const { return (int64_t)free_.size(); }
+  py::object alloc(int64_t n) {
+    if (n > (int64_t)free_.size()) return py::none();
+    py::array_t<int32_t> out((py::ssize_t)n);
+    int32_t* o = out.mutable_data();
+    for (int64_t i = 0; i < n; ++i) {
+      o[i] = free_.back();
+      free_.pop_back();
+      is_free_[o[i]] = 0;
+    }
+    return std::move(out);
+  }
+  void free_pages(i32arr pages) {
+    const int32_t* p = pages.data();
+    for (py::ssize_t i = 0; i < pages.size(); ++i) {
+      if (p[i] <= 0 || p[i] >= n_ || is_free_[p[i]]) throw std::runtime_error("double free / invalid free of KV page " + std::to_string(p[i]));
+      is_free_[p[i]] = 1;
+      free_.push_back(p[i]);
+    }
+  }
+  bool is_free(int64_t p) const { return is_free_[p] != 0; }
+
+ private:
+  int64_t n_;
+  std::vector<int32_t> free_;
+  std::vector<uint8_t> is_free_;
+};
+
+// 64-bit FNV-1a chained page hash (parent hash folded in) — keys for KV events / L3 storage
+// (reference: mem_cache/cpp_utils/hash_binding.cpp)
+static std::vector<uint64_t> hash_pages(i32arr tokens, int page_size, uint64_t seed) {
+  const int32_t* t = tokens.data();
+  const int64_t n = tokens.size() / page_size;
+  std::vector<uint64_t> out((size_t)n);
+  uint64_t prev = seed;
+  for (int64_t p = 0; p < n; ++p) {
+    uint64_t h = 1469598103934665603ull ^ prev;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(t + p * page_size);
+    for (size_t i = 0; i < sizeof(int32_t) * (size_t)page_size; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    out[(size_t)p] = h;
+    prev = h;
+  }
+  return out;
+}
+
+PYBIND11_MODULE(sglb_rt, m) {
+  m.doc() = "sglang_b200 host runtime (C++)";
+  py::class_<RadixTree>(m, "RadixTree")
+      .def(py::init<int, int>(), py::arg("page_size"), py::arg("policy") = 0)
+      .def("reset", &RadixTree::reset)
+      .def("match_prefix", [](RadixTree& t, i32arr tokens, int64_t extra_key) {
+        int32_t last = -1;
+        auto pages = t.match_prefix(tokens.data(), tokens.size(), extra_key, &last);
+        return py::make_tuple(to_np(pages), last);
+      })
+      .def("insert", [](RadixTree& t, i32arr tokens, i32arr pages, int64_t extra_key, int32_t priority) {
+        return t.insert(tokens.data(), tokens.size(), pages.data(), pages.size(), extra_key, priority);
+      })
+      .def("inc_lock_ref", &RadixTree::inc_lock_ref)
+      .def("dec_lock_ref", &RadixTree::dec_lock_ref)
+      .def("lock_cost", &RadixTree::lock_cost)
+      .def("evict", [](RadixTree& t, int64_t n) { return to_np(t.evict(n)); })
+      .def("evictable_pages", &RadixTree::evictable_pages)
+      .def("protected_pages", &RadixTree::protected_pages)
+      .def("all_pages", [](RadixTree& t) { return to_np(t.all_pages()); })
+      .def("num_nodes", &RadixTree::num_nodes);
+
+  py::class_<PageAllocator>(m, "PageAllocator")
+      .def(py::init<int64_t>())
+      .def("clear", &PageAllocator::clear)
+      .def("available", &PageAllocator::available)
+      .def("alloc", &PageAllocator::alloc)
+      .def("free", &PageAllocator::free_pages)
+      .def("is_free", &PageAllocator::is_free);
+
+  py::class_<NgramCorpus>(m, "NgramCorpus")
+      .def(py::init<int, int64_t>(), py::arg("max_depth") = 8, py::arg("max_nodes") = 1 << 22)
+      .def("reset", &NgramCorpus::reset)
+      .def("insert", [](NgramCorpus& c, i32arr toks) { py::gil_scoped_release r; c.insert(toks.data(), toks.size()); })
+      .def("match_chain", [](NgramCorpus& c, i32arr ctx, int max_draft, int min_match) {
+        return to_np(c.match_chain(ctx.data(), ctx.size(), max_draft, min_match));
+      }, py::arg("context"), py::arg("max_draft"), py::arg("min_match") = 1)
+      .def("match_tree", [](NgramCorpus& c, i32arr ctx, int max_nodes, int branch, int min_match) {
+        std::vector<int32_t> toks, parents;
+        c.match_tree(ctx.data(), ctx.size(), max_nodes, branch, min_match, &toks, &parents);
+        return py::make_tuple(to_np(toks), to_np(parents));
+      }, py::arg("context"), py::arg("max_nodes"), py::arg("branch") = 2, py::arg("min_match") = 1)
+      .def("num_nodes", &NgramCorpus::num_nodes);
+
+  m.def("hash_pages", &hash_pages, py::arg("tokens"), py::arg("page_size"), py::arg("seed") = 0);
+}

@@ -1,0 +1,485 @@
+"""Engine: the in-process (offline) API and the core that the HTTP server wraps.
+
+Parity: reference ``python/sglang/srt/entrypoints/engine.py:207`` (``generate:360``, ``async_generate``, ``encode``,
+``flush_cache``, sessions, profiling, weight-update family ``:1396-1509``, LoRA load/unload, memory release/resume,
+``shutdown:1258``) and the front half of ``managers/tokenizer_manager.py:386`` (tokenise, request state,
+``_handle_batch_output:2166`` -> meta_info).
+
+Topology (B200-first): ONE process per GPU.  The front half (tokeniser, detokeniser, request states) and the
+scheduler share that process; two drive modes exist:
+* synchronous: ``generate`` steps the scheduler itself until its requests finish — zero IPC, deterministic, and the
+  only mode in which every TP rank can run SPMD under ``torchrun`` (all ranks make identical scheduling decisions);
+* background: ``start_background_loop`` runs the scheduler on a thread fed by a thread-safe inbox; used by the HTTP
+  server and ``async_generate``.  With TP>1, rank 0 broadcasts each iteration's new requests over the Gloo group
+  (reference ``request_receiver.py:153-216``).
+"""
+from __future__ import annotations
+
+import asyncio
+import dataclasses
+import logging
+import queue
+import threading
+import time
+import uuid
+from typing import Any, AsyncIterator, Dict, Iterator, List, Optional, Union
+
+import torch
+
+from ..configs.model_config import load_model_config
+from ..managers import io_struct as ios
+from ..managers.detokenizer import Detokenizer
+from ..managers.scheduler import Scheduler
+from ..model_executor.model_runner import ModelRunner
+from ..parallel import parallel_state as ps
+from ..sampling.sampling_params import SamplingParams
+from ..server_args import ServerArgs
+from ..utils.tokenizer import get_tokenizer
+
+logger = logging.getLogger(__name__)
+
+
+class ReqState:
+    __slots__ = ("rid", "text", "output_ids", "finished", "meta", "out_q", "created", "first_token_time", "obj", "logprobs",
+                 "input_logprobs", "top_logprobs", "embedding", "hidden_states", "last_emit")
+
+    def __init__(self, rid: str, obj: Any, stream_q: Optional[Any]):
+        self.rid, self.obj, self.out_q = rid, obj, stream_q
+        self.text = ""
+        self.output_ids: List[int] = []
+        self.finished = False
+        self.meta: Dict[str, Any] = {}
+        self.created = time.perf_counter()
+        self.first_token_time: Optional[float] = None
+        self.logprobs: List[Any] = []
+        self.input_logprobs: Any = None
+        self.top_logprobs: List[Any] = []
+        self.embedding = None
+        self.hidden_states = None
+        self.last_emit = 0
+
+    def result(self) -> Dict[str, Any]:
+        out = {"text": self.text, "output_ids": list(self.output_ids), "meta_info": dict(self.meta)}
+        if self.embedding is not None:
+            out = {"embedding": self.embedding, "meta_info": dict(self.meta)}
+        return out
+
+
+class Engine:
+    def __init__(self, server_args: Optional[ServerArgs] = None, **kwargs: Any):
+        self.server_args = server_args or ServerArgs(**kwargs)
+        a = self.server_args
+        logging.basicConfig(level=getattr(logging, a.log_level.upper(), logging.INFO),
+                            format="[%(asctime)s %(name)s] %(message)s")
+        world = a.tp_size * a.pp_size
+        if world > 1:
+            ps.init_distributed(a.tp_size, a.pp_size, a.ep_size, device=a.device, enable_nvl=a.comm_backend != "nccl")
+        else:
+            if a.device == "cuda":
+                torch.cuda.set_device(a.base_gpu_id)
+            ps.set_state(None)
+            ps.get_state()
+        st = ps.get_state()
+        self.tp_rank, self.pp_rank = st.tp.rank, st.pp.rank
+        self.is_driver = st.rank == 0
+        self.model_config = load_model_config(a.model_path, None, a.context_length)
+        self.runner = ModelRunner(a, self.model_config)
+        self.tokenizer = None if a.skip_tokenizer_init else get_tokenizer(
+            a.tokenizer_path, self.model_config.vocab_size, self.model_config.eos_token_id, self.model_config.bos_token_id,
+            a.trust_remote_code)
+        self.detok = Detokenizer(self.tokenizer) if self.tokenizer is not None else None
+        emits_output = st.tp.rank == 0 and st.pp.is_last if st.pp.world_size > 1 else st.tp.rank == 0
+        self.scheduler = Scheduler(a, self.runner, self.tokenizer, self._on_scheduler_output, 0 if emits_output else 1)
+        self._install_optional_components()
+        self.states: Dict[str, ReqState] = {}
+        self._lock = threading.RLock()
+        self._inbox: "queue.Queue[Any]" = queue.Queue()
+        self._bg_thread: Optional[threading.Thread] = None
+        self._bg_stop = threading.Event()
+        self._wake = threading.Event()
+        self.metrics = None
+        if a.enable_metrics:
+            from ..observability.metrics import MetricsCollector
+
+            self.metrics = MetricsCollector(a.served_model_name)
+            self.scheduler.metrics = self.metrics
+        self.weight_version = "default"
+        self.start_time = time.time()
+
+    def _install_optional_components(self) -> None:
+        a = self.server_args
+        if a.grammar_backend != "none" and self.tokenizer is not None:
+            try:
+                from ..constrained.grammar_manager import GrammarManager
+
+                self.scheduler.grammar_manager = GrammarManager(self.tokenizer, self.model_config.vocab_size, a.grammar_backend)
+            except Exception as e:  # grammar backends are optional at import time
+                logger.warning("grammar backend unavailable: %s", e)
+        if a.speculative_algorithm:
+            from ..speculative.spec_worker import create_spec_worker
+
+            self.scheduler.spec_worker = create_spec_worker(a, self.runner, self.scheduler)
+        if a.enable_lora:
+            from ..lora.lora_manager import LoRAManager
+
+            self.runner.lora_manager = LoRAManager(self.runner, a.max_loras_per_batch, a.max_lora_rank)
+            for p in a.lora_paths or []:
+                name, _, path = p.partition("=")
+                self.runner.lora_manager.load_adapter(name, path or name)
+        if a.enable_hierarchical_cache:
+            from ..mem_cache.hicache import attach_hicache
+
+            attach_hicache(self.scheduler, self.runner, a)
+
+    # ================================================================== request construction
+    def _tokenize(self, g: ios.GenerateReqInput) -> ios.TokenizedGenerateReqInput:
+        sp = dict(g.sampling_params or {})
+        if g.input_ids is not None:
+            ids, text = list(g.input_ids), g.text
+        else:
+            if self.tokenizer is None:
+                raise ValueError("text input requires a tokenizer (skip_tokenizer_init is set)")
+            text = g.text
+            ids = self.tokenizer.encode(text)
+            bos = getattr(self.tokenizer, "bos_token_id", None)
+            if isinstance(self.tokenizer, object) and type(self.tokenizer).__name__ == "ByteTokenizer" and bos is not None:
+                ids = [bos] + ids
+        mm = None
+        if g.image_data is not None and self.model_config.is_multimodal:
+            from ..multimodal.processor import process_images
+
+            ids, mm = process_images(ids, g.image_data, self.model_config, self.tokenizer)
+        SamplingParams.from_dict(sp).verify(self.model_config.vocab_size)
+        return ios.TokenizedGenerateReqInput(
+            rid=g.rid or uuid.uuid4().hex, input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),
+            logprob_start_len=int(g.logprob_start_len), top_logprobs_num=int(g.top_logprobs_num), stream=bool(g.stream),
+            return_hidden_states=g.return_hidden_states, lora_id=g.lora_path, session_params=g.session_params, mm_inputs=mm,
+            custom_logit_processor=g.custom_logit_processor, bootstrap_host=g.bootstrap_host, bootstrap_port=g.bootstrap_port,
+            bootstrap_room=g.bootstrap_room, priority=g.priority, extra_key=g.extra_key, created_time=time.perf_counter())
+
+    def _submit(self, g: ios.GenerateReqInput, stream_q: Optional[Any] = None, is_embedding: bool = False) -> ReqState:
+        t = self._tokenize(g)
+        t.is_embedding = is_embedding
+        stt = ReqState(t.rid, g, stream_q)
+        stt.meta = {"id": t.rid, "prompt_tokens": len(t.input_ids), "completion_tokens": 0, "cached_tokens": 0,
+                    "finish_reason": None, "weight_version": self.weight_version}
+        with self._lock:
+            self.states[t.rid] = stt
+        if self._bg_thread is not None:
+            self._inbox.put(t)
+            self._wake.set()
+        else:
+            self.scheduler.handle_request(t)
+        return stt
+
+    # ================================================================== output path
+    def _on_scheduler_output(self, msg: ios.BatchTokenIDOutput) -> None:
+        out = self.detok.process(msg) if self.detok is not None else ios.BatchStrOutput(
+            rids=msg.rids, finished_reasons=msg.finished_reasons, output_strs=[""] * len(msg.rids), output_ids=msg.output_ids,
+            prompt_tokens=msg.prompt_tokens, completion_tokens=msg.completion_tokens, cached_tokens=msg.cached_tokens,
+            output_logprobs=msg.output_logprobs, input_logprobs=msg.input_logprobs, top_logprobs=msg.top_logprobs,
+            spec_verify_ct=msg.spec_verify_ct, spec_accepted_tokens=msg.spec_accepted_tokens, embeddings=msg.embeddings,
+            hidden_states=msg.hidden_states)
+        now = time.perf_counter()
+        for i, rid in enumerate(out.rids):
+            st = self.states.get(rid)
+            if st is None:
+                continue
+            st.text += out.output_strs[i]
+            st.output_ids.extend(out.output_ids[i])
+            if st.first_token_time is None and out.output_ids[i]:
+                st.first_token_time = now
+            m = st.meta
+            m["completion_tokens"] = out.completion_tokens[i]
+            m["cached_tokens"] = out.cached_tokens[i]
+            if out.output_logprobs is not None and out.output_logprobs[i] is not None:
+                st.logprobs.extend(out.output_logprobs[i])
+                m["output_token_logprobs"] = [(lp, tid, None) for lp, tid in st.logprobs]
+                if out.input_logprobs is not None and out.input_logprobs[i] is not None:
+                    m["input_token_logprobs"] = [(lp, tid, None) for lp, tid in out.input_logprobs[i]]
+                if out.top_logprobs is not None and out.top_logprobs[i]:
+                    st.top_logprobs.extend(out.top_logprobs[i])
+                    m["output_top_logprobs"] = st.top_logprobs
+            if out.spec_verify_ct is not None:
+                m["spec_verify_ct"] = out.spec_verify_ct[i]
+                v = max(1, out.spec_verify_ct[i])
+                m["spec_accept_length"] = 1.0 + out.spec_accepted_tokens[i] / v
+                m["spec_accepted_drafts"] = out.spec_accepted_tokens[i]
+            if out.embeddings is not None and out.embeddings[i] is not None:
+                st.embedding = out.embeddings[i]
+            if out.hidden_states is not None and out.hidden_states[i]:
+                m["hidden_states"] = out.hidden_states[i]
+            fr = out.finished_reasons[i]
+            if fr is not None:
+                st.finished = True
+                m["finish_reason"] = fr
+                m["e2e_latency"] = now - st.created
+                if st.first_token_time is not None:
+                    m["ttft"] = st.first_token_time - st.created
+                if self.metrics is not None:
+                    self.metrics.observe_request(m)
+            if st.out_q is not None:
+                st.out_q.put(st.result() if not st.finished else {**st.result(), "_done": True})
+            if st.finished:
+                with self._lock:
+                    self.states.pop(rid, None)
+
+    # ================================================================== public API
+    def generate(self, prompt: Optional[Union[str, List[str]]] = None, sampling_params: Optional[Union[Dict, List[Dict]]] = None,
+                 input_ids: Optional[Union[List[int], List[List[int]]]] = None, image_data: Any = None,
+                 return_logprob: Union[bool, List[bool]] = False, logprob_start_len: Union[int, List[int]] = -1,
+                 top_logprobs_num: Union[int, List[int]] = 0, lora_path: Any = None, stream: bool = False,
+                 return_hidden_states: bool = False, rid: Any = None, priority: Optional[int] = None,
+                 session_params: Optional[Dict] = None, extra_key: Optional[str] = None):
+        g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, sampling_params=sampling_params,
+                                 return_logprob=return_logprob, logprob_start_len=logprob_start_len,
+                                 top_logprobs_num=top_logprobs_num, lora_path=lora_path, stream=stream,
+                                 return_hidden_states=return_hidden_states, rid=rid, priority=priority,
+                                 session_params=session_params, extra_key=extra_key)
+        is_batch = g.is_batch()
+        singles = g.normalize()
+        if stream:
+            if is_batch or len(singles) != 1:
+                raise ValueError("stream=True supports a single request")
+            return self._stream_one(singles[0])
+        states = [self._submit(s, None) for s in singles]
+        self._drive(states)
+        res = [s.result() for s in states]
+        return res if (is_batch or len(res) > 1) else res[0]
+
+    def _drive(self, states: List[ReqState]) -> None:
+        if self._bg_thread is not None:
+            while not all(s.finished for s in states):
+                time.sleep(0.0005)
+            return
+        sch = self.scheduler
+        while sch.has_work():
+            sch.step()
+        sch.drain()
+        if self.is_driver or self.scheduler.tp_rank == 0:
+            pending = [s for s in states if not s.finished]
+            if pending:
+                raise RuntimeError(f"{len(pending)} requests did not finish (scheduler idle)")
+
+    def _stream_one(self, g: ios.GenerateReqInput) -> Iterator[Dict[str, Any]]:
+        q: "queue.Queue[Dict[str, Any]]" = queue.Queue()
+        g.stream = True
+        st = self._submit(g, q)
+        sch = self.scheduler
+        while True:
+            if self._bg_thread is None:
+                while q.empty() and sch.has_work():
+                    sch.step()
+                if q.empty():
+                    sch.drain()
+            try:
+                item = q.get(timeout=60 if self._bg_thread is not None else 0.001)
+            except queue.Empty:
+                if self._bg_thread is None and not sch.has_work():
+                    return
+                continue
+            done = item.pop("_done", False)
+            yield item
+            if done:
+                return
+
+    async def async_generate(self, prompt=None, sampling_params=None, input_ids=None, image_data=None, stream: bool = False,
+                             **kw) -> Union[Dict[str, Any], AsyncIterator[Dict[str, Any]]]:
+        self.start_background_loop()
+        loop = asyncio.get_running_loop()
+        g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, sampling_params=sampling_params,
+                                 stream=stream, **kw)
+        singles = g.normalize()
+        aq: "asyncio.Queue[Dict[str, Any]]" = asyncio.Queue()
+
+        class _Bridge:
+            def put(self_inner, item):
+                loop.call_soon_threadsafe(aq.put_nowait, item)
+
+        states = [self._submit(s, _Bridge()) for s in singles]
+
+        async def gen():
+            remaining = len(states)
+            while remaining:
+                item = await aq.get()
+                if item.pop("_done", False):
+                    remaining -= 1
+                    yield item
+                elif stream:
+                    yield item
+
+        if stream:
+            return gen()
+        outs = [o async for o in gen()]
+        by_id = {o["meta_info"]["id"]: o for o in outs}
+        res = [by_id[s.rid] for s in states]
+        return res if g.is_batch() or len(res) > 1 else res[0]
+
+    def encode(self, prompt: Union[str, List[str]], image_data: Any = None) -> Any:
+        g = ios.GenerateReqInput(text=prompt, image_data=image_data, sampling_params={"max_new_tokens": 1})
+        states = [self._submit(s, None, is_embedding=True) for s in g.normalize()]
+        self._drive(states)
+        res = [s.result() for s in states]
+        return res if g.is_batch() else res[0]
+
+    def score(self, query: str, items: List[str], label_token_ids: List[int], apply_softmax: bool = True) -> List[List[float]]:
+        """P(label token | query + item) for each item (reference tokenizer_manager_score_mixin)"""
+        outs = self.generate([query + it for it in items], {"max_new_tokens": 1, "temperature": 0}, return_logprob=True,
+                             top_logprobs_num=max(20, len(label_token_ids)))
+        scores = []
+        for o in outs:
+            top = dict((tid, lp) for lp, tid in (o["meta_info"].get("output_top_logprobs") or [[]])[0])
+            row = [top.get(t, -1e9) for t in label_token_ids]
+            if apply_softmax:
+                row = torch.softmax(torch.tensor(row), 0).tolist()
+            scores.append(row)
+        return scores
+
+    def rerank(self, query: str, documents: List[str]) -> List[Dict[str, Any]]:
+        embs = self.encode([query] + documents)
+        q = torch.tensor(embs[0]["embedding"])
+        sc = [float(torch.dot(q, torch.tensor(e["embedding"]))) for e in embs[1:]]
+        order = sorted(range(len(documents)), key=lambda i: -sc[i])
+        return [{"index": i, "score": sc[i], "document": documents[i]} for i in order]
+
+    # ---- control plane
+    def _control(self, msg: Any) -> Any:
+        if self._bg_thread is not None:
+            box: "queue.Queue[Any]" = queue.Queue()
+            self._inbox.put((msg, box))
+            self._wake.set()
+            return box.get()
+        return self.scheduler.handle_request(msg)
+
+    def abort_request(self, rid: str = "", abort_all: bool = False) -> None:
+        self._control(ios.AbortReq(rid=rid, abort_all=abort_all))
+
+    def flush_cache(self) -> bool:
+        return self._control(ios.FlushCacheReq()).success
+
+    def get_server_info(self) -> Dict[str, Any]:
+        st = self._control(ios.GetInternalStateReq()).state
+        return {**self.server_args.to_dict(), "internal_states": [st], "version": "0.1.0", "weight_version": self.weight_version,
+                "model_config": dataclasses.asdict(self.model_config)}
+
+    def get_load(self) -> Dict[str, Any]:
+        return dataclasses.asdict(self._control(ios.GetLoadReq()))
+
+    def start_profile(self, output_dir: Optional[str] = None, num_steps: Optional[int] = None, activities=None,
+                      profile_by_stage: bool = False) -> Any:
+        return self._control(ios.ProfileReq("start", output_dir, num_steps, activities, profile_by_stage))
+
+    def stop_profile(self) -> Any:
+        return self._control(ios.ProfileReq("stop"))
+
+    def update_weights_from_disk(self, model_path: str, load_format: Optional[str] = None) -> Any:
+        r = self._control(ios.UpdateWeightsFromDiskReq(model_path, load_format))
+        if r.success:
+            self.weight_version = model_path
+        return r
+
+    def update_weights_from_tensor(self, named_tensors: Any, flush_cache: bool = True) -> Any:
+        return self._control(ios.UpdateWeightsFromTensorReq(named_tensors, flush_cache))
+
+    def get_weights_by_name(self, name: str, truncate_size: int = 100) -> Any:
+        return self._control(ios.GetWeightsByNameReq(name, truncate_size)).parameter
+
+    def release_memory_occupation(self, tags: Optional[List[str]] = None) -> Any:
+        return self._control(ios.ReleaseMemoryOccupationReq(tags))
+
+    def resume_memory_occupation(self, tags: Optional[List[str]] = None) -> Any:
+        return self._control(ios.ResumeMemoryOccupationReq(tags))
+
+    def load_lora_adapter(self, lora_name: str, lora_path: str) -> Any:
+        return self._control(ios.LoadLoRAAdapterReq(lora_name, lora_path))
+
+    def unload_lora_adapter(self, lora_name: str) -> Any:
+        return self._control(ios.UnloadLoRAAdapterReq(lora_name))
+
+    def open_session(self, capacity_of_str_len: int = 0, session_id: Optional[str] = None) -> Optional[str]:
+        return self._control(ios.OpenSessionReq(capacity_of_str_len, session_id)).session_id
+
+    def close_session(self, session_id: str) -> None:
+        self._control(ios.CloseSessionReq(session_id))
+
+    def pause_generation(self, mode: str = "abort") -> Any:
+        return self._control(ios.PauseGenerationReq(mode))
+
+    def continue_generation(self) -> Any:
+        return self._control(ios.ContinueGenerationReq())
+
+    def save_sharded_model(self, path: str) -> None:
+        from ..model_loader.loader import save_sharded_state
+
+        save_sharded_state(self.runner.model, path, ps.get_state().rank)
+
+    # ================================================================== background loop
+    def start_background_loop(self) -> None:
+        if self._bg_thread is not None:
+            return
+        self._bg_stop.clear()
+        self._bg_thread = threading.Thread(target=self._bg_loop, name="sglb-scheduler", daemon=True)
+        self._bg_thread.start()
+
+    def _bg_loop(self) -> None:
+        sch = self.scheduler
+        tp = ps.get_state().tp
+        if self.server_args.device == "cuda":
+            torch.cuda.set_device(self.runner.device)
+        while not self._bg_stop.is_set():
+            new: List[Any] = []
+            if self.is_driver:
+                while True:
+                    try:
+                        new.append(self._inbox.get_nowait())
+                    except queue.Empty:
+                        break
+            if tp.world_size > 1:
+                payload = [m if not isinstance(m, tuple) else m[0] for m in new] if self.is_driver else None
+                payload = tp.broadcast_pyobj(payload, src=0)
+                if not self.is_driver:
+                    new = payload
+            for m in new:
+                try:
+                    if isinstance(m, tuple):
+                        msg, box = m
+                        box.put(sch.handle_request(msg))
+                    else:
+                        sch.handle_request(m)
+                except Exception as e:  # a bad request must not kill the loop
+                    logger.exception("request handling failed: %s", e)
+                    if isinstance(m, tuple):
+                        m[1].put(ios.GenericResp(False, str(e)))
+            if sch.has_work():
+                try:
+                    sch.step()
+                except Exception:
+                    logger.exception("scheduler step failed; aborting in-flight requests")
+                    self._fail_all()
+                    raise
+            else:
+                sch.drain()
+                self._wake.wait(timeout=0.002)
+                self._wake.clear()
+
+    def _fail_all(self) -> None:
+        with self._lock:
+            for st in list(self.states.values()):
+                st.finished = True
+                st.meta["finish_reason"] = {"type": "abort", "message": "engine failure"}
+                if st.out_q is not None:
+                    st.out_q.put({**st.result(), "_done": True})
+            self.states.clear()
+
+    def shutdown(self) -> None:
+        self._bg_stop.set()
+        self._wake.set()
+        if self._bg_thread is not None:
+            self._bg_thread.join(timeout=10)
+            self._bg_thread = None
+
+    def __enter__(self) -> "Engine":
+        return self
+
+    def __exit__(self, *a: Any) -> None:
+        self.shutdown()

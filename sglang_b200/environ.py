@@ -1,0 +1,107 @@
+"""Typed environment-variable registry.
+
+Parity target: reference ``python/sglang/srt/environ.py:41-120`` (EnvBool/EnvInt/...
+descriptors with ``get/set/override/is_set``).  Ours is a small declarative table:
+every variable the runtime reads is declared once here so ``envs.dump()`` can print
+the effective configuration and tests can ``override`` values hermetically.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Any, Callable, Dict, Generic, Iterator, Optional, TypeVar
+
+T = TypeVar("T")
+_REGISTRY: Dict[str, "EnvVar"] = {}
+
+
+class EnvVar(Generic[T]):
+    def __init__(self, name: str, default: T, parse: Callable[[str], T], doc: str = ""):
+        self.name, self.default, self._parse, self.doc = name, default, parse, doc
+        _REGISTRY[name] = self
+
+    def is_set(self) -> bool:
+        return self.name in os.environ
+
+    def get(self) -> T:
+        raw = os.environ.get(self.name)
+        if raw is None:
+            return self.default
+        try:
+            return self._parse(raw)
+        except Exception as e:  # a bad value must fail loudly, not silently default
+            raise ValueError(f"invalid value {raw!r} for env {self.name}: {e}") from e
+
+    def set(self, value: Any) -> None:
+        os.environ[self.name] = str(value)
+
+    def clear(self) -> None:
+        os.environ.pop(self.name, None)
+
+    @contextlib.contextmanager
+    def override(self, value: Any) -> Iterator[None]:
+        old = os.environ.get(self.name)
+        os.environ[self.name] = str(value)
+        try:
+            yield
+        finally:
+            if old is None:
+                os.environ.pop(self.name, None)
+            else:
+                os.environ[self.name] = old
+
+
+def _bool(s: str) -> bool:
+    s = s.strip().lower()
+    if s in ("1", "true", "yes", "on"):
+        return True
+    if s in ("0", "false", "no", "off", ""):
+        return False
+    raise ValueError("expected a boolean")
+
+
+def EnvBool(name: str, default: bool, doc: str = "") -> EnvVar[bool]:
+    return EnvVar(name, default, _bool, doc)
+
+
+def EnvInt(name: str, default: int, doc: str = "") -> EnvVar[int]:
+    return EnvVar(name, default, int, doc)
+
+
+def EnvFloat(name: str, default: float, doc: str = "") -> EnvVar[float]:
+    return EnvVar(name, default, float, doc)
+
+
+def EnvStr(name: str, default: Optional[str], doc: str = "") -> EnvVar[Optional[str]]:
+    return EnvVar(name, default, str, doc)
+
+
+class _Envs:
+    # --- build / kernels
+    SGLB_REQUIRE_NATIVE = EnvBool("SGLB_REQUIRE_NATIVE", True, "fail loudly if the CUDA extension is missing on a GPU box")
+    SGLB_FORCE_TORCH_OPS = EnvBool("SGLB_FORCE_TORCH_OPS", False, "debug: route every op through the fp32 torch reference")
+    SGLB_ATTN_IMPL = EnvStr("SGLB_ATTN_IMPL", "auto", "auto|tc (tcgen05)|simt (reference-grade CUDA)")
+    SGLB_GEMM_IMPL = EnvStr("SGLB_GEMM_IMPL", "auto", "auto|tc (own tcgen05 GEMM)|lib (cuBLASLt)")
+    SGLB_DISABLE_CUDA_GRAPH = EnvBool("SGLB_DISABLE_CUDA_GRAPH", False)
+    SGLB_KERNEL_LAUNCH_COUNT = EnvBool("SGLB_KERNEL_LAUNCH_COUNT", True, "count native kernel launches")
+    # --- scheduler test hooks (reference: SGLANG_TEST_RETRACT etc., environ.py:384-393)
+    SGLB_TEST_RETRACT = EnvBool("SGLB_TEST_RETRACT", False, "force a decode retraction every N steps")
+    SGLB_TEST_RETRACT_INTERVAL = EnvInt("SGLB_TEST_RETRACT_INTERVAL", 3)
+    SGLB_TEST_STUCK_SCHEDULER = EnvFloat("SGLB_TEST_STUCK_SCHEDULER", 0.0, "sleep seconds inside a forward (watchdog tests)")
+    SGLB_TEST_DISAGG_FAILURE_PROB = EnvFloat("SGLB_TEST_DISAGG_FAILURE_PROB", 0.0)
+    SGLB_STRICT_MEM_CHECK = EnvBool("SGLB_STRICT_MEM_CHECK", False, "run the pool invariant checker every busy step")
+    SGLB_SIMULATE_ACC_LEN = EnvFloat("SGLB_SIMULATE_ACC_LEN", -1.0, "simulated speculative accept length")
+    # --- KV canary (reference: S/kv_canary)
+    SGLB_KV_CANARY = EnvStr("SGLB_KV_CANARY", "none", "none|log|raise")
+    # --- distributed
+    SGLB_COMM_IMPL = EnvStr("SGLB_COMM_IMPL", "auto", "auto|nvl (own P2P/multicast kernels)|nccl")
+    SGLB_NVL_MAX_BYTES = EnvInt("SGLB_NVL_MAX_BYTES", 64 << 20, "symmetric arena bytes per rank")
+    # --- observability
+    SGLB_TORCH_PROFILER_DIR = EnvStr("SGLB_TORCH_PROFILER_DIR", "/tmp/sglb_profiles")
+    SGLB_LOG_LEVEL = EnvStr("SGLB_LOG_LEVEL", "info")
+
+    def dump(self) -> Dict[str, Any]:
+        return {k: v.get() for k, v in _REGISTRY.items()}
+
+
+envs = _Envs()

@@ -1,0 +1,89 @@
+"""Norm / rotary / attention layer modules used by every model.
+
+Parity: reference ``python/sglang/srt/layers/layernorm.py:423`` (RMSNorm with fused residual add),
+``rotary_embedding/*`` (cos/sin cache, neox & gptj, llama3 scaling), ``radix_attention.py:91`` (model-facing
+attention op that delegates to the backend).  Here RoPE, the paged KV-cache write and the attention call are one
+layer: ``RadixAttention.forward(q, k, v, fb)`` -> ``ops.rope_kv_write`` (one kernel) -> ``ops.paged_attention``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..model_executor.forward_batch import ForwardBatch
+from ..ops import torch_ref
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, hidden_size: int, eps: float = 1e-6, dtype=torch.bfloat16, gemma: bool = False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(hidden_size, dtype=dtype) if gemma else torch.ones(hidden_size, dtype=dtype),
+                                   requires_grad=False)
+        self.eps = eps
+        self.gemma = gemma
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
+        """residual given: (in place) residual += x; x = norm(residual); returns (x, residual)"""
+        if residual is None:
+            return ops.rmsnorm(x, self.weight, self.eps, gemma=self.gemma)
+        ops.fused_add_rmsnorm(x, residual, self.weight, self.eps, gemma=self.gemma)
+        return x, residual
+
+
+class RotaryEmbedding:
+    """holds the fp32 cos|sin cache [max_pos, rotary_dim]"""
+    _cache = {}
+
+    def __init__(self, head_dim: int, max_position: int, base: float, rope_scaling=None, is_neox: bool = True,
+                 partial_rotary_factor: float = 1.0, device="cpu"):
+        self.is_neox = is_neox
+        rd = int(head_dim * partial_rotary_factor)
+        key = (head_dim, rd, max_position, base, str(rope_scaling), str(device))
+        if key not in RotaryEmbedding._cache:
+            RotaryEmbedding._cache[key] = torch_ref.build_cos_sin_cache(head_dim, max_position, base, rope_scaling, rd).to(device)
+        self.cos_sin = RotaryEmbedding._cache[key]
+
+
+class RadixAttention(nn.Module):
+    def __init__(self, num_heads: int, head_dim: int, num_kv_heads: int, layer_id: int, scale: Optional[float] = None,
+                 rope: Optional[RotaryEmbedding] = None, sliding_window: int = -1, logit_cap: float = 0.0):
+        super().__init__()
+        self.num_heads, self.head_dim, self.num_kv_heads, self.layer_id = num_heads, head_dim, num_kv_heads, layer_id
+        self.scale = scale if scale is not None else head_dim ** -0.5
+        self.rope = rope
+        self.window = sliding_window
+        self.logit_cap = logit_cap
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
+        """q [T, Hq*D], k/v [T, Hkv*D] (views into the fused QKV output)"""
+        T = q.shape[0]
+        q3 = q.view(T, self.num_heads, self.head_dim)
+        k3 = k.view(T, self.num_kv_heads, self.head_dim)
+        v3 = v.view(T, self.num_kv_heads, self.head_dim)
+        pool = fb.kv_pool
+        kc, vc = pool.k(self.layer_id), pool.v(self.layer_id)
+        if self.rope is not None:
+            ops.rope_kv_write(q3, k3, v3, fb.positions, self.rope.cos_sin, kc, vc, fb.out_cache_loc, self.rope.is_neox,
+                              pool.k_scale, pool.v_scale)
+        else:
+            loc = fb.out_cache_loc.long()
+            kc[loc] = k3.to(kc.dtype)
+            vc[loc] = v3.to(vc.dtype)
+        o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
+                                fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
+                                k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
+                                workspace=fb.attn_workspace, custom_mask=fb.custom_mask)
+        return o.view(T, self.num_heads * self.head_dim)
+
+
+def get_act_and_mul(name: str):
+    if name == "silu":
+        return ops.silu_and_mul
+    if name in ("gelu_pytorch_tanh", "gelu_tanh", "gelu_new"):
+        return lambda x: ops.gelu_and_mul(x, "tanh")
+    if name == "gelu":
+        return lambda x: ops.gelu_and_mul(x, "none")
+    raise ValueError(f"unsupported activation {name}")

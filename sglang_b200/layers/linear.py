@@ -1,0 +1,187 @@
+"""Tensor-parallel linear layers + vocab-parallel embedding / LM head.
+
+Parity: reference ``python/sglang/srt/layers/linear.py`` (``ReplicatedLinear:204``, ``ColumnParallelLinear:302``,
+``MergedColumnParallelLinear:507``, ``QKVParallelLinear:936``, ``RowParallelLinear:1407`` forward ``:1596`` ->
+all-reduce ``:1643-1662``) and ``vocab_parallel_embedding.py:188,591``.  Weight shards are ``[out_local, in]``
+(K-major) which is exactly the B-operand layout of the tcgen05 GEMM.
+
+Quantisation plugs in through ``quant_method`` (``layers/quantization.py``): ``create_weights`` /
+``process_weights_after_loading`` / ``apply``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..parallel.parallel_state import get_tp_group
+from .quantization import QuantMethod, UnquantizedMethod
+
+
+def _divide(a: int, b: int) -> int:
+    assert a % b == 0, f"{a} is not divisible by {b}"
+    return a // b
+
+
+class LinearBase(nn.Module):
+    def __init__(self, in_features: int, out_features: int, bias: bool, dtype: torch.dtype,
+                 quant: Optional[QuantMethod] = None, prefix: str = ""):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.quant = quant or UnquantizedMethod()
+        self.prefix = prefix
+        self.quant.create_weights(self, in_features, out_features, dtype)
+        self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype), requires_grad=False) if bias else None
+
+    def apply(self, x: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        shp = x.shape
+        y = self.quant.apply(self, x.reshape(-1, shp[-1]), bias)
+        return y.view(*shp[:-1], y.shape[-1])
+
+
+class ReplicatedLinear(LinearBase):
+    def __init__(self, in_features, out_features, bias=False, dtype=torch.bfloat16, quant=None, prefix=""):
+        super().__init__(in_features, out_features, bias, dtype, quant, prefix)
+
+    def forward(self, x):
+        return self.apply(x, self.bias)
+
+    def weight_loader(self, param: torch.Tensor, loaded: torch.Tensor, shard_id=None) -> None:
+        param.data.copy_(loaded)
+
+
+class ColumnParallelLinear(LinearBase):
+    def __init__(self, in_features, out_features, bias=False, gather_output=False, dtype=torch.bfloat16, quant=None, prefix="",
+                 tp_group=None):
+        self.tp = tp_group or get_tp_group()
+        self.gather_output = gather_output
+        self.out_total = out_features
+        super().__init__(in_features, _divide(out_features, self.tp.world_size), bias, dtype, quant, prefix)
+
+    def forward(self, x):
+        y = self.apply(x, self.bias)
+        if self.gather_output and self.tp.world_size > 1:
+            y = self.tp.all_gather(y, dim=-1)
+        return y
+
+    def weight_loader(self, param, loaded, shard_id=None):
+        n = param.shape[0]
+        param.data.copy_(loaded.narrow(0, self.tp.rank * n, n))
+
+
+class MergedColumnParallelLinear(LinearBase):
+    """several column-parallel matrices sharing the input (gate_up_proj); each is sharded separately"""
+
+    def __init__(self, in_features, out_sizes: List[int], bias=False, dtype=torch.bfloat16, quant=None, prefix="", tp_group=None):
+        self.tp = tp_group or get_tp_group()
+        self.out_sizes = out_sizes
+        self.local_sizes = [_divide(s, self.tp.world_size) for s in out_sizes]
+        super().__init__(in_features, sum(self.local_sizes), bias, dtype, quant, prefix)
+
+    def forward(self, x):
+        return self.apply(x, self.bias)
+
+    def weight_loader(self, param, loaded, shard_id: Optional[int] = None):
+        if shard_id is None:  # already merged checkpoint tensor
+            off = 0
+            chunks = []
+            for s, ls in zip(self.out_sizes, self.local_sizes):
+                chunks.append(loaded.narrow(0, off + self.tp.rank * ls, ls))
+                off += s
+            param.data.copy_(torch.cat(chunks, 0))
+            return
+        ls = self.local_sizes[shard_id]
+        start = sum(self.local_sizes[:shard_id])
+        param.data.narrow(0, start, ls).copy_(loaded.narrow(0, self.tp.rank * ls, ls))
+
+
+class QKVParallelLinear(LinearBase):
+    def __init__(self, hidden_size, head_dim, num_heads, num_kv_heads, bias=False, dtype=torch.bfloat16, quant=None, prefix="",
+                 tp_group=None):
+        self.tp = tp_group or get_tp_group()
+        tp = self.tp.world_size
+        self.head_dim = head_dim
+        self.num_heads = _divide(num_heads, tp)
+        if num_kv_heads >= tp:
+            self.num_kv_heads, self.kv_replicas = _divide(num_kv_heads, tp), 1
+        else:  # replicate KV heads when tp > num_kv_heads (reference linear.py:936)
+            self.num_kv_heads, self.kv_replicas = 1, _divide(tp, num_kv_heads)
+        self.q_size = self.num_heads * head_dim
+        self.kv_size = self.num_kv_heads * head_dim
+        super().__init__(hidden_size, self.q_size + 2 * self.kv_size, bias, dtype, quant, prefix)
+
+    def forward(self, x):
+        return self.apply(x, self.bias)
+
+    def weight_loader(self, param, loaded, shard_id: Optional[str] = None):
+        r = self.tp.rank
+        if shard_id == "q":
+            param.data.narrow(0, 0, self.q_size).copy_(loaded.narrow(0, r * self.q_size, self.q_size))
+        elif shard_id in ("k", "v"):
+            off = self.q_size + (0 if shard_id == "k" else self.kv_size)
+            src = (r // self.kv_replicas) * self.kv_size
+            param.data.narrow(0, off, self.kv_size).copy_(loaded.narrow(0, src, self.kv_size))
+        else:
+            raise ValueError(shard_id)
+
+
+class RowParallelLinear(LinearBase):
+    """input features sharded; partial sums are all-reduced (or left partial when the caller fuses the reduction
+    into the next op: ``reduce_results=False``)."""
+
+    def __init__(self, in_features, out_features, bias=False, reduce_results=True, dtype=torch.bfloat16, quant=None, prefix="",
+                 tp_group=None):
+        self.tp = tp_group or get_tp_group()
+        self.reduce_results = reduce_results
+        self.in_total = in_features
+        super().__init__(_divide(in_features, self.tp.world_size), out_features, bias, dtype, quant, prefix)
+
+    def forward(self, x):
+        # bias is added once (rank 0) so the reduction stays a pure sum
+        y = self.apply(x, self.bias if (self.bias is not None and self.tp.rank == 0) else None)
+        if self.reduce_results and self.tp.world_size > 1:
+            nvl = self.tp.nvl
+            y = self.tp.all_reduce(y)
+        return y
+
+    def weight_loader(self, param, loaded, shard_id=None):
+        if param.dim() == 1:
+            param.data.copy_(loaded)
+            return
+        k = param.shape[1]
+        param.data.copy_(loaded.narrow(1, self.tp.rank * k, k))
+
+
+class VocabParallelEmbedding(nn.Module):
+    def __init__(self, vocab_size: int, hidden_size: int, dtype=torch.bfloat16, tp_group=None, pad_to: int = 64):
+        super().__init__()
+        self.tp = tp_group or get_tp_group()
+        tp = self.tp.world_size
+        self.vocab_size = vocab_size
+        self.padded_vocab = (vocab_size + pad_to * tp - 1) // (pad_to * tp) * (pad_to * tp)
+        self.local_vocab = self.padded_vocab // tp
+        self.vocab_start = self.tp.rank * self.local_vocab
+        self.weight = nn.Parameter(torch.zeros(self.local_vocab, hidden_size, dtype=dtype), requires_grad=False)
+
+    def forward(self, ids: torch.Tensor, gather_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = ops.embedding(self.weight, ids, gather_idx, self.vocab_start)
+        if self.tp.world_size > 1:
+            y = self.tp.all_reduce(y)
+        return y
+
+    def weight_loader(self, param, loaded, shard_id=None):
+        n = min(self.local_vocab, max(0, loaded.shape[0] - self.vocab_start))
+        if n > 0:
+            param.data[:n].copy_(loaded.narrow(0, self.vocab_start, n))
+
+
+class ParallelLMHead(VocabParallelEmbedding):
+    """vocab-sharded LM head; logits are all-gathered (reference logits_processor.py:338)"""
+
+    def logits(self, hidden: torch.Tensor) -> torch.Tensor:
+        y = ops.linear(hidden, self.weight)
+        if self.tp.world_size > 1:
+            y = self.tp.all_gather(y, dim=-1)
+        return y[:, : self.vocab_size]

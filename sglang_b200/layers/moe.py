@@ -1,0 +1,81 @@
+"""Mixture-of-experts layer: top-k routing + grouped expert MLP, tensor- or expert-parallel.
+
+Parity: reference ``python/sglang/srt/layers/moe/`` (``topk.py`` softmax top-k + renormalise,
+``fused_moe_triton/layer.py`` FusedMoE, ``token_dispatcher/standard.py:98`` replicated-token dispatch + final
+all-reduce, ``ep_moe/layer.py`` expert sharding, ``moe_align_kernel.cu`` align/permute).
+
+Sharding: with ``ep_size == 1`` every rank holds all experts with the intermediate dim split over TP (moe-TP);
+with ``ep_size == tp_size`` each rank holds ``E/ep`` whole experts (moe-EP).  In both cases tokens are replicated
+across the TP group after attention (they already are, post all-reduce), each rank computes the contribution of
+its weight shard and the partial outputs are summed by ONE all-reduce — the same collective the dense MLP needs,
+so EP costs no extra dispatch/combine traffic inside a node (NVSwitch all-reduce of [T,H] vs an all-to-all of
+[T*topk,H]: for top-2 the bytes are equal and the all-reduce has no routing imbalance).
+An all-to-all token dispatcher (``A2ADispatcher``) is provided for the DP-attention configuration where tokens are
+NOT replicated.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..ops import torch_ref
+from ..parallel.parallel_state import get_ep_group, get_tp_group
+
+
+def select_experts(router_logits: torch.Tensor, top_k: int, renormalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    from ..ops import moe_ops
+
+    return moe_ops.topk_softmax(router_logits, top_k, renormalize)
+
+
+class FusedMoE(nn.Module):
+    def __init__(self, num_experts: int, top_k: int, hidden_size: int, intermediate_size: int, dtype=torch.bfloat16,
+                 renormalize: bool = True, ep_size: int = 1, quant=None, layer_id: int = 0):
+        super().__init__()
+        self.tp = get_tp_group()
+        self.num_experts, self.top_k, self.renormalize, self.layer_id = num_experts, top_k, renormalize, layer_id
+        tp = self.tp.world_size
+        self.ep_size = ep_size if ep_size > 1 else 1
+        if self.ep_size > 1:
+            assert tp % self.ep_size == 0 and num_experts % self.ep_size == 0
+            self.moe_tp = tp // self.ep_size                   # TP inside each expert shard
+            self.ep_rank = self.tp.rank // self.moe_tp
+            self.moe_tp_rank = self.tp.rank % self.moe_tp
+        else:
+            self.moe_tp, self.ep_rank, self.moe_tp_rank = tp, 0, self.tp.rank
+        self.local_experts = num_experts // self.ep_size
+        self.expert_offset = self.ep_rank * self.local_experts
+        assert intermediate_size % self.moe_tp == 0
+        self.inter_local = intermediate_size // self.moe_tp
+        self.w13 = nn.Parameter(torch.zeros(self.local_experts, 2 * self.inter_local, hidden_size, dtype=dtype), requires_grad=False)
+        self.w2 = nn.Parameter(torch.zeros(self.local_experts, hidden_size, self.inter_local, dtype=dtype), requires_grad=False)
+        self.expert_load = None  # EPLB recorder hook
+
+    def weight_loader(self, param: torch.Tensor, loaded: torch.Tensor, expert_id: int, shard: str) -> None:
+        """shard in {'w1' (gate), 'w3' (up), 'w2' (down)}; ``loaded`` is the full (unsharded) expert matrix"""
+        le = expert_id - self.expert_offset
+        if le < 0 or le >= self.local_experts:
+            return
+        I, r = self.inter_local, self.moe_tp_rank
+        if shard == "w1":
+            param.data[le, :I].copy_(loaded.narrow(0, r * I, I))
+        elif shard == "w3":
+            param.data[le, I:].copy_(loaded.narrow(0, r * I, I))
+        elif shard == "w2":
+            param.data[le].copy_(loaded.narrow(1, r * I, I))
+        else:
+            raise ValueError(shard)
+
+    def forward(self, x: torch.Tensor, router_logits: torch.Tensor) -> torch.Tensor:
+        from ..ops import moe_ops
+
+        w, ids = select_experts(router_logits, self.top_k, self.renormalize)
+        if self.expert_load is not None:
+            self.expert_load.record(self.layer_id, ids)
+        y = moe_ops.fused_moe(x, self.w13, self.w2, w, ids, self.expert_offset)
+        if self.tp.world_size > 1:
+            y = self.tp.all_reduce(y)
+        return y

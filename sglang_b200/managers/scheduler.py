@@ -1,0 +1,698 @@
+"""Continuous-batching scheduler (one per GPU rank).
+
+Parity: reference ``python/sglang/srt/managers/scheduler.py`` (``event_loop_normal:1748``,
+``event_loop_overlap:1783``, ``get_next_batch_to_run:3080``, ``_get_new_batch_prefill_raw:3252``,
+``update_running_batch:3566``, ``run_batch:3711``, ``process_batch_result:4035``, ``flush_cache:4376``,
+``abort_request:4567``) and ``scheduler_components/batch_result_processor.py``.
+
+Design (B200-first): the scheduler owns only host state.  A step (1) drains the inbox, (2) forms a batch
+(prefill-first, chunked prefill, retract-on-OOM), (3) hands it to the worker which launches the GPU work
+asynchronously, (4) processes the *previous* step's result while the GPU runs (one-iteration-lag overlap;
+next-token ids never touch the host on the critical path: the sampler writes them to a device buffer
+indexed by request slot and the next decode gathers from it).
+"""
+from __future__ import annotations
+
+import logging
+import time
+from collections import deque
+from typing import Any, Callable, Deque, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from ..environ import envs
+from ..mem_cache.allocator import PagedAllocator
+from ..mem_cache.kv_manager import KVManager
+from ..mem_cache.radix_cache import create_radix_cache
+from ..sampling.sampling_params import SamplingParams
+from ..server_args import ServerArgs
+from . import io_struct as ios
+from .schedule_batch import (FINISH_ABORT, FINISH_LENGTH, ForwardMode, Req, ScheduleBatch)
+from .schedule_policy import AddResult, PrefillAdder, SchedulePolicy
+
+logger = logging.getLogger(__name__)
+
+
+class Scheduler:
+    def __init__(self, server_args: ServerArgs, worker: Any, tokenizer: Any = None,
+                 send_to_detokenizer: Optional[Callable[[Any], None]] = None, tp_rank: int = 0):
+        self.args = server_args
+        self.worker = worker
+        self.tokenizer = tokenizer
+        self.tp_rank = tp_rank
+        self.send_to_detokenizer = send_to_detokenizer or (lambda m: None)
+        self.page_size = server_args.page_size
+
+        info = worker.get_memory_info()  # {"num_pages", "max_context_len", "max_running"}
+        self.max_context_len = info["max_context_len"]
+        self.max_running = info["max_running"]
+        self.allocator = PagedAllocator(info["num_pages"], self.page_size)
+        self.tree = create_radix_cache(self.allocator, self.page_size, server_args.radix_eviction_policy,
+                                       disable=server_args.disable_radix_cache, impl=server_args.radix_cache_impl,
+                                       enable_kv_events=server_args.enable_kv_events)
+        self.kv = KVManager(self.allocator, self.tree, self.page_size, self.max_running, self.max_context_len)
+        worker.attach_kv_manager(self.kv)
+        self.policy = SchedulePolicy(server_args.schedule_policy, self.kv, server_args.enable_priority_scheduling,
+                                     server_args.random_seed)
+
+        self.waiting_queue: List[Req] = []
+        self.running_batch = ScheduleBatch(reqs=[], forward_mode=ForwardMode.DECODE)
+        self.running_batch.init_decode_state()
+        self.last_batch: Optional[ScheduleBatch] = None
+        self.chunked_req: Optional[Req] = None
+        self.pending: Deque[Tuple[ScheduleBatch, Any]] = deque()
+        self.enable_overlap = not server_args.disable_overlap_schedule and worker.supports_overlap()
+        self.grammar_queue: List[Req] = []
+        self.grammar_manager = None
+        self.spec_worker = None
+        self.sessions: Dict[str, Any] = {}
+        self.paused = False
+
+        # new-token-ratio estimator (reference scheduler.py:3580-3611)
+        cons = server_args.schedule_conservativeness
+        self.init_new_token_ratio = min(0.7 * cons, 1.0)
+        self.min_new_token_ratio = min(self.init_new_token_ratio * 0.14, 1.0)
+        self.new_token_ratio_decay = (self.init_new_token_ratio - self.min_new_token_ratio) / 600
+        self.new_token_ratio = self.init_new_token_ratio
+
+        self.forward_ct = 0
+        self.decode_ct = 0
+        self.num_retracted = 0
+        self.num_generated_tokens = 0
+        self.num_prefill_tokens = 0
+        self.num_cached_tokens = 0
+        self.last_decode_log = time.perf_counter()
+        self.last_decode_tokens = 0
+        self.gen_throughput = 0.0
+        self.metrics = None
+        self.watchdog_last_progress = time.perf_counter()
+        self.batch_records: List[Dict[str, Any]] = []   # scripted-runtime hook (reference scheduler_hook.py:46-53)
+        self.record_batches = server_args.scripted_scheduler
+        self.eos_token_ids = set(worker.get_eos_token_ids())
+
+    # ================================================================== request intake
+    def handle_request(self, msg: Any) -> Optional[Any]:
+        if isinstance(msg, ios.TokenizedGenerateReqInput):
+            return self.handle_generate_request(msg)
+        if isinstance(msg, ios.AbortReq):
+            return self.abort_request(msg)
+        if isinstance(msg, ios.FlushCacheReq):
+            return ios.FlushCacheResp(success=self.flush_cache())
+        if isinstance(msg, ios.GetInternalStateReq):
+            return ios.GetInternalStateResp(state=self.get_internal_state())
+        if isinstance(msg, ios.HealthCheckReq):
+            return ios.HealthCheckResp(ok=True, forward_ct=self.forward_ct)
+        if isinstance(msg, ios.GetLoadReq):
+            return ios.GetLoadResp(num_running_reqs=len(self.running_batch.reqs), num_waiting_reqs=len(self.waiting_queue),
+                                   num_tokens=int(self.kv.total_pages() - self.kv.available_pages()) * self.page_size,
+                                   token_usage=self.kv.token_usage())
+        if isinstance(msg, ios.PauseGenerationReq):
+            return self.pause_generation(msg.mode)
+        if isinstance(msg, ios.ContinueGenerationReq):
+            self.paused = False
+            return ios.GenericResp()
+        if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq, ios.GetWeightsByNameReq,
+                            ios.ReleaseMemoryOccupationReq, ios.ResumeMemoryOccupationReq, ios.ProfileReq,
+                            ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq)):
+            self.drain()
+            if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq)):
+                self.flush_cache()
+            return self.worker.handle_control(msg)
+        if isinstance(msg, ios.OpenSessionReq):
+            sid = msg.session_id or f"sess-{len(self.sessions)}"
+            ok = sid not in self.sessions
+            if ok:
+                self.sessions[sid] = {"reqs": []}
+            return ios.OpenSessionResp(session_id=sid, success=ok)
+        if isinstance(msg, ios.CloseSessionReq):
+            self.sessions.pop(msg.session_id, None)
+            return ios.GenericResp()
+        raise TypeError(f"unknown message {type(msg)}")
+
+    def handle_generate_request(self, m: ios.TokenizedGenerateReqInput) -> None:
+        sp = SamplingParams.from_dict(m.sampling_params)
+        req = Req(m.rid, m.input_ids, sp, origin_input_text=m.input_text, return_logprob=m.return_logprob,
+                  top_logprobs_num=m.top_logprobs_num, logprob_start_len=m.logprob_start_len, stream=m.stream,
+                  lora_id=m.lora_id, extra_key=m.extra_key, priority=m.priority, eos_token_ids=self.eos_token_ids,
+                  mm_inputs=m.mm_inputs, is_embedding=m.is_embedding, return_hidden_states=m.return_hidden_states)
+        req.trace_context = m.trace_context
+        if m.created_time:
+            req.created_time = m.created_time
+        # validation (reference scheduler.py:2414-2783)
+        n_in = len(req.origin_input_ids)
+        if n_in == 0:
+            return self._reject(req, "empty prompt")
+        if n_in >= self.max_context_len:
+            return self._reject(req, f"prompt ({n_in} tokens) exceeds the context length {self.max_context_len}")
+        sp.max_new_tokens = min(sp.max_new_tokens, self.max_context_len - n_in)
+        if self.args.max_queued_requests is not None and len(self.waiting_queue) >= self.args.max_queued_requests:
+            return self._reject(req, "the request queue is full", 503)
+        total_pages = (n_in + sp.max_new_tokens + self.page_size - 1) // self.page_size
+        if (n_in + self.page_size) // self.page_size + 1 > self.kv.total_pages():
+            return self._reject(req, "prompt does not fit in the KV cache")
+        if sp.has_grammar and self.grammar_manager is not None:
+            ready = self.grammar_manager.attach(req)
+            if not ready:
+                self.grammar_queue.append(req)
+                return None
+            if req.to_abort is not None:
+                return self._reject(req, req.to_abort.kw.get("message", "invalid grammar"))
+        elif sp.has_grammar:
+            return self._reject(req, "grammar-constrained decoding requested but no grammar backend is enabled")
+        if m.session_params and m.session_params.get("id") in self.sessions:
+            req.session_id = m.session_params["id"]
+        self.waiting_queue.append(req)
+        return None
+
+    def _reject(self, req: Req, msg: str, code: int = 400) -> None:
+        req.finished_reason = FINISH_ABORT(msg, code)
+        self.stream_output([req])
+
+    def abort_request(self, m: ios.AbortReq) -> None:
+        hit = lambda r: m.abort_all or r.rid == m.rid or (m.rid and r.rid.startswith(m.rid))
+        keep = []
+        for r in self.waiting_queue:
+            if hit(r):
+                r.finished_reason = FINISH_ABORT()
+                if r.req_slot is not None:
+                    self.kv.release(r, insert=False)
+                self.stream_output([r])
+            else:
+                keep.append(r)
+        self.waiting_queue = keep
+        for r in self.running_batch.reqs + ([self.chunked_req] if self.chunked_req else []):
+            if hit(r) and not r.finished():
+                r.to_abort = FINISH_ABORT()   # picked up at the next result processing
+        return None
+
+    def pause_generation(self, mode: str) -> Any:
+        self.drain()
+        self.paused = True
+        if mode == "abort":
+            self.abort_request(ios.AbortReq(abort_all=True))
+            self.paused = False
+        elif mode == "retract":
+            self._retract(self.running_batch, list(range(len(self.running_batch.reqs))))
+        return ios.GenericResp()
+
+    def flush_cache(self) -> bool:
+        self.drain()
+        if self.running_batch.reqs or self.waiting_queue and any(r.req_slot is not None for r in self.waiting_queue) \
+                or self.chunked_req is not None:
+            logger.warning("flush_cache refused: requests in flight")
+            return False
+        self.tree.reset()
+        self.allocator.clear()
+        self.kv.slots.clear()
+        self.kv.page_table[:] = 0
+        self.kv.take_deltas()
+        self.worker.flush()
+        self.new_token_ratio = self.init_new_token_ratio
+        return True
+
+    # ================================================================== batch formation
+    def get_next_batch_to_run(self) -> Optional[ScheduleBatch]:
+        if self.paused:
+            return None
+        # merge the last prefill batch into the running (decode) batch (reference :3133-3157)
+        if self.last_batch is not None and self.last_batch.forward_mode.is_extend():
+            lb = self.last_batch
+            keep = [i for i, r in enumerate(lb.reqs) if not r.finished() and r is not self.chunked_req
+                    and not r.is_embedding]
+            if keep:
+                lb.reqs = [lb.reqs[i] for i in keep]
+                lb.init_decode_state()
+                self.running_batch.merge_batch(lb)
+            self.last_batch = None
+
+        self._poll_grammar_queue()
+        new_batch = self._get_new_batch_prefill()
+        if new_batch is not None:
+            return new_batch
+        if self.running_batch.reqs:
+            b = self._update_running_batch()
+            return b
+        return None
+
+    def _poll_grammar_queue(self) -> None:
+        if not self.grammar_queue:
+            return
+        still = []
+        for r in self.grammar_queue:
+            if self.grammar_manager.poll(r):
+                if r.to_abort is not None:
+                    self._reject(r, r.to_abort.kw.get("message", "invalid grammar"))
+                else:
+                    self.waiting_queue.append(r)
+            else:
+                still.append(r)
+        self.grammar_queue = still
+
+    def _get_new_batch_prefill(self) -> Optional[ScheduleBatch]:
+        if not self.waiting_queue and self.chunked_req is None:
+            return None
+        running = self.running_batch.reqs
+        if len(running) >= self.max_running and self.chunked_req is None:
+            return None
+        if envs.SGLB_TEST_RETRACT.get() and len(running) > 0 and self.chunked_req is None and \
+                self.decode_ct % max(2, envs.SGLB_TEST_RETRACT_INTERVAL.get()) != 0:
+            pass
+        self.policy.calc_priority(self.waiting_queue)
+        adder = PrefillAdder(self.kv, self.page_size, self.new_token_ratio, self.args.max_prefill_tokens,
+                             self.args.chunked_prefill_size, running, self.max_running)
+        if self.chunked_req is not None:
+            ok = adder.add_chunked_req(self.chunked_req)
+            if not ok:
+                return None
+        admitted = []
+        for req in self.waiting_queue:
+            res = adder.add_one_req(req)
+            if res == AddResult.CONTINUE:
+                admitted.append(req)
+                if adder.new_chunked_req is not None:
+                    break
+                continue
+            break
+        if admitted:
+            ids = set(map(id, admitted))
+            self.waiting_queue = [r for r in self.waiting_queue if id(r) not in ids]
+        if not adder.can_run:
+            return None
+        prev_chunked = self.chunked_req
+        self.chunked_req = adder.new_chunked_req
+        batch = ScheduleBatch(reqs=adder.can_run, forward_mode=ForwardMode.EXTEND, chunked_req=self.chunked_req)
+        if not self._prepare_for_extend(batch):
+            # allocation failed despite the budget (fragmentation of reserves): put everything back
+            for r in batch.reqs:
+                if r is prev_chunked:
+                    continue
+                self.kv.release(r, insert=False)
+                r.is_chunked = 0
+                self.waiting_queue.insert(0, r)
+            self.chunked_req = prev_chunked
+            return None
+        return batch
+
+    def _prepare_for_extend(self, batch: ScheduleBatch) -> bool:
+        """allocate pages, build token-level arrays (reference prepare_for_extend:2378)"""
+        ids, pos, loc, qlens, plens, slots, seqlens, sample = [], [], [], [], [], [], [], []
+        for r in batch.reqs:
+            if not self.kv.alloc_for_extend(r, r.fill_len):
+                return False
+        for r in batch.reqs:
+            all_ids = r.all_ids()
+            s, e = r.prefix_len, r.fill_len
+            ids.append(np.asarray(all_ids[s:e], dtype=np.int32))
+            pos.append(np.arange(s, e, dtype=np.int32))
+            loc.append(self.kv.slots_for(r, s, e))
+            qlens.append(e - s)
+            plens.append(s)
+            slots.append(r.req_slot)
+            seqlens.append(e)
+            sample.append(e == len(all_ids))  # last chunk -> produces a token
+            r.kv_len = e   # committed at launch: later steps are stream-ordered behind this one
+            if r.queue_time_start is not None:
+                r.queue_time_end = time.perf_counter()
+            batch.return_logprob |= r.return_logprob
+            batch.has_grammar |= r.grammar is not None
+        batch.input_ids = np.concatenate(ids)
+        batch.positions = np.concatenate(pos)
+        batch.out_cache_loc = np.concatenate(loc)
+        batch.q_lens = np.asarray(qlens, dtype=np.int32)
+        batch.prefix_lens = np.asarray(plens, dtype=np.int32)
+        batch.req_slots = np.asarray(slots, dtype=np.int32)
+        batch.seq_lens = np.asarray(seqlens, dtype=np.int32)
+        batch.sample_mask = np.asarray(sample, dtype=bool)
+        batch.pt_rows, batch.pt_cols, batch.pt_vals = self.kv.take_deltas()
+        self.num_prefill_tokens += int(batch.q_lens.sum())
+        self.num_cached_tokens += int(batch.prefix_lens.sum())
+        return True
+
+    def _update_running_batch(self) -> Optional[ScheduleBatch]:
+        """decode step for the running batch; retract on OOM (reference update_running_batch:3566)"""
+        rb = self.running_batch
+        keep = [i for i, r in enumerate(rb.reqs) if not r.finished()]
+        rb.filter_batch(keep)
+        if not rb.reqs:
+            return None
+        force_retract = envs.SGLB_TEST_RETRACT.get() and self.decode_ct > 0 and \
+            self.decode_ct % envs.SGLB_TEST_RETRACT_INTERVAL.get() == 0 and len(rb.reqs) > 1
+        positions = rb.seq_lens.copy()   # index of the token written this step
+        loc = None if force_retract else self.kv.alloc_for_decode(rb.reqs, rb.req_slots, positions)
+        if loc is None:
+            self.drain()   # never retract under an in-flight batch
+            keep = [i for i, r in enumerate(rb.reqs) if not r.finished()]
+            rb.filter_batch(keep)
+            if not rb.reqs:
+                return None
+            positions = rb.seq_lens.copy()
+            loc = None if force_retract else self.kv.alloc_for_decode(rb.reqs, rb.req_slots, positions)
+            while loc is None:
+                if len(rb.reqs) <= 1 and not force_retract:
+                    # cannot make progress: abort the last request
+                    r = rb.reqs[0]
+                    r.finished_reason = FINISH_ABORT("out of KV cache memory", 500)
+                    self.kv.release(r, insert=False)
+                    self.stream_output([r])
+                    rb.filter_batch([])
+                    return None
+                victims = self._pick_retract_victims(rb, force_retract)
+                force_retract = False
+                self._retract(rb, victims)
+                positions = rb.seq_lens.copy()
+                loc = self.kv.alloc_for_decode(rb.reqs, rb.req_slots, positions)
+            self.new_token_ratio = min(1.0, self.new_token_ratio + 0.2)   # be more conservative after a retract
+        else:
+            self.new_token_ratio = max(self.min_new_token_ratio, self.new_token_ratio - self.new_token_ratio_decay)
+        rb.forward_mode = ForwardMode.DECODE
+        rb.positions = positions.astype(np.int32)
+        rb.out_cache_loc = loc
+        rb.seq_lens = rb.seq_lens + 1
+        for r in rb.reqs:
+            r.kv_len += 1
+        rb.q_lens = None
+        rb.input_ids = None
+        rb.sample_mask = None
+        rb.pt_rows, rb.pt_cols, rb.pt_vals = self.kv.take_deltas()
+        rb.has_grammar = any(r.grammar is not None for r in rb.reqs)
+        rb.return_logprob = any(r.return_logprob for r in rb.reqs)
+        # the worker gets a *snapshot* so later filter/merge of running_batch cannot race with it
+        snap = ScheduleBatch(reqs=list(rb.reqs), forward_mode=ForwardMode.DECODE, seq_lens=rb.seq_lens.copy(),
+                             req_slots=rb.req_slots.copy(), positions=rb.positions, out_cache_loc=rb.out_cache_loc,
+                             pt_rows=rb.pt_rows, pt_cols=rb.pt_cols, pt_vals=rb.pt_vals,
+                             return_logprob=rb.return_logprob, has_grammar=rb.has_grammar)
+        self.decode_ct += 1
+        return snap
+
+    def _pick_retract_victims(self, rb: ScheduleBatch, force: bool) -> List[int]:
+        """reference retract_decode:2825/2889 — retract the requests with the fewest generated tokens first
+        (cheapest to recompute), longest prompts breaking ties"""
+        order = sorted(range(len(rb.reqs)), key=lambda i: (len(rb.reqs[i].output_ids), -len(rb.reqs[i].origin_input_ids)))
+        need = self.kv.pages_needed_for_decode(rb.seq_lens)
+        victims, freed = [], 0
+        for i in order:
+            if len(victims) >= len(rb.reqs) - 1:
+                break
+            victims.append(i)
+            freed += rb.reqs[i].num_pages - rb.reqs[i].num_cached_pages
+            if force or freed + self.kv.available_pages() >= need + len(rb.reqs):
+                break
+        return victims
+
+    def _retract(self, rb: ScheduleBatch, victims: List[int]) -> None:
+        vs = set(victims)
+        for i in victims:
+            r = rb.reqs[i]
+            self.kv.release(r, insert=True)   # computed prefix stays reusable in the tree
+            r.reset_for_retract()
+            self.waiting_queue.insert(0, r)
+            self.num_retracted += 1
+        rb.filter_batch([i for i in range(len(rb.reqs)) if i not in vs])
+
+    # ================================================================== run + results
+    def run_batch(self, batch: ScheduleBatch) -> Any:
+        self.forward_ct += 1
+        batch.launch_time = time.perf_counter()
+        if self.record_batches:
+            self.batch_records.append({"mode": batch.forward_mode.name, "rids": [r.rid for r in batch.reqs],
+                                       "chunked_rid": batch.chunked_req.rid if batch.chunked_req else None,
+                                       "tokens": int(batch.q_lens.sum()) if batch.q_lens is not None else len(batch.reqs)})
+        stuck = envs.SGLB_TEST_STUCK_SCHEDULER.get()
+        if stuck > 0:
+            time.sleep(stuck)
+        if self.spec_worker is not None and batch.forward_mode.is_decode():
+            return self.spec_worker.forward_batch_speculative(batch)
+        return self.worker.forward_batch_generation(batch)
+
+    def process_batch_result(self, batch: ScheduleBatch, result: Any) -> None:
+        result.wait()
+        self.watchdog_last_progress = time.perf_counter()
+        if batch.forward_mode.is_extend():
+            self._process_prefill_result(batch, result)
+        else:
+            self._process_decode_result(batch, result)
+
+    def _process_prefill_result(self, batch: ScheduleBatch, result: Any) -> None:
+        toks = result.next_token_ids
+        out: List[Req] = []
+        now = time.perf_counter()
+        j = 0
+        for i, r in enumerate(batch.reqs):
+            produces = bool(batch.sample_mask[i])
+            if r.is_embedding:
+                r.embedding = result.embeddings[i] if result.embeddings is not None else None
+                r.finished_reason = FINISH_LENGTH(0)
+                self.kv.release(r)
+                out.append(r)
+                continue
+            if not produces:
+                # chunk of a longer prompt: publish the computed prefix (reference cache_unfinished_req)
+                r.is_chunked = max(0, r.is_chunked - 1)
+                self.kv.cache_unfinished(r)
+                continue
+            if r.return_logprob and result.input_logprobs is not None:
+                r.input_token_logprobs = result.input_logprobs[i]
+            if r.finished():       # aborted while in flight
+                continue
+            tok = int(toks[i])
+            self._append_token(r, tok, result, i)
+            if r.first_token_time is None:
+                r.first_token_time = now
+            r.check_finished(self.tokenizer)
+            if r.to_abort is not None and not r.finished():
+                r.finished_reason = r.to_abort
+            if r.finished():
+                r.finished_time = now
+                r.kv_len = min(r.kv_len, r.seqlen - 1)
+                self.kv.release(r)
+            else:
+                self.kv.cache_unfinished(r)
+            out.append(r)
+        d = self.kv.take_deltas()
+        if d[0].size:
+            self._carry_deltas(d)
+        self.stream_output(out)
+
+    def _carry_deltas(self, d) -> None:
+        # deltas produced while processing results ride with the next batch
+        self.kv._delta_rows.insert(0, d[0]); self.kv._delta_cols.insert(0, d[1]); self.kv._delta_vals.insert(0, d[2])
+
+    def _append_token(self, r: Req, tok: int, result: Any, i: int) -> None:
+        r.output_ids.append(tok)
+        self.num_generated_tokens += 1
+        if r.return_logprob and result.next_token_logprobs is not None:
+            r.output_token_logprobs.append((float(result.next_token_logprobs[i]), tok))
+            if r.top_logprobs_num > 0 and result.top_logprobs is not None:
+                r.output_top_logprobs.append(result.top_logprobs[i])
+        if r.return_hidden_states and result.hidden_states is not None:
+            r.hidden_states.append(result.hidden_states[i])
+        if r.grammar is not None:
+            try:
+                r.grammar.accept_token(tok)
+            except Exception as e:  # grammar rejected a sampled token: abort that request only
+                r.to_abort = FINISH_ABORT(f"grammar error: {e}", 500)
+
+    def _process_decode_result(self, batch: ScheduleBatch, result: Any) -> None:
+        toks = result.next_token_ids
+        out: List[Req] = []
+        now = time.perf_counter()
+        accept = getattr(result, "accept_lens", None)
+        for i, r in enumerate(batch.reqs):
+            if r.finished() or r.req_slot is None:
+                continue        # finished (or retracted) one step earlier; this lagging result is discarded
+            if accept is not None:
+                n_new = int(accept[i])
+                for t in result.accepted_tokens[i][:n_new]:
+                    self._append_token(r, int(t), result, i)
+                r.spec_verify_ct += 1
+                r.spec_accepted_tokens += n_new - 1
+            else:
+                n_new = 1
+                self._append_token(r, int(toks[i]), result, i)
+            r.check_finished(self.tokenizer, n_new)
+            if r.to_abort is not None and not r.finished():
+                r.finished_reason = r.to_abort
+            if r.finished():
+                r.finished_time = now
+                # with overlap a lagging step may already have bumped kv_len; the KV of the final token is
+                # never needed, so clamp to what was really computed for tokens of all_ids()
+                r.kv_len = min(r.kv_len, r.seqlen - 1)
+                self.kv.release(r)
+            elif r.grammar is not None and self.args.enable_jump_forward:
+                self._try_jump_forward(r)
+            out.append(r)
+        d = self.kv.take_deltas()
+        if d[0].size:
+            self._carry_deltas(d)
+        self.stream_output(out)
+        if self.decode_ct % max(1, self.args.decode_log_interval) == 0:
+            self._log_decode_stats()
+
+    def _try_jump_forward(self, r: Req) -> None:
+        """Compressed-FSM jump-forward (reference v0.2 semantics; API ``base_grammar_backend.py:120-147``):
+        when the grammar admits exactly one continuation string, append its tokens and re-prefill."""
+        jf = r.grammar.try_jump_forward(self.tokenizer) if hasattr(r.grammar, "try_jump_forward") else None
+        if not jf:
+            return
+        new_tokens = r.grammar.jump_forward_tokens(jf, self.tokenizer, r.output_ids)
+        if not new_tokens:
+            return
+        room = r.sampling_params.max_new_tokens - len(r.output_ids)
+        new_tokens = new_tokens[: max(0, room - 1)]
+        if not new_tokens:
+            return
+        for t in new_tokens:
+            r.output_ids.append(int(t))
+            r.grammar.accept_token(int(t))
+        self.num_generated_tokens += len(new_tokens)
+        r.jump_forward_tokens.extend(new_tokens)
+        # leave the decode batch and re-enter through the prefill path (KV of the prefix is reused via the tree)
+        rb = self.running_batch
+        if r in rb.reqs:
+            rb.filter_batch([i for i, x in enumerate(rb.reqs) if x is not r])
+        r.kv_len = min(r.kv_len, r.seqlen - 1 - len(new_tokens))
+        self.kv.release(r, insert=True)
+        r.reset_for_retract()
+        r.is_retracted = False
+        self.waiting_queue.insert(0, r)
+
+    # ================================================================== output streaming
+    def stream_output(self, reqs: List[Req]) -> None:
+        """reference scheduler_components/output_streamer.py:113"""
+        sel = []
+        for r in reqs:
+            if r.finished():
+                sel.append(r)
+            elif r.stream:
+                interval = r.sampling_params.stream_interval or self.args.stream_interval
+                if len(r.output_ids) - r.sent_offset >= interval:
+                    sel.append(r)
+        if not sel or self.tp_rank != 0:
+            for r in sel:
+                r.sent_offset = len(r.output_ids)
+            return
+        msg = ios.BatchTokenIDOutput(
+            rids=[r.rid for r in sel],
+            finished_reasons=[r.finished_reason.to_json() if r.finished() else None for r in sel],
+            output_ids=[r.output_ids[r.sent_offset:] for r in sel],
+            read_offsets=[r.sent_offset for r in sel],
+            prompt_tokens=[len(r.origin_input_ids) for r in sel],
+            completion_tokens=[len(r.output_ids) for r in sel],
+            cached_tokens=[r.cached_tokens for r in sel],
+            skip_special_tokens=[r.sampling_params.skip_special_tokens for r in sel],
+            no_stop_trim=[r.sampling_params.no_stop_trim for r in sel],
+            stop_strs=[r.sampling_params.stop for r in sel],
+        )
+        if any(r.return_logprob for r in sel):
+            msg.output_logprobs = [r.output_token_logprobs[r.sent_offset:] if r.return_logprob else None for r in sel]
+            msg.input_logprobs = [r.input_token_logprobs if (r.return_logprob and r.sent_offset == 0) else None for r in sel]
+            msg.top_logprobs = [r.output_top_logprobs[r.sent_offset:] if r.return_logprob else None for r in sel]
+        if any(r.spec_verify_ct for r in sel):
+            msg.spec_verify_ct = [r.spec_verify_ct for r in sel]
+            msg.spec_accepted_tokens = [r.spec_accepted_tokens for r in sel]
+        if any(r.is_embedding for r in sel):
+            msg.embeddings = [r.embedding for r in sel]
+        if any(r.return_hidden_states for r in sel):
+            msg.hidden_states = [r.hidden_states for r in sel]
+        for r in sel:
+            r.sent_offset = len(r.output_ids)
+        self.send_to_detokenizer(msg)
+
+    # ================================================================== loops
+    def step(self) -> bool:
+        """One scheduler iteration.  Returns False when there is nothing to do."""
+        batch = self.get_next_batch_to_run()
+        if batch is None:
+            if self.pending:
+                self.drain()
+                return True
+            self._on_idle()
+            return False
+        need_sync = (not self.enable_overlap) or batch.has_grammar or (self.pending and self.pending[-1][0].has_grammar)
+        if need_sync:
+            self.drain()
+            if batch.has_grammar and batch.forward_mode.is_decode():
+                # requests may have finished / jumped forward while draining
+                alive = [i for i, r in enumerate(batch.reqs) if not r.finished() and r.req_slot is not None]
+                if len(alive) != len(batch.reqs):
+                    self._undo_decode_prepare(batch, alive)
+                    if not alive:
+                        return True
+        result = self.run_batch(batch)
+        self.last_batch = batch
+        self.pending.append((batch, result))
+        while len(self.pending) > (1 if self.enable_overlap and not need_sync else 0):
+            b, res = self.pending.popleft()
+            self.process_batch_result(b, res)
+        if envs.SGLB_STRICT_MEM_CHECK.get():
+            self.check_invariants()
+        return True
+
+    def _undo_decode_prepare(self, batch: ScheduleBatch, alive: List[int]) -> None:
+        idx = np.asarray(alive, dtype=np.int64)
+        batch.reqs = [batch.reqs[i] for i in alive]
+        for name in ("seq_lens", "req_slots", "positions", "out_cache_loc"):
+            setattr(batch, name, getattr(batch, name)[idx])
+
+    def drain(self) -> None:
+        while self.pending:
+            b, res = self.pending.popleft()
+            self.process_batch_result(b, res)
+
+    def has_work(self) -> bool:
+        return bool(self.waiting_queue or self.running_batch.reqs or self.chunked_req is not None or self.pending
+                    or self.grammar_queue or (self.last_batch is not None and self.last_batch.forward_mode.is_extend()))
+
+    def run_until_idle(self, max_steps: int = 1 << 60) -> int:
+        n = 0
+        while self.has_work() and n < max_steps:
+            self.step()
+            n += 1
+        self.drain()
+        return n
+
+    def _on_idle(self) -> None:
+        self.new_token_ratio = self.init_new_token_ratio
+        if not self.has_work():
+            self.check_invariants()
+
+    # ================================================================== introspection
+    def live_reqs(self) -> List[Req]:
+        out = list(self.running_batch.reqs)
+        if self.chunked_req is not None and self.chunked_req not in out:
+            out.append(self.chunked_req)
+        if self.last_batch is not None:
+            out.extend(r for r in self.last_batch.reqs if r not in out)
+        out.extend(r for r in self.waiting_queue if r.req_slot is not None and r not in out)
+        return out
+
+    def check_invariants(self) -> None:
+        self.kv.check_invariants(self.live_reqs())
+
+    def get_internal_state(self) -> Dict[str, Any]:
+        return {
+            "forward_ct": self.forward_ct, "num_running_reqs": len(self.running_batch.reqs),
+            "num_waiting_reqs": len(self.waiting_queue), "token_usage": self.kv.token_usage(),
+            "available_pages": self.kv.available_pages(), "total_pages": self.kv.total_pages(),
+            "evictable_pages": self.tree.evictable_pages(), "protected_pages": self.tree.protected_pages(),
+            "new_token_ratio": self.new_token_ratio, "num_retracted_reqs": self.num_retracted,
+            "num_generated_tokens": self.num_generated_tokens, "num_prefill_tokens": self.num_prefill_tokens,
+            "num_cached_tokens": self.num_cached_tokens, "gen_throughput": self.gen_throughput,
+            "cache_hit_rate": self.num_cached_tokens / max(1, self.num_cached_tokens + self.num_prefill_tokens),
+            "max_running_requests": self.max_running, "max_context_len": self.max_context_len,
+            "page_size": self.page_size, "overlap": self.enable_overlap,
+        }
+
+    def _log_decode_stats(self) -> None:
+        now = time.perf_counter()
+        dt = now - self.last_decode_log
+        if dt <= 0:
+            return
+        self.gen_throughput = (self.num_generated_tokens - self.last_decode_tokens) / dt
+        self.last_decode_log, self.last_decode_tokens = now, self.num_generated_tokens
+        logger.info("Decode batch. #running-req: %d, #token: %d, token usage: %.2f, gen throughput (token/s): %.2f, "
+                    "#queue-req: %d", len(self.running_batch.reqs),
+                    (self.kv.total_pages() - self.kv.available_pages()) * self.page_size, self.kv.token_usage(),
+                    self.gen_throughput, len(self.waiting_queue))
+        if self.metrics is not None:
+            self.metrics.log_stats(self.get_internal_state())

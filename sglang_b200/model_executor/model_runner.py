@@ -1,0 +1,529 @@
+"""ModelRunner: owns the model, the KV pool, device-side request state and the CUDA-graph decode path.
+
+Parity: reference ``python/sglang/srt/model_executor/model_runner.py:285`` (``initialize:642``, ``load_model:1072``,
+pool sizing ``pool_configurator.py``, ``forward:1520``, ``sample:1792``), ``managers/tp_worker.py:299``
+(``forward_batch_generation:574``), ``runner/decode_cuda_graph_runner.py:200`` (capture per batch-size bucket,
+``load_batch:1240``, ``execute:1386``) and ``managers/overlap_utils.py:246`` (FutureMap).
+
+B200-first notes
+* one H2D copy per step (``BatchPacker``), page table kept on device and patched by deltas;
+* sampled tokens are scattered into ``next_token_buf[req_slot]`` by the sampling kernel and gathered by the next
+  decode's embedding kernel: the "future map" is a device array, the host only reads results one step late;
+* decode runs as ONE ``cudaGraphLaunch`` per step (embedding -> layers -> LM head -> sampling);
+* everything is enqueued on a private stream; results are copied to pinned memory and fenced with an event.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..configs.model_config import ModelConfig, load_model_config
+from ..environ import envs
+from ..managers import io_struct as ios
+from ..managers.schedule_batch import ForwardMode, ScheduleBatch
+from ..mem_cache.memory_pool import KVPool
+from ..model_loader.loader import load_model
+from ..parallel.parallel_state import get_pp_group, get_state, get_tp_group
+from ..server_args import ServerArgs
+from .forward_batch import BatchPacker, ForwardBatch, SamplingTensors
+
+logger = logging.getLogger(__name__)
+_DT = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
+
+
+class BatchResult:
+    """Asynchronous result of one step; ``wait()`` blocks until the device->host copy has landed."""
+
+    def __init__(self) -> None:
+        self.event: Optional[torch.cuda.Event] = None
+        self._tok_host: Optional[torch.Tensor] = None
+        self._lp_host: Optional[torch.Tensor] = None
+        self.next_token_ids: Optional[np.ndarray] = None   # aligned with batch.reqs (non-sampled rows = -1)
+        self.next_token_logprobs: Optional[np.ndarray] = None
+        self.top_logprobs: Any = None
+        self.input_logprobs: Any = None
+        self.embeddings: Any = None
+        self.hidden_states: Any = None
+        self.sample_rows: Optional[np.ndarray] = None
+        self.batch_size = 0
+        self.d2h_bytes = 0
+        self.accept_lens = None
+        self.accepted_tokens = None
+
+    def wait(self) -> None:
+        if self.next_token_ids is not None or self._tok_host is None:
+            return
+        if self.event is not None:
+            self.event.synchronize()
+        toks = self._tok_host.numpy()
+        out = np.full(self.batch_size, -1, dtype=np.int64)
+        out[self.sample_rows] = toks[: self.sample_rows.size]
+        self.next_token_ids = out
+        if self._lp_host is not None:
+            lp = np.zeros(self.batch_size, dtype=np.float32)
+            lp[self.sample_rows] = self._lp_host.numpy()[: self.sample_rows.size]
+            self.next_token_logprobs = lp
+
+
+class ModelRunner:
+    def __init__(self, server_args: ServerArgs, model_config: Optional[ModelConfig] = None):
+        self.args = server_args
+        self.cfg = model_config or load_model_config(server_args.model_path, json.loads(server_args.json_model_override_args or "{}"),
+                                                     server_args.context_length)
+        st = get_state()
+        self.tp, self.pp = st.tp, st.pp
+        self.is_cuda = server_args.device == "cuda"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.is_cuda else torch.device("cpu")
+        self.dtype = _DT[self.cfg.dtype] if self.is_cuda or self.cfg.dtype != "bfloat16" else torch.float32
+        if not self.is_cuda and self.cfg.dtype == "bfloat16":
+            self.cfg.dtype = "float32"      # CPU tier runs fp32
+            self.dtype = torch.float32
+        if self.is_cuda:
+            ops.load_native()
+            if server_args.gemm_backend in ("tc", "lib"):
+                envs.SGLB_GEMM_IMPL.set(server_args.gemm_backend)
+            if server_args.attention_backend in ("tc", "simt"):
+                envs.SGLB_ATTN_IMPL.set(server_args.attention_backend)
+        self.page_size = server_args.page_size
+        torch.manual_seed(server_args.random_seed)
+        t0 = time.perf_counter()
+        if self.cfg.is_moe:
+            from ..models import mixtral
+
+            mixtral.set_ep_size(server_args.ep_size)
+        self.model = load_model(self.cfg, server_args.model_path, server_args.load_format, self.device, server_args.quantization,
+                                server_args.random_seed)
+        self.load_time = time.perf_counter() - t0
+        self.weight_bytes = sum(p.numel() * p.element_size() for p in self.model.parameters())
+        self.stream = torch.cuda.Stream(self.device) if self.is_cuda else None
+        self.kv_manager = None
+        self._init_memory()
+        self.packer = BatchPacker(self.device)
+        # pinned staging rings: the host may run up to two steps ahead of the device (overlap scheduling), so a
+        # staging buffer is only reused after >= 4 later steps
+        self._stage_ring: List[torch.Tensor] = []
+        self._res_ring: List[Any] = []
+        self._ring_i = 0
+        if self.is_cuda:
+            n_stage = 8 * max(self.max_running, 512) + 2 + 3 * 8192
+            self._stage_ring = [torch.zeros(n_stage, dtype=torch.int32).pin_memory() for _ in range(4)]
+            self._res_ring = [(torch.zeros(self.max_running + 8, dtype=torch.int32).pin_memory(),
+                               torch.zeros(self.max_running + 8, dtype=torch.float32).pin_memory()) for _ in range(8)]
+        self.graphs: Dict[int, Any] = {}
+        self.graph_bs: List[int] = []
+        self.graph_launches = 0       # kernels replayed through CUDA graphs (for gpu_launches accounting)
+        self.step_counter = 0
+        self.forward_ct = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.lora_manager = None
+        self.profiler = None
+        self.expert_recorder = None
+        if self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1:
+            with torch.cuda.stream(self.stream):
+                self._capture_graphs()
+            self.stream.synchronize()
+
+    # ------------------------------------------------------------------ memory
+    def _init_memory(self) -> None:
+        cfg, a = self.cfg, self.args
+        n_layers = len(self.model.model.layers)
+        kv_heads = self.model.model.layers[0].self_attn.attn.num_kv_heads if n_layers else cfg.num_key_value_heads
+        kv_dtype = self.dtype
+        if a.kv_cache_dtype in ("fp8_e4m3", "fp8"):
+            kv_dtype = torch.float8_e4m3fn
+        per_page = KVPool.bytes_per_page(self.page_size, n_layers, kv_heads, cfg.head_dim, kv_dtype)
+        self.max_context_len = a.context_length or cfg.max_position_embeddings
+        if self.is_cuda:
+            free, total = torch.cuda.mem_get_info(self.device)
+            budget = int(total * a.mem_fraction_static) - (total - free)
+            # activation head-room for the largest prefill chunk (QKV + MLP intermediates), logits and graphs
+            chunk = a.chunked_prefill_size or a.max_prefill_tokens
+            act = chunk * (cfg.hidden_size * 6 + (cfg.intermediate_size // self.tp.world_size) * 3 * 2) * 2
+            budget -= act
+            num_pages = max(16, budget // per_page)
+        else:
+            num_pages = 4096 // self.page_size + 1
+        if a.max_total_tokens:
+            num_pages = min(num_pages, a.max_total_tokens // self.page_size + 1)
+        if self.tp.world_size > 1:   # all ranks must agree (reference: min over TP ranks)
+            t = torch.tensor([num_pages], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.tp.device_group)
+            num_pages = int(t.item())
+        self.num_pages = int(num_pages)
+        self.kv_pool = KVPool(self.num_pages, self.page_size, n_layers, kv_heads, cfg.head_dim, kv_dtype, str(self.device))
+        tokens = (self.num_pages - 1) * self.page_size
+        self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
+        max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
+        self.page_table = torch.zeros(self.max_running + 1, max_pages_per_req, dtype=torch.int32, device=self.device)
+        self.next_token_buf = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
+        logger.info("KV pool: %d pages x %d tokens (%.2f GB), max_running=%d, weights %.2f GB", self.num_pages, self.page_size,
+                    self.num_pages * per_page / 2 ** 30, self.max_running, self.weight_bytes / 2 ** 30)
+
+    def get_memory_info(self) -> Dict[str, int]:
+        return {"num_pages": self.num_pages, "max_context_len": self.max_context_len, "max_running": self.max_running}
+
+    def attach_kv_manager(self, kv: Any) -> None:
+        self.kv_manager = kv
+        assert kv.page_table.shape[1] <= self.page_table.shape[1] + 1
+        if kv.page_table.shape[1] != self.page_table.shape[1]:
+            self.page_table = torch.zeros(self.max_running + 1, kv.page_table.shape[1], dtype=torch.int32, device=self.device)
+
+    def get_eos_token_ids(self) -> List[int]:
+        return self.cfg.eos_token_ids
+
+    def supports_overlap(self) -> bool:
+        return True
+
+    def flush(self) -> None:
+        self.page_table.zero_()
+
+    # ------------------------------------------------------------------ attention split heuristic
+    def _pick_splits(self, bs: int, max_kv: int) -> int:
+        if not self.is_cuda:
+            return 1
+        kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads
+        ctas = bs * kvh
+        tiles = (max_kv + 127) // 128
+        if ctas >= 148 or tiles <= 2:
+            return 1
+        return int(max(1, min(tiles, 8, (148 * 2) // max(1, ctas))))
+
+    # ------------------------------------------------------------------ forward
+    def forward_batch_generation(self, sb: ScheduleBatch) -> BatchResult:
+        self.forward_ct += 1
+        if self.is_cuda:
+            with torch.cuda.stream(self.stream):
+                return self._forward(sb)
+        return self._forward(sb)
+
+    @torch.no_grad()
+    def _forward(self, sb: ScheduleBatch) -> BatchResult:
+        B = len(sb.reqs)
+        decode = sb.forward_mode.is_decode()
+        self.step_counter += 1
+        use_graph = decode and self.graphs and not sb.return_logprob and not sb.has_grammar and sb.spec_info is None and \
+            B <= self.graph_bs[-1] and not any(r.sampling_params.logit_bias or r.sampling_params.frequency_penalty
+                                               or r.sampling_params.presence_penalty or r.sampling_params.repetition_penalty != 1.0
+                                               for r in sb.reqs) and self.lora_manager is None
+        if use_graph:
+            return self._forward_graph(sb)
+        fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
+        self.h2d_bytes += fb.h2d_bytes
+        fb.num_splits = self._pick_splits(B, fb.max_kv_len) if decode else 1
+        self._attach_mm(sb, fb)
+        if self.lora_manager is not None:
+            self.lora_manager.prepare_batch(sb, fb)
+        if not self.pp.is_first:
+            fb.pp_hidden = self._pp_recv(fb.num_tokens)
+        hidden = self.model(fb)
+        res = BatchResult()
+        res.batch_size = B
+        if not self.pp.is_last:
+            self._pp_send(hidden)
+            return self._pp_result(sb, res)
+        samp_rows = np.arange(B) if decode else np.flatnonzero(sb.sample_mask)
+        res.sample_rows = samp_rows
+        if samp_rows.size == 0:
+            res.next_token_ids = np.full(B, -1, dtype=np.int64)
+            return res
+        h_last = hidden if decode else ops.gather_rows(hidden, fb.last_idx)
+        if getattr(self.model, "is_embedding", False) or any(r.is_embedding for r in sb.reqs):
+            emb = self.model.pool(h_last) if hasattr(self.model, "pool") else torch.nn.functional.normalize(h_last.float(), dim=-1)
+            embs = emb.cpu().tolist()
+            res.embeddings = [None] * B
+            for j, i in enumerate(samp_rows.tolist()):
+                res.embeddings[i] = embs[j]
+            res.next_token_ids = np.full(B, -1, dtype=np.int64)
+            return res
+        logits = self.model.compute_logits(h_last)
+        if any(r.return_hidden_states for r in sb.reqs):
+            hs = h_last.float().cpu().tolist()
+            res.hidden_states = [None] * B
+            for j, i in enumerate(samp_rows.tolist()):
+                res.hidden_states[i] = hs[j]
+        reqs = [sb.reqs[i] for i in samp_rows.tolist()]
+        logits = self._preprocess_logits(logits, reqs, fb)
+        lp_out = torch.empty(len(reqs), dtype=torch.float32, device=self.device) if sb.return_logprob else None
+        toks = self.sample(logits, fb, lp_out)
+        if sb.return_logprob:
+            self._extra_logprobs(sb, fb, hidden, logits, res, samp_rows)
+        self._finish_result(res, toks, lp_out)
+        return res
+
+    def sample(self, logits: torch.Tensor, fb: ForwardBatch, lp_out: Optional[torch.Tensor]) -> torch.Tensor:
+        s = fb.sampling
+        if self.args.sampling_backend == "token_oracle" and self.token_oracle is not None:
+            return self.token_oracle(fb, logits)
+        return ops.sample(logits, s.temperature, s.top_k, s.top_p, s.min_p, s.seeds, fb.sample_slots, fb.next_token_buf,
+                          lp_out, global_seed=self.args.random_seed, step=self.step_counter)
+
+    token_oracle = None
+
+    def _finish_result(self, res: BatchResult, toks: torch.Tensor, lp: Optional[torch.Tensor]) -> None:
+        n = toks.numel()
+        if self.is_cuda:
+            self._ring_i += 1
+            th, lh = self._res_ring[self._ring_i % len(self._res_ring)]
+            res._tok_host = th[:n]
+            res._tok_host.copy_(toks, non_blocking=True)
+            if lp is not None:
+                res._lp_host = lh[:n]
+                res._lp_host.copy_(lp, non_blocking=True)
+            res.event = torch.cuda.Event()
+            res.event.record(torch.cuda.current_stream())
+        else:
+            res._tok_host = toks.to(torch.int32).cpu()
+            res._lp_host = lp.cpu() if lp is not None else None
+        res.d2h_bytes = n * 4 + (n * 4 if lp is not None else 0)
+        self.d2h_bytes += res.d2h_bytes
+
+    # ---- logits post-processing (grammar mask, penalties, logit bias) — reference sampling_batch_info.py:240,301
+    def _preprocess_logits(self, logits: torch.Tensor, reqs: List[Any], fb: ForwardBatch) -> torch.Tensor:
+        need_f32 = fb.sampling.has_penalty
+        if need_f32:
+            logits = logits.float()
+            V = logits.shape[1]
+            for j, r in enumerate(reqs):
+                sp = r.sampling_params
+                if sp.logit_bias:
+                    idx = torch.tensor([int(k) for k in sp.logit_bias], device=self.device)
+                    logits[j, idx] += torch.tensor(list(sp.logit_bias.values()), device=self.device, dtype=logits.dtype)
+                if sp.frequency_penalty or sp.presence_penalty or sp.repetition_penalty != 1.0:
+                    counts = torch.zeros(1, V, dtype=torch.int32, device=self.device)
+                    if r.output_ids:
+                        out = torch.tensor(r.output_ids, device=self.device)
+                        counts[0].index_add_(0, out, torch.ones_like(out, dtype=torch.int32))
+                    pm = torch.zeros(1, V, dtype=torch.uint8, device=self.device)
+                    if sp.repetition_penalty != 1.0:
+                        pm[0, torch.tensor(r.origin_input_ids, device=self.device)] = 1
+                    row = logits[j:j + 1]
+                    ops.apply_penalties(row, counts, pm, torch.tensor([sp.frequency_penalty], device=self.device),
+                                        torch.tensor([sp.presence_penalty], device=self.device),
+                                        torch.tensor([sp.repetition_penalty], device=self.device))
+        g_rows = [j for j, r in enumerate(reqs) if r.grammar is not None]
+        if g_rows:
+            V = logits.shape[1]
+            words = (V + 31) // 32
+            bm = np.full((len(g_rows), words), -1, dtype=np.int32)
+            for k, j in enumerate(g_rows):
+                reqs[j].grammar.fill_vocab_mask(bm[k], V)
+            bm_t = torch.from_numpy(bm).to(self.device)
+            ops.apply_token_bitmask(logits, bm_t, torch.tensor(g_rows, dtype=torch.int32, device=self.device))
+        for j, r in enumerate(reqs):
+            if len(r.output_ids) < r.sampling_params.min_new_tokens:
+                stops = list(r.eos_token_ids) + list(r.sampling_params.stop_token_ids)
+                if stops:
+                    logits[j, torch.tensor(stops, device=self.device)] = float("-inf")
+        return logits
+
+    def _extra_logprobs(self, sb: ScheduleBatch, fb: ForwardBatch, hidden, logits, res: BatchResult, samp_rows) -> None:
+        """top-k logprobs of the sampled position and prompt (input) logprobs — library ops, off the hot path"""
+        lsm = torch.log_softmax(logits.float(), dim=-1)
+        res.top_logprobs = [None] * len(sb.reqs)
+        for j, i in enumerate(samp_rows.tolist()):
+            k = sb.reqs[i].top_logprobs_num
+            if k > 0:
+                v, idx = lsm[j].topk(k)
+                res.top_logprobs[i] = list(zip(v.tolist(), idx.tolist()))
+        if sb.forward_mode.is_extend() and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs):
+            all_logits = torch.log_softmax(self.model.compute_logits(hidden).float(), dim=-1)
+            res.input_logprobs = [None] * len(sb.reqs)
+            cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
+            for i, r in enumerate(sb.reqs):
+                if not (r.return_logprob and r.logprob_start_len >= 0):
+                    continue
+                s, e = int(cu[i]), int(cu[i + 1])
+                ids = torch.from_numpy(sb.input_ids[s + 1:e].astype(np.int64)).to(self.device)
+                lp = all_logits[s:e - 1].gather(1, ids[:, None]).squeeze(1).tolist()
+                start = max(0, r.logprob_start_len - int(sb.prefix_lens[i]))
+                res.input_logprobs[i] = [(None, int(sb.input_ids[s]))] * (1 if start == 0 else 0) + \
+                    [(float(a), int(b)) for a, b in zip(lp, ids.tolist())][start:]
+
+    def _attach_mm(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
+        if not sb.forward_mode.is_extend() or not any(r.mm_inputs for r in sb.reqs):
+            return
+        from ..multimodal.embed import build_mm_embeds
+
+        fb.mm_embeds = build_mm_embeds(self.model, sb, self.device, self.dtype)
+
+    # ------------------------------------------------------------------ pipeline parallel hand-off
+    def _pp_recv(self, T: int):
+        H = self.cfg.hidden_size
+        h = torch.empty(T, H, dtype=self.dtype, device=self.device)
+        r = torch.empty(T, H, dtype=self.dtype, device=self.device)
+        self.pp.recv(h, self.pp.rank - 1)
+        self.pp.recv(r, self.pp.rank - 1)
+        return h, r
+
+    def _pp_send(self, hr) -> None:
+        h, r = hr
+        self.pp.send(h.contiguous(), self.pp.rank + 1)
+        self.pp.send(r.contiguous(), self.pp.rank + 1)
+
+    def _pp_result(self, sb: ScheduleBatch, res: BatchResult) -> BatchResult:
+        """non-last stages learn the sampled ids from the last stage (they need them for the next decode input)"""
+        B = len(sb.reqs)
+        decode = sb.forward_mode.is_decode()
+        rows = np.arange(B) if decode else np.flatnonzero(sb.sample_mask)
+        res.sample_rows = rows
+        toks = torch.empty(max(1, rows.size), dtype=torch.int32, device=self.device)
+        if rows.size:
+            self.pp.broadcast(toks, src=self.pp.world_size - 1)
+            slots = torch.from_numpy(sb.req_slots[rows].astype(np.int64)).to(self.device)
+            self.next_token_buf[slots] = toks[: rows.size]
+        self._finish_result(res, toks[: rows.size], None)
+        return res
+
+    # ------------------------------------------------------------------ CUDA graph decode path
+    def _capture_graphs(self) -> None:
+        a = self.args
+        max_bs = min(a.cuda_graph_max_bs, self.max_running)
+        bs_list = a.cuda_graph_bs or sorted({b for b in ([1, 2, 4, 8, 12, 16, 24, 32, 48, 64, 96, 128, 160, 192, 224, 256] +
+                                                         list(range(320, 4097, 64))) if b <= max_bs} | {max_bs})
+        self.graph_bs = sorted(bs_list)
+        t0 = time.perf_counter()
+        pool = None
+        kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads
+        for bs in reversed(self.graph_bs):
+            g = _DecodeGraph(self, bs)
+            g.capture(pool)
+            pool = g.graph.pool()
+            self.graphs[bs] = g
+        logger.info("captured %d decode graphs (bs %s..%s) in %.1fs", len(self.graphs), self.graph_bs[0], self.graph_bs[-1],
+                    time.perf_counter() - t0)
+
+    def _forward_graph(self, sb: ScheduleBatch) -> BatchResult:
+        B = len(sb.reqs)
+        import bisect
+
+        bs = self.graph_bs[bisect.bisect_left(self.graph_bs, B)]
+        g = self.graphs[bs]
+        # page-table deltas are applied eagerly (their count is unbounded), then one graph launch
+        nd = 0 if sb.pt_rows is None else sb.pt_rows.size
+        g.load(sb, self.step_counter, self.args.random_seed)
+        if nd:
+            d = g.delta_views(nd)
+            ops.apply_pt_delta(self.page_table, d[0], d[1], d[2])
+        g.graph.replay()
+        self.graph_launches += g.num_kernels
+        res = BatchResult()
+        res.batch_size = B
+        res.sample_rows = np.arange(B)
+        self._finish_result(res, g.out_tokens[:B], None)
+        return res
+
+    # ------------------------------------------------------------------ control plane (weights, profiling, LoRA)
+    def handle_control(self, msg: Any) -> Any:
+        from . import control
+
+        return control.handle(self, msg)
+
+
+class _DecodeGraph:
+    """One captured decode step for a fixed (padded) batch size."""
+
+    def __init__(self, runner: ModelRunner, bs: int):
+        self.r = runner
+        self.bs = bs
+        dev = runner.device
+        # static int region: positions | out_cache_loc | req_slots | seq_lens | step(2) | temperature | top_p | min_p | top_k
+        self.n_int = 8 * bs + 2
+        self.static = torch.zeros(self.n_int + 3 * 8192, dtype=torch.int32, device=dev)
+        s = self.static
+        self.positions, self.out_cache_loc, self.req_slots, self.seq_lens = s[0:bs], s[bs:2 * bs], s[2 * bs:3 * bs], s[3 * bs:4 * bs]
+        self.step = s[4 * bs:4 * bs + 2].view(torch.int64)
+        o = 4 * bs + 2
+        self.temperature = s[o:o + bs].view(torch.float32)
+        self.top_p = s[o + bs:o + 2 * bs].view(torch.float32)
+        self.min_p = s[o + 2 * bs:o + 3 * bs].view(torch.float32)
+        self.top_k = s[o + 3 * bs:o + 4 * bs]
+        self.out_tokens = torch.zeros(bs, dtype=torch.int32, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.num_kernels = 0
+        self.num_splits = runner._pick_splits(bs, min(runner.max_context_len, 4096))
+        self.workspace = None
+        if self.num_splits > 1:
+            a0 = runner.model.model.layers[0].self_attn.attn
+            self.workspace = (torch.empty(self.num_splits, bs, a0.num_heads, a0.head_dim, dtype=torch.float32, device=dev),
+                              torch.empty(self.num_splits, bs, a0.num_heads, dtype=torch.float32, device=dev))
+
+    def _fb(self) -> ForwardBatch:
+        r = self.r
+        samp = SamplingTensors(self.temperature, self.top_k, self.top_p, self.min_p)
+        return ForwardBatch(mode=ForwardMode.DECODE, batch_size=self.bs, num_tokens=self.bs, input_ids=None,
+                            positions=self.positions, out_cache_loc=self.out_cache_loc, req_slots=self.req_slots,
+                            seq_lens=self.seq_lens, cu_q=None, q_lens=None, last_idx=None, sample_slots=self.req_slots,
+                            max_q_len=1, max_kv_len=r.max_context_len, page_table=r.page_table, page_size=r.page_size,
+                            kv_pool=r.kv_pool, num_splits=self.num_splits, attn_workspace=self.workspace, sampling=samp,
+                            next_token_buf=r.next_token_buf)
+
+    def _run(self) -> None:
+        r = self.r
+        fb = self._fb()
+        hidden = r.model(fb)
+        logits = r.model.compute_logits(hidden)
+        torch.ops.sglb.sample(logits, self.temperature, self.top_k, self.top_p, self.min_p, None, self.req_slots,
+                              r.next_token_buf, self.out_tokens, None, int(r.args.random_seed), self.step, 0)
+
+    def capture(self, pool) -> None:
+        # neutral padding values
+        bs = self.bs
+        host = torch.zeros(self.static.numel(), dtype=torch.int32)
+        hn = host.numpy()
+        hn[3 * bs:4 * bs] = 1                       # seq_lens = 1
+        o = 4 * bs + 2
+        hn[o:o + 2 * bs] = np.float32(1.0).view(np.int32)   # temperature, top_p
+        hn[o + 3 * bs:o + 4 * bs] = 1               # top_k = 1 (greedy)
+        self.static.copy_(host)
+        stream = torch.cuda.current_stream()
+        for _ in range(2):   # warm-up outside capture (cuBLAS workspaces, lazy inits)
+            self._run()
+        stream.synchronize()
+        c0 = ops.launch_count()
+        with torch.cuda.graph(self.graph, pool=pool, stream=stream):
+            self._run()
+        self.num_kernels = ops.launch_count() - c0
+
+    def load(self, sb: ScheduleBatch, step: int, seed: int) -> None:
+        B, bs = len(sb.reqs), self.bs
+        r_ = self.r
+        r_._ring_i += 1
+        host = r_._stage_ring[r_._ring_i % len(r_._stage_ring)]
+        h = host.numpy()
+        h[0:B] = sb.positions; h[B:bs] = 0
+        h[bs:bs + B] = sb.out_cache_loc; h[bs + B:2 * bs] = 0
+        h[2 * bs:2 * bs + B] = sb.req_slots; h[2 * bs + B:3 * bs] = 0
+        h[3 * bs:3 * bs + B] = sb.seq_lens; h[3 * bs + B:4 * bs] = 1
+        h[4 * bs:4 * bs + 2] = np.asarray([step], dtype=np.int64).view(np.int32)
+        o = 4 * bs + 2
+        sp = [r.sampling_params for r in sb.reqs]
+        h[o:o + B] = np.asarray([p.temperature for p in sp], dtype=np.float32).view(np.int32)
+        h[o + B:o + bs] = np.float32(1.0).view(np.int32)
+        h[o + bs:o + bs + B] = np.asarray([p.top_p for p in sp], dtype=np.float32).view(np.int32)
+        h[o + bs + B:o + 2 * bs] = np.float32(1.0).view(np.int32)
+        h[o + 2 * bs:o + 2 * bs + B] = np.asarray([p.min_p for p in sp], dtype=np.float32).view(np.int32)
+        h[o + 2 * bs + B:o + 3 * bs] = 0
+        h[o + 3 * bs:o + 3 * bs + B] = np.asarray([min(p.top_k, 1 << 30) for p in sp], dtype=np.int32)
+        h[o + 3 * bs + B:o + 4 * bs] = 1
+        n = self.n_int
+        nd = 0 if sb.pt_rows is None else sb.pt_rows.size
+        if nd:
+            if n + 3 * nd > h.size:
+                raise RuntimeError("page-table delta overflow in graph staging buffer")
+            h[n:n + nd] = sb.pt_rows; h[n + nd:n + 2 * nd] = sb.pt_cols; h[n + 2 * nd:n + 3 * nd] = sb.pt_vals
+        tot = n + 3 * nd
+        self.static[:tot].copy_(host[:tot], non_blocking=True)
+        self.r.h2d_bytes += tot * 4
+
+    def delta_views(self, nd: int):
+        n = self.n_int
+        s = self.static
+        return s[n:n + nd], s[n + nd:n + 2 * nd], s[n + 2 * nd:n + 3 * nd]

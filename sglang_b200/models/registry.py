@@ -1,0 +1,38 @@
+"""Architecture registry (reference ``python/sglang/srt/models/registry.py:20`` EntryClass scan)."""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+_REGISTRY: Dict[str, Callable] = {}
+
+
+def register_model(arch: str, cls: Callable) -> None:
+    _REGISTRY[arch] = cls
+
+
+def get_model_class(arch: str):
+    _ensure()
+    if arch not in _REGISTRY:
+        raise ValueError(f"unsupported architecture {arch!r}; supported: {sorted(_REGISTRY)}")
+    return _REGISTRY[arch]
+
+
+def supported_architectures():
+    _ensure()
+    return sorted(_REGISTRY)
+
+
+def _ensure() -> None:
+    if _REGISTRY:
+        return
+    from . import llama, llava, mixtral
+
+    for name in ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM", "Qwen3ForCausalLM", "GemmaForCausalLM"):
+        register_model(name, getattr(llama, name))
+    register_model("MixtralForCausalLM", mixtral.MixtralForCausalLM)
+    register_model("LlavaForConditionalGeneration", llava.LlavaForConditionalGeneration)
+    register_model("LlavaLlamaForCausalLM", llava.LlavaForConditionalGeneration)
+    from . import embedding as _emb
+
+    register_model("LlamaEmbeddingModel", _emb.LlamaEmbeddingModel)
+    register_model("LlamaForSequenceClassification", _emb.LlamaForSequenceClassification)

@@ -1,0 +1,277 @@
+"""Op front door.  CUDA tensors -> our sm_100a kernels (``torch.ops.sglb.*`` from ``_C.so``); CPU tensors ->
+the fp32 torch reference (``torch_ref``) so the scheduler/model stack is testable without a GPU.
+
+There is no multi-backend dispatch on the GPU: if the extension is missing on a CUDA box the ops raise
+(``SGLB_REQUIRE_NATIVE``), they never fall back silently (the driver records which .so files were loaded).
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Optional, Tuple
+
+import torch
+
+from ..environ import envs
+from . import torch_ref
+
+_SO = Path(__file__).resolve().parent.parent / "_C.so"
+_loaded = False
+_load_error: Optional[str] = None
+
+
+def load_native(build_if_missing: bool = False) -> bool:
+    global _loaded, _load_error
+    if _loaded:
+        return True
+    if not _SO.exists() and build_if_missing:
+        from .. import build as _b
+
+        _b.build_all()
+    try:
+        torch.ops.load_library(str(_SO))
+        _loaded = True
+    except Exception as e:  # pragma: no cover - depends on the box
+        _load_error = f"{type(e).__name__}: {e}"
+    return _loaded
+
+
+def native_available() -> bool:
+    return load_native()
+
+
+def _use_native(t: torch.Tensor) -> bool:
+    if not t.is_cuda or envs.SGLB_FORCE_TORCH_OPS.get():
+        return False
+    if not load_native():
+        if envs.SGLB_REQUIRE_NATIVE.get():
+            raise RuntimeError(f"sglang_b200 CUDA extension not loaded ({_load_error}); run `python -m sglang_b200.build`")
+        return False
+    return True
+
+
+def launch_count() -> int:
+    return int(torch.ops.sglb.launch_count()) if _loaded else 0
+
+
+def reset_launch_count() -> None:
+    if _loaded:
+        torch.ops.sglb.reset_launch_count()
+
+
+# ------------------------------------------------------------------ norms / activations
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None, gemma: bool = False) -> torch.Tensor:
+    if _use_native(x) and x.dtype == torch.bfloat16:
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        out = torch.empty_like(x2) if out is None else out.view(-1, shp[-1])
+        torch.ops.sglb.rmsnorm(x2, None, weight, out, eps, gemma)
+        return out.view(shp)
+    r = torch_ref.gemma_rmsnorm(x, weight, eps) if gemma else torch_ref.rmsnorm(x, weight, eps)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def fused_add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float, gemma: bool = False) -> None:
+    """residual += x ; x = rmsnorm(residual) * w   (in place)"""
+    if _use_native(x) and x.dtype == torch.bfloat16:
+        torch.ops.sglb.rmsnorm(x, residual, weight, x, eps, gemma)
+        return
+    if gemma:
+        s = x.float() + residual.float()
+        residual.copy_(s.to(residual.dtype))
+        x.copy_(torch_ref.gemma_rmsnorm(residual, weight, eps))
+    else:
+        torch_ref.fused_add_rmsnorm(x, residual, weight, eps)
+
+
+def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    if _use_native(x) and x.dtype == torch.bfloat16:
+        out = torch.empty(x.shape[0], x.shape[1] // 2, dtype=x.dtype, device=x.device)
+        torch.ops.sglb.act_and_mul(x, out, 0)
+        return out
+    return torch_ref.silu_and_mul(x)
+
+
+def gelu_and_mul(x: torch.Tensor, approximate: str = "none") -> torch.Tensor:
+    if _use_native(x) and x.dtype == torch.bfloat16:
+        out = torch.empty(x.shape[0], x.shape[1] // 2, dtype=x.dtype, device=x.device)
+        torch.ops.sglb.act_and_mul(x, out, 2 if approximate == "tanh" else 1)
+        return out
+    return torch_ref.gelu_and_mul(x, approximate)
+
+
+# ------------------------------------------------------------------ rope + KV write
+def rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox: bool = True,
+                  k_scale: float = 1.0, v_scale: float = 1.0) -> None:
+    if _use_native(q) and q.dtype == torch.bfloat16:
+        torch.ops.sglb.rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox, k_scale, v_scale)
+        return
+    torch_ref.rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox, k_scale, v_scale)
+
+
+# ------------------------------------------------------------------ attention
+def attn_impl() -> int:
+    v = envs.SGLB_ATTN_IMPL.get()
+    return 1 if v == "simt" else 0
+
+
+def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, q_lens, max_q_len: int, page_size: int,
+                    scale: float, causal: bool = True, window: int = -1, logit_cap: float = 0.0, k_scale: float = 1.0,
+                    v_scale: float = 1.0, num_splits: int = 1, workspace=None, tok2req=None, out=None, lse=None,
+                    impl: Optional[int] = None, custom_mask=None):
+    """q [T,Hq,D]; caches [slots,Hkv,D]; cu_q None => decode (q_len 1)."""
+    if _use_native(q) and q.dtype == torch.bfloat16 and custom_mask is None:
+        if out is None:
+            out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+        impl = attn_impl() if impl is None else impl
+        D = q.shape[-1]
+        Hq, Hkv = q.shape[1], k_cache.shape[1]
+        G = Hq // Hkv
+        if impl == 0 and (D != 128 or k_cache.dtype != torch.bfloat16 or 128 % G != 0 or page_size < 8 or page_size > 128):
+            impl = 1
+        part_o = part_lse = None
+        if impl == 0 and num_splits > 1:
+            if workspace is None:
+                T = q.shape[0]
+                part_o = torch.empty(num_splits, T, Hq, D, dtype=torch.float32, device=q.device)
+                part_lse = torch.empty(num_splits, T, Hq, dtype=torch.float32, device=q.device)
+            else:
+                part_o, part_lse = workspace
+        else:
+            num_splits = 1
+        if impl == 1 and cu_q is not None and tok2req is None:
+            ql = cu_q[1:] - cu_q[:-1]
+            tok2req = torch.repeat_interleave(torch.arange(ql.numel(), device=q.device, dtype=torch.int32), ql.long()).to(torch.int32)
+        torch.ops.sglb.attn_fwd(q, k_cache, v_cache, out, lse, part_o, part_lse, page_table, req_slots, seq_lens, cu_q, tok2req,
+                                int(max_q_len), int(page_size), int(num_splits), float(scale), bool(causal), int(window),
+                                float(logit_cap), float(k_scale), float(v_scale), int(impl))
+        return out
+    r = torch_ref.paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, q_lens, page_size, scale, causal,
+                                  window, logit_cap, k_scale, v_scale, custom_mask=custom_mask, return_lse=lse is not None)
+    if lse is not None:
+        o, l = r
+        lse.copy_(l)
+        r = o
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+# ------------------------------------------------------------------ GEMM
+EPI_NONE, EPI_BIAS, EPI_SILU_MUL = 0, 1, 2
+
+
+def gemm_impl() -> str:
+    return envs.SGLB_GEMM_IMPL.get()
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, impl: Optional[str] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T,K] @ w[N,K]^T.  impl: 'tc' = our tcgen05 GEMM, 'lib' = cuBLASLt (plain library GEMM)."""
+    impl = impl or gemm_impl()
+    if impl in ("tc", "auto") and _use_native(x) and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 \
+            and x.dim() == 2 and x.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and x.stride(0) % 8 == 0 and x.stride(1) == 1 \
+            and impl == "tc":
+        if out is None:
+            out = torch.empty(x.shape[0], w.shape[0], dtype=x.dtype, device=x.device)
+        torch.ops.sglb.gemm(x, w, out, bias, EPI_BIAS if bias is not None else EPI_NONE, 0)
+        return out
+    r = torch.nn.functional.linear(x, w, bias)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, bn: int = 0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n_out = w.shape[0] // 2 if epilogue == EPI_SILU_MUL else w.shape[0]
+    if out is None:
+        out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
+    torch.ops.sglb.gemm(x, w, out, bias, epilogue, bn)
+    return out
+
+
+# ------------------------------------------------------------------ misc index ops
+def apply_pt_delta(page_table: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n: Optional[torch.Tensor] = None,
+                   n_max: Optional[int] = None) -> None:
+    n_max = rows.numel() if n_max is None else n_max
+    if n_max == 0:
+        return
+    if _use_native(page_table):
+        torch.ops.sglb.apply_pt_delta(page_table, rows, cols, vals, n, n_max)
+        return
+    page_table[rows.long(), cols.long()] = vals
+
+
+def embedding(weight: torch.Tensor, ids: torch.Tensor, gather_idx: Optional[torch.Tensor] = None, vocab_start: int = 0) -> torch.Tensor:
+    T = ids.shape[0] if gather_idx is None else gather_idx.shape[0]
+    if _use_native(weight) and weight.dtype == torch.bfloat16:
+        out = torch.empty(T, weight.shape[1], dtype=weight.dtype, device=weight.device)
+        torch.ops.sglb.embedding(weight, ids, gather_idx, out, vocab_start)
+        return out
+    if gather_idx is not None:
+        ids = ids[gather_idx.long()]
+    idl = ids.long() - vocab_start
+    ok = (idl >= 0) & (idl < weight.shape[0])
+    out = torch.nn.functional.embedding(idl.clamp(0, weight.shape[0] - 1), weight)
+    return out * ok[:, None].to(out.dtype)
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    if _use_native(x) and x.dtype == torch.bfloat16:
+        out = torch.empty(idx.shape[0], x.shape[1], dtype=x.dtype, device=x.device)
+        torch.ops.sglb.gather_rows(x, idx, out)
+        return out
+    return x[idx.long()]
+
+
+# ------------------------------------------------------------------ sampling
+def sample(logits, temperature, top_k, top_p, min_p, seeds=None, out_slots=None, next_token_buf=None, out_logprobs=None,
+           global_seed: int = 0, step_ptr=None, step: int = 0, generator=None) -> torch.Tensor:
+    B = logits.shape[0]
+    if _use_native(logits):
+        out = torch.empty(B, dtype=torch.int32, device=logits.device)
+        torch.ops.sglb.sample(logits, temperature, top_k, top_p, min_p, seeds, out_slots, next_token_buf, out, out_logprobs,
+                              int(global_seed) & 0x7FFFFFFFFFFFFFFF, step_ptr, int(step))
+        return out
+    g = generator
+    if g is None:
+        g = torch.Generator(device="cpu")
+        g.manual_seed((int(global_seed) * 1000003 + int(step)) & 0x7FFFFFFF)
+    u = torch.rand(B, generator=g).to(logits.device)
+    tok = torch_ref.sample(logits, temperature, top_k, top_p, min_p, u).to(torch.int32)
+    if out_logprobs is not None:
+        lp = torch.log_softmax(logits.float() / temperature.clamp(min=1e-6)[:, None], dim=-1)
+        out_logprobs.copy_(lp.gather(1, tok.long()[:, None]).squeeze(1))
+    if next_token_buf is not None and out_slots is not None:
+        next_token_buf[out_slots.long()] = tok
+    return tok
+
+
+def apply_token_bitmask(logits: torch.Tensor, bitmask: torch.Tensor, row_idx: Optional[torch.Tensor] = None) -> None:
+    if _use_native(logits):
+        torch.ops.sglb.apply_token_bitmask(logits, bitmask, row_idx)
+        return
+    if row_idx is None:
+        torch_ref.apply_token_bitmask(logits, bitmask)
+    else:
+        sub = logits[row_idx.long()]
+        torch_ref.apply_token_bitmask(sub, bitmask)
+        logits[row_idx.long()] = sub
+
+
+def apply_penalties(logits, counts, prompt_mask, freq, pres, rep) -> None:
+    if _use_native(logits) and logits.dtype == torch.float32:
+        torch.ops.sglb.apply_penalties(logits, counts, prompt_mask, freq, pres, rep)
+        return
+    pm = prompt_mask.bool() if prompt_mask is not None else torch.zeros_like(counts, dtype=torch.bool)
+    torch_ref.apply_penalties(logits, counts, pm, freq, pres, rep)
+
+
+def merge_attn_states(o1, lse1, o2, lse2):
+    return torch_ref.merge_attn_states(o1, lse1, o2, lse2)

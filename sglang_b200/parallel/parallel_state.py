@@ -1,0 +1,257 @@
+"""Process groups: one process per GPU, ``torch.distributed`` (NCCL on CUDA, Gloo on CPU) for the plumbing.
+
+Parity: reference ``python/sglang/srt/distributed/parallel_state.py`` (``GroupCoordinator:237``,
+``init_distributed_environment:2236``, ``initialize_model_parallel:2328``: world / TP / PP / EP groups, a CPU
+(Gloo) twin of every group for control-plane objects, ``all_reduce:648`` dispatch).
+
+B200-first: a GroupCoordinator may carry an ``NvlComm`` (``parallel/nvl_comm.py``: symmetric-memory arena with
+peer + multicast pointers over NVSwitch).  ``all_reduce`` uses our one-shot / two-shot kernels when the message
+fits the arena, and the fused GEMM+all-reduce path bypasses this API entirely (see ``layers/linear.py``).
+NCCL stays for bootstrap, large prefill messages, PP send/recv and as the measured baseline.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from dataclasses import dataclass
+from typing import Any, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GroupCoordinator:
+    def __init__(self, ranks: List[int], rank: int, device: torch.device, name: str):
+        self.ranks = ranks
+        self.world_size = len(ranks)
+        self.rank_in_group = ranks.index(rank) if rank in ranks else -1
+        self.global_rank = rank
+        self.device = device
+        self.name = name
+        self.device_group = None
+        self.cpu_group = None
+        self.nvl = None  # NvlComm
+        self.comm_bytes = 0
+        self.comm_calls = 0
+
+    # ---- properties
+    @property
+    def rank(self) -> int:
+        return self.rank_in_group
+
+    @property
+    def is_first(self) -> bool:
+        return self.rank_in_group == 0
+
+    @property
+    def is_last(self) -> bool:
+        return self.rank_in_group == self.world_size - 1
+
+    # ---- collectives
+    def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
+        if self.world_size == 1:
+            return x
+        self.comm_calls += 1
+        self.comm_bytes += x.numel() * x.element_size()
+        if self.nvl is not None and self.nvl.can_all_reduce(x):
+            return self.nvl.all_reduce(x)
+        dist.all_reduce(x, group=self.device_group)
+        return x
+
+    def all_gather(self, x: torch.Tensor, dim: int = -1) -> torch.Tensor:
+        if self.world_size == 1:
+            return x
+        if dim < 0:
+            dim += x.dim()
+        out = torch.empty((self.world_size,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.device_group)
+        out = out.movedim(0, dim)
+        shp = list(x.shape)
+        shp[dim] *= self.world_size
+        return out.reshape(shp)
+
+    def reduce_scatter(self, x: torch.Tensor) -> torch.Tensor:
+        """x [world*n, ...] -> [n, ...] (sum over ranks of each rank's slice)"""
+        if self.world_size == 1:
+            return x
+        out = torch.empty((x.shape[0] // self.world_size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, x.contiguous(), group=self.device_group)
+        return out
+
+    def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor, out_splits=None, in_splits=None) -> torch.Tensor:
+        if self.world_size == 1:
+            out.copy_(inp)
+            return out
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.device_group)
+        return out
+
+    def broadcast(self, x: torch.Tensor, src: int = 0) -> torch.Tensor:
+        if self.world_size == 1:
+            return x
+        dist.broadcast(x, src=self.ranks[src], group=self.device_group)
+        return x
+
+    def send(self, x: torch.Tensor, dst: int) -> None:
+        dist.send(x, dst=self.ranks[dst], group=self.device_group)
+
+    def recv(self, x: torch.Tensor, src: int) -> torch.Tensor:
+        dist.recv(x, src=self.ranks[src], group=self.device_group)
+        return x
+
+    def barrier(self) -> None:
+        if self.world_size > 1:
+            dist.barrier(group=self.cpu_group)
+
+    def broadcast_pyobj(self, obj: Any, src: int = 0) -> Any:
+        """control-plane object broadcast over the Gloo twin (reference ``broadcast_pyobj``)"""
+        if self.world_size == 1:
+            return obj
+        lst = [obj if self.rank_in_group == src else None]
+        dist.broadcast_object_list(lst, src=self.ranks[src], group=self.cpu_group)
+        return lst[0]
+
+    def all_gather_pyobj(self, obj: Any) -> List[Any]:
+        if self.world_size == 1:
+            return [obj]
+        out = [None] * self.world_size
+        dist.all_gather_object(out, obj, group=self.cpu_group)
+        return out
+
+    def send_pyobj(self, obj: Any, dst: int) -> None:
+        dist.send_object_list([obj], dst=self.ranks[dst], group=self.cpu_group)
+
+    def recv_pyobj(self, src: int) -> Any:
+        lst = [None]
+        dist.recv_object_list(lst, src=self.ranks[src], group=self.cpu_group)
+        return lst[0]
+
+
+@dataclass
+class ParallelState:
+    world: GroupCoordinator
+    tp: GroupCoordinator
+    pp: GroupCoordinator
+    ep: GroupCoordinator
+    rank: int
+    world_size: int
+    local_rank: int
+
+
+_STATE: Optional[ParallelState] = None
+
+
+def _single(device: torch.device) -> ParallelState:
+    g = lambda n: GroupCoordinator([0], 0, device, n)
+    return ParallelState(g("world"), g("tp"), g("pp"), g("ep"), 0, 1, 0)
+
+
+def compute_group_ranks(world_size: int, tp_size: int, pp_size: int, ep_size: int = 1):
+    """Rank layout (reference ``initialize_model_parallel`` docstring :2363-2390): TP is the fastest-varying
+    dimension, PP the slowest; EP groups partition each TP group into contiguous blocks of ``ep_size``."""
+    assert world_size == tp_size * pp_size, (world_size, tp_size, pp_size)
+    tp_groups = [list(range(p * tp_size, (p + 1) * tp_size)) for p in range(pp_size)]
+    pp_groups = [list(range(t, world_size, tp_size)) for t in range(tp_size)]
+    ep_groups = []
+    for g in tp_groups:
+        for i in range(0, tp_size, max(1, ep_size)):
+            ep_groups.append(g[i:i + max(1, ep_size)])
+    return tp_groups, pp_groups, ep_groups
+
+
+def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, device: Optional[str] = None,
+                     init_method: Optional[str] = None, rank: Optional[int] = None, world_size: Optional[int] = None,
+                     enable_nvl: bool = True, timeout_s: int = 600) -> ParallelState:
+    global _STATE
+    use_cuda = (device or ("cuda" if torch.cuda.is_available() else "cpu")).startswith("cuda")
+    ws = tp_size * pp_size
+    if ws == 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+        _STATE = _single(dev)
+        return _STATE
+    rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+    world_size = int(os.environ.get("WORLD_SIZE", ws)) if world_size is None else world_size
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    assert world_size == ws, f"world size {world_size} != tp*pp {ws}"
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+    else:
+        dev = torch.device("cpu")
+    if not dist.is_initialized():
+        import datetime
+
+        if init_method is None:
+            addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+            port = os.environ.get("MASTER_PORT", "29500")
+            init_method = f"tcp://{addr}:{port}"
+        kw = {}
+        if use_cuda:
+            kw["device_id"] = dev
+        dist.init_process_group(backend="nccl" if use_cuda else "gloo", init_method=init_method, rank=rank,
+                                world_size=world_size, timeout=datetime.timedelta(seconds=timeout_s), **kw)
+
+    def make(groups, name) -> GroupCoordinator:
+        mine = None
+        for ranks in groups:
+            dg = dist.new_group(ranks, backend="nccl" if use_cuda else "gloo") if len(ranks) > 1 else None
+            cg = dist.new_group(ranks, backend="gloo") if len(ranks) > 1 else None
+            if rank in ranks:
+                mine = GroupCoordinator(ranks, rank, dev, name)
+                mine.device_group, mine.cpu_group = dg, cg
+        return mine
+
+    tp_groups, pp_groups, ep_groups = compute_group_ranks(world_size, tp_size, pp_size, ep_size)
+    world = make([list(range(world_size))], "world")
+    tp = make(tp_groups, "tp")
+    pp = make(pp_groups, "pp")
+    ep = make(ep_groups, "ep")
+    _STATE = ParallelState(world, tp, pp, ep, rank, world_size, local_rank)
+    if use_cuda and enable_nvl and tp.world_size > 1:
+        try:
+            from .nvl_comm import NvlComm
+
+            tp.nvl = NvlComm.create(tp)
+        except Exception as e:  # keep NCCL as the fallback; say so loudly
+            import logging
+
+            logging.getLogger(__name__).warning("NVL symmetric-memory comm unavailable, using NCCL only: %s", e)
+    return _STATE
+
+
+def get_state() -> ParallelState:
+    global _STATE
+    if _STATE is None:
+        _STATE = _single(torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+    return _STATE
+
+
+def set_state(s: Optional[ParallelState]) -> None:
+    global _STATE
+    _STATE = s
+
+
+def get_tp_group() -> GroupCoordinator:
+    return get_state().tp
+
+
+def get_pp_group() -> GroupCoordinator:
+    return get_state().pp
+
+
+def get_ep_group() -> GroupCoordinator:
+    return get_state().ep
+
+
+def get_tp_rank() -> int:
+    return get_state().tp.rank
+
+
+def get_tp_size() -> int:
+    return get_state().tp.world_size
+
+
+def destroy_distributed() -> None:
+    global _STATE
+    _STATE = None
+    if dist.is_initialized():
+        dist.destroy_process_group()

@@ -1,0 +1,256 @@
+"""ServerArgs: the single config dataclass, with auto-derived CLI flags.
+
+Parity: reference ``python/sglang/srt/server_args.py:473-3642`` (dataclass + auto CLI),
+``:3643`` resolution pipeline, ``:9970`` PortArgs.  Ours keeps the same flag names where a
+user-facing flag exists in the reference (``--model-path``, ``--tp-size``, ``--mem-fraction-static``,
+``--chunked-prefill-size``, ``--max-running-requests``, ``--schedule-policy``, ...), and a small
+ordered resolution pipeline (``_resolve``) instead of ~90 handlers because there is exactly one
+hardware target (B200, sm_100a).
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import json
+import os
+import tempfile
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+
+@dataclass
+class ServerArgs:
+    # --- model
+    model_path: str = "dummy:tiny-llama"
+    tokenizer_path: Optional[str] = None
+    load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state
+    dtype: str = "bfloat16"
+    kv_cache_dtype: str = "auto"  # auto|bf16|fp8_e4m3
+    quantization: Optional[str] = None  # None|fp8|fp8_block|w4a16|w8a8_int8(unsupported)
+    context_length: Optional[int] = None
+    trust_remote_code: bool = False
+    served_model_name: Optional[str] = None
+    chat_template: Optional[str] = None
+    is_embedding: bool = False
+    skip_tokenizer_init: bool = False
+    revision: Optional[str] = None
+    json_model_override_args: str = "{}"
+    # --- server
+    host: str = "127.0.0.1"
+    port: int = 30000
+    api_key: Optional[str] = None
+    admin_api_key: Optional[str] = None
+    log_level: str = "info"
+    log_requests: bool = False
+    enable_metrics: bool = False
+    enable_trace: bool = False
+    otlp_traces_endpoint: str = "localhost:4317"
+    decode_log_interval: int = 40
+    watchdog_timeout: float = 300.0
+    soft_watchdog_timeout: Optional[float] = None
+    crash_dump_folder: Optional[str] = None
+    # --- memory / scheduling
+    mem_fraction_static: Optional[float] = None
+    max_running_requests: Optional[int] = None
+    max_queued_requests: Optional[int] = None
+    max_total_tokens: Optional[int] = None
+    max_prefill_tokens: int = 16384
+    chunked_prefill_size: Optional[int] = None
+    page_size: int = 32
+    schedule_policy: str = "fcfs"  # lpm|fcfs|dfs-weight|lof|random
+    enable_priority_scheduling: bool = False
+    schedule_conservativeness: float = 1.0
+    enable_mixed_chunk: bool = False
+    disable_radix_cache: bool = False
+    radix_eviction_policy: str = "lru"  # lru|lfu|fifo|mru|filo|priority
+    radix_cache_impl: str = "auto"  # auto|cpp|python
+    disable_overlap_schedule: bool = False
+    stream_interval: int = 1
+    num_continuous_decode_steps: int = 1
+    # --- parallelism
+    tp_size: int = 1
+    pp_size: int = 1
+    dp_size: int = 1
+    ep_size: int = 1
+    enable_dp_attention: bool = False
+    enable_prefill_cp: bool = False
+    cp_size: int = 1
+    dcp_size: int = 1
+    load_balance_method: str = "round_robin"
+    dist_init_addr: Optional[str] = None
+    nnodes: int = 1
+    node_rank: int = 0
+    base_gpu_id: int = 0
+    nccl_port: Optional[int] = None
+    comm_backend: str = "auto"  # auto|nvl|nccl
+    enable_fused_gemm_allreduce: bool = True
+    launch_mode: str = "inproc"  # inproc (SPMD / single process) | subprocess (ZMQ)
+    # --- kernels / runtime
+    attention_backend: str = "auto"  # auto|tc|simt|torch_native
+    sampling_backend: str = "auto"  # auto|native|pytorch|token_oracle
+    gemm_backend: str = "auto"  # auto|tc|lib
+    disable_cuda_graph: bool = False
+    cuda_graph_max_bs: Optional[int] = None
+    cuda_graph_bs: Optional[List[int]] = None
+    enable_deterministic_inference: bool = False
+    random_seed: int = 0
+    device: str = "auto"
+    # --- speculative decoding
+    speculative_algorithm: Optional[str] = None  # EAGLE|NGRAM|STANDALONE
+    speculative_draft_model_path: Optional[str] = None
+    speculative_num_steps: int = 3
+    speculative_eagle_topk: int = 1
+    speculative_num_draft_tokens: int = 4
+    # --- grammar
+    grammar_backend: str = "auto"  # auto|xgrammar|regex_fsm|none
+    enable_jump_forward: bool = True
+    reasoning_parser: Optional[str] = None
+    tool_call_parser: Optional[str] = None
+    # --- LoRA
+    enable_lora: bool = False
+    lora_paths: Optional[List[str]] = None
+    max_loras_per_batch: int = 8
+    max_lora_rank: int = 64
+    # --- HiCache
+    enable_hierarchical_cache: bool = False
+    hicache_ratio: float = 2.0
+    hicache_write_policy: str = "write_through"
+    hicache_storage_backend: Optional[str] = None  # file
+    hicache_storage_dir: Optional[str] = None
+    # --- PD disaggregation
+    disaggregation_mode: str = "null"  # null|prefill|decode
+    disaggregation_transfer_backend: str = "nvlink"  # nvlink|fake|tcp
+    disaggregation_bootstrap_port: int = 8998
+    # --- multimodal
+    enable_multimodal: Optional[bool] = None
+    mm_attention_backend: Optional[str] = None
+    # --- debugging
+    kv_canary: str = "none"
+    enable_kv_events: bool = False
+    scripted_scheduler: bool = False
+
+    # ------------------------------------------------------------------ resolution
+    def __post_init__(self) -> None:
+        self._resolve()
+
+    def _resolve(self) -> None:
+        if self.tokenizer_path is None:
+            self.tokenizer_path = self.model_path
+        if self.served_model_name is None:
+            self.served_model_name = self.model_path
+        if self.device == "auto":
+            try:
+                import torch
+
+                self.device = "cuda" if torch.cuda.is_available() else "cpu"
+            except Exception:
+                self.device = "cpu"
+        if self.load_format == "auto":
+            self.load_format = "dummy" if self.model_path.startswith("dummy:") else "safetensors"
+        if self.page_size < 1 or (self.page_size & (self.page_size - 1)):
+            raise ValueError("--page-size must be a power of two")
+        if self.chunked_prefill_size is None:
+            # B200: 180 GB HBM3e -> large chunks keep the tcgen05 prefill kernels compute-bound
+            self.chunked_prefill_size = 8192 if self.device == "cuda" else 512
+        if self.chunked_prefill_size is not None and self.chunked_prefill_size <= 0:
+            self.chunked_prefill_size = None  # disabled
+        if self.mem_fraction_static is None:
+            self.mem_fraction_static = 0.88 if self.tp_size == 1 else 0.85
+        if self.schedule_policy not in ("lpm", "fcfs", "dfs-weight", "lof", "random"):
+            raise ValueError(f"unknown schedule policy {self.schedule_policy}")
+        if self.disable_radix_cache and self.schedule_policy in ("lpm", "dfs-weight"):
+            self.schedule_policy = "fcfs"
+        world = self.tp_size * self.pp_size
+        if self.ep_size > 1 and self.tp_size % self.ep_size != 0:
+            raise ValueError("ep_size must divide tp_size (experts are sharded inside the TP group)")
+        if self.enable_dp_attention and self.dp_size > self.tp_size:
+            raise ValueError("dp attention requires dp_size <= tp_size")
+        if self.cuda_graph_max_bs is None:
+            self.cuda_graph_max_bs = 512 if self.tp_size == 1 else 256
+        if self.device != "cuda":
+            self.disable_cuda_graph = True
+        if self.speculative_algorithm is not None:
+            self.speculative_algorithm = self.speculative_algorithm.upper()
+            self.disable_overlap_schedule = True
+        if self.disaggregation_mode not in ("null", "prefill", "decode"):
+            raise ValueError("bad --disaggregation-mode")
+        if self.attention_backend == "auto":
+            self.attention_backend = "tc" if self.device == "cuda" else "torch_native"
+        if self.sampling_backend == "auto":
+            self.sampling_backend = "native" if self.device == "cuda" else "pytorch"
+        self.world_size = world
+
+    # ------------------------------------------------------------------ CLI
+    @staticmethod
+    def add_cli_args(parser: argparse.ArgumentParser) -> None:
+        for f in dataclasses.fields(ServerArgs):
+            flag = "--" + f.name.replace("_", "-")
+            aliases = {"tp_size": ["--tp"], "pp_size": ["--pp"], "dp_size": ["--dp"], "ep_size": ["--ep"],
+                       "model_path": ["--model"]}.get(f.name, [])
+            t = f.type
+            default = f.default if f.default is not dataclasses.MISSING else None
+            if t in ("bool", bool):
+                parser.add_argument(flag, *aliases, action="store_true", default=default)
+            elif "List[int]" in str(t):
+                parser.add_argument(flag, *aliases, type=int, nargs="+", default=default)
+            elif "List[str]" in str(t):
+                parser.add_argument(flag, *aliases, type=str, nargs="+", default=default)
+            elif "int" in str(t):
+                parser.add_argument(flag, *aliases, type=int, default=default)
+            elif "float" in str(t):
+                parser.add_argument(flag, *aliases, type=float, default=default)
+            else:
+                parser.add_argument(flag, *aliases, type=str, default=default)
+        parser.add_argument("--config", type=str, default=None, help="YAML/JSON file merged under CLI flags")
+
+    @classmethod
+    def from_cli_args(cls, ns: argparse.Namespace) -> "ServerArgs":
+        names = {f.name for f in dataclasses.fields(cls)}
+        kw = {k: v for k, v in vars(ns).items() if k in names}
+        cfg = getattr(ns, "config", None)
+        if cfg:
+            kw = {**_load_config_file(cfg), **{k: v for k, v in kw.items() if v is not None}}
+        return cls(**kw)
+
+    def to_dict(self) -> Dict[str, Any]:
+        return dataclasses.asdict(self)
+
+    def url(self) -> str:
+        return f"http://{self.host}:{self.port}"
+
+
+def _load_config_file(path: str) -> Dict[str, Any]:
+    with open(path) as f:
+        text = f.read()
+    if path.endswith((".yaml", ".yml")):
+        import yaml
+
+        d = yaml.safe_load(text) or {}
+    else:
+        d = json.loads(text)
+    return {k.replace("-", "_"): v for k, v in d.items()}
+
+
+def prepare_server_args(argv: List[str]) -> ServerArgs:
+    parser = argparse.ArgumentParser("sglang_b200")
+    ServerArgs.add_cli_args(parser)
+    return ServerArgs.from_cli_args(parser.parse_args(argv))
+
+
+@dataclass
+class PortArgs:
+    """IPC endpoint names (reference ``server_args.py:9970-10080``)."""
+
+    tokenizer_ipc_name: str
+    scheduler_input_ipc_name: str
+    detokenizer_ipc_name: str
+    rpc_ipc_name: str
+    metrics_ipc_name: str
+    nccl_port: int
+
+    @staticmethod
+    def init_new(server_args: ServerArgs) -> "PortArgs":
+        d = tempfile.mkdtemp(prefix="sglb_ipc_")
+        mk = lambda n: f"ipc://{os.path.join(d, n)}"
+        port = server_args.nccl_port or (server_args.port + 1007)
+        return PortArgs(mk("tok"), mk("sched"), mk("detok"), mk("rpc"), mk("metrics"), port)

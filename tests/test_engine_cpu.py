@@ -1,0 +1,122 @@
+"""BASELINE config #1: radix prefix cache + continuous batching correctness on a 2-layer transformer, CPU, world=1.
+Batched/chunked/retracted/cached generation must reproduce one-request-at-a-time greedy outputs token for token
+(reference strategy: mock-model e2e + scheduler kits)."""
+import numpy as np
+import pytest
+
+import sglang_b200 as sgl
+from sglang_b200.environ import envs
+
+
+def _prompts(n, rng, lo=5, hi=60, shared=0):
+    base = rng.integers(3, 200, size=shared).tolist()
+    return [base + rng.integers(3, 200, size=int(rng.integers(lo, hi))).tolist() for _ in range(n)]
+
+
+@pytest.fixture(scope="module")
+def ref_engine():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, disable_radix_cache=True, chunked_prefill_size=-1,
+                     disable_overlap_schedule=True, max_running_requests=1)
+    yield eng
+    eng.shutdown()
+
+
+def _ref(ref_engine, prompts, max_new):
+    return [ref_engine.generate(input_ids=p, sampling_params={"max_new_tokens": m, "temperature": 0, "ignore_eos": True})["output_ids"]
+            for p, m in zip(prompts, max_new)]
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("page_size", [1, 4])
+def test_continuous_batching_matches_sequential(ref_engine, overlap, page_size):
+    rng = np.random.default_rng(1)
+    prompts = _prompts(12, rng, shared=9)
+    max_new = rng.integers(1, 20, size=12).tolist()
+    want = _ref(ref_engine, prompts, max_new)
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=page_size, disable_overlap_schedule=not overlap,
+                     chunked_prefill_size=32, max_running_requests=5)
+    sps = [{"max_new_tokens": m, "temperature": 0, "ignore_eos": True} for m in max_new]
+    got = eng.generate(input_ids=prompts, sampling_params=sps)
+    assert [g["output_ids"] for g in got] == want
+    # second pass: everything page-aligned is served from the radix cache, outputs unchanged
+    got2 = eng.generate(input_ids=prompts, sampling_params=sps)
+    assert [g["output_ids"] for g in got2] == want
+    assert sum(g["meta_info"]["cached_tokens"] for g in got2) > 0
+    eng.scheduler.check_invariants()
+    st = eng.scheduler.get_internal_state()
+    assert st["available_pages"] == st["total_pages"]    # every page is free or evictable once idle
+
+
+def test_chunked_prefill_long_prompt(ref_engine):
+    rng = np.random.default_rng(2)
+    prompts = _prompts(3, rng, lo=150, hi=300)
+    want = _ref(ref_engine, prompts, [6] * 3)
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=64, scripted_scheduler=True)
+    got = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True})
+    assert [g["output_ids"] for g in got] == want
+    recs = eng.scheduler.batch_records
+    assert any(r["chunked_rid"] for r in recs), "a long prompt must have been chunked"
+    assert max(r["tokens"] for r in recs if r["mode"] == "EXTEND") <= 64
+
+
+def test_retract_decode_recovers(ref_engine):
+    rng = np.random.default_rng(3)
+    prompts = _prompts(6, rng)
+    want = _ref(ref_engine, prompts, [24] * 6)
+    with envs.SGLB_TEST_RETRACT.override(True), envs.SGLB_TEST_RETRACT_INTERVAL.override(4):
+        eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+        got = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 24, "temperature": 0, "ignore_eos": True})
+    assert eng.scheduler.num_retracted > 0
+    assert [g["output_ids"] for g in got] == want
+    eng.scheduler.check_invariants()
+
+
+def test_kv_pressure_eviction_and_oom_retract(ref_engine):
+    rng = np.random.default_rng(4)
+    prompts = _prompts(10, rng, lo=20, hi=40)
+    want = _ref(ref_engine, prompts, [30] * 10)
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=400, schedule_conservativeness=0.3)
+    got = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 30, "temperature": 0, "ignore_eos": True})
+    assert [g["output_ids"] for g in got] == want
+    eng.scheduler.check_invariants()
+
+
+def test_stop_conditions_and_stream():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    full = eng.generate("abc", {"max_new_tokens": 12, "temperature": 0, "ignore_eos": True})
+    ids = full["output_ids"]
+    out = eng.generate("abc", {"max_new_tokens": 12, "temperature": 0, "ignore_eos": True, "stop_token_ids": [ids[3]]})
+    assert out["output_ids"] == ids[: ids.index(ids[3]) + 1] and out["meta_info"]["finish_reason"]["type"] == "stop"
+    chunks = list(eng.generate("abc", {"max_new_tokens": 12, "temperature": 0, "ignore_eos": True}, stream=True))
+    assert chunks[-1]["output_ids"] == ids and chunks[-1]["meta_info"]["finish_reason"]["type"] == "length"
+    assert len(chunks) >= 2
+
+
+def test_sampling_seeded_and_logprobs():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    sp = {"max_new_tokens": 8, "temperature": 0.9, "top_p": 0.9, "top_k": 50, "sampling_seed": 7, "ignore_eos": True}
+    a = eng.generate("hello", dict(sp))
+    g = eng.generate("hello", {"max_new_tokens": 4, "temperature": 0, "ignore_eos": True}, return_logprob=True, top_logprobs_num=3,
+                     logprob_start_len=0)
+    lps = g["meta_info"]["output_token_logprobs"]
+    assert len(lps) == 4 and all(lp <= 0 for lp, _, _ in lps)
+    tops = g["meta_info"]["output_top_logprobs"]
+    assert all(abs(t[0][0] - lp[0]) < 1e-4 for t, lp in zip(tops, lps))   # greedy token is the top-1
+    assert len(g["meta_info"]["input_token_logprobs"]) == g["meta_info"]["prompt_tokens"]
+    assert len(a["output_ids"]) == 8
+
+
+def test_abort_and_priority():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, enable_priority_scheduling=True, max_running_requests=1,
+                     scripted_scheduler=True)
+    outs = eng.generate(["low low low", "high high high"], {"max_new_tokens": 3, "temperature": 0, "ignore_eos": True},
+                        priority=None, rid=["lo", "hi"])
+    assert len(outs) == 2
+    from sglang_b200.managers import io_struct as ios
+
+    eng.scheduler.handle_request(eng._tokenize(ios.GenerateReqInput(text="to be aborted", rid="ab", sampling_params={"max_new_tokens": 50})))
+    eng.abort_request("ab")
+    while eng.scheduler.has_work():
+        eng.scheduler.step()
+    eng.scheduler.check_invariants()
+    assert eng.flush_cache()
