@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): output tokens/s (whole box, device-timed, max over ranks) + p50 TTFT for
+Llama-3-8B bf16 at TP = --gpus, synthetic ShareGPT-shaped request trace, random-init weights.
+
+A *step* = serving one complete trace (``--num-prompts`` requests, request-rate = inf, continuous batching with
+chunked prefill + radix cache) through the engine.  ``value``   : trace replayed from pre-tokenised ids, timed with
+CUDA events on the engine stream (max over ranks).  ``e2e.value``: the same trace through the public API
+``Engine.generate(text prompts) -> text``: tokenisation, per-step pinned-host->device metadata copies, device->host
+token reads and detokenisation all inside a barrier+synchronize-bracketed wall-clock region.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8
+    python bench.py --impl reference ...     # the unmodified reference from baseline/_ref (if it can run)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--num-prompts", type=int, default=256)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--attention-backend", default=os.environ.get("SGLB_BENCH_ATTN", "auto"))
+    ap.add_argument("--gemm-backend", default=os.environ.get("SGLB_BENCH_GEMM", "auto"))
+    ap.add_argument("--page-size", type=int, default=32)
+    ap.add_argument("--max-running", type=int, default=256)
+    ap.add_argument("--disable-cuda-graph", action="store_true")
+    ap.add_argument("--disable-overlap", action="store_true")
+    ap.add_argument("--comm-backend", default="auto")
+    ap.add_argument("--quantization", default=None)
+    return ap.parse_args()
+
+
+def sharegpt_shaped_trace(n: int, seed: int, max_in: int = 2048, max_out: int = 1024):
+    """(prompt_len, output_len) pairs with ShareGPT-like heavy-tailed (log-normal) lengths; the dataset itself is not
+    available offline (reference sampler: python/sglang/benchmark/datasets/sharegpt.py:82-129)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    pin = np.clip(rng.lognormal(mean=5.2, sigma=1.0, size=n), 4, max_in).astype(int)     # median ~180, mean ~300
+    pout = np.clip(rng.lognormal(mean=4.95, sigma=0.9, size=n), 4, max_out).astype(int)  # median ~140, mean ~210
+    return pin.tolist(), pout.tolist()
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index: int = 0, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.stop_evt = threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_evt.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report that rather than fake numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        import statistics
+
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
+
+
+def run_reference(args) -> None:
+    """The unmodified reference from baseline/_ref through its own public API (sglang.Engine)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    why = None
+    if not os.path.isdir(os.path.join(ref, "sglang")):
+        why = "baseline/_ref not installed (pip --no-index --no-deps install of /root/reference/python)"
+    else:
+        sys.path.insert(0, ref)
+        try:
+            import sglang  # noqa: F401
+            from sglang.srt.entrypoints.engine import Engine  # noqa: F401
+        except Exception as e:
+            why = f"reference installs (--no-deps) but cannot import offline: {type(e).__name__}: {str(e)[:160]}"
+    if why is None:
+        try:
+            _run_reference_engine(args)
+            return
+        except Exception as e:
+            why = f"reference engine failed to run: {type(e).__name__}: {str(e)[:200]}"
+    rank = int(os.environ.get("RANK", 0))
+    if rank == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def _run_reference_engine(args) -> None:
+    import statistics
+
+    import torch
+    import sglang as sgl
+
+    pin, pout = sharegpt_shaped_trace(args.num_prompts, args.seed)
+    import numpy as np
+
+    rng = np.random.default_rng(args.seed + 1)
+    prompts = [rng.integers(1000, 100000, size=n).tolist() for n in pin]
+    eng = sgl.Engine(model_path=os.environ.get("SGLB_REF_MODEL_PATH", "meta-llama/Meta-Llama-3-8B"), load_format="dummy",
+                     tp_size=args.gpus, skip_tokenizer_init=True, max_running_requests=args.max_running)
+    sps = [{"max_new_tokens": m, "temperature": 0, "ignore_eos": True} for m in pout]
+    for _ in range(args.warmup):
+        eng.generate(input_ids=prompts, sampling_params=sps)
+    times = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.generate(input_ids=prompts, sampling_params=sps)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    tot = sum(pout)
+    ms = 1000 * sum(times) / len(times)
+    print(json.dumps({"impl": "reference", "metric": "output_tokens_per_s", "value": tot / (ms / 1000), "unit": "tok/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"model": "llama-3-8b", "global_batch": args.num_prompts, "parallelism": f"tp{args.gpus}"}}))
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import sglang_b200 as sgl
+    from sglang_b200 import ops
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    eng = sgl.Engine(model_path=f"dummy:{args.model}", tp_size=args.gpus, page_size=args.page_size,
+                     attention_backend=args.attention_backend, gemm_backend=args.gemm_backend, max_running_requests=args.max_running,
+                     cuda_graph_max_bs=args.max_running, disable_cuda_graph=args.disable_cuda_graph,
+                     disable_overlap_schedule=args.disable_overlap, comm_backend=args.comm_backend, quantization=args.quantization,
+                     log_level="warning", base_gpu_id=local_rank, random_seed=args.seed)
+    pin, pout = sharegpt_shaped_trace(args.num_prompts, args.seed)
+    rng = np.random.default_rng(args.seed + 1)
+    V = eng.model_config.vocab_size
+    tok = eng.tokenizer
+    sps = [{"max_new_tokens": m, "temperature": 0, "ignore_eos": True} for m in pout]
+    total_out = int(sum(pout))
+    total_in = int(sum(pin))
+
+    def fresh_ids(step: int):
+        r = np.random.default_rng(args.seed + 100 + step)   # new content every step: no cross-step radix hits
+        return [r.integers(300, V - 1000, size=n).tolist() for n in pin]
+
+    def fresh_text(step: int):
+        r = np.random.default_rng(args.seed + 5000 + step)
+        return ["".join(chr(c) for c in r.integers(97, 123, size=max(1, n - 1))) for n in pin]   # n-1 bytes + BOS = n tokens
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    stream = eng.runner.stream
+    # ------------------------------------------------------------------ device-timed region (pre-tokenised ids)
+    for w in range(args.warmup):
+        eng.generate(input_ids=fresh_ids(-1 - w), sampling_params=sps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    c0, g0 = ops.launch_count(), eng.runner.graph_launches
+    h0, d0 = eng.runner.h2d_bytes, eng.runner.d2h_bytes
+    f0 = eng.runner.forward_ct
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(args.steps):
+        eng.generate(input_ids=fresh_ids(k), sampling_params=sps)
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = (ops.launch_count() - c0) + (eng.runner.graph_launches - g0)
+    fwd = eng.runner.forward_ct - f0
+    h2d = (eng.runner.h2d_bytes - h0) / max(1, fwd)
+    d2h = (eng.runner.d2h_bytes - d0) / max(1, fwd)
+    # ------------------------------------------------------------------ end-to-end region (public text API)
+    ttfts = []
+    for w in range(min(1, args.warmup)):
+        eng.generate(fresh_text(-1 - w), sps)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        outs = eng.generate(fresh_text(k), sps)
+        if rank == 0:
+            ttfts.extend(o["meta_info"].get("ttft", 0.0) for o in outs)
+            assert all(isinstance(o["text"], str) for o in outs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_evt.set()
+    sampler.join(timeout=2)
+
+    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        value = total_out * args.steps / (dev_ms / 1000.0)
+        e2e_value = total_out * args.steps / (e2e_ms / 1000.0)
+        import statistics
+
+        print(json.dumps({
+            "metric": "output_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16" if not args.quantization else args.quantization, "data": "synthetic",
+            "config": {"model": args.model, "global_batch": args.num_prompts, "seq_len": f"sharegpt-shaped lognormal: mean in {total_in // args.num_prompts} / out {total_out // args.num_prompts}",
+                       "parallelism": f"tp{args.gpus}", "step": "one full trace (request-rate inf, continuous batching)",
+                       "l2": "inputs_larger_than_L2 (16 GB weights + KV streamed every decode step)",
+                       "attention_backend": eng.server_args.attention_backend, "gemm_backend": os.environ.get("SGLB_GEMM_IMPL", "auto"),
+                       "cuda_graph": not args.disable_cuda_graph, "overlap_schedule": eng.scheduler.enable_overlap,
+                       "page_size": args.page_size, "max_running": args.max_running, "input_tokens_per_step": total_in,
+                       "output_tokens_per_step": total_out, "total_tokens_per_s": (total_in + total_out) * args.steps / (dev_ms / 1000.0)},
+            "p50_ttft_ms": 1000.0 * statistics.median(ttfts) if ttfts else None,
+            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "text prompts -> tokenizer -> engine -> detokenizer -> text; bytes are per engine forward step"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "impl": "ours"}))
+    eng.shutdown()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,252 @@
+"""GPU numerics cases: every CUDA kernel against the plain-PyTorch fp32 reference of the same op (``ops.torch_ref``).
+
+Each case is runnable in isolation (``python tests/gpu_cases.py <case>``) so that a device-side trap in an experimental
+kernel cannot poison the CUDA context of the other cases; ``tests/test_kernels_gpu.py`` drives them under pytest.
+"""
+import json
+import math
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+from sglang_b200 import ops
+from sglang_b200.ops import torch_ref
+
+DEV = "cuda"
+
+
+def _close(a, b, atol, rtol, name):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = (err > tol).float().mean().item()
+    mx = err.max().item()
+    assert bad < 1e-3 and math.isfinite(mx), f"{name}: max err {mx:.4g}, {bad * 100:.3f}% out of tol (atol={atol}, rtol={rtol})"
+    return mx
+
+
+def case_rmsnorm():
+    torch.manual_seed(0)
+    for T, H in [(1, 4096), (37, 4096), (5, 8192), (3, 1024), (2, 14336)]:
+        x = torch.randn(T, H, device=DEV, dtype=torch.bfloat16)
+        w = torch.randn(H, device=DEV, dtype=torch.bfloat16)
+        _close(ops.rmsnorm(x, w, 1e-5), torch_ref.rmsnorm(x, w, 1e-5), 2e-2, 2e-2, f"rmsnorm {T}x{H}")
+        _close(ops.rmsnorm(x, w, 1e-6, gemma=True), torch_ref.gemma_rmsnorm(x, w, 1e-6), 3e-2, 2e-2, "gemma_rmsnorm")
+        r = torch.randn(T, H, device=DEV, dtype=torch.bfloat16)
+        x1, r1, x2, r2 = x.clone(), r.clone(), x.clone(), r.clone()
+        ops.fused_add_rmsnorm(x1, r1, w, 1e-5)
+        torch_ref.fused_add_rmsnorm(x2, r2, w, 1e-5)
+        _close(r1, r2, 1e-2, 1e-2, "fused_add residual")
+        _close(x1, x2, 3e-2, 2e-2, "fused_add out")
+    # strided input rows (view into a wider buffer)
+    big = torch.randn(9, 3 * 1024, device=DEV, dtype=torch.bfloat16)
+    v = big[:, 1024:2048]
+    w = torch.ones(1024, device=DEV, dtype=torch.bfloat16)
+    _close(ops.rmsnorm(v, w, 1e-5), torch_ref.rmsnorm(v, w, 1e-5), 2e-2, 2e-2, "rmsnorm strided")
+
+
+def case_act():
+    torch.manual_seed(0)
+    for T, I in [(1, 14336), (33, 14336), (7, 1024)]:
+        x = torch.randn(T, 2 * I, device=DEV, dtype=torch.bfloat16)
+        _close(ops.silu_and_mul(x), torch_ref.silu_and_mul(x), 2e-2, 2e-2, "silu_and_mul")
+        _close(ops.gelu_and_mul(x, "tanh"), torch_ref.gelu_and_mul(x, "tanh"), 2e-2, 2e-2, "gelu_tanh_and_mul")
+        _close(ops.gelu_and_mul(x), torch_ref.gelu_and_mul(x), 2e-2, 2e-2, "gelu_and_mul")
+
+
+def case_rope():
+    torch.manual_seed(0)
+    for (Hq, Hkv, D, rot, neox) in [(32, 8, 128, 128, True), (4, 2, 128, 128, False), (8, 8, 64, 32, True)]:
+        T, slots = 19, 64
+        qkv = torch.randn(T, (Hq + 2 * Hkv) * D, device=DEV, dtype=torch.bfloat16)
+        q, k, v = qkv.split([Hq * D, Hkv * D, Hkv * D], dim=-1)
+        q3, k3, v3 = q.view(T, Hq, D), k.view(T, Hkv, D), v.view(T, Hkv, D)
+        pos = torch.randint(0, 500, (T,), device=DEV, dtype=torch.int32)
+        cs = torch_ref.build_cos_sin_cache(D, 512, 10000.0, None, rot).to(DEV)
+        loc = torch.randperm(slots, device=DEV)[:T].to(torch.int32)
+        kc = torch.zeros(slots, Hkv, D, device=DEV, dtype=torch.bfloat16)
+        vc = torch.zeros_like(kc)
+        q_ref, k_ref = torch_ref.apply_rope(q3, pos, cs, neox), torch_ref.apply_rope(k3, pos, cs, neox)
+        ops.rope_kv_write(q3, k3, v3, pos, cs, kc, vc, loc, neox)
+        _close(q3, q_ref, 2e-2, 2e-2, "rope q")
+        _close(kc[loc.long()], k_ref, 2e-2, 2e-2, "rope k->cache")
+        _close(vc[loc.long()], v3, 0, 0, "v->cache")
+
+
+def _attn_setup(B, q_lens, seq_lens, Hq, Hkv, D, ps, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    T = int(sum(q_lens))
+    max_pages = (max(seq_lens) + ps - 1) // ps + 4
+    need = sum((s + ps - 1) // ps for s in seq_lens)
+    n_pages = need + 8
+    perm = (torch.randperm(n_pages - 1, generator=g) + 1).tolist()
+    pt = torch.zeros(B + 3, max_pages, dtype=torch.int32)
+    slots = torch.tensor([b + 1 for b in range(B)], dtype=torch.int32)
+    it = iter(perm)
+    for b, s in enumerate(seq_lens):
+        for i in range((s + ps - 1) // ps):
+            pt[b + 1, i] = next(it)
+    kc = (torch.randn(n_pages * ps, Hkv, D, generator=g) * 0.5).to(dtype)
+    vc = (torch.randn(n_pages * ps, Hkv, D, generator=g) * 0.5).to(dtype)
+    q = (torch.randn(T, Hq, D, generator=g) * 0.5).to(dtype)
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor(q_lens).cumsum(0)
+    return dict(q=q.to(DEV), kc=kc.to(DEV), vc=vc.to(DEV), pt=pt.to(DEV), slots=slots.to(DEV),
+                seq=torch.tensor(seq_lens, dtype=torch.int32, device=DEV), cu=cu.to(DEV),
+                ql=torch.tensor(q_lens, dtype=torch.int32, device=DEV), T=T)
+
+
+def _attn_check(impl, B, q_lens, seq_lens, Hq=32, Hkv=8, D=128, ps=32, decode=False, splits=1, window=-1, cap=0.0, name=""):
+    s = _attn_setup(B, q_lens, seq_lens, Hq, Hkv, D, ps)
+    scale = D ** -0.5
+    ref = torch_ref.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None if decode else s["ql"], ps, scale,
+                                    True, window, cap)
+    out = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None if decode else s["cu"],
+                              None if decode else s["ql"], max(q_lens), ps, scale, True, window, cap, num_splits=splits, impl=impl)
+    torch.cuda.synchronize()
+    return _close(out, ref, 2e-2, 3e-2, f"attn[{'tc' if impl == 0 else 'simt'}] {name}")
+
+
+def case_attn_simt():
+    _attn_check(1, 3, [5, 17, 1], [5, 40, 33], name="prefill")
+    _attn_check(1, 4, [1, 1, 1, 1], [7, 64, 129, 300], decode=True, name="decode")
+    _attn_check(1, 2, [9, 4], [50, 90], Hq=4, Hkv=4, D=64, ps=4, name="mha d64")
+    _attn_check(1, 2, [9, 4], [50, 90], window=16, name="window")
+
+
+def case_attn_tc_decode():
+    _attn_check(0, 1, [1], [100], decode=True, name="decode 1x100")
+    _attn_check(0, 5, [1] * 5, [1, 31, 128, 129, 700], decode=True, name="decode ragged")
+    _attn_check(0, 3, [1] * 3, [257, 1000, 64], decode=True, ps=16, name="decode ps16")
+    _attn_check(0, 2, [1] * 2, [513, 90], decode=True, ps=128, name="decode ps128")
+
+
+def case_attn_tc_prefill():
+    _attn_check(0, 1, [64], [64], name="prefill 64")
+    _attn_check(0, 1, [200], [200], name="prefill 200 (multi q tile, diag)")
+    _attn_check(0, 3, [5, 130, 33], [5, 130, 33], name="prefill ragged")
+    _attn_check(0, 2, [40, 7], [300, 135], name="extend with prefix")
+    _attn_check(0, 1, [300], [300], Hq=8, Hkv=8, name="mha G=1")
+    _attn_check(0, 1, [100], [400], Hq=16, Hkv=2, name="G=8")
+
+
+def case_attn_tc_split():
+    _attn_check(0, 2, [1, 1], [900, 130], decode=True, splits=4, name="decode split4")
+    _attn_check(0, 1, [1], [40], decode=True, splits=8, name="decode split8 short (empty splits)")
+    _attn_check(0, 1, [50], [700], splits=2, name="prefill split2")
+
+
+def case_attn_tc_window():
+    _attn_check(0, 2, [60, 1], [400, 300], window=128, name="sliding window")
+    _attn_check(0, 1, [33], [200], cap=30.0, name="logit cap")
+
+
+def case_gemm_tc():
+    torch.manual_seed(0)
+    for (M, N, K, bn) in [(128, 128, 64, 128), (128, 256, 512, 128), (1, 4096, 4096, 32), (37, 6144, 4096, 64), (300, 4096, 14336, 128),
+                          (1000, 1024, 4096, 256), (64, 28672, 4096, 0), (2048, 6144, 4096, 0), (5, 2048, 512, 0), (130, 4096, 320, 64)]:
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) * 0.5).to(torch.bfloat16)
+        ref = a.float() @ w.float().t()
+        out = ops.gemm_tc(a, w, bn=bn)
+        torch.cuda.synchronize()
+        _close(out, ref, 0.5 if K > 4096 else 0.25, 2e-2, f"gemm {M}x{N}x{K} bn={bn}")
+    # bias epilogue + strided A (column slice of a wider buffer) + strided out
+    a_big = (torch.randn(70, 3 * 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    a = a_big[:, 1024:2048]
+    w = (torch.randn(512, 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    b = torch.randn(512, device=DEV).to(torch.bfloat16)
+    out = ops.gemm_tc(a, w, bias=b, epilogue=ops.EPI_BIAS)
+    _close(out, a.float() @ w.float().t() + b.float(), 0.25, 2e-2, "gemm bias strided")
+    # fused SiLU*mul epilogue with 16-wide interleaved gate/up rows
+    I, K, M = 1024, 512, 50
+    gate = (torch.randn(I, K, device=DEV) * 0.2).to(torch.bfloat16)
+    up = (torch.randn(I, K, device=DEV) * 0.2).to(torch.bfloat16)
+    inter = torch.stack([gate.view(I // 16, 16, K), up.view(I // 16, 16, K)], dim=1).reshape(2 * I, K).contiguous()
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    out = ops.gemm_tc(a, inter, epilogue=ops.EPI_SILU_MUL)
+    ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    _close(out, ref, 0.1, 3e-2, "gemm silu_mul epilogue")
+
+
+def case_sampling():
+    torch.manual_seed(0)
+    B, V = 16, 32000
+    logits = torch.randn(B, V, device=DEV) * 3
+    ones = torch.ones(B, device=DEV)
+    greedy = torch.ones(B, dtype=torch.int32, device=DEV)
+    tok = ops.sample(logits, ones, greedy, ones, torch.zeros(B, device=DEV))
+    assert torch.equal(tok.long(), logits.argmax(-1)), "greedy argmax mismatch"
+    tokb = ops.sample(logits.to(torch.bfloat16), ones, greedy, ones, torch.zeros(B, device=DEV))
+    assert torch.equal(tokb.long(), logits.to(torch.bfloat16).float().argmax(-1)), "greedy bf16 mismatch"
+    # top-k: samples always inside the top-k set; top-p: inside the nucleus; frequencies roughly follow probs
+    k = 5
+    topk_idx = logits.topk(k, -1).indices
+    lp = torch.empty(B, device=DEV)
+    buf = torch.zeros(64, dtype=torch.int32, device=DEV)
+    slots = torch.arange(1, B + 1, dtype=torch.int32, device=DEV)
+    for step in range(50):
+        t = ops.sample(logits, ones, torch.full((B,), k, dtype=torch.int32, device=DEV), ones, torch.zeros(B, device=DEV),
+                       out_slots=slots, next_token_buf=buf, out_logprobs=lp, global_seed=3, step=step)
+        assert (topk_idx == t.long()[:, None]).any(-1).all(), "top-k sample outside top-k"
+        assert torch.equal(buf[1:B + 1], t), "next_token_buf scatter"
+        ref_lp = torch.log_softmax(logits, -1).gather(1, t.long()[:, None]).squeeze(1)
+        _close(lp, ref_lp, 1e-3, 1e-3, "sample logprob")
+    probs = torch.softmax(logits[0] / 0.7, -1)
+    sp, si = probs.sort(descending=True)
+    nucleus = set(si[: int((sp.cumsum(0) < 0.8).sum().item()) + 1].tolist())
+    cnt = {}
+    N = 400
+    one = logits[:1].expand(N, V).contiguous()
+    t = ops.sample(one, torch.full((N,), 0.7, device=DEV), torch.full((N,), 1 << 30, dtype=torch.int32, device=DEV),
+                   torch.full((N,), 0.8, device=DEV), torch.zeros(N, device=DEV), global_seed=11, step=1)
+    for x in t.tolist():
+        assert x in nucleus, "top-p sample outside nucleus"
+        cnt[x] = cnt.get(x, 0) + 1
+    top1 = int(si[0])
+    expect = float(sp[0] / sp[: len(nucleus)].sum())
+    assert abs(cnt.get(top1, 0) / N - expect) < 0.12, (cnt.get(top1, 0) / N, expect)
+    # bitmask
+    lg = torch.randn(4, 1000, device=DEV)
+    bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (2, 32), dtype=torch.int32, device=DEV)
+    ref = lg.clone()
+    sub = ref[[1, 3]]
+    torch_ref.apply_token_bitmask(sub, bm)
+    ref[[1, 3]] = sub
+    ops.apply_token_bitmask(lg, bm, torch.tensor([1, 3], dtype=torch.int32, device=DEV))
+    assert torch.equal(torch.isinf(lg), torch.isinf(ref)) and torch.allclose(lg[~torch.isinf(lg)], ref[~torch.isinf(ref)])
+
+
+def case_misc():
+    pt = torch.zeros(8, 16, dtype=torch.int32, device=DEV)
+    rows = torch.tensor([1, 1, 5], dtype=torch.int32, device=DEV)
+    cols = torch.tensor([0, 3, 15], dtype=torch.int32, device=DEV)
+    vals = torch.tensor([7, 8, 9], dtype=torch.int32, device=DEV)
+    ops.apply_pt_delta(pt, rows, cols, vals)
+    assert pt[1, 0] == 7 and pt[1, 3] == 8 and pt[5, 15] == 9 and pt.sum() == 24
+    w = torch.randn(100, 256, device=DEV, dtype=torch.bfloat16)
+    ids = torch.tensor([3, 99, 0, 50], dtype=torch.int32, device=DEV)
+    assert torch.equal(ops.embedding(w, ids), w[ids.long()])
+    buf = torch.tensor([0, 42, 7, 9], dtype=torch.int32, device=DEV)
+    g = torch.tensor([2, 1], dtype=torch.int32, device=DEV)
+    assert torch.equal(ops.embedding(w, buf, g), w[[7, 42]])
+    e = ops.embedding(w, ids, None, vocab_start=50)   # ids below the shard start -> zeros
+    assert torch.equal(e[0], torch.zeros_like(e[0])) and torch.equal(e[1], w[49])
+    x = torch.randn(10, 256, device=DEV, dtype=torch.bfloat16)
+    assert torch.equal(ops.gather_rows(x, torch.tensor([9, 0], dtype=torch.int32, device=DEV)), x[[9, 0]])
+
+
+CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    t0 = time.time()
+    assert ops.load_native(), "native extension failed to load"
+    CASES[name]()
+    torch.cuda.synchronize()
+    print(json.dumps({"case": name, "ok": True, "seconds": round(time.time() - t0, 2)}))
