@@ -1,0 +1,322 @@
+"""HTTP server: native routes + OpenAI-compatible routes over one ``Engine``.
+
+Parity: reference ``python/sglang/srt/entrypoints/http_server.py`` (routes ``:654-2041``: /health, /health_generate,
+/get_model_info, /get_server_info, /get_load, /flush_cache, /generate, /encode, /abort_request, profiling,
+weight-update family, LoRA load/unload, sessions, pause/continue, /metrics, /v1/*; admin-key guard; warm-up request
+``_execute_server_warmup:2186``; ``launch_server:2766``).
+
+Process model: rank 0 hosts FastAPI + tokenizer/detokenizer + scheduler thread; ranks 1..N-1 (TP/PP peers) are spawned
+as plain worker processes running the same scheduler loop and receive each iteration's requests by Gloo broadcast.
+"""
+import asyncio
+import json
+import logging
+import multiprocessing as mp
+import os
+import socket
+import sys
+import threading
+import time
+from typing import Any, Dict, Optional
+
+from fastapi import FastAPI, Request
+from fastapi.responses import JSONResponse, Response, StreamingResponse
+
+from ..managers import io_struct as ios
+from ..server_args import ServerArgs, prepare_server_args
+from .openai import protocol as P
+from .openai.serving import OpenAIServing
+
+logger = logging.getLogger(__name__)
+
+
+def create_app(engine: Any):
+    app = FastAPI(title="sglang_b200")
+    serving = OpenAIServing(engine)
+    args: ServerArgs = engine.server_args
+    app.state.engine = engine
+
+    def err(msg: str, code: int = 400) -> JSONResponse:
+        return JSONResponse({"error": {"message": msg, "type": "BadRequestError", "code": code}}, status_code=code)
+
+    @app.middleware("http")
+    async def auth(request: Request, call_next):
+        path = request.url.path
+        key = request.headers.get("authorization", "").removeprefix("Bearer ").strip()
+        admin_paths = ("/update_weights", "/flush_cache", "/release_memory", "/resume_memory", "/load_lora", "/unload_lora",
+                       "/start_profile", "/stop_profile", "/pause_generation", "/continue_generation", "/configure_logging")
+        if args.admin_api_key and path.startswith(admin_paths) and key != args.admin_api_key:
+            return err("admin API key required", 401)
+        if args.api_key and path.startswith(("/v1", "/generate", "/encode")) and key not in (args.api_key, args.admin_api_key):
+            return err("invalid API key", 401)
+        return await call_next(request)
+
+    # ------------------------------------------------------------------ health / info
+    @app.get("/health")
+    async def health():
+        return Response(status_code=200)
+
+    @app.get("/health_generate")
+    async def health_generate():
+        try:
+            out = await asyncio.wait_for(engine.async_generate(input_ids=[1, 2, 3], sampling_params={"max_new_tokens": 1, "temperature": 0}), 30)
+            return Response(status_code=200 if out["meta_info"]["completion_tokens"] >= 1 else 503)
+        except Exception:
+            return Response(status_code=503)
+
+    @app.get("/get_model_info")
+    async def model_info():
+        return {"model_path": args.model_path, "tokenizer_path": args.tokenizer_path, "is_generation": not args.is_embedding,
+                "architecture": engine.model_config.architecture, "weight_version": engine.weight_version}
+
+    @app.get("/get_server_info")
+    async def server_info():
+        return await _ctl(engine.get_server_info)
+
+    @app.get("/get_load")
+    @app.get("/v1/loads")
+    async def get_load():
+        return await _ctl(engine.get_load)
+
+    @app.get("/metrics")
+    async def metrics():
+        if engine.metrics is None:
+            return err("metrics are disabled (--enable-metrics)", 404)
+        return Response(engine.metrics.render(engine.scheduler.get_internal_state()), media_type="text/plain; version=0.0.4")
+
+    async def _ctl(fn, *a):
+        return await asyncio.get_running_loop().run_in_executor(None, fn, *a)
+
+    # ------------------------------------------------------------------ native generate
+    @app.post("/generate")
+    async def generate(request: Request):
+        body = await request.json()
+        allowed = {f for f in ios.GenerateReqInput.__dataclass_fields__}
+        kw = {k: v for k, v in body.items() if k in allowed}
+        stream = bool(kw.pop("stream", False))
+        prompt = kw.pop("text", None)
+        try:
+            if stream:
+                gen = await engine.async_generate(prompt, stream=True, **kw)
+
+                async def sse():
+                    async for o in gen:
+                        yield "data: " + json.dumps(o) + "\n\n"
+                    yield "data: [DONE]\n\n"
+
+                return StreamingResponse(sse(), media_type="text/event-stream")
+            return await engine.async_generate(prompt, **kw)
+        except ValueError as e:
+            return err(str(e))
+
+    @app.post("/encode")
+    async def encode(request: Request):
+        body = await request.json()
+        return await _ctl(engine.encode, body.get("text"))
+
+    @app.post("/abort_request")
+    async def abort(request: Request):
+        body = await request.json()
+        await _ctl(engine.abort_request, body.get("rid", ""), bool(body.get("abort_all", False)))
+        return {"success": True}
+
+    @app.api_route("/flush_cache", methods=["GET", "POST"])
+    async def flush():
+        ok = await _ctl(engine.flush_cache)
+        return Response("Cache flushed.\n" if ok else "Flush refused: requests in flight.\n", status_code=200 if ok else 400)
+
+    # ------------------------------------------------------------------ admin: profiling / weights / memory / LoRA / sessions
+    @app.api_route("/start_profile", methods=["GET", "POST"])
+    async def start_profile(request: Request):
+        body = await request.json() if request.method == "POST" and await request.body() else {}
+        r = await _ctl(engine.start_profile, body.get("output_dir"), body.get("num_steps"), body.get("activities"))
+        return {"success": r.success, "message": r.message}
+
+    @app.api_route("/stop_profile", methods=["GET", "POST"])
+    async def stop_profile():
+        r = await _ctl(engine.stop_profile)
+        return {"success": r.success, "message": r.message}
+
+    @app.post("/update_weights_from_disk")
+    async def update_disk(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.update_weights_from_disk, b["model_path"], b.get("load_format"))
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
+    @app.post("/update_weights_from_tensor")
+    async def update_tensor(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.update_weights_from_tensor, [(k, v) for k, v in b["named_tensors"]], b.get("flush_cache", True))
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
+    @app.api_route("/get_weights_by_name", methods=["GET", "POST"])
+    async def get_weights(request: Request):
+        b = await request.json()
+        return await _ctl(engine.get_weights_by_name, b["name"], b.get("truncate_size", 100))
+
+    @app.api_route("/release_memory_occupation", methods=["GET", "POST"])
+    async def release(request: Request):
+        b = await request.json() if await request.body() else {}
+        r = await _ctl(engine.release_memory_occupation, b.get("tags"))
+        return {"success": r.success, "message": r.message}
+
+    @app.api_route("/resume_memory_occupation", methods=["GET", "POST"])
+    async def resume(request: Request):
+        b = await request.json() if await request.body() else {}
+        r = await _ctl(engine.resume_memory_occupation, b.get("tags"))
+        return {"success": r.success, "message": r.message}
+
+    @app.post("/load_lora_adapter")
+    async def load_lora(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.load_lora_adapter, b["lora_name"], b["lora_path"])
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
+    @app.post("/unload_lora_adapter")
+    async def unload_lora(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.unload_lora_adapter, b["lora_name"])
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
+    @app.api_route("/open_session", methods=["GET", "POST"])
+    async def open_session(request: Request):
+        b = await request.json() if await request.body() else {}
+        return await _ctl(engine.open_session, b.get("capacity_of_str_len", 0), b.get("session_id"))
+
+    @app.api_route("/close_session", methods=["GET", "POST"])
+    async def close_session(request: Request):
+        b = await request.json()
+        await _ctl(engine.close_session, b["session_id"])
+        return Response(status_code=200)
+
+    @app.post("/pause_generation")
+    async def pause(request: Request):
+        b = await request.json() if await request.body() else {}
+        await _ctl(engine.pause_generation, b.get("mode", "abort"))
+        return {"success": True}
+
+    @app.post("/continue_generation")
+    async def cont():
+        await _ctl(engine.continue_generation)
+        return {"success": True}
+
+    @app.api_route("/configure_logging", methods=["GET", "POST"])
+    async def configure_logging(request: Request):
+        b = await request.json() if await request.body() else {}
+        if "log_level" in b:
+            logging.getLogger().setLevel(getattr(logging, str(b["log_level"]).upper(), logging.INFO))
+        if "log_requests" in b:
+            args.log_requests = bool(b["log_requests"])
+        return Response(status_code=200)
+
+    # ------------------------------------------------------------------ OpenAI-compatible
+    @app.get("/v1/models")
+    async def v1_models():
+        return serving.models()
+
+    @app.post("/v1/completions")
+    async def v1_completions(r: P.CompletionRequest):
+        try:
+            out = await serving.completions(r)
+        except ValueError as e:
+            return err(str(e))
+        return StreamingResponse(out, media_type="text/event-stream") if r.stream else out
+
+    @app.post("/v1/chat/completions")
+    async def v1_chat(r: P.ChatCompletionRequest):
+        try:
+            out = await serving.chat_completions(r)
+        except ValueError as e:
+            return err(str(e))
+        return StreamingResponse(out, media_type="text/event-stream") if r.stream else out
+
+    @app.post("/v1/embeddings")
+    async def v1_embeddings(r: P.EmbeddingRequest):
+        return await serving.embeddings(r)
+
+    @app.post("/v1/tokenize")
+    @app.post("/tokenize")
+    async def v1_tokenize(r: P.TokenizeRequest):
+        return serving.tokenize(r)
+
+    @app.post("/v1/detokenize")
+    @app.post("/detokenize")
+    async def v1_detokenize(r: P.DetokenizeRequest):
+        return serving.detokenize(r)
+
+    @app.post("/v1/score")
+    async def v1_score(r: P.ScoringRequest):
+        s = await _ctl(engine.score, r.query, r.items, r.label_token_ids, r.apply_softmax)
+        return {"scores": s, "model": r.model, "object": "scoring"}
+
+    @app.post("/v1/rerank")
+    async def v1_rerank(r: P.RerankRequest):
+        res = await _ctl(engine.rerank, r.query, r.documents)
+        return res[: r.top_n] if r.top_n else res
+
+    return app
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _peer_main(args: ServerArgs, rank: int, world: int, master_port: int) -> None:
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(master_port))
+    from .engine import Engine
+
+    eng = Engine(server_args=args)
+    eng.start_background_loop()
+    eng._bg_thread.join()
+
+
+def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) -> None:
+    import uvicorn
+
+    from .engine import Engine
+
+    world = server_args.tp_size * server_args.pp_size
+    peers = []
+    if world > 1 and "RANK" not in os.environ:
+        port = server_args.nccl_port or _free_port()
+        ctx = mp.get_context("spawn")
+        for r in range(1, world):
+            p = ctx.Process(target=_peer_main, args=(server_args, r, world, port), daemon=True)
+            p.start()
+            peers.append(p)
+        os.environ.update(RANK="0", LOCAL_RANK="0", WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    engine = Engine(server_args=server_args)
+    engine.start_background_loop()
+    if int(os.environ.get("RANK", 0)) != 0:
+        engine._bg_thread.join()
+        return
+    app = create_app(engine)
+
+    @app.on_event("startup")
+    async def _warm():
+        try:   # one real request through the whole stack (reference _wait_and_warmup)
+            await engine.async_generate(input_ids=[1, 2, 3, 4], sampling_params={"max_new_tokens": 2, "temperature": 0})
+            logger.info("The server is fired up and ready to roll!")
+        except Exception as e:
+            logger.error("warm-up request failed: %s", e)
+        if ready_event is not None:
+            ready_event.set()
+
+    try:
+        uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5)
+    finally:
+        engine.shutdown()
+        for p in peers:
+            p.terminate()
+
+
+def main(argv=None) -> None:
+    launch_server(prepare_server_args(sys.argv[1:] if argv is None else argv))
+
+
+if __name__ == "__main__":
+    main()

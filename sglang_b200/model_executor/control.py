@@ -1,0 +1,154 @@
+"""Control-plane handlers executed by the model runner between steps: live weight updates (RL), weight
+introspection, memory release/resume, profiling, LoRA adapters, expert-distribution recording.
+
+Parity: reference ``model_executor/model_runner_components/weight_updater.py``, ``entrypoints/engine.py:1396-1648``
+(update_weights_from_{disk,tensor,distributed}, get_weights_by_name, release/resume_memory_occupation),
+``managers/scheduler_components/profiler_manager.py:53`` (torch profiler start/stop, per-rank traces).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import time
+from typing import Any, Dict, List, Tuple
+
+import torch
+
+from ..managers import io_struct as ios
+
+logger = logging.getLogger(__name__)
+
+
+def handle(runner: Any, msg: Any) -> Any:
+    if isinstance(msg, ios.UpdateWeightsFromDiskReq):
+        return _update_from_disk(runner, msg)
+    if isinstance(msg, ios.UpdateWeightsFromTensorReq):
+        return _update_from_tensor(runner, msg)
+    if isinstance(msg, ios.GetWeightsByNameReq):
+        return _get_weights(runner, msg)
+    if isinstance(msg, ios.ReleaseMemoryOccupationReq):
+        return _release(runner, msg)
+    if isinstance(msg, ios.ResumeMemoryOccupationReq):
+        return _resume(runner, msg)
+    if isinstance(msg, ios.ProfileReq):
+        return _profile(runner, msg)
+    if isinstance(msg, ios.LoadLoRAAdapterReq):
+        if runner.lora_manager is None:
+            return ios.GenericResp(False, "LoRA is not enabled (--enable-lora)")
+        runner.lora_manager.load_adapter(msg.lora_name, msg.lora_path)
+        return ios.GenericResp(True, f"loaded {msg.lora_name}")
+    if isinstance(msg, ios.UnloadLoRAAdapterReq):
+        if runner.lora_manager is None:
+            return ios.GenericResp(False, "LoRA is not enabled (--enable-lora)")
+        runner.lora_manager.unload_adapter(msg.lora_name)
+        return ios.GenericResp(True, f"unloaded {msg.lora_name}")
+    if isinstance(msg, ios.ExpertDistributionReq):
+        from ..eplb.expert_distribution import handle_request
+
+        return handle_request(runner, msg)
+    raise TypeError(type(msg))
+
+
+def _sync(runner) -> None:
+    if runner.is_cuda:
+        torch.cuda.synchronize(runner.device)
+
+
+def _update_from_disk(runner, msg) -> ios.UpdateWeightsResp:
+    from ..model_loader.loader import iter_pt, iter_safetensors, process_weights_after_loading
+
+    _sync(runner)
+    try:
+        it = iter_pt(msg.model_path) if msg.load_format == "pt" else iter_safetensors(msg.model_path)
+        n = len(runner.model.load_weights(it))
+        process_weights_after_loading(runner.model)
+    except Exception as e:
+        logger.exception("update_weights_from_disk failed")
+        return ios.UpdateWeightsResp(False, f"{type(e).__name__}: {e}")
+    _recapture(runner)
+    return ios.UpdateWeightsResp(True, f"loaded {n} tensors from {msg.model_path}")
+
+
+def _update_from_tensor(runner, msg) -> ios.UpdateWeightsResp:
+    """named_tensors: list of (name, tensor | nested list).  Full (unsharded) tensors; each rank takes its shard."""
+    _sync(runner)
+    try:
+        items: List[Tuple[str, torch.Tensor]] = []
+        for name, t in msg.named_tensors:
+            items.append((name, t if isinstance(t, torch.Tensor) else torch.tensor(t)))
+        dtype = next(runner.model.parameters()).dtype
+        n = len(runner.model.load_weights((k, v.to(dtype)) for k, v in items))
+    except Exception as e:
+        logger.exception("update_weights_from_tensor failed")
+        return ios.UpdateWeightsResp(False, f"{type(e).__name__}: {e}")
+    return ios.UpdateWeightsResp(True, f"updated {n} tensors")
+
+
+def _get_weights(runner, msg) -> ios.GetWeightsByNameResp:
+    params = dict(runner.model.named_parameters())
+    if msg.name not in params:
+        return ios.GetWeightsByNameResp(None)
+    return ios.GetWeightsByNameResp(params[msg.name].detach().float().flatten()[: msg.truncate_size].cpu().tolist())
+
+
+def _release(runner, msg) -> ios.GenericResp:
+    """free the KV pool (and optionally park the weights on the host) so a co-located trainer can use the HBM"""
+    tags = msg.tags or ["kv_cache", "weights"]
+    _sync(runner)
+    if "kv_cache" in tags and runner.kv_pool.buf is not None:
+        runner._released_kv_shape = (tuple(runner.kv_pool.buf.shape), runner.kv_pool.buf.dtype)
+        runner.kv_pool.buf = None
+        runner.graphs.clear()
+    if "weights" in tags:
+        runner._parked = {k: p.data.to("cpu", non_blocking=False) for k, p in runner.model.named_parameters()}
+        for p in runner.model.parameters():
+            p.data = torch.empty(0, dtype=p.dtype, device=p.device)
+    if runner.is_cuda:
+        torch.cuda.empty_cache()
+    return ios.GenericResp(True, f"released {tags}")
+
+
+def _resume(runner, msg) -> ios.GenericResp:
+    tags = msg.tags or ["kv_cache", "weights"]
+    if "weights" in tags and getattr(runner, "_parked", None):
+        for k, p in runner.model.named_parameters():
+            p.data = runner._parked[k].to(runner.device)
+        runner._parked = None
+    if "kv_cache" in tags and runner.kv_pool.buf is None:
+        shape, dt = runner._released_kv_shape
+        runner.kv_pool.buf = torch.zeros(shape, dtype=dt, device=runner.device)
+        _recapture(runner)
+    return ios.GenericResp(True, f"resumed {tags}")
+
+
+def _recapture(runner) -> None:
+    # CUDA graphs hold raw pointers to the KV pool; weights are updated in place so they stay valid
+    if runner.is_cuda and not runner.graphs and not runner.args.disable_cuda_graph and runner.pp.world_size == 1:
+        with torch.cuda.stream(runner.stream):
+            runner._capture_graphs()
+        runner.stream.synchronize()
+
+
+def _profile(runner, msg) -> ios.ProfileResp:
+    from torch.profiler import ProfilerActivity, profile
+
+    if msg.action == "start":
+        if runner.profiler is not None:
+            return ios.ProfileResp(False, "profiler already running")
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if runner.is_cuda else [])
+        out = msg.output_dir or os.environ.get("SGLB_TORCH_PROFILER_DIR", "/tmp/sglb_profiles")
+        os.makedirs(out, exist_ok=True)
+        runner.profiler = profile(activities=acts, record_shapes=True, with_stack=False)
+        runner.profiler.__enter__()
+        runner._profile_dir = out
+        runner._profile_stop_at = runner.forward_ct + msg.num_steps if msg.num_steps else None
+        return ios.ProfileResp(True, f"profiling to {out}")
+    if runner.profiler is None:
+        return ios.ProfileResp(False, "profiler not running")
+    runner.profiler.__exit__(None, None, None)
+    from ..parallel.parallel_state import get_state
+
+    path = os.path.join(runner._profile_dir, f"trace-rank{get_state().rank}-{int(time.time())}.json")
+    runner.profiler.export_chrome_trace(path)
+    runner.profiler = None
+    return ios.ProfileResp(True, path)

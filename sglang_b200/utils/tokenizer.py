@@ -29,7 +29,9 @@ class ByteTokenizer:
         return self.vocab_size
 
     def encode(self, text: str, add_special_tokens: bool = False) -> List[int]:
+        sp = set(self.all_special_ids)
         ids = [b % self._nbytes for b in text.encode("utf-8")]
+        ids = [i if i not in sp else 63 for i in ids]   # a byte that collides with a special id becomes '?'
         return ([self.bos_token_id] + ids) if add_special_tokens else ids
 
     def __call__(self, text, add_special_tokens: bool = False, **kw) -> Dict[str, Any]:
@@ -39,9 +41,10 @@ class ByteTokenizer:
 
     def decode(self, ids: Sequence[int], skip_special_tokens: bool = True, **kw) -> str:
         out = bytearray()
+        sp = set(self.all_special_ids)
         for i in ids:
             i = int(i)
-            if i < self._nbytes:
+            if i < self._nbytes and i not in sp:
                 out.append(i)
             elif not skip_special_tokens:
                 name = {self.bos_token_id: "<bos>", self.eos_token_id: "<eos>", self.pad_token_id: "<pad>",
