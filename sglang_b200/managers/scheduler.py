@@ -218,7 +218,7 @@ class Scheduler:
         if self.last_batch is not None and self.last_batch.forward_mode.is_extend():
             lb = self.last_batch
             keep = [i for i, r in enumerate(lb.reqs) if not r.finished() and r is not self.chunked_req
-                    and not r.is_embedding]
+                    and not r.is_embedding and r.sampling_params.max_new_tokens > 0]
             if keep:
                 lb.reqs = [lb.reqs[i] for i in keep]
                 lb.init_decode_state()
@@ -453,6 +453,13 @@ class Scheduler:
             if r.return_logprob and result.input_logprobs is not None:
                 r.input_token_logprobs = result.input_logprobs[i]
             if r.finished():       # aborted while in flight
+                continue
+            if r.sampling_params.max_new_tokens == 0:   # prefill-only (cache warm-up / prompt scoring)
+                r.finished_reason = FINISH_LENGTH(0)
+                r.finished_time = now
+                r.kv_len = min(r.kv_len, r.seqlen)
+                self.kv.release(r)
+                out.append(r)
                 continue
             tok = int(toks[i])
             self._append_token(r, tok, result, i)
