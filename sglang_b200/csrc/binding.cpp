@@ -193,9 +193,36 @@ void bump_counts(at::Tensor counts, const at::Tensor& tokens) {
   count();
 }
 
+void nvl_allreduce(const at::Tensor& buf_ptrs, const at::Tensor& flag_ptrs, int64_t mc_ptr, int64_t slot_off, int64_t rank,
+                   int64_t world, at::Tensor out, at::Tensor epoch, at::Tensor done, int64_t channel, int64_t algo) {
+  CHECK_CUDA(out); CHECK_BF16(out); TORCH_CHECK(out.is_contiguous() && !buf_ptrs.is_cuda() && !flag_ptrs.is_cuda());
+  c10::cuda::CUDAGuard g(out.device());
+  sglb::nvl_allreduce(buf_ptrs.data_ptr<int64_t>(), flag_ptrs.data_ptr<int64_t>(), mc_ptr, slot_off, (int)rank, (int)world,
+                      out.data_ptr(), (int)out.numel(), reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                      reinterpret_cast<uint32_t*>(done.data_ptr<int>()), (int)channel, (int)algo, num_sms(), cur_stream());
+  count();
+}
+
+void nvl_ar_add_rmsnorm(const at::Tensor& buf_ptrs, const at::Tensor& flag_ptrs, int64_t mc_ptr, int64_t slot_off, int64_t rank,
+                        int64_t world, c10::optional<at::Tensor> residual, const at::Tensor& w, at::Tensor out, double eps, bool gemma,
+                        at::Tensor epoch, at::Tensor done, int64_t channel) {
+  CHECK_CUDA(out); CHECK_BF16(out); CHECK_BF16(w); TORCH_CHECK(out.is_contiguous() && out.dim() == 2);
+  if (residual.has_value()) TORCH_CHECK(residual->is_contiguous());
+  c10::cuda::CUDAGuard g(out.device());
+  sglb::nvl_ar_add_rmsnorm(buf_ptrs.data_ptr<int64_t>(), flag_ptrs.data_ptr<int64_t>(), mc_ptr, slot_off, (int)rank, (int)world,
+                           residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), out.data_ptr(), (int)out.size(0),
+                           (int)out.size(1), (float)eps, gemma, reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                           reinterpret_cast<uint32_t*>(done.data_ptr<int>()), (int)channel, num_sms(), cur_stream());
+  count();
+}
+
 }  // namespace
 
 TORCH_LIBRARY(sglb, m) {
+  m.def("nvl_allreduce(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!) out, "
+        "Tensor(b!) epoch, Tensor(c!) done, int channel, int algo) -> ()", &nvl_allreduce);
+  m.def("nvl_ar_add_rmsnorm(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!)? residual, "
+        "Tensor w, Tensor(b!) out, float eps, bool gemma, Tensor(c!) epoch, Tensor(d!) done, int channel) -> ()", &nvl_ar_add_rmsnorm);
   m.def("launch_count() -> int", &launch_count);
   m.def("reset_launch_count() -> ()", &reset_launch_count);
   m.def("gemm_pick_bn(int M, int N, int K) -> int", &gemm_pick_bn);

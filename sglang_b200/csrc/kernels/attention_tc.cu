@@ -20,11 +20,12 @@
 namespace sglb {
 
 constexpr int ATT_D = 128;          // head dim
-constexpr int ATT_KT = 128;         // kv tile
+// kv tile KT is a template parameter: 128 for prefill (compute-bound, 1 CTA/SM), 64 for decode (latency-bound: 256
+// TMEM columns + 96 KB smem so two CTAs share an SM and overlap their load -> MMA -> softmax chains)
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 32 KB (Q, K or V tile)
 constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
-constexpr int ATT_SMEM = 5 * ATT_TILE_BYTES + 1024 + 256;
+template <int KT> constexpr int att_smem_bytes() { return ATT_TILE_BYTES + 4 * KT * ATT_D * 2 + 1024 + 256; }
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units; lazy rescale (FA4-style)
 
 struct AttnParams {
@@ -41,7 +42,8 @@ struct AttnParams {
   int causal, window;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int KT>
+__global__ void __launch_bounds__(ATT_THREADS, (KT <= 64) ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   const int b = blockIdx.z;
@@ -59,8 +61,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int kv_hi = p.causal ? min(seq_len, prefix + t_hi) : seq_len;
   int kv_lo = 0;
   if (p.window > 0) kv_lo = max(0, prefix + t0 - p.window + 1);
-  const int tile_lo_all = kv_lo / ATT_KT;
-  const int tile_hi_all = (kv_hi + ATT_KT - 1) / ATT_KT;
+  constexpr int KV_TILE_BYTES = KT * ATT_D * 2;      // K or V tile
+  constexpr int KV_HALF_BYTES = KV_TILE_BYTES / 2;   // one 64-wide d-block of the tile
+  constexpr int TMEM_COLS = (KT <= 64) ? 256 : 512;  // S0 | S1 | O(128)
+  const int tile_lo_all = kv_lo / KT;
+  const int tile_hi_all = (kv_hi + KT - 1) / KT;
   const int per_split = (tile_hi_all - tile_lo_all + p.num_splits - 1) / p.num_splits;
   const int tile_begin = tile_lo_all + split * per_split;
   const int tile_end = min(tile_hi_all, tile_begin + per_split);
@@ -86,9 +91,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;       // 2 stages
-  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;   // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  uint8_t* sK = smem + ATT_TILE_BYTES;                       // 2 stages
+  uint8_t* sV = smem + ATT_TILE_BYTES + 2 * KV_TILE_BYTES;   // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES + 4 * KV_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -111,15 +116,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S0 = tmem_base;          // S buffers: cols [0,128) and [128,256); P aliases cols [0,64) of each
-  const uint32_t tmem_O = tmem_base + 256;     // O: cols [256,384)
+  const uint32_t tmem_S0 = tmem_base;           // S buffers: cols [0,KT) and [KT,2KT); P aliases the first KT/2 cols of each
+  const uint32_t tmem_O = tmem_base + 2 * KT;   // O: 128 cols
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ producer
@@ -127,44 +132,45 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_4d(sQ, &tmQ, q_full, 0, 0, kvh, q_start + t0);
     tma_load_4d(sQ + ATT_HALF_BYTES, &tmQ, q_full, 64, 0, kvh, q_start + t0);
     const int ps = p.page_size;
-    const int pages_per_tile = ATT_KT / ps;
+    const int pages_per_tile = KT / ps;
     const int* pt = p.page_table + (size_t)p.req_slots[b] * p.pt_stride;
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const int pg0 = (tile_begin + j) * pages_per_tile;
       mbar_wait(&k_empty[st], ph ^ 1);
-      mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+      mbar_expect_tx(&k_full[st], KV_TILE_BYTES);
       for (int i = 0; i < pages_per_tile; ++i) {
         const int page = pt[min(pg0 + i, p.pt_stride - 1)];
-        uint8_t* dst = sK + st * ATT_TILE_BYTES + i * ps * 128;
+        uint8_t* dst = sK + st * KV_TILE_BYTES + i * ps * 128;
         tma_load_3d(dst, &tmK, &k_full[st], 0, kvh, page * ps);
-        tma_load_3d(dst + ATT_HALF_BYTES, &tmK, &k_full[st], 64, kvh, page * ps);
+        tma_load_3d(dst + KV_HALF_BYTES, &tmK, &k_full[st], 64, kvh, page * ps);
       }
       mbar_wait(&v_empty[st], ph ^ 1);
-      mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+      mbar_expect_tx(&v_full[st], KV_TILE_BYTES);
       for (int i = 0; i < pages_per_tile; ++i) {
         const int page = pt[min(pg0 + i, p.pt_stride - 1)];
-        uint8_t* dst = sV + st * ATT_TILE_BYTES + i * ps * 128;
+        uint8_t* dst = sV + st * KV_TILE_BYTES + i * ps * 128;
         tma_load_3d(dst, &tmV, &v_full[st], 0, kvh, page * ps);
-        tma_load_3d(dst + ATT_HALF_BYTES, &tmV, &v_full[st], 64, kvh, page * ps);
+        tma_load_3d(dst + KV_HALF_BYTES, &tmV, &v_full[st], 64, kvh, page * ps);
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, 128, ATT_KT, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, 128, KT, 0, 0);
     constexpr uint32_t idesc_o = make_idesc(UMMA_BF16, UMMA_BF16, 128, ATT_D, 0, 1);   // B (V) is MN-major
     const uint32_t q_addr = smem_u32(sQ);
     auto issue_S = [&](int j) {
       const int st = j & 1;
       mbar_wait(&k_full[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+      const uint32_t k_addr = smem_u32(sK + st * KV_TILE_BYTES);
 #pragma unroll
       for (int k = 0; k < ATT_D / 16; ++k) {
-        const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
-        umma_f16_ss(tmem_S0 + st * 128, make_smem_desc_sw128(q_addr + off, 0, 1024),
-                    make_smem_desc_sw128(k_addr + off, 0, 1024), idesc_s, k != 0);
+        const uint32_t qoff = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
+        const uint32_t koff = (k >> 2) * KV_HALF_BYTES + (k & 3) * 32;
+        umma_f16_ss(tmem_S0 + st * KT, make_smem_desc_sw128(q_addr + qoff, 0, 1024),
+                    make_smem_desc_sw128(k_addr + koff, 0, 1024), idesc_s, k != 0);
       }
       umma_commit(&k_empty[st]);
       umma_commit(&s_full[st]);
@@ -178,11 +184,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&p_full[st], ph);
       mbar_wait(&v_full[st], ph);
       tc_fence_after();
-      const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+      const uint32_t v_addr = smem_u32(sV + st * KV_TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < ATT_KT / 16; ++k) {
+      for (int k = 0; k < KT / 16; ++k) {
         // A = P (bf16 pairs in TMEM: 16 K-elements = 8 columns), B = V rows [16k, 16k+16) (MN-major)
-        umma_f16_ts(tmem_O, tmem_S0 + st * 128 + k * 8, make_smem_desc_sw128(v_addr + k * 2048, ATT_HALF_BYTES, 1024),
+        umma_f16_ts(tmem_O, tmem_S0 + st * KT + k * 8, make_smem_desc_sw128(v_addr + k * 2048, KV_HALF_BYTES, 1024),
                     idesc_o, (j | k) != 0);
       }
       umma_commit(&v_empty[st]);
@@ -205,17 +211,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
       if (warp_valid) {
-        const uint32_t s_addr = tmem_S0 + lane_addr + st * 128;
-        uint32_t sr[4][32];
+        constexpr int NC = KT / 32;
+        const uint32_t s_addr = tmem_S0 + lane_addr + st * KT;
+        uint32_t sr[NC][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr[c]);
+        for (int c = 0; c < NC; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr[c]);
         tmem_ld_wait();
-        const int kv0 = (tile_begin + j) * ATT_KT;
-        const bool need_mask = (kv0 + ATT_KT > kv_hi) || (p.causal && kv0 + ATT_KT - 1 > prefix + t0) ||
+        const int kv0 = (tile_begin + j) * KT;
+        const bool need_mask = (kv0 + KT > kv_hi) || (p.causal && kv0 + KT - 1 > prefix + t0) ||
                                (p.window > 0 && kv0 < prefix + t_hi - p.window);
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float s = __uint_as_float(sr[c][i]) * p.scale_log2;
@@ -262,9 +269,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         m_i = m_use;
         const float m_sub = (m_i == -INFINITY) ? 0.f : m_i;
         float psum = 0.f;
-        const uint32_t p_addr = tmem_S0 + lane_addr + st * 128;
+        const uint32_t p_addr = tmem_S0 + lane_addr + st * KT;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -330,7 +337,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // merge split-KV partials: one warp per (token, head) row
@@ -383,13 +390,24 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
   p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens; p.cu_q = cu_q;
   p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.T = T;
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.causal = causal; p.window = window;
-  static bool configured = false;
-  if (!configured) {
-    SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
-  }
   dim3 grid((max_q_len + TQ - 1) / TQ, Hkv * num_splits, B);
-  attn_fwd_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  // decode (one query token per request) is latency-bound: small KV tiles, two CTAs per SM
+  const bool small = (cu_q == nullptr) && page_size <= 64;
+  if (small) {
+    static bool configured64 = false;
+    if (!configured64) {
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem_bytes<64>()));
+      configured64 = true;
+    }
+    attn_fwd_tc_kernel<64><<<grid, ATT_THREADS, att_smem_bytes<64>(), stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    static bool configured128 = false;
+    if (!configured128) {
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem_bytes<128>()));
+      configured128 = true;
+    }
+    attn_fwd_tc_kernel<128><<<grid, ATT_THREADS, att_smem_bytes<128>(), stream>>>(tmQ, tmK, tmV, p);
+  }
   SGLB_CUDA_CHECK(cudaGetLastError());
   if (num_splits > 1) {
     const int rows = T * Hq;

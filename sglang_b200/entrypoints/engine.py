@@ -179,7 +179,7 @@ class Engine:
             prompt_tokens=msg.prompt_tokens, completion_tokens=msg.completion_tokens, cached_tokens=msg.cached_tokens,
             output_logprobs=msg.output_logprobs, input_logprobs=msg.input_logprobs, top_logprobs=msg.top_logprobs,
             spec_verify_ct=msg.spec_verify_ct, spec_accepted_tokens=msg.spec_accepted_tokens, embeddings=msg.embeddings,
-            hidden_states=msg.hidden_states)
+            hidden_states=msg.hidden_states, ttfts=msg.ttfts, queue_times=msg.queue_times)
         now = time.perf_counter()
         for i, rid in enumerate(out.rids):
             st = self.states.get(rid)
@@ -214,7 +214,10 @@ class Engine:
                 st.finished = True
                 m["finish_reason"] = fr
                 m["e2e_latency"] = now - st.created
-                if st.first_token_time is not None:
+                if out.ttfts is not None and out.ttfts[i] is not None:
+                    m["ttft"] = out.ttfts[i]          # measured by the scheduler at the step that produced token 1
+                    m["queue_time"] = out.queue_times[i] if out.queue_times else None
+                elif st.first_token_time is not None:
                     m["ttft"] = st.first_token_time - st.created
                 if self.metrics is not None:
                     self.metrics.observe_request(m)

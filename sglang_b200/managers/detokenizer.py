@@ -80,4 +80,4 @@ class Detokenizer:
             prompt_tokens=msg.prompt_tokens, completion_tokens=msg.completion_tokens, cached_tokens=msg.cached_tokens,
             output_logprobs=msg.output_logprobs, input_logprobs=msg.input_logprobs, top_logprobs=msg.top_logprobs,
             spec_verify_ct=msg.spec_verify_ct, spec_accepted_tokens=msg.spec_accepted_tokens, embeddings=msg.embeddings,
-            hidden_states=msg.hidden_states)
+            hidden_states=msg.hidden_states, ttfts=msg.ttfts, queue_times=msg.queue_times)

@@ -187,6 +187,8 @@ class BatchTokenIDOutput:
     spec_accepted_tokens: Optional[List[int]] = None
     embeddings: Optional[List[Any]] = None
     hidden_states: Optional[List[Any]] = None
+    ttfts: Optional[List[Optional[float]]] = None      # scheduler-measured time to first token (s)
+    queue_times: Optional[List[Optional[float]]] = None
 
 
 @message
@@ -205,6 +207,8 @@ class BatchStrOutput:
     spec_accepted_tokens: Optional[List[int]] = None
     embeddings: Optional[List[Any]] = None
     hidden_states: Optional[List[Any]] = None
+    ttfts: Optional[List[Optional[float]]] = None
+    queue_times: Optional[List[Optional[float]]] = None
 
 
 # --------------------------------------------------------------------------- control plane

@@ -601,6 +601,8 @@ class Scheduler:
             msg.embeddings = [r.embedding for r in sel]
         if any(r.return_hidden_states for r in sel):
             msg.hidden_states = [r.hidden_states for r in sel]
+        msg.ttfts = [(r.first_token_time - r.created_time) if r.first_token_time is not None else None for r in sel]
+        msg.queue_times = [(getattr(r, 'queue_time_end', None) or r.created_time) - r.created_time for r in sel]
         for r in sel:
             r.sent_offset = len(r.output_ids)
         self.send_to_detokenizer(msg)

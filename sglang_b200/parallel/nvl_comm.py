@@ -1,0 +1,107 @@
+"""NvlComm: symmetric-memory arena over NVLink 5 / NVSwitch + the collectives built on it.
+
+Stands in for the reference's custom all-reduce v1/v2 (``distributed/device_communicators/custom_all_reduce_v2.py:98``),
+torch-symm-mem AR (``torch_symm_mem.py:34-185``) and FlashInfer AR+RMSNorm fusion (``layers/flashinfer_comm_fusion.py``).
+Plumbing (allocation, handle exchange, peer + multicast mapping) is delegated to ``torch.distributed._symmetric_memory``
+(CUDA VMM + fabric/posix-fd handles underneath); every kernel that touches the arena is ours
+(``csrc/comm/nvl_allreduce.cu``, ``csrc/comm/gemm_allreduce.cu``).
+
+Arena layout per rank (identical on all ranks):  slot[parity] = [ input region | result region ], parity = epoch & 1.
+Hazard argument for double buffering: call k writes slot k%2 *before* its flag round; a slow peer may still be reading
+slot (k-1)%2 from call k-1, never slot k%2, because having passed the flag round of call k-1 implies it finished all
+reads of call k-2.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, List, Optional
+
+import torch
+
+from ..environ import envs
+
+logger = logging.getLogger(__name__)
+
+CH_ONESHOT, CH_TWOSHOT, CH_FUSED_NORM, CH_GEMM = 0, 1, 2, 3
+NUM_CHANNELS = 8
+
+
+class NvlComm:
+    def __init__(self, group: Any, buf: torch.Tensor, hdl: Any, slot_bytes: int):
+        self.group = group
+        self.rank, self.world = group.rank, group.world_size
+        self.buf, self.hdl = buf, hdl
+        self.slot_bytes = slot_bytes
+        dev = buf.device
+        self.buf_ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64)
+        self.flag_ptrs = torch.tensor([int(p) for p in hdl.signal_pad_ptrs], dtype=torch.int64)
+        self.mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        # per-channel epoch counters + completion counters (device memory; graph-replay safe)
+        self.epochs = torch.zeros(NUM_CHANNELS, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(NUM_CHANNELS, 2, dtype=torch.int32, device=dev)
+        self.host_epoch = [0] * NUM_CHANNELS   # host mirror used only to pick the slot parity
+        self.max_oneshot_bytes = 512 * 1024    # crossover measured by the reference on B200x8 (k3_ar_fusion.py:36-38)
+        self.calls = 0
+
+    @classmethod
+    def create(cls, group: Any) -> "NvlComm":
+        import torch.distributed._symmetric_memory as symm_mem
+
+        total = envs.SGLB_NVL_MAX_BYTES.get()
+        slot = total // 2
+        dev = group.device
+        buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(buf, group.device_group.group_name)
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        group.barrier()
+        c = cls(group, buf, hdl, slot)
+        logger.info("NVL arena: %d MiB/rank, world=%d, multicast=%s", total >> 20, c.world, bool(c.mc_ptr))
+        return c
+
+    # ------------------------------------------------------------------ helpers
+    def _slot(self, channel: int) -> int:
+        """byte offset of the slot used by the NEXT call on this channel, and advance the host mirror"""
+        self.host_epoch[channel] += 1
+        return (self.host_epoch[channel] & 1) * self.slot_bytes
+
+    def slot_view(self, offset: int, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[offset:offset + nbytes].view(dtype).view(*shape)
+
+    def can_all_reduce(self, x: torch.Tensor) -> bool:
+        nbytes = x.numel() * x.element_size()
+        return (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
+                and 2 * nbytes <= self.slot_bytes and not torch.cuda.is_current_stream_capturing() or
+                (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0 and 2 * nbytes <= self.slot_bytes))
+
+    # ------------------------------------------------------------------ collectives
+    def all_reduce(self, x: torch.Tensor, algo: Optional[int] = None) -> torch.Tensor:
+        nbytes = x.numel() * x.element_size()
+        if algo is None:
+            algo = 0 if nbytes <= self.max_oneshot_bytes else 1
+        ch = CH_ONESHOT if algo == 0 else CH_TWOSHOT
+        off = self._slot(ch)
+        self.slot_view(off, x.shape).copy_(x)      # stage into the arena (the fused GEMM epilogue writes here directly)
+        out = torch.empty_like(x)
+        torch.ops.sglb.nvl_allreduce(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, out, self.epochs[ch:ch + 1],
+                                     self.done[ch], ch, algo)
+        self.calls += 1
+        return out
+
+    def stage(self, channel: int, shape, dtype=torch.bfloat16):
+        """reserve this call's arena slot; returns (offset, view).  The producer (GEMM) writes its partial output there."""
+        off = self._slot(channel)
+        return off, self.slot_view(off, shape, dtype)
+
+    def fused_allreduce_add_rmsnorm(self, off: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
+                                    eps: float, gemma: bool = False) -> None:
+        """consumer side of a row-parallel GEMM whose partial output already sits in arena slot ``off``"""
+        T, H = out.shape
+        ch = CH_FUSED_NORM
+        torch.ops.sglb.nvl_ar_add_rmsnorm(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, residual, weight, out,
+                                          float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch], ch)
+        self.calls += 1
