@@ -42,7 +42,7 @@ struct AttnParams {
   int causal, window;
 };
 
-template <int KT>
+template <int KT, bool HAS_CAP>
 __global__ void __launch_bounds__(ATT_THREADS, (KT <= 64) ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -204,6 +204,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int q_pos = prefix + tok;               // absolute position of this query token
     const uint32_t lane_addr = (uint32_t)(q << 5) << 16;
     float m_i = -INFINITY, l_i = 0.f;
+    // loop-invariant uniforms hoisted into registers
+    const float scale_log2 = p.scale_log2;
+    const float cap = p.logit_cap, inv_cap = HAS_CAP ? 1.f / p.logit_cap : 0.f;
+    const float scale_nat = scale_log2 * 0.6931471805599453f, inv_scale_nat = 1.f / scale_nat;
+    const int kv_last = p.causal ? min(seq_len - 1, q_pos) : seq_len - 1;
+    const int kv_first = p.window > 0 ? q_pos - p.window + 1 : -(1 << 30);
 
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
@@ -220,28 +226,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int kv0 = (tile_begin + j) * KT;
         const bool need_mask = (kv0 + KT > kv_hi) || (p.causal && kv0 + KT - 1 > prefix + t0) ||
                                (p.window > 0 && kv0 < prefix + t_hi - p.window);
-        float mx = -INFINITY;
+        // The inner loops are kept branch-free and tiny (the 128-wide body is fully unrolled: any per-element branch or
+        // constant-bank reload multiplies into thousands of instructions and thrashes the instruction cache).
+        if (HAS_CAP) {   // Gemma-2 style soft-capping (separate template instance): rewrite raw so raw*scale_log2 is the capped logit
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(sr[c][i]) * p.scale_log2;
-            if (p.logit_cap > 0.f) {
-              // s is in log2 units: cap * tanh(x / cap) with x = s * ln2
-              const float x = s * 0.6931471805599453f;
-              s = p.logit_cap * tanhf(x / p.logit_cap) * 1.4426950408889634f;
+            for (int i = 0; i < 32; ++i) {
+              const float x = __uint_as_float(sr[c][i]) * scale_nat;
+              sr[c][i] = __float_as_uint(cap * tanhf(x * inv_cap) * inv_scale_nat);
             }
-            if (need_mask) {
-              const int kv = kv0 + c * 32 + i;
-              bool ok = kv < seq_len;
-              if (p.causal) ok = ok && (kv <= q_pos);
-              if (p.window > 0) ok = ok && (kv > q_pos - p.window);
-              if (!ok) s = -INFINITY;
+        }
+        float mx_raw = -INFINITY;
+        if (need_mask) {
+          const int hi = kv_last - kv0;     // columns > hi are masked   (per-thread: causal / sequence end)
+          const int lo = kv_first - kv0;    // columns < lo are masked   (sliding window)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = c * 32 + i;
+              const float v = (col > hi || col < lo) ? -INFINITY : __uint_as_float(sr[c][i]);
+              sr[c][i] = __float_as_uint(v);
+              mx_raw = fmaxf(mx_raw, v);
             }
-            sr[c][i] = __float_as_uint(s);
-            mx = fmaxf(mx, s);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(sr[c][i]));
           }
         }
+        const float mx = mx_raw * scale_log2;   // scale_log2 > 0: max commutes with the scaling
         const float m_new = fmaxf(m_i, mx);
         const bool first = (j == 0);
         const bool need = (!first) && (m_new > m_i + ATT_RESCALE_THRESHOLD);
@@ -275,8 +292,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = exp2f(__uint_as_float(sr[c][i]) - m_sub);
-            const float p1 = exp2f(__uint_as_float(sr[c][i + 1]) - m_sub);
+            // p = 2^(raw*scale - m): one FFMA + one MUFU.EX2 per element
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), scale_log2, -m_sub));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), scale_log2, -m_sub));
             psum += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
@@ -393,21 +411,20 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
   dim3 grid((max_q_len + TQ - 1) / TQ, Hkv * num_splits, B);
   // decode (one query token per request) is latency-bound: small KV tiles, two CTAs per SM
   const bool small = (cu_q == nullptr) && page_size <= 64;
-  if (small) {
-    static bool configured64 = false;
-    if (!configured64) {
-      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem_bytes<64>()));
-      configured64 = true;
-    }
-    attn_fwd_tc_kernel<64><<<grid, ATT_THREADS, att_smem_bytes<64>(), stream>>>(tmQ, tmK, tmV, p);
-  } else {
-    static bool configured128 = false;
-    if (!configured128) {
-      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem_bytes<128>()));
-      configured128 = true;
-    }
-    attn_fwd_tc_kernel<128><<<grid, ATT_THREADS, att_smem_bytes<128>(), stream>>>(tmQ, tmK, tmV, p);
-  }
+  const bool capped = logit_cap > 0.f;
+#define SGLB_ATT_LAUNCH(KT_, CAP_)                                                                                         \
+  do {                                                                                                                    \
+    static bool configured = false;                                                                                       \
+    if (!configured) {                                                                                                    \
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<KT_, CAP_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           att_smem_bytes<KT_>()));                                                       \
+      configured = true;                                                                                                  \
+    }                                                                                                                     \
+    attn_fwd_tc_kernel<KT_, CAP_><<<grid, ATT_THREADS, att_smem_bytes<KT_>(), stream>>>(tmQ, tmK, tmV, p);                \
+  } while (0)
+  if (small) { if (capped) SGLB_ATT_LAUNCH(64, true); else SGLB_ATT_LAUNCH(64, false); }
+  else { if (capped) SGLB_ATT_LAUNCH(128, true); else SGLB_ATT_LAUNCH(128, false); }
+#undef SGLB_ATT_LAUNCH
   SGLB_CUDA_CHECK(cudaGetLastError());
   if (num_splits > 1) {
     const int rows = T * Hq;

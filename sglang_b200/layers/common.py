@@ -27,6 +27,10 @@ class RMSNorm(nn.Module):
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
         """residual given: (in place) residual += x; x = norm(residual); returns (x, residual)"""
+        if hasattr(x, "nvl"):   # PendingAllReduce: cross-rank sum + residual add + norm in ONE kernel
+            out = torch.empty(x.T, x.H, dtype=self.weight.dtype, device=self.weight.device)
+            x.nvl.fused_allreduce_add_rmsnorm(x.off, residual, self.weight, out, self.eps, self.gemma)
+            return out, residual
         if residual is None:
             return ops.rmsnorm(x, self.weight, self.eps, gemma=self.gemma)
         ops.fused_add_rmsnorm(x, residual, self.weight, self.eps, gemma=self.gemma)

@@ -20,6 +20,23 @@ from ..parallel.parallel_state import get_tp_group
 from .quantization import QuantMethod, UnquantizedMethod
 
 
+class PendingAllReduce:
+    """Handle for partial sums that sit in this call's NVL arena slot on every rank (not yet reduced)."""
+    __slots__ = ("nvl", "off", "T", "H")
+
+    def __init__(self, nvl, off: int, T: int, H: int):
+        self.nvl, self.off, self.T, self.H = nvl, off, T, H
+
+    def resolve(self) -> torch.Tensor:
+        """plain all-reduce of the parked partials (used when the consumer is not an RMSNorm)"""
+        from ..parallel.nvl_comm import CH_FUSED_NORM
+
+        out = torch.empty(self.T, self.H, dtype=torch.bfloat16, device=self.nvl.buf.device)
+        ones = None
+        self.nvl.allreduce_from_slot(self.off, out)
+        return out
+
+
 def _divide(a: int, b: int) -> int:
     assert a % b == 0, f"{a} is not divisible by {b}"
     return a // b
@@ -138,12 +155,30 @@ class RowParallelLinear(LinearBase):
         self.in_total = in_features
         super().__init__(_divide(in_features, self.tp.world_size), out_features, bias, dtype, quant, prefix)
 
-    def forward(self, x):
-        # bias is added once (rank 0) so the reduction stays a pure sum
-        y = self.apply(x, self.bias if (self.bias is not None and self.tp.rank == 0) else None)
-        if self.reduce_results and self.tp.world_size > 1:
-            nvl = self.tp.nvl
-            y = self.tp.all_reduce(y)
+    # messages up to this size take the fused path: the GEMM writes its partial product straight into the NVL arena and the
+    # *next* RMSNorm kernel performs the cross-rank sum (+ residual + norm) while pulling the peers' rows over NVLink.
+    FUSED_AR_MAX_BYTES = 1 << 20
+
+    def forward(self, x, defer_reduce: bool = False):
+        """``defer_reduce``: return a ``PendingAllReduce`` (partial sums parked in the symmetric arena) instead of
+        reducing; the consumer must be ``RMSNorm.forward_pending``."""
+        bias = self.bias if (self.bias is not None and self.tp.rank == 0) else None   # added once: the reduction stays a pure sum
+        tp = self.tp
+        if tp.world_size == 1:
+            return self.apply(x, bias)
+        nvl = tp.nvl
+        T = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
+        nbytes = T * self.out_features * 2
+        if (defer_reduce and self.reduce_results and nvl is not None and x.dim() == 2 and nbytes <= self.FUSED_AR_MAX_BYTES
+                and isinstance(self.quant, UnquantizedMethod) and bias is None and x.dtype == torch.bfloat16):
+            from ..parallel.nvl_comm import CH_FUSED_NORM
+
+            off, view = nvl.stage(CH_FUSED_NORM, (T, self.out_features))
+            ops.linear(x, self.weight, None, out=view)
+            return PendingAllReduce(nvl, off, T, self.out_features)
+        y = self.apply(x, bias)
+        if self.reduce_results:
+            y = tp.all_reduce(y)
         return y
 
     def weight_loader(self, param, loaded, shard_id=None):

@@ -487,9 +487,17 @@ class _DecodeGraph:
         for _ in range(2):   # warm-up outside capture (cuBLAS workspaces, lazy inits)
             self._run()
         stream.synchronize()
+        nvl = self.r.tp.nvl
+        if nvl is not None:
+            self.r.tp.barrier()       # all ranks finished their eager warm-up collectives before anyone records
+            nvl.begin_capture()       # collectives recorded into the graph use the graph arena region, parity from 0
         c0 = ops.launch_count()
-        with torch.cuda.graph(self.graph, pool=pool, stream=stream):
-            self._run()
+        try:
+            with torch.cuda.graph(self.graph, pool=pool, stream=stream):
+                self._run()
+        finally:
+            if nvl is not None:
+                nvl.end_capture()
         self.num_kernels = ops.launch_count() - c0
 
     def load(self, sb: ScheduleBatch, step: int, seed: int) -> None:

@@ -32,11 +32,66 @@ def build_model(cfg: ModelConfig, device: torch.device, quant: Optional[str] = N
     return model.eval()
 
 
+def dummy_checkpoint_iterator(cfg: ModelConfig, device: torch.device, dtype: torch.dtype, seed: int = 0,
+                              scale: float = 0.02) -> Iterator[Tuple[str, torch.Tensor]]:
+    """A synthetic *HF-named, unsharded* checkpoint generated tensor by tensor on the device from name-hashed seeds.
+    Feeding it through ``model.load_weights`` makes dummy weights independent of the TP/PP/EP layout (every rank slices
+    the same global tensor), which is what lets TP=N runs be compared with TP=1 and exercises the real loader path."""
+    def rnd(name: str, *shape: int) -> torch.Tensor:
+        g = torch.Generator(device=device)
+        g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+        return torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, scale, generator=g).to(dtype)
+
+    H, V, D = cfg.hidden_size, cfg.vocab_size, cfg.head_dim
+    Hq, Hkv, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
+    gemma = cfg.architecture.startswith("Gemma")
+    norm = (lambda n: torch.zeros(n, dtype=dtype, device=device)) if gemma else (lambda n: torch.ones(n, dtype=dtype, device=device))
+    yield "model.embed_tokens.weight", rnd("model.embed_tokens.weight", V, H)
+    for i in range(cfg.num_hidden_layers):
+        p = f"model.layers.{i}."
+        for nm, n_out in (("q_proj", Hq * D), ("k_proj", Hkv * D), ("v_proj", Hkv * D)):
+            yield p + f"self_attn.{nm}.weight", rnd(p + nm, n_out, H)
+            if cfg.attention_bias:
+                yield p + f"self_attn.{nm}.bias", rnd(p + nm + ".bias", n_out)
+        yield p + "self_attn.o_proj.weight", rnd(p + "o_proj", H, Hq * D)
+        if cfg.qk_norm:
+            yield p + "self_attn.q_norm.weight", norm(D)
+            yield p + "self_attn.k_norm.weight", norm(D)
+        if cfg.is_moe:
+            yield p + "block_sparse_moe.gate.weight", rnd(p + "gate", cfg.num_local_experts, H)
+            Im = cfg.moe_intermediate_size
+            for e in range(cfg.num_local_experts):
+                q = p + f"block_sparse_moe.experts.{e}."
+                yield q + "w1.weight", rnd(q + "w1", Im, H)
+                yield q + "w3.weight", rnd(q + "w3", Im, H)
+                yield q + "w2.weight", rnd(q + "w2", H, Im)
+        else:
+            yield p + "mlp.gate_proj.weight", rnd(p + "gate_proj", I, H)
+            yield p + "mlp.up_proj.weight", rnd(p + "up_proj", I, H)
+            yield p + "mlp.down_proj.weight", rnd(p + "down_proj", H, I)
+        yield p + "input_layernorm.weight", norm(H)
+        yield p + "post_attention_layernorm.weight", norm(H)
+    yield "model.norm.weight", norm(H)
+    if not cfg.tie_word_embeddings:
+        yield "lm_head.weight", rnd("lm_head.weight", V, H)
+
+
 @torch.no_grad()
-def init_dummy_weights(model: nn.Module, seed: int = 0, scale: float = 0.02) -> None:
-    """N(0, scale) for matrices, ones for norm weights (zeros for gemma-style), zeros for biases.
-    The seed of each tensor is a hash of its *global* name so results do not depend on sharding order."""
-    for name, p in model.named_parameters():
+def init_dummy_weights(model: nn.Module, seed: int = 0, scale: float = 0.02, cfg: Optional[ModelConfig] = None) -> None:
+    """Random-init weights of the real architecture (reference ``DummyModelLoader``).  The language model is filled
+    through the layout-independent synthetic checkpoint above; anything it does not cover (vision tower, heads) gets a
+    per-parameter name-seeded init."""
+    params = dict(model.named_parameters())
+    if cfg is not None and hasattr(model, "load_weights"):
+        for p in params.values():
+            if p.numel():
+                p.data.view(-1)[:1].fill_(float("nan"))
+        first = next(iter(params.values()))
+        model.load_weights(dummy_checkpoint_iterator(cfg, first.device, first.dtype, seed, scale))
+        todo = {n: p for n, p in params.items() if p.numel() and bool(torch.isnan(p.data.view(-1)[0].float()))}
+    else:
+        todo = params
+    for name, p in todo.items():
         if p.dim() <= 1:
             if name.endswith("bias"):
                 p.zero_()
@@ -78,7 +133,7 @@ def load_model(cfg: ModelConfig, model_path: str, load_format: str, device: torc
                seed: int = 0) -> nn.Module:
     model = build_model(cfg, device, quant)
     if load_format == "dummy":
-        init_dummy_weights(model, seed)
+        init_dummy_weights(model, seed, cfg=cfg)
     elif load_format in ("safetensors", "auto"):
         model.load_weights(iter_safetensors(model_path))
     elif load_format == "pt":

@@ -40,7 +40,7 @@ class LlamaMLP(nn.Module):
         self.act = get_act_and_mul(cfg.hidden_act)
 
     def forward(self, x):
-        return self.down_proj(self.act(self.gate_up_proj(x)))
+        return self.down_proj(self.act(self.gate_up_proj(x)), defer_reduce=True)
 
 
 class LlamaAttention(nn.Module):
@@ -68,7 +68,7 @@ class LlamaAttention(nn.Module):
             q = self.q_norm(q.reshape(T * self.attn.num_heads, self.head_dim)).view(T, self.q_size)
             k = self.k_norm(k.reshape(T * self.attn.num_kv_heads, self.head_dim)).view(T, self.kv_size)
         o = self.attn(q, k, v, fb)
-        return self.o_proj(o)
+        return self.o_proj(o, defer_reduce=True)
 
 
 class LlamaDecoderLayer(nn.Module):
@@ -131,6 +131,8 @@ class LlamaModel(nn.Module):
         for layer in self.layers:
             h, residual = layer(h, residual, fb)
         if not self.pp.is_last:
+            if hasattr(h, "resolve"):
+                h = h.resolve()
             return h, residual
         h, _ = self.norm(h, residual)
         return h

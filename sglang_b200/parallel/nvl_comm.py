@@ -40,6 +40,8 @@ class NvlComm:
         self.epochs = torch.zeros(NUM_CHANNELS, dtype=torch.int32, device=dev)
         self.done = torch.zeros(NUM_CHANNELS, 2, dtype=torch.int32, device=dev)
         self.host_epoch = [0] * NUM_CHANNELS   # host mirror used only to pick the slot parity
+        self.graph_epoch = [0] * NUM_CHANNELS
+        self.capturing = False
         self.max_oneshot_bytes = 512 * 1024    # crossover measured by the reference on B200x8 (k3_ar_fusion.py:36-38)
         self.calls = 0
 
@@ -48,7 +50,7 @@ class NvlComm:
         import torch.distributed._symmetric_memory as symm_mem
 
         total = envs.SGLB_NVL_MAX_BYTES.get()
-        slot = total // 2
+        slot = total // 4          # {eager, graph} x {even, odd}
         dev = group.device
         buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         hdl = symm_mem.rendezvous(buf, group.device_group.group_name)
@@ -61,9 +63,22 @@ class NvlComm:
 
     # ------------------------------------------------------------------ helpers
     def _slot(self, channel: int) -> int:
-        """byte offset of the slot used by the NEXT call on this channel, and advance the host mirror"""
-        self.host_epoch[channel] += 1
-        return (self.host_epoch[channel] & 1) * self.slot_bytes
+        """byte offset of the slot used by the NEXT call on this channel, and advance the host mirror.
+        The arena has two regions x two parities: eager calls alternate inside region 0; calls recorded into a CUDA
+        graph alternate inside region 1 starting from parity 0 at every capture (a forward pass stages an even number of
+        times per channel, so back-to-back replays of any graphs keep alternating, and an eager step followed by a graph
+        replay — or vice versa — never reuses the slot of the immediately preceding collective)."""
+        ctr = self.graph_epoch if self.capturing else self.host_epoch
+        ctr[channel] += 1
+        region = 1 if self.capturing else 0
+        return region * 2 * self.slot_bytes + (ctr[channel] & 1) * self.slot_bytes
+
+    def begin_capture(self) -> None:
+        self.capturing = True
+        self.graph_epoch = [0] * NUM_CHANNELS
+
+    def end_capture(self) -> None:
+        self.capturing = False
 
     def slot_view(self, offset: int, shape, dtype=torch.bfloat16) -> torch.Tensor:
         n = 1
@@ -75,8 +90,7 @@ class NvlComm:
     def can_all_reduce(self, x: torch.Tensor) -> bool:
         nbytes = x.numel() * x.element_size()
         return (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
-                and 2 * nbytes <= self.slot_bytes and not torch.cuda.is_current_stream_capturing() or
-                (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0 and 2 * nbytes <= self.slot_bytes))
+                and 2 * nbytes <= self.slot_bytes)
 
     # ------------------------------------------------------------------ collectives
     def all_reduce(self, x: torch.Tensor, algo: Optional[int] = None) -> torch.Tensor:
@@ -96,6 +110,12 @@ class NvlComm:
         """reserve this call's arena slot; returns (offset, view).  The producer (GEMM) writes its partial output there."""
         off = self._slot(channel)
         return off, self.slot_view(off, shape, dtype)
+
+    def allreduce_from_slot(self, off: int, out: torch.Tensor, channel: int = CH_FUSED_NORM) -> None:
+        """one-shot all-reduce of partials that a producer already wrote into slot ``off`` (no staging copy)"""
+        torch.ops.sglb.nvl_allreduce(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, out,
+                                     self.epochs[channel:channel + 1], self.done[channel], channel, 0)
+        self.calls += 1
 
     def fused_allreduce_add_rmsnorm(self, off: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
                                     eps: float, gemma: bool = False) -> None:
