@@ -114,6 +114,14 @@ class KVManager:
             req.num_pages += need
         return True
 
+    def trim(self, req, n_tokens: int) -> None:
+        """give back pages beyond those needed for ``n_tokens`` tokens (speculative decoding over-allocates for drafts)"""
+        need = max((n_tokens + self.ps - 1) // self.ps, req.num_cached_pages)
+        if req.num_pages > need:
+            extra = self.page_table[req.req_slot, need:req.num_pages].copy()
+            self.allocator.free(extra)
+            req.num_pages = need
+
     def slots_for(self, req, start: int, end: int) -> np.ndarray:
         pos = np.arange(start, end, dtype=np.int64)
         return (self.page_table[req.req_slot, pos // self.ps].astype(np.int64) * self.ps + pos % self.ps).astype(np.int32)

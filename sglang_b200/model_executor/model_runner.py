@@ -38,6 +38,14 @@ logger = logging.getLogger(__name__)
 _DT = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
 
 
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class BatchResult:
     """Asynchronous result of one step; ``wait()`` blocks until the device->host copy has landed."""
 
@@ -257,6 +265,36 @@ class ModelRunner:
             self._extra_logprobs(sb, fb, hidden, logits, res, samp_rows)
         self._finish_result(res, toks, lp_out)
         return res
+
+    @torch.no_grad()
+    def forward_verify(self, sb: ScheduleBatch) -> np.ndarray:
+        """Speculative verification: ragged extend over [last_token, drafts...] of every request; returns the target
+        model's sample at EVERY fed position (int64 [T]).  Synchronous (speculative decoding disables overlap)."""
+        self.forward_ct += 1
+        self.step_counter += 1
+        ctx = torch.cuda.stream(self.stream) if self.is_cuda else _null_ctx()
+        with ctx:
+            fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
+            self.h2d_bytes += fb.h2d_bytes
+            hidden = self.model(fb)
+            logits = self.model.compute_logits(hidden)          # [T, V]
+            reps = torch.from_numpy(sb.q_lens.astype(np.int64)).to(self.device)
+            s = fb.sampling
+            rep = lambda t: torch.repeat_interleave(t, reps)
+            g_rows = [i for i, r in enumerate(sb.reqs) if r.grammar is not None]
+            if g_rows:
+                cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
+                V = logits.shape[1]
+                bm = np.full((len(g_rows), (V + 31) // 32), -1, dtype=np.int32)
+                for k, i in enumerate(g_rows):
+                    sb.reqs[i].grammar.fill_vocab_mask(bm[k], V)
+                rows = torch.tensor([int(cu[i]) for i in g_rows], dtype=torch.int32, device=self.device)
+                ops.apply_token_bitmask(logits, torch.from_numpy(bm).to(self.device), rows)
+            toks = ops.sample(logits, rep(s.temperature), rep(s.top_k), rep(s.top_p), rep(s.min_p), None, None, None, None,
+                              global_seed=self.args.random_seed, step=self.step_counter)
+            out = toks.cpu().numpy().astype(np.int64)
+        self.d2h_bytes += out.size * 4
+        return out
 
     def sample(self, logits: torch.Tensor, fb: ForwardBatch, lp_out: Optional[torch.Tensor]) -> torch.Tensor:
         s = fb.sampling

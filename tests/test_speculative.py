@@ -1,0 +1,48 @@
+"""Speculative decoding: greedy outputs identical to plain decoding; drafts get accepted on repetitive text
+(reference: test/registered/spec/* + spec_decoding_kit accept-length gate)."""
+import numpy as np
+import pytest
+
+import sglang_b200 as sgl
+
+
+def _prompts():
+    rng = np.random.default_rng(0)
+    base = rng.integers(3, 200, size=12).tolist()
+    return [base * 4, rng.integers(3, 200, size=30).tolist(), (base[:5] * 9)[:40]]
+
+
+@pytest.mark.parametrize("algo", ["NGRAM", "STANDALONE"])
+def test_spec_greedy_equals_plain(algo):
+    prompts = _prompts()
+    sp = {"max_new_tokens": 40, "temperature": 0, "ignore_eos": True}
+    plain = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    want = [o["output_ids"] for o in plain.generate(input_ids=prompts, sampling_params=sp)]
+    kw = dict(speculative_draft_model_path="dummy:tiny-llama") if algo == "STANDALONE" else {}
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, speculative_algorithm=algo, speculative_num_draft_tokens=4, **kw)
+    outs = eng.generate(input_ids=prompts, sampling_params=sp)
+    assert [o["output_ids"] for o in outs] == want
+    w = eng.scheduler.spec_worker
+    assert w.total_verify > 0
+    if algo == "STANDALONE":
+        # the draft model IS the target model (same seed offset differs -> different weights), acceptance is not guaranteed
+        assert w.total_drafted > 0
+    m = outs[0]["meta_info"]
+    assert m["spec_verify_ct"] > 0 and m["spec_accept_length"] >= 1.0
+    eng.scheduler.check_invariants()
+
+
+def test_ngram_accepts_on_repetition():
+    # a model that has already generated this continuation once: the corpus must predict it the second time
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, speculative_algorithm="NGRAM", speculative_num_draft_tokens=6,
+                     disable_radix_cache=True)
+    p = np.random.default_rng(5).integers(3, 200, size=20).tolist()
+    sp = {"max_new_tokens": 48, "temperature": 0, "ignore_eos": True}
+    a = eng.generate(input_ids=p, sampling_params=sp)
+    w = eng.scheduler.spec_worker
+    v1 = w.total_verify
+    b = eng.generate(input_ids=p, sampling_params=sp)
+    assert a["output_ids"] == b["output_ids"]
+    steps2 = w.total_verify - v1
+    assert steps2 < 48 * 0.6, f"second pass should need far fewer target steps ({steps2})"
+    assert b["meta_info"]["spec_accept_length"] > 1.5
