@@ -1,0 +1,227 @@
+"""Hierarchical KV cache: L1 device pages -> L2 pinned host pages -> L3 storage (files).
+
+Parity: reference ``python/sglang/srt/mem_cache/hiradix_cache.py:77`` (HiRadixCache), ``managers/cache_controller.py``
+(HiCacheController: write-through / write-back, load-back on hit), ``memory_pool_host.py`` (host pools),
+``hicache_storage.py:150,361`` (storage backends; ``HiCacheFile``), page transfer kernels ``kernels/aot/csrc/kvcacheio/transfer.cu``.
+
+Design: the radix node keeps ``host_pages`` next to ``pages``.  Eviction of a device node with a host copy only drops
+the device pages (the node stays in the tree as *host-resident*); a later prefix match that reaches a host-resident node
+re-allocates device pages and loads the KV back with one strided H2D copy per node (the KV pool is a single tensor whose
+page dimension is contiguous per (layer, K|V) plane, so a page set moves as one ``index_copy_``).  L3 spills host pages
+to files named by the chained page hash (``sglb_rt.hash_pages``), giving cross-restart prefix reuse.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .memory_pool import HostKVPool, KVPool
+from .radix_cache import _EMPTY, RadixCache, TreeNode
+
+logger = logging.getLogger(__name__)
+
+
+class FileStorage:
+    """L3: one file per page hash (reference HiCacheFile)"""
+
+    def __init__(self, root: str):
+        self.root = root
+        os.makedirs(root, exist_ok=True)
+
+    def _p(self, h: int) -> str:
+        return os.path.join(self.root, f"{h:016x}.kv")
+
+    def exists(self, h: int) -> bool:
+        return os.path.exists(self._p(h))
+
+    def put(self, h: int, page: torch.Tensor) -> None:
+        tmp = self._p(h) + ".tmp"
+        torch.save(page.contiguous().cpu(), tmp)
+        os.replace(tmp, self._p(h))
+
+    def get(self, h: int) -> Optional[torch.Tensor]:
+        try:
+            return torch.load(self._p(h), map_location="cpu", weights_only=True)
+        except FileNotFoundError:
+            return None
+
+
+class HiRadixCache(RadixCache):
+    def __init__(self, allocator: Any, page_size: int, kv_pool: KVPool, host_pages: int, eviction_policy: str = "lru",
+                 write_policy: str = "write_through", storage: Optional[FileStorage] = None):
+        super().__init__(allocator, page_size, eviction_policy)
+        self.kv_pool = kv_pool
+        self.host = HostKVPool(host_pages, kv_pool, pin=kv_pool.buf.is_cuda)
+        self.write_policy = write_policy
+        self.storage = storage
+        self.stats = {"host_writes": 0, "host_hits_pages": 0, "l3_writes": 0, "l3_hits_pages": 0, "host_evictions": 0}
+
+    # ---- L1 -> L2
+    def _backup(self, node: TreeNode) -> bool:
+        if node.host_pages is not None:
+            return True
+        n = int(node.pages.size)
+        hp = self.host.alloc(n)
+        if hp is None:
+            self._evict_host(n)
+            hp = self.host.alloc(n)
+            if hp is None:
+                return False
+        dev = torch.from_numpy(node.pages.astype(np.int64)).to(self.kv_pool.buf.device)
+        data = self.kv_pool.gather_pages(dev)                    # [L, 2, n, ps, H, D]
+        self.host.buf[:, :, torch.from_numpy(hp.astype(np.int64))] = data.to("cpu")
+        node.host_pages = hp
+        self.stats["host_writes"] += n
+        if self.storage is not None:
+            self._spill_l3(node)
+        return True
+
+    def _spill_l3(self, node: TreeNode) -> None:
+        from .. import sglb_rt
+
+        key = self._full_key(node)
+        hashes = sglb_rt.hash_pages(key, self.page_size)
+        n = int(node.host_pages.size)
+        for h, hp in zip(hashes[-n:], node.host_pages.tolist()):
+            if not self.storage.exists(h):
+                self.storage.put(h, self.host.buf[:, :, hp])
+                self.stats["l3_writes"] += 1
+
+    def _full_key(self, node: TreeNode) -> np.ndarray:
+        parts = []
+        while node is not None and node.parent is not None:
+            parts.append(node.key)
+            node = node.parent
+        return np.concatenate(parts[::-1]) if parts else _EMPTY
+
+    def _evict_host(self, n: int) -> None:
+        """drop host copies of the coldest host-only nodes"""
+        cands = []
+        stack = list(self.roots.values())
+        while stack:
+            x = stack.pop()
+            stack.extend(x.children.values())
+            if x.parent is not None and x.evicted and x.host_pages is not None and not x.children and x.lock_ref == 0:
+                cands.append(x)
+        cands.sort(key=lambda x: x.last_access)
+        freed = 0
+        for x in cands:
+            self.host.free(x.host_pages)
+            freed += x.host_pages.size
+            x.host_pages = None
+            del x.parent.children[self._child_key(x.key)]
+            self.stats["host_evictions"] += 1
+            if freed >= n:
+                break
+
+    def insert(self, token_ids, pages, extra_key: Any = None, priority: int = 0) -> int:
+        m = super().insert(token_ids, pages, extra_key, priority)
+        if self.write_policy == "write_through":
+            _, node = RadixCache.match_prefix(self, token_ids, extra_key)
+            while node is not None and node.parent is not None and node.host_pages is None and not node.evicted:
+                self._backup(node)
+                node = node.parent
+        return m
+
+    def evict(self, num_pages: int, on_evict=None) -> int:
+        def keep(node: TreeNode) -> bool:
+            return self._backup(node)
+
+        return super().evict(num_pages, on_evict=keep)
+
+    # ---- L2 / L3 -> L1
+    def match_prefix(self, token_ids, extra_key: Any = None):
+        pages, node = super().match_prefix(token_ids, extra_key)
+        key = np.asarray(token_ids, dtype=np.int32)
+        key = key[: key.size - key.size % self.page_size]
+        off = int(pages.size) * self.page_size
+        out = [pages] if pages.size else []
+        while off < key.size:
+            child = node.children.get(self._child_key(key, off))
+            if child is None or not child.evicted or child.host_pages is None:
+                break
+            m = self._match_len_pages(child.key, key[off:])
+            if m == 0:
+                break
+            if m * self.page_size < child.key.size:
+                child = self._split(child, m)
+            if not self._load_back(child):
+                break
+            out.append(child.pages)
+            node = child
+            off += m * self.page_size
+        if off < key.size and self.storage is not None:
+            node, more = self._load_from_l3(node, key, off, extra_key)
+            if more is not None:
+                out.append(more)
+        return (np.concatenate(out) if out else _EMPTY), node
+
+    def _load_back(self, node: TreeNode) -> bool:
+        n = int(node.host_pages.size)
+        short = n - self.allocator.available_pages()
+        if short > 0:
+            super().evict(short, on_evict=lambda x: self._backup(x))
+        dev_pages = self.allocator.alloc(n)
+        if dev_pages is None:
+            return False
+        data = self.host.buf[:, :, torch.from_numpy(node.host_pages.astype(np.int64))]
+        self.kv_pool.scatter_pages(torch.from_numpy(dev_pages.astype(np.int64)).to(self.kv_pool.buf.device),
+                                   data.to(self.kv_pool.buf.device, non_blocking=True))
+        node.pages = dev_pages
+        self._evictable_pages += n if node.lock_ref == 0 else 0
+        self._protected_pages += n if node.lock_ref > 0 else 0
+        node.last_access = self._now()
+        self.stats["host_hits_pages"] += n
+        return True
+
+    def _load_from_l3(self, node: TreeNode, key: np.ndarray, off: int, extra_key: Any):
+        from .. import sglb_rt
+
+        hashes = sglb_rt.hash_pages(key, self.page_size)
+        first = off // self.page_size
+        got: List[torch.Tensor] = []
+        for h in hashes[first:]:
+            if not self.storage.exists(h):
+                break
+            t = self.storage.get(h)
+            if t is None:
+                break
+            got.append(t)
+        if not got:
+            return node, None
+        n = len(got)
+        dev_pages = self.allocator.alloc(n)
+        if dev_pages is None:
+            return node, None
+        data = torch.stack(got, dim=2).to(self.kv_pool.buf.device)
+        self.kv_pool.scatter_pages(torch.from_numpy(dev_pages.astype(np.int64)).to(self.kv_pool.buf.device), data)
+        end = off + n * self.page_size
+        RadixCache.insert(self, key[:end], np.concatenate([self._pages_along(key[:off], extra_key), dev_pages]), extra_key)
+        self.stats["l3_hits_pages"] += n
+        pages, node2 = RadixCache.match_prefix(self, key[:end], extra_key)
+        return node2, dev_pages
+
+    def _pages_along(self, key: np.ndarray, extra_key: Any) -> np.ndarray:
+        if key.size == 0:
+            return _EMPTY
+        p, _ = RadixCache.match_prefix(self, key, extra_key)
+        return p
+
+
+def attach_hicache(scheduler: Any, runner: Any, args: Any) -> HiRadixCache:
+    dev_pages = scheduler.allocator.total_pages
+    host_pages = max(8, int(dev_pages * args.hicache_ratio))
+    if runner.is_cuda:
+        # bound pinned memory to something sane for a dev box; production sizes it from --hicache-ratio
+        per_page = runner.kv_pool.buf[:, :, :1].numel() * runner.kv_pool.buf.element_size() * runner.page_size
+        host_pages = min(host_pages, max(8, int(64 * (1 << 30) // max(1, per_page))))
+    storage = FileStorage(args.hicache_storage_dir or "/tmp/sglb_hicache") if args.hicache_storage_backend == "file" else None
+    tree = HiRadixCache(scheduler.allocator, scheduler.page_size, runner.kv_pool, host_pages, args.radix_eviction_policy,
+                        args.hicache_write_policy, storage)
+    scheduler.tree = tree
+    scheduler.kv.tree = tree
+    return tree

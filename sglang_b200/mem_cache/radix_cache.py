@@ -165,7 +165,7 @@ class RadixCache:
         new = TreeNode()
         new.parent = child.parent
         new.key = child.key[: m_pages * ps]
-        new.pages = child.pages[:m_pages]
+        new.pages = None if child.pages is None else child.pages[:m_pages]   # None: host-resident (HiCache) node
         new.lock_ref = child.lock_ref
         new.last_access, new.created, new.hit_count, new.priority = (child.last_access, child.created,
                                                                      child.hit_count, child.priority)
@@ -173,7 +173,8 @@ class RadixCache:
             new.host_pages, child.host_pages = child.host_pages[:m_pages], child.host_pages[m_pages:]
         child.parent.children[self._child_key(new.key)] = new
         child.key = child.key[m_pages * ps:]
-        child.pages = child.pages[m_pages:]
+        if child.pages is not None:
+            child.pages = child.pages[m_pages:]
         child.parent = new
         new.children[self._child_key(child.key)] = child
         return new
