@@ -52,8 +52,13 @@ class NvlComm:
         total = envs.SGLB_NVL_MAX_BYTES.get()
         slot = total // 4          # {eager, graph} x {even, odd}
         dev = group.device
+        gname = group.device_group.group_name
+        try:   # older torch needs an explicit opt-in per group; newer versions made it a no-op / deprecated
+            symm_mem.enable_symm_mem_for_group(gname)
+        except Exception:
+            pass
         buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
-        hdl = symm_mem.rendezvous(buf, group.device_group.group_name)
+        hdl = symm_mem.rendezvous(buf, gname)
         buf.zero_()
         torch.cuda.synchronize(dev)
         group.barrier()
