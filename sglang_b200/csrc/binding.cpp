@@ -216,9 +216,38 @@ void nvl_ar_add_rmsnorm(const at::Tensor& buf_ptrs, const at::Tensor& flag_ptrs,
   count();
 }
 
+// fused GEMM + all-reduce producer: a[M,K] @ w[N,K]^T pushed into slot [rank] of every peer's arena
+void gemm_push(const at::Tensor& a, const at::Tensor& w, const at::Tensor& peer_slot_ptrs, const at::Tensor& peer_flag_ptrs,
+               int64_t rank, int64_t world, at::Tensor epoch, at::Tensor done, int64_t bn) {
+  CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.size(1) == w.size(1) && !peer_slot_ptrs.is_cuda() && !peer_flag_ptrs.is_cuda());
+  c10::cuda::CUDAGuard g(a.device());
+  sglb::gemm_bf16_tc_push(a.data_ptr(), w.data_ptr(), (int)a.size(0), (int)w.size(0), (int)a.size(1), (int)a.stride(0), (int)w.stride(0),
+                          peer_slot_ptrs.data_ptr<int64_t>(), peer_flag_ptrs.data_ptr<int64_t>(), (int)rank, (int)world,
+                          reinterpret_cast<const uint32_t*>(epoch.data_ptr<int>()), reinterpret_cast<uint32_t*>(done.data_ptr<int>()),
+                          (int)bn, num_sms(), cur_stream());
+  count();
+}
+
+void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10::optional<at::Tensor> residual, const at::Tensor& w,
+                                  at::Tensor out, int64_t world, double eps, bool gemma, at::Tensor epoch, at::Tensor done) {
+  CHECK_CUDA(out); CHECK_BF16(out); CHECK_BF16(w); CHECK_BF16(slot); TORCH_CHECK(out.is_contiguous() && out.dim() == 2);
+  c10::cuda::CUDAGuard g(out.device());
+  sglb::nvl_local_reduce_add_rmsnorm(slot.data_ptr(), reinterpret_cast<uint32_t*>(flags_ptr),
+                                     residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), out.data_ptr(),
+                                     (int)out.size(0), (int)out.size(1), (int)world, (float)eps, gemma,
+                                     reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()), reinterpret_cast<uint32_t*>(done.data_ptr<int>()),
+                                     num_sms(), cur_stream());
+  count();
+}
+
 }  // namespace
 
 TORCH_LIBRARY(sglb, m) {
+  m.def("gemm_push(Tensor a, Tensor w, Tensor peer_slot_ptrs, Tensor peer_flag_ptrs, int rank, int world, Tensor(a!) epoch, "
+        "Tensor(b!) done, int bn) -> ()", &gemm_push);
+  m.def("nvl_local_reduce_add_rmsnorm(Tensor slot, int flags_ptr, Tensor(a!)? residual, Tensor w, Tensor(b!) out, int world, float eps, "
+        "bool gemma, Tensor(c!) epoch, Tensor(d!) done) -> ()", &nvl_local_reduce_add_rmsnorm);
   m.def("nvl_allreduce(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!) out, "
         "Tensor(b!) epoch, Tensor(c!) done, int channel, int algo) -> ()", &nvl_allreduce);
   m.def("nvl_ar_add_rmsnorm(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!)? residual, "

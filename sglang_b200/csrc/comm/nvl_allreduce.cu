@@ -212,6 +212,88 @@ __global__ void __launch_bounds__(256) nvl_ar_add_rmsnorm_kernel(NvlPeers P, __n
   epoch_end(epoch_ptr, done_ctr, epoch);
 }
 
+// ---------------------------------------------------------------- consumer of the push-GEMM (gemm_tc.cu EPI_PUSH)
+// All `world` partial copies of the [T,H] activation already sit in THIS rank's arena slot (layout [world][T][H]); wait
+// for every source rank's flag, then sum locally (+ residual) and normalise.  No NVLink traffic in this kernel.
+template <int MAXV>
+__global__ void __launch_bounds__(256) nvl_local_reduce_add_rmsnorm_kernel(const __nv_bfloat16* __restrict__ slot, uint32_t* flags,
+                                                                           __nv_bfloat16* __restrict__ residual,
+                                                                           const __nv_bfloat16* __restrict__ w,
+                                                                           __nv_bfloat16* __restrict__ out, int T, int H, int world,
+                                                                           float eps, uint32_t* epoch_ptr, uint32_t* done_ctr, int gemma) {
+  const uint32_t epoch = epoch_begin(epoch_ptr);
+  if (threadIdx.x < world) {
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+      if (++spins > (1u << 26)) {
+        printf("sglb nvl: push-flag timeout waiting on rank=%d epoch=%u have=%u\n", threadIdx.x, epoch, ld_acquire_sys(flags + threadIdx.x));
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int nvec = H >> 3;
+  const size_t stride = (size_t)T * H;
+  __shared__ float red[8];
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    float v[MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = threadIdx.x + i * 256;
+      if (vi < nvec) {
+        float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t off = (size_t)row * H + (size_t)vi * 8;
+#pragma unroll
+        for (int r = 0; r < NVL_MAX_RANKS; ++r)
+          if (r < world) acc_bf16x8(a, ld_peer128(slot + r * stride + off));   // written by peers: bypass stale L1 lines
+        if (residual) {
+          acc_bf16x8(a, ld128(residual + off));
+          const U4 s = pack8(a);
+          st128(residual + off, s);
+          a[0] = bf16_lo(s.x); a[1] = bf16_hi(s.x); a[2] = bf16_lo(s.y); a[3] = bf16_hi(s.y);
+          a[4] = bf16_lo(s.z); a[5] = bf16_hi(s.z); a[6] = bf16_lo(s.w); a[7] = bf16_hi(s.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[i][k] = a[k]; ss += a[k] * a[k]; }
+      }
+    }
+    ss = warp_sum(ss);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float rs = rsqrtf(tot / H + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = threadIdx.x + i * 256;
+      if (vi < nvec) {
+        const U4 ww = ldg128(w + (size_t)vi * 8);
+        const float g[8] = {bf16_lo(ww.x), bf16_hi(ww.x), bf16_lo(ww.y), bf16_hi(ww.y), bf16_lo(ww.z), bf16_hi(ww.z), bf16_lo(ww.w), bf16_hi(ww.w)};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = v[i][k] * rs * (gemma ? 1.f + g[k] : g[k]);
+        st128(out + (size_t)row * H + (size_t)vi * 8, pack8(o));
+      }
+    }
+  }
+  epoch_end(epoch_ptr, done_ctr, epoch);
+}
+
+void nvl_local_reduce_add_rmsnorm(const void* slot, uint32_t* flags, void* residual, const void* w, void* out, int T, int H, int world,
+                                  float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms, cudaStream_t stream) {
+  if (H % 8 || H > 256 * 8 * 8) throw std::runtime_error("sglb nvl reduce+norm: H must be a multiple of 8 and <= 16384");
+  const int grid = max(1, min(T, num_sms * 4));
+  const int nvec = H / 8;
+  auto S = (const __nv_bfloat16*)slot; auto R = (__nv_bfloat16*)residual; auto W = (const __nv_bfloat16*)w; auto O = (__nv_bfloat16*)out;
+#define SGLB_LRN(MV) nvl_local_reduce_add_rmsnorm_kernel<MV><<<grid, 256, 0, stream>>>(S, flags, R, W, O, T, H, world, eps, epoch_ptr, done_ctr, gemma)
+  if (nvec <= 256) SGLB_LRN(1); else if (nvec <= 512) SGLB_LRN(2); else if (nvec <= 1024) SGLB_LRN(4); else SGLB_LRN(8);
+#undef SGLB_LRN
+  SGLB_CUDA_CHECK(cudaGetLastError());
+}
+
 static NvlPeers make_peers(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc_ptr, int64_t slot_off, int rank, int world) {
   if (world > NVL_MAX_RANKS) throw std::runtime_error("sglb nvl: world size > 8");
   NvlPeers P;

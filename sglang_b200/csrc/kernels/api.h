@@ -53,4 +53,10 @@ void nvl_ar_add_rmsnorm(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64
                         void* residual, const void* w, void* out, int T, int H, float eps, bool gemma, uint32_t* epoch_ptr,
                         uint32_t* done_ctr, int channel, int num_sms, cudaStream_t stream);
 
+void gemm_bf16_tc_push(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int64_t* peer_slot_ptrs,
+                       const int64_t* peer_flag_ptrs, int rank, int world, const uint32_t* epoch_ptr, uint32_t* done_ctr, int bn,
+                       int num_sms, cudaStream_t stream);
+void nvl_local_reduce_add_rmsnorm(const void* slot, uint32_t* flags, void* residual, const void* w, void* out, int T, int H, int world,
+                                  float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms, cudaStream_t stream);
+
 }  // namespace sglb

@@ -17,7 +17,20 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 
-enum GemmEpilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_SILU_MUL = 2 };
+enum GemmEpilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_SILU_MUL = 2, EPI_PUSH = 3 };
+
+// EPI_PUSH: fused GEMM + all-reduce producer.  The epilogue stores every output tile into slot [rank] of EVERY peer's
+// symmetric arena (P2P stores over NVLink / NVSwitch, peer pointers mapped into this address space), tile by tile while
+// the tensor core already works on the next tile; the last CTA to finish publishes `epoch` to all peers with a
+// system-scope release store.  The consumer (nvl_local_reduce_add_rmsnorm_kernel) then only reads LOCAL memory.
+struct GemmPush {
+  __nv_bfloat16* peer_slot[8];   // peer r's arena slot base for this call: layout [world][M][ldc]
+  uint32_t* peer_flags[8];       // peer r's flag array for this channel: flags[src_rank]
+  const uint32_t* epoch_ptr;     // device-resident epoch (the consumer kernel advances it)
+  uint32_t* done_ctr;            // local CTA-completion counter
+  long long slot_stride;         // elements between two source ranks' regions (= M * ldc)
+  int rank, world;
+};
 
 template <int BN>
 struct GemmCfg {
@@ -32,7 +45,8 @@ struct GemmCfg {
 template <int BN, int EPI, bool A_FP8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int ldc) {
+               __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int ldc,
+               const GemmPush push) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -155,8 +169,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   f[0] += bf16_lo(b.x); f[1] += bf16_hi(b.x); f[2] += bf16_lo(b.y); f[3] += bf16_hi(b.y);
                   f[4] += bf16_lo(b.z); f[5] += bf16_hi(b.z); f[6] += bf16_lo(b.w); f[7] += bf16_hi(b.w);
                 }
-                st128(C + (size_t)row * ldc + col,
-                      U4{pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])});
+                const U4 o = U4{pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])};
+                if (EPI == EPI_PUSH) {
+                  const size_t off = (size_t)push.rank * push.slot_stride + (size_t)row * ldc + col;
+#pragma unroll
+                  for (int r = 0; r < 8; ++r)
+                    if (r < push.world) st128(push.peer_slot[r] + off, o);
+                } else {
+                  st128(C + (size_t)row * ldc + col, o);
+                }
               }
             }
           }
@@ -169,14 +190,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (EPI == EPI_PUSH) {
+    // every thread that stored to peers makes its stores visible system-wide before the CTA signs off
+    if (warp >= 4) __threadfence_system();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (EPI == EPI_PUSH && threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(push.done_ctr, 1u);
+    if (t == gridDim.x - 1) {           // last CTA of this rank: all tiles of all CTAs are out -> publish
+      *push.done_ctr = 0;
+      __threadfence_system();
+      const uint32_t epoch = *((volatile const uint32_t*)push.epoch_ptr) + 1;
+      for (int r = 0; r < push.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(push.peer_flags[r] + push.rank), "r"(epoch) : "memory");
+    }
+  }
 }
 
 template <int BN, int EPI>
 static void launch_gemm(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw,
-                        int ldc, int num_sms, cudaStream_t stream) {
+                        int ldc, int num_sms, cudaStream_t stream, const GemmPush& push) {
   using Cfg = GemmCfg<BN>;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sAs[1] = {(uint64_t)lda * 2};
   uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sBs[1] = {(uint64_t)ldw * 2};
@@ -191,18 +227,18 @@ static void launch_gemm(const void* A, const void* W, void* C, const void* bias,
   }
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, (__nv_bfloat16*)C, (const __nv_bfloat16*)bias, M, N, K, ldc);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, (__nv_bfloat16*)C, (const __nv_bfloat16*)bias, M, N, K, ldc, push);
   SGLB_CUDA_CHECK(cudaGetLastError());
 }
 
 template <int EPI>
 static void dispatch_bn(int bn, const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda,
-                        int ldw, int ldc, int num_sms, cudaStream_t stream) {
+                        int ldw, int ldc, int num_sms, cudaStream_t stream, const GemmPush& push = GemmPush{}) {
   switch (bn) {
-    case 32: launch_gemm<32, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
-    case 64: launch_gemm<64, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
-    case 128: launch_gemm<128, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
-    case 256: launch_gemm<256, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case 32: launch_gemm<32, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
+    case 64: launch_gemm<64, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
+    case 128: launch_gemm<128, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
+    case 256: launch_gemm<256, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
     default: throw std::runtime_error("sglb gemm: unsupported BN");
   }
 }
@@ -232,6 +268,23 @@ void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M
     case EPI_SILU_MUL: dispatch_bn<EPI_SILU_MUL>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
     default: throw std::runtime_error("sglb gemm: bad epilogue");
   }
+}
+
+// Fused GEMM + all-reduce producer: C is not written locally; every tile goes to slot [rank] of every peer's arena.
+void gemm_bf16_tc_push(const void* A, const void* W, int M, int N, int K, int lda, int ldw, const int64_t* peer_slot_ptrs,
+                       const int64_t* peer_flag_ptrs, int rank, int world, const uint32_t* epoch_ptr, uint32_t* done_ctr, int bn,
+                       int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return;
+  if (K % 8 || N % 8 || lda % 8 || ldw % 8) throw std::runtime_error("sglb gemm push: K, N, lda, ldw must be multiples of 8");
+  if (world > 8) throw std::runtime_error("sglb gemm push: world size > 8");
+  GemmPush p{};
+  for (int r = 0; r < world; ++r) {
+    p.peer_slot[r] = reinterpret_cast<__nv_bfloat16*>(peer_slot_ptrs[r]);
+    p.peer_flags[r] = reinterpret_cast<uint32_t*>(peer_flag_ptrs[r]);
+  }
+  p.epoch_ptr = epoch_ptr; p.done_ctr = done_ctr; p.slot_stride = (long long)M * N; p.rank = rank; p.world = world;
+  if (bn <= 0) bn = gemm_pick_bn(M, N, K, num_sms);
+  dispatch_bn<EPI_PUSH>(bn, A, W, nullptr, nullptr, M, N, K, lda, ldw, N, num_sms, stream, p);
 }
 
 }  // namespace sglb

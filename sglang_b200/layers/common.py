@@ -29,7 +29,7 @@ class RMSNorm(nn.Module):
         """residual given: (in place) residual += x; x = norm(residual); returns (x, residual)"""
         if hasattr(x, "nvl"):   # PendingAllReduce: cross-rank sum + residual add + norm in ONE kernel
             out = torch.empty(x.T, x.H, dtype=self.weight.dtype, device=self.weight.device)
-            x.nvl.fused_allreduce_add_rmsnorm(x.off, residual, self.weight, out, self.eps, self.gemma)
+            x.consume_norm(residual, self.weight, out, self.eps, self.gemma)
             return out, residual
         if residual is None:
             return ops.rmsnorm(x, self.weight, self.eps, gemma=self.gemma)

@@ -22,17 +22,22 @@ from .quantization import QuantMethod, UnquantizedMethod
 
 class PendingAllReduce:
     """Handle for partial sums that sit in this call's NVL arena slot on every rank (not yet reduced)."""
-    __slots__ = ("nvl", "off", "T", "H")
+    __slots__ = ("nvl", "off", "T", "H", "mode")
 
-    def __init__(self, nvl, off: int, T: int, H: int):
-        self.nvl, self.off, self.T, self.H = nvl, off, T, H
+    def __init__(self, nvl, off: int, T: int, H: int, mode: str = "pull"):
+        self.nvl, self.off, self.T, self.H, self.mode = nvl, off, T, H, mode
+
+    def consume_norm(self, residual, weight: torch.Tensor, out: torch.Tensor, eps: float, gemma: bool) -> None:
+        """cross-rank sum + residual add + RMSNorm in one kernel"""
+        if self.mode == "push":     # partials of all ranks were pushed into OUR arena by the peers' GEMM epilogues
+            self.nvl.push_reduce_add_rmsnorm(self.off, self.T, self.H, residual, weight, out, eps, gemma)
+        else:                       # partials sit in each producer's arena: pull them over NVLink
+            self.nvl.fused_allreduce_add_rmsnorm(self.off, residual, weight, out, eps, gemma)
 
     def resolve(self) -> torch.Tensor:
         """plain all-reduce of the parked partials (used when the consumer is not an RMSNorm)"""
-        from ..parallel.nvl_comm import CH_FUSED_NORM
-
         out = torch.empty(self.T, self.H, dtype=torch.bfloat16, device=self.nvl.buf.device)
-        ones = None
+        assert self.mode == "pull", "push-mode partials are always consumed by an RMSNorm (push is disabled under PP)"
         self.nvl.allreduce_from_slot(self.off, out)
         return out
 
@@ -171,11 +176,17 @@ class RowParallelLinear(LinearBase):
         nbytes = T * self.out_features * 2
         if (defer_reduce and self.reduce_results and nvl is not None and x.dim() == 2 and nbytes <= self.FUSED_AR_MAX_BYTES
                 and isinstance(self.quant, UnquantizedMethod) and bias is None and x.dtype == torch.bfloat16):
+            from ..environ import envs
             from ..parallel.nvl_comm import CH_FUSED_NORM
+            from ..parallel.parallel_state import get_pp_group
 
+            if envs.SGLB_FUSED_AR.get() == "push" and get_pp_group().world_size == 1 and x.stride(0) % 8 == 0:
+                # ONE kernel: tcgen05 GEMM whose epilogue pushes each tile into every peer's arena (+ flag publication)
+                off = nvl.gemm_push(x, self.weight)
+                return PendingAllReduce(nvl, off, T, self.out_features, "push")
             off, view = nvl.stage(CH_FUSED_NORM, (T, self.out_features))
             ops.linear(x, self.weight, None, out=view)
-            return PendingAllReduce(nvl, off, T, self.out_features)
+            return PendingAllReduce(nvl, off, T, self.out_features, "pull")
         y = self.apply(x, bias)
         if self.reduce_results:
             y = tp.all_reduce(y)

@@ -24,6 +24,8 @@ logger = logging.getLogger(__name__)
 
 CH_ONESHOT, CH_TWOSHOT, CH_FUSED_NORM, CH_GEMM = 0, 1, 2, 3
 NUM_CHANNELS = 8
+MAX_RANKS = 8          # must match NVL_MAX_RANKS in csrc/comm/nvl_allreduce.cu
+FLAG_OFFSET = 1024
 
 
 class NvlComm:
@@ -34,7 +36,8 @@ class NvlComm:
         self.slot_bytes = slot_bytes
         dev = buf.device
         self.buf_ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64)
-        self.flag_ptrs = torch.tensor([int(p) for p in hdl.signal_pad_ptrs], dtype=torch.int64)
+        # our flag words live FLAG_OFFSET bytes into each rank's signal pad (the head of the pad is left to torch's own ops)
+        self.flag_ptrs = torch.tensor([int(p) + FLAG_OFFSET for p in hdl.signal_pad_ptrs], dtype=torch.int64)
         self.mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
         # per-channel epoch counters + completion counters (device memory; graph-replay safe)
         self.epochs = torch.zeros(NUM_CHANNELS, dtype=torch.int32, device=dev)
@@ -60,6 +63,11 @@ class NvlComm:
         buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         hdl = symm_mem.rendezvous(buf, gname)
         buf.zero_()
+        try:   # zero our flag words in the local signal pad
+            pad = hdl.get_signal_pad(hdl.rank)
+            pad.view(torch.uint8)[FLAG_OFFSET:FLAG_OFFSET + NUM_CHANNELS * MAX_RANKS * 4].zero_()
+        except Exception:
+            pass
         torch.cuda.synchronize(dev)
         group.barrier()
         c = cls(group, buf, hdl, slot)
@@ -129,4 +137,26 @@ class NvlComm:
         ch = CH_FUSED_NORM
         torch.ops.sglb.nvl_ar_add_rmsnorm(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, residual, weight, out,
                                           float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch], ch)
+        self.calls += 1
+
+    # ------------------------------------------------------------------ fused GEMM + all-reduce (push)
+    def gemm_push(self, x: torch.Tensor, w: torch.Tensor, bn: int = 0) -> int:
+        """x[T,K] @ w[N,K]^T computed by the tcgen05 GEMM whose epilogue stores every tile into slot [rank] of EVERY peer's
+        arena and finally publishes this call's epoch to all peers.  Returns the slot offset for ``push_reduce_add_rmsnorm``."""
+        T, N = x.shape[0], w.shape[0]
+        assert self.world * T * N * 2 <= self.slot_bytes, "NVL arena slot too small for this GEMM output"
+        ch = CH_GEMM
+        off = self._slot(ch)
+        slots = self.buf_ptrs + off
+        flags = self.flag_ptrs + ch * MAX_RANKS * 4
+        torch.ops.sglb.gemm_push(x, w, slots, flags, self.rank, self.world, self.epochs[ch:ch + 1], self.done[ch, 1:], bn)
+        self.calls += 1
+        return off
+
+    def push_reduce_add_rmsnorm(self, off: int, T: int, H: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
+                                eps: float, gemma: bool = False) -> None:
+        ch = CH_GEMM
+        slot = self.slot_view(off, (self.world, T, H))
+        torch.ops.sglb.nvl_local_reduce_add_rmsnorm(slot, int(self.flag_ptrs[self.rank]) + ch * MAX_RANKS * 4, residual, weight, out,
+                                                    self.world, float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch])
         self.calls += 1

@@ -79,6 +79,31 @@ for T, H in ((1, 4096), (64, 4096), (128, 8192)):
     res[f"fused_ar_norm_T{T}_H{H}_us"] = {"fused": 1000 * timed(fused), "nccl_plus_norm": 1000 * timed(unfused)}
 log("fused ar+norm ok", json.dumps({k: v for k, v in res.items() if k.startswith("fused")}))
 
+# ---------------- 2b. fused GEMM(+push) -> local reduce + residual + RMSNorm  vs  cuBLAS + NCCL all-reduce + norm
+for T, K, H in ((16, 4096 // world, 4096), (64, 14336 // world, 4096), (128, 4096 // world, 4096)):
+    torch.manual_seed(1000 + rank)
+    x = (torch.randn(T, K, device=dev) * 0.3).to(torch.bfloat16)
+    wgt = (torch.randn(H, K, device=dev) * 0.05).to(torch.bfloat16)
+    torch.manual_seed(7)
+    resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); nw = torch.randn(H, device=dev).to(torch.bfloat16)
+    full = (x.float() @ wgt.float().t()); dist.all_reduce(full)
+    r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
+    torch_ref.fused_add_rmsnorm(x_ref, r_ref, nw, 1e-5)
+    out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
+    off = nvl.gemm_push(x, wgt)
+    nvl.push_reduce_add_rmsnorm(off, T, H, r2, nw, out, 1e-5)
+    torch.cuda.synchronize()
+    e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
+    assert e1 < 0.25 and e2 < 0.15, ("push", T, K, H, e1, e2)
+    def push():
+        o = nvl.gemm_push(x, wgt); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5)
+    def pull():
+        o, v = nvl.stage(CH_FUSED_NORM, (T, H)); torch.matmul(x, wgt.t(), out=v); nvl.fused_allreduce_add_rmsnorm(o, r2, nw, out, 1e-5)
+    def base():
+        y = torch.nn.functional.linear(x, wgt); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, nw, 1e-5)
+    res[f"gemm_ar_norm_T{T}_K{K}_us"] = {"push_fused": 1000 * timed(push), "pull_fused": 1000 * timed(pull), "cublas_nccl_norm": 1000 * timed(base)}
+log("gemm+ar+norm ok", json.dumps({k: v for k, v in res.items() if k.startswith("gemm_ar")}))
+
 # ---------------- 3. TP engine == TP=1 reference
 ps.set_state(None)
 import sglang_b200 as sgl
