@@ -209,7 +209,10 @@ class ServerArgs:
         kw = {k: v for k, v in vars(ns).items() if k in names}
         cfg = getattr(ns, "config", None)
         if cfg:
-            kw = {**_load_config_file(cfg), **{k: v for k, v in kw.items() if v is not None}}
+            # the file provides defaults; a CLI flag wins only when it was actually given (differs from the built-in default)
+            defaults = {f.name: f.default for f in dataclasses.fields(cls)}
+            explicit = {k: v for k, v in kw.items() if v is not None and v != defaults.get(k)}
+            kw = {**{k: v for k, v in kw.items() if v is not None}, **_load_config_file(cfg), **explicit}
         return cls(**kw)
 
     def to_dict(self) -> Dict[str, Any]:
