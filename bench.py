@@ -19,6 +19,10 @@ import json
 import os
 import sys
 import threading
+import faulthandler
+if os.environ.get("SGLB_HANG_DUMP_S"):
+    faulthandler.dump_traceback_later(int(os.environ["SGLB_HANG_DUMP_S"]), repeat=False, exit=True)
+
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -164,6 +164,9 @@ def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, devic
     global _STATE
     use_cuda = (device or ("cuda" if torch.cuda.is_available() else "cpu")).startswith("cuda")
     ws = tp_size * pp_size
+    if (_STATE is not None and ws > 1 and _STATE.world_size == ws and _STATE.tp.world_size == tp_size
+            and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size)):
+        return _STATE       # idempotent: a second Engine in the same SPMD job reuses the groups and the NVL arena
     if ws == 1:
         dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
         _STATE = _single(dev)

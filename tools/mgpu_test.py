@@ -1,9 +1,16 @@
 """Multi-GPU checks (run under torchrun): NVL collectives vs NCCL (numerics + device-timed latency, max over ranks) and
-TP engine == TP=1 engine on the same synthetic checkpoint.   torchrun --nproc-per-node N tools/mgpu_test.py [ref.json]"""
+TP engine == TP=1 engine on the same synthetic checkpoint.   torchrun --nproc-per-node N tools/mgpu_test.py [ref.json]
+
+Every section is isolated: a failure is recorded (with its traceback, per rank, in gpurun_out/mgpu_rank{r}.log) and the
+next section still runs, so one GPU call answers as many questions as possible."""
+import faulthandler
 import json
 import os
 import sys
-import time
+import traceback
+
+if os.environ.get("SGLB_HANG_DUMP_S"):
+    faulthandler.dump_traceback_later(int(os.environ["SGLB_HANG_DUMP_S"]), repeat=False, exit=True)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,19 +18,46 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+_rlog = open(os.path.join(ROOT, "gpurun_out", f"mgpu_rank{rank}.log"), "w")
+
+
+def log(*a):
+    msg = " ".join(str(x) for x in a)
+    _rlog.write(msg + "\n"); _rlog.flush()
+    if rank == 0:
+        print(f"[rank {rank}]", msg, flush=True)
+
+
+import logging
+logging.basicConfig(level=logging.INFO, stream=_rlog)
+
 from sglang_b200 import ops
 from sglang_b200.ops import torch_ref
 from sglang_b200.parallel import parallel_state as ps
 
-rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 st = ps.init_distributed(tp_size=world, device="cuda")
 tp = st.tp
 dev = tp.device
 ops.load_native()
-res = {"world": world, "nvl": tp.nvl is not None, "multicast": bool(tp.nvl and tp.nvl.mc_ptr)}
-log = lambda *a: print(f"[rank {rank}]", *a, flush=True) if rank == 0 else None
-assert tp.nvl is not None, "NVL comm failed to initialise"
 nvl = tp.nvl
+res = {"world": world, "nvl": nvl is not None, "multicast": bool(nvl and nvl.mc_ptr)}
+failures = []
+log("init ok", res)
+
+
+def section(name):
+    def deco(fn):
+        try:
+            fn()
+            torch.cuda.synchronize()
+            log(f"SECTION {name}: ok")
+        except BaseException as e:  # noqa: BLE001 — includes CUDA errors; record and carry on (a sticky CUDA error fails the rest too)
+            failures.append(name)
+            log(f"SECTION {name}: FAILED {type(e).__name__}: {e}\n{traceback.format_exc()}")
+        return fn
+    return deco
 
 
 def timed(fn, iters=20, warm=5):
@@ -40,89 +74,130 @@ def timed(fn, iters=20, warm=5):
     return float(t)
 
 
-# ---------------- 1. all-reduce numerics + latency
-torch.manual_seed(100 + rank)
-lat = {}
-for n in (4096, 32768, 262144, 1 << 20, 4 << 20):      # elements (bf16)
-    x = (torch.randn(n, device=dev) * 0.5).to(torch.bfloat16)
-    ref = x.float().clone(); dist.all_reduce(ref)
-    for algo, nm in ((0, "oneshot"), (1, "twoshot")):
-        y = nvl.all_reduce(x.clone(), algo=algo)
-        err = (y.float() - ref).abs().max().item()
-        assert err < 0.05 * world, f"nvl {nm} n={n} err={err}"
-        lat[f"{nm}_{n*2}B_us"] = 1000 * timed(lambda: nvl.all_reduce(x, algo=algo))
-    z = x.clone()
-    lat[f"nccl_{n*2}B_us"] = 1000 * timed(lambda: dist.all_reduce(z))
-res["allreduce_us"] = lat
-log("allreduce ok", json.dumps({k: round(v, 1) for k, v in lat.items()}))
+if nvl is None:
+    failures.append("nvl_init")
+    log("NVL comm failed to initialise (see warning above); collective sections skipped")
+else:
+    from sglang_b200.parallel.nvl_comm import CH_FUSED_NORM
 
-# ---------------- 2. fused all-reduce + residual + RMSNorm
-from sglang_b200.parallel.nvl_comm import CH_FUSED_NORM
-for T, H in ((1, 4096), (64, 4096), (128, 8192)):
-    part = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16)
-    torch.manual_seed(7)     # same residual / weight on every rank
-    resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); w = torch.randn(H, device=dev).to(torch.bfloat16)
-    full = part.float().clone(); dist.all_reduce(full)
-    r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
-    torch_ref.fused_add_rmsnorm(x_ref, r_ref, w, 1e-5)
-    off, view = nvl.stage(CH_FUSED_NORM, (T, H)); view.copy_(part)
-    out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
-    nvl.fused_allreduce_add_rmsnorm(off, r2, w, out, 1e-5)
-    torch.cuda.synchronize()
-    e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
-    assert e1 < 0.15 and e2 < 0.1, (T, H, e1, e2)
-    def fused():
-        o, v = nvl.stage(CH_FUSED_NORM, (T, H)); v.copy_(part)
-        nvl.fused_allreduce_add_rmsnorm(o, r2, w, out, 1e-5)
-    def unfused():
-        y = part.clone(); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, w, 1e-5)
-    res[f"fused_ar_norm_T{T}_H{H}_us"] = {"fused": 1000 * timed(fused), "nccl_plus_norm": 1000 * timed(unfused)}
-log("fused ar+norm ok", json.dumps({k: v for k, v in res.items() if k.startswith("fused")}))
+    @section("peer_write")
+    def _peer():
+        # the most basic property: a store through a peer pointer is visible to the peer after a barrier
+        v = nvl.slot_view(0, (world, 8), torch.int32)
+        v.zero_(); torch.cuda.synchronize(); dist.barrier()
+        for r in range(world):
+            peer = nvl.hdl.get_buffer(r, (world, 8), torch.int32, 0)
+            peer[rank].fill_(rank + 1)
+        torch.cuda.synchronize(); dist.barrier()
+        got = v[:, 0].tolist()
+        assert got == [r + 1 for r in range(world)], got
+        v.zero_(); torch.cuda.synchronize(); dist.barrier()
 
-# ---------------- 2b. fused GEMM(+push) -> local reduce + residual + RMSNorm  vs  cuBLAS + NCCL all-reduce + norm
-for T, K, H in ((16, 4096 // world, 4096), (64, 14336 // world, 4096), (128, 4096 // world, 4096)):
-    torch.manual_seed(1000 + rank)
-    x = (torch.randn(T, K, device=dev) * 0.3).to(torch.bfloat16)
-    wgt = (torch.randn(H, K, device=dev) * 0.05).to(torch.bfloat16)
-    torch.manual_seed(7)
-    resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); nw = torch.randn(H, device=dev).to(torch.bfloat16)
-    full = (x.float() @ wgt.float().t()); dist.all_reduce(full)
-    r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
-    torch_ref.fused_add_rmsnorm(x_ref, r_ref, nw, 1e-5)
-    out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
-    off = nvl.gemm_push(x, wgt)
-    nvl.push_reduce_add_rmsnorm(off, T, H, r2, nw, out, 1e-5)
-    torch.cuda.synchronize()
-    e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
-    assert e1 < 0.25 and e2 < 0.15, ("push", T, K, H, e1, e2)
-    def push():
-        o = nvl.gemm_push(x, wgt); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5)
-    def pull():
-        o, v = nvl.stage(CH_FUSED_NORM, (T, H)); torch.matmul(x, wgt.t(), out=v); nvl.fused_allreduce_add_rmsnorm(o, r2, nw, out, 1e-5)
-    def base():
-        y = torch.nn.functional.linear(x, wgt); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, nw, 1e-5)
-    res[f"gemm_ar_norm_T{T}_K{K}_us"] = {"push_fused": 1000 * timed(push), "pull_fused": 1000 * timed(pull), "cublas_nccl_norm": 1000 * timed(base)}
-log("gemm+ar+norm ok", json.dumps({k: v for k, v in res.items() if k.startswith("gemm_ar")}))
+    @section("allreduce")
+    def _ar():
+        torch.manual_seed(100 + rank)
+        lat = {}
+        for n in (4096, 32768, 262144, 1 << 20, 4 << 20):      # elements (bf16)
+            x = (torch.randn(n, device=dev) * 0.5).to(torch.bfloat16)
+            ref = x.float().clone(); dist.all_reduce(ref)
+            for algo, nm in ((0, "oneshot"), (1, "twoshot")):
+                y = nvl.all_reduce(x.clone(), algo=algo)
+                err = (y.float() - ref).abs().max().item()
+                log(f"  nvl {nm} n={n} err={err:.4f}")
+                assert err < 0.05 * world, f"nvl {nm} n={n} err={err}"
+                lat[f"{nm}_{n*2}B_us"] = 1000 * timed(lambda: nvl.all_reduce(x, algo=algo))
+            z = x.clone()
+            lat[f"nccl_{n*2}B_us"] = 1000 * timed(lambda: dist.all_reduce(z))
+        res["allreduce_us"] = lat
+        log("allreduce", json.dumps({k: round(v, 1) for k, v in lat.items()}))
 
-# ---------------- 3. TP engine == TP=1 reference
-ps.set_state(None)
-import sglang_b200 as sgl
-rng = np.random.default_rng(0)
-prompts = [rng.integers(3, 2000, size=int(n)).tolist() for n in rng.integers(5, 300, size=12)]
-eng = sgl.Engine(model_path="dummy:tiny-llama-gpu", tp_size=world, page_size=32, chunked_prefill_size=256, cuda_graph_max_bs=16,
-                 mem_fraction_static=0.2, max_running_requests=16, log_level="warning", base_gpu_id=rank)
-outs = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 24, "temperature": 0, "ignore_eos": True})
+    @section("fused_ar_norm")
+    def _fused():
+        for T, H in ((1, 4096), (64, 4096), (128, 8192)):
+            torch.manual_seed(200 + rank)
+            part = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16)
+            torch.manual_seed(7)     # same residual / weight on every rank
+            resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); w = torch.randn(H, device=dev).to(torch.bfloat16)
+            full = part.float().clone(); dist.all_reduce(full)
+            r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
+            torch_ref.fused_add_rmsnorm(x_ref, r_ref, w, 1e-5)
+            off, view = nvl.stage(CH_FUSED_NORM, (T, H)); view.copy_(part)
+            out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
+            nvl.fused_allreduce_add_rmsnorm(off, r2, w, out, 1e-5)
+            torch.cuda.synchronize()
+            e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
+            log(f"  fused T={T} H={H} err_out={e1:.4f} err_resid={e2:.4f}")
+            assert e1 < 0.15 and e2 < 0.1, (T, H, e1, e2)
+
+            def fused():
+                o, v = nvl.stage(CH_FUSED_NORM, (T, H)); v.copy_(part)
+                nvl.fused_allreduce_add_rmsnorm(o, r2, w, out, 1e-5)
+
+            def unfused():
+                y = part.clone(); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, w, 1e-5)
+
+            res[f"fused_ar_norm_T{T}_H{H}_us"] = {"fused": 1000 * timed(fused), "nccl_plus_norm": 1000 * timed(unfused)}
+        log("fused ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("fused")}))
+
+    @section("gemm_push")
+    def _push():
+        for T, K, H in ((16, 4096 // world, 4096), (64, 14336 // world, 4096), (128, 4096 // world, 4096)):
+            torch.manual_seed(1000 + rank)
+            x = (torch.randn(T, K, device=dev) * 0.3).to(torch.bfloat16)
+            wgt = (torch.randn(H, K, device=dev) * 0.05).to(torch.bfloat16)
+            torch.manual_seed(7)
+            resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); nw = torch.randn(H, device=dev).to(torch.bfloat16)
+            full = (x.float() @ wgt.float().t()); dist.all_reduce(full)
+            r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
+            torch_ref.fused_add_rmsnorm(x_ref, r_ref, nw, 1e-5)
+            out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
+            off = nvl.gemm_push(x, wgt)
+            nvl.push_reduce_add_rmsnorm(off, T, H, r2, nw, out, 1e-5)
+            torch.cuda.synchronize()
+            e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
+            log(f"  push T={T} K={K} H={H} err_out={e1:.4f} err_resid={e2:.4f}")
+            assert e1 < 0.25 and e2 < 0.15, ("push", T, K, H, e1, e2)
+
+            def push():
+                o = nvl.gemm_push(x, wgt); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5)
+
+            def pull():
+                o, v = nvl.stage(CH_FUSED_NORM, (T, H)); torch.matmul(x, wgt.t(), out=v); nvl.fused_allreduce_add_rmsnorm(o, r2, nw, out, 1e-5)
+
+            def base():
+                y = torch.nn.functional.linear(x, wgt); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, nw, 1e-5)
+
+            res[f"gemm_ar_norm_T{T}_K{K}_us"] = {"push_fused": 1000 * timed(push), "pull_fused": 1000 * timed(pull),
+                                                 "cublas_nccl_norm": 1000 * timed(base)}
+        log("gemm+ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("gemm_ar")}))
+
+
+# ---------------- TP engine == TP=1 reference (runs with whatever comm survived above)
+@section("tp_engine")
+def _engine():
+    import sglang_b200 as sgl
+
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(3, 2000, size=int(n)).tolist() for n in rng.integers(5, 300, size=12)]
+    eng = sgl.Engine(model_path="dummy:tiny-llama-gpu", tp_size=world, page_size=32, chunked_prefill_size=256, cuda_graph_max_bs=16,
+                     mem_fraction_static=0.2, max_running_requests=16, log_level="warning", base_gpu_id=rank)
+    log("engine built; nvl =", eng.runner.tp.nvl is not None)
+    outs = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 24, "temperature": 0, "ignore_eos": True})
+    if rank == 0:
+        got = [o["output_ids"] for o in outs]
+        if len(sys.argv) > 1 and os.path.exists(sys.argv[1]):
+            want = json.load(open(sys.argv[1]))
+            same = sum(a == b for a, b in zip(got, want)); first = sum(a[:4] == b[:4] for a, b in zip(got, want))
+            res["tp_vs_tp1"] = {"identical": same, "first4_identical": first, "n": len(want)}
+            log("TP engine vs TP=1:", res["tp_vs_tp1"])
+            assert first >= len(want) - 1 and same >= len(want) - 4, res["tp_vs_tp1"]
+        res["nvl_calls"] = eng.runner.tp.nvl.calls if eng.runner.tp.nvl else 0
+    eng.shutdown()
+
+
+res["failures"] = failures
 if rank == 0:
-    got = [o["output_ids"] for o in outs]
-    if len(sys.argv) > 1 and os.path.exists(sys.argv[1]):
-        want = json.load(open(sys.argv[1]))
-        same = sum(a == b for a, b in zip(got, want)); first = sum(a[:4] == b[:4] for a, b in zip(got, want))
-        res["tp_vs_tp1"] = {"identical": same, "first4_identical": first, "n": len(want)}
-        log("TP engine vs TP=1:", res["tp_vs_tp1"])
-        assert first >= len(want) - 1 and same >= len(want) - 4, res["tp_vs_tp1"]
-    res["nvl_calls"] = eng.runner.tp.nvl.calls if eng.runner.tp.nvl else 0
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"mgpu_{world}.json"), "w"), indent=1)
-    print("MGPU OK", json.dumps(res)[:1500])
-eng.shutdown()
-dist.barrier()
+    print("MGPU", "OK" if not failures else f"FAILED {failures}", json.dumps(res)[:2500], flush=True)
+_rlog.close()
+os._exit(1 if failures else 0)
