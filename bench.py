@@ -264,9 +264,13 @@ def main() -> None:
                     "note": "text prompts -> tokenizer -> engine -> detokenizer -> text; bytes are per engine forward step"},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "impl": "ours"}))
     eng.shutdown()
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        # NCCL communicator teardown can block for minutes when CUDA graphs still reference the communicator's streams;
+        # the result line is out and every rank has passed the barrier, so leave without running the destructors.
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

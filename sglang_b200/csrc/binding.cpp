@@ -241,9 +241,110 @@ void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10
   count();
 }
 
+void per_token_group_quant_fp8(const at::Tensor& x, at::Tensor q, at::Tensor scales, int64_t group, bool ue8m0) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_LAST_CONTIG(x);
+  TORCH_CHECK(group == 128, "fp8 activation quant: group size must be 128");
+  TORCH_CHECK(x.dim() == 2 && q.is_contiguous() && q.element_size() == 1 && scales.scalar_type() == at::kFloat && scales.is_contiguous());
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::per_token_group_quant_fp8(x.data_ptr(), q.data_ptr(), scales.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.stride(0),
+                                  ue8m0, cur_stream());
+  count();
+}
+
+// out[M,N] bf16 = block-scaled (xq[M,K] e4m3, xs[M,K/128]) @ (wq[N,K] e4m3, ws[N/128,K/128])^T
+void gemm_fp8_block(const at::Tensor& xq, const at::Tensor& xs, const at::Tensor& wq, const at::Tensor& ws, at::Tensor out) {
+  CHECK_CUDA(xq); CHECK_BF16(out); CHECK_LAST_CONTIG(xq); CHECK_LAST_CONTIG(wq); CHECK_LAST_CONTIG(out);
+  TORCH_CHECK(xq.element_size() == 1 && wq.element_size() == 1 && xq.dim() == 2 && wq.dim() == 2 && xq.size(1) == wq.size(1));
+  TORCH_CHECK(xs.scalar_type() == at::kFloat && ws.scalar_type() == at::kFloat && xs.stride(-1) == 1 && ws.stride(-1) == 1);
+  const int64_t kg = (xq.size(1) + 127) / 128;
+  TORCH_CHECK(xs.size(0) == xq.size(0) && xs.size(1) == kg && ws.size(0) == (wq.size(0) + 127) / 128 && ws.size(1) == kg,
+              "fp8 block gemm: scale shapes must be [M, K/128] and [N/128, K/128]");
+  c10::cuda::CUDAGuard g(xq.device());
+  sglb::gemm_fp8_block(xq.data_ptr(), xs.data_ptr<float>(), wq.data_ptr(), ws.data_ptr<float>(), out.data_ptr(), (int)xq.size(0),
+                       (int)wq.size(0), (int)xq.size(1), (int)xq.stride(0), (int)wq.stride(0), (int)out.stride(0), (int)xs.stride(0),
+                       (int)ws.stride(0), num_sms(), cur_stream());
+  count();
+}
+
+void moe_topk_softmax(const at::Tensor& logits, at::Tensor out_w, at::Tensor out_ids, bool renorm) {
+  CHECK_CUDA(logits); CHECK_LAST_CONTIG(logits); CHECK_I32(out_ids);
+  TORCH_CHECK(logits.dim() == 2 && out_w.scalar_type() == at::kFloat && out_w.is_contiguous() && out_ids.is_contiguous());
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(bf16 || logits.scalar_type() == at::kFloat, "router logits must be bf16 or fp32");
+  c10::cuda::CUDAGuard g(logits.device());
+  sglb::moe_topk_softmax(logits.data_ptr(), bf16, out_w.data_ptr<float>(), out_ids.data_ptr<int>(), (int)logits.size(0),
+                         (int)logits.size(1), (int)out_ids.size(1), (int)logits.stride(0), renorm, cur_stream());
+  count();
+}
+
+// Whole expert MLP block on expert-sorted rows: align -> gather -> grouped GEMM (silu(gate)*up fused) -> grouped GEMM (routing
+// weight fused) -> combine.  With peer pointers the combine pushes its result into every peer's NVLink arena instead of `out`.
+void moe_grouped_mlp_impl(const at::Tensor& x, const at::Tensor& w13, const at::Tensor& w2, const at::Tensor& topk_w,
+                          const at::Tensor& topk_ids, c10::optional<at::Tensor> out, int64_t expert_offset,
+                          const int64_t* peer_slots, const int64_t* peer_flags, int rank, int world, const uint32_t* epoch,
+                          uint32_t* done) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_BF16(w13); CHECK_BF16(w2); CHECK_I32(topk_ids); CHECK_LAST_CONTIG(x);
+  TORCH_CHECK(x.dim() == 2 && w13.dim() == 3 && w2.dim() == 3 && w13.is_contiguous() && w2.is_contiguous());
+  TORCH_CHECK(topk_w.scalar_type() == at::kFloat && topk_w.is_contiguous() && topk_ids.is_contiguous());
+  const int T = (int)x.size(0), H = (int)x.size(1), K = (int)topk_ids.size(1), E = (int)w13.size(0), I = (int)w2.size(2);
+  TORCH_CHECK(w13.size(1) == 2 * I && w13.size(2) == H && w2.size(1) == H && w2.size(0) == E);
+  if (T == 0) return;
+  c10::cuda::CUDAGuard g(x.device());
+  auto stream = cur_stream();
+  const int pairs = T * K;
+  const int max_tiles = (pairs + 127) / 128 + E;
+  const int cap = max_tiles * 128;
+  auto i32 = x.options().dtype(at::kInt);
+  auto meta = at::empty({cap + pairs + max_tiles + 1}, i32);
+  int* sorted_row = meta.data_ptr<int>();
+  int* inv_pos = sorted_row + cap;
+  int* tile_expert = inv_pos + pairs;
+  int* num_tiles = tile_expert + max_tiles;
+  auto row_w = at::empty({cap}, x.options().dtype(at::kFloat));
+  sglb::moe_align(topk_ids.data_ptr<int>(), topk_w.data_ptr<float>(), pairs, E, (int)expert_offset, sorted_row, inv_pos,
+                  row_w.data_ptr<float>(), tile_expert, num_tiles, max_tiles, stream);
+  auto xs = at::empty({cap, H}, x.options());
+  sglb::moe_gather(x.data_ptr(), sorted_row, num_tiles, xs.data_ptr(), H, (int)x.stride(0), K, cap, num_sms(), stream);
+  auto h = at::empty({cap, I}, x.options());
+  sglb::gemm_bf16_tc_grouped(xs.data_ptr(), w13.data_ptr(), h.data_ptr(), nullptr, cap, I, H, H, I, E, tile_expert, num_tiles, true,
+                             num_sms(), stream);
+  auto& ys = xs;   // the gathered inputs are dead once the first GEMM has run (same stream): reuse as the [cap, H] output
+  sglb::gemm_bf16_tc_grouped(h.data_ptr(), w2.data_ptr(), ys.data_ptr(), row_w.data_ptr<float>(), cap, H, I, I, H, E, tile_expert,
+                             num_tiles, false, num_sms(), stream);
+  if (peer_slots) {
+    sglb::moe_combine_push(ys.data_ptr(), inv_pos, nullptr, T, H, K, peer_slots, peer_flags, rank, world, epoch, done, num_sms(), stream);
+  } else {
+    TORCH_CHECK(out.has_value() && out->is_contiguous());
+    sglb::moe_combine(ys.data_ptr(), inv_pos, nullptr, out->data_ptr(), T, H, K, num_sms(), stream);
+  }
+  count(5);
+}
+
+void moe_grouped_mlp(const at::Tensor& x, const at::Tensor& w13, const at::Tensor& w2, const at::Tensor& topk_w,
+                     const at::Tensor& topk_ids, at::Tensor out, int64_t expert_offset) {
+  CHECK_BF16(out);
+  moe_grouped_mlp_impl(x, w13, w2, topk_w, topk_ids, out, expert_offset, nullptr, nullptr, 0, 1, nullptr, nullptr);
+}
+
+void moe_grouped_mlp_push(const at::Tensor& x, const at::Tensor& w13, const at::Tensor& w2, const at::Tensor& topk_w,
+                          const at::Tensor& topk_ids, int64_t expert_offset, const at::Tensor& peer_slot_ptrs,
+                          const at::Tensor& peer_flag_ptrs, int64_t rank, int64_t world, at::Tensor epoch, at::Tensor done) {
+  TORCH_CHECK(!peer_slot_ptrs.is_cuda() && !peer_flag_ptrs.is_cuda());
+  moe_grouped_mlp_impl(x, w13, w2, topk_w, topk_ids, c10::nullopt, expert_offset, peer_slot_ptrs.data_ptr<int64_t>(),
+                       peer_flag_ptrs.data_ptr<int64_t>(), (int)rank, (int)world, reinterpret_cast<const uint32_t*>(epoch.data_ptr<int>()),
+                       reinterpret_cast<uint32_t*>(done.data_ptr<int>()));
+}
+
 }  // namespace
 
 TORCH_LIBRARY(sglb, m) {
+  m.def("per_token_group_quant_fp8(Tensor x, Tensor(a!) q, Tensor(b!) scales, int group, bool ue8m0) -> ()", &per_token_group_quant_fp8);
+  m.def("gemm_fp8_block(Tensor xq, Tensor xs, Tensor wq, Tensor ws, Tensor(a!) out) -> ()", &gemm_fp8_block);
+  m.def("moe_topk_softmax(Tensor logits, Tensor(a!) out_w, Tensor(b!) out_ids, bool renorm) -> ()", &moe_topk_softmax);
+  m.def("moe_grouped_mlp(Tensor x, Tensor w13, Tensor w2, Tensor topk_w, Tensor topk_ids, Tensor(a!) out, int expert_offset) -> ()",
+        &moe_grouped_mlp);
+  m.def("moe_grouped_mlp_push(Tensor x, Tensor w13, Tensor w2, Tensor topk_w, Tensor topk_ids, int expert_offset, Tensor peer_slot_ptrs, "
+        "Tensor peer_flag_ptrs, int rank, int world, Tensor(a!) epoch, Tensor(b!) done) -> ()", &moe_grouped_mlp_push);
   m.def("gemm_push(Tensor a, Tensor w, Tensor peer_slot_ptrs, Tensor peer_flag_ptrs, int rank, int world, Tensor(a!) epoch, "
         "Tensor(b!) done, int bn) -> ()", &gemm_push);
   m.def("nvl_local_reduce_add_rmsnorm(Tensor slot, int flags_ptr, Tensor(a!)? residual, Tensor w, Tensor(b!) out, int world, float eps, "

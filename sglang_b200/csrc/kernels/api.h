@@ -33,6 +33,27 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
 void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc,
                   int epilogue, int bn, int num_sms, cudaStream_t stream);
 int gemm_pick_bn(int M, int N, int K, int num_sms);
+void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* row_scale, int M_cap, int n_out, int K, int lda,
+                          int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
+                          cudaStream_t stream);
+
+// gemm_fp8.cu
+void gemm_fp8_block(const void* A, const float* xs, const void* W, const float* ws, void* C, int M, int N, int K, int lda, int ldw,
+                    int ldc, int xs_stride, int ws_stride, int num_sms, cudaStream_t stream);
+void per_token_group_quant_fp8(const void* x, void* q, float* scales, int M, int K, int x_stride, bool ue8m0, cudaStream_t stream);
+
+// moe.cu
+void moe_topk_softmax(const void* logits, bool bf16, float* out_w, int* out_ids, int T, int E, int K, int stride, bool renorm,
+                      cudaStream_t stream);
+void moe_align(const int* topk_ids, const float* topk_w, int n_pairs, int E, int expert_offset, int* sorted_row, int* inv_pos,
+               float* row_w, int* tile_expert, int* num_tiles, int max_tiles, cudaStream_t stream);
+void moe_gather(const void* x, const int* sorted_row, const int* num_tiles, void* xs, int H, int x_stride, int K, int cap_rows,
+                int num_sms, cudaStream_t stream);
+void moe_combine(const void* ys, const int* inv_pos, const float* pair_w, void* out, int T, int H, int K, int num_sms,
+                 cudaStream_t stream);
+void moe_combine_push(const void* ys, const int* inv_pos, const float* pair_w, int T, int H, int K, const int64_t* peer_slot_ptrs,
+                      const int64_t* peer_flag_ptrs, int rank, int world, const uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms,
+                      cudaStream_t stream);
 
 // sampling.cu
 void sample(const void* logits, bool bf16, int B, int V, int stride, const float* temperature, const int* top_k,

@@ -11,13 +11,21 @@
 #include "common.cuh"
 #include "tma_host.h"
 
+#include <algorithm>
+
 namespace sglb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 
-enum GemmEpilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_SILU_MUL = 2, EPI_PUSH = 3 };
+enum GemmEpilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_SILU_MUL = 2, EPI_PUSH = 3, EPI_SILU_SPLIT = 4, EPI_ROWSCALE = 5 };
+// EPI_SILU_SPLIT: W = [gate rows (n_half) ; up rows (n_half)] un-interleaved (the checkpoint layout).  Each B stage is
+//   filled by TWO TMA boxes of BN/2 rows — gate rows j.. and up rows n_half+j.. — so one UMMA of width BN produces the
+//   gate half in accumulator columns [0,BN/2) and the matching up half in [BN/2,BN); the epilogue writes silu(g)*u.
+// EPI_ROWSCALE : C[row,:] = acc[row,:] * scale[row]  (fp32 per-row scale passed through `bias`; MoE routing weights).
+// GROUPED      : A rows are expert-sorted and padded to 128-row tiles; W is [E][N][K] behind a 3-D tensor map and
+//   tile_expert[m_tile] selects the expert slab; the number of live M tiles is read from device memory.
 
 // EPI_PUSH: fused GEMM + all-reduce producer.  The epilogue stores every output tile into slot [rank] of EVERY peer's
 // symmetric arena (P2P stores over NVLink / NVSwitch, peer pointers mapped into this address space), tile by tile while
@@ -42,11 +50,13 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, bool A_FP8>
+template <int BN, int EPI, bool GROUPED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ bias, int M, int N, int K, int ldc,
-               const GemmPush push) {
+               const GemmPush push, const int* __restrict__ tile_expert, const int* __restrict__ num_m_tiles_ptr, int n_half) {
+  constexpr bool SPLIT = (EPI == EPI_SILU_SPLIT);
+  constexpr int BN_OUT = SPLIT ? BN / 2 : BN;       // output columns covered by one tile
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -62,8 +72,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  const int n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = GROUPED ? min(__ldg(num_m_tiles_ptr), (M + GEMM_BM - 1) / GEMM_BM) : (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN_OUT - 1) / BN_OUT;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
 
@@ -90,11 +100,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const int expert = GROUPED ? __ldg(tile_expert + m_blk) : 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
         tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+        uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
+        if constexpr (GROUPED) {
+          tma_load_3d(b_dst, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN_OUT, expert);
+          if constexpr (SPLIT) tma_load_3d(b_dst + Cfg::B_BYTES / 2, &tmB, &full[stage], kb * GEMM_BK, n_half + n_blk * BN_OUT, expert);
+        } else {
+          tma_load_2d(b_dst, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN_OUT);
+          if constexpr (SPLIT) tma_load_2d(b_dst + Cfg::B_BYTES / 2, &tmB, &full[stage], kb * GEMM_BK, n_half + n_blk * BN_OUT);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -133,10 +151,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      float row_scale = 1.f;
+      if (EPI == EPI_ROWSCALE && row < M) row_scale = __ldg(reinterpret_cast<const float*>(bias) + row);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < BN_OUT / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
+        if constexpr (SPLIT) {
+          uint32_t u[32];
+          tmem_ld_32x32b_x32(t_row + BN / 2 + c * 32, u);
+          tmem_ld_wait();
+          const int col0 = n_blk * BN_OUT + c * 32;
+          if (row < M) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              if (col0 + v * 8 < N) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float g0 = __uint_as_float(r[v * 8 + 2 * i]), g1 = __uint_as_float(r[v * 8 + 2 * i + 1]);
+                  const float u0 = __uint_as_float(u[v * 8 + 2 * i]), u1 = __uint_as_float(u[v * 8 + 2 * i + 1]);
+                  o[i] = pack_bf16(g0 / (1.f + __expf(-g0)) * u0, g1 / (1.f + __expf(-g1)) * u1);
+                }
+                st128(C + (size_t)row * ldc + col0 + v * 8, U4{o[0], o[1], o[2], o[3]});
+              }
+            }
+          }
+          continue;
+        }
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
         if (EPI == EPI_SILU_MUL) {
@@ -164,6 +206,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]);
+                if (EPI == EPI_ROWSCALE) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] *= row_scale;
+                }
                 if (EPI == EPI_BIAS) {
                   U4 b = ldg128(bias + col);
                   f[0] += bf16_lo(b.x); f[1] += bf16_hi(b.x); f[2] += bf16_lo(b.y); f[3] += bf16_hi(b.y);
@@ -210,35 +256,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int EPI>
+// host-side extras: expert-grouped B ([E][rows][K], 3-D tensor map) and the split gate/up epilogue
+struct GemmExtra {
+  int num_experts = 0;                 // > 0 -> GROUPED
+  const int* tile_expert = nullptr;    // [max m tiles]
+  const int* num_m_tiles = nullptr;    // device scalar
+  int w_rows = 0;                      // rows of W per expert (N for plain epilogues, 2*n_half for EPI_SILU_SPLIT)
+  int n_half = 0;                      // EPI_SILU_SPLIT: row offset of the `up` half
+};
+
+template <int BN, int EPI, bool GROUPED>
 static void launch_gemm(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw,
-                        int ldc, int num_sms, cudaStream_t stream, const GemmPush& push) {
+                        int ldc, int num_sms, cudaStream_t stream, const GemmPush& push, const GemmExtra& ex) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool SPLIT = (EPI == EPI_SILU_SPLIT);
+  constexpr int BN_OUT = SPLIT ? BN / 2 : BN;
+  const int w_rows = ex.w_rows > 0 ? ex.w_rows : N;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sAs[1] = {(uint64_t)lda * 2};
-  uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sBs[1] = {(uint64_t)ldw * 2};
-  uint32_t bA[2] = {GEMM_BK, GEMM_BM}, bB[2] = {GEMM_BK, (uint32_t)BN};
+  uint32_t bA[2] = {GEMM_BK, GEMM_BM};
   CUtensorMap tmA = make_tmap(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, sAs, bA, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap tmB = make_tmap(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, sBs, bB, CU_TENSOR_MAP_SWIZZLE_128B);
-  auto kern = gemm_tc_kernel<BN, EPI, false>;
+  CUtensorMap tmB;
+  if (GROUPED) {
+    uint64_t dB[3] = {(uint64_t)K, (uint64_t)w_rows, (uint64_t)ex.num_experts};
+    uint64_t sBs[2] = {(uint64_t)ldw * 2, (uint64_t)w_rows * ldw * 2};
+    uint32_t bB[3] = {GEMM_BK, (uint32_t)BN_OUT, 1};
+    tmB = make_tmap(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dB, sBs, bB, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)w_rows}, sBs[1] = {(uint64_t)ldw * 2};
+    uint32_t bB[2] = {GEMM_BK, (uint32_t)BN_OUT};
+    tmB = make_tmap(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, sBs, bB, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  auto kern = gemm_tc_kernel<BN, EPI, GROUPED>;
   static bool configured = false;
   if (!configured) {
     SGLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
-  const int grid = min(m_tiles * n_tiles, num_sms);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, (__nv_bfloat16*)C, (const __nv_bfloat16*)bias, M, N, K, ldc, push);
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN_OUT - 1) / BN_OUT;
+  const int grid = (int)std::min<long long>((long long)m_tiles * n_tiles, num_sms);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, (__nv_bfloat16*)C, (const __nv_bfloat16*)bias, M, N, K, ldc, push,
+                                                        ex.tile_expert, ex.num_m_tiles, ex.n_half);
   SGLB_CUDA_CHECK(cudaGetLastError());
 }
 
-template <int EPI>
+template <int EPI, bool GROUPED = false>
 static void dispatch_bn(int bn, const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda,
-                        int ldw, int ldc, int num_sms, cudaStream_t stream, const GemmPush& push = GemmPush{}) {
+                        int ldw, int ldc, int num_sms, cudaStream_t stream, const GemmPush& push = GemmPush{},
+                        const GemmExtra& ex = GemmExtra{}) {
   switch (bn) {
-    case 32: launch_gemm<32, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
-    case 64: launch_gemm<64, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
-    case 128: launch_gemm<128, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
-    case 256: launch_gemm<256, EPI>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push); break;
+    case 32: launch_gemm<32, EPI, GROUPED>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push, ex); break;
+    case 64: launch_gemm<64, EPI, GROUPED>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push, ex); break;
+    case 128: launch_gemm<128, EPI, GROUPED>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push, ex); break;
+    case 256: launch_gemm<256, EPI, GROUPED>(A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream, push, ex); break;
     default: throw std::runtime_error("sglb gemm: unsupported BN");
   }
 }
@@ -266,7 +335,58 @@ void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M
     case EPI_NONE: dispatch_bn<EPI_NONE>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
     case EPI_BIAS: dispatch_bn<EPI_BIAS>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
     case EPI_SILU_MUL: dispatch_bn<EPI_SILU_MUL>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case EPI_ROWSCALE: dispatch_bn<EPI_ROWSCALE>(bn, A, W, C, bias, M, N, K, lda, ldw, ldc, num_sms, stream); break;
+    case EPI_SILU_SPLIT: {
+      // W is [2*n_half, K] = [gate ; up]; C is [M, n_half].  N counts W rows on entry.
+      const int n_half = N / 2;
+      if (bn <= 0 || n_half % (bn / 2)) {
+        bn = 0;
+        const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+        for (int cand : {256, 128, 64, 32}) {
+          if (n_half % (cand / 2)) continue;
+          bn = cand;
+          if ((long long)m_tiles * (n_half / (cand / 2)) >= num_sms) break;
+        }
+        if (!bn) throw std::runtime_error("sglb gemm: split-silu needs intermediate size % 16 == 0");
+      }
+      GemmExtra ex; ex.w_rows = N; ex.n_half = n_half;
+      dispatch_bn<EPI_SILU_SPLIT>(bn, A, W, C, bias, M, n_half, K, lda, ldw, ldc, num_sms, stream, GemmPush{}, ex);
+      break;
+    }
     default: throw std::runtime_error("sglb gemm: bad epilogue");
+  }
+}
+
+// Expert-grouped GEMM over expert-sorted, 128-row-padded activations (see moe.cu for the alignment kernels).
+//   split_silu: W = [E][2*n_out][K] (gate;up), C = [M_cap][n_out] = silu(gate)*up
+//   else      : W = [E][n_out][K],             C = [M_cap][n_out] = acc * row_scale[row]   (row_scale may be null)
+void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* row_scale, int M_cap, int n_out, int K, int lda,
+                          int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
+                          cudaStream_t stream) {
+  if (M_cap <= 0 || n_out <= 0) return;
+  if (K % 8 || n_out % 16 || lda % 8) throw std::runtime_error("sglb grouped gemm: K % 8, n_out % 16, lda % 8 required");
+  GemmExtra ex; ex.num_experts = num_experts; ex.tile_expert = tile_expert; ex.num_m_tiles = num_m_tiles;
+  const int m_tiles = M_cap / GEMM_BM;
+  int bn = 0;
+  if (split_silu) {
+    ex.w_rows = 2 * n_out; ex.n_half = n_out;
+    for (int cand : {256, 128, 64, 32}) {
+      if (n_out % (cand / 2)) continue;
+      bn = cand;
+      if ((long long)m_tiles * (n_out / (cand / 2)) >= 2LL * num_sms) break;
+    }
+    if (!bn) throw std::runtime_error("sglb grouped gemm: bad intermediate size");
+    dispatch_bn<EPI_SILU_SPLIT, true>(bn, A, W, C, nullptr, M_cap, n_out, K, lda, K, ldc, num_sms, stream, GemmPush{}, ex);
+  } else {
+    ex.w_rows = n_out;
+    for (int cand : {256, 128, 64, 32}) {
+      if (n_out % cand) continue;
+      bn = cand;
+      if ((long long)m_tiles * (n_out / cand) >= 2LL * num_sms) break;
+    }
+    if (!bn) throw std::runtime_error("sglb grouped gemm: n_out must be a multiple of 32");
+    if (row_scale) dispatch_bn<EPI_ROWSCALE, true>(bn, A, W, C, row_scale, M_cap, n_out, K, lda, K, ldc, num_sms, stream, GemmPush{}, ex);
+    else dispatch_bn<EPI_NONE, true>(bn, A, W, C, nullptr, M_cap, n_out, K, lda, K, ldc, num_sms, stream, GemmPush{}, ex);
   }
 }
 

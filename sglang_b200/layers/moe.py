@@ -75,7 +75,18 @@ class FusedMoE(nn.Module):
         w, ids = select_experts(router_logits, self.top_k, self.renormalize)
         if self.expert_load is not None:
             self.expert_load.record(self.layer_id, ids)
+        tp = self.tp
+        if (tp.world_size > 1 and tp.nvl is not None and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
+                and moe_ops._has("moe_grouped_mlp_push") and tp.world_size * x.numel() * 2 <= tp.nvl.slot_bytes):
+            from ..environ import envs
+            from ..parallel.parallel_state import get_pp_group
+            from .linear import PendingAllReduce
+
+            if envs.SGLB_FUSED_AR.get() == "push" and get_pp_group().world_size == 1:
+                # combine kernel pushes the partial sums to every peer; the next RMSNorm reduces them locally
+                off = tp.nvl.moe_push(x, self.w13, self.w2, w, ids.to(torch.int32), self.expert_offset)
+                return PendingAllReduce(tp.nvl, off, x.shape[0], x.shape[1], "push")
         y = moe_ops.fused_moe(x, self.w13, self.w2, w, ids, self.expert_offset)
-        if self.tp.world_size > 1:
-            y = self.tp.all_reduce(y)
+        if tp.world_size > 1:
+            y = tp.all_reduce(y)
         return y

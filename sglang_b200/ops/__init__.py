@@ -162,7 +162,7 @@ def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, 
 
 
 # ------------------------------------------------------------------ GEMM
-EPI_NONE, EPI_BIAS, EPI_SILU_MUL = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_SILU_MUL, EPI_PUSH, EPI_SILU_SPLIT, EPI_ROWSCALE = 0, 1, 2, 3, 4, 5
 
 
 def gemm_impl() -> str:
@@ -180,6 +180,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
             out = torch.empty(x.shape[0], w.shape[0], dtype=x.dtype, device=x.device)
         torch.ops.sglb.gemm(x, w, out, bias, EPI_BIAS if bias is not None else EPI_NONE, 0)
         return out
+    if out is not None and bias is None and x.dim() == 2 and out.is_contiguous():
+        return torch.mm(x, w.t(), out=out)       # cuBLAS writes straight into the caller's buffer (e.g. an NVL arena slot)
     r = torch.nn.functional.linear(x, w, bias)
     if out is not None:
         out.copy_(r)
@@ -189,7 +191,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, bn: int = 0,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    n_out = w.shape[0] // 2 if epilogue == EPI_SILU_MUL else w.shape[0]
+    n_out = w.shape[0] // 2 if epilogue in (EPI_SILU_MUL, EPI_SILU_SPLIT) else w.shape[0]
     if out is None:
         out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
     torch.ops.sglb.gemm(x, w, out, bias, epilogue, bn)

@@ -153,6 +153,20 @@ class NvlComm:
         self.calls += 1
         return off
 
+    def moe_push(self, x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: torch.Tensor, topk_ids: torch.Tensor,
+                 expert_offset: int) -> int:
+        """expert MLP block (align -> gather -> grouped GEMMs -> combine) whose combine kernel stores this rank's partial
+        [T,H] straight into slot [rank] of every peer's arena: the expert-parallel reduction costs no kernel of its own."""
+        T, H = x.shape
+        assert self.world * T * H * 2 <= self.slot_bytes, "NVL arena slot too small for this MoE output"
+        ch = CH_GEMM
+        off = self._slot(ch)
+        torch.ops.sglb.moe_grouped_mlp_push(x, w13, w2, topk_w, topk_ids, expert_offset, self.buf_ptrs + off,
+                                            self.flag_ptrs + ch * MAX_RANKS * 4, self.rank, self.world, self.epochs[ch:ch + 1],
+                                            self.done[ch, 1:])
+        self.calls += 1
+        return off
+
     def push_reduce_add_rmsnorm(self, off: int, T: int, H: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
                                 eps: float, gemma: bool = False) -> None:
         ch = CH_GEMM

@@ -174,6 +174,86 @@ def case_gemm_tc():
     _close(out, ref, 0.1, 3e-2, "gemm silu_mul epilogue")
 
 
+def case_gemm_split_silu():
+    """un-interleaved [gate;up] weights, silu(g)*u fused in the tcgen05 epilogue (EPI_SILU_SPLIT)"""
+    torch.manual_seed(1)
+    for (M, I, K, bn) in [(50, 1024, 512, 0), (300, 1792, 4096, 0), (7, 14336, 4096, 0), (1000, 2048, 1024, 256), (64, 1040, 256, 0)]:
+        gate = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        up = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        w = torch.cat([gate, up], 0).contiguous()
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        out = torch.empty(M, I, device=DEV, dtype=torch.bfloat16)
+        torch.ops.sglb.gemm(a, w, out, None, ops.EPI_SILU_SPLIT, bn)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+        _close(out, ref, 0.1, 3e-2, f"gemm split-silu {M}x{I}x{K}")
+
+
+def case_moe():
+    from sglang_b200.ops import moe_ops
+
+    torch.manual_seed(2)
+    # routing
+    for T, E, K in [(1, 8, 2), (77, 8, 2), (300, 64, 6), (33, 256, 8), (5, 160, 6)]:
+        for dt in (torch.float32, torch.bfloat16):
+            logits = (torch.randn(T, E, device=DEV) * 2).to(dt)
+            for renorm in (True, False):
+                w, ids = moe_ops.topk_softmax(logits, K, renorm)
+                rw, rids = torch_ref.moe_topk_softmax(logits.float(), K, renorm)
+                torch.cuda.synchronize()
+                # compare as sets of (id -> weight): ties in bf16 logits may legitimately reorder equal experts
+                probs = torch.softmax(logits.float(), -1)
+                got = torch.gather(probs, 1, ids.long())
+                want = torch.gather(probs, 1, rids.long())
+                assert torch.allclose(got.sort(-1).values, want.sort(-1).values, atol=1e-6), f"topk ids T={T} E={E} K={K}"
+                exp_w = got / got.sum(-1, keepdim=True) if renorm else got
+                _close(w, exp_w, 1e-5, 1e-4, f"topk weights T={T} E={E} K={K} renorm={renorm}")
+    # full expert MLP vs fp32 reference (also with an expert offset = expert-parallel shard)
+    for T, E, K, H, I, off, Etot in [(1, 8, 2, 512, 256, 0, 8), (37, 8, 2, 1024, 512, 0, 8), (300, 8, 2, 1024, 1792, 0, 8),
+                                     (64, 4, 2, 512, 256, 4, 8), (513, 16, 4, 256, 128, 0, 16), (16, 8, 2, 4096, 14336, 0, 8)]:
+        x = (torch.randn(T, H, device=DEV) * 0.5).to(torch.bfloat16)
+        w13 = (torch.randn(E, 2 * I, H, device=DEV) * (1.0 / math.sqrt(H))).to(torch.bfloat16)
+        w2 = (torch.randn(E, H, I, device=DEV) * (1.0 / math.sqrt(I))).to(torch.bfloat16)
+        logits = torch.randn(T, Etot, device=DEV)
+        tw, ids = moe_ops.topk_softmax(logits, K, True)
+        out = moe_ops.fused_moe(x, w13, w2, tw, ids, off)
+        torch.cuda.synchronize()
+        ref = torch_ref.fused_moe(x.float(), w13.float(), w2.float(), tw, ids, off)
+        _close(out, ref, 3e-2, 3e-2, f"fused_moe T={T} E={E} K={K} H={H} I={I} off={off}")
+        out2 = moe_ops.fused_moe(x, w13, w2, tw, ids, off)
+        assert torch.equal(out, out2), "fused_moe must be run-to-run deterministic"
+    assert moe_ops._has("moe_grouped_mlp") and moe_ops._has("moe_topk_softmax"), "native MoE ops missing"
+
+
+def case_fp8():
+    """activation quantiser + block-scaled fp8 tcgen05 GEMM vs the fp32 dequantised reference"""
+    from sglang_b200.ops import quant_ops
+
+    assert quant_ops._has("gemm_fp8_block") and quant_ops._has("per_token_group_quant_fp8"), "native fp8 ops missing"
+    torch.manual_seed(3)
+    for (M, N, K) in [(1, 512, 512), (37, 4096, 4096), (300, 1024, 7168), (128, 384, 256), (1000, 2048, 1024), (16, 28672, 4096),
+                      (64, 576, 1536)]:
+        x = (torch.randn(M, K, device=DEV) * 0.7).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) * 0.05)
+        for ue in (False, True):
+            xq, xs = quant_ops.per_token_group_quant_fp8(x, 128, ue)
+            rq, rs = torch_ref.per_token_group_quant_fp8(x, 128, ue)
+            _close(xs, rs, 1e-7, 1e-5, f"fp8 act scales {M}x{K}")
+            # dequantised values must agree (bit-equality of fp8 codes can differ by 1 ulp on round-to-nearest ties)
+            dq = xq.float().view(M, K // 128, 128) * xs[..., None]
+            dr = rq.float().view(M, K // 128, 128) * rs[..., None]
+            _close(dq, dr, 0.04, 0.07, f"fp8 act quant {M}x{K}")
+            wq, ws = torch_ref.block_quant_weight_fp8(w, 128, ue)
+            out = quant_ops.fp8_block_linear(x, wq, ws, 128, ue)
+            torch.cuda.synchronize()
+            ref = torch_ref.fp8_block_gemm(xq, xs, wq, ws, 128, torch.float32)
+            _close(out, ref, 0.05, 2e-2, f"fp8 block gemm {M}x{N}x{K} ue8m0={ue}")
+            # and the quantised product is a faithful approximation of the bf16 one
+            full = x.float() @ w.t()
+            rel = ((out.float() - full).norm() / full.norm()).item()
+            assert rel < 0.06, f"fp8 gemm {M}x{N}x{K}: relative error vs unquantised {rel:.3f}"
+
+
 def case_sampling():
     torch.manual_seed(0)
     B, V = 16, 32000

@@ -74,6 +74,39 @@ def timed(fn, iters=20, warm=5):
     return float(t)
 
 
+def timed_graph(fn, per_graph=4, iters=20):
+    """device time per call with launch overhead removed: `per_graph` calls captured in one CUDA graph (even count, so the
+    arena slot parity keeps alternating across replays), replayed `iters` times; max over ranks"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize(); dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    if nvl is not None:
+        nvl.begin_capture()
+    try:
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(per_graph):
+                fn()
+    finally:
+        if nvl is not None:
+            nvl.end_capture()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize(); dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        g.replay()
+    e.record(); torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / (iters * per_graph)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
 if nvl is None:
     failures.append("nvl_init")
     log("NVL comm failed to initialise (see warning above); collective sections skipped")
@@ -106,8 +139,10 @@ else:
                 log(f"  nvl {nm} n={n} err={err:.4f}")
                 assert err < 0.05 * world, f"nvl {nm} n={n} err={err}"
                 lat[f"{nm}_{n*2}B_us"] = 1000 * timed(lambda: nvl.all_reduce(x, algo=algo))
+                lat[f"{nm}_{n*2}B_graph_us"] = 1000 * timed_graph(lambda: nvl.all_reduce(x, algo=algo))
             z = x.clone()
             lat[f"nccl_{n*2}B_us"] = 1000 * timed(lambda: dist.all_reduce(z))
+            lat[f"nccl_{n*2}B_graph_us"] = 1000 * timed_graph(lambda: dist.all_reduce(z))
         res["allreduce_us"] = lat
         log("allreduce", json.dumps({k: round(v, 1) for k, v in lat.items()}))
 
@@ -136,7 +171,8 @@ else:
             def unfused():
                 y = part.clone(); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, w, 1e-5)
 
-            res[f"fused_ar_norm_T{T}_H{H}_us"] = {"fused": 1000 * timed(fused), "nccl_plus_norm": 1000 * timed(unfused)}
+            res[f"fused_ar_norm_T{T}_H{H}_us"] = {"fused": 1000 * timed(fused), "nccl_plus_norm": 1000 * timed(unfused),
+                                                  "fused_graph": 1000 * timed_graph(fused), "nccl_plus_norm_graph": 1000 * timed_graph(unfused)}
         log("fused ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("fused")}))
 
     @section("gemm_push")
@@ -168,8 +204,45 @@ else:
                 y = torch.nn.functional.linear(x, wgt); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, nw, 1e-5)
 
             res[f"gemm_ar_norm_T{T}_K{K}_us"] = {"push_fused": 1000 * timed(push), "pull_fused": 1000 * timed(pull),
-                                                 "cublas_nccl_norm": 1000 * timed(base)}
+                                                 "cublas_nccl_norm": 1000 * timed(base), "push_fused_graph": 1000 * timed_graph(push),
+                                                 "pull_fused_graph": 1000 * timed_graph(pull), "cublas_nccl_norm_graph": 1000 * timed_graph(base)}
         log("gemm+ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("gemm_ar")}))
+
+
+    @section("moe_push")
+    def _moe_push():
+        """expert-parallel MoE block whose combine kernel pushes straight into the peers' arenas, vs fp32 reference"""
+        from sglang_b200.ops import moe_ops
+
+        for T, E, K, H, I in ((16, 8, 2, 1024, 512), (200, 8, 2, 2048, 1024)):
+            torch.manual_seed(5)          # identical tokens / router / weights on every rank (tokens are replicated post-attention)
+            x = (torch.randn(T, H, device=dev) * 0.5).to(torch.bfloat16)
+            w13 = (torch.randn(E, 2 * I, H, device=dev) / H ** 0.5).to(torch.bfloat16)
+            w2 = (torch.randn(E, H, I, device=dev) / I ** 0.5).to(torch.bfloat16)
+            logits = torch.randn(T, E, device=dev)
+            resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); nw = torch.randn(H, device=dev).to(torch.bfloat16)
+            tw, ids = moe_ops.topk_softmax(logits, K, True)
+            le = E // world
+            y_ref = torch_ref.fused_moe(x.float(), w13.float(), w2.float(), tw, ids, 0)
+            r_ref = resid.clone(); x_ref = y_ref.to(torch.bfloat16)
+            torch_ref.fused_add_rmsnorm(x_ref, r_ref, nw, 1e-5)
+            w13_l, w2_l = w13[rank * le:(rank + 1) * le].contiguous(), w2[rank * le:(rank + 1) * le].contiguous()
+            out = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r2 = resid.clone()
+            off = nvl.moe_push(x, w13_l, w2_l, tw, ids, rank * le)
+            nvl.push_reduce_add_rmsnorm(off, T, H, r2, nw, out, 1e-5)
+            torch.cuda.synchronize()
+            e1 = (out.float() - x_ref.float()).abs().max().item(); e2 = (r2.float() - r_ref.float()).abs().max().item()
+            log(f"  moe push T={T} E={E} H={H} err_out={e1:.4f} err_resid={e2:.4f}")
+            assert e1 < 0.3 and e2 < 0.15, ("moe_push", T, e1, e2)
+
+            def fused():
+                o = nvl.moe_push(x, w13_l, w2_l, tw, ids, rank * le); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5)
+
+            def base():
+                y = moe_ops.fused_moe(x, w13_l, w2_l, tw, ids, rank * le); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r2, nw, 1e-5)
+
+            res[f"moe_ar_norm_T{T}_us"] = {"push_fused_graph": 1000 * timed_graph(fused), "nccl_graph": 1000 * timed_graph(base)}
+        log("moe push", json.dumps({k: v for k, v in res.items() if k.startswith("moe_ar")}))
 
 
 # ---------------- TP engine == TP=1 reference (runs with whatever comm survived above)
@@ -183,14 +256,24 @@ def _engine():
                      mem_fraction_static=0.2, max_running_requests=16, log_level="warning", base_gpu_id=rank)
     log("engine built; nvl =", eng.runner.tp.nvl is not None)
     outs = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 24, "temperature": 0, "ignore_eos": True})
+    lp = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 1, "temperature": 0, "ignore_eos": True}, return_logprob=True,
+                      logprob_start_len=0)
     if rank == 0:
         got = [o["output_ids"] for o in outs]
         if len(sys.argv) > 1 and os.path.exists(sys.argv[1]):
-            want = json.load(open(sys.argv[1]))
-            same = sum(a == b for a, b in zip(got, want)); first = sum(a[:4] == b[:4] for a, b in zip(got, want))
-            res["tp_vs_tp1"] = {"identical": same, "first4_identical": first, "n": len(want)}
+            ref = json.load(open(sys.argv[1]))
+            want = ref["output_ids"]
+            same = sum(a == b for a, b in zip(got, want)); first = sum(a[:1] == b[:1] for a, b in zip(got, want))
+            # numerics oracle: teacher-forced prompt logprobs must agree (bf16 reduction order differs between TP degrees)
+            errs = []
+            for o, r in zip(lp, ref["input_logprobs"]):
+                g = [float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None]
+                assert len(g) == len(r), (len(g), len(r))
+                errs.append(max(abs(a - b) for a, b in zip(g, r)) if g else 0.0)
+            res["tp_vs_tp1"] = {"identical": same, "first_token_identical": first, "n": len(want), "max_logprob_err": max(errs)}
             log("TP engine vs TP=1:", res["tp_vs_tp1"])
-            assert first >= len(want) - 1 and same >= len(want) - 4, res["tp_vs_tp1"]
+            assert max(errs) < 0.08, res["tp_vs_tp1"]
+            assert first >= len(want) - 3, res["tp_vs_tp1"]
         res["nvl_calls"] = eng.runner.tp.nvl.calls if eng.runner.tp.nvl else 0
     eng.shutdown()
 
