@@ -55,7 +55,7 @@ void act_and_mul(const at::Tensor& x, at::Tensor out, int64_t act) {
 
 void rope_kv_write(at::Tensor q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& positions,
                    const at::Tensor& cos_sin, at::Tensor k_cache, at::Tensor v_cache, const at::Tensor& out_loc, bool neox,
-                   double k_scale, double v_scale) {
+                   double k_scale, double v_scale, int64_t nslabs, int64_t slab_stride) {
   CHECK_CUDA(q); CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_I32(positions); CHECK_I32(out_loc);
   TORCH_CHECK(q.dim() == 3 && k.dim() == 3 && v.dim() == 3, "q/k/v must be [T, H, D]");
   TORCH_CHECK(cos_sin.scalar_type() == at::kFloat && cos_sin.is_contiguous());
@@ -67,7 +67,8 @@ void rope_kv_write(at::Tensor q, const at::Tensor& k, const at::Tensor& v, const
   sglb::rope_kv_write(q.data_ptr(), k.data_ptr(), v.data_ptr(), positions.data_ptr<int>(), cos_sin.data_ptr<float>(),
                       k_cache.data_ptr(), v_cache.data_ptr(), out_loc.data_ptr<int>(), (int)q.size(0), (int)q.size(1),
                       (int)k.size(1), (int)q.size(2), (int)cos_sin.size(1), (int)q.stride(0), (int)k.stride(0),
-                      (int)v.stride(0), neox, fp8, (float)k_scale, (float)v_scale, cur_stream());
+                      (int)v.stride(0), neox, fp8, (float)k_scale, (float)v_scale, (int)std::max<int64_t>(1, nslabs), (long long)slab_stride,
+                      cur_stream());
   count();
 }
 
@@ -230,14 +231,57 @@ void gemm_push(const at::Tensor& a, const at::Tensor& w, const at::Tensor& peer_
 }
 
 void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10::optional<at::Tensor> residual, const at::Tensor& w,
-                                  at::Tensor out, int64_t world, double eps, bool gemma, at::Tensor epoch, at::Tensor done) {
+                                  at::Tensor out, int64_t world, int64_t nslabs, double eps, bool gemma, at::Tensor epoch, at::Tensor done) {
   CHECK_CUDA(out); CHECK_BF16(out); CHECK_BF16(w); CHECK_BF16(slot); TORCH_CHECK(out.is_contiguous() && out.dim() == 2);
   c10::cuda::CUDAGuard g(out.device());
   sglb::nvl_local_reduce_add_rmsnorm(slot.data_ptr(), reinterpret_cast<uint32_t*>(flags_ptr),
                                      residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), out.data_ptr(),
-                                     (int)out.size(0), (int)out.size(1), (int)world, (float)eps, gemma,
+                                     (int)out.size(0), (int)out.size(1), (int)world, (int)nslabs, (float)eps, gemma,
                                      reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()), reinterpret_cast<uint32_t*>(done.data_ptr<int>()),
                                      num_sms(), cur_stream());
+  count();
+}
+
+// decode-shape GEMM (M <= 256): out is [M, N] (splits == 1) or a slab workspace [splits, M, N] that the consumer sums
+int64_t gemm_skinny_splits(int64_t M, int64_t N, int64_t K, int64_t max_splits) {
+  return sglb::gemm_skinny_splits((int)M, (int)N, (int)K, (int)max_splits, num_sms());
+}
+int64_t gemm_skinny_norm_splits(int64_t K, int64_t s) { return sglb::gemm_skinny_norm_splits((int)K, (int)s); }
+void gemm_skinny(const at::Tensor& a, const at::Tensor& w, at::Tensor out, c10::optional<at::Tensor> bias, int64_t epilogue,
+                 int64_t splits) {
+  CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_BF16(out); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w); CHECK_LAST_CONTIG(out);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.size(1) == w.size(1));
+  const int M = (int)a.size(0), K = (int)a.size(1);
+  const int N = epilogue == 4 ? (int)w.size(0) / 2 : (int)w.size(0);
+  TORCH_CHECK(splits >= 1 && (splits == 1 ? out.dim() == 2 : (out.dim() == 3 && out.size(0) >= splits && out.is_contiguous())));
+  TORCH_CHECK(out.size(-1) == N && out.size(-2) == M, "gemm_skinny: bad output shape");
+  c10::cuda::CUDAGuard g(a.device());
+  sglb::gemm_bf16_skinny(a.data_ptr(), w.data_ptr(), out.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, M, N, K,
+                         (int)a.stride(0), (int)w.stride(0), (int)out.stride(-2), (int)epilogue, (int)splits,
+                         splits > 1 ? (long long)out.stride(0) : 0, cur_stream());
+  count();
+}
+void gemm_skinny_push(const at::Tensor& a, const at::Tensor& w, int64_t splits, const at::Tensor& peer_slot_ptrs,
+                      const at::Tensor& peer_flag_ptrs, int64_t rank, int64_t world, at::Tensor epoch, at::Tensor done) {
+  CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.size(1) == w.size(1) && !peer_slot_ptrs.is_cuda() && !peer_flag_ptrs.is_cuda());
+  c10::cuda::CUDAGuard g(a.device());
+  sglb::gemm_bf16_skinny_push(a.data_ptr(), w.data_ptr(), (int)a.size(0), (int)w.size(0), (int)a.size(1), (int)a.stride(0),
+                              (int)w.stride(0), (int)splits, peer_slot_ptrs.data_ptr<int64_t>(), peer_flag_ptrs.data_ptr<int64_t>(),
+                              (int)rank, (int)world, reinterpret_cast<const uint32_t*>(epoch.data_ptr<int>()),
+                              reinterpret_cast<uint32_t*>(done.data_ptr<int>()), cur_stream());
+  count();
+}
+// out = rmsnorm(residual += sum_s slabs[s]) — the consumer of a LOCAL split-K GEMM (no flags, stream order is enough)
+void slab_reduce_add_rmsnorm(const at::Tensor& slabs, c10::optional<at::Tensor> residual, const at::Tensor& w, at::Tensor out,
+                             double eps, bool gemma) {
+  CHECK_CUDA(out); CHECK_BF16(out); CHECK_BF16(w); CHECK_BF16(slabs);
+  TORCH_CHECK(slabs.dim() == 3 && slabs.is_contiguous() && out.is_contiguous() && out.dim() == 2);
+  TORCH_CHECK(slabs.size(1) == out.size(0) && slabs.size(2) == out.size(1) && slabs.size(0) <= 64, "slab_reduce: bad shapes");
+  c10::cuda::CUDAGuard g(out.device());
+  sglb::nvl_local_reduce_add_rmsnorm(slabs.data_ptr(), nullptr, residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(),
+                                     out.data_ptr(), (int)out.size(0), (int)out.size(1), 0, (int)slabs.size(0), (float)eps, gemma, nullptr,
+                                     nullptr, num_sms(), cur_stream());
   count();
 }
 
@@ -338,6 +382,13 @@ void moe_grouped_mlp_push(const at::Tensor& x, const at::Tensor& w13, const at::
 }  // namespace
 
 TORCH_LIBRARY(sglb, m) {
+  m.def("gemm_skinny_splits(int M, int N, int K, int max_splits) -> int", &gemm_skinny_splits);
+  m.def("gemm_skinny_norm_splits(int K, int s) -> int", &gemm_skinny_norm_splits);
+  m.def("gemm_skinny(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int splits) -> ()", &gemm_skinny);
+  m.def("gemm_skinny_push(Tensor a, Tensor w, int splits, Tensor peer_slot_ptrs, Tensor peer_flag_ptrs, int rank, int world, "
+        "Tensor(a!) epoch, Tensor(b!) done) -> ()", &gemm_skinny_push);
+  m.def("slab_reduce_add_rmsnorm(Tensor slabs, Tensor(a!)? residual, Tensor w, Tensor(b!) out, float eps, bool gemma) -> ()",
+        &slab_reduce_add_rmsnorm);
   m.def("per_token_group_quant_fp8(Tensor x, Tensor(a!) q, Tensor(b!) scales, int group, bool ue8m0) -> ()", &per_token_group_quant_fp8);
   m.def("gemm_fp8_block(Tensor xq, Tensor xs, Tensor wq, Tensor ws, Tensor(a!) out) -> ()", &gemm_fp8_block);
   m.def("moe_topk_softmax(Tensor logits, Tensor(a!) out_w, Tensor(b!) out_ids, bool renorm) -> ()", &moe_topk_softmax);
@@ -347,7 +398,7 @@ TORCH_LIBRARY(sglb, m) {
         "Tensor peer_flag_ptrs, int rank, int world, Tensor(a!) epoch, Tensor(b!) done) -> ()", &moe_grouped_mlp_push);
   m.def("gemm_push(Tensor a, Tensor w, Tensor peer_slot_ptrs, Tensor peer_flag_ptrs, int rank, int world, Tensor(a!) epoch, "
         "Tensor(b!) done, int bn) -> ()", &gemm_push);
-  m.def("nvl_local_reduce_add_rmsnorm(Tensor slot, int flags_ptr, Tensor(a!)? residual, Tensor w, Tensor(b!) out, int world, float eps, "
+  m.def("nvl_local_reduce_add_rmsnorm(Tensor slot, int flags_ptr, Tensor(a!)? residual, Tensor w, Tensor(b!) out, int world, int nslabs, float eps, "
         "bool gemma, Tensor(c!) epoch, Tensor(d!) done) -> ()", &nvl_local_reduce_add_rmsnorm);
   m.def("nvl_allreduce(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!) out, "
         "Tensor(b!) epoch, Tensor(c!) done, int channel, int algo) -> ()", &nvl_allreduce);
@@ -359,7 +410,7 @@ TORCH_LIBRARY(sglb, m) {
   m.def("rmsnorm(Tensor(a!) x, Tensor(b!)? residual, Tensor w, Tensor(c!) out, float eps, bool gemma) -> ()", &rmsnorm);
   m.def("act_and_mul(Tensor x, Tensor(a!) out, int act) -> ()", &act_and_mul);
   m.def("rope_kv_write(Tensor(a!) q, Tensor k, Tensor v, Tensor positions, Tensor cos_sin, Tensor(b!) k_cache, "
-        "Tensor(c!) v_cache, Tensor out_loc, bool neox, float k_scale, float v_scale) -> ()", &rope_kv_write);
+        "Tensor(c!) v_cache, Tensor out_loc, bool neox, float k_scale, float v_scale, int nslabs=1, int slab_stride=0) -> ()", &rope_kv_write);
   m.def("apply_pt_delta(Tensor(a!) page_table, Tensor rows, Tensor cols, Tensor vals, Tensor? n, int n_max) -> ()", &apply_pt_delta);
   m.def("embedding(Tensor weight, Tensor ids, Tensor? gather_idx, Tensor(a!) out, int vocab_start) -> ()", &embedding);
   m.def("gather_rows(Tensor x, Tensor idx, Tensor(a!) out) -> ()", &gather_rows);

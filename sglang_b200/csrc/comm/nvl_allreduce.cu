@@ -220,9 +220,11 @@ __global__ void __launch_bounds__(256) nvl_local_reduce_add_rmsnorm_kernel(const
                                                                            __nv_bfloat16* __restrict__ residual,
                                                                            const __nv_bfloat16* __restrict__ w,
                                                                            __nv_bfloat16* __restrict__ out, int T, int H, int world,
-                                                                           float eps, uint32_t* epoch_ptr, uint32_t* done_ctr, int gemma) {
-  const uint32_t epoch = epoch_begin(epoch_ptr);
-  if (threadIdx.x < world) {
+                                                                           int nslabs, float eps, uint32_t* epoch_ptr, uint32_t* done_ctr,
+                                                                           int gemma) {
+  // flags == nullptr: the slabs were produced by a LOCAL split-K GEMM on this stream (no cross-rank wait, no epoch)
+  const uint32_t epoch = epoch_ptr ? epoch_begin(epoch_ptr) : 0;
+  if (flags && threadIdx.x < world) {
     uint32_t spins = 0;
     while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
       if (++spins > (1u << 26)) {
@@ -244,9 +246,8 @@ __global__ void __launch_bounds__(256) nvl_local_reduce_add_rmsnorm_kernel(const
       if (vi < nvec) {
         float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const size_t off = (size_t)row * H + (size_t)vi * 8;
-#pragma unroll
-        for (int r = 0; r < NVL_MAX_RANKS; ++r)
-          if (r < world) acc_bf16x8(a, ld_peer128(slot + r * stride + off));   // written by peers: bypass stale L1 lines
+#pragma unroll 4
+        for (int r = 0; r < nslabs; ++r) acc_bf16x8(a, ld_peer128(slot + r * stride + off));   // written by peers: bypass stale L1 lines
         if (residual) {
           acc_bf16x8(a, ld128(residual + off));
           const U4 s = pack8(a);
@@ -279,16 +280,17 @@ __global__ void __launch_bounds__(256) nvl_local_reduce_add_rmsnorm_kernel(const
       }
     }
   }
-  epoch_end(epoch_ptr, done_ctr, epoch);
+  if (epoch_ptr) epoch_end(epoch_ptr, done_ctr, epoch);
 }
 
 void nvl_local_reduce_add_rmsnorm(const void* slot, uint32_t* flags, void* residual, const void* w, void* out, int T, int H, int world,
-                                  float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms, cudaStream_t stream) {
+                                  int nslabs, float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms,
+                                  cudaStream_t stream) {
   if (H % 8 || H > 256 * 8 * 8) throw std::runtime_error("sglb nvl reduce+norm: H must be a multiple of 8 and <= 16384");
   const int grid = max(1, min(T, num_sms * 4));
   const int nvec = H / 8;
   auto S = (const __nv_bfloat16*)slot; auto R = (__nv_bfloat16*)residual; auto W = (const __nv_bfloat16*)w; auto O = (__nv_bfloat16*)out;
-#define SGLB_LRN(MV) nvl_local_reduce_add_rmsnorm_kernel<MV><<<grid, 256, 0, stream>>>(S, flags, R, W, O, T, H, world, eps, epoch_ptr, done_ctr, gemma)
+#define SGLB_LRN(MV) nvl_local_reduce_add_rmsnorm_kernel<MV><<<grid, 256, 0, stream>>>(S, flags, R, W, O, T, H, world, nslabs, eps, epoch_ptr, done_ctr, gemma)
   if (nvec <= 256) SGLB_LRN(1); else if (nvec <= 512) SGLB_LRN(2); else if (nvec <= 1024) SGLB_LRN(4); else SGLB_LRN(8);
 #undef SGLB_LRN
   SGLB_CUDA_CHECK(cudaGetLastError());

@@ -12,7 +12,8 @@ void rmsnorm(void* x, void* residual, const void* w, void* out, int T, int H, in
 void act_and_mul(const void* x, void* out, int T, int I, int x_stride, int act, cudaStream_t stream);
 void rope_kv_write(void* q, const void* k, const void* v, const int* positions, const float* cos_sin, void* k_cache,
                    void* v_cache, const int* out_loc, int T, int Hq, int Hkv, int D, int rot, int q_stride, int k_stride,
-                   int v_stride, bool neox, bool fp8_cache, float k_scale, float v_scale, cudaStream_t stream);
+                   int v_stride, bool neox, bool fp8_cache, float k_scale, float v_scale, int nslabs, long long slab_stride,
+                   cudaStream_t stream);
 void apply_pt_delta(int* page_table, int stride, const int* rows, const int* cols, const int* vals, const int* n_ptr,
                     int n_max, cudaStream_t stream);
 void embedding(const void* weight, const int* ids, const int* gather_idx, void* out, int T, int H, int vocab, int vocab_start,
@@ -36,6 +37,15 @@ int gemm_pick_bn(int M, int N, int K, int num_sms);
 void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* row_scale, int M_cap, int n_out, int K, int lda,
                           int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
                           cudaStream_t stream);
+
+// gemm_skinny.cu (decode shapes: swap-AB, split-K slabs, transposed epilogue, optional NVLink push)
+int gemm_skinny_splits(int M, int N, int K, int max_splits, int num_sms);
+int gemm_skinny_norm_splits(int K, int s);
+void gemm_bf16_skinny(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc,
+                      int epilogue, int splits, long long slab_stride, cudaStream_t stream);
+void gemm_bf16_skinny_push(const void* A, const void* W, int M, int N, int K, int lda, int ldw, int splits, const int64_t* peer_slot_ptrs,
+                           const int64_t* peer_flag_ptrs, int rank, int world, const uint32_t* epoch_ptr, uint32_t* done_ctr,
+                           cudaStream_t stream);
 
 // gemm_fp8.cu
 void gemm_fp8_block(const void* A, const float* xs, const void* W, const float* ws, void* C, int M, int N, int K, int lda, int ldw,
@@ -78,6 +88,7 @@ void gemm_bf16_tc_push(const void* A, const void* W, int M, int N, int K, int ld
                        const int64_t* peer_flag_ptrs, int rank, int world, const uint32_t* epoch_ptr, uint32_t* done_ctr, int bn,
                        int num_sms, cudaStream_t stream);
 void nvl_local_reduce_add_rmsnorm(const void* slot, uint32_t* flags, void* residual, const void* w, void* out, int T, int H, int world,
-                                  float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms, cudaStream_t stream);
+                                  int nslabs, float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr, int num_sms,
+                                  cudaStream_t stream);
 
 }  // namespace sglb

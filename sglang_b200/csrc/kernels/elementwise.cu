@@ -138,13 +138,24 @@ __device__ __forceinline__ void store_cache2<__nv_fp8_e4m3>(__nv_fp8_e4m3* dst, 
   dst[0] = x; dst[1] = y;
 }
 
+// bf16 pair load that also folds split-K partial slabs (gemm_skinny.cu): value = sum_s p[s * slab_stride]
+__device__ __forceinline__ void ld2_slabs(const __nv_bfloat16* p, int nslabs, long long slab_stride, float& a, float& b) {
+  uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  a = bf16_lo(w); b = bf16_hi(w);
+  for (int s = 1; s < nslabs; ++s) {
+    w = *reinterpret_cast<const uint32_t*>(p + (size_t)s * slab_stride);
+    a += bf16_lo(w); b += bf16_hi(w);
+  }
+}
+
 template <typename CacheT, bool NEOX>
 __global__ void __launch_bounds__(256) rope_kv_write_kernel(__nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                             const __nv_bfloat16* __restrict__ v, const int* __restrict__ positions,
                                                             const float* __restrict__ cos_sin, CacheT* __restrict__ k_cache,
                                                             CacheT* __restrict__ v_cache, const int* __restrict__ out_loc, int T,
                                                             int Hq, int Hkv, int D, int rot, int q_stride, int k_stride,
-                                                            int v_stride, float k_inv_scale, float v_inv_scale) {
+                                                            int v_stride, float k_inv_scale, float v_inv_scale, int nslabs,
+                                                            long long slab_stride) {
   const int heads = Hq + 2 * Hkv;
   const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gw >= (long)T * heads) return;
@@ -162,9 +173,8 @@ __global__ void __launch_bounds__(256) rope_kv_write_kernel(__nv_bfloat16* __res
     for (int i = lane * 2; i < half; i += 64) {
       float x1a, x1b, x2a, x2b, c0, c1, s0, s1;
       if (NEOX) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(src + i);
-        const uint32_t b = *reinterpret_cast<const uint32_t*>(src + half + i);
-        x1a = bf16_lo(a); x1b = bf16_hi(a); x2a = bf16_lo(b); x2b = bf16_hi(b);
+        ld2_slabs(src + i, nslabs, slab_stride, x1a, x1b);
+        ld2_slabs(src + half + i, nslabs, slab_stride, x2a, x2b);
         c0 = cs[i]; c1 = cs[i + 1]; s0 = cs[half + i]; s1 = cs[half + i + 1];
         const float o1a = x1a * c0 - x2a * s0, o1b = x1b * c1 - x2b * s1;
         const float o2a = x2a * c0 + x1a * s0, o2b = x2b * c1 + x1b * s1;
@@ -177,9 +187,8 @@ __global__ void __launch_bounds__(256) rope_kv_write_kernel(__nv_bfloat16* __res
         }
       } else {
         // gptj / interleaved: pairs (2j, 2j+1); this lane handles j = i, i+1
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * i);
-        const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 2 * i + 2);
-        x1a = bf16_lo(a); x2a = bf16_hi(a); x1b = bf16_lo(b); x2b = bf16_hi(b);
+        ld2_slabs(src + 2 * i, nslabs, slab_stride, x1a, x2a);
+        ld2_slabs(src + 2 * i + 2, nslabs, slab_stride, x1b, x2b);
         c0 = cs[i]; c1 = cs[i + 1]; s0 = cs[half + i]; s1 = cs[half + i + 1];
         const float oa0 = x1a * c0 - x2a * s0, oa1 = x2a * c0 + x1a * s0;
         const float ob0 = x1b * c1 - x2b * s1, ob1 = x2b * c1 + x1b * s1;
@@ -195,8 +204,15 @@ __global__ void __launch_bounds__(256) rope_kv_write_kernel(__nv_bfloat16* __res
     // pass-through part (rot < D)
     if (!is_q) {
       for (int i = rot + lane * 2; i < D; i += 64) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(src + i);
-        store_cache2<CacheT>(cdst + i, bf16_lo(a), bf16_hi(a), k_inv_scale);
+        float a, b;
+        ld2_slabs(src + i, nslabs, slab_stride, a, b);
+        store_cache2<CacheT>(cdst + i, a, b, k_inv_scale);
+      }
+    } else if (nslabs > 1) {
+      for (int i = rot + lane * 2; i < D; i += 64) {
+        float a, b;
+        ld2_slabs(src + i, nslabs, slab_stride, a, b);
+        *reinterpret_cast<uint32_t*>(qdst + i) = pack_bf16(a, b);
       }
     }
   } else {
@@ -204,15 +220,17 @@ __global__ void __launch_bounds__(256) rope_kv_write_kernel(__nv_bfloat16* __res
     const __nv_bfloat16* src = v + (size_t)t * v_stride + hv * D;
     CacheT* cdst = v_cache + ((size_t)out_loc[t] * Hkv + hv) * D;
     for (int i = lane * 2; i < D; i += 64) {
-      const uint32_t a = *reinterpret_cast<const uint32_t*>(src + i);
-      store_cache2<CacheT>(cdst + i, bf16_lo(a), bf16_hi(a), v_inv_scale);
+      float a, b;
+      ld2_slabs(src + i, nslabs, slab_stride, a, b);
+      store_cache2<CacheT>(cdst + i, a, b, v_inv_scale);
     }
   }
 }
 
 void rope_kv_write(void* q, const void* k, const void* v, const int* positions, const float* cos_sin, void* k_cache,
                    void* v_cache, const int* out_loc, int T, int Hq, int Hkv, int D, int rot, int q_stride, int k_stride,
-                   int v_stride, bool neox, bool fp8_cache, float k_scale, float v_scale, cudaStream_t stream) {
+                   int v_stride, bool neox, bool fp8_cache, float k_scale, float v_scale, int nslabs, long long slab_stride,
+                   cudaStream_t stream) {
   if (T <= 0) return;
   if (rot % 4 || D % 2) throw std::runtime_error("sglb rope: rotary_dim must be a multiple of 4");
   const long warps = (long)T * (Hq + 2 * Hkv);
@@ -220,7 +238,8 @@ void rope_kv_write(void* q, const void* k, const void* v, const int* positions, 
   auto Q = (__nv_bfloat16*)q; auto K = (const __nv_bfloat16*)k; auto V = (const __nv_bfloat16*)v;
 #define RL(CT, NX)                                                                                                  \
   rope_kv_write_kernel<CT, NX><<<grid, 256, 0, stream>>>(Q, K, V, positions, cos_sin, (CT*)k_cache, (CT*)v_cache, out_loc, T, \
-                                                         Hq, Hkv, D, rot, q_stride, k_stride, v_stride, 1.f / k_scale, 1.f / v_scale)
+                                                         Hq, Hkv, D, rot, q_stride, k_stride, v_stride, 1.f / k_scale, 1.f / v_scale, \
+                                                         nslabs, slab_stride)
   if (fp8_cache) { if (neox) RL(__nv_fp8_e4m3, true); else RL(__nv_fp8_e4m3, false); }
   else { if (neox) RL(__nv_bfloat16, true); else RL(__nv_bfloat16, false); }
 #undef RL

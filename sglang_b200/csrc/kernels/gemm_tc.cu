@@ -271,6 +271,7 @@ static void launch_gemm(const void* A, const void* W, void* C, const void* bias,
   using Cfg = GemmCfg<BN>;
   constexpr bool SPLIT = (EPI == EPI_SILU_SPLIT);
   constexpr int BN_OUT = SPLIT ? BN / 2 : BN;
+  if (SPLIT && BN < 64) throw std::runtime_error("sglb gemm: split-silu epilogue needs BN >= 64");
   const int w_rows = ex.w_rows > 0 ? ex.w_rows : N;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sAs[1] = {(uint64_t)lda * 2};
   uint32_t bA[2] = {GEMM_BK, GEMM_BM};
@@ -339,15 +340,15 @@ void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M
     case EPI_SILU_SPLIT: {
       // W is [2*n_half, K] = [gate ; up]; C is [M, n_half].  N counts W rows on entry.
       const int n_half = N / 2;
-      if (bn <= 0 || n_half % (bn / 2)) {
+      if (bn < 64 || n_half % (bn / 2)) {      // the epilogue walks 32-column chunks of each half: BN/2 >= 32
         bn = 0;
         const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-        for (int cand : {256, 128, 64, 32}) {
+        for (int cand : {256, 128, 64}) {
           if (n_half % (cand / 2)) continue;
           bn = cand;
           if ((long long)m_tiles * (n_half / (cand / 2)) >= num_sms) break;
         }
-        if (!bn) throw std::runtime_error("sglb gemm: split-silu needs intermediate size % 16 == 0");
+        if (!bn) throw std::runtime_error("sglb gemm: split-silu needs intermediate size % 32 == 0");
       }
       GemmExtra ex; ex.w_rows = N; ex.n_half = n_half;
       dispatch_bn<EPI_SILU_SPLIT>(bn, A, W, C, bias, M, n_half, K, lda, ldw, ldc, num_sms, stream, GemmPush{}, ex);
@@ -364,13 +365,13 @@ void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* ro
                           int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
                           cudaStream_t stream) {
   if (M_cap <= 0 || n_out <= 0) return;
-  if (K % 8 || n_out % 16 || lda % 8) throw std::runtime_error("sglb grouped gemm: K % 8, n_out % 16, lda % 8 required");
+  if (K % 8 || n_out % 32 || lda % 8) throw std::runtime_error("sglb grouped gemm: K % 8, n_out % 32, lda % 8 required");
   GemmExtra ex; ex.num_experts = num_experts; ex.tile_expert = tile_expert; ex.num_m_tiles = num_m_tiles;
   const int m_tiles = M_cap / GEMM_BM;
   int bn = 0;
   if (split_silu) {
     ex.w_rows = 2 * n_out; ex.n_half = n_out;
-    for (int cand : {256, 128, 64, 32}) {
+    for (int cand : {256, 128, 64}) {
       if (n_out % (cand / 2)) continue;
       bn = cand;
       if ((long long)m_tiles * (n_out / (cand / 2)) >= 2LL * num_sms) break;

@@ -27,7 +27,7 @@ class RMSNorm(nn.Module):
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
         """residual given: (in place) residual += x; x = norm(residual); returns (x, residual)"""
-        if hasattr(x, "nvl"):   # PendingAllReduce: cross-rank sum + residual add + norm in ONE kernel
+        if hasattr(x, "consume_norm"):   # PendingAllReduce / PendingSlabs: (cross-rank | split-K) sum + residual add + norm in ONE kernel
             out = torch.empty(x.T, x.H, dtype=self.weight.dtype, device=self.weight.device)
             x.consume_norm(residual, self.weight, out, self.eps, self.gemma)
             return out, residual
@@ -61,8 +61,10 @@ class RadixAttention(nn.Module):
         self.window = sliding_window
         self.logit_cap = logit_cap
 
-    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
-        """q [T, Hq*D], k/v [T, Hkv*D] (views into the fused QKV output)"""
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fb: ForwardBatch, nslabs: int = 1,
+                slab_stride: int = 0) -> torch.Tensor:
+        """q [T, Hq*D], k/v [T, Hkv*D] (views into the fused QKV output; with ``nslabs > 1`` into slab 0 of a split-K QKV GEMM
+        whose partials the RoPE kernel sums)"""
         T = q.shape[0]
         q3 = q.view(T, self.num_heads, self.head_dim)
         k3 = k.view(T, self.num_kv_heads, self.head_dim)
@@ -71,8 +73,9 @@ class RadixAttention(nn.Module):
         kc, vc = pool.k(self.layer_id), pool.v(self.layer_id)
         if self.rope is not None:
             ops.rope_kv_write(q3, k3, v3, fb.positions, self.rope.cos_sin, kc, vc, fb.out_cache_loc, self.rope.is_neox,
-                              pool.k_scale, pool.v_scale)
+                              pool.k_scale, pool.v_scale, nslabs, slab_stride)
         else:
+            assert nslabs == 1
             loc = fb.out_cache_loc.long()
             kc[loc] = k3.to(kc.dtype)
             vc[loc] = v3.to(vc.dtype)

@@ -22,15 +22,15 @@ from .quantization import QuantMethod, UnquantizedMethod
 
 class PendingAllReduce:
     """Handle for partial sums that sit in this call's NVL arena slot on every rank (not yet reduced)."""
-    __slots__ = ("nvl", "off", "T", "H", "mode")
+    __slots__ = ("nvl", "off", "T", "H", "mode", "splits")
 
-    def __init__(self, nvl, off: int, T: int, H: int, mode: str = "pull"):
-        self.nvl, self.off, self.T, self.H, self.mode = nvl, off, T, H, mode
+    def __init__(self, nvl, off: int, T: int, H: int, mode: str = "pull", splits: int = 1):
+        self.nvl, self.off, self.T, self.H, self.mode, self.splits = nvl, off, T, H, mode, splits
 
     def consume_norm(self, residual, weight: torch.Tensor, out: torch.Tensor, eps: float, gemma: bool) -> None:
         """cross-rank sum + residual add + RMSNorm in one kernel"""
         if self.mode == "push":     # partials of all ranks were pushed into OUR arena by the peers' GEMM epilogues
-            self.nvl.push_reduce_add_rmsnorm(self.off, self.T, self.H, residual, weight, out, eps, gemma)
+            self.nvl.push_reduce_add_rmsnorm(self.off, self.T, self.H, residual, weight, out, eps, gemma, self.splits)
         else:                       # partials sit in each producer's arena: pull them over NVLink
             self.nvl.fused_allreduce_add_rmsnorm(self.off, residual, weight, out, eps, gemma)
 
@@ -40,6 +40,26 @@ class PendingAllReduce:
         assert self.mode == "pull", "push-mode partials are always consumed by an RMSNorm (push is disabled under PP)"
         self.nvl.allreduce_from_slot(self.off, out)
         return out
+
+
+class PendingSlabs:
+    """split-K partial products [splits, T, H] of a LOCAL decode-shape GEMM (ops.gemm_skinny_slabs); the next RMSNorm sums
+    the slabs, adds the residual and normalises in one kernel."""
+    __slots__ = ("slabs", "T", "H")
+
+    def __init__(self, slabs: torch.Tensor):
+        self.slabs, self.T, self.H = slabs, slabs.shape[1], slabs.shape[2]
+
+    def consume_norm(self, residual, weight: torch.Tensor, out: torch.Tensor, eps: float, gemma: bool) -> None:
+        torch.ops.sglb.slab_reduce_add_rmsnorm(self.slabs, residual, weight, out, eps, gemma)
+
+    def resolve(self) -> torch.Tensor:
+        return self.slabs[0] if self.slabs.shape[0] == 1 else self.slabs.float().sum(0).to(self.slabs.dtype)
+
+
+def _skinny_allowed(layer, x: torch.Tensor) -> bool:
+    return (getattr(layer, "fast_path_ok", True) and isinstance(layer.quant, UnquantizedMethod) and ops.gemm_impl() != "lib"
+            and ops.skinny_ok(x, layer.weight))
 
 
 def _divide(a: int, b: int) -> int:
@@ -170,18 +190,24 @@ class RowParallelLinear(LinearBase):
         bias = self.bias if (self.bias is not None and self.tp.rank == 0) else None   # added once: the reduction stays a pure sum
         tp = self.tp
         if tp.world_size == 1:
+            if defer_reduce and bias is None and _skinny_allowed(self, x):
+                return PendingSlabs(ops.gemm_skinny_slabs(x, self.weight))      # reduced inside the next RMSNorm kernel
             return self.apply(x, bias)
         nvl = tp.nvl
         T = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
         nbytes = T * self.out_features * 2
         if (defer_reduce and self.reduce_results and nvl is not None and x.dim() == 2 and nbytes <= self.FUSED_AR_MAX_BYTES
-                and isinstance(self.quant, UnquantizedMethod) and bias is None and x.dtype == torch.bfloat16):
+                and isinstance(self.quant, UnquantizedMethod) and bias is None and x.dtype == torch.bfloat16
+                and getattr(self, "fast_path_ok", True)):
             from ..environ import envs
             from ..parallel.nvl_comm import CH_FUSED_NORM
             from ..parallel.parallel_state import get_pp_group
 
             if envs.SGLB_FUSED_AR.get() == "push" and get_pp_group().world_size == 1 and x.stride(0) % 8 == 0:
                 # ONE kernel: tcgen05 GEMM whose epilogue pushes each tile into every peer's arena (+ flag publication)
+                if _skinny_allowed(self, x):      # decode shape: swap-AB + split-K, slabs [world*splits] summed by the consumer
+                    off, splits = nvl.gemm_push_skinny(x, self.weight)
+                    return PendingAllReduce(nvl, off, T, self.out_features, "push", splits)
                 off = nvl.gemm_push(x, self.weight)
                 return PendingAllReduce(nvl, off, T, self.out_features, "push")
             off, view = nvl.stage(CH_FUSED_NORM, (T, self.out_features))

@@ -166,3 +166,4 @@ def _install(mod: Any, layer_idx: int, mod_name: str) -> None:
         return y
 
     mod.apply = apply_with_lora
+    mod.fast_path_ok = False     # fused GEMM paths bypass .apply(); keep them off for adapter-wrapped layers

@@ -16,7 +16,7 @@ from .. import ops
 from ..configs.model_config import ModelConfig
 from ..layers.common import RadixAttention, RMSNorm, RotaryEmbedding, get_act_and_mul
 from ..layers.linear import (MergedColumnParallelLinear, ParallelLMHead, QKVParallelLinear, RowParallelLinear,
-                             VocabParallelEmbedding)
+                             VocabParallelEmbedding, _skinny_allowed)
 from ..layers.quantization import get_quant_method
 from ..model_executor.forward_batch import ForwardBatch
 from ..parallel.parallel_state import get_pp_group, get_tp_group
@@ -38,9 +38,15 @@ class LlamaMLP(nn.Module):
         self.down_proj = RowParallelLinear(cfg.intermediate_size, cfg.hidden_size, cfg.mlp_bias, True, dtype, quant,
                                            prefix + ".down_proj")
         self.act = get_act_and_mul(cfg.hidden_act)
+        self.fuse_silu = cfg.hidden_act == "silu" and not cfg.mlp_bias
 
     def forward(self, x):
-        return self.down_proj(self.act(self.gate_up_proj(x)), defer_reduce=True)
+        if self.fuse_silu and x.dim() == 2 and _skinny_allowed(self.gate_up_proj, x):
+            # decode shapes: ONE tcgen05 kernel for gate_up_proj + SiLU*mul ([gate; up] rows paired inside each tile)
+            h = ops.gemm_skinny(x, self.gate_up_proj.weight, silu_split=True)
+        else:
+            h = self.act(self.gate_up_proj(x))
+        return self.down_proj(h, defer_reduce=True)
 
 
 class LlamaAttention(nn.Module):
@@ -61,6 +67,12 @@ class LlamaAttention(nn.Module):
                                    rope=rope, sliding_window=window, logit_cap=cfg.attn_logit_softcapping)
 
     def forward(self, x: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
+        if not self.qk_norm and self.attn.rope is not None and x.dim() == 2 and _skinny_allowed(self.qkv_proj, x):
+            # decode shapes: split-K QKV GEMM; the RoPE + KV-write kernel folds the partial slabs while it reads q/k/v
+            slabs = ops.gemm_skinny_slabs(x, self.qkv_proj.weight, self.qkv_proj.bias)
+            q, k, v = slabs[0].split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+            o = self.attn(q, k, v, fb, nslabs=slabs.shape[0], slab_stride=slabs.stride(0))
+            return self.o_proj(o, defer_reduce=True)
         qkv = self.qkv_proj(x)
         q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
         if self.qk_norm:

@@ -105,10 +105,14 @@ def gelu_and_mul(x: torch.Tensor, approximate: str = "none") -> torch.Tensor:
 
 # ------------------------------------------------------------------ rope + KV write
 def rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox: bool = True,
-                  k_scale: float = 1.0, v_scale: float = 1.0) -> None:
+                  k_scale: float = 1.0, v_scale: float = 1.0, nslabs: int = 1, slab_stride: int = 0) -> None:
+    """``nslabs > 1``: q/k/v are slab 0 of a split-K QKV GEMM; the kernel sums the slabs while it rotates (q is written back
+    into slab 0, k/v go to the cache)."""
     if _use_native(q) and q.dtype == torch.bfloat16:
-        torch.ops.sglb.rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox, k_scale, v_scale)
+        torch.ops.sglb.rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox, k_scale, v_scale,
+                                     nslabs, slab_stride)
         return
+    assert nslabs == 1
     torch_ref.rope_kv_write(q, k, v, positions, cos_sin, k_cache, v_cache, out_cache_loc, is_neox, k_scale, v_scale)
 
 
@@ -195,6 +199,49 @@ def gemm_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     if out is None:
         out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
     torch.ops.sglb.gemm(x, w, out, bias, epilogue, bn)
+    return out
+
+
+# ------------------------------------------------------------------ decode-shape ("skinny") GEMM: swap-AB + split-K slabs
+SKINNY_MAX_M = 256
+
+
+def skinny_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """decode-shape policy: tokens <= 256, bf16, 16-byte aligned rows (``SGLB_SKINNY=0`` disables, ``1`` forces the check only)"""
+    mode = envs.SGLB_SKINNY.get()
+    return (mode != "off" and x.is_cuda and x.dim() == 2 and 0 < x.shape[0] <= SKINNY_MAX_M and x.dtype == torch.bfloat16
+            and w.dtype == torch.bfloat16 and w.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.shape[1] % 8 == 0
+            and w.shape[0] % 8 == 0 and _use_native(x))
+
+
+def gemm_skinny(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, silu_split: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[T<=256,K] @ w[N,K]^T in one pass (no K split).  ``silu_split``: w = [gate; up] -> silu(x@gate^T) * (x@up^T)"""
+    n_out = w.shape[0] // 2 if silu_split else w.shape[0]
+    if out is None:
+        out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
+    torch.ops.sglb.gemm_skinny(x, w, out, bias, EPI_SILU_SPLIT if silu_split else (EPI_BIAS if bias is not None else EPI_NONE), 1)
+    return out
+
+
+def gemm_skinny_slabs(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, max_splits: int = 8) -> torch.Tensor:
+    """split-K partials [splits, T, N] (bf16); the consumer sums the slabs (``slab_reduce_add_rmsnorm``, ``rope_kv_write``)"""
+    T, K = x.shape
+    N = w.shape[0]
+    s = int(torch.ops.sglb.gemm_skinny_splits(T, N, K, max_splits))
+    slabs = torch.empty(s, T, N, dtype=x.dtype, device=x.device)
+    if s == 1:
+        torch.ops.sglb.gemm_skinny(x, w, slabs[0], bias, EPI_BIAS if bias is not None else EPI_NONE, 1)
+    else:
+        torch.ops.sglb.gemm_skinny(x, w, slabs, bias, EPI_BIAS if bias is not None else EPI_NONE, s)
+    return slabs
+
+
+def slab_reduce_add_rmsnorm(slabs: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, eps: float,
+                            gemma: bool = False) -> torch.Tensor:
+    """out = rmsnorm(residual += sum_s slabs[s]) * w    (residual updated in place when given)"""
+    out = torch.empty(slabs.shape[1], slabs.shape[2], dtype=slabs.dtype, device=slabs.device)
+    torch.ops.sglb.slab_reduce_add_rmsnorm(slabs, residual, weight, out, eps, gemma)
     return out
 
 

@@ -167,10 +167,28 @@ class NvlComm:
         self.calls += 1
         return off
 
-    def push_reduce_add_rmsnorm(self, off: int, T: int, H: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
-                                eps: float, gemma: bool = False) -> None:
+    def gemm_push_skinny(self, x: torch.Tensor, w: torch.Tensor, max_splits: int = 4):
+        """decode-shape variant of ``gemm_push`` (csrc/kernels/gemm_skinny.cu): W streams as the UMMA M operand, K is split so
+        ~one CTA per SM is busy, and every (rank, split) partial lands as slab [rank*splits + split] in every peer's arena.
+        Returns (slot offset, splits) for ``push_reduce_add_rmsnorm``."""
+        T, K = x.shape
+        N = w.shape[0]
+        splits = int(torch.ops.sglb.gemm_skinny_splits(T, N, K, max_splits))
+        while splits > 1 and self.world * splits * T * N * 2 > self.slot_bytes:
+            splits = int(torch.ops.sglb.gemm_skinny_norm_splits(K, splits - 1))
+        assert self.world * splits * T * N * 2 <= self.slot_bytes, "NVL arena slot too small for this GEMM output"
         ch = CH_GEMM
-        slot = self.slot_view(off, (self.world, T, H))
+        off = self._slot(ch)
+        torch.ops.sglb.gemm_skinny_push(x, w, splits, self.buf_ptrs + off, self.flag_ptrs + ch * MAX_RANKS * 4, self.rank, self.world,
+                                        self.epochs[ch:ch + 1], self.done[ch, 1:])
+        self.calls += 1
+        return off, splits
+
+    def push_reduce_add_rmsnorm(self, off: int, T: int, H: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
+                                eps: float, gemma: bool = False, splits: int = 1) -> None:
+        ch = CH_GEMM
+        nslabs = self.world * splits
+        slot = self.slot_view(off, (nslabs, T, H))
         torch.ops.sglb.nvl_local_reduce_add_rmsnorm(slot, int(self.flag_ptrs[self.rank]) + ch * MAX_RANKS * 4, residual, weight, out,
-                                                    self.world, float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch])
+                                                    self.world, nslabs, float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch])
         self.calls += 1

@@ -177,7 +177,7 @@ def case_gemm_tc():
 def case_gemm_split_silu():
     """un-interleaved [gate;up] weights, silu(g)*u fused in the tcgen05 epilogue (EPI_SILU_SPLIT)"""
     torch.manual_seed(1)
-    for (M, I, K, bn) in [(50, 1024, 512, 0), (300, 1792, 4096, 0), (7, 14336, 4096, 0), (1000, 2048, 1024, 256), (64, 1040, 256, 0)]:
+    for (M, I, K, bn) in [(50, 1024, 512, 0), (300, 1792, 4096, 0), (7, 14336, 4096, 0), (1000, 2048, 1024, 256), (64, 1056, 256, 0)]:
         gate = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
         up = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
         w = torch.cat([gate, up], 0).contiguous()
@@ -252,6 +252,67 @@ def case_fp8():
             full = x.float() @ w.t()
             rel = ((out.float() - full).norm() / full.norm()).item()
             assert rel < 0.06, f"fp8 gemm {M}x{N}x{K}: relative error vs unquantised {rel:.3f}"
+
+
+def case_gemm_skinny():
+    """decode-shape swap-AB GEMM: plain / bias / split-K slabs (+ fused consumers) / fused split-SiLU"""
+    torch.manual_seed(4)
+    for (M, N, K) in [(1, 4096, 4096), (16, 6144, 4096), (37, 4096, 14336), (64, 28672, 4096), (100, 1024, 512), (128, 4096, 4096),
+                      (200, 6144, 4096), (256, 4096, 14336), (256, 2048, 7168), (5, 128256, 512), (48, 1000, 264)]:
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) * 0.5).to(torch.bfloat16)
+        ref = a.float() @ w.float().t()
+        out = ops.gemm_skinny(a, w)
+        torch.cuda.synchronize()
+        _close(out, ref, 0.5 if K > 4096 else 0.25, 2e-2, f"skinny {M}x{N}x{K}")
+        slabs = ops.gemm_skinny_slabs(a, w)
+        torch.cuda.synchronize()
+        _close(slabs.float().sum(0), ref, 0.6 if K > 4096 else 0.3, 2e-2, f"skinny slabs({slabs.shape[0]}) {M}x{N}x{K}")
+    # bias + strided A
+    a_big = (torch.randn(70, 3 * 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    a = a_big[:, 1024:2048]
+    w = (torch.randn(512, 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    b = torch.randn(512, device=DEV).to(torch.bfloat16)
+    _close(ops.gemm_skinny(a, w, bias=b), a.float() @ w.float().t() + b.float(), 0.25, 2e-2, "skinny bias strided")
+    sl = ops.gemm_skinny_slabs(a, w, bias=b)
+    _close(sl.float().sum(0), a.float() @ w.float().t() + b.float(), 0.3, 2e-2, "skinny slabs bias")
+    # fused SiLU*mul on [gate; up]
+    for (M, I, K) in [(50, 1024, 512), (256, 14336, 4096), (7, 1792, 4096), (33, 1000, 256)]:
+        gate = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        up = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        out = ops.gemm_skinny(a, torch.cat([gate, up], 0).contiguous(), silu_split=True)
+        ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+        _close(out, ref, 0.1, 3e-2, f"skinny split-silu {M}x{I}x{K}")
+    # consumer 1: slabs -> residual add + RMSNorm
+    T, H, K = 40, 4096, 14336
+    a = (torch.randn(T, K, device=DEV) * 0.3).to(torch.bfloat16); w = (torch.randn(H, K, device=DEV) * 0.02).to(torch.bfloat16)
+    resid = (torch.randn(T, H, device=DEV) * 0.3).to(torch.bfloat16); nw = torch.randn(H, device=DEV).to(torch.bfloat16)
+    slabs = ops.gemm_skinny_slabs(a, w)
+    assert slabs.shape[0] > 1
+    r2 = resid.clone()
+    out = ops.slab_reduce_add_rmsnorm(slabs, r2, nw, 1e-5)
+    x_ref = (a.float() @ w.float().t()).to(torch.bfloat16); r_ref = resid.clone()
+    torch_ref.fused_add_rmsnorm(x_ref, r_ref, nw, 1e-5)
+    _close(r2, r_ref, 0.06, 2e-2, "slab reduce residual"); _close(out, x_ref, 0.15, 3e-2, "slab reduce norm")
+    # consumer 2: slabs -> RoPE + KV write (q rotated in slab 0, k/v summed into the cache)
+    T, Hq, Hkv, D, ps = 9, 32, 8, 128, 32
+    N = (Hq + 2 * Hkv) * D
+    x = (torch.randn(T, 4096, device=DEV) * 0.3).to(torch.bfloat16); wq = (torch.randn(N, 4096, device=DEV) * 0.03).to(torch.bfloat16)
+    slabs = ops.gemm_skinny_slabs(x, wq)
+    assert slabs.shape[0] > 1
+    full = slabs.float().sum(0).to(torch.bfloat16)
+    pos = torch.arange(5, 5 + T, dtype=torch.int32, device=DEV); loc = torch.arange(3, 3 + T, dtype=torch.int32, device=DEV)
+    cs = torch_ref.build_cos_sin_cache(D, 4096, 10000.0, None, D).to(DEV)
+    kc = torch.zeros(64, Hkv, D, device=DEV, dtype=torch.bfloat16); vc = torch.zeros_like(kc)
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(kc)
+    q, k, v = slabs[0].split([Hq * D, Hkv * D, Hkv * D], -1)
+    ops.rope_kv_write(q.view(T, Hq, D), k.view(T, Hkv, D), v.view(T, Hkv, D), pos, cs, kc, vc, loc, True, 1.0, 1.0, slabs.shape[0], slabs.stride(0))
+    qf, kf, vf = full.clone().split([Hq * D, Hkv * D, Hkv * D], -1)
+    qf = qf.contiguous().view(T, Hq, D)
+    torch_ref.rope_kv_write(qf, kf.contiguous().view(T, Hkv, D), vf.contiguous().view(T, Hkv, D), pos, cs, kc2, vc2, loc, True, 1.0, 1.0)
+    torch.cuda.synchronize()
+    _close(q.reshape(T, Hq, D), qf, 0.05, 2e-2, "slab rope q"); _close(kc, kc2, 0.05, 2e-2, "slab rope k"); _close(vc, vc2, 0.05, 2e-2, "slab rope v")
 
 
 def case_sampling():
