@@ -115,14 +115,23 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
   const int B = (int)req_slots.size(0);
   const bool fp8 = k_cache.scalar_type() == at::kFloat8_e4m3fn;
   c10::cuda::CUDAGuard g(q.device());
-  if (impl == 0) {
+  if (impl == 0 || impl == 2) {
     TORCH_CHECK(!fp8, "tcgen05 attention: fp8 KV cache not yet supported (use impl=1)");
     if (num_splits > 1) TORCH_CHECK(part_o.has_value() && part_lse.has_value(), "split-KV needs workspaces");
+    // impl 2: persistent CTAs + atomic work counter (one zero-initialised [next, done] pair per device, reset by the kernel)
+    static at::Tensor sched[16];
+    int* sched_ptr = nullptr;
+    if (impl == 2) {
+      const int di = q.get_device();
+      TORCH_CHECK(di >= 0 && di < 16);
+      if (!sched[di].defined()) sched[di] = at::zeros({2}, q.options().dtype(at::kInt));
+      sched_ptr = sched[di].data_ptr<int>();
+    }
     sglb::attn_fwd_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),
                       opt_mptr<float>(part_o), opt_mptr<float>(part_lse), page_table.data_ptr<int>(),
                       (int)page_table.stride(0), req_slots.data_ptr<int>(), seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), B, T,
                       (int)q.stride(0), (int)max_q_len, Hq, Hkv, D, (int)k_cache.size(0), (int)page_size, (int)num_splits,
-                      (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, cur_stream());
+                      (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, sched_ptr, num_sms(), cur_stream());
     count(num_splits > 1 ? 2 : 1);
   } else {
     sglb::attn_fwd_simt(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),

@@ -254,6 +254,9 @@ def create_app(engine: Any):
         res = await _ctl(engine.rerank, r.query, r.documents)
         return res[: r.top_n] if r.top_n else res
 
+    from .adapters import install_adapters
+
+    install_adapters(app, engine, serving)
     return app
 
 

@@ -82,6 +82,7 @@ class _Envs:
     SGLB_FORCE_TORCH_OPS = EnvBool("SGLB_FORCE_TORCH_OPS", False, "debug: route every op through the fp32 torch reference")
     SGLB_ATTN_IMPL = EnvStr("SGLB_ATTN_IMPL", "auto", "auto|tc (tcgen05)|simt (reference-grade CUDA)")
     SGLB_GEMM_IMPL = EnvStr("SGLB_GEMM_IMPL", "auto", "auto|tc (own tcgen05 GEMM)|lib (cuBLASLt)")
+    SGLB_ATTN_PERSIST = EnvBool("SGLB_ATTN_PERSIST", True, "persistent-CTA attention with an atomic work queue (pipelines across requests)")
     SGLB_SKINNY = EnvStr("SGLB_SKINNY", "on", "on|off: decode-shape (<=256 tokens) swap-AB split-K tcgen05 GEMM with fused consumers")
     SGLB_DISABLE_CUDA_GRAPH = EnvBool("SGLB_DISABLE_CUDA_GRAPH", False)
     SGLB_KERNEL_LAUNCH_COUNT = EnvBool("SGLB_KERNEL_LAUNCH_COUNT", True, "count native kernel launches")

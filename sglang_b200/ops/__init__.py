@@ -137,7 +137,7 @@ def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, 
         if impl == 0 and (D != 128 or k_cache.dtype != torch.bfloat16 or 128 % G != 0 or page_size < 8 or page_size > 128):
             impl = 1
         part_o = part_lse = None
-        if impl == 0 and num_splits > 1:
+        if impl in (0, 2) and num_splits > 1:
             if workspace is None:
                 T = q.shape[0]
                 part_o = torch.empty(num_splits, T, Hq, D, dtype=torch.float32, device=q.device)
@@ -149,6 +149,8 @@ def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, 
         if impl == 1 and cu_q is not None and tok2req is None:
             ql = cu_q[1:] - cu_q[:-1]
             tok2req = torch.repeat_interleave(torch.arange(ql.numel(), device=q.device, dtype=torch.int32), ql.long()).to(torch.int32)
+        if impl == 0 and envs.SGLB_ATTN_PERSIST.get():
+            impl = 2        # same kernel family, persistent CTAs with an atomic work queue (falls back to the classic launch when small)
         torch.ops.sglb.attn_fwd(q, k_cache, v_cache, out, lse, part_o, part_lse, page_table, req_slots, seq_lens, cu_q, tok2req,
                                 int(max_q_len), int(page_size), int(num_splits), float(scale), bool(causal), int(window),
                                 float(logit_cap), float(k_scale), float(v_scale), int(impl))

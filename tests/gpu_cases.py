@@ -141,6 +141,34 @@ def case_attn_tc_split():
     _attn_check(0, 1, [50], [700], splits=2, name="prefill split2")
 
 
+def case_attn_tc_persist():
+    """persistent-CTA scheduling (taken when work items > resident CTAs): must match the reference AND the classic launch"""
+    import numpy as np
+    from sglang_b200.environ import envs
+
+    rng = np.random.default_rng(7)
+    assert envs.SGLB_ATTN_PERSIST.get()
+    lens = rng.integers(1, 900, 400).tolist()
+    _attn_check(0, 400, [1] * 400, lens, decode=True, name="persist decode ragged x400 (3200 items)")
+    _attn_check(0, 64, [1] * 64, rng.integers(1, 2000, 64).tolist(), decode=True, splits=8, name="persist decode split8 (4096 items, empty splits)")
+    ql = rng.integers(1, 600, 40).tolist()
+    _attn_check(0, 40, ql, [a + int(b) for a, b in zip(ql, rng.integers(0, 300, 40))], name="persist ragged extend x40")
+    _attn_check(0, 300, [1] * 300, rng.integers(1, 600, 300).tolist(), decode=True, ps=16, cap=30.0, name="persist decode softcap ps16")
+    # bit-level agreement with the classic launch is not required (same math, different CTA->item mapping), numerics are
+    s = _attn_setup(400, [1] * 400, lens, 32, 8, 128, 32)
+    a = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, impl=0)
+    envs.SGLB_ATTN_PERSIST.set(False)
+    b = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, impl=0)
+    envs.SGLB_ATTN_PERSIST.set(True)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), "persistent and classic launches must agree exactly (identical per-item arithmetic)"
+    # back-to-back launches re-use the scheduler counter: run several and re-check
+    for _ in range(5):
+        a2 = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, impl=0)
+    torch.cuda.synchronize()
+    assert torch.equal(a, a2)
+
+
 def case_attn_tc_window():
     _attn_check(0, 2, [60, 1], [400, 300], window=128, name="sliding window")
     _attn_check(0, 1, [33], [200], cap=30.0, name="logit cap")

@@ -77,3 +77,46 @@ def test_tokenize_embeddings_metrics_admin(client):
     up = client.post("/update_weights_from_tensor", json={"named_tensors": [["model.norm.weight", [2.0] * 64]]}).json()
     assert up["success"]
     assert client.post("/get_weights_by_name", json={"name": "model.norm.weight", "truncate_size": 2}).json() == [2.0, 2.0]
+
+
+def test_anthropic_messages(client):
+    body = {"model": "m", "max_tokens": 5, "temperature": 0, "system": "be brief",
+            "messages": [{"role": "user", "content": [{"type": "text", "text": "ping"}]}]}
+    j = client.post("/v1/messages", json=body).json()
+    assert j["type"] == "message" and j["role"] == "assistant" and j["stop_reason"] == "max_tokens"
+    assert j["usage"]["output_tokens"] == 5 and j["content"][0]["type"] == "text"
+    with client.stream("POST", "/v1/messages", json={**body, "stream": True}) as s:
+        events = [l[7:] for l in s.iter_lines() if l.startswith("event: ")]
+    assert events[0] == "message_start" and events[-1] == "message_stop" and "content_block_delta" in events
+    assert client.post("/v1/messages/count_tokens", json=body).json()["input_tokens"] > 0
+
+
+def test_ollama_api(client):
+    assert client.get("/api/tags").json()["models"][0]["name"] == "dummy:tiny-llama"
+    j = client.post("/api/generate", json={"model": "m", "prompt": "hello", "stream": False, "options": {"num_predict": 4, "temperature": 0}}).json()
+    assert j["done"] and j["eval_count"] == 4 and isinstance(j["response"], str)
+    with client.stream("POST", "/api/generate", json={"model": "m", "prompt": "hello", "options": {"num_predict": 4, "temperature": 0}}) as s:
+        lines = [json.loads(l) for l in s.iter_lines() if l]
+    assert lines[-1]["done"] and "".join(x["response"] for x in lines) == j["response"]
+    j = client.post("/api/chat", json={"model": "m", "messages": [{"role": "user", "content": "hi"}], "stream": False,
+                                       "options": {"num_predict": 3}}).json()
+    assert j["done"] and j["message"]["role"] == "assistant" and j["eval_count"] == 3
+    with client.stream("POST", "/api/chat", json={"model": "m", "messages": [{"role": "user", "content": "hi"}], "options": {"num_predict": 3}}) as s:
+        lines = [json.loads(l) for l in s.iter_lines() if l]
+    assert lines[-1]["done"]
+
+
+def test_sagemaker_vertex_responses(client):
+    assert client.get("/ping").status_code == 200
+    j = client.post("/invocations", json={"model": "m", "messages": [{"role": "user", "content": "x"}], "max_tokens": 3}).json()
+    assert j["usage"]["completion_tokens"] == 3
+    j = client.post("/invocations", json={"text": "abc", "sampling_params": {"max_new_tokens": 2}}).json()
+    assert j["meta_info"]["completion_tokens"] == 2
+    j = client.post("/vertex_generate", json={"instances": [{"text": "a"}, {"text": "bb"}], "parameters": {"max_new_tokens": 2}}).json()
+    assert len(j["predictions"]) == 2 and j["predictions"][0]["meta_info"]["completion_tokens"] == 2
+    j = client.post("/v1/responses", json={"model": "m", "input": "hello", "max_output_tokens": 4, "instructions": "short"}).json()
+    assert j["object"] == "response" and j["status"] == "completed" and j["usage"]["output_tokens"] == 4
+    with client.stream("POST", "/v1/responses", json={"model": "m", "input": [{"role": "user", "content": [{"type": "input_text", "text": "yo"}]}],
+                                                      "max_output_tokens": 4, "stream": True}) as s:
+        events = [l[7:] for l in s.iter_lines() if l.startswith("event: ")]
+    assert events[0] == "response.created" and events[-1] == "response.completed"
