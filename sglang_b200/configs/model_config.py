@@ -42,6 +42,16 @@ class ModelConfig:
     num_experts_per_tok: int = 0
     moe_intermediate_size: Optional[int] = None
     norm_topk_prob: bool = True
+    shared_expert_intermediate_size: Optional[int] = None      # Qwen2-MoE sigmoid-gated shared expert
+    decoder_sparse_step: int = 1
+    mlp_only_layers: Optional[List[int]] = None
+    # Gemma-2 / Granite extras
+    query_pre_attn_scalar: Optional[float] = None
+    layer_types: Optional[List[str]] = None
+    embedding_multiplier: Optional[float] = None
+    residual_multiplier: Optional[float] = None
+    attention_multiplier: Optional[float] = None
+    logits_scaling: Optional[float] = None
     # multimodal (LLaVA-style)
     vision: Optional[Dict[str, Any]] = None
     image_token_id: Optional[int] = None
@@ -111,7 +121,42 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                        rope_theta=10000.0, dtype="float32", image_token_id=500,
                        vision={"hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 2, "num_attention_heads": 2,
                                "image_size": 28, "patch_size": 14, "select_layer": -2, "projector_hidden_act": "gelu"}),
+    "tiny-phi3": dict(architecture="Phi3ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
+    "tiny-internlm2": dict(architecture="InternLM2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                           num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                           rope_theta=10000.0, dtype="float32"),
+    "tiny-qwen2-moe": dict(architecture="Qwen2MoeForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=3,
+                           num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                           attention_bias=True, num_local_experts=4, num_experts_per_tok=2, moe_intermediate_size=32,
+                           shared_expert_intermediate_size=64, norm_topk_prob=False, mlp_only_layers=[0], rope_theta=10000.0,
+                           dtype="float32"),
+    "tiny-qwen3-moe": dict(architecture="Qwen3MoeForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                           num_attention_heads=4, num_key_value_heads=2, head_dim=32, vocab_size=512, max_position_embeddings=512,
+                           qk_norm=True, num_local_experts=8, num_experts_per_tok=2, moe_intermediate_size=32, rope_theta=10000.0,
+                           dtype="float32"),
+    "tiny-gemma2": dict(architecture="Gemma2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=4,
+                        num_attention_heads=4, num_key_value_heads=2, head_dim=32, vocab_size=512, max_position_embeddings=512,
+                        hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True, sliding_window=16, attn_logit_softcapping=50.0,
+                        final_logit_softcapping=30.0, query_pre_attn_scalar=32, rope_theta=10000.0, dtype="float32"),
+    "tiny-granite": dict(architecture="GraniteForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                         embedding_multiplier=12.0, residual_multiplier=0.22, attention_multiplier=0.0078125 * 8, logits_scaling=8.0,
+                         tie_word_embeddings=True, rope_theta=10000.0, dtype="float32"),
+    "tiny-olmo2": dict(architecture="Olmo2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0,
+                       dtype="float32"),
     # ---- real architectures (random-init offline)
+    "qwen3-30b-a3b": dict(architecture="Qwen3MoeForCausalLM", hidden_size=2048, intermediate_size=6144, num_hidden_layers=48,
+                          num_attention_heads=32, num_key_value_heads=4, head_dim=128, vocab_size=151936, max_position_embeddings=40960,
+                          rope_theta=1000000.0, qk_norm=True, rms_norm_eps=1e-6, num_local_experts=128, num_experts_per_tok=8,
+                          moe_intermediate_size=768, eos_token_id=[151643, 151645]),
+    "gemma-2-9b": dict(architecture="Gemma2ForCausalLM", hidden_size=3584, intermediate_size=14336, num_hidden_layers=42,
+                       num_attention_heads=16, num_key_value_heads=8, head_dim=256, vocab_size=256000, max_position_embeddings=8192,
+                       hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True, sliding_window=4096, attn_logit_softcapping=50.0,
+                       final_logit_softcapping=30.0, query_pre_attn_scalar=256, rope_theta=10000.0, rms_norm_eps=1e-6),
+    "phi-3-mini": dict(architecture="Phi3ForCausalLM", hidden_size=3072, intermediate_size=8192, num_hidden_layers=32,
+                       num_attention_heads=32, num_key_value_heads=32, vocab_size=32064, max_position_embeddings=4096, rope_theta=10000.0),
     "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
                        num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, rope_theta=500000.0,
                        bos_token_id=128000, eos_token_id=[128001, 128009]),
@@ -143,6 +188,8 @@ PRESETS: Dict[str, Dict[str, Any]] = {
 }
 
 _HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM"}
+# HF config keys that differ from our field names
+_HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts"}
 
 
 def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = None, context_length: Optional[int] = None) -> ModelConfig:
@@ -160,6 +207,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             hf = json.load(f)
         text = hf.get("text_config", hf)
         fields = {f.name for f in dataclasses.fields(ModelConfig)}
+        text = {_HF_KEY_MAP.get(k, k): v for k, v in text.items()}
         kw = {k: v for k, v in text.items() if k in fields}
         arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)

@@ -105,7 +105,8 @@ class LlamaDecoderLayer(nn.Module):
 
 
 class LlamaModel(nn.Module):
-    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, mlp_cls=LlamaMLP, device="cpu"):
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, mlp_cls=LlamaMLP, device="cpu", layer_cls=None):
+        layer_cls = layer_cls or LlamaDecoderLayer
         super().__init__()
         self.cfg = cfg
         dtype = _DT[cfg.dtype]
@@ -118,7 +119,7 @@ class LlamaModel(nn.Module):
         rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
                                cfg.partial_rotary_factor, device)
         self.layers = nn.ModuleList([
-            LlamaDecoderLayer(cfg, i - self.start_layer, dtype, quant_factory(), rope, f"model.layers.{i}", mlp_cls)
+            layer_cls(cfg, i - self.start_layer, dtype, quant_factory(), rope, f"model.layers.{i}", mlp_cls)
             for i in range(self.start_layer, self.end_layer)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, self.gemma) if pp.is_last else None
 
@@ -146,11 +147,14 @@ class LlamaModel(nn.Module):
             if hasattr(h, "resolve"):
                 h = h.resolve()
             return h, residual
+        if residual is None:      # families whose layers keep the residual stream in h (Gemma-2, Granite, OLMo-2)
+            return self.norm(h.resolve() if hasattr(h, "resolve") else h)
         h, _ = self.norm(h, residual)
         return h
 
 
 class LlamaForCausalLM(nn.Module):
+    decoder_layer_cls = None      # subclasses may swap the decoder layer (models/families.py)
     # checkpoint name -> (merged param name, shard id)   (reference llama.py:663 stacked_params_mapping)
     stacked_params = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v"),
                       (".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
@@ -158,7 +162,7 @@ class LlamaForCausalLM(nn.Module):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__()
         self.cfg = cfg
-        self.model = LlamaModel(cfg, quant_name, self._mlp_cls(), device)
+        self.model = LlamaModel(cfg, quant_name, self._mlp_cls(), device, getattr(self, "decoder_layer_cls", None))
         pp = get_pp_group()
         if pp.is_last:
             if cfg.tie_word_embeddings and pp.is_first:

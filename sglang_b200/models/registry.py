@@ -32,6 +32,11 @@ def _ensure() -> None:
     register_model("MixtralForCausalLM", mixtral.MixtralForCausalLM)
     register_model("LlavaForConditionalGeneration", llava.LlavaForConditionalGeneration)
     register_model("LlavaLlamaForCausalLM", llava.LlavaForConditionalGeneration)
+    from . import families as _fam
+
+    for name in ("Phi3ForCausalLM", "InternLM2ForCausalLM", "Qwen2MoeForCausalLM", "Qwen3MoeForCausalLM", "Gemma2ForCausalLM",
+                 "GraniteForCausalLM", "Olmo2ForCausalLM"):
+        register_model(name, getattr(_fam, name))
     from . import embedding as _emb
 
     register_model("LlamaEmbeddingModel", _emb.LlamaEmbeddingModel)
