@@ -83,7 +83,8 @@ class _Envs:
     SGLB_ATTN_IMPL = EnvStr("SGLB_ATTN_IMPL", "auto", "auto|tc (tcgen05)|simt (reference-grade CUDA)")
     SGLB_GEMM_IMPL = EnvStr("SGLB_GEMM_IMPL", "auto", "auto|tc (own tcgen05 GEMM)|lib (cuBLASLt)")
     SGLB_ATTN_PERSIST = EnvBool("SGLB_ATTN_PERSIST", True, "persistent-CTA attention with an atomic work queue (pipelines across requests)")
-    SGLB_SKINNY = EnvStr("SGLB_SKINNY", "on", "on|off: decode-shape (<=256 tokens) swap-AB split-K tcgen05 GEMM with fused consumers")
+    SGLB_SKINNY = EnvStr("SGLB_SKINNY", "tp", "tp|on|off: decode-shape (<=256 tokens) swap-AB split-K tcgen05 GEMM — tp: only as the fused "
+                         "GEMM+all-reduce producer; on: every decode GEMM with fused consumers")
     SGLB_DISABLE_CUDA_GRAPH = EnvBool("SGLB_DISABLE_CUDA_GRAPH", False)
     SGLB_KERNEL_LAUNCH_COUNT = EnvBool("SGLB_KERNEL_LAUNCH_COUNT", True, "count native kernel launches")
     # --- scheduler test hooks (reference: SGLANG_TEST_RETRACT etc., environ.py:384-393)

