@@ -262,7 +262,7 @@ class FunctionCallParser:
             return delta, []
         r = self.detector.detect_and_parse(text, self.tools)
         new_calls = r.calls[self._sent_calls:]
-        self._sent_calls = len(r.calls)
+        self._sent_calls = max(self._sent_calls, len(r.calls))     # a call, once emitted, stays emitted (partial closers may un-match)
         # only text before the first marker is safe to emit
         cut = text.find(bot) if bot and bot in text else len(r.normal_text)
         safe = text[:cut] if bot else r.normal_text

@@ -87,3 +87,51 @@ def test_router_policies():
     assert ch.select(ws, "x", "user-42") is ch.select(ws, "y", "user-42")
     ws[0].inflight = 50
     assert Policy("power_of_two").select(ws[:2], "").url == "http://b"
+
+
+def test_more_tool_call_formats():
+    import json
+
+    from sglang_b200.function_call.function_call_parser import DETECTORS, FunctionCallParser
+
+    tools = [{"type": "function", "function": {"name": "get_weather", "parameters": {"type": "object", "properties": {
+        "city": {"type": "string"}, "days": {"type": "integer"}, "detail": {"type": "boolean"}}}}}]
+    want = {"city": "Paris", "days": 3}
+    samples = {
+        "hermes": 'ok <tool_call>\n{"name": "get_weather", "arguments": {"city": "Paris", "days": 3}}\n</tool_call>',
+        "internlm": 'hm<|action_start|><|plugin|>{"name": "get_weather", "parameters": {"city": "Paris", "days": 3}}<|action_end|>',
+        "cohere_command4": '<|START_ACTION|>[{"tool_call_id": "0", "tool_name": "get_weather", "parameters": {"city": "Paris", "days": 3}}]<|END_ACTION|>',
+        "lfm2": 'sure <|tool_call_start|>[get_weather(city="Paris", days=3)]<|tool_call_end|>',
+        "deepseekv31": '<｜tool▁calls▁begin｜><｜tool▁call▁begin｜>get_weather<｜tool▁sep｜>{"city": "Paris", "days": 3}<｜tool▁call▁end｜><｜tool▁calls▁end｜>',
+        "kimi_k2": '<|tool_calls_section_begin|><|tool_call_begin|>functions.get_weather:0<|tool_call_argument_begin|>{"city": "Paris", "days": 3}<|tool_call_end|><|tool_calls_section_end|>',
+        "gpt-oss": '<|start|>assistant<|channel|>commentary to=functions.get_weather <|constrain|>json<|message|>{"city": "Paris", "days": 3}<|call|>',
+        "qwen3_coder": '<tool_call>\n<function=get_weather>\n<parameter=city>\nParis\n</parameter>\n<parameter=days>\n3\n</parameter>\n</function>\n</tool_call>',
+        "glm45": '<tool_call>get_weather\n<arg_key>city</arg_key>\n<arg_value>Paris</arg_value>\n<arg_key>days</arg_key>\n<arg_value>3</arg_value>\n</tool_call>',
+        "minimax-m2": '<minimax:tool_call>\n<invoke name="get_weather">\n<parameter name="city">Paris</parameter>\n<parameter name="days">3</parameter>\n</invoke>\n</minimax:tool_call>',
+        "deepseekv32": '<｜DSML｜function_calls>\n<｜DSML｜invoke name="get_weather">\n<｜DSML｜parameter name="city" string="true">Paris</｜DSML｜parameter>\n<｜DSML｜parameter name="days" string="false">3</｜DSML｜parameter>\n</｜DSML｜invoke>\n</｜DSML｜function_calls>',
+        "step3": '<｜tool_calls_begin｜><｜tool_call_begin｜>function<｜tool_sep｜><steptml:invoke name="get_weather">\n<steptml:parameter name="city">Paris</steptml:parameter>\n<steptml:parameter name="days">3</steptml:parameter>\n</steptml:invoke><｜tool_call_end｜><｜tool_calls_end｜>',
+        "dots": '<dots_function_call>\n<invoke name="get_weather">\n<parameter name="city">Paris</parameter>\n<parameter name="days">3</parameter>\n</invoke>\n</dots_function_call>',
+        "minicpm5": '<function name="get_weather"><param name="city">Paris</param><param name="days">3</param></function>',
+    }
+    assert len(DETECTORS) >= 25
+    for fmt, text in samples.items():
+        p = FunctionCallParser(tools, fmt)
+        assert p.has_tool_call(text), fmt
+        normal, calls = p.parse_non_stream(text)
+        assert len(calls) == 1 and calls[0].name == "get_weather", (fmt, calls)
+        assert json.loads(calls[0].parameters) == want, (fmt, calls[0].parameters)
+        assert "get_weather" not in normal, (fmt, normal)
+        # streaming: feed char by char, exactly one call must come out and no marker text may leak
+        sp = FunctionCallParser(tools, fmt)
+        out_text, out_calls = "", []
+        for ch in text:
+            d, cs = sp.parse_stream_chunk(ch)
+            out_text += d
+            out_calls += cs
+        assert len(out_calls) == 1 and json.loads(out_calls[0].parameters) == want, (fmt, out_calls)
+        assert "get_weather" not in out_text, (fmt, out_text)
+        st = p.get_structural_constraint("required")
+        assert st["structures"][0]["begin"] and st["structures"][0]["schema"]["type"] == "object"
+    # unknown function names are ignored
+    p = FunctionCallParser(tools, "hermes")
+    assert p.parse_non_stream('<tool_call>{"name": "nope", "arguments": {}}</tool_call>')[1] == []
