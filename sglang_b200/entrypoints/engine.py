@@ -89,6 +89,11 @@ class Engine:
             a.trust_remote_code)
         self.detok = Detokenizer(self.tokenizer) if self.tokenizer is not None else None
         emits_output = st.tp.rank == 0 and st.pp.is_last if st.pp.world_size > 1 else st.tp.rank == 0
+        # pipeline parallel: the LAST stage samples, rank 0 talks to the client -> the last stage's tp-rank-0 relays every step's
+        # output messages to rank 0 over the Gloo twin of the world group (both run the same SPMD loop, one hand-off per step)
+        self._relay_src = (st.pp.world_size - 1) * st.tp.world_size if st.pp.world_size > 1 else None
+        self._relay_buf: List[Any] = []
+        self._world = st.world
         self.scheduler = Scheduler(a, self.runner, self.tokenizer, self._on_scheduler_output, 0 if emits_output else 1)
         self._install_optional_components()
         self.states: Dict[str, ReqState] = {}
@@ -151,7 +156,7 @@ class Engine:
             ids, mm = process_images(ids, g.image_data, self.model_config, self.tokenizer)
         SamplingParams.from_dict(sp).verify(self.model_config.vocab_size)
         return ios.TokenizedGenerateReqInput(
-            rid=g.rid or uuid.uuid4().hex, input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),
+            rid=g.rid or self._new_rid(), input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),
             logprob_start_len=int(g.logprob_start_len), top_logprobs_num=int(g.top_logprobs_num), stream=bool(g.stream),
             return_hidden_states=g.return_hidden_states, lora_id=g.lora_path, session_params=g.session_params, mm_inputs=mm,
             custom_logit_processor=g.custom_logit_processor, bootstrap_host=g.bootstrap_host, bootstrap_port=g.bootstrap_port,
@@ -173,7 +178,29 @@ class Engine:
         return stt
 
     # ================================================================== output path
-    def _on_scheduler_output(self, msg: ios.BatchTokenIDOutput) -> None:
+    def _new_rid(self) -> str:
+        """request ids must agree on every rank of an SPMD job (results are matched by id when a later pipeline stage relays them)"""
+        if self._world.world_size > 1:
+            self._rid_ctr = getattr(self, "_rid_ctr", 0) + 1
+            return f"req-{self._rid_ctr:08d}"
+        return uuid.uuid4().hex
+
+    def _relay_sync(self) -> None:
+        """PP only: ship this step's output messages from the sampling stage to rank 0 (no-op otherwise)"""
+        if self._relay_src is None:
+            return
+        rank = ps.get_state().rank
+        if rank == self._relay_src:
+            self._world.send_pyobj(self._relay_buf, 0)
+            self._relay_buf = []
+        elif rank == 0:
+            for m in self._world.recv_pyobj(self._relay_src):
+                self._on_scheduler_output(m, relayed=True)
+
+    def _on_scheduler_output(self, msg: ios.BatchTokenIDOutput, relayed: bool = False) -> None:
+        if self._relay_src is not None and not relayed and ps.get_state().rank == self._relay_src:
+            self._relay_buf.append(msg)
+            return
         out = self.detok.process(msg) if self.detok is not None else ios.BatchStrOutput(
             rids=msg.rids, finished_reasons=msg.finished_reasons, output_strs=[""] * len(msg.rids), output_ids=msg.output_ids,
             prompt_tokens=msg.prompt_tokens, completion_tokens=msg.completion_tokens, cached_tokens=msg.cached_tokens,
@@ -258,8 +285,10 @@ class Engine:
         sch = self.scheduler
         while sch.has_work():
             sch.step()
+            self._relay_sync()
         sch.drain()
-        if self.is_driver or self.scheduler.tp_rank == 0:
+        self._relay_sync()
+        if self.is_driver:
             pending = [s for s in states if not s.finished]
             if pending:
                 raise RuntimeError(f"{len(pending)} requests did not finish (scheduler idle)")
@@ -437,9 +466,9 @@ class Engine:
                         new.append(self._inbox.get_nowait())
                     except queue.Empty:
                         break
-            if tp.world_size > 1:
+            if self._world.world_size > 1:      # every rank of the TP x PP world runs the same loop on the same requests
                 payload = [m if not isinstance(m, tuple) else m[0] for m in new] if self.is_driver else None
-                payload = tp.broadcast_pyobj(payload, src=0)
+                payload = self._world.broadcast_pyobj(payload, src=0)
                 if not self.is_driver:
                     new = payload
             for m in new:
@@ -456,12 +485,14 @@ class Engine:
             if sch.has_work():
                 try:
                     sch.step()
+                    self._relay_sync()
                 except Exception:
                     logger.exception("scheduler step failed; aborting in-flight requests")
                     self._fail_all()
                     raise
             else:
                 sch.drain()
+                self._relay_sync()
                 self._wake.wait(timeout=0.002)
                 self._wake.clear()
 

@@ -125,7 +125,7 @@ class GenerateReqInput:
                 sp_ij["n"] = 1
                 r = dataclasses.replace(
                     self, text=texts[i], input_ids=ids[i], sampling_params=sp_ij, image_data=img,
-                    rid=(rid if (rid and par == 1) else (f"{rid}-{j}" if rid else uuid.uuid4().hex)),
+                    rid=(rid if (rid and par == 1) else (f"{rid}-{j}" if rid else None)),     # None: the engine assigns (SPMD-consistent) ids
                     return_logprob=pick(self.return_logprob, i), logprob_start_len=pick(self.logprob_start_len, i),
                     top_logprobs_num=pick(self.top_logprobs_num, i), lora_path=pick(self.lora_path, i),
                 )

@@ -261,6 +261,9 @@ class ModelRunner:
         logits = self._preprocess_logits(logits, reqs, fb)
         lp_out = torch.empty(len(reqs), dtype=torch.float32, device=self.device) if sb.return_logprob else None
         toks = self.sample(logits, fb, lp_out)
+        if self.pp.world_size > 1:      # earlier stages need the sampled ids as their next decode input (see _pp_result)
+            t32 = toks.to(torch.int32).contiguous()
+            self.pp.broadcast(t32, src=self.pp.world_size - 1)
         if sb.return_logprob:
             self._extra_logprobs(sb, fb, hidden, logits, res, samp_rows)
         self._finish_result(res, toks, lp_out)

@@ -63,9 +63,13 @@ class GroupCoordinator:
             return x
         if dim < 0:
             dim += x.dim()
-        out = torch.empty((self.world_size,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(out, x.contiguous(), group=self.device_group)
-        out = out.movedim(0, dim)
+        x = x.contiguous()
+        if x.dim() == 0:
+            x = x.view(1)
+        # flat [world * n0, ...] output: the layout both NCCL and Gloo accept for all_gather_into_tensor
+        flat = torch.empty((self.world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(flat, x, group=self.device_group)
+        out = flat.view((self.world_size,) + tuple(x.shape)).movedim(0, dim)
         shp = list(x.shape)
         shp[dim] *= self.world_size
         return out.reshape(shp)

@@ -1,0 +1,23 @@
+"""SPMD worker for the multi-process CPU tests (gloo): every rank builds the same Engine and drives the same requests; rank 0
+prints the result as one JSON line.   env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT;  argv: json config"""
+import faulthandler
+import json
+import os
+import sys
+
+if os.environ.get("SGLB_HANG_DUMP_S"):
+    faulthandler.dump_traceback_later(int(os.environ["SGLB_HANG_DUMP_S"]), exit=True)
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+cfg = json.loads(sys.argv[1])
+import sglang_b200 as sgl  # noqa: E402
+
+eng = sgl.Engine(log_level="error", device="cpu", **cfg["engine"])
+outs = eng.generate(input_ids=cfg["prompts"], sampling_params=cfg["sampling"], **cfg.get("gen_kw", {}))
+if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives outputs
+    res = {"ids": [o["output_ids"] for o in outs]}
+    if cfg.get("gen_kw", {}).get("return_logprob"):
+        res["lp"] = [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in outs]
+    print("RESULT " + json.dumps(res), flush=True)
+eng.shutdown()
+os._exit(0)
