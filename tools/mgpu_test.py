@@ -194,6 +194,18 @@ else:
             log(f"  push T={T} K={K} H={H} err_out={e1:.4f} err_resid={e2:.4f}")
             assert e1 < 0.25 and e2 < 0.15, ("push", T, K, H, e1, e2)
 
+            # decode-shape variant: swap-AB + split-K slabs pushed to every peer
+            out_s = torch.empty(T, H, device=dev, dtype=torch.bfloat16); r3 = resid.clone()
+            off_s, splits = nvl.gemm_push_skinny(x, wgt)
+            nvl.push_reduce_add_rmsnorm(off_s, T, H, r3, nw, out_s, 1e-5, splits=splits)
+            torch.cuda.synchronize()
+            e3 = (out_s.float() - x_ref.float()).abs().max().item(); e4 = (r3.float() - r_ref.float()).abs().max().item()
+            log(f"  push-skinny T={T} K={K} H={H} splits={splits} err_out={e3:.4f} err_resid={e4:.4f}")
+            assert e3 < 0.25 and e4 < 0.15, ("push-skinny", T, K, H, e3, e4)
+
+            def push_skinny():
+                o, s = nvl.gemm_push_skinny(x, wgt); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5, splits=s)
+
             def push():
                 o = nvl.gemm_push(x, wgt); nvl.push_reduce_add_rmsnorm(o, T, H, r2, nw, out, 1e-5)
 
@@ -205,6 +217,7 @@ else:
 
             res[f"gemm_ar_norm_T{T}_K{K}_us"] = {"push_fused": 1000 * timed(push), "pull_fused": 1000 * timed(pull),
                                                  "cublas_nccl_norm": 1000 * timed(base), "push_fused_graph": 1000 * timed_graph(push),
+                                                 "push_skinny_graph": 1000 * timed_graph(push_skinny),
                                                  "pull_fused_graph": 1000 * timed_graph(pull), "cublas_nccl_norm_graph": 1000 * timed_graph(base)}
         log("gemm+ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("gemm_ar")}))
 
