@@ -219,6 +219,8 @@ class Engine:
             m = st.meta
             m["completion_tokens"] = out.completion_tokens[i]
             m["cached_tokens"] = out.cached_tokens[i]
+            if out.prompt_tokens is not None and out.prompt_tokens[i]:
+                m["prompt_tokens"] = out.prompt_tokens[i]      # authoritative (sessions prepend history inside the scheduler)
             if out.output_logprobs is not None and out.output_logprobs[i] is not None:
                 st.logprobs.extend(out.output_logprobs[i])
                 m["output_token_logprobs"] = [(lp, tid, None) for lp, tid in st.logprobs]

@@ -51,6 +51,9 @@ class Scheduler:
                                        disable=server_args.disable_radix_cache, impl=server_args.radix_cache_impl,
                                        enable_kv_events=server_args.enable_kv_events)
         self.kv = KVManager(self.allocator, self.tree, self.page_size, self.max_running, self.max_context_len)
+        from .session_controller import SessionController
+
+        self.sessions = SessionController(self.tree, self.page_size)
         worker.attach_kv_manager(self.kv)
         self.policy = SchedulePolicy(server_args.schedule_policy, self.kv, server_args.enable_priority_scheduling,
                                      server_args.random_seed)
@@ -65,7 +68,6 @@ class Scheduler:
         self.grammar_queue: List[Req] = []
         self.grammar_manager = None
         self.spec_worker = None
-        self.sessions: Dict[str, Any] = {}
         self.paused = False
 
         # new-token-ratio estimator (reference scheduler.py:3580-3611)
@@ -119,18 +121,21 @@ class Scheduler:
                 self.flush_cache()
             return self.worker.handle_control(msg)
         if isinstance(msg, ios.OpenSessionReq):
-            sid = msg.session_id or f"sess-{len(self.sessions)}"
-            ok = sid not in self.sessions
-            if ok:
-                self.sessions[sid] = {"reqs": []}
+            sid, ok = self.sessions.open(msg.session_id, int(msg.capacity_of_str_len or 0))
             return ios.OpenSessionResp(session_id=sid, success=ok)
         if isinstance(msg, ios.CloseSessionReq):
-            self.sessions.pop(msg.session_id, None)
+            self.sessions.close(msg.session_id)
             return ios.GenericResp()
         raise TypeError(f"unknown message {type(msg)}")
 
     def handle_generate_request(self, m: ios.TokenizedGenerateReqInput) -> None:
         sp = SamplingParams.from_dict(m.sampling_params)
+        session_err, session_id = None, None
+        if m.session_params and m.session_params.get("id") is not None:
+            # continue an earlier turn of the session: history (token ids) + this request's new input
+            full, session_err = self.sessions.build_input(m.session_params, list(m.input_ids), m.rid)
+            if full is not None:
+                m.input_ids, session_id = full, m.session_params["id"]
         req = Req(m.rid, m.input_ids, sp, origin_input_text=m.input_text, return_logprob=m.return_logprob,
                   top_logprobs_num=m.top_logprobs_num, logprob_start_len=m.logprob_start_len, stream=m.stream,
                   lora_id=m.lora_id, extra_key=m.extra_key, priority=m.priority, eos_token_ids=self.eos_token_ids,
@@ -138,6 +143,9 @@ class Scheduler:
         req.trace_context = m.trace_context
         if m.created_time:
             req.created_time = m.created_time
+        req.session_id = session_id
+        if session_err is not None:
+            return self._reject(req, session_err)
         # validation (reference scheduler.py:2414-2783)
         n_in = len(req.origin_input_ids)
         if n_in == 0:
@@ -159,8 +167,6 @@ class Scheduler:
                 return self._reject(req, req.to_abort.kw.get("message", "invalid grammar"))
         elif sp.has_grammar:
             return self._reject(req, "grammar-constrained decoding requested but no grammar backend is enabled")
-        if m.session_params and m.session_params.get("id") in self.sessions:
-            req.session_id = m.session_params["id"]
         self.waiting_queue.append(req)
         return None
 
@@ -201,6 +207,7 @@ class Scheduler:
                 or self.chunked_req is not None:
             logger.warning("flush_cache refused: requests in flight")
             return False
+        self.sessions.unpin_all()
         self.tree.reset()
         self.allocator.clear()
         self.kv.slots.clear()
@@ -568,6 +575,12 @@ class Scheduler:
         """reference scheduler_components/output_streamer.py:113"""
         sel = []
         for r in reqs:
+            if r.session_id is not None and r.finished() and not getattr(r, "_session_closed", False):
+                r._session_closed = True
+                if r.finished_reason.kind == "abort":
+                    self.sessions.on_aborted(r.session_id, r.rid)
+                else:
+                    self.sessions.on_finished(r.session_id, r.rid, r.output_ids, r.extra_key)
             if r.finished():
                 sel.append(r)
             elif r.stream:
