@@ -43,6 +43,18 @@ __device__ __forceinline__ U4 ld_peer128(const void* p) {
   return r;
 }
 
+// NVLS (NVSwitch multicast) primitives: one load returns the SUM over every rank's copy (the switch reduces in fp32), one store
+// lands in every rank's copy.  `p` is an address inside the multicast alias of the symmetric arena.
+__device__ __forceinline__ U4 mc_ld_reduce_bf16x8(const void* p) {
+  U4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st_bf16x8(void* p, const U4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Publish `epoch` to every peer on `channel`, then wait until every peer has published it to us.
 // Called by all threads of a block; threads [0, world) do the flag traffic.
 __device__ __forceinline__ void nvl_barrier(const NvlPeers& P, int channel, uint32_t epoch) {
@@ -87,6 +99,9 @@ __device__ __forceinline__ void epoch_end(uint32_t* epoch_ptr, uint32_t* done_ct
 }
 
 // ---------------------------------------------------------------- one-shot all-reduce (bf16, n multiple of 8)
+// WEAK: plain (weak) 128-bit loads after the acquire of the flag round instead of relaxed.sys loads — this kernel never read the
+// peers' slots before the barrier, so no stale L1 line can exist; weak loads pipeline better over NVLink.
+template <bool WEAK>
 __global__ void __launch_bounds__(512) nvl_allreduce_oneshot_kernel(NvlPeers P, __nv_bfloat16* __restrict__ out, int n,
                                                                     uint32_t* epoch_ptr, uint32_t* done_ctr, int channel) {
   const uint32_t epoch = epoch_begin(epoch_ptr);
@@ -94,9 +109,16 @@ __global__ void __launch_bounds__(512) nvl_allreduce_oneshot_kernel(NvlPeers P, 
   const int nvec = n >> 3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    U4 v[NVL_MAX_RANKS];
 #pragma unroll
     for (int r = 0; r < NVL_MAX_RANKS; ++r)
-      if (r < P.world) acc_bf16x8(a, ld_peer128(reinterpret_cast<const __nv_bfloat16*>(P.buf[r]) + (size_t)i * 8));
+      if (r < P.world) {
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(P.buf[r]) + (size_t)i * 8;
+        v[r] = WEAK ? ld128(src) : ld_peer128(src);
+      }
+#pragma unroll
+    for (int r = 0; r < NVL_MAX_RANKS; ++r)
+      if (r < P.world) acc_bf16x8(a, v[r]);
     st128(out + (size_t)i * 8, pack8(a));
   }
   epoch_end(epoch_ptr, done_ctr, epoch);
@@ -153,6 +175,56 @@ __global__ void __launch_bounds__(512) nvl_allreduce_twoshot_kernel(NvlPeers P, 
   }
 }
 
+// ---------------------------------------------------------------- NVLS one-shot: out[i] = multimem.ld_reduce(arena[i])
+// One flag round, then every rank pulls the already-reduced vector through the switch: inbound traffic per rank is n bytes
+// (not (world-1) * n as in the peer-pull one-shot) and there is ONE load instruction per 16 bytes regardless of world size.
+__global__ void __launch_bounds__(512) nvl_allreduce_nvls_oneshot_kernel(NvlPeers P, __nv_bfloat16* __restrict__ out, int n,
+                                                                         uint32_t* epoch_ptr, uint32_t* done_ctr, int channel) {
+  const uint32_t epoch = epoch_begin(epoch_ptr);
+  nvl_barrier(P, channel, epoch);
+  const int nvec = n >> 3;
+  const __nv_bfloat16* mc = reinterpret_cast<const __nv_bfloat16*>(P.mc_buf);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x)
+    st128(out + (size_t)i * 8, mc_ld_reduce_bf16x8(mc + (size_t)i * 8));
+  epoch_end(epoch_ptr, done_ctr, epoch);
+}
+
+// ---------------------------------------------------------------- NVLS two-shot: reduce-scatter by ld_reduce + all-gather by multimem.st
+// rank r reduces slice r through the switch and broadcasts it into the result region of EVERY rank's slot with one multicast
+// store per 16 bytes; bandwidth-optimal for prefill-size messages (each byte crosses each link once in, once out).
+__global__ void __launch_bounds__(512) nvl_allreduce_nvls_twoshot_kernel(NvlPeers P, __nv_bfloat16* __restrict__ out, int n,
+                                                                         uint32_t* epoch_ptr, uint32_t* done_ctr, int channel) {
+  const uint32_t epoch = epoch_begin(epoch_ptr);
+  nvl_barrier(P, channel, 2 * epoch - 1);
+  const int nvec = n >> 3;
+  const int per = (nvec + P.world - 1) / P.world;
+  const int lo = P.rank * per, hi = min(nvec, lo + per);
+  __nv_bfloat16* mc = reinterpret_cast<__nv_bfloat16*>(P.mc_buf);
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x)
+    mc_st_bf16x8(mc + (size_t)n + (size_t)i * 8, mc_ld_reduce_bf16x8(mc + (size_t)i * 8));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(done_ctr + 1, 1);
+    while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {}
+  }
+  nvl_barrier(P, channel, 2 * epoch);
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(P.buf[P.rank]) + (size_t)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x)
+    st128(out + (size_t)i * 8, ld_peer128(res + (size_t)i * 8));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(done_ctr, 1);
+    if (t == gridDim.x - 1) {
+      *done_ctr = 0;
+      *(done_ctr + 1) = 0;
+      __threadfence();
+      *((volatile uint32_t*)epoch_ptr) = epoch;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- fused all-reduce + residual add + RMSNorm
 // partial rows of every rank sit in the arena slots; one CTA per token row.
 //   residual[t] += sum_r partial_r[t] ; out[t] = rmsnorm(residual[t]) * w
@@ -174,9 +246,13 @@ __global__ void __launch_bounds__(256) nvl_ar_add_rmsnorm_kernel(NvlPeers P, __n
       if (vi < nvec) {
         float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const size_t off = (size_t)row * H + (size_t)vi * 8;
+        if (P.mc_buf) {      // NVLS: the switch returns the cross-rank sum in one load
+          acc_bf16x8(a, mc_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(P.mc_buf) + off));
+        } else {
 #pragma unroll
-        for (int r = 0; r < NVL_MAX_RANKS; ++r)
-          if (r < P.world) acc_bf16x8(a, ld_peer128(reinterpret_cast<const __nv_bfloat16*>(P.buf[r]) + off));
+          for (int r = 0; r < NVL_MAX_RANKS; ++r)
+            if (r < P.world) acc_bf16x8(a, ld_peer128(reinterpret_cast<const __nv_bfloat16*>(P.buf[r]) + off));
+        }
         if (residual) {
           acc_bf16x8(a, ld128(residual + off));
           const U4 s = pack8(a);
@@ -314,9 +390,17 @@ void nvl_allreduce(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc
   if (n % 8) throw std::runtime_error("sglb nvl allreduce: element count must be a multiple of 8");
   NvlPeers P = make_peers(buf_ptrs, flag_ptrs, mc_ptr, slot_off, rank, world);
   const int nvec = n / 8;
-  if (algo == 0) {
+  if (algo >= 2 && !P.mc_buf) throw std::runtime_error("sglb nvl allreduce: NVLS algorithms need a multicast mapping");
+  if (algo == 2) {
     const int grid = max(1, min((nvec + 511) / 512, num_sms));
-    nvl_allreduce_oneshot_kernel<<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);
+    nvl_allreduce_nvls_oneshot_kernel<<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);
+  } else if (algo == 3) {
+    const int grid = max(1, min((nvec / world + 511) / 512, num_sms / 2));   // co-resident (spin on the local counter)
+    nvl_allreduce_nvls_twoshot_kernel<<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);
+  } else if (algo == 0 || algo == 4) {
+    const int grid = max(1, min((nvec + 511) / 512, num_sms));
+    if (algo == 4) nvl_allreduce_oneshot_kernel<true><<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);
+    else nvl_allreduce_oneshot_kernel<false><<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);
   } else {
     const int grid = max(1, min((nvec / world + 511) / 512, num_sms / 2));   // all blocks must be co-resident (spin)
     nvl_allreduce_twoshot_kernel<<<grid, 512, 0, stream>>>(P, (__nv_bfloat16*)out, n, epoch_ptr, done_ctr, channel);

@@ -99,6 +99,7 @@ class _Envs:
     # --- distributed
     SGLB_COMM_IMPL = EnvStr("SGLB_COMM_IMPL", "auto", "auto|nvl (own P2P/multicast kernels)|nccl")
     SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "push", "push (GEMM epilogue stores into peers) | pull (consumer loads from peers) | off")
+    SGLB_NVLS = EnvBool("SGLB_NVLS", True, "use NVSwitch multicast (multimem.ld_reduce / multimem.st) in the NVL collectives when available")
     SGLB_NVL_MAX_BYTES = EnvInt("SGLB_NVL_MAX_BYTES", 512 << 20, "symmetric arena bytes per rank")
     # --- observability
     SGLB_TORCH_PROFILER_DIR = EnvStr("SGLB_TORCH_PROFILER_DIR", "/tmp/sglb_profiles")

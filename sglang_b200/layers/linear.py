@@ -190,7 +190,7 @@ class RowParallelLinear(LinearBase):
 
     # messages up to this size take the fused path: the GEMM writes its partial product straight into the NVL arena and the
     # *next* RMSNorm kernel performs the cross-rank sum (+ residual + norm) while pulling the peers' rows over NVLink.
-    FUSED_AR_MAX_BYTES = 1 << 20
+    FUSED_AR_MAX_BYTES = 16 << 20      # [T, H] bf16 partials up to e.g. 2048 x 4096: every decode batch and most prefill chunks
 
     def forward(self, x, defer_reduce: bool = False):
         """``defer_reduce``: return a ``PendingAllReduce`` (partial sums parked in the symmetric arena) instead of

@@ -45,8 +45,11 @@ class NvlComm:
         self.host_epoch = [0] * NUM_CHANNELS   # host mirror used only to pick the slot parity
         self.graph_epoch = [0] * NUM_CHANNELS
         self.capturing = False
-        self.max_oneshot_bytes = 512 * 1024    # crossover measured by the reference on B200x8 (k3_ar_fusion.py:36-38)
+        # one-shot -> two-shot crossover: 512 KB on 8 GPUs (reference k3_ar_fusion.py:36-38); with two ranks a reduce-scatter +
+        # all-gather moves exactly the same bytes as the one-shot exchange, so two-shot never wins (measured: profiles/mgpu_tp2_r1.md)
+        self.max_oneshot_bytes = (1 << 40) if self.world == 2 else 512 * 1024
         self.calls = 0
+        self.use_nvls = bool(self.mc_ptr) and envs.SGLB_NVLS.get()      # NVSwitch in-network reduction when a multicast alias exists
 
     @classmethod
     def create(cls, group: Any) -> "NvlComm":
@@ -109,8 +112,10 @@ class NvlComm:
     def all_reduce(self, x: torch.Tensor, algo: Optional[int] = None) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
         if algo is None:
-            algo = 0 if nbytes <= self.max_oneshot_bytes else 1
-        ch = CH_ONESHOT if algo == 0 else CH_TWOSHOT
+            # algo 0/1: peer pull one-/two-shot; 2/3: NVLS (switch-side reduction: multimem.ld_reduce / multimem.st)
+            small = nbytes <= self.max_oneshot_bytes
+            algo = (2 if small else 3) if self.use_nvls else (0 if small else 1)
+        ch = CH_ONESHOT if algo in (0, 2, 4) else CH_TWOSHOT
         off = self._slot(ch)
         self.slot_view(off, x.shape).copy_(x)      # stage into the arena (the fused GEMM epilogue writes here directly)
         out = torch.empty_like(x)
@@ -127,7 +132,7 @@ class NvlComm:
     def allreduce_from_slot(self, off: int, out: torch.Tensor, channel: int = CH_FUSED_NORM) -> None:
         """one-shot all-reduce of partials that a producer already wrote into slot ``off`` (no staging copy)"""
         torch.ops.sglb.nvl_allreduce(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, out,
-                                     self.epochs[channel:channel + 1], self.done[channel], channel, 0)
+                                     self.epochs[channel:channel + 1], self.done[channel], channel, 2 if self.use_nvls else 0)
         self.calls += 1
 
     def fused_allreduce_add_rmsnorm(self, off: int, residual: Optional[torch.Tensor], weight: torch.Tensor, out: torch.Tensor,
@@ -135,7 +140,7 @@ class NvlComm:
         """consumer side of a row-parallel GEMM whose partial output already sits in arena slot ``off``"""
         T, H = out.shape
         ch = CH_FUSED_NORM
-        torch.ops.sglb.nvl_ar_add_rmsnorm(self.buf_ptrs, self.flag_ptrs, self.mc_ptr, off, self.rank, self.world, residual, weight, out,
+        torch.ops.sglb.nvl_ar_add_rmsnorm(self.buf_ptrs, self.flag_ptrs, self.mc_ptr if self.use_nvls else 0, off, self.rank, self.world, residual, weight, out,
                                           float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch], ch)
         self.calls += 1
 
