@@ -135,3 +135,29 @@ def test_more_tool_call_formats():
     # unknown function names are ignored
     p = FunctionCallParser(tools, "hermes")
     assert p.parse_non_stream('<tool_call>{"name": "nope", "arguments": {}}</tool_call>')[1] == []
+
+
+def test_jit_build_cache_and_weak_ref(tmp_path, monkeypatch):
+    import torch
+
+    from sglang_b200 import jit
+
+    monkeypatch.setenv("SGLB_JIT_CACHE", str(tmp_path))
+    jit._LOADED.clear()
+    so = jit.build("sglb_jit_weak_ref", [jit.CSRC_JIT / "weak_ref.cpp"])
+    assert so.exists() and so.parent.parent == tmp_path
+    t0 = so.stat().st_mtime
+    assert jit.build("sglb_jit_weak_ref", [jit.CSRC_JIT / "weak_ref.cpp"]) == so and so.stat().st_mtime == t0      # cache hit, no rebuild
+    x = torch.arange(12, dtype=torch.float32).view(3, 4)
+    w = jit.weak_ref_tensor(x[:, 1:3])
+    assert w.data_ptr() == x[:, 1:3].data_ptr() and w.shape == (3, 2) and w.stride() == (4, 1)
+    x[0, 1] = 42.0
+    assert w[0, 0] == 42.0
+    # a different flag set is a different cache entry
+    so2 = jit.build("sglb_jit_weak_ref", [jit.CSRC_JIT / "weak_ref.cpp"], extra_cflags=["-DSGLB_JIT_TEST_FLAG=1"])
+    assert so2 != so and so2.exists()
+    # inline source: a tiny CPU op
+    src = '#include <torch/library.h>\n#include <torch/types.h>\nstatic at::Tensor twice(const at::Tensor& t) { return t * 2; }\n' \
+          'TORCH_LIBRARY(sglb_jit_t, m) { m.def("twice(Tensor t) -> Tensor", &twice); }\n'
+    jit.load_inline("sglb_jit_t", src, is_cuda=False)
+    assert torch.equal(torch.ops.sglb_jit_t.twice(torch.ones(3)), torch.full((3,), 2.0))
