@@ -36,12 +36,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3-8b")
-    ap.add_argument("--num-prompts", type=int, default=256)
+    ap.add_argument("--num-prompts", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--attention-backend", default=os.environ.get("SGLB_BENCH_ATTN", "auto"))
     ap.add_argument("--gemm-backend", default=os.environ.get("SGLB_BENCH_GEMM", "auto"))
     ap.add_argument("--page-size", type=int, default=32)
-    ap.add_argument("--max-running", type=int, default=256)
+    ap.add_argument("--max-running", type=int, default=1024)
     ap.add_argument("--disable-cuda-graph", action="store_true")
     ap.add_argument("--disable-overlap", action="store_true")
     ap.add_argument("--comm-backend", default="auto")

@@ -101,6 +101,8 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                        vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
     "tiny-llama-gpu": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
                            num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
+    "tiny-llama-gpu8": dict(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8,
+                            num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
     "tiny-mixtral": dict(architecture="MixtralForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
                          num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
                          num_local_experts=4, num_experts_per_tok=2, rope_theta=10000.0, dtype="float32"),

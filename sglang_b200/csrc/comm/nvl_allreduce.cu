@@ -55,22 +55,31 @@ __device__ __forceinline__ void mc_st_bf16x8(void* p, const U4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Publish `epoch` to every peer on `channel`, then wait until every peer has published it to us.
-// Called by all threads of a block; threads [0, world) do the flag traffic.
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Flag round: publish `epoch` to every peer on `channel`, then wait until every peer has published it to us.
+// Called by all threads of every block.  Only block 0 PUBLISHES (the data being announced was produced by an earlier kernel on this
+// stream, so one release store per peer is enough — measured: with every CTA issuing sys-scope fences + remote stores the flag
+// round cost ~7 us on 2 x B200); every block polls its own rank's (local) flag words with relaxed loads and fences once.
 __device__ __forceinline__ void nvl_barrier(const NvlPeers& P, int channel, uint32_t epoch) {
   __syncthreads();
   if (threadIdx.x < P.world) {
-    __threadfence_system();
-    st_release_sys(P.flags[threadIdx.x] + channel * NVL_MAX_RANKS + P.rank, epoch);
+    if (blockIdx.x == 0) st_release_sys(P.flags[threadIdx.x] + channel * NVL_MAX_RANKS + P.rank, epoch);
     const uint32_t* mine = P.flags[P.rank] + channel * NVL_MAX_RANKS + threadIdx.x;
     uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) {
       if (++spins > (1u << 26)) {
         printf("sglb nvl: barrier timeout rank=%d waiting on rank=%d channel=%d epoch=%u have=%u\n", P.rank, threadIdx.x, channel,
                epoch, ld_acquire_sys(mine));
         __trap();
       }
     }
+    fence_acquire_sys();
   }
   __syncthreads();
 }

@@ -79,3 +79,15 @@ def test_tp2_qwen_bias_and_gqa_replication():
     for preset in ("tiny-qwen2", "tiny-gemma"):
         kw = dict(model_path=f"dummy:{preset}", page_size=4)
         _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))
+
+
+def test_world4_layouts():
+    """TP=4 with KV-head replication, EP=4 / EP=2 x moe-TP=2, and TP=2 x PP=2 on four gloo ranks"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=32)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 4}, 4, LP), ref)
+    _check(_run({**kw, "tp_size": 2, "pp_size": 2}, 4, LP), ref)
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 4, "ep_size": 4}, 4, LP), ref)
+    _check(_run({**kw, "tp_size": 4, "ep_size": 2}, 4, LP), ref)
