@@ -27,6 +27,7 @@ from typing import Any, AsyncIterator, Dict, Iterator, List, Optional, Union
 import torch
 
 from ..configs.model_config import load_model_config
+from ..environ import envs
 from ..managers import io_struct as ios
 from ..managers.detokenizer import Detokenizer
 from ..managers.scheduler import Scheduler
@@ -452,6 +453,23 @@ class Engine:
         if self._bg_thread is not None:
             return
         self._bg_stop.clear()
+        self._shm_bcast = None
+        if self._world.world_size > 1 and self.server_args.nnodes == 1 and envs.SGLB_SHM_BROADCAST.get():
+            # single node: per-iteration request fan-out over a shared-memory ring instead of a Gloo collective
+            from ..parallel.shm_broadcast import ShmBroadcaster
+
+            try:
+                if self.is_driver:
+                    self._shm_bcast = ShmBroadcaster(self._world.world_size - 1)
+                    self._world.broadcast_pyobj(self._shm_bcast.handle(), src=0)
+                else:
+                    h = self._world.broadcast_pyobj(None, src=0)
+                    self._shm_bcast = ShmBroadcaster.attach(h, ps.get_state().rank - 1) if h is not None else None
+            except Exception as e:      # /dev/shm unavailable: keep the Gloo path
+                logger.warning("shared-memory broadcast unavailable (%s); using Gloo", e)
+                if self.is_driver:
+                    self._world.broadcast_pyobj(None, src=0)
+                self._shm_bcast = None
         self._bg_thread = threading.Thread(target=self._bg_loop, name="sglb-scheduler", daemon=True)
         self._bg_thread.start()
 
@@ -470,7 +488,10 @@ class Engine:
                         break
             if self._world.world_size > 1:      # every rank of the TP x PP world runs the same loop on the same requests
                 payload = [m if not isinstance(m, tuple) else m[0] for m in new] if self.is_driver else None
-                payload = self._world.broadcast_pyobj(payload, src=0)
+                if self._shm_bcast is not None:
+                    payload = self._shm_bcast.broadcast(payload, timeout=None)
+                else:
+                    payload = self._world.broadcast_pyobj(payload, src=0)
                 if not self.is_driver:
                     new = payload
             for m in new:

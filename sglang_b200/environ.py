@@ -99,6 +99,7 @@ class _Envs:
     # --- distributed
     SGLB_COMM_IMPL = EnvStr("SGLB_COMM_IMPL", "auto", "auto|nvl (own P2P/multicast kernels)|nccl")
     SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "push", "push (GEMM epilogue stores into peers) | pull (consumer loads from peers) | off")
+    SGLB_SHM_BROADCAST = EnvBool("SGLB_SHM_BROADCAST", True, "single-node control-plane fan-out over a shared-memory ring (else Gloo)")
     SGLB_NVLS = EnvBool("SGLB_NVLS", True, "use NVSwitch multicast (multimem.ld_reduce / multimem.st) in the NVL collectives when available")
     SGLB_NVL_MAX_BYTES = EnvInt("SGLB_NVL_MAX_BYTES", 512 << 20, "symmetric arena bytes per rank")
     # --- observability

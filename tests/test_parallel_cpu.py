@@ -91,3 +91,49 @@ def test_world4_layouts():
     ref = _run(kw, 1, LP)
     _check(_run({**kw, "tp_size": 4, "ep_size": 4}, 4, LP), ref)
     _check(_run({**kw, "tp_size": 4, "ep_size": 2}, 4, LP), ref)
+
+
+def test_shm_broadcast_ring_multi_reader():
+    import pickle
+
+    from sglang_b200.parallel.shm_broadcast import ShmBroadcaster
+
+    w = ShmBroadcaster(2, max_chunk_bytes=4096, n_chunks=4)
+    h = w.handle()
+    arg = pickle.dumps((h.name, h.n_readers, h.max_chunk_bytes, h.n_chunks)).hex()
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_shm_reader.py"), arg, str(r)], stdout=subprocess.PIPE, text=True,
+                              env=dict(os.environ, PYTHONPATH=ROOT)) for r in range(2)]
+    want = 0
+    for i in range(300):                      # far more messages than chunks; some span several chunks
+        blob = b"x" * (10 if i % 7 else 20000)
+        o = {"x": list(range(i % 50)), "blob": blob}
+        want += sum(o["x"]) + len(blob)
+        w.broadcast(o, timeout=30)
+    w.broadcast(None, timeout=30)
+    for p in procs:
+        out, _ = p.communicate(timeout=60)
+        assert p.returncode == 0 and out.strip() == f"SUM {want}", out
+    w.close()
+
+
+@pytest.mark.parametrize("shm", ["1", "0"])
+def test_tp2_server_mode_background_loop(shm):
+    """request fan-out to the peer rank over the shm ring (and over Gloo when disabled) gives the single-process results"""
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   PYTHONPATH=ROOT, OMP_NUM_THREADS="2", SGLB_SHM_BROADCAST=shm, PEER_LIFETIME="25")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_mp_server_worker.py")], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True, cwd=ROOT))
+    o, e = procs[0].communicate(timeout=200)
+    assert procs[0].returncode == 0, e[-3000:]
+    got = json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][-1][7:])
+    procs[1].kill()
+    import sglang_b200 as sgl
+
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, log_level="error")
+    sp = {"max_new_tokens": 6, "temperature": 0, "ignore_eos": True}
+    ref = [eng.generate(input_ids=p, sampling_params=sp)["output_ids"] for p in ([5, 6, 7, 8, 9], [3, 4], list(range(20, 50)), [9, 8, 7], [1, 2, 3, 4])]
+    eng.shutdown()
+    assert got == ref
