@@ -413,6 +413,20 @@ class Engine:
             self.weight_version = model_path
         return r
 
+    def init_weights_update_group(self, master_address: str, master_port: int, rank_offset: int, world_size: int,
+                                  group_name: str = "weight_update_group", backend: str = "nccl") -> Any:
+        return self._control(ios.InitWeightsUpdateGroupReq(master_address, master_port, rank_offset, world_size, group_name, backend))
+
+    def destroy_weights_update_group(self, group_name: str = "weight_update_group") -> Any:
+        return self._control(ios.DestroyWeightsUpdateGroupReq(group_name))
+
+    def update_weights_from_distributed(self, names: List[str], dtypes: List[str], shapes: List[List[int]],
+                                        group_name: str = "weight_update_group", flush_cache: bool = True) -> Any:
+        r = self._control(ios.UpdateWeightsFromDistributedReq(names, dtypes, shapes, group_name, flush_cache))
+        if r.success:
+            self.weight_version = f"distributed:{group_name}"
+        return r
+
     def update_weights_from_tensor(self, named_tensors: Any, flush_cache: bool = True) -> Any:
         return self._control(ios.UpdateWeightsFromTensorReq(named_tensors, flush_cache))
 

@@ -254,6 +254,26 @@ def create_app(engine: Any):
         res = await _ctl(engine.rerank, r.query, r.documents)
         return res[: r.top_n] if r.top_n else res
 
+    @app.post("/init_weights_update_group")
+    async def init_weights_update_group(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.init_weights_update_group, b["master_address"], int(b["master_port"]), int(b.get("rank_offset", 1)),
+                       int(b["world_size"]), b.get("group_name", "weight_update_group"), b.get("backend", "nccl"))
+        return {"success": r.success, "message": r.message}
+
+    @app.post("/update_weights_from_distributed")
+    async def update_weights_from_distributed(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.update_weights_from_distributed, b["names"], b["dtypes"], b["shapes"], b.get("group_name", "weight_update_group"),
+                       bool(b.get("flush_cache", True)))
+        return {"success": r.success, "message": r.message}
+
+    @app.post("/destroy_weights_update_group")
+    async def destroy_weights_update_group(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.destroy_weights_update_group, b.get("group_name", "weight_update_group"))
+        return {"success": r.success, "message": r.message}
+
     from .adapters import install_adapters
 
     install_adapters(app, engine, serving)

@@ -266,6 +266,31 @@ class UpdateWeightsFromTensorReq:
 
 
 @message
+class InitWeightsUpdateGroupReq:
+    """join a dedicated process group with an external trainer (rank 0) — reference engine.init_weights_update_group"""
+    master_address: str = "127.0.0.1"
+    master_port: int = 0
+    rank_offset: int = 1
+    world_size: int = 2
+    group_name: str = "weight_update_group"
+    backend: str = "nccl"
+
+
+@message
+class DestroyWeightsUpdateGroupReq:
+    group_name: str = "weight_update_group"
+
+
+@message
+class UpdateWeightsFromDistributedReq:
+    names: Any = None
+    dtypes: Any = None
+    shapes: Any = None
+    group_name: str = "weight_update_group"
+    flush_cache: bool = True
+
+
+@message
 class UpdateWeightsResp:
     success: bool = True
     message: str = ""

@@ -114,10 +114,12 @@ class Scheduler:
             self.paused = False
             return ios.GenericResp()
         if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq, ios.GetWeightsByNameReq,
+                            ios.InitWeightsUpdateGroupReq, ios.DestroyWeightsUpdateGroupReq, ios.UpdateWeightsFromDistributedReq,
                             ios.ReleaseMemoryOccupationReq, ios.ResumeMemoryOccupationReq, ios.ProfileReq,
                             ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq)):
             self.drain()
-            if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq)):
+            if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq)) or \
+                    (isinstance(msg, ios.UpdateWeightsFromDistributedReq) and msg.flush_cache):
                 self.flush_cache()
             return self.worker.handle_control(msg)
         if isinstance(msg, ios.OpenSessionReq):

@@ -26,6 +26,13 @@ def handle(runner: Any, msg: Any) -> Any:
         return _update_from_tensor(runner, msg)
     if isinstance(msg, ios.GetWeightsByNameReq):
         return _get_weights(runner, msg)
+    if isinstance(msg, ios.InitWeightsUpdateGroupReq):
+        return _init_update_group(runner, msg)
+    if isinstance(msg, ios.DestroyWeightsUpdateGroupReq):
+        getattr(runner, "_update_groups", {}).pop(msg.group_name, None)
+        return ios.GenericResp(True, f"destroyed {msg.group_name}")
+    if isinstance(msg, ios.UpdateWeightsFromDistributedReq):
+        return _update_from_distributed(runner, msg)
     if isinstance(msg, ios.ReleaseMemoryOccupationReq):
         return _release(runner, msg)
     if isinstance(msg, ios.ResumeMemoryOccupationReq):
@@ -82,6 +89,58 @@ def _update_from_tensor(runner, msg) -> ios.UpdateWeightsResp:
         logger.exception("update_weights_from_tensor failed")
         return ios.UpdateWeightsResp(False, f"{type(e).__name__}: {e}")
     return ios.UpdateWeightsResp(True, f"updated {n} tensors")
+
+
+def _init_update_group(runner, msg) -> ios.GenericResp:
+    """Standalone communicator with an external trainer process (its rank 0 broadcasts fresh weights after every RL step).
+    Reference: ``model_runner_components/weight_updater.py`` ``init_weights_update_group`` (custom process group over a TCP store;
+    our rank = rank_offset + tp_rank).  Built from a private TCPStore + ProcessGroup{NCCL,Gloo} so it does not touch the serving
+    job's default group."""
+    import datetime
+
+    import torch.distributed as dist
+
+    rank = msg.rank_offset + runner.tp.rank
+    backend = msg.backend if runner.is_cuda else "gloo"
+    try:
+        store = dist.TCPStore(msg.master_address, int(msg.master_port), msg.world_size, is_master=False,
+                              timeout=datetime.timedelta(seconds=120))
+        store = dist.PrefixStore(msg.group_name, store)
+        if backend == "nccl":
+            pg = dist.ProcessGroupNCCL(store, rank, msg.world_size, dist.ProcessGroupNCCL.Options())
+        else:
+            pg = dist.ProcessGroupGloo(store, rank, msg.world_size, datetime.timedelta(seconds=120))
+    except Exception as e:
+        logger.exception("init_weights_update_group failed")
+        return ios.GenericResp(False, f"{type(e).__name__}: {e}")
+    if not hasattr(runner, "_update_groups"):
+        runner._update_groups = {}
+    runner._update_groups[msg.group_name] = pg
+    return ios.GenericResp(True, f"joined {msg.group_name} as rank {rank}/{msg.world_size} ({backend})")
+
+
+def _update_from_distributed(runner, msg) -> ios.UpdateWeightsResp:
+    """receive full (unsharded) tensors by broadcast from the trainer (rank 0) and load each rank's shard"""
+    import torch.distributed as dist
+
+    pg = getattr(runner, "_update_groups", {}).get(msg.group_name)
+    if pg is None:
+        return ios.UpdateWeightsResp(False, f"weight update group {msg.group_name!r} is not initialised")
+    _sync(runner)
+    dt = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
+    try:
+        pdtype = next(runner.model.parameters()).dtype
+        n = 0
+        for name, dtype, shape in zip(msg.names, msg.dtypes, msg.shapes):
+            t = torch.empty(tuple(shape), dtype=dt.get(str(dtype).replace("torch.", ""), torch.float32), device=runner.device)
+            opts = dist.BroadcastOptions()
+            opts.rootRank = 0
+            pg.broadcast([t], opts).wait()
+            n += len(runner.model.load_weights([(name, t.to(pdtype))]))
+    except Exception as e:
+        logger.exception("update_weights_from_distributed failed")
+        return ios.UpdateWeightsResp(False, f"{type(e).__name__}: {e}")
+    return ios.UpdateWeightsResp(True, f"updated {n} tensors over {msg.group_name}")
 
 
 def _get_weights(runner, msg) -> ios.GetWeightsByNameResp:

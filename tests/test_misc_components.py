@@ -161,3 +161,46 @@ def test_jit_build_cache_and_weak_ref(tmp_path, monkeypatch):
           'TORCH_LIBRARY(sglb_jit_t, m) { m.def("twice(Tensor t) -> Tensor", &twice); }\n'
     jit.load_inline("sglb_jit_t", src, is_cuda=False)
     assert torch.equal(torch.ops.sglb_jit_t.twice(torch.ones(3)), torch.full((3,), 2.0))
+
+
+def test_update_weights_from_distributed_group():
+    """RL weight sync: an external 'trainer' (rank 0 of a private gloo group) broadcasts a tensor, the engine loads it"""
+    import datetime
+    import socket
+    import threading
+
+    import torch
+    import torch.distributed as dist
+
+    import sglang_b200 as sgl
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, log_level="error")
+    name = "model.layers.0.mlp.down_proj.weight"
+    shape = list(dict(eng.runner.model.named_parameters())[name].shape)
+    new = torch.full(shape, 0.125)
+    before = eng.generate(input_ids=[5, 6, 7, 8], sampling_params={"max_new_tokens": 4, "temperature": 0})["output_ids"]
+    err = []
+
+    def trainer():
+        try:
+            store = dist.TCPStore("127.0.0.1", port, 2, is_master=True, timeout=datetime.timedelta(seconds=60))
+            pg = dist.ProcessGroupGloo(dist.PrefixStore("weight_update_group", store), 0, 2, datetime.timedelta(seconds=60))
+            opts = dist.BroadcastOptions(); opts.rootRank = 0
+            pg.broadcast([new.clone()], opts).wait()
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+
+    th = threading.Thread(target=trainer); th.start()
+    r = eng.init_weights_update_group("127.0.0.1", port, 1, 2, backend="gloo")
+    assert r.success, r.message
+    r = eng.update_weights_from_distributed([name], ["float32"], [shape])
+    th.join(timeout=60)
+    assert not err and r.success, (err, r.message)
+    got = torch.tensor(eng.get_weights_by_name(name, 8))
+    assert torch.allclose(got, torch.full((8,), 0.125))
+    after = eng.generate(input_ids=[5, 6, 7, 8], sampling_params={"max_new_tokens": 4, "temperature": 0})
+    assert after["meta_info"]["cached_tokens"] == 0          # the radix cache was flushed with the old weights
+    assert eng.update_weights_from_distributed([name], ["float32"], [shape], group_name="nope").success is False
+    assert eng.destroy_weights_update_group().success
+    eng.shutdown()
