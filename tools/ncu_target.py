@@ -31,5 +31,38 @@ elif what.startswith("gemm"):
     o = torch.empty(M, 6144, device=dev, dtype=torch.bfloat16)
     for _ in range(n):
         torch.ops.sglb.gemm(a, w, o, None, 0, 0)
+elif what == "attn_decode_persist":
+    B = 512
+    s = _attn_setup(B, [1] * B, [512] * B, 32, 8, 128, 32)
+    out = torch.empty_like(s["q"])
+    for _ in range(n):
+        ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, impl=0, out=out)
+elif what == "skinny":
+    a = torch.randn(64, 14336, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(4096, 14336, device=dev, dtype=torch.bfloat16) * 0.02
+    for _ in range(n):
+        ops.gemm_skinny_slabs(a, w)
+elif what == "skinny_silu":
+    a = torch.randn(64, 4096, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(2 * 14336, 4096, device=dev, dtype=torch.bfloat16) * 0.02
+    for _ in range(n):
+        ops.gemm_skinny(a, w, silu_split=True)
+elif what == "fp8":
+    from sglang_b200.ops import quant_ops, torch_ref
+    x = torch.randn(2048, 4096, device=dev, dtype=torch.bfloat16)
+    wq, ws = torch_ref.block_quant_weight_fp8(torch.randn(14336, 4096, device=dev) * 0.02, 128, False)
+    xq, xs = quant_ops.per_token_group_quant_fp8(x, 128, False)
+    out = torch.empty(2048, 14336, device=dev, dtype=torch.bfloat16)
+    for _ in range(n):
+        torch.ops.sglb.gemm_fp8_block(xq, xs, wq, ws, out)
+elif what == "moe":
+    from sglang_b200.ops import moe_ops
+    T, E, K, H, I = 2048, 8, 2, 4096, 14336
+    x = torch.randn(T, H, device=dev, dtype=torch.bfloat16) * 0.5
+    w13 = torch.randn(E, 2 * I, H, device=dev, dtype=torch.bfloat16) * 0.02
+    w2 = torch.randn(E, H, I, device=dev, dtype=torch.bfloat16) * 0.02
+    tw, ids = moe_ops.topk_softmax(torch.randn(T, E, device=dev), K, True)
+    for _ in range(n):
+        moe_ops.fused_moe(x, w13, w2, tw, ids, 0)
 torch.cuda.synchronize()
 print("done", what)
