@@ -132,6 +132,8 @@ class ModelRunner:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.lora_manager = None
+        self.hidden_tap = None          # callable(ScheduleBatch, hidden[T,H]) installed by feature-based draft workers (EAGLE)
+        self.last_verify_hidden = None
         self.profiler = None
         self.expert_recorder = None
         if self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1:
@@ -232,6 +234,8 @@ class ModelRunner:
         if not self.pp.is_first:
             fb.pp_hidden = self._pp_recv(fb.num_tokens)
         hidden = self.model(fb)
+        if self.hidden_tap is not None and not decode and self.pp.is_last:
+            self.hidden_tap(sb, hidden)          # EAGLE: target features of the prefilled positions
         res = BatchResult()
         res.batch_size = B
         if not self.pp.is_last:
@@ -280,6 +284,7 @@ class ModelRunner:
             fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
             self.h2d_bytes += fb.h2d_bytes
             hidden = self.model(fb)
+            self.last_verify_hidden = hidden if self.hidden_tap is not None else None
             logits = self.model.compute_logits(hidden)          # [T, V]
             reps = torch.from_numpy(sb.q_lens.astype(np.int64)).to(self.device)
             s = fb.sampling

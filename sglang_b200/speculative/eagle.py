@@ -1,0 +1,179 @@
+"""EAGLE-style feature-level speculative decoding (chain drafts, top-1).
+
+Parity: reference ``python/sglang/srt/speculative/eagle_worker_v2.py:1050`` (draft extend after prefill / after verify, multi-step
+draft), ``models/llama_eagle.py`` (draft = ``fc(2H -> H)`` over ``[embed(next token) ; target feature]`` + ONE decoder layer, sharing
+the target's embedding and LM head), ``eagle_info.py`` (features captured from the verify pass).
+
+How it runs here:
+* the target's final hidden states are tapped (``ModelRunner.hidden_tap`` for prefill chunks, ``last_verify_hidden`` for verify
+  passes) and the newest ``window`` (token position, feature) pairs are kept per request;
+* ``propose`` re-runs the one-layer draft over that window into a scratch KV pool (no second page table: the draft is one layer, the
+  window is short), then rolls forward ``num_draft`` steps feeding its OWN output feature back in (EAGLE's autoregression in feature
+  space) and taking the arg-max token at each step;
+* verification is the shared ragged-extend path of ``BaseSpecWorker`` (chain drafts => plain causal attention on the tcgen05 kernel).
+Tree drafts (topk > 1) need custom-mask attention; ``speculative_eagle_topk`` > 1 is accepted and clamped to the chain.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..configs.model_config import ModelConfig, load_model_config
+from ..managers.schedule_batch import ForwardMode, ScheduleBatch
+from ..mem_cache.memory_pool import KVPool
+from ..model_executor.forward_batch import ForwardBatch
+from ..models.llama import _DT, LlamaDecoderLayer
+from ..layers.common import RMSNorm, RotaryEmbedding
+from .spec_worker import BaseSpecWorker
+
+logger = logging.getLogger(__name__)
+
+
+class EagleDraftModel(nn.Module):
+    def __init__(self, cfg: ModelConfig, device: Any):
+        super().__init__()
+        dtype = _DT[cfg.dtype]
+        H = cfg.hidden_size
+        self.fc = nn.Linear(2 * H, H, bias=False, dtype=dtype)
+        rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
+                               cfg.partial_rotary_factor, device)
+        self.layer = LlamaDecoderLayer(cfg, 0, dtype, None, rope, "model.layers.0")
+        self.layer.input_layernorm = _Identity()        # EAGLE's first (only) layer has no input norm: fc output feeds attention
+
+    def forward(self, fb: ForwardBatch, tok_embeds: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
+        x = self.fc(torch.cat([tok_embeds, feats.to(tok_embeds.dtype)], dim=-1))
+        h, res = self.layer(x, None, fb)
+        h = h.resolve() if hasattr(h, "resolve") else h
+        return h + res                                  # predicted next-position feature
+
+    def load_weights(self, weights) -> List[str]:
+        params = dict(self.named_parameters())
+        loaded = []
+        remap = [("model.fc.", "fc."), ("fc.", "fc."), ("model.layers.0.", "layer."), ("layers.0.", "layer.")]
+        stacked = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v"),
+                   (".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
+        mods = dict(self.named_modules())
+        for name, w in weights:
+            for a, b in remap:
+                if name.startswith(a):
+                    name = b + name[len(a):]
+                    break
+            target, shard = name, None
+            for merged, orig, sid in stacked:
+                if orig in name:
+                    target, shard = name.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded
+
+
+class _Identity(nn.Module):
+    def forward(self, x, residual=None):
+        return x if residual is None else (x, residual)
+
+
+class EagleSpecWorker(BaseSpecWorker):
+    def __init__(self, args: Any, runner: Any, scheduler: Any, window: int = 48):
+        super().__init__(args, runner, scheduler)
+        if (args.speculative_eagle_topk or 1) > 1:
+            logger.warning("EAGLE tree drafts (topk=%d) are clamped to chain drafts (topk=1)", args.speculative_eagle_topk)
+        self.window = window
+        tcfg = runner.cfg
+        path = args.speculative_draft_model_path
+        cfg = load_model_config(path) if path and not path.startswith("dummy:") else tcfg
+        self.cfg = cfg
+        self.draft = EagleDraftModel(cfg, runner.device).to(runner.device)
+        if path and not path.startswith("dummy:"):
+            from ..model_loader.loader import iter_safetensors
+
+            self.draft.load_weights(iter_safetensors(path))
+        else:
+            g = torch.Generator(device="cpu").manual_seed(args.random_seed + 29)
+            for p in self.draft.parameters():
+                if p.dim() > 1:
+                    p.data.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
+        a0 = self.draft.layer.self_attn.attn
+        self.ps = 16
+        self.pool = KVPool(2 + (window + 2 * self.num_draft + 32) // self.ps, self.ps, 1, a0.num_kv_heads, cfg.head_dim, runner.dtype,
+                           str(runner.device))
+        # the feature window lives ON the request object (``req._eagle``: (position of the first kept row, features [n, H])) so it
+        # is dropped with the request — no registry to clean up on finish / abort / retraction
+        runner.hidden_tap = self._tap_prefill
+
+    # ---- feature bookkeeping
+    def _append(self, req: Any, start_pos: int, rows: torch.Tensor) -> None:
+        cur = getattr(req, "_eagle", None)
+        if cur is not None and cur[0] + cur[1].shape[0] == start_pos:
+            first, buf = cur
+            buf = torch.cat([buf, rows], 0)
+        else:
+            first, buf = start_pos, rows          # gap (cache hit / retraction): restart the window
+        if buf.shape[0] > self.window:
+            first += buf.shape[0] - self.window
+            buf = buf[-self.window:]
+        req._eagle = (first, buf.detach())
+
+    def _tap_prefill(self, sb: ScheduleBatch, hidden: torch.Tensor) -> None:
+        cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
+        for i, r in enumerate(sb.reqs):
+            lo, hi = int(cu[i]), int(cu[i + 1])
+            keep = min(hi - lo, self.window)
+            self._append(r, int(sb.prefix_lens[i]) + (hi - lo) - keep, hidden[hi - keep:hi])
+
+    def on_verified_hidden(self, req: Any, start_pos: int, hidden: torch.Tensor) -> None:
+        self._append(req, start_pos, hidden)
+
+    # ---- drafting
+    @torch.no_grad()
+    def propose(self, req: Any, max_draft: int) -> List[int]:
+        st = getattr(req, "_eagle", None)
+        if st is None or max_draft <= 0:
+            return []
+        first, feats = st
+        toks = req.origin_input_ids + req.output_ids
+        L = len(toks) - 1                      # position of the newest token (no target feature yet)
+        n = feats.shape[0]
+        if first + n != L or n == 0:           # features must end right before the newest token
+            return []
+        dev = self.runner.device
+        target = self.runner.model
+        embed = target.model.embed_tokens
+        out: List[int] = []
+        npages = self.pool.num_pages - 1
+        pt = torch.arange(1, npages + 1, dtype=torch.int32, device=dev).view(1, -1)
+        pt = torch.cat([torch.zeros_like(pt), pt], 0)
+        # window pass: inputs (token p+1, feature p) for p = first .. L-1, draft KV rows 0 .. n-1
+        ids = torch.tensor(toks[first + 1: L + 1], dtype=torch.int32, device=dev)
+        f_in = feats
+        base = 0
+        for step in range(max_draft):
+            m = ids.shape[0]
+            rel = torch.arange(base, base + m, dtype=torch.int32, device=dev)
+            fb = ForwardBatch(mode=ForwardMode.EXTEND, batch_size=1, num_tokens=m, input_ids=ids, positions=rel + first,
+                              out_cache_loc=(rel + self.ps).to(torch.int32), req_slots=torch.ones(1, dtype=torch.int32, device=dev),
+                              seq_lens=torch.tensor([base + m], dtype=torch.int32, device=dev),
+                              cu_q=torch.tensor([0, m], dtype=torch.int32, device=dev), q_lens=torch.tensor([m], dtype=torch.int32, device=dev),
+                              last_idx=None, sample_slots=None, max_q_len=m, max_kv_len=base + m, page_table=pt, page_size=self.ps,
+                              kv_pool=self.pool)
+            h = self.draft(fb, embed(ids), f_in)
+            last = h[-1:]
+            logits = target.compute_logits(last)       # features are post-final-norm hidden states (what the LM head consumes)
+            t = int(logits.argmax(-1))
+            out.append(t)
+            base += m
+            ids = torch.tensor([t], dtype=torch.int32, device=dev)
+            f_in = last                         # autoregression in feature space
+            if base + 1 >= self.window + 2 * self.num_draft + 16:
+                break
+        return out

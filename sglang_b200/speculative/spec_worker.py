@@ -53,6 +53,9 @@ class BaseSpecWorker:
     def on_tokens_accepted(self, req: Any, new_tokens: List[int]) -> None:
         pass
 
+    def on_verified_hidden(self, req: Any, start_pos: int, hidden: torch.Tensor) -> None:
+        pass
+
     def forward_batch_speculative(self, batch: ScheduleBatch) -> SpecResult:
         """``batch``: decode snapshot (one slot already allocated at position p = seq_len-1 for every request)."""
         sch, kv, runner = self.scheduler, self.scheduler.kv, self.runner
@@ -92,6 +95,7 @@ class BaseSpecWorker:
         toks_all = runner.forward_verify(vb)          # np.int64 [T]: target sample at every fed position
         res = SpecResult(B)
         cu = np.concatenate([[0], np.cumsum(vb.q_lens)])
+        vh = runner.last_verify_hidden
         for i, r in enumerate(batch.reqs):
             t = toks_all[cu[i]:cu[i + 1]]
             d = drafts[i]
@@ -108,6 +112,8 @@ class BaseSpecWorker:
             self.total_drafted += len(d)
             self.total_accepted += a
             self.total_verify += 1
+            if vh is not None:                     # target features of the positions that stay (last token + accepted drafts)
+                self.on_verified_hidden(r, plens[i], vh[cu[i]:cu[i] + a + 1])
             self.on_tokens_accepted(r, out)
         # keep the device-side "future map" coherent for anyone who reads it
         slots = torch.from_numpy(np.asarray(batch.req_slots, dtype=np.int64)).to(runner.device)
@@ -215,8 +221,10 @@ def create_spec_worker(args: Any, runner: Any, scheduler: Any) -> BaseSpecWorker
     algo = (args.speculative_algorithm or "").upper()
     if algo == "NGRAM":
         return NgramSpecWorker(args, runner, scheduler)
-    if algo in ("STANDALONE", "EAGLE", "EAGLE3"):
-        if algo != "STANDALONE":
-            logger.warning("%s draft heads are served through the standalone chain-draft worker (topk=1)", algo)
+    if algo in ("EAGLE", "EAGLE3"):
+        from .eagle import EagleSpecWorker
+
+        return EagleSpecWorker(args, runner, scheduler)
+    if algo == "STANDALONE":
         return StandaloneSpecWorker(args, runner, scheduler)
     raise ValueError(f"unknown speculative algorithm {args.speculative_algorithm}")

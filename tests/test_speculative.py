@@ -46,3 +46,21 @@ def test_ngram_accepts_on_repetition():
     steps2 = w.total_verify - v1
     assert steps2 < 48 * 0.6, f"second pass should need far fewer target steps ({steps2})"
     assert b["meta_info"]["spec_accept_length"] > 1.5
+
+
+def test_eagle_chain_drafts_exact_and_feature_window():
+    """EAGLE worker: outputs identical to plain greedy decoding whatever the draft quality; features tapped from prefill + verify"""
+    prompts = _prompts()
+    sp = {"max_new_tokens": 24, "temperature": 0, "ignore_eos": True}
+    plain = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    want = [o["output_ids"] for o in plain.generate(input_ids=prompts, sampling_params=sp)]
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, speculative_algorithm="EAGLE", speculative_num_draft_tokens=3,
+                     chunked_prefill_size=16)
+    outs = eng.generate(input_ids=prompts, sampling_params=sp)
+    assert [o["output_ids"] for o in outs] == want
+    w = eng.scheduler.spec_worker
+    assert type(w).__name__ == "EagleSpecWorker" and w.total_verify > 0 and w.total_drafted > 0
+    eng.scheduler.check_invariants()
+    # a draft that IS a perfect predictor: make the draft layer output the target feature of the next position by construction is not
+    # possible with random weights, so check the mechanics instead — drafts are proposed from step one and bounded by num_draft
+    assert w.total_drafted <= w.total_verify * 3
