@@ -45,6 +45,20 @@ class ModelConfig:
     shared_expert_intermediate_size: Optional[int] = None      # Qwen2-MoE sigmoid-gated shared expert
     decoder_sparse_step: int = 1
     mlp_only_layers: Optional[List[int]] = None
+    # DeepSeek-V2/V3: MLA + DeepSeekMoE
+    q_lora_rank: Optional[int] = None
+    kv_lora_rank: Optional[int] = None
+    qk_nope_head_dim: int = 0
+    qk_rope_head_dim: int = 0
+    v_head_dim: int = 0
+    n_shared_experts: Optional[int] = None
+    first_k_dense_replace: int = 0
+    moe_layer_freq: int = 1
+    n_group: Optional[int] = None
+    topk_group: Optional[int] = None
+    routed_scaling_factor: float = 1.0
+    scoring_func: str = "softmax"
+    topk_method: str = "greedy"
     # Gemma-2 / Granite extras
     query_pre_attn_scalar: Optional[float] = None
     layer_types: Optional[List[str]] = None
@@ -123,6 +137,18 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                        rope_theta=10000.0, dtype="float32", image_token_id=500,
                        vision={"hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 2, "num_attention_heads": 2,
                                "image_size": 28, "patch_size": 14, "select_layer": -2, "projector_hidden_act": "gelu"}),
+    "tiny-deepseek-v2": dict(architecture="DeepseekV2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=3,
+                             num_attention_heads=4, num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0,
+                             kv_lora_rank=32, q_lora_rank=None, qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16,
+                             num_local_experts=8, num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1,
+                             first_k_dense_replace=1, n_group=4, topk_group=2, routed_scaling_factor=1.0, norm_topk_prob=False,
+                             rope_is_neox=False, dtype="float32"),
+    "tiny-deepseek-v3": dict(architecture="DeepseekV3ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=3,
+                             num_attention_heads=4, num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0,
+                             kv_lora_rank=32, q_lora_rank=24, qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16,
+                             num_local_experts=8, num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1,
+                             first_k_dense_replace=1, n_group=4, topk_group=2, routed_scaling_factor=2.5, norm_topk_prob=True,
+                             scoring_func="sigmoid", topk_method="noaux_tc", rope_is_neox=False, dtype="float32"),
     "tiny-phi3": dict(architecture="Phi3ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
                       num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
     "tiny-internlm2": dict(architecture="InternLM2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
@@ -149,6 +175,12 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                        num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0,
                        dtype="float32"),
     # ---- real architectures (random-init offline)
+    "deepseek-v2-lite": dict(architecture="DeepseekV2ForCausalLM", hidden_size=2048, intermediate_size=10944, num_hidden_layers=27,
+                             num_attention_heads=16, num_key_value_heads=16, vocab_size=102400, max_position_embeddings=163840,
+                             rope_theta=10000.0, kv_lora_rank=512, q_lora_rank=None, qk_nope_head_dim=128, qk_rope_head_dim=64,
+                             v_head_dim=128, num_local_experts=64, num_experts_per_tok=6, moe_intermediate_size=1408, n_shared_experts=2,
+                             first_k_dense_replace=1, n_group=1, topk_group=1, routed_scaling_factor=1.0, norm_topk_prob=False,
+                             rope_is_neox=False, rms_norm_eps=1e-6, bos_token_id=100000, eos_token_id=100001),
     "qwen3-30b-a3b": dict(architecture="Qwen3MoeForCausalLM", hidden_size=2048, intermediate_size=6144, num_hidden_layers=48,
                           num_attention_heads=32, num_key_value_heads=4, head_dim=128, vocab_size=151936, max_position_embeddings=40960,
                           rope_theta=1000000.0, qk_norm=True, rms_norm_eps=1e-6, num_local_experts=128, num_experts_per_tok=8,

@@ -70,9 +70,14 @@ class FusedMoE(nn.Module):
             raise ValueError(shard)
 
     def forward(self, x: torch.Tensor, router_logits: torch.Tensor) -> torch.Tensor:
+        w, ids = select_experts(router_logits, self.top_k, self.renormalize)
+        return self.forward_routed(x, w, ids)
+
+    def forward_routed(self, x: torch.Tensor, w: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """expert MLPs for an externally computed routing (``w`` fp32 [T,K], ``ids`` int32 [T,K] global expert ids) — grouped /
+        biased / sigmoid routers (DeepSeek) live in the model file"""
         from ..ops import moe_ops
 
-        w, ids = select_experts(router_logits, self.top_k, self.renormalize)
         if self.expert_load is not None:
             self.expert_load.record(self.layer_id, ids)
         tp = self.tp

@@ -136,7 +136,8 @@ class ModelRunner:
         self.last_verify_hidden = None
         self.profiler = None
         self.expert_recorder = None
-        if self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1:
+        if (self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1
+                and getattr(self.model, "supports_cuda_graph", True)):
             with torch.cuda.stream(self.stream):
                 self._capture_graphs()
             self.stream.synchronize()
@@ -145,11 +146,13 @@ class ModelRunner:
     def _init_memory(self) -> None:
         cfg, a = self.cfg, self.args
         n_layers = len(self.model.model.layers)
-        kv_heads = self.model.model.layers[0].self_attn.attn.num_kv_heads if n_layers else cfg.num_key_value_heads
+        a0 = self.model.model.layers[0].self_attn.attn if n_layers else None
+        kv_heads = a0.num_kv_heads if a0 is not None else cfg.num_key_value_heads
+        kv_dim = getattr(a0, "kv_head_dim", None) or cfg.head_dim      # MLA caches one 576-wide latent row per token
         kv_dtype = self.dtype
         if a.kv_cache_dtype in ("fp8_e4m3", "fp8"):
             kv_dtype = torch.float8_e4m3fn
-        per_page = KVPool.bytes_per_page(self.page_size, n_layers, kv_heads, cfg.head_dim, kv_dtype)
+        per_page = KVPool.bytes_per_page(self.page_size, n_layers, kv_heads, kv_dim, kv_dtype)
         self.max_context_len = a.context_length or cfg.max_position_embeddings
         if self.is_cuda:
             free, total = torch.cuda.mem_get_info(self.device)
@@ -168,7 +171,7 @@ class ModelRunner:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.tp.device_group)
             num_pages = int(t.item())
         self.num_pages = int(num_pages)
-        self.kv_pool = KVPool(self.num_pages, self.page_size, n_layers, kv_heads, cfg.head_dim, kv_dtype, str(self.device))
+        self.kv_pool = KVPool(self.num_pages, self.page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
         tokens = (self.num_pages - 1) * self.page_size
         self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1

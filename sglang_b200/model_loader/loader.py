@@ -87,7 +87,11 @@ def init_dummy_weights(model: nn.Module, seed: int = 0, scale: float = 0.02, cfg
             if p.numel():
                 p.data.view(-1)[:1].fill_(float("nan"))
         first = next(iter(params.values()))
-        model.load_weights(dummy_checkpoint_iterator(cfg, first.device, first.dtype, seed, scale))
+        # families whose tensors are not Llama-shaped describe their own full-size synthetic checkpoint (same loader path, so the
+        # result is independent of the TP/EP/PP layout)
+        it = model.dummy_checkpoint(cfg, first.device, first.dtype, seed, scale) if hasattr(model, "dummy_checkpoint") else \
+            dummy_checkpoint_iterator(cfg, first.device, first.dtype, seed, scale)
+        model.load_weights(it)
         todo = {n: p for n, p in params.items() if p.numel() and bool(torch.isnan(p.data.view(-1)[0].float()))}
     else:
         todo = params

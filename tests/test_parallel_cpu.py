@@ -137,3 +137,10 @@ def test_tp2_server_mode_background_loop(shm):
     ref = [eng.generate(input_ids=p, sampling_params=sp)["output_ids"] for p in ([5, 6, 7, 8, 9], [3, 4], list(range(20, 50)), [9, 8, 7], [1, 2, 3, 4])]
     eng.shutdown()
     assert got == ref
+
+
+def test_deepseek_mla_tp2_ep2():
+    kw = dict(model_path="dummy:tiny-deepseek-v3", page_size=4)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), ref, atol=5e-3)
+    _check(_run({**kw, "tp_size": 2, "ep_size": 2}, 2, LP), ref, atol=5e-3)
