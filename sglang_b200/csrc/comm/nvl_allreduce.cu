@@ -55,6 +55,16 @@ __device__ __forceinline__ void mc_st_bf16x8(void* p, const U4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Wall-clock bound for every cross-rank wait: ranks of an SPMD job may legitimately skew by seconds at trace boundaries (host-side work),
+// so the bound is TIME (globaltimer, 45 s), not a spin count; a protocol bug still ends in a trap with a message instead of a hung box.
+__device__ __forceinline__ bool nvl_wait_expired(uint32_t& spins, unsigned long long& t0) {
+  if ((++spins & 0xfffu) != 0) return false;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0) { t0 = now; return false; }
+  return now - t0 > 45ull * 1000ull * 1000ull * 1000ull;
+}
+
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -72,10 +82,11 @@ __device__ __forceinline__ void nvl_barrier(const NvlPeers& P, int channel, uint
     if (blockIdx.x == 0) st_release_sys(P.flags[threadIdx.x] + channel * NVL_MAX_RANKS + P.rank, epoch);
     const uint32_t* mine = P.flags[P.rank] + channel * NVL_MAX_RANKS + threadIdx.x;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) {
-      if (++spins > (1u << 26)) {
-        printf("sglb nvl: barrier timeout rank=%d waiting on rank=%d channel=%d epoch=%u have=%u\n", P.rank, threadIdx.x, channel,
-               epoch, ld_acquire_sys(mine));
+      if (nvl_wait_expired(spins, t0)) {
+        printf("sglb nvl: barrier timeout (45 s) rank=%d block=%d waiting on rank=%d channel=%d epoch=%u have=%u\n", P.rank, blockIdx.x,
+               threadIdx.x, channel, epoch, ld_acquire_sys(mine));
         __trap();
       }
     }
@@ -165,7 +176,11 @@ __global__ void __launch_bounds__(512) nvl_allreduce_twoshot_kernel(NvlPeers P, 
   __syncthreads();
   // every block waits until the whole grid has pushed (spin on the local counter), then the 2nd flag round
   if (threadIdx.x == 0) {
-    while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {}
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {
+      if (nvl_wait_expired(spins, t0)) { printf("sglb nvl: two-shot grid counter timeout rank=%d block=%d\n", P.rank, blockIdx.x); __trap(); }
+    }
   }
   nvl_barrier(P, channel, 2 * epoch);
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(P.buf[P.rank]) + (size_t)n;
@@ -215,7 +230,11 @@ __global__ void __launch_bounds__(512) nvl_allreduce_nvls_twoshot_kernel(NvlPeer
   if (threadIdx.x == 0) {
     __threadfence_system();
     atomicAdd(done_ctr + 1, 1);
-    while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {}
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {
+      if (nvl_wait_expired(spins, t0)) { printf("sglb nvl: NVLS two-shot grid counter timeout rank=%d block=%d\n", P.rank, blockIdx.x); __trap(); }
+    }
   }
   nvl_barrier(P, channel, 2 * epoch);
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(P.buf[P.rank]) + (size_t)n;
@@ -311,12 +330,15 @@ __global__ void __launch_bounds__(256) nvl_local_reduce_add_rmsnorm_kernel(const
   const uint32_t epoch = epoch_ptr ? epoch_begin(epoch_ptr) : 0;
   if (flags && threadIdx.x < world) {
     uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-      if (++spins > (1u << 26)) {
-        printf("sglb nvl: push-flag timeout waiting on rank=%d epoch=%u have=%u\n", threadIdx.x, epoch, ld_acquire_sys(flags + threadIdx.x));
+    unsigned long long t0 = 0;
+    while ((int32_t)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
+      if (nvl_wait_expired(spins, t0)) {
+        printf("sglb nvl: push-flag timeout (45 s) block=%d waiting on rank=%d epoch=%u have=%u\n", blockIdx.x, threadIdx.x, epoch,
+               ld_acquire_sys(flags + threadIdx.x));
         __trap();
       }
     }
+    fence_acquire_sys();
   }
   __syncthreads();
   const int nvec = H >> 3;
