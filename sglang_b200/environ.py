@@ -98,7 +98,9 @@ class _Envs:
     SGLB_KV_CANARY = EnvStr("SGLB_KV_CANARY", "none", "none|log|raise")
     # --- distributed
     SGLB_COMM_IMPL = EnvStr("SGLB_COMM_IMPL", "auto", "auto|nvl (own P2P/multicast kernels)|nccl")
-    SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "push", "push (GEMM epilogue stores into peers) | pull (consumer loads from peers) | off")
+    SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "pull", "pull (GEMM writes its partial into the local arena slot, the next norm kernel reduces across "
+                           "ranks via peer loads / NVLS) | push (GEMM epilogue stores into every peer, norm reduces locally) | off.  Measured: "
+                           "pull wins at 2 and 8 GPUs (push issues O(world) remote stores per rank; profiles/mgpu_tp8_r1.md)")
     SGLB_SHM_BROADCAST = EnvBool("SGLB_SHM_BROADCAST", True, "single-node control-plane fan-out over a shared-memory ring (else Gloo)")
     SGLB_NVLS = EnvBool("SGLB_NVLS", True, "use NVSwitch multicast (multimem.ld_reduce / multimem.st) in the NVL collectives when available")
     SGLB_NVL_MAX_BYTES = EnvInt("SGLB_NVL_MAX_BYTES", 512 << 20, "symmetric arena bytes per rank")
