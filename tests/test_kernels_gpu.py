@@ -88,3 +88,30 @@ print(json.dumps({{"ids": [o["output_ids"] for o in out],
     same = sum(a == b for a, b in zip(t["ids"], r["ids"]))
     first = sum(a[:1] == b[:1] for a, b in zip(t["ids"], r["ids"]))
     assert first >= len(r["ids"]) - 2 and same >= len(r["ids"]) // 2, (same, first)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["tiny-mixtral-gpu"])
+def test_moe_engine_gpu_native_vs_torch_ops(model):
+    """Mixtral-style engine on the GPU: native kernels (MoE block, tcgen05 attention, CUDA graphs) vs the same engine with every op forced
+    onto the fp32 torch references — teacher-forced prompt logprobs must agree"""
+    code = f'''
+import json
+import sglang_b200 as sgl
+import numpy as np
+rng = np.random.default_rng(1)
+prompts = [rng.integers(3, 2000, size=int(n)).tolist() for n in rng.integers(5, 200, size=8)]
+eng = sgl.Engine(model_path="dummy:{model}", page_size=32, chunked_prefill_size=256, cuda_graph_max_bs=8, mem_fraction_static=0.2, max_running_requests=8)
+lp = eng.generate(input_ids=prompts, sampling_params={{"max_new_tokens": 4, "temperature": 0, "ignore_eos": True}}, return_logprob=True, logprob_start_len=0)
+print(json.dumps({{"lp": [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in lp],
+                  "dlp": [[float(t[0]) for t in o["meta_info"]["output_token_logprobs"]] for o in lp], "ids": [o["output_ids"] for o in lp]}}))
+'''
+    outs = {}
+    for tag, env in (("native", {}), ("ref", {"SGLB_FORCE_TORCH_OPS": "1", "SGLB_DISABLE_CUDA_GRAPH": "1"})):
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, **env), cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-4000:]
+        outs[tag] = json.loads(p.stdout.strip().splitlines()[-1])
+    err = max(max(abs(a - b) for a, b in zip(x, y)) for x, y in zip(outs["native"]["lp"], outs["ref"]["lp"]) if x)
+    assert err < 0.08, f"prompt logprob mismatch {err}"
+    first = sum(a[:1] == b[:1] for a, b in zip(outs["native"]["ids"], outs["ref"]["ids"]))
+    assert first >= 6, (first, outs["native"]["ids"], outs["ref"]["ids"])

@@ -22,14 +22,14 @@ def t(fn, it=7):
         torch.cuda.synchronize(); s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
     return sorted(ts)[len(ts) // 2]
 res = {"fp8": {}, "moe": {}}
-shapes = {"8b_gate_up": (28672, 4096), "8b_down": (4096, 14336), "70b_tp8_qkv": (1280, 8192), "70b_tp8_gate_up": (7168, 8192), "70b_tp8_down": (8192, 3584)}
+shapes = {"8b_gate_up": (28672, 4096), "70b_tp8_qkv": (1280, 8192), "70b_tp8_gate_up": (7168, 8192), "70b_tp8_down": (8192, 3584)}
 for name, (N, K) in shapes.items():
     w = torch.randn(N, K, device=dev) * 0.02
     wq, ws = torch_ref.block_quant_weight_fp8(w, 128, False)
     wb = w.to(torch.bfloat16)
     wq_t = wq.t()   # column-major view for _scaled_mm
     one = torch.ones(1, device=dev)
-    for M in (16, 256, 2048, 8192):
+    for M in (16, 256, 4096):
         x = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         xq, xs = quant_ops.per_token_group_quant_fp8(x, 128, False)
@@ -49,7 +49,7 @@ for name, (N, K) in shapes.items():
 E, K, H, I = 8, 2, 4096, 14336
 w13 = torch.randn(E, 2 * I, H, device=dev, dtype=torch.bfloat16) * 0.02
 w2 = torch.randn(E, H, I, device=dev, dtype=torch.bfloat16) * 0.02
-for T in (16, 64, 256, 2048, 8192):
+for T in (16, 256, 2048, 8192):
     x = torch.randn(T, H, device=dev, dtype=torch.bfloat16) * 0.5
     tw, ids = moe_ops.topk_softmax(torch.randn(T, E, device=dev), K, True)
     ms_n = t(lambda: moe_ops.fused_moe(x, w13, w2, tw, ids, 0))
