@@ -74,7 +74,8 @@ class Engine:
                             format="[%(asctime)s %(name)s] %(message)s")
         world = a.tp_size * a.pp_size
         if world > 1:
-            ps.init_distributed(a.tp_size, a.pp_size, a.ep_size, device=a.device, enable_nvl=a.comm_backend != "nccl")
+            ps.init_distributed(a.tp_size, a.pp_size, a.ep_size, device=a.device, enable_nvl=a.comm_backend != "nccl",
+                                attn_dp_size=a.dp_size if a.enable_dp_attention else 1)
         else:
             if a.device == "cuda":
                 torch.cuda.set_device(a.base_gpu_id)
@@ -90,6 +91,13 @@ class Engine:
             a.trust_remote_code)
         self.detok = Detokenizer(self.tokenizer) if self.tokenizer is not None else None
         emits_output = st.tp.rank == 0 and st.pp.is_last if st.pp.world_size > 1 else st.tp.rank == 0
+        # DP-attention: every attention group serves its own requests (round-robin by arrival); the first rank of each group emits
+        # that group's outputs and all of them are gathered to rank 0 once per iteration
+        self._dp = st.attn_dp_size if a.enable_dp_attention else 1
+        self._dp_rank = st.attn_dp_rank
+        self._dp_ctr = 0
+        if self._dp > 1:
+            emits_output = st.attn_tp.rank == 0
         # pipeline parallel: the LAST stage samples, rank 0 talks to the client -> the last stage's tp-rank-0 relays every step's
         # output messages to rank 0 over the Gloo twin of the world group (both run the same SPMD loop, one hand-off per step)
         self._relay_src = (st.pp.world_size - 1) * st.tp.world_size if st.pp.world_size > 1 else None
@@ -171,6 +179,12 @@ class Engine:
                     "finish_reason": None, "weight_version": self.weight_version}
         with self._lock:
             self.states[t.rid] = stt
+        if self._dp > 1:
+            owner = self._dp_ctr % self._dp            # deterministic on every rank (SPMD): arrival order round-robin
+            self._dp_ctr += 1
+            stt.meta["dp_rank"] = owner
+            if owner != self._dp_rank:
+                return stt                              # another attention group serves it; rank 0 still tracks its state
         if self._bg_thread is not None:
             self._inbox.put(t)
             self._wake.set()
@@ -179,6 +193,17 @@ class Engine:
         return stt
 
     # ================================================================== output path
+    def _any_rank_has_work(self) -> bool:
+        """DP-attention: groups hold different requests, so the loop condition must be global (one tiny Gloo all-reduce per iteration)"""
+        mine = self.scheduler.has_work()
+        if self._dp <= 1:
+            return mine
+        import torch.distributed as dist
+
+        t = torch.tensor([1 if mine else 0], dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._world.cpu_group)
+        return bool(t.item())
+
     def _new_rid(self) -> str:
         """request ids must agree on every rank of an SPMD job (results are matched by id when a later pipeline stage relays them)"""
         if self._world.world_size > 1:
@@ -188,6 +213,15 @@ class Engine:
 
     def _relay_sync(self) -> None:
         """PP only: ship this step's output messages from the sampling stage to rank 0 (no-op otherwise)"""
+        if self._dp > 1:
+            # every group's emitter contributes this iteration's messages; rank 0 consumes all of them (its own come back too)
+            allm = self._world.all_gather_pyobj(self._relay_buf)
+            self._relay_buf = []
+            if ps.get_state().rank == 0:
+                for msgs in allm:
+                    for m in msgs:
+                        self._on_scheduler_output(m, relayed=True)
+            return
         if self._relay_src is None:
             return
         rank = ps.get_state().rank
@@ -199,7 +233,7 @@ class Engine:
                 self._on_scheduler_output(m, relayed=True)
 
     def _on_scheduler_output(self, msg: ios.BatchTokenIDOutput, relayed: bool = False) -> None:
-        if self._relay_src is not None and not relayed and ps.get_state().rank == self._relay_src:
+        if not relayed and (self._dp > 1 or (self._relay_src is not None and ps.get_state().rank == self._relay_src)):
             self._relay_buf.append(msg)
             return
         out = self.detok.process(msg) if self.detok is not None else ios.BatchStrOutput(
@@ -286,7 +320,7 @@ class Engine:
                 time.sleep(0.0005)
             return
         sch = self.scheduler
-        while sch.has_work():
+        while self._any_rank_has_work():
             sch.step()
             self._relay_sync()
         sch.drain()

@@ -626,6 +626,11 @@ class Scheduler:
     def step(self) -> bool:
         """One scheduler iteration.  Returns False when there is nothing to do."""
         batch = self.get_next_batch_to_run()
+        if batch is None and self.args.enable_dp_attention:
+            self.drain()
+            self.worker.forward_idle()        # keep the other DP groups' collectives matched
+            self._on_idle()
+            return False
         if batch is None:
             if self.pending:
                 self.drain()

@@ -137,7 +137,7 @@ class ModelRunner:
         self.profiler = None
         self.expert_recorder = None
         if (self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1
-                and getattr(self.model, "supports_cuda_graph", True)):
+                and getattr(self.model, "supports_cuda_graph", True) and not server_args.enable_dp_attention):
             with torch.cuda.stream(self.stream):
                 self._capture_graphs()
             self.stream.synchronize()
@@ -218,7 +218,33 @@ class ModelRunner:
         return self._forward(sb)
 
     @torch.no_grad()
+    def forward_idle(self) -> None:
+        """DP-attention: this group has no batch this iteration but the other groups do — run the same layer sequence on ZERO local
+        tokens so that every gather / all-reduce of the step completes (reference scheduler_components/dp_attn.py idle batches)."""
+        from ..layers.dp_attention import get_dp_ctx
+
+        ctx = get_dp_ctx()
+        if ctx is None:
+            return
+        self.forward_ct += 1
+        ctx.begin()
+        dev = self.device
+        z = lambda: torch.zeros(0, dtype=torch.int32, device=dev)
+        fb = ForwardBatch(mode=ForwardMode.EXTEND, batch_size=0, num_tokens=0, input_ids=z(), positions=z(), out_cache_loc=z(),
+                          req_slots=z(), seq_lens=z(), cu_q=torch.zeros(1, dtype=torch.int32, device=dev), q_lens=z(), last_idx=z(),
+                          sample_slots=z(), max_q_len=0, max_kv_len=0, page_table=self.page_table, page_size=self.page_size,
+                          kv_pool=self.kv_pool, next_token_buf=self.next_token_buf)
+        hidden = self.model(fb)
+        self.model.compute_logits(hidden[:0])        # the LM head gathers sampled rows across groups as well ...
+        self.model.compute_logits(hidden[:0], key="logits_all")     # ... and the rows of a prompt-logprob pass
+
+    @torch.no_grad()
     def _forward(self, sb: ScheduleBatch) -> BatchResult:
+        from ..layers.dp_attention import get_dp_ctx
+
+        _dp = get_dp_ctx()
+        if _dp is not None:
+            _dp.begin()
         B = len(sb.reqs)
         decode = sb.forward_mode.is_decode()
         self.step_counter += 1
@@ -246,6 +272,16 @@ class ModelRunner:
             return self._pp_result(sb, res)
         samp_rows = np.arange(B) if decode else np.flatnonzero(sb.sample_mask)
         res.sample_rows = samp_rows
+        if _dp is not None:
+            # DP-attention: the LM head is vocab-parallel over ALL groups -> every group calls it exactly twice per forward (sampled
+            # rows, then the rows of a prompt-logprob pass), with zero rows when it has nothing to contribute
+            self._dp_all_logits = None
+            need_all = (not decode) and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs)
+            if samp_rows.size == 0:
+                self.model.compute_logits(hidden[:0])
+                self.model.compute_logits(hidden if need_all else hidden[:0], key="logits_all")
+                res.next_token_ids = np.full(B, -1, dtype=np.int64)
+                return res
         if samp_rows.size == 0:
             res.next_token_ids = np.full(B, -1, dtype=np.int64)
             return res
@@ -259,6 +295,9 @@ class ModelRunner:
             res.next_token_ids = np.full(B, -1, dtype=np.int64)
             return res
         logits = self.model.compute_logits(h_last)
+        if _dp is not None:
+            al = self.model.compute_logits(hidden if need_all else hidden[:0], key="logits_all")
+            self._dp_all_logits = al if need_all else None
         if any(r.return_hidden_states for r in sb.reqs):
             hs = h_last.float().cpu().tolist()
             res.hidden_states = [None] * B
@@ -383,7 +422,8 @@ class ModelRunner:
                 v, idx = lsm[j].topk(k)
                 res.top_logprobs[i] = list(zip(v.tolist(), idx.tolist()))
         if sb.forward_mode.is_extend() and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs):
-            all_logits = torch.log_softmax(self.model.compute_logits(hidden).float(), dim=-1)
+            pre = getattr(self, "_dp_all_logits", None)      # DP-attention computed it collectively above
+            all_logits = torch.log_softmax((pre if pre is not None else self.model.compute_logits(hidden)).float(), dim=-1)
             res.input_logprobs = [None] * len(sb.reqs)
             cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
             for i, r in enumerate(sb.reqs):

@@ -209,8 +209,8 @@ class GraniteForCausalLM(LlamaForCausalLM):
             inputs_embeds = self.model.embed(fb) * float(self.cfg.embedding_multiplier)
         return self.model(fb, inputs_embeds)
 
-    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
-        y = super().compute_logits(hidden)
+    def compute_logits(self, hidden: torch.Tensor, key: str = "logits") -> torch.Tensor:
+        y = super().compute_logits(hidden, key)
         return y / float(self.cfg.logits_scaling) if (self.cfg.logits_scaling or 1.0) != 1.0 else y
 
 

@@ -19,7 +19,8 @@ from ..layers.linear import (MergedColumnParallelLinear, ParallelLMHead, QKVPara
                              VocabParallelEmbedding, _skinny_allowed)
 from ..layers.quantization import get_quant_method
 from ..model_executor.forward_batch import ForwardBatch
-from ..parallel.parallel_state import get_pp_group, get_tp_group
+from ..layers.dp_attention import get_dp_ctx
+from ..parallel.parallel_state import get_attn_tp_group, get_pp_group, get_tp_group
 
 _DT = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
 
@@ -52,10 +53,11 @@ class LlamaMLP(nn.Module):
 class LlamaAttention(nn.Module):
     def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope: RotaryEmbedding, prefix: str):
         super().__init__()
+        atp = get_attn_tp_group()          # == the TP group unless DP-attention is on
         self.qkv_proj = QKVParallelLinear(cfg.hidden_size, cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads,
-                                          cfg.attention_bias, dtype, quant, prefix + ".qkv_proj")
+                                          cfg.attention_bias, dtype, quant, prefix + ".qkv_proj", tp_group=atp)
         self.o_proj = RowParallelLinear(cfg.num_attention_heads * cfg.head_dim, cfg.hidden_size, False, True, dtype, quant,
-                                        prefix + ".o_proj")
+                                        prefix + ".o_proj", tp_group=atp)
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         self.head_dim = cfg.head_dim
         self.qk_norm = cfg.qk_norm
@@ -100,6 +102,12 @@ class LlamaDecoderLayer(nn.Module):
             h, residual = self.input_layernorm(h, residual)
         h = self.self_attn(h, fb)
         h, residual = self.post_attention_layernorm(h, residual)
+        ctx = get_dp_ctx()
+        if ctx is not None:
+            # DP-attention: the MLP / MoE is parallel over the whole TP group -> run it on the union of all groups' tokens
+            y = self.mlp(ctx.gather(h, "tokens"))
+            y = y.resolve() if hasattr(y, "resolve") else y
+            return ctx.slice(y, "tokens"), residual
         h = self.mlp(h)
         return h, residual
 
@@ -124,7 +132,11 @@ class LlamaModel(nn.Module):
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, self.gemma) if pp.is_last else None
 
     def embed(self, fb: ForwardBatch) -> torch.Tensor:
-        if fb.input_ids is None:   # decode: token ids live on the device, indexed by request slot
+        ctx = get_dp_ctx()
+        if ctx is not None:        # vocab-parallel over the full TP group: embed the union of the groups' token ids, keep ours
+            ids = fb.next_token_buf[fb.req_slots.long()] if fb.input_ids is None else fb.input_ids
+            h = ctx.slice(self.embed_tokens(ctx.gather(ids.to(torch.int32), "tokens")), "tokens")
+        elif fb.input_ids is None:   # decode: token ids live on the device, indexed by request slot
             h = self.embed_tokens(fb.next_token_buf, fb.req_slots)
         else:
             h = self.embed_tokens(fb.input_ids)
@@ -178,12 +190,19 @@ class LlamaForCausalLM(nn.Module):
     def forward(self, fb: ForwardBatch, inputs_embeds=None):
         return self.model(fb, inputs_embeds)
 
-    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
+    def compute_logits(self, hidden: torch.Tensor, key: str = "logits") -> torch.Tensor:
+        """``key`` names the row set under DP-attention (sampled rows vs all rows of a prompt-logprob pass): every group must make
+        the same sequence of calls per forward, with zero rows when it has nothing to contribute"""
         head = self.lm_head if self.lm_head is not None else self.model.embed_tokens
+        ctx = get_dp_ctx()
+        if ctx is not None:
+            hidden = ctx.gather(hidden, key)
         y = ops.linear(hidden, head.weight)
         tp = get_tp_group()
         if tp.world_size > 1:
             y = tp.all_gather(y, dim=-1)
+        if ctx is not None:
+            y = ctx.slice(y, key)
         y = y[:, : self.cfg.vocab_size]
         if self.cfg.final_logit_softcapping > 0:
             c = self.cfg.final_logit_softcapping

@@ -139,6 +139,11 @@ class ParallelState:
     rank: int
     world_size: int
     local_rank: int
+    # DP-attention: attention is tensor-parallel only inside ``attn_tp`` (tp_size / dp_size consecutive ranks); each of the
+    # ``attn_dp_size`` groups serves its own requests, the MLP / MoE / vocab layers stay parallel over the full ``tp`` group
+    attn_tp: Any = None
+    attn_dp_rank: int = 0
+    attn_dp_size: int = 1
 
 
 _STATE: Optional[ParallelState] = None
@@ -146,7 +151,8 @@ _STATE: Optional[ParallelState] = None
 
 def _single(device: torch.device) -> ParallelState:
     g = lambda n: GroupCoordinator([0], 0, device, n)
-    return ParallelState(g("world"), g("tp"), g("pp"), g("ep"), 0, 1, 0)
+    tp = g("tp")
+    return ParallelState(g("world"), tp, g("pp"), g("ep"), 0, 1, 0, tp, 0, 1)
 
 
 def compute_group_ranks(world_size: int, tp_size: int, pp_size: int, ep_size: int = 1):
@@ -164,12 +170,12 @@ def compute_group_ranks(world_size: int, tp_size: int, pp_size: int, ep_size: in
 
 def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, device: Optional[str] = None,
                      init_method: Optional[str] = None, rank: Optional[int] = None, world_size: Optional[int] = None,
-                     enable_nvl: bool = True, timeout_s: int = 600) -> ParallelState:
+                     enable_nvl: bool = True, timeout_s: int = 600, attn_dp_size: int = 1) -> ParallelState:
     global _STATE
     use_cuda = (device or ("cuda" if torch.cuda.is_available() else "cpu")).startswith("cuda")
     ws = tp_size * pp_size
     if (_STATE is not None and ws > 1 and _STATE.world_size == ws and _STATE.tp.world_size == tp_size
-            and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size)):
+            and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size) and _STATE.attn_dp_size == max(1, attn_dp_size)):
         return _STATE       # idempotent: a second Engine in the same SPMD job reuses the groups and the NVL arena
     if ws == 1:
         dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
@@ -212,7 +218,14 @@ def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, devic
     tp = make(tp_groups, "tp")
     pp = make(pp_groups, "pp")
     ep = make(ep_groups, "ep")
-    _STATE = ParallelState(world, tp, pp, ep, rank, world_size, local_rank)
+    attn_tp, dp_rank = tp, 0
+    if attn_dp_size > 1:
+        assert tp_size % attn_dp_size == 0, "dp attention: dp_size must divide tp_size"
+        a = tp_size // attn_dp_size
+        groups = [g[i:i + a] for g in tp_groups for i in range(0, tp_size, a)]
+        attn_tp = make(groups, "attn_tp")
+        dp_rank = tp.rank // a
+    _STATE = ParallelState(world, tp, pp, ep, rank, world_size, local_rank, attn_tp, dp_rank, max(1, attn_dp_size))
     if use_cuda and enable_nvl and tp.world_size > 1:
         try:
             from .nvl_comm import NvlComm
@@ -247,6 +260,11 @@ def get_pp_group() -> GroupCoordinator:
 
 def get_ep_group() -> GroupCoordinator:
     return get_state().ep
+
+
+def get_attn_tp_group() -> GroupCoordinator:
+    st = get_state()
+    return st.attn_tp if st.attn_tp is not None else st.tp
 
 
 def get_tp_rank() -> int:

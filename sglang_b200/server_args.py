@@ -163,8 +163,12 @@ class ServerArgs:
         world = self.tp_size * self.pp_size
         if self.ep_size > 1 and self.tp_size % self.ep_size != 0:
             raise ValueError("ep_size must divide tp_size (experts are sharded inside the TP group)")
-        if self.enable_dp_attention and self.dp_size > self.tp_size:
-            raise ValueError("dp attention requires dp_size <= tp_size")
+        if self.enable_dp_attention:
+            if self.dp_size > self.tp_size or self.tp_size % max(1, self.dp_size):
+                raise ValueError("dp attention requires dp_size to divide tp_size")
+            # groups take different batches every step: one synchronous forward per iteration on every rank, no graph replay
+            self.disable_overlap_schedule = True
+            self.disable_cuda_graph = True
         if self.cuda_graph_max_bs is None:
             self.cuda_graph_max_bs = 512 if self.tp_size == 1 else 256
         if self.device != "cuda":

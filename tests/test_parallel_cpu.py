@@ -144,3 +144,14 @@ def test_deepseek_mla_tp2_ep2():
     ref = _run(kw, 1, LP)
     _check(_run({**kw, "tp_size": 2}, 2, LP), ref, atol=5e-3)
     _check(_run({**kw, "tp_size": 2, "ep_size": 2}, 2, LP), ref, atol=5e-3)
+
+
+def test_dp_attention_tp2_dp2_and_tp4_dp2():
+    """DP-attention: requests are split between attention groups, MLP runs on the gathered tokens over the full TP group; results must
+    equal the single-process engine (more requests than groups, uneven lengths -> idle batches at the tail)"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=32)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 2, "dp_size": 2, "enable_dp_attention": True}, 2, LP), ref)
+    _check(_run({**kw, "tp_size": 4, "dp_size": 2, "enable_dp_attention": True}, 4, LP), ref)
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
+    _check(_run({**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True}, 2, LP), _run(kw, 1, LP))
