@@ -73,11 +73,56 @@ class FusedMoE(nn.Module):
         w, ids = select_experts(router_logits, self.top_k, self.renormalize)
         return self.forward_routed(x, w, ids)
 
+    def forward_a2a(self, x: torch.Tensor, w: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """All-to-all expert dispatch for DP-attention (tokens are NOT replicated across ranks): every (token, k) pair travels to the
+        rank that owns its expert, the owners run their experts on what they received, results travel back and are combined with the
+        routing weights on the home rank.  Reference: ``token_dispatcher/{deepep,flashinfer}.py`` dispatch/combine; here over
+        ``all_to_all_single`` (NCCL on NVLink / Gloo on the CPU tier).  Requires whole experts per rank (ep_size == tp_size)."""
+        from ..ops import moe_ops
+
+        tp = self.tp
+        W = tp.world_size
+        assert self.moe_tp == 1 and self.ep_size == W, "all-to-all dispatch needs ep_size == tp_size"
+        self._a2a_calls = getattr(self, "_a2a_calls", 0) + 1
+        T, H = x.shape
+        K = ids.shape[1]
+        flat_e = ids.reshape(-1).long()
+        dest = flat_e // self.local_experts
+        order = torch.argsort(dest, stable=True)
+        send_counts = torch.bincount(dest, minlength=W)
+        recv_counts = torch.empty_like(send_counts)
+        tp.all_to_all_single(recv_counts, send_counts)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        tok = order // K
+        send_x = x.index_select(0, tok).contiguous()
+        send_e = flat_e.index_select(0, order).to(torch.int32).contiguous()
+        R = int(sum(rc))
+        recv_x = torch.empty(R, H, dtype=x.dtype, device=x.device)
+        recv_e = torch.empty(R, dtype=torch.int32, device=x.device)
+        tp.all_to_all_single(recv_x, send_x, rc, sc)
+        tp.all_to_all_single(recv_e, send_e, rc, sc)
+        if self.expert_load is not None:
+            self.expert_load.record(self.layer_id, ids)
+        if R:
+            ones = torch.ones(R, 1, dtype=torch.float32, device=x.device)
+            y = moe_ops.fused_moe(recv_x, self.w13, self.w2, ones, recv_e.view(R, 1), self.expert_offset)
+        else:
+            y = recv_x
+        back = torch.empty(send_x.shape[0], H, dtype=x.dtype, device=x.device)
+        tp.all_to_all_single(back, y.contiguous(), sc, rc)
+        out = torch.zeros(T, H, dtype=torch.float32, device=x.device)
+        out.index_add_(0, tok, back.float() * w.reshape(-1).index_select(0, order).float()[:, None])
+        return out.to(x.dtype)
+
     def forward_routed(self, x: torch.Tensor, w: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         """expert MLPs for an externally computed routing (``w`` fp32 [T,K], ``ids`` int32 [T,K] global expert ids) — grouped /
         biased / sigmoid routers (DeepSeek) live in the model file"""
         from ..ops import moe_ops
+        from .dp_attention import get_dp_ctx
 
+        ctx = get_dp_ctx()
+        if ctx is not None and getattr(ctx, "a2a_active", False):
+            return self.forward_a2a(x, w, ids)
         if self.expert_load is not None:
             self.expert_load.record(self.layer_id, ids)
         tp = self.tp

@@ -19,6 +19,7 @@ from ..layers.linear import (MergedColumnParallelLinear, ParallelLMHead, QKVPara
                              VocabParallelEmbedding, _skinny_allowed)
 from ..layers.quantization import get_quant_method
 from ..model_executor.forward_batch import ForwardBatch
+from ..environ import envs
 from ..layers.dp_attention import get_dp_ctx
 from ..parallel.parallel_state import get_attn_tp_group, get_pp_group, get_tp_group
 
@@ -104,6 +105,15 @@ class LlamaDecoderLayer(nn.Module):
         h, residual = self.post_attention_layernorm(h, residual)
         ctx = get_dp_ctx()
         if ctx is not None:
+            experts = getattr(self.mlp, "experts", None)
+            if (experts is not None and envs.SGLB_MOE_A2A.get() and experts.ep_size == experts.tp.world_size and experts.moe_tp == 1
+                    and getattr(self.mlp, "shared_experts", None) is None and getattr(self.mlp, "shared_expert", None) is None):
+                # expert-parallel MoE without shared experts: tokens stay home, only routed (token, k) pairs cross ranks (all-to-all)
+                ctx.a2a_active = True
+                try:
+                    return self.mlp(h), residual
+                finally:
+                    ctx.a2a_active = False
             # DP-attention: the MLP / MoE is parallel over the whole TP group -> run it on the union of all groups' tokens
             y = self.mlp(ctx.gather(h, "tokens"))
             y = y.resolve() if hasattr(y, "resolve") else y

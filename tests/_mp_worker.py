@@ -19,5 +19,8 @@ if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives out
     if cfg.get("gen_kw", {}).get("return_logprob"):
         res["lp"] = [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in outs]
     print("RESULT " + json.dumps(res), flush=True)
+if os.environ.get("SGLB_TEST_EXPECT_A2A"):
+    ex = eng.runner.model.model.layers[0].mlp.experts
+    assert getattr(ex, "_a2a_calls", 0) > 0, "the all-to-all dispatcher was expected to run"
 eng.shutdown()
 os._exit(0)

@@ -23,13 +23,13 @@ def _free_port() -> int:
     return p
 
 
-def _run(engine_kw, world, gen_kw=None):
+def _run(engine_kw, world, gen_kw=None, extra_env=None):
     cfg = json.dumps({"engine": engine_kw, "prompts": PROMPTS, "sampling": SAMPLING, "gen_kw": gen_kw or {}})
     port = _free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+                   PYTHONPATH=ROOT, OMP_NUM_THREADS="2", **(extra_env or {}))
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_mp_worker.py"), cfg], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True, cwd=ROOT))
     outs = []
@@ -154,4 +154,7 @@ def test_dp_attention_tp2_dp2_and_tp4_dp2():
     _check(_run({**kw, "tp_size": 2, "dp_size": 2, "enable_dp_attention": True}, 2, LP), ref)
     _check(_run({**kw, "tp_size": 4, "dp_size": 2, "enable_dp_attention": True}, 4, LP), ref)
     kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
-    _check(_run({**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True}, 2, LP), _run(kw, 1, LP))
+    ref = _run(kw, 1, LP)
+    dpk = {**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True}
+    _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1", "SGLB_TEST_EXPECT_A2A": "1"}), ref)      # all-to-all expert dispatch / combine
+    _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "0"}), ref)                                   # gather-all-tokens dispatcher
