@@ -6,6 +6,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "kv_indexer.h"
 #include "ngram_corpus.h"
 #include "radix_tree.h"
 
@@ -118,6 +119,15 @@ PYBIND11_MODULE(sglb_rt, m) {
         return py::make_tuple(to_np(toks), to_np(parents));
       }, py::arg("context"), py::arg("max_nodes"), py::arg("branch") = 2, py::arg("min_match") = 1)
       .def("num_nodes", &NgramCorpus::num_nodes);
+
+  py::class_<sglb::KvIndexer>(m, "KvIndexer")
+      .def(py::init<>())
+      .def("stored", &sglb::KvIndexer::stored, py::call_guard<py::gil_scoped_release>())
+      .def("removed", &sglb::KvIndexer::removed, py::call_guard<py::gil_scoped_release>())
+      .def("clear_worker", &sglb::KvIndexer::clear_worker, py::call_guard<py::gil_scoped_release>())
+      .def("match", &sglb::KvIndexer::match, py::call_guard<py::gil_scoped_release>())
+      .def("num_blocks", &sglb::KvIndexer::num_blocks)
+      .def("worker_blocks", &sglb::KvIndexer::worker_blocks);
 
   m.def("hash_pages", &hash_pages, py::arg("tokens"), py::arg("page_size"), py::arg("seed") = 0);
 }

@@ -426,6 +426,11 @@ class Engine:
     def flush_cache(self) -> bool:
         return self._control(ios.FlushCacheReq()).success
 
+    def take_kv_events(self) -> Dict[str, Any]:
+        """KV-cache events since the last call (needs ``enable_kv_events``): feed for a KV-aware router / indexer"""
+        r = self._control(ios.GetKvEventsReq())
+        return {"events": r.events or [], "page_size": r.page_size}
+
     def get_server_info(self) -> Dict[str, Any]:
         st = self._control(ios.GetInternalStateReq()).state
         return {**self.server_args.to_dict(), "internal_states": [st], "version": "0.1.0", "weight_version": self.weight_version,

@@ -254,6 +254,10 @@ def create_app(engine: Any):
         res = await _ctl(engine.rerank, r.query, r.documents)
         return res[: r.top_n] if r.top_n else res
 
+    @app.get("/kv_events")
+    async def kv_events():
+        return await _ctl(engine.take_kv_events)
+
     @app.post("/init_weights_update_group")
     async def init_weights_update_group(request: Request):
         b = await request.json()

@@ -384,6 +384,18 @@ class GetLoadReq:
 
 
 @message
+class GetKvEventsReq:
+    """drain the radix cache's KV events (BlockStored / BlockRemoved / AllBlocksCleared with chained page hashes)"""
+    pass
+
+
+@message
+class GetKvEventsResp:
+    events: Any = None
+    page_size: int = 1
+
+
+@message
 class GetLoadResp:
     num_running_reqs: int = 0
     num_waiting_reqs: int = 0

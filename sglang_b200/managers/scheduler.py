@@ -104,6 +104,9 @@ class Scheduler:
             return ios.GetInternalStateResp(state=self.get_internal_state())
         if isinstance(msg, ios.HealthCheckReq):
             return ios.HealthCheckResp(ok=True, forward_ct=self.forward_ct)
+        if isinstance(msg, ios.GetKvEventsReq):
+            ev = self.tree.take_kv_events() if hasattr(self.tree, "take_kv_events") else []
+            return ios.GetKvEventsResp([list(e) for e in ev], self.page_size)
         if isinstance(msg, ios.GetLoadReq):
             return ios.GetLoadResp(num_running_reqs=len(self.running_batch.reqs), num_waiting_reqs=len(self.waiting_queue),
                                    num_tokens=int(self.kv.total_pages() - self.kv.available_pages()) * self.page_size,

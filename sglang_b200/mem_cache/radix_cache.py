@@ -27,7 +27,7 @@ _EMPTY = np.empty(0, dtype=np.int32)
 
 class TreeNode:
     __slots__ = ("children", "parent", "key", "pages", "lock_ref", "last_access", "hit_count", "created",
-                 "priority", "host_pages", "id")
+                 "priority", "host_pages", "id", "hashes")
     _ctr = 0
 
     def __init__(self) -> None:
@@ -41,6 +41,7 @@ class TreeNode:
         self.created = 0.0
         self.hit_count = 0
         self.priority = 0
+        self.hashes: Optional[np.ndarray] = None     # chained 64-bit page hashes (only when KV events are enabled)
         TreeNode._ctr += 1
         self.id = TreeNode._ctr
 
@@ -60,6 +61,34 @@ _POLICIES: Dict[str, Callable[[TreeNode], Any]] = {
     "filo": lambda n: -n.created,
     "priority": lambda n: (n.priority, n.last_access),
 }
+
+
+def _root_seed(extra_key: Any) -> int:
+    """namespace seed of the hash chain (LoRA adapter / cache salt): requests in different namespaces never share a prefix"""
+    if extra_key is None:
+        return 0
+    import zlib
+
+    return zlib.crc32(str(extra_key).encode()) + 1
+
+
+def chain_hashes(tokens: np.ndarray, page_size: int, seed: int = 0) -> np.ndarray:
+    """64-bit FNV-1a page hashes, each folding in its predecessor (C++ ``sglb_rt.hash_pages``; numpy fallback)"""
+    try:
+        from .. import sglb_rt
+
+        return np.asarray(sglb_rt.hash_pages(np.ascontiguousarray(tokens, dtype=np.int32), page_size, int(seed)), dtype=np.uint64)
+    except Exception:
+        out, prev = [], int(seed)
+        b = np.ascontiguousarray(tokens, dtype=np.int32).view(np.uint8)
+        step = 4 * page_size
+        for p in range(len(tokens) // page_size):
+            h = 1469598103934665603 ^ prev
+            for v in b[p * step:(p + 1) * step].tolist():
+                h = ((h ^ v) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+            out.append(h)
+            prev = h
+        return np.asarray(out, dtype=np.uint64)
 
 
 class RadixCache:
@@ -171,6 +200,8 @@ class RadixCache:
                                                                      child.hit_count, child.priority)
         if child.host_pages is not None:
             new.host_pages, child.host_pages = child.host_pages[:m_pages], child.host_pages[m_pages:]
+        if child.hashes is not None:
+            new.hashes, child.hashes = child.hashes[:m_pages], child.hashes[m_pages:]
         child.parent.children[self._child_key(new.key)] = new
         child.key = child.key[m_pages * ps:]
         if child.pages is not None:
@@ -222,7 +253,10 @@ class RadixCache:
             node.children[self._child_key(new.key)] = new
             self._evictable_pages += new.pages.size
             if self.enable_kv_events:
-                self.kv_events.append(("BlockStored", new.pages.tolist()))
+                # chained page hashes identify the PREFIX, so a fleet-level index can match requests without seeing page ids
+                parent_hash = int(node.hashes[-1]) if node.hashes is not None and node.hashes.size else _root_seed(extra_key)
+                new.hashes = chain_hashes(new.key, ps, parent_hash)
+                self.kv_events.append(("BlockStored", {"pages": new.pages.tolist(), "hashes": new.hashes.tolist(), "parent_hash": parent_hash}))
         return matched
 
     # ------------------------------------------------------------------ locking
@@ -280,7 +314,7 @@ class RadixCache:
             freed += n.pages.size
             self._evictable_pages -= n.pages.size
             if self.enable_kv_events:
-                self.kv_events.append(("BlockRemoved", n.pages.tolist()))
+                self.kv_events.append(("BlockRemoved", {"pages": n.pages.tolist(), "hashes": n.hashes.tolist() if n.hashes is not None else []}))
             parent = n.parent
             if keep_host and n.host_pages is not None:
                 n.pages = None  # stays in the tree as a host-resident node

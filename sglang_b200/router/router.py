@@ -35,6 +35,7 @@ class Worker:
     opened_at: float = 0.0           # circuit breaker: time the circuit opened (0 = closed)
     served: int = 0
     tree: Any = None
+    index: int = 0                   # stable id used by the KV indexer
 
     def available(self, now: float, cooldown: float) -> bool:
         if not self.healthy:
@@ -93,7 +94,60 @@ class Policy:
                 if best.tree.num_nodes() > self.max_tree_nodes:
                     best.tree.evict(best.tree.evictable_pages() // 4)
             return best
+        if n == "kv_aware":
+            return self._select_kv_aware(workers, text)
         raise ValueError(f"unknown policy {n}")
+
+    # ---- KV-event driven routing (reference: experimental/sgl-router + sgl-kv-indexer): exact longest cached prefix per worker
+    def attach_kv_index(self, tokenizer: Any, page_size: int) -> None:
+        from .. import sglb_rt
+
+        self.kv_index = sglb_rt.KvIndexer()
+        self.kv_tokenizer, self.kv_page_size = tokenizer, page_size
+
+    def apply_kv_events(self, worker_idx: int, events: List[Any]) -> None:
+        for kind, payload in events:
+            if kind == "BlockStored":
+                self.kv_index.stored(worker_idx, [int(h) for h in payload["hashes"]])
+            elif kind == "BlockRemoved":
+                self.kv_index.removed(worker_idx, [int(h) for h in payload["hashes"]])
+            elif kind == "AllBlocksCleared":
+                self.kv_index.clear_worker(worker_idx)
+
+    def _select_kv_aware(self, workers: List[Worker], text_or_ids: Any) -> Worker:
+        from ..mem_cache.radix_cache import chain_hashes
+
+        loads = [w.inflight for w in workers]
+        lo, hi = min(loads), max(loads)
+        imbalanced = (hi - lo) > self.balance_abs and hi > self.balance_rel * max(1, lo)
+        ids = text_or_ids if not isinstance(text_or_ids, str) else self.kv_tokenizer(text_or_ids)
+        hashes = chain_hashes(np.asarray(ids, dtype=np.int32), self.kv_page_size, 0).tolist()
+        best = None
+        if hashes and not imbalanced:
+            by_idx = {w.index: w for w in workers}
+            m = [(depth, -by_idx[wi].inflight, wi) for wi, depth in self.kv_index.match(hashes) if wi in by_idx]
+            if m:
+                depth, _, wi = max(m)
+                if depth >= self.cache_threshold * len(hashes):
+                    best = by_idx[wi]
+        return best if best is not None else min(workers, key=lambda w: w.inflight)
+
+
+def make_engine_tokenizer(tokenizer_path: Optional[str]):
+    """text -> token ids exactly as a worker tokenises a `/generate` text prompt (so prefix hashes line up with the workers' events)"""
+    from ..configs.model_config import load_model_config
+    from ..utils.tokenizer import get_tokenizer
+
+    path = tokenizer_path or "dummy:tiny-llama"
+    cfg = load_model_config(path) if path.startswith("dummy:") or __import__("os").path.isdir(path) else None
+    tok = get_tokenizer(path, cfg.vocab_size if cfg else 32000, cfg.eos_token_id if cfg else 2, cfg.bos_token_id if cfg else 1, False)
+    byte_tok = type(tok).__name__ == "ByteTokenizer"
+
+    def enc(text: str) -> List[int]:
+        ids = tok.encode(text)
+        return ([tok.bos_token_id] + ids) if byte_tok and getattr(tok, "bos_token_id", None) is not None else ids
+
+    return enc
 
 
 class Router:
@@ -103,6 +157,8 @@ class Router:
         self.workers: List[Worker] = [Worker(u.rstrip("/")) for u in worker_urls]
         self.workers += [Worker(u.rstrip("/"), "prefill") for u in (prefill_urls or [])]
         self.workers += [Worker(u.rstrip("/"), "decode") for u in (decode_urls or [])]
+        for i, w in enumerate(self.workers):
+            w.index = i
         self.policy = Policy(policy)
         self.max_retries, self.cb_threshold, self.cb_cooldown = max_retries, cb_threshold, cb_cooldown
         self.health_interval = health_interval
@@ -161,9 +217,13 @@ class Router:
         async def on_start(app):
             router.session = ClientSession(timeout=ClientTimeout(total=3600))
             app["health"] = asyncio.create_task(router._health_loop())
+            if router.policy.name == "kv_aware":
+                app["kv"] = asyncio.create_task(router._kv_event_loop())
 
         async def on_stop(app):
             app["health"].cancel()
+            if "kv" in app:
+                app["kv"].cancel()
             await router.session.close()
 
         async def proxy(request: "web.Request"):
@@ -240,6 +300,22 @@ class Router:
         app.router.add_route("*", "/{tail:.*}", proxy)
         return app
 
+    async def _kv_event_loop(self, period: float = 0.05) -> None:
+        """pull every worker's KV events (``GET /kv_events``, workers run with --enable-kv-events) into the shared index"""
+        while True:
+            for w in list(self.workers):
+                if not w.healthy:
+                    continue
+                try:
+                    async with self.session.get(w.url + "/kv_events", timeout=__import__("aiohttp").ClientTimeout(total=3)) as r:
+                        if r.status == 200:
+                            d = await r.json()
+                            self.policy.kv_page_size = int(d.get("page_size", self.policy.kv_page_size))
+                            self.policy.apply_kv_events(w.index, d.get("events", []))
+                except Exception:
+                    pass
+            await asyncio.sleep(period)
+
     async def _health_loop(self) -> None:
         while True:
             for w in list(self.workers):
@@ -259,7 +335,9 @@ def main(argv: Optional[List[str]] = None) -> None:
     ap.add_argument("--prefill-urls", nargs="*", default=[])
     ap.add_argument("--decode-urls", nargs="*", default=[])
     ap.add_argument("--policy", default="cache_aware", choices=["random", "round_robin", "cache_aware", "power_of_two", "prefix_hash",
-                                                                "consistent_hashing"])
+                                                                "consistent_hashing", "kv_aware"])
+    ap.add_argument("--tokenizer-path", default=None, help="kv_aware: tokenizer used to hash request prefixes (dummy:<preset> = byte tokenizer)")
+    ap.add_argument("--page-size", type=int, default=32, help="kv_aware: KV page size of the workers (refreshed from /kv_events)")
     ap.add_argument("--host", default="127.0.0.1")
     ap.add_argument("--port", type=int, default=8080)
     ap.add_argument("--max-retries", type=int, default=3)
@@ -267,6 +345,8 @@ def main(argv: Optional[List[str]] = None) -> None:
     ap.add_argument("--api-key", default=None)
     a = ap.parse_args(argv)
     r = Router(a.worker_urls, a.policy, a.prefill_urls, a.decode_urls, a.max_retries, rate_limit=a.rate_limit, api_key=a.api_key)
+    if a.policy == "kv_aware":
+        r.policy.attach_kv_index(make_engine_tokenizer(a.tokenizer_path), a.page_size)
     web.run_app(r.build_app(), host=a.host, port=a.port)
 
 

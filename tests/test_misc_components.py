@@ -204,3 +204,52 @@ def test_update_weights_from_distributed_group():
     assert eng.update_weights_from_distributed([name], ["float32"], [shape], group_name="nope").success is False
     assert eng.destroy_weights_update_group().success
     eng.shutdown()
+
+
+def test_kv_indexer_and_kv_aware_routing():
+    """C++ KvIndexer + KV-event-driven routing: the worker that really holds a request's prefix (per its radix-cache events) is chosen"""
+    import numpy as np
+
+    import sglang_b200 as sgl
+    from sglang_b200 import sglb_rt
+    from sglang_b200.mem_cache.radix_cache import chain_hashes
+    from sglang_b200.router.router import Policy, Worker, make_engine_tokenizer
+
+    idx = sglb_rt.KvIndexer()
+    h = chain_hashes(np.arange(64, dtype=np.int32), 4, 0).tolist()
+    idx.stored(0, h[:10]); idx.stored(1, h[:4]); idx.stored(1, [123456789])
+    assert dict(idx.match(h)) == {0: 10, 1: 4} and idx.worker_blocks(1) == 5
+    idx.removed(0, h[6:10])
+    assert dict(idx.match(h)) == {0: 6, 1: 4}
+    idx.clear_worker(1)
+    assert dict(idx.match(h)) == {0: 6} and idx.worker_blocks(1) == 0 and idx.num_blocks() == 6
+    assert idx.match([42]) == []
+    # chained: the same page content under a different prefix hashes differently
+    a = chain_hashes(np.asarray([1, 2, 3, 4, 9, 9, 9, 9], dtype=np.int32), 4, 0)
+    b = chain_hashes(np.asarray([5, 6, 7, 8, 9, 9, 9, 9], dtype=np.int32), 4, 0)
+    assert a[1] != b[1] and chain_hashes(np.asarray([1, 2, 3, 4], dtype=np.int32), 4, 0)[0] == a[0]
+
+    # two engines with KV events on; worker 0 serves a long document, worker 1 something else
+    engs = [sgl.Engine(model_path="dummy:tiny-llama", page_size=4, enable_kv_events=True, log_level="error") for _ in range(2)]
+    pol = Policy("kv_aware")
+    pol.attach_kv_index(make_engine_tokenizer("dummy:tiny-llama"), 4)
+    workers = [Worker("http://w0", index=0), Worker("http://w1", index=1)]
+    doc = "the quick brown fox jumps over the lazy dog " * 6
+    sp = {"max_new_tokens": 2, "temperature": 0}
+    engs[0].generate(doc + "question one", sp)
+    engs[1].generate("completely different text that shares nothing with it " * 4, sp)
+    for i, e in enumerate(engs):
+        ev = e.take_kv_events()
+        assert ev["page_size"] == 4 and any(k == "BlockStored" for k, _ in ev["events"])
+        pol.apply_kv_events(i, ev["events"])
+    assert pol._select_kv_aware(workers, doc + "question two") is workers[0]
+    assert pol._select_kv_aware(workers, "completely different text that shares nothing with it " * 4 + "tail") is workers[1]
+    workers[1].inflight = 3
+    assert pol._select_kv_aware(workers, "never seen before prompt") is workers[0]         # no match -> least loaded
+    # eviction / flush events remove the prefix from the index
+    engs[0].flush_cache()
+    pol.apply_kv_events(0, engs[0].take_kv_events()["events"])
+    workers[1].inflight = 0; workers[0].inflight = 2
+    assert pol._select_kv_aware(workers, doc + "question three") is workers[1]
+    for e in engs:
+        e.shutdown()
