@@ -45,6 +45,10 @@ class ModelConfig:
     shared_expert_intermediate_size: Optional[int] = None      # Qwen2-MoE sigmoid-gated shared expert
     decoder_sparse_step: int = 1
     mlp_only_layers: Optional[List[int]] = None
+    # classic pre-LayerNorm decoders (GPT-2 / OPT / GPT-NeoX / StarCoder2)
+    pos_emb: str = "rope"            # rope | learned
+    pos_offset: int = 0              # OPT stores positions shifted by 2
+    parallel_residual: bool = False  # NeoX: x + attn(ln1 x) + mlp(ln2 x)
     # DeepSeek-V2/V3: MLA + DeepSeekMoE
     q_lora_rank: Optional[int] = None
     kv_lora_rank: Optional[int] = None
@@ -149,6 +153,18 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                              num_local_experts=8, num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1,
                              first_k_dense_replace=1, n_group=4, topk_group=2, routed_scaling_factor=2.5, norm_topk_prob=True,
                              scoring_func="sigmoid", topk_method="noaux_tc", rope_is_neox=False, dtype="float32"),
+    "tiny-gpt2": dict(architecture="GPT2LMHeadModel", hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, pos_emb="learned", tie_word_embeddings=True,
+                      hidden_act="gelu_new", dtype="float32"),
+    "tiny-opt": dict(architecture="OPTForCausalLM", hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, pos_emb="learned", pos_offset=2,
+                     tie_word_embeddings=True, hidden_act="relu", dtype="float32"),
+    "tiny-neox": dict(architecture="GPTNeoXForCausalLM", hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, partial_rotary_factor=0.25, parallel_residual=True,
+                      hidden_act="gelu", rope_theta=10000.0, dtype="float32"),
+    "tiny-starcoder2": dict(architecture="Starcoder2ForCausalLM", hidden_size=64, intermediate_size=256, num_hidden_layers=2,
+                            num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=512,
+                            hidden_act="gelu_pytorch_tanh", rope_theta=10000.0, sliding_window=64, tie_word_embeddings=True, dtype="float32"),
     "tiny-phi3": dict(architecture="Phi3ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
                       num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
     "tiny-internlm2": dict(architecture="InternLM2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
@@ -223,7 +239,16 @@ PRESETS: Dict[str, Dict[str, Any]] = {
 
 _HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM"}
 # HF config keys that differ from our field names
-_HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts"}
+_HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts", "n_embd": "hidden_size", "n_layer": "num_hidden_layers",
+               "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
+               "activation_function": "hidden_act", "layer_norm_epsilon": "rms_norm_eps", "layer_norm_eps": "rms_norm_eps",
+               "norm_epsilon": "rms_norm_eps", "ffn_dim": "intermediate_size", "rotary_pct": "partial_rotary_factor",
+               "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta"}
+# per-architecture defaults for fields HF configs leave implicit
+_ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
+                  "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),
+                  "GPTNeoXForCausalLM": dict(parallel_residual=True, hidden_act="gelu"),
+                  "Starcoder2ForCausalLM": dict(hidden_act="gelu_pytorch_tanh")}
 
 
 def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = None, context_length: Optional[int] = None) -> ModelConfig:
@@ -245,6 +270,12 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         kw = {k: v for k, v in text.items() if k in fields}
         arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
+        for k, v in _ARCH_DEFAULTS.get(arch, {}).items():
+            kw.setdefault(k, v)
+        if arch in _ARCH_DEFAULTS:
+            kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
+            if kw.get("intermediate_size") is None:
+                kw["intermediate_size"] = 4 * kw["hidden_size"]
         if "vision_config" in hf:
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

@@ -37,6 +37,10 @@ def _ensure() -> None:
     for name in ("Phi3ForCausalLM", "InternLM2ForCausalLM", "Qwen2MoeForCausalLM", "Qwen3MoeForCausalLM", "Gemma2ForCausalLM",
                  "GraniteForCausalLM", "Olmo2ForCausalLM"):
         register_model(name, getattr(_fam, name))
+    from . import classic as _cl
+
+    for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM"):
+        register_model(name, getattr(_cl, name))
     from . import deepseek as _ds
 
     register_model("DeepseekV2ForCausalLM", _ds.DeepseekV2ForCausalLM)

@@ -169,3 +169,87 @@ def test_deepseek_mla_moe(preset):
     want = att.o_proj(ref)
     assert torch.allclose(out if not hasattr(out, "resolve") else out.resolve(), want, atol=2e-4, rtol=2e-3)
     eng.shutdown()
+
+
+@pytest.mark.parametrize("preset", ["tiny-gpt2", "tiny-opt", "tiny-neox", "tiny-starcoder2"])
+def test_classic_families_generate(preset):
+    test_family_generates(preset)
+
+
+def test_classic_checkpoint_dialects():
+    """GPT-2 (Conv1D + fused c_attn), OPT (decoder.* names), NeoX (head-interleaved query_key_value) load into the canonical layout"""
+    from sglang_b200.models.classic import ClassicForCausalLM
+
+    def canon(preset):
+        cfg = load_model_config(f"dummy:{preset}")
+        ps.set_state(None)
+        m = get_model_class(cfg.architecture)(cfg)
+        m.load_weights(ClassicForCausalLM.dummy_checkpoint(cfg, torch.device("cpu"), torch.float32, 3))
+        return cfg, m
+
+    # GPT-2
+    cfg, ref = canon("tiny-gpt2")
+    H = cfg.hidden_size
+    ck = []
+    for n, p in ref.named_parameters():
+        w = p.data.clone()
+        n2 = n.replace("model.embed_tokens.", "transformer.wte.").replace("model.embed_positions.", "transformer.wpe.").replace("model.norm.", "transformer.ln_f.")
+        if ".layers." in n:
+            lid = n.split(".")[2]
+            rest = n.split(".", 3)[3]
+            pre = f"transformer.h.{lid}."
+            kind = rest.rsplit(".", 1)[1]
+            tr = (lambda x: x.t().contiguous()) if kind == "weight" else (lambda x: x)
+            if rest.startswith("self_attn.qkv_proj"):
+                ck.append((pre + "attn.c_attn." + kind, tr(w))); continue
+            m_ = {"input_layernorm": "ln_1", "post_attention_layernorm": "ln_2"}
+            for a, b in m_.items():
+                if rest.startswith(a):
+                    ck.append((pre + b + "." + kind, w)); break
+            else:
+                for a, b in (("self_attn.o_proj", "attn.c_proj"), ("mlp.fc1", "mlp.c_fc"), ("mlp.fc2", "mlp.c_proj")):
+                    if rest.startswith(a):
+                        ck.append((pre + b + "." + kind, tr(w)))
+            continue
+        ck.append((n2, w))
+    ps.set_state(None)
+    m = get_model_class("GPT2LMHeadModel")(cfg)
+    m.load_weights(iter(ck))
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), m.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+    # NeoX: interleave q/k/v per head
+    cfg, ref = canon("tiny-neox")
+    nh, D = cfg.num_attention_heads, cfg.head_dim
+    ck = []
+    for n, p in ref.named_parameters():
+        w = p.data.clone()
+        n2 = n.replace("model.embed_tokens.", "gpt_neox.embed_in.").replace("model.norm.", "gpt_neox.final_layer_norm.").replace("lm_head.", "embed_out.")
+        n2 = n2.replace("model.layers.", "gpt_neox.layers.").replace(".self_attn.o_proj.", ".attention.dense.").replace(".mlp.fc1.", ".mlp.dense_h_to_4h.").replace(".mlp.fc2.", ".mlp.dense_4h_to_h.")
+        if ".self_attn.qkv_proj." in n:
+            q, k, v = w.split([nh * D] * 3, 0)
+            inter = torch.stack([q.view(nh, D, *w.shape[1:]), k.view(nh, D, *w.shape[1:]), v.view(nh, D, *w.shape[1:])], 1).reshape(3 * nh * D, *w.shape[1:])
+            ck.append((n2.replace(".self_attn.qkv_proj.", ".attention.query_key_value."), inter)); continue
+        ck.append((n2, w))
+    ps.set_state(None)
+    m = get_model_class("GPTNeoXForCausalLM")(cfg)
+    m.load_weights(iter(ck))
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), m.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+    # OPT
+    cfg, ref = canon("tiny-opt")
+    ck = []
+    for n, p in ref.named_parameters():
+        n2 = n.replace("model.norm.", "model.decoder.final_layer_norm.") if n.startswith("model.norm.") else n.replace("model.", "model.decoder.", 1)
+        n2 = n2.replace(".self_attn.o_proj.", ".self_attn.out_proj.").replace(".input_layernorm.", ".self_attn_layer_norm.")
+        n2 = n2.replace(".post_attention_layernorm.", ".final_layer_norm.").replace(".mlp.fc1.", ".fc1.").replace(".mlp.fc2.", ".fc2.")
+        if ".self_attn.qkv_proj." in n:
+            q, k, v = p.data.chunk(3, 0)
+            for nm, t in (("q_proj", q), ("k_proj", k), ("v_proj", v)):
+                ck.append((n2.replace("qkv_proj", nm), t.clone()))
+            continue
+        ck.append((n2, p.data.clone()))
+    ps.set_state(None)
+    m = get_model_class("OPTForCausalLM")(cfg)
+    m.load_weights(iter(ck))
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), m.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1

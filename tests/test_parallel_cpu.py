@@ -158,3 +158,9 @@ def test_dp_attention_tp2_dp2_and_tp4_dp2():
     dpk = {**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True}
     _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1", "SGLB_TEST_EXPECT_A2A": "1"}), ref)      # all-to-all expert dispatch / combine
     _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "0"}), ref)                                   # gather-all-tokens dispatcher
+
+
+def test_classic_family_tp2():
+    for preset in ("tiny-gpt2", "tiny-neox"):
+        kw = dict(model_path=f"dummy:{preset}", page_size=4)
+        _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))
