@@ -219,6 +219,9 @@ class GPT2LMHeadModel(ClassicForCausalLM):
 
     def remap(self, name, w):
         H = self.cfg.hidden_size
+        if name.startswith("model."):         # already canonical (synthetic checkpoint)
+            yield name, w
+            return
         name = name[len("transformer."):] if name.startswith("transformer.") else name
         if name in ("wte.weight",):
             yield "model.embed_tokens.weight", w
