@@ -84,7 +84,7 @@ class Engine:
         st = ps.get_state()
         self.tp_rank, self.pp_rank = st.tp.rank, st.pp.rank
         self.is_driver = st.rank == 0
-        self.model_config = load_model_config(a.model_path, None, a.context_length)
+        self.model_config = load_model_config(a.model_path, __import__('json').loads(a.json_model_override_args or '{}') or None, a.context_length)
         self.runner = ModelRunner(a, self.model_config)
         self.tokenizer = None if a.skip_tokenizer_init else get_tokenizer(
             a.tokenizer_path, self.model_config.vocab_size, self.model_config.eos_token_id, self.model_config.bos_token_id,

@@ -77,6 +77,10 @@ class Scheduler:
         self.new_token_ratio_decay = (self.init_new_token_ratio - self.min_new_token_ratio) / 600
         self.new_token_ratio = self.init_new_token_ratio
 
+        self.prefill_delayer = None
+        self.min_free_slots_delayer = None
+        self._init_delayers()
+
         self.forward_ct = 0
         self.decode_ct = 0
         self.num_retracted = 0
@@ -238,13 +242,51 @@ class Scheduler:
             self.last_batch = None
 
         self._poll_grammar_queue()
-        new_batch = self._get_new_batch_prefill()
+        allow = self._prefill_allowed() if (self.prefill_delayer is not None or self.min_free_slots_delayer is not None) else True
+        new_batch = self._get_new_batch_prefill() if allow else None
         if new_batch is not None:
+            if self.prefill_delayer is not None:
+                self.prefill_delayer.observe_prefill(len(new_batch.reqs))
             return new_batch
         if self.running_batch.reqs:
             b = self._update_running_batch()
             return b
         return None
+
+    def _init_delayers(self) -> None:
+        a = self.args
+        from .prefill_delayer import MinFreeSlotsDelayer, PrefillDelayer, resolve_min_free_slots
+
+        n = resolve_min_free_slots(a.min_free_slots, self.max_running)
+        if n is not None:
+            self.min_free_slots_delayer = MinFreeSlotsDelayer(n)
+        if not a.enable_prefill_delayer:
+            return
+        gather = None
+        if a.enable_dp_attention:
+            from ..parallel import parallel_state as ps
+
+            st = ps.get_state()
+            stride = max(1, st.tp.world_size // max(1, st.attn_dp_size))
+            gather = lambda row: st.tp.all_gather_pyobj(row)[::stride]       # one row per DP group (its attention-TP rank 0)
+        self.prefill_delayer = PrefillDelayer(gather, a.dp_size, a.enable_dp_attention, a.prefill_delayer_max_delay_passes,
+                                              a.prefill_delayer_token_usage_low_watermark, a.prefill_delayer_queue_min_ratio,
+                                              a.prefill_delayer_max_delay_ms, a.prefill_max_requests)
+
+    def _prefill_allowed(self) -> bool:
+        """one negotiation per scheduler pass on every rank (also with nothing to prefill: keeps the gather matched)"""
+        running = len(self.running_batch.reqs)
+        if self.min_free_slots_delayer is not None and self.chunked_req is None and self.waiting_queue and \
+                self.min_free_slots_delayer.should_delay(running, self.max_running - running):
+            local_ok = False
+        else:
+            local_ok = True
+        if self.prefill_delayer is None:
+            return local_ok
+        prefillable = local_ok and bool(self.waiting_queue) and self.chunked_req is None and running < self.max_running
+        d = self.prefill_delayer.negotiate(prefillable, self.kv.token_usage(), running, len(self.waiting_queue), self.max_running)
+        # a chunked request in flight always continues (its pages are already held)
+        return local_ok and (d.allow or self.chunked_req is not None)
 
     def _poll_grammar_queue(self) -> None:
         if not self.grammar_queue:

@@ -67,6 +67,13 @@ class ServerArgs:
     disable_overlap_schedule: bool = False
     stream_interval: int = 1
     num_continuous_decode_steps: int = 1
+    enable_prefill_delayer: bool = False
+    prefill_delayer_max_delay_passes: int = 30
+    prefill_delayer_token_usage_low_watermark: Optional[float] = None
+    prefill_delayer_queue_min_ratio: Optional[float] = None
+    prefill_delayer_max_delay_ms: Optional[float] = None
+    prefill_max_requests: Optional[int] = None
+    min_free_slots: Optional[int] = None
     # --- parallelism
     tp_size: int = 1
     pp_size: int = 1

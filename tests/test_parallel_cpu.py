@@ -164,3 +164,11 @@ def test_classic_family_tp2():
     for preset in ("tiny-gpt2", "tiny-neox"):
         kw = dict(model_path=f"dummy:{preset}", page_size=4)
         _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))
+
+
+def test_dp_attention_with_prefill_delayer():
+    """the delayer's per-pass gather must stay matched across DP groups (uneven load -> 'mixed' passes are delayed, bounded)"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 2, "dp_size": 2, "enable_dp_attention": True, "enable_prefill_delayer": True,
+                 "prefill_delayer_max_delay_passes": 3}, 2, LP), ref)
