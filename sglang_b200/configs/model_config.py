@@ -259,11 +259,16 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             raise ValueError(f"unknown preset {name!r}; available: {sorted(PRESETS)}")
         kw = {**PRESETS[name], **overrides, "name": name}
     else:
-        cfg_file = os.path.join(model_path, "config.json")
-        if not os.path.exists(cfg_file):
-            raise FileNotFoundError(f"{cfg_file} not found (offline box: use dummy:<preset> or a local HF directory)")
-        with open(cfg_file) as f:
-            hf = json.load(f)
+        if os.path.isfile(model_path) and model_path.endswith(".gguf"):
+            from ..model_loader.gguf import GGUFFile, config_from_gguf
+
+            hf = config_from_gguf(GGUFFile(model_path))
+        else:
+            cfg_file = os.path.join(model_path, "config.json")
+            if not os.path.exists(cfg_file):
+                raise FileNotFoundError(f"{cfg_file} not found (offline box: use dummy:<preset>, a local HF directory or a .gguf file)")
+            with open(cfg_file) as f:
+                hf = json.load(f)
         text = hf.get("text_config", hf)
         fields = {f.name for f in dataclasses.fields(ModelConfig)}
         text = {_HF_KEY_MAP.get(k, k): v for k, v in text.items()}

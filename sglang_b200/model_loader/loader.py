@@ -138,6 +138,10 @@ def load_model(cfg: ModelConfig, model_path: str, load_format: str, device: torc
     model = build_model(cfg, device, quant)
     if load_format == "dummy":
         init_dummy_weights(model, seed, cfg=cfg)
+    elif load_format == "gguf" or (load_format == "auto" and model_path.endswith(".gguf") and os.path.isfile(model_path)):
+        from .gguf import iter_gguf
+
+        model.load_weights(iter_gguf(model_path, next(model.parameters()).dtype))
     elif load_format in ("safetensors", "auto"):
         model.load_weights(iter_safetensors(model_path))
     elif load_format == "pt":

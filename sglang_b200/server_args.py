@@ -23,7 +23,7 @@ class ServerArgs:
     # --- model
     model_path: str = "dummy:tiny-llama"
     tokenizer_path: Optional[str] = None
-    load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state
+    load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf
     dtype: str = "bfloat16"
     kv_cache_dtype: str = "auto"  # auto|bf16|fp8_e4m3
     quantization: Optional[str] = None  # None|fp8|fp8_block|w4a16|w8a8_int8(unsupported)
@@ -153,7 +153,7 @@ class ServerArgs:
             except Exception:
                 self.device = "cpu"
         if self.load_format == "auto":
-            self.load_format = "dummy" if self.model_path.startswith("dummy:") else "safetensors"
+            self.load_format = "dummy" if self.model_path.startswith("dummy:") else ("gguf" if self.model_path.endswith(".gguf") else "safetensors")
         if self.page_size < 1 or (self.page_size & (self.page_size - 1)):
             raise ValueError("--page-size must be a power of two")
         if self.chunked_prefill_size is None:

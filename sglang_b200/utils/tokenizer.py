@@ -99,5 +99,11 @@ def get_tokenizer(path: Optional[str], vocab_size: int = 512, eos_token_id: Any 
         from transformers import AutoTokenizer
 
         return AutoTokenizer.from_pretrained(path, trust_remote_code=trust_remote_code, local_files_only=True)
+    if path and os.path.isfile(path) and path.endswith(".gguf"):
+        from ..model_loader.gguf import GGUFFile, GGUFTokenizer
+
+        md = GGUFFile(path).metadata
+        if "tokenizer.ggml.tokens" in md:
+            return GGUFTokenizer(md)
     eos = eos_token_id[0] if isinstance(eos_token_id, (list, tuple)) else eos_token_id
     return ByteTokenizer(vocab_size, eos, bos_token_id)
