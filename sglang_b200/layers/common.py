@@ -71,19 +71,57 @@ class RadixAttention(nn.Module):
         v3 = v.view(T, self.num_kv_heads, self.head_dim)
         pool = fb.kv_pool
         kc, vc = pool.k(self.layer_id), pool.v(self.layer_id)
+        dcp = getattr(fb, "dcp", None)
+        out_loc = fb.out_cache_loc if dcp is None else dcp.local_loc
         if self.rope is not None:
-            ops.rope_kv_write(q3, k3, v3, fb.positions, self.rope.cos_sin, kc, vc, fb.out_cache_loc, self.rope.is_neox,
+            ops.rope_kv_write(q3, k3, v3, fb.positions, self.rope.cos_sin, kc, vc, out_loc, self.rope.is_neox,
                               pool.k_scale, pool.v_scale, nslabs, slab_stride)
         else:
             assert nslabs == 1
-            loc = fb.out_cache_loc.long()
+            loc = out_loc.long()
             kc[loc] = k3.to(kc.dtype)
             vc[loc] = v3.to(vc.dtype)
+        if dcp is not None:
+            return self._forward_dcp(q3, kc, vc, fb, dcp, pool)
         o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
                                 workspace=fb.attn_workspace, custom_mask=fb.custom_mask)
         return o.view(T, self.num_heads * self.head_dim)
+
+
+def _radix_forward_dcp(self, q3, kc, vc, fb, dcp, pool):
+    """decode context parallel attention (layers/dcp.py): gather the group's query heads, attend to this rank's token shard, merge"""
+    from ..parallel.parallel_state import get_dcp_group
+    from .dcp import merge_partials
+
+    assert self.window <= 0, "DCP: sliding-window attention is not supported"
+    g = get_dcp_group()
+    T = q3.shape[0]
+    qg = g.all_gather(q3.contiguous(), dim=1)                              # [T, Hg, D]
+    Hg = qg.shape[1]
+    lse = torch.full((T, Hg), float("-inf"), dtype=torch.float32, device=q3.device)
+    kw = dict(window=-1, logit_cap=self.logit_cap, k_scale=pool.k_scale, v_scale=pool.v_scale)
+    if fb.mode.is_decode() and fb.cu_q is None:
+        o = torch.empty_like(qg)
+        ops.paged_attention(qg, kc, vc, fb.page_table, fb.req_slots, dcp.local_lens, None, None, 1, dcp.local_page_size, self.scale,
+                            causal=True, out=o, lse=lse, **kw)
+        lse = torch.where(dcp.empty.unsqueeze(-1), torch.full_like(lse, float("-inf")), lse)
+    else:
+        o = torch.zeros_like(qg)
+        if dcp.v_rows.numel():
+            qv = qg[dcp.v_rows].contiguous()
+            ov = torch.empty_like(qv)
+            lv = torch.empty(qv.shape[0], Hg, dtype=torch.float32, device=q3.device)
+            ops.paged_attention(qv, kc, vc, fb.page_table, dcp.v_slots, dcp.v_seq_lens, dcp.v_cu_q, dcp.v_q_lens, dcp.v_max_q,
+                                dcp.local_page_size, self.scale, causal=True, out=ov, lse=lv, **kw)
+            o[dcp.v_rows] = ov
+            lse[dcp.v_rows] = lv
+    out = merge_partials(g, o, lse)
+    return out.to(q3.dtype).reshape(T, self.num_heads * self.head_dim)
+
+
+RadixAttention._forward_dcp = _radix_forward_dcp
 
 
 def get_act_and_mul(name: str):

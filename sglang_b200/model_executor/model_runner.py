@@ -100,6 +100,10 @@ class ModelRunner:
             if server_args.attention_backend in ("tc", "simt"):
                 envs.SGLB_ATTN_IMPL.set(server_args.attention_backend)
         self.page_size = server_args.page_size
+        from ..parallel.parallel_state import get_dcp_group
+
+        self.dcp = get_dcp_group()
+        self.local_page_size = self.page_size // (self.dcp.world_size if self.dcp is not None else 1)
         torch.manual_seed(server_args.random_seed)
         t0 = time.perf_counter()
         if self.cfg.is_moe:
@@ -137,7 +141,7 @@ class ModelRunner:
         self.profiler = None
         self.expert_recorder = None
         if (self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1
-                and getattr(self.model, "supports_cuda_graph", True) and not server_args.enable_dp_attention):
+                and getattr(self.model, "supports_cuda_graph", True) and not server_args.enable_dp_attention and self.dcp is None):
             with torch.cuda.stream(self.stream):
                 self._capture_graphs()
             self.stream.synchronize()
@@ -152,7 +156,12 @@ class ModelRunner:
         kv_dtype = self.dtype
         if a.kv_cache_dtype in ("fp8_e4m3", "fp8"):
             kv_dtype = torch.float8_e4m3fn
-        per_page = KVPool.bytes_per_page(self.page_size, n_layers, kv_heads, kv_dim, kv_dtype)
+        if self.dcp is not None:
+            assert self.page_size % self.dcp.world_size == 0, "DCP: --page-size must be a multiple of --dcp-size"
+            q0 = self.model.model.layers[0].self_attn.qkv_proj if n_layers and hasattr(self.model.model.layers[0].self_attn, "qkv_proj") else None
+            assert q0 is not None and getattr(q0, "kv_replicas", 1) % self.dcp.world_size == 0, \
+                "DCP: dcp_size must divide the KV-head replication factor tp_size / num_kv_heads (nothing to de-duplicate otherwise)"
+        per_page = KVPool.bytes_per_page(self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype)
         self.max_context_len = a.context_length or cfg.max_position_embeddings
         if self.is_cuda:
             free, total = torch.cuda.mem_get_info(self.device)
@@ -171,7 +180,7 @@ class ModelRunner:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.tp.device_group)
             num_pages = int(t.item())
         self.num_pages = int(num_pages)
-        self.kv_pool = KVPool(self.num_pages, self.page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
+        self.kv_pool = KVPool(self.num_pages, self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
         tokens = (self.num_pages - 1) * self.page_size
         self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
@@ -197,6 +206,17 @@ class ModelRunner:
 
     def flush(self) -> None:
         self.page_table.zero_()
+
+    def _attach_dcp(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
+        if self.dcp is None:
+            return
+        from ..layers.dcp import build_meta
+
+        decode = sb.forward_mode.is_decode() and fb.cu_q is None
+        fb.dcp = build_meta(self.dcp, self.page_size, fb.out_cache_loc, fb.seq_lens, decode, fb.seq_lens_cpu, fb.q_lens_cpu,
+                            np.asarray(sb.req_slots) if not decode else None)
+        fb.page_size = self.local_page_size
+        fb.num_splits = 1
 
     # ------------------------------------------------------------------ attention split heuristic
     def _pick_splits(self, bs: int, max_kv: int) -> int:
@@ -257,6 +277,7 @@ class ModelRunner:
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
         self.h2d_bytes += fb.h2d_bytes
         fb.num_splits = self._pick_splits(B, fb.max_kv_len) if decode else 1
+        self._attach_dcp(sb, fb)
         self._attach_mm(sb, fb)
         if self.lora_manager is not None:
             self.lora_manager.prepare_batch(sb, fb)
@@ -325,6 +346,7 @@ class ModelRunner:
         with ctx:
             fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
             self.h2d_bytes += fb.h2d_bytes
+            self._attach_dcp(sb, fb)
             hidden = self.model(fb)
             self.last_verify_hidden = hidden if self.hidden_tap is not None else None
             logits = self.model.compute_logits(hidden)          # [T, V]

@@ -66,6 +66,7 @@ class GroupCoordinator:
         x = x.contiguous()
         if x.dim() == 0:
             x = x.view(1)
+        self.comm_calls += 1
         # flat [world * n0, ...] output: the layout both NCCL and Gloo accept for all_gather_into_tensor
         flat = torch.empty((self.world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(flat, x, group=self.device_group)
@@ -78,7 +79,12 @@ class GroupCoordinator:
         """x [world*n, ...] -> [n, ...] (sum over ranks of each rank's slice)"""
         if self.world_size == 1:
             return x
-        out = torch.empty((x.shape[0] // self.world_size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        n = x.shape[0] // self.world_size
+        if not x.is_cuda:       # Gloo has no reduce-scatter: all-reduce and keep this rank's slice (CPU tier only)
+            x = x.contiguous().clone()
+            dist.all_reduce(x, group=self.device_group)
+            return x[self.rank_in_group * n:(self.rank_in_group + 1) * n].contiguous()
+        out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.reduce_scatter_tensor(out, x.contiguous(), group=self.device_group)
         return out
 
@@ -144,6 +150,9 @@ class ParallelState:
     attn_tp: Any = None
     attn_dp_rank: int = 0
     attn_dp_size: int = 1
+    # decode context parallelism: ``dcp`` = consecutive ranks of the attention-TP group that hold the SAME (replicated) KV head and
+    # split the tokens of every sequence between them (layers/dcp.py)
+    dcp: Any = None
 
 
 _STATE: Optional[ParallelState] = None
@@ -170,12 +179,13 @@ def compute_group_ranks(world_size: int, tp_size: int, pp_size: int, ep_size: in
 
 def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, device: Optional[str] = None,
                      init_method: Optional[str] = None, rank: Optional[int] = None, world_size: Optional[int] = None,
-                     enable_nvl: bool = True, timeout_s: int = 600, attn_dp_size: int = 1) -> ParallelState:
+                     enable_nvl: bool = True, timeout_s: int = 600, attn_dp_size: int = 1, dcp_size: int = 1) -> ParallelState:
     global _STATE
     use_cuda = (device or ("cuda" if torch.cuda.is_available() else "cpu")).startswith("cuda")
     ws = tp_size * pp_size
     if (_STATE is not None and ws > 1 and _STATE.world_size == ws and _STATE.tp.world_size == tp_size
-            and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size) and _STATE.attn_dp_size == max(1, attn_dp_size)):
+            and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size) and _STATE.attn_dp_size == max(1, attn_dp_size)
+            and (_STATE.dcp.world_size if _STATE.dcp is not None else 1) == max(1, dcp_size)):
         return _STATE       # idempotent: a second Engine in the same SPMD job reuses the groups and the NVL arena
     if ws == 1:
         dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
@@ -226,6 +236,11 @@ def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, devic
         attn_tp = make(groups, "attn_tp")
         dp_rank = tp.rank // a
     _STATE = ParallelState(world, tp, pp, ep, rank, world_size, local_rank, attn_tp, dp_rank, max(1, attn_dp_size))
+    if dcp_size > 1:
+        a = tp_size // max(1, attn_dp_size)
+        assert a % dcp_size == 0, "dcp_size must divide the attention-TP size"
+        attn_groups = [g[i:i + a] for g in tp_groups for i in range(0, tp_size, a)]
+        _STATE.dcp = make([g[i:i + dcp_size] for g in attn_groups for i in range(0, a, dcp_size)], "dcp")
     if use_cuda and enable_nvl and tp.world_size > 1:
         try:
             from .nvl_comm import NvlComm
@@ -265,6 +280,11 @@ def get_ep_group() -> GroupCoordinator:
 def get_attn_tp_group() -> GroupCoordinator:
     st = get_state()
     return st.attn_tp if st.attn_tp is not None else st.tp
+
+
+def get_dcp_group() -> Optional[GroupCoordinator]:
+    d = get_state().dcp
+    return d if d is not None and d.world_size > 1 else None
 
 
 def get_tp_rank() -> int:

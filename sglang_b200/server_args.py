@@ -176,6 +176,12 @@ class ServerArgs:
             # groups take different batches every step: one synchronous forward per iteration on every rank, no graph replay
             self.disable_overlap_schedule = True
             self.disable_cuda_graph = True
+        if self.dcp_size > 1:
+            attn_tp = self.tp_size // (self.dp_size if self.enable_dp_attention else 1)
+            if attn_tp % self.dcp_size:
+                raise ValueError("dcp_size must divide the attention TP size")
+            if self.page_size % self.dcp_size:
+                raise ValueError("page_size must be a multiple of dcp_size (each rank stores page_size / dcp_size tokens of every page)")
         if self.cuda_graph_max_bs is None:
             self.cuda_graph_max_bs = 512 if self.tp_size == 1 else 256
         if self.device != "cuda":

@@ -22,5 +22,8 @@ if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives out
 if os.environ.get("SGLB_TEST_EXPECT_A2A"):
     ex = eng.runner.model.model.layers[0].mlp.experts
     assert getattr(ex, "_a2a_calls", 0) > 0, "the all-to-all dispatcher was expected to run"
+if os.environ.get("SGLB_TEST_EXPECT_DCP"):
+    assert eng.runner.dcp is not None and eng.runner.kv_pool.page_size * eng.runner.dcp.world_size == eng.runner.page_size
+    assert eng.runner.dcp.comm_calls > 0, "DCP collectives were expected to run"
 eng.shutdown()
 os._exit(0)

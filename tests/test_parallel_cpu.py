@@ -172,3 +172,15 @@ def test_dp_attention_with_prefill_delayer():
     ref = _run(kw, 1, LP)
     _check(_run({**kw, "tp_size": 2, "dp_size": 2, "enable_dp_attention": True, "enable_prefill_delayer": True,
                  "prefill_delayer_max_delay_passes": 3}, 2, LP), ref)
+
+
+def test_decode_context_parallel_matches_single():
+    """DCP: the two ranks that would hold copies of the single KV head split the tokens instead (token p on rank p % 2); prefill runs as
+    per-residue virtual requests, decode on the local shard, partials merged by LSE -> must equal the single-process engine, with chunked
+    prefill, prefix reuse (second wave shares a prefix) and sequences shorter than the group"""
+    over = json.dumps({"num_key_value_heads": 1})
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, json_model_override_args=over, chunked_prefill_size=16)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 2, "dcp_size": 2}, 2, LP, {"SGLB_TEST_EXPECT_DCP": "1"}), ref)
+    _check(_run({**kw, "tp_size": 4, "dcp_size": 2, "page_size": 8}, 4, LP), _run({**kw, "page_size": 8}, 1, LP))
+    _check(_run({**kw, "tp_size": 4, "dcp_size": 4}, 4, LP), ref)
