@@ -75,7 +75,8 @@ class Engine:
         world = a.tp_size * a.pp_size
         if world > 1:
             ps.init_distributed(a.tp_size, a.pp_size, a.ep_size, device=a.device, enable_nvl=a.comm_backend != "nccl",
-                                attn_dp_size=a.dp_size if a.enable_dp_attention else 1, dcp_size=a.dcp_size)
+                                attn_dp_size=a.dp_size if a.enable_dp_attention else 1, dcp_size=a.dcp_size,
+                                cp_size=a.cp_size if a.enable_prefill_cp else 1)
         else:
             if a.device == "cuda":
                 torch.cuda.set_device(a.base_gpu_id)

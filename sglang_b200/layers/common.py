@@ -83,6 +83,12 @@ class RadixAttention(nn.Module):
             vc[loc] = v3.to(vc.dtype)
         if dcp is not None:
             return self._forward_dcp(q3, kc, vc, fb, dcp, pool)
+        cp = getattr(fb, "cp", None)
+        if cp is not None:       # context-parallel prefill: the other groups' K/V rows of this layer (layers/cp.py)
+            from ..parallel.parallel_state import get_cp_group
+            from .cp import gather_write_kv
+
+            gather_write_kv(get_cp_group(), cp, out_loc, kc, vc)
         o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,

@@ -27,6 +27,7 @@ class DpAttnContext:
         self.dp_size, self.dp_rank = st.attn_dp_size, st.attn_dp_rank
         self.attn_tp_size = st.tp.world_size // st.attn_dp_size
         self._counts: Dict[str, List[int]] = {}
+        self.cp_active = False      # prefill-CP reuses this context, but only inside a context-parallel prefill (layers/cp.py)
 
     def begin(self) -> None:
         self._counts = {}
@@ -64,6 +65,19 @@ def get_dp_ctx() -> Optional[DpAttnContext]:
     st = get_state()
     if st.attn_dp_size <= 1:
         _CTX = None
+        return None
+    if _CTX is None or _CTX.tp is not st.tp:
+        _CTX = DpAttnContext()
+    if st.cp_mode and not _CTX.cp_active:
+        return None         # outside a CP prefill every group holds every token: the plain tensor-parallel path is exact
+    return _CTX
+
+
+def get_cp_ctx() -> Optional[DpAttnContext]:
+    """the (possibly inactive) shared context of prefill-CP mode"""
+    global _CTX
+    st = get_state()
+    if not st.cp_mode:
         return None
     if _CTX is None or _CTX.tp is not st.tp:
         _CTX = DpAttnContext()

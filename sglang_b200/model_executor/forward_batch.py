@@ -65,6 +65,7 @@ class ForwardBatch:
     seq_lens_cpu: Optional[np.ndarray] = None
     q_lens_cpu: Optional[np.ndarray] = None
     pp_hidden: Any = None
+    cp: Any = None                   # layers/cp.py CpMeta inside a context-parallel prefill
     dcp: Any = None                  # layers/dcp.py DcpMeta when decode context parallelism is on
 
 

@@ -103,6 +103,13 @@ class ModelRunner:
         from ..parallel.parallel_state import get_dcp_group
 
         self.dcp = get_dcp_group()
+        from ..parallel.parallel_state import get_cp_group, get_state as _gs
+
+        self.cp = get_cp_group()
+        self.cp_rank = _gs().attn_dp_rank if self.cp is not None else 0
+        self.cp_min_tokens = max(2 * (self.cp.world_size if self.cp is not None else 1), envs.SGLB_CP_MIN_TOKENS.get())
+        self.cp_forwards = 0
+        assert self.cp is None or self.dcp is None, "prefill CP and decode CP are separate modes"
         self.local_page_size = self.page_size // (self.dcp.world_size if self.dcp is not None else 1)
         torch.manual_seed(server_args.random_seed)
         t0 = time.perf_counter()
@@ -207,6 +214,35 @@ class ModelRunner:
     def flush(self) -> None:
         self.page_table.zero_()
 
+    # ------------------------------------------------------------------ prefill context parallelism (layers/cp.py)
+    def _cp_eligible(self, sb: ScheduleBatch, fb: ForwardBatch) -> bool:
+        return (fb.cu_q is not None and fb.input_ids is not None and fb.num_tokens >= self.cp_min_tokens and fb.mm_embeds is None
+                and self.lora_manager is None and sb.spec_info is None and fb.custom_mask is None and self.pp.world_size == 1)
+
+    def _forward_cp(self, sb: ScheduleBatch, fb: ForwardBatch) -> torch.Tensor:
+        """run the decoder stack on this attention group's zig-zag slice of the rows; returns the hidden states of ALL rows, original order"""
+        import dataclasses as _dc
+
+        from ..layers.cp import build_meta
+        from ..layers.dp_attention import get_cp_ctx
+
+        st_rank = self.cp_rank
+        meta = build_meta(st_rank, self.cp.world_size, fb.seq_lens_cpu, fb.q_lens_cpu, np.asarray(sb.req_slots), fb.out_cache_loc)
+        rows = meta.rows
+        lfb = _dc.replace(fb, batch_size=int(meta.v_slots.numel()), num_tokens=int(rows.numel()), input_ids=fb.input_ids[rows],
+                          positions=fb.positions[rows], out_cache_loc=fb.out_cache_loc[rows], req_slots=meta.v_slots,
+                          seq_lens=meta.v_seq_lens, cu_q=meta.v_cu_q, q_lens=meta.v_q_lens, max_q_len=meta.v_max_q, cp=meta, num_splits=1)
+        ctx = get_cp_ctx()
+        ctx.begin()
+        ctx.cp_active = True
+        try:
+            hidden = self.model(lfb)
+            full = ctx.gather(hidden, "tokens")
+        finally:
+            ctx.cp_active = False
+        self.cp_forwards += 1
+        return full[meta.inv_perm]
+
     def _attach_dcp(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
         if self.dcp is None:
             return
@@ -283,7 +319,7 @@ class ModelRunner:
             self.lora_manager.prepare_batch(sb, fb)
         if not self.pp.is_first:
             fb.pp_hidden = self._pp_recv(fb.num_tokens)
-        hidden = self.model(fb)
+        hidden = self._forward_cp(sb, fb) if (self.cp is not None and not decode and self._cp_eligible(sb, fb)) else self.model(fb)
         if self.hidden_tap is not None and not decode and self.pp.is_last:
             self.hidden_tap(sb, hidden)          # EAGLE: target features of the prefilled positions
         res = BatchResult()

@@ -142,10 +142,14 @@ def load_model(cfg: ModelConfig, model_path: str, load_format: str, device: torc
         from .gguf import iter_gguf
 
         model.load_weights(iter_gguf(model_path, next(model.parameters()).dtype))
-    elif load_format in ("safetensors", "auto"):
-        model.load_weights(iter_safetensors(model_path))
-    elif load_format == "pt":
-        model.load_weights(iter_pt(model_path))
+    elif load_format in ("safetensors", "auto", "pt"):
+        it = iter_pt(model_path) if load_format == "pt" else iter_safetensors(model_path)
+        from .quant_adapters import adapt_quantized_checkpoint, read_quant_config
+
+        qcfg = read_quant_config(model_path)
+        if qcfg:      # AWQ / GPTQ / compressed-tensors / fp8 / ModelOpt / mxfp4 / bitsandbytes checkpoint: de-quantise into the serving dtype
+            it = adapt_quantized_checkpoint(it, qcfg, next(model.parameters()).dtype, keep_block_fp8=quant in ("fp8_block", "mxfp8"))
+        model.load_weights(it)
     elif load_format == "sharded_state":
         load_sharded_state(model, model_path)
     else:

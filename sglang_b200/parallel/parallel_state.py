@@ -153,6 +153,10 @@ class ParallelState:
     # decode context parallelism: ``dcp`` = consecutive ranks of the attention-TP group that hold the SAME (replicated) KV head and
     # split the tokens of every sequence between them (layers/dcp.py)
     dcp: Any = None
+    # prefill context parallelism: the TP group is split into ``cp_size`` attention groups exactly like DP-attention, but the groups share
+    # every request: in a prefill each takes a zig-zag slice of the query rows and all-gathers K/V over ``cp`` (layers/cp.py)
+    cp: Any = None
+    cp_mode: bool = False
 
 
 _STATE: Optional[ParallelState] = None
@@ -179,13 +183,16 @@ def compute_group_ranks(world_size: int, tp_size: int, pp_size: int, ep_size: in
 
 def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, device: Optional[str] = None,
                      init_method: Optional[str] = None, rank: Optional[int] = None, world_size: Optional[int] = None,
-                     enable_nvl: bool = True, timeout_s: int = 600, attn_dp_size: int = 1, dcp_size: int = 1) -> ParallelState:
+                     enable_nvl: bool = True, timeout_s: int = 600, attn_dp_size: int = 1, dcp_size: int = 1, cp_size: int = 1) -> ParallelState:
     global _STATE
+    if cp_size > 1:
+        assert attn_dp_size == 1, "prefill CP and DP-attention both partition the TP group: enable one of them"
+        attn_dp_size = cp_size
     use_cuda = (device or ("cuda" if torch.cuda.is_available() else "cpu")).startswith("cuda")
     ws = tp_size * pp_size
     if (_STATE is not None and ws > 1 and _STATE.world_size == ws and _STATE.tp.world_size == tp_size
             and _STATE.pp.world_size == pp_size and _STATE.ep.world_size == max(1, ep_size) and _STATE.attn_dp_size == max(1, attn_dp_size)
-            and (_STATE.dcp.world_size if _STATE.dcp is not None else 1) == max(1, dcp_size)):
+            and (_STATE.dcp.world_size if _STATE.dcp is not None else 1) == max(1, dcp_size) and _STATE.cp_mode == (cp_size > 1)):
         return _STATE       # idempotent: a second Engine in the same SPMD job reuses the groups and the NVL arena
     if ws == 1:
         dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
@@ -236,6 +243,10 @@ def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, devic
         attn_tp = make(groups, "attn_tp")
         dp_rank = tp.rank // a
     _STATE = ParallelState(world, tp, pp, ep, rank, world_size, local_rank, attn_tp, dp_rank, max(1, attn_dp_size))
+    if cp_size > 1:
+        a = tp_size // cp_size
+        _STATE.cp = make([[g[i + j * a] for j in range(cp_size)] for g in tp_groups for i in range(a)], "cp")
+        _STATE.cp_mode = True
     if dcp_size > 1:
         a = tp_size // max(1, attn_dp_size)
         assert a % dcp_size == 0, "dcp_size must divide the attention-TP size"
@@ -280,6 +291,11 @@ def get_ep_group() -> GroupCoordinator:
 def get_attn_tp_group() -> GroupCoordinator:
     st = get_state()
     return st.attn_tp if st.attn_tp is not None else st.tp
+
+
+def get_cp_group() -> Optional[GroupCoordinator]:
+    st = get_state()
+    return st.cp if st.cp_mode and st.cp is not None and st.cp.world_size > 1 else None
 
 
 def get_dcp_group() -> Optional[GroupCoordinator]:

@@ -176,6 +176,11 @@ class ServerArgs:
             # groups take different batches every step: one synchronous forward per iteration on every rank, no graph replay
             self.disable_overlap_schedule = True
             self.disable_cuda_graph = True
+        if self.cp_size > 1:
+            self.enable_prefill_cp = True
+        if self.enable_prefill_cp:
+            if self.cp_size <= 1 or self.tp_size % self.cp_size or self.enable_dp_attention or self.pp_size > 1 or self.dcp_size > 1:
+                raise ValueError("prefill CP: cp_size (> 1) must divide tp_size; not combinable with DP-attention, PP or DCP")
         if self.dcp_size > 1:
             attn_tp = self.tp_size // (self.dp_size if self.enable_dp_attention else 1)
             if attn_tp % self.dcp_size:

@@ -25,5 +25,7 @@ if os.environ.get("SGLB_TEST_EXPECT_A2A"):
 if os.environ.get("SGLB_TEST_EXPECT_DCP"):
     assert eng.runner.dcp is not None and eng.runner.kv_pool.page_size * eng.runner.dcp.world_size == eng.runner.page_size
     assert eng.runner.dcp.comm_calls > 0, "DCP collectives were expected to run"
+if os.environ.get("SGLB_TEST_EXPECT_CP"):
+    assert eng.runner.cp is not None and eng.runner.cp_forwards > 0, "context-parallel prefills were expected to run"
 eng.shutdown()
 os._exit(0)

@@ -184,3 +184,15 @@ def test_decode_context_parallel_matches_single():
     _check(_run({**kw, "tp_size": 2, "dcp_size": 2}, 2, LP, {"SGLB_TEST_EXPECT_DCP": "1"}), ref)
     _check(_run({**kw, "tp_size": 4, "dcp_size": 2, "page_size": 8}, 4, LP), _run({**kw, "page_size": 8}, 1, LP))
     _check(_run({**kw, "tp_size": 4, "dcp_size": 4}, 4, LP), ref)
+
+
+def test_prefill_context_parallel_matches_single():
+    """prefill CP: every request's new rows are zig-zag split between the attention groups (K/V all-gathered per layer), decode runs the
+    plain TP path on the replicated KV; chunked prefill + uneven tiny requests exercise empty blocks"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=32)
+    ref = _run(kw, 1, LP)
+    env = {"SGLB_CP_MIN_TOKENS": "1", "SGLB_TEST_EXPECT_CP": "1"}
+    _check(_run({**kw, "tp_size": 2, "cp_size": 2}, 2, LP, env), ref)
+    _check(_run({**kw, "tp_size": 4, "cp_size": 2}, 4, LP, env), ref)
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
+    _check(_run({**kw, "tp_size": 2, "cp_size": 2, "ep_size": 2}, 2, LP, env), _run(kw, 1, LP))
