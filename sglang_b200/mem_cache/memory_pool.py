@@ -37,6 +37,14 @@ class KVPool:
     def v(self, layer: int) -> torch.Tensor:
         return self.buf[layer, 1]
 
+    def move_slots(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        """copy KV rows ``src -> dst`` in every layer (gather first: the two sets may overlap).  Tree speculative decoding compacts the
+        accepted path of a verified token tree into consecutive positions with this (reference ``move_kv_cache`` for topk > 1)."""
+        if src.numel() == 0:
+            return
+        rows = self.buf.index_select(2, src.long())
+        self.buf.index_copy_(2, dst.long(), rows)
+
     # page-granular views for transfer engines (PD disaggregation / HiCache)
     def page_view(self) -> torch.Tensor:
         """[layers, 2, num_pages, page_size, kv_heads, head_dim]"""

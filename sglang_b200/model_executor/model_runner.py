@@ -383,6 +383,10 @@ class ModelRunner:
             fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
             self.h2d_bytes += fb.h2d_bytes
             self._attach_dcp(sb, fb)
+            cm = (sb.spec_info or {}).get("custom_mask") if isinstance(sb.spec_info, dict) else None
+            if cm is not None:       # token-tree verification: every node attends to the prefix and its own ancestors only
+                assert self.dcp is None, "tree drafts + DCP: not supported"
+                fb.custom_mask = torch.from_numpy(cm).to(self.device)
             hidden = self.model(fb)
             self.last_verify_hidden = hidden if self.hidden_tap is not None else None
             logits = self.model.compute_logits(hidden)          # [T, V]

@@ -86,8 +86,7 @@ class _Identity(nn.Module):
 class EagleSpecWorker(BaseSpecWorker):
     def __init__(self, args: Any, runner: Any, scheduler: Any, window: int = 48):
         super().__init__(args, runner, scheduler)
-        if (args.speculative_eagle_topk or 1) > 1:
-            logger.warning("EAGLE tree drafts (topk=%d) are clamped to chain drafts (topk=1)", args.speculative_eagle_topk)
+        self.topk = max(1, int(args.speculative_eagle_topk or 1))
         self.window = window
         tcfg = runner.cfg
         path = args.speculative_draft_model_path
@@ -105,7 +104,7 @@ class EagleSpecWorker(BaseSpecWorker):
                     p.data.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
         a0 = self.draft.layer.self_attn.attn
         self.ps = 16
-        self.pool = KVPool(2 + (window + 2 * self.num_draft + 32) // self.ps, self.ps, 1, a0.num_kv_heads, cfg.head_dim, runner.dtype,
+        self.pool = KVPool(2 + (window + 2 * self.num_draft + self.topk * max(1, args.speculative_num_steps) + 32) // self.ps, self.ps, 1, a0.num_kv_heads, cfg.head_dim, runner.dtype,
                            str(runner.device))
         # the feature window lives ON the request object (``req._eagle``: (position of the first kept row, features [n, H])) so it
         # is dropped with the request — no registry to clean up on finish / abort / retraction
@@ -177,3 +176,89 @@ class EagleSpecWorker(BaseSpecWorker):
             if base + 1 >= self.window + 2 * self.num_draft + 16:
                 break
         return out
+
+    @torch.no_grad()
+    def propose_tree(self, req: Any, max_nodes: int):
+        """EAGLE-2 style token tree (``--speculative-eagle-topk k > 1``): the window pass scores the children of the last token; at every
+        further depth the ``k`` best frontier nodes (by cumulative log-probability) are expanded in ONE draft forward whose tree mask lets
+        a node see the window and its own ancestors; the ``max_nodes`` best candidates overall form the tree.  Cumulative scores never
+        increase along a path, so the best-N set is closed under "parent of" (reference eagle_utils.py build_tree / organize_draft_results)."""
+        if self.topk <= 1:
+            return super().propose_tree(req, max_nodes)
+        st = getattr(req, "_eagle", None)
+        if st is None or max_nodes <= 0:
+            return [], []
+        first, feats = st
+        toks = req.origin_input_ids + req.output_ids
+        L = len(toks) - 1
+        n = feats.shape[0]
+        if first + n != L or n == 0:
+            return [], []
+        dev, target, k = self.runner.device, self.runner.model, self.topk
+        embed = target.model.embed_tokens
+        npages = self.pool.num_pages - 1
+        pt = torch.arange(1, npages + 1, dtype=torch.int32, device=dev).view(1, -1)
+        pt = torch.cat([torch.zeros_like(pt), pt], 0)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+
+        def run(ids, f_in, positions, base, mask):
+            m = ids.shape[0]
+            rel = torch.arange(base, base + m, dtype=torch.int32, device=dev)
+            fb = ForwardBatch(mode=ForwardMode.EXTEND, batch_size=1, num_tokens=m, input_ids=ids, positions=positions,
+                              out_cache_loc=(rel + self.ps).to(torch.int32), req_slots=torch.ones(1, dtype=torch.int32, device=dev),
+                              seq_lens=i32([base + m]), cu_q=i32([0, m]), q_lens=i32([m]), last_idx=None, sample_slots=None, max_q_len=m,
+                              max_kv_len=base + m, page_table=pt, page_size=self.ps, kv_pool=self.pool, custom_mask=mask)
+            return self.draft(fb, embed(ids), f_in)
+
+        ids = i32(toks[first + 1: L + 1])
+        h = run(ids, feats, torch.arange(n, dtype=torch.int32, device=dev) + first, 0, None)
+        # candidate pool: (score, token, parent candidate index or -1, depth, feature row to feed when expanded)
+        cand_tok: List[int] = []
+        cand_par: List[int] = []
+        cand_score: List[float] = []
+        cand_depth: List[int] = []
+        row_of: dict = {}                 # candidate index -> draft KV row (only expanded candidates have one)
+        feat_of: dict = {}                # candidate index -> the parent's output feature (input of this candidate's expansion)
+
+        def add_children(parent: int, feat: torch.Tensor, score: float, depth: int) -> List[int]:
+            lp = torch.log_softmax(target.compute_logits(feat).float(), -1)[0]
+            v, t = torch.topk(lp, k)
+            out = []
+            for s_, t_ in zip(v.tolist(), t.tolist()):
+                cand_tok.append(int(t_))
+                cand_par.append(parent)
+                cand_score.append(score + float(s_))
+                cand_depth.append(depth)
+                feat_of[len(cand_tok) - 1] = feat
+                out.append(len(cand_tok) - 1)
+            return out
+
+        frontier = add_children(-1, h[-1:], 0.0, 1)
+        base = n
+        steps = max(1, int(self.args.speculative_num_steps))
+        cap = self.pool.num_slots - self.ps - 1
+        for _ in range(steps - 1):
+            if len(cand_tok) >= 4 * max_nodes or base + len(frontier) >= cap:
+                break
+            m = len(frontier)
+            mask = torch.zeros(m, base + m, dtype=torch.bool, device=dev)
+            mask[:, :n] = True
+            for j, c in enumerate(frontier):
+                a = cand_par[c]
+                while a >= 0:
+                    mask[j, row_of[a]] = True
+                    a = cand_par[a]
+                mask[j, base + j] = True
+                row_of[c] = base + j
+            hx = run(i32([cand_tok[c] for c in frontier]), torch.cat([feat_of[c] for c in frontier], 0),
+                     i32([first + n - 1 + cand_depth[c] for c in frontier]), base, mask.reshape(-1))
+            base += m
+            new = []
+            for j, c in enumerate(frontier):
+                new += add_children(c, hx[j: j + 1], cand_score[c], cand_depth[c] + 1)
+            frontier = sorted(new, key=lambda c: (-cand_score[c], c))[:k]
+        order = sorted(range(len(cand_tok)), key=lambda c: (-cand_score[c], c))[:max_nodes]
+        keep = sorted(order)                                  # creation order is topological
+        idx = {c: j for j, c in enumerate(keep)}
+        assert all(cand_par[c] < 0 or cand_par[c] in idx for c in keep)
+        return [cand_tok[c] for c in keep], [idx[cand_par[c]] if cand_par[c] >= 0 else -1 for c in keep]

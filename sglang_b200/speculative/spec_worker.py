@@ -15,7 +15,7 @@ target model would (greedy => identical output to non-speculative decoding).
 from __future__ import annotations
 
 import logging
-from typing import Any, List, Optional
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 import torch
@@ -46,9 +46,17 @@ class BaseSpecWorker:
         self.total_drafted = 0
         self.total_accepted = 0
         self.total_verify = 0
+        self.total_tree_verifies = 0       # verifications that needed a tree mask
+        self.total_kv_moves = 0            # KV rows compacted after accepting a non-leading path
 
     def propose(self, req: Any, max_draft: int) -> List[int]:
         raise NotImplementedError
+
+    def propose_tree(self, req: Any, max_nodes: int):
+        """(tokens, parents): a draft token TREE in topological order; ``parents[i]`` is the index of node i's parent among the drafts, -1 for
+        children of the last committed token.  Default: the chain from ``propose`` (reference eagle_utils build_tree / ngram tree mask)."""
+        d = self.propose(req, max_nodes)
+        return d, list(range(-1, len(d) - 1))
 
     def on_tokens_accepted(self, req: Any, new_tokens: List[int]) -> None:
         pass
@@ -62,19 +70,28 @@ class BaseSpecWorker:
         B = len(batch.reqs)
         ids, pos, loc, qlens, plens = [], [], [], [], []
         drafts: List[List[int]] = []
+        trees: List[List[int]] = []
+        any_tree = False
         for i, r in enumerate(batch.reqs):
             p = int(batch.positions[i])
             room = min(self.num_draft, r.sampling_params.max_new_tokens - len(r.output_ids) - 1,
                        sch.max_context_len - p - 2)
-            d = self.propose(r, room) if room > 0 else []
+            d, par = self.propose_tree(r, room) if room > 0 else ([], [])
             if r.grammar is not None:
-                d = []      # grammar-constrained requests verify one token at a time (masks depend on accepted text)
+                d, par = [], []      # grammar-constrained requests verify one token at a time (masks depend on accepted text)
             if d and not kv.alloc_for_extend(r, p + len(d) + 1):
-                d = []      # no KV room for the draft: fall back to plain decode for this request
+                d, par = [], []      # no KV room for the draft: fall back to plain decode for this request
+            d, par = list(d), [int(x) for x in par]
             drafts.append(d)
+            trees.append(par)
+            depth = [0] * (len(d) + 1)           # node 0 = the last committed token; draft j is node j + 1
+            for j, pj in enumerate(par):
+                assert -1 <= pj < j, "draft tree must be in topological order"
+                depth[j + 1] = depth[pj + 1] + 1
+                any_tree |= pj != j - 1
             last = r.output_ids[-1] if r.output_ids else r.origin_input_ids[-1]
             ids.append(np.asarray([last] + d, dtype=np.int32))
-            pos.append(np.arange(p, p + len(d) + 1, dtype=np.int32))
+            pos.append(p + np.asarray(depth, dtype=np.int32))
             loc.append(kv.slots_for(r, p, p + len(d) + 1))
             qlens.append(len(d) + 1)
             plens.append(p)
@@ -91,30 +108,63 @@ class BaseSpecWorker:
         d1 = kv.take_deltas()
         vb.pt_rows, vb.pt_cols, vb.pt_vals = (np.concatenate([a, b]) for a, b in zip(d0, d1))
         vb.spec_info = {"verify_all_positions": True}
+        if any_tree:
+            self.total_tree_verifies += 1
+            masks = []
+            for i in range(B):
+                ql, p = qlens[i], plens[i]
+                m = np.zeros((ql, p + ql), dtype=bool)
+                m[:, :p] = True
+                m[:, p] = True                        # every node descends from the last committed token
+                for j, pj in enumerate(trees[i]):
+                    m[j + 1, p: p + ql] = m[pj + 1, p: p + ql]
+                    m[j + 1, p + j + 1] = True
+                masks.append(m.reshape(-1))
+            vb.spec_info["custom_mask"] = np.concatenate(masks)
         vb.has_grammar = batch.has_grammar
-        toks_all = runner.forward_verify(vb)          # np.int64 [T]: target sample at every fed position
+        toks_all = runner.forward_verify(vb)          # np.int64 [T]: target sample at every fed node
         res = SpecResult(B)
         cu = np.concatenate([[0], np.cumsum(vb.q_lens)])
         vh = runner.last_verify_hidden
+        mv_src, mv_dst = [], []
         for i, r in enumerate(batch.reqs):
             t = toks_all[cu[i]:cu[i + 1]]
-            d = drafts[i]
-            a = 0
-            while a < len(d) and int(t[a]) == d[a]:
-                a += 1
-            out = [int(x) for x in t[: a + 1]]    # a accepted drafts (== target samples) + the bonus/correction token
+            d, par = drafts[i], trees[i]
+            kids: Dict[int, List[int]] = {}
+            for j, pj in enumerate(par):
+                kids.setdefault(pj + 1, []).append(j + 1)
+            node, path = 0, []                     # walk: follow the child that equals the target's sample at the current node
+            while True:
+                nxt = next((c for c in kids.get(node, ()) if d[c - 1] == int(t[node])), None)
+                if nxt is None:
+                    break
+                path.append(nxt)
+                node = nxt
+            a = len(path)
+            out = [d[c - 1] for c in path] + [int(t[node])]     # accepted drafts (== target samples) + the bonus / correction token
+            if path != list(range(1, a + 1)):      # accepted nodes are not the first a slots: compact their KV rows
+                sl = loc[i]
+                mv_src.append(sl[np.asarray(path, dtype=np.int64)])
+                mv_dst.append(sl[1: a + 1])
             res.accept_lens[i] = len(out)
             res.accepted_tokens[i] = out
             res.next_token_ids[i] = out[-1]
             r.kv_len += a                          # KV of last_token and the a accepted drafts is now valid
             batch.seq_lens[i] += a
-            kv.trim(r, r.kv_len)                   # rejected drafts' pages go back (next decode re-allocates on demand)
             self.total_drafted += len(d)
             self.total_accepted += a
             self.total_verify += 1
-            if vh is not None:                     # target features of the positions that stay (last token + accepted drafts)
-                self.on_verified_hidden(r, plens[i], vh[cu[i]:cu[i] + a + 1])
+            if vh is not None:                     # target features of the nodes that stay (last token + accepted path)
+                rows = torch.as_tensor([0] + path, dtype=torch.long, device=vh.device) + int(cu[i])
+                self.on_verified_hidden(r, plens[i], vh[rows])
             self.on_tokens_accepted(r, out)
+        if mv_src:
+            self.total_kv_moves += int(sum(x.size for x in mv_src))
+            dev = runner.device
+            runner.kv_pool.move_slots(torch.from_numpy(np.concatenate(mv_src).astype(np.int64)).to(dev),
+                                      torch.from_numpy(np.concatenate(mv_dst).astype(np.int64)).to(dev))
+        for r in batch.reqs:
+            kv.trim(r, r.kv_len)                   # rejected drafts' pages go back (next decode re-allocates on demand)
         # keep the device-side "future map" coherent for anyone who reads it
         slots = torch.from_numpy(np.asarray(batch.req_slots, dtype=np.int64)).to(runner.device)
         runner.next_token_buf[slots] = torch.from_numpy(res.next_token_ids.astype(np.int32)).to(runner.device)
@@ -145,12 +195,21 @@ class NgramSpecWorker(BaseSpecWorker):
         self.max_depth = max_depth
         self._seen_prompt = set()
 
-    def propose(self, req: Any, max_draft: int) -> List[int]:
+    def _ctx(self, req: Any) -> np.ndarray:
         if id(req) not in self._seen_prompt:
             self._seen_prompt.add(id(req))
             self.corpus.insert(np.asarray(req.origin_input_ids, dtype=np.int32))
-        ctx = (req.origin_input_ids + req.output_ids)[-self.max_depth:]
-        return self.corpus.match_chain(np.asarray(ctx, dtype=np.int32), max_draft, 2).tolist()
+        return np.asarray((req.origin_input_ids + req.output_ids)[-self.max_depth:], dtype=np.int32)
+
+    def propose(self, req: Any, max_draft: int) -> List[int]:
+        return self.corpus.match_chain(self._ctx(req), max_draft, 2).tolist()
+
+    def propose_tree(self, req: Any, max_nodes: int):
+        branch = int(self.args.speculative_eagle_topk or 1)
+        if branch <= 1:
+            return super().propose_tree(req, max_nodes)
+        toks, parents = self.corpus.match_tree(self._ctx(req), max_nodes, branch, 2)      # breadth-first over the trie's continuations
+        return np.asarray(toks).tolist(), np.asarray(parents).tolist()
 
     def on_tokens_accepted(self, req: Any, new_tokens: List[int]) -> None:
         tail = (req.origin_input_ids + req.output_ids)[-(self.max_depth - 1):] + list(new_tokens)
