@@ -6,6 +6,9 @@
 #include <cstring>
 #include <stdexcept>
 
+#include <thread>
+
+#include "image_ops.h"
 #include "kv_indexer.h"
 #include "ngram_corpus.h"
 #include "radix_tree.h"
@@ -130,4 +133,54 @@ PYBIND11_MODULE(sglb_rt, m) {
       .def("worker_blocks", &sglb::KvIndexer::worker_blocks);
 
   m.def("hash_pages", &hash_pages, py::arg("tokens"), py::arg("page_size"), py::arg("seed") = 0);
+
+  // ---- image preprocessing (image_ops.cpp)
+  using u8arr = py::array_t<uint8_t, py::array::c_style | py::array::forcecast>;
+  using f32arr = py::array_t<float, py::array::c_style | py::array::forcecast>;
+  m.def("image_resize", [](u8arr img, int out_h, int out_w, int filter) {
+    if (img.ndim() != 3) throw std::runtime_error("image_resize: expected HWC uint8");
+    const int h = (int)img.shape(0), w = (int)img.shape(1), c = (int)img.shape(2);
+    py::array_t<uint8_t> out({out_h, out_w, c});
+    {
+      py::gil_scoped_release r;
+      resize_u8(img.data(), h, w, c, out.mutable_data(), out_h, out_w, (Filter)filter);
+    }
+    return out;
+  }, py::arg("img"), py::arg("out_h"), py::arg("out_w"), py::arg("filter") = 3);
+  m.def("clip_preprocess_batch", [](std::vector<u8arr> imgs, int size, f32arr mean, f32arr std_, int filter, int threads) {
+    const int n = (int)imgs.size();
+    py::array_t<float> out({n, 3, size, size});
+    float* o = out.mutable_data();
+    std::vector<const uint8_t*> ptr(n);
+    std::vector<int> hs(n), ws(n);
+    for (int i = 0; i < n; ++i) {
+      if (imgs[i].ndim() != 3 || imgs[i].shape(2) != 3) throw std::runtime_error("clip_preprocess_batch: expected HxWx3 uint8 images");
+      ptr[i] = imgs[i].data(); hs[i] = (int)imgs[i].shape(0); ws[i] = (int)imgs[i].shape(1);
+    }
+    const float* mp = mean.data();
+    const float* sp = std_.data();
+    {
+      py::gil_scoped_release r;
+      const int nt = std::max(1, std::min(threads, n));
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&, t] {
+          for (int i = t; i < n; i += nt) clip_preprocess(ptr[i], hs[i], ws[i], o + (size_t)i * 3 * size * size, size, mp, sp, (Filter)filter);
+        });
+      for (auto& th : pool) th.join();
+    }
+    return out;
+  }, py::arg("imgs"), py::arg("size"), py::arg("mean"), py::arg("std"), py::arg("filter") = 3, py::arg("threads") = 4);
+  m.def("patchify", [](f32arr chw, int patch, int merge, int temporal) {
+    if (chw.ndim() != 3 || chw.shape(0) != 3) throw std::runtime_error("patchify: expected [3, H, W] float32");
+    const int H = (int)chw.shape(1), W = (int)chw.shape(2);
+    if (H % (patch * merge) || W % (patch * merge)) throw std::runtime_error("patchify: H and W must be multiples of patch * merge");
+    py::array_t<float> out({(H / patch) * (W / patch), 3 * temporal * patch * patch});
+    patchify(chw.data(), H, W, patch, merge, temporal, out.mutable_data());
+    return out;
+  }, py::arg("chw"), py::arg("patch"), py::arg("merge") = 1, py::arg("temporal") = 1);
+  m.def("hash_bytes", [](py::buffer b) {
+    py::buffer_info info = b.request();
+    return hash_bytes((const uint8_t*)info.ptr, (int64_t)info.size * info.itemsize);
+  });
 }

@@ -66,8 +66,40 @@ def clip_preprocess(img: np.ndarray, size: int) -> np.ndarray:
     return arr.transpose(2, 0, 1)
 
 
+def _native():
+    """the C++ image pipeline (csrc/runtime/image_ops.cpp: Pillow-exact fixed-point resize, crop+normalise, patchify, hashing), or None"""
+    try:
+        from .. import sglb_rt
+
+        return sglb_rt if hasattr(sglb_rt, "clip_preprocess_batch") else None
+    except Exception:
+        return None
+
+
+def clip_preprocess_batch(imgs: List[np.ndarray], size: int, threads: int = 4) -> np.ndarray:
+    """[N, 3, size, size] float32; native thread pool when the runtime is built, Pillow otherwise (bit-identical resize)"""
+    rt = _native()
+    if rt is not None and imgs:
+        return rt.clip_preprocess_batch([np.ascontiguousarray(a) for a in imgs], size, CLIP_MEAN, CLIP_STD, 3, threads)
+    return np.stack([clip_preprocess(a, size) for a in imgs])
+
+
+def patchify(chw: np.ndarray, patch: int, merge: int = 1, temporal: int = 1) -> np.ndarray:
+    """[3, H, W] -> [(H/p)(W/p), 3*t*p*p] patch rows in (merge x merge)-block order (Qwen2-VL flattening)"""
+    rt = _native()
+    if rt is not None:
+        return rt.patchify(np.ascontiguousarray(chw, dtype=np.float32), patch, merge, temporal)
+    C, H, W = chw.shape
+    gh, gw = H // patch, W // patch
+    x = np.repeat(chw[:, None], temporal, 1).reshape(C, temporal, gh // merge, merge, patch, gw // merge, merge, patch)
+    return np.ascontiguousarray(x.transpose(2, 5, 3, 6, 0, 1, 4, 7)).reshape(gh * gw, C * temporal * patch * patch)
+
+
 def image_hash(img: np.ndarray) -> int:
-    return int.from_bytes(hashlib.sha256(img.tobytes()).digest()[:8], "little")
+    rt = _native()
+    if rt is not None:
+        return int(rt.hash_bytes(np.ascontiguousarray(img))) & ((1 << 63) - 1)
+    return int.from_bytes(hashlib.sha256(img.tobytes()).digest()[:8], "little") & ((1 << 63) - 1)
 
 
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any) -> Tuple[List[int], Dict[str, Any]]:
@@ -78,7 +110,7 @@ def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: A
     n_tok = (size // patch) ** 2
     imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
     arrs = [load_image(x) for x in imgs]
-    pixels = np.stack([clip_preprocess(a, size) for a in arrs])
+    pixels = clip_preprocess_batch(arrs, size)
     img_tok = cfg.image_token_id if cfg.image_token_id is not None else getattr(tokenizer, "image_token_id", None)
     if img_tok is None:
         raise ValueError("model config has no image_token_id")
