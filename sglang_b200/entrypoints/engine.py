@@ -163,7 +163,7 @@ class Engine:
         if g.image_data is not None and self.model_config.is_multimodal:
             from ..multimodal.processor import process_images
 
-            ids, mm = process_images(ids, g.image_data, self.model_config, self.tokenizer)
+            ids, mm = process_images(ids, g.image_data, self.model_config, self.tokenizer, self._encoder_client())
         SamplingParams.from_dict(sp).verify(self.model_config.vocab_size)
         return ios.TokenizedGenerateReqInput(
             rid=g.rid or self._new_rid(), input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),
@@ -171,6 +171,17 @@ class Engine:
             return_hidden_states=g.return_hidden_states, lora_id=g.lora_path, session_params=g.session_params, mm_inputs=mm,
             custom_logit_processor=g.custom_logit_processor, bootstrap_host=g.bootstrap_host, bootstrap_port=g.bootstrap_port,
             bootstrap_room=g.bootstrap_room, priority=g.priority, extra_key=g.extra_key, created_time=time.perf_counter())
+
+    def _encoder_client(self):
+        """EPD: client of the vision-encoder fleet (``--encoder-urls``), None when images are encoded locally"""
+        if not self.server_args.encoder_urls:
+            return None
+        c = getattr(self, "_enc_client", None)
+        if c is None:
+            from ..disaggregation.encoder import EncoderClient
+
+            c = self._enc_client = EncoderClient(self.server_args.encoder_urls)
+        return c
 
     def _submit(self, g: ios.GenerateReqInput, stream_q: Optional[Any] = None, is_embedding: bool = False) -> ReqState:
         t = self._tokenize(g)

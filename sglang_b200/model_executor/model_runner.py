@@ -117,6 +117,8 @@ class ModelRunner:
             from ..models import mixtral
 
             mixtral.set_ep_size(server_args.ep_size)
+        if server_args.language_only and self.cfg.vision:
+            self.cfg.vision = {**self.cfg.vision, "skip_tower": True}
         self.model = load_model(self.cfg, server_args.model_path, server_args.load_format, self.device, server_args.quantization,
                                 server_args.random_seed)
         self.load_time = time.perf_counter() - t0

@@ -103,7 +103,9 @@ def init_dummy_weights(model: nn.Module, seed: int = 0, scale: float = 0.02, cfg
                 gemma = getattr(dict(model.named_modules()).get(name.rsplit(".", 1)[0]), "gemma", False)
                 p.fill_(0.0 if gemma else 1.0)
             else:
-                p.normal_(0.0, scale)
+                g1 = torch.Generator(device=p.device)
+                g1.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+                p.normal_(0.0, scale, generator=g1)
             continue
         g = torch.Generator(device=p.device)
         g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)

@@ -77,6 +77,10 @@ class LlavaForConditionalGeneration(LlamaForCausalLM):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__(cfg, quant_name, device)
         dtype = _DT[cfg.dtype]
+        if cfg.vision.get("skip_tower"):      # EPD --language-only: image rows arrive as embeddings from an encoder server
+            self.vision_tower = self.projector = None
+            self.num_image_tokens = (cfg.vision["image_size"] // cfg.vision["patch_size"]) ** 2
+            return
         self.vision_tower = CLIPVisionTower(cfg.vision, dtype)
         vh = cfg.vision["hidden_size"]
         self.projector = nn.Sequential(nn.Linear(vh, cfg.hidden_size, dtype=dtype), nn.GELU(),
@@ -105,6 +109,6 @@ class LlavaForConditionalGeneration(LlamaForCausalLM):
             if n in own:
                 own[n].data.copy_(w.reshape(own[n].shape))
                 loaded.append(name)
-            elif not n.startswith("vision_tower"):
+            elif not n.startswith(("vision_tower", "projector.", "multi_modal_projector")):
                 rest.append((name, w))
         return loaded + super().load_weights(rest)

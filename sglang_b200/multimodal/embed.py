@@ -26,7 +26,12 @@ def build_mm_embeds(model: Any, sb: Any, device: torch.device, dtype: torch.dtyp
             continue
         key = (id(mm), 0)
         emb = _ENC_CACHE.get(key)
+        if emb is None and mm.get("image_embeds") is not None:      # EPD: an encoder server already produced the LM-space rows
+            emb = torch.as_tensor(np.asarray(mm["image_embeds"]), device=device).to(dtype).view(len(mm["image_offsets"]), n_tok, -1)
+            _ENC_CACHE[key] = emb
         if emb is None:
+            if not hasattr(model, "encode_images") or getattr(model, "vision_tower", None) is None:
+                raise RuntimeError("this server was started --language-only: images need --encoder-urls (no local vision tower)")
             px = torch.tensor(mm["pixel_values"], dtype=torch.float32, device=device)
             emb = model.encode_images(px.to(dtype)).view(len(mm["image_offsets"]), n_tok, -1)
             if len(_ENC_CACHE) >= _ENC_CACHE_MAX:

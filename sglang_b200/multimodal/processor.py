@@ -102,7 +102,7 @@ def image_hash(img: np.ndarray) -> int:
     return int.from_bytes(hashlib.sha256(img.tobytes()).digest()[:8], "little") & ((1 << 63) - 1)
 
 
-def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any) -> Tuple[List[int], Dict[str, Any]]:
+def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
     """returns (expanded ids, mm_inputs).  mm_inputs: pixel_values [N,3,S,S] float32 (nested lists for IPC),
     image_offsets (start index of every image's pad run), pad_values, num_image_tokens."""
     v = cfg.vision
@@ -147,5 +147,9 @@ def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: A
         pads = [pad] + pads
         out = run + out
         k += 1
-    mm = {"pixel_values": pixels.tolist(), "image_offsets": offsets, "pad_values": pads, "num_image_tokens": n_tok}
+    if encoder is not None:       # EPD: ship the pixel blocks to the encoder fleet now, carry embeddings instead of pixels
+        emb = encoder.encode(pixels, [image_hash(a) for a in arrs])
+        mm = {"image_embeds": emb, "image_offsets": offsets, "pad_values": pads, "num_image_tokens": n_tok}
+    else:
+        mm = {"pixel_values": pixels.tolist(), "image_offsets": offsets, "pad_values": pads, "num_image_tokens": n_tok}
     return out, mm

@@ -129,6 +129,9 @@ class ServerArgs:
     disaggregation_transfer_backend: str = "nvlink"  # nvlink|fake|tcp
     disaggregation_bootstrap_port: int = 8998
     # --- multimodal
+    encoder_only: bool = False            # EPD: serve only the vision tower (disaggregation/encoder.py)
+    language_only: bool = False           # EPD: do not load the vision tower; images require --encoder-urls
+    encoder_urls: Optional[List[str]] = None
     enable_multimodal: Optional[bool] = None
     mm_attention_backend: Optional[str] = None
     # --- debugging

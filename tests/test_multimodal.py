@@ -38,3 +38,44 @@ def test_image_changes_logits():
     lx = [v for v, _, _ in x["meta_info"]["output_token_logprobs"]]
     ly = [v for v, _, _ in y["meta_info"]["output_token_logprobs"]]
     assert lx != ly, "vision features must reach the language model"
+
+
+def test_encoder_disaggregation_matches_colocated():
+    """EPD: a vision-encoder-only server + a --language-only engine (no vision weights) produce the same tokens as the colocated model;
+    repeated images are served from the encoder's content-addressed cache without re-sending pixels"""
+    import socket
+    import threading
+
+    import uvicorn
+
+    from sglang_b200.disaggregation.encoder import VisionEncoder, build_encoder_app
+    from sglang_b200.lang.backend.runtime_endpoint import _wait_http
+
+    sp = {"max_new_tokens": 6, "temperature": 0, "ignore_eos": True}
+    prompts = [("USER: <image>\nWhat? ASSISTANT:", _img(5)), ("<image> and <image> compare", [_img(6), _img(5)])]
+    ref_eng = sgl.Engine(model_path="dummy:tiny-llava", page_size=4, disable_radix_cache=True)
+    ref = [ref_eng.generate(t, sp, image_data=im, return_logprob=True) for t, im in prompts]
+    ref_eng.shutdown()
+
+    enc = VisionEncoder("dummy:tiny-llava", "cpu")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    server = uvicorn.Server(uvicorn.Config(build_encoder_app(enc), host="127.0.0.1", port=port, log_level="error"))
+    t = threading.Thread(target=server.run, daemon=True)
+    t.start()
+    try:
+        _wait_http(f"http://127.0.0.1:{port}", 30)
+        eng = sgl.Engine(model_path="dummy:tiny-llava", page_size=4, disable_radix_cache=True, language_only=True,
+                         encoder_urls=[f"http://127.0.0.1:{port}"])
+        assert eng.runner.model.vision_tower is None
+        got = [eng.generate(t_, sp, image_data=im, return_logprob=True) for t_, im in prompts]
+        for a, b in zip(ref, got):
+            assert a["output_ids"] == b["output_ids"]
+            la = [v for v, _, _ in a["meta_info"]["output_token_logprobs"]]
+            lb = [v for v, _, _ in b["meta_info"]["output_token_logprobs"]]
+            assert max(abs(x - y) for x, y in zip(la, lb)) < 5e-2      # embeddings travel as fp16
+        assert enc.stats["encoded"] == 2 and enc.stats["cache_hits"] == 1          # image 5 was encoded once
+        assert eng._enc_client.stats["pixels_skipped"] == 1
+        eng.shutdown()
+    finally:
+        server.should_exit = True
+        t.join(timeout=10)
