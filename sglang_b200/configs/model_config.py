@@ -63,6 +63,7 @@ class ModelConfig:
     routed_scaling_factor: float = 1.0
     scoring_func: str = "softmax"
     topk_method: str = "greedy"
+    swiglu_limit: Optional[float] = None        # GPT-OSS clamped SwiGLU
     # Gemma-2 / Granite extras
     query_pre_attn_scalar: Optional[float] = None
     layer_types: Optional[List[str]] = None
@@ -70,6 +71,8 @@ class ModelConfig:
     residual_multiplier: Optional[float] = None
     attention_multiplier: Optional[float] = None
     logits_scaling: Optional[float] = None
+    # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
+    mamba: Optional[Dict[str, Any]] = None
     # multimodal (LLaVA-style)
     vision: Optional[Dict[str, Any]] = None
     image_token_id: Optional[int] = None
@@ -117,6 +120,19 @@ PRESETS: Dict[str, Dict[str, Any]] = {
     # ---- tiny CPU-test models
     "tiny-llama": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
                        vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
+    "tiny-gpt-oss": dict(architecture="GptOssForCausalLM", hidden_size=64, intermediate_size=32, moe_intermediate_size=32, num_hidden_layers=4,
+                         num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512, dtype="float32",
+                         num_local_experts=4, num_experts_per_tok=2, sliding_window=8, attention_bias=True, swiglu_limit=7.0, rope_theta=150000.0,
+                         layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"],
+                         rope_scaling={"rope_type": "yarn", "factor": 4.0, "beta_fast": 32.0, "beta_slow": 1.0, "truncate": False,
+                                       "original_max_position_embeddings": 128}),
+    "tiny-mamba2": dict(architecture="Mamba2ForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, dtype="float32", tie_word_embeddings=True,
+                        mamba=dict(num_heads=8, head_dim=16, d_state=16, d_conv=4, n_groups=1, norm_groups=1, chunk_size=8)),
+    "tiny-nemotron-h": dict(architecture="NemotronHForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=6,
+                            num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512,
+                            dtype="float32", mamba=dict(num_heads=8, head_dim=16, d_state=16, d_conv=4, n_groups=2, norm_groups=2,
+                                                        chunk_size=8, pattern="M-M*-M")),
     "tiny-llama-gpu": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
                            num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
     "tiny-llama-gpu8": dict(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8,
@@ -243,7 +259,7 @@ _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_loca
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
                "activation_function": "hidden_act", "layer_norm_epsilon": "rms_norm_eps", "layer_norm_eps": "rms_norm_eps",
                "norm_epsilon": "rms_norm_eps", "ffn_dim": "intermediate_size", "rotary_pct": "partial_rotary_factor",
-               "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta"}
+               "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta", "experts_per_token": "num_experts_per_tok"}
 # per-architecture defaults for fields HF configs leave implicit
 _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
                   "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),
@@ -281,6 +297,20 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
             if kw.get("intermediate_size") is None:
                 kw["intermediate_size"] = 4 * kw["hidden_size"]
+        if arch in ("NemotronHForCausalLM", "Mamba2ForCausalLM"):
+            hid = text["hidden_size"]
+            heads = text.get("mamba_num_heads") or text.get("num_heads") or (text.get("expand", 2) * hid // text.get("head_dim", 64))
+            hd = text.get("mamba_head_dim") or text.get("head_dim") or (text.get("expand", 2) * hid // heads)
+            ngroups = text.get("n_groups", 1)
+            kw["mamba"] = {"num_heads": heads, "head_dim": hd, "d_state": text.get("ssm_state_size") or text.get("state_size", 128),
+                           "d_conv": text.get("conv_kernel", 4), "n_groups": ngroups, "chunk_size": text.get("chunk_size", 64),
+                           "use_bias": text.get("use_bias", False), "use_conv_bias": text.get("use_conv_bias", True),
+                           "norm_groups": ngroups if arch == "NemotronHForCausalLM" else 1,
+                           "pattern": text.get("hybrid_override_pattern") if arch == "NemotronHForCausalLM" else None}
+            kw["rms_norm_eps"] = text.get("layer_norm_epsilon", text.get("rms_norm_eps", 1e-5))
+            kw.setdefault("num_key_value_heads", text.get("num_key_value_heads", kw.get("num_attention_heads", 1)))
+            if arch == "NemotronHForCausalLM" and text.get("attention_head_dim"):
+                kw["head_dim"] = text["attention_head_dim"]
         if "vision_config" in hf:
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

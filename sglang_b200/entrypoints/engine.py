@@ -104,6 +104,11 @@ class Engine:
         self._relay_src = (st.pp.world_size - 1) * st.tp.world_size if st.pp.world_size > 1 else None
         self._relay_buf: List[Any] = []
         self._world = st.world
+        if getattr(self.runner.model, "disable_radix_cache", False) and not a.disable_radix_cache:
+            logger.info("%s keeps recurrent state per request: prefix caching disabled", type(self.runner.model).__name__)
+            a.disable_radix_cache = True
+            if a.schedule_policy in ("lpm", "dfs-weight"):
+                a.schedule_policy = "fcfs"
         self.scheduler = Scheduler(a, self.runner, self.tokenizer, self._on_scheduler_output, 0 if emits_output else 1)
         self._install_optional_components()
         self.states: Dict[str, ReqState] = {}

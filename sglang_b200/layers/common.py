@@ -89,10 +89,14 @@ class RadixAttention(nn.Module):
             from .cp import gather_write_kv
 
             gather_write_kv(get_cp_group(), cp, out_loc, kc, vc)
+        sinks = getattr(self, "sinks", None)
+        lse = torch.empty(T, self.num_heads, dtype=torch.float32, device=q3.device) if sinks is not None else None
         o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
-                                workspace=fb.attn_workspace, custom_mask=fb.custom_mask)
+                                workspace=fb.attn_workspace, custom_mask=fb.custom_mask, lse=lse)
+        if sinks is not None:       # attention sinks (GPT-OSS): exp(sink_h) joins the soft-max denominator only -> o * sigmoid(lse - sink_h)
+            o = (o.float() * torch.sigmoid(lse - sinks[None, :]).unsqueeze(-1)).to(o.dtype)
         return o.view(T, self.num_heads * self.head_dim)
 
 

@@ -499,13 +499,17 @@ class Scheduler:
                 self.kv.release(r)
                 out.append(r)
                 continue
+            if r.return_logprob and result.input_logprobs is not None and result.input_logprobs[i] is not None and \
+                    not (r.retraction_count > 0 and r.output_ids):       # a re-prefill after retraction reported its prompt already
+                if r.input_token_logprobs is None:       # first computed chunk: the first reported token has no logprob of its own
+                    first = max(int(batch.prefix_lens[i]), r.logprob_start_len)
+                    r.input_token_logprobs = [(None, int(r.origin_input_ids[first]))] if first < len(r.origin_input_ids) else []
+                r.input_token_logprobs = r.input_token_logprobs + result.input_logprobs[i]
             if not produces:
                 # chunk of a longer prompt: publish the computed prefix (reference cache_unfinished_req)
                 r.is_chunked = max(0, r.is_chunked - 1)
                 self.kv.cache_unfinished(r)
                 continue
-            if r.return_logprob and result.input_logprobs is not None:
-                r.input_token_logprobs = result.input_logprobs[i]
             if r.finished():       # aborted while in flight
                 continue
             if r.sampling_params.max_new_tokens == 0:   # prefill-only (cache warm-up / prompt scoring)

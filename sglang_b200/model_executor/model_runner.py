@@ -194,6 +194,8 @@ class ModelRunner:
         self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
         self.page_table = torch.zeros(self.max_running + 1, max_pages_per_req, dtype=torch.int32, device=self.device)
+        # recurrent (SSM) state of hybrid / Mamba decoders, indexed by request slot like the page table (models/mamba.py)
+        self.kv_pool.mamba = self.model.make_mamba_pool(self.max_running + 1, self.device) if hasattr(self.model, "make_mamba_pool") else None
         self.next_token_buf = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
         logger.info("KV pool: %d pages x %d tokens (%.2f GB), max_running=%d, weights %.2f GB", self.num_pages, self.page_size,
                     self.num_pages * per_page / 2 ** 30, self.max_running, self.weight_bytes / 2 ** 30)
@@ -259,6 +261,8 @@ class ModelRunner:
     # ------------------------------------------------------------------ attention split heuristic
     def _pick_splits(self, bs: int, max_kv: int) -> int:
         if not self.is_cuda:
+            return 1
+        if not len(self.model.model.layers):
             return 1
         kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads
         ctas = bs * kvh
@@ -338,11 +342,16 @@ class ModelRunner:
             need_all = (not decode) and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs)
             if samp_rows.size == 0:
                 self.model.compute_logits(hidden[:0])
-                self.model.compute_logits(hidden if need_all else hidden[:0], key="logits_all")
+                al = self.model.compute_logits(hidden if need_all else hidden[:0], key="logits_all")
                 res.next_token_ids = np.full(B, -1, dtype=np.int64)
+                if need_all:
+                    self._dp_all_logits = al
+                    self._input_logprobs(sb, hidden, res)
                 return res
         if samp_rows.size == 0:
             res.next_token_ids = np.full(B, -1, dtype=np.int64)
+            if sb.return_logprob and _dp is None:
+                self._input_logprobs(sb, hidden, res)
             return res
         h_last = hidden if decode else ops.gather_rows(hidden, fb.last_idx)
         if getattr(self.model, "is_embedding", False) or any(r.is_embedding for r in sb.reqs):
@@ -485,20 +494,31 @@ class ModelRunner:
             if k > 0:
                 v, idx = lsm[j].topk(k)
                 res.top_logprobs[i] = list(zip(v.tolist(), idx.tolist()))
-        if sb.forward_mode.is_extend() and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs):
-            pre = getattr(self, "_dp_all_logits", None)      # DP-attention computed it collectively above
-            all_logits = torch.log_softmax((pre if pre is not None else self.model.compute_logits(hidden)).float(), dim=-1)
-            res.input_logprobs = [None] * len(sb.reqs)
-            cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
-            for i, r in enumerate(sb.reqs):
-                if not (r.return_logprob and r.logprob_start_len >= 0):
-                    continue
-                s, e = int(cu[i]), int(cu[i + 1])
-                ids = torch.from_numpy(sb.input_ids[s + 1:e].astype(np.int64)).to(self.device)
-                lp = all_logits[s:e - 1].gather(1, ids[:, None]).squeeze(1).tolist()
-                start = max(0, r.logprob_start_len - int(sb.prefix_lens[i]))
-                res.input_logprobs[i] = [(None, int(sb.input_ids[s]))] * (1 if start == 0 else 0) + \
-                    [(float(a), int(b)) for a, b in zip(lp, ids.tolist())][start:]
+        self._input_logprobs(sb, hidden, res)
+
+    def _input_logprobs(self, sb: ScheduleBatch, hidden, res: BatchResult) -> None:
+        """prompt (input) logprobs of THIS chunk: for every prompt position ``pos`` in ``(max(chunk_begin, logprob_start_len), chunk_end]``
+        the logprob of token ``pos`` given everything before it (row ``pos - 1`` of the chunk) — the last one belongs to the first token of
+        the NEXT chunk, so chunked prefill loses nothing.  The scheduler concatenates the chunks (reference logprob_processor input path)."""
+        if not (sb.forward_mode.is_extend() and any(r.return_logprob and r.logprob_start_len >= 0 for r in sb.reqs)):
+            return
+        pre = getattr(self, "_dp_all_logits", None)      # DP-attention computed it collectively
+        all_logits = torch.log_softmax((pre if pre is not None else self.model.compute_logits(hidden)).float(), dim=-1)
+        res.input_logprobs = [None] * len(sb.reqs)
+        cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
+        for i, r in enumerate(sb.reqs):
+            if not (r.return_logprob and r.logprob_start_len >= 0):
+                continue
+            cb, ce = int(sb.prefix_lens[i]), int(sb.prefix_lens[i] + sb.q_lens[i])
+            full = r.origin_input_ids
+            lo, hi = max(cb, r.logprob_start_len) + 1, min(ce, len(full) - 1)
+            if hi < lo:
+                res.input_logprobs[i] = []
+                continue
+            rows = torch.arange(lo - 1 - cb, hi - cb, device=self.device) + int(cu[i])
+            ids = torch.tensor(full[lo: hi + 1], dtype=torch.int64, device=self.device)
+            lp = all_logits[rows].gather(1, ids[:, None]).squeeze(1).tolist()
+            res.input_logprobs[i] = [(float(a), int(b)) for a, b in zip(lp, ids.tolist())]
 
     def _attach_mm(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
         if not sb.forward_mode.is_extend() or not any(r.mm_inputs for r in sb.reqs):

@@ -240,7 +240,9 @@ def adapt_quantized_checkpoint(it: Iterable[Tuple[str, torch.Tensor]], qcfg: Opt
             p = pending[pre]
             if "blocks" in p and "scales" in p:
                 pending.pop(pre)
-                yield pre, dequant_mxfp4(p["blocks"], p["scales"]).to(dtype)
+                w = dequant_mxfp4(p["blocks"], p["scales"]).to(dtype)
+                # stacked expert tensors are stored [E, out, in] in MXFP4 checkpoints but [E, in, out] in the bf16 ones: emit the latter
+                yield pre, (w.transpose(1, 2).contiguous() if w.dim() == 3 else w)
             elif {"qweight", "qzeros", "scales"} <= set(p) and ("g_idx" in p or (qcfg.get("quant_method") or "").lower() == "awq"):
                 yield from flush(pre)
     for pre in list(pending):

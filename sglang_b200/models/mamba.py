@@ -1,0 +1,414 @@
+"""State-space and hybrid decoders: Mamba-2 (``Mamba2ForCausalLM``) and Nemotron-H style hybrids (``NemotronHForCausalLM``: every layer is
+``x + mixer(norm(x))`` with the mixer chosen per layer by a pattern string — ``M`` Mamba-2, ``*`` attention, ``-`` MLP).
+
+Parity: reference ``python/sglang/srt/models/{mamba2,nemotron_h}.py``, ``layers/attention/mamba/*`` (mixer, causal-conv1d and selective-scan
+ops), ``mem_cache/memory_pool.py`` ``MambaPool`` (per-request conv + SSM state), hybrid-linear attention backend wrapper.
+
+How it fits this engine:
+
+* recurrent state lives in a ``MambaPool`` indexed by the *request slot* (the same index the page table uses), so continuous batching,
+  chunked prefill (the state simply carries over between chunks), retraction (a re-prefill starts from position 0 and re-initialises the
+  state) and the overlap scheduler need no special cases; attention layers of a hybrid use the ordinary paged KV pool;
+* prefix caching is switched off for these families (a radix hit would skip tokens whose state was never computed — the reference's
+  ``MambaRadixCache`` keeps state snapshots; not carried over yet);
+* prefill uses the chunked *SSD* formulation of Mamba-2 (intra-chunk work is three batched GEMM-shaped contractions, inter-chunk a short
+  scan over chunk states) — the shape a tcgen05 kernel wants; decode is the one-step recurrence.  Both are plain PyTorch here: exactness
+  first (tests check the SSD path against the step recurrence), a fused sm_100a selective-scan/conv kernel is the follow-up;
+* tensor parallelism shards heads (and B/C groups) — z | x | B | C | dt blocks of ``in_proj`` and the conv channels are sliced per block.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..configs.model_config import ModelConfig
+from ..layers.common import RadixAttention, RMSNorm
+from ..layers.linear import ColumnParallelLinear, ParallelLMHead, QKVParallelLinear, RowParallelLinear, VocabParallelEmbedding
+from ..model_executor.forward_batch import ForwardBatch
+from ..parallel.parallel_state import get_pp_group, get_tp_group
+from .llama import _DT
+
+
+class MambaPool:
+    """conv_state [L, slots, conv_dim, k-1], ssm_state [L, slots, H, P, N] (fp32), slot = request slot"""
+
+    def __init__(self, num_layers: int, slots: int, conv_dim: int, d_conv: int, heads: int, head_dim: int, d_state: int, dtype, device):
+        self.conv = torch.zeros(num_layers, slots, conv_dim, d_conv - 1, dtype=dtype, device=device)
+        self.ssm = torch.zeros(num_layers, slots, heads, head_dim, d_state, dtype=torch.float32, device=device)
+
+    def bytes(self) -> int:
+        return self.conv.numel() * self.conv.element_size() + self.ssm.numel() * 4
+
+
+def _segsum(x: torch.Tensor) -> torch.Tensor:
+    """stable segment sum: out[..., i, j] = sum_{j < k <= i} x[..., k] (lower triangle), -inf above the diagonal"""
+    T = x.size(-1)
+    x = x[..., None].expand(*x.shape, T)
+    lower = torch.tril(torch.ones(T, T, dtype=torch.bool, device=x.device), -1)
+    x = x.masked_fill(~lower, 0)
+    s = torch.cumsum(x, dim=-2)
+    keep = torch.tril(torch.ones(T, T, dtype=torch.bool, device=x.device), 0)
+    return s.masked_fill(~keep, float("-inf"))
+
+
+def ssd_chunk_scan(x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, state: torch.Tensor,
+                   chunk: int = 64) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Mamba-2 SSD over one sequence.  x [T, H, P], dt [T, H] (after softplus), A [H] (negative), B / C [T, H, N] (already expanded from
+    groups), state [H, P, N] fp32 -> (y [T, H, P] fp32 WITHOUT the D skip term, final state)."""
+    T, H, P = x.shape
+    pad = (-T) % chunk
+    if pad:
+        z = lambda t: F.pad(t, (0, 0) * (t.dim() - 1) + (0, pad))
+        x, dt, B, C = z(x), z(dt), z(B), z(C)          # dt = 0 on the padding: decay 1, no input -> the state is untouched
+    c = (T + pad) // chunk
+    X = (x.float() * dt.float()[..., None]).view(c, chunk, H, P)
+    Ad = (dt.float() * A.float()[None, :]).view(c, chunk, H).permute(2, 0, 1)           # [H, c, q]
+    Bc, Cc = B.float().view(c, chunk, H, -1), C.float().view(c, chunk, H, -1)
+    Acs = torch.cumsum(Ad, dim=-1)
+    L = torch.exp(_segsum(Ad))                                                          # [H, c, q, q]
+    Yd = torch.einsum("clhn,cshn,hcls,cshp->clhp", Cc, Bc, L, X)
+    decay = torch.exp(Acs[..., -1:] - Acs)                                              # [H, c, q]
+    st = torch.einsum("clhn,hcl,clhp->chpn", Bc, decay, X)                              # chunk-local end states
+    st = torch.cat([state.float()[None], st], 0)                                        # [c + 1, H, P, N]
+    dc = torch.exp(_segsum(F.pad(Acs[..., -1], (1, 0))))                                # [H, c + 1, c + 1]
+    ns = torch.einsum("hzc,chpn->zhpn", dc, st)
+    prev, final = ns[:-1], ns[-1]
+    Yo = torch.einsum("clhn,chpn,hcl->clhp", Cc, prev, torch.exp(Acs))
+    return (Yd + Yo).reshape(c * chunk, H, P)[:T], final
+
+
+def ssm_step(x, dt, A, B, C, state):
+    """one token per row: x [R, H, P], dt [R, H], B / C [R, H, N], state [R, H, P, N] (updated in place) -> y [R, H, P] fp32"""
+    dA = torch.exp(dt.float() * A.float()[None, :])
+    state.mul_(dA[..., None, None]).add_((dt.float()[..., None] * x.float())[..., None] * B.float()[:, :, None, :])
+    return torch.einsum("rhpn,rhn->rhp", state, C.float())
+
+
+class Mamba2Mixer(nn.Module):
+    def __init__(self, cfg: ModelConfig, layer_idx: int, dtype, prefix: str):
+        super().__init__()
+        tp = get_tp_group()
+        self.tp = tp
+        W = tp.world_size
+        m = cfg.mamba
+        self.H_total, self.P, self.N, self.G_total, self.k = m["num_heads"], m["head_dim"], m["d_state"], m["n_groups"], m["d_conv"]
+        assert self.H_total % W == 0 and (self.G_total % W == 0 or self.G_total == 1), \
+            "Mamba-2 TP: heads must be divisible by tp_size, B/C groups divisible or a single (replicated) group"
+        self.group_replicated = self.G_total % W != 0
+        self.H, self.G = self.H_total // W, (self.G_total if self.group_replicated else self.G_total // W)
+        self.d_inner = self.H * self.P
+        self.conv_dim = self.d_inner + 2 * self.G * self.N
+        self.layer_idx = layer_idx                      # index into the MambaPool
+        self.chunk = m.get("chunk_size", 64)
+        proj_out = 2 * self.d_inner + 2 * self.G * self.N + self.H
+        self.in_proj = nn.Linear(cfg.hidden_size, proj_out, bias=m.get("use_bias", False), dtype=dtype)
+        self.conv_weight = nn.Parameter(torch.zeros(self.conv_dim, self.k, dtype=dtype), requires_grad=False)
+        self.conv_bias = nn.Parameter(torch.zeros(self.conv_dim, dtype=dtype), requires_grad=False) if m.get("use_conv_bias", True) else None
+        self.A_log = nn.Parameter(torch.zeros(self.H, dtype=torch.float32), requires_grad=False)
+        self.D = nn.Parameter(torch.ones(self.H, dtype=torch.float32), requires_grad=False)
+        self.dt_bias = nn.Parameter(torch.zeros(self.H, dtype=torch.float32), requires_grad=False)
+        self.norm_weight = nn.Parameter(torch.ones(self.d_inner, dtype=dtype), requires_grad=False)
+        ng = int(m.get("norm_groups", self.G_total))          # Nemotron-H: one RMS group per B/C group; HF Mamba-2: a single full-width group
+        assert ng == 1 or ng % W == 0
+        self.norm_groups = max(1, ng // W)
+        self.norm_full_width = ng == 1 and W > 1                # the variance then spans all ranks' channels
+        self.eps = cfg.rms_norm_eps
+        self.out_proj = RowParallelLinear(self.H_total * self.P, cfg.hidden_size, m.get("use_bias", False), True, dtype, None, prefix + ".out_proj")
+        for p in self.in_proj.parameters():
+            p.requires_grad_(False)
+
+    # ---- sharded loading: the fused tensors are [z | x | B | C | dt] (in_proj rows) and [x | B | C] (conv channels)
+    def _blocks(self, with_z_dt: bool) -> List[Tuple[int, int]]:
+        W, r = self.tp.world_size, self.tp.rank
+        di, gn = self.H_total * self.P, self.G_total * self.N
+        segs = ([di] if with_z_dt else []) + [di, gn, gn] + ([self.H_total] if with_z_dt else [])
+        out, off = [], 0
+        for s in segs:
+            if s == gn and self.group_replicated:
+                out.append((off, s))
+            else:
+                out.append((off + r * (s // W), s // W))
+            off += s
+        return out
+
+    def load_fused(self, param: torch.Tensor, w: torch.Tensor, with_z_dt: bool) -> None:
+        parts = [w.narrow(0, o, n) for o, n in self._blocks(with_z_dt)]
+        param.data.copy_(torch.cat(parts, 0).reshape(param.shape))
+
+    def load_heads(self, param: torch.Tensor, w: torch.Tensor, per_head: int = 1) -> None:
+        n = param.shape[0]
+        param.data.copy_(w.narrow(0, self.tp.rank * n, n).to(param.dtype))
+
+    # ---- compute
+    def _gated_norm(self, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        y = y.float() * F.silu(z.float())
+        if self.norm_full_width:
+            ss = y.pow(2).sum(-1, keepdim=True)
+            ss = self.tp.all_reduce(ss.contiguous())
+            return (y * torch.rsqrt(ss / (self.H_total * self.P) + self.eps) * self.norm_weight.float()).to(z.dtype)
+        g = self.norm_groups
+        yg = y.view(y.shape[0], g, -1)
+        yg = yg * torch.rsqrt(yg.pow(2).mean(-1, keepdim=True) + self.eps)
+        return (yg.view(y.shape[0], -1) * self.norm_weight.float()).to(z.dtype)
+
+    def forward(self, h: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
+        pool: MambaPool = fb.kv_pool.mamba
+        conv_s, ssm_s = pool.conv[self.layer_idx], pool.ssm[self.layer_idx]
+        T = h.shape[0]
+        zxbcdt = self.in_proj(h)
+        di, gn = self.d_inner, self.G * self.N
+        z, xBC, dt = zxbcdt.split([di, di + 2 * gn, self.H], dim=-1)
+        dt = F.softplus(dt.float() + self.dt_bias)
+        A = -torch.exp(self.A_log)
+        rep = self.H // self.G
+        slots = fb.req_slots.long()
+        if fb.cu_q is None:      # decode: one token per request, state rows gathered by request slot
+            cs = conv_s[slots]                                              # [B, conv_dim, k-1]
+            win = torch.cat([cs, xBC.unsqueeze(-1)], -1)                    # [B, conv_dim, k]
+            conv_s[slots] = win[..., 1:]
+            u = (win.float() * self.conv_weight.float()[None]).sum(-1)
+            if self.conv_bias is not None:
+                u = u + self.conv_bias.float()
+            u = F.silu(u)
+            x, Bm, Cm = u.split([di, gn, gn], dim=-1)
+            st = ssm_s[slots]
+            y = ssm_step(x.view(T, self.H, self.P), dt, A, Bm.view(T, self.G, self.N).repeat_interleave(rep, 1),
+                         Cm.view(T, self.G, self.N).repeat_interleave(rep, 1), st)
+            ssm_s[slots] = st
+            y = y + self.D[None, :, None] * x.view(T, self.H, self.P).float()
+        else:
+            ys = []
+            ql, sl = fb.q_lens_cpu, fb.seq_lens_cpu
+            off = 0
+            for b in range(len(ql)):
+                n, s = int(ql[b]), int(slots[b])
+                fresh = int(sl[b]) - n == 0
+                xb = xBC[off:off + n]                                       # [n, conv_dim]
+                prev = torch.zeros_like(conv_s[s]) if fresh else conv_s[s]
+                seq = torch.cat([prev.t(), xb], 0)                          # [k-1+n, conv_dim]
+                conv_s[s] = seq[-(self.k - 1):].t()
+                u = F.conv1d(seq.t().unsqueeze(0).float(), self.conv_weight.float().unsqueeze(1),
+                             self.conv_bias.float() if self.conv_bias is not None else None, groups=self.conv_dim)[0].t()      # [n, conv_dim]
+                u = F.silu(u)
+                x, Bm, Cm = u.split([di, gn, gn], dim=-1)
+                st0 = torch.zeros_like(ssm_s[s]) if fresh else ssm_s[s]
+                xh = x.view(n, self.H, self.P)
+                yb, stN = ssd_chunk_scan(xh, dt[off:off + n], A, Bm.view(n, self.G, self.N).repeat_interleave(rep, 1),
+                                         Cm.view(n, self.G, self.N).repeat_interleave(rep, 1), st0, self.chunk)
+                ssm_s[s] = stN
+                ys.append(yb + self.D[None, :, None] * xh.float())
+                off += n
+            y = torch.cat(ys, 0) if ys else torch.zeros(0, self.H, self.P, device=h.device)
+        y = self._gated_norm(y.reshape(T, di), z)
+        return self.out_proj(y.to(h.dtype))
+
+
+class _ReluSqMLP(nn.Module):
+    def __init__(self, cfg: ModelConfig, dtype, prefix: str):
+        super().__init__()
+        self.up_proj = ColumnParallelLinear(cfg.hidden_size, cfg.intermediate_size, cfg.mlp_bias, False, dtype, None, prefix + ".up_proj")
+        self.down_proj = RowParallelLinear(cfg.intermediate_size, cfg.hidden_size, cfg.mlp_bias, True, dtype, None, prefix + ".down_proj")
+
+    def forward(self, x, fb=None):
+        return self.down_proj(torch.relu(self.up_proj(x)).pow(2))
+
+
+class _Attn(nn.Module):
+    """Nemotron-H attention block: no positional encoding (the SSM layers carry order), GQA"""
+
+    def __init__(self, cfg: ModelConfig, attn_idx: int, dtype, prefix: str):
+        super().__init__()
+        self.qkv_proj = QKVParallelLinear(cfg.hidden_size, cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.attention_bias,
+                                          dtype, None, prefix + ".qkv_proj")
+        self.o_proj = RowParallelLinear(cfg.num_attention_heads * cfg.head_dim, cfg.hidden_size, cfg.attention_bias, True, dtype, None,
+                                        prefix + ".o_proj")
+        self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
+        self.attn = RadixAttention(self.qkv_proj.num_heads, cfg.head_dim, self.qkv_proj.num_kv_heads, attn_idx, rope=None)
+
+    def forward(self, x, fb: ForwardBatch):
+        q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        return self.o_proj(self.attn(q.contiguous(), k.contiguous(), v.contiguous(), fb))
+
+
+class _Block(nn.Module):
+    def __init__(self, kind: str, mixer: nn.Module, cfg: ModelConfig, dtype):
+        super().__init__()
+        self.kind = kind
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.mixer = mixer
+        if kind == "attention":
+            self.self_attn = mixer          # the runner sizes the KV pool from ``layers[i].self_attn.attn``
+
+    def forward(self, x, fb):
+        y = self.mixer(self.norm(x), fb)
+        y = y.resolve() if hasattr(y, "resolve") else y
+        return x + y
+
+
+class HybridBackbone(nn.Module):
+    def __init__(self, cfg: ModelConfig, device):
+        super().__init__()
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        assert get_pp_group().world_size == 1, "hybrid / SSM decoders: pipeline parallelism is not wired"
+        self.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        kinds = {"M": "mamba", "*": "attention", "-": "mlp"}
+        pat = cfg.mamba.get("pattern") or "M" * cfg.num_hidden_layers
+        assert len(pat) == cfg.num_hidden_layers, "hybrid pattern length must equal num_hidden_layers"
+        blocks, n_m, n_a = [], 0, 0
+        for i, ch in enumerate(pat):
+            kind = kinds[ch]
+            pre = f"model.layers.{i}.mixer"
+            if kind == "mamba":
+                mixer, n_m = Mamba2Mixer(cfg, n_m, dtype, pre), n_m + 1
+            elif kind == "attention":
+                mixer, n_a = _Attn(cfg, n_a, dtype, pre), n_a + 1
+            else:
+                mixer = _ReluSqMLP(cfg, dtype, pre)
+            blocks.append(_Block(kind, mixer, cfg, dtype))
+        self.all_layers = nn.ModuleList(blocks)
+        self.num_mamba, self.num_attn = n_m, n_a
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    @property
+    def layers(self):
+        """what the runner iterates to size the paged KV pool: the attention blocks only"""
+        return [b for b in self.all_layers if b.kind == "attention"]
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        if inputs_embeds is not None:
+            h = inputs_embeds
+        elif fb.input_ids is None:
+            h = self.embed_tokens(fb.next_token_buf, fb.req_slots)
+        else:
+            h = self.embed_tokens(fb.input_ids)
+        for blk in self.all_layers:
+            h = blk(h, fb)
+        return self.norm(h)
+
+
+class NemotronHForCausalLM(nn.Module):
+    """canonical names: model.embed_tokens, model.layers.N.norm, model.layers.N.mixer.{in_proj, conv1d, A_log, D, dt_bias, norm, out_proj |
+    q_proj, k_proj, v_proj, o_proj | up_proj, down_proj}, model.norm, lm_head.  HF checkpoints say ``backbone.`` / ``embeddings`` / ``norm_f``."""
+    supports_cuda_graph = False
+    disable_radix_cache = True
+    stacked_params = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v")]
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__()
+        self.cfg = cfg
+        self.model = HybridBackbone(cfg, device)
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, _DT[cfg.dtype])
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        return self.model(fb, inputs_embeds)
+
+    def compute_logits(self, hidden: torch.Tensor, key: str = "logits") -> torch.Tensor:
+        head = self.lm_head if self.lm_head is not None else self.model.embed_tokens
+        y = ops.linear(hidden, head.weight)
+        tp = get_tp_group()
+        if tp.world_size > 1:
+            y = tp.all_gather(y, dim=-1)
+        return y[:, : self.cfg.vocab_size]
+
+    # ---- recurrent state
+    def make_mamba_pool(self, slots: int, device) -> Optional[MambaPool]:
+        m = next((b.mixer for b in self.model.all_layers if b.kind == "mamba"), None)
+        if m is None:
+            return None
+        return MambaPool(self.model.num_mamba, slots, m.conv_dim, m.k, m.H, m.P, m.N, _DT[self.cfg.dtype], device)
+
+    # ---- weights
+    @staticmethod
+    def remap(name: str) -> str:
+        name = name.replace("backbone.", "model.", 1) if name.startswith("backbone.") else name
+        return name.replace("model.embeddings.", "model.embed_tokens.").replace("model.norm_f.", "model.norm.")
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        params = dict(self.named_parameters())
+        mods = dict(self.named_modules())
+        loaded = []
+        for name, w in weights:
+            name = self.remap(name).replace("model.layers.", "model.all_layers.")
+            if name == "lm_head.weight" and self.lm_head is None:
+                continue
+            mixer_name = name[: name.index(".mixer") + 6] if ".mixer." in name else None
+            mixer = mods.get(mixer_name) if mixer_name else None
+            if isinstance(mixer, Mamba2Mixer):
+                leaf = name[len(mixer_name) + 1:]
+                if leaf in ("in_proj.weight", "in_proj.bias"):
+                    mixer.load_fused(params[name], w, True)
+                elif leaf == "conv1d.weight":
+                    mixer.load_fused(mixer.conv_weight, w.reshape(w.shape[0], -1), False)
+                elif leaf == "conv1d.bias":
+                    mixer.load_fused(mixer.conv_bias, w, False)
+                elif leaf in ("A_log", "D", "dt_bias"):
+                    mixer.load_heads(getattr(mixer, leaf), w)
+                elif leaf == "norm.weight":
+                    mixer.load_heads(mixer.norm_weight, w)
+                elif leaf.startswith("out_proj."):
+                    mixer.out_proj.weight_loader(params[name], w)
+                else:
+                    continue
+                loaded.append(name)
+                continue
+            target, shard = name, None
+            for merged, orig, sid in self.stacked_params:
+                if orig + "." in name:
+                    target, shard = name.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded
+
+    def dummy_checkpoint(self, cfg: ModelConfig, device, dtype, seed: int = 0, scale: float = 0.02):
+        """full-size (unsharded) synthetic checkpoint in HF naming, independent of the TP layout"""
+        def rnd(name, *shape, s=scale):
+            g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+            return (torch.randn(*shape, generator=g) * s).to(dtype)
+
+        m = cfg.mamba
+        H, P, N, G, k = m["num_heads"], m["head_dim"], m["d_state"], m["n_groups"], m["d_conv"]
+        di, hid = H * P, cfg.hidden_size
+        yield "backbone.embeddings.weight", rnd("emb", cfg.vocab_size, hid)
+        pat = m.get("pattern") or "M" * cfg.num_hidden_layers
+        for i, ch in enumerate(pat):
+            pre = f"backbone.layers.{i}."
+            yield pre + "norm.weight", torch.ones(hid, dtype=dtype)
+            if ch == "M":
+                yield pre + "mixer.in_proj.weight", rnd(pre + "in", 2 * di + 2 * G * N + H, hid)
+                yield pre + "mixer.conv1d.weight", rnd(pre + "cw", di + 2 * G * N, 1, k, s=0.3)
+                yield pre + "mixer.conv1d.bias", rnd(pre + "cb", di + 2 * G * N, s=0.1)
+                g = torch.Generator(device="cpu").manual_seed(zlib.crc32((pre + "A").encode()) & 0x7FFFFFFF)
+                yield pre + "mixer.A_log", torch.log(torch.rand(H, generator=g) * 3 + 0.5)
+                yield pre + "mixer.D", torch.ones(H) + rnd(pre + "D", H, s=0.1).float()
+                yield pre + "mixer.dt_bias", rnd(pre + "dtb", H, s=0.5).float() - 1.0
+                yield pre + "mixer.norm.weight", torch.ones(di, dtype=dtype) + rnd(pre + "nw", di, s=0.05)
+                yield pre + "mixer.out_proj.weight", rnd(pre + "out", hid, di)
+            elif ch == "*":
+                hd, nh, nkv = cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads
+                yield pre + "mixer.q_proj.weight", rnd(pre + "q", nh * hd, hid)
+                yield pre + "mixer.k_proj.weight", rnd(pre + "k", nkv * hd, hid)
+                yield pre + "mixer.v_proj.weight", rnd(pre + "v", nkv * hd, hid)
+                yield pre + "mixer.o_proj.weight", rnd(pre + "o", hid, nh * hd)
+            else:
+                yield pre + "mixer.up_proj.weight", rnd(pre + "up", cfg.intermediate_size, hid)
+                yield pre + "mixer.down_proj.weight", rnd(pre + "down", hid, cfg.intermediate_size)
+        yield "backbone.norm_f.weight", torch.ones(hid, dtype=dtype)
+        if not cfg.tie_word_embeddings:
+            yield "lm_head.weight", rnd("lm_head", cfg.vocab_size, hid)
+
+
+class Mamba2ForCausalLM(NemotronHForCausalLM):
+    """pure Mamba-2 stack (every layer is an SSM mixer); same checkpoint naming (``backbone.layers.N.mixer.*``)"""

@@ -41,6 +41,13 @@ def _ensure() -> None:
 
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import gpt_oss as _go
+
+    register_model("GptOssForCausalLM", _go.GptOssForCausalLM)
+    from . import mamba as _mb
+
+    register_model("NemotronHForCausalLM", _mb.NemotronHForCausalLM)
+    register_model("Mamba2ForCausalLM", _mb.Mamba2ForCausalLM)
     from . import deepseek as _ds
 
     register_model("DeepseekV2ForCausalLM", _ds.DeepseekV2ForCausalLM)

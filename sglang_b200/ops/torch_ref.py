@@ -66,9 +66,51 @@ def build_cos_sin_cache(head_dim: int, max_pos: int, base: float = 10000.0, rope
         inv_freq = scaled
     elif rope_scaling and rope_scaling.get("rope_type", rope_scaling.get("type")) == "linear":
         inv_freq = inv_freq / rope_scaling.get("factor", 1.0)
+    mscale = 1.0
+    kind = (rope_scaling or {}).get("rope_type", (rope_scaling or {}).get("type"))
+    if kind in ("yarn", "deepseek_yarn"):
+        # YaRN (reference rotary_embedding yarn / deepseek_yarn): interpolate the low frequencies by ``factor``, keep the high ones, blend
+        # linearly between the two correction dims; cos / sin carry the attention temperature ("mscale")
+        rs = rope_scaling
+        factor = float(rs.get("factor", 1.0))
+        old = rs.get("original_max_position_embeddings", max_pos)
+        fast, slow = rs.get("beta_fast", 32), rs.get("beta_slow", 1)
+        corr = lambda rot: (rd * math.log(old / (rot * 2 * math.pi))) / (2 * math.log(base))
+        lo, hi = corr(fast), corr(slow)
+        if rs.get("truncate", True):
+            lo, hi = math.floor(lo), math.ceil(hi)
+        lo, hi = max(lo, 0), min(hi, rd - 1)
+        if lo == hi:
+            hi += 0.001
+        ramp = ((torch.arange(rd // 2, dtype=torch.float32) - lo) / (hi - lo)).clamp(0, 1)
+        extrap_mask = 1 - ramp
+        inv_freq = inv_freq / factor * (1 - extrap_mask) + inv_freq * extrap_mask
+        get_ms = lambda sc, m=1.0: 1.0 if sc <= 1 else 0.1 * m * math.log(sc) + 1.0
+        if rs.get("attention_factor") is not None:
+            mscale = float(rs["attention_factor"])
+        elif rs.get("mscale") and rs.get("mscale_all_dim"):
+            mscale = get_ms(factor, rs["mscale"]) / get_ms(factor, rs["mscale_all_dim"])
+        else:
+            mscale = get_ms(factor)
+    elif kind in ("longrope", "su"):
+        # Phi-3 LongRoPE: per-dimension rescale factors (short / long table chosen by the served context length)
+        rs = rope_scaling
+        old = rs.get("original_max_position_embeddings", max_pos)
+        ext = torch.tensor(rs["long_factor"] if max_pos > old else rs["short_factor"], dtype=torch.float32)
+        inv_freq = inv_freq / ext
+        sc = max_pos / old
+        mscale = 1.0 if sc <= 1.0 else math.sqrt(1 + math.log(sc) / math.log(old))
+    elif kind == "dynamic":
+        # dynamic NTK evaluated at the served context length (static table: one base for all positions)
+        rs = rope_scaling
+        factor = float(rs.get("factor", 1.0))
+        old = rs.get("original_max_position_embeddings", max_pos)
+        if max_pos > old:
+            nb = base * ((factor * max_pos / old) - (factor - 1)) ** (rd / (rd - 2))
+            inv_freq = 1.0 / (nb ** (torch.arange(0, rd, 2, dtype=torch.float32) / rd))
     t = torch.arange(max_pos, dtype=torch.float32)
     freqs = torch.outer(t, inv_freq)
-    return torch.cat([freqs.cos(), freqs.sin()], dim=-1)
+    return torch.cat([freqs.cos() * mscale, freqs.sin() * mscale], dim=-1)
 
 
 def apply_rope(x: torch.Tensor, positions: torch.Tensor, cos_sin: torch.Tensor, is_neox: bool = True) -> torch.Tensor:

@@ -196,3 +196,16 @@ def test_prefill_context_parallel_matches_single():
     _check(_run({**kw, "tp_size": 4, "cp_size": 2}, 4, LP, env), ref)
     kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
     _check(_run({**kw, "tp_size": 2, "cp_size": 2, "ep_size": 2}, 2, LP, env), _run(kw, 1, LP))
+
+
+def test_hybrid_mamba_tp2():
+    """Mamba-2 heads / B-C groups / conv channels sharded over TP (fused in_proj and conv tensors sliced per block), attention layers of the
+    hybrid on the paged pool; single replicated group + full-width gated norm (all-reduced variance) for the pure Mamba-2 preset"""
+    for preset in ("tiny-nemotron-h", "tiny-mamba2"):
+        kw = dict(model_path=f"dummy:{preset}", page_size=4, chunked_prefill_size=16)
+        _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))
+
+
+def test_gpt_oss_tp2():
+    kw = dict(model_path="dummy:tiny-gpt-oss", page_size=4, chunked_prefill_size=16)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))

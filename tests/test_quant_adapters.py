@@ -111,7 +111,7 @@ def test_adapter_stream_mixed_checkpoint():
     torch.testing.assert_close(out["m.l0.q_proj.weight"], awq)
     torch.testing.assert_close(out["m.l0.o_proj.weight"], wf.float() * 2.0)
     torch.testing.assert_close(out["m.l0.up.weight"], wf.float() * blk)
-    torch.testing.assert_close(out["m.l0.experts.w13"], (Q._FP4[idx] * 0.5))
+    torch.testing.assert_close(out["m.l0.experts.w13"], (Q._FP4[idx] * 0.5).transpose(1, 2))
     assert out["m.norm.weight"].shape == (K,) and "m.l0.q_proj.bias" in out and out["m.embed.weight"].shape == (4, K)
     assert not any(k.endswith(("qweight", "qzeros", "scales", "weight_scale", "input_scale")) for k in out)
     kept = dict(Q.adapt_quantized_checkpoint(iter(stream), {"quant_method": "fp8"}, torch.float32, keep_block_fp8=True))
