@@ -120,6 +120,11 @@ PRESETS: Dict[str, Dict[str, Any]] = {
     # ---- tiny CPU-test models
     "tiny-llama": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
                        vocab_size=512, max_position_embeddings=512, rope_theta=10000.0, dtype="float32"),
+    "tiny-qwen2-vl": dict(architecture="Qwen2VLForConditionalGeneration", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                          num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=2048, attention_bias=True,
+                          rope_theta=10000.0, dtype="float32", image_token_id=500, rope_scaling={"type": "mrope", "mrope_section": [2, 3, 3]},
+                          vision={"embed_dim": 32, "depth": 2, "num_heads": 2, "hidden_size": 64, "mlp_ratio": 2, "patch_size": 14,
+                                  "spatial_merge_size": 2, "temporal_patch_size": 2, "min_pixels": 28 * 28, "max_pixels": 28 * 28 * 12}),
     "tiny-gpt-oss": dict(architecture="GptOssForCausalLM", hidden_size=64, intermediate_size=32, moe_intermediate_size=32, num_hidden_layers=4,
                          num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512, dtype="float32",
                          num_local_experts=4, num_experts_per_tok=2, sliding_window=8, attention_bias=True, swiglu_limit=7.0, rope_theta=150000.0,
@@ -288,6 +293,13 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         text = hf.get("text_config", hf)
         fields = {f.name for f in dataclasses.fields(ModelConfig)}
         text = {_HF_KEY_MAP.get(k, k): v for k, v in text.items()}
+        rp = text.get("rope_parameters")          # transformers >= 5: theta and scaling live in one dict
+        if isinstance(rp, dict):
+            if rp.get("rope_theta") is not None:
+                text.setdefault("rope_theta", rp["rope_theta"])
+            sc = {k: v for k, v in rp.items() if k != "rope_theta"}
+            if text.get("rope_scaling") is None and (sc.get("rope_type", "default") != "default" or "mrope_section" in sc):
+                text["rope_scaling"] = sc
         kw = {k: v for k, v in text.items() if k in fields}
         arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
@@ -311,7 +323,15 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", text.get("num_key_value_heads", kw.get("num_attention_heads", 1)))
             if arch == "NemotronHForCausalLM" and text.get("attention_head_dim"):
                 kw["head_dim"] = text["attention_head_dim"]
-        if "vision_config" in hf:
+        if arch == "Qwen2VLForConditionalGeneration":
+            vc = hf["vision_config"]
+            kw["vision"] = {"embed_dim": vc.get("embed_dim", 1280), "depth": vc.get("depth", 32), "num_heads": vc.get("num_heads", 16),
+                            "hidden_size": vc.get("hidden_size", kw["hidden_size"]), "mlp_ratio": vc.get("mlp_ratio", 4),
+                            "patch_size": vc.get("patch_size", 14), "spatial_merge_size": vc.get("spatial_merge_size", 2),
+                            "temporal_patch_size": vc.get("temporal_patch_size", 2)}
+            kw["image_token_id"] = hf.get("image_token_id", 151655)
+            kw.setdefault("attention_bias", True)
+        elif "vision_config" in hf:
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))

@@ -74,8 +74,9 @@ class RadixAttention(nn.Module):
         dcp = getattr(fb, "dcp", None)
         out_loc = fb.out_cache_loc if dcp is None else dcp.local_loc
         if self.rope is not None:
-            ops.rope_kv_write(q3, k3, v3, fb.positions, self.rope.cos_sin, kc, vc, out_loc, self.rope.is_neox,
-                              pool.k_scale, pool.v_scale, nslabs, slab_stride)
+            ov = fb.rope_override            # M-RoPE: a per-token cos/sin table indexed by row number instead of the position table
+            ops.rope_kv_write(q3, k3, v3, fb.positions if ov is None else ov[1], self.rope.cos_sin if ov is None else ov[0], kc, vc, out_loc,
+                              self.rope.is_neox, pool.k_scale, pool.v_scale, nslabs, slab_stride)
         else:
             assert nslabs == 1
             loc = out_loc.long()

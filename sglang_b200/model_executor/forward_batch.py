@@ -65,6 +65,8 @@ class ForwardBatch:
     seq_lens_cpu: Optional[np.ndarray] = None
     q_lens_cpu: Optional[np.ndarray] = None
     pp_hidden: Any = None
+    rope_override: Any = None        # (cos_sin rows [T, rot], row index [T]): per-token rotary table (M-RoPE)
+    mrope_positions: Any = None      # i64 [3, T]
     cp: Any = None                   # layers/cp.py CpMeta inside a context-parallel prefill
     dcp: Any = None                  # layers/dcp.py DcpMeta when decode context parallelism is on
 

@@ -197,6 +197,8 @@ class ModelRunner:
         # recurrent (SSM) state of hybrid / Mamba decoders, indexed by request slot like the page table (models/mamba.py)
         self.kv_pool.mamba = self.model.make_mamba_pool(self.max_running + 1, self.device) if hasattr(self.model, "make_mamba_pool") else None
         self.next_token_buf = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
+        if getattr(self.model, "is_mrope", False):
+            self.model.mrope_delta = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
         logger.info("KV pool: %d pages x %d tokens (%.2f GB), max_running=%d, weights %.2f GB", self.num_pages, self.page_size,
                     self.num_pages * per_page / 2 ** 30, self.max_running, self.weight_bytes / 2 ** 30)
 
@@ -221,7 +223,8 @@ class ModelRunner:
     # ------------------------------------------------------------------ prefill context parallelism (layers/cp.py)
     def _cp_eligible(self, sb: ScheduleBatch, fb: ForwardBatch) -> bool:
         return (fb.cu_q is not None and fb.input_ids is not None and fb.num_tokens >= self.cp_min_tokens and fb.mm_embeds is None
-                and self.lora_manager is None and sb.spec_info is None and fb.custom_mask is None and self.pp.world_size == 1)
+                and self.lora_manager is None and sb.spec_info is None and fb.custom_mask is None and self.pp.world_size == 1
+                and not getattr(self.model, "is_mrope", False))
 
     def _forward_cp(self, sb: ScheduleBatch, fb: ForwardBatch) -> torch.Tensor:
         """run the decoder stack on this attention group's zig-zag slice of the rows; returns the hidden states of ALL rows, original order"""
@@ -521,11 +524,37 @@ class ModelRunner:
             res.input_logprobs[i] = [(float(a), int(b)) for a, b in zip(lp, ids.tolist())]
 
     def _attach_mm(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
-        if not sb.forward_mode.is_extend() or not any(r.mm_inputs for r in sb.reqs):
+        if not sb.forward_mode.is_extend():
+            return
+        if getattr(self.model, "is_mrope", False):
+            self._attach_mrope(sb, fb)
+        if not any(r.mm_inputs for r in sb.reqs):
             return
         from ..multimodal.embed import build_mm_embeds
 
         fb.mm_embeds = build_mm_embeds(self.model, sb, self.device, self.dtype)
+
+    def _attach_mrope(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
+        """M-RoPE (Qwen2-VL): 3-axis rotary positions of this chunk's tokens + the per-request decode delta (models/qwen2_vl.py)"""
+        m = self.model
+        if m.mrope_delta is None:
+            m.mrope_delta = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
+        cols, deltas = [], []
+        for i, r in enumerate(sb.reqs):
+            s, e = int(sb.prefix_lens[i]), int(sb.prefix_lens[i] + sb.q_lens[i])
+            mm = r.mm_inputs or {}
+            tab, d = mm.get("mrope_positions"), int(mm.get("mrope_delta", 0))
+            p = np.arange(s, e, dtype=np.int64)
+            if tab is None:
+                cols.append(np.stack([p, p, p]))
+            else:
+                tab = np.asarray(tab, dtype=np.int64)
+                n = tab.shape[1]
+                cols.append(np.concatenate([tab[:, s:min(e, n)], np.stack([p[p >= n] + d] * 3)], 1))
+            deltas.append(d)
+        fb.mrope_positions = torch.from_numpy(np.concatenate(cols, 1)).to(self.device)
+        slots = torch.from_numpy(np.asarray(sb.req_slots, dtype=np.int64)).to(self.device)
+        m.mrope_delta[slots] = torch.tensor(deltas, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------ pipeline parallel hand-off
     def _pp_recv(self, T: int):

@@ -1,0 +1,185 @@
+"""Qwen2-VL: dynamic-resolution vision transformer (2-D rotary, per-image full attention, 2x2 patch merger) feeding a Qwen2 decoder that
+uses multimodal rotary positions (M-RoPE: temporal / height / width position per token, one rotary section each).
+
+Parity: reference ``python/sglang/srt/models/qwen2_vl.py`` (``Qwen2VisionTransformer``, ``Qwen2VLForConditionalGeneration``),
+``layers/rotary_embedding`` mrope variant, ``multimodal/processors/qwen_vl.py`` (smart resize, patch flattening, rope index).
+
+Engine integration without touching the kernels:
+
+* M-RoPE = ordinary RoPE whose cos/sin row is assembled per token from three positions.  ``prepare_mrope`` builds that [T, rot] table once
+  per forward (gathering the three sections from the model's cos/sin cache) and the fused RoPE + KV-write kernel simply indexes it by row
+  number (``fb.rope_override``).  Text-only tokens have three equal positions and reduce to plain RoPE;
+* decode positions are ``sequence position + delta`` with a per-request delta (images occupy fewer rotary positions than tokens) kept in a
+  device vector indexed by request slot — pure device arithmetic, graph-capturable;
+* image rows are spliced into the prompt embeddings by the shared ``multimodal/embed.py`` path (variable token count per image).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..configs.model_config import ModelConfig
+from ..model_executor.forward_batch import ForwardBatch
+from .llama import _DT, LlamaForCausalLM
+
+
+# ------------------------------------------------------------------------------------------------ vision tower
+def _rot_half(x):
+    a, b = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat([-b, a], -1)
+
+
+class VisionBlock(nn.Module):
+    def __init__(self, dim: int, heads: int, mlp_ratio: float, dtype):
+        super().__init__()
+        self.heads = heads
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6, dtype=dtype)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6, dtype=dtype)
+        self.qkv = nn.Linear(dim, 3 * dim, dtype=dtype)
+        self.proj = nn.Linear(dim, dim, dtype=dtype)
+        self.fc1 = nn.Linear(dim, int(dim * mlp_ratio), dtype=dtype)
+        self.fc2 = nn.Linear(int(dim * mlp_ratio), dim, dtype=dtype)
+
+    def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seg: List[int]) -> torch.Tensor:
+        N, D = x.shape
+        q, k, v = self.qkv(self.norm1(x)).view(N, 3, self.heads, D // self.heads).unbind(1)
+        q = (q.float() * cos[:, None] + _rot_half(q.float()) * sin[:, None]).to(x.dtype)
+        k = (k.float() * cos[:, None] + _rot_half(k.float()) * sin[:, None]).to(x.dtype)
+        outs, s = [], 0
+        for n in seg:           # full attention inside one image (frame group), nothing across images
+            o = F.scaled_dot_product_attention(q[s:s + n].transpose(0, 1), k[s:s + n].transpose(0, 1), v[s:s + n].transpose(0, 1))
+            outs.append(o.transpose(0, 1).reshape(n, D))
+            s += n
+        x = x + self.proj(torch.cat(outs, 0))
+        h = self.fc1(self.norm2(x))
+        return x + self.fc2(h * torch.sigmoid(1.702 * h))            # quick-GELU
+
+
+class Qwen2VisionTransformer(nn.Module):
+    def __init__(self, v: Dict[str, Any], dtype):
+        super().__init__()
+        self.embed_dim, self.heads, self.patch, self.merge, self.tps = v["embed_dim"], v["num_heads"], v["patch_size"], v["spatial_merge_size"], \
+            v.get("temporal_patch_size", 2)
+        self.patch_embed = nn.Linear(3 * self.tps * self.patch * self.patch, self.embed_dim, bias=False, dtype=dtype)      # Conv3d with stride = kernel
+        self.blocks = nn.ModuleList([VisionBlock(self.embed_dim, self.heads, v.get("mlp_ratio", 4), dtype) for _ in range(v["depth"])])
+        self.ln_q = nn.LayerNorm(self.embed_dim, eps=1e-6, dtype=dtype)
+        m = self.embed_dim * self.merge ** 2
+        self.merger = nn.Sequential(nn.Linear(m, m, dtype=dtype), nn.GELU(), nn.Linear(m, v["hidden_size"], dtype=dtype))
+        hd = self.embed_dim // self.heads
+        self.register_buffer("inv_freq", 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float32) / (hd // 2))), persistent=False)
+
+    def rot_pos_emb(self, grid_thw: np.ndarray) -> Tuple[torch.Tensor, torch.Tensor]:
+        ids = []
+        m = self.merge
+        for t, h, w in grid_thw.tolist():
+            hp = np.arange(h)[:, None].repeat(w, 1).reshape(h // m, m, w // m, m).transpose(0, 2, 1, 3).reshape(-1)
+            wp = np.arange(w)[None, :].repeat(h, 0).reshape(h // m, m, w // m, m).transpose(0, 2, 1, 3).reshape(-1)
+            ids.append(np.tile(np.stack([hp, wp], -1), (t, 1)))
+        ids = torch.from_numpy(np.concatenate(ids)).to(self.inv_freq.device)
+        freqs = torch.outer(torch.arange(int(grid_thw[:, 1:].max()), dtype=torch.float32, device=self.inv_freq.device), self.inv_freq)
+        emb = freqs[ids].flatten(1)                     # [N, head_dim / 2]: h frequencies | w frequencies
+        emb = torch.cat([emb, emb], -1)
+        return emb.cos(), emb.sin()
+
+    def forward(self, patches: torch.Tensor, grid_thw: np.ndarray) -> torch.Tensor:
+        """patches [N, 3*tps*p*p] (merge-block order), grid_thw [n_img, 3] -> [N / merge^2, hidden]"""
+        x = self.patch_embed(patches)
+        cos, sin = self.rot_pos_emb(grid_thw)
+        seg = []
+        for t, h, w in grid_thw.tolist():
+            seg += [h * w] * t
+        for blk in self.blocks:
+            x = blk(x, cos, sin, seg)
+        return self.merger(self.ln_q(x).view(-1, self.embed_dim * self.merge ** 2))
+
+
+# ------------------------------------------------------------------------------------------------ M-RoPE helpers
+def mrope_index(ids: List[int], grids: List[Tuple[int, int, int]], image_token: int, merge: int) -> Tuple[np.ndarray, int]:
+    """[3, len(ids)] rotary positions (temporal, height, width) and the delta ``next position - len(ids)`` for decode (reference
+    ``get_rope_index``).  ``grids``: (t, h, w) in PATCH units for every image, in prompt order; its placeholder run has t*h*w/merge^2 tokens."""
+    pos = np.zeros((3, len(ids)), dtype=np.int64)
+    i, st, g = 0, 0, 0
+    arr = np.asarray(ids)
+    n = len(ids)
+    while i < n:
+        if arr[i] == image_token and g < len(grids):
+            t, h, w = grids[g]
+            h, w = h // merge, w // merge
+            cnt = t * h * w
+            ti = np.arange(t)[:, None, None].repeat(h, 1).repeat(w, 2).reshape(-1)
+            hi = np.arange(h)[None, :, None].repeat(t, 0).repeat(w, 2).reshape(-1)
+            wi = np.arange(w)[None, None, :].repeat(t, 0).repeat(h, 1).reshape(-1)
+            pos[:, i:i + cnt] = np.stack([ti, hi, wi]) + st
+            st += max(t, h, w)
+            i += cnt
+            g += 1
+        else:
+            pos[:, i] = st
+            st += 1
+            i += 1
+    return pos, st - n
+
+
+def prepare_mrope(fb: ForwardBatch, cos_sin: torch.Tensor, pos3: torch.Tensor, sections: List[int]) -> None:
+    """assemble the per-token cos/sin rows: rotary dims [0, s0) follow the temporal position, [s0, s0+s1) height, the rest width"""
+    half = cos_sin.shape[1] // 2
+    sel = torch.repeat_interleave(torch.arange(3, device=cos_sin.device), torch.tensor(sections, device=cos_sin.device))[:half]      # [half] -> axis
+    p = pos3.long()[sel, :].t()                                             # [T, half]: which position feeds each rotary pair
+    d = torch.arange(half, device=cos_sin.device)[None, :]
+    rows = torch.cat([cos_sin[p, d], cos_sin[p, d + half]], -1)             # [T, rot]
+    fb.rope_override = (rows.contiguous(), torch.arange(rows.shape[0], dtype=torch.int32, device=rows.device))
+
+
+class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
+    is_mrope = True
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        v = cfg.vision
+        self.visual = None if v.get("skip_tower") else Qwen2VisionTransformer(v, _DT[cfg.dtype])
+        self.vision_tower = self.visual            # name the shared multimodal plumbing looks for
+        self.merge = v["spatial_merge_size"]
+        self.sections = list((cfg.rope_scaling or {}).get("mrope_section", [cfg.head_dim // 2]))
+        self.mrope_delta: Optional[torch.Tensor] = None       # [max_slots] i32, set per request at prefill (ModelRunner allocates)
+
+    # ---- vision
+    @torch.no_grad()
+    def encode_images(self, patches: torch.Tensor, grid_thw: Any = None) -> torch.Tensor:
+        return self.visual(patches, np.asarray(grid_thw, dtype=np.int64).reshape(-1, 3))
+
+    # ---- language model with M-RoPE
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        cs = self.model.layers[0].self_attn.attn.rope.cos_sin if len(self.model.layers) else None
+        if cs is not None:
+            pos3 = getattr(fb, "mrope_positions", None)
+            if pos3 is None and self.mrope_delta is not None:      # decode (or text-only extend): all three axes advance together
+                p = fb.positions.long() + self.mrope_delta[fb.req_slots.long()].long() if fb.cu_q is None else fb.positions.long()
+                pos3 = p[None, :].expand(3, -1)
+            if pos3 is not None:
+                prepare_mrope(fb, cs, pos3.clamp(max=cs.shape[0] - 1), self.sections)
+        return self.model(fb, inputs_embeds)
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        own = dict(self.named_parameters())
+        rest, loaded = [], []
+        for name, w in weights:
+            if name.startswith("model.visual."):                 # transformers >= 4.52 nests both halves under ``model.``
+                name = name[len("model."):]
+            elif name.startswith("model.language_model."):
+                name = "model." + name[len("model.language_model."):]
+            if name.startswith("visual."):
+                if self.visual is None:
+                    continue
+                n = name.replace(".attn.qkv.", ".qkv.").replace(".attn.proj.", ".proj.").replace(".mlp.fc1.", ".fc1.").replace(".mlp.fc2.", ".fc2.") \
+                    .replace("visual.merger.ln_q.", "visual.ln_q.").replace("visual.merger.mlp.", "visual.merger.").replace("visual.patch_embed.proj.", "visual.patch_embed.")
+                if n in own:
+                    own[n].data.copy_(w.reshape(own[n].shape))
+                    loaded.append(name)
+                continue
+            rest.append((name[len("language_model."):] if name.startswith("language_model.") else name, w))
+        return loaded + super().load_weights(rest)

@@ -41,6 +41,9 @@ def _ensure() -> None:
 
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import qwen2_vl as _qv
+
+    register_model("Qwen2VLForConditionalGeneration", _qv.Qwen2VLForConditionalGeneration)
     from . import gpt_oss as _go
 
     register_model("GptOssForCausalLM", _go.GptOssForCausalLM)

@@ -12,36 +12,51 @@ _ENC_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
 _ENC_CACHE_MAX = 64
 
 
+def _encode(model: Any, mm: Dict[str, Any], device: torch.device, dtype: torch.dtype):
+    """-> list of [tokens_k, hidden] tensors, one per image"""
+    counts = mm.get("image_token_counts") or [mm["num_image_tokens"]] * len(mm["image_offsets"])
+    if mm.get("image_embeds") is not None:      # EPD: an encoder server already produced the LM-space rows
+        e = mm["image_embeds"]
+        flat = torch.as_tensor(np.asarray(e), device=device).to(dtype)
+        flat = flat.reshape(-1, flat.shape[-1])
+    else:
+        if not hasattr(model, "encode_images") or getattr(model, "vision_tower", None) is None:
+            raise RuntimeError("this server was started --language-only: images need --encoder-urls (no local vision tower)")
+        if mm.get("pixel_patches") is not None:     # dynamic-resolution towers (Qwen2-VL): flattened patches + grids
+            px = torch.as_tensor(np.asarray(mm["pixel_patches"], dtype=np.float32), device=device)
+            flat = model.encode_images(px.to(dtype), mm["grid_thw"])
+        else:
+            px = torch.tensor(mm["pixel_values"], dtype=torch.float32, device=device)
+            flat = model.encode_images(px.to(dtype))
+        flat = flat.reshape(-1, flat.shape[-1])
+    assert flat.shape[0] == sum(counts), (flat.shape, counts)
+    return list(flat.split(counts, 0))
+
+
 def build_mm_embeds(model: Any, sb: Any, device: torch.device, dtype: torch.dtype) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     rows, feats = [], []
     cu = np.concatenate([[0], np.cumsum(sb.q_lens)])
     for i, r in enumerate(sb.reqs):
         mm = r.mm_inputs
-        if not mm:
+        if not mm or not mm.get("image_offsets"):
             continue
         s, e = int(sb.prefix_lens[i]), int(sb.prefix_lens[i] + sb.q_lens[i])
-        n_tok = mm["num_image_tokens"]
-        need = [k for k, off in enumerate(mm["image_offsets"]) if off < e and off + n_tok > s]
+        counts = mm.get("image_token_counts") or [mm["num_image_tokens"]] * len(mm["image_offsets"])
+        need = [k for k, off in enumerate(mm["image_offsets"]) if off < e and off + counts[k] > s]
         if not need:
             continue
         key = (id(mm), 0)
         emb = _ENC_CACHE.get(key)
-        if emb is None and mm.get("image_embeds") is not None:      # EPD: an encoder server already produced the LM-space rows
-            emb = torch.as_tensor(np.asarray(mm["image_embeds"]), device=device).to(dtype).view(len(mm["image_offsets"]), n_tok, -1)
-            _ENC_CACHE[key] = emb
         if emb is None:
-            if not hasattr(model, "encode_images") or getattr(model, "vision_tower", None) is None:
-                raise RuntimeError("this server was started --language-only: images need --encoder-urls (no local vision tower)")
-            px = torch.tensor(mm["pixel_values"], dtype=torch.float32, device=device)
-            emb = model.encode_images(px.to(dtype)).view(len(mm["image_offsets"]), n_tok, -1)
+            emb = _encode(model, mm, device, dtype)
             if len(_ENC_CACHE) >= _ENC_CACHE_MAX:
                 _ENC_CACHE.pop(next(iter(_ENC_CACHE)))
             _ENC_CACHE[key] = emb
         for k in need:
             off = mm["image_offsets"][k]
-            a, b = max(off, s), min(off + n_tok, e)
+            a, b = max(off, s), min(off + counts[k], e)
             rows.append(torch.arange(int(cu[i]) + a - s, int(cu[i]) + b - s, device=device))
-            feats.append(emb[k, a - off:b - off])
+            feats.append(emb[k][a - off:b - off])
     if not rows:
         return None
     return torch.cat(rows), torch.cat(feats)

@@ -102,7 +102,85 @@ def image_hash(img: np.ndarray) -> int:
     return int.from_bytes(hashlib.sha256(img.tobytes()).digest()[:8], "little") & ((1 << 63) - 1)
 
 
+def smart_resize(h: int, w: int, factor: int = 28, min_pixels: int = 56 * 56, max_pixels: int = 14 * 14 * 4 * 1280) -> Tuple[int, int]:
+    """Qwen2-VL dynamic resolution: both sides multiples of ``factor``, area inside [min_pixels, max_pixels], aspect ratio kept"""
+    import math
+
+    if max(h, w) / min(h, w) > 200:
+        raise ValueError("image aspect ratio must be below 200")
+    hb, wb = max(factor, round(h / factor) * factor), max(factor, round(w / factor) * factor)
+    if hb * wb > max_pixels:
+        beta = math.sqrt((h * w) / max_pixels)
+        hb, wb = math.floor(h / beta / factor) * factor, math.floor(w / beta / factor) * factor
+    elif hb * wb < min_pixels:
+        beta = math.sqrt(min_pixels / (h * w))
+        hb, wb = math.ceil(h * beta / factor) * factor, math.ceil(w * beta / factor) * factor
+    return hb, wb
+
+
+def qwen_vl_patches(img: np.ndarray, patch: int, merge: int, temporal: int, min_pixels: int, max_pixels: int) -> Tuple[np.ndarray, Tuple[int, int, int]]:
+    """uint8 HWC -> (flattened patches [gh*gw, 3*t*p*p] in merge-block order, (1, gh, gw))"""
+    h, w = img.shape[:2]
+    nh, nw = smart_resize(h, w, patch * merge, min_pixels, max_pixels)
+    rt = _native()
+    if rt is not None:
+        r = rt.image_resize(np.ascontiguousarray(img), nh, nw, 3)
+    else:
+        from PIL import Image
+
+        r = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
+    chw = ((r.astype(np.float32) / 255.0 - CLIP_MEAN) / CLIP_STD).transpose(2, 0, 1)
+    return patchify(np.ascontiguousarray(chw), patch, merge, temporal), (1, nh // patch, nw // patch)
+
+
+def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None):
+    """Qwen2-VL: every image placeholder token expands to ``gh * gw / merge^2`` pad tokens (hash-derived ids for the radix cache); returns the
+    patches, grids, M-RoPE position table and decode delta (reference multimodal/processors/qwen_vl.py)"""
+    from ..models.qwen2_vl import mrope_index
+
+    v = cfg.vision
+    patch, merge, tps = v["patch_size"], v["spatial_merge_size"], v.get("temporal_patch_size", 2)
+    imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
+    arrs = [load_image(x) for x in imgs]
+    pp = [qwen_vl_patches(a, patch, merge, tps, v.get("min_pixels", 56 * 56), v.get("max_pixels", 14 * 14 * 4 * 1280)) for a in arrs]
+    img_tok, V = cfg.image_token_id, cfg.vocab_size
+    out, offsets, counts, pads, k = [], [], [], [], 0
+    for t in input_ids:
+        if t == img_tok and k < len(arrs):
+            g = pp[k][1]
+            n = g[0] * g[1] * g[2] // (merge * merge)
+            h = image_hash(arrs[k])
+            offsets.append(len(out))
+            counts.append(n)
+            pads.append(int(h % max(1, V - 1)))
+            out.extend([img_tok] * n)
+            k += 1
+        else:
+            out.append(t)
+    if k < len(arrs):
+        raise ValueError(f"{len(arrs)} images but only {k} image placeholder tokens in the prompt")
+    pos, delta = mrope_index(out, [g for _, g in pp], img_tok, merge)
+    # the placeholder ids themselves never reach the model (their embedding rows are overwritten): replace them with hash-derived ids so
+    # that different images never share a radix-cache key
+    for off, n, k_ in zip(offsets, counts, range(len(arrs))):
+        h = image_hash(arrs[k_])
+        out[off:off + n] = [pads[k_] if (j & 1) == 0 else int((h >> 17) % max(1, V - 1)) for j in range(n)]
+    mm: Dict[str, Any] = {"image_offsets": offsets, "image_token_counts": counts, "pad_values": pads, "num_image_tokens": 0,
+                          "grid_thw": [list(g) for _, g in pp], "mrope_positions": pos, "mrope_delta": int(delta)}
+    patches = np.concatenate([p for p, _ in pp]) if pp else np.zeros((0, 3 * tps * patch * patch), np.float32)
+    if encoder is not None:
+        raise NotImplementedError("EPD for dynamic-resolution towers is not wired yet")
+    mm["pixel_patches"] = patches
+    return out, mm
+
+
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
+    if cfg.architecture.startswith("Qwen2VL"):
+        return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
+    return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)
+
+
+def _process_images_clip(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
     """returns (expanded ids, mm_inputs).  mm_inputs: pixel_values [N,3,S,S] float32 (nested lists for IPC),
     image_offsets (start index of every image's pad run), pad_values, num_image_tokens."""
     v = cfg.vision
