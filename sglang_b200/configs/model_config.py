@@ -92,7 +92,9 @@ class ModelConfig:
     @property
     def eos_token_ids(self) -> List[int]:
         e = self.eos_token_id
-        return list(e) if isinstance(e, (list, tuple)) else [int(e)]
+        if e is None:          # config.json without an EOS id (generation_config.json / the tokenizer supply it): nothing stops on its own
+            return []
+        return [int(x) for x in e] if isinstance(e, (list, tuple)) else [int(e)]
 
     @property
     def is_moe(self) -> bool:
@@ -269,7 +271,12 @@ _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_loca
 _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
                   "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),
                   "GPTNeoXForCausalLM": dict(parallel_residual=True, hidden_act="gelu"),
-                  "Starcoder2ForCausalLM": dict(hidden_act="gelu_pytorch_tanh")}
+                  "Starcoder2ForCausalLM": dict(hidden_act="gelu_pytorch_tanh"),
+                  "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
+                  "Qwen2VLForConditionalGeneration": dict(attention_bias=True),
+                  "DeepseekV3ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", rope_is_neox=False),
+                  "DeepseekV2ForCausalLM": dict(rope_is_neox=False),
+                  "Qwen3ForCausalLM": dict(qk_norm=True), "Qwen3MoeForCausalLM": dict(qk_norm=True)}
 
 
 def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = None, context_length: Optional[int] = None) -> ModelConfig:
@@ -297,7 +304,9 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         if isinstance(rp, dict):
             if rp.get("rope_theta") is not None:
                 text.setdefault("rope_theta", rp["rope_theta"])
-            sc = {k: v for k, v in rp.items() if k != "rope_theta"}
+            if rp.get("partial_rotary_factor") is not None:
+                text.setdefault("partial_rotary_factor", rp["partial_rotary_factor"])
+            sc = {k: v for k, v in rp.items() if k not in ("rope_theta", "partial_rotary_factor")}
             if text.get("rope_scaling") is None and (sc.get("rope_type", "default") != "default" or "mrope_section" in sc):
                 text["rope_scaling"] = sc
         kw = {k: v for k, v in text.items() if k in fields}
@@ -318,7 +327,18 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                            "d_conv": text.get("conv_kernel", 4), "n_groups": ngroups, "chunk_size": text.get("chunk_size", 64),
                            "use_bias": text.get("use_bias", False), "use_conv_bias": text.get("use_conv_bias", True),
                            "norm_groups": ngroups if arch == "NemotronHForCausalLM" else 1,
-                           "pattern": text.get("hybrid_override_pattern") if arch == "NemotronHForCausalLM" else None}
+                           "pattern": None, "dt_limit": list(text.get("time_step_limit") or (0.0, float("inf")))}
+            if arch == "NemotronHForCausalLM":
+                pat = text.get("hybrid_override_pattern")
+                if not pat and text.get("layers_block_type"):
+                    pat = "".join({"mamba": "M", "attention": "*", "mlp": "-", "moe": "E"}[t] for t in text["layers_block_type"])
+                if pat and "E" in pat:
+                    raise ValueError("Nemotron-H with MoE blocks ('E' in the hybrid pattern) is not supported yet")
+                kw["mamba"]["pattern"] = pat
+                if pat:
+                    kw["num_hidden_layers"] = len(pat)
+                kw["num_local_experts"] = kw["num_experts_per_tok"] = 0
+                kw["mamba"]["use_bias"] = text.get("mamba_proj_bias", text.get("use_bias", False))
             kw["rms_norm_eps"] = text.get("layer_norm_epsilon", text.get("rms_norm_eps", 1e-5))
             kw.setdefault("num_key_value_heads", text.get("num_key_value_heads", kw.get("num_attention_heads", 1)))
             if arch == "NemotronHForCausalLM" and text.get("attention_head_dim"):
@@ -335,7 +355,9 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))
-        kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype", "bfloat16"), "bfloat16")
+        kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype") or hf.get("dtype") or text.get("dtype") or "bfloat16", "bfloat16")
+        if text.get("hidden_activation"):          # Gemma-2 spells it differently
+            kw["hidden_act"] = text["hidden_activation"]
         kw["name"] = os.path.basename(model_path.rstrip("/"))
         kw.update(overrides)
     cfg = ModelConfig(**kw)

@@ -118,6 +118,10 @@ class Mamba2Mixer(nn.Module):
         self.norm_groups = max(1, ng // W)
         self.norm_full_width = ng == 1 and W > 1                # the variance then spans all ranks' channels
         self.eps = cfg.rms_norm_eps
+        num = lambda v, d: float(v) if isinstance(v, (int, float)) else d       # JSON has no literal for infinity: anything else means "unbounded"
+        lim = m.get("dt_limit") or (0.0, float("inf"))
+        lim = (num(lim[0], 0.0), num(lim[1], float("inf")))
+        self.dt_limit = lim if (lim[0] > 0 or lim[1] != float("inf")) else None
         self.out_proj = RowParallelLinear(self.H_total * self.P, cfg.hidden_size, m.get("use_bias", False), True, dtype, None, prefix + ".out_proj")
         for p in self.in_proj.parameters():
             p.requires_grad_(False)
@@ -164,6 +168,8 @@ class Mamba2Mixer(nn.Module):
         di, gn = self.d_inner, self.G * self.N
         z, xBC, dt = zxbcdt.split([di, di + 2 * gn, self.H], dim=-1)
         dt = F.softplus(dt.float() + self.dt_bias)
+        if self.dt_limit is not None:
+            dt = dt.clamp(self.dt_limit[0], self.dt_limit[1])
         A = -torch.exp(self.A_log)
         rep = self.H // self.G
         slots = fb.req_slots.long()
@@ -327,7 +333,8 @@ class NemotronHForCausalLM(nn.Module):
     @staticmethod
     def remap(name: str) -> str:
         name = name.replace("backbone.", "model.", 1) if name.startswith("backbone.") else name
-        return name.replace("model.embeddings.", "model.embed_tokens.").replace("model.norm_f.", "model.norm.")
+        return name.replace("model.embeddings.", "model.embed_tokens.").replace("model.embedding.", "model.embed_tokens.").replace(
+            "model.norm_f.", "model.norm.")
 
     def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
         params = dict(self.named_parameters())
