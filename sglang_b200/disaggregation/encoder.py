@@ -82,6 +82,8 @@ class VisionEncoder:
         from ..model_loader.loader import iter_safetensors
 
         for name, w in iter_safetensors(model_path):
+            if name.startswith(("model.vision_tower", "model.multi_modal_projector")):
+                name = name[len("model."):]
             if not (name.startswith("vision_tower") or name.startswith("multi_modal_projector")):
                 continue
             n = name.replace("vision_tower.vision_model.embeddings.", "vision_tower.").replace(

@@ -98,8 +98,15 @@ class LlavaForConditionalGeneration(LlamaForCausalLM):
         rest, loaded = [], []
         for name, w in weights:
             n = name
+            # checkpoint dialects: llava-1.5-hf ("language_model.model.*", "vision_tower.*", "multi_modal_projector.*") and the newer
+            # transformers layout that nests all three under "model."
+            for pre in ("vision_tower.", "multi_modal_projector.", "language_model."):
+                if n.startswith("model." + pre):
+                    n = n[len("model."):]
+                    break
             if n.startswith("language_model."):
-                rest.append((n[len("language_model."):], w))
+                n = n[len("language_model."):]
+                rest.append((n if n.startswith(("model.", "lm_head.")) else "model." + n, w))
                 continue
             n = n.replace("vision_tower.vision_model.embeddings.", "vision_tower.").replace(
                 "vision_tower.vision_model.encoder.layers.", "vision_tower.layers.").replace(

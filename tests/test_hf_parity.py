@@ -98,3 +98,41 @@ def test_family_matches_hf(name, tmp_path):
     n = len(ids)
     for j, tok in enumerate(o["output_ids"]):
         assert abs(float(lp[n - 1 + j, tok]) - dec[j]) < 3e-3, (name, j)
+
+
+def test_llava_matches_hf(tmp_path):
+    """LLaVA-1.5 layout: CLIP tower (feature layer -2, CLS dropped) + 2-layer projector + Llama; preprocessing, image-row splicing and the
+    checkpoint dialect of the installed transformers"""
+    from sglang_b200.multimodal import processor as P
+
+    torch.manual_seed(0)
+    cfg = tf.LlavaConfig(text_config=dict(model_type="llama", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                          num_key_value_heads=2, vocab_size=512, max_position_embeddings=1024, rope_theta=10000.0),
+                         vision_config=dict(model_type="clip_vision_model", hidden_size=32, intermediate_size=64, num_hidden_layers=3,
+                                            num_attention_heads=2, image_size=28, patch_size=14, projection_dim=32),
+                         image_token_index=500, vision_feature_layer=-2, vision_feature_select_strategy="default", projector_hidden_act="gelu")
+    hf = tf.LlavaForConditionalGeneration(cfg).float().eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.08)
+    d = str(tmp_path / "llava")
+    hf.save_pretrained(d, safe_serialization=True)
+    img = np.random.default_rng(0).integers(0, 255, size=(40, 50, 3), dtype=np.uint8)
+    ids = [5, 6, 500, 7, 8, 9]
+    e = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error", disable_radix_cache=True)
+    o = e.generate(input_ids=ids, image_data=[img], sampling_params={"max_new_tokens": 4, "temperature": 0, "ignore_eos": True},
+                   return_logprob=True, logprob_start_len=0)
+    ex, mm = P.process_images(ids, [img], e.model_config, None)
+    e.shutdown()
+    hf_ids, n = list(ex), mm["num_image_tokens"]
+    for off in mm["image_offsets"]:
+        hf_ids[off:off + n] = [500] * n
+    full = hf_ids + o["output_ids"]
+    with torch.no_grad():
+        lp = torch.log_softmax(hf(input_ids=torch.tensor([full]), pixel_values=torch.tensor(mm["pixel_values"])).logits[0].float(), -1)
+    got = [v for v, _, _ in o["meta_info"]["input_token_logprobs"][1:]]
+    ref = [float(lp[t, full[t + 1]]) for t in range(len(hf_ids) - 1)]
+    assert max(abs(ref[t] - got[t]) for t in range(len(hf_ids) - 1) if hf_ids[t + 1] != 500) < 2e-3
+    dec = [v for v, _, _ in o["meta_info"]["output_token_logprobs"]]
+    assert max(abs(float(lp[len(hf_ids) - 1 + j, tok]) - dec[j]) for j, tok in enumerate(o["output_ids"])) < 2e-3
