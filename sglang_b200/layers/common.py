@@ -60,6 +60,7 @@ class RadixAttention(nn.Module):
         self.rope = rope
         self.window = sliding_window
         self.logit_cap = logit_cap
+        self.sinks = None            # [num_heads] fp32 learned attention sinks (GPT-OSS), see forward
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fb: ForwardBatch, nslabs: int = 1,
                 slab_stride: int = 0) -> torch.Tensor:
@@ -90,7 +91,7 @@ class RadixAttention(nn.Module):
             from .cp import gather_write_kv
 
             gather_write_kv(get_cp_group(), cp, out_loc, kc, vc)
-        sinks = getattr(self, "sinks", None)
+        sinks = self.sinks
         lse = torch.empty(T, self.num_heads, dtype=torch.float32, device=q3.device) if sinks is not None else None
         o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
