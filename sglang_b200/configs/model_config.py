@@ -64,6 +64,14 @@ class ModelConfig:
     scoring_func: str = "softmax"
     topk_method: str = "greedy"
     swiglu_limit: Optional[float] = None        # GPT-OSS clamped SwiGLU
+    # Llama-variant switches (SeedOss / Ernie-4.5 / Helium / Arcee / SmolLM3 / OLMo-3 / GLM / Gemma-3 / Cohere / Nemotron ...)
+    attention_out_bias: Optional[bool] = None   # o_proj bias (defaults to no bias)
+    mlp_gated: bool = True                      # False: up_proj -> act -> down_proj (Arcee, Nemotron)
+    no_rope_layers: Optional[List[int]] = None  # SmolLM3: 0 = this layer applies no rotary embedding
+    rope_local_base_freq: Optional[float] = None   # Gemma-3: rope base of the sliding-window layers
+    logit_scale: Optional[float] = None         # Cohere
+    norm_type: str = "rms"                      # rms | layernorm (Cohere: weight only) | layernorm1p (Nemotron: 1 + weight, bias)
+    use_qk_norm: bool = False                   # Cohere-2 style flag in HF configs
     # Gemma-2 / Granite extras
     query_pre_attn_scalar: Optional[float] = None
     layer_types: Optional[List[str]] = None
@@ -84,6 +92,8 @@ class ModelConfig:
     name: str = ""
 
     def __post_init__(self) -> None:
+        self.attn_logit_softcapping = float(self.attn_logit_softcapping or 0.0)        # HF writes an explicit null for "off"
+        self.final_logit_softcapping = float(self.final_logit_softcapping or 0.0)
         if self.head_dim is None:
             self.head_dim = self.hidden_size // self.num_attention_heads
         if self.moe_intermediate_size is None:
@@ -260,7 +270,9 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                          max_position_embeddings=4096, rope_theta=10000.0, image_token_id=32000, vision=_CLIP_L_336),
 }
 
-_HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM"}
+_HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM", "SeedOssForCausalLM": "LlamaForCausalLM", "HeliumForCausalLM": "LlamaForCausalLM",
+                "Ernie4_5ForCausalLM": "LlamaForCausalLM", "ArceeForCausalLM": "LlamaForCausalLM", "SmolLM3ForCausalLM": "LlamaForCausalLM",
+                "Ministral3ForCausalLM": "LlamaForCausalLM", "Olmo3ForCausalLM": "Olmo2ForCausalLM", "KimiK2ForCausalLM": "DeepseekV3ForCausalLM"}
 # HF config keys that differ from our field names
 _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts", "n_embd": "hidden_size", "n_layer": "num_hidden_layers",
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
@@ -274,6 +286,14 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Starcoder2ForCausalLM": dict(hidden_act="gelu_pytorch_tanh"),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True),
+                  "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
+                  "OlmoeForCausalLM": dict(norm_topk_prob=False),
+                  "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
+                  "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"),
+                  "GlmForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
+                  "Glm4ForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
+                  "NemotronForCausalLM": dict(mlp_gated=False, hidden_act="relu2", norm_type="layernorm1p", partial_rotary_factor=0.5),
+                  "CohereForCausalLM": dict(norm_type="layernorm", rope_is_neox=False, tie_word_embeddings=True, logit_scale=0.0625),
                   "DeepseekV3ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", rope_is_neox=False),
                   "DeepseekV2ForCausalLM": dict(rope_is_neox=False),
                   "Qwen3ForCausalLM": dict(qk_norm=True), "Qwen3MoeForCausalLM": dict(qk_norm=True)}
@@ -301,6 +321,11 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         fields = {f.name for f in dataclasses.fields(ModelConfig)}
         text = {_HF_KEY_MAP.get(k, k): v for k, v in text.items()}
         rp = text.get("rope_parameters")          # transformers >= 5: theta and scaling live in one dict
+        if isinstance(rp, dict) and "full_attention" in rp:      # Gemma-3: one entry per layer type
+            loc = rp.get("sliding_attention") or {}
+            if loc.get("rope_theta") is not None:
+                text.setdefault("rope_local_base_freq", loc["rope_theta"])
+            rp = rp["full_attention"]
         if isinstance(rp, dict):
             if rp.get("rope_theta") is not None:
                 text.setdefault("rope_theta", rp["rope_theta"])
@@ -356,6 +381,12 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))
         kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype") or hf.get("dtype") or text.get("dtype") or "bfloat16", "bfloat16")
+        if arch == "Ernie4_5ForCausalLM" and text.get("use_bias") is not None:
+            kw["attention_bias"] = kw["attention_out_bias"] = kw["mlp_bias"] = bool(text["use_bias"])
+        if arch in ("NemotronForCausalLM",) and text.get("norm_eps") is not None:
+            kw["rms_norm_eps"] = text["norm_eps"]
+        if text.get("use_sliding_window") is False:       # Qwen2 / SmolLM3 ship a window size next to a switch that disables it
+            kw["sliding_window"] = None
         if text.get("hidden_activation"):          # Gemma-2 spells it differently
             kw["hidden_act"] = text["hidden_activation"]
         kw["name"] = os.path.basename(model_path.rstrip("/"))

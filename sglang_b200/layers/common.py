@@ -136,6 +136,17 @@ def _radix_forward_dcp(self, q3, kc, vc, fb, dcp, pool):
 RadixAttention._forward_dcp = _radix_forward_dcp
 
 
+def get_act(name: str):
+    """plain (non-gated) activations"""
+    import torch.nn.functional as F
+
+    if name == "relu2":
+        return lambda x: torch.relu(x).square()
+    if name in ("gelu_pytorch_tanh", "gelu_tanh", "gelu_new", "gelu_fast"):
+        return lambda x: F.gelu(x, approximate="tanh")
+    return {"gelu": F.gelu, "relu": torch.relu, "silu": F.silu}[name]
+
+
 def get_act_and_mul(name: str):
     if name == "silu":
         return ops.silu_and_mul

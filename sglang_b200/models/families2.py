@@ -1,0 +1,259 @@
+"""More decoder families on the shared Llama skeleton: GLM / GLM-4, Gemma-3 (text), Cohere (Command-R), OLMoE, Nemotron (dense).
+
+Parity: reference ``python/sglang/srt/models/{glm4,gemma3_causal,commandr,olmoe,nemotron}.py``.  Every class here is checked against the Hugging Face
+implementation in ``tests/test_hf_parity.py`` (tiny random model -> ``save_pretrained`` -> served from disk).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..configs.model_config import ModelConfig
+from ..layers.common import RMSNorm, RotaryEmbedding
+from ..layers.linear import ReplicatedLinear
+from ..layers.moe import FusedMoE
+from ..model_executor.forward_batch import ForwardBatch
+from ..parallel.parallel_state import get_tp_group
+from .llama import LlamaAttention, LlamaDecoderLayer, LlamaForCausalLM, LlamaMLP, _layer_id
+
+
+def _resolve(y):
+    return y.resolve() if hasattr(y, "resolve") else y
+
+
+def _gid(prefix: str) -> int:
+    return int(prefix.rsplit(".", 1)[1])
+
+
+# ---------------------------------------------------------------- GLM / GLM-4 (fused gate_up in the checkpoint, sandwich norms in GLM-4)
+class GlmForCausalLM(LlamaForCausalLM):
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        def split():
+            for name, w in weights:
+                if ".mlp.gate_up_proj." in name:        # [gate; up] stacked on the output dim
+                    g, u = w.chunk(2, dim=0)
+                    yield name.replace("gate_up_proj", "gate_proj"), g
+                    yield name.replace("gate_up_proj", "up_proj"), u
+                else:
+                    yield name, w
+        return super().load_weights(split())
+
+
+class Glm4DecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        self.post_self_attn_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.post_mlp_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        a = _resolve(self.self_attn(self.input_layernorm(h), fb))
+        h = h + self.post_self_attn_layernorm(a)
+        m = _resolve(self.mlp(self.post_attention_layernorm(h)))
+        return h + self.post_mlp_layernorm(m), None
+
+
+class Glm4ForCausalLM(GlmForCausalLM):
+    decoder_layer_cls = Glm4DecoderLayer
+
+
+# ---------------------------------------------------------------- Gemma-3 text (per-head q/k norm, local/global rope bases, sandwich norms)
+class Gemma3DecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        self.pre_feedforward_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, True)
+        self.post_feedforward_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, True)
+        sa = self.self_attn
+        sa.qk_norm = True
+        sa.q_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype, True)
+        sa.k_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype, True)
+        gid = _gid(prefix)
+        kinds = cfg.layer_types or ["full_attention" if (i + 1) % 6 == 0 else "sliding_attention" for i in range(cfg.num_hidden_layers)]
+        local = kinds[gid] == "sliding_attention"
+        sa.attn.window = cfg.sliding_window if (local and cfg.sliding_window) else -1
+        if local and cfg.rope_local_base_freq:
+            sa.attn.rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_local_base_freq, None, cfg.rope_is_neox, 1.0,
+                                           rope.cos_sin.device)
+        if cfg.query_pre_attn_scalar:
+            sa.attn.scale = float(cfg.query_pre_attn_scalar) ** -0.5
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        a = _resolve(self.self_attn(self.input_layernorm(h), fb))
+        h = h + self.post_attention_layernorm(a)
+        m = _resolve(self.mlp(self.pre_feedforward_layernorm(h)))
+        return h + self.post_feedforward_layernorm(m), None
+
+
+class Gemma3ForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = Gemma3DecoderLayer
+
+    def load_weights(self, weights):
+        return super().load_weights((n[len("language_model."):] if n.startswith("language_model.") else n, w) for n, w in weights)
+
+
+# ---------------------------------------------------------------- Cohere / Command-R (mean-centred LayerNorm, parallel block, logit scale)
+class CohereNorm(nn.Module):
+    def __init__(self, shape, eps: float, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(shape, dtype=dtype), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        f = x.float()
+        f = f - f.mean(-1, keepdim=True)
+        return (f * torch.rsqrt(f.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight.float()).to(x.dtype)
+
+
+class CohereAttention(LlamaAttention):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix)
+        self.use_qk = bool(cfg.use_qk_norm)
+        if self.use_qk:
+            self.q_norm = CohereNorm((self.attn.num_heads, cfg.head_dim), cfg.rms_norm_eps, dtype)
+            self.k_norm = CohereNorm((self.attn.num_kv_heads, cfg.head_dim), cfg.rms_norm_eps, dtype)
+        self.qk_norm = False
+
+    def forward(self, x: torch.Tensor, fb: ForwardBatch):
+        if not self.use_qk:
+            return super().forward(x, fb)
+        T = x.shape[0]
+        q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        q = self.q_norm(q.reshape(T, self.attn.num_heads, self.head_dim)).reshape(T, self.q_size)
+        k = self.k_norm(k.reshape(T, self.attn.num_kv_heads, self.head_dim)).reshape(T, self.kv_size)
+        return self.o_proj(self.attn(q, k, v.contiguous(), fb))
+
+
+class CohereDecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        self.self_attn = CohereAttention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
+        self.input_layernorm = CohereNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        del self.post_attention_layernorm
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        x = self.input_layernorm(h)
+        return h + _resolve(self.self_attn(x, fb)) + _resolve(self.mlp(x)), None
+
+
+class CohereForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = CohereDecoderLayer
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        self.model.norm = CohereNorm(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype)
+
+    def compute_logits(self, hidden: torch.Tensor, key: str = "logits") -> torch.Tensor:
+        y = super().compute_logits(hidden, key)
+        return y * float(self.cfg.logit_scale) if self.cfg.logit_scale else y
+
+    def load_weights(self, weights):
+        tp = get_tp_group()
+
+        def fix():
+            for n, w in weights:
+                if n.endswith(("q_norm.weight", "k_norm.weight")) and w.dim() == 2 and tp.world_size > 1:       # [heads, head_dim]: shard heads
+                    per = max(1, w.shape[0] // tp.world_size)
+                    w = w[(tp.rank * per) % w.shape[0]:(tp.rank * per) % w.shape[0] + per]
+                yield n, w
+        return super().load_weights(fix())
+
+
+# ---------------------------------------------------------------- OLMoE (full-width q/k RMSNorm + softmax top-k experts)
+class OlmoeMoE(nn.Module):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, prefix: str):
+        super().__init__()
+        from .mixtral import _EP_SIZE
+
+        self.gate = ReplicatedLinear(cfg.hidden_size, cfg.num_local_experts, False, dtype, None, prefix + ".gate")
+        self.experts = FusedMoE(cfg.num_local_experts, cfg.num_experts_per_tok, cfg.hidden_size, cfg.moe_intermediate_size, dtype,
+                                cfg.norm_topk_prob, _EP_SIZE["v"], quant, layer_id)
+
+    def forward(self, x):
+        return self.experts(x, self.gate(x))
+
+
+class OlmoeDecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        from .families import Olmo2Attention
+
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, OlmoeMoE)
+        self.self_attn = Olmo2Attention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
+
+
+class OlmoeForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = OlmoeDecoderLayer
+
+    def _mlp_cls(self):
+        return OlmoeMoE
+
+    def load_weights(self, weights):
+        mods = dict(self.named_modules())
+        rest, loaded = [], []
+        for name, w in weights:
+            if ".mlp.experts." in name:
+                lid = _layer_id(name)
+                if not (self.model.start_layer <= lid < self.model.end_layer):
+                    continue
+                mod = mods[f"model.layers.{lid - self.model.start_layer}.mlp.experts"]
+                tail = name.split(".experts.")[1]
+                if tail.split(".")[0].isdigit():                      # per-expert tensors
+                    eid, proj = int(tail.split(".")[0]), tail.split(".")[1]
+                    shard = {"gate_proj": "w1", "up_proj": "w3", "down_proj": "w2"}[proj]
+                    mod.weight_loader(mod.w2 if shard == "w2" else mod.w13, w, eid, shard)
+                elif tail.startswith("gate_up_proj"):                 # stacked [E, 2I, H]
+                    for e in range(w.shape[0]):
+                        g, u = w[e].chunk(2, dim=0)
+                        mod.weight_loader(mod.w13, g, e, "w1")
+                        mod.weight_loader(mod.w13, u, e, "w3")
+                elif tail.startswith("down_proj"):                    # stacked [E, H, I]
+                    for e in range(w.shape[0]):
+                        mod.weight_loader(mod.w2, w[e], e, "w2")
+                loaded.append(name)
+            else:
+                rest.append((name, w))
+        return loaded + super().load_weights(rest)
+
+
+# ---------------------------------------------------------------- Nemotron (dense): LayerNorm1P, partial rotary, squared-ReLU MLP
+class LayerNorm1P(nn.Module):
+    def __init__(self, n: int, eps: float, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(n, dtype=dtype), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(n, dtype=dtype), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x, residual=None):
+        if residual is not None:
+            x = x + residual
+            residual = x
+        y = F.layer_norm(x.float(), (x.shape[-1],), self.weight.float() + 1.0, self.bias.float(), self.eps).to(x.dtype)
+        return y if residual is None else (y, residual)
+
+
+class NemotronDecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        self.input_layernorm = LayerNorm1P(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.post_attention_layernorm = LayerNorm1P(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        h = h + _resolve(self.self_attn(self.input_layernorm(h), fb))
+        return h + _resolve(self.mlp(self.post_attention_layernorm(h))), None
+
+
+class NemotronForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = NemotronDecoderLayer
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        self.model.norm = LayerNorm1P(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype)

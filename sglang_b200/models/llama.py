@@ -42,6 +42,11 @@ class LlamaMLP(nn.Module):
         self.act = get_act_and_mul(cfg.hidden_act)
         self.fuse_silu = cfg.hidden_act == "silu" and not cfg.mlp_bias
 
+    def __new__(cls, cfg: ModelConfig, *a, **kw):
+        if cls is LlamaMLP and not cfg.mlp_gated:
+            return super().__new__(PlainMLP)
+        return super().__new__(cls)
+
     def forward(self, x):
         if self.fuse_silu and x.dim() == 2 and _skinny_allowed(self.gate_up_proj, x):
             # decode shapes: ONE tcgen05 kernel for gate_up_proj + SiLU*mul ([gate; up] rows paired inside each tile)
@@ -51,26 +56,47 @@ class LlamaMLP(nn.Module):
         return self.down_proj(h, defer_reduce=True)
 
 
+class PlainMLP(LlamaMLP):
+    """non-gated MLP (Arcee, Nemotron): up_proj -> activation -> down_proj"""
+
+    def __init__(self, cfg: ModelConfig, dtype, quant, prefix: str):
+        nn.Module.__init__(self)
+        from ..layers.common import get_act
+        from ..layers.linear import ColumnParallelLinear
+
+        self.up_proj = ColumnParallelLinear(cfg.hidden_size, cfg.intermediate_size, cfg.mlp_bias, False, dtype, quant, prefix + ".up_proj")
+        self.down_proj = RowParallelLinear(cfg.intermediate_size, cfg.hidden_size, cfg.mlp_bias, True, dtype, quant, prefix + ".down_proj")
+        self.act = get_act(cfg.hidden_act)
+
+    def forward(self, x):
+        return self.down_proj(self.act(self.up_proj(x)), defer_reduce=True)
+
+
 class LlamaAttention(nn.Module):
     def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope: RotaryEmbedding, prefix: str):
         super().__init__()
         atp = get_attn_tp_group()          # == the TP group unless DP-attention is on
         self.qkv_proj = QKVParallelLinear(cfg.hidden_size, cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads,
                                           cfg.attention_bias, dtype, quant, prefix + ".qkv_proj", tp_group=atp)
-        self.o_proj = RowParallelLinear(cfg.num_attention_heads * cfg.head_dim, cfg.hidden_size, False, True, dtype, quant,
+        self.o_proj = RowParallelLinear(cfg.num_attention_heads * cfg.head_dim, cfg.hidden_size, bool(cfg.attention_out_bias), True, dtype, quant,
                                         prefix + ".o_proj", tp_group=atp)
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         self.head_dim = cfg.head_dim
         self.qk_norm = cfg.qk_norm
+        gid = int(prefix.split(".layers.")[1].split(".")[0]) if ".layers." in prefix else layer_id      # global layer index
+        if cfg.no_rope_layers is not None and gid < len(cfg.no_rope_layers) and not cfg.no_rope_layers[gid]:
+            rope = None                                                                                  # SmolLM3 NoPE layers
         if cfg.qk_norm:
             self.q_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
             self.k_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
         window = cfg.sliding_window if (cfg.sliding_window and cfg.sliding_window > 0) else -1
+        if cfg.layer_types is not None and gid < len(cfg.layer_types) and cfg.layer_types[gid] != "sliding_attention":
+            window = -1
         self.attn = RadixAttention(self.qkv_proj.num_heads, cfg.head_dim, self.qkv_proj.num_kv_heads, layer_id,
                                    rope=rope, sliding_window=window, logit_cap=cfg.attn_logit_softcapping)
 
     def forward(self, x: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
-        if not self.qk_norm and self.attn.rope is not None and x.dim() == 2 and _skinny_allowed(self.qkv_proj, x):
+        if not self.qk_norm and self.attn.rope is not None and x.dim() == 2 and _skinny_allowed(self.qkv_proj, x) and self.o_proj.bias is None:
             # decode shapes: split-K QKV GEMM; the RoPE + KV-write kernel folds the partial slabs while it reads q/k/v
             slabs = ops.gemm_skinny_slabs(x, self.qkv_proj.weight, self.qkv_proj.bias)
             q, k, v = slabs[0].split([self.q_size, self.kv_size, self.kv_size], dim=-1)
@@ -184,6 +210,8 @@ class LlamaForCausalLM(nn.Module):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__()
         self.cfg = cfg
+        if not cfg.mlp_gated:       # checkpoints of non-gated MLPs have a real ".up_proj": do not fold it into a gate_up pair
+            self.stacked_params = [t for t in self.stacked_params if t[0] != ".gate_up_proj"]
         self.model = LlamaModel(cfg, quant_name, self._mlp_cls(), device, getattr(self, "decoder_layer_cls", None))
         pp = get_pp_group()
         if pp.is_last:

@@ -41,6 +41,11 @@ def _ensure() -> None:
 
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import families2 as _f2
+
+    for name in ("GlmForCausalLM", "Glm4ForCausalLM", "Gemma3ForCausalLM", "CohereForCausalLM", "OlmoeForCausalLM", "NemotronForCausalLM"):
+        register_model(name, getattr(_f2, name))
+    register_model("Gemma3ForConditionalGeneration", _f2.Gemma3ForCausalLM)      # text tower of the multimodal checkpoint
     from . import qwen2_vl as _qv
 
     register_model("Qwen2VLForConditionalGeneration", _qv.Qwen2VLForConditionalGeneration)

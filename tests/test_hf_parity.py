@@ -30,6 +30,22 @@ CASES = {
                                                                  num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512,
                                                                  hybrid_override_pattern="MM*M", mamba_num_heads=8, mamba_head_dim=16, ssm_state_size=16,
                                                                  conv_kernel=4, n_groups=2, chunk_size=8, tie_word_embeddings=False)),
+    "seed-oss": ("SeedOssConfig", "SeedOssForCausalLM", dict(BASE, head_dim=16, attention_bias=True, attention_out_bias=True)),
+    "helium": ("HeliumConfig", "HeliumForCausalLM", dict(BASE, head_dim=16)),
+    "ernie4.5": ("Ernie4_5Config", "Ernie4_5ForCausalLM", dict(BASE, head_dim=16, use_bias=True)),
+    "arcee": ("ArceeConfig", "ArceeForCausalLM", dict(BASE, head_dim=16)),
+    "smollm3": ("SmolLM3Config", "SmolLM3ForCausalLM", dict(BASE, pad_token_id=0, num_hidden_layers=4, no_rope_layers=[1, 1, 0, 1], use_sliding_window=True,
+                                                            sliding_window=8, layer_types=["full_attention", "sliding_attention"] * 2)),
+    "ministral3": ("Ministral3Config", "Ministral3ForCausalLM", dict(BASE, head_dim=16, sliding_window=None)),
+    "olmo3": ("Olmo3Config", "Olmo3ForCausalLM", dict(BASE, sliding_window=8, layer_types=["sliding_attention", "full_attention"])),
+    "glm": ("GlmConfig", "GlmForCausalLM", dict(BASE, head_dim=16, pad_token_id=0)),
+    "glm4": ("Glm4Config", "Glm4ForCausalLM", dict(BASE, head_dim=16, pad_token_id=0)),
+    "gemma3": ("Gemma3TextConfig", "Gemma3ForCausalLM", dict(BASE, num_hidden_layers=3, head_dim=16, sliding_window=8, query_pre_attn_scalar=16,
+                                                             layer_types=["sliding_attention", "sliding_attention", "full_attention"],
+                                                             tie_word_embeddings=True, rope_local_base_freq=10000.0, rope_theta=1000000.0)),
+    "cohere": ("CohereConfig", "CohereForCausalLM", dict(BASE, pad_token_id=0, use_qk_norm=True, logit_scale=0.25, tie_word_embeddings=True)),
+    "olmoe": ("OlmoeConfig", "OlmoeForCausalLM", dict(BASE, pad_token_id=0, num_experts=4, num_experts_per_tok=2)),
+    "nemotron": ("NemotronConfig", "NemotronForCausalLM", dict(BASE, head_dim=16, partial_rotary_factor=0.5)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
