@@ -284,6 +284,9 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),
                   "GPTNeoXForCausalLM": dict(parallel_residual=True, hidden_act="gelu"),
                   "Starcoder2ForCausalLM": dict(hidden_act="gelu_pytorch_tanh"),
+                  "PhiForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", partial_rotary_factor=0.5),
+                  "GPTJForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", rope_is_neox=False),
+                  "GPTBigCodeForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_pytorch_tanh"),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
@@ -337,6 +340,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         kw = {k: v for k, v in text.items() if k in fields}
         arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
+        kw.setdefault("rope_theta", 10000.0)          # the Hugging Face default when a config does not say (this dataclass defaults to Llama-3's)
         for k, v in _ARCH_DEFAULTS.get(arch, {}).items():
             kw.setdefault(k, v)
         if arch in _ARCH_DEFAULTS:
@@ -385,6 +389,10 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["attention_bias"] = kw["attention_out_bias"] = kw["mlp_bias"] = bool(text["use_bias"])
         if arch in ("NemotronForCausalLM",) and text.get("norm_eps") is not None:
             kw["rms_norm_eps"] = text["norm_eps"]
+        if arch == "GPTJForCausalLM" and text.get("rotary_dim"):
+            kw["partial_rotary_factor"] = text["rotary_dim"] / (kw["hidden_size"] // kw["num_attention_heads"])
+        if arch == "GPTBigCodeForCausalLM":
+            kw["num_key_value_heads"] = 1 if text.get("multi_query", True) else kw["num_attention_heads"]
         if text.get("use_sliding_window") is False:       # Qwen2 / SmolLM3 ship a window size next to a switch that disables it
             kw["sliding_window"] = None
         if text.get("hidden_activation"):          # Gemma-2 spells it differently

@@ -79,11 +79,13 @@ class ClassicLayer(nn.Module):
         self.self_attn = ClassicAttention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
         self.mlp = ClassicMLP(cfg, dtype, quant, prefix + ".mlp")
         self.parallel = bool(cfg.parallel_residual)
+        self.shared_ln = cfg.norm_type == "shared_layernorm"       # Phi / GPT-J: ONE LayerNorm feeds both branches of the parallel block
 
     def forward(self, x, fb: ForwardBatch):
-        a = self.self_attn(self.input_layernorm(x), fb)
+        n = self.input_layernorm(x)
+        a = self.self_attn(n, fb)
         if self.parallel:
-            return x + a + self.mlp(self.post_attention_layernorm(x))
+            return x + a + self.mlp(n if self.shared_ln else self.post_attention_layernorm(x))
         x = x + a
         return x + self.mlp(self.post_attention_layernorm(x))
 
@@ -136,6 +138,7 @@ class ClassicForCausalLM(nn.Module):
         self.cfg = cfg
         self.model = ClassicModel(cfg, quant_name, device)
         self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, _DT[cfg.dtype])
+        self.lm_head_bias = nn.Parameter(torch.zeros(cfg.vocab_size, dtype=_DT[cfg.dtype]), requires_grad=False)      # Phi / GPT-J (zero otherwise)
 
     def forward(self, fb: ForwardBatch, inputs_embeds=None):
         return self.model(fb, inputs_embeds)
@@ -146,7 +149,7 @@ class ClassicForCausalLM(nn.Module):
         tp = get_tp_group()
         if tp.world_size > 1:
             y = tp.all_gather(y, dim=-1)
-        return y[:, : self.cfg.vocab_size]
+        return y[:, : self.cfg.vocab_size] + self.lm_head_bias
 
     # ---- checkpoint dialects
     def remap(self, name: str, w: torch.Tensor) -> Iterable[Tuple[str, torch.Tensor]]:
@@ -158,6 +161,10 @@ class ClassicForCausalLM(nn.Module):
         loaded: List[str] = []
         for raw_name, raw_w in weights:
             for name, w in self.remap(raw_name, raw_w):
+                if name == "lm_head.bias":
+                    self.lm_head_bias.data.copy_(w[: self.lm_head_bias.shape[0]])
+                    loaded.append(name)
+                    continue
                 if name.startswith("lm_head") and self.lm_head is None:
                     continue
                 target, shard = name, None
@@ -277,3 +284,59 @@ class GPTNeoXForCausalLM(ClassicForCausalLM):
         if "rotary_emb" in name or name.endswith(".attention.bias") or name.endswith(".masked_bias"):
             return
         yield name, w
+
+
+class PhiForCausalLM(ClassicForCausalLM):
+    """phi-1 / phi-2: parallel block with one shared LayerNorm, partial rotary, biased lm_head"""
+
+    def remap(self, name, w):
+        yield name.replace(".self_attn.dense.", ".self_attn.o_proj.").replace("model.final_layernorm.", "model.norm."), w
+
+
+class GPTJForCausalLM(ClassicForCausalLM):
+    def remap(self, name, w):
+        if name.startswith("model."):
+            yield name, w
+            return
+        name = name.replace("transformer.wte.", "model.embed_tokens.").replace("transformer.ln_f.", "model.norm.").replace("transformer.h.", "model.layers.")
+        name = name.replace(".ln_1.", ".input_layernorm.").replace(".attn.out_proj.", ".self_attn.o_proj.").replace(".attn.", ".self_attn.")
+        name = name.replace(".mlp.fc_in.", ".mlp.fc1.").replace(".mlp.fc_out.", ".mlp.fc2.")
+        if name.endswith((".self_attn.bias", ".masked_bias")):
+            return
+        yield name, w
+
+
+class GPTBigCodeForCausalLM(ClassicForCausalLM):
+    """StarCoder-1 / SantaCoder: GPT-2 layout with nn.Linear weights and multi-query attention (fused c_attn = [q | k | v])"""
+
+    def remap(self, name, w):
+        cfg = self.cfg
+        if name.startswith("model."):
+            yield name, w
+            return
+        name = name[len("transformer."):] if name.startswith("transformer.") else name
+        if name == "wte.weight":
+            yield "model.embed_tokens.weight", w
+        elif name == "wpe.weight":
+            yield "model.embed_positions.weight", w
+        elif name.startswith("ln_f."):
+            yield "model.norm." + name[5:], w
+        elif name.startswith("h."):
+            _, lid, rest = name.split(".", 2)
+            p, leaf = f"model.layers.{lid}.", rest.rsplit(".", 1)[1]
+            if rest.startswith("ln_1."):
+                yield p + "input_layernorm." + leaf, w
+            elif rest.startswith("ln_2."):
+                yield p + "post_attention_layernorm." + leaf, w
+            elif rest.startswith("attn.c_attn."):
+                q, kv = cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim
+                for nm, part in zip(("q_proj", "k_proj", "v_proj"), w.split([q, kv, kv], dim=0)):
+                    yield p + f"self_attn.{nm}." + leaf, part
+            elif rest.startswith("attn.c_proj."):
+                yield p + "self_attn.o_proj." + leaf, w
+            elif rest.startswith("mlp.c_fc."):
+                yield p + "mlp.fc1." + leaf, w
+            elif rest.startswith("mlp.c_proj."):
+                yield p + "mlp.fc2." + leaf, w
+        elif name == "lm_head.weight":
+            yield name, w

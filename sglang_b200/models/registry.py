@@ -39,7 +39,8 @@ def _ensure() -> None:
         register_model(name, getattr(_fam, name))
     from . import classic as _cl
 
-    for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM"):
+    for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM", "PhiForCausalLM", "GPTJForCausalLM",
+                 "GPTBigCodeForCausalLM"):
         register_model(name, getattr(_cl, name))
     from . import families2 as _f2
 

@@ -46,6 +46,11 @@ CASES = {
     "cohere": ("CohereConfig", "CohereForCausalLM", dict(BASE, pad_token_id=0, use_qk_norm=True, logit_scale=0.25, tie_word_embeddings=True)),
     "olmoe": ("OlmoeConfig", "OlmoeForCausalLM", dict(BASE, pad_token_id=0, num_experts=4, num_experts_per_tok=2)),
     "nemotron": ("NemotronConfig", "NemotronForCausalLM", dict(BASE, head_dim=16, partial_rotary_factor=0.5)),
+    "phi": ("PhiConfig", "PhiForCausalLM", dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=512,
+                                                max_position_embeddings=512, partial_rotary_factor=0.5)),
+    "gptj": ("GPTJConfig", "GPTJForCausalLM", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512, rotary_dim=8)),
+    "gpt-bigcode": ("GPTBigCodeConfig", "GPTBigCodeForCausalLM", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512, n_inner=128,
+                                                                    multi_query=True)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
