@@ -81,6 +81,8 @@ class ModelConfig:
     logits_scaling: Optional[float] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
     mamba: Optional[Dict[str, Any]] = None
+    # speech encoder of encoder-decoder ASR models (models/whisper.py)
+    audio: Optional[Dict[str, Any]] = None
     # multimodal (LLaVA-style)
     vision: Optional[Dict[str, Any]] = None
     image_token_id: Optional[int] = None
@@ -137,6 +139,11 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                           rope_theta=10000.0, dtype="float32", image_token_id=500, rope_scaling={"type": "mrope", "mrope_section": [2, 3, 3]},
                           vision={"embed_dim": 32, "depth": 2, "num_heads": 2, "hidden_size": 64, "mlp_ratio": 2, "patch_size": 14,
                                   "spatial_merge_size": 2, "temporal_patch_size": 2, "min_pixels": 28 * 28, "max_pixels": 28 * 28 * 12}),
+    "tiny-whisper": dict(architecture="WhisperForConditionalGeneration", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=4, head_dim=16, vocab_size=512, max_position_embeddings=128, pos_emb="learned",
+                         hidden_act="gelu", tie_word_embeddings=True, dtype="float32",
+                         audio={"d_model": 64, "encoder_layers": 2, "encoder_attention_heads": 4, "encoder_ffn_dim": 128, "num_mel_bins": 80,
+                                "max_source_positions": 100, "chunk_length": 2}),
     "tiny-gpt-oss": dict(architecture="GptOssForCausalLM", hidden_size=64, intermediate_size=32, moe_intermediate_size=32, num_hidden_layers=4,
                          num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512, dtype="float32",
                          num_local_experts=4, num_experts_per_tok=2, sliding_window=8, attention_bias=True, swiglu_limit=7.0, rope_theta=150000.0,
@@ -372,6 +379,13 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", text.get("num_key_value_heads", kw.get("num_attention_heads", 1)))
             if arch == "NemotronHForCausalLM" and text.get("attention_head_dim"):
                 kw["head_dim"] = text["attention_head_dim"]
+        if arch == "WhisperForConditionalGeneration":
+            kw.update(hidden_size=hf["d_model"], num_hidden_layers=hf["decoder_layers"], num_attention_heads=hf["decoder_attention_heads"],
+                      num_key_value_heads=hf["decoder_attention_heads"], intermediate_size=hf["decoder_ffn_dim"],
+                      max_position_embeddings=hf.get("max_target_positions", 448), hidden_act=hf.get("activation_function", "gelu"),
+                      rms_norm_eps=1e-5, pos_emb="learned", tie_word_embeddings=True, head_dim=hf["d_model"] // hf["decoder_attention_heads"])
+            kw["audio"] = {k: hf[k] for k in ("d_model", "encoder_layers", "encoder_attention_heads", "encoder_ffn_dim", "num_mel_bins",
+                                              "max_source_positions")}
         if arch == "Qwen2VLForConditionalGeneration":
             vc = hf["vision_config"]
             kw["vision"] = {"embed_dim": vc.get("embed_dim", 1280), "depth": vc.get("depth", 32), "num_heads": vc.get("num_heads", 16),

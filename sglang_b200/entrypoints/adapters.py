@@ -11,12 +11,13 @@ sampling params, tool calls and streaming stay in ``OpenAIServing``) and transla
 from __future__ import annotations
 
 import json
+import re
 import time
 import uuid
 from typing import Any, AsyncIterator, Dict, List, Optional
 
 from fastapi import Request
-from fastapi.responses import JSONResponse, StreamingResponse
+from fastapi.responses import JSONResponse, PlainTextResponse, StreamingResponse
 
 from .openai import protocol as P
 
@@ -160,8 +161,69 @@ def _ollama_options(body: Dict[str, Any]) -> Dict[str, Any]:
     return kw
 
 
+def parse_multipart(body: bytes, content_type: str) -> Dict[str, Any]:
+    """minimal multipart/form-data reader (no python-multipart in the image): {field: str | bytes (file parts)}"""
+    m = re.search(r'boundary="?([^";]+)"?', content_type or "")
+    if not m:
+        raise ValueError("multipart body without a boundary")
+    out: Dict[str, Any] = {}
+    for part in body.split(b"--" + m.group(1).encode()):
+        part = part.strip(b"\r\n")
+        if not part or part == b"--" or b"\r\n\r\n" not in part:
+            continue
+        head, data = part.split(b"\r\n\r\n", 1)
+        hd = head.decode("utf-8", "replace")
+        nm = re.search(r'name="([^"]*)"', hd)
+        if not nm:
+            continue
+        out[nm.group(1)] = data if "filename=" in hd else data.decode("utf-8", "replace")
+    return out
+
+
+def _whisper_prompt_ids(tokenizer: Any, language: Optional[str], task: str = "transcribe") -> List[int]:
+    toks = ["<|startoftranscript|>"] + ([f"<|{language}|>"] if language else []) + [f"<|{task}|>", "<|notimestamps|>"]
+    ids = tokenizer.convert_tokens_to_ids(toks)
+    if any(i is None for i in ids):
+        raise ValueError("the tokenizer has no Whisper control tokens; pass prompt_ids")
+    return [int(i) for i in ids]
+
+
 def install_adapters(app: Any, engine: Any, serving: Any) -> None:
     model_name = engine.server_args.served_model_name
+
+    # ----- speech to text (reference entrypoints/openai/serving_transcription.py)
+    @app.post("/v1/audio/transcriptions")
+    async def transcriptions(request: Request):
+        ctype = request.headers.get("content-type", "")
+        raw = await request.body()
+        try:
+            if ctype.startswith("multipart/"):
+                form = parse_multipart(raw, ctype)
+                audio = form.get("file")
+            else:
+                form = json.loads(raw or b"{}")
+                audio = form.get("audio") or form.get("file")
+            if audio is None:
+                raise ValueError("no audio: send a multipart 'file' part or a JSON 'audio' (base64 WAV)")
+            if engine.model_config.audio is None:
+                raise ValueError(f"{model_name} is not a speech model")
+            ids = form.get("prompt_ids")
+            if isinstance(ids, str):
+                ids = json.loads(ids)
+            if ids is None:
+                ids = _whisper_prompt_ids(engine.tokenizer, form.get("language") or "en")
+            sp = {"max_new_tokens": int(form.get("max_tokens") or engine.model_config.max_position_embeddings - len(ids) - 1),
+                  "temperature": float(form.get("temperature") or 0.0)}
+            o = await engine.async_generate(input_ids=[int(i) for i in ids], sampling_params=sp, audio_data=audio)
+        except (ValueError, KeyError, TypeError) as e:
+            return JSONResponse({"error": {"message": str(e), "type": "invalid_request_error"}}, status_code=400)
+        text = o.get("text")
+        if text is None and engine.tokenizer is not None:
+            text = engine.tokenizer.decode(o["output_ids"], skip_special_tokens=True)
+        if (form.get("response_format") or "json") == "text":
+            return PlainTextResponse(text or "")
+        return {"text": text or "", "output_ids": o["output_ids"], "usage": {"type": "tokens", "input_tokens": o["meta_info"]["prompt_tokens"],
+                                                                            "output_tokens": o["meta_info"]["completion_tokens"]}}
 
     # ----- Anthropic
     @app.post("/v1/messages")

@@ -169,6 +169,10 @@ class Engine:
             from ..multimodal.processor import process_images
 
             ids, mm = process_images(ids, g.image_data, self.model_config, self.tokenizer, self._encoder_client())
+        if g.audio_data is not None and self.model_config.audio is not None:
+            from ..multimodal.audio import process_audio
+
+            mm = process_audio(g.audio_data, self.model_config)
         SamplingParams.from_dict(sp).verify(self.model_config.vocab_size)
         return ios.TokenizedGenerateReqInput(
             rid=g.rid or self._new_rid(), input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),
@@ -314,8 +318,8 @@ class Engine:
                  return_logprob: Union[bool, List[bool]] = False, logprob_start_len: Union[int, List[int]] = -1,
                  top_logprobs_num: Union[int, List[int]] = 0, lora_path: Any = None, stream: bool = False,
                  return_hidden_states: bool = False, rid: Any = None, priority: Optional[int] = None,
-                 session_params: Optional[Dict] = None, extra_key: Optional[str] = None):
-        g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, sampling_params=sampling_params,
+                 session_params: Optional[Dict] = None, extra_key: Optional[str] = None, audio_data: Any = None):
+        g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, audio_data=audio_data, sampling_params=sampling_params,
                                  return_logprob=return_logprob, logprob_start_len=logprob_start_len,
                                  top_logprobs_num=top_logprobs_num, lora_path=lora_path, stream=stream,
                                  return_hidden_states=return_hidden_states, rid=rid, priority=priority,

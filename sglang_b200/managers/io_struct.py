@@ -8,6 +8,8 @@ control messages).  Messages are plain dataclasses serialised as tagged msgpack 
 from __future__ import annotations
 
 import dataclasses
+
+import numpy as np
 import uuid
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Union
@@ -120,11 +122,14 @@ class GenerateReqInput:
             img = self.image_data
             if self.is_batch() and isinstance(img, list) and len(img) == n:
                 img = img[i]
+            aud = self.audio_data
+            if self.is_batch() and isinstance(aud, list) and len(aud) == n and not np.isscalar(aud[0]):
+                aud = aud[i]
             for j in range(par):
                 sp_ij = dict(sp_i)
                 sp_ij["n"] = 1
                 r = dataclasses.replace(
-                    self, text=texts[i], input_ids=ids[i], sampling_params=sp_ij, image_data=img,
+                    self, text=texts[i], input_ids=ids[i], sampling_params=sp_ij, image_data=img, audio_data=aud,
                     rid=(rid if (rid and par == 1) else (f"{rid}-{j}" if rid else None)),     # None: the engine assigns (SPMD-consistent) ids
                     return_logprob=pick(self.return_logprob, i), logprob_start_len=pick(self.logprob_start_len, i),
                     top_logprobs_num=pick(self.top_logprobs_num, i), lora_path=pick(self.lora_path, i),

@@ -528,6 +528,9 @@ class ModelRunner:
             return
         if getattr(self.model, "is_mrope", False):
             self._attach_mrope(sb, fb)
+        if hasattr(self.model, "prepare_batch"):       # encoder-decoder models: run the encoder of requests that start here (models/whisper.py)
+            self.model.prepare_batch(sb, fb, self)
+            return
         if not any(r.mm_inputs for r in sb.reqs):
             return
         from ..multimodal.embed import build_mm_embeds
