@@ -493,6 +493,12 @@ class Engine:
     def get_weights_by_name(self, name: str, truncate_size: int = 100) -> Any:
         return self._control(ios.GetWeightsByNameReq(name, truncate_size)).parameter
 
+    def weights_checker(self, action: str = "checksum") -> Any:
+        return self._control(ios.WeightsCheckerReq(action))
+
+    def slow_down(self, forward_sleep_time: Optional[float]) -> Any:
+        return self._control(ios.SlowDownReq(forward_sleep_time))
+
     def release_memory_occupation(self, tags: Optional[List[str]] = None) -> Any:
         return self._control(ios.ReleaseMemoryOccupationReq(tags))
 
@@ -585,6 +591,7 @@ class Engine:
                     self._relay_sync()
                 except Exception:
                     logger.exception("scheduler step failed; aborting in-flight requests")
+                    self.dump_requests_before_crash()
                     self._fail_all()
                     raise
             else:
@@ -592,6 +599,34 @@ class Engine:
                 self._relay_sync()
                 self._wake.wait(timeout=0.002)
                 self._wake.clear()
+
+    def dump_requests_before_crash(self) -> Optional[str]:
+        """``--crash-dump-folder``: write the in-flight and queued requests (ids, token ids, sampling params, progress) plus the scheduler's
+        internal state to a JSON file for offline replay (reference tokenizer_manager.dump_requests_before_crash:2986)"""
+        folder = self.server_args.crash_dump_folder
+        if not folder:
+            return None
+        import json
+        import os
+
+        try:
+            os.makedirs(folder, exist_ok=True)
+            sch = self.scheduler
+            reqs = []
+            for where, lst in (("running", sch.running_batch.reqs), ("waiting", sch.waiting_queue)):
+                for r in lst:
+                    reqs.append({"rid": r.rid, "state": where, "input_ids": list(r.origin_input_ids), "output_ids": list(r.output_ids),
+                                 "sampling_params": getattr(r.sampling_params, "__dict__", {}), "kv_len": int(r.kv_len),
+                                 "retractions": int(r.retraction_count)})
+            path = os.path.join(folder, f"crash_dump_{int(time.time())}_rank{ps.get_state().rank}.json")
+            with open(path, "w") as f:
+                json.dump({"time": time.time(), "server_args": self.server_args.to_dict(), "internal_state": sch.get_internal_state(),
+                           "requests": reqs}, f, default=str)
+            logger.error("crash dump with %d requests written to %s", len(reqs), path)
+            return path
+        except Exception:
+            logger.exception("writing the crash dump failed")
+            return None
 
     def _fail_all(self) -> None:
         with self._lock:

@@ -154,6 +154,27 @@ def create_app(engine: Any):
         b = await request.json()
         return await _ctl(engine.get_weights_by_name, b["name"], b.get("truncate_size", 100))
 
+    @app.api_route("/weights_checker", methods=["GET", "POST"])
+    async def weights_checker(request: Request):
+        b = await request.json() if await request.body() else {}
+        r = await _ctl(engine.weights_checker, b.get("action", "checksum"))
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
+    @app.api_route("/slow_down", methods=["GET", "POST"])
+    async def slow_down(request: Request):
+        b = await request.json() if await request.body() else {}
+        r = await _ctl(engine.slow_down, b.get("forward_sleep_time"))
+        return {"success": r.success, "message": r.message}
+
+    @app.api_route("/set_trace_level", methods=["GET", "POST"])
+    async def set_trace_level(request: Request):
+        from ..observability.trace import get_tracer, init_tracing
+
+        b = await request.json() if await request.body() else {}
+        lv = int(b.get("level", request.query_params.get("level", 1)))
+        (get_tracer() or init_tracing(lv)).set_level(lv)
+        return {"success": True, "level": lv}
+
     @app.api_route("/release_memory_occupation", methods=["GET", "POST"])
     async def release(request: Request):
         b = await request.json() if await request.body() else {}

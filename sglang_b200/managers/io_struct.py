@@ -308,6 +308,18 @@ class GetWeightsByNameReq:
 
 
 @message
+class WeightsCheckerReq:
+    """checksum every parameter shard (reference /weights_checker, utils/weight_checker.py): compare instances / ranks / before-after a swap"""
+    action: str = "checksum"       # checksum | snapshot | compare (against the stored snapshot)
+
+
+@message
+class SlowDownReq:
+    """fault injection (reference /slow_down): sleep this long before every forward; None / 0 clears"""
+    forward_sleep_time: Optional[float] = None
+
+
+@message
 class GetWeightsByNameResp:
     parameter: Any = None
 

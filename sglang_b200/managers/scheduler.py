@@ -14,6 +14,7 @@ indexed by request slot and the next decode gathers from it).
 from __future__ import annotations
 
 import logging
+import os
 import time
 from collections import deque
 from typing import Any, Callable, Deque, Dict, List, Optional, Tuple
@@ -77,6 +78,8 @@ class Scheduler:
         self.new_token_ratio_decay = (self.init_new_token_ratio - self.min_new_token_ratio) / 600
         self.new_token_ratio = self.init_new_token_ratio
 
+        self.forward_sleep_time: Optional[float] = None
+        self.consensus_mode = os.environ.get("SGLB_RANK_CONSENSUS", "off")
         self.prefill_delayer = None
         self.min_free_slots_delayer = None
         self._init_delayers()
@@ -115,6 +118,9 @@ class Scheduler:
             return ios.GetLoadResp(num_running_reqs=len(self.running_batch.reqs), num_waiting_reqs=len(self.waiting_queue),
                                    num_tokens=int(self.kv.total_pages() - self.kv.available_pages()) * self.page_size,
                                    token_usage=self.kv.token_usage())
+        if isinstance(msg, ios.SlowDownReq):
+            self.forward_sleep_time = msg.forward_sleep_time or None
+            return ios.GenericResp(True, f"forward sleep = {self.forward_sleep_time}")
         if isinstance(msg, ios.PauseGenerationReq):
             return self.pause_generation(msg.mode)
         if isinstance(msg, ios.ContinueGenerationReq):
@@ -123,7 +129,7 @@ class Scheduler:
         if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq, ios.GetWeightsByNameReq,
                             ios.InitWeightsUpdateGroupReq, ios.DestroyWeightsUpdateGroupReq, ios.UpdateWeightsFromDistributedReq,
                             ios.ReleaseMemoryOccupationReq, ios.ResumeMemoryOccupationReq, ios.ProfileReq,
-                            ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq)):
+                            ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq, ios.WeightsCheckerReq)):
             self.drain()
             if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq)) or \
                     (isinstance(msg, ios.UpdateWeightsFromDistributedReq) and msg.flush_cache):
@@ -466,6 +472,15 @@ class Scheduler:
     # ================================================================== run + results
     def run_batch(self, batch: ScheduleBatch) -> Any:
         self.forward_ct += 1
+        if self.forward_sleep_time:
+            time.sleep(self.forward_sleep_time)
+        if self.consensus_mode != "off":        # SPMD: every TP rank must have formed the identical batch (utils/rank_consensus.py)
+            from ..parallel import parallel_state as ps
+            from ..utils.rank_consensus import check_consensus
+
+            tp = ps.get_state().attn_tp if self.args.enable_dp_attention else ps.get_state().tp
+            check_consensus(tp, (int(batch.forward_mode.value) if hasattr(batch.forward_mode, "value") else str(batch.forward_mode),
+                                 [r.rid for r in batch.reqs], np.asarray(batch.seq_lens).tolist()), "Scheduler.run_batch", self.consensus_mode)
         batch.launch_time = time.perf_counter()
         if self.record_batches:
             self.batch_records.append({"mode": batch.forward_mode.name, "rids": [r.rid for r in batch.reqs],

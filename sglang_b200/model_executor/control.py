@@ -26,6 +26,8 @@ def handle(runner: Any, msg: Any) -> Any:
         return _update_from_tensor(runner, msg)
     if isinstance(msg, ios.GetWeightsByNameReq):
         return _get_weights(runner, msg)
+    if isinstance(msg, ios.WeightsCheckerReq):
+        return _weights_checker(runner, msg)
     if isinstance(msg, ios.InitWeightsUpdateGroupReq):
         return _init_update_group(runner, msg)
     if isinstance(msg, ios.DestroyWeightsUpdateGroupReq):
@@ -54,6 +56,28 @@ def handle(runner: Any, msg: Any) -> Any:
 
         return handle_request(runner, msg)
     raise TypeError(type(msg))
+
+
+def _weights_checker(runner: Any, msg: Any) -> Any:
+    """per-parameter checksums of THIS rank's shards: sum and a position-weighted sum in fp64 (any flipped / permuted element changes it)"""
+    sums = {}
+    for n, p in runner.model.named_parameters():
+        f = p.detach().double().reshape(-1)
+        if p.dtype == torch.float8_e4m3fn:
+            f = p.detach().view(torch.uint8).double().reshape(-1)
+        w = torch.arange(1, f.numel() + 1, dtype=torch.float64, device=f.device) % 8191
+        sums[n] = (float(f.sum()), float((f * w).sum()))
+    total = float(sum(abs(a) + abs(b) for a, b in sums.values()))
+    if msg.action == "snapshot":
+        runner._weights_snapshot = sums
+        return ios.GenericResp(True, f"snapshot of {len(sums)} tensors (fingerprint {total:.6e})")
+    if msg.action == "compare":
+        snap = getattr(runner, "_weights_snapshot", None)
+        if snap is None:
+            return ios.GenericResp(False, "no snapshot to compare against")
+        diff = sorted(n for n in sums if snap.get(n) != sums[n])
+        return ios.GenericResp(not diff, "identical" if not diff else f"{len(diff)} tensors changed: {diff[:8]}")
+    return ios.GenericResp(True, __import__("json").dumps({"fingerprint": total, "num_tensors": len(sums), "checksums": sums}))
 
 
 def _sync(runner) -> None:

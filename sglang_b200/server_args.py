@@ -259,10 +259,39 @@ def _load_config_file(path: str) -> Dict[str, Any]:
     return {k.replace("-", "_"): v for k, v in d.items()}
 
 
+def _merge_config_file(argv: List[str]) -> List[str]:
+    """``--config file.yaml``: keys become flags placed BEFORE the command line, so explicit flags win (reference server_args_config_parser.py)"""
+    if "--config" not in argv:
+        return argv
+    i = argv.index("--config")
+    path = argv[i + 1]
+    rest = argv[:i] + argv[i + 2:]
+    import yaml
+
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+    if not isinstance(cfg, dict):
+        raise ValueError(f"{path}: expected a mapping of flag names to values")
+    extra: List[str] = []
+    for k, v in cfg.items():
+        flag = "--" + str(k).replace("_", "-")
+        if isinstance(v, bool):
+            if v:
+                extra.append(flag)
+        elif isinstance(v, (list, tuple)):
+            extra += [flag] + [str(x) for x in v]
+        elif v is not None:
+            extra += [flag, json.dumps(v) if isinstance(v, dict) else str(v)]
+    return extra + rest
+
+
 def prepare_server_args(argv: List[str]) -> ServerArgs:
     parser = argparse.ArgumentParser("sglang_b200")
     ServerArgs.add_cli_args(parser)
-    return ServerArgs.from_cli_args(parser.parse_args(argv))
+    from .plugins import load_plugins
+
+    load_plugins()          # out-of-tree models / grammar backends / spec algorithms register themselves before the args are resolved
+    return ServerArgs.from_cli_args(parser.parse_args(_merge_config_file(list(argv))))
 
 
 @dataclass

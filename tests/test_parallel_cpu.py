@@ -209,3 +209,9 @@ def test_hybrid_mamba_tp2():
 def test_gpt_oss_tp2():
     kw = dict(model_path="dummy:tiny-gpt-oss", page_size=4, chunked_prefill_size=16)
     _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP))
+
+
+def test_rank_consensus_checker_passes_on_spmd_scheduler():
+    """SGLB_RANK_CONSENSUS=crash: every batch decision of the two SPMD schedulers is hashed and min/max-reduced; a healthy run never diverges"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=16)
+    _check(_run({**kw, "tp_size": 2}, 2, LP, {"SGLB_RANK_CONSENSUS": "crash"}), _run(kw, 1, LP))
