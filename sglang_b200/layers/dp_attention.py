@@ -27,12 +27,14 @@ class DpAttnContext:
         self.dp_size, self.dp_rank = st.attn_dp_size, st.attn_dp_rank
         self.attn_tp_size = st.tp.world_size // st.attn_dp_size
         self._counts: Dict[str, List[int]] = {}
+        self.mb = 0                 # two-batch overlap: which micro-batch the current layer call belongs to (separate row counts)
         self.cp_active = False      # prefill-CP reuses this context, but only inside a context-parallel prefill (layers/cp.py)
 
     def begin(self) -> None:
         self._counts = {}
 
     def counts(self, key: str, n_local: int, device: torch.device) -> List[int]:
+        key = f"{key}#{self.mb}"
         c = self._counts.get(key)
         if c is None:
             t = torch.tensor([n_local], dtype=torch.int64, device=device)
@@ -51,7 +53,7 @@ class DpAttnContext:
         return torch.cat(parts, 0) if parts else x.new_zeros((0,) + tuple(x.shape[1:]))
 
     def slice(self, y: torch.Tensor, key: str) -> torch.Tensor:
-        cnt = self._counts[key]
+        cnt = self._counts[f"{key}#{self.mb}"]
         off = sum(cnt[: self.dp_rank])
         return y[off: off + cnt[self.dp_rank]]
 

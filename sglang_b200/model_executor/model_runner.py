@@ -35,6 +35,15 @@ from ..server_args import ServerArgs
 from .forward_batch import BatchPacker, ForwardBatch, SamplingTensors
 
 logger = logging.getLogger(__name__)
+
+
+def _llama_forward():
+    from ..models.llama import LlamaForCausalLM
+
+    return LlamaForCausalLM.forward
+
+
+_LLAMA_FORWARD = _llama_forward()
 _DT = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
 
 
@@ -250,6 +259,93 @@ class ModelRunner:
         self.cp_forwards += 1
         return full[meta.inv_perm]
 
+    # ------------------------------------------------------------------ two-batch overlap (reference batch_overlap/two_batch_overlap.py)
+    def _tbo_static_ok(self) -> bool:
+        m = getattr(self.model, "model", None)
+        return (m is not None and hasattr(m, "embed") and self.pp.world_size == 1 and self.lora_manager is None and self.dcp is None
+                and self.cp is None and not getattr(self.model, "is_mrope", False) and type(self.model).forward is _LLAMA_FORWARD)
+
+    def _tbo_eligible(self, sb: ScheduleBatch, fb: ForwardBatch) -> bool:
+        from ..layers.dp_attention import get_dp_ctx
+
+        if not self._tbo_static_ok():
+            return False
+        if get_dp_ctx() is not None:
+            # DP-attention: every group must issue the same collective sequence -> the decision may only depend on static facts; a group
+            # with fewer than two requests runs an EMPTY second micro-batch (and idle groups two empty ones, see forward_idle)
+            return self.cfg.vision is None
+        return len(sb.reqs) >= 2 and fb.mm_embeds is None and sb.spec_info is None and fb.custom_mask is None
+
+    def _forward_tbo(self, sb: ScheduleBatch, fb: ForwardBatch) -> torch.Tensor:
+        """Split the batch by requests into two micro-batches of near-equal token count and walk the decoder stack layer by layer, alternating
+        between them on two streams: while one micro-batch waits for its MoE all-to-all / TP all-reduce the other one's attention and GEMMs
+        keep the SMs busy.  On one stream (CPU tier) this is just a different evaluation order, so outputs are identical by construction."""
+        import dataclasses as _dc
+
+        from ..layers.dp_attention import get_dp_ctx
+
+        decode = fb.cu_q is None
+        B = fb.batch_size
+        if decode:
+            k = (B + 1) // 2
+            cuts = [(0, k, 0, k), (k, B, k, B)]                                   # (req lo, req hi, row lo, row hi)
+        elif B < 2:
+            T = fb.num_tokens
+            cuts = [(0, B, 0, T), (B, B, T, T)]                                   # second micro-batch empty (DP-attention lock-step)
+        else:
+            cu = np.concatenate([[0], np.cumsum(fb.q_lens_cpu)])
+            k = int(np.argmin(np.abs(cu[1:-1] - cu[-1] / 2))) + 1
+            cuts = [(0, k, 0, int(cu[k])), (k, B, int(cu[k]), int(cu[-1]))]
+        parts = []
+        for (r0, r1, t0, t1) in cuts:
+            kw = dict(batch_size=r1 - r0, num_tokens=t1 - t0, positions=fb.positions[t0:t1], out_cache_loc=fb.out_cache_loc[t0:t1],
+                      req_slots=fb.req_slots[r0:r1], seq_lens=fb.seq_lens[r0:r1], input_ids=None if fb.input_ids is None else fb.input_ids[t0:t1],
+                      seq_lens_cpu=None if fb.seq_lens_cpu is None else fb.seq_lens_cpu[r0:r1], num_splits=1, attn_workspace=None)
+            if not decode:
+                ql = fb.q_lens[r0:r1]
+                qc = fb.q_lens_cpu[r0:r1] if fb.q_lens_cpu is not None else np.zeros(0, np.int32)
+                sc = fb.seq_lens_cpu[r0:r1] if fb.seq_lens_cpu is not None else np.zeros(0, np.int32)
+                kw.update(q_lens=ql, cu_q=(fb.cu_q[r0:r1 + 1] - fb.cu_q[r0]).contiguous(), q_lens_cpu=qc,
+                          max_q_len=int(qc.max()) if qc.size else 0, max_kv_len=int(sc.max()) if sc.size else 0)
+            parts.append(_dc.replace(fb, **kw))
+        m = self.model.model
+        ctx = get_dp_ctx()
+        streams = None
+        if self.is_cuda:
+            if getattr(self, "_tbo_streams", None) is None:
+                self._tbo_streams = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+            streams = self._tbo_streams
+            cur = torch.cuda.current_stream()
+            for s_ in streams:
+                s_.wait_stream(cur)
+
+        def on(i):
+            if ctx is not None:
+                ctx.mb = i
+            return torch.cuda.stream(streams[i]) if streams else _null_ctx()
+
+        st = []
+        for i, f in enumerate(parts):
+            with on(i):
+                st.append((m.embed(f), None))
+        for layer in m.layers:
+            for i, f in enumerate(parts):
+                with on(i):
+                    st[i] = layer(st[i][0], st[i][1], f)
+        outs = []
+        for i, f in enumerate(parts):
+            with on(i):
+                h, r = st[i]
+                h = h.resolve() if hasattr(h, "resolve") else h
+                outs.append(m.norm(h) if r is None else m.norm(h, r)[0])
+        if streams:
+            for s_ in streams:
+                torch.cuda.current_stream().wait_stream(s_)
+        if ctx is not None:
+            ctx.mb = 0
+        self.tbo_forwards = getattr(self, "tbo_forwards", 0) + 1
+        return torch.cat(outs, 0)
+
     def _attach_dcp(self, sb: ScheduleBatch, fb: ForwardBatch) -> None:
         if self.dcp is None:
             return
@@ -299,7 +395,8 @@ class ModelRunner:
                           req_slots=z(), seq_lens=z(), cu_q=torch.zeros(1, dtype=torch.int32, device=dev), q_lens=z(), last_idx=z(),
                           sample_slots=z(), max_q_len=0, max_kv_len=0, page_table=self.page_table, page_size=self.page_size,
                           kv_pool=self.kv_pool, next_token_buf=self.next_token_buf)
-        hidden = self.model(fb)
+        hidden = self._forward_tbo(None, fb) if (self.args.enable_two_batch_overlap and self._tbo_static_ok() and self.cfg.vision is None) \
+            else self.model(fb)
         self.model.compute_logits(hidden[:0])        # the LM head gathers sampled rows across groups as well ...
         self.model.compute_logits(hidden[:0], key="logits_all")     # ... and the rows of a prompt-logprob pass
 
@@ -328,7 +425,12 @@ class ModelRunner:
             self.lora_manager.prepare_batch(sb, fb)
         if not self.pp.is_first:
             fb.pp_hidden = self._pp_recv(fb.num_tokens)
-        hidden = self._forward_cp(sb, fb) if (self.cp is not None and not decode and self._cp_eligible(sb, fb)) else self.model(fb)
+        if self.cp is not None and not decode and self._cp_eligible(sb, fb):
+            hidden = self._forward_cp(sb, fb)
+        elif self.args.enable_two_batch_overlap and self._tbo_eligible(sb, fb):
+            hidden = self._forward_tbo(sb, fb)
+        else:
+            hidden = self.model(fb)
         if self.hidden_tap is not None and not decode and self.pp.is_last:
             self.hidden_tap(sb, hidden)          # EAGLE: target features of the prefilled positions
         res = BatchResult()

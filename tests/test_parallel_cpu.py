@@ -23,8 +23,8 @@ def _free_port() -> int:
     return p
 
 
-def _run(engine_kw, world, gen_kw=None, extra_env=None):
-    cfg = json.dumps({"engine": engine_kw, "prompts": PROMPTS, "sampling": SAMPLING, "gen_kw": gen_kw or {}})
+def _run(engine_kw, world, gen_kw=None, extra_env=None, prompts=None):
+    cfg = json.dumps({"engine": engine_kw, "prompts": prompts or PROMPTS, "sampling": SAMPLING, "gen_kw": gen_kw or {}})
     port = _free_port()
     procs = []
     for r in range(world):
@@ -215,3 +215,16 @@ def test_rank_consensus_checker_passes_on_spmd_scheduler():
     """SGLB_RANK_CONSENSUS=crash: every batch decision of the two SPMD schedulers is hashed and min/max-reduced; a healthy run never diverges"""
     kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=16)
     _check(_run({**kw, "tp_size": 2}, 2, LP, {"SGLB_RANK_CONSENSUS": "crash"}), _run(kw, 1, LP))
+
+
+def test_two_batch_overlap_with_dp_attention_a2a():
+    """TBO under DP-attention + expert-parallel all-to-all: the two micro-batches of every group interleave their gathers / all-to-alls"""
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
+    ref = _run(kw, 1, LP)
+    dpk = {**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True, "enable_two_batch_overlap": True}
+    _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1"}), ref)
+    _check(_run({**kw, "tp_size": 2, "enable_two_batch_overlap": True}, 2, LP), ref)
+    # uneven load: 3 requests over 2 groups -> one group prefills / decodes a single request (empty second micro-batch) while the other
+    # splits two; idle forwards at the tail run two empty micro-batches
+    odd = PROMPTS[:3]
+    _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1"}, prompts=odd), _run(kw, 1, LP, prompts=odd))
