@@ -296,6 +296,8 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "GPTBigCodeForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_pytorch_tanh"),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True),
+                  "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
+                  "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
                   "OlmoeForCausalLM": dict(norm_topk_prob=False),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),

@@ -221,6 +221,13 @@ class DeepseekV2ForCausalLM(LlamaForCausalLM):
     stacked_params = [(".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
 
     def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        loaded, rest = load_moe_tensors(self, weights)
+        return loaded + super().load_weights(rest)
+
+
+def load_moe_tensors(self, weights):
+    """route the DeepSeek-style expert / router tensors into ``FusedMoE`` and the gate; returns (loaded names, remaining (name, tensor) pairs)"""
+    if True:
         rest, loaded = [], []
         modules = dict(self.named_modules())
         shard_of = {"gate_proj": "w1", "up_proj": "w3", "down_proj": "w2"}
@@ -244,7 +251,7 @@ class DeepseekV2ForCausalLM(LlamaForCausalLM):
                     loaded.append(name)
             else:
                 rest.append((name, w))
-        return loaded + super().load_weights(rest)
+        return loaded, rest
 
 
 class DeepseekV3ForCausalLM(DeepseekV2ForCausalLM):

@@ -257,3 +257,38 @@ class NemotronForCausalLM(LlamaForCausalLM):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__(cfg, quant_name, device)
         self.model.norm = LayerNorm1P(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype)
+
+
+# ---------------------------------------------------------------- GLM-4.5 (Glm4Moe) and dots.llm1: DeepSeek-V3 style MoE + ordinary GQA attention
+def _ds():
+    from . import deepseek
+
+    return deepseek
+
+
+class _DsMoeLayer(LlamaDecoderLayer):
+    """standard attention; dense MLP for the first ``first_k_dense_replace`` layers, DeepSeek MoE (sigmoid router + correction bias, grouped
+    top-k, shared experts, routed scaling) afterwards"""
+
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        if cfg.num_local_experts > 0 and _gid(prefix) >= (cfg.first_k_dense_replace or 0):
+            self.mlp = _ds().DeepseekV2MoE(cfg, layer_id, dtype, quant, prefix + ".mlp")
+        if cfg.use_qk_norm:
+            sa = self.self_attn
+            sa.qk_norm = True
+            sa.q_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
+            sa.k_norm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
+
+
+class Glm4MoeForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = _DsMoeLayer
+
+    def load_weights(self, weights):
+        # expert / router tensors use the DeepSeek names: reuse that loader, everything else is Llama-shaped
+        loaded, rest = _ds().load_moe_tensors(self, weights)
+        return loaded + super().load_weights(rest)
+
+
+class Dots1ForCausalLM(Glm4MoeForCausalLM):
+    pass

@@ -51,6 +51,12 @@ CASES = {
     "gptj": ("GPTJConfig", "GPTJForCausalLM", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512, rotary_dim=8)),
     "gpt-bigcode": ("GPTBigCodeConfig", "GPTBigCodeForCausalLM", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512, n_inner=128,
                                                                     multi_query=True)),
+    "glm4-moe": ("Glm4MoeConfig", "Glm4MoeForCausalLM", dict(BASE, num_hidden_layers=3, head_dim=16, pad_token_id=0, n_routed_experts=8,
+                                                             num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1,
+                                                             n_group=2, topk_group=1, routed_scaling_factor=1.5, norm_topk_prob=True, use_qk_norm=True)),
+    "dots1": ("Dots1Config", "Dots1ForCausalLM", dict(BASE, num_hidden_layers=3, head_dim=16, n_routed_experts=8, num_experts_per_tok=2,
+                                                      moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1, n_group=2, topk_group=1,
+                                                      routed_scaling_factor=1.5, norm_topk_prob=True)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
