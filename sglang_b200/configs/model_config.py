@@ -295,7 +295,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "GPTJForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", rope_is_neox=False),
                   "GPTBigCodeForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_pytorch_tanh"),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
-                  "Qwen2VLForConditionalGeneration": dict(attention_bias=True),
+                  "Qwen2VLForConditionalGeneration": dict(attention_bias=True), "Qwen2_5_VLForConditionalGeneration": dict(attention_bias=True),
                   "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
@@ -388,6 +388,15 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                       rms_norm_eps=1e-5, pos_emb="learned", tie_word_embeddings=True, head_dim=hf["d_model"] // hf["decoder_attention_heads"])
             kw["audio"] = {k: hf[k] for k in ("d_model", "encoder_layers", "encoder_attention_heads", "encoder_ffn_dim", "num_mel_bins",
                                               "max_source_positions")}
+        if arch == "Qwen2_5_VLForConditionalGeneration":
+            vc = hf["vision_config"]
+            kw["vision"] = {"variant": "qwen2.5", "embed_dim": vc.get("hidden_size", 1280), "depth": vc.get("depth", 32),
+                            "num_heads": vc.get("num_heads", 16), "hidden_size": vc.get("out_hidden_size", kw["hidden_size"]),
+                            "intermediate_size": vc.get("intermediate_size", 3420), "patch_size": vc.get("patch_size", 14),
+                            "spatial_merge_size": vc.get("spatial_merge_size", 2), "temporal_patch_size": vc.get("temporal_patch_size", 2),
+                            "window_size": vc.get("window_size", 112), "fullatt_block_indexes": vc.get("fullatt_block_indexes", [7, 15, 23, 31])}
+            kw["image_token_id"] = hf.get("image_token_id", 151655)
+            kw.setdefault("attention_bias", True)
         if arch == "Qwen2VLForConditionalGeneration":
             vc = hf["vision_config"]
             kw["vision"] = {"embed_dim": vc.get("embed_dim", 1280), "depth": vc.get("depth", 32), "num_heads": vc.get("num_heads", 16),
@@ -396,7 +405,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf:
+        elif "vision_config" in hf and arch != "Qwen2_5_VLForConditionalGeneration":
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))

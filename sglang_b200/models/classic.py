@@ -138,7 +138,7 @@ class ClassicForCausalLM(nn.Module):
         self.cfg = cfg
         self.model = ClassicModel(cfg, quant_name, device)
         self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, _DT[cfg.dtype])
-        self.lm_head_bias = nn.Parameter(torch.zeros(cfg.vocab_size, dtype=_DT[cfg.dtype]), requires_grad=False)      # Phi / GPT-J (zero otherwise)
+        self.register_buffer("lm_head_bias", torch.zeros(cfg.vocab_size, dtype=_DT[cfg.dtype]), persistent=False)      # Phi / GPT-J (zero otherwise)
 
     def forward(self, fb: ForwardBatch, inputs_embeds=None):
         return self.model(fb, inputs_embeds)
@@ -162,7 +162,7 @@ class ClassicForCausalLM(nn.Module):
         for raw_name, raw_w in weights:
             for name, w in self.remap(raw_name, raw_w):
                 if name == "lm_head.bias":
-                    self.lm_head_bias.data.copy_(w[: self.lm_head_bias.shape[0]])
+                    self.lm_head_bias.copy_(w[: self.lm_head_bias.shape[0]])
                     loaded.append(name)
                     continue
                 if name.startswith("lm_head") and self.lm_head is None:

@@ -98,6 +98,96 @@ class Qwen2VisionTransformer(nn.Module):
         return self.merger(self.ln_q(x).view(-1, self.embed_dim * self.merge ** 2))
 
 
+class _VRMS(nn.Module):
+    def __init__(self, n: int, dtype, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n, dtype=dtype), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x):
+        f = x.float()
+        return (f * torch.rsqrt(f.pow(2).mean(-1, keepdim=True) + self.eps)).to(x.dtype) * self.weight
+
+
+class VisionBlock25(nn.Module):
+    """Qwen2.5-VL block: RMSNorm, biased SwiGLU MLP; attention is full inside the segments it is given (windows or whole frames)"""
+
+    def __init__(self, dim: int, heads: int, inter: int, dtype):
+        super().__init__()
+        self.heads = heads
+        self.norm1, self.norm2 = _VRMS(dim, dtype), _VRMS(dim, dtype)
+        self.qkv, self.proj = nn.Linear(dim, 3 * dim, dtype=dtype), nn.Linear(dim, dim, dtype=dtype)
+        self.gate_proj, self.up_proj = nn.Linear(dim, inter, dtype=dtype), nn.Linear(dim, inter, dtype=dtype)
+        self.down_proj = nn.Linear(inter, dim, dtype=dtype)
+
+    def forward(self, x, cos, sin, seg: List[int]):
+        N, D = x.shape
+        q, k, v = self.qkv(self.norm1(x)).view(N, 3, self.heads, D // self.heads).unbind(1)
+        q = (q.float() * cos[:, None] + _rot_half(q.float()) * sin[:, None]).to(x.dtype)
+        k = (k.float() * cos[:, None] + _rot_half(k.float()) * sin[:, None]).to(x.dtype)
+        outs, s = [], 0
+        for n in seg:
+            o = F.scaled_dot_product_attention(q[s:s + n].transpose(0, 1), k[s:s + n].transpose(0, 1), v[s:s + n].transpose(0, 1))
+            outs.append(o.transpose(0, 1).reshape(n, D))
+            s += n
+        x = x + self.proj(torch.cat(outs, 0))
+        h = self.norm2(x)
+        return x + self.down_proj(F.silu(self.gate_proj(h)) * self.up_proj(h))
+
+
+class Qwen25VisionTransformer(Qwen2VisionTransformer):
+    """Qwen2.5-VL tower: most blocks attend inside ``window_size`` pixel windows (patches are re-ordered window-major for that), the blocks
+    listed in ``fullatt_block_indexes`` attend over the whole frame; merger with RMSNorm"""
+
+    def __init__(self, v: Dict[str, Any], dtype):
+        nn.Module.__init__(self)
+        self.embed_dim, self.heads, self.patch, self.merge, self.tps = v["embed_dim"], v["num_heads"], v["patch_size"], v["spatial_merge_size"], \
+            v.get("temporal_patch_size", 2)
+        self.window, self.full_blocks = v.get("window_size", 112), set(v.get("fullatt_block_indexes", []))
+        self.patch_embed = nn.Linear(3 * self.tps * self.patch * self.patch, self.embed_dim, bias=False, dtype=dtype)
+        self.blocks = nn.ModuleList([VisionBlock25(self.embed_dim, self.heads, v["intermediate_size"], dtype) for _ in range(v["depth"])])
+        self.ln_q = _VRMS(self.embed_dim, dtype)
+        m = self.embed_dim * self.merge ** 2
+        self.merger = nn.Sequential(nn.Linear(m, m, dtype=dtype), nn.GELU(), nn.Linear(m, v["hidden_size"], dtype=dtype))
+        hd = self.embed_dim // self.heads
+        self.register_buffer("inv_freq", 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float32) / (hd // 2))), persistent=False)
+
+    def window_index(self, grid_thw: np.ndarray):
+        """order of the merge-blocks that makes every window contiguous + the window segment lengths in patches"""
+        order, seg, base = [], [], 0
+        ws = self.window // self.merge // self.patch
+        unit = self.merge ** 2
+        for t, h, w in grid_thw.tolist():
+            lh, lw = h // self.merge, w // self.merge
+            idx = np.arange(t * lh * lw).reshape(t, lh, lw)
+            ph, pw = ws - lh % ws, ws - lw % ws
+            pad = np.pad(idx, ((0, 0), (0, ph), (0, pw)), constant_values=-100)
+            nh, nw = (lh + ph) // ws, (lw + pw) // ws
+            pad = pad.reshape(t, nh, ws, nw, ws).transpose(0, 1, 3, 2, 4).reshape(t, nh * nw, ws, ws)
+            cnt = (pad != -100).sum((2, 3)).reshape(-1)
+            flat = pad.reshape(-1)
+            order.append(flat[flat != -100] + base)
+            seg += [int(c) * unit for c in cnt if c > 0]
+            base += t * lh * lw
+        return np.concatenate(order), seg
+
+    def forward(self, patches: torch.Tensor, grid_thw: np.ndarray) -> torch.Tensor:
+        x = self.patch_embed(patches)
+        cos, sin = self.rot_pos_emb(grid_thw)
+        order, win_seg = self.window_index(grid_thw)
+        unit = self.merge ** 2
+        oi = torch.from_numpy(order).to(x.device)
+        regroup = lambda t: t.view(-1, unit, t.shape[-1])[oi].reshape(-1, t.shape[-1])
+        x, cos, sin = regroup(x), regroup(cos), regroup(sin)
+        full_seg = []
+        for t, h, w in grid_thw.tolist():
+            full_seg += [h * w] * t
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, cos, sin, full_seg if i in self.full_blocks else win_seg)
+        y = self.merger(self.ln_q(x).view(-1, self.embed_dim * unit))
+        return y[torch.argsort(oi)]
+
+
 # ------------------------------------------------------------------------------------------------ M-RoPE helpers
 def mrope_index(ids: List[int], grids: List[Tuple[int, int, int]], image_token: int, merge: int) -> Tuple[np.ndarray, int]:
     """[3, len(ids)] rotary positions (temporal, height, width) and the delta ``next position - len(ids)`` for decode (reference
@@ -141,7 +231,8 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__(cfg, quant_name, device)
         v = cfg.vision
-        self.visual = None if v.get("skip_tower") else Qwen2VisionTransformer(v, _DT[cfg.dtype])
+        tower = Qwen25VisionTransformer if v.get("variant") == "qwen2.5" else Qwen2VisionTransformer
+        self.visual = None if v.get("skip_tower") else tower(v, _DT[cfg.dtype])
         self.vision_tower = self.visual            # name the shared multimodal plumbing looks for
         self.merge = v["spatial_merge_size"]
         self.sections = list((cfg.rope_scaling or {}).get("mrope_section", [cfg.head_dim // 2]))
@@ -176,6 +267,7 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
                 if self.visual is None:
                     continue
                 n = name.replace(".attn.qkv.", ".qkv.").replace(".attn.proj.", ".proj.").replace(".mlp.fc1.", ".fc1.").replace(".mlp.fc2.", ".fc2.") \
+                    .replace(".mlp.gate_proj.", ".gate_proj.").replace(".mlp.up_proj.", ".up_proj.").replace(".mlp.down_proj.", ".down_proj.") \
                     .replace("visual.merger.ln_q.", "visual.ln_q.").replace("visual.merger.mlp.", "visual.merger.").replace("visual.patch_embed.proj.", "visual.patch_embed.")
                 if n in own:
                     own[n].data.copy_(w.reshape(own[n].shape))
@@ -183,3 +275,7 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
                 continue
             rest.append((name[len("language_model."):] if name.startswith("language_model.") else name, w))
         return loaded + super().load_weights(rest)
+
+
+class Qwen2_5_VLForConditionalGeneration(Qwen2VLForConditionalGeneration):
+    """same language model and M-RoPE; windowed vision tower (``vision['variant'] == 'qwen2.5'`` is set by the config loader)"""

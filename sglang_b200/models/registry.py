@@ -54,6 +54,7 @@ def _ensure() -> None:
     from . import qwen2_vl as _qv
 
     register_model("Qwen2VLForConditionalGeneration", _qv.Qwen2VLForConditionalGeneration)
+    register_model("Qwen2_5_VLForConditionalGeneration", _qv.Qwen2_5_VLForConditionalGeneration)
     from . import gpt_oss as _go
 
     register_model("GptOssForCausalLM", _go.GptOssForCausalLM)

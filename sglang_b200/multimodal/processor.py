@@ -175,7 +175,7 @@ def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, toke
 
 
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
-    if cfg.architecture.startswith("Qwen2VL"):
+    if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
     return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)
 

@@ -12,10 +12,27 @@ from sglang_b200.multimodal import processor as P
 tf = pytest.importorskip("transformers")
 
 
-def _hf_model(tmp_path):
+def _hf_model(tmp_path, v25=False):
     from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
 
     torch.manual_seed(0)
+    if v25:
+        from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+
+        cfg = Qwen2_5_VLConfig(text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                                vocab_size=512, max_position_embeddings=2048, rope_theta=10000.0,
+                                                rope_scaling={"type": "mrope", "mrope_section": [2, 3, 3]}, tie_word_embeddings=False),
+                               vision_config=dict(hidden_size=32, out_hidden_size=64, intermediate_size=48, depth=3, num_heads=2, patch_size=14,
+                                                  spatial_merge_size=2, temporal_patch_size=2, window_size=56, fullatt_block_indexes=[1],
+                                                  tokens_per_second=1),      # (this transformers build scales an IMAGE's temporal position by it)
+                               image_token_id=500, video_token_id=501, vision_start_token_id=502)
+        m = Qwen2_5_VLForConditionalGeneration(cfg).float().eval()
+        for p in m.parameters():
+            if p.dim() > 1:
+                torch.nn.init.normal_(p, std=0.08)
+        d = tmp_path / "qwen25vl"
+        m.save_pretrained(str(d), safe_serialization=True)
+        return m, str(d)
     cfg = Qwen2VLConfig(text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
                                          vocab_size=512, max_position_embeddings=2048, rope_theta=10000.0,
                                          rope_scaling={"type": "mrope", "mrope_section": [2, 3, 3]}, tie_word_embeddings=False),
@@ -38,13 +55,15 @@ def test_smart_resize_and_patch_layout_match_hf():
         assert P.smart_resize(h, w, 28, 56 * 56, 28 * 28 * 100) == smart_resize(h, w, 28, 56 * 56, 28 * 28 * 100)
 
 
-def test_engine_matches_hf(tmp_path):
-    hf, path = _hf_model(tmp_path)
+@pytest.mark.parametrize("v25", [False, True])
+def test_engine_matches_hf(tmp_path, v25):
+    hf, path = _hf_model(tmp_path, v25)
     rng = np.random.default_rng(0)
-    imgs = [rng.integers(0, 255, size=(60, 90, 3), dtype=np.uint8), rng.integers(0, 255, size=(100, 56, 3), dtype=np.uint8)]
+    # 2.5: windows of 56 px = 2x2 merge blocks; the images below give partial windows on both axes
+    imgs = [rng.integers(0, 255, size=(60, 90, 3), dtype=np.uint8), rng.integers(0, 255, size=(150, 56, 3), dtype=np.uint8)]
     ids = [5, 6, 502, 500, 7, 8, 9, 502, 500, 10, 11, 12, 13]
     eng = sgl.Engine(model_path=path, device="cpu", page_size=4, skip_tokenizer_init=True, chunked_prefill_size=16, disable_radix_cache=True)
-    assert type(eng.runner.model).__name__ == "Qwen2VLForConditionalGeneration"
+    assert type(eng.runner.model).__name__ == ("Qwen2_5_VLForConditionalGeneration" if v25 else "Qwen2VLForConditionalGeneration")
     o = eng.generate(input_ids=ids, image_data=imgs, sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True},
                      return_logprob=True, logprob_start_len=0)
     # the HF side: same patches / grids, placeholder runs expanded with the image token id
