@@ -348,6 +348,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                 text["rope_scaling"] = sc
         kw = {k: v for k, v in text.items() if k in fields}
         arch = (hf.get("architectures") or ["LlamaForCausalLM"])[0]
+        if "text_config" in hf and hf.get("tie_word_embeddings") is not None:
+            kw["tie_word_embeddings"] = bool(hf["tie_word_embeddings"])          # composite configs decide at the top level
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
         kw.setdefault("rope_theta", 10000.0)          # the Hugging Face default when a config does not say (this dataclass defaults to Llama-3's)
         for k, v in _ARCH_DEFAULTS.get(arch, {}).items():
@@ -388,6 +390,20 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                       rms_norm_eps=1e-5, pos_emb="learned", tie_word_embeddings=True, head_dim=hf["d_model"] // hf["decoder_attention_heads"])
             kw["audio"] = {k: hf[k] for k in ("d_model", "encoder_layers", "encoder_attention_heads", "encoder_ffn_dim", "num_mel_bins",
                                               "max_source_positions")}
+        if arch == "InternVLForConditionalGeneration":
+            vc = hf["vision_config"]
+            size = vc.get("image_size", 448)
+            kw["vision"] = {"kind": "internvl", "hidden_size": vc["hidden_size"], "intermediate_size": vc["intermediate_size"],
+                            "num_hidden_layers": vc["num_hidden_layers"], "num_attention_heads": vc["num_attention_heads"],
+                            "image_size": size[0] if isinstance(size, (list, tuple)) else size,
+                            "patch_size": (vc.get("patch_size", 14)[0] if isinstance(vc.get("patch_size", 14), (list, tuple)) else vc.get("patch_size", 14)),
+                            "attention_bias": vc.get("attention_bias", False), "use_qk_norm": vc.get("use_qk_norm", False),
+                            "norm_type": vc.get("norm_type", "layer_norm"), "layer_norm_eps": vc.get("layer_norm_eps", 1e-6),
+                            "hidden_act": vc.get("hidden_act", "gelu"), "select_layer": hf.get("vision_feature_layer", -1),
+                            "downsample_ratio": hf.get("downsample_ratio", 0.5)}
+            kw["image_token_id"] = hf.get("image_token_id", 151667)
+            if (hf.get("text_config") or {}).get("model_type", "qwen2") == "qwen2":
+                kw.setdefault("attention_bias", True)
         if arch == "Qwen2_5_VLForConditionalGeneration":
             vc = hf["vision_config"]
             kw["vision"] = {"variant": "qwen2.5", "embed_dim": vc.get("hidden_size", 1280), "depth": vc.get("depth", 32),
@@ -405,7 +421,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch != "Qwen2_5_VLForConditionalGeneration":
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))

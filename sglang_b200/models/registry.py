@@ -42,6 +42,9 @@ def _ensure() -> None:
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM", "PhiForCausalLM", "GPTJForCausalLM",
                  "GPTBigCodeForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import internvl as _iv
+
+    register_model("InternVLForConditionalGeneration", _iv.InternVLForConditionalGeneration)
     from . import whisper as _wh
 
     register_model("WhisperForConditionalGeneration", _wh.WhisperForConditionalGeneration)

@@ -26,7 +26,7 @@ def _encode(model: Any, mm: Dict[str, Any], device: torch.device, dtype: torch.d
             px = torch.as_tensor(np.asarray(mm["pixel_patches"], dtype=np.float32), device=device)
             flat = model.encode_images(px.to(dtype), mm["grid_thw"])
         else:
-            px = torch.tensor(mm["pixel_values"], dtype=torch.float32, device=device)
+            px = torch.as_tensor(np.asarray(mm["pixel_values"], dtype=np.float32), device=device)
             flat = model.encode_images(px.to(dtype))
         flat = flat.reshape(-1, flat.shape[-1])
     assert flat.shape[0] == sum(counts), (flat.shape, counts)

@@ -174,7 +174,68 @@ def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, toke
     return out, mm
 
 
+IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], dtype=np.float32)
+IMAGENET_STD = np.array([0.229, 0.224, 0.225], dtype=np.float32)
+
+
+def internvl_tiles(img: np.ndarray, size: int = 448, min_tiles: int = 1, max_tiles: int = 12, thumbnail: bool = True) -> np.ndarray:
+    """InternVL dynamic tiling: pick the (cols, rows) grid with cols*rows in [min, max] whose aspect ratio is closest to the image's (ties go
+    to the larger grid when the image has enough pixels), resize to the grid, cut ``size`` tiles, append a thumbnail -> [n, 3, size, size]"""
+    h, w = img.shape[:2]
+    ar = w / h
+    grids = sorted({(i, j) for n in range(min_tiles, max_tiles + 1) for i in range(1, n + 1) for j in range(1, n + 1) if min_tiles <= i * j <= max_tiles},
+                   key=lambda g: g[0] * g[1])
+    best, best_d = (1, 1), float("inf")
+    for g in grids:
+        d = abs(ar - g[0] / g[1])
+        if d < best_d or (d == best_d and w * h > 0.5 * size * size * g[0] * g[1]):
+            best, best_d = g, d
+    rt = _native()
+
+    def resize(a, hh, ww):
+        if rt is not None:
+            return rt.image_resize(np.ascontiguousarray(a), hh, ww, 3)
+        from PIL import Image
+
+        return np.asarray(Image.fromarray(a).resize((ww, hh), Image.BICUBIC))
+
+    big = resize(img, size * best[1], size * best[0])
+    tiles = [big[r * size:(r + 1) * size, c * size:(c + 1) * size] for r in range(best[1]) for c in range(best[0])]
+    if thumbnail and len(tiles) > 1:
+        tiles.append(resize(img, size, size))
+    arr = np.stack(tiles).astype(np.float32) / 255.0
+    return np.ascontiguousarray(((arr - IMAGENET_MEAN) / IMAGENET_STD).transpose(0, 3, 1, 2))
+
+
+def process_images_internvl(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None):
+    v = cfg.vision
+    per_tile = int((v["image_size"] // v["patch_size"]) ** 2 * v.get("downsample_ratio", 0.5) ** 2)
+    imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
+    arrs = [load_image(x) for x in imgs]
+    tiles = [internvl_tiles(a, v["image_size"], max_tiles=v.get("max_tiles", 12)) for a in arrs]
+    img_tok, V = cfg.image_token_id, cfg.vocab_size
+    out, offsets, counts, pads, k = [], [], [], [], 0
+    for t in input_ids:
+        if t == img_tok and k < len(arrs):
+            n = tiles[k].shape[0] * per_tile
+            h = image_hash(arrs[k])
+            offsets.append(len(out))
+            counts.append(n)
+            pads.append(int(h % max(1, V - 1)))
+            out.extend([pads[-1] if (j & 1) == 0 else int((h >> 17) % max(1, V - 1)) for j in range(n)])
+            k += 1
+        else:
+            out.append(t)
+    if k < len(arrs):
+        raise ValueError(f"{len(arrs)} images but only {k} image placeholder tokens in the prompt")
+    mm = {"image_offsets": offsets, "image_token_counts": counts, "pad_values": pads, "num_image_tokens": per_tile,
+          "pixel_values": np.concatenate(tiles) if tiles else np.zeros((0, 3, v["image_size"], v["image_size"]), np.float32)}
+    return out, mm
+
+
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
+    if cfg.architecture.startswith("InternVL"):
+        return process_images_internvl(input_ids, image_data, cfg, tokenizer, encoder)
     if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
     return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)

@@ -163,3 +163,43 @@ def test_llava_matches_hf(tmp_path):
     assert max(abs(ref[t] - got[t]) for t in range(len(hf_ids) - 1) if hf_ids[t + 1] != 500) < 2e-3
     dec = [v for v, _, _ in o["meta_info"]["output_token_logprobs"]]
     assert max(abs(float(lp[len(hf_ids) - 1 + j, tok]) - dec[j]) for j, tok in enumerate(o["output_ids"])) < 2e-3
+
+
+def test_internvl_matches_hf(tmp_path):
+    """InternViT (CLS, layer scale, qk-norm off) -> pixel shuffle -> projector -> Qwen2; two images, one tiled 2x1 + thumbnail"""
+    from sglang_b200.multimodal import processor as P
+
+    torch.manual_seed(0)
+    cfg = tf.InternVLConfig(text_config=dict(model_type="qwen2", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                             num_key_value_heads=2, vocab_size=512, max_position_embeddings=2048, rope_theta=10000.0),
+                            vision_config=dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, image_size=[56, 56],
+                                               patch_size=[14, 14], use_qk_norm=False, norm_type="layer_norm", layer_scale_init_value=0.5),
+                            image_token_id=500, downsample_ratio=0.5, vision_feature_layer=-1)
+    hf = tf.InternVLForConditionalGeneration(cfg).float().eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if p.dim() > 1 or "lambda" in n or "cls_token" in n:
+                p.normal_(0, 0.08) if p.dim() > 1 else p.add_(torch.randn_like(p) * 0.1)
+    d = str(tmp_path / "internvl")
+    hf.save_pretrained(d, safe_serialization=True)
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 255, size=(50, 110, 3), dtype=np.uint8), rng.integers(0, 255, size=(60, 60, 3), dtype=np.uint8)]
+    ids = [5, 6, 500, 7, 8, 500, 9, 10]
+    e = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error", disable_radix_cache=True,
+                   chunked_prefill_size=16)
+    o = e.generate(input_ids=ids, image_data=imgs, sampling_params={"max_new_tokens": 4, "temperature": 0, "ignore_eos": True},
+                   return_logprob=True, logprob_start_len=0)
+    ex, mm = P.process_images(ids, imgs, e.model_config, None)
+    e.shutdown()
+    assert mm["image_token_counts"] == [3 * 4, 1 * 4]          # 2x1 grid + thumbnail, then a single tile; 4 tokens per 56-px tile
+    hf_ids = list(ex)
+    for off, n in zip(mm["image_offsets"], mm["image_token_counts"]):
+        hf_ids[off:off + n] = [500] * n
+    full = hf_ids + o["output_ids"]
+    with torch.no_grad():
+        lp = torch.log_softmax(hf(input_ids=torch.tensor([full]), pixel_values=torch.from_numpy(mm["pixel_values"])).logits[0].float(), -1)
+    got = [v for v, _, _ in o["meta_info"]["input_token_logprobs"][1:]]
+    ref = [float(lp[t, full[t + 1]]) for t in range(len(hf_ids) - 1)]
+    assert max(abs(ref[t] - got[t]) for t in range(len(hf_ids) - 1) if hf_ids[t + 1] != 500) < 2e-3
+    dec = [v for v, _, _ in o["meta_info"]["output_token_logprobs"]]
+    assert max(abs(float(lp[len(hf_ids) - 1 + j, tok]) - dec[j]) for j, tok in enumerate(o["output_ids"])) < 2e-3
