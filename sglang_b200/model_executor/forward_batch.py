@@ -65,6 +65,8 @@ class ForwardBatch:
     seq_lens_cpu: Optional[np.ndarray] = None
     q_lens_cpu: Optional[np.ndarray] = None
     pp_hidden: Any = None
+    capture_aux: Any = None          # EAGLE-3: set of (global) layer indices whose input hidden state is captured ...
+    aux_hidden: Any = None           # ... into this [T, n_aux * H] tensor by the model
     rope_override: Any = None        # (cos_sin rows [T, rot], row index [T]): per-token rotary table (M-RoPE)
     mrope_positions: Any = None      # i64 [3, T]
     cp: Any = None                   # layers/cp.py CpMeta inside a context-parallel prefill

@@ -156,6 +156,7 @@ class ModelRunner:
         self.lora_manager = None
         self.hidden_tap = None          # callable(ScheduleBatch, hidden[T,H]) installed by feature-based draft workers (EAGLE)
         self.last_verify_hidden = None
+        self.aux_layer_ids = None       # EAGLE-3: capture the hidden states entering these layers instead of the final one
         self.profiler = None
         self.expert_recorder = None
         if (self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1
@@ -232,6 +233,7 @@ class ModelRunner:
     # ------------------------------------------------------------------ prefill context parallelism (layers/cp.py)
     def _cp_eligible(self, sb: ScheduleBatch, fb: ForwardBatch) -> bool:
         return (fb.cu_q is not None and fb.input_ids is not None and fb.num_tokens >= self.cp_min_tokens and fb.mm_embeds is None
+                and self.aux_layer_ids is None
                 and self.lora_manager is None and sb.spec_info is None and fb.custom_mask is None and self.pp.world_size == 1
                 and not getattr(self.model, "is_mrope", False))
 
@@ -263,6 +265,7 @@ class ModelRunner:
     def _tbo_static_ok(self) -> bool:
         m = getattr(self.model, "model", None)
         return (m is not None and hasattr(m, "embed") and self.pp.world_size == 1 and self.lora_manager is None and self.dcp is None
+                and self.aux_layer_ids is None
                 and self.cp is None and not getattr(self.model, "is_mrope", False) and type(self.model).forward is _LLAMA_FORWARD)
 
     def _tbo_eligible(self, sb: ScheduleBatch, fb: ForwardBatch) -> bool:
@@ -425,6 +428,8 @@ class ModelRunner:
             self.lora_manager.prepare_batch(sb, fb)
         if not self.pp.is_first:
             fb.pp_hidden = self._pp_recv(fb.num_tokens)
+        if self.aux_layer_ids is not None and not decode:
+            fb.capture_aux = self.aux_layer_ids
         if self.cp is not None and not decode and self._cp_eligible(sb, fb):
             hidden = self._forward_cp(sb, fb)
         elif self.args.enable_two_batch_overlap and self._tbo_eligible(sb, fb):
@@ -432,7 +437,7 @@ class ModelRunner:
         else:
             hidden = self.model(fb)
         if self.hidden_tap is not None and not decode and self.pp.is_last:
-            self.hidden_tap(sb, hidden)          # EAGLE: target features of the prefilled positions
+            self.hidden_tap(sb, hidden if fb.aux_hidden is None else fb.aux_hidden)      # EAGLE: target features of the prefilled positions
         res = BatchResult()
         res.batch_size = B
         if not self.pp.is_last:
@@ -503,8 +508,10 @@ class ModelRunner:
             if cm is not None:       # token-tree verification: every node attends to the prefix and its own ancestors only
                 assert self.dcp is None, "tree drafts + DCP: not supported"
                 fb.custom_mask = torch.from_numpy(cm).to(self.device)
+            if self.aux_layer_ids is not None:
+                fb.capture_aux = self.aux_layer_ids
             hidden = self.model(fb)
-            self.last_verify_hidden = hidden if self.hidden_tap is not None else None
+            self.last_verify_hidden = (hidden if fb.aux_hidden is None else fb.aux_hidden) if self.hidden_tap is not None else None
             logits = self.model.compute_logits(hidden)          # [T, V]
             reps = torch.from_numpy(sb.q_lens.astype(np.int64)).to(self.device)
             s = fb.sampling

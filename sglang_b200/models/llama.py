@@ -189,8 +189,15 @@ class LlamaModel(nn.Module):
             residual = None
         else:
             h, residual = fb.pp_hidden
-        for layer in self.layers:
+        cap = fb.capture_aux
+        aux = [] if cap is not None else None
+        for i, layer in enumerate(self.layers):
+            if cap is not None and (i + self.start_layer) in cap:       # EAGLE-3 auxiliary features: the residual stream entering this layer
+                h = h.resolve() if hasattr(h, "resolve") else h
+                aux.append(h if residual is None else h + residual)
             h, residual = layer(h, residual, fb)
+        if aux:
+            fb.aux_hidden = torch.cat(aux, dim=-1)
         if not self.pp.is_last:
             if hasattr(h, "resolve"):
                 h = h.resolve()

@@ -262,3 +262,167 @@ class EagleSpecWorker(BaseSpecWorker):
         idx = {c: j for j, c in enumerate(keep)}
         assert all(cand_par[c] < 0 or cand_par[c] in idx for c in keep)
         return [cand_tok[c] for c in keep], [idx[cand_par[c]] if cand_par[c] >= 0 else -1 for c in keep]
+
+
+# ================================================================================================ EAGLE-3
+class Eagle3DraftModel(nn.Module):
+    """EAGLE-3 draft (reference ``models/llama_eagle3.py``): ``fc`` fuses the hidden states of several target layers (low / mid / high) into one
+    feature; ONE decoder layer whose attention reads ``[input_layernorm(embed(token)) ; hidden_norm(feature)]`` (2H wide); own final norm and
+    LM head over a reduced draft vocabulary with a ``d2t`` offset table back to target ids.  Later draft steps feed the layer's own
+    pre-norm output back in as the feature."""
+
+    def __init__(self, cfg: ModelConfig, device: Any, n_aux: int = 3, target_hidden: Optional[int] = None, draft_vocab: Optional[int] = None):
+        super().__init__()
+        from ..layers.linear import QKVParallelLinear
+
+        dtype = _DT[cfg.dtype]
+        H = cfg.hidden_size
+        self.n_aux, self.Ht = n_aux, target_hidden or H
+        self.fc = nn.Linear(self.Ht * n_aux, H, bias=False, dtype=dtype)
+        rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
+                               cfg.partial_rotary_factor, device)
+        self.layer = LlamaDecoderLayer(cfg, 0, dtype, None, rope, "model.layers.0")
+        sa = self.layer.self_attn
+        sa.qkv_proj = QKVParallelLinear(2 * H, cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.attention_bias, dtype, None,
+                                        "model.layers.0.self_attn.qkv_proj", tp_group=sa.qkv_proj.tp)
+        self.layer.hidden_norm = RMSNorm(H, cfg.rms_norm_eps, dtype)
+        self.norm = RMSNorm(H, cfg.rms_norm_eps, dtype)
+        self.draft_vocab = draft_vocab or cfg.vocab_size
+        self.lm_head = nn.Linear(H, self.draft_vocab, bias=False, dtype=dtype)
+        self.register_buffer("d2t", torch.zeros(self.draft_vocab, dtype=torch.long), persistent=False)
+
+    def fuse(self, aux: torch.Tensor) -> torch.Tensor:
+        return self.fc(aux.to(self.fc.weight.dtype))
+
+    def forward(self, fb: ForwardBatch, tok_embeds: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        L = self.layer
+        residual = hidden
+        x = torch.cat([L.input_layernorm(tok_embeds), L.hidden_norm(hidden)], dim=-1)
+        a = L.self_attn(x, fb)
+        a = a.resolve() if hasattr(a, "resolve") else a
+        h, residual = L.post_attention_layernorm(a, residual.clone())
+        m = L.mlp(h)
+        m = m.resolve() if hasattr(m, "resolve") else m
+        normed, pre = self.norm(m, residual)
+        return normed, pre                  # (what the draft LM head reads, the feature the next draft step consumes)
+
+    def to_target_ids(self, draft_ids: torch.Tensor) -> torch.Tensor:
+        return draft_ids + self.d2t[draft_ids]
+
+    def load_weights(self, weights) -> List[str]:
+        params = dict(self.named_parameters())
+        loaded = []
+        stacked = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v"),
+                   (".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
+        mods = dict(self.named_modules())
+        for name, w in weights:
+            if name == "d2t":
+                self.d2t.copy_(w.to(torch.long)[: self.d2t.shape[0]])
+                loaded.append(name)
+                continue
+            n = name
+            for a, b in (("model.midlayer.", "layer."), ("midlayer.", "layer."), ("model.layers.0.", "layer."), ("layers.0.", "layer."),
+                         ("model.fc.", "fc."), ("model.norm.", "norm.")):
+                if n.startswith(a):
+                    n = b + n[len(a):]
+                    break
+            target, shard = n, None
+            for merged, orig, sid in stacked:
+                if orig + "." in n:
+                    target, shard = n.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded
+
+
+def default_aux_layers(num_layers: int) -> List[int]:
+    """the three taps EAGLE-3 trains with: low, middle, high (reference ``set_eagle3_layers_to_capture``: [2, L // 2, L - 3])"""
+    return sorted({min(num_layers - 1, max(0, x)) for x in (2, num_layers // 2, num_layers - 3)})
+
+
+class Eagle3SpecWorker(EagleSpecWorker):
+    """features = concatenated target hidden states of ``aux_layers`` (captured inside the target's forward); chain drafts"""
+
+    def __init__(self, args: Any, runner: Any, scheduler: Any, window: int = 48):
+        BaseSpecWorker.__init__(self, args, runner, scheduler)
+        self.topk, self.window = 1, window
+        tcfg = runner.cfg
+        path = args.speculative_draft_model_path
+        real = bool(path) and not path.startswith("dummy:")
+        cfg = load_model_config(path) if real else tcfg
+        extra = {}
+        if real:
+            import json
+            import os
+
+            with open(os.path.join(path, "config.json")) as f:
+                extra = json.load(f)
+        ec = extra.get("eagle_config") or {}
+        self.aux_layers = list(ec.get("eagle_aux_hidden_state_layer_ids") or default_aux_layers(tcfg.num_hidden_layers))
+        self.cfg = cfg
+        self.draft = Eagle3DraftModel(cfg, runner.device, len(self.aux_layers), extra.get("target_hidden_size") or tcfg.hidden_size,
+                                      extra.get("draft_vocab_size")).to(runner.device)
+        if real:
+            from ..model_loader.loader import iter_safetensors
+
+            got = self.draft.load_weights(iter_safetensors(path))
+            if not any(n.startswith("lm_head") for n in got):      # checkpoints without a head share the target's
+                head = runner.model.lm_head if runner.model.lm_head is not None else runner.model.model.embed_tokens
+                self.draft.lm_head.weight.data.copy_(head.weight[: self.draft.draft_vocab])
+        else:
+            g = torch.Generator(device="cpu").manual_seed(args.random_seed + 31)
+            for p in self.draft.parameters():
+                if p.dim() > 1:
+                    p.data.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
+        a0 = self.draft.layer.self_attn.attn
+        self.ps = 16
+        self.pool = KVPool(2 + (window + 2 * self.num_draft + 32) // self.ps, self.ps, 1, a0.num_kv_heads, cfg.head_dim, runner.dtype, str(runner.device))
+        runner.aux_layer_ids = set(self.aux_layers)
+        runner.hidden_tap = self._tap_prefill
+
+    @torch.no_grad()
+    def propose(self, req: Any, max_draft: int) -> List[int]:
+        st = getattr(req, "_eagle", None)
+        if st is None or max_draft <= 0:
+            return []
+        first, feats = st
+        toks = req.origin_input_ids + req.output_ids
+        L = len(toks) - 1
+        n = feats.shape[0]
+        if first + n != L or n == 0:
+            return []
+        dev = self.runner.device
+        embed = self.runner.model.model.embed_tokens
+        npages = self.pool.num_pages - 1
+        pt = torch.arange(1, npages + 1, dtype=torch.int32, device=dev).view(1, -1)
+        pt = torch.cat([torch.zeros_like(pt), pt], 0)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        ids = i32(toks[first + 1: L + 1])
+        hidden = self.draft.fuse(feats)                      # [n, H]: one fused feature per window position
+        out: List[int] = []
+        base = 0
+        for _ in range(max_draft):
+            m = ids.shape[0]
+            rel = torch.arange(base, base + m, dtype=torch.int32, device=dev)
+            fb = ForwardBatch(mode=ForwardMode.EXTEND, batch_size=1, num_tokens=m, input_ids=ids, positions=rel + first,
+                              out_cache_loc=(rel + self.ps).to(torch.int32), req_slots=torch.ones(1, dtype=torch.int32, device=dev),
+                              seq_lens=i32([base + m]), cu_q=i32([0, m]), q_lens=i32([m]), last_idx=None, sample_slots=None, max_q_len=m,
+                              max_kv_len=base + m, page_table=pt, page_size=self.ps, kv_pool=self.pool)
+            normed, pre = self.draft(fb, embed(ids), hidden)
+            t = int(self.draft.to_target_ids(self.draft.lm_head(normed[-1:]).argmax(-1))[0])
+            out.append(t)
+            base += m
+            ids, hidden = i32([t]), pre[-1:]                 # autoregression on the draft's own (pre-norm) feature
+            if base + 1 >= self.window + 2 * self.num_draft + 16:
+                break
+        return out
+
+    def propose_tree(self, req: Any, max_nodes: int):
+        return BaseSpecWorker.propose_tree(self, req, max_nodes)

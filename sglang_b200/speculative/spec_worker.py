@@ -280,7 +280,11 @@ def create_spec_worker(args: Any, runner: Any, scheduler: Any) -> BaseSpecWorker
     algo = (args.speculative_algorithm or "").upper()
     if algo == "NGRAM":
         return NgramSpecWorker(args, runner, scheduler)
-    if algo in ("EAGLE", "EAGLE3"):
+    if algo == "EAGLE3":
+        from .eagle import Eagle3SpecWorker
+
+        return Eagle3SpecWorker(args, runner, scheduler)
+    if algo == "EAGLE":
         from .eagle import EagleSpecWorker
 
         return EagleSpecWorker(args, runner, scheduler)

@@ -135,3 +135,66 @@ def test_eagle_tree_drafts_exact():
     assert w.total_tree_verifies > 0
     eng.scheduler.check_invariants()
     eng.shutdown()
+
+
+def test_eagle3_multi_layer_features_exact_and_checkpoint_loading(tmp_path):
+    """EAGLE-3: hidden states of three target layers are captured inside the target forward, fused by ``fc`` and drafted through the 2H-wide
+    layer; outputs stay exact; a checkpoint in the published layout (midlayer.*, fc, norm, lm_head over a reduced vocabulary, d2t) loads"""
+    import json
+
+    from safetensors.torch import save_file
+
+    from sglang_b200.speculative.eagle import Eagle3DraftModel, default_aux_layers
+
+    prompts = _prompts()
+    sp = {"max_new_tokens": 24, "temperature": 0, "ignore_eos": True}
+    plain = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, json_model_override_args=json.dumps({"num_hidden_layers": 6}))
+    want = [o["output_ids"] for o in plain.generate(input_ids=prompts, sampling_params=sp)]
+    cfg = plain.model_config
+    plain.shutdown()
+    assert default_aux_layers(6) == [2, 3] and default_aux_layers(32) == [2, 16, 29]
+    # a draft checkpoint in the public naming, reduced draft vocabulary of 128 ids with a d2t table
+    torch_mod = __import__("torch")
+    torch_mod.manual_seed(0)
+    ref = Eagle3DraftModel(cfg, "cpu", n_aux=2, draft_vocab=128)
+    sd = {}
+    for n, p in ref.named_parameters():
+        w = torch_mod.randn_like(p) * 0.05 if p.dim() > 1 else torch_mod.ones_like(p)
+        p.data.copy_(w)
+        n2 = n.replace("layer.", "midlayer.", 1) if n.startswith("layer.") else n
+        if ".qkv_proj." in n2:
+            q, k, v = w.split([cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim])
+            for nm, part in (("q_proj", q), ("k_proj", k), ("v_proj", v)):
+                sd[n2.replace("qkv_proj", nm)] = part.contiguous()
+        elif ".gate_up_proj." in n2:
+            g, u = w.chunk(2)
+            sd[n2.replace("gate_up_proj", "gate_proj")], sd[n2.replace("gate_up_proj", "up_proj")] = g.contiguous(), u.contiguous()
+        else:
+            sd[n2] = w.contiguous()
+    sd["d2t"] = torch_mod.arange(128) * 3            # draft id i -> target id 4 i
+    d = tmp_path / "eagle3"
+    d.mkdir()
+    save_file(sd, str(d / "model.safetensors"))
+    hf = {"architectures": ["LlamaForCausalLMEagle3"], "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+          "num_hidden_layers": 1, "num_attention_heads": cfg.num_attention_heads, "num_key_value_heads": cfg.num_key_value_heads,
+          "vocab_size": cfg.vocab_size, "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps,
+          "rope_theta": cfg.rope_theta, "torch_dtype": "float32", "draft_vocab_size": 128, "target_hidden_size": cfg.hidden_size,
+          "eagle_config": {"eagle_aux_hidden_state_layer_ids": [1, 4]}}
+    (d / "config.json").write_text(json.dumps(hf))
+    for path in (None, str(d)):
+        eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, json_model_override_args=json.dumps({"num_hidden_layers": 6}),
+                         speculative_algorithm="EAGLE3", speculative_num_draft_tokens=3, chunked_prefill_size=16,
+                         speculative_draft_model_path=path)
+        w = eng.scheduler.spec_worker
+        assert type(w).__name__ == "Eagle3SpecWorker" and eng.runner.aux_layer_ids == ({1, 4} if path else {2, 3})
+        outs = eng.generate(input_ids=prompts, sampling_params=sp)
+        assert [o["output_ids"] for o in outs] == want
+        assert w.total_drafted > 0 and w.total_verify > 0
+        if path:
+            assert w.draft.draft_vocab == 128 and int(w.draft.d2t[5]) == 15
+            got = dict(w.draft.named_parameters())
+            for n, p in ref.named_parameters():
+                assert torch_mod.equal(got[n], p), n
+            feats = next(iter([r for r in []]), None)
+        eng.scheduler.check_invariants()
+        eng.shutdown()
