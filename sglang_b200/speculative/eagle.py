@@ -92,7 +92,7 @@ class EagleSpecWorker(BaseSpecWorker):
         path = args.speculative_draft_model_path
         cfg = load_model_config(path) if path and not path.startswith("dummy:") else tcfg
         self.cfg = cfg
-        self.draft = EagleDraftModel(cfg, runner.device).to(runner.device)
+        self.draft = self.make_draft(cfg, runner).to(runner.device)
         if path and not path.startswith("dummy:"):
             from ..model_loader.loader import iter_safetensors
 
@@ -104,11 +104,14 @@ class EagleSpecWorker(BaseSpecWorker):
                     p.data.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
         a0 = self.draft.layer.self_attn.attn
         self.ps = 16
-        self.pool = KVPool(2 + (window + 2 * self.num_draft + self.topk * max(1, args.speculative_num_steps) + 32) // self.ps, self.ps, 1, a0.num_kv_heads, cfg.head_dim, runner.dtype,
-                           str(runner.device))
+        self.pool = KVPool(2 + (window + 2 * self.num_draft + self.topk * max(1, args.speculative_num_steps) + 32) // self.ps, self.ps, 1, a0.num_kv_heads,
+                           getattr(a0, "kv_head_dim", None) or cfg.head_dim, runner.dtype, str(runner.device))
         # the feature window lives ON the request object (``req._eagle``: (position of the first kept row, features [n, H])) so it
         # is dropped with the request — no registry to clean up on finish / abort / retraction
         runner.hidden_tap = self._tap_prefill
+
+    def make_draft(self, cfg: ModelConfig, runner: Any) -> nn.Module:
+        return EagleDraftModel(cfg, runner.device)
 
     # ---- feature bookkeeping
     def _append(self, req: Any, start_pos: int, rows: torch.Tensor) -> None:
@@ -426,3 +429,87 @@ class Eagle3SpecWorker(EagleSpecWorker):
 
     def propose_tree(self, req: Any, max_nodes: int):
         return BaseSpecWorker.propose_tree(self, req, max_nodes)
+
+
+# ================================================================================================ MTP / NextN (DeepSeek-V3 style)
+class MtpDraftModel(nn.Module):
+    """multi-token-prediction module shipped inside the target checkpoint as layer ``num_hidden_layers`` (reference ``models/deepseek_nextn.py``):
+    ``eh_proj([enorm(embed(token)) ; hnorm(previous hidden)])`` -> one full decoder layer of the target's own kind (MLA + MoE for DeepSeek) ->
+    ``shared_head.norm``; the LM head is the target's.  Same driver as EAGLE: autoregression on its own output hidden state."""
+
+    def __init__(self, cfg: ModelConfig, device: Any, layer_cls: Any):
+        super().__init__()
+        dtype = _DT[cfg.dtype]
+        H = cfg.hidden_size
+        self.enorm, self.hnorm = RMSNorm(H, cfg.rms_norm_eps, dtype), RMSNorm(H, cfg.rms_norm_eps, dtype)
+        self.eh_proj = nn.Linear(2 * H, H, bias=False, dtype=dtype)
+        rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
+                               cfg.partial_rotary_factor, device)
+        # the MTP layer sits AFTER the dense prefix: build it with the index of the last layer so MoE families make it sparse
+        self.layer = layer_cls(cfg, 0, dtype, None, rope, f"model.layers.{cfg.num_hidden_layers - 1}")
+        self.norm = RMSNorm(H, cfg.rms_norm_eps, dtype)
+        self.src_layer = cfg.num_hidden_layers
+
+    def forward(self, fb: ForwardBatch, tok_embeds: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
+        x = self.eh_proj(torch.cat([self.enorm(tok_embeds), self.hnorm(feats.to(tok_embeds.dtype))], dim=-1))
+        h, res = self.layer(x, None, fb)
+        h = h.resolve() if hasattr(h, "resolve") else h
+        return self.norm(h) if res is None else self.norm(h, res)[0]
+
+    def load_weights(self, weights) -> List[str]:
+        """picks ``model.layers.{L}.*`` out of the TARGET checkpoint"""
+        pre = f"model.layers.{self.src_layer}."
+        params = dict(self.named_parameters())
+        mods = dict(self.named_modules())
+        stacked = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v"),
+                   (".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
+        shard_of = {"gate_proj": "w1", "up_proj": "w3", "down_proj": "w2"}
+        loaded = []
+        for name, w in weights:
+            if not name.startswith(pre):
+                continue
+            n = name[len(pre):]
+            if n.startswith(("embed_tokens.", "shared_head.head.")):
+                continue                        # shared with the target
+            n = n.replace("shared_head.norm.", "norm.") if n.startswith("shared_head.norm.") else (n if n.startswith(("enorm.", "hnorm.", "eh_proj.")) else "layer." + n)
+            if ".mlp.experts." in n and n.split(".experts.")[1].split(".")[0].isdigit():
+                ex = mods.get("layer.mlp.experts")
+                if ex is not None:
+                    eid, proj = int(n.split(".experts.")[1].split(".")[0]), n.split(".")[-2]
+                    ex.weight_loader(ex.w2 if proj == "down_proj" else ex.w13, w, eid, shard_of[proj])
+                    loaded.append(name)
+                continue
+            if n.endswith("mlp.gate.e_score_correction_bias"):
+                g = mods.get("layer.mlp.gate")
+                if g is not None and getattr(g, "e_score_correction_bias", None) is not None:
+                    g.e_score_correction_bias.data.copy_(w.float())
+                    loaded.append(name)
+                continue
+            target, shard = n, None
+            for merged, orig, sid in stacked:
+                if orig + "." in n:
+                    target, shard = n.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded
+
+
+class MtpSpecWorker(EagleSpecWorker):
+    """``--speculative-algorithm NEXTN`` (alias MTP): the draft is the target checkpoint's own MTP layer (``--speculative-draft-model-path``
+    defaults to the target path)"""
+
+    def __init__(self, args: Any, runner: Any, scheduler: Any, window: int = 48):
+        if not args.speculative_draft_model_path and not str(args.model_path).startswith("dummy:"):
+            args.speculative_draft_model_path = args.model_path
+        super().__init__(args, runner, scheduler, window)
+
+    def make_draft(self, cfg: ModelConfig, runner: Any) -> nn.Module:
+        layer_cls = type(runner.model.model.layers[-1])
+        return MtpDraftModel(runner.cfg, runner.device, layer_cls)

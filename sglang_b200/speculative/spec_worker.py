@@ -280,6 +280,10 @@ def create_spec_worker(args: Any, runner: Any, scheduler: Any) -> BaseSpecWorker
     algo = (args.speculative_algorithm or "").upper()
     if algo == "NGRAM":
         return NgramSpecWorker(args, runner, scheduler)
+    if algo in ("NEXTN", "MTP"):
+        from .eagle import MtpSpecWorker
+
+        return MtpSpecWorker(args, runner, scheduler)
     if algo == "EAGLE3":
         from .eagle import Eagle3SpecWorker
 

@@ -198,3 +198,58 @@ def test_eagle3_multi_layer_features_exact_and_checkpoint_loading(tmp_path):
             feats = next(iter([r for r in []]), None)
         eng.scheduler.check_invariants()
         eng.shutdown()
+
+
+@pytest.mark.parametrize("preset", ["tiny-llama", "tiny-deepseek-v3"])
+def test_mtp_nextn_draft_from_target_checkpoint(tmp_path, preset):
+    """NEXTN: the draft module is layer ``num_hidden_layers`` of the target checkpoint (enorm / hnorm / eh_proj / a full decoder layer of the
+    target's kind / shared_head.norm); loads from the same directory, outputs stay exact"""
+    import json
+
+    import torch
+    from safetensors.torch import save_file
+
+    from sglang_b200.configs.model_config import load_model_config
+
+    cfg = load_model_config(f"dummy:{preset}")
+    plain = sgl.Engine(model_path=f"dummy:{preset}", page_size=4)
+    model = plain.runner.model
+    it = model.dummy_checkpoint(cfg, "cpu", torch.float32, 0) if hasattr(model, "dummy_checkpoint") else None
+    if it is None:
+        from sglang_b200.model_loader.loader import dummy_checkpoint_iterator
+
+        it = dummy_checkpoint_iterator(cfg, torch.device("cpu"), torch.float32, 0)
+    sd = {n: w.contiguous() for n, w in it}
+    L = cfg.num_hidden_layers
+    g = torch.Generator().manual_seed(1)
+    last = f"model.layers.{L - 1}."
+    for n in [k for k in sd if k.startswith(last)]:                       # the MTP layer has the shape of the last decoder layer
+        sd[f"model.layers.{L}." + n[len(last):]] = torch.randn(sd[n].shape, generator=g) * 0.05 if sd[n].dim() > 1 else sd[n].clone()
+    H = cfg.hidden_size
+    sd[f"model.layers.{L}.enorm.weight"], sd[f"model.layers.{L}.hnorm.weight"] = torch.ones(H), torch.ones(H)
+    sd[f"model.layers.{L}.eh_proj.weight"] = torch.randn(H, 2 * H, generator=g) * 0.05
+    sd[f"model.layers.{L}.shared_head.norm.weight"] = torch.ones(H)
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    save_file(sd, str(d / "model.safetensors"))
+    import dataclasses
+
+    hf = {k: v for k, v in dataclasses.asdict(cfg).items() if v is not None and k not in ("name", "architecture", "dtype", "mamba", "vision", "audio")}
+    hf.update(architectures=[cfg.architecture], torch_dtype="float32", n_routed_experts=cfg.num_local_experts or None)
+    (d / "config.json").write_text(json.dumps({k: v for k, v in hf.items() if v is not None}))
+    prompts = _prompts()
+    sp = {"max_new_tokens": 20, "temperature": 0, "ignore_eos": True}
+    plain.shutdown()
+    ref = sgl.Engine(model_path=str(d), page_size=4, skip_tokenizer_init=True)
+    want = [o["output_ids"] for o in ref.generate(input_ids=prompts, sampling_params=sp)]
+    ref.shutdown()
+    eng = sgl.Engine(model_path=str(d), page_size=4, skip_tokenizer_init=True, speculative_algorithm="NEXTN", speculative_num_draft_tokens=3)
+    w = eng.scheduler.spec_worker
+    assert type(w).__name__ == "MtpSpecWorker" and type(w.draft.layer).__name__ == type(eng.runner.model.model.layers[-1]).__name__
+    loaded = torch.load if False else None
+    assert float(w.draft.eh_proj.weight.abs().sum()) > 0 and torch.equal(w.draft.eh_proj.weight, sd[f"model.layers.{L}.eh_proj.weight"])
+    outs = eng.generate(input_ids=prompts, sampling_params=sp)
+    assert [o["output_ids"] for o in outs] == want
+    assert w.total_drafted > 0
+    eng.scheduler.check_invariants()
+    eng.shutdown()
