@@ -154,6 +154,31 @@ def create_app(engine: Any):
         b = await request.json()
         return await _ctl(engine.get_weights_by_name, b["name"], b.get("truncate_size", 100))
 
+    @app.api_route("/hicache/storage-backend", methods=["GET", "PUT", "DELETE"])
+    async def hicache_storage_backend(request: Request):
+        """inspect / attach / detach the L3 storage of the hierarchical cache at run time (reference http_server.py:1078-1141)"""
+        from ..mem_cache.hicache_storage import create_storage
+
+        tree = engine.scheduler.tree
+        if not hasattr(tree, "storage"):
+            return JSONResponse({"success": False, "message": "hierarchical cache is not enabled"}, status_code=400)
+        if request.method == "GET":
+            return {"attached": tree.storage is not None, "stats": tree.storage.stats() if tree.storage is not None else {}}
+        if request.method == "DELETE":
+            if tree.storage is not None:
+                tree.storage.close()
+            tree.storage = None
+            return {"success": True, "message": "detached"}
+        b = await request.json()
+        try:
+            new = create_storage(b["backend"], b.get("config") or {})
+        except (ValueError, KeyError) as e:
+            return JSONResponse({"success": False, "message": str(e)}, status_code=400)
+        if tree.storage is not None:
+            tree.storage.close()
+        tree.storage = new
+        return {"success": True, "message": f"attached {b['backend']}"}
+
     @app.api_route("/weights_checker", methods=["GET", "POST"])
     async def weights_checker(request: Request):
         b = await request.json() if await request.body() else {}

@@ -12,6 +12,7 @@ to files named by the chained page hash (``sglb_rt.hash_pages``), giving cross-r
 """
 from __future__ import annotations
 
+import json
 import logging
 import os
 from typing import Any, Dict, List, Optional, Tuple
@@ -25,29 +26,7 @@ from .radix_cache import _EMPTY, RadixCache, TreeNode
 logger = logging.getLogger(__name__)
 
 
-class FileStorage:
-    """L3: one file per page hash (reference HiCacheFile)"""
-
-    def __init__(self, root: str):
-        self.root = root
-        os.makedirs(root, exist_ok=True)
-
-    def _p(self, h: int) -> str:
-        return os.path.join(self.root, f"{h:016x}.kv")
-
-    def exists(self, h: int) -> bool:
-        return os.path.exists(self._p(h))
-
-    def put(self, h: int, page: torch.Tensor) -> None:
-        tmp = self._p(h) + ".tmp"
-        torch.save(page.contiguous().cpu(), tmp)
-        os.replace(tmp, self._p(h))
-
-    def get(self, h: int) -> Optional[torch.Tensor]:
-        try:
-            return torch.load(self._p(h), map_location="cpu", weights_only=True)
-        except FileNotFoundError:
-            return None
+from .hicache_storage import FileStorage, HiCacheStorage, create_storage  # noqa: E402,F401  (FileStorage re-exported for callers)
 
 
 class HiRadixCache(RadixCache):
@@ -219,7 +198,10 @@ def attach_hicache(scheduler: Any, runner: Any, args: Any) -> HiRadixCache:
         # bound pinned memory to something sane for a dev box; production sizes it from --hicache-ratio
         per_page = runner.kv_pool.buf[:, :, :1].numel() * runner.kv_pool.buf.element_size() * runner.page_size
         host_pages = min(host_pages, max(8, int(64 * (1 << 30) // max(1, per_page))))
-    storage = FileStorage(args.hicache_storage_dir or "/tmp/sglb_hicache") if args.hicache_storage_backend == "file" else None
+    extra = json.loads(args.hicache_storage_backend_extra_config) if getattr(args, "hicache_storage_backend_extra_config", None) else {}
+    if args.hicache_storage_dir:
+        extra.setdefault("dir", args.hicache_storage_dir)
+    storage = create_storage(args.hicache_storage_backend, extra)
     tree = HiRadixCache(scheduler.allocator, scheduler.page_size, runner.kv_pool, host_pages, args.radix_eviction_policy,
                         args.hicache_write_policy, storage)
     scheduler.tree = tree

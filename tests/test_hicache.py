@@ -4,9 +4,24 @@ import numpy as np
 import sglang_b200 as sgl
 
 
-def test_host_tier_roundtrip_and_l3(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("backend", ["file", "shm", "memory", "remote"])
+def test_host_tier_roundtrip_and_l3(tmp_path, backend):
+    import json
+
+    from sglang_b200.mem_cache.hicache_storage import PageServer
+
+    extra, srv = {}, None
+    if backend == "remote":
+        srv = PageServer("127.0.0.1", 0).start()
+        extra = {"port": srv.port}
+    elif backend == "shm":
+        extra = {"name": f"sglb_test_{tmp_path.name}"}
     eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=256, enable_hierarchical_cache=True,
-                     hicache_ratio=4.0, hicache_storage_backend="file", hicache_storage_dir=str(tmp_path), radix_cache_impl="python")
+                     hicache_ratio=4.0, hicache_storage_backend=backend, hicache_storage_dir=str(tmp_path) if backend == "file" else None,
+                     hicache_storage_backend_extra_config=json.dumps(extra), radix_cache_impl="python")
     rng = np.random.default_rng(0)
     sp = {"max_new_tokens": 4, "temperature": 0, "ignore_eos": True}
     A = rng.integers(3, 200, size=100).tolist()
@@ -26,3 +41,34 @@ def test_host_tier_roundtrip_and_l3(tmp_path):
     third = eng.generate(input_ids=A, sampling_params=sp)
     assert third["output_ids"] == ref["output_ids"]
     assert tree.stats["l3_hits_pages"] > 0 and third["meta_info"]["cached_tokens"] > 0
+    assert tree.storage.stats().get("backend", backend) in (backend, "memory")
+    if backend == "remote":
+        # a SECOND engine sharing the page server gets the prefix without ever having computed it
+        eng2 = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=256, enable_hierarchical_cache=True, hicache_ratio=4.0,
+                          hicache_storage_backend=f"remote://127.0.0.1:{srv.port}", radix_cache_impl="python")
+        o = eng2.generate(input_ids=A, sampling_params=sp)
+        assert o["output_ids"] == ref["output_ids"] and o["meta_info"]["cached_tokens"] > 0
+        eng2.shutdown()
+        srv.shutdown()
+    if backend == "shm":
+        import shutil
+
+        shutil.rmtree(tree.storage.root, ignore_errors=True)
+    eng.shutdown()
+
+
+def test_runtime_attach_detach_storage_backend():
+    from fastapi.testclient import TestClient
+
+    from sglang_b200.entrypoints.http_server import create_app
+
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=256, enable_hierarchical_cache=True, hicache_ratio=2.0,
+                     radix_cache_impl="python", log_level="error")
+    with TestClient(create_app(eng)) as c:
+        assert c.get("/hicache/storage-backend").json()["attached"] is False
+        assert c.put("/hicache/storage-backend", json={"backend": "memory", "config": {"capacity_pages": 64}}).json()["success"]
+        assert c.get("/hicache/storage-backend").json() == {"attached": True, "stats": {"backend": "memory", "pages": 0, "hits": 0, "misses": 0}}
+        assert c.put("/hicache/storage-backend", json={"backend": "nope"}).status_code == 400
+        assert c.delete("/hicache/storage-backend").json()["success"]
+        assert c.get("/hicache/storage-backend").json()["attached"] is False
+    eng.shutdown()
