@@ -493,6 +493,10 @@ class Engine:
     def get_weights_by_name(self, name: str, truncate_size: int = 100) -> Any:
         return self._control(ios.GetWeightsByNameReq(name, truncate_size)).parameter
 
+    def send_weights_to_remote_instance(self, master_address: str, master_port: int, group_name: str = "remote_instance_load",
+                                        backend: str = "nccl") -> Any:
+        return self._control(ios.SendWeightsToRemoteInstanceReq(master_address, int(master_port), group_name, backend))
+
     def weights_checker(self, action: str = "checksum") -> Any:
         return self._control(ios.WeightsCheckerReq(action))
 

@@ -179,6 +179,13 @@ def create_app(engine: Any):
         tree.storage = new
         return {"success": True, "message": f"attached {b['backend']}"}
 
+    @app.post("/send_weights_to_remote_instance")
+    async def send_weights_to_remote_instance(request: Request):
+        b = await request.json()
+        r = await _ctl(engine.send_weights_to_remote_instance, b["master_address"], b["master_port"], b.get("group_name", "remote_instance_load"),
+                       b.get("backend", "nccl"))
+        return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
+
     @app.api_route("/weights_checker", methods=["GET", "POST"])
     async def weights_checker(request: Request):
         b = await request.json() if await request.body() else {}

@@ -308,6 +308,16 @@ class GetWeightsByNameReq:
 
 
 @message
+class SendWeightsToRemoteInstanceReq:
+    """seed side of the remote-instance loader: join a 2-rank group per TP rank (the new instance hosts the store at
+    ``master_address:master_port + tp_rank``) and broadcast every local parameter shard"""
+    master_address: str = "127.0.0.1"
+    master_port: int = 0
+    group_name: str = "remote_instance_load"
+    backend: str = "nccl"
+
+
+@message
 class WeightsCheckerReq:
     """checksum every parameter shard (reference /weights_checker, utils/weight_checker.py): compare instances / ranks / before-after a swap"""
     action: str = "checksum"       # checksum | snapshot | compare (against the stored snapshot)

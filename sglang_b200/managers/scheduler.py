@@ -129,7 +129,8 @@ class Scheduler:
         if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq, ios.GetWeightsByNameReq,
                             ios.InitWeightsUpdateGroupReq, ios.DestroyWeightsUpdateGroupReq, ios.UpdateWeightsFromDistributedReq,
                             ios.ReleaseMemoryOccupationReq, ios.ResumeMemoryOccupationReq, ios.ProfileReq,
-                            ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq, ios.WeightsCheckerReq)):
+                            ios.LoadLoRAAdapterReq, ios.UnloadLoRAAdapterReq, ios.ExpertDistributionReq, ios.WeightsCheckerReq,
+                            ios.SendWeightsToRemoteInstanceReq)):
             self.drain()
             if isinstance(msg, (ios.UpdateWeightsFromDiskReq, ios.UpdateWeightsFromTensorReq)) or \
                     (isinstance(msg, ios.UpdateWeightsFromDistributedReq) and msg.flush_cache):

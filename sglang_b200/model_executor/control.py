@@ -26,6 +26,8 @@ def handle(runner: Any, msg: Any) -> Any:
         return _update_from_tensor(runner, msg)
     if isinstance(msg, ios.GetWeightsByNameReq):
         return _get_weights(runner, msg)
+    if isinstance(msg, ios.SendWeightsToRemoteInstanceReq):
+        return _send_weights_to_remote(runner, msg)
     if isinstance(msg, ios.WeightsCheckerReq):
         return _weights_checker(runner, msg)
     if isinstance(msg, ios.InitWeightsUpdateGroupReq):
@@ -56,6 +58,91 @@ def handle(runner: Any, msg: Any) -> Any:
 
         return handle_request(runner, msg)
     raise TypeError(type(msg))
+
+
+def _p2p_group(address: str, port: int, name: str, rank: int, cuda: bool, backend: str, is_master: bool):
+    import datetime
+
+    import torch.distributed as dist
+
+    store = dist.PrefixStore(name, dist.TCPStore(address, int(port), 2, is_master=is_master, timeout=datetime.timedelta(seconds=120)))
+    if cuda and backend == "nccl":
+        return dist.ProcessGroupNCCL(store, rank, 2, dist.ProcessGroupNCCL.Options())
+    return dist.ProcessGroupGloo(store, rank, 2, datetime.timedelta(seconds=120))
+
+
+def _send_weights_to_remote(runner: Any, msg: Any) -> Any:
+    """remote-instance loader, seed side (reference loader.py:3268 RemoteInstanceModelLoader + /send_weights_to_remote_instance): this rank's
+    shards go to the same TP rank of the new instance, parameter by parameter, in ``named_parameters`` order (identical layouts on both sides)"""
+    import torch.distributed as dist
+
+    _sync(runner)
+    try:
+        pg = _p2p_group(msg.master_address, msg.master_port + runner.tp.rank, msg.group_name, 0, runner.is_cuda, msg.backend, False)
+        opts = dist.BroadcastOptions()
+        opts.rootRank = 0
+        n = 0
+        for _, p in runner.model.named_parameters():
+            t = p.data if p.dtype != torch.float8_e4m3fn else p.data.view(torch.uint8)
+            pg.broadcast([t.contiguous()], opts).wait()
+            n += 1
+        for _, b in runner.model.named_buffers():
+            if b.numel() and b.dtype.is_floating_point:
+                pg.broadcast([b.data.contiguous()], opts).wait()
+        _sync(runner)
+        return ios.GenericResp(True, f"sent {n} tensors")
+    except Exception as e:
+        logger.exception("send_weights_to_remote_instance failed")
+        return ios.GenericResp(False, f"{type(e).__name__}: {e}")
+
+
+def receive_weights_from_seed(model: torch.nn.Module, seed_url: str, tp_rank: int, cuda: bool, port: int, address: str = "127.0.0.1",
+                              backend: str = "nccl", group_name: str = "remote_instance_load") -> int:
+    """remote-instance loader, new-instance side: host the rendezvous store, ask the seed to start sending (rank 0 posts the request), receive"""
+    import json
+    import threading
+    import urllib.request
+
+    import torch.distributed as dist
+
+    err: list = []
+
+    def ask():
+        try:
+            body = json.dumps({"master_address": address, "master_port": port, "group_name": group_name, "backend": backend}).encode()
+            req = urllib.request.Request(seed_url.rstrip("/") + "/send_weights_to_remote_instance", data=body,
+                                         headers={"Content-Type": "application/json"}, method="POST")
+            with urllib.request.urlopen(req, timeout=600) as r:
+                j = json.loads(r.read())
+                if not j.get("success"):
+                    err.append(j.get("message"))
+        except Exception as e:      # noqa: BLE001
+            err.append(repr(e))
+
+    th = None
+    if tp_rank == 0:
+        th = threading.Thread(target=ask, daemon=True)
+        th.start()
+    pg = _p2p_group(address, port + tp_rank, group_name, 1, cuda, backend, True)
+    opts = dist.BroadcastOptions()
+    opts.rootRank = 0
+    n = 0
+    for _, p in model.named_parameters():
+        t = p.data if p.dtype != torch.float8_e4m3fn else p.data.view(torch.uint8)
+        buf = torch.empty_like(t)
+        pg.broadcast([buf], opts).wait()
+        t.copy_(buf)
+        n += 1
+    for _, b in model.named_buffers():
+        if b.numel() and b.dtype.is_floating_point:
+            buf = torch.empty_like(b.data)
+            pg.broadcast([buf], opts).wait()
+            b.data.copy_(buf)
+    if th is not None:
+        th.join(timeout=600)
+    if err:
+        raise RuntimeError(f"seed instance failed to send weights: {err[0]}")
+    return n
 
 
 def _weights_checker(runner: Any, msg: Any) -> Any:

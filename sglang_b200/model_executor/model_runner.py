@@ -128,8 +128,14 @@ class ModelRunner:
             mixtral.set_ep_size(server_args.ep_size)
         if server_args.language_only and self.cfg.vision:
             self.cfg.vision = {**self.cfg.vision, "skip_tower": True}
+        remote = None
+        if server_args.load_format == "remote_instance":
+            remote = {"seed_url": f"http://{server_args.remote_instance_weight_loader_seed_instance_ip}:"
+                                  f"{server_args.remote_instance_weight_loader_seed_instance_service_port}",
+                      "port": server_args.remote_instance_weight_loader_send_weights_group_port, "address": server_args.host
+                      if server_args.host not in ("0.0.0.0", "") else "127.0.0.1"}
         self.model = load_model(self.cfg, server_args.model_path, server_args.load_format, self.device, server_args.quantization,
-                                server_args.random_seed)
+                                server_args.random_seed, remote)
         self.load_time = time.perf_counter() - t0
         self.weight_bytes = sum(p.numel() * p.element_size() for p in self.model.parameters())
         self.stream = torch.cuda.Stream(self.device) if self.is_cuda else None

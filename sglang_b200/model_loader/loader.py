@@ -136,8 +136,17 @@ def iter_pt(path: str) -> Iterator[Tuple[str, torch.Tensor]]:
 
 
 def load_model(cfg: ModelConfig, model_path: str, load_format: str, device: torch.device, quant: Optional[str] = None,
-               seed: int = 0) -> nn.Module:
+               seed: int = 0, remote: Optional[dict] = None) -> nn.Module:
     model = build_model(cfg, device, quant)
+    if load_format == "remote_instance":
+        # clone the weights of a RUNNING instance with the same parallel layout (reference RemoteInstanceModelLoader): no disk, no re-sharding
+        from ..model_executor.control import receive_weights_from_seed
+        from ..parallel.parallel_state import get_tp_group
+
+        process_weights_after_loading(model)          # bring the parameters into their runtime format first; the seed sends that format
+        receive_weights_from_seed(model, remote["seed_url"], get_tp_group().rank, device.type == "cuda", int(remote["port"]),
+                                  remote.get("address", "127.0.0.1"))
+        return model
     if load_format == "dummy":
         init_dummy_weights(model, seed, cfg=cfg)
     elif load_format == "gguf" or (load_format == "auto" and model_path.endswith(".gguf") and os.path.isfile(model_path)):

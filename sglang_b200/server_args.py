@@ -23,7 +23,10 @@ class ServerArgs:
     # --- model
     model_path: str = "dummy:tiny-llama"
     tokenizer_path: Optional[str] = None
-    load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf
+    load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf|remote_instance
+    remote_instance_weight_loader_seed_instance_ip: Optional[str] = None
+    remote_instance_weight_loader_seed_instance_service_port: Optional[int] = None
+    remote_instance_weight_loader_send_weights_group_port: int = 31500
     dtype: str = "bfloat16"
     kv_cache_dtype: str = "auto"  # auto|bf16|fp8_e4m3
     quantization: Optional[str] = None  # None|fp8|fp8_block|w4a16|w8a8_int8(unsupported)

@@ -253,3 +253,41 @@ def test_kv_indexer_and_kv_aware_routing():
     assert pol._select_kv_aware(workers, doc + "question three") is workers[1]
     for e in engs:
         e.shutdown()
+
+
+def test_remote_instance_loader_clones_a_running_server():
+    """load_format=remote_instance: a new engine pulls every parameter from a running seed instance over a private 2-rank group (no disk)"""
+    import socket
+    import threading
+
+    import torch
+    import uvicorn
+
+    import sglang_b200 as sgl
+    from sglang_b200.entrypoints.http_server import create_app
+    from sglang_b200.lang.backend.runtime_endpoint import _wait_http
+
+    def free_port():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+        return p
+
+    seed = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, random_seed=11, log_level="error")
+    seed.start_background_loop()
+    port = free_port()
+    server = uvicorn.Server(uvicorn.Config(create_app(seed), host="127.0.0.1", port=port, log_level="error"))
+    t = threading.Thread(target=server.run, daemon=True)
+    t.start()
+    try:
+        _wait_http(f"http://127.0.0.1:{port}", 30)
+        new = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, random_seed=0, log_level="error", load_format="remote_instance",
+                         remote_instance_weight_loader_seed_instance_ip="127.0.0.1", remote_instance_weight_loader_seed_instance_service_port=port,
+                         remote_instance_weight_loader_send_weights_group_port=free_port())
+        a, b = dict(seed.runner.model.named_parameters()), dict(new.runner.model.named_parameters())
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+        sp = {"max_new_tokens": 5, "temperature": 0, "ignore_eos": True}
+        assert new.generate(input_ids=[5, 6, 7, 8], sampling_params=sp)["output_ids"] == seed.generate(input_ids=[5, 6, 7, 8], sampling_params=sp)["output_ids"]
+        new.shutdown()
+    finally:
+        server.should_exit = True
+        t.join(timeout=10)
+        seed.shutdown()
