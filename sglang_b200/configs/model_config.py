@@ -342,7 +342,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             if rp.get("rope_theta") is not None:
                 text.setdefault("rope_theta", rp["rope_theta"])
             if rp.get("partial_rotary_factor") is not None:
-                text.setdefault("partial_rotary_factor", rp["partial_rotary_factor"])
+                text["partial_rotary_factor"] = rp["partial_rotary_factor"]          # authoritative in transformers >= 5
             sc = {k: v for k, v in rp.items() if k not in ("rope_theta", "partial_rotary_factor")}
             if text.get("rope_scaling") is None and (sc.get("rope_type", "default") != "default" or "mrope_section" in sc):
                 text["rope_scaling"] = sc
@@ -358,6 +358,18 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
             if kw.get("intermediate_size") is None:
                 kw["intermediate_size"] = 4 * kw["hidden_size"]
+        if arch == "BambaForCausalLM":
+            hid = text["hidden_size"]
+            heads = text.get("mamba_n_heads", 128)
+            dh = text.get("mamba_d_head", "auto")
+            dh = (text.get("mamba_expand", 2) * hid // heads) if dh in ("auto", None) else dh
+            kinds = text.get("layers_block_type") or ["attention" if i in (text.get("attn_layer_indices") or []) else "mamba"
+                                                      for i in range(text["num_hidden_layers"])]
+            kw["mamba"] = {"num_heads": heads, "head_dim": dh, "d_state": text.get("mamba_d_state", 256), "d_conv": text.get("mamba_d_conv", 4),
+                           "n_groups": text.get("mamba_n_groups", 1), "chunk_size": text.get("mamba_chunk_size", 256),
+                           "use_bias": text.get("mamba_proj_bias", False), "use_conv_bias": text.get("mamba_conv_bias", True), "norm_groups": 1,
+                           "pattern": "".join("M" if k == "mamba" else "*" for k in kinds)}
+            kw["partial_rotary_factor"] = (text.get("rope_parameters") or {}).get("partial_rotary_factor", text.get("partial_rotary_factor", 0.5))
         if arch in ("NemotronHForCausalLM", "Mamba2ForCausalLM"):
             hid = text["hidden_size"]
             heads = text.get("mamba_num_heads") or text.get("num_heads") or (text.get("expand", 2) * hid // text.get("head_dim", 64))

@@ -419,3 +419,131 @@ class NemotronHForCausalLM(nn.Module):
 
 class Mamba2ForCausalLM(NemotronHForCausalLM):
     """pure Mamba-2 stack (every layer is an SSM mixer); same checkpoint naming (``backbone.layers.N.mixer.*``)"""
+
+
+# ================================================================================================ Bamba (Mamba-2 / attention mixers + a gated MLP in EVERY layer)
+class _BambaBlock(nn.Module):
+    def __init__(self, cfg: ModelConfig, kind: str, idx: int, gid: int, dtype, rope):
+        super().__init__()
+        from .llama import LlamaAttention, LlamaMLP
+
+        self.kind = kind
+        pre = f"model.layers.{gid}"
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.pre_ff_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        if kind == "mamba":
+            self.mamba = Mamba2Mixer(cfg, idx, dtype, pre + ".mamba")
+        else:
+            self.self_attn = LlamaAttention(cfg, idx, dtype, None, rope, pre + ".self_attn")
+        self.feed_forward = LlamaMLP(cfg, dtype, None, pre + ".feed_forward")
+
+    def forward(self, x, fb):
+        h = self.input_layernorm(x)
+        y = self.mamba(h, fb) if self.kind == "mamba" else self.self_attn(h, fb)
+        x = x + (y.resolve() if hasattr(y, "resolve") else y)
+        m = self.feed_forward(self.pre_ff_layernorm(x))
+        return x + (m.resolve() if hasattr(m, "resolve") else m)
+
+
+class BambaBackbone(nn.Module):
+    def __init__(self, cfg: ModelConfig, device):
+        super().__init__()
+        from ..layers.common import RotaryEmbedding
+
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        assert get_pp_group().world_size == 1
+        self.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
+                               cfg.partial_rotary_factor, device)
+        pat = cfg.mamba["pattern"]
+        blocks, n_m, n_a = [], 0, 0
+        for i, ch in enumerate(pat):
+            if ch == "M":
+                blocks.append(_BambaBlock(cfg, "mamba", n_m, i, dtype, rope))
+                n_m += 1
+            else:
+                blocks.append(_BambaBlock(cfg, "attention", n_a, i, dtype, rope))
+                n_a += 1
+        self.all_layers = nn.ModuleList(blocks)
+        self.num_mamba, self.num_attn = n_m, n_a
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    @property
+    def layers(self):
+        return [b for b in self.all_layers if b.kind == "attention"]
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        if inputs_embeds is not None:
+            h = inputs_embeds
+        elif fb.input_ids is None:
+            h = self.embed_tokens(fb.next_token_buf, fb.req_slots)
+        else:
+            h = self.embed_tokens(fb.input_ids)
+        for blk in self.all_layers:
+            h = blk(h, fb)
+        return self.norm(h)
+
+
+class BambaForCausalLM(NemotronHForCausalLM):
+    stacked_params = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v"),
+                      (".gate_up_proj", ".gate_proj", 0), (".gate_up_proj", ".up_proj", 1)]
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        nn.Module.__init__(self)
+        self.cfg = cfg
+        self.model = BambaBackbone(cfg, device)
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, _DT[cfg.dtype])
+
+    def make_mamba_pool(self, slots: int, device) -> Optional[MambaPool]:
+        m = next((b.mamba for b in self.model.all_layers if b.kind == "mamba"), None)
+        if m is None:
+            return None
+        return MambaPool(self.model.num_mamba, slots, m.conv_dim, m.k, m.H, m.P, m.N, _DT[self.cfg.dtype], device)
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        from .llama import _load_stacked_bias
+
+        params = dict(self.named_parameters())
+        mods = dict(self.named_modules())
+        loaded = []
+        for name, w in weights:
+            name = name.replace("model.final_layernorm.", "model.norm.").replace("model.layers.", "model.all_layers.")
+            if name == "lm_head.weight" and self.lm_head is None:
+                continue
+            if ".mamba." in name:
+                mixer_name = name[: name.index(".mamba") + 6]
+                mixer, leaf = mods[mixer_name], name[name.index(".mamba") + 7:]
+                if leaf in ("in_proj.weight", "in_proj.bias"):
+                    mixer.load_fused(params[name], w, True)
+                elif leaf == "conv1d.weight":
+                    mixer.load_fused(mixer.conv_weight, w.reshape(w.shape[0], -1), False)
+                elif leaf == "conv1d.bias":
+                    mixer.load_fused(mixer.conv_bias, w, False)
+                elif leaf in ("A_log", "D", "dt_bias"):
+                    mixer.load_heads(getattr(mixer, leaf), w)
+                elif leaf == "norm.weight":
+                    mixer.load_heads(mixer.norm_weight, w)
+                elif leaf.startswith("out_proj."):
+                    mixer.out_proj.weight_loader(params[name], w)
+                else:
+                    continue
+                loaded.append(name)
+                continue
+            target, shard = name, None
+            for merged, orig, sid in self.stacked_params:
+                if orig + "." in name:
+                    target, shard = name.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                if target.endswith(".bias") and shard is not None:
+                    _load_stacked_bias(mod, params[target], w, shard)
+                else:
+                    mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded

@@ -65,6 +65,7 @@ def _ensure() -> None:
 
     register_model("NemotronHForCausalLM", _mb.NemotronHForCausalLM)
     register_model("Mamba2ForCausalLM", _mb.Mamba2ForCausalLM)
+    register_model("BambaForCausalLM", _mb.BambaForCausalLM)
     from . import deepseek as _ds
 
     register_model("DeepseekV2ForCausalLM", _ds.DeepseekV2ForCausalLM)

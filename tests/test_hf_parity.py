@@ -57,6 +57,9 @@ CASES = {
     "dots1": ("Dots1Config", "Dots1ForCausalLM", dict(BASE, num_hidden_layers=3, head_dim=16, n_routed_experts=8, num_experts_per_tok=2,
                                                       moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1, n_group=2, topk_group=1,
                                                       routed_scaling_factor=1.5, norm_topk_prob=True)),
+    "bamba": ("BambaConfig", "BambaForCausalLM", dict(BASE, num_hidden_layers=3, attn_layer_indices=[1], mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2,
+                                                      mamba_d_state=16, mamba_d_conv=4, mamba_expand=2, mamba_chunk_size=8, pad_token_id=0,
+                                                      rope_parameters={"rope_theta": 10000.0, "rope_type": "default", "partial_rotary_factor": 1.0})),  # (this transformers build rotates the full head for Bamba whatever the factor says)
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
