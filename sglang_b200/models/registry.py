@@ -22,9 +22,20 @@ def supported_architectures():
     return sorted(_REGISTRY)
 
 
+_BUILTINS_DONE = False
+
+
 def _ensure() -> None:
-    if _REGISTRY:
+    global _BUILTINS_DONE
+    if _BUILTINS_DONE:        # (a flag, not "registry non-empty": plugins may register architectures before the built-ins are imported)
         return
+    _BUILTINS_DONE = True
+    plugin_entries = dict(_REGISTRY)
+    _register_builtins()
+    _REGISTRY.update(plugin_entries)      # an out-of-tree class registered under a built-in name wins
+
+
+def _register_builtins() -> None:
     from . import llama, llava, mixtral
 
     for name in ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM", "Qwen3ForCausalLM", "GemmaForCausalLM"):
