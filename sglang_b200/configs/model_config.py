@@ -358,6 +358,30 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
             if kw.get("intermediate_size") is None:
                 kw["intermediate_size"] = 4 * kw["hidden_size"]
+        if arch in ("MambaForCausalLM", "FalconMambaForCausalLM"):
+            hid = text["hidden_size"]
+            kw["mamba"] = {"d_inner": text.get("intermediate_size") or text.get("expand", 2) * hid, "d_state": text.get("state_size", 16),
+                           "d_conv": text.get("conv_kernel", 4), "dt_rank": text.get("time_step_rank") if isinstance(text.get("time_step_rank"), int)
+                           else -(-hid // 16), "use_bias": text.get("use_bias", False), "use_conv_bias": text.get("use_conv_bias", True),
+                           "bcdt_norm": "plain" if arch == "FalconMambaForCausalLM" else None, "mixer_rms_eps": text.get("mixer_rms_eps", 1e-6),
+                           "pattern": "M" * text["num_hidden_layers"]}
+            kw["rms_norm_eps"] = text.get("layer_norm_epsilon", 1e-5)
+            kw["intermediate_size"] = kw["mamba"]["d_inner"]
+            kw.setdefault("num_attention_heads", 1)
+            kw.setdefault("tie_word_embeddings", True)
+        if arch == "JambaForCausalLM":
+            hid, L = text["hidden_size"], text["num_hidden_layers"]
+            kinds = text.get("layers_block_type") or ["attention" if i % text.get("attn_layer_period", 8) == text.get("attn_layer_offset", 4) else "mamba"
+                                                      for i in range(L)]
+            ne = text.get("layers_num_experts") or [text.get("num_local_experts", text.get("num_experts", 16)) if i % text.get("expert_layer_period", 2) == text.get("expert_layer_offset", 1)
+                                                    else 1 for i in range(L)]
+            dtr = text.get("mamba_dt_rank", "auto")
+            kw["mamba"] = {"d_inner": text.get("mamba_expand", 2) * hid, "d_state": text.get("mamba_d_state", 16), "d_conv": text.get("mamba_d_conv", 4),
+                           "dt_rank": -(-hid // 16) if dtr in ("auto", None) else dtr, "use_bias": text.get("mamba_proj_bias", False),
+                           "use_conv_bias": text.get("mamba_conv_bias", True), "bcdt_norm": "weight",
+                           "pattern": "".join("M" if k == "mamba" else "*" for k in kinds), "moe_layers": [int(n > 1) for n in ne]}
+            kw["num_local_experts"] = max(ne) if max(ne) > 1 else 0
+            kw["num_experts_per_tok"] = text.get("num_experts_per_tok", 2)
         if arch == "BambaForCausalLM":
             hid = text["hidden_size"]
             heads = text.get("mamba_n_heads", 128)

@@ -547,3 +547,338 @@ class BambaForCausalLM(NemotronHForCausalLM):
                 params[target].data.copy_(w)
             loaded.append(name)
         return loaded
+
+
+# ================================================================================================ Mamba-1 (selective scan per channel): Mamba, FalconMamba, Jamba
+def selective_scan_chunked(u, dt, A, B, C, state, chunk: int = 16):
+    """u, dt [T, Dn]; A [Dn, N] (negative); B, C [T, N]; state [Dn, N] fp32 -> (y [T, Dn] without the D skip, final state).
+    h_t = exp(dt_t A) h_{t-1} + dt_t B_t u_t, y_t = h_t . C_t.  Inside a chunk the recurrence is solved in closed form with decay factors
+    exp(sum_{s<k<=t} dt_k A) (all <= 1, so nothing overflows); chunks are chained through the carried state."""
+    T, Dn = u.shape
+    u, dt, B, C, A = u.float(), dt.float(), B.float(), C.float(), A.float()
+    ys = []
+    for s in range(0, T, chunk):
+        e = min(T, s + chunk)
+        q = e - s
+        la = dt[s:e, :, None] * A[None]                                   # [q, Dn, N] log decay per step
+        cs = torch.cumsum(la, 0)
+        inp = (dt[s:e] * u[s:e])[:, :, None] * B[s:e, None, :]            # [q, Dn, N]
+        # L[t, k] = exp(cs_t - cs_k) for k <= t
+        diff = cs[:, None] - cs[None, :]                                  # [q, q, Dn, N]
+        mask = torch.tril(torch.ones(q, q, dtype=torch.bool, device=u.device))[:, :, None, None]
+        L = torch.exp(diff.masked_fill(~mask, float("-inf")))
+        h = torch.exp(cs) * state[None] + torch.einsum("tkdn,kdn->tdn", L, inp)
+        ys.append(torch.einsum("tdn,tn->td", h, C[s:e]))
+        state = h[-1]
+    return (torch.cat(ys, 0) if ys else u.new_zeros(0, Dn)), state
+
+
+class Mamba1Mixer(nn.Module):
+    def __init__(self, cfg: ModelConfig, layer_idx: int, dtype, prefix: str):
+        super().__init__()
+        tp = get_tp_group()
+        self.tp = tp
+        W = tp.world_size
+        m = cfg.mamba
+        self.Dn_total, self.N, self.k, self.R = m["d_inner"], m["d_state"], m["d_conv"], m["dt_rank"]
+        assert self.Dn_total % W == 0
+        self.Dn = self.Dn_total // W
+        self.layer_idx = layer_idx
+        self.in_proj = nn.Linear(cfg.hidden_size, 2 * self.Dn, bias=m.get("use_bias", False), dtype=dtype)          # local [x | z] channels
+        self.conv_weight = nn.Parameter(torch.zeros(self.Dn, self.k, dtype=dtype), requires_grad=False)
+        self.conv_bias = nn.Parameter(torch.zeros(self.Dn, dtype=dtype), requires_grad=False) if m.get("use_conv_bias", True) else None
+        self.x_proj = RowParallelLinear(self.Dn_total, self.R + 2 * self.N, False, True, dtype, None, prefix + ".x_proj")
+        self.dt_proj = nn.Linear(self.R, self.Dn, bias=True, dtype=dtype)
+        self.A_log = nn.Parameter(torch.zeros(self.Dn, self.N, dtype=torch.float32), requires_grad=False)
+        self.D = nn.Parameter(torch.ones(self.Dn, dtype=torch.float32), requires_grad=False)
+        self.out_proj = RowParallelLinear(self.Dn_total, cfg.hidden_size, m.get("use_bias", False), True, dtype, None, prefix + ".out_proj")
+        kind = m.get("bcdt_norm")            # None | "plain" (FalconMamba: weightless RMS) | "weight" (Jamba)
+        self.bcdt = kind
+        self.eps = m.get("mixer_rms_eps", cfg.rms_norm_eps)
+        if kind == "weight":
+            self.dt_layernorm, self.b_layernorm, self.c_layernorm = RMSNorm(self.R, cfg.rms_norm_eps, dtype), RMSNorm(self.N, cfg.rms_norm_eps, dtype), \
+                RMSNorm(self.N, cfg.rms_norm_eps, dtype)
+        for p in list(self.in_proj.parameters()) + list(self.dt_proj.parameters()):
+            p.requires_grad_(False)
+        self.chunk = m.get("scan_chunk", 16)
+        # MambaPool geometry: heads = local channels, head_dim = 1
+        self.conv_dim, self.H, self.P = self.Dn, self.Dn, 1
+
+    def shard(self, w: torch.Tensor, dim: int = 0) -> torch.Tensor:
+        return w.narrow(dim, self.tp.rank * self.Dn, self.Dn)
+
+    def _n(self, t, mod):
+        if self.bcdt == "weight":
+            return mod(t.contiguous())
+        if self.bcdt == "plain":
+            f = t.float()
+            return (f * torch.rsqrt(f.pow(2).mean(-1, keepdim=True) + self.eps)).to(t.dtype)
+        return t
+
+    def forward(self, h: torch.Tensor, fb: ForwardBatch) -> torch.Tensor:
+        pool: MambaPool = fb.kv_pool.mamba
+        conv_s, ssm_s = pool.conv[self.layer_idx], pool.ssm[self.layer_idx]          # [slots, Dn, k-1], [slots, Dn, 1, N]
+        T = h.shape[0]
+        x, z = self.in_proj(h).split([self.Dn, self.Dn], dim=-1)
+        A = -torch.exp(self.A_log)
+        slots = fb.req_slots.long()
+        decode = fb.cu_q is None
+        if decode:
+            win = torch.cat([conv_s[slots], x.unsqueeze(-1)], -1)
+            conv_s[slots] = win[..., 1:]
+            u = (win.float() * self.conv_weight.float()[None]).sum(-1)
+        else:
+            outs, off = [], 0
+            for b in range(len(fb.q_lens_cpu)):
+                n, s = int(fb.q_lens_cpu[b]), int(slots[b])
+                fresh = int(fb.seq_lens_cpu[b]) - n == 0
+                seq = torch.cat([(torch.zeros_like(conv_s[s]) if fresh else conv_s[s]).t(), x[off:off + n]], 0)
+                conv_s[s] = seq[-(self.k - 1):].t()
+                outs.append(F.conv1d(seq.t().unsqueeze(0).float(), self.conv_weight.float().unsqueeze(1), None, groups=self.Dn)[0].t())
+                off += n
+            u = torch.cat(outs, 0) if outs else x.new_zeros(0, self.Dn).float()
+        if self.conv_bias is not None:
+            u = u + self.conv_bias.float()
+        u = F.silu(u).to(h.dtype)
+        dbc = self.x_proj(u)
+        dbc = dbc.resolve() if hasattr(dbc, "resolve") else dbc
+        dtr, Bm, Cm = dbc.split([self.R, self.N, self.N], dim=-1)
+        dtr, Bm, Cm = self._n(dtr, getattr(self, "dt_layernorm", None)), self._n(Bm, getattr(self, "b_layernorm", None)), \
+            self._n(Cm, getattr(self, "c_layernorm", None))
+        dt = F.softplus(self.dt_proj(dtr).float())
+        if decode:
+            st = ssm_s[slots][:, :, 0]                                                 # [B, Dn, N]
+            st = torch.exp(dt[:, :, None] * A[None]) * st + (dt * u.float())[:, :, None] * Bm.float()[:, None, :]
+            ssm_s[slots] = st.unsqueeze(2)
+            y = torch.einsum("bdn,bn->bd", st, Cm.float())
+        else:
+            ys, off = [], 0
+            for b in range(len(fb.q_lens_cpu)):
+                n, s = int(fb.q_lens_cpu[b]), int(slots[b])
+                fresh = int(fb.seq_lens_cpu[b]) - n == 0
+                st0 = torch.zeros_like(ssm_s[s][:, 0]) if fresh else ssm_s[s][:, 0]
+                yb, stN = selective_scan_chunked(u[off:off + n], dt[off:off + n], A, Bm[off:off + n], Cm[off:off + n], st0, self.chunk)
+                ssm_s[s] = stN.unsqueeze(1)
+                ys.append(yb)
+                off += n
+            y = torch.cat(ys, 0) if ys else u.new_zeros(0, self.Dn).float()
+        y = (y + self.D[None] * u.float()) * F.silu(z.float())
+        return self.out_proj(y.to(h.dtype))
+
+
+def _load_mamba1(mixer: Mamba1Mixer, leaf: str, w: torch.Tensor, params: Dict[str, torch.Tensor], full: str) -> bool:
+    if leaf in ("in_proj.weight", "in_proj.bias"):
+        x, z = w.chunk(2, 0)
+        params[full].data.copy_(torch.cat([mixer.shard(x), mixer.shard(z)], 0))
+    elif leaf == "conv1d.weight":
+        mixer.conv_weight.data.copy_(mixer.shard(w.reshape(w.shape[0], -1)))
+    elif leaf == "conv1d.bias":
+        mixer.conv_bias.data.copy_(mixer.shard(w))
+    elif leaf == "x_proj.weight":
+        mixer.x_proj.weight_loader(params[full], w)
+    elif leaf in ("dt_proj.weight", "dt_proj.bias"):
+        params[full].data.copy_(mixer.shard(w))
+    elif leaf in ("A_log", "D"):
+        getattr(mixer, leaf).data.copy_(mixer.shard(w).float())
+    elif leaf.startswith("out_proj."):
+        mixer.out_proj.weight_loader(params[full], w) if leaf.endswith("weight") else params[full].data.copy_(w)
+    elif leaf.split(".")[0] in ("dt_layernorm", "b_layernorm", "c_layernorm"):
+        params[full].data.copy_(w)
+    else:
+        return False
+    return True
+
+
+class _M1Block(nn.Module):
+    def __init__(self, cfg, idx, dtype, prefix):
+        super().__init__()
+        self.kind = "mamba"
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.mixer = Mamba1Mixer(cfg, idx, dtype, prefix + ".mixer")
+
+    def forward(self, x, fb):
+        y = self.mixer(self.norm(x), fb)
+        return x + (y.resolve() if hasattr(y, "resolve") else y)
+
+
+class MambaForCausalLM(NemotronHForCausalLM):
+    """Mamba-1 (state-spaces/mamba-*-hf) and FalconMamba (``cfg.mamba['bcdt_norm'] == 'plain'``)"""
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        nn.Module.__init__(self)
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        bb = nn.Module()
+        bb.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        bb.all_layers = nn.ModuleList([_M1Block(cfg, i, dtype, f"model.layers.{i}") for i in range(cfg.num_hidden_layers)])
+        bb.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        bb.layers, bb.num_mamba = [], cfg.num_hidden_layers
+        self.model = bb
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, dtype)
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        m = self.model
+        h = inputs_embeds if inputs_embeds is not None else (m.embed_tokens(fb.next_token_buf, fb.req_slots) if fb.input_ids is None
+                                                             else m.embed_tokens(fb.input_ids))
+        for blk in m.all_layers:
+            h = blk(h, fb)
+        return m.norm(h)
+
+    def make_mamba_pool(self, slots: int, device) -> Optional[MambaPool]:
+        mx = self.model.all_layers[0].mixer
+        return MambaPool(self.model.num_mamba, slots, mx.Dn, mx.k, mx.Dn, 1, mx.N, _DT[self.cfg.dtype], device)
+
+    def load_weights(self, weights):
+        params = dict(self.named_parameters())
+        mods = dict(self.named_modules())
+        loaded = []
+        for name, w in weights:
+            n = self.remap(name).replace("model.layers.", "model.all_layers.")
+            if n == "lm_head.weight" and self.lm_head is None:
+                continue
+            if ".mixer." in n:
+                mn = n[: n.index(".mixer") + 6]
+                if _load_mamba1(mods[mn], n[len(mn) + 1:], w, params, n):
+                    loaded.append(name)
+                continue
+            if n in params:
+                mod = mods[n.rsplit(".", 1)[0]]
+                mod.weight_loader(params[n], w) if hasattr(mod, "weight_loader") else params[n].data.copy_(w)
+                loaded.append(name)
+        return loaded
+
+    def dummy_checkpoint(self, cfg, device, dtype, seed: int = 0, scale: float = 0.02):
+        for n, p in self.named_parameters():
+            g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(n.encode())) & 0x7FFFFFFF)
+            if n.endswith("A_log"):
+                p.data.copy_(torch.log(torch.rand(p.shape, generator=g) * 3 + 0.5))
+            elif p.dim() > 1:
+                p.data.copy_((torch.randn(p.shape, generator=g) * 0.05).to(p.dtype))
+            elif "norm" in n or n.endswith(".D"):
+                p.data.fill_(1.0)
+            else:
+                p.data.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
+        return iter(())
+
+
+class FalconMambaForCausalLM(MambaForCausalLM):
+    pass
+
+
+# ---- Jamba: Mamba-1 mixers with normalised dt / B / C, attention without positional encoding, MoE every other layer
+class _JambaMoE(nn.Module):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, prefix: str):
+        super().__init__()
+        from ..layers.linear import ReplicatedLinear
+        from ..layers.moe import FusedMoE
+        from .mixtral import _EP_SIZE
+
+        self.router = ReplicatedLinear(cfg.hidden_size, cfg.num_local_experts, False, dtype, None, prefix + ".router")
+        self.experts = FusedMoE(cfg.num_local_experts, cfg.num_experts_per_tok, cfg.hidden_size, cfg.intermediate_size, dtype, False, _EP_SIZE["v"],
+                                None, layer_id)
+
+    def forward(self, x):
+        return self.experts(x, self.router(x))
+
+
+class _JambaBlock(nn.Module):
+    def __init__(self, cfg: ModelConfig, kind: str, idx: int, gid: int, moe: bool, dtype):
+        super().__init__()
+        from .llama import LlamaAttention, LlamaMLP
+
+        self.kind = kind
+        pre = f"model.layers.{gid}"
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.pre_ff_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        if kind == "mamba":
+            self.mamba = Mamba1Mixer(cfg, idx, dtype, pre + ".mamba")
+        else:
+            self.self_attn = LlamaAttention(cfg, idx, dtype, None, None, pre + ".self_attn")          # Jamba attention has no rotary embedding
+        self.feed_forward = _JambaMoE(cfg, gid, dtype, pre + ".feed_forward") if moe else LlamaMLP(cfg, dtype, None, pre + ".feed_forward")
+
+    def forward(self, x, fb):
+        h = self.input_layernorm(x)
+        y = self.mamba(h, fb) if self.kind == "mamba" else self.self_attn(h, fb)
+        x = x + (y.resolve() if hasattr(y, "resolve") else y)
+        m = self.feed_forward(self.pre_ff_layernorm(x))
+        return x + (m.resolve() if hasattr(m, "resolve") else m)
+
+
+class JambaForCausalLM(BambaForCausalLM):
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        nn.Module.__init__(self)
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        bb = nn.Module()
+        bb.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        blocks, n_m, n_a = [], 0, 0
+        for i, ch in enumerate(cfg.mamba["pattern"]):
+            moe = bool(cfg.mamba["moe_layers"][i])
+            if ch == "M":
+                blocks.append(_JambaBlock(cfg, "mamba", n_m, i, moe, dtype))
+                n_m += 1
+            else:
+                blocks.append(_JambaBlock(cfg, "attention", n_a, i, moe, dtype))
+                n_a += 1
+        bb.all_layers = nn.ModuleList(blocks)
+        bb.num_mamba, bb.num_attn = n_m, n_a
+        bb.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        bb.layers = [b for b in blocks if b.kind == "attention"]
+        self.model = bb
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, dtype)
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        return MambaForCausalLM.forward(self, fb, inputs_embeds)
+
+    def make_mamba_pool(self, slots: int, device) -> Optional[MambaPool]:
+        mx = next((b.mamba for b in self.model.all_layers if b.kind == "mamba"), None)
+        return None if mx is None else MambaPool(self.model.num_mamba, slots, mx.Dn, mx.k, mx.Dn, 1, mx.N, _DT[self.cfg.dtype], device)
+
+    def load_weights(self, weights):
+        from .llama import _load_stacked_bias
+
+        params = dict(self.named_parameters())
+        mods = dict(self.named_modules())
+        loaded = []
+        for name, w in weights:
+            n = name.replace("model.final_layernorm.", "model.norm.").replace("model.layers.", "model.all_layers.")
+            if n == "lm_head.weight" and self.lm_head is None:
+                continue
+            if ".mamba." in n:
+                mn = n[: n.index(".mamba") + 6]
+                if _load_mamba1(mods[mn], n[len(mn) + 1:], w, params, n):
+                    loaded.append(name)
+                continue
+            if ".feed_forward.experts." in n:
+                ex = mods[n[: n.index(".experts") + 8]]
+                tail = n.split(".experts.")[1]
+                if tail.split(".")[0].isdigit():
+                    eid, proj = int(tail.split(".")[0]), tail.split(".")[1]
+                    ex.weight_loader(ex.w2 if proj == "down_proj" else ex.w13, w, eid, {"gate_proj": "w1", "up_proj": "w3", "down_proj": "w2"}[proj])
+                elif tail.startswith("gate_up_proj"):
+                    for e in range(w.shape[0]):
+                        g_, u_ = w[e].chunk(2, 0)
+                        ex.weight_loader(ex.w13, g_, e, "w1")
+                        ex.weight_loader(ex.w13, u_, e, "w3")
+                elif tail.startswith("down_proj"):
+                    for e in range(w.shape[0]):
+                        ex.weight_loader(ex.w2, w[e], e, "w2")
+                loaded.append(name)
+                continue
+            target, shard = n, None
+            for merged, orig, sid in self.stacked_params:
+                if orig + "." in n:
+                    target, shard = n.replace(orig, merged), sid
+                    break
+            if target not in params:
+                continue
+            mod = mods[target.rsplit(".", 1)[0]]
+            if hasattr(mod, "weight_loader"):
+                if target.endswith(".bias") and shard is not None:
+                    _load_stacked_bias(mod, params[target], w, shard)
+                else:
+                    mod.weight_loader(params[target], w, shard) if shard is not None else mod.weight_loader(params[target], w)
+            else:
+                params[target].data.copy_(w)
+            loaded.append(name)
+        return loaded

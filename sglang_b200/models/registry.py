@@ -29,10 +29,10 @@ def _ensure() -> None:
     global _BUILTINS_DONE
     if _BUILTINS_DONE:        # (a flag, not "registry non-empty": plugins may register architectures before the built-ins are imported)
         return
-    _BUILTINS_DONE = True
     plugin_entries = dict(_REGISTRY)
     _register_builtins()
     _REGISTRY.update(plugin_entries)      # an out-of-tree class registered under a built-in name wins
+    _BUILTINS_DONE = True
 
 
 def _register_builtins() -> None:
@@ -77,6 +77,8 @@ def _register_builtins() -> None:
     register_model("NemotronHForCausalLM", _mb.NemotronHForCausalLM)
     register_model("Mamba2ForCausalLM", _mb.Mamba2ForCausalLM)
     register_model("BambaForCausalLM", _mb.BambaForCausalLM)
+    for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM"):
+        register_model(name, getattr(_mb, name))
     from . import deepseek as _ds
 
     register_model("DeepseekV2ForCausalLM", _ds.DeepseekV2ForCausalLM)

@@ -60,6 +60,13 @@ CASES = {
     "bamba": ("BambaConfig", "BambaForCausalLM", dict(BASE, num_hidden_layers=3, attn_layer_indices=[1], mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2,
                                                       mamba_d_state=16, mamba_d_conv=4, mamba_expand=2, mamba_chunk_size=8, pad_token_id=0,
                                                       rope_parameters={"rope_theta": 10000.0, "rope_type": "default", "partial_rotary_factor": 1.0})),  # (this transformers build rotates the full head for Bamba whatever the factor says)
+    "mamba1": ("MambaConfig", "MambaForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, state_size=8, conv_kernel=4, expand=2,
+                                                       time_step_rank=4, pad_token_id=0)),
+    "falcon-mamba": ("FalconMambaConfig", "FalconMambaForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, state_size=8, conv_kernel=4,
+                                                                       expand=2, time_step_rank=4, pad_token_id=0)),
+    "jamba": ("JambaConfig", "JambaForCausalLM", dict(BASE, num_hidden_layers=4, attn_layer_period=2, attn_layer_offset=1, expert_layer_period=2,
+                                                      expert_layer_offset=1, num_experts=4, num_experts_per_tok=2, mamba_d_state=8, mamba_d_conv=4,
+                                                      mamba_expand=2, mamba_dt_rank=4, pad_token_id=0, use_mamba_kernels=False)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),

@@ -228,3 +228,25 @@ def test_two_batch_overlap_with_dp_attention_a2a():
     # splits two; idle forwards at the tail run two empty micro-batches
     odd = PROMPTS[:3]
     _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1"}, prompts=odd), _run(kw, 1, LP, prompts=odd))
+
+
+def test_mamba1_jamba_tp2(tmp_path):
+    """Mamba-1 channels sharded over TP (row-parallel x_proj with an all-reduce for dt / B / C), Jamba = Mamba-1 + attention + MoE"""
+    import transformers as tf
+
+    import torch
+
+    torch.manual_seed(0)
+    cfg = tf.JambaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                         max_position_embeddings=512, attn_layer_period=2, attn_layer_offset=1, expert_layer_period=2, expert_layer_offset=1,
+                         num_experts=4, num_experts_per_tok=2, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2, mamba_dt_rank=4, pad_token_id=0,
+                         use_mamba_kernels=False)
+    hf = tf.JambaForCausalLM(cfg).float()
+    with torch.no_grad():
+        for p in hf.parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.08)
+    d = str(tmp_path / "jamba")
+    hf.save_pretrained(d, safe_serialization=True)
+    kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP), atol=5e-3)
