@@ -79,6 +79,8 @@ class ModelConfig:
     residual_multiplier: Optional[float] = None
     attention_multiplier: Optional[float] = None
     logits_scaling: Optional[float] = None
+    # Qwen3-Next gated DeltaNet layers: num_k_heads, num_v_heads, k_head_dim, v_head_dim, conv_kernel (models/qwen3_next.py)
+    linear_attn: Optional[Dict[str, Any]] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
     mamba: Optional[Dict[str, Any]] = None
     # speech encoder of encoder-decoder ASR models (models/whisper.py)
@@ -358,6 +360,14 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
             if kw.get("intermediate_size") is None:
                 kw["intermediate_size"] = 4 * kw["hidden_size"]
+        if arch == "Qwen3NextForCausalLM":
+            kw["linear_attn"] = {"num_k_heads": text.get("linear_num_key_heads", 16), "num_v_heads": text.get("linear_num_value_heads", 32),
+                                 "k_head_dim": text.get("linear_key_head_dim", 128), "v_head_dim": text.get("linear_value_head_dim", 128),
+                                 "conv_kernel": text.get("linear_conv_kernel_dim", 4)}
+            L = text["num_hidden_layers"]
+            kw["layer_types"] = text.get("layer_types") or ["full_attention" if (i + 1) % text.get("full_attention_interval", 4) == 0
+                                                            else "linear_attention" for i in range(L)]
+            kw.setdefault("partial_rotary_factor", 0.25)
         if arch in ("MambaForCausalLM", "FalconMambaForCausalLM"):
             hid = text["hidden_size"]
             kw["mamba"] = {"d_inner": text.get("intermediate_size") or text.get("expand", 2) * hid, "d_state": text.get("state_size", 16),

@@ -53,6 +53,9 @@ def _register_builtins() -> None:
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM", "PhiForCausalLM", "GPTJForCausalLM",
                  "GPTBigCodeForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import qwen3_next as _qn
+
+    register_model("Qwen3NextForCausalLM", _qn.Qwen3NextForCausalLM)
     from . import internvl as _iv
 
     register_model("InternVLForConditionalGeneration", _iv.InternVLForConditionalGeneration)

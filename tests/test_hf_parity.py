@@ -67,6 +67,12 @@ CASES = {
     "jamba": ("JambaConfig", "JambaForCausalLM", dict(BASE, num_hidden_layers=4, attn_layer_period=2, attn_layer_offset=1, expert_layer_period=2,
                                                       expert_layer_offset=1, num_experts=4, num_experts_per_tok=2, mamba_d_state=8, mamba_d_conv=4,
                                                       mamba_expand=2, mamba_dt_rank=4, pad_token_id=0, use_mamba_kernels=False)),
+    "qwen3-next": ("Qwen3NextConfig", "Qwen3NextForCausalLM", dict(BASE, num_hidden_layers=4, head_dim=16, partial_rotary_factor=0.25,
+                                                                 linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=8,
+                                                                 linear_value_head_dim=8, linear_conv_kernel_dim=4, num_experts=4, num_experts_per_tok=2,
+                                                                 moe_intermediate_size=32, shared_expert_intermediate_size=48, decoder_sparse_step=1,
+                                                                 mlp_only_layers=[], norm_topk_prob=True,
+                                                                 layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"])),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),

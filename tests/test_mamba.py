@@ -76,3 +76,19 @@ def test_retraction_reprefills_state():
     finally:
         os.environ.pop("SGLB_TEST_RETRACT", None)
         envs.SGLB_TEST_RETRACT.set(False)
+
+
+def test_gated_delta_chunked_equals_recurrence():
+    from sglang_b200.models.qwen3_next import gated_delta_chunked, gated_delta_step
+
+    torch.manual_seed(0)
+    T, H, Dk, Dv = 150, 3, 8, 16
+    q, k, v = torch.randn(T, H, Dk), torch.randn(T, H, Dk), torch.randn(T, H, Dv)
+    g, beta = -torch.rand(T, H) * 0.5, torch.rand(T, H)
+    st0 = torch.randn(H, Dk, Dv) * 0.3
+    st = st0.clone()[None]
+    ref = torch.stack([gated_delta_step(q[t:t + 1], k[t:t + 1], v[t:t + 1], g[t:t + 1], beta[t:t + 1], st)[0] for t in range(T)])
+    for chunk in (16, 64):
+        o, fin = gated_delta_chunked(q, k, v, g, beta, st0, chunk)
+        torch.testing.assert_close(o, ref, atol=2e-4, rtol=2e-4)
+        torch.testing.assert_close(fin, st[0], atol=2e-4, rtol=2e-4)

@@ -250,3 +250,25 @@ def test_mamba1_jamba_tp2(tmp_path):
     hf.save_pretrained(d, safe_serialization=True)
     kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
     _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP), atol=5e-3)
+
+
+def test_qwen3_next_tp2(tmp_path):
+    """gated DeltaNet heads (k-head groups), conv channels and the gated softmax attention sharded over TP"""
+    import torch
+    import transformers as tf
+
+    torch.manual_seed(0)
+    cfg = tf.Qwen3NextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                             max_position_embeddings=512, head_dim=16, partial_rotary_factor=0.25, linear_num_key_heads=2, linear_num_value_heads=4,
+                             linear_key_head_dim=8, linear_value_head_dim=8, linear_conv_kernel_dim=4, num_experts=4, num_experts_per_tok=2,
+                             moe_intermediate_size=32, shared_expert_intermediate_size=48, decoder_sparse_step=1, mlp_only_layers=[],
+                             layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"], tie_word_embeddings=False)
+    hf = tf.Qwen3NextForCausalLM(cfg).float()
+    with torch.no_grad():
+        for p in hf.parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.08)
+    d = str(tmp_path / "q3n")
+    hf.save_pretrained(d, safe_serialization=True)
+    kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP), atol=5e-3)
