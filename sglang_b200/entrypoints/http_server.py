@@ -345,8 +345,9 @@ def _free_port() -> int:
     return p
 
 
-def _peer_main(args: ServerArgs, rank: int, world: int, master_port: int) -> None:
-    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(master_port))
+def _peer_main(args: ServerArgs, rank: int, world: int, master_port: int, master_addr: str = "127.0.0.1", local_rank: Optional[int] = None) -> None:
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank if local_rank is None else local_rank), WORLD_SIZE=str(world), MASTER_ADDR=master_addr,
+                      MASTER_PORT=str(master_port))
     from .engine import Engine
 
     eng = Engine(server_args=args)
@@ -362,13 +363,26 @@ def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) ->
     world = server_args.tp_size * server_args.pp_size
     peers = []
     if world > 1 and "RANK" not in os.environ:
-        port = server_args.nccl_port or _free_port()
+        # multi-node (reference --nnodes / --node-rank / --dist-init-addr): node i owns the consecutive global ranks
+        # [i * world / nnodes, (i + 1) * world / nnodes); every node spawns its own ranks, rendezvous at dist_init_addr; node 0 serves HTTP
+        nn, nr = max(1, server_args.nnodes), server_args.node_rank
+        if world % nn:
+            raise ValueError("tp_size * pp_size must be divisible by nnodes")
+        per = world // nn
+        if nn > 1:
+            if not server_args.dist_init_addr:
+                raise ValueError("--nnodes > 1 needs --dist-init-addr host:port")
+            addr, port = server_args.dist_init_addr.rsplit(":", 1)
+            port = int(port)
+        else:
+            addr, port = "127.0.0.1", server_args.nccl_port or _free_port()
+        first = nr * per
         ctx = mp.get_context("spawn")
-        for r in range(1, world):
-            p = ctx.Process(target=_peer_main, args=(server_args, r, world, port), daemon=True)
+        for lr in range(1, per):
+            p = ctx.Process(target=_peer_main, args=(server_args, first + lr, world, port, addr, lr), daemon=True)
             p.start()
             peers.append(p)
-        os.environ.update(RANK="0", LOCAL_RANK="0", WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        os.environ.update(RANK=str(first), LOCAL_RANK="0", WORLD_SIZE=str(world), MASTER_ADDR=addr, MASTER_PORT=str(port))
     engine = Engine(server_args=server_args)
     engine.start_background_loop()
     if int(os.environ.get("RANK", 0)) != 0:

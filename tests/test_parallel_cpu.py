@@ -272,3 +272,43 @@ def test_qwen3_next_tp2(tmp_path):
     hf.save_pretrained(d, safe_serialization=True)
     kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
     _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP), atol=5e-3)
+
+
+def test_multi_node_launch_two_nodes_tp4():
+    """``--nnodes 2``: two launch_server invocations (one per "node", both on this host) each spawn their local ranks and rendezvous at
+    --dist-init-addr; node 0 serves HTTP for the whole TP=4 job"""
+    import signal
+    import time
+    import urllib.request
+
+    http, rdv = _free_port(), _free_port()
+    procs = []
+    try:
+        for node in (0, 1):
+            env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            procs.append(subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu",
+                                           "--page-size", "4", "--tp", "4", "--nnodes", "2", "--node-rank", str(node), "--dist-init-addr",
+                                           f"127.0.0.1:{rdv}", "--port", str(http), "--log-level", "error", "--skip-tokenizer-init"],
+                                          env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, start_new_session=True))
+        body = json.dumps({"input_ids": PROMPTS[0], "sampling_params": SAMPLING}).encode()
+        out, t0 = None, time.time()
+        while time.time() - t0 < 180:
+            if any(p.poll() is not None for p in procs):
+                raise AssertionError("a node exited: " + "".join((p.stderr.read() or "")[-1500:] for p in procs if p.poll() is not None))
+            try:
+                req = urllib.request.Request(f"http://127.0.0.1:{http}/generate", data=body, headers={"Content-Type": "application/json"})
+                out = json.loads(urllib.request.urlopen(req, timeout=60).read())
+                break
+            except OSError:
+                time.sleep(1.0)
+        assert out is not None, "server did not come up"
+        ref = _run(dict(model_path="dummy:tiny-llama", page_size=4), 1)
+        assert out["output_ids"] == ref["ids"][0]
+    finally:
+        for p in procs:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)       # the node's own process group: launcher + the ranks it spawned
+            except ProcessLookupError:
+                pass
