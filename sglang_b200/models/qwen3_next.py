@@ -188,50 +188,40 @@ class GatedDeltaNet(nn.Module):
 
 
 class GatedAttention(nn.Module):
-    """softmax attention whose q projection also emits a per-channel output gate; per-head zero-centred q/k norm, partial rotary"""
+    """softmax attention whose q projection also emits a per-channel output gate; per-head zero-centred q/k norm, partial rotary.
+    The checkpoint's q_proj rows are [head][q (hd) | gate (hd)]: to the fused QKV linear that is simply ``2 * heads`` heads of width ``hd``
+    (pairs stay together under TP because heads are sharded contiguously)."""
 
     def __init__(self, cfg: ModelConfig, layer_id: int, dtype, rope, prefix: str):
         super().__init__()
-        tp = get_tp_group()
         hd = cfg.head_dim
-        self.qkv_proj = QKVParallelLinear(cfg.hidden_size, 2 * hd, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.attention_bias, dtype, None,
+        self.qkv_proj = QKVParallelLinear(cfg.hidden_size, hd, 2 * cfg.num_attention_heads, cfg.num_key_value_heads, cfg.attention_bias, dtype, None,
                                           prefix + ".qkv_proj")
-        # QKVParallelLinear sized every head 2*hd wide; k / v only use the first hd columns of theirs (kept simple: separate views below)
-        self.nh, self.nkv, self.hd = self.qkv_proj.num_heads, self.qkv_proj.num_kv_heads, hd
+        self.nh, self.nkv, self.hd = self.qkv_proj.num_heads // 2, self.qkv_proj.num_kv_heads, hd
         self.o_proj = RowParallelLinear(cfg.num_attention_heads * hd, cfg.hidden_size, cfg.attention_bias, True, dtype, None, prefix + ".o_proj")
         self.q_norm, self.k_norm = RMSNorm(hd, cfg.rms_norm_eps, dtype, True), RMSNorm(hd, cfg.rms_norm_eps, dtype, True)
         self.attn = RadixAttention(self.nh, hd, self.nkv, layer_id, rope=rope)
 
     def load(self, leaf: str, w: torch.Tensor) -> bool:
-        """q_proj [(heads, 2 hd), H]; k_proj / v_proj [(kv heads, hd), H] are padded to the 2*hd head width of the fused parameter"""
         proj, kind = leaf.split(".")[0], leaf.split(".")[1]
         if proj not in ("q_proj", "k_proj", "v_proj"):
             return False
-        p = self.qkv_proj.weight if kind == "weight" else self.qkv_proj.bias
-        tail = tuple(w.shape[1:])
-        if proj != "q_proj":
-            heads = w.shape[0] // self.hd
-            wp = torch.zeros((heads, 2 * self.hd) + tail, dtype=w.dtype)
-            wp[:, : self.hd] = w.view((heads, self.hd) + tail)
-            w = wp.view((heads * 2 * self.hd,) + tail)
         if kind == "weight":
-            self.qkv_proj.weight_loader(p, w, proj[0])
+            self.qkv_proj.weight_loader(self.qkv_proj.weight, w, proj[0])
         else:
             from .llama import _load_stacked_bias
 
-            _load_stacked_bias(self.qkv_proj, p, w, proj[0])
+            _load_stacked_bias(self.qkv_proj, self.qkv_proj.bias, w, proj[0])
         return True
 
     def forward(self, x: torch.Tensor, fb: ForwardBatch):
         T = x.shape[0]
-        q2, k2, v2 = self.qkv_proj(x).split([self.qkv_proj.q_size, self.qkv_proj.kv_size, self.qkv_proj.kv_size], dim=-1)
+        q2, k, v = self.qkv_proj(x).split([self.qkv_proj.q_size, self.qkv_proj.kv_size, self.qkv_proj.kv_size], dim=-1)
         q2 = q2.view(T, self.nh, 2 * self.hd)
         q, gate = q2[..., : self.hd], q2[..., self.hd:].reshape(T, self.nh * self.hd)
-        k = k2.view(T, self.nkv, 2 * self.hd)[..., : self.hd]
-        v = v2.view(T, self.nkv, 2 * self.hd)[..., : self.hd]
         q = self.q_norm(q.reshape(T * self.nh, self.hd)).view(T, self.nh * self.hd)
         k = self.k_norm(k.reshape(T * self.nkv, self.hd)).view(T, self.nkv * self.hd)
-        o = self.attn(q.contiguous(), k.contiguous(), v.reshape(T, self.nkv * self.hd).contiguous(), fb)
+        o = self.attn(q.contiguous(), k.contiguous(), v.contiguous(), fb)
         return self.o_proj(o * torch.sigmoid(gate.float()).to(o.dtype))
 
 
