@@ -83,6 +83,8 @@ class ModelConfig:
     linear_attn: Optional[Dict[str, Any]] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
     mamba: Optional[Dict[str, Any]] = None
+    num_labels: int = 1                              # classification / reward heads
+    encoder: Optional[Dict[str, Any]] = None         # encoder-only models (BERT / RoBERTa): type_vocab_size, sep_token_id
     # speech encoder of encoder-decoder ASR models (models/whisper.py)
     audio: Optional[Dict[str, Any]] = None
     # multimodal (LLaVA-style)
@@ -296,7 +298,8 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "PhiForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", partial_rotary_factor=0.5),
                   "GPTJForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", rope_is_neox=False),
                   "GPTBigCodeForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_pytorch_tanh"),
-                  "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
+                  "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2ForSequenceClassification": dict(attention_bias=True),
+                  "Qwen2Model": dict(attention_bias=True), "Qwen3ForSequenceClassification": dict(qk_norm=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True), "Qwen2_5_VLForConditionalGeneration": dict(attention_bias=True),
                   "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
@@ -429,6 +432,15 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", text.get("num_key_value_heads", kw.get("num_attention_heads", 1)))
             if arch == "NemotronHForCausalLM" and text.get("attention_head_dim"):
                 kw["head_dim"] = text["attention_head_dim"]
+        if hf.get("num_labels") is not None or hf.get("id2label"):
+            kw["num_labels"] = int(hf.get("num_labels") or len(hf["id2label"]))
+        if arch in ("BertModel", "XLMRobertaModel", "RobertaModel", "BertForSequenceClassification", "XLMRobertaForSequenceClassification",
+                    "RobertaForSequenceClassification"):
+            kw["encoder"] = {"type_vocab_size": hf.get("type_vocab_size", 2), "sep_token_id": hf.get("sep_token_id", 102 if arch.startswith("Bert") else 2)}
+            kw["rms_norm_eps"] = hf.get("layer_norm_eps", 1e-12)
+            kw["num_key_value_heads"] = hf["num_attention_heads"]
+            kw["pos_emb"] = "learned"
+            kw.setdefault("hidden_act", hf.get("hidden_act", "gelu"))
         if arch == "WhisperForConditionalGeneration":
             kw.update(hidden_size=hf["d_model"], num_hidden_layers=hf["decoder_layers"], num_attention_heads=hf["decoder_attention_heads"],
                       num_key_value_heads=hf["decoder_attention_heads"], intermediate_size=hf["decoder_ffn_dim"],

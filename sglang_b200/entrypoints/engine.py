@@ -104,6 +104,8 @@ class Engine:
         self._relay_src = (st.pp.world_size - 1) * st.tp.world_size if st.pp.world_size > 1 else None
         self._relay_buf: List[Any] = []
         self._world = st.world
+        if getattr(self.runner.model, "disable_chunked_prefill", False):
+            a.chunked_prefill_size = None       # encoder-only models attend bidirectionally: a request is always encoded in one pass
         if getattr(self.runner.model, "disable_radix_cache", False) and not a.disable_radix_cache:
             logger.info("%s keeps recurrent state per request: prefix caching disabled", type(self.runner.model).__name__)
             a.disable_radix_cache = True
@@ -405,8 +407,8 @@ class Engine:
         res = [by_id[s.rid] for s in states]
         return res if g.is_batch() or len(res) > 1 else res[0]
 
-    def encode(self, prompt: Union[str, List[str]], image_data: Any = None) -> Any:
-        g = ios.GenerateReqInput(text=prompt, image_data=image_data, sampling_params={"max_new_tokens": 1})
+    def encode(self, prompt: Union[str, List[str], None] = None, image_data: Any = None, input_ids: Any = None) -> Any:
+        g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, sampling_params={"max_new_tokens": 1})
         states = [self._submit(s, None, is_embedding=True) for s in g.normalize()]
         self._drive(states)
         res = [s.result() for s in states]

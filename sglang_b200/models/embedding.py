@@ -23,9 +23,14 @@ class LlamaEmbeddingModel(LlamaForCausalLM):
 class LlamaForSequenceClassification(LlamaForCausalLM):
     is_embedding = True
 
-    def __init__(self, cfg, quant_name: Optional[str] = None, device="cpu", num_labels: int = 1):
+    def __init__(self, cfg, quant_name: Optional[str] = None, device="cpu", num_labels: Optional[int] = None):
         super().__init__(cfg, quant_name, device)
-        self.score = nn.Linear(cfg.hidden_size, num_labels, bias=False, dtype=_DT[cfg.dtype])
+        self.score = nn.Linear(cfg.hidden_size, num_labels or cfg.num_labels, bias=False, dtype=_DT[cfg.dtype])
 
     def pool(self, hidden_last: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         return self.score(hidden_last).float()
+
+
+def make_classifier(base_cls):
+    """``<Family>ForSequenceClassification``: the family's decoder + a bias-free ``score`` head on the last token (reward models, classifiers)"""
+    return type(base_cls.__name__.replace("ForCausalLM", "") + "ForSequenceClassification", (LlamaForSequenceClassification, base_cls), {})

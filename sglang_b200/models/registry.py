@@ -90,3 +90,15 @@ def _register_builtins() -> None:
 
     register_model("LlamaEmbeddingModel", _emb.LlamaEmbeddingModel)
     register_model("LlamaForSequenceClassification", _emb.LlamaForSequenceClassification)
+    for fam in ("Qwen2", "Qwen3", "Gemma2", "Phi3", "Gemma"):
+        if fam + "ForCausalLM" in _REGISTRY:
+            register_model(fam + "ForSequenceClassification", _emb.make_classifier(_REGISTRY[fam + "ForCausalLM"]))
+    register_model("MistralForSequenceClassification", _emb.LlamaForSequenceClassification)
+    register_model("MistralModel", _emb.LlamaEmbeddingModel)
+    register_model("Qwen2Model", type("Qwen2EmbeddingModel", (_emb.LlamaEmbeddingModel,), {}))
+    from . import bert as _bert
+
+    for name in ("BertModel", "XLMRobertaModel", "BertForSequenceClassification", "XLMRobertaForSequenceClassification"):
+        register_model(name, getattr(_bert, name))
+    register_model("RobertaModel", _bert.XLMRobertaModel)
+    register_model("RobertaForSequenceClassification", _bert.XLMRobertaForSequenceClassification)
