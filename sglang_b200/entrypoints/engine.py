@@ -428,6 +428,19 @@ class Engine:
         return scores
 
     def rerank(self, query: str, documents: List[str]) -> List[Dict[str, Any]]:
+        if type(self.runner.model).__name__.endswith("ForSequenceClassification") and self.tokenizer is not None:
+            # cross-encoder (bge-reranker, ms-marco-MiniLM, ...): ONE pass over "<cls> query <sep> document <sep>", the head's logit is the score
+            # (reference CrossEncodingPooler / serving_rerank)
+            tk = self.tokenizer
+            try:
+                pairs = [tk(query, d, truncation=True, max_length=self.model_config.max_position_embeddings - 2)["input_ids"] for d in documents]
+            except TypeError:          # tokenizers without pair encoding: join with the separator ourselves
+                sep = getattr(tk, "sep_token_id", None)
+                pairs = [tk.encode(query) + ([sep] if sep is not None else []) + tk.encode(d)[1:] for d in documents]
+            outs = self.encode(input_ids=pairs)
+            sc = [float(o["embedding"][0]) for o in (outs if isinstance(outs, list) else [outs])]
+            order = sorted(range(len(documents)), key=lambda i: -sc[i])
+            return [{"index": i, "score": sc[i], "document": documents[i]} for i in order]
         embs = self.encode([query] + documents)
         q = torch.tensor(embs[0]["embedding"])
         sc = [float(torch.dot(q, torch.tensor(e["embedding"]))) for e in embs[1:]]

@@ -78,3 +78,38 @@ def test_decoder_classifier_matches_hf(name, cfgname, tmp_path):
         with torch.no_grad():
             ref = hf(input_ids=torch.tensor([ids])).logits[0]
         assert torch.allclose(torch.tensor(o["embedding"]), ref, atol=2e-3)
+
+
+def test_rerank_uses_the_cross_encoder_head(tmp_path):
+    """/v1/rerank on a ...ForSequenceClassification model scores (query, document) PAIRS in one pass each"""
+    torch.manual_seed(1)
+    cfg = tf.XLMRobertaConfig(**ENC, num_labels=1)
+    hf = _randomise(tf.XLMRobertaForSequenceClassification(cfg))
+    d = str(tmp_path / "rr")
+    hf.save_pretrained(d, safe_serialization=True)
+
+    class PairTok:          # minimal pair tokenizer: bytes + 5, <s>=0 </s>=2
+        sep_token_id = 2
+
+        def encode(self, t):
+            return [0] + [5 + (b % 200) for b in t.encode()] + [2]
+
+        def __call__(self, a, b=None, **kw):
+            ids = self.encode(a) + ([2] + self.encode(b)[1:] if b is not None else [])
+            return {"input_ids": ids}
+
+        def decode(self, ids, **kw):
+            return ""
+
+    e = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error")
+    e.tokenizer = PairTok()
+    docs = ["alpha beta", "gamma", "delta epsilon zeta"]
+    got = e.rerank("what is alpha", docs)
+    e.shutdown()
+    tk = PairTok()
+    ref = []
+    for dd in docs:
+        with torch.no_grad():
+            ref.append(float(hf(input_ids=torch.tensor([tk("what is alpha", dd)["input_ids"]])).logits[0, 0]))
+    assert [r["index"] for r in got] == sorted(range(3), key=lambda i: -ref[i])
+    assert all(abs(r["score"] - ref[r["index"]]) < 2e-4 for r in got)
