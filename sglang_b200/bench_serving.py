@@ -13,7 +13,6 @@ import argparse
 import asyncio
 import json
 import random
-import sys
 import time
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple

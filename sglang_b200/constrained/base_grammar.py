@@ -7,7 +7,7 @@ it is applied on the device by ``ops.apply_token_bitmask`` (``csrc/kernels/sampl
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional
 
 import numpy as np
 

@@ -18,7 +18,7 @@ import logging
 import threading
 import urllib.request
 from collections import OrderedDict
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -16,7 +16,6 @@ Intra-node NVLink peer copies reuse the NVL arena machinery and are wired throug
 from __future__ import annotations
 
 import enum
-import io
 import logging
 import pickle
 import queue

@@ -15,9 +15,8 @@ import multiprocessing as mp
 import os
 import socket
 import sys
-import threading
 import time
-from typing import Any, Dict, Optional
+from typing import Any, Optional
 
 from fastapi import FastAPI, Request
 from fastapi.responses import JSONResponse, Response, StreamingResponse

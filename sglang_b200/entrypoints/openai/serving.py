@@ -7,7 +7,6 @@ Parity: reference ``python/sglang/srt/entrypoints/openai/`` (``serving_base.py:2
 from __future__ import annotations
 
 import json
-import time
 from typing import Any, AsyncIterator, Dict, List, Optional, Tuple
 
 from ...function_call.function_call_parser import FunctionCallParser

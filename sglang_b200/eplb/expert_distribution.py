@@ -8,7 +8,7 @@ apply by permuting the expert dimension of ``w13``/``w2`` and the router's outpu
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 import numpy as np
 import torch

@@ -19,7 +19,7 @@ import hashlib
 import os
 import subprocess
 from pathlib import Path
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Sequence
 
 ROOT = Path(__file__).resolve().parent
 CSRC_JIT = ROOT / "csrc" / "jit"

@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import re
-from typing import Any, Callable, List, Optional, Union
+from typing import Any, Callable, List, Optional
 
 from .choices import (ChoicesSamplingMethod, greedy_token_selection, token_length_normalized,  # noqa: F401
                       unconditional_likelihood_normalized)

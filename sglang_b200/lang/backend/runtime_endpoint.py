@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import atexit
 import json
-import multiprocessing as mp
 import os
 import socket
 import subprocess

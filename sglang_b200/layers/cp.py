@@ -21,7 +21,7 @@ relative to the quadratic attention it removes at long sequence lengths).
 from __future__ import annotations
 
 import dataclasses
-from typing import Any, List, Optional
+from typing import Any, List
 
 import numpy as np
 import torch

@@ -10,7 +10,7 @@ Quantisation plugs in through ``quant_method`` (``layers/quantization.py``): ``c
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 from torch import nn

@@ -15,7 +15,7 @@ NOT replicated.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 from torch import nn

@@ -7,7 +7,7 @@ process (or in-line for the offline engine); the C++ HTTP front end can host the
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List
 
 from . import io_struct as ios
 

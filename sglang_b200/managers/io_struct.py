@@ -10,7 +10,6 @@ from __future__ import annotations
 import dataclasses
 
 import numpy as np
-import uuid
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Union
 

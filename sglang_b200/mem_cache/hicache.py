@@ -14,8 +14,7 @@ from __future__ import annotations
 
 import json
 import logging
-import os
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, List, Optional
 
 import numpy as np
 import torch

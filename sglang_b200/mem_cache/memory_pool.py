@@ -9,7 +9,7 @@ HiCache page transfers are strided copies of one tensor, (c) a page is contiguou
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Optional
 
 import numpy as np
 import torch

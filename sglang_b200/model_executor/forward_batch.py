@@ -10,7 +10,7 @@ in a second (float) region of the same buffer.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, List, Optional
 
 import numpy as np

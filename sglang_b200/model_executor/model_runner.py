@@ -17,7 +17,6 @@ from __future__ import annotations
 import json
 import logging
 import time
-from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional
 
 import numpy as np

@@ -9,10 +9,9 @@ host staging, so a 70B random init costs seconds, and all TP ranks agree on repl
 from __future__ import annotations
 
 import glob
-import json
 import os
 import zlib
-from typing import Dict, Iterable, Iterator, Optional, Tuple
+from typing import Iterator, Optional, Tuple
 
 import torch
 from torch import nn

@@ -14,7 +14,7 @@ fused or as ``Conv1D``).
 from __future__ import annotations
 
 import zlib
-from typing import Any, Dict, Iterable, List, Optional, Tuple
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 from torch import nn
@@ -25,7 +25,7 @@ from ..layers.common import RadixAttention, RotaryEmbedding
 from ..layers.linear import ColumnParallelLinear, ParallelLMHead, QKVParallelLinear, RowParallelLinear, VocabParallelEmbedding
 from ..model_executor.forward_batch import ForwardBatch
 from ..parallel.parallel_state import get_attn_tp_group, get_pp_group, get_tp_group
-from .llama import _DT, _layer_id, _load_stacked_bias, pp_layer_range
+from .llama import _DT, _load_stacked_bias
 
 _ACT = {"gelu": lambda x: torch.nn.functional.gelu(x), "gelu_new": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),
         "gelu_pytorch_tanh": lambda x: torch.nn.functional.gelu(x, approximate="tanh"), "gelu_fast": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),

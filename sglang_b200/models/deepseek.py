@@ -15,7 +15,7 @@ yet, so CUDA graphs are disabled for these models (``supports_cuda_graph = False
 from __future__ import annotations
 
 import math
-from typing import Any, Iterable, List, Optional, Tuple
+from typing import Iterable, List, Tuple
 
 import torch
 from torch import nn

@@ -12,7 +12,7 @@ elementwise op after the unmodified tcgen05 / reference attention (also exact un
 from __future__ import annotations
 
 import zlib
-from typing import Iterable, List, Optional, Tuple
+from typing import Iterable, List, Tuple
 
 import torch
 from torch import nn

@@ -7,7 +7,7 @@ Parity: reference ``python/sglang/srt/models/llama.py`` (``LlamaMLP:111``, ``Lla
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
 from torch import nn

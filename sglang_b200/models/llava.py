@@ -14,7 +14,6 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..configs.model_config import ModelConfig
-from ..model_executor.forward_batch import ForwardBatch
 from .llama import _DT, LlamaForCausalLM
 
 

@@ -19,7 +19,7 @@ How it fits this engine:
 from __future__ import annotations
 
 import zlib
-from typing import Any, Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F

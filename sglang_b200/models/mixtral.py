@@ -5,7 +5,7 @@ Parity: reference ``python/sglang/srt/models/mixtral.py`` (MixtralMoE block: rep
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Tuple
+from typing import Iterable, List, Tuple
 
 import torch
 from torch import nn

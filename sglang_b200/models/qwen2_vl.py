@@ -15,7 +15,6 @@ Engine integration without touching the kernels:
 """
 from __future__ import annotations
 
-import math
 from typing import Any, Dict, Iterable, List, Optional, Tuple
 
 import numpy as np

@@ -9,7 +9,7 @@ import base64
 import io
 import os
 import wave
-from typing import Any, Tuple
+from typing import Any
 
 import numpy as np
 import torch

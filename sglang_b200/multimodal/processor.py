@@ -12,7 +12,7 @@ import base64
 import hashlib
 import io
 import os
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Tuple
 
 import numpy as np
 import torch

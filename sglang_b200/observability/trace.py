@@ -6,11 +6,10 @@ from __future__ import annotations
 
 import collections
 import json
-import os
 import threading
 import time
 import uuid
-from typing import Any, Deque, Dict, List, Optional
+from typing import Any, Deque, Dict, Optional
 
 _LOCK = threading.Lock()
 

@@ -14,7 +14,7 @@ reads of call k-2.
 from __future__ import annotations
 
 import logging
-from typing import Any, List, Optional
+from typing import Any, Optional
 
 import torch
 

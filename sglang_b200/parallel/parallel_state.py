@@ -12,7 +12,6 @@ NCCL stays for bootstrap, large prefill messages, PP send/recv and as the measur
 from __future__ import annotations
 
 import os
-import pickle
 from dataclasses import dataclass
 from typing import Any, List, Optional
 

@@ -7,7 +7,7 @@ json_schema | regex | ebnf | structural_tag (mutually exclusive), n, ignore_eos,
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Union
 
 _SAMPLING_EPS = 1e-6

@@ -16,7 +16,7 @@ Tree drafts (topk > 1) need custom-mask attention; ``speculative_eagle_topk`` > 
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, List, Optional, Tuple
 
 import numpy as np
 import torch

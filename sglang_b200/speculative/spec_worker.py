@@ -15,7 +15,7 @@ target model would (greedy => identical output to non-speculative decoding).
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List
 
 import numpy as np
 import torch

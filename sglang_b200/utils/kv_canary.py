@@ -12,7 +12,7 @@ free or wrong prefix-cache hit shows up as a mismatch.
 from __future__ import annotations
 
 import logging
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Callable, List, Optional
 
 import numpy as np
 
