@@ -395,12 +395,15 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                            "pattern": "".join("M" if k == "mamba" else "*" for k in kinds), "moe_layers": [int(n > 1) for n in ne]}
             kw["num_local_experts"] = max(ne) if max(ne) > 1 else 0
             kw["num_experts_per_tok"] = text.get("num_experts_per_tok", 2)
-        if arch == "BambaForCausalLM":
+        if arch == "GraniteMoeHybridForCausalLM":
+            kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size")
+            kw["pos_emb"] = "rope" if text.get("position_embedding_type", "rope") == "rope" else "none"
+        if arch in ("BambaForCausalLM", "GraniteMoeHybridForCausalLM"):
             hid = text["hidden_size"]
             heads = text.get("mamba_n_heads", 128)
             dh = text.get("mamba_d_head", "auto")
             dh = (text.get("mamba_expand", 2) * hid // heads) if dh in ("auto", None) else dh
-            kinds = text.get("layers_block_type") or ["attention" if i in (text.get("attn_layer_indices") or []) else "mamba"
+            kinds = text.get("layers_block_type") or text.get("layer_types") or ["attention" if i in (text.get("attn_layer_indices") or []) else "mamba"
                                                       for i in range(text["num_hidden_layers"])]
             kw["mamba"] = {"num_heads": heads, "head_dim": dh, "d_state": text.get("mamba_d_state", 256), "d_conv": text.get("mamba_d_conv", 4),
                            "n_groups": text.get("mamba_n_groups", 1), "chunk_size": text.get("mamba_chunk_size", 256),

@@ -882,3 +882,131 @@ class JambaForCausalLM(BambaForCausalLM):
                 params[target].data.copy_(w)
             loaded.append(name)
         return loaded
+
+
+# ================================================================================================ Granite 4 (GraniteMoeHybrid): Mamba-2 / attention mixers, MoE + shared MLP, Granite multipliers
+class _GraniteMoE(nn.Module):
+    def __init__(self, cfg: ModelConfig, gid: int, dtype, prefix: str):
+        super().__init__()
+        from ..layers.linear import ReplicatedLinear
+        from ..layers.moe import FusedMoE
+        from .mixtral import _EP_SIZE
+
+        self.router = ReplicatedLinear(cfg.hidden_size, cfg.num_local_experts, False, dtype, None, prefix + ".router")
+        self.experts = FusedMoE(cfg.num_local_experts, cfg.num_experts_per_tok, cfg.hidden_size, cfg.intermediate_size, dtype, True, _EP_SIZE["v"], None, gid)
+
+    def forward(self, x):
+        return self.experts(x, self.router(x))
+
+
+class _SharedMLP(nn.Module):
+    def __init__(self, cfg: ModelConfig, dtype, prefix: str):
+        super().__init__()
+        from ..layers.linear import MergedColumnParallelLinear
+
+        S = cfg.shared_expert_intermediate_size
+        self.gate_up_proj = MergedColumnParallelLinear(cfg.hidden_size, [S, S], False, dtype, None, prefix + ".gate_up_proj")
+        self.down_proj = RowParallelLinear(S, cfg.hidden_size, False, True, dtype, None, prefix + ".down_proj")
+
+    def forward(self, x):
+        return self.down_proj(ops.silu_and_mul(self.gate_up_proj(x)))
+
+
+class _GraniteHybridBlock(nn.Module):
+    def __init__(self, cfg: ModelConfig, kind: str, idx: int, gid: int, dtype, rope):
+        super().__init__()
+        from .llama import LlamaAttention
+
+        self.kind = kind
+        pre = f"model.layers.{gid}"
+        self.rm = float(cfg.residual_multiplier or 1.0)
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        if kind == "mamba":
+            self.mamba = Mamba2Mixer(cfg, idx, dtype, pre + ".mamba")
+        else:
+            self.self_attn = LlamaAttention(cfg, idx, dtype, None, rope, pre + ".self_attn")
+            if cfg.attention_multiplier:
+                self.self_attn.attn.scale = float(cfg.attention_multiplier)
+        self.block_sparse_moe = _GraniteMoE(cfg, gid, dtype, pre + ".block_sparse_moe") if cfg.num_local_experts > 0 else None
+        self.shared_mlp = _SharedMLP(cfg, dtype, pre + ".shared_mlp") if cfg.shared_expert_intermediate_size else None
+
+    def forward(self, x, fb):
+        r = lambda y: y.resolve() if hasattr(y, "resolve") else y
+        h = self.input_layernorm(x)
+        x = x + r(self.mamba(h, fb) if self.kind == "mamba" else self.self_attn(h, fb)) * self.rm
+        h = self.post_attention_layernorm(x)
+        y = r(self.block_sparse_moe(h)) if self.block_sparse_moe is not None else 0
+        if self.shared_mlp is not None:
+            y = y + r(self.shared_mlp(h))
+        return x + y * self.rm
+
+
+class GraniteMoeHybridForCausalLM(BambaForCausalLM):
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        nn.Module.__init__(self)
+        from ..layers.common import RotaryEmbedding
+
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        bb = nn.Module()
+        bb.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        rope = None
+        if cfg.pos_emb == "rope":
+            rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox, cfg.partial_rotary_factor,
+                                   device)
+        blocks, n_m, n_a = [], 0, 0
+        for i, ch in enumerate(cfg.mamba["pattern"]):
+            if ch == "M":
+                blocks.append(_GraniteHybridBlock(cfg, "mamba", n_m, i, dtype, rope))
+                n_m += 1
+            else:
+                blocks.append(_GraniteHybridBlock(cfg, "attention", n_a, i, dtype, rope))
+                n_a += 1
+        bb.all_layers = nn.ModuleList(blocks)
+        bb.num_mamba, bb.num_attn = n_m, n_a
+        bb.layers = [b for b in blocks if b.kind == "attention"]
+        bb.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.model = bb
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, dtype)
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        m = self.model
+        h = inputs_embeds if inputs_embeds is not None else (m.embed_tokens(fb.next_token_buf, fb.req_slots) if fb.input_ids is None
+                                                             else m.embed_tokens(fb.input_ids))
+        if self.cfg.embedding_multiplier:
+            h = h * float(self.cfg.embedding_multiplier)
+        for blk in m.all_layers:
+            h = blk(h, fb)
+        return m.norm(h)
+
+    def compute_logits(self, hidden, key: str = "logits"):
+        y = super().compute_logits(hidden, key)
+        return y / float(self.cfg.logits_scaling) if (self.cfg.logits_scaling or 1.0) != 1.0 else y
+
+    def load_weights(self, weights):
+        mods = dict(self.named_modules())
+
+        def rename():
+            for name, w in weights:
+                n = name.replace("model.layers.", "model.all_layers.")
+                if ".block_sparse_moe.router.layer." in n:
+                    yield name.replace(".router.layer.", ".router."), w
+                elif ".block_sparse_moe.input_linear.weight" in n or ".block_sparse_moe.output_linear.weight" in n:
+                    ex = mods[n[: n.index(".block_sparse_moe") + 17] + ".experts"]
+                    for e in range(w.shape[0]):
+                        if "input_linear" in n:
+                            g_, u_ = w[e].chunk(2, 0)
+                            ex.weight_loader(ex.w13, g_, e, "w1")
+                            ex.weight_loader(ex.w13, u_, e, "w3")
+                        else:
+                            ex.weight_loader(ex.w2, w[e], e, "w2")
+                elif ".shared_mlp.input_linear.weight" in n:
+                    g_, u_ = w.chunk(2, 0)
+                    yield name.replace("input_linear", "gate_proj"), g_
+                    yield name.replace("input_linear", "up_proj"), u_
+                elif ".shared_mlp.output_linear.weight" in n:
+                    yield name.replace("output_linear", "down_proj"), w
+                else:
+                    yield name, w
+        return super().load_weights(rename())

@@ -80,7 +80,7 @@ def _register_builtins() -> None:
     register_model("NemotronHForCausalLM", _mb.NemotronHForCausalLM)
     register_model("Mamba2ForCausalLM", _mb.Mamba2ForCausalLM)
     register_model("BambaForCausalLM", _mb.BambaForCausalLM)
-    for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM"):
+    for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM", "GraniteMoeHybridForCausalLM"):
         register_model(name, getattr(_mb, name))
     from . import deepseek as _ds
 

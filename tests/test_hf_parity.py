@@ -73,6 +73,10 @@ CASES = {
                                                                  moe_intermediate_size=32, shared_expert_intermediate_size=48, decoder_sparse_step=1,
                                                                  mlp_only_layers=[], norm_topk_prob=True,
                                                                  layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"])),
+    "granite4-hybrid": ("GraniteMoeHybridConfig", "GraniteMoeHybridForCausalLM", dict(
+        BASE, num_hidden_layers=3, layer_types=["mamba", "attention", "mamba"], mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=16,
+        mamba_d_conv=4, mamba_expand=2, mamba_chunk_size=8, num_local_experts=4, num_experts_per_tok=2, shared_intermediate_size=48,
+        embedding_multiplier=3.0, residual_multiplier=0.5, attention_multiplier=0.2, logits_scaling=2.0, position_embedding_type="nope", pad_token_id=0)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
