@@ -101,6 +101,7 @@ class _Envs:
     SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "pull", "pull (GEMM writes its partial into the local arena slot, the next norm kernel reduces across "
                            "ranks via peer loads / NVLS) | push (GEMM epilogue stores into every peer, norm reduces locally) | off.  Measured: "
                            "pull wins at 2 and 8 GPUs (push issues O(world) remote stores per rank; profiles/mgpu_tp8_r1.md)")
+    SGLB_SP_MIN_TOKENS = EnvInt("SGLB_SP_MIN_TOKENS", 512, "sequence parallelism: prefills with fewer new tokens keep the fused all-reduce + norm path")
     SGLB_CP_MIN_TOKENS = EnvInt("SGLB_CP_MIN_TOKENS", 1024, "prefill CP: batches with fewer new tokens run the plain TP path (KV all-gather would dominate)")
     SGLB_MOE_A2A = EnvBool("SGLB_MOE_A2A", True, "DP-attention + expert parallel: all-to-all token dispatch/combine instead of gather-all-tokens")
     SGLB_SHM_BROADCAST = EnvBool("SGLB_SHM_BROADCAST", True, "single-node control-plane fan-out over a shared-memory ring (else Gloo)")

@@ -15,6 +15,7 @@ from typing import List, Optional
 import torch
 from torch import nn
 
+from .sp import get_sp_ctx
 from .. import ops
 from ..parallel.parallel_state import get_tp_group
 from .quantization import QuantMethod, UnquantizedMethod
@@ -197,6 +198,10 @@ class RowParallelLinear(LinearBase):
         reducing; the consumer must be ``RMSNorm.forward_pending``."""
         bias = self.bias if (self.bias is not None and self.tp.rank == 0) else None   # added once: the reduction stays a pure sum
         tp = self.tp
+        if tp.world_size > 1 and self.reduce_results:
+            sp = get_sp_ctx()
+            if sp is not None and sp.group is tp:       # sequence parallel: the reduction ends scattered over the token rows (layers/sp.py)
+                return sp.reduce_scatter(self.apply(x, bias))
         if tp.world_size == 1:
             if defer_reduce and bias is None and _skinny_allowed(self, x):
                 return PendingSlabs(ops.gemm_skinny_slabs(x, self.weight))      # reduced inside the next RMSNorm kernel

@@ -267,6 +267,20 @@ class ModelRunner:
         return full[meta.inv_perm]
 
     # ------------------------------------------------------------------ two-batch overlap (reference batch_overlap/two_batch_overlap.py)
+    def _sp_eligible(self, fb: ForwardBatch) -> bool:
+        """sequence parallel prefill: plain Llama-shaped dense decoders (every layer runs ``LlamaDecoderLayer.forward`` with a dense MLP)"""
+        from ..layers.dp_attention import get_dp_ctx
+        from ..models.llama import LlamaDecoderLayer, LlamaMLP
+
+        m = getattr(self.model, "model", None)
+        ok = getattr(self, "_sp_static", None)
+        if ok is None:
+            ok = (self.tp.world_size > 1 and self.pp.world_size == 1 and m is not None and hasattr(m, "embed") and self.lora_manager is None
+                  and self.cp is None and self.dcp is None and type(self.model).forward is _LLAMA_FORWARD
+                  and all(type(l).forward is LlamaDecoderLayer.forward and isinstance(l.mlp, LlamaMLP) for l in m.layers))
+            self._sp_static = ok
+        return ok and get_dp_ctx() is None and fb.capture_aux is None and fb.num_tokens >= envs.SGLB_SP_MIN_TOKENS.get()
+
     def _tbo_static_ok(self) -> bool:
         m = getattr(self.model, "model", None)
         return (m is not None and hasattr(m, "embed") and self.pp.world_size == 1 and self.lora_manager is None and self.dcp is None
@@ -439,6 +453,15 @@ class ModelRunner:
             hidden = self._forward_cp(sb, fb)
         elif self.args.enable_two_batch_overlap and self._tbo_eligible(sb, fb):
             hidden = self._forward_tbo(sb, fb)
+        elif self.args.enable_sp and not decode and self._sp_eligible(fb):
+            from ..layers.sp import sp_context
+
+            sp = sp_context()
+            sp.begin(self.tp, fb.num_tokens)
+            try:
+                hidden = self.model(fb)
+            finally:
+                sp.end()
         else:
             hidden = self.model(fb)
         if self.hidden_tap is not None and not decode and self.pp.is_last:

@@ -21,6 +21,7 @@ from ..layers.quantization import get_quant_method
 from ..model_executor.forward_batch import ForwardBatch
 from ..environ import envs
 from ..layers.dp_attention import get_dp_ctx
+from ..layers.sp import get_sp_ctx
 from ..parallel.parallel_state import get_attn_tp_group, get_pp_group, get_tp_group
 
 _DT = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}
@@ -127,6 +128,13 @@ class LlamaDecoderLayer(nn.Module):
             h = self.input_layernorm(h)
         else:
             h, residual = self.input_layernorm(h, residual)
+        sp = get_sp_ctx()
+        if sp is not None:
+            # sequence parallel: h / residual are this rank's rows; gather before each tensor-parallel block, whose row-parallel GEMM
+            # (o_proj, down_proj) hands back reduce-scattered rows
+            h = self.self_attn(sp.gather(h)[: sp.T], fb)
+            h, residual = self.post_attention_layernorm(h, residual)
+            return self.mlp(sp.gather(h)), residual
         h = self.self_attn(h, fb)
         h, residual = self.post_attention_layernorm(h, residual)
         ctx = get_dp_ctx()
@@ -189,6 +197,9 @@ class LlamaModel(nn.Module):
             residual = None
         else:
             h, residual = fb.pp_hidden
+        sp = get_sp_ctx()
+        if sp is not None:
+            h = sp.scatter(h)
         cap = fb.capture_aux
         aux = [] if cap is not None else None
         for i, layer in enumerate(self.layers):
@@ -205,6 +216,8 @@ class LlamaModel(nn.Module):
         if residual is None:      # families whose layers keep the residual stream in h (Gemma-2, Granite, OLMo-2)
             return self.norm(h.resolve() if hasattr(h, "resolve") else h)
         h, _ = self.norm(h, residual)
+        if sp is not None:
+            h = sp.gather(h)[: sp.T]
         return h
 
 

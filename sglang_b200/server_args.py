@@ -83,6 +83,7 @@ class ServerArgs:
     dp_size: int = 1
     ep_size: int = 1
     enable_dp_attention: bool = False
+    enable_sp: bool = False                    # sequence parallelism for the token-wise half of TP prefills (layers/sp.py)
     enable_two_batch_overlap: bool = False     # TBO: split every batch in two micro-batches and interleave them layer by layer on two streams
     enable_prefill_cp: bool = False
     cp_size: int = 1

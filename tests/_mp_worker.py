@@ -27,5 +27,9 @@ if os.environ.get("SGLB_TEST_EXPECT_DCP"):
     assert eng.runner.dcp.comm_calls > 0, "DCP collectives were expected to run"
 if os.environ.get("SGLB_TEST_EXPECT_CP"):
     assert eng.runner.cp is not None and eng.runner.cp_forwards > 0, "context-parallel prefills were expected to run"
+if os.environ.get("SGLB_TEST_EXPECT_SP"):
+    from sglang_b200.layers.sp import sp_context
+
+    assert sp_context().forwards > 0, "sequence-parallel prefills were expected to run"
 eng.shutdown()
 os._exit(0)

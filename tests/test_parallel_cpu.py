@@ -312,3 +312,15 @@ def test_multi_node_launch_two_nodes_tp4():
                 os.killpg(p.pid, signal.SIGKILL)       # the node's own process group: launcher + the ranks it spawned
             except ProcessLookupError:
                 pass
+
+
+def test_sequence_parallel_prefill():
+    """--enable-sp: residual stream scattered over the token rows between the TP blocks (reduce-scatter after o_proj / down_proj, all-gather
+    before qkv / gate_up); token counts not divisible by tp exercise the padding; decode keeps the plain path"""
+    env = {"SGLB_SP_MIN_TOKENS": "1", "SGLB_TEST_EXPECT_SP": "1"}
+    for preset in ("tiny-llama", "tiny-phi3"):
+        kw = dict(model_path=f"dummy:{preset}", page_size=4, chunked_prefill_size=32)
+        ref = _run(kw, 1, LP)
+        _check(_run({**kw, "tp_size": 2, "enable_sp": True}, 2, LP, env), ref)
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=32)
+    _check(_run({**kw, "tp_size": 4, "enable_sp": True}, 4, LP, env), _run(kw, 1, LP))
