@@ -68,6 +68,7 @@ class DataParallelController:
         d = dataclasses.asdict(server_args)
         d = {k: v for k, v in d.items() if k in {f.name for f in dataclasses.fields(ServerArgs)}}
         d["dp_size"] = 1
+        self._ctx, self._replica_args = ctx, d
         self.inqs = [ctx.Queue() for _ in range(self.dp)]
         self.outq = ctx.Queue()
         self.procs = [ctx.Process(target=_replica_main, args=(d, r, self.inqs[r], self.outq), daemon=True) for r in range(self.dp)]
@@ -96,10 +97,14 @@ class DataParallelController:
         logger.info("%d DP replicas ready in %.1fs", self.dp, time.time() - t0)
 
     # ------------------------------------------------------------------ dispatch
-    def _pick(self) -> int:
+    def _pick(self, bootstrap_room: Optional[int] = None) -> int:
         live = [i for i in range(self.dp) if self.alive[i]]
         if not live:
             raise RuntimeError("no live data-parallel replica")
+        if self.policy == "follow_bootstrap_room" and bootstrap_room is not None:
+            # PD disaggregation: the prefill and the decode fleet must pick the SAME dp rank for a request without talking to each other
+            # (reference data_parallel_controller follow_bootstrap_room): the room id decides
+            return live[int(bootstrap_room) % len(live)]
         if self.policy == "total_requests":
             return min(live, key=lambda i: self.inflight_reqs[i])
         if self.policy == "total_tokens":
@@ -114,7 +119,8 @@ class DataParallelController:
             int((sampling_params or {}).get("max_new_tokens", 128))
         box: "queue.Queue[Any]" = queue.Queue()
         with self._lock:
-            r = routed_dp_rank if routed_dp_rank is not None and self.alive[routed_dp_rank] else self._pick()
+            r = routed_dp_rank if routed_dp_rank is not None and 0 <= routed_dp_rank < self.dp and self.alive[routed_dp_rank] \
+                else self._pick(kw.get("bootstrap_room"))
             self._waiters[rid], self._owner[rid], self._cost[rid] = box, r, cost
             self.inflight_reqs[r] += 1
             self.inflight_tokens[r] += cost
@@ -143,6 +149,10 @@ class DataParallelController:
                 kind, rid, out = self.outq.get(timeout=0.2)
             except queue.Empty:
                 continue
+            if kind == "ready":             # a replica added / restarted at run time
+                self._pending_ready = getattr(self, "_pending_ready", set())
+                self._pending_ready.add(rid)
+                continue
             with self._lock:
                 box = self._waiters.pop(rid, None)
                 r = self._owner.pop(rid, None)
@@ -167,6 +177,56 @@ class DataParallelController:
                             self._cost.pop(rid, None)
                             if box is not None:
                                 box.put(("error", f"replica {r} died"))
+
+    # ------------------------------------------------------------------ elastic replicas (reference elastic workers :234-300)
+    def add_replica(self, timeout: float = 600.0) -> int:
+        """start one more replica at run time; returns its dp rank"""
+        with self._lock:
+            r = self.dp
+            self.inqs.append(self._ctx.Queue())
+            p = self._ctx.Process(target=_replica_main, args=(self._replica_args, r, self.inqs[r], self.outq), daemon=True)
+            self.procs.append(p)
+            self.alive.append(False)
+            self.inflight_reqs.append(0)
+            self.inflight_tokens.append(0)
+            self.dp += 1
+        self._pending_ready = getattr(self, "_pending_ready", set())
+        p.start()
+        t0 = time.time()
+        while r not in self._pending_ready:          # the collector thread sees the "ready" message
+            if time.time() - t0 > timeout or not p.is_alive():
+                raise RuntimeError(f"replica {r} failed to start")
+            time.sleep(0.05)
+        self.alive[r] = True
+        return r
+
+    def remove_replica(self, r: int, drain_timeout: float = 60.0) -> None:
+        """stop routing to replica ``r``, let its in-flight requests finish, then stop the process"""
+        self.alive[r] = False
+        t0 = time.time()
+        while self.inflight_reqs[r] > 0 and time.time() - t0 < drain_timeout:
+            time.sleep(0.05)
+        self.inqs[r].put(None)
+        self.procs[r].join(timeout=10)
+        if self.procs[r].is_alive():
+            self.procs[r].terminate()
+
+    def restart_replica(self, r: int, timeout: float = 600.0) -> None:
+        """bring a dead replica back under the same rank"""
+        assert not self.procs[r].is_alive(), "replica still running"
+        self.inqs[r] = self._ctx.Queue()
+        p = self._ctx.Process(target=_replica_main, args=(self._replica_args, r, self.inqs[r], self.outq), daemon=True)
+        self.procs[r] = p
+        self._pending_ready = getattr(self, "_pending_ready", set())
+        self._pending_ready.discard(r)
+        p.start()
+        t0 = time.time()
+        while r not in self._pending_ready:
+            if time.time() - t0 > timeout or not p.is_alive():
+                raise RuntimeError(f"replica {r} failed to restart")
+            time.sleep(0.05)
+        self.inflight_reqs[r] = self.inflight_tokens[r] = 0
+        self.alive[r] = True
 
     def shutdown(self) -> None:
         self._stop.set()

@@ -26,5 +26,17 @@ def test_dp_dispatch_and_failover():
             time.sleep(0.1)
         assert not c.alive[1]
         assert len(c.generate("after failover", sp)["output_ids"]) == 6   # traffic continues on the survivor
+        # elastic: bring rank 1 back, add a third replica, drain and remove it again
+        c.restart_replica(1)
+        assert c.alive == [True, True] and c.generate("hello dp", sp, routed_dp_rank=1)["output_ids"] == a["output_ids"]
+        r = c.add_replica()
+        assert r == 2 and c.dp == 3 and c.generate("hello dp", sp, routed_dp_rank=2)["output_ids"] == a["output_ids"]
+        c.remove_replica(2)
+        assert not c.alive[2] and len(c.generate("after scale-down", sp)["output_ids"]) == 6
+        # PD: both fleets derive the dp rank from the bootstrap room
+        c.policy = "follow_bootstrap_room"
+        with c._lock:
+            picks = [c._pick(room) for room in (0, 1, 2, 3, 10, 11)]
+        assert picks == [0, 1, 0, 1, 0, 1]
     finally:
         c.shutdown()
