@@ -79,6 +79,8 @@ class ModelConfig:
     residual_multiplier: Optional[float] = None
     attention_multiplier: Optional[float] = None
     logits_scaling: Optional[float] = None
+    # Llama-4: no_rope_layers, moe_layers, intermediate_size_mlp, attention_chunk_size, use_qk_norm, attn_temperature_tuning, floor_scale, attn_scale
+    llama4: Optional[Dict[str, Any]] = None
     # Qwen3-Next gated DeltaNet layers: num_k_heads, num_v_heads, k_head_dim, v_head_dim, conv_kernel (models/qwen3_next.py)
     linear_attn: Optional[Dict[str, Any]] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
@@ -363,6 +365,17 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
             if kw.get("intermediate_size") is None:
                 kw["intermediate_size"] = 4 * kw["hidden_size"]
+        if arch in ("Llama4ForCausalLM", "Llama4ForConditionalGeneration"):
+            L = text["num_hidden_layers"]
+            nr = text.get("no_rope_layers") or [int((i + 1) % 4 != 0) for i in range(L)]
+            step = text.get("interleave_moe_layer_step", 1)
+            kw["llama4"] = {"no_rope_layers": nr, "moe_layers": text.get("moe_layers") or list(range(step - 1, L, step)),
+                            "intermediate_size_mlp": text.get("intermediate_size_mlp"), "attention_chunk_size": text.get("attention_chunk_size", 8192),
+                            "use_qk_norm": text.get("use_qk_norm", True), "attn_temperature_tuning": text.get("attn_temperature_tuning", True),
+                            "floor_scale": text.get("floor_scale", 8192), "attn_scale": text.get("attn_scale", 0.1)}
+            kw["layer_types"] = text.get("layer_types") or ["chunked_attention" if r else "full_attention" for r in nr]
+            kw["rope_is_neox"] = False
+            kw["architecture"] = "Llama4ForCausalLM"
         if arch == "Qwen3NextForCausalLM":
             kw["linear_attn"] = {"num_k_heads": text.get("linear_num_key_heads", 16), "num_v_heads": text.get("linear_num_value_heads", 32),
                                  "k_head_dim": text.get("linear_key_head_dim", 128), "v_head_dim": text.get("linear_value_head_dim", 128),

@@ -61,6 +61,7 @@ class RadixAttention(nn.Module):
         self.window = sliding_window
         self.logit_cap = logit_cap
         self.sinks = None            # [num_heads] fp32 learned attention sinks (GPT-OSS), see forward
+        self.chunk = 0               # > 0: attend only inside fixed position chunks (Llama-4 local layers)
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fb: ForwardBatch, nslabs: int = 1,
                 slab_stride: int = 0) -> torch.Tensor:
@@ -93,13 +94,33 @@ class RadixAttention(nn.Module):
             gather_write_kv(get_cp_group(), cp, out_loc, kc, vc)
         sinks = self.sinks
         lse = torch.empty(T, self.num_heads, dtype=torch.float32, device=q3.device) if sinks is not None else None
+        mask = fb.custom_mask if not self.chunk else chunk_attention_mask(fb, self.chunk)
         o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
-                                workspace=fb.attn_workspace, custom_mask=fb.custom_mask, lse=lse)
+                                workspace=fb.attn_workspace, custom_mask=mask, lse=lse)
         if sinks is not None:       # attention sinks (GPT-OSS): exp(sink_h) joins the soft-max denominator only -> o * sigmoid(lse - sink_h)
             o = (o.float() * torch.sigmoid(lse - sinks[None, :]).unsqueeze(-1)).to(o.dtype)
         return o.view(T, self.num_heads * self.head_dim)
+
+
+def chunk_attention_mask(fb: ForwardBatch, chunk: int) -> torch.Tensor:
+    """flattened per-request [q_len, kv_len] masks "same chunk and causal" (Llama-4 chunked attention), cached on the batch"""
+    cache = fb.__dict__.setdefault("_chunk_masks", {})
+    if chunk in cache:
+        return cache[chunk]
+    import numpy as np
+
+    sl = np.asarray(fb.seq_lens_cpu if fb.seq_lens_cpu is not None else fb.seq_lens.cpu().numpy())
+    ql = np.ones_like(sl) if fb.cu_q is None else np.asarray(fb.q_lens_cpu)
+    parts = []
+    for L, n in zip(sl.tolist(), ql.tolist()):
+        qp = torch.arange(L - n, L)[:, None]
+        kp = torch.arange(L)[None, :]
+        parts.append(((kp <= qp) & (kp // chunk == qp // chunk)).reshape(-1))
+    m = torch.cat(parts).to(fb.seq_lens.device) if parts else torch.zeros(0, dtype=torch.bool, device=fb.seq_lens.device)
+    cache[chunk] = m
+    return m
 
 
 def _radix_forward_dcp(self, q3, kc, vc, fb, dcp, pool):

@@ -53,6 +53,10 @@ def _register_builtins() -> None:
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM", "PhiForCausalLM", "GPTJForCausalLM",
                  "GPTBigCodeForCausalLM"):
         register_model(name, getattr(_cl, name))
+    from . import llama4 as _l4
+
+    register_model("Llama4ForCausalLM", _l4.Llama4ForCausalLM)
+    register_model("Llama4ForConditionalGeneration", _l4.Llama4ForCausalLM)       # text tower of the multimodal checkpoint
     from . import qwen3_next as _qn
 
     register_model("Qwen3NextForCausalLM", _qn.Qwen3NextForCausalLM)

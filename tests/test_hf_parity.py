@@ -77,6 +77,10 @@ CASES = {
         BASE, num_hidden_layers=3, layer_types=["mamba", "attention", "mamba"], mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=16,
         mamba_d_conv=4, mamba_expand=2, mamba_chunk_size=8, num_local_experts=4, num_experts_per_tok=2, shared_intermediate_size=48,
         embedding_multiplier=3.0, residual_multiplier=0.5, attention_multiplier=0.2, logits_scaling=2.0, position_embedding_type="nope", pad_token_id=0)),
+    "llama4": ("Llama4TextConfig", "Llama4ForCausalLM", dict(BASE, num_hidden_layers=4, head_dim=16, intermediate_size=32, intermediate_size_mlp=96,
+                                                           num_local_experts=4, num_experts_per_tok=1, interleave_moe_layer_step=2,
+                                                           no_rope_layers=[1, 1, 1, 0], attention_chunk_size=8, use_qk_norm=True,
+                                                           attn_temperature_tuning=True, floor_scale=4, attn_scale=0.3, pad_token_id=0)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
