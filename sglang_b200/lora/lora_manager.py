@@ -9,6 +9,10 @@ delta ``(x_seg @ A^T) @ B^T * scaling`` is computed per segment with two skinny 
 cache is namespaced by adapter id (``Req.extra_key``) so KV computed under one adapter is never reused under another.
 Adapter weights live in a paged pool of ``max_loras_per_batch`` slots on the device; the registry on the host can hold
 more (LRU eviction of device slots).
+
+Tensor parallelism: adapters are sharded exactly like the layer they modify.  Column-parallel layers (qkv, gate_up) keep ``A`` whole and take the
+rows of ``B`` that belong to this rank's heads / channels (KV heads follow the base layer's replication rule); row-parallel layers (o_proj,
+down_proj) take the matching input columns of ``A`` and keep ``B`` whole — their delta is a partial sum that rides the layer's own all-reduce.
 """
 from __future__ import annotations
 
@@ -49,13 +53,40 @@ def _dummy_adapter(name: str, spec: str, model: Any, device, dtype) -> LoRAAdapt
             mods.update({"gate_up_proj": layer.mlp.gate_up_proj, "down_proj": layer.mlp.down_proj})
         for mod_name, mod in mods.items():
             subs = TARGETS[mod_name]
+            W = mod.tp.world_size if getattr(mod, "tp", None) is not None else 1
             outs = _sub_out_sizes(mod_name, mod)
             for sub, n_out in zip(subs, outs):
                 g.manual_seed(zlib.crc32(f"{name}/{li}/{sub}".encode()) & 0x7FFFFFFF)
-                A = torch.empty(rank, mod.in_features, dtype=torch.float32, device=device).normal_(0, 0.05, generator=g).to(dtype)
-                B = torch.empty(n_out, rank, dtype=torch.float32, device=device).normal_(0, 0.05, generator=g).to(dtype)
-                ad.weights[(li, sub)] = (A, B)
+                # full-size factors (identical on every rank), then this rank's shard: results do not depend on the TP layout
+                full_in = mod.in_features * (W if mod_name in ("o_proj", "down_proj") else 1)
+                if mod_name in ("o_proj", "down_proj"):
+                    full_out = n_out
+                elif mod_name == "qkv_proj" and sub != "q_proj":
+                    full_out = n_out * max(1, W // getattr(mod, "kv_replicas", 1))
+                else:
+                    full_out = n_out * W
+                A = torch.empty(rank, full_in, dtype=torch.float32, device=device).normal_(0, 0.05, generator=g).to(dtype)
+                B = torch.empty(full_out, rank, dtype=torch.float32, device=device).normal_(0, 0.05, generator=g).to(dtype)
+                ad.weights[(li, sub)] = shard_adapter_weight(mod_name, sub, mod, A, B)
     return ad
+
+
+def shard_adapter_weight(mod_name: str, sub: str, mod: Any, A: torch.Tensor, B: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """full (unsharded) LoRA factors of one checkpoint sub-module -> this rank's factors (see module docstring)"""
+    tp = getattr(mod, "tp", None)
+    if tp is None or tp.world_size == 1:
+        return A, B
+    r = tp.rank
+    if mod_name in ("o_proj", "down_proj"):                      # row parallel: input features sharded
+        k = mod.in_features
+        return A[:, r * k:(r + 1) * k].contiguous(), B
+    if mod_name == "qkv_proj":
+        if sub == "q_proj":
+            return A, B[r * mod.q_size:(r + 1) * mod.q_size].contiguous()
+        src = (r // getattr(mod, "kv_replicas", 1)) * mod.kv_size
+        return A, B[src:src + mod.kv_size].contiguous()
+    n = list(mod.local_sizes)[0 if sub == "gate_proj" else 1]     # gate_up: both halves sharded alike
+    return A, B[r * n:(r + 1) * n].contiguous()
 
 
 def _sub_out_sizes(mod_name: str, mod: Any) -> List[int]:
@@ -73,15 +104,36 @@ def _load_peft_adapter(name: str, path: str, model: Any, device, dtype) -> LoRAA
     ad = LoRAAdapter(name, int(cfg["r"]), float(cfg.get("lora_alpha", cfg["r"])))
     f = os.path.join(path, "adapter_model.safetensors")
     sd = load_file(f) if os.path.exists(f) else torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu", weights_only=True)
-    pat = re.compile(r"layers\.(\d+)\..*?(q_proj|k_proj|v_proj|o_proj|gate_proj|up_proj|down_proj)\.lora_(A|B)")
+    pat = re.compile(r"layers\.(\d+)\..*?(q_proj|k_proj|v_proj|o_proj|gate_proj|up_proj|down_proj|qkv_proj|gate_up_proj)\.lora_(A|B)")
     tmp: Dict[Tuple[int, str], Dict[str, torch.Tensor]] = {}
     for k, v in sd.items():
         m = pat.search(k)
         if m:
             tmp.setdefault((int(m.group(1)), m.group(2)), {})[m.group(3)] = v.to(device=device, dtype=dtype)
-    for key, ab in tmp.items():
-        if "A" in ab and "B" in ab:
-            ad.weights[key] = (ab["A"], ab["B"])
+    layers = model.model.layers
+    where = {"q_proj": "qkv_proj", "k_proj": "qkv_proj", "v_proj": "qkv_proj", "o_proj": "o_proj", "gate_proj": "gate_up_proj", "up_proj": "gate_up_proj",
+             "down_proj": "down_proj"}
+    for (li, sub), ab in tmp.items():
+        if not ("A" in ab and "B" in ab) or li >= len(layers):
+            continue
+        layer = layers[li]
+        mods = {"qkv_proj": layer.self_attn.qkv_proj, "o_proj": layer.self_attn.o_proj, "gate_up_proj": getattr(layer.mlp, "gate_up_proj", None),
+                "down_proj": getattr(layer.mlp, "down_proj", None)}
+        if sub in ("qkv_proj", "gate_up_proj"):          # adapters trained on fused projections (Phi-3 style): split B by the fused layout
+            mod = mods[sub]
+            if mod is None:
+                continue
+            W = mod.tp.world_size
+            if sub == "qkv_proj":
+                sizes = [mod.q_size * W, mod.kv_size * max(1, W // getattr(mod, "kv_replicas", 1))] + [mod.kv_size * max(1, W // getattr(mod, "kv_replicas", 1))]
+            else:
+                sizes = [n * W for n in mod.local_sizes]
+            for part, Bp in zip(TARGETS[sub], ab["B"].split(sizes, 0)):
+                ad.weights[(li, part)] = shard_adapter_weight(sub, part, mod, ab["A"], Bp)
+            continue
+        mod = mods[where[sub]]
+        if mod is not None:
+            ad.weights[(li, sub)] = shard_adapter_weight(where[sub], sub, mod, ab["A"], ab["B"])
     if not ad.weights:
         raise ValueError(f"no LoRA weights found under {path}")
     return ad
@@ -92,8 +144,6 @@ class LoRAManager:
         self.runner = runner
         self.max_per_batch, self.max_rank = max_loras_per_batch, max_lora_rank
         self.adapters: "OrderedDict[str, LoRAAdapter]" = OrderedDict()
-        if runner.tp.world_size > 1:
-            raise NotImplementedError("LoRA with tensor parallelism is not supported yet (adapters are unsharded)")
         self._wrap_model()
 
     # ------------------------------------------------------------------ registry

@@ -324,3 +324,12 @@ def test_sequence_parallel_prefill():
         _check(_run({**kw, "tp_size": 2, "enable_sp": True}, 2, LP, env), ref)
     kw = dict(model_path="dummy:tiny-llama", page_size=4, chunked_prefill_size=32)
     _check(_run({**kw, "tp_size": 4, "enable_sp": True}, 4, LP, env), _run(kw, 1, LP))
+
+
+def test_lora_tp2_matches_single():
+    """adapters sharded like their layers (B rows of column-parallel, A columns of row-parallel projections); mixed batch of two adapters + base"""
+    kw = dict(model_path="dummy:tiny-llama", page_size=4, enable_lora=True, lora_paths=["a=dummy:rank=4", "b=dummy:rank=8"])
+    gen = {**LP, "lora_path": ["a", None, "b", "a"]}
+    ref = _run(kw, 1, gen)
+    _check(_run({**kw, "tp_size": 2}, 2, gen), ref)
+    assert ref["ids"] != _run(dict(model_path="dummy:tiny-llama", page_size=4), 1, LP)["ids"]
