@@ -16,8 +16,13 @@ logger = logging.getLogger(__name__)
 
 
 class GrammarManager:
-    def __init__(self, tokenizer: Any, vocab_size: int, backend: str = "auto", jump_forward_backend: Optional[str] = None):
+    def __init__(self, tokenizer: Any, vocab_size: int, backend: str = "auto", jump_forward_backend: Optional[str] = None,
+                 reasoning_parser: Optional[str] = None):
+        from .reasoner_grammar import think_end_ids
+
         self.backend = create_grammar_backend(backend, tokenizer, vocab_size)
+        # with a reasoning parser the grammar constrains the answer only (constrained/reasoner_grammar.py)
+        GrammarManager.think_end = think_end_ids(tokenizer, reasoning_parser)
         self.backend_name = type(self.backend).__name__
         self.pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sglb-grammar")
         self.cache: Dict[Tuple[str, str], Any] = {}     # key -> compiled template grammar | Exception
@@ -62,6 +67,11 @@ class GrammarManager:
             req.to_abort = FINISH_ABORT(f"invalid grammar: {compiled}", 400)
         else:
             req.grammar = compiled.copy()
+            end = getattr(GrammarManager, "think_end", None)
+            if end:
+                from .reasoner_grammar import ReasonerGrammar
+
+                req.grammar = ReasonerGrammar(req.grammar, end)
 
     def shutdown(self) -> None:
         self.pool.shutdown(wait=False, cancel_futures=True)

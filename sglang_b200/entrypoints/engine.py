@@ -134,7 +134,8 @@ class Engine:
             try:
                 from ..constrained.grammar_manager import GrammarManager
 
-                self.scheduler.grammar_manager = GrammarManager(self.tokenizer, self.model_config.vocab_size, a.grammar_backend)
+                self.scheduler.grammar_manager = GrammarManager(self.tokenizer, self.model_config.vocab_size, a.grammar_backend,
+                                                                 reasoning_parser=a.reasoning_parser)
             except Exception as e:  # grammar backends are optional at import time
                 logger.warning("grammar backend unavailable: %s", e)
         if a.speculative_algorithm:
@@ -511,6 +512,11 @@ class Engine:
     def send_weights_to_remote_instance(self, master_address: str, master_port: int, group_name: str = "remote_instance_load",
                                         backend: str = "nccl") -> Any:
         return self._control(ios.SendWeightsToRemoteInstanceReq(master_address, int(master_port), group_name, backend))
+
+    def collective_rpc(self, method: str, **kwargs: Any) -> Any:
+        """call ``method(**kwargs)`` on the scheduler (or its model runner) of EVERY rank (reference Engine.collective_rpc); returns this
+        rank's result"""
+        return self._control(ios.RpcReq(method, kwargs)).result
 
     def weights_checker(self, action: str = "checksum") -> Any:
         return self._control(ios.WeightsCheckerReq(action))

@@ -307,6 +307,19 @@ class GetWeightsByNameReq:
 
 
 @message
+class RpcReq:
+    method: str = ""
+    kwargs: Optional[Dict[str, Any]] = None
+
+
+@message
+class RpcResp:
+    success: bool = True
+    result: Any = None
+    message: str = ""
+
+
+@message
 class SendWeightsToRemoteInstanceReq:
     """seed side of the remote-instance loader: join a 2-rank group per TP rank (the new instance hosts the store at
     ``master_address:master_port + tp_rank``) and broadcast every local parameter shard"""

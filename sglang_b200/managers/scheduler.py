@@ -118,6 +118,15 @@ class Scheduler:
             return ios.GetLoadResp(num_running_reqs=len(self.running_batch.reqs), num_waiting_reqs=len(self.waiting_queue),
                                    num_tokens=int(self.kv.total_pages() - self.kv.available_pages()) * self.page_size,
                                    token_usage=self.kv.token_usage())
+        if isinstance(msg, ios.RpcReq):
+            self.drain()
+            target = self if hasattr(self, msg.method) else self.worker
+            if msg.method.startswith("_") or not hasattr(target, msg.method):
+                return ios.RpcResp(False, None, f"no public method {msg.method!r} on the scheduler or the model runner")
+            try:
+                return ios.RpcResp(True, getattr(target, msg.method)(**(msg.kwargs or {})))
+            except Exception as e:      # noqa: BLE001 - reported to the caller
+                return ios.RpcResp(False, None, f"{type(e).__name__}: {e}")
         if isinstance(msg, ios.SlowDownReq):
             self.forward_sleep_time = msg.forward_sleep_time or None
             return ios.GenericResp(True, f"forward sleep = {self.forward_sleep_time}")

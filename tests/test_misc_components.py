@@ -291,3 +291,69 @@ def test_remote_instance_loader_clones_a_running_server():
         server.should_exit = True
         t.join(timeout=10)
         seed.shutdown()
+
+
+def test_reasoner_grammar_constrains_only_after_think_end():
+    import numpy as np
+
+    from sglang_b200.constrained.base_grammar import BaseGrammar
+    from sglang_b200.constrained.reasoner_grammar import ReasonerGrammar
+
+    class OnlyToken7(BaseGrammar):
+        def __init__(self):
+            self.seen = []
+
+        def accept_token(self, t):
+            assert t == 7
+            self.seen.append(t)
+
+        def fill_vocab_mask(self, row, V):
+            row[:] = 0
+            row[0] = 1 << 7
+
+        def is_terminated(self):
+            return len(self.seen) >= 2
+
+        def copy(self):
+            c = OnlyToken7()
+            c.seen = list(self.seen)
+            return c
+
+    g = ReasonerGrammar(OnlyToken7(), end_ids=[50, 51])
+    row = np.zeros(2, dtype=np.int32)
+    g.fill_vocab_mask(row, 64)
+    assert (row == -1).all()                                  # thinking: everything allowed
+    for t in (3, 50, 9, 50, 51):                              # "50 9" is not the marker; "50 51" is
+        g.accept_token(t)
+    assert not g.in_reasoning
+    g.fill_vocab_mask(row, 64)
+    assert row[0] == 1 << 7 and row[1] == 0                   # answering: the inner grammar rules
+    c = g.copy()
+    g.accept_token(7)
+    g.accept_token(7)
+    assert g.is_terminated() and not c.is_terminated()
+
+
+def test_collective_rpc_and_batch_tokenizer():
+    import asyncio
+
+    from sglang_b200.utils.batch_tokenizer import AsyncDynamicBatchTokenizer
+
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error")
+    assert eng.collective_rpc("get_memory_info")["num_pages"] > 0          # a model-runner method
+    assert eng.collective_rpc("has_work") is False                          # a scheduler method
+    with pytest.raises(Exception):
+        r = eng._control(sgl.managers.io_struct.RpcReq("_private", {}))
+        assert not r.success
+        raise RuntimeError(r.message)
+    tk = eng.tokenizer
+
+    async def run():
+        bt = AsyncDynamicBatchTokenizer(tk, max_batch_size=8, batch_wait_timeout_s=0.02)
+        outs = await asyncio.gather(*[bt.encode(f"hello {i}") for i in range(10)])
+        return outs, bt.batches
+
+    outs, batches = asyncio.run(run())
+    assert outs == [tk.encode(f"hello {i}") for i in range(10)]
+    assert sum(batches) == 10 and max(batches) > 1                          # concurrent requests were coalesced
+    eng.shutdown()
