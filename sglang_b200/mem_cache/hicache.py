@@ -34,7 +34,10 @@ class HiRadixCache(RadixCache):
         super().__init__(allocator, page_size, eviction_policy)
         self.kv_pool = kv_pool
         self.host = HostKVPool(host_pages, kv_pool, pin=kv_pool.buf.is_cuda)
+        if write_policy not in ("write_through", "write_through_selective", "write_back"):
+            raise ValueError(f"unknown hicache write policy {write_policy!r}")
         self.write_policy = write_policy
+        self.selective_hits = 2
         self.storage = storage
         self.stats = {"host_writes": 0, "host_hits_pages": 0, "l3_writes": 0, "l3_hits_pages": 0, "host_evictions": 0}
 
@@ -64,10 +67,12 @@ class HiRadixCache(RadixCache):
         key = self._full_key(node)
         hashes = sglb_rt.hash_pages(key, self.page_size)
         n = int(node.host_pages.size)
-        for h, hp in zip(hashes[-n:], node.host_pages.tolist()):
-            if not self.storage.exists(h):
-                self.storage.put(h, self.host.buf[:, :, hp])
-                self.stats["l3_writes"] += 1
+        hs = [int(h) for h in hashes[-n:]]
+        have = self.storage.batch_exists(hs)                      # one round trip for the whole node, then one for the missing pages
+        todo = [(h, hp) for h, hp, ok in zip(hs, node.host_pages.tolist(), have) if not ok]
+        if todo:
+            self.storage.batch_put([h for h, _ in todo], [self.host.buf[:, :, hp] for _, hp in todo])
+            self.stats["l3_writes"] += len(todo)
 
     def _full_key(self, node: TreeNode) -> np.ndarray:
         parts = []
@@ -98,10 +103,13 @@ class HiRadixCache(RadixCache):
 
     def insert(self, token_ids, pages, extra_key: Any = None, priority: int = 0) -> int:
         m = super().insert(token_ids, pages, extra_key, priority)
-        if self.write_policy == "write_through":
+        if self.write_policy in ("write_through", "write_through_selective"):
+            # write_through: every new node is copied to the host tier right away; write_through_selective: only nodes that were HIT at
+            # least ``selective_hits`` times (hot prefixes) — one-off prompts are backed up lazily at eviction like write_back
             _, node = RadixCache.match_prefix(self, token_ids, extra_key)
             while node is not None and node.parent is not None and node.host_pages is None and not node.evicted:
-                self._backup(node)
+                if self.write_policy == "write_through" or node.hit_count >= self.selective_hits:
+                    self._backup(node)
                 node = node.parent
         return m
 
@@ -161,11 +169,11 @@ class HiRadixCache(RadixCache):
 
         hashes = sglb_rt.hash_pages(key, self.page_size)
         first = off // self.page_size
+        hs = [int(h) for h in hashes[first:]]
+        have = self.storage.batch_exists(hs) if hs else []
+        n_ok = next((i for i, ok in enumerate(have) if not ok), len(have))          # longest stored run from the first missing page
         got: List[torch.Tensor] = []
-        for h in hashes[first:]:
-            if not self.storage.exists(h):
-                break
-            t = self.storage.get(h)
+        for t in (self.storage.batch_get(hs[:n_ok]) if n_ok else []):
             if t is None:
                 break
             got.append(t)

@@ -72,3 +72,23 @@ def test_runtime_attach_detach_storage_backend():
         assert c.delete("/hicache/storage-backend").json()["success"]
         assert c.get("/hicache/storage-backend").json()["attached"] is False
     eng.shutdown()
+
+
+def test_write_policies():
+    """write_through backs every prefix up at insert; write_through_selective only prefixes that were hit again; write_back only at eviction"""
+    rng = np.random.default_rng(1)
+    sp = {"max_new_tokens": 2, "temperature": 0, "ignore_eos": True}
+    A = rng.integers(3, 200, size=40).tolist()
+    writes = {}
+    for pol in ("write_through", "write_through_selective", "write_back"):
+        eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=4096, enable_hierarchical_cache=True, hicache_ratio=2.0,
+                         hicache_write_policy=pol, radix_cache_impl="python", log_level="error")
+        eng.generate(input_ids=A, sampling_params=sp)
+        first = eng.scheduler.tree.stats["host_writes"]
+        eng.generate(input_ids=A + [7, 8, 9, 10, 11, 12, 13, 14], sampling_params=sp)       # hits the A prefix twice over
+        eng.generate(input_ids=A + [20, 21, 22, 23, 24, 25, 26, 27], sampling_params=sp)
+        writes[pol] = (first, eng.scheduler.tree.stats["host_writes"])
+        eng.shutdown()
+    assert writes["write_through"][0] > 0
+    assert writes["write_through_selective"][0] == 0 and writes["write_through_selective"][1] > 0
+    assert writes["write_back"] == (0, 0)
