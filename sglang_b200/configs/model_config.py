@@ -150,6 +150,11 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                          hidden_act="gelu", tie_word_embeddings=True, dtype="float32",
                          audio={"d_model": 64, "encoder_layers": 2, "encoder_attention_heads": 4, "encoder_ffn_dim": 128, "num_mel_bins": 80,
                                 "max_source_positions": 100, "chunk_length": 2}),
+    "tiny-internvl": dict(architecture="InternVLForConditionalGeneration", hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                          num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=2048, attention_bias=True,
+                          rope_theta=10000.0, dtype="float32", image_token_id=500,
+                          vision={"kind": "internvl", "hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 2, "num_attention_heads": 2,
+                                  "image_size": 56, "patch_size": 14, "downsample_ratio": 0.5, "select_layer": -1, "max_tiles": 4}),
     "tiny-gpt-oss": dict(architecture="GptOssForCausalLM", hidden_size=64, intermediate_size=32, moe_intermediate_size=32, num_hidden_layers=4,
                          num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512, dtype="float32",
                          num_local_experts=4, num_experts_per_tok=2, sliding_window=8, attention_bias=True, swiglu_limit=7.0, rope_theta=150000.0,

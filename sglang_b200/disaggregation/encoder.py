@@ -44,81 +44,75 @@ def _from_npy(b: bytes) -> np.ndarray:
 
 
 class VisionEncoder:
-    """the vision half of a VLM checkpoint (no language model weights are allocated)"""
+    """the vision half of a VLM checkpoint: the model class is instantiated with ZERO decoder layers, so any registered multimodal architecture
+    (LLaVA, Qwen2-VL / 2.5-VL, InternVL) brings its own tower / projector / checkpoint mapping and no language-model weights are allocated"""
 
     def __init__(self, model_path: str, device: str = "cpu", dtype: Optional[torch.dtype] = None, cache_items: int = 256, seed: int = 0):
-        from ..models.llava import CLIPVisionTower
+        import dataclasses
+
+        from ..model_loader.loader import build_model, init_dummy_weights, iter_safetensors
+        from ..parallel import parallel_state as ps
 
         self.cfg: ModelConfig = load_model_config(model_path)
         if not self.cfg.is_multimodal:
             raise ValueError(f"{model_path}: not a multimodal model, nothing to encode")
         self.device = torch.device(device)
-        self.dtype = dtype or {"float32": torch.float32, "float16": torch.float16}.get(self.cfg.dtype, torch.bfloat16)
-        v = self.cfg.vision
-        self.tower = CLIPVisionTower(v, self.dtype)
-        H = self.cfg.hidden_size
-        self.projector = torch.nn.Sequential(torch.nn.Linear(v["hidden_size"], H, dtype=self.dtype), torch.nn.GELU(),
-                                             torch.nn.Linear(H, H, dtype=self.dtype))
-        self.num_image_tokens = self.tower.num_patches
-        self._load(model_path, seed)
-        self.tower.to(self.device).eval()
-        self.projector.to(self.device).eval()
+        cfg0 = dataclasses.replace(self.cfg, num_hidden_layers=0, layer_types=None)
+        if dtype is not None:
+            cfg0.dtype = {torch.float32: "float32", torch.float16: "float16"}.get(dtype, "bfloat16")
+        ps.get_state()
+        self.model = build_model(cfg0, self.device, None)
+        self.dtype = next(self.model.parameters()).dtype
+        if model_path.startswith("dummy:"):
+            init_dummy_weights(self.model, seed, cfg=None)      # name-seeded: identical to the tower inside the full dummy model
+        else:
+            self.model.load_weights((n, w) for n, w in iter_safetensors(model_path) if ".layers." not in n or "vision" in n or "visual" in n)
+        self.model.eval()
+        self.num_image_tokens = getattr(self.model, "num_image_tokens", 0)
         self._cache: "OrderedDict[int, np.ndarray]" = OrderedDict()
         self._cache_items = cache_items
         self._lock = threading.Lock()
         self.stats = {"encoded": 0, "cache_hits": 0, "requests": 0}
 
-    def _load(self, model_path: str, seed: int) -> None:
-        own = {("vision_tower." + n): p for n, p in self.tower.named_parameters()}
-        own.update({("projector." + n): p for n, p in self.projector.named_parameters()})
-        if model_path.startswith("dummy:"):
-            # the same name-seeded synthetic initialisation the full model gets (model_loader.loader.init_dummy_weights)
-            from ..model_loader.loader import init_dummy_weights
-
-            holder = torch.nn.Module()
-            holder.vision_tower, holder.projector = self.tower, self.projector
-            init_dummy_weights(holder, seed, cfg=None)
-            return
-        from ..model_loader.loader import iter_safetensors
-
-        for name, w in iter_safetensors(model_path):
-            if name.startswith(("model.vision_tower", "model.multi_modal_projector")):
-                name = name[len("model."):]
-            if not (name.startswith("vision_tower") or name.startswith("multi_modal_projector")):
-                continue
-            n = name.replace("vision_tower.vision_model.embeddings.", "vision_tower.").replace(
-                "vision_tower.vision_model.encoder.layers.", "vision_tower.layers.").replace(
-                "vision_tower.vision_model.pre_layrnorm", "vision_tower.pre_layrnorm").replace(".self_attn.", ".").replace(
-                ".mlp.fc", ".fc").replace("multi_modal_projector.linear_1", "projector.0").replace("multi_modal_projector.linear_2", "projector.2")
-            if n in own:
-                own[n].data.copy_(w.reshape(own[n].shape))
-
     @torch.no_grad()
-    def encode(self, pixels: np.ndarray, hashes: Optional[Sequence[int]] = None) -> np.ndarray:
-        """pixels [N, 3, S, S] float32 -> [N, n_tokens, hidden] float16; rows whose hash is cached are not recomputed"""
-        n = pixels.shape[0]
-        hashes = list(hashes) if hashes is not None else [None] * n
-        out: List[Optional[np.ndarray]] = [None] * n
+    def _encode_one(self, arr: np.ndarray, grid: Optional[Sequence[int]]) -> np.ndarray:
+        t = torch.from_numpy(np.array(arr, dtype=np.float32, copy=True)).to(self.device, self.dtype)
+        if grid is not None:                      # dynamic-resolution towers: flattened patches + (t, h, w)
+            e = self.model.encode_images(t, [list(grid)])
+        else:                                     # fixed-size tiles [n, 3, S, S] (LLaVA: n = 1, InternVL: n tiles)
+            e = self.model.encode_images(t if t.dim() == 4 else t[None])
+        return e.reshape(-1, e.shape[-1]).to(torch.float16).cpu().numpy()
+
+    def encode_items(self, items: Sequence[dict]) -> List[np.ndarray]:
+        """items: {"hash": int, "array": ndarray | None (None = expected in the cache), "grid": [t, h, w] | None} -> per-item [tokens, hidden]"""
+        out: List[Optional[np.ndarray]] = [None] * len(items)
         with self._lock:
-            for i, h in enumerate(hashes):
+            for i, it in enumerate(items):
+                h = it.get("hash")
                 if h is not None and h in self._cache:
                     self._cache.move_to_end(h)
                     out[i] = self._cache[h]
                     self.stats["cache_hits"] += 1
-        todo = [i for i in range(n) if out[i] is None]
-        if todo:
-            px = torch.from_numpy(np.ascontiguousarray(pixels[todo])).to(self.device, self.dtype)
-            emb = self.projector(self.tower(px)).to(torch.float16).cpu().numpy()
-            self.stats["encoded"] += len(todo)
-            with self._lock:
-                for j, i in enumerate(todo):
-                    out[i] = emb[j]
-                    if hashes[i] is not None:
-                        self._cache[hashes[i]] = emb[j]
-                        while len(self._cache) > self._cache_items:
-                            self._cache.popitem(last=False)
+        for i, it in enumerate(items):
+            if out[i] is not None:
+                continue
+            if it.get("array") is None:
+                raise KeyError(it.get("hash"))
+            emb = self._encode_one(it["array"], it.get("grid"))
+            self.stats["encoded"] += 1
+            out[i] = emb
+            if it.get("hash") is not None:
+                with self._lock:
+                    self._cache[it["hash"]] = emb
+                    while len(self._cache) > self._cache_items:
+                        self._cache.popitem(last=False)
         self.stats["requests"] += 1
-        return np.stack(out)
+        return out          # type: ignore[return-value]
+
+    def encode(self, pixels: np.ndarray, hashes: Optional[Sequence[int]] = None) -> np.ndarray:
+        """fixed-size convenience form: pixels [N, 3, S, S] -> [N, n_tokens, hidden]"""
+        hs = list(hashes) if hashes is not None else [None] * pixels.shape[0]
+        return np.stack(self.encode_items([{"hash": h, "array": pixels[i], "grid": None} for i, h in enumerate(hs)]))
 
     def cached(self, hashes: Sequence[int]) -> List[bool]:
         with self._lock:
@@ -143,30 +137,32 @@ def build_encoder_app(enc: VisionEncoder):
 
     @app.post("/encode")
     async def encode(req: Request):
-        """body: 4-byte little-endian header length, JSON header {"hashes": [...], "have": [bool...]}, then the .npy pixel block of the
-        images with ``have == false`` (in order)"""
+        """body: u32 header length, JSON header {"items": [{"hash", "have", "shape", "grid"}]}, then the raw float32 arrays of the items with
+        ``have == false`` back to back.  Reply: u32 header length, JSON {"counts": [...]}, float16 embeddings of all items concatenated."""
         raw = await req.body()
         hl = int.from_bytes(raw[:4], "little")
         hdr = json.loads(raw[4:4 + hl])
-        hashes = [int(h) for h in hdr["hashes"]]
-        have = hdr.get("have") or [False] * len(hashes)
-        sent = _from_npy(raw[4 + hl:]) if len(raw) > 4 + hl else np.zeros((0, 3, 1, 1), np.float32)
-        S = sent.shape[-1] if sent.shape[0] else enc.cfg.vision["image_size"]
-        pixels = np.zeros((len(hashes), 3, S, S), np.float32)
-        k = 0
-        for i, hv in enumerate(have):
-            if not hv:
-                pixels[i] = sent[k]
-                k += 1
-        if any(have) and not all(c or not hv for c, hv in zip(enc.cached(hashes), have)):
+        off, items = 4 + hl, []
+        for it in hdr["items"]:
+            arr = None
+            if not it.get("have"):
+                n = int(np.prod(it["shape"])) * 4
+                arr = np.frombuffer(raw[off:off + n], dtype=np.float32).reshape(it["shape"])
+                off += n
+            items.append({"hash": int(it["hash"]), "array": arr, "grid": it.get("grid")})
+        try:
+            embs = enc.encode_items(items)
+        except KeyError:
             return Response(status_code=409, content=b"cache miss for a hash the client assumed present")
-        return Response(content=_npy(enc.encode(pixels, hashes)), media_type="application/octet-stream")
+        out_hdr = json.dumps({"counts": [int(e.shape[0]) for e in embs], "hidden": int(embs[0].shape[1]) if embs else 0}).encode()
+        return Response(content=len(out_hdr).to_bytes(4, "little") + out_hdr + b"".join(np.ascontiguousarray(e).tobytes() for e in embs),
+                        media_type="application/octet-stream")
 
     return app
 
 
 class EncoderClient:
-    """language-server side: pixel blocks -> embeddings via the encoder fleet"""
+    """language-server side: image arrays -> embeddings via the encoder fleet"""
 
     def __init__(self, urls: Sequence[str], timeout: float = 60.0):
         self.urls = [u.rstrip("/") for u in urls]
@@ -178,35 +174,46 @@ class EncoderClient:
         with urllib.request.urlopen(req, timeout=self.timeout) as r:
             return r.read()
 
-    def encode(self, pixels: np.ndarray, hashes: Sequence[int]) -> np.ndarray:
-        out: List[Optional[np.ndarray]] = [None] * len(hashes)
+    def encode_items(self, items: Sequence[dict]) -> List[np.ndarray]:
+        """items: {"hash", "array" float32, "grid" | None}; one encoder per item by ``hash % len(urls)`` (repeats meet their cache)"""
+        out: List[Optional[np.ndarray]] = [None] * len(items)
         by_url: Dict[str, List[int]] = {}
-        for i, h in enumerate(hashes):
-            by_url.setdefault(self.urls[int(h) % len(self.urls)], []).append(i)
+        for i, it in enumerate(items):
+            by_url.setdefault(self.urls[int(it["hash"]) % len(self.urls)], []).append(i)
         for url, idx in by_url.items():
-            hs = [int(hashes[i]) for i in idx]
+            hs = [int(items[i]["hash"]) for i in idx]
             try:
                 have = json.loads(self._post(url + "/encode/probe", json.dumps({"hashes": hs}).encode(), "application/json"))["cached"]
             except Exception:
                 have = [False] * len(hs)
             for attempt in range(2):
-                hdr = json.dumps({"hashes": hs, "have": have}).encode()
-                miss = [i for i, hv in zip(idx, have) if not hv]
-                body = len(hdr).to_bytes(4, "little") + hdr + (_npy(np.ascontiguousarray(pixels[miss], dtype=np.float32)) if miss else b"")
+                meta = [{"hash": hs[j], "have": bool(have[j]), "shape": list(items[i]["array"].shape), "grid": items[i].get("grid")}
+                        for j, i in enumerate(idx)]
+                hdr = json.dumps({"items": meta}).encode()
+                body = len(hdr).to_bytes(4, "little") + hdr + b"".join(
+                    np.ascontiguousarray(items[i]["array"], dtype=np.float32).tobytes() for j, i in enumerate(idx) if not have[j])
                 try:
-                    emb = _from_npy(self._post(url + "/encode", body))
+                    raw = self._post(url + "/encode", body)
                     break
                 except urllib.error.HTTPError as e:      # evicted between probe and encode: resend everything once
                     if e.code == 409 and attempt == 0:
                         have = [False] * len(hs)
                         continue
                     raise
-            self.stats["requests"] += 1
-            self.stats["pixels_sent"] += len(miss)
-            self.stats["pixels_skipped"] += len(idx) - len(miss)
+            hl = int.from_bytes(raw[:4], "little")
+            rh = json.loads(raw[4:4 + hl])
+            flat = np.frombuffer(raw[4 + hl:], dtype=np.float16).reshape(-1, rh["hidden"]) if rh["hidden"] else np.zeros((0, 0), np.float16)
+            o = 0
             for j, i in enumerate(idx):
-                out[i] = emb[j]
-        return np.stack(out)
+                out[i] = flat[o:o + rh["counts"][j]]
+                o += rh["counts"][j]
+            self.stats["requests"] += 1
+            self.stats["pixels_sent"] += sum(1 for hv in have if not hv)
+            self.stats["pixels_skipped"] += sum(1 for hv in have if hv)
+        return out          # type: ignore[return-value]
+
+    def encode(self, pixels: np.ndarray, hashes: Sequence[int]) -> np.ndarray:
+        return np.stack(self.encode_items([{"hash": h, "array": pixels[i], "grid": None} for i, h in enumerate(hashes)]))
 
 
 def launch_encoder_server(model_path: str, host: str = "127.0.0.1", port: int = 30010, device: str = "auto", **kw) -> None:

@@ -168,9 +168,11 @@ def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, toke
     mm: Dict[str, Any] = {"image_offsets": offsets, "image_token_counts": counts, "pad_values": pads, "num_image_tokens": 0,
                           "grid_thw": [list(g) for _, g in pp], "mrope_positions": pos, "mrope_delta": int(delta)}
     patches = np.concatenate([p for p, _ in pp]) if pp else np.zeros((0, 3 * tps * patch * patch), np.float32)
-    if encoder is not None:
-        raise NotImplementedError("EPD for dynamic-resolution towers is not wired yet")
-    mm["pixel_patches"] = patches
+    if encoder is not None:       # EPD: one item per image (its patches + grid), embeddings come back per image
+        embs = encoder.encode_items([{"hash": image_hash(a), "array": p_, "grid": list(g_)} for a, (p_, g_) in zip(arrs, pp)])
+        mm["image_embeds"] = np.concatenate(embs) if embs else np.zeros((0, cfg.hidden_size), np.float16)
+    else:
+        mm["pixel_patches"] = patches
     return out, mm
 
 
@@ -228,8 +230,12 @@ def process_images_internvl(input_ids: List[int], image_data: Any, cfg: Any, tok
             out.append(t)
     if k < len(arrs):
         raise ValueError(f"{len(arrs)} images but only {k} image placeholder tokens in the prompt")
-    mm = {"image_offsets": offsets, "image_token_counts": counts, "pad_values": pads, "num_image_tokens": per_tile,
-          "pixel_values": np.concatenate(tiles) if tiles else np.zeros((0, 3, v["image_size"], v["image_size"]), np.float32)}
+    mm = {"image_offsets": offsets, "image_token_counts": counts, "pad_values": pads, "num_image_tokens": per_tile}
+    if encoder is not None:       # EPD: one item per image = all of its tiles
+        embs = encoder.encode_items([{"hash": image_hash(a), "array": t_, "grid": None} for a, t_ in zip(arrs, tiles)])
+        mm["image_embeds"] = np.concatenate(embs) if embs else np.zeros((0, cfg.hidden_size), np.float16)
+    else:
+        mm["pixel_values"] = np.concatenate(tiles) if tiles else np.zeros((0, 3, v["image_size"], v["image_size"]), np.float32)
     return out, mm
 
 

@@ -79,3 +79,47 @@ def test_encoder_disaggregation_matches_colocated():
     finally:
         server.should_exit = True
         t.join(timeout=10)
+
+
+import pytest
+
+
+@pytest.mark.parametrize("preset", ["tiny-qwen2-vl", "tiny-internvl"])
+def test_encoder_disaggregation_dynamic_towers(preset):
+    """EPD for dynamic-resolution (Qwen2-VL: patches + grid) and tiled (InternVL) towers: per-image items, per-image embedding cache"""
+    import socket
+    import threading
+
+    import uvicorn
+
+    from sglang_b200.disaggregation.encoder import VisionEncoder, build_encoder_app
+    from sglang_b200.lang.backend.runtime_endpoint import _wait_http
+
+    sp = {"max_new_tokens": 5, "temperature": 0, "ignore_eos": True}
+    a, b = _img(7), np.random.default_rng(8).integers(0, 255, size=(70, 130, 3), dtype=np.uint8)
+    reqs = [([5, 6, 500, 7, 8], [a]), ([5, 500, 6, 500, 9], [b, a])]
+    ref_eng = sgl.Engine(model_path=f"dummy:{preset}", page_size=4, disable_radix_cache=True, log_level="error")
+    ref = [ref_eng.generate(input_ids=ids, sampling_params=sp, image_data=im, return_logprob=True) for ids, im in reqs]
+    ref_eng.shutdown()
+    enc = VisionEncoder(f"dummy:{preset}", "cpu")
+    assert len(getattr(enc.model.model, "layers", [])) == 0               # no decoder layers were allocated
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    server = uvicorn.Server(uvicorn.Config(build_encoder_app(enc), host="127.0.0.1", port=port, log_level="error"))
+    t = threading.Thread(target=server.run, daemon=True)
+    t.start()
+    try:
+        _wait_http(f"http://127.0.0.1:{port}", 30)
+        eng = sgl.Engine(model_path=f"dummy:{preset}", page_size=4, disable_radix_cache=True, language_only=True, log_level="error",
+                         encoder_urls=[f"http://127.0.0.1:{port}"])
+        assert eng.runner.model.vision_tower is None
+        got = [eng.generate(input_ids=ids, sampling_params=sp, image_data=im, return_logprob=True) for ids, im in reqs]
+        for x, y in zip(ref, got):
+            assert x["output_ids"] == y["output_ids"] and x["meta_info"]["prompt_tokens"] == y["meta_info"]["prompt_tokens"]
+            lx = [v for v, _, _ in x["meta_info"]["output_token_logprobs"]]
+            ly = [v for v, _, _ in y["meta_info"]["output_token_logprobs"]]
+            assert max(abs(p - q) for p, q in zip(lx, ly)) < 5e-2
+        assert enc.stats["encoded"] == 2 and enc.stats["cache_hits"] == 1            # image `a` encoded once, served from the cache the second time
+        eng.shutdown()
+    finally:
+        server.should_exit = True
+        t.join(timeout=10)
