@@ -81,6 +81,7 @@ class ModelConfig:
     logits_scaling: Optional[float] = None
     # Llama-4: no_rope_layers, moe_layers, intermediate_size_mlp, attention_chunk_size, use_qk_norm, attn_temperature_tuning, floor_scale, attn_scale
     llama4: Optional[Dict[str, Any]] = None
+    falcon_h1: Optional[Dict[str, Any]] = None       # Falcon-H1 muP multipliers (folded into the weights at load)
     # Qwen3-Next gated DeltaNet layers: num_k_heads, num_v_heads, k_head_dim, v_head_dim, conv_kernel (models/qwen3_next.py)
     linear_attn: Optional[Dict[str, Any]] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
@@ -413,10 +414,14 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                            "pattern": "".join("M" if k == "mamba" else "*" for k in kinds), "moe_layers": [int(n > 1) for n in ne]}
             kw["num_local_experts"] = max(ne) if max(ne) > 1 else 0
             kw["num_experts_per_tok"] = text.get("num_experts_per_tok", 2)
+        if arch == "FalconH1ForCausalLM":
+            kw["falcon_h1"] = {k: text.get(k) for k in ("ssm_multipliers", "ssm_in_multiplier", "ssm_out_multiplier", "attention_in_multiplier",
+                                                        "attention_out_multiplier", "key_multiplier", "mlp_multipliers", "lm_head_multiplier")
+                               if text.get(k) is not None}
         if arch == "GraniteMoeHybridForCausalLM":
             kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size")
             kw["pos_emb"] = "rope" if text.get("position_embedding_type", "rope") == "rope" else "none"
-        if arch in ("BambaForCausalLM", "GraniteMoeHybridForCausalLM"):
+        if arch in ("BambaForCausalLM", "GraniteMoeHybridForCausalLM", "FalconH1ForCausalLM"):
             hid = text["hidden_size"]
             heads = text.get("mamba_n_heads", 128)
             dh = text.get("mamba_d_head", "auto")
@@ -428,6 +433,12 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                            "use_bias": text.get("mamba_proj_bias", False), "use_conv_bias": text.get("mamba_conv_bias", True), "norm_groups": 1,
                            "pattern": "".join("M" if k == "mamba" else "*" for k in kinds)}
             kw["partial_rotary_factor"] = (text.get("rope_parameters") or {}).get("partial_rotary_factor", text.get("partial_rotary_factor", 0.5))
+            if arch == "FalconH1ForCausalLM":
+                kw["mamba"].update(norm_groups=text.get("mamba_n_groups", 1), rms_norm=bool(text.get("mamba_rms_norm", False)),
+                                   norm_before_gate=bool(text.get("mamba_norm_before_gate", True)), pattern="M" * text["num_hidden_layers"])
+                kw["partial_rotary_factor"] = (text.get("rope_parameters") or {}).get("partial_rotary_factor", 1.0)
+                if text.get("mamba_d_ssm"):
+                    kw["mamba"]["num_heads"] = text["mamba_d_ssm"] // kw["mamba"]["head_dim"]
         if arch in ("NemotronHForCausalLM", "Mamba2ForCausalLM"):
             hid = text["hidden_size"]
             heads = text.get("mamba_num_heads") or text.get("num_heads") or (text.get("expand", 2) * hid // text.get("head_dim", 64))

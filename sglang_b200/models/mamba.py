@@ -117,6 +117,7 @@ class Mamba2Mixer(nn.Module):
         assert ng == 1 or ng % W == 0
         self.norm_groups = max(1, ng // W)
         self.norm_full_width = ng == 1 and W > 1                # the variance then spans all ranks' channels
+        self.use_norm, self.norm_before_gate = bool(m.get("rms_norm", True)), bool(m.get("norm_before_gate", False))
         self.eps = cfg.rms_norm_eps
         num = lambda v, d: float(v) if isinstance(v, (int, float)) else d       # JSON has no literal for infinity: anything else means "unbounded"
         lim = m.get("dt_limit") or (0.0, float("inf"))
@@ -150,6 +151,13 @@ class Mamba2Mixer(nn.Module):
 
     # ---- compute
     def _gated_norm(self, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        if not self.use_norm:                                   # Falcon-H1 without mamba_rms_norm: gate only
+            return (y.float() * F.silu(z.float())).to(z.dtype)
+        if self.norm_before_gate:                               # normalise first, gate afterwards
+            g = self.norm_groups
+            yg = y.float().view(y.shape[0], g, -1)
+            yg = yg * torch.rsqrt(yg.pow(2).mean(-1, keepdim=True) + self.eps)
+            return (yg.view(y.shape[0], -1) * self.norm_weight.float() * F.silu(z.float())).to(z.dtype)
         y = y.float() * F.silu(z.float())
         if self.norm_full_width:
             ss = y.pow(2).sum(-1, keepdim=True)
@@ -1010,3 +1018,86 @@ class GraniteMoeHybridForCausalLM(BambaForCausalLM):
                 else:
                     yield name, w
         return super().load_weights(rename())
+
+
+# ================================================================================================ Falcon-H1: Mamba-2 and attention IN PARALLEL in every layer + muP multipliers
+class _FalconH1Block(nn.Module):
+    def __init__(self, cfg: ModelConfig, idx: int, dtype, rope):
+        super().__init__()
+        from .llama import LlamaAttention, LlamaMLP
+
+        self.kind = "attention"            # every layer owns a KV-cache layer (and a MambaPool layer)
+        pre = f"model.layers.{idx}"
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.pre_ff_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.mamba = Mamba2Mixer(cfg, idx, dtype, pre + ".mamba")
+        self.self_attn = LlamaAttention(cfg, idx, dtype, None, rope, pre + ".self_attn")
+        self.feed_forward = LlamaMLP(cfg, dtype, None, pre + ".feed_forward")
+
+    def forward(self, x, fb):
+        r = lambda y: y.resolve() if hasattr(y, "resolve") else y
+        h = self.input_layernorm(x)
+        x = x + r(self.mamba(h, fb)) + r(self.self_attn(h, fb))         # the muP multipliers are folded into the weights at load time
+        return x + r(self.feed_forward(self.pre_ff_layernorm(x)))
+
+
+class FalconH1ForCausalLM(BambaForCausalLM):
+    """all scalar muP multipliers (ssm in / out, per-section zxbcdt, attention in / out, key, MLP gate / down) are folded into the projection weights
+    when the checkpoint is loaded; only the embedding and LM-head multipliers remain at run time"""
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        nn.Module.__init__(self)
+        from ..layers.common import RotaryEmbedding
+
+        self.cfg = cfg
+        dtype = _DT[cfg.dtype]
+        bb = nn.Module()
+        bb.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype)
+        rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox, cfg.partial_rotary_factor, device)
+        blocks = [_FalconH1Block(cfg, i, dtype, rope) for i in range(cfg.num_hidden_layers)]
+        bb.all_layers = nn.ModuleList(blocks)
+        bb.num_mamba = bb.num_attn = cfg.num_hidden_layers
+        bb.layers = blocks
+        bb.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+        self.model = bb
+        self.lm_head = None if cfg.tie_word_embeddings else ParallelLMHead(cfg.vocab_size, cfg.hidden_size, dtype)
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        m = self.model
+        h = inputs_embeds if inputs_embeds is not None else (m.embed_tokens(fb.next_token_buf, fb.req_slots) if fb.input_ids is None
+                                                             else m.embed_tokens(fb.input_ids))
+        h = h * float(self.cfg.embedding_multiplier or 1.0)
+        for blk in m.all_layers:
+            h = blk(h, fb)
+        return m.norm(h)
+
+    def compute_logits(self, hidden, key: str = "logits"):
+        return NemotronHForCausalLM.compute_logits(self, hidden, key) * float(self.cfg.falcon_h1.get("lm_head_multiplier", 1.0))
+
+    def make_mamba_pool(self, slots: int, device) -> Optional[MambaPool]:
+        mx = self.model.all_layers[0].mamba
+        return MambaPool(self.model.num_mamba, slots, mx.conv_dim, mx.k, mx.H, mx.P, mx.N, _DT[self.cfg.dtype], device)
+
+    def load_weights(self, weights):
+        f = self.cfg.falcon_h1
+        m = self.cfg.mamba
+        di, gn, H = m["num_heads"] * m["head_dim"], m["n_groups"] * m["d_state"], m["num_heads"]
+        zx = f.get("ssm_multipliers") or [1.0] * 5
+        mup = torch.cat([torch.full((n,), float(v)) for n, v in zip((di, di, gn, gn, H), zx)]) * float(f.get("ssm_in_multiplier", 1.0))
+        gate_m, down_m = f.get("mlp_multipliers") or (1.0, 1.0)
+        scale = {".self_attn.q_proj.": float(f.get("attention_in_multiplier", 1.0)), ".self_attn.v_proj.": float(f.get("attention_in_multiplier", 1.0)),
+                 ".self_attn.k_proj.": float(f.get("attention_in_multiplier", 1.0)) * float(f.get("key_multiplier", 1.0)),
+                 ".self_attn.o_proj.": float(f.get("attention_out_multiplier", 1.0)), ".mamba.out_proj.": float(f.get("ssm_out_multiplier", 1.0)),
+                 ".feed_forward.gate_proj.": float(gate_m), ".feed_forward.down_proj.": float(down_m)}
+
+        def fold():
+            for name, w in weights:
+                if name.endswith(".mamba.in_proj.weight"):
+                    w = w * mup[:, None].to(w.dtype)
+                else:
+                    for k, v in scale.items():
+                        if k in name and v != 1.0:
+                            w = w * v
+                            break
+                yield name, w
+        return super().load_weights(fold())

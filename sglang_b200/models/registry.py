@@ -84,7 +84,7 @@ def _register_builtins() -> None:
     register_model("NemotronHForCausalLM", _mb.NemotronHForCausalLM)
     register_model("Mamba2ForCausalLM", _mb.Mamba2ForCausalLM)
     register_model("BambaForCausalLM", _mb.BambaForCausalLM)
-    for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM", "GraniteMoeHybridForCausalLM"):
+    for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM", "GraniteMoeHybridForCausalLM", "FalconH1ForCausalLM"):
         register_model(name, getattr(_mb, name))
     from . import deepseek as _ds
 

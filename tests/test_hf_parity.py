@@ -81,6 +81,17 @@ CASES = {
                                                            num_local_experts=4, num_experts_per_tok=1, interleave_moe_layer_step=2,
                                                            no_rope_layers=[1, 1, 1, 0], attention_chunk_size=8, use_qk_norm=True,
                                                            attn_temperature_tuning=True, floor_scale=4, attn_scale=0.3, pad_token_id=0)),
+    "falcon-h1": ("FalconH1Config", "FalconH1ForCausalLM", dict(
+        BASE, num_hidden_layers=2, mamba_n_heads=8, mamba_d_head=16, mamba_d_ssm=128, mamba_n_groups=2, mamba_d_state=16, mamba_d_conv=4, mamba_expand=2,
+        mamba_chunk_size=8, mamba_rms_norm=True, mamba_norm_before_gate=False, ssm_multipliers=[0.5, 1.5, 0.7, 1.3, 0.9], ssm_in_multiplier=1.2,
+        ssm_out_multiplier=0.8, attention_in_multiplier=1.1, attention_out_multiplier=0.9, key_multiplier=0.6, mlp_multipliers=[0.7, 1.4],
+        embedding_multiplier=2.0, lm_head_multiplier=0.5, pad_token_id=0)),
+    "falcon-h1-norm-before-gate": ("FalconH1Config", "FalconH1ForCausalLM", dict(
+        BASE, num_hidden_layers=2, mamba_n_heads=8, mamba_d_head=16, mamba_d_ssm=128, mamba_n_groups=2, mamba_d_state=16, mamba_d_conv=4, mamba_expand=2,
+        mamba_chunk_size=8, mamba_rms_norm=True, mamba_norm_before_gate=True, pad_token_id=0)),
+    "falcon-h1-no-norm": ("FalconH1Config", "FalconH1ForCausalLM", dict(
+        BASE, num_hidden_layers=2, mamba_n_heads=8, mamba_d_head=16, mamba_d_ssm=128, mamba_n_groups=1, mamba_d_state=16, mamba_d_conv=4, mamba_expand=2,
+        mamba_chunk_size=8, mamba_rms_norm=False, pad_token_id=0)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
