@@ -418,6 +418,11 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["falcon_h1"] = {k: text.get(k) for k in ("ssm_multipliers", "ssm_in_multiplier", "ssm_out_multiplier", "attention_in_multiplier",
                                                         "attention_out_multiplier", "key_multiplier", "mlp_multipliers", "lm_head_multiplier")
                                if text.get(k) is not None}
+        if arch in ("GraniteMoeForCausalLM", "GraniteMoeSharedForCausalLM"):      # Granite 3.x MoE = the Granite-4 block without Mamba layers
+            kw["mamba"] = {"pattern": "*" * text["num_hidden_layers"], "num_heads": 1, "head_dim": 1, "d_state": 1, "d_conv": 2, "n_groups": 1}
+            kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size") if arch == "GraniteMoeSharedForCausalLM" else None
+            kw["pos_emb"] = "rope"
+            kw["architecture"] = "GraniteMoeHybridForCausalLM"
         if arch == "GraniteMoeHybridForCausalLM":
             kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size")
             kw["pos_emb"] = "rope" if text.get("position_embedding_type", "rope") == "rope" else "none"

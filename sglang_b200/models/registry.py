@@ -86,6 +86,8 @@ def _register_builtins() -> None:
     register_model("BambaForCausalLM", _mb.BambaForCausalLM)
     for name in ("MambaForCausalLM", "FalconMambaForCausalLM", "JambaForCausalLM", "GraniteMoeHybridForCausalLM", "FalconH1ForCausalLM"):
         register_model(name, getattr(_mb, name))
+    register_model("GraniteMoeForCausalLM", _mb.GraniteMoeHybridForCausalLM)          # Granite 3.x MoE: the same block, attention-only pattern
+    register_model("GraniteMoeSharedForCausalLM", _mb.GraniteMoeHybridForCausalLM)
     from . import deepseek as _ds
 
     register_model("DeepseekV2ForCausalLM", _ds.DeepseekV2ForCausalLM)

@@ -92,6 +92,12 @@ CASES = {
     "falcon-h1-no-norm": ("FalconH1Config", "FalconH1ForCausalLM", dict(
         BASE, num_hidden_layers=2, mamba_n_heads=8, mamba_d_head=16, mamba_d_ssm=128, mamba_n_groups=1, mamba_d_state=16, mamba_d_conv=4, mamba_expand=2,
         mamba_chunk_size=8, mamba_rms_norm=False, pad_token_id=0)),
+    "granite-moe": ("GraniteMoeConfig", "GraniteMoeForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2, embedding_multiplier=3.0,
+                                                                    residual_multiplier=0.5, attention_multiplier=0.2, logits_scaling=2.0, pad_token_id=0)),
+    "granite-moe-shared": ("GraniteMoeSharedConfig", "GraniteMoeSharedForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2,
+                                                                                       shared_intermediate_size=48, embedding_multiplier=3.0,
+                                                                                       residual_multiplier=0.5, attention_multiplier=0.2,
+                                                                                       logits_scaling=2.0, pad_token_id=0)),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
