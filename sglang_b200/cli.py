@@ -1,4 +1,4 @@
-"""``python -m sglang_b200.cli {serve,generate,bench-serving,router,version}`` (reference ``python/sglang/cli/main.py:12-45``)."""
+"""``python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,version}`` (reference ``python/sglang/cli/main.py:12-45``)."""
 from __future__ import annotations
 
 import json
@@ -36,12 +36,16 @@ def main(argv=None) -> None:
         from .router.router import main as rt
 
         rt(argv)
+    elif cmd in ("diffusion", "generate-image"):                  # the reference's `sglang generate` (multimodal_gen) product
+        from .multimodal_gen.pipeline import main as dm
+
+        dm(argv)
     elif cmd == "version":
         from . import __version__
 
         print(__version__)
     else:
-        print("usage: python -m sglang_b200.cli {serve,generate,bench-serving,router,version} [args]")
+        print("usage: python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,version} [args]")
 
 
 if __name__ == "__main__":
