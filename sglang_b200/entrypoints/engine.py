@@ -138,7 +138,7 @@ class Engine:
                                                                  reasoning_parser=a.reasoning_parser)
             except Exception as e:  # grammar backends are optional at import time
                 logger.warning("grammar backend unavailable: %s", e)
-        if a.speculative_algorithm:
+        if a.speculative_algorithm or a.dllm_algorithm:
             from ..speculative.spec_worker import create_spec_worker
 
             self.scheduler.spec_worker = create_spec_worker(a, self.runner, self.scheduler)

@@ -541,6 +541,7 @@ class ModelRunner:
             hidden = self.model(fb)
             self.last_verify_hidden = (hidden if fb.aux_hidden is None else fb.aux_hidden) if self.hidden_tap is not None else None
             logits = self.model.compute_logits(hidden)          # [T, V]
+            self.last_verify_logits = logits if isinstance(sb.spec_info, dict) and sb.spec_info.get("return_logits") else None
             reps = torch.from_numpy(sb.q_lens.astype(np.int64)).to(self.device)
             s = fb.sampling
             rep = lambda t: torch.repeat_interleave(t, reps)
@@ -567,6 +568,7 @@ class ModelRunner:
                           lp_out, global_seed=self.args.random_seed, step=self.step_counter)
 
     token_oracle = None
+    last_verify_logits = None
 
     def _finish_result(self, res: BatchResult, toks: torch.Tensor, lp: Optional[torch.Tensor]) -> None:
         n = toks.numel()

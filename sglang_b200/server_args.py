@@ -109,6 +109,10 @@ class ServerArgs:
     device: str = "auto"
     # --- speculative decoding
     speculative_algorithm: Optional[str] = None  # EAGLE|NGRAM|STANDALONE
+    dllm_algorithm: Optional[str] = None         # diffusion-LLM block decoding: LowConfidence | JointThreshold | a registered plug-in
+    dllm_algorithm_config: Optional[str] = None  # YAML path or inline JSON: threshold, edit_threshold, block_size, mask_id, ...
+    dllm_block_size: Optional[int] = None
+    dllm_mask_id: Optional[int] = None
     speculative_draft_model_path: Optional[str] = None
     speculative_num_steps: int = 3
     speculative_eagle_topk: int = 1
@@ -202,6 +206,10 @@ class ServerArgs:
             self.disable_cuda_graph = True
         if self.speculative_algorithm is not None:
             self.speculative_algorithm = self.speculative_algorithm.upper()
+            self.disable_overlap_schedule = True
+        if self.dllm_algorithm is not None:
+            if self.speculative_algorithm is not None:
+                raise ValueError("--dllm-algorithm and --speculative-algorithm are mutually exclusive")
             self.disable_overlap_schedule = True
         if self.disaggregation_mode not in ("null", "prefill", "decode"):
             raise ValueError("bad --disaggregation-mode")

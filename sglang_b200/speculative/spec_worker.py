@@ -278,6 +278,10 @@ class StandaloneSpecWorker(BaseSpecWorker):
 
 def create_spec_worker(args: Any, runner: Any, scheduler: Any) -> BaseSpecWorker:
     algo = (args.speculative_algorithm or "").upper()
+    if getattr(args, "dllm_algorithm", None):
+        from ..dllm import DllmWorker
+
+        return DllmWorker(args, runner, scheduler)
     if algo == "NGRAM":
         return NgramSpecWorker(args, runner, scheduler)
     if algo in ("NEXTN", "MTP"):
