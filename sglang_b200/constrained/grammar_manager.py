@@ -68,7 +68,7 @@ class GrammarManager:
         else:
             req.grammar = compiled.copy()
             end = getattr(GrammarManager, "think_end", None)
-            if end:
+            if end and (getattr(req.sampling_params, "custom_params", None) or {}).get("require_reasoning"):
                 from .reasoner_grammar import ReasonerGrammar
 
                 req.grammar = ReasonerGrammar(req.grammar, end)

@@ -157,6 +157,11 @@ class OpenAIServing:
             st = parser.get_structural_constraint(r.tool_choice)
             if st is not None:
                 sp["structural_tag"] = json.dumps(st)
+        ck = r.chat_template_kwargs or {}
+        if self.args.reasoning_parser and ck.get("enable_thinking", True) and ck.get("thinking", True) and \
+                any(k in sp for k in ("regex", "ebnf", "json_schema", "structural_tag")):
+            # the model will think first: the grammar must only bind the answer (reference serving_chat.py require_reasoning)
+            sp["custom_params"] = dict(sp.get("custom_params") or {}, require_reasoning=True)
         return sp
 
     async def chat_completions(self, r: P.ChatCompletionRequest):

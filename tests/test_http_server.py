@@ -58,7 +58,8 @@ def test_openai_completions_and_chat(client):
     assert chunks[-1]["usage"]["completion_tokens"] == 4
     # response_format -> grammar
     r = client.post("/v1/chat/completions", json={"model": "m", "messages": [{"role": "user", "content": "json"}], "max_tokens": 60,
-                                                  "response_format": {"type": "regex", "pattern": "(ab)+c"}, "temperature": 0.5})
+                                                  "response_format": {"type": "regex", "pattern": "(ab)+c"}, "temperature": 0.5,
+                                                  "chat_template_kwargs": {"enable_thinking": False}})
     import re
 
     assert re.fullmatch("(ab)+c", r.json()["choices"][0]["message"]["content"])

@@ -357,3 +357,25 @@ def test_collective_rpc_and_batch_tokenizer():
     assert outs == [tk.encode(f"hello {i}") for i in range(10)]
     assert sum(batches) == 10 and max(batches) > 1                          # concurrent requests were coalesced
     eng.shutdown()
+
+
+def test_grammar_manager_wraps_only_requests_that_will_reason():
+    from types import SimpleNamespace
+
+    from sglang_b200.constrained.grammar_manager import GrammarManager
+    from sglang_b200.constrained.reasoner_grammar import ReasonerGrammar
+
+    class G:
+        def copy(self):
+            return G()
+
+    old = getattr(GrammarManager, "think_end", None)
+    GrammarManager.think_end = [42]
+    try:
+        plain = SimpleNamespace(sampling_params=SimpleNamespace(custom_params=None), grammar=None, to_abort=None)
+        think = SimpleNamespace(sampling_params=SimpleNamespace(custom_params={"require_reasoning": True}), grammar=None, to_abort=None)
+        GrammarManager._bind(plain, G())
+        GrammarManager._bind(think, G())
+        assert isinstance(plain.grammar, G) and isinstance(think.grammar, ReasonerGrammar)
+    finally:
+        GrammarManager.think_end = old
