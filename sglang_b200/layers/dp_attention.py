@@ -32,6 +32,11 @@ class DpAttnContext:
 
     def begin(self) -> None:
         self._counts = {}
+        from .dwdp import get_dwdp_manager
+
+        m = get_dwdp_manager()
+        if m is not None:
+            m.reset()
 
     def counts(self, key: str, n_local: int, device: torch.device) -> List[int]:
         key = f"{key}#{self.mb}"

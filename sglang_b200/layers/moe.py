@@ -122,6 +122,11 @@ class FusedMoE(nn.Module):
 
         ctx = get_dp_ctx()
         if ctx is not None and getattr(ctx, "a2a_active", False):
+            from .dwdp import get_dwdp_manager
+
+            mgr = get_dwdp_manager()
+            if mgr is not None and mgr.use(ctx, x):          # big prefill: move the weights, not the tokens (layers/dwdp.py)
+                return mgr.forward(self, x, w, ids)
             return self.forward_a2a(x, w, ids)
         if self.expert_load is not None:
             self.expert_load.record(self.layer_id, ids)

@@ -164,6 +164,13 @@ class ModelRunner:
         self.aux_layer_ids = None       # EAGLE-3: capture the hidden states entering these layers instead of the final one
         self.profiler = None
         self.expert_recorder = None
+        self.dwdp = None
+        if getattr(server_args, "enable_dwdp", False):
+            if not server_args.enable_dp_attention:
+                raise ValueError("--enable-dwdp rides on DP-attention (tokens stay on their rank)")
+            from ..layers import dwdp as _dwdp
+
+            _dwdp.attach(self, server_args.dwdp_min_tokens)
         if (self.is_cuda and not server_args.disable_cuda_graph and not envs.SGLB_DISABLE_CUDA_GRAPH.get() and self.pp.world_size == 1
                 and getattr(self.model, "supports_cuda_graph", True) and not server_args.enable_dp_attention and self.dcp is None):
             with torch.cuda.stream(self.stream):

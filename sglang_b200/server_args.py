@@ -109,6 +109,8 @@ class ServerArgs:
     device: str = "auto"
     # --- speculative decoding
     speculative_algorithm: Optional[str] = None  # EAGLE|NGRAM|STANDALONE
+    enable_dwdp: bool = False                    # DP-attention + EP prefill: prefetch peers' expert weights instead of dispatching tokens
+    dwdp_min_tokens: int = 1024                  # DP-wide new-token count from which a forward uses DWDP
     dllm_algorithm: Optional[str] = None         # diffusion-LLM block decoding: LowConfidence | JointThreshold | a registered plug-in
     dllm_algorithm_config: Optional[str] = None  # YAML path or inline JSON: threshold, edit_threshold, block_size, mask_id, ...
     dllm_block_size: Optional[int] = None

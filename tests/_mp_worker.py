@@ -18,6 +18,10 @@ if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives out
     res = {"ids": [o["output_ids"] for o in outs]}
     if cfg.get("gen_kw", {}).get("return_logprob"):
         res["lp"] = [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in outs]
+    if getattr(eng.runner, "dwdp", None) is not None:
+        m = eng.runner.dwdp
+        res["dwdp"] = {"forwards": m.num_forwards, "prefetches": m.num_prefetches, "bytes": m.bytes_moved,
+                       "a2a_calls": sum(getattr(l, "_a2a_calls", 0) for l in m.layers)}
     print("RESULT " + json.dumps(res), flush=True)
 if os.environ.get("SGLB_TEST_EXPECT_A2A"):
     ex = eng.runner.model.model.layers[0].mlp.experts

@@ -230,6 +230,18 @@ def test_two_batch_overlap_with_dp_attention_a2a():
     _check(_run(dpk, 2, LP, {"SGLB_MOE_A2A": "1"}, prompts=odd), _run(kw, 1, LP, prompts=odd))
 
 
+def test_dwdp_prefetched_expert_weights_match_all_to_all_dispatch():
+    """DWDP: prefills above the token threshold all-gather the peers' experts (layer-ahead) and run every expert locally; decode
+    steps stay on the all-to-all path.  Both must agree with the single-process engine."""
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4)
+    ref = _run(kw, 1, LP)
+    dpk = {**kw, "tp_size": 2, "dp_size": 2, "ep_size": 2, "enable_dp_attention": True, "enable_dwdp": True, "dwdp_min_tokens": 8}
+    out = _run(dpk, 2, LP, {"SGLB_MOE_A2A": "1"})
+    _check(out, ref)
+    st = out["dwdp"]
+    assert st["forwards"] > 0 and st["prefetches"] >= st["forwards"] // 2 and st["a2a_calls"] > 0      # prefill used DWDP, decode used a2a
+
+
 def test_mamba1_jamba_tp2(tmp_path):
     """Mamba-1 channels sharded over TP (row-parallel x_proj with an all-reduce for dt / B / C), Jamba = Mamba-1 + attention + MoE"""
     import transformers as tf
