@@ -191,6 +191,21 @@ def create_app(engine: Any):
         r = await _ctl(engine.weights_checker, b.get("action", "checksum"))
         return JSONResponse({"success": r.success, "message": r.message}, status_code=200 if r.success else 400)
 
+    def _rpc_route(path: str, method: str):
+        async def handler(request: Request):
+            b = await request.json() if await request.body() else {}
+            try:
+                return {"success": True, "result": await _ctl(lambda: engine.collective_rpc(method, **b))}
+            except Exception as e:      # noqa: BLE001 - surfaced to the operator
+                return JSONResponse({"success": False, "message": f"{type(e).__name__}: {e}"}, status_code=400)
+
+        app.add_api_route(path, handler, methods=["POST"])
+
+    # expert placement: live EPLB re-plan (optionally with redundant slots), host backups, and rank-fault recovery (eplb/placement.py)
+    _rpc_route("/eplb_rebalance", "eplb_rebalance")
+    _rpc_route("/build_expert_backup", "build_expert_backup")
+    _rpc_route("/elastic_ep_recover", "elastic_ep_recover")
+
     @app.api_route("/slow_down", methods=["GET", "POST"])
     async def slow_down(request: Request):
         b = await request.json() if await request.body() else {}

@@ -89,8 +89,6 @@ class DwdpManager:
 
         self.num_forwards += 1
         w13, w2 = self.weights(self.index[id(layer)])
-        if layer.expert_load is not None:
-            layer.expert_load.record(layer.layer_id, ids)
         if x.shape[0] == 0:
             return x
         return moe_ops.fused_moe(x, w13, w2, w, ids, 0)

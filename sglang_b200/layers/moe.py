@@ -53,6 +53,8 @@ class FusedMoE(nn.Module):
         self.w13 = nn.Parameter(torch.zeros(self.local_experts, 2 * self.inter_local, hidden_size, dtype=dtype), requires_grad=False)
         self.w2 = nn.Parameter(torch.zeros(self.local_experts, hidden_size, self.inter_local, dtype=dtype), requires_grad=False)
         self.expert_load = None  # EPLB recorder hook
+        self.placement = None    # eplb/placement.py ExpertPlacement once experts are replicated / moved; None = contiguous default
+        self.rep_table = self.rep_count = None
 
     def weight_loader(self, param: torch.Tensor, loaded: torch.Tensor, expert_id: int, shard: str) -> None:
         """shard in {'w1' (gate), 'w3' (up), 'w2' (down)}; ``loaded`` is the full (unsharded) expert matrix"""
@@ -68,6 +70,23 @@ class FusedMoE(nn.Module):
             param.data[le].copy_(loaded.narrow(1, r * I, I))
         else:
             raise ValueError(shard)
+
+    def set_placement(self, pl, w13: torch.Tensor, w2: torch.Tensor) -> None:
+        """Adopt a physical placement (eplb/placement.py): ``w13``/``w2`` are this rank's new slot contents."""
+        assert self.moe_tp == 1 or pl.ep_size == self.ep_size
+        self.placement = pl
+        self.w13 = nn.Parameter(w13, requires_grad=False)
+        self.w2 = nn.Parameter(w2, requires_grad=False)
+        self.local_experts = pl.slots
+        self.expert_offset = self.ep_rank * pl.slots
+        self.rep_table, self.rep_count = pl.tables(self.num_experts, w13.device)
+
+    def to_physical(self, ids: torch.Tensor) -> torch.Tensor:
+        """logical expert ids [T, K] -> physical slot ids; replicas of a hot expert take its tokens round-robin by token index"""
+        lid = ids.long()
+        T, K = lid.shape
+        pick = (torch.arange(T, device=ids.device)[:, None] + torch.arange(K, device=ids.device)[None]) % self.rep_count[lid]
+        return self.rep_table[lid, pick].to(ids.dtype)
 
     def forward(self, x: torch.Tensor, router_logits: torch.Tensor) -> torch.Tensor:
         w, ids = select_experts(router_logits, self.top_k, self.renormalize)
@@ -101,8 +120,6 @@ class FusedMoE(nn.Module):
         recv_e = torch.empty(R, dtype=torch.int32, device=x.device)
         tp.all_to_all_single(recv_x, send_x, rc, sc)
         tp.all_to_all_single(recv_e, send_e, rc, sc)
-        if self.expert_load is not None:
-            self.expert_load.record(self.layer_id, ids)
         if R:
             ones = torch.ones(R, 1, dtype=torch.float32, device=x.device)
             y = moe_ops.fused_moe(recv_x, self.w13, self.w2, ones, recv_e.view(R, 1), self.expert_offset)
@@ -121,6 +138,10 @@ class FusedMoE(nn.Module):
         from .dp_attention import get_dp_ctx
 
         ctx = get_dp_ctx()
+        if self.expert_load is not None:
+            self.expert_load.record(self.layer_id, ids)          # logical ids: what the rebalancer plans on
+        if self.rep_table is not None:
+            ids = self.to_physical(ids)
         if ctx is not None and getattr(ctx, "a2a_active", False):
             from .dwdp import get_dwdp_manager
 
@@ -128,8 +149,6 @@ class FusedMoE(nn.Module):
             if mgr is not None and mgr.use(ctx, x):          # big prefill: move the weights, not the tokens (layers/dwdp.py)
                 return mgr.forward(self, x, w, ids)
             return self.forward_a2a(x, w, ids)
-        if self.expert_load is not None:
-            self.expert_load.record(self.layer_id, ids)
         tp = self.tp
         if (tp.world_size > 1 and tp.nvl is not None and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
                 and moe_ops._has("moe_grouped_mlp_push") and tp.world_size * x.numel() * 2 <= tp.nvl.slot_bytes):

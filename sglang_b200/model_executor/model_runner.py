@@ -529,6 +529,22 @@ class ModelRunner:
         return res
 
     @torch.no_grad()
+    # ---- expert placement (eplb/placement.py); reached via Engine.collective_rpc so every rank moves together
+    def build_expert_backup(self):
+        from ..eplb import placement
+
+        return placement.build_backup(self)
+
+    def eplb_rebalance(self, redundant_slots_per_rank: int = 0, load=None):
+        from ..eplb import placement
+
+        return placement.rebalance(self, redundant_slots_per_rank, load)
+
+    def elastic_ep_recover(self, dead_ranks):
+        from ..eplb import placement
+
+        return placement.recover(self, dead_ranks)
+
     def forward_verify(self, sb: ScheduleBatch) -> np.ndarray:
         """Speculative verification: ragged extend over [last_token, drafts...] of every request; returns the target
         model's sample at EVERY fed position (int64 [T]).  Synchronous (speculative decoding disables overlap)."""

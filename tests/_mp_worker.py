@@ -14,8 +14,20 @@ import sglang_b200 as sgl  # noqa: E402
 
 eng = sgl.Engine(log_level="error", device="cpu", **cfg["engine"])
 outs = eng.generate(input_ids=cfg["prompts"], sampling_params=cfg["sampling"], **cfg.get("gen_kw", {}))
+rpc_out = []
+for step in cfg.get("rpc", []):              # control actions between two generations (every rank issues them: SPMD)
+    if step.get("zero_rank") is not None:    # fault injection: wipe a "dead" rank's expert memory so nothing can silently read it
+        if int(os.environ.get("RANK", 0)) == step["zero_rank"]:
+            for m in eng.runner.model.modules():
+                if m.__class__.__name__ == "FusedMoE":
+                    m.w13.data.zero_(), m.w2.data.zero_()
+        continue
+    rpc_out.append(eng.collective_rpc(step["method"], **step.get("kwargs", {})))
+outs2 = eng.generate(input_ids=cfg["prompts"], sampling_params=cfg["sampling"], **cfg.get("gen_kw", {})) if cfg.get("rpc") else None
 if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives outputs
     res = {"ids": [o["output_ids"] for o in outs]}
+    if outs2 is not None:
+        res["ids2"], res["rpc"] = [o["output_ids"] for o in outs2], rpc_out
     if cfg.get("gen_kw", {}).get("return_logprob"):
         res["lp"] = [[float(t[0]) for t in o["meta_info"]["input_token_logprobs"] if t[0] is not None] for o in outs]
     if getattr(eng.runner, "dwdp", None) is not None:

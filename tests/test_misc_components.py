@@ -379,3 +379,25 @@ def test_grammar_manager_wraps_only_requests_that_will_reason():
         assert isinstance(plain.grammar, G) and isinstance(think.grammar, ReasonerGrammar)
     finally:
         GrammarManager.think_end = old
+
+
+def test_expert_placement_planner_replicates_hot_experts_and_skips_dead_ranks():
+    import numpy as np
+
+    from sglang_b200.eplb.placement import ExpertPlacement, imbalance, plan
+
+    load = np.asarray([900.0, 10, 10, 10, 10, 10, 10, 40])
+    base = ExpertPlacement.default(8, 4)
+    pl = plan(load, ep_size=4, slots=3, live=None)                     # 12 slots for 8 experts: 4 replicas to hand out
+    reps = pl.replicas(8)
+    assert len(reps[0]) >= 3 and all(len(r) >= 1 for r in reps)         # the hot expert is replicated, nobody is dropped
+    assert len({p // 3 for p in reps[0]}) == len(reps[0])               # its replicas sit on different ranks
+    assert imbalance(load, pl) < 0.6 * imbalance(load, base)
+    dead = plan(load, ep_size=4, slots=3, live=[0, 2, 3])               # rank 1 lost: 9 slots still hold all 8 experts
+    assert (dead.phys_to_logical[1] == -1).all() and all(dead.replicas(8))
+    tab, cnt = dead.tables(8, "cpu")
+    assert tab.shape[0] == 8 and int(cnt.min()) == 1 and not any(int(p) // 3 == 1 for p in tab.flatten())
+    import pytest
+
+    with pytest.raises(ValueError):
+        plan(load, ep_size=4, slots=2, live=[0])                        # 2 slots cannot hold 8 experts

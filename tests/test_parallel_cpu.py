@@ -23,8 +23,8 @@ def _free_port() -> int:
     return p
 
 
-def _run(engine_kw, world, gen_kw=None, extra_env=None, prompts=None):
-    cfg = json.dumps({"engine": engine_kw, "prompts": prompts or PROMPTS, "sampling": SAMPLING, "gen_kw": gen_kw or {}})
+def _run(engine_kw, world, gen_kw=None, extra_env=None, prompts=None, rpc=None):
+    cfg = json.dumps({"engine": engine_kw, "prompts": prompts or PROMPTS, "sampling": SAMPLING, "gen_kw": gen_kw or {}, "rpc": rpc or []})
     port = _free_port()
     procs = []
     for r in range(world):
@@ -240,6 +240,23 @@ def test_dwdp_prefetched_expert_weights_match_all_to_all_dispatch():
     _check(out, ref)
     st = out["dwdp"]
     assert st["forwards"] > 0 and st["prefetches"] >= st["forwards"] // 2 and st["a2a_calls"] > 0      # prefill used DWDP, decode used a2a
+
+
+def test_eplb_redundant_experts_and_elastic_ep_rank_loss():
+    """EP2: (1) re-plan with one redundant slot per rank from a skewed load — weights move between ranks, hot experts get replicas, tokens
+    are unchanged; (2) rank 1 'dies' (its expert memory is wiped): the survivor restores rank 1's experts from its host backup and serves
+    every expert alone."""
+    kw = dict(model_path="dummy:tiny-mixtral", page_size=4, disable_radix_cache=True)
+    ref = _run(kw, 1)
+    load = [[100.0, 1.0, 1.0, 50.0]] * 2
+    out = _run({**kw, "tp_size": 2, "ep_size": 2}, 2, rpc=[{"method": "eplb_rebalance", "kwargs": {"redundant_slots_per_rank": 1, "load": load}}])
+    assert out["ids"] == ref["ids"] and out["ids2"] == ref["ids"]
+    r = out["rpc"][0]
+    assert r["slots"] == 3 and max(r["imbalance_after"]) < max(r["imbalance_before"]) and r["moves"]["peer"] > 0
+    out = _run({**kw, "tp_size": 2, "ep_size": 2}, 2, rpc=[{"method": "build_expert_backup"}, {"zero_rank": 1},
+                                                           {"method": "elastic_ep_recover", "kwargs": {"dead_ranks": [1]}}])
+    assert out["ids"] == ref["ids"] and out["ids2"] == ref["ids"]
+    assert out["rpc"][0]["experts"] == 4 and out["rpc"][1]["live_ranks"] == [0] and out["rpc"][1]["moves"]["backup"] == 4    # 2 experts x 2 layers
 
 
 def test_mamba1_jamba_tp2(tmp_path):
