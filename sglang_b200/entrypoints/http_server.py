@@ -348,6 +348,9 @@ def create_app(engine: Any):
     from .adapters import install_adapters
 
     install_adapters(app, engine, serving)
+    from .realtime import install_realtime
+
+    install_realtime(app, engine, serving)
     return app
 
 
