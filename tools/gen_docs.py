@@ -68,6 +68,8 @@ def http_api() -> str:
     seen = {}
     for r in app.routes:
         p, m = getattr(r, "path", None), getattr(r, "methods", None)
+        if p and m is None and r.__class__.__name__ == "APIWebSocketRoute":
+            m = {"WEBSOCKET"}
         if p and m and not p.startswith(("/docs", "/openapi", "/redoc")):
             seen.setdefault(p, set()).update(x for x in m if x not in ("HEAD", "OPTIONS"))
     for p in sorted(seen):
