@@ -291,7 +291,8 @@ PRESETS: Dict[str, Dict[str, Any]] = {
 
 _HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM", "SeedOssForCausalLM": "LlamaForCausalLM", "HeliumForCausalLM": "LlamaForCausalLM",
                 "Ernie4_5ForCausalLM": "LlamaForCausalLM", "ArceeForCausalLM": "LlamaForCausalLM", "SmolLM3ForCausalLM": "LlamaForCausalLM",
-                "Ministral3ForCausalLM": "LlamaForCausalLM", "Olmo3ForCausalLM": "Olmo2ForCausalLM", "KimiK2ForCausalLM": "DeepseekV3ForCausalLM"}
+                "Ministral3ForCausalLM": "LlamaForCausalLM", "Olmo3ForCausalLM": "Olmo2ForCausalLM", "KimiK2ForCausalLM": "DeepseekV3ForCausalLM",
+                "CwmForCausalLM": "LlamaForCausalLM", "Cohere2ForCausalLM": "CohereForCausalLM"}
 # HF config keys that differ from our field names
 _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts", "n_embd": "hidden_size", "n_layer": "num_hidden_layers",
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
@@ -365,7 +366,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["tie_word_embeddings"] = bool(hf["tie_word_embeddings"])          # composite configs decide at the top level
         kw["architecture"] = _HF_ARCH_MAP.get(arch, arch)
         kw.setdefault("rope_theta", 10000.0)          # the Hugging Face default when a config does not say (this dataclass defaults to Llama-3's)
-        for k, v in _ARCH_DEFAULTS.get(arch, {}).items():
+        for k, v in (_ARCH_DEFAULTS.get(arch) or _ARCH_DEFAULTS.get(kw["architecture"], {})).items():      # aliases inherit their base family's implicit fields
             kw.setdefault(k, v)
         if arch in _ARCH_DEFAULTS:
             kw.setdefault("num_key_value_heads", kw.get("num_attention_heads", 1))
@@ -423,6 +424,11 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size") if arch == "GraniteMoeSharedForCausalLM" else None
             kw["pos_emb"] = "rope"
             kw["architecture"] = "GraniteMoeHybridForCausalLM"
+        if arch == "Cohere2ForCausalLM":             # Command R7B / A: rotary only on the sliding-window layers, global layers are NoPE
+            lt = text.get("layer_types") or [("full_attention" if (i + 1) % text.get("sliding_window_pattern", 4) == 0 else "sliding_attention")
+                                             for i in range(text["num_hidden_layers"])]
+            kw["layer_types"] = lt
+            kw["no_rope_layers"] = [int(t == "sliding_attention") for t in lt]
         if arch == "GraniteMoeHybridForCausalLM":
             kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size")
             kw["pos_emb"] = "rope" if text.get("position_embedding_type", "rope") == "rope" else "none"

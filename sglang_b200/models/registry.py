@@ -31,6 +31,11 @@ def _ensure() -> None:
         return
     plugin_entries = dict(_REGISTRY)
     _register_builtins()
+    from ..configs.model_config import _HF_ARCH_MAP
+
+    for alias, base in _HF_ARCH_MAP.items():          # checkpoints whose architecture is a configuration of a registered family
+        if base in _REGISTRY:
+            _REGISTRY.setdefault(alias, _REGISTRY[base])
     _REGISTRY.update(plugin_entries)      # an out-of-tree class registered under a built-in name wins
     _BUILTINS_DONE = True
 

@@ -98,6 +98,10 @@ CASES = {
                                                                                        shared_intermediate_size=48, embedding_multiplier=3.0,
                                                                                        residual_multiplier=0.5, attention_multiplier=0.2,
                                                                                        logits_scaling=2.0, pad_token_id=0)),
+    "cwm": ("CwmConfig", "CwmForCausalLM", dict(BASE, pad_token_id=0, num_hidden_layers=4, sliding_window=8,
+                                                layer_types=["full_attention", "sliding_attention", "sliding_attention", "full_attention"])),
+    "cohere2": ("Cohere2Config", "Cohere2ForCausalLM", dict(BASE, pad_token_id=0, num_hidden_layers=4, sliding_window=8, logit_scale=0.25, tie_word_embeddings=True,
+                                                            layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"])),
     "mistral": ("MistralConfig", "MistralForCausalLM", dict(BASE, sliding_window=None)),
     "qwen2": ("Qwen2Config", "Qwen2ForCausalLM", dict(BASE)),
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
