@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "vllm"])
     ap.add_argument("--model", default="llama-3-8b")
     ap.add_argument("--num-prompts", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=0)
@@ -101,65 +101,90 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
 
 
+def _run_arm_subprocess(script: str, extra: list, args, timeout_s: float):
+    """runs one baseline arm in a clean child interpreter (its own sys.path / env) and returns (json line | None, failure text)"""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", script), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
+           str(args.warmup), "--model", args.model, "--num-prompts", str(args.num_prompts), "--seed", str(args.seed), "--max-running",
+           str(args.max_running)] + extra
+    import signal
+    import types
+
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)      # the arm's own process group (engine + its TP workers), nothing else
+        except Exception:
+            pass
+        out, err = proc.communicate()
+        return None, f"timeout after {timeout_s:.0f}s"
+    finally:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)      # stragglers of a crashed engine must not hold the GPU for the next arm
+        except Exception:
+            pass
+    p = types.SimpleNamespace(stdout=out or "", stderr=err or "", returncode=proc.returncode)
+    for ln in reversed(p.stdout.splitlines()):
+        ln = ln.strip()
+        if ln.startswith("{") and '"metric"' in ln:
+            try:
+                return json.loads(ln), ""
+            except Exception:
+                pass
+    tail = (p.stderr or p.stdout or "").strip().splitlines()
+    why = next((t for t in reversed(tail) if "Error" in t or "error" in t or "Exception" in t), tail[-1] if tail else f"rc={p.returncode}")
+    log = os.path.join(ROOT, "gpurun_out", f"baseline_{script.replace('.py', '')}_{'_'.join(extra).replace('--', '') or 'run'}.log")
+    try:
+        os.makedirs(os.path.dirname(log), exist_ok=True)
+        with open(log, "w") as f:
+            f.write(p.stdout[-20000:] + "\n=== stderr ===\n" + p.stderr[-60000:])
+    except Exception:
+        pass
+    return None, f"rc={p.returncode}: {why[:240]}"
+
+
 def run_reference(args) -> None:
-    """The unmodified reference from baseline/_ref through its own public API (sglang.Engine)."""
-    ref = os.path.join(ROOT, "baseline", "_ref")
-    why = None
-    if not os.path.isdir(os.path.join(ref, "sglang")):
-        why = "baseline/_ref not installed (pip --no-index --no-deps install of /root/reference/python)"
-    else:
-        sys.path.insert(0, ref)
-        try:
-            import sglang  # noqa: F401
-            from sglang.srt.entrypoints.engine import Engine  # noqa: F401
-        except Exception as e:
-            why = f"reference installs (--no-deps) but cannot import offline: {type(e).__name__}: {str(e)[:160]}"
-    if why is None:
-        try:
-            _run_reference_engine(args)
-            return
-        except Exception as e:
-            why = f"reference engine failed to run: {type(e).__name__}: {str(e)[:200]}"
+    """The unmodified reference from baseline/_ref through its own public API (sglang.Engine): baseline/run_reference.py.  Under torchrun only
+    rank 0 drives it (the reference spawns and wires its own TP workers); the other ranks leave."""
     rank = int(os.environ.get("RANK", 0))
-    if rank == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}))
+    if rank != 0:
+        return
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "sglang")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed (pip --no-index --no-deps install of /root/reference/python)"}))
+        return
+    modes = [m for m in os.environ.get("SGLB_REF_MODES", "stock,fi,degraded").split(",") if m]
+    fails = []
+    budget = 900.0 + 60.0 * (args.steps + args.warmup)
+    for m in modes:
+        line, why = _run_arm_subprocess("run_reference.py", ["--mode", m], args, budget)
+        if line is not None:
+            if fails:
+                line["config"]["modes_that_failed"] = fails
+            print(json.dumps(line), flush=True)
+            return
+        fails.append(f"{m}: {why}")
+    print(json.dumps({"impl": "reference", "unavailable": "; ".join(fails)[:900]}), flush=True)
 
 
-def _run_reference_engine(args) -> None:
-    import statistics
-
-    import torch
-    import sglang as sgl
-
-    pin, pout = sharegpt_shaped_trace(args.num_prompts, args.seed)
-    import numpy as np
-
-    rng = np.random.default_rng(args.seed + 1)
-    prompts = [rng.integers(1000, 100000, size=n).tolist() for n in pin]
-    eng = sgl.Engine(model_path=os.environ.get("SGLB_REF_MODEL_PATH", "meta-llama/Meta-Llama-3-8B"), load_format="dummy",
-                     tp_size=args.gpus, skip_tokenizer_init=True, max_running_requests=args.max_running)
-    sps = [{"max_new_tokens": m, "temperature": 0, "ignore_eos": True} for m in pout]
-    for _ in range(args.warmup):
-        eng.generate(input_ids=prompts, sampling_params=sps)
-    times = []
-    for _ in range(args.steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        eng.generate(input_ids=prompts, sampling_params=sps)
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    tot = sum(pout)
-    ms = 1000 * sum(times) / len(times)
-    print(json.dumps({"impl": "reference", "metric": "output_tokens_per_s", "value": tot / (ms / 1000), "unit": "tok/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                      "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                      "config": {"model": "llama-3-8b", "global_batch": args.num_prompts, "parallelism": f"tp{args.gpus}"}}))
+def run_vllm(args) -> None:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    line, why = _run_arm_subprocess("run_vllm.py", [], args, 900.0 + 60.0 * (args.steps + args.warmup))
+    print(json.dumps(line if line is not None else {"impl": "vllm", "unavailable": why}), flush=True)
 
 
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "vllm":
+        run_vllm(args)
         return
     import numpy as np
     import torch

@@ -166,6 +166,9 @@ void sample(const at::Tensor& logits, const at::Tensor& temperature, const at::T
   TORCH_CHECK(logits.dim() == 2);
   const bool bf16 = logits.scalar_type() == at::kBFloat16;
   TORCH_CHECK(bf16 || logits.scalar_type() == at::kFloat, "logits must be bf16 or fp32");
+  if (seeds.has_value())
+    TORCH_CHECK(seeds->dim() == 2 && seeds->size(0) == logits.size(0) && seeds->size(1) == 2 && seeds->is_contiguous() &&
+                seeds->scalar_type() == at::kLong, "seeds must be int64 [B, 2] = (seed, output position | -1)");
   c10::cuda::CUDAGuard g(logits.device());
   sglb::sample(logits.data_ptr(), bf16, (int)logits.size(0), (int)logits.size(1), (int)logits.stride(0),
                temperature.data_ptr<float>(), top_k.data_ptr<int>(), top_p.data_ptr<float>(), min_p.data_ptr<float>(),

@@ -45,6 +45,8 @@ struct AttnParams {
   // persistent variant: work items = the (x, y, z) cells of the classic grid, handed out by an atomic counter
   int gx, gy, total_items;
   int* sched;         // [0] next item, [1] CTAs finished (the last one resets both: graph-replay safe)
+  int legacy_epilogue_wait;   // FAULT INJECTION ONLY (SGLB_ATTN_LEGACY_EPILOGUE=1): re-creates the round-1 epilogue hand-off (wait on o_done by
+                              // tile parity) so tools/attn_stress.py can reproduce the premature-pass race / the TP>=4 deadlock it caused
 };
 
 template <int KT, bool HAS_CAP>
@@ -106,8 +108,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2]
   uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* o_done = bars + 13;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* o_done = bars + 13;    // every PV tile (lazy-rescale hand-off: exactly one phase behind the waiter)
+  uint64_t* o_final = bars + 14;   // the LAST PV tile only (epilogue hand-off).  Waiting on o_done by tile parity in the epilogue was a
+                                   // protocol flaw: a warp that had not observed phase L-1 passes try_wait.parity(L&1) while the barrier
+                                   // is still two phases behind (PV(L-1) in flight) and reads O early.
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -117,7 +122,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
     }
-    mbar_init(o_done, 1);
+    mbar_init(o_done, 1); mbar_init(o_final, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -198,6 +203,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       umma_commit(&v_empty[st]);
       umma_commit(o_done);
+      if (j + 1 == n_tiles) umma_commit(o_final);
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ softmax + epilogue
@@ -313,7 +319,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 
     // ---- epilogue: wait for the last PV, normalise, store
-    mbar_wait(o_done, (uint32_t)((n_tiles - 1) & 1));
+    if (p.legacy_epilogue_wait) mbar_wait(o_done, (uint32_t)((n_tiles - 1) & 1));
+    else mbar_wait(o_final, 0);
     tc_fence_after();
     if (warp_valid) {
       const float inv_l = (l_i > 0.f) ? 1.f / l_i : 0.f;
@@ -399,8 +406,12 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   uint64_t* o_free = bars + 15;
   uint64_t* item_full = bars + 16;   // [2]
   uint64_t* item_empty = bars + 18;  // [2]
-  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 20);   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* o_final = bars + 20;     // last PV of an item (phase = item ordinal): the epilogue hand-off, see the classic kernel
+  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 21);   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 23);   // [6] per-warp role state, dumped on a wait timeout
+#define SGLB_ATT_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
+#define SGLB_ATT_WAIT(bar_, par_) mbar_wait((bar_), (par_), dbg, 6)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -411,9 +422,10 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
       mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5);   // MMA thread + 4 softmax warps
     }
-    mbar_init(o_done, 1); mbar_init(o_free, 4);
+    mbar_init(o_done, 1); mbar_init(o_free, 4); mbar_init(o_final, 1);
     fence_barrier_init();
   }
+  if (lane == 0) dbg[warp] = 0;
   if (warp == 1) {
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
@@ -456,15 +468,16 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
-      mbar_wait(&item_empty[slot], ((n_it >> 1) & 1) ^ 1);
+      SGLB_ATT_WAIT(&item_empty[slot], ((n_it >> 1) & 1) ^ 1);
       const int idx = atomicAdd(p.sched, 1);
+      SGLB_ATT_DBG(1, n_it, g);
       s_item[slot] = idx;
       mbar_arrive(&item_full[slot]);
       ++n_it;
       if (idx >= p.total_items) break;
       const Item it = decode_item(idx);
       if (it.n_tiles == 0) continue;
-      mbar_wait(q_empty, (n_q & 1) ^ 1);
+      SGLB_ATT_WAIT(q_empty, (n_q & 1) ^ 1);
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_4d(sQ, &tmQ, q_full, 0, 0, it.kvh, it.q_start + it.t0);
       tma_load_4d(sQ + ATT_HALF_BYTES, &tmQ, q_full, 64, 0, it.kvh, it.q_start + it.t0);
@@ -476,7 +489,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const int st = g & 1;
         const uint32_t ph = (g >> 1) & 1;
         const int pg0 = (it.tile_begin + j) * pages_per_tile;
-        mbar_wait(&k_empty[st], ph ^ 1);
+        SGLB_ATT_WAIT(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], KV_TILE_BYTES);
         for (int i = 0; i < pages_per_tile; ++i) {
           const int page = pt[min(pg0 + i, p.pt_stride - 1)];
@@ -484,7 +497,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, page * ps);
           tma_load_3d(dst + KV_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, page * ps);
         }
-        mbar_wait(&v_empty[st], ph ^ 1);
+        SGLB_ATT_WAIT(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], KV_TILE_BYTES);
         for (int i = 0; i < pages_per_tile; ++i) {
           const int page = pt[min(pg0 + i, p.pt_stride - 1)];
@@ -502,7 +515,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
-      mbar_wait(&item_full[slot], (n_it >> 1) & 1);
+      SGLB_ATT_WAIT(&item_full[slot], (n_it >> 1) & 1);
       const int idx = s_item[slot];
       mbar_arrive(&item_empty[slot]);
       ++n_it;
@@ -510,9 +523,10 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       const Item it = decode_item(idx);
       if (it.n_tiles == 0) continue;
       const int n_tiles = it.n_tiles;
+      SGLB_ATT_DBG(2, n_q, g);
       auto issue_S = [&](uint32_t gt, bool last) {
         const int st = gt & 1;
-        mbar_wait(&k_full[st], (gt >> 1) & 1);
+        SGLB_ATT_WAIT(&k_full[st], (gt >> 1) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * KV_TILE_BYTES);
 #pragma unroll
@@ -526,16 +540,16 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         umma_commit(&s_full[st]);
         if (last) umma_commit(q_empty);            // the Q tile is dead once the item's last S has been computed
       };
-      mbar_wait(q_full, n_q & 1);
+      SGLB_ATT_WAIT(q_full, n_q & 1);
       issue_S(g, n_tiles == 1);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t gt = g + j;
         const int st = gt & 1;
         const uint32_t ph = (gt >> 1) & 1;
         if (j + 1 < n_tiles) issue_S(gt + 1, j + 2 == n_tiles);
-        mbar_wait(&p_full[st], ph);
-        mbar_wait(&v_full[st], ph);
-        if (j == 0) mbar_wait(o_free, (n_q & 1) ^ 1);   // previous item's epilogue has read O
+        SGLB_ATT_WAIT(&p_full[st], ph);
+        SGLB_ATT_WAIT(&v_full[st], ph);
+        if (j == 0) SGLB_ATT_WAIT(o_free, (n_q & 1) ^ 1);   // previous item's epilogue has read O
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * KV_TILE_BYTES);
 #pragma unroll
@@ -544,6 +558,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                       (j | k) != 0);
         umma_commit(&v_empty[st]);
         umma_commit(o_done);
+        if (j + 1 == n_tiles) umma_commit(o_final);
       }
       g += n_tiles;
       ++n_q;
@@ -556,10 +571,10 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const float scale_log2 = p.scale_log2;
     const float cap = p.logit_cap, inv_cap = HAS_CAP ? 1.f / p.logit_cap : 0.f;
     const float scale_nat = scale_log2 * 0.6931471805599453f, inv_scale_nat = 1.f / scale_nat;
-    uint32_t n_it = 0, g = 0;
+    uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
-      mbar_wait(&item_full[slot], (n_it >> 1) & 1);
+      SGLB_ATT_WAIT(&item_full[slot], (n_it >> 1) & 1);
       const int idx = s_item[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(&item_empty[slot]);
@@ -582,6 +597,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         continue;
       }
       const int n_tiles = it.n_tiles;
+      if (lane == 0) SGLB_ATT_DBG(3, n_q, g);
       const int q_pos = it.prefix + tok;
       float m_i = -INFINITY, l_i = 0.f;
       const int kv_last = p.causal ? min(it.seq_len - 1, q_pos) : it.seq_len - 1;
@@ -590,7 +606,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const uint32_t gt = g + j;
         const int st = gt & 1;
         const uint32_t ph = (gt >> 1) & 1;
-        mbar_wait(&s_full[st], ph);
+        SGLB_ATT_WAIT(&s_full[st], ph);
         tc_fence_after();
         if (warp_valid) {
           constexpr int NC = KT / 32;
@@ -641,7 +657,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             m_use = m_new;
           } else if (__any_sync(0xffffffffu, need)) {
             const float f = (m_new == -INFINITY) ? 1.f : exp2f(m_i - m_new);
-            mbar_wait(o_done, (gt - 1) & 1);
+            SGLB_ATT_WAIT(o_done, (gt - 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
@@ -681,7 +697,10 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       g += n_tiles;
 
       // ---- epilogue: wait for the item's last PV, normalise, store, then hand O back to the MMA warp
-      mbar_wait(o_done, (g - 1) & 1);
+      if (lane == 0) SGLB_ATT_DBG(4, n_q, g);
+      if (p.legacy_epilogue_wait) SGLB_ATT_WAIT(o_done, (g - 1) & 1);
+      else SGLB_ATT_WAIT(o_final, n_q & 1);
+      ++n_q;
       tc_fence_after();
       if (warp_valid) {
         const float inv_l = (l_i > 0.f) ? 1.f / l_i : 0.f;
@@ -730,6 +749,8 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     }
   }
 
+#undef SGLB_ATT_DBG
+#undef SGLB_ATT_WAIT
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -793,6 +814,8 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.causal = causal; p.window = window;
   dim3 grid((max_q_len + TQ - 1) / TQ, Hkv * num_splits, B);
   p.gx = (int)grid.x; p.gy = (int)grid.y; p.total_items = (int)(grid.x * grid.y * grid.z); p.sched = sched;
+  static const int legacy = [] { const char* e = getenv("SGLB_ATTN_LEGACY_EPILOGUE"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.legacy_epilogue_wait = legacy;
   // decode (one query token per request) is latency-bound: small KV tiles, two CTAs per SM
   const bool small = (cu_q == nullptr) && page_size <= 64;
   const bool capped = logit_cap > 0.f;

@@ -79,17 +79,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must trap (visible as a CUDA error) instead of hanging the GPU box.
-#ifndef SGLB_MBAR_SPIN_LIMIT
-#define SGLB_MBAR_SPIN_LIMIT (1u << 28)
+// Bounded wait: a protocol bug must trap (visible as a CUDA error) instead of hanging the GPU box.  The bound is WALL-CLOCK
+// (%globaltimer), not a spin count: try_wait suspends for a hardware-dependent time, so a count misfires under load and fires late when
+// idle.  On expiry the waiter prints who it is, the raw barrier word and (optionally) a per-CTA role-state array, then traps.
+#ifndef SGLB_MBAR_TIMEOUT_NS
+#define SGLB_MBAR_TIMEOUT_NS 10000000000ull   // 10 s
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_timeout_trap(uint64_t* bar, uint32_t parity, const volatile uint32_t* dbg, int ndbg) {
+  uint64_t raw;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(raw) : "r"(smem_u32(bar)));
+  printf("sglb: mbarrier wait timeout block=(%d,%d,%d) thread=%d bar_off=0x%x parity=%u raw=0x%llx\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, smem_u32(bar) & 0x3ffff, parity, (unsigned long long)raw);
+  for (int i = 0; i < ndbg; ++i) printf("sglb:   block=%d role[%d]=0x%08x\n", blockIdx.x, i, dbg[i]);
+  // give the other stuck roles of this CTA a moment to print their own line before the context dies
+  const uint64_t t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < 50000000ull) {}
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const volatile uint32_t* dbg = nullptr, int ndbg = 0) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SGLB_MBAR_SPIN_LIMIT) {
-      printf("sglb: mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=%p parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, (void*)bar, parity);
-      __trap();
+    if ((++spins & 0xfffu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SGLB_MBAR_TIMEOUT_NS) mbar_timeout_trap(bar, parity, dbg, ndbg);
     }
   }
 }

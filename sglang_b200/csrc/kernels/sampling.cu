@@ -58,7 +58,7 @@ struct SampleParams {
   const int* top_k;           // [B]  (1 => greedy)
   const float* top_p;         // [B]
   const float* min_p;         // [B]
-  const long long* seeds;     // [B] per-request seed (or null -> global seed)
+  const long long* seeds;     // [B, 2] (per-request seed, per-request output position) or null; position < 0 -> this row uses the global stream
   const int* out_slots;       // [B] scatter index into next_token_buf (or null)
   int* next_token_buf;        // [max_reqs+1]
   int* out_tokens;            // [B]
@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(const T* __restric
     }
     s_chunk[tid] = cm;
     const float total = block_reduce_sum(cm, red);
-    const unsigned long long seed = p.seeds ? (unsigned long long)p.seeds[row] : p.global_seed;
+    // a seeded request draws from (its seed, ITS OWN output position): the stream does not depend on which step / row / batch the scheduler
+    // happened to put it in (the first version mixed the global step counter in, so seeded output changed with scheduling)
+    const bool own = p.seeds && p.seeds[2 * row + 1] >= 0;
     const long long step = p.step_ptr ? *p.step_ptr : p.step;
-    const float u = rng_uniform(seed, (unsigned long long)(p.seeds ? 0 : row), (unsigned long long)step) * total;
+    const float u = (own ? rng_uniform((unsigned long long)p.seeds[2 * row], 0ull, (unsigned long long)p.seeds[2 * row + 1])
+                         : rng_uniform(p.global_seed, (unsigned long long)row, (unsigned long long)step)) * total;
     if (tid == 0) {
       float run = 0.f; int pick = SAMP_THREADS - 1;
       for (int t = 0; t < SAMP_THREADS; ++t) {

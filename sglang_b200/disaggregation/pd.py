@@ -9,15 +9,18 @@ Design: a prefill instance runs the prompt, keeps the request's KV pages alive u
 ``(room, token ids, first sampled token, KV pages [L,2,n,ps,H,D])`` to the decode instance named in the request's
 bootstrap fields.  The decode instance pre-allocates pages, scatters the received KV into its pool (one strided copy: the
 pool is a single tensor with a contiguous page dimension per plane) and inserts the request straight into the running
-decode batch — no prefill on the decode side.  Transports: ``tcp`` (length-prefixed msgpack header + raw tensor bytes;
+decode batch — no prefill on the decode side.  Transports: ``tcp`` (magic + length-prefixed JSON header + HMAC-SHA256 under ``SGLB_DISAGG_SECRET`` + raw tensor bytes;
 works between any two processes), ``fake`` (same process, zero-copy hand-off; the unit-test / warm-up transport).
 Intra-node NVLink peer copies reuse the NVL arena machinery and are wired through the same ``KVTransport`` interface.
 """
 from __future__ import annotations
 
 import enum
+import hashlib
+import hmac
+import json
 import logging
-import pickle
+import os
 import queue
 import random
 import socket
@@ -35,6 +38,16 @@ from ..managers.schedule_batch import FINISH_ABORT, Req
 from ..sampling.sampling_params import SamplingParams
 
 logger = logging.getLogger(__name__)
+
+
+def _json_default(o):
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, (set, tuple)):
+        return list(o)
+    raise TypeError(f"KV header field of type {type(o).__name__} is not serialisable")
 
 
 class KVPoll(enum.IntEnum):
@@ -92,11 +105,14 @@ class FakeTransport(KVTransport):
 
 
 class TcpTransport(KVTransport):
-    def __init__(self, listen: Optional[Tuple[str, int]] = None):
+    def __init__(self, listen: Optional[Tuple[str, int]] = None, secret: Optional[str] = None):
         self.inbox: "queue.Queue[KVPayload]" = queue.Queue()
         self._stop = threading.Event()
         self.sock = None
+        self._key = (secret if secret is not None else os.environ.get("SGLB_DISAGG_SECRET", "")).encode()
         if listen is not None:
+            if not self._key and listen[0] not in ("127.0.0.1", "localhost", "::1"):
+                logger.warning("PD KV listener on %s without SGLB_DISAGG_SECRET: any host that can reach the port can inject KV payloads", listen[0])
             self.sock = socket.socket()
             self.sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
             self.sock.bind(listen)
@@ -125,16 +141,47 @@ class TcpTransport(KVTransport):
             buf.extend(chunk)
         return bytes(buf)
 
+    # Wire format (no executable payloads — the first version unpickled the header of ANY inbound connection, i.e. remote code execution
+    # for whoever could reach the bootstrap port):
+    #   b"SGLBKV1\0" | u32 header_len | header (UTF-8 JSON) | 32-byte HMAC-SHA256(secret, header) | raw KV bytes
+    # dtype names go through an allow-list; the shared secret comes from SGLB_DISAGG_SECRET (both instances) and is verified in constant time.
+    MAGIC = b"SGLBKV1\0"
+    DTYPES = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32, "uint8": torch.uint8,
+              "float8_e4m3fn": torch.float8_e4m3fn}
+    MAX_HEADER = 64 << 20
+
+    def _secret(self) -> bytes:
+        return self._key
+
     def _recv(self, c: socket.socket) -> None:
         try:
             with c:
-                (hl,) = struct.unpack("<Q", self._read(c, 8))
-                head = pickle.loads(self._read(c, hl))
+                if self._read(c, 8) != self.MAGIC:
+                    raise ValueError("bad magic")
+                (hl,) = struct.unpack("<I", self._read(c, 4))
+                if hl > self.MAX_HEADER:
+                    raise ValueError("header too large")
+                hraw = self._read(c, hl)
+                mac = self._read(c, 32)
+                if not hmac.compare_digest(mac, hmac.new(self._secret(), hraw, hashlib.sha256).digest()):
+                    raise PermissionError("KV payload rejected: HMAC mismatch (SGLB_DISAGG_SECRET differs between the instances?)")
+                head = json.loads(hraw.decode("utf-8"))
                 kv = None
-                if head["kv_bytes"]:
-                    raw = self._read(c, head["kv_bytes"])
-                    kv = torch.frombuffer(bytearray(raw), dtype=torch.uint8).view(head["kv_dtype"]).view(head["kv_shape"])
-                self.inbox.put(KVPayload(kv=kv, **head["fields"]))
+                nbytes = int(head["kv_bytes"])
+                if nbytes:
+                    dt = self.DTYPES[head["kv_dtype"]]          # KeyError -> rejected: only plain tensor dtypes
+                    shape = tuple(int(x) for x in head["kv_shape"])
+                    n = 1
+                    for d in shape:
+                        n *= d
+                    if n * torch.empty(0, dtype=dt).element_size() != nbytes or nbytes > (64 << 30):
+                        raise ValueError("kv_shape does not match kv_bytes")
+                    raw = self._read(c, nbytes)
+                    kv = torch.frombuffer(bytearray(raw), dtype=torch.uint8).view(dt).view(shape)
+                f = head["fields"]
+                self.inbox.put(KVPayload(kv=kv, room=int(f["room"]), rid=str(f["rid"]), input_ids=[int(t) for t in f["input_ids"]],
+                                         first_token=int(f["first_token"]), sampling_params=dict(f["sampling_params"] or {}),
+                                         n_tokens=int(f["n_tokens"]), stream=bool(f["stream"])))
                 c.sendall(b"OK")
         except Exception as e:
             logger.error("KV receive failed: %s", e)
@@ -145,11 +192,13 @@ class TcpTransport(KVTransport):
         try:
             kv = payload.kv.contiguous().cpu() if payload.kv is not None else None
             fields = {k: getattr(payload, k) for k in ("room", "rid", "input_ids", "first_token", "sampling_params", "n_tokens", "stream")}
+            fields["input_ids"] = [int(t) for t in fields["input_ids"]]
             raw = kv.view(torch.uint8).numpy().tobytes() if kv is not None else b""
-            head = pickle.dumps({"fields": fields, "kv_bytes": len(raw), "kv_dtype": kv.dtype if kv is not None else None,
-                                 "kv_shape": tuple(kv.shape) if kv is not None else None})
+            head = json.dumps({"fields": fields, "kv_bytes": len(raw), "kv_dtype": str(kv.dtype).replace("torch.", "") if kv is not None else None,
+                               "kv_shape": list(kv.shape) if kv is not None else None}, default=_json_default).encode("utf-8")
+            mac = hmac.new(self._secret(), head, hashlib.sha256).digest()
             with socket.create_connection(tuple(addr), timeout=30) as c:
-                c.sendall(struct.pack("<Q", len(head)) + head + raw)
+                c.sendall(self.MAGIC + struct.pack("<I", len(head)) + head + mac + raw)
                 return self._read(c, 2) == b"OK"
         except Exception as e:
             logger.error("KV send to %s failed: %s", addr, e)

@@ -354,23 +354,62 @@ def make_server(engine: Any, host: str = "127.0.0.1", port: int = 0, max_workers
         mk = grpc.unary_stream_rpc_method_handler if stream else grpc.unary_unary_rpc_method_handler
         handlers[name] = mk(wrap_stream(fn) if stream else wrap(fn), request_deserializer=MSG[req].FromString,
                             response_serializer=MSG[resp].SerializeToString)
-    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
+    sa = getattr(engine, "server_args", None)
+    api_key, admin_key = getattr(sa, "api_key", None), getattr(sa, "admin_api_key", None)
+    interceptors = [_AuthInterceptor(api_key, admin_key)] if (api_key or admin_key) else []
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers), interceptors=interceptors)
     server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(f"{PACKAGE}.{SERVICE}", handlers),))
-    bound = server.add_insecure_port(f"{host}:{port}")
+    cert, pkey = getattr(sa, "ssl_certfile", None), getattr(sa, "ssl_keyfile", None)
+    if cert and pkey:
+        with open(pkey, "rb") as fk, open(cert, "rb") as fc:
+            creds = grpc.ssl_server_credentials(((fk.read(), fc.read()),))
+        bound = server.add_secure_port(f"{host}:{port}", creds)
+    else:
+        bound = server.add_insecure_port(f"{host}:{port}")
     return server, bound
+
+
+class _AuthInterceptor(grpc.ServerInterceptor):
+    """same policy table as the HTTP middleware (utils/auth.py): bearer token in the ``authorization`` metadata entry"""
+
+    def __init__(self, api_key: Optional[str], admin_key: Optional[str]):
+        self.api_key, self.admin_key = api_key, admin_key
+
+    def intercept_service(self, continuation, handler_call_details):
+        from ..utils import auth as _auth
+
+        md = dict(handler_call_details.invocation_metadata or ())
+        ok, msg = _auth.decide_grpc(handler_call_details.method, md.get("authorization"), self.api_key, self.admin_key)
+        if ok:
+            return continuation(handler_call_details)
+        handler = continuation(handler_call_details)
+
+        def deny(request, context):
+            context.abort(grpc.StatusCode.UNAUTHENTICATED, msg or "invalid API key")
+
+        if handler is not None and handler.response_streaming:
+            def deny_stream(request, context):
+                context.abort(grpc.StatusCode.UNAUTHENTICATED, msg or "invalid API key")
+                yield  # pragma: no cover
+            return grpc.unary_stream_rpc_method_handler(deny_stream, request_deserializer=handler.request_deserializer,
+                                                        response_serializer=handler.response_serializer)
+        return grpc.unary_unary_rpc_method_handler(deny, request_deserializer=getattr(handler, "request_deserializer", None),
+                                                   response_serializer=getattr(handler, "response_serializer", None))
 
 
 class SglbGrpcClient:
     """minimal typed client (tests, router, bench): ``client.call("HealthCheck", MSG["Empty"]())``"""
 
-    def __init__(self, target: str):
+    def __init__(self, target: str, api_key: Optional[str] = None):
         self.channel = grpc.insecure_channel(target)
+        self.metadata = (("authorization", f"Bearer {api_key}"),) if api_key else None
 
     def call(self, rpc: str, request: Any):
         req, resp, stream = RPCS[rpc]
         path = f"/{PACKAGE}.{SERVICE}/{rpc}"
         mk = self.channel.unary_stream if stream else self.channel.unary_unary
-        return mk(path, request_serializer=MSG[req].SerializeToString, response_deserializer=MSG[resp].FromString)(request)
+        return mk(path, request_serializer=MSG[req].SerializeToString, response_deserializer=MSG[resp].FromString)(request,
+                                                                                                                  metadata=self.metadata)
 
     def close(self) -> None:
         self.channel.close()

@@ -40,14 +40,13 @@ def create_app(engine: Any):
 
     @app.middleware("http")
     async def auth(request: Request, call_next):
-        path = request.url.path
-        key = request.headers.get("authorization", "").removeprefix("Bearer ").strip()
-        admin_paths = ("/update_weights", "/flush_cache", "/release_memory", "/resume_memory", "/load_lora", "/unload_lora",
-                       "/start_profile", "/stop_profile", "/pause_generation", "/continue_generation", "/configure_logging")
-        if args.admin_api_key and path.startswith(admin_paths) and key != args.admin_api_key:
-            return err("admin API key required", 401)
-        if args.api_key and path.startswith(("/v1", "/generate", "/encode")) and key not in (args.api_key, args.admin_api_key):
-            return err("invalid API key", 401)
+        # deny by default (utils/auth.py): every route except /health*, /ping and /metrics needs a key once one is configured
+        from ..utils import auth as _auth
+
+        ok, code, msg = _auth.decide(request.method, request.url.path, request.headers.get("authorization"), args.api_key,
+                                     args.admin_api_key)
+        if not ok:
+            return err(msg, code)
         return await call_next(request)
 
     # ------------------------------------------------------------------ health / info

@@ -206,8 +206,11 @@ class RealtimeSession:
 def install_realtime(app: Any, engine: Any, serving: Any) -> None:
     @app.websocket("/v1/realtime")
     async def realtime(ws: WebSocket):
-        key = engine.server_args.api_key
-        if key and ws.headers.get("authorization") != f"Bearer {key}":
+        from ..utils import auth as _auth
+
+        ok, _, _ = _auth.decide("GET", "/v1/realtime", ws.headers.get("authorization"), engine.server_args.api_key,
+                                engine.server_args.admin_api_key)
+        if not ok:
             await ws.close(code=4401)
             return
         await ws.accept()

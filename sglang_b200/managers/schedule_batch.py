@@ -237,6 +237,18 @@ class ScheduleBatch:
     def batch_size(self) -> int:
         return len(self.reqs)
 
+    def needs_host_state(self) -> bool:
+        """True when sampling this batch reads per-request HOST state that must be current: penalties / logit bias (output-token counts),
+        min_new_tokens still active (EOS suppression), per-request seeds (stream position), hidden-state return.  Such a batch cannot run
+        one step ahead of result processing (overlap) and does not fit the captured decode graph, whose sampler sees only static tensors."""
+        for r in self.reqs:
+            sp = r.sampling_params
+            if (sp.frequency_penalty or sp.presence_penalty or sp.repetition_penalty != 1.0 or sp.logit_bias
+                    or sp.sampling_seed is not None or getattr(r, "return_hidden_states", False)
+                    or (sp.min_new_tokens and len(r.output_ids) < sp.min_new_tokens + 1)):
+                return True
+        return False
+
     def is_empty(self) -> bool:
         return len(self.reqs) == 0
 

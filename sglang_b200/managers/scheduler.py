@@ -211,7 +211,18 @@ class Scheduler:
             else:
                 keep.append(r)
         self.waiting_queue = keep
-        for r in self.running_batch.reqs + ([self.chunked_req] if self.chunked_req else []):
+        # requests still compiling a grammar hold no KV yet: finish them here (they would otherwise be admitted after the abort)
+        still = []
+        for r in self.grammar_queue:
+            if hit(r):
+                r.finished_reason = FINISH_ABORT()
+                self.stream_output([r])
+            else:
+                still.append(r)
+        self.grammar_queue = still
+        # everything that holds KV: the decode batch, the chunked request AND the prefill that has just run but is not merged yet
+        # (self.last_batch) — the one-iteration window the first version missed, which silently dropped the abort
+        for r in self.live_reqs():
             if hit(r) and not r.finished():
                 r.to_abort = FINISH_ABORT()   # picked up at the next result processing
         return None
@@ -228,10 +239,12 @@ class Scheduler:
 
     def flush_cache(self) -> bool:
         self.drain()
-        if self.running_batch.reqs or self.waiting_queue and any(r.req_slot is not None for r in self.waiting_queue) \
-                or self.chunked_req is not None:
+        # live_reqs() covers running, chunked, waiting-with-KV and the just-run prefill (self.last_batch) that is not merged into the
+        # running batch yet; flushing under the latter reset the tree / allocator beneath live requests (dec_lock_ref underflow)
+        if any(not r.finished() for r in self.live_reqs()):
             logger.warning("flush_cache refused: requests in flight")
             return False
+        self.last_batch = None
         self.sessions.unpin_all()
         self.tree.reset()
         self.allocator.clear()
@@ -417,6 +430,9 @@ class Scheduler:
                 return None
             positions = rb.seq_lens.copy()
             loc = None if force_retract else self.kv.alloc_for_decode(rb.reqs, rb.req_slots, positions)
+            while loc is None and not force_retract and self.sessions.unpin_lru(8):
+                # KV pressure: session pins are an optimisation — give their pages back before retracting / aborting live requests
+                loc = self.kv.alloc_for_decode(rb.reqs, rb.req_slots, positions)
             while loc is None:
                 if len(rb.reqs) <= 1 and not force_retract:
                     # cannot make progress: abort the last request
@@ -711,7 +727,10 @@ class Scheduler:
                 return True
             self._on_idle()
             return False
-        need_sync = (not self.enable_overlap) or batch.has_grammar or (self.pending and self.pending[-1][0].has_grammar)
+        # grammar state, penalties, min_new_tokens and per-request seeds read host-side request state: it must not lag by a step
+        host_state = batch.needs_host_state()
+        need_sync = (not self.enable_overlap) or batch.has_grammar or host_state or \
+            (self.pending and (self.pending[-1][0].has_grammar or self.pending[-1][0].needs_host_state()))
         if need_sync:
             self.drain()
             if batch.has_grammar and batch.forward_mode.is_decode():

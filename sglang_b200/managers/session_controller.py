@@ -9,6 +9,7 @@ closing the session (or superseding the turn) unpins it.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -32,20 +33,32 @@ class Session:
 
 
 class SessionController:
-    def __init__(self, tree: Any, page_size: int):
+    """``max_sessions`` bounds open sessions (the route may be reachable by any API-key holder); ``max_pinned`` bounds how many sessions keep
+    their newest turn PINNED in the radix tree — beyond it the least-recently-finished pin is dropped (the history stays as token ids and is
+    simply recomputed / re-matched), and ``unpin_lru`` lets the scheduler reclaim pins under KV pressure before it retracts or aborts."""
+
+    def __init__(self, tree: Any, page_size: int, max_sessions: int = 4096, max_pinned: int = 256):
         self.tree, self.ps = tree, page_size
         self.sessions: Dict[str, Session] = {}
+        self.max_sessions, self.max_pinned = max_sessions, max_pinned
+        self._pin_order: "OrderedDict[str, SessionTurn]" = OrderedDict()     # session id -> pinned turn, oldest first
+        self._n_opened = 0
 
     # ---- lifecycle
-    def open(self, session_id: Optional[str], capacity: int = 0) -> Tuple[str, bool]:
-        sid = session_id or f"sess-{len(self.sessions)}"
+    def open(self, session_id: Optional[str], capacity: int = 0) -> Tuple[Optional[str], bool]:
+        if session_id is None:
+            self._n_opened += 1
+        sid = session_id or f"sess-{self._n_opened}"
         if sid in self.sessions:
             return sid, False
+        if len(self.sessions) >= self.max_sessions:
+            return None, False
         self.sessions[sid] = Session(sid, capacity)
         return sid, True
 
     def close(self, session_id: str) -> None:
         s = self.sessions.pop(session_id, None)
+        self._pin_order.pop(session_id, None)
         if s is not None:
             for t in s.turns.values():
                 self._unpin(t)
@@ -103,6 +116,11 @@ class SessionController:
                 if len(pages) and node is not None:
                     self.tree.inc_lock_ref(node)
                     t.pinned_node = node
+                    self._pin_order.pop(session_id, None)
+                    self._pin_order[session_id] = t
+                    while len(self._pin_order) > self.max_pinned:
+                        _, old = self._pin_order.popitem(last=False)
+                        self._unpin(old)
             except Exception:      # pinning is an optimisation; the history itself is kept as token ids
                 t.pinned_node = None
 
@@ -120,8 +138,18 @@ class SessionController:
             finally:
                 t.pinned_node = None
 
+    def unpin_lru(self, n: int = 1) -> int:
+        """KV pressure: drop the ``n`` oldest session pins (their pages become evictable); returns how many were dropped"""
+        k = 0
+        while self._pin_order and k < n:
+            _, old = self._pin_order.popitem(last=False)
+            self._unpin(old)
+            k += 1
+        return k
+
     def unpin_all(self) -> None:
         """cache flush: the tree is about to be reset, drop every pin (token histories stay)"""
+        self._pin_order.clear()
         for s in self.sessions.values():
             for t in s.turns.values():
                 t.pinned_node = None

@@ -67,9 +67,10 @@ def _root_seed(extra_key: Any) -> int:
     """namespace seed of the hash chain (LoRA adapter / cache salt): requests in different namespaces never share a prefix"""
     if extra_key is None:
         return 0
-    import zlib
+    import hashlib
 
-    return zlib.crc32(str(extra_key).encode()) + 1
+    # 63-bit keyed digest (a 32-bit CRC made a collision between two cache salts / adapter ids merge their KV namespaces)
+    return (int.from_bytes(hashlib.blake2b(repr(extra_key).encode(), digest_size=8, key=b"sglb-radix-ns").digest(), "little") >> 1) | 1
 
 
 def chain_hashes(tokens: np.ndarray, page_size: int, seed: int = 0) -> np.ndarray:

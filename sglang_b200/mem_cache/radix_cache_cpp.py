@@ -13,12 +13,19 @@ _POLICY = {"lru": 0, "lfu": 1, "fifo": 2, "mru": 3, "filo": 4, "priority": 5}
 _EMPTY = np.empty(0, dtype=np.int32)
 
 
+_NS_IDS: dict = {}     # interned namespace ids: exact (a 32-bit CRC of the salt let two salts collide and share KV)
+
+
 def _key(extra_key: Any) -> int:
     if extra_key is None:
         return 0
-    if isinstance(extra_key, int):
+    if isinstance(extra_key, int) and not isinstance(extra_key, bool) and 0 <= extra_key < (1 << 40):
         return extra_key + 1
-    return (zlib.crc32(repr(extra_key).encode()) << 16) | 0x8001
+    k = repr(extra_key)
+    v = _NS_IDS.get(k)
+    if v is None:
+        v = _NS_IDS[k] = (1 << 41) + len(_NS_IDS)
+    return v
 
 
 class _NodeHandle(int):

@@ -155,8 +155,10 @@ class BatchPacker:
             apply_delta(page_table, v("pt_rows"), v("pt_cols"), v("pt_vals"))
         seeds = None
         if any(p.sampling_seed is not None for p in sp):
-            seeds = torch.tensor([p.sampling_seed if p.sampling_seed is not None else 0 for p in sp], dtype=torch.int64,
-                                 device=self.device)
+            # (seed, the request's own output position): scheduling-independent streams; -1 = unseeded row (global stream).  The position
+            # is exact because the scheduler drains the pipeline before a batch that needs host-side sampling state (needs_host_state)
+            seeds = torch.tensor([[r.sampling_params.sampling_seed, len(r.output_ids)] if r.sampling_params.sampling_seed is not None
+                                  else [0, -1] for r in reqs], dtype=torch.int64, device=self.device)
         sampling = SamplingTensors(
             temperature=v("temperature").view(torch.float32), top_k=v("top_k"), top_p=v("top_p").view(torch.float32),
             min_p=v("min_p").view(torch.float32), all_greedy=bool((topk == 1).all()) if Bs else True,

@@ -439,10 +439,10 @@ class ModelRunner:
         B = len(sb.reqs)
         decode = sb.forward_mode.is_decode()
         self.step_counter += 1
+        # the captured sampler sees only the static tensors: anything that needs per-request host state (penalties, logit bias, active
+        # min_new_tokens -> EOS mask, per-request seeds, hidden-state return) takes the eager path (ScheduleBatch.needs_host_state)
         use_graph = decode and self.graphs and not sb.return_logprob and not sb.has_grammar and sb.spec_info is None and \
-            B <= self.graph_bs[-1] and not any(r.sampling_params.logit_bias or r.sampling_params.frequency_penalty
-                                               or r.sampling_params.presence_penalty or r.sampling_params.repetition_penalty != 1.0
-                                               for r in sb.reqs) and self.lora_manager is None
+            B <= self.graph_bs[-1] and not sb.needs_host_state() and self.lora_manager is None
         if use_graph:
             return self._forward_graph(sb)
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)

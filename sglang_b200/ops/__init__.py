@@ -293,7 +293,14 @@ def sample(logits, temperature, top_k, top_p, min_p, seeds=None, out_slots=None,
     if g is None:
         g = torch.Generator(device="cpu")
         g.manual_seed((int(global_seed) * 1000003 + int(step)) & 0x7FFFFFFF)
-    u = torch.rand(B, generator=g).to(logits.device)
+    u = torch.rand(B, generator=g)
+    if seeds is not None:      # seeded rows: one uniform from (seed, own output position) — same contract as the kernel
+        for j, (sd, pos) in enumerate(seeds.tolist()):
+            if pos >= 0:
+                gj = torch.Generator(device="cpu")
+                gj.manual_seed(((int(sd) * 0x9E3779B1) ^ (int(pos) * 0x85EBCA6B + 0x5bd1e995)) & 0x7FFFFFFFFFFFFFFF)
+                u[j] = torch.rand(1, generator=gj)[0]
+    u = u.to(logits.device)
     tok = torch_ref.sample(logits, temperature, top_k, top_p, min_p, u).to(torch.int32)
     if out_logprobs is not None:
         lp = torch.log_softmax(logits.float() / temperature.clamp(min=1e-6)[:, None], dim=-1)

@@ -57,3 +57,42 @@ def test_pd_transfer_failure_is_reported():
             pre.scheduler.step()
     assert p.failed == 1 and p.sent == 0
     pre.scheduler.check_invariants()
+
+
+def test_tcp_transport_rejects_pickles_and_wrong_secret(monkeypatch):
+    """the listener used to pickle.loads() the header of any inbound connection (RCE).  The wire format is now magic + JSON + HMAC:
+    a pickle blob, a wrong secret and a non-allow-listed dtype are all dropped without touching the inbox."""
+    import pickle
+    import socket
+    import struct
+    import time
+
+    import torch
+
+    from sglang_b200.disaggregation.pd import KVPayload, TcpTransport
+
+    monkeypatch.setenv("SGLB_DISAGG_SECRET", "s3cret")
+    rx = TcpTransport(("127.0.0.1", 0))
+    tx = TcpTransport()
+    pay = KVPayload(room=3, rid="r", input_ids=[1, 2, 3], first_token=9, sampling_params={"max_new_tokens": 4},
+                    kv=torch.arange(24, dtype=torch.bfloat16).view(1, 2, 1, 3, 2, 2), n_tokens=3)
+    assert tx.send(("127.0.0.1", rx.port), pay)
+    got = rx.poll()
+    assert len(got) == 1 and got[0].rid == "r" and torch.equal(got[0].kv, pay.kv) and got[0].sampling_params == {"max_new_tokens": 4}
+
+    class Boom:
+        def __reduce__(self):
+            return (exec, ("raise SystemExit('pickle executed')",))
+
+    blob = pickle.dumps(Boom())
+    with socket.create_connection(("127.0.0.1", rx.port), timeout=5) as c:       # the round-1 frame: u64 length + pickle
+        c.sendall(struct.pack("<Q", len(blob)) + blob)
+        c.settimeout(2)
+        try:
+            assert c.recv(2) != b"OK"
+        except (socket.timeout, ConnectionError):
+            pass
+    assert not TcpTransport(secret="other").send(("127.0.0.1", rx.port), pay)     # signed with the wrong key: no OK comes back ...
+    time.sleep(0.2)
+    assert rx.poll() == []                                                          # ... and nothing reached the inbox
+    rx.close()

@@ -120,3 +120,58 @@ def test_abort_and_priority():
         eng.scheduler.step()
     eng.scheduler.check_invariants()
     assert eng.flush_cache()
+
+
+def test_flush_and_abort_see_the_unmerged_prefill_batch():
+    """between a prefill step and the next iteration the batch lives only in scheduler.last_batch.  flush_cache() used to succeed
+    there (tree / allocator reset under live requests -> 'dec_lock_ref underflow' kills the scheduler) and abort_request() missed it."""
+    from sglang_b200.managers import io_struct as ios
+
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, disable_overlap_schedule=True, scripted_scheduler=True)
+    sch = eng.scheduler
+    sch.handle_request(eng._tokenize(ios.GenerateReqInput(text="the quick brown fox jumps", rid="lb", sampling_params={"max_new_tokens": 40, "ignore_eos": True})))
+    sch.step()                                           # prefill ran; the request now sits in last_batch only
+    assert sch.last_batch is not None and not sch.running_batch.reqs
+    assert eng.flush_cache() is False                    # refused: KV pages are held by the unmerged batch
+    sch.step(); sch.step()
+    sch.check_invariants()
+    # abort in the same window
+    sch.handle_request(eng._tokenize(ios.GenerateReqInput(text="another prompt to abort", rid="second", sampling_params={"max_new_tokens": 40, "ignore_eos": True})))
+    eng.abort_request("lb")
+    for _ in range(10):
+        sch.step()
+        if sch.last_batch is not None and sch.last_batch.forward_mode.is_extend() and any(r.rid == "second" for r in sch.last_batch.reqs):
+            break
+    else:
+        raise AssertionError("the second request never prefilled")
+    eng.abort_request("second")                             # "second" is in last_batch right now
+    n = 0
+    while sch.has_work():
+        sch.step()
+        n += 1
+        assert n < 20, "aborted requests kept generating"
+    sch.check_invariants()
+    assert eng.flush_cache() is True
+    eng.shutdown()
+
+
+def test_seeded_sampling_is_scheduling_independent_and_min_new_tokens_holds_under_overlap():
+    """a per-request seed must give the same text whatever the batch composition / step the scheduler picks (the RNG counter is the
+    request's own output position), and min_new_tokens must suppress EOS exactly that long in overlap mode too."""
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    assert eng.scheduler.enable_overlap
+    sp = {"max_new_tokens": 12, "temperature": 1.3, "top_p": 0.95, "top_k": 40, "sampling_seed": 1234, "ignore_eos": True}
+    alone = eng.generate("seeded request", dict(sp))["output_ids"]
+    eng.flush_cache()
+    noise = {"max_new_tokens": 5, "temperature": 1.0, "ignore_eos": True}
+    outs = eng.generate(["a b c d e f", "seeded request", "other text here", "zzz"], [noise, dict(sp), noise, dict(noise, max_new_tokens=17)])
+    assert outs[1]["output_ids"] == alone
+    again = eng.generate("seeded request", dict(sp))["output_ids"]     # radix hit this time: different prefill shape, same stream
+    assert again == alone
+    # min_new_tokens: make every token an EOS candidate by declaring the greedy continuation a stop token
+    g = eng.generate("stop me", {"max_new_tokens": 10, "temperature": 0, "ignore_eos": True})["output_ids"]
+    first = g[0]
+    o = eng.generate("stop me", {"max_new_tokens": 10, "temperature": 0, "stop_token_ids": [first], "min_new_tokens": 4})
+    ids = o["output_ids"]
+    assert len(ids) >= 4 and first not in ids[:4], ids
+    eng.shutdown()
