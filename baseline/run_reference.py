@@ -14,6 +14,7 @@ reference's own switch ``SGLANG_SKIP_SGL_KERNEL_VERSION_CHECK=1``.
 
 Modes (tried in order by bench.py until one produces a line; the one that ran is recorded in ``config.reference_mode``):
   stock      the reference's own defaults on sm_100: trtllm_mha attention (FlashInfer trtllm-gen cubins), FlashInfer sampling, CUDA graphs
+             (+ --bf16-gemm-backend torch in every mode, see MODES)
   fi         --attention-backend flashinfer
   degraded   --attention-backend triton --sampling-backend pytorch          
 """
@@ -40,10 +41,12 @@ os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
 sys.path[:0] = [os.path.join(HERE, "ref_shims"), os.path.join(HERE, "_ref")]
 sys.path.append(ROOT)
 
+# every mode carries the reference's own --bf16-gemm-backend torch: its sm_100 default ("cutedsl") imports cutlass.cute.experimental, which the
+# image's nvidia-cutlass-dsl refuses below CUDA toolkit 13.1 (this image: 12.9) — F.linear / cuBLAS is the reference's documented alternative
 MODES = {
-    "stock": {},
-    "fi": {"attention_backend": "flashinfer"},
-    "degraded": {"attention_backend": "triton", "sampling_backend": "pytorch"},
+    "stock": {"bf16_gemm_backend": "torch"},
+    "fi": {"bf16_gemm_backend": "torch", "attention_backend": "flashinfer"},
+    "degraded": {"bf16_gemm_backend": "torch", "attention_backend": "triton", "sampling_backend": "pytorch"},
 }
 
 
@@ -105,7 +108,7 @@ def main() -> None:
                        "seq_len": f"sharegpt-shaped lognormal: mean in {total_in // a.num_prompts} / out {total_out // a.num_prompts}",
                        "parallelism": f"tp{a.gpus}", "step": "one full trace (request-rate inf, continuous batching)",
                        "l2": "inputs_larger_than_L2 (16 GB weights + KV streamed every decode step)",
-                       "reference_mode": a.mode,
+                       "reference_mode": a.mode, "reference_flags": MODES[a.mode],
                        "attention_backend": getattr(sa, "attention_backend", None), "sampling_backend": getattr(sa, "sampling_backend", None),
                        "page_size": getattr(sa, "page_size", None), "cuda_graph": not getattr(sa, "disable_cuda_graph", False),
                        "max_running": a.max_running, "input_tokens_per_step": total_in, "output_tokens_per_step": total_out,

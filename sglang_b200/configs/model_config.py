@@ -262,6 +262,13 @@ PRESETS: Dict[str, Dict[str, Any]] = {
     "llama-3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
                        num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, rope_theta=500000.0,
                        bos_token_id=128000, eos_token_id=[128001, 128009]),
+    # per-rank shapes of llama-3-8b at TP=4 / TP=8 on ONE GPU (no collectives): kernel repro / stress presets (tools/attn_stress.py)
+    "llama-3-8b-tp4shard": dict(hidden_size=4096, intermediate_size=3584, num_hidden_layers=32, num_attention_heads=8, head_dim=128,
+                                num_key_value_heads=2, vocab_size=32064, max_position_embeddings=8192, rope_theta=500000.0,
+                                bos_token_id=1, eos_token_id=[2]),
+    "llama-3-8b-tp8shard": dict(hidden_size=4096, intermediate_size=1792, num_hidden_layers=32, num_attention_heads=4, head_dim=128,
+                                num_key_value_heads=1, vocab_size=16032, max_position_embeddings=8192, rope_theta=500000.0,
+                                bos_token_id=1, eos_token_id=[2]),
     "llama-3.1-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
                          num_key_value_heads=8, vocab_size=128256, max_position_embeddings=131072, rope_theta=500000.0,
                          rope_scaling=_LLAMA3_ROPE, bos_token_id=128000, eos_token_id=[128001, 128008, 128009]),

@@ -254,6 +254,22 @@ void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10
   count();
 }
 
+// persistent stream-K decode GEMM (M <= 256): out[M, N] = a[M, K] @ w[N, K]^T (+bias) ; epilogue 4: w = [gate; up], out[M, N/2] = silu(g) * u
+void gemm_streamk(const at::Tensor& a, const at::Tensor& w, at::Tensor out, c10::optional<at::Tensor> bias, int64_t epilogue) {
+  CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_BF16(out); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w); CHECK_LAST_CONTIG(out);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && out.dim() == 2 && a.size(1) == w.size(1));
+  const int M = (int)a.size(0), K = (int)a.size(1);
+  const int N = epilogue == 4 ? (int)w.size(0) / 2 : (int)w.size(0);
+  TORCH_CHECK(out.size(1) == N && out.size(0) == M, "gemm_streamk: bad output shape");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.data_ptr()) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(w.data_ptr()) & 15) == 0, "gemm_streamk: operands must be 16-byte aligned (TMA)");
+  if (epilogue == 1) TORCH_CHECK(bias.has_value() && bias->numel() == N);
+  c10::cuda::CUDAGuard g(a.device());
+  sglb::gemm_bf16_streamk(a.data_ptr(), w.data_ptr(), out.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, M, N, K,
+                          (int)a.stride(0), (int)w.stride(0), (int)out.stride(0), (int)epilogue, num_sms(), cur_stream());
+  count();
+}
+
 // decode-shape GEMM (M <= 256): out is [M, N] (splits == 1) or a slab workspace [splits, M, N] that the consumer sums
 int64_t gemm_skinny_splits(int64_t M, int64_t N, int64_t K, int64_t max_splits) {
   return sglb::gemm_skinny_splits((int)M, (int)N, (int)K, (int)max_splits, num_sms());
@@ -394,6 +410,7 @@ void moe_grouped_mlp_push(const at::Tensor& x, const at::Tensor& w13, const at::
 }  // namespace
 
 TORCH_LIBRARY(sglb, m) {
+  m.def("gemm_streamk(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue) -> ()", &gemm_streamk);
   m.def("gemm_skinny_splits(int M, int N, int K, int max_splits) -> int", &gemm_skinny_splits);
   m.def("gemm_skinny_norm_splits(int K, int s) -> int", &gemm_skinny_norm_splits);
   m.def("gemm_skinny(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int splits) -> ()", &gemm_skinny);

@@ -39,6 +39,10 @@ void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* ro
                           int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
                           cudaStream_t stream);
 
+// gemm_streamk.cu (decode shapes: persistent stream-K swap-AB weight streaming, in-kernel fixup, TMA-store epilogue, fused split-SiLU)
+void gemm_bf16_streamk(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc, int epilogue,
+                       int num_sms, cudaStream_t stream);
+
 // gemm_skinny.cu (decode shapes: swap-AB, split-K slabs, transposed epilogue, optional NVLink push)
 int gemm_skinny_splits(int M, int N, int K, int max_splits, int num_sms);
 int gemm_skinny_norm_splits(int K, int s);

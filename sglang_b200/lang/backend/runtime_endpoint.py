@@ -46,9 +46,9 @@ class BaseBackend:
 
     # subclasses implement _generate_raw(payload) -> dict | list and _generate_stream(payload)
     def _payload(self, s: Any, sp: SglSamplingParams, **extra: Any) -> Dict[str, Any]:
-        p: Dict[str, Any] = {"text": s.text_, "sampling_params": {"skip_special_tokens": True, **sp.to_srt_kwargs()}}
-        if s.images_:
-            p["image_data"] = s.images_ if len(s.images_) > 1 else s.images_[0]
+        p: Dict[str, Any] = {"text": s.prompt, "sampling_params": {"skip_special_tokens": True, **sp.to_srt_kwargs()}}
+        if s.images:
+            p["image_data"] = s.images if len(s.images) > 1 else s.images[0]
         for k in ("return_logprob", "logprob_start_len", "top_logprobs_num"):
             v = getattr(sp, k)
             if v is not None:
@@ -75,10 +75,10 @@ class BaseBackend:
         assert temperature <= 1e-5, "select only supports greedy decisions"
         method = choices_method or token_length_normalized
         # 1. cache the prefix and learn its token length
-        base = self._generate_raw({"text": s.text_, "sampling_params": {"max_new_tokens": 0, "temperature": 0}})
+        base = self._generate_raw({"text": s.prompt, "sampling_params": {"max_new_tokens": 0, "temperature": 0}})
         prompt_len = base["meta_info"]["prompt_tokens"]
         # 2. prompt logprobs of every continuation
-        objs = self._generate_raw({"text": [s.text_ + c for c in choices], "sampling_params": {"max_new_tokens": 0, "temperature": 0},
+        objs = self._generate_raw({"text": [s.prompt + c for c in choices], "sampling_params": {"max_new_tokens": 0, "temperature": 0},
                                    "return_logprob": True, "logprob_start_len": max(prompt_len - 2, 0)})
         input_lp, norm = [], []
         for o in objs:

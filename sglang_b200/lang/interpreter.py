@@ -1,63 +1,123 @@
-"""Interpreter for sgl programs.
+"""Executor for ``sgl`` programs: a deferred op log that is evaluated on demand.
 
-Parity: reference ``python/sglang/lang/interpreter.py`` (``run_program:57``, ``run_program_batch:93``,
-``StreamExecutor:274`` with its worker thread ``:422`` and ``_execute :461`` dispatch — fill ``:505``, gen ``:593``,
-select ``:647``, image ``:524``, fork ``:370``; ``ProgramState:852`` with ``fork:888``, text / messages / variable
-access and streaming iterators).
+Public surface (what programs and ``SglFunction.run / run_batch`` see) matches the reference frontend — ``ProgramState`` with ``+=``,
+role helpers, ``fork / join``, ``text() / messages()``, ``state["var"]``, ``text_iter`` — see reference ``python/sglang/lang/interpreter.py``
+(``run_program:57``, ``run_program_batch:93``, ``ProgramState:852``).
+
+The machinery underneath is different by design.  The reference gives every program state a worker thread, a queue and one
+``threading.Event`` per variable.  Here a state is a plain value object:
+
+  * ``state += expr`` only APPENDS to the state's op log (``_Pending``) — nothing runs;
+  * a *demand* (reading a variable, ``text()``, ``fork``, the end of a non-streaming ``run``) drains the log in order on the calling
+    thread (``_drain``): constant text is concatenated into the ``Transcript``, ``gen`` / ``select`` call the backend;
+  * ``stream=True`` needs no thread either: evaluation is written as generators (``_steps`` -> ``_eval`` -> the backend's chunk stream), and
+    ``text_iter`` simply iterates them — every ``next()`` advances the program until the next piece of text exists (pull-based streaming);
+  * concurrency exists exactly where requests can overlap on the server: the branches of a ``fork`` (and the programs of ``run_batch``) are
+    drained together on one shared pool (``_POOL``) when they are joined, so N branches put N requests in flight at once.
+
+Backends receive the state itself and read ``state.prompt`` / ``state.images`` (``lang/backend/runtime_endpoint.py``).
 """
 from __future__ import annotations
 
-import queue
+import itertools
 import threading
-import uuid
+from collections import deque
 from concurrent.futures import ThreadPoolExecutor
-from typing import Any, Dict, Iterator, List, Optional, Union
+from typing import Any, Deque, Dict, Iterator, List, Optional, Tuple, Union
 
 from .ir import (SglArgument, SglCommitLazy, SglConcateAndAppend, SglConstantText, SglExpr, SglExprList, SglFunction, SglGen,
                  SglImage, SglRoleBegin, SglRoleEnd, SglSamplingParams, SglSelect, SglSeparateReasoning, SglVarScopeBegin,
                  SglVarScopeEnd, SglVideo)
 
+_POOL = ThreadPoolExecutor(max_workers=64, thread_name_prefix="sgl-prog")
+_ids = itertools.count()
 
+
+class Transcript:
+    """what the model will see: text pieces, image inputs and the chat-message view of the same content"""
+
+    __slots__ = ("pieces", "images", "turn_images", "messages", "open_role", "role_mark")
+
+    def __init__(self) -> None:
+        self.pieces: List[str] = []
+        self.images: List[Any] = []
+        self.turn_images: List[Any] = []
+        self.messages: List[Dict[str, Any]] = []
+        self.open_role: Optional[str] = None
+        self.role_mark = 0              # len(text) where the open role's own content starts
+
+    def text(self) -> str:
+        if len(self.pieces) > 1:        # collapse so repeated reads stay O(total)
+            self.pieces = ["".join(self.pieces)]
+        return self.pieces[0] if self.pieces else ""
+
+    def __len__(self) -> int:
+        return sum(len(p) for p in self.pieces)
+
+    def write(self, s: str) -> None:
+        if s:
+            self.pieces.append(s)
+
+    def branch(self) -> "Transcript":
+        t = Transcript()
+        t.pieces = [self.text()]
+        t.images, t.turn_images = list(self.images), list(self.turn_images)
+        t.messages = [dict(m) for m in self.messages]
+        t.open_role, t.role_mark = self.open_role, self.role_mark
+        return t
+
+
+class _Ctx:
+    """per-run constants shared by a program state and all of its forks"""
+
+    __slots__ = ("backend", "arguments", "defaults", "template", "stream")
+
+    def __init__(self, backend: Any, arguments: Dict[str, Any], defaults: SglSamplingParams, stream: bool):
+        self.backend, self.arguments, self.defaults, self.stream = backend, arguments, defaults, stream
+        self.template = backend.get_chat_template()
+
+
+def _unwrap_backend(backend: Any) -> Any:
+    backend = getattr(backend, "endpoint", backend)
+    assert backend is not None, "set a backend with sgl.set_default_backend(...) or pass backend="
+    return backend
+
+
+# ------------------------------------------------------------------------------------------------------------------ entry points
 def run_program(program: SglFunction, backend: Any, func_args, func_kwargs: Dict[str, Any], default_sp: SglSamplingParams,
                 stream: bool, sync: bool = False, use_thread: bool = True) -> "ProgramState":
-    if hasattr(backend, "endpoint"):
-        backend = backend.endpoint
-    assert backend is not None, "set a backend with sgl.set_default_backend(...) or pass backend="
-    stream_executor = StreamExecutor(backend, func_kwargs, default_sp, chat_template=None, stream=stream, use_thread=use_thread)
-    state = ProgramState(stream_executor)
-    if stream:
-        t = threading.Thread(target=_run_internal, args=(state, program, func_args, func_kwargs, sync), daemon=True)
-        t.start()
-        return state
-    _run_internal(state, program, func_args, func_kwargs, sync)
-    return state
-
-
-def _run_internal(state: "ProgramState", program: SglFunction, func_args, func_kwargs, sync: bool) -> None:
+    """build the op log by running the user function, then (unless streaming) evaluate it.  ``use_thread`` is accepted for API
+    compatibility; there is no per-program thread to turn off."""
+    state = ProgramState(_Ctx(_unwrap_backend(backend), func_kwargs, default_sp, stream), Transcript())
     try:
         state.ret_value = program.func(state, *func_args, **func_kwargs)
+        if not stream:
+            state._drain()
     except Exception as e:
-        state.stream_executor.error_ = e
+        state._fail(e)
         raise
     finally:
-        state.stream_executor.end()
-    if sync:
-        state.stream_executor.sync()
+        if not stream:
+            state._close()
+    return state
 
 
 def run_program_batch(program: SglFunction, backend: Any, batch_arguments: List[Dict[str, Any]], default_sp: SglSamplingParams,
                       num_threads: Union[str, int], progress_bar: bool) -> List["ProgramState"]:
-    if hasattr(backend, "endpoint"):
-        backend = backend.endpoint
+    backend = _unwrap_backend(backend)
     if len(batch_arguments) > 1:
         cache_program(program, backend, batch_arguments[0])
-    n = max(16, 64) if num_threads == "auto" else int(num_threads)
-    n = min(n, len(batch_arguments))
-    if n <= 1:
-        return [run_program(program, backend, (), a, default_sp, False, True) for a in batch_arguments]
-    with ThreadPoolExecutor(n) as ex:
-        futs = [ex.submit(run_program, program, backend, (), a, default_sp, False, True) for a in batch_arguments]
-        return [f.result() for f in futs]
+    width = len(batch_arguments) if num_threads == "auto" else max(1, min(int(num_threads), len(batch_arguments)))
+    one = lambda a: run_program(program, backend, (), a, default_sp, False, True)      # noqa: E731
+    if width <= 1:
+        return [one(a) for a in batch_arguments]
+    gate = threading.Semaphore(width)
+
+    def gated(a):
+        with gate:
+            return one(a)
+
+    return [f.result() for f in [_POOL.submit(gated, a) for a in batch_arguments]]
 
 
 def cache_program(program: SglFunction, backend: Any, example_args: Optional[Dict[str, Any]] = None) -> None:
@@ -72,376 +132,240 @@ def cache_program(program: SglFunction, backend: Any, example_args: Optional[Dic
         backend.cache_prefix(prefix)
 
 
-class StreamExecutor:
-    def __init__(self, backend: Any, arguments: Dict[str, Any], default_sampling_para: SglSamplingParams, chat_template: Any,
-                 stream: bool, use_thread: bool = True):
-        self.sid = uuid.uuid4().hex
-        self.backend = backend
-        self.arguments = arguments
-        self.default_sampling_para = default_sampling_para
-        self.stream = stream
-        self.variables: Dict[str, Any] = {}
-        self.variable_event: Dict[str, threading.Event] = {}
-        self.meta_info: Dict[str, Any] = {}
-        self.is_finished = False
-        self.error_: Optional[Exception] = None
-        self.text_ = ""
-        self.messages_: List[Dict[str, Any]] = []
-        self.chat_template = chat_template or backend.get_chat_template()
-        self.cur_role: Optional[str] = None
-        self.cur_role_begin_pos = 0
-        self.images_: List[Any] = []
-        self.cur_images: List[Any] = []
-        self.fork_start_text_pos: Optional[int] = None
-        self.stream_text_event = threading.Event() if stream else None
-        self.stream_var_event: Dict[str, threading.Event] = {}
-        self.use_thread = use_thread
-        if use_thread:
-            self.queue: "queue.Queue[Optional[SglExpr]]" = queue.Queue()
-            self.worker = threading.Thread(target=self._thread_worker_func, daemon=True)
-            self.worker.start()
+# ------------------------------------------------------------------------------------------------------------------ the state
+class _Pending:
+    """the deferred op log of one state (appends from the program, pops from whoever demands a value)"""
 
-    # ---- submission
-    def submit(self, expr: SglExpr) -> None:
-        self._init_var_event(expr)
-        if self.use_thread:
-            self.queue.put(expr)
-        else:
-            self._execute(expr)
+    __slots__ = ("ops", "lock")
 
-    def sync(self) -> None:
-        if self.use_thread:
-            self.queue.join()
+    def __init__(self) -> None:
+        self.ops: Deque[Any] = deque()
+        self.lock = threading.RLock()
 
-    def get_var(self, name: str) -> Any:
-        if name in self.variable_event:
-            self.variable_event[name].wait()
-        if self.error_ is not None:
-            raise self.error_
-        return self.variables[name]
 
-    def set_var(self, name: str, value: Any) -> None:
-        self.variables[name] = value
-
-    def get_meta_info(self, name: str, timeout: Optional[float] = None) -> Any:
-        if name in self.variable_event and not self.variable_event[name].wait(timeout):
-            return None
-        return self.meta_info.get(name)
-
-    def fork(self, size: int = 1, position_ids_offset: Optional[List[int]] = None) -> List["StreamExecutor"]:
-        if size > 1:
-            self.submit(SglCommitLazy())
-        self.sync()
-        exes = [StreamExecutor(self.backend, self.arguments, self.default_sampling_para, self.chat_template, self.stream,
-                               self.use_thread) for _ in range(size)]
-        for e in exes:
-            e.variables = dict(self.variables)
-            e.text_ = str(self.text_)
-            e.messages_ = list(self.messages_)
-            e.cur_role, e.cur_role_begin_pos = self.cur_role, self.cur_role_begin_pos
-            e.fork_start_text_pos = len(self.text_)
-            e.images_ = list(self.images_)
-        return exes
-
-    def text(self) -> str:
-        self.sync()
-        return self.text_
-
-    def messages(self) -> List[Dict[str, Any]]:
-        self.sync()
-        return self.messages_
-
-    def end(self) -> None:
-        if self.use_thread:
-            if self.worker.is_alive():
-                self.queue.put(None)
-        self.backend.end_program(self)
-
-    def _thread_worker_func(self) -> None:
-        error = None
-        while True:
-            expr = self.queue.get()
-            if expr is None:
-                self.queue.task_done()
-                break
-            try:
-                if error is None:
-                    self._execute(expr)
-            except Exception as e:
-                error = self.error_ = e
-            self.queue.task_done()
-            if self.stream_text_event:
-                self.stream_text_event.set()
-        if error is not None:
-            for ev in self.variable_event.values():
-                ev.set()
-            for ev in self.stream_var_event.values():
-                ev.set()
-        if self.stream_text_event:
-            self.stream_text_event.set()
-        self.is_finished = True
-
-    # ---- execution
-    def _init_var_event(self, expr: SglExpr) -> None:
-        if isinstance(expr, (SglGen, SglSelect, SglVarScopeBegin)):
-            if expr.name is not None:
-                self.variable_event[expr.name] = threading.Event()
-                if self.stream:
-                    self.stream_var_event[expr.name] = threading.Event()
-        elif isinstance(expr, SglExprList):
-            for e in expr.expr_list:
-                self._init_var_event(e)
-        elif isinstance(expr, SglSeparateReasoning):
-            self._init_var_event(expr.expr)
-
-    def _execute(self, other: Any) -> None:
-        if isinstance(other, str):
-            other = SglConstantText(other)
-        if isinstance(other, SglConstantText):
-            self._execute_fill(other.value)
-        elif isinstance(other, SglGen):
-            self._execute_gen(other)
-        elif isinstance(other, SglSelect):
-            self._execute_select(other)
-        elif isinstance(other, SglExprList):
-            for x in other.expr_list:
-                self._execute(x)
-        elif isinstance(other, SglRoleBegin):
-            self._execute_role_begin(other)
-        elif isinstance(other, SglRoleEnd):
-            self._execute_role_end(other)
-        elif isinstance(other, SglImage):
-            self._execute_image(other)
-        elif isinstance(other, SglVideo):
-            self._execute_image(SglImage(other.path))
-        elif isinstance(other, SglVarScopeBegin):
-            self.variables[f"__scope_{other.name}"] = len(self.text_)
-        elif isinstance(other, SglVarScopeEnd):
-            start = self.variables.pop(f"__scope_{other.name}")
-            self.variables[other.name] = self.text_[start:]
-            self.variable_event[other.name].set()
-        elif isinstance(other, SglCommitLazy):
-            self.backend.commit_lazy_operations(self)
-        elif isinstance(other, SglConcateAndAppend):
-            for st in other.states:
-                self._execute_fill(st.text()[st.stream_executor.fork_start_text_pos or 0:])
-        elif isinstance(other, SglSeparateReasoning):
-            self._execute_separate_reasoning(other)
-        elif isinstance(other, SglArgument):
-            self._execute_fill(str(other.value))
-        else:
-            raise ValueError(f"unknown expression type {type(other)}")
-
-    def _execute_fill(self, value: str) -> None:
-        self.text_ += str(value)
-
-    def _execute_image(self, expr: SglImage) -> None:
-        self.images_.append(expr.path)
-        self.cur_images.append(expr.path)
-        self.text_ += self.chat_template.image_token
-
-    def _resolve_sp(self, sp: SglSamplingParams) -> SglSamplingParams:
-        out = self.default_sampling_para.clone()
-        defaults = SglSamplingParams()
-        for f in sp.__dataclass_fields__:
-            v = getattr(sp, f)
-            if v != getattr(defaults, f):
-                setattr(out, f, v)
-        return out
-
-    def _execute_gen(self, expr: SglGen) -> None:
-        sp = self._resolve_sp(expr.sampling_params)
-        name = expr.name
-        if not self.stream:
-            comp, meta = self.backend.generate(self, sampling_params=sp)
-            if isinstance(comp, list):   # n > 1
-                self.text_ += comp[0]
-            else:
-                self.text_ += comp
-            val = comp
-            if sp.dtype in ("int", int) and isinstance(comp, str):
-                try:
-                    val = int(comp.strip().split()[0])
-                except Exception:
-                    val = comp
-            self.variables[name] = val
-            self.meta_info[name] = meta
-            if name in self.variable_event:
-                self.variable_event[name].set()
-        else:
-            self.variables[name] = ""
-            self.stream_var_event[name].set()
-            for comp, meta in self.backend.generate_stream(self, sampling_params=sp):
-                self.text_ += comp
-                self.variables[name] += comp
-                self.meta_info[name] = meta
-                self.stream_var_event[name].set()
-                self.stream_text_event.set()
-            self.variable_event[name].set()
-            self.stream_var_event[name].set()
-
-    def _execute_select(self, expr: SglSelect) -> None:
-        decision = self.backend.select(self, expr.choices, expr.temperature, expr.choices_method)
-        if expr.name is not None:
-            self.variables[expr.name] = decision.decision
-            self.meta_info[expr.name] = decision.meta_info
-            self.variable_event[expr.name].set()
-            if self.stream_var_event:
-                self.stream_var_event[expr.name].set()
-        self.text_ += decision.decision
-
-    def _execute_role_begin(self, expr: SglRoleBegin) -> None:
-        assert self.cur_role is None, "nested roles are not allowed"
-        if len(self.messages_) == 0 and expr.role != "system":
-            default_system = self.chat_template.default_system_prompt
-            if default_system:
-                self._execute_role_begin(SglRoleBegin("system"))
-                self._execute_fill(default_system)
-                self._execute_role_end(SglRoleEnd("system"))
-        self.cur_role = expr.role
-        prefix, _ = self.chat_template.get_prefix_and_suffix(expr.role, self.messages_)
-        self._execute_fill(prefix)
-        self.cur_role_begin_pos = len(self.text_)
-
-    def _execute_role_end(self, expr: SglRoleEnd) -> None:
-        new_text = self.text_[self.cur_role_begin_pos:].lstrip()
-        _, suffix = self.chat_template.get_prefix_and_suffix(expr.role, self.messages_)
-        self._execute_fill(suffix)
-        if self.cur_images:
-            content: Any = [{"type": "text", "text": new_text}] + [{"type": "image_url", "image_url": {"url": p}} for p in self.cur_images]
-            self.cur_images = []
-        else:
-            content = new_text
-        self.messages_.append({"role": expr.role, "content": content})
-        self.cur_role = None
-
-    def _execute_separate_reasoning(self, expr: SglSeparateReasoning) -> None:
-        from ..parser.reasoning_parser import ReasoningParser
-
-        inner = expr.expr
-        self._execute(inner)
-        names = [inner.name] if isinstance(inner, (SglGen, SglSelect)) else [e.name for e in getattr(inner, "expr_list", []) if hasattr(e, "name")]
-        for n in names:
-            if n is None:
-                continue
-            r, c = ReasoningParser(expr.model_type).parse_non_stream(self.variables[n])
-            self.variables[f"{n}_reasoning_content"] = r or ""
-            self.variables[n] = c
+def _flatten(expr: Any) -> Iterator[Any]:
+    if isinstance(expr, SglExprList):
+        for e in expr.expr_list:
+            yield from _flatten(e)
+    else:
+        yield expr
 
 
 class ProgramState:
-    def __init__(self, stream_executor: StreamExecutor):
-        self.stream_executor = stream_executor
+    def __init__(self, ctx: _Ctx, transcript: Transcript, variables: Optional[Dict[str, Any]] = None, fork_mark: Optional[int] = None):
+        self.sid = f"prog-{next(_ids)}"
+        self._ctx = ctx
+        self._tr = transcript
+        self._vars: Dict[str, Any] = dict(variables or {})
+        self._meta: Dict[str, Any] = {}
+        self._log = _Pending()
+        self._declared: set = set()          # variable names that WILL exist once the log is drained
+        self._scopes: Dict[str, int] = {}
+        self._err: Optional[BaseException] = None
+        self._closed = False
+        self._fork_mark = fork_mark          # len(text) at the fork point (join(mode="concate_and_append") appends what came after)
         self.ret_value: Any = None
 
-    # ---- role context managers
-    class _Role:
-        def __init__(self, state: "ProgramState", role: str):
-            self.s, self.role = state, role
+    # ---- what a backend reads
+    @property
+    def prompt(self) -> str:
+        return self._tr.text()
 
-        def __enter__(self):
-            self.s.stream_executor.submit(SglRoleBegin(self.role))
-            return self.s
+    @property
+    def images(self) -> List[Any]:
+        return self._tr.images
 
-        def __exit__(self, *a):
-            self.s.stream_executor.submit(SglRoleEnd(self.role))
-
-    def system(self, expr: Any = None):
-        return self._role_common("system", expr)
-
-    def user(self, expr: Any = None):
-        return self._role_common("user", expr)
-
-    def assistant(self, expr: Any = None):
-        return self._role_common("assistant", expr)
-
-    def _role_common(self, role: str, expr: Any):
-        if expr is None:
-            return ProgramState._Role(self, role)
-        self.stream_executor.submit(SglExprList([SglRoleBegin(role), expr if isinstance(expr, SglExpr) else SglConstantText(str(expr)),
-                                                 SglRoleEnd(role)]))
-        return self
-
-    def var_scope(self, name: str):
-        s = self
-
-        class _Scope:
-            def __enter__(self_inner):
-                s.stream_executor.submit(SglVarScopeBegin(name))
-
-            def __exit__(self_inner, *a):
-                s.stream_executor.submit(SglVarScopeEnd(name))
-
-        return _Scope()
-
-    def fork(self, size: int = 1, position_ids_offset: Optional[List[int]] = None) -> "ProgramStateGroup":
-        return ProgramStateGroup([ProgramState(x) for x in self.stream_executor.fork(size, position_ids_offset)], self)
-
-    def copy(self, position_ids_offset=None) -> "ProgramState":
-        return self.fork(1, position_ids_offset)[0]
-
-    def text(self) -> str:
-        return self.stream_executor.text()
-
-    def messages(self) -> List[Dict[str, Any]]:
-        return self.stream_executor.messages()
-
-    def sync(self) -> None:
-        self.stream_executor.sync()
-
-    def error(self) -> Optional[Exception]:
-        return self.stream_executor.error_
-
-    def text_iter(self, var_name: Optional[str] = None) -> Iterator[str]:
-        se = self.stream_executor
-        assert se.stream, "text_iter requires run(..., stream=True)"
-        prev = 0
-        if var_name is None:
-            while True:
-                se.stream_text_event.wait()
-                se.stream_text_event.clear()
-                out = str(se.text_[prev:])
-                prev += len(out)
-                if out:
-                    yield out
-                if se.is_finished:
-                    out = str(se.text_[prev:])
-                    if out:
-                        yield out
-                    break
-        else:
-            while var_name not in se.stream_var_event:
-                if se.is_finished:
-                    return
-                threading.Event().wait(0.001)
-            ev = se.stream_var_event[var_name]
-            while True:
-                ev.wait()
-                ev.clear()
-                out = str(se.variables.get(var_name, "")[prev:])
-                prev += len(out)
-                if out:
-                    yield out
-                if se.variable_event[var_name].is_set():
-                    out = str(se.variables.get(var_name, "")[prev:])
-                    if out:
-                        yield out
-                    break
-
-    def get_var(self, name: str) -> Any:
-        return self.stream_executor.get_var(name)
-
-    def set_var(self, name: str, value: Any) -> None:
-        self.stream_executor.set_var(name, value)
-
-    def get_meta_info(self, name: str) -> Any:
-        return self.stream_executor.get_meta_info(name)
-
+    # ---- building the log
     def __iadd__(self, other: Any) -> "ProgramState":
         if other is None:
             raise ValueError("tried to append None to the state")
-        self.stream_executor.submit(other if isinstance(other, SglExpr) else SglConstantText(str(other)))
+        expr = other if isinstance(other, SglExpr) else SglConstantText(str(other))
+        with self._log.lock:
+            for e in _flatten(expr):
+                inner = e.expr if isinstance(e, SglSeparateReasoning) else e
+                for leaf in _flatten(inner):
+                    name = getattr(leaf, "name", None)
+                    if name is not None and isinstance(leaf, (SglGen, SglSelect, SglVarScopeBegin)):
+                        self._declared.add(name)
+                self._log.ops.append(e)
         return self
+
+    def _role_ops(self, role: str, expr: Any) -> Any:
+        if expr is None:
+            return _RoleBlock(self, role)
+        self += SglExprList([SglRoleBegin(role), expr if isinstance(expr, SglExpr) else SglConstantText(str(expr)), SglRoleEnd(role)])
+        return self
+
+    def system(self, expr: Any = None):
+        return self._role_ops("system", expr)
+
+    def user(self, expr: Any = None):
+        return self._role_ops("user", expr)
+
+    def assistant(self, expr: Any = None):
+        return self._role_ops("assistant", expr)
+
+    def var_scope(self, name: str) -> "_ScopeBlock":
+        return _ScopeBlock(self, name)
+
+    # ---- evaluation
+    def _fail(self, e: BaseException) -> None:
+        self._err = e
+
+    def _close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            try:
+                self._ctx.backend.end_program(self)
+            except Exception:
+                pass
+
+    def _steps(self, until: Optional[str] = None, live: bool = False) -> Iterator[Tuple[str, Optional[str]]]:
+        """evaluate pending ops in order, yielding ``(piece, variable)`` for every piece of text the moment it is appended (``variable``
+        names the gen / select it belongs to).  Stops early once variable ``until`` exists.  ``live``: ask the backend for chunk streams."""
+        while True:
+            if self._err is not None:
+                raise self._err
+            if until is not None and until in self._vars:
+                return
+            with self._log.lock:
+                if not self._log.ops:
+                    return
+                op = self._log.ops.popleft()
+            try:
+                yield from self._eval(op, live)
+            except Exception as e:
+                self._fail(e)
+                raise
+
+    def _drain(self, until: Optional[str] = None) -> None:
+        for _ in self._steps(until):
+            pass
+
+    def _emit(self, piece: str, var: Optional[str] = None) -> Iterator[Tuple[str, Optional[str]]]:
+        self._tr.write(piece)
+        if piece:
+            yield piece, var
+
+    def _eval(self, op: Any, live: bool) -> Iterator[Tuple[str, Optional[str]]]:
+        tr, tpl = self._tr, self._ctx.template
+        if isinstance(op, SglConstantText):
+            yield from self._emit(op.value)
+        elif isinstance(op, SglArgument):
+            yield from self._emit(str(op.value))
+        elif isinstance(op, SglGen):
+            yield from self._eval_gen(op, live)
+        elif isinstance(op, SglSelect):
+            d = self._ctx.backend.select(self, op.choices, op.temperature, op.choices_method)
+            if op.name is not None:
+                self._vars[op.name], self._meta[op.name] = d.decision, d.meta_info
+            yield from self._emit(d.decision, op.name)
+        elif isinstance(op, SglRoleBegin):
+            if tr.open_role is not None:
+                raise ValueError("nested roles are not allowed")
+            if not tr.messages and op.role != "system" and tpl.default_system_prompt:
+                for sub in (SglRoleBegin("system"), SglConstantText(tpl.default_system_prompt), SglRoleEnd("system")):
+                    yield from self._eval(sub, live)
+            yield from self._emit(tpl.get_prefix_and_suffix(op.role, tr.messages)[0])
+            tr.open_role, tr.role_mark = op.role, len(tr)
+        elif isinstance(op, SglRoleEnd):
+            body = tr.text()[tr.role_mark:].lstrip()
+            yield from self._emit(tpl.get_prefix_and_suffix(op.role, tr.messages)[1])
+            content: Any = body
+            if tr.turn_images:
+                content = [{"type": "text", "text": body}] + [{"type": "image_url", "image_url": {"url": p}} for p in tr.turn_images]
+                tr.turn_images = []
+            tr.messages.append({"role": op.role, "content": content})
+            tr.open_role = None
+        elif isinstance(op, (SglImage, SglVideo)):
+            tr.images.append(op.path)
+            tr.turn_images.append(op.path)
+            yield from self._emit(tpl.image_token)
+        elif isinstance(op, SglVarScopeBegin):
+            self._scopes[op.name] = len(tr)
+        elif isinstance(op, SglVarScopeEnd):
+            self._vars[op.name] = tr.text()[self._scopes.pop(op.name):]
+        elif isinstance(op, SglCommitLazy):
+            self._ctx.backend.commit_lazy_operations(self)
+        elif isinstance(op, SglConcateAndAppend):
+            for child in op.states:
+                child._drain()
+                yield from self._emit(child._tr.text()[child._fork_mark or 0:])
+        elif isinstance(op, SglSeparateReasoning):
+            yield from self._eval_reasoning(op, live)
+        else:
+            raise ValueError(f"unknown expression type {type(op)}")
+
+    def _sampling(self, sp: SglSamplingParams) -> SglSamplingParams:
+        """per-call parameters override the run's defaults field by field (a field left at its dataclass default does not)"""
+        merged, blank = self._ctx.defaults.clone(), SglSamplingParams()
+        for f in sp.__dataclass_fields__:
+            if getattr(sp, f) != getattr(blank, f):
+                setattr(merged, f, getattr(sp, f))
+        return merged
+
+    def _eval_gen(self, op: SglGen, live: bool) -> Iterator[Tuple[str, Optional[str]]]:
+        sp, name, be = self._sampling(op.sampling_params), op.name, self._ctx.backend
+        if live:
+            acc: List[str] = []
+            meta: Any = None
+            for piece, meta in be.generate_stream(self, sampling_params=sp):
+                acc.append(piece)
+                yield from self._emit(piece, name)
+            self._vars[name], self._meta[name] = "".join(acc), meta       # the variable exists once its stream is complete
+            return
+        out, meta = be.generate(self, sampling_params=sp)
+        yield from self._emit(out[0] if isinstance(out, list) else out, name)      # n > 1: the first sample continues the text
+        val: Any = out
+        if sp.dtype in ("int", int) and isinstance(out, str):
+            try:
+                val = int(out.strip().split()[0])
+            except Exception:
+                val = out
+        self._vars[name], self._meta[name] = val, meta
+
+    def _eval_reasoning(self, op: SglSeparateReasoning, live: bool) -> Iterator[Tuple[str, Optional[str]]]:
+        from ..parser.reasoning_parser import ReasoningParser
+
+        leaves = list(_flatten(op.expr))
+        for leaf in leaves:
+            yield from self._eval(leaf, live)
+        for leaf in leaves:
+            n = getattr(leaf, "name", None)
+            if n is not None and isinstance(leaf, (SglGen, SglSelect)):
+                thought, answer = ReasoningParser(op.model_type).parse_non_stream(self._vars[n])
+                self._vars[f"{n}_reasoning_content"] = thought or ""
+                self._vars[n] = answer
+
+    # ---- reading results (each read is a demand)
+    def sync(self) -> None:
+        self._drain()
+
+    def text(self) -> str:
+        self._drain()
+        return self._tr.text()
+
+    def messages(self) -> List[Dict[str, Any]]:
+        self._drain()
+        return self._tr.messages
+
+    def error(self) -> Optional[BaseException]:
+        return self._err
+
+    def get_var(self, name: str) -> Any:
+        if name not in self._vars:
+            self._drain(until=name)
+        if self._err is not None:
+            raise self._err
+        return self._vars[name]
+
+    def set_var(self, name: str, value: Any) -> None:
+        self._vars[name] = value
+
+    def get_meta_info(self, name: str, timeout: Optional[float] = None) -> Any:
+        if name not in self._meta and name in self._declared:
+            self._drain(until=name)
+        return self._meta.get(name)
 
     def __getitem__(self, name: str) -> Any:
         return self.get_var(name)
@@ -450,40 +374,109 @@ class ProgramState:
         self.set_var(name, value)
 
     def __contains__(self, name: str) -> bool:
-        return name in self.stream_executor.variables
+        return name in self._vars or name in self._declared
 
     def __repr__(self) -> str:
         return f"ProgramState({self.text()})"
+
+    def text_iter(self, var_name: Optional[str] = None) -> Iterator[str]:
+        """pull-based streaming: iterating this generator IS what runs the program's remaining ops — each ``next()`` advances the op log
+        until the next piece of text exists (for a ``gen`` that is the next chunk of the backend's stream).  Text that was already
+        produced, because the program itself demanded a value earlier, is yielded first."""
+        assert self._ctx.stream, "text_iter requires run(..., stream=True)"
+        if var_name is None:
+            done = self._tr.text()
+            if done:
+                yield done
+        elif var_name in self._vars:
+            if self._vars[var_name]:
+                yield str(self._vars[var_name])
+            return
+        try:
+            for piece, var in self._steps(until=var_name, live=True):
+                if var_name is None or var == var_name:
+                    yield piece
+        finally:
+            if var_name is None and not self._log.ops:
+                self._close()
+
+    # ---- fork / join
+    def fork(self, size: int = 1, position_ids_offset: Optional[List[int]] = None) -> "ProgramStateGroup":
+        if size > 1:
+            self += SglCommitLazy()
+        self._drain()
+        mark = len(self._tr)
+        kids = [ProgramState(self._ctx, self._tr.branch(), self._vars, fork_mark=mark) for _ in range(size)]
+        return ProgramStateGroup(kids, self)
+
+    def copy(self, position_ids_offset=None) -> "ProgramState":
+        return self.fork(1, position_ids_offset)[0]
+
+
+class _RoleBlock:
+    """``with s.user(): ...``"""
+
+    def __init__(self, state: ProgramState, role: str):
+        self.state, self.role = state, role
+
+    def __enter__(self) -> ProgramState:
+        self.state += SglRoleBegin(self.role)
+        return self.state
+
+    def __exit__(self, *exc) -> None:
+        self.state += SglRoleEnd(self.role)
+
+
+class _ScopeBlock:
+    """``with s.var_scope("name"): ...`` captures the text produced inside the block as a variable"""
+
+    def __init__(self, state: ProgramState, name: str):
+        self.state, self.name = state, name
+
+    def __enter__(self) -> None:
+        self.state += SglVarScopeBegin(self.name)
+
+    def __exit__(self, *exc) -> None:
+        self.state += SglVarScopeEnd(self.name)
 
 
 class ProgramStateGroup:
     def __init__(self, states: List[ProgramState], src_state: Optional[ProgramState] = None):
         self.states, self.src_state = states, src_state
 
+    def _drain_all(self) -> None:
+        """all branches at once: each pending ``gen`` becomes an in-flight request, the server batches them"""
+        if len(self.states) == 1:
+            self.states[0]._drain()
+            return
+        for f in [_POOL.submit(s._drain) for s in self.states]:
+            f.result()
+
     def join(self, mode: str = "gather_variable") -> None:
         if mode == "gather_variable":
-            src_vars = self.src_state.stream_executor.variables
-            src_events = self.src_state.stream_executor.variable_event
-            for s in self.states:
-                s.stream_executor.sync()
-            keys = set().union(*[set(s.stream_executor.variables) for s in self.states])
-            for k in keys:
-                vals = [s.stream_executor.variables.get(k) for s in self.states]
-                src_vars[k] = vals
-                if k in src_events:
-                    src_events[k].set()
+            self._drain_all()
+            names = set().union(*[set(s._vars) for s in self.states]) if self.states else set()
+            for k in names:
+                self.src_state._vars[k] = [s._vars.get(k) for s in self.states]
         elif mode == "concate_and_append":
-            self.src_state.stream_executor.submit(SglConcateAndAppend(self.states))
+            self._drain_all()
+            self.src_state += SglConcateAndAppend(self.states)
         else:
             raise ValueError(mode)
         for s in self.states:
-            s.stream_executor.end()
+            s._close()
 
     def __getitem__(self, i: int) -> ProgramState:
         return self.states[i]
 
-    def __setitem__(self, i: int, v: ProgramState) -> None:
+    def __setitem__(self, i: int, v: ProgramState) -> None:       # ``forks[i] += x`` re-assigns the same object
         pass
+
+    def __iter__(self) -> Iterator[ProgramState]:
+        return iter(self.states)
+
+    def __len__(self) -> int:
+        return len(self.states)
 
     def __iadd__(self, other: Any) -> "ProgramStateGroup":
         if isinstance(other, (list, tuple)):
@@ -496,6 +489,3 @@ class ProgramStateGroup:
             for s in self.states:
                 s += other
         return self
-
-    def __len__(self) -> int:
-        return len(self.states)

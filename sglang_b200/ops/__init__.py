@@ -225,6 +225,17 @@ def gemm_skinny(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def gemm_streamk(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, silu_split: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[T<=256,K] @ w[N,K]^T on the persistent stream-K tcgen05 kernel (csrc/kernels/gemm_streamk.cu): every SM streams an equal share of
+    the weights, split tiles are reduced in-kernel (deterministic), TMA-store epilogue.  ``silu_split``: w = [gate; up] -> silu(g) * u."""
+    n_out = w.shape[0] // 2 if silu_split else w.shape[0]
+    if out is None:
+        out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
+    torch.ops.sglb.gemm_streamk(x, w, out, bias, EPI_SILU_SPLIT if silu_split else (EPI_BIAS if bias is not None else EPI_NONE))
+    return out
+
+
 def gemm_skinny_slabs(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, max_splits: int = 8) -> torch.Tensor:
     """split-K partials [splits, T, N] (bf16); the consumer sums the slabs (``slab_reduce_add_rmsnorm``, ``rope_kv_write``)"""
     T, K = x.shape

@@ -343,6 +343,66 @@ def case_gemm_skinny():
     _close(q.reshape(T, Hq, D), qf, 0.05, 2e-2, "slab rope q"); _close(kc, kc2, 0.05, 2e-2, "slab rope k"); _close(vc, vc2, 0.05, 2e-2, "slab rope v")
 
 
+def case_gemm_streamk():
+    """persistent stream-K decode GEMM: plain / bias / strided / fused split-SiLU, every token bucket, tiles split across 1..5 CTAs, M edge
+    clipping by the TMA store, bit-determinism across launches (the fixup sums partials in contributor order, not arrival order)"""
+    torch.manual_seed(11)
+    for (M, N, K) in [(1, 4096, 4096), (16, 6144, 4096), (17, 6144, 4096), (37, 4096, 14336), (64, 28672, 4096), (100, 1024, 512),
+                      (128, 4096, 4096), (200, 6144, 4096), (256, 4096, 14336), (256, 2048, 7168), (5, 128256, 512), (48, 1000, 264),
+                      (3, 128, 64), (33, 256, 8192), (129, 28672, 4096)]:
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) * 0.5).to(torch.bfloat16)
+        ref = a.float() @ w.float().t()
+        out = ops.gemm_streamk(a, w)
+        out2 = ops.gemm_streamk(a, w)
+        torch.cuda.synchronize()
+        _close(out, ref, 0.5 if K > 4096 else 0.25, 2e-2, f"streamk {M}x{N}x{K}")
+        assert torch.equal(out, out2), f"streamk {M}x{N}x{K}: not bit-deterministic"
+    # output rows beyond M must stay untouched (TMA store clipping) — write into a view of a larger poisoned buffer
+    big = torch.full((80, 4096), 7.0, device=DEV, dtype=torch.bfloat16)
+    a = (torch.randn(50, 4096, device=DEV) * 0.5).to(torch.bfloat16); w = (torch.randn(4096, 4096, device=DEV) * 0.05).to(torch.bfloat16)
+    ops.gemm_streamk(a, w, out=big[:50])
+    torch.cuda.synchronize()
+    _close(big[:50], a.float() @ w.float().t(), 0.1, 2e-2, "streamk clip")
+    assert bool((big[50:] == 7.0).all()), "streamk wrote past M"
+    # bias + strided A
+    a_big = (torch.randn(70, 3 * 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    a = a_big[:, 1024:2048]
+    w = (torch.randn(512, 1024, device=DEV) * 0.5).to(torch.bfloat16)
+    b = torch.randn(512, device=DEV).to(torch.bfloat16)
+    _close(ops.gemm_streamk(a, w, bias=b), a.float() @ w.float().t() + b.float(), 0.25, 2e-2, "streamk bias strided")
+    w2 = (torch.randn(6144, 4096, device=DEV) * 0.05).to(torch.bfloat16); b2 = torch.randn(6144, device=DEV).to(torch.bfloat16)
+    a2 = (torch.randn(30, 4096, device=DEV) * 0.5).to(torch.bfloat16)
+    _close(ops.gemm_streamk(a2, w2, bias=b2), a2.float() @ w2.float().t() + b2.float(), 0.1, 2e-2, "streamk bias split tiles")
+    # fused SiLU*mul on [gate; up]
+    for (M, I, K) in [(50, 1024, 512), (256, 14336, 4096), (7, 1792, 4096), (33, 1000, 256), (64, 14336, 4096), (130, 3584, 4096)]:
+        gate = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        up = (torch.randn(I, K, device=DEV) * 0.1).to(torch.bfloat16)
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        out = ops.gemm_streamk(a, torch.cat([gate, up], 0).contiguous(), silu_split=True)
+        ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+        torch.cuda.synchronize()
+        _close(out, ref, 0.1, 3e-2, f"streamk split-silu {M}x{I}x{K}")
+    # CUDA-graph replay: counters re-armed by the finisher, workspace reused
+    a = (torch.randn(24, 4096, device=DEV) * 0.5).to(torch.bfloat16); w = (torch.randn(6144, 4096, device=DEV) * 0.05).to(torch.bfloat16)
+    out = torch.empty(24, 6144, device=DEV, dtype=torch.bfloat16)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.gemm_streamk(a, w, out=out)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        ops.gemm_streamk(a, w, out=out)
+    first = None
+    for _ in range(5):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        first = out.clone() if first is None else first
+        assert torch.equal(out, first)
+    _close(out, a.float() @ w.float().t(), 0.1, 2e-2, "streamk graph replay")
+
+
 def case_sampling():
     torch.manual_seed(0)
     B, V = 16, 32000
