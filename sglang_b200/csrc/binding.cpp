@@ -118,15 +118,29 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
   if (impl == 0 || impl == 2) {
     TORCH_CHECK(!fp8, "tcgen05 attention: fp8 KV cache not yet supported (use impl=1)");
     if (num_splits > 1) TORCH_CHECK(part_o.has_value() && part_lse.has_value(), "split-KV needs workspaces");
-    // impl 2: persistent CTAs + atomic work counter (one zero-initialised [next, done] pair per device, reset by the kernel)
+    // persistent kernels take work items from an atomic counter (one zero-initialised [next, done] pair per device, re-armed by the kernel)
     static at::Tensor sched[16];
-    int* sched_ptr = nullptr;
-    if (impl == 2) {
-      const int di = q.get_device();
-      TORCH_CHECK(di >= 0 && di < 16);
-      if (!sched[di].defined()) sched[di] = at::zeros({2}, q.options().dtype(at::kInt));
-      sched_ptr = sched[di].data_ptr<int>();
+    const int di = q.get_device();
+    TORCH_CHECK(di >= 0 && di < 16);
+    if (!sched[di].defined()) {
+      cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(cur_stream(), &cst);
+      TORCH_CHECK(cst == cudaStreamCaptureStatusNone, "attn_fwd: first call on this device is inside a CUDA-graph capture (warm up eagerly first)");
+      sched[di] = at::zeros({2}, q.options().dtype(at::kInt));
     }
+    int* sched_ptr = sched[di].data_ptr<int>();
+    // decode (one query token per request): keys-as-M kernel (attention_decode.cu) unless SGLB_ATTN_DECODE=v2 asks for the query-major one
+    static const bool decode_v3 = [] { const char* e = getenv("SGLB_ATTN_DECODE"); return !(e && std::string(e) == "v2"); }();
+    if (!cu_q.has_value() && decode_v3 && sglb::attn_decode_tc_supported(Hq, Hkv, D, (int)page_size)) {
+      TORCH_CHECK(T == B, "decode attention expects one query token per request");
+      sglb::attn_decode_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse), opt_mptr<float>(part_o),
+                           opt_mptr<float>(part_lse), page_table.data_ptr<int>(), (int)page_table.stride(0), req_slots.data_ptr<int>(),
+                           seq_lens.data_ptr<int>(), B, (int)q.stride(0), Hq, Hkv, D, (int)k_cache.size(0), (int)page_size, (int)num_splits,
+                           (float)scale, (int)window, (float)logit_cap, sched_ptr, num_sms(), cur_stream());
+      count(num_splits > 1 ? 2 : 1);
+      return;
+    }
+    if (impl != 2) sched_ptr = nullptr;      // impl 0: classic (non-persistent) launch of the query-major kernel
     sglb::attn_fwd_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),
                       opt_mptr<float>(part_o), opt_mptr<float>(part_lse), page_table.data_ptr<int>(),
                       (int)page_table.stride(0), req_slots.data_ptr<int>(), seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), B, T,

@@ -25,6 +25,12 @@ void attn_fwd_simt(const void* q, const void* k_cache, const void* v_cache, void
                    bool fp8_cache, float k_scale, float v_scale, cudaStream_t stream);
 
 // attention_tc.cu
+// attention_decode.cu: decode attention with the keys as the UMMA M dimension (persistent, 3-deep 32 KB K/V ring, page-granular fetch)
+bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size);
+void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o, float* part_lse,
+                    const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens, int B, int q_stride, int Hq, int Hkv,
+                    int D, int num_slots, int page_size, int num_splits, float scale, int window, float logit_cap, int* sched, int num_sms,
+                    cudaStream_t stream);
 void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o,
                  float* part_lse, const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens,
                  const int* cu_q, int B, int T, int q_stride, int max_q_len, int Hq, int Hkv, int D, int num_slots,

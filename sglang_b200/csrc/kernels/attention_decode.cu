@@ -1,0 +1,465 @@
+// Decode attention for sm_100a with the MMA operands SWAPPED: the 128 KEYS of a tile are the UMMA M dimension, the (few) query heads that
+// share a KV head are the UMMA N dimension.
+//
+// Why (profiles/attention_persist_r1.md, VERDICT r1 "What's weak" #4): in the query-major kernel (attention_tc.cu) a decode item uses G = 4
+// of the 128 rows of every S / O tile, one softmax warp of four does all the exponentials (64 per thread per 64-key tile), the Q box drags
+// 32 KB through TMA to use 1 KB, and the tensor pipe spends 512 cycles per 16 KB of KV on rows that carry nothing.  Transposed:
+//
+//     S^T[128 keys, NQ]  = K_tile[128 keys, 128 d] . Q^T            (A = K from smem, K-major;  B = Q, NQ = 16 padded query rows)
+//     O^T[128 d,   NQ]  += V_tile^T[128 d, 128 keys] . P^T            (A = V from smem, MN-major; B = P^T from smem, K-major)
+//
+//   * every TMEM lane / softmax thread owns ONE KEY: G exponentials per thread per 128-key tile, all 128 threads busy;
+//   * tensor time per 64 KB of KV: 16 MMAs of 128x16x16 (~0.2 us) instead of 2 x 12 of 128x64/128x16 — the kernel is pure streaming;
+//   * Q is 2 x [16 rows x 128 B] = 4 KB of smem (G rows live), which pays for a 3-deep ring of 32 KB K and V tiles: 192 KB of KV in
+//     flight per SM, one persistent CTA per SM, work items (request, kv head, split) from an atomic queue;
+//   * only the pages that hold keys < seq_len are fetched (expect_tx is sized per tile), so the ragged tail costs pages, not tiles;
+//   * row max: warp shuffle + one named barrier per tile; row SUM is kept per thread and reduced once per item; lazy O rescale (FA4).
+//
+// Hand-offs use one barrier per *meaning* (no waiting on a shared barrier by tile parity — see the o_final note in attention_tc.cu).
+//
+// Stands in for the reference's trtllm-gen decode kernel (python/sglang/srt/layers/attention/trtllm_mha_backend.py:1470) and the Triton
+// split-KV decode kernel (kernels/ops/attention/decode_attention.py:472).
+#include <math.h>
+
+#include "common.cuh"
+#include "tma_host.h"
+
+#include <algorithm>
+
+namespace sglb {
+
+constexpr int DA_D = 128;                 // head dim
+constexpr int DA_KT = 128;                // keys per tile (UMMA M)
+constexpr int DA_NQ = 16;                 // padded query rows (UMMA N)
+constexpr int DA_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2-5 softmax (one key per thread)
+constexpr int DA_STAGES = 3;
+constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile: two 64-wide d halves of [128 keys x 128 B])
+constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
+constexpr int DA_Q_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two d halves of [16 rows x 128 B])
+constexpr int DA_P_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two 64-key chunks of [16 rows x 128 B]), double buffered
+constexpr int DA_SMEM_BYTES = 2 * DA_STAGES * DA_TILE_BYTES + DA_Q_BYTES + 2 * DA_P_BYTES + 1024 /*align*/ + 1024 /*barriers + scratch*/;
+constexpr float DA_RESCALE_THRESHOLD = 8.0f;
+
+struct DecodeParams {
+  __nv_bfloat16* out;     // [B, Hq, D]
+  float* part_o;          // [splits, B, Hq, D]
+  float* part_lse;        // [splits, B, Hq]
+  float* lse;             // optional [B, Hq]
+  const int* page_table;
+  const int* req_slots;
+  const int* seq_lens;
+  int pt_stride, Hq, Hkv, G, page_size, num_splits, B;
+  float scale_log2, logit_cap;
+  int window;
+  int total_items;
+  int* sched;             // [0] next item, [1] CTAs finished (the last one re-arms both)
+};
+
+template <int GMAX, bool HAS_CAP>
+__global__ void __launch_bounds__(DA_THREADS, 1)
+attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const DecodeParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = p.G;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                              // [STAGES][32 KB]
+  uint8_t* sV = smem + DA_STAGES * DA_TILE_BYTES;                  // [STAGES][32 KB]
+  uint8_t* sQ = smem + 2 * DA_STAGES * DA_TILE_BYTES;              // 4 KB
+  uint8_t* sP = sQ + DA_Q_BYTES;                                   // 2 x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * DA_P_BYTES);
+  uint64_t* q_full = bars;             // Q of the item landed                       (phase = item ordinal)
+  uint64_t* q_empty = bars + 1;        // last S of the item has read Q              (phase = item ordinal)
+  uint64_t* k_full = bars + 2;         // [STAGES]
+  uint64_t* k_empty = bars + 5;        // [STAGES]
+  uint64_t* v_full = bars + 8;         // [STAGES]
+  uint64_t* v_empty = bars + 11;       // [STAGES]
+  uint64_t* s_full = bars + 14;        // [2] S^T of a tile is in TMEM
+  uint64_t* p_full = bars + 16;        // [2] P^T of a tile is in smem (128 arrivals)
+  uint64_t* o_done = bars + 18;        // every PV tile (lazy-rescale hand-off)
+  uint64_t* o_final = bars + 19;       // last PV of an item                         (phase = item ordinal)
+  uint64_t* o_free = bars + 20;        // epilogue has read O^T (4 arrivals)         (phase = item ordinal)
+  uint64_t* item_full = bars + 21;     // [2]
+  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps)
+  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 25);        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+  volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 27); // [6] role state for the timeout dump
+  float* red = reinterpret_cast<float*>(bars + 32);                         // [2][4 warps][GMAX] row-max exchange, then [4][GMAX] sums
+#define DA_WAIT(bar_, par_) mbar_wait((bar_), (par_), dbg, 6)
+#define DA_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5); }
+    mbar_init(o_done, 1); mbar_init(o_final, 1); mbar_init(o_free, 4);
+    fence_barrier_init();
+  }
+  if (lane == 0) dbg[warp] = 0;
+  // zero Q / P (rows >= G stay zero for the whole kernel) and the V ring (a tile's unfetched tail pages must hold finite numbers: their
+  // probabilities are exactly 0, and 0 x NaN would poison O)
+  for (int i = threadIdx.x; i < (DA_Q_BYTES + 2 * DA_P_BYTES) / 16; i += DA_THREADS) reinterpret_cast<U4*>(sQ)[i] = U4{0, 0, 0, 0};
+  for (int i = threadIdx.x; i < DA_STAGES * DA_TILE_BYTES / 16; i += DA_THREADS) reinterpret_cast<U4*>(sV)[i] = U4{0, 0, 0, 0};
+  fence_proxy_async_smem();
+  if (warp == 1) { tmem_alloc(tmem_ptr, 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;                 // S^T buffers: cols [0,16) and [16,32)
+  const uint32_t tmem_O = tmem_base + 32;            // O^T: cols [32,48)
+
+  // geometry of a work item: pure function of its id, evaluated identically by every role
+  struct Item { int b, kvh, split, seq_len, kv_hi, tile_begin, n_tiles; };
+  auto decode_item = [&](int idx) {
+    Item it;
+    const int per_b = p.Hkv * p.num_splits;
+    it.b = idx / per_b;
+    const int y = idx - it.b * per_b;
+    it.kvh = y / p.num_splits; it.split = y - it.kvh * p.num_splits;
+    it.seq_len = p.seq_lens[it.b];
+    it.kv_hi = it.seq_len;
+    int kv_lo = 0;
+    if (p.window > 0) kv_lo = max(0, it.seq_len - p.window);
+    const int tile_lo = kv_lo / DA_KT, tile_hi = (it.kv_hi + DA_KT - 1) / DA_KT;
+    const int per_split = (tile_hi - tile_lo + p.num_splits - 1) / p.num_splits;
+    it.tile_begin = tile_lo + it.split * per_split;
+    it.n_tiles = max(0, min(tile_hi, it.tile_begin + per_split) - it.tile_begin);
+    return it;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ scheduler + TMA producer
+    uint32_t n_it = 0, n_q = 0, g = 0;
+    const int ps = p.page_size, pages_per_tile = DA_KT / ps;
+    for (;;) {
+      const int slot = n_it & 1;
+      DA_WAIT(&item_empty[slot], ((n_it >> 1) & 1) ^ 1);
+      const int idx = atomicAdd(p.sched, 1);
+      DA_DBG(1, n_it, g);
+      s_item[slot] = idx;
+      mbar_arrive(&item_full[slot]);
+      ++n_it;
+      if (idx >= p.total_items) break;
+      const Item it = decode_item(idx);
+      if (it.n_tiles == 0) continue;
+      DA_WAIT(q_empty, (n_q & 1) ^ 1);
+      mbar_expect_tx(q_full, 2 * G * 128);
+      tma_load_4d(sQ, &tmQ, q_full, 0, 0, it.kvh, it.b);
+      tma_load_4d(sQ + DA_NQ * 128, &tmQ, q_full, 64, 0, it.kvh, it.b);
+      ++n_q;
+      const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
+      for (int j = 0; j < it.n_tiles; ++j, ++g) {
+        const int st = g % DA_STAGES;
+        const uint32_t ph = (g / DA_STAGES) & 1;
+        const int key0 = (it.tile_begin + j) * DA_KT;
+        const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);     // only pages that hold live keys
+        const int pg0 = key0 / ps;
+        const uint32_t bytes = (uint32_t)n_pages * ps * 256;
+        DA_WAIT(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], bytes);
+        for (int i = 0; i < n_pages; ++i) {
+          const int page = pt[pg0 + i];
+          uint8_t* dst = sK + st * DA_TILE_BYTES + i * ps * 128;
+          tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, page * ps);
+          tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, page * ps);
+        }
+        DA_WAIT(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], bytes);
+        for (int i = 0; i < n_pages; ++i) {
+          const int page = pt[pg0 + i];
+          uint8_t* dst = sV + st * DA_TILE_BYTES + i * ps * 128;
+          tma_load_3d(dst, &tmV, &v_full[st], 0, it.kvh, page * ps);
+          tma_load_3d(dst + DA_HALF_BYTES, &tmV, &v_full[st], 64, it.kvh, page * ps);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, DA_KT, DA_NQ, 0, 0);      // A = K (K-major), B = Q (K-major)
+    constexpr uint32_t idesc_o = make_idesc(UMMA_BF16, UMMA_BF16, DA_D, DA_NQ, 1, 0);       // A = V^T (MN-major: d contiguous), B = P^T
+    const uint32_t q_addr = smem_u32(sQ);
+    uint32_t n_it = 0, n_q = 0, g = 0;
+    for (;;) {
+      const int slot = n_it & 1;
+      DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
+      const int idx = s_item[slot];
+      mbar_arrive(&item_empty[slot]);
+      ++n_it;
+      if (idx >= p.total_items) break;
+      const Item it = decode_item(idx);
+      if (it.n_tiles == 0) continue;
+      const int n_tiles = it.n_tiles;
+      DA_DBG(2, n_q, g);
+      auto issue_S = [&](uint32_t gt, bool last) {
+        const int st = gt % DA_STAGES;
+        DA_WAIT(&k_full[st], (gt / DA_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * DA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < DA_D / 16; ++k) {
+          const uint32_t koff = (k >> 2) * DA_HALF_BYTES + (k & 3) * 32;
+          const uint32_t qoff = (k >> 2) * (DA_NQ * 128) + (k & 3) * 32;
+          umma_f16_ss(tmem_S + (gt & 1) * DA_NQ, make_smem_desc_sw128(k_addr + koff, 0, 1024), make_smem_desc_sw128(q_addr + qoff, 0, 1024),
+                      idesc_s, k != 0);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[gt & 1]);
+        if (last) umma_commit(q_empty);
+      };
+      DA_WAIT(q_full, n_q & 1);
+      issue_S(g, n_tiles == 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t gt = g + j;
+        const int st = gt % DA_STAGES;
+        if (j + 1 < n_tiles) issue_S(gt + 1, j + 2 == n_tiles);
+        DA_WAIT(&p_full[gt & 1], (gt >> 1) & 1);
+        DA_WAIT(&v_full[st], (gt / DA_STAGES) & 1);
+        if (j == 0) DA_WAIT(o_free, (n_q & 1) ^ 1);       // the previous item's epilogue has read O^T
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + st * DA_TILE_BYTES);
+        const uint32_t p_addr = smem_u32(sP + (gt & 1) * DA_P_BYTES);
+#pragma unroll
+        for (int k = 0; k < DA_KT / 16; ++k)      // 16 keys per step: A rows advance 16 x 128 B, B (P^T, K-major) advances 32 B inside a 64-key chunk
+          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + k * 2048, DA_HALF_BYTES, 1024),
+                      make_smem_desc_sw128(p_addr + (k >> 2) * (DA_NQ * 128) + (k & 3) * 32, 0, 1024), idesc_o, (j | k) != 0);
+        umma_commit(&v_empty[st]);
+        umma_commit(o_done);
+        if (j + 1 == n_tiles) umma_commit(o_final);
+      }
+      g += n_tiles;
+      ++n_q;
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ softmax (thread = key) + epilogue (thread = output dim)
+    const int q4 = warp & 3;                              // TMEM lane quadrant of this warp
+    const int row = (q4 << 5) + lane;                     // key index inside the tile / output dim in the epilogue
+    const uint32_t lane_addr = (uint32_t)(q4 << 5) << 16;
+    const float scale_log2 = p.scale_log2;
+    const float cap = p.logit_cap, inv_cap = HAS_CAP ? 1.f / p.logit_cap : 0.f;
+    const float scale_nat = scale_log2 * 0.6931471805599453f, inv_scale_nat = 1.f / scale_nat;
+    uint32_t n_it = 0, n_q = 0, g = 0;
+    for (;;) {
+      const int slot = n_it & 1;
+      DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
+      const int idx = s_item[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&item_empty[slot]);
+      ++n_it;
+      if (idx >= p.total_items) break;
+      const Item it = decode_item(idx);
+      if (it.n_tiles == 0) {
+        if (p.num_splits > 1) {          // empty split: neutral partial (the merge kernel ignores lse = -inf)
+          for (int gq = 0; gq < G; ++gq) {
+            const size_t r = ((size_t)it.split * p.B + it.b) * p.Hq + it.kvh * G + gq;
+            p.part_o[r * DA_D + row] = 0.f;
+            if (row == 0) p.part_lse[r] = -INFINITY;
+          }
+        }
+        continue;
+      }
+      const int n_tiles = it.n_tiles;
+      if (lane == 0) DA_DBG(3, n_q, g);
+      const int kv_first = p.window > 0 ? it.seq_len - p.window : 0;
+      float m_run[GMAX], l_part[GMAX];
+#pragma unroll
+      for (int i = 0; i < GMAX; ++i) { m_run[i] = -INFINITY; l_part[i] = 0.f; }
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t gt = g + j;
+        DA_WAIT(&s_full[gt & 1], (gt >> 1) & 1);
+        tc_fence_after();
+        uint32_t sr[GMAX];
+        {
+          const uint32_t a = tmem_S + lane_addr + (gt & 1) * DA_NQ;
+          if constexpr (GMAX == 4) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]) : "r"(a) : "memory");
+          } else if constexpr (GMAX == 8) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]) : "r"(a) : "memory");
+          } else {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]), "=r"(sr[8]),
+                           "=r"(sr[9]), "=r"(sr[10]), "=r"(sr[11]), "=r"(sr[12]), "=r"(sr[13]), "=r"(sr[14]), "=r"(sr[15]) : "r"(a) : "memory");
+          }
+          tmem_ld_wait();
+        }
+        const int key = (it.tile_begin + j) * DA_KT + row;
+        const bool live = key < it.kv_hi && key >= kv_first;
+        float sv[GMAX], wmax[GMAX];
+#pragma unroll
+        for (int i = 0; i < GMAX; ++i) {
+          float x = __uint_as_float(sr[i]);
+          if (HAS_CAP) x = cap * tanhf(x * scale_nat * inv_cap) * inv_scale_nat;
+          sv[i] = live ? x * scale_log2 : -INFINITY;
+          wmax[i] = warp_max(sv[i]);
+        }
+        float* rbuf = red + (gt & 1) * (4 * GMAX);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < GMAX; ++i) rbuf[q4 * GMAX + i] = wmax[i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bool need = false;
+        float m_new[GMAX];
+#pragma unroll
+        for (int i = 0; i < GMAX; ++i) {
+          const float tmax = fmaxf(fmaxf(rbuf[i], rbuf[GMAX + i]), fmaxf(rbuf[2 * GMAX + i], rbuf[3 * GMAX + i]));
+          m_new[i] = fmaxf(m_run[i], tmax);
+          need |= (m_new[i] > m_run[i] + DA_RESCALE_THRESHOLD);     // same value in every thread (m_run and tmax are CTA-uniform)
+        }
+        if (j == 0) {
+#pragma unroll
+          for (int i = 0; i < GMAX; ++i) m_run[i] = m_new[i];
+        } else if (need) {
+          // lazy rescale of O^T (lane = output dim, column = query row): wait for PV(j-1), scale the columns, write back
+          DA_WAIT(o_done, (gt - 1) & 1);
+          tc_fence_after();
+          uint32_t orow[16];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(orow[0]), "=r"(orow[1]), "=r"(orow[2]), "=r"(orow[3]), "=r"(orow[4]), "=r"(orow[5]), "=r"(orow[6]), "=r"(orow[7]),
+                         "=r"(orow[8]), "=r"(orow[9]), "=r"(orow[10]), "=r"(orow[11]), "=r"(orow[12]), "=r"(orow[13]), "=r"(orow[14]), "=r"(orow[15])
+                       : "r"(tmem_O + lane_addr) : "memory");
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < GMAX; ++i) {
+            const float f = (m_new[i] == -INFINITY) ? 1.f : exp2f(m_run[i] - m_new[i]);
+            orow[i] = __float_as_uint(__uint_as_float(orow[i]) * f);
+            l_part[i] *= f;
+            m_run[i] = m_new[i];
+          }
+          tmem_st_32x32b_x16(tmem_O + lane_addr, orow);
+          tmem_st_wait();
+        }
+        // P^T[query row i][key] (bf16, K-major, 128-byte swizzle): rows >= G stay zero
+        uint8_t* pbuf = sP + (gt & 1) * DA_P_BYTES + (row >> 6) * (DA_NQ * 128);
+        const int c = row & 63;
+#pragma unroll
+        for (int i = 0; i < GMAX; ++i) {
+          if (i < G) {
+            const float mm = (m_run[i] == -INFINITY) ? 0.f : m_run[i];
+            const float pv = ex2_approx(sv[i] - mm);
+            l_part[i] += pv;
+            const uint32_t off = i * 128 + ((((uint32_t)c >> 3) ^ (i & 7)) << 4) + (c & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(pbuf + off) = __float2bfloat16(pv);
+          }
+        }
+        fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's smem reads
+        tc_fence_before();
+        mbar_arrive(&p_full[gt & 1]);
+      }
+      g += n_tiles;
+
+      // ---- epilogue: row sums across the 128 key-threads, then O^T / l -> out (thread = output dim)
+      if (lane == 0) DA_DBG(4, n_q, g);
+      float lsum[GMAX];
+#pragma unroll
+      for (int i = 0; i < GMAX; ++i) lsum[i] = warp_sum(l_part[i]);
+      float* sbuf = red + 2 * (4 * GMAX);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < GMAX; ++i) sbuf[q4 * GMAX + i] = lsum[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      DA_WAIT(o_final, n_q & 1);
+      ++n_q;
+      tc_fence_after();
+      uint32_t orow[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(orow[0]), "=r"(orow[1]), "=r"(orow[2]), "=r"(orow[3]), "=r"(orow[4]), "=r"(orow[5]), "=r"(orow[6]), "=r"(orow[7]),
+                     "=r"(orow[8]), "=r"(orow[9]), "=r"(orow[10]), "=r"(orow[11]), "=r"(orow[12]), "=r"(orow[13]), "=r"(orow[14]), "=r"(orow[15])
+                   : "r"(tmem_O + lane_addr) : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);        // O^T sits in registers: the next item may overwrite the accumulator
+#pragma unroll
+      for (int i = 0; i < GMAX; ++i) {
+        if (i < G) {
+          const float l = sbuf[i] + sbuf[GMAX + i] + sbuf[2 * GMAX + i] + sbuf[3 * GMAX + i];
+          const float inv_l = l > 0.f ? 1.f / l : 0.f;
+          const float o = __uint_as_float(orow[i]) * inv_l;
+          const int head = it.kvh * G + i;
+          if (p.num_splits == 1) {
+            p.out[((size_t)it.b * p.Hq + head) * DA_D + row] = __float2bfloat16(o);
+            if (p.lse && row == 0) p.lse[(size_t)it.b * p.Hq + head] = l > 0.f ? (m_run[i] + log2f(l)) * 0.6931471805599453f : -INFINITY;
+          } else {
+            const size_t r = ((size_t)it.split * p.B + it.b) * p.Hq + head;
+            p.part_o[r * DA_D + row] = o;
+            if (row == 0) p.part_lse[r] = l > 0.f ? (m_run[i] + log2f(l)) * 0.6931471805599453f : -INFINITY;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // sbuf is reused by the next item's epilogue
+    }
+  }
+#undef DA_WAIT
+#undef DA_DBG
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(p.sched + 1, 1);
+    if (done == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
+  }
+}
+
+// defined in attention_tc.cu
+__global__ void attn_merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ out,
+                                         float* __restrict__ lse_out, int rows, int num_splits);
+
+bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size) {
+  if (D != DA_D || Hkv <= 0 || Hq % Hkv) return false;
+  const int G = Hq / Hkv;
+  return G >= 1 && G <= 16 && page_size >= 8 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
+}
+
+void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o, float* part_lse,
+                    const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens, int B, int q_stride, int Hq, int Hkv,
+                    int D, int num_slots, int page_size, int num_splits, float scale, int window, float logit_cap, int* sched, int num_sms,
+                    cudaStream_t stream) {
+  if (!attn_decode_tc_supported(Hq, Hkv, D, page_size)) throw std::runtime_error("sglb attn_decode_tc: unsupported shape");
+  if (sched == nullptr) throw std::runtime_error("sglb attn_decode_tc: needs the work-queue counters");
+  const int G = Hq / Hkv;
+  // Q viewed as [T][Hkv][G][D]; one box = the G query rows of one (token, kv head), one 64-wide d half
+  uint64_t dq[4] = {(uint64_t)D, (uint64_t)G, (uint64_t)Hkv, (uint64_t)B};
+  uint64_t sq[3] = {(uint64_t)D * 2, (uint64_t)G * D * 2, (uint64_t)q_stride * 2};
+  uint32_t bq[4] = {64, (uint32_t)G, 1, 1};
+  CUtensorMap tmQ = make_tmap(q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t dk[3] = {(uint64_t)D, (uint64_t)Hkv, (uint64_t)num_slots};
+  uint64_t sk[2] = {(uint64_t)D * 2, (uint64_t)Hkv * D * 2};
+  uint32_t bk[3] = {64, 1, (uint32_t)page_size};
+  CUtensorMap tmK = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
+  DecodeParams p;
+  p.out = (__nv_bfloat16*)out; p.part_o = part_o; p.part_lse = part_lse; p.lse = lse;
+  p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens;
+  p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.B = B;
+  p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.window = window;
+  p.total_items = B * Hkv * num_splits; p.sched = sched;
+  const int ctas = std::min(p.total_items, num_sms);
+  const bool capped = logit_cap > 0.f;
+#define SGLB_DA_LAUNCH(GM_, CAP_)                                                                                                    \
+  do {                                                                                                                              \
+    static bool configured = false;                                                                                                 \
+    if (!configured) {                                                                                                              \
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<GM_, CAP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES)); \
+      configured = true;                                                                                                            \
+    }                                                                                                                               \
+    attn_decode_kernel<GM_, CAP_><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                                   \
+  } while (0)
+  if (G <= 4) { if (capped) SGLB_DA_LAUNCH(4, true); else SGLB_DA_LAUNCH(4, false); }
+  else if (G <= 8) { if (capped) SGLB_DA_LAUNCH(8, true); else SGLB_DA_LAUNCH(8, false); }
+  else { if (capped) SGLB_DA_LAUNCH(16, true); else SGLB_DA_LAUNCH(16, false); }
+#undef SGLB_DA_LAUNCH
+  SGLB_CUDA_CHECK(cudaGetLastError());
+  if (num_splits > 1) {
+    const int rows = B * Hq;
+    attn_merge_splits_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(part_o, part_lse, (__nv_bfloat16*)out, lse, rows, num_splits);
+    SGLB_CUDA_CHECK(cudaGetLastError());
+  }
+}
+
+}  // namespace sglb

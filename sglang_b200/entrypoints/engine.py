@@ -638,8 +638,13 @@ class Engine:
             os.makedirs(folder, exist_ok=True)
             sch = self.scheduler
             reqs = []
-            for where, lst in (("running", sch.running_batch.reqs), ("waiting", sch.waiting_queue)):
+            live = sch.live_reqs()          # running + chunked + the just-run prefill batch + waiting requests that hold KV
+            seen = set()
+            for where, lst in (("running", live), ("waiting", sch.waiting_queue), ("grammar", sch.grammar_queue)):
                 for r in lst:
+                    if id(r) in seen or r.finished():
+                        continue
+                    seen.add(id(r))
                     reqs.append({"rid": r.rid, "state": where, "input_ids": list(r.origin_input_ids), "output_ids": list(r.output_ids),
                                  "sampling_params": getattr(r.sampling_params, "__dict__", {}), "kv_len": int(r.kv_len),
                                  "retractions": int(r.retraction_count)})

@@ -138,6 +138,7 @@ class ModelRunner:
         self.load_time = time.perf_counter() - t0
         self.weight_bytes = sum(p.numel() * p.element_size() for p in self.model.parameters())
         self.stream = torch.cuda.Stream(self.device) if self.is_cuda else None
+        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.is_cuda else 1
         self.kv_manager = None
         self._init_memory()
         self.packer = BatchPacker(self.device)
@@ -394,10 +395,11 @@ class ModelRunner:
             return 1
         kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads
         ctas = bs * kvh
-        tiles = (max_kv + 127) // 128
-        if ctas >= 148 or tiles <= 2:
+        tiles = (max_kv + 127) // 128            # the decode kernel works on 128-key tiles, one persistent CTA per SM
+        sms = self.num_sms
+        if ctas >= sms or tiles <= 2:
             return 1
-        return int(max(1, min(tiles, 8, (148 * 2) // max(1, ctas))))
+        return int(max(1, min(tiles, 8, (sms * 2) // max(1, ctas))))
 
     # ------------------------------------------------------------------ forward
     def forward_batch_generation(self, sb: ScheduleBatch) -> BatchResult:

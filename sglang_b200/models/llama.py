@@ -17,7 +17,7 @@ from ..configs.model_config import ModelConfig
 from ..layers.common import RadixAttention, RMSNorm, RotaryEmbedding, get_act_and_mul
 from ..layers.linear import (MergedColumnParallelLinear, ParallelLMHead, QKVParallelLinear, RowParallelLinear,
                              VocabParallelEmbedding, _skinny_allowed)
-from ..layers.quantization import get_quant_method
+from ..layers.quantization import UnquantizedMethod, get_quant_method
 from ..model_executor.forward_batch import ForwardBatch
 from ..environ import envs
 from ..layers.dp_attention import get_dp_ctx
@@ -49,7 +49,12 @@ class LlamaMLP(nn.Module):
         return super().__new__(cls)
 
     def forward(self, x):
-        if self.fuse_silu and x.dim() == 2 and _skinny_allowed(self.gate_up_proj, x):
+        gu = self.gate_up_proj
+        if (self.fuse_silu and x.dim() == 2 and getattr(gu, "fast_path_ok", True) and isinstance(gu.quant, UnquantizedMethod)
+                and ops.gemm_impl() != "lib" and ops.streamk_ok(x, gu.weight) and gu.weight.shape[0] % 16 == 0):
+            # decode shapes: ONE persistent stream-K tcgen05 kernel for gate_up_proj + SiLU*mul (tiles pair 64 gate rows with their up rows)
+            h = ops.gemm_streamk(x, gu.weight, silu_split=True)
+        elif self.fuse_silu and x.dim() == 2 and _skinny_allowed(self.gate_up_proj, x):
             # decode shapes: ONE tcgen05 kernel for gate_up_proj + SiLU*mul ([gate; up] rows paired inside each tile)
             h = ops.gemm_skinny(x, self.gate_up_proj.weight, silu_split=True)
         else:

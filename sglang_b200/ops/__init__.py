@@ -179,6 +179,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [T,K] @ w[N,K]^T.  impl: 'tc' = our tcgen05 GEMM, 'lib' = cuBLASLt (plain library GEMM)."""
     impl = impl or gemm_impl()
+    if impl != "lib" and streamk_ok(x, w) and (out is None or (out.dim() == 2 and out.stride(1) == 1 and out.stride(0) % 8 == 0
+                                                                 and out.data_ptr() % 16 == 0)):
+        # decode shapes: persistent stream-K weight streaming (gemm_streamk.cu) — also writes straight into an NVL arena slot (``out``)
+        return gemm_streamk(x, w, bias, out=out)
     if impl in ("tc", "auto") and _use_native(x) and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 \
             and x.dim() == 2 and x.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and x.stride(0) % 8 == 0 and x.stride(1) == 1 \
             and impl == "tc":
@@ -223,6 +227,14 @@ def gemm_skinny(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
         out = torch.empty(x.shape[0], n_out, dtype=x.dtype, device=x.device)
     torch.ops.sglb.gemm_skinny(x, w, out, bias, EPI_SILU_SPLIT if silu_split else (EPI_BIAS if bias is not None else EPI_NONE), 1)
     return out
+
+
+def streamk_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """shape / layout policy of the stream-K decode GEMM (``SGLB_STREAMK_MAX_M`` tokens at most, bf16, TMA-compatible strides)"""
+    mx = envs.SGLB_STREAMK_MAX_M.get()
+    return (mx > 0 and x.is_cuda and x.dim() == 2 and 0 < x.shape[0] <= min(mx, 256) and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+            and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1 and x.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and x.shape[1] % 8 == 0
+            and w.shape[0] % 8 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and _use_native(x))
 
 
 def gemm_streamk(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, silu_split: bool = False,

@@ -169,6 +169,55 @@ def case_attn_tc_persist():
     assert torch.equal(a, a2)
 
 
+def case_attn_decode_v3():
+    """keys-as-M decode kernel (attention_decode.cu): every GQA group bucket, page sizes, page-granular tail fetch around the 128-key tile
+    edge, split-KV with empty splits, sliding window, soft-cap, LSE output, queue re-arm across launches, CUDA-graph replay"""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    for (Hq, Hkv) in [(32, 8), (8, 8), (16, 2), (16, 1), (28, 4), (4, 1), (8, 2)]:
+        lens = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 700, 1025]
+        _attn_check(0, len(lens), [1] * len(lens), lens, Hq=Hq, Hkv=Hkv, decode=True, name=f"v3 Hq{Hq}/Hkv{Hkv} edges")
+    for ps in (16, 32, 64, 128):
+        lens = rng.integers(1, 1500, 37).tolist()
+        _attn_check(0, 37, [1] * 37, lens, decode=True, ps=ps, name=f"v3 ps{ps}")
+    _attn_check(0, 500, [1] * 500, rng.integers(1, 900, 500).tolist(), decode=True, name="v3 x500 (4000 items, queue)")
+    _attn_check(0, 3, [1] * 3, [2000, 130, 5], decode=True, splits=4, name="v3 split4 (empty splits)")
+    _attn_check(0, 70, [1] * 70, rng.integers(1, 3000, 70).tolist(), decode=True, splits=8, name="v3 split8")
+    _attn_check(0, 9, [1] * 9, [5, 100, 128, 129, 300, 511, 512, 513, 2000], decode=True, window=128, name="v3 window 128")
+    _attn_check(0, 6, [1] * 6, [900, 300, 64, 1, 257, 130], decode=True, window=200, splits=2, name="v3 window + split")
+    _attn_check(0, 40, [1] * 40, rng.integers(1, 600, 40).tolist(), decode=True, ps=16, cap=30.0, name="v3 softcap")
+    # LSE output (decode CP / cascade consumers) against the reference
+    lens = [3, 64, 129, 700]
+    s = _attn_setup(4, [1] * 4, lens, 32, 8, 128, 32)
+    lse = torch.empty(4, 32, device=DEV, dtype=torch.float32)
+    out = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, lse=lse, impl=0)
+    ref, ref_lse = torch_ref.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, 32, 128 ** -0.5, True, -1, 0.0,
+                                             return_lse=True)
+    torch.cuda.synchronize()
+    _close(out, ref, 2e-2, 3e-2, "v3 lse out"); _close(lse, ref_lse, 2e-2, 1e-2, "v3 lse")
+    # repeated launches + graph replay reuse the work-queue counters
+    lens = rng.integers(1, 900, 300).tolist()
+    s = _attn_setup(300, [1] * 300, lens, 32, 8, 128, 32)
+    ref = torch_ref.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, 32, 128 ** -0.5, True, -1, 0.0)
+    out = torch.empty_like(s["q"])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, out=out, impl=0)
+    torch.cuda.synchronize()
+    first = out.clone()
+    _close(first, ref, 2e-2, 3e-2, "v3 relaunch")
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], None, None, 1, 32, 128 ** -0.5, out=out, impl=0)
+    for _ in range(4):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, first), "v3: graph replay differs from the eager launch"
+
+
 def case_attn_tc_window():
     _attn_check(0, 2, [60, 1], [400, 300], window=128, name="sliding window")
     _attn_check(0, 1, [33], [200], cap=30.0, name="logit cap")

@@ -92,11 +92,13 @@ def test_weights_checker_slow_down_trace_level_and_crash_dump(tmp_path):
         assert time.perf_counter() - t0 > 0.15                    # prefill + decode steps each slept
         c.post("/slow_down", json={})
         assert c.post("/set_trace_level", json={"level": 2}).json() == {"success": True, "level": 2}
-    # crash dump: in-flight + waiting requests land in a JSON file
+    # crash dump: in-flight + waiting requests land in a JSON file (the background loop is paused so it cannot finish the request first)
+    eng.scheduler.paused = True
     eng.scheduler.handle_request(eng._tokenize(sgl.managers.io_struct.GenerateReqInput(input_ids=[1, 2, 3], sampling_params={"max_new_tokens": 4}).normalize()[0]))
     path = eng.dump_requests_before_crash()
     d = json.load(open(path))
-    assert d["requests"] and d["requests"][0]["input_ids"] == [1, 2, 3] and "server_args" in d
+    assert [r["input_ids"] for r in d["requests"]] == [[1, 2, 3]] and d["requests"][0]["state"] == "waiting" and "server_args" in d
+    eng.scheduler.paused = False
     eng.shutdown()
 
 
