@@ -237,6 +237,10 @@ def main() -> None:
     c0, g0 = ops.launch_count(), eng.runner.graph_launches
     h0, d0 = eng.runner.h2d_bytes, eng.runner.d2h_bytes
     f0 = eng.runner.forward_ct
+    from sglang_b200.model_executor.model_runner import BatchResult
+
+    w0, sw0, sc0 = BatchResult.wait_s, eng.scheduler.step_wall_s, eng.scheduler.step_calls
+    t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for k in range(args.steps):
@@ -244,6 +248,13 @@ def main() -> None:
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    wall_ms = 1000.0 * (time.perf_counter() - t_wall0)
+    n_sched = max(1, eng.scheduler.step_calls - sc0)
+    # where a scheduler iteration goes: host = Python time inside Scheduler.step() that was NOT spent blocked on a CUDA event; the device side is
+    # the whole timed region / forward steps (graph replays back to back: a gap shows up as device_ms_per_step > the kernels' own time)
+    host_split = {"scheduler_iterations": n_sched, "host_ms_per_iteration": 1000.0 * ((eng.scheduler.step_wall_s - sw0) - (BatchResult.wait_s - w0)) / n_sched,
+                  "blocked_on_device_ms_per_iteration": 1000.0 * (BatchResult.wait_s - w0) / n_sched,
+                  "outside_scheduler_ms_per_iteration": (wall_ms - 1000.0 * (eng.scheduler.step_wall_s - sw0)) / n_sched}
     launches = (ops.launch_count() - c0) + (eng.runner.graph_launches - g0)
     fwd = eng.runner.forward_ct - f0
     h2d = (eng.runner.h2d_bytes - h0) / max(1, fwd)
@@ -287,7 +298,8 @@ def main() -> None:
             "p50_ttft_ms": 1000.0 * statistics.median(ttfts) if ttfts else None,
             "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "text prompts -> tokenizer -> engine -> detokenizer -> text; bytes are per engine forward step"},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "impl": "ours"}))
+            "gpu_launches": int(launches), "step_split": {**host_split, "device_ms_per_forward": dev_ms / max(1, fwd), "forward_steps": int(fwd)},
+            "clocks": sampler.summary(), "impl": "ours"}))
     eng.shutdown()
     sys.stdout.flush()
     if world > 1:

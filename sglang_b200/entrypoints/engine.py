@@ -42,7 +42,7 @@ logger = logging.getLogger(__name__)
 
 class ReqState:
     __slots__ = ("rid", "text", "output_ids", "finished", "meta", "out_q", "created", "first_token_time", "obj", "logprobs",
-                 "input_logprobs", "top_logprobs", "embedding", "hidden_states", "last_emit")
+                 "input_logprobs", "top_logprobs", "embedding", "hidden_states", "last_emit", "done")
 
     def __init__(self, rid: str, obj: Any, stream_q: Optional[Any]):
         self.rid, self.obj, self.out_q = rid, obj, stream_q
@@ -58,6 +58,7 @@ class ReqState:
         self.embedding = None
         self.hidden_states = None
         self.last_emit = 0
+        self.done = threading.Event()      # set when the final output has been applied (multi-process front end waits on it)
 
     def result(self) -> Dict[str, Any]:
         out = {"text": self.text, "output_ids": list(self.output_ids), "meta_info": dict(self.meta)}
@@ -209,12 +210,17 @@ class Engine:
             stt.meta["dp_rank"] = owner
             if owner != self._dp_rank:
                 return stt                              # another attention group serves it; rank 0 still tracks its state
+        self._dispatch(t)
+        return stt
+
+    def _dispatch(self, t: ios.TokenizedGenerateReqInput) -> None:
+        """hand a tokenised request to the scheduler: its inbox (background loop), a direct call (offline), or — in the multi-process front
+        end (managers/multiprocess.py) — a ZMQ frame"""
         if self._bg_thread is not None:
             self._inbox.put(t)
             self._wake.set()
         else:
             self.scheduler.handle_request(t)
-        return stt
 
     # ================================================================== output path
     def _any_rank_has_work(self) -> bool:
@@ -266,6 +272,10 @@ class Engine:
             output_logprobs=msg.output_logprobs, input_logprobs=msg.input_logprobs, top_logprobs=msg.top_logprobs,
             spec_verify_ct=msg.spec_verify_ct, spec_accepted_tokens=msg.spec_accepted_tokens, embeddings=msg.embeddings,
             hidden_states=msg.hidden_states, ttfts=msg.ttfts, queue_times=msg.queue_times)
+        self._apply_output(out)
+
+    def _apply_output(self, out: ios.BatchStrOutput) -> None:
+        """fold one detokenised batch into the request states and wake their waiters (called in-process, or by the front end's receive thread)"""
         now = time.perf_counter()
         for i, rid in enumerate(out.rids):
             st = self.states.get(rid)
@@ -314,6 +324,7 @@ class Engine:
             if st.finished:
                 with self._lock:
                     self.states.pop(rid, None)
+                st.done.set()
 
     # ================================================================== public API
     def generate(self, prompt: Optional[Union[str, List[str]]] = None, sampling_params: Optional[Union[Dict, List[Dict]]] = None,

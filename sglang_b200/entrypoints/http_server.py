@@ -371,11 +371,8 @@ def _peer_main(args: ServerArgs, rank: int, world: int, master_port: int, master
     eng._bg_thread.join()
 
 
-def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) -> None:
-    import uvicorn
-
-    from .engine import Engine
-
+def spawn_peers(server_args: ServerArgs) -> list:
+    """start this node's TP x PP ranks > 0 as worker processes and export RANK / MASTER_* for the calling (first local) rank"""
     world = server_args.tp_size * server_args.pp_size
     peers = []
     if world > 1 and "RANK" not in os.environ:
@@ -399,11 +396,34 @@ def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) ->
             p.start()
             peers.append(p)
         os.environ.update(RANK=str(first), LOCAL_RANK="0", WORLD_SIZE=str(world), MASTER_ADDR=addr, MASTER_PORT=str(port))
+    return peers
+
+
+def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) -> None:
+    import uvicorn
+
+    from .engine import Engine
+
+    if server_args.enable_multi_process_frontend and "RANK" not in os.environ and not os.environ.get("SGLB_IN_SCHEDULER_PROCESS"):
+        # this process keeps HTTP + tokenizer + request states; the scheduler (and through it the TP x PP peers) and the detokenizer run in
+        # their own processes (reference engine.py:905 _launch_subprocesses)
+        from ..managers.multiprocess import FrontendEngine
+
+        engine = FrontendEngine(server_args)
+        _serve(engine, server_args, ready_event, [])
+        return
+    peers = spawn_peers(server_args)
     engine = Engine(server_args=server_args)
     engine.start_background_loop()
     if int(os.environ.get("RANK", 0)) != 0:
         engine._bg_thread.join()
         return
+    _serve(engine, server_args, ready_event, peers)
+
+
+def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], peers: list) -> None:
+    import uvicorn
+
     app = create_app(engine)
 
     @app.on_event("startup")

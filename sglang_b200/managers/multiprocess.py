@@ -1,0 +1,332 @@
+"""Multi-process serving topology: front end (HTTP + tokenizer + request states) | scheduler process(es) | detokenizer process.
+
+Parity: reference ``python/sglang/srt/entrypoints/engine.py:905-1003`` (``_launch_subprocesses``: scheduler procs + detokenizer proc +
+TokenizerManager in the main process, wired with ZMQ), ``managers/tokenizer_manager.py:386,765`` and ``managers/detokenizer_manager.py``.
+
+Why it exists here: the default topology keeps one process per GPU (tokenizer, detokenizer, request states and the scheduler loop share it —
+zero IPC for the offline ``Engine``).  Behind an HTTP server that means FastAPI handlers, tokenisation, detokenisation and SSE serialisation
+all contend for the scheduler thread's GIL.  ``--enable-multi-process-frontend`` moves everything that is not scheduling out of that process:
+
+    front end (this process)  --PUSH tokenised requests-->  scheduler process (rank 0; spawns / drives its TP x PP peers as before)
+          ^                                                      |
+          |                                                      +--PUSH BatchTokenIDOutput-->  detokenizer process
+          +----------------PULL BatchStrOutput--------------------------------------------------------+
+    control RPCs: front end DEALER <-> scheduler ROUTER (request id correlated, any number in flight)
+
+Messages are the tagged msgpack frames of ``managers/io_struct.py`` (no pickles on the wire); sockets are ``ipc://`` files in a private
+temp dir.  ``FrontendEngine`` subclasses ``Engine`` and overrides exactly the three seams that touch the scheduler (``_submit``,
+``_control`` and the drive loop), so every public method, the OpenAI layer and the adapters work unchanged on top of it.
+"""
+from __future__ import annotations
+
+import itertools
+import logging
+import multiprocessing as mp
+import os
+import queue
+import tempfile
+import threading
+import time
+from typing import Any, Dict, List, Optional
+
+from . import io_struct as ios
+from ..server_args import ServerArgs
+
+logger = logging.getLogger(__name__)
+
+
+def _ipc_names() -> Dict[str, str]:
+    d = tempfile.mkdtemp(prefix="sglb-ipc-")
+    return {k: f"ipc://{d}/{k}" for k in ("req", "tok", "str", "ctl")}
+
+
+# ------------------------------------------------------------------------------------------------------------------ scheduler process
+def scheduler_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready: Any) -> None:
+    """rank-0 scheduler process: a regular ``Engine`` (it spawns / joins its TP x PP peers exactly as the single-process server does)
+    whose input comes from ZMQ and whose token-id outputs go to the detokenizer process"""
+    import zmq
+
+    from ..entrypoints.engine import Engine
+
+    try:
+        os.environ["SGLB_IN_SCHEDULER_PROCESS"] = "1"
+        from ..entrypoints.http_server import spawn_peers
+
+        peers = spawn_peers(server_args)      # TP x PP ranks > 0 (sets RANK / MASTER_* for this process when world > 1)
+        eng = Engine(server_args=server_args)
+        ctx = zmq.Context(2)
+        s_req = ctx.socket(zmq.PULL); s_req.bind(ipc["req"])
+        s_tok = ctx.socket(zmq.PUSH); s_tok.connect(ipc["tok"])
+        s_ctl = ctx.socket(zmq.ROUTER); s_ctl.bind(ipc["ctl"])
+        send_lock = threading.Lock()
+
+        def forward(msg: ios.BatchTokenIDOutput, relayed: bool = False) -> None:
+            s_tok.send(ios.encode(msg))      # called from the scheduler thread only
+
+        eng.scheduler.send_to_detokenizer = forward      # raw token ids leave the process; text is made elsewhere
+        eng.start_background_loop()
+        ready.put({"ok": True, "memory": eng.runner.get_memory_info(), "max_context_len": eng.scheduler.max_context_len,
+                   "weight_bytes": int(eng.runner.weight_bytes)})
+    except Exception as e:      # noqa: BLE001
+        logger.exception("scheduler process failed to start")
+        ready.put({"ok": False, "error": f"{type(e).__name__}: {e}"})
+        return
+
+    def run_ctl(ident: bytes, cid: bytes, msg: Any) -> None:
+        try:
+            rep = eng._control(msg)
+        except Exception as e:      # noqa: BLE001
+            rep = ios.GenericResp(False, f"{type(e).__name__}: {e}")
+        with send_lock:
+            s_ctl.send_multipart([ident, cid, ios.encode(rep)])
+
+    poller = zmq.Poller()
+    poller.register(s_req, zmq.POLLIN)
+    poller.register(s_ctl, zmq.POLLIN)
+    while True:
+        for sock, _ in poller.poll(1000):
+            if sock is s_req:
+                while True:
+                    try:
+                        buf = s_req.recv(zmq.NOBLOCK)
+                    except zmq.Again:
+                        break
+                    eng._inbox.put(ios.decode(buf))
+                eng._wake.set()
+            else:
+                ident, cid, buf = s_ctl.recv_multipart()
+                msg = ios.decode(buf)
+                if isinstance(msg, ios.ShutdownReq):
+                    with send_lock:
+                        s_ctl.send_multipart([ident, cid, ios.encode(ios.GenericResp(True, "bye"))])
+                    s_tok.send(ios.encode(ios.ShutdownReq()))      # the detokenizer leaves too
+                    eng.shutdown()
+                    for p in peers:
+                        p.terminate()
+                    return
+                # control messages may block (drain, weight load): never stall the request socket behind them
+                threading.Thread(target=run_ctl, args=(ident, cid, msg), daemon=True).start()
+        if eng._bg_thread is not None and not eng._bg_thread.is_alive():
+            logger.error("scheduler loop died; leaving the scheduler process")
+            return
+
+
+# ------------------------------------------------------------------------------------------------------------------ detokenizer process
+def detokenizer_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready: Any) -> None:
+    import zmq
+
+    from ..configs.model_config import load_model_config
+    from ..utils.tokenizer import get_tokenizer
+    from .detokenizer import Detokenizer
+
+    try:
+        cfg = load_model_config(server_args.model_path, None, server_args.context_length)
+        tok = get_tokenizer(server_args.tokenizer_path, cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id, server_args.trust_remote_code)
+        detok = Detokenizer(tok)
+        ctx = zmq.Context(1)
+        s_tok = ctx.socket(zmq.PULL); s_tok.bind(ipc["tok"])
+        s_str = ctx.socket(zmq.PUSH); s_str.connect(ipc["str"])
+        ready.put({"ok": True})
+    except Exception as e:      # noqa: BLE001
+        ready.put({"ok": False, "error": f"{type(e).__name__}: {e}"})
+        return
+    while True:
+        msg = ios.decode(s_tok.recv())
+        if isinstance(msg, ios.ShutdownReq):
+            return
+        s_str.send(ios.encode(detok.process(msg)))
+
+
+# ------------------------------------------------------------------------------------------------------------------ front end
+class _Sentinel:
+    """stands in for the scheduler thread object: the base class only asks ``is not None``"""
+
+    def join(self, timeout: Optional[float] = None) -> None:
+        pass
+
+    def is_alive(self) -> bool:
+        return True
+
+
+class FrontendEngine:
+    """Factory: builds an ``Engine`` subclass instance whose scheduler lives in another process"""
+
+    def __new__(cls, server_args: Optional[ServerArgs] = None, **kwargs: Any):
+        from ..entrypoints.engine import Engine
+
+        class _Frontend(Engine):
+            def __init__(self, a: ServerArgs):
+                import zmq
+
+                from ..configs.model_config import load_model_config
+                from ..utils.tokenizer import get_tokenizer
+
+                self.server_args = a
+                logging.basicConfig(level=getattr(logging, a.log_level.upper(), logging.INFO), format="[%(asctime)s %(name)s] %(message)s")
+                self.model_config = load_model_config(a.model_path, __import__("json").loads(a.json_model_override_args or "{}") or None,
+                                                      a.context_length)
+                self.tokenizer = None if a.skip_tokenizer_init else get_tokenizer(
+                    a.tokenizer_path, self.model_config.vocab_size, self.model_config.eos_token_id, self.model_config.bos_token_id,
+                    a.trust_remote_code)
+                self.detok = None
+                self.is_driver, self.tp_rank, self.pp_rank = True, 0, 0
+                self._dp, self._dp_rank, self._dp_ctr = 1, 0, 0
+                self._relay_src, self._relay_buf = None, []
+                self._world = _SoloWorld()
+                self.states: Dict[str, Any] = {}
+                self._lock = threading.RLock()
+                self._inbox = queue.Queue()
+                self._bg_stop, self._wake = threading.Event(), threading.Event()
+                self._bg_thread = _Sentinel()
+                self.metrics = None
+                if a.enable_metrics:
+                    from ..observability.metrics import MetricsCollector
+
+                    self.metrics = MetricsCollector(a.served_model_name)
+                self.weight_version = "default"
+                self.start_time = time.time()
+                self.runner = _RunnerView(self)
+                self.scheduler = _SchedulerView(self)
+                # ---- processes and sockets
+                self._ipc = _ipc_names()
+                spawn = mp.get_context("spawn")
+                rq_s, rq_d = spawn.Queue(), spawn.Queue()
+                self._ctx = zmq.Context(2)
+                self._s_str = self._ctx.socket(zmq.PULL); self._s_str.bind(self._ipc["str"])
+                self._p_detok = spawn.Process(target=detokenizer_process_main, args=(a, self._ipc, rq_d), daemon=True, name="sglb-detokenizer")
+                self._p_detok.start()
+                r = rq_d.get(timeout=600)
+                if not r.get("ok"):
+                    raise RuntimeError(f"detokenizer process failed: {r.get('error')}")
+                self._p_sched = spawn.Process(target=scheduler_process_main, args=(a, self._ipc, rq_s), daemon=False, name="sglb-scheduler")
+                self._p_sched.start()
+                r = rq_s.get(timeout=3600)
+                if not r.get("ok"):
+                    raise RuntimeError(f"scheduler process failed: {r.get('error')}")
+                self._sched_info = r
+                self._s_req = self._ctx.socket(zmq.PUSH); self._s_req.connect(self._ipc["req"])
+                self._s_ctl = self._ctx.socket(zmq.DEALER); self._s_ctl.connect(self._ipc["ctl"])
+                self._req_lock, self._ctl_lock = threading.Lock(), threading.Lock()
+                self._ctl_ids = itertools.count(1)
+                self._ctl_wait: Dict[bytes, "queue.Queue[Any]"] = {}
+                self._closed = False
+                threading.Thread(target=self._recv_outputs, daemon=True, name="sglb-front-out").start()
+                threading.Thread(target=self._recv_ctl, daemon=True, name="sglb-front-ctl").start()
+
+            # ---- seams
+            def _dispatch(self, t: ios.TokenizedGenerateReqInput) -> None:
+                with self._req_lock:
+                    self._s_req.send(ios.encode(t))
+
+            def _control(self, msg: Any) -> Any:
+                cid = str(next(self._ctl_ids)).encode()
+                box: "queue.Queue[Any]" = queue.Queue()
+                self._ctl_wait[cid] = box
+                with self._ctl_lock:
+                    self._s_ctl.send_multipart([cid, ios.encode(msg)])
+                rep = box.get()
+                self._ctl_wait.pop(cid, None)
+                return rep
+
+            def _recv_ctl(self) -> None:
+                import zmq
+
+                while not self._closed:
+                    try:
+                        if not self._s_ctl.poll(500):
+                            continue
+                        cid, buf = self._s_ctl.recv_multipart()
+                    except zmq.ZMQError:
+                        return
+                    box = self._ctl_wait.get(cid)
+                    if box is not None:
+                        box.put(ios.decode(buf))
+
+            def _recv_outputs(self) -> None:
+                import zmq
+
+                while not self._closed:
+                    try:
+                        if not self._s_str.poll(500):
+                            continue
+                        out = ios.decode(self._s_str.recv())
+                    except zmq.ZMQError:
+                        return
+                    try:
+                        self._apply_output(out)
+                    except Exception:      # noqa: BLE001
+                        logger.exception("applying a detokenizer batch failed")
+
+            def start_background_loop(self) -> None:
+                pass
+
+            def _drive(self, states: List[Any]) -> None:
+                for st in states:
+                    st.done.wait()
+
+            def dump_requests_before_crash(self) -> Optional[str]:
+                return None
+
+            def shutdown(self) -> None:
+                if self._closed:
+                    return
+                try:
+                    self._control(ios.ShutdownReq())
+                except Exception:      # noqa: BLE001
+                    pass
+                self._closed = True
+                for p in (self._p_sched, self._p_detok):
+                    p.join(timeout=10)
+                    if p.is_alive():
+                        p.terminate()
+                        p.join(timeout=5)
+                self._ctx.destroy(linger=0)
+
+        return _Frontend(server_args or ServerArgs(**kwargs))
+
+
+class _SoloWorld:
+    """the front end is not a rank of the model-parallel world"""
+
+    world_size = 1
+
+
+class _RunnerView:
+    """the runner facts the API layer reports (sizes), taken from the scheduler process's start-up hand-shake"""
+
+    def __init__(self, front: Any):
+        self._f = front
+        self.model = None
+        self.lora_manager = None
+
+    @property
+    def weight_bytes(self) -> int:
+        return int(self._f._sched_info["weight_bytes"])
+
+    @property
+    def max_context_len(self) -> int:
+        return int(self._f._sched_info["max_context_len"])
+
+    def get_memory_info(self) -> Dict[str, int]:
+        return dict(self._f._sched_info["memory"])
+
+
+class _SchedulerView:
+    """the few scheduler attributes the HTTP layer reads, answered over the control channel"""
+
+    def __init__(self, front: Any):
+        self._f = front
+
+    @property
+    def max_context_len(self) -> int:
+        return int(self._f._sched_info["max_context_len"])
+
+    def get_internal_state(self) -> Dict[str, Any]:
+        return self._f._control(ios.GetInternalStateReq()).state
+
+    def has_work(self) -> bool:
+        return bool(self._f.states)
+
+    @property
+    def tree(self) -> Any:
+        raise AttributeError("the radix tree lives in the scheduler process (use /get_server_info or the KV-event stream)")

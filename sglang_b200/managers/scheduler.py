@@ -63,6 +63,8 @@ class Scheduler:
         self.running_batch = ScheduleBatch(reqs=[], forward_mode=ForwardMode.DECODE)
         self.running_batch.init_decode_state()
         self.last_batch: Optional[ScheduleBatch] = None
+        self.step_wall_s = 0.0
+        self.step_calls = 0
         self.chunked_req: Optional[Req] = None
         self.pending: Deque[Tuple[ScheduleBatch, Any]] = deque()
         self.enable_overlap = not server_args.disable_overlap_schedule and worker.supports_overlap()
@@ -715,6 +717,14 @@ class Scheduler:
     # ================================================================== loops
     def step(self) -> bool:
         """One scheduler iteration.  Returns False when there is nothing to do."""
+        t0 = time.perf_counter()
+        try:
+            return self._step()
+        finally:
+            self.step_wall_s += time.perf_counter() - t0      # minus BatchResult.wait_s = pure host time (bench.py reports the split)
+            self.step_calls += 1
+
+    def _step(self) -> bool:
         batch = self.get_next_batch_to_run()
         if batch is None and self.args.enable_dp_attention:
             self.drain()

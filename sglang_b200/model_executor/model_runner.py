@@ -57,6 +57,8 @@ class _null_ctx:
 class BatchResult:
     """Asynchronous result of one step; ``wait()`` blocks until the device->host copy has landed."""
 
+    wait_s = 0.0      # class-wide: seconds the host spent blocked in event.synchronize()
+
     def __init__(self) -> None:
         self.event: Optional[torch.cuda.Event] = None
         self._tok_host: Optional[torch.Tensor] = None
@@ -77,7 +79,9 @@ class BatchResult:
         if self.next_token_ids is not None or self._tok_host is None:
             return
         if self.event is not None:
+            t0 = time.perf_counter()
             self.event.synchronize()
+            BatchResult.wait_s += time.perf_counter() - t0      # host blocked on the device (accounting for bench.py's host/device split)
         toks = self._tok_host.numpy()
         out = np.full(self.batch_size, -1, dtype=np.int64)
         out[self.sample_rows] = toks[: self.sample_rows.size]

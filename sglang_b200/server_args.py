@@ -41,6 +41,7 @@ class ServerArgs:
     # --- server
     host: str = "127.0.0.1"
     port: int = 30000
+    enable_multi_process_frontend: bool = False   # HTTP + tokenizer | scheduler | detokenizer in separate processes (managers/multiprocess.py)
     api_key: Optional[str] = None
     admin_api_key: Optional[str] = None
     log_level: str = "info"
