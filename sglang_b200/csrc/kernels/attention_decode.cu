@@ -37,7 +37,7 @@ constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile:
 constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
 constexpr int DA_Q_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two d halves of [16 rows x 128 B])
 constexpr int DA_P_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two 64-key chunks of [16 rows x 128 B]), double buffered
-constexpr int DA_SMEM_BYTES = 2 * DA_STAGES * DA_TILE_BYTES + DA_Q_BYTES + 2 * DA_P_BYTES + 1024 /*align*/ + 1024 /*barriers + scratch*/;
+constexpr int DA_SMEM_BYTES = 2 * DA_STAGES * DA_TILE_BYTES + 2 * DA_Q_BYTES + 2 * DA_P_BYTES + 1024 /*align*/ + 1024 /*barriers + scratch*/;
 constexpr float DA_RESCALE_THRESHOLD = 8.0f;
 
 struct DecodeParams {
@@ -65,11 +65,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                                              // [STAGES][32 KB]
   uint8_t* sV = smem + DA_STAGES * DA_TILE_BYTES;                  // [STAGES][32 KB]
-  uint8_t* sQ = smem + 2 * DA_STAGES * DA_TILE_BYTES;              // 4 KB
-  uint8_t* sP = sQ + DA_Q_BYTES;                                   // 2 x 4 KB
+  uint8_t* sQ = smem + 2 * DA_STAGES * DA_TILE_BYTES;              // 2 x 4 KB: the next item's Q lands while the current item computes
+  uint8_t* sP = sQ + 2 * DA_Q_BYTES;                               // 2 x 4 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * DA_P_BYTES);
-  uint64_t* q_full = bars;             // Q of the item landed                       (phase = item ordinal)
-  uint64_t* q_empty = bars + 1;        // last S of the item has read Q              (phase = item ordinal)
+  uint64_t* q_full = bars;             // [2] Q of the item landed                   (slot = item ordinal & 1, phase = ordinal >> 1)
+  uint64_t* q_empty = bars + 30;       // [2] last S of the item has read Q  (bars 27..29 hold the 6 debug words)
   uint64_t* k_full = bars + 2;         // [STAGES]
   uint64_t* k_empty = bars + 5;        // [STAGES]
   uint64_t* v_full = bars + 8;         // [STAGES]
@@ -90,7 +90,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5); }
     mbar_init(o_done, 1); mbar_init(o_final, 1); mbar_init(o_free, 4);
@@ -99,7 +99,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (lane == 0) dbg[warp] = 0;
   // zero Q / P (rows >= G stay zero for the whole kernel) and the V ring (a tile's unfetched tail pages must hold finite numbers: their
   // probabilities are exactly 0, and 0 x NaN would poison O)
-  for (int i = threadIdx.x; i < (DA_Q_BYTES + 2 * DA_P_BYTES) / 16; i += DA_THREADS) reinterpret_cast<U4*>(sQ)[i] = U4{0, 0, 0, 0};
+  for (int i = threadIdx.x; i < (2 * DA_Q_BYTES + 2 * DA_P_BYTES) / 16; i += DA_THREADS) reinterpret_cast<U4*>(sQ)[i] = U4{0, 0, 0, 0};
   for (int i = threadIdx.x; i < DA_STAGES * DA_TILE_BYTES / 16; i += DA_THREADS) reinterpret_cast<U4*>(sV)[i] = U4{0, 0, 0, 0};
   fence_proxy_async_smem();
   if (warp == 1) { tmem_alloc(tmem_ptr, 64); tmem_relinquish(); }
@@ -133,10 +133,14 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------------------------------------ scheduler + TMA producer
     uint32_t n_it = 0, n_q = 0, g = 0;
     const int ps = p.page_size, pages_per_tile = DA_KT / ps;
+    int next_idx = atomicAdd(p.sched, 1);
     for (;;) {
       const int slot = n_it & 1;
       DA_WAIT(&item_empty[slot], ((n_it >> 1) & 1) ^ 1);
-      const int idx = atomicAdd(p.sched, 1);
+      // the queue atomic is a ~1 us L2 round trip: fetch the NEXT item's index now and consume it one iteration later, so the round trip
+      // overlaps this item's TMA issue instead of stalling the only thread that feeds the ring
+      const int idx = next_idx;
+      if (idx < p.total_items) next_idx = atomicAdd(p.sched, 1);
       DA_DBG(1, n_it, g);
       s_item[slot] = idx;
       mbar_arrive(&item_full[slot]);
@@ -144,11 +148,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (idx >= p.total_items) break;
       const Item it = decode_item(idx);
       if (it.n_tiles == 0) continue;
-      DA_WAIT(q_empty, (n_q & 1) ^ 1);
-      mbar_expect_tx(q_full, 2 * G * 128);
-      tma_load_4d(sQ, &tmQ, q_full, 0, 0, it.kvh, it.b);
-      tma_load_4d(sQ + DA_NQ * 128, &tmQ, q_full, 64, 0, it.kvh, it.b);
-      ++n_q;
+      {
+        const int qs = n_q & 1;
+        uint8_t* qdst = sQ + qs * DA_Q_BYTES;
+        DA_WAIT(&q_empty[qs], ((n_q >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], 2 * G * 128);
+        tma_load_4d(qdst, &tmQ, &q_full[qs], 0, 0, it.kvh, it.b);
+        tma_load_4d(qdst + DA_NQ * 128, &tmQ, &q_full[qs], 64, 0, it.kvh, it.b);
+        ++n_q;
+      }
       const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
       for (int j = 0; j < it.n_tiles; ++j, ++g) {
         const int st = g % DA_STAGES;
@@ -179,7 +187,6 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, DA_KT, DA_NQ, 0, 0);      // A = K (K-major), B = Q (K-major)
     constexpr uint32_t idesc_o = make_idesc(UMMA_BF16, UMMA_BF16, DA_D, DA_NQ, 1, 0);       // A = V^T (MN-major: d contiguous), B = P^T
-    const uint32_t q_addr = smem_u32(sQ);
     uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
@@ -191,6 +198,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const Item it = decode_item(idx);
       if (it.n_tiles == 0) continue;
       const int n_tiles = it.n_tiles;
+      const int qs = n_q & 1;
+      const uint32_t q_addr = smem_u32(sQ + qs * DA_Q_BYTES);
       DA_DBG(2, n_q, g);
       auto issue_S = [&](uint32_t gt, bool last) {
         const int st = gt % DA_STAGES;
@@ -206,9 +215,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[gt & 1]);
-        if (last) umma_commit(q_empty);
+        if (last) umma_commit(&q_empty[qs]);
       };
-      DA_WAIT(q_full, n_q & 1);
+      DA_WAIT(&q_full[qs], (n_q >> 1) & 1);
       issue_S(g, n_tiles == 1);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t gt = g + j;

@@ -264,17 +264,33 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #pragma unroll 1
           for (int tok0 = 0; tok0 < MT; tok0 += TOK) {
             if (tok0 < p.M) {
-              // 128 threads x float4 = four 512-byte token rows per step (coalesced), contributors summed in rank order
+              // 128 threads x float4 = four 512-byte token rows per step (coalesced).  All contributors' loads are issued BEFORE the first add
+              // (independent L2 round trips in flight together); the sum itself runs in contributor order -> bit-deterministic.
+              const float* base0 = p.ws + (size_t)tok0 * STK_BF;
+              size_t coff[8];
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) {
+                const int c = c_first + min(cc, n_contrib - 1);
+                const int slot = (stk_cut(U, c, G) >= lo) ? 0 : 1;   // tile t is c's first segment unless c's range starts before it
+                coff[cc] = ((size_t)c * 2 + slot) * (size_t)(STK_BF * MT);
+              }
 #pragma unroll 1
               for (int idx = et; idx < TOK * (STK_BF / 4); idx += 128) {
                 const int tok = idx / (STK_BF / 4), grp = idx % (STK_BF / 4);
+                const size_t eoff = (size_t)tok * STK_BF + grp * 4;
+                float4 v[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                  if (cc < n_contrib) v[cc] = __ldcg(reinterpret_cast<const float4*>(base0 + coff[cc] + eoff));
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int cc = 0; cc < n_contrib; ++cc) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                  if (cc < n_contrib) { acc.x += v[cc].x; acc.y += v[cc].y; acc.z += v[cc].z; acc.w += v[cc].w; }
+                for (int cc = 8; cc < n_contrib; ++cc) {            // more than 8 contributors (tiny N, huge K): plain loop
                   const int c = c_first + cc;
-                  const int slot = (stk_cut(U, c, G) >= lo) ? 0 : 1;   // tile t is c's first segment unless c's range starts before it
-                  const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)c * 2 + slot) * (size_t)(STK_BF * MT) +
-                                                                         (size_t)(tok0 + tok) * STK_BF + grp * 4));
-                  acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                  const int slot = (stk_cut(U, c, G) >= lo) ? 0 : 1;
+                  const float4 w = __ldcg(reinterpret_cast<const float4*>(base0 + ((size_t)c * 2 + slot) * (size_t)(STK_BF * MT) + eoff));
+                  acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
                 }
                 if (EPI == STK_EPI_BIAS) {
                   const int f0 = t * STK_BF + grp * 4;

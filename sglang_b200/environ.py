@@ -85,8 +85,9 @@ class _Envs:
     SGLB_ATTN_PERSIST = EnvBool("SGLB_ATTN_PERSIST", True, "persistent-CTA attention with an atomic work queue (pipelines across requests)")
     SGLB_SKINNY = EnvStr("SGLB_SKINNY", "tp", "tp|on|off: decode-shape (<=256 tokens) swap-AB split-K tcgen05 GEMM — tp: only as the fused "
                          "GEMM+all-reduce producer; on: every decode GEMM with fused consumers")
-    SGLB_STREAMK_MAX_M = EnvInt("SGLB_STREAMK_MAX_M", 256, "bf16 GEMMs with <= this many tokens run on the persistent stream-K tcgen05 kernel "
-                                "(gemm_streamk.cu); 0 = never (cuBLAS)")
+    SGLB_STREAMK_MAX_M = EnvInt("SGLB_STREAMK_MAX_M", 0, "bf16 GEMMs with <= this many tokens run on the persistent stream-K tcgen05 kernel "
+                                "(gemm_streamk.cu); 0 = never (cuBLAS).  Default 0: measured in-graph it does not beat the library yet "
+                                "(profiles/gemm_streamk_r2.md)")
     SGLB_ATTN_DECODE = EnvStr("SGLB_ATTN_DECODE", "v3", "v3 = keys-as-M decode kernel (attention_decode.cu) | v2 = query-major kernel")
     SGLB_DISABLE_CUDA_GRAPH = EnvBool("SGLB_DISABLE_CUDA_GRAPH", False)
     SGLB_KERNEL_LAUNCH_COUNT = EnvBool("SGLB_KERNEL_LAUNCH_COUNT", True, "count native kernel launches")
