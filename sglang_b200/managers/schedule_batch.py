@@ -108,6 +108,8 @@ class Req:
         # output / streaming state
         self.finished_reason: Optional[FinishReason] = None
         self.to_abort: Optional[FinishReason] = None
+        self.host_state_flag: Optional[int] = None      # cached static part of ScheduleBatch.needs_host_state()
+        self.samp4: Optional[tuple] = None               # cached (temperature, top_p, min_p, top_k) row for the packed step buffer
         self.sent_offset = 0            # number of output tokens already streamed
         self.decoded_text = ""          # scheduler-side incremental detokenisation (stop strings only)
         self.stop_check_offset = 0
@@ -242,10 +244,16 @@ class ScheduleBatch:
         min_new_tokens still active (EOS suppression), per-request seeds (stream position), hidden-state return.  Such a batch cannot run
         one step ahead of result processing (overlap) and does not fit the captured decode graph, whose sampler sees only static tensors."""
         for r in self.reqs:
-            sp = r.sampling_params
-            if (sp.frequency_penalty or sp.presence_penalty or sp.repetition_penalty != 1.0 or sp.logit_bias
-                    or sp.sampling_seed is not None or getattr(r, "return_hidden_states", False)
-                    or (sp.min_new_tokens and len(r.output_ids) < sp.min_new_tokens + 1)):
+            f = r.host_state_flag
+            if f is None:      # static part, computed once per request: 0 = never, 1 = always, 2 = while min_new_tokens is active
+                sp = r.sampling_params
+                if (sp.frequency_penalty or sp.presence_penalty or sp.repetition_penalty != 1.0 or sp.logit_bias
+                        or sp.sampling_seed is not None or getattr(r, "return_hidden_states", False)):
+                    f = 1
+                else:
+                    f = 2 if sp.min_new_tokens else 0
+                r.host_state_flag = f
+            if f == 1 or (f == 2 and len(r.output_ids) < r.sampling_params.min_new_tokens + 1):
                 return True
         return False
 

@@ -416,7 +416,7 @@ class Scheduler:
     def _update_running_batch(self) -> Optional[ScheduleBatch]:
         """decode step for the running batch; retract on OOM (reference update_running_batch:3566)"""
         rb = self.running_batch
-        keep = [i for i, r in enumerate(rb.reqs) if not r.finished()]
+        keep = [i for i, r in enumerate(rb.reqs) if r.finished_reason is None]
         rb.filter_batch(keep)
         if not rb.reqs:
             return None
@@ -456,14 +456,17 @@ class Scheduler:
         rb.positions = positions.astype(np.int32)
         rb.out_cache_loc = loc
         rb.seq_lens = rb.seq_lens + 1
-        for r in rb.reqs:
-            r.kv_len += 1
         rb.q_lens = None
         rb.input_ids = None
         rb.sample_mask = None
         rb.pt_rows, rb.pt_cols, rb.pt_vals = self.kv.take_deltas()
-        rb.has_grammar = any(r.grammar is not None for r in rb.reqs)
-        rb.return_logprob = any(r.return_logprob for r in rb.reqs)
+        rb.has_grammar = rb.return_logprob = False
+        for r in rb.reqs:
+            r.kv_len += 1
+            if r.grammar is not None:
+                rb.has_grammar = True
+            if r.return_logprob:
+                rb.return_logprob = True
         # the worker gets a *snapshot* so later filter/merge of running_batch cannot race with it
         snap = ScheduleBatch(reqs=list(rb.reqs), forward_mode=ForwardMode.DECODE, seq_lens=rb.seq_lens.copy(),
                              req_slots=rb.req_slots.copy(), positions=rb.positions, out_cache_loc=rb.out_cache_loc,
@@ -605,30 +608,56 @@ class Scheduler:
         out: List[Req] = []
         now = time.perf_counter()
         accept = getattr(result, "accept_lens", None)
-        for i, r in enumerate(batch.reqs):
-            if r.finished() or r.req_slot is None:
-                continue        # finished (or retracted) one step earlier; this lagging result is discarded
-            if accept is not None:
-                n_new = int(accept[i])
-                for t in result.accepted_tokens[i][:n_new]:
-                    self._append_token(r, int(t), result, i)
-                r.spec_verify_ct += 1
-                r.spec_accepted_tokens += n_new - 1
-            else:
-                n_new = 1
-                self._append_token(r, int(toks[i]), result, i)
-            r.check_finished(self.tokenizer, n_new)
-            if r.to_abort is not None and not r.finished():
-                r.finished_reason = r.to_abort
-            if r.finished():
-                r.finished_time = now
-                # with overlap a lagging step may already have bumped kv_len; the KV of the final token is
-                # never needed, so clamp to what was really computed for tokens of all_ids()
-                r.kv_len = min(r.kv_len, r.seqlen - 1)
-                self.kv.release(r)
-            elif r.grammar is not None and self.args.enable_jump_forward:
-                self._try_jump_forward(r)
-            out.append(r)
+        if accept is None and not batch.return_logprob and not batch.has_grammar and result.hidden_states is None:
+            # plain decode (the hot case): one tight loop, the finish test inlined — at 1024 running requests the generic path below costs
+            # ~1.8 ms of Python per iteration, more than a TP=8 decode step takes on the device (tools/host_step_bench.py)
+            tl = toks.tolist()
+            tokenizer = self.tokenizer
+            n_app = 0
+            for i, r in enumerate(batch.reqs):
+                if r.finished_reason is not None or r.req_slot is None:
+                    continue        # finished (or retracted) one step earlier; this lagging result is discarded
+                tok = tl[i]
+                oids = r.output_ids
+                oids.append(tok)
+                n_app += 1
+                sp = r.sampling_params
+                if (len(oids) >= sp.max_new_tokens or r.to_abort is not None or sp.stop or sp.stop_regex or sp.stop_token_ids
+                        or (not sp.ignore_eos and tok in r.eos_token_ids)):
+                    r.check_finished(tokenizer, 1)           # rare: let the full rule set decide
+                    if r.to_abort is not None and r.finished_reason is None:
+                        r.finished_reason = r.to_abort
+                    if r.finished_reason is not None:
+                        r.finished_time = now
+                        r.kv_len = min(r.kv_len, r.seqlen - 1)
+                        self.kv.release(r)
+                out.append(r)
+            self.num_generated_tokens += n_app
+        else:
+            for i, r in enumerate(batch.reqs):
+                if r.finished() or r.req_slot is None:
+                    continue        # finished (or retracted) one step earlier; this lagging result is discarded
+                if accept is not None:
+                    n_new = int(accept[i])
+                    for t in result.accepted_tokens[i][:n_new]:
+                        self._append_token(r, int(t), result, i)
+                    r.spec_verify_ct += 1
+                    r.spec_accepted_tokens += n_new - 1
+                else:
+                    n_new = 1
+                    self._append_token(r, int(toks[i]), result, i)
+                r.check_finished(self.tokenizer, n_new)
+                if r.to_abort is not None and not r.finished():
+                    r.finished_reason = r.to_abort
+                if r.finished():
+                    r.finished_time = now
+                    # with overlap a lagging step may already have bumped kv_len; the KV of the final token is
+                    # never needed, so clamp to what was really computed for tokens of all_ids()
+                    r.kv_len = min(r.kv_len, r.seqlen - 1)
+                    self.kv.release(r)
+                elif r.grammar is not None and self.args.enable_jump_forward:
+                    self._try_jump_forward(r)
+                out.append(r)
         d = self.kv.take_deltas()
         if d[0].size:
             self._carry_deltas(d)
@@ -669,13 +698,14 @@ class Scheduler:
         """reference scheduler_components/output_streamer.py:113"""
         sel = []
         for r in reqs:
-            if r.session_id is not None and r.finished() and not getattr(r, "_session_closed", False):
+            fin = r.finished_reason is not None
+            if fin and r.session_id is not None and not getattr(r, "_session_closed", False):
                 r._session_closed = True
                 if r.finished_reason.kind == "abort":
                     self.sessions.on_aborted(r.session_id, r.rid)
                 else:
                     self.sessions.on_finished(r.session_id, r.rid, r.output_ids, r.extra_key)
-            if r.finished():
+            if fin:
                 sel.append(r)
             elif r.stream:
                 interval = r.sampling_params.stream_interval or self.args.stream_interval
