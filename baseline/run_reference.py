@@ -43,10 +43,13 @@ sys.path.append(ROOT)
 
 # every mode carries the reference's own --bf16-gemm-backend torch: its sm_100 default ("cutedsl") imports cutlass.cute.experimental, which the
 # image's nvidia-cutlass-dsl refuses below CUDA toolkit 13.1 (this image: 12.9) — F.linear / cuBLAS is the reference's documented alternative
+# --mem-fraction-static 0.8: with its own default (0.854 on this part) the reference runs out of memory while capturing its prefill CUDA graphs
+# on this image (run D: "Tried to allocate 420 MiB ... 178.2 GiB in use"); lowering the fraction is the reference's documented remedy.
+_COMMON = {"bf16_gemm_backend": "torch", "mem_fraction_static": 0.8}
 MODES = {
-    "stock": {"bf16_gemm_backend": "torch"},
-    "fi": {"bf16_gemm_backend": "torch", "attention_backend": "flashinfer"},
-    "degraded": {"bf16_gemm_backend": "torch", "attention_backend": "triton", "sampling_backend": "pytorch"},
+    "stock": dict(_COMMON),
+    "fi": dict(_COMMON, attention_backend="flashinfer"),
+    "degraded": dict(_COMMON, attention_backend="triton", sampling_backend="pytorch"),
 }
 
 

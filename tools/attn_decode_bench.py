@@ -36,7 +36,10 @@ CASES = {
     "tp8shard_bs1024_ragged": (1, rng.integers(32, 1500, 1024).tolist(), 1),
 }
 res = {}
+only = sys.argv[2] if len(sys.argv) > 2 else None          # optional: one case only (ncu captures)
 for name, (Hkv, lens, splits) in CASES.items():
+    if only and only not in name:
+        continue
     B, Hq, ps = len(lens), Hkv * 4, 32
     s = _attn_setup(B, [1] * B, lens, Hq, Hkv, 128, ps)
     out = torch.empty_like(s["q"])
@@ -65,4 +68,5 @@ for name, (Hkv, lens, splits) in CASES.items():
         res[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     print(tag, name, res[name], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump({"impl": tag, "hbm_gbs_measured": peaks["hbm_gbs"], "cases": res}, open(os.path.join(ROOT, "gpurun_out", f"attn_decode_bench_{tag}.json"), "w"), indent=1)
+if not only:
+    json.dump({"impl": tag, "hbm_gbs_measured": peaks["hbm_gbs"], "cases": res}, open(os.path.join(ROOT, "gpurun_out", f"attn_decode_bench_{tag}.json"), "w"), indent=1)
