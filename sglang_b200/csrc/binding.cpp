@@ -268,6 +268,23 @@ void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10
   count();
 }
 
+// y[perm[i], :] += B[slot] (A[slot] x[perm[i], :])  for the tokens listed in the tile table (see kernels/lora.cu)
+void lora_sgmv(const at::Tensor& x, const at::Tensor& a_pool, const at::Tensor& b_pool, const at::Tensor& tile_slot,
+               const at::Tensor& tile_start, const at::Tensor& tile_cnt, const at::Tensor& perm, at::Tensor h, at::Tensor y, int64_t b1, int64_t b2) {
+  CHECK_CUDA(x); CHECK_BF16(x); CHECK_BF16(y); CHECK_BF16(a_pool); CHECK_BF16(b_pool); CHECK_LAST_CONTIG(x); CHECK_LAST_CONTIG(y);
+  CHECK_I32(tile_slot); CHECK_I32(tile_start); CHECK_I32(tile_cnt); CHECK_I32(perm);
+  TORCH_CHECK(a_pool.dim() == 4 && b_pool.dim() == 3 && a_pool.is_contiguous() && b_pool.is_contiguous() && x.dim() == 2 && y.dim() == 2);
+  TORCH_CHECK(h.scalar_type() == at::kFloat && h.is_contiguous());
+  const int n_sub = (int)a_pool.size(1), R = (int)a_pool.size(2), K = (int)a_pool.size(3), N = (int)b_pool.size(1);
+  TORCH_CHECK(x.size(1) == K && y.size(1) == N && b_pool.size(2) == R && b_pool.size(0) == a_pool.size(0));
+  TORCH_CHECK(h.numel() >= perm.numel() * n_sub * R, "lora_sgmv: scratch too small");
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::lora_sgmv(x.data_ptr(), (int)x.stride(0), a_pool.data_ptr(), b_pool.data_ptr(), R, n_sub, K, N, (int)b1, (int)b2, tile_slot.data_ptr<int>(),
+                  tile_start.data_ptr<int>(), tile_cnt.data_ptr<int>(), perm.data_ptr<int>(), (int)tile_slot.numel(), h.data_ptr<float>(),
+                  y.data_ptr(), (int)y.stride(0), cur_stream());
+  count(2);
+}
+
 // persistent stream-K decode GEMM (M <= 256): out[M, N] = a[M, K] @ w[N, K]^T (+bias) ; epilogue 4: w = [gate; up], out[M, N/2] = silu(g) * u
 void gemm_streamk(const at::Tensor& a, const at::Tensor& w, at::Tensor out, c10::optional<at::Tensor> bias, int64_t epilogue) {
   CHECK_CUDA(a); CHECK_BF16(a); CHECK_BF16(w); CHECK_BF16(out); CHECK_LAST_CONTIG(a); CHECK_LAST_CONTIG(w); CHECK_LAST_CONTIG(out);
@@ -425,6 +442,8 @@ void moe_grouped_mlp_push(const at::Tensor& x, const at::Tensor& w13, const at::
 
 TORCH_LIBRARY(sglb, m) {
   m.def("gemm_streamk(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue) -> ()", &gemm_streamk);
+  m.def("lora_sgmv(Tensor x, Tensor a_pool, Tensor b_pool, Tensor tile_slot, Tensor tile_start, Tensor tile_cnt, Tensor perm, Tensor(a!) h, "
+        "Tensor(b!) y, int b1, int b2) -> ()", &lora_sgmv);
   m.def("gemm_skinny_splits(int M, int N, int K, int max_splits) -> int", &gemm_skinny_splits);
   m.def("gemm_skinny_norm_splits(int K, int s) -> int", &gemm_skinny_norm_splits);
   m.def("gemm_skinny(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int splits) -> ()", &gemm_skinny);

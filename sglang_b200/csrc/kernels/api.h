@@ -45,6 +45,11 @@ void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* ro
                           int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
                           cudaStream_t stream);
 
+// lora.cu: segment-grouped multi-adapter LoRA (shrink + expand) over a slot-paged adapter pool; static metadata -> graph-capturable
+void lora_sgmv(const void* x, int ldx, const void* A_pool, const void* B_pool, int rank_cap, int n_sub, int K, int N, int b1, int b2,
+               const int* tile_slot, const int* tile_start, const int* tile_cnt, const int* perm, int tile_cap, float* h, void* y, int ldy,
+               cudaStream_t stream);
+
 // gemm_streamk.cu (decode shapes: persistent stream-K swap-AB weight streaming, in-kernel fixup, TMA-store epilogue, fused split-SiLU)
 void gemm_bf16_streamk(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc, int epilogue,
                        int num_sms, cudaStream_t stream);

@@ -150,6 +150,7 @@ class Engine:
             for p in a.lora_paths or []:
                 name, _, path = p.partition("=")
                 self.runner.lora_manager.load_adapter(name, path or name)
+            self.runner.recapture_graphs()        # decode graphs must contain the SGMV kernels the manager just wrapped in
         if a.enable_hierarchical_cache:
             from ..mem_cache.hicache import attach_hicache
 

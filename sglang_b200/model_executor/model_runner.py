@@ -448,7 +448,7 @@ class ModelRunner:
         # the captured sampler sees only the static tensors: anything that needs per-request host state (penalties, logit bias, active
         # min_new_tokens -> EOS mask, per-request seeds, hidden-state return) takes the eager path (ScheduleBatch.needs_host_state)
         use_graph = decode and self.graphs and not sb.return_logprob and not sb.has_grammar and sb.spec_info is None and \
-            B <= self.graph_bs[-1] and not sb.needs_host_state() and self.lora_manager is None
+            B <= self.graph_bs[-1] and not sb.needs_host_state()
         if use_graph:
             return self._forward_graph(sb)
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
@@ -773,6 +773,17 @@ class ModelRunner:
         logger.info("captured %d decode graphs (bs %s..%s) in %.1fs", len(self.graphs), self.graph_bs[0], self.graph_bs[-1],
                     time.perf_counter() - t0)
 
+    def recapture_graphs(self) -> None:
+        """components installed after construction that change what a decode step launches (the LoRA manager wraps every projection with
+        its SGMV kernels) call this so the captured graphs contain them"""
+        if not self.graphs:
+            return
+        self.graphs.clear()
+        self.graph_bs = []
+        with torch.cuda.stream(self.stream):
+            self._capture_graphs()
+        self.stream.synchronize()
+
     def _forward_graph(self, sb: ScheduleBatch) -> BatchResult:
         B = len(sb.reqs)
         import bisect
@@ -782,6 +793,8 @@ class ModelRunner:
         # page-table deltas are applied eagerly (their count is unbounded), then one graph launch
         nd = 0 if sb.pt_rows is None else sb.pt_rows.size
         g.load(sb, self.step_counter, self.args.random_seed)
+        if self.lora_manager is not None:
+            self.lora_manager.prepare_batch(sb)          # refresh the static tile table the captured SGMV kernels read
         if nd:
             d = g.delta_views(nd)
             ops.apply_pt_delta(self.page_table, d[0], d[1], d[2])
