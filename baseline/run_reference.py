@@ -45,11 +45,17 @@ sys.path.append(ROOT)
 # image's nvidia-cutlass-dsl refuses below CUDA toolkit 13.1 (this image: 12.9) — F.linear / cuBLAS is the reference's documented alternative
 # --mem-fraction-static 0.8: with its own default (0.854 on this part) the reference runs out of memory while capturing its prefill CUDA graphs
 # on this image (run D: "Tried to allocate 420 MiB ... 178.2 GiB in use"); lowering the fraction is the reference's documented remedy.
-_COMMON = {"bf16_gemm_backend": "torch", "mem_fraction_static": 0.8}
+# --cuda-graph-max-bs-prefill 2048: at its default (16384 tokens x 74 shapes) every captured prefill shape took 10-15 GB on this torch build and the
+# capture ran the 178 GB card out of memory at ANY mem fraction (runs D / E); 2048 is the value the reference's own OOM message recommends.  The
+# `*_nopg` modes (--disable-prefill-cuda-graph) are the second fallback.
+_COMMON = {"bf16_gemm_backend": "torch", "mem_fraction_static": 0.8, "cuda_graph_max_bs_prefill": 2048}
+_NOPG = {"bf16_gemm_backend": "torch", "mem_fraction_static": 0.8, "disable_prefill_cuda_graph": True}
 MODES = {
     "stock": dict(_COMMON),
     "fi": dict(_COMMON, attention_backend="flashinfer"),
+    "fi_nopg": dict(_NOPG, attention_backend="flashinfer"),
     "degraded": dict(_COMMON, attention_backend="triton", sampling_backend="pytorch"),
+    "degraded_nopg": dict(_NOPG, attention_backend="triton", sampling_backend="pytorch"),
 }
 
 

@@ -156,7 +156,7 @@ def run_reference(args) -> None:
     if not os.path.isdir(os.path.join(ref, "sglang")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed (pip --no-index --no-deps install of /root/reference/python)"}))
         return
-    modes = [m for m in os.environ.get("SGLB_REF_MODES", "stock,fi,degraded").split(",") if m]
+    modes = [m for m in os.environ.get("SGLB_REF_MODES", "stock,fi,fi_nopg,degraded,degraded_nopg").split(",") if m]
     fails = []
     budget = 900.0 + 60.0 * (args.steps + args.warmup)
     for m in modes:
