@@ -268,6 +268,20 @@ void nvl_local_reduce_add_rmsnorm(const at::Tensor& slot, int64_t flags_ptr, c10
   count();
 }
 
+// HiCache page mover: dev_buf [planes, slots, ...] <-> pinned host_buf; page indices as int32 DEVICE tensors; strides in bytes
+void kv_transfer_pages(at::Tensor dev_buf, at::Tensor host_buf, const at::Tensor& dev_pages, const at::Tensor& host_pages, int64_t planes,
+                       int64_t dev_plane_stride, int64_t host_plane_stride, int64_t host_page_stride, int64_t chunk_bytes, bool to_host) {
+  CHECK_CUDA(dev_buf); CHECK_I32(dev_pages); CHECK_I32(host_pages);
+  TORCH_CHECK(!host_buf.is_cuda() && host_buf.is_pinned(), "kv_transfer_pages: the host pool must be pinned memory");
+  TORCH_CHECK(dev_pages.is_cuda() && host_pages.is_cuda() && dev_pages.numel() == host_pages.numel());
+  c10::cuda::CUDAGuard g(dev_buf.device());
+  void* hptr = nullptr;
+  TORCH_CHECK(cudaHostGetDevicePointer(&hptr, host_buf.data_ptr(), 0) == cudaSuccess, "kv_transfer_pages: host pool is not device-mapped");
+  sglb::kv_transfer_pages(dev_buf.data_ptr(), hptr, dev_pages.data_ptr<int>(), host_pages.data_ptr<int>(), (int)dev_pages.numel(), (int)planes,
+                          dev_plane_stride, host_plane_stride, host_page_stride, (int)chunk_bytes, to_host, cur_stream());
+  count();
+}
+
 // y[perm[i], :] += B[slot] (A[slot] x[perm[i], :])  for the tokens listed in the tile table (see kernels/lora.cu)
 void lora_sgmv(const at::Tensor& x, const at::Tensor& a_pool, const at::Tensor& b_pool, const at::Tensor& tile_slot,
                const at::Tensor& tile_start, const at::Tensor& tile_cnt, const at::Tensor& perm, at::Tensor h, at::Tensor y, int64_t b1, int64_t b2) {
@@ -442,6 +456,8 @@ void moe_grouped_mlp_push(const at::Tensor& x, const at::Tensor& w13, const at::
 
 TORCH_LIBRARY(sglb, m) {
   m.def("gemm_streamk(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue) -> ()", &gemm_streamk);
+  m.def("kv_transfer_pages(Tensor(a!) dev_buf, Tensor(b!) host_buf, Tensor dev_pages, Tensor host_pages, int planes, int dev_plane_stride, "
+        "int host_plane_stride, int host_page_stride, int chunk_bytes, bool to_host) -> ()", &kv_transfer_pages);
   m.def("lora_sgmv(Tensor x, Tensor a_pool, Tensor b_pool, Tensor tile_slot, Tensor tile_start, Tensor tile_cnt, Tensor perm, Tensor(a!) h, "
         "Tensor(b!) y, int b1, int b2) -> ()", &lora_sgmv);
   m.def("gemm_skinny_splits(int M, int N, int K, int max_splits) -> int", &gemm_skinny_splits);

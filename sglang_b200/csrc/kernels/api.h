@@ -45,6 +45,10 @@ void gemm_bf16_tc_grouped(const void* A, const void* W, void* C, const float* ro
                           int ldc, int num_experts, const int* tile_expert, const int* num_m_tiles, bool split_silu, int num_sms,
                           cudaStream_t stream);
 
+// kvio.cu: device pool <-> pinned host pool page movers (HiCache L1 <-> L2), zero-copy over UVA, layer_first / page_first host layouts
+void kv_transfer_pages(void* dev, void* host_devptr, const int* dev_pages, const int* host_pages, int n, int planes, long long dev_plane_stride,
+                       long long host_plane_stride, long long host_page_stride, int chunk_bytes, bool to_host, cudaStream_t stream);
+
 // lora.cu: segment-grouped multi-adapter LoRA (shrink + expand) over a slot-paged adapter pool; static metadata -> graph-capturable
 void lora_sgmv(const void* x, int ldx, const void* A_pool, const void* B_pool, int rank_cap, int n_sub, int K, int N, int b1, int b2,
                const int* tile_slot, const int* tile_start, const int* tile_cnt, const int* perm, int tile_cap, float* h, void* y, int ldy,

@@ -30,10 +30,10 @@ from .hicache_storage import FileStorage, HiCacheStorage, create_storage  # noqa
 
 class HiRadixCache(RadixCache):
     def __init__(self, allocator: Any, page_size: int, kv_pool: KVPool, host_pages: int, eviction_policy: str = "lru",
-                 write_policy: str = "write_through", storage: Optional[FileStorage] = None):
+                 write_policy: str = "write_through", storage: Optional[FileStorage] = None, mem_layout: str = "layer_first"):
         super().__init__(allocator, page_size, eviction_policy)
         self.kv_pool = kv_pool
-        self.host = HostKVPool(host_pages, kv_pool, pin=kv_pool.buf.is_cuda)
+        self.host = HostKVPool(host_pages, kv_pool, pin=kv_pool.buf.is_cuda, layout=mem_layout)
         if write_policy not in ("write_through", "write_through_selective", "write_back"):
             raise ValueError(f"unknown hicache write policy {write_policy!r}")
         self.write_policy = write_policy
@@ -52,9 +52,7 @@ class HiRadixCache(RadixCache):
             hp = self.host.alloc(n)
             if hp is None:
                 return False
-        dev = torch.from_numpy(node.pages.astype(np.int64)).to(self.kv_pool.buf.device)
-        data = self.kv_pool.gather_pages(dev)                    # [L, 2, n, ps, H, D]
-        self.host.buf[:, :, torch.from_numpy(hp.astype(np.int64))] = data.to("cpu")
+        self.host.write_from_device(self.kv_pool, node.pages, hp)      # kvio.cu page mover on CUDA (one launch, all layers)
         node.host_pages = hp
         self.stats["host_writes"] += n
         if self.storage is not None:
@@ -71,7 +69,7 @@ class HiRadixCache(RadixCache):
         have = self.storage.batch_exists(hs)                      # one round trip for the whole node, then one for the missing pages
         todo = [(h, hp) for h, hp, ok in zip(hs, node.host_pages.tolist(), have) if not ok]
         if todo:
-            self.storage.batch_put([h for h, _ in todo], [self.host.buf[:, :, hp] for _, hp in todo])
+            self.storage.batch_put([h for h, _ in todo], [self.host.page(hp) for _, hp in todo])
             self.stats["l3_writes"] += len(todo)
 
     def _full_key(self, node: TreeNode) -> np.ndarray:
@@ -154,9 +152,7 @@ class HiRadixCache(RadixCache):
         dev_pages = self.allocator.alloc(n)
         if dev_pages is None:
             return False
-        data = self.host.buf[:, :, torch.from_numpy(node.host_pages.astype(np.int64))]
-        self.kv_pool.scatter_pages(torch.from_numpy(dev_pages.astype(np.int64)).to(self.kv_pool.buf.device),
-                                   data.to(self.kv_pool.buf.device, non_blocking=True))
+        self.host.read_to_device(self.kv_pool, node.host_pages, dev_pages)
         node.pages = dev_pages
         self._evictable_pages += n if node.lock_ref == 0 else 0
         self._protected_pages += n if node.lock_ref > 0 else 0
@@ -210,7 +206,7 @@ def attach_hicache(scheduler: Any, runner: Any, args: Any) -> HiRadixCache:
         extra.setdefault("dir", args.hicache_storage_dir)
     storage = create_storage(args.hicache_storage_backend, extra)
     tree = HiRadixCache(scheduler.allocator, scheduler.page_size, runner.kv_pool, host_pages, args.radix_eviction_policy,
-                        args.hicache_write_policy, storage)
+                        args.hicache_write_policy, storage, getattr(args, "hicache_mem_layout", "layer_first"))
     scheduler.tree = tree
     scheduler.kv.tree = tree
     return tree

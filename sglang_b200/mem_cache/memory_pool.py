@@ -58,15 +58,77 @@ class KVPool:
 
 
 class HostKVPool:
-    """Pinned-host mirror used by the HiCache L2 tier (reference ``memory_pool_host.py``)."""
+    """Pinned-host mirror used by the HiCache L2 tier (reference ``memory_pool_host.py``).
 
-    def __init__(self, num_pages: int, like: KVPool, pin: bool = True):
-        self.num_pages = num_pages
-        shape = (like.num_layers, 2, num_pages, like.page_size, like.num_kv_heads, like.head_dim)
+    Layouts (``--hicache-mem-layout``): ``layer_first`` ``[L, 2, pages, ps, H, D]`` mirrors the device pool; ``page_first``
+    ``[pages, L, 2, ps, H, D]`` makes every host page ONE contiguous record, which is what the L3 storage back ends read and write.
+    On CUDA pages move with ``csrc/kernels/kvio.cu`` (one launch for all layers, the SMs address the pinned pool directly over UVA);
+    on CPU (tests) with index copies."""
+
+    def __init__(self, num_pages: int, like: KVPool, pin: bool = True, layout: str = "layer_first"):
+        assert layout in ("layer_first", "page_first"), layout
+        self.num_pages, self.layout = num_pages, layout
+        L, ps, H, D = like.num_layers, like.page_size, like.num_kv_heads, like.head_dim
+        shape = (L, 2, num_pages, ps, H, D) if layout == "layer_first" else (num_pages, L, 2, ps, H, D)
         self.buf = torch.empty(shape, dtype=like.dtype, device="cpu")
         if pin and torch.cuda.is_available():
             self.buf = self.buf.pin_memory()
+        self.planes = L * 2
+        self.chunk_bytes = ps * H * D * self.buf.element_size()
         self._free = list(range(num_pages - 1, -1, -1))
+        self.kernel_transfers = 0
+
+    # ---- page access independent of the layout
+    def page(self, hp: int) -> torch.Tensor:
+        """[L, 2, ps, H, D] view of one host page"""
+        return self.buf[:, :, hp] if self.layout == "layer_first" else self.buf[hp]
+
+    def _strides(self):
+        cb = self.chunk_bytes
+        if self.layout == "layer_first":
+            return self.num_pages * cb, cb          # plane stride, page stride
+        return cb, self.planes * cb
+
+    def _use_kernel(self, like: KVPool) -> bool:
+        if not (like.buf.is_cuda and self.buf.is_pinned()):
+            return False
+        from .. import ops
+
+        return ops.load_native()
+
+    def write_from_device(self, like: KVPool, dev_pages: np.ndarray, host_pages: np.ndarray) -> None:
+        """device pages -> host pages (all layers, K and V)"""
+        if self._use_kernel(like):
+            dev = like.buf.device
+            dp = torch.from_numpy(np.ascontiguousarray(dev_pages, dtype=np.int32)).to(dev)
+            hp = torch.from_numpy(np.ascontiguousarray(host_pages, dtype=np.int32)).to(dev)
+            ps_, hs_ = self._strides()
+            torch.ops.sglb.kv_transfer_pages(like.buf, self.buf, dp, hp, self.planes, like.num_slots * like.num_kv_heads * like.head_dim *
+                                             like.buf.element_size(), ps_, hs_, self.chunk_bytes, True)
+            torch.cuda.current_stream().synchronize()      # the host copy must be complete before the device pages are recycled
+            self.kernel_transfers += 1
+            return
+        data = like.gather_pages(torch.from_numpy(np.asarray(dev_pages, dtype=np.int64)).to(like.buf.device)).to("cpu")   # [L, 2, n, ps, H, D]
+        idx = torch.from_numpy(np.asarray(host_pages, dtype=np.int64))
+        if self.layout == "layer_first":
+            self.buf[:, :, idx] = data
+        else:
+            self.buf[idx] = data.permute(2, 0, 1, 3, 4, 5)
+
+    def read_to_device(self, like: KVPool, host_pages: np.ndarray, dev_pages: np.ndarray) -> None:
+        """host pages -> device pages"""
+        if self._use_kernel(like):
+            dev = like.buf.device
+            dp = torch.from_numpy(np.ascontiguousarray(dev_pages, dtype=np.int32)).to(dev)
+            hp = torch.from_numpy(np.ascontiguousarray(host_pages, dtype=np.int32)).to(dev)
+            ps_, hs_ = self._strides()
+            torch.ops.sglb.kv_transfer_pages(like.buf, self.buf, dp, hp, self.planes, like.num_slots * like.num_kv_heads * like.head_dim *
+                                             like.buf.element_size(), ps_, hs_, self.chunk_bytes, False)
+            self.kernel_transfers += 1
+            return
+        idx = torch.from_numpy(np.asarray(host_pages, dtype=np.int64))
+        data = self.buf[:, :, idx] if self.layout == "layer_first" else self.buf[idx].permute(1, 2, 0, 3, 4, 5)
+        like.scatter_pages(torch.from_numpy(np.asarray(dev_pages, dtype=np.int64)).to(like.buf.device), data.to(like.buf.device))
 
     def available(self) -> int:
         return len(self._free)

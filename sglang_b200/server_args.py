@@ -134,6 +134,7 @@ class ServerArgs:
     enable_hierarchical_cache: bool = False
     hicache_ratio: float = 2.0
     hicache_write_policy: str = "write_through"
+    hicache_mem_layout: str = "layer_first"   # layer_first | page_first (host pool layout; page_first = one contiguous record per page for L3 IO)
     hicache_storage_backend: Optional[str] = None  # file | shm | memory | remote | remote://host:port | <registered plugin backend>
     hicache_storage_backend_extra_config: Optional[str] = None   # JSON passed to the backend factory
     hicache_storage_dir: Optional[str] = None

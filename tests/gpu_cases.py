@@ -514,6 +514,35 @@ def case_lora():
     assert outs_[0] == outs_[1], f"graph vs eager LoRA decode differ: {outs_}"
 
 
+def case_kvio():
+    """HiCache page movers (kvio.cu): device pool -> pinned host pool -> other device pages, both host layouts, all layers in one launch"""
+    from sglang_b200.mem_cache.memory_pool import HostKVPool, KVPool
+
+    torch.manual_seed(9)
+    pool = KVPool(num_pages=40, page_size=32, num_layers=3, num_kv_heads=2, head_dim=128, dtype=torch.bfloat16, device=DEV)
+    pool.buf.copy_(torch.randn_like(pool.buf.float()).to(torch.bfloat16))
+    for layout in ("layer_first", "page_first"):
+        host = HostKVPool(16, pool, pin=True, layout=layout)
+        host.buf.zero_()
+        dev_pages = np.asarray([3, 17, 5, 39, 0], dtype=np.int32)
+        hp = host.alloc(5)
+        host.write_from_device(pool, dev_pages, hp)
+        assert host.kernel_transfers == 1, "the CUDA page mover was not used"
+        want = pool.gather_pages(torch.from_numpy(dev_pages.astype(np.int64)).to(DEV)).cpu()      # [L, 2, n, ps, H, D]
+        for i, h in enumerate(hp.tolist()):
+            assert torch.equal(host.page(h), want[:, :, i]), f"{layout}: host page {h} differs"
+        untouched = [h for h in range(16) if h not in hp.tolist()]
+        assert all(bool((host.page(h) == 0).all()) for h in untouched), "transfer wrote outside its pages"
+        dst = np.asarray([20, 21, 22, 23, 24], dtype=np.int32)
+        before = pool.buf.clone()
+        host.read_to_device(pool, hp, dst)
+        torch.cuda.synchronize()
+        got = pool.gather_pages(torch.from_numpy(dst.astype(np.int64)).to(DEV)).cpu()
+        assert torch.equal(got, want), f"{layout}: load-back differs"
+        keep = torch.ones(40, dtype=torch.bool); keep[torch.from_numpy(dst.astype(np.int64))] = False
+        assert torch.equal(pool.page_view()[:, :, keep.to(DEV)], before.view_as(pool.page_view())[:, :, keep.to(DEV)]), "load-back touched other pages"
+
+
 def case_sampling():
     torch.manual_seed(0)
     B, V = 16, 32000

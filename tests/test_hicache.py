@@ -7,8 +7,9 @@ import sglang_b200 as sgl
 import pytest
 
 
-@pytest.mark.parametrize("backend", ["file", "shm", "memory", "remote"])
-def test_host_tier_roundtrip_and_l3(tmp_path, backend):
+@pytest.mark.parametrize("backend,layout", [("file", "layer_first"), ("shm", "layer_first"), ("memory", "page_first"), ("remote", "layer_first"),
+                                            ("file", "page_first")])
+def test_host_tier_roundtrip_and_l3(tmp_path, backend, layout):
     import json
 
     from sglang_b200.mem_cache.hicache_storage import PageServer
@@ -21,7 +22,8 @@ def test_host_tier_roundtrip_and_l3(tmp_path, backend):
         extra = {"name": f"sglb_test_{tmp_path.name}"}
     eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, max_total_tokens=256, enable_hierarchical_cache=True,
                      hicache_ratio=4.0, hicache_storage_backend=backend, hicache_storage_dir=str(tmp_path) if backend == "file" else None,
-                     hicache_storage_backend_extra_config=json.dumps(extra), radix_cache_impl="python")
+                     hicache_storage_backend_extra_config=json.dumps(extra), radix_cache_impl="python", hicache_mem_layout=layout)
+    assert eng.scheduler.tree.host.layout == layout
     rng = np.random.default_rng(0)
     sp = {"max_new_tokens": 4, "temperature": 0, "ignore_eos": True}
     A = rng.integers(3, 200, size=100).tolist()
