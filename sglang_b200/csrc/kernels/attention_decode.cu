@@ -31,13 +31,13 @@ namespace sglb {
 constexpr int DA_D = 128;                 // head dim
 constexpr int DA_KT = 128;                // keys per tile (UMMA M)
 constexpr int DA_NQ = 16;                 // padded query rows (UMMA N)
-constexpr int DA_THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 the two softmax groups (one key per thread)
+constexpr int DA_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2-5 softmax (one key per thread)
 constexpr int DA_STAGES = 3;
 constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile: two 64-wide d halves of [128 keys x 128 B])
 constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
 constexpr int DA_Q_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two d halves of [16 rows x 128 B])
 constexpr int DA_P_BYTES = 2 * DA_NQ * 128;              // 4 KB   (two 64-key chunks of [16 rows x 128 B]), double buffered
-constexpr int DA_SMEM_BYTES = 2 * DA_STAGES * DA_TILE_BYTES + 2 * DA_Q_BYTES + 2 * DA_P_BYTES + 1024 /*align*/ + 3072 /*barriers + scratch*/;
+constexpr int DA_SMEM_BYTES = 2 * DA_STAGES * DA_TILE_BYTES + 2 * DA_Q_BYTES + 2 * DA_P_BYTES + 1024 /*align*/ + 1024 /*barriers + scratch*/;
 constexpr float DA_RESCALE_THRESHOLD = 8.0f;
 
 struct DecodeParams {
@@ -69,36 +69,31 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sP = sQ + 2 * DA_Q_BYTES;                               // 2 x 4 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * DA_P_BYTES);
   uint64_t* q_full = bars;             // [2] Q of the item landed                   (slot = item ordinal & 1, phase = ordinal >> 1)
+  uint64_t* q_empty = bars + 30;       // [2] last S of the item has read Q  (bars 27..29 hold the 6 debug words)
   uint64_t* k_full = bars + 2;         // [STAGES]
   uint64_t* k_empty = bars + 5;        // [STAGES]
   uint64_t* v_full = bars + 8;         // [STAGES]
   uint64_t* v_empty = bars + 11;       // [STAGES]
-  uint64_t* s_full = bars + 14;        // [2 groups] S^T of the group's tile is in TMEM     (phase = the group's running tile count)
-  uint64_t* p_full = bars + 16;        // [2 groups] P^T of the group's tile is in smem (128 arrivals)
-  uint64_t* o_done = bars + 18;        // [2 groups] every PV of the group (lazy-rescale hand-off)
-  uint64_t* o_final = bars + 20;       // [2 groups] the group's last PV of an item        (phase = items in which the group had tiles)
-  uint64_t* o_free = bars + 22;        // epilogue has read both O^T (4 arrivals)          (phase = item ordinal)
-  uint64_t* item_full = bars + 23;     // [2]
-  uint64_t* item_empty = bars + 25;    // [2]  (MMA thread + 8 softmax warps)
-  uint64_t* q_empty = bars + 27;       // [2] last S of the item has read Q
-  uint64_t* stats_full = bars + 29;    // [2] group 1 published (m, l) of the item         (slot = item ordinal & 1)
-  uint64_t* stats_empty = bars + 31;   // [2] group 0 has read them
-  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 33);        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
-  volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 35); // [10] role state for the timeout dump (bars 35..39)
-  float* red = reinterpret_cast<float*>(bars + 40);     // [2 groups][2][4][GMAX] row max, [2 groups][4][GMAX] row sums, [2][2][GMAX] group-1 stats
-#define DA_WAIT(bar_, par_) mbar_wait((bar_), (par_), dbg, 10)
+  uint64_t* s_full = bars + 14;        // [2] S^T of a tile is in TMEM
+  uint64_t* p_full = bars + 16;        // [2] P^T of a tile is in smem (128 arrivals)
+  uint64_t* o_done = bars + 18;        // every PV tile (lazy-rescale hand-off)
+  uint64_t* o_final = bars + 19;       // last PV of an item                         (phase = item ordinal)
+  uint64_t* o_free = bars + 20;        // epilogue has read O^T (4 arrivals)         (phase = item ordinal)
+  uint64_t* item_full = bars + 21;     // [2]
+  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps)
+  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 25);        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+  volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 27); // [6] role state for the timeout dump
+  float* red = reinterpret_cast<float*>(bars + 32);                         // [2][4 warps][GMAX] row-max exchange, then [4][GMAX] sums
+#define DA_WAIT(bar_, par_) mbar_wait((bar_), (par_), dbg, 6)
 #define DA_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 9);
-      mbar_init(&o_done[i], 1); mbar_init(&o_final[i], 1); mbar_init(&stats_full[i], 1); mbar_init(&stats_empty[i], 1);
-    }
-    mbar_init(o_free, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5); }
+    mbar_init(o_done, 1); mbar_init(o_final, 1); mbar_init(o_free, 4);
     fence_barrier_init();
   }
   if (lane == 0) dbg[warp] = 0;
@@ -112,8 +107,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;                 // S^T of group 0 / 1: cols [0,16) and [16,32)
-  const uint32_t tmem_O = tmem_base + 32;            // O^T of group 0 / 1: cols [32,48) and [48,64)
+  const uint32_t tmem_S = tmem_base;                 // S^T buffers: cols [0,16) and [16,32)
+  const uint32_t tmem_O = tmem_base + 32;            // O^T: cols [32,48)
 
   // geometry of a work item: pure function of its id, evaluated identically by every role
   struct Item { int b, kvh, split, seq_len, kv_hi, tile_begin, n_tiles; };
@@ -190,13 +185,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
-    // tile j of an item belongs to softmax group j & 1: S^T[grp], P[grp] and the accumulator O^T[grp] are that group's private buffers, so two
-    // tiles are always in flight (one being exponentiated by each group) and the ~3 k-cycle softmax chain of a tile is no longer the SM's
-    // throughput limit (ncu of the single-group version: 60 % of DRAM peak, trtllm-gen 83 %; profiles/attn_decode_r2.md)
     constexpr uint32_t idesc_s = make_idesc(UMMA_BF16, UMMA_BF16, DA_KT, DA_NQ, 0, 0);      // A = K (K-major), B = Q (K-major)
     constexpr uint32_t idesc_o = make_idesc(UMMA_BF16, UMMA_BF16, DA_D, DA_NQ, 1, 0);       // A = V^T (MN-major: d contiguous), B = P^T
     uint32_t n_it = 0, n_q = 0, g = 0;
-    uint32_t cg[2] = {0, 0};             // per-group running tile counters (phases of s_full / p_full / o_done)
     for (;;) {
       const int slot = n_it & 1;
       DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
@@ -210,9 +201,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int qs = n_q & 1;
       const uint32_t q_addr = smem_u32(sQ + qs * DA_Q_BYTES);
       DA_DBG(2, n_q, g);
-      auto issue_S = [&](int j) {
-        const uint32_t gt = g + j;
-        const int st = gt % DA_STAGES, grp = j & 1;
+      auto issue_S = [&](uint32_t gt, bool last) {
+        const int st = gt % DA_STAGES;
         DA_WAIT(&k_full[st], (gt / DA_STAGES) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * DA_TILE_BYTES);
@@ -220,52 +210,45 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int k = 0; k < DA_D / 16; ++k) {
           const uint32_t koff = (k >> 2) * DA_HALF_BYTES + (k & 3) * 32;
           const uint32_t qoff = (k >> 2) * (DA_NQ * 128) + (k & 3) * 32;
-          umma_f16_ss(tmem_S + grp * DA_NQ, make_smem_desc_sw128(k_addr + koff, 0, 1024), make_smem_desc_sw128(q_addr + qoff, 0, 1024),
+          umma_f16_ss(tmem_S + (gt & 1) * DA_NQ, make_smem_desc_sw128(k_addr + koff, 0, 1024), make_smem_desc_sw128(q_addr + qoff, 0, 1024),
                       idesc_s, k != 0);
         }
         umma_commit(&k_empty[st]);
-        umma_commit(&s_full[grp]);
-        if (j + 1 == n_tiles) umma_commit(&q_empty[qs]);
+        umma_commit(&s_full[gt & 1]);
+        if (last) umma_commit(&q_empty[qs]);
       };
       DA_WAIT(&q_full[qs], (n_q >> 1) & 1);
-      issue_S(0);
-      if (n_tiles > 1) issue_S(1);
+      issue_S(g, n_tiles == 1);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t gt = g + j;
-        const int st = gt % DA_STAGES, grp = j & 1;
-        DA_WAIT(&p_full[grp], cg[grp] & 1);
+        const int st = gt % DA_STAGES;
+        if (j + 1 < n_tiles) issue_S(gt + 1, j + 2 == n_tiles);
+        DA_WAIT(&p_full[gt & 1], (gt >> 1) & 1);
         DA_WAIT(&v_full[st], (gt / DA_STAGES) & 1);
-        if (j == 0) DA_WAIT(o_free, (n_q & 1) ^ 1);       // the previous item's epilogue has read BOTH accumulators
+        if (j == 0) DA_WAIT(o_free, (n_q & 1) ^ 1);       // the previous item's epilogue has read O^T
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * DA_TILE_BYTES);
-        const uint32_t p_addr = smem_u32(sP + grp * DA_P_BYTES);
+        const uint32_t p_addr = smem_u32(sP + (gt & 1) * DA_P_BYTES);
 #pragma unroll
         for (int k = 0; k < DA_KT / 16; ++k)      // 16 keys per step: A rows advance 16 x 128 B, B (P^T, K-major) advances 32 B inside a 64-key chunk
-          umma_f16_ss(tmem_O + grp * DA_NQ, make_smem_desc_sw128(v_addr + k * 2048, DA_HALF_BYTES, 1024),
-                      make_smem_desc_sw128(p_addr + (k >> 2) * (DA_NQ * 128) + (k & 3) * 32, 0, 1024), idesc_o, (j >= 2 || k != 0) ? 1u : 0u);
+          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + k * 2048, DA_HALF_BYTES, 1024),
+                      make_smem_desc_sw128(p_addr + (k >> 2) * (DA_NQ * 128) + (k & 3) * 32, 0, 1024), idesc_o, (j | k) != 0);
         umma_commit(&v_empty[st]);
-        umma_commit(&o_done[grp]);
-        if (j + 2 >= n_tiles) umma_commit(&o_final[grp]);          // this group's last tile of the item
-        ++cg[grp];
-        if (j + 2 < n_tiles) issue_S(j + 2);                       // S^T[grp] and P[grp] are free again: PV(j) above is ordered before it
+        umma_commit(o_done);
+        if (j + 1 == n_tiles) umma_commit(o_final);
       }
       g += n_tiles;
       ++n_q;
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ softmax groups (thread = key); group 0 also runs the item epilogue
-    const int grp = (warp - 2) >> 2;                      // warps 2-5 -> group 0, warps 6-9 -> group 1
+    // ------------------------------------------------------------ softmax (thread = key) + epilogue (thread = output dim)
     const int q4 = warp & 3;                              // TMEM lane quadrant of this warp
     const int row = (q4 << 5) + lane;                     // key index inside the tile / output dim in the epilogue
     const uint32_t lane_addr = (uint32_t)(q4 << 5) << 16;
     const float scale_log2 = p.scale_log2;
     const float cap = p.logit_cap, inv_cap = HAS_CAP ? 1.f / p.logit_cap : 0.f;
     const float scale_nat = scale_log2 * 0.6931471805599453f, inv_scale_nat = 1.f / scale_nat;
-    float* red_g = red + grp * (2 * 4 * GMAX);           // [2][4 warps][GMAX] row-max exchange of this group
-    float* sum_g = red + 2 * (2 * 4 * GMAX) + grp * (4 * GMAX);
-    float* stats = red + 2 * (2 * 4 * GMAX) + 2 * (4 * GMAX);      // [2 item parities][2 (m, l)][GMAX]: group 1 -> group 0
-    const uint32_t tS = tmem_S + grp * DA_NQ + lane_addr, tO = tmem_O + grp * DA_NQ + lane_addr;
-    uint32_t n_it = 0, n_q = 0, c = 0, q0 = 0, q1 = 0;    // c: this group's running tile counter; q0/q1: items in which group 0/1 had tiles
+    uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
       DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
@@ -276,7 +259,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (idx >= p.total_items) break;
       const Item it = decode_item(idx);
       if (it.n_tiles == 0) {
-        if (p.num_splits > 1 && grp == 0) {          // empty split: neutral partial (the merge kernel ignores lse = -inf)
+        if (p.num_splits > 1) {          // empty split: neutral partial (the merge kernel ignores lse = -inf)
           for (int gq = 0; gq < G; ++gq) {
             const size_t r = ((size_t)it.split * p.B + it.b) * p.Hq + it.kvh * G + gq;
             p.part_o[r * DA_D + row] = 0.f;
@@ -286,28 +269,30 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         continue;
       }
       const int n_tiles = it.n_tiles;
-      const int n_mine = (n_tiles - grp + 1) >> 1;     // tiles grp, grp + 2, ...
-      if (lane == 0) DA_DBG(3, n_q, c);
+      if (lane == 0) DA_DBG(3, n_q, g);
       const int kv_first = p.window > 0 ? it.seq_len - p.window : 0;
       float m_run[GMAX], l_part[GMAX];
 #pragma unroll
       for (int i = 0; i < GMAX; ++i) { m_run[i] = -INFINITY; l_part[i] = 0.f; }
-      for (int k = 0; k < n_mine; ++k, ++c) {
-        const int j = grp + 2 * k;
-        DA_WAIT(&s_full[grp], c & 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t gt = g + j;
+        DA_WAIT(&s_full[gt & 1], (gt >> 1) & 1);
         tc_fence_after();
         uint32_t sr[GMAX];
-        if constexpr (GMAX == 4) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]) : "r"(tS) : "memory");
-        } else if constexpr (GMAX == 8) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]) : "r"(tS) : "memory");
-        } else {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                       : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]), "=r"(sr[8]),
-                         "=r"(sr[9]), "=r"(sr[10]), "=r"(sr[11]), "=r"(sr[12]), "=r"(sr[13]), "=r"(sr[14]), "=r"(sr[15]) : "r"(tS) : "memory");
+        {
+          const uint32_t a = tmem_S + lane_addr + (gt & 1) * DA_NQ;
+          if constexpr (GMAX == 4) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]) : "r"(a) : "memory");
+          } else if constexpr (GMAX == 8) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]) : "r"(a) : "memory");
+          } else {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(sr[0]), "=r"(sr[1]), "=r"(sr[2]), "=r"(sr[3]), "=r"(sr[4]), "=r"(sr[5]), "=r"(sr[6]), "=r"(sr[7]), "=r"(sr[8]),
+                           "=r"(sr[9]), "=r"(sr[10]), "=r"(sr[11]), "=r"(sr[12]), "=r"(sr[13]), "=r"(sr[14]), "=r"(sr[15]) : "r"(a) : "memory");
+          }
+          tmem_ld_wait();
         }
-        tmem_ld_wait();
         const int key = (it.tile_begin + j) * DA_KT + row;
         const bool live = key < it.kv_hi && key >= kv_first;
         float sv[GMAX], wmax[GMAX];
@@ -318,32 +303,32 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           sv[i] = live ? x * scale_log2 : -INFINITY;
           wmax[i] = warp_max(sv[i]);
         }
-        float* rbuf = red_g + (c & 1) * (4 * GMAX);
+        float* rbuf = red + (gt & 1) * (4 * GMAX);
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < GMAX; ++i) rbuf[q4 * GMAX + i] = wmax[i];
         }
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         bool need = false;
         float m_new[GMAX];
 #pragma unroll
         for (int i = 0; i < GMAX; ++i) {
           const float tmax = fmaxf(fmaxf(rbuf[i], rbuf[GMAX + i]), fmaxf(rbuf[2 * GMAX + i], rbuf[3 * GMAX + i]));
           m_new[i] = fmaxf(m_run[i], tmax);
-          need |= (m_new[i] > m_run[i] + DA_RESCALE_THRESHOLD);     // group-uniform (m_run and tmax are identical in all 128 threads)
+          need |= (m_new[i] > m_run[i] + DA_RESCALE_THRESHOLD);     // same value in every thread (m_run and tmax are CTA-uniform)
         }
-        if (k == 0) {
+        if (j == 0) {
 #pragma unroll
           for (int i = 0; i < GMAX; ++i) m_run[i] = m_new[i];
         } else if (need) {
-          // lazy rescale of this group's O^T (lane = output dim, column = query row): wait for its previous PV, scale, write back
-          DA_WAIT(&o_done[grp], (c - 1) & 1);
+          // lazy rescale of O^T (lane = output dim, column = query row): wait for PV(j-1), scale the columns, write back
+          DA_WAIT(o_done, (gt - 1) & 1);
           tc_fence_after();
           uint32_t orow[16];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                        : "=r"(orow[0]), "=r"(orow[1]), "=r"(orow[2]), "=r"(orow[3]), "=r"(orow[4]), "=r"(orow[5]), "=r"(orow[6]), "=r"(orow[7]),
                          "=r"(orow[8]), "=r"(orow[9]), "=r"(orow[10]), "=r"(orow[11]), "=r"(orow[12]), "=r"(orow[13]), "=r"(orow[14]), "=r"(orow[15])
-                       : "r"(tO) : "memory");
+                       : "r"(tmem_O + lane_addr) : "memory");
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < GMAX; ++i) {
@@ -352,104 +337,69 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             l_part[i] *= f;
             m_run[i] = m_new[i];
           }
-          tmem_st_32x32b_x16(tO, orow);
+          tmem_st_32x32b_x16(tmem_O + lane_addr, orow);
           tmem_st_wait();
         }
-        // P^T[query row i][key] (bf16, K-major, 128-byte swizzle) into this group's buffer: rows >= G stay zero
-        uint8_t* pbuf = sP + grp * DA_P_BYTES + (row >> 6) * (DA_NQ * 128);
-        const int cc = row & 63;
+        // P^T[query row i][key] (bf16, K-major, 128-byte swizzle): rows >= G stay zero
+        uint8_t* pbuf = sP + (gt & 1) * DA_P_BYTES + (row >> 6) * (DA_NQ * 128);
+        const int c = row & 63;
 #pragma unroll
         for (int i = 0; i < GMAX; ++i) {
           if (i < G) {
             const float mm = (m_run[i] == -INFINITY) ? 0.f : m_run[i];
             const float pv = ex2_approx(sv[i] - mm);
             l_part[i] += pv;
-            const uint32_t off = i * 128 + ((((uint32_t)cc >> 3) ^ (i & 7)) << 4) + (cc & 7) * 2;
+            const uint32_t off = i * 128 + ((((uint32_t)c >> 3) ^ (i & 7)) << 4) + (c & 7) * 2;
             *reinterpret_cast<__nv_bfloat16*>(pbuf + off) = __float2bfloat16(pv);
           }
         }
         fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's smem reads
         tc_fence_before();
-        mbar_arrive(&p_full[grp]);
+        mbar_arrive(&p_full[gt & 1]);
       }
+      g += n_tiles;
 
-      // ---- per-group row sums across the 128 key-threads
+      // ---- epilogue: row sums across the 128 key-threads, then O^T / l -> out (thread = output dim)
+      if (lane == 0) DA_DBG(4, n_q, g);
       float lsum[GMAX];
 #pragma unroll
       for (int i = 0; i < GMAX; ++i) lsum[i] = warp_sum(l_part[i]);
+      float* sbuf = red + 2 * (4 * GMAX);
       if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < GMAX; ++i) sum_g[q4 * GMAX + i] = lsum[i];
+        for (int i = 0; i < GMAX; ++i) sbuf[q4 * GMAX + i] = lsum[i];
       }
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-      float l_tot[GMAX];
-#pragma unroll
-      for (int i = 0; i < GMAX; ++i) l_tot[i] = sum_g[i] + sum_g[GMAX + i] + sum_g[2 * GMAX + i] + sum_g[3 * GMAX + i];
-      const int sb = n_q & 1;
-      float* st_buf = stats + sb * (2 * GMAX);
-      if (grp == 1) {
-        // hand (m, l) of the odd tiles to group 0; O^T[1] itself is read by group 0 straight from TMEM after o_final[1]
-        if (row == 0) {
-          DA_WAIT(&stats_empty[sb], ((n_q >> 1) & 1) ^ 1);
-#pragma unroll
-          for (int i = 0; i < GMAX; ++i) { st_buf[i] = m_run[i]; st_buf[GMAX + i] = l_tot[i]; }
-          mbar_arrive(&stats_full[sb]);
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");      // sum_g is reused by this group's next item
-        ++n_q;
-        continue;
-      }
-      // ---- group 0: merge the two partial softmax states, normalise, store (thread = output dim)
-      if (lane == 0) DA_DBG(4, n_q, c);
-      DA_WAIT(&o_final[0], q0 & 1);
-      ++q0;
-      DA_WAIT(&stats_full[sb], (n_q >> 1) & 1);
-      float m1[GMAX], l1[GMAX];
-#pragma unroll
-      for (int i = 0; i < GMAX; ++i) { m1[i] = st_buf[i]; l1[i] = st_buf[GMAX + i]; }
-      const bool two = n_tiles >= 2;
-      if (two) { DA_WAIT(&o_final[1], q1 & 1); ++q1; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      DA_WAIT(o_final, n_q & 1);
+      ++n_q;
       tc_fence_after();
-      uint32_t o0[16], o1[16];
+      uint32_t orow[16];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                   : "=r"(o0[0]), "=r"(o0[1]), "=r"(o0[2]), "=r"(o0[3]), "=r"(o0[4]), "=r"(o0[5]), "=r"(o0[6]), "=r"(o0[7]),
-                     "=r"(o0[8]), "=r"(o0[9]), "=r"(o0[10]), "=r"(o0[11]), "=r"(o0[12]), "=r"(o0[13]), "=r"(o0[14]), "=r"(o0[15])
+                   : "=r"(orow[0]), "=r"(orow[1]), "=r"(orow[2]), "=r"(orow[3]), "=r"(orow[4]), "=r"(orow[5]), "=r"(orow[6]), "=r"(orow[7]),
+                     "=r"(orow[8]), "=r"(orow[9]), "=r"(orow[10]), "=r"(orow[11]), "=r"(orow[12]), "=r"(orow[13]), "=r"(orow[14]), "=r"(orow[15])
                    : "r"(tmem_O + lane_addr) : "memory");
-      if (two) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(o1[0]), "=r"(o1[1]), "=r"(o1[2]), "=r"(o1[3]), "=r"(o1[4]), "=r"(o1[5]), "=r"(o1[6]), "=r"(o1[7]),
-                       "=r"(o1[8]), "=r"(o1[9]), "=r"(o1[10]), "=r"(o1[11]), "=r"(o1[12]), "=r"(o1[13]), "=r"(o1[14]), "=r"(o1[15])
-                     : "r"(tmem_O + DA_NQ + lane_addr) : "memory");
-      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);        // both accumulators sit in registers: the next item may overwrite them
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // every group-0 thread has read the stats (and sum_g)
-      if (row == 0) mbar_arrive(&stats_empty[sb]);
+      if (lane == 0) mbar_arrive(o_free);        // O^T sits in registers: the next item may overwrite the accumulator
 #pragma unroll
       for (int i = 0; i < GMAX; ++i) {
         if (i < G) {
-          const float mb = two ? m1[i] : -INFINITY;
-          const float m = fmaxf(m_run[i], mb);
-          const float f0 = (m_run[i] == -INFINITY) ? 0.f : exp2f(m_run[i] - m);
-          const float f1 = (mb == -INFINITY) ? 0.f : exp2f(mb - m);
-          const float l = l_tot[i] * f0 + (two ? l1[i] * f1 : 0.f);
+          const float l = sbuf[i] + sbuf[GMAX + i] + sbuf[2 * GMAX + i] + sbuf[3 * GMAX + i];
           const float inv_l = l > 0.f ? 1.f / l : 0.f;
-          const float o = (__uint_as_float(o0[i]) * f0 + (two ? __uint_as_float(o1[i]) * f1 : 0.f)) * inv_l;
+          const float o = __uint_as_float(orow[i]) * inv_l;
           const int head = it.kvh * G + i;
-          const float lse = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
           if (p.num_splits == 1) {
             p.out[((size_t)it.b * p.Hq + head) * DA_D + row] = __float2bfloat16(o);
-            if (p.lse && row == 0) p.lse[(size_t)it.b * p.Hq + head] = lse;
+            if (p.lse && row == 0) p.lse[(size_t)it.b * p.Hq + head] = l > 0.f ? (m_run[i] + log2f(l)) * 0.6931471805599453f : -INFINITY;
           } else {
             const size_t r = ((size_t)it.split * p.B + it.b) * p.Hq + head;
             p.part_o[r * DA_D + row] = o;
-            if (row == 0) p.part_lse[r] = lse;
+            if (row == 0) p.part_lse[r] = l > 0.f ? (m_run[i] + log2f(l)) * 0.6931471805599453f : -INFINITY;
           }
         }
       }
-      ++n_q;
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // sbuf is reused by the next item's epilogue
     }
   }
 #undef DA_WAIT

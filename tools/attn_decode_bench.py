@@ -34,6 +34,9 @@ CASES = {
     "bs512_ctx400": (8, [400] * 512, 1), "bs64_ctx2048": (8, [2048] * 64, 1), "bs16_ctx1024_split": (8, [1024] * 16, 4),
     "bs8_ctx4096_split8": (8, [4096] * 8, 8), "tp4shard_bs512_ragged": (2, rng.integers(32, 1500, 512).tolist(), 1),
     "tp8shard_bs1024_ragged": (1, rng.integers(32, 1500, 1024).tolist(), 1),
+    # layout probes: Hkv = 1 makes every (page, head) one contiguous 8 KB run; same bytes as the Hkv = 8 cases above
+    "probe_hkv1_bs2048_ctx512": (1, [512] * 2048, 1),
+    "probe_hkv1_bs8192_ragged": (1, np.clip(rng.lognormal(5.9, 0.7, 8192), 8, 3000).astype(int).tolist(), 1),
 }
 res = {}
 only = sys.argv[2] if len(sys.argv) > 2 else None          # optional: one case only (ncu captures)
