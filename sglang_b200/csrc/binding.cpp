@@ -193,6 +193,29 @@ void sample(const at::Tensor& logits, const at::Tensor& temperature, const at::T
   count();
 }
 
+void greedy_shard(const at::Tensor& logits, int64_t v_valid, int64_t v_offset, int64_t rank, int64_t tp, at::Tensor buf) {
+  CHECK_CUDA(logits); CHECK_LAST_CONTIG(logits); CHECK_CUDA(buf);
+  TORCH_CHECK(logits.dim() == 2 && buf.dim() == 3 && buf.size(0) == tp && buf.size(2) == 4 && buf.is_contiguous() &&
+              buf.scalar_type() == at::kBFloat16 && buf.size(1) >= logits.size(0), "greedy_shard: buf must be bf16 [tp, Bpad >= B, 4]");
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(bf16 || logits.scalar_type() == at::kFloat, "logits must be bf16 or fp32");
+  TORCH_CHECK(v_valid >= 0 && v_valid <= logits.size(1) && v_offset + v_valid < (1 << 24) && rank >= 0 && rank < tp);
+  c10::cuda::CUDAGuard g(logits.device());
+  sglb::greedy_shard(logits.data_ptr(), bf16, (int)logits.size(0), (int)logits.stride(0), (int)v_valid, (int)v_offset, (int)rank, (int)tp,
+                     (int)buf.size(1), buf.data_ptr(), cur_stream());
+  count();
+}
+void greedy_merge(const at::Tensor& buf, int64_t B, c10::optional<at::Tensor> out_slots, c10::optional<at::Tensor> next_token_buf,
+                  at::Tensor out_tokens) {
+  CHECK_CUDA(buf); CHECK_I32(out_tokens);
+  TORCH_CHECK(buf.dim() == 3 && buf.size(2) == 4 && buf.is_contiguous() && buf.scalar_type() == at::kBFloat16 && B <= buf.size(1) &&
+              out_tokens.numel() >= B);
+  c10::cuda::CUDAGuard g(buf.device());
+  sglb::greedy_merge(buf.data_ptr(), (int)buf.size(0), (int)buf.size(1), (int)B, opt_ptr<int>(out_slots), opt_mptr<int>(next_token_buf),
+                     out_tokens.data_ptr<int>(), cur_stream());
+  count();
+}
+
 void apply_token_bitmask(at::Tensor logits, const at::Tensor& bitmask, c10::optional<at::Tensor> row_idx) {
   CHECK_CUDA(logits); CHECK_I32(bitmask); TORCH_CHECK(bitmask.is_contiguous() && logits.dim() == 2);
   const bool bf16 = logits.scalar_type() == at::kBFloat16;
@@ -500,6 +523,8 @@ TORCH_LIBRARY(sglb, m) {
   m.def("sample(Tensor logits, Tensor temperature, Tensor top_k, Tensor top_p, Tensor min_p, Tensor? seeds, "
         "Tensor? out_slots, Tensor(a!)? next_token_buf, Tensor(b!) out_tokens, Tensor(c!)? out_logprobs, int global_seed, "
         "Tensor? step_ptr, int step) -> ()", &sample);
+  m.def("greedy_shard(Tensor logits, int v_valid, int v_offset, int rank, int tp, Tensor(a!) buf) -> ()", &greedy_shard);
+  m.def("greedy_merge(Tensor buf, int B, Tensor? out_slots, Tensor(a!)? next_token_buf, Tensor(b!) out_tokens) -> ()", &greedy_merge);
   m.def("apply_token_bitmask(Tensor(a!) logits, Tensor bitmask, Tensor? row_idx) -> ()", &apply_token_bitmask);
   m.def("apply_penalties(Tensor(a!) logits, Tensor counts, Tensor? prompt_mask, Tensor freq, Tensor pres, Tensor rep) -> ()",
         &apply_penalties);

@@ -90,6 +90,9 @@ void sample(const void* logits, bool bf16, int B, int V, int stride, const float
             const float* top_p, const float* min_p, const long long* seeds, const int* out_slots, int* next_token_buf,
             int* out_tokens, float* out_logprobs, unsigned long long global_seed, const long long* step_ptr, long long step,
             cudaStream_t stream);
+void greedy_shard(const void* logits, bool bf16, int B, int stride, int v_valid, int v_offset, int rank, int tp, int b_pad, void* buf,
+                  cudaStream_t stream);
+void greedy_merge(const void* buf, int tp, int b_pad, int B, const int* out_slots, int* next_token_buf, int* out_tokens, cudaStream_t stream);
 void apply_token_bitmask(void* logits, bool bf16, const int* bitmask, const int* row_idx, int n_rows, int V, int stride,
                          cudaStream_t stream);
 void apply_penalties(float* logits, const int* counts, const unsigned char* prompt_mask, const float* freq, const float* pres,

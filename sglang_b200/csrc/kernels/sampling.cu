@@ -245,6 +245,79 @@ void sample(const void* logits, bool bf16, int B, int V, int stride, const float
 }
 
 // ---------------------------------------------------------------- grammar bitmask: logits[b, v] = -inf where bit == 0
+// ---- vocab-parallel greedy decoding: no [B, V] logits all-gather on the TP decode path.
+// Every rank takes the argmax of its own vocabulary shard and publishes 4 bf16 words per row — (max logit, idx byte 0, 1, 2), all exactly
+// representable — into its own [rank] plane of a [tp, Bpad, 4] buffer whose other planes it zeroes; the arena all-reduce (a sum with
+// zeros: exact) then is an all-gather of 8 bytes per (rank, row), and greedy_merge_kernel picks the winner (ties -> lowest global index,
+// as torch.argmax on the gathered row would).  Reference counterpart: the full-logits all-gather in layers/logits_processor.py:877-905.
+template <typename T>
+__global__ void __launch_bounds__(SAMP_THREADS) greedy_shard_kernel(const T* __restrict__ logits, int stride, int v_valid, int v_offset,
+                                                                    int rank, int tp, int b_pad, __nv_bfloat16* __restrict__ buf) {
+  __shared__ float red[32];
+  __shared__ int s_arg;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const T* lr = logits + (size_t)row * stride;
+  float mx = -INFINITY; int am = 0x7fffffff;
+  for (int i = tid; i < v_valid; i += SAMP_THREADS) {
+    const float v = to_f<T>(lr[i]);
+    if (v > mx) { mx = v; am = i; }
+  }
+  const float gmax = block_reduce_max(mx, red);
+  if (tid == 0) s_arg = 0x7fffffff;
+  __syncthreads();
+  if (mx == gmax && am != 0x7fffffff) atomicMin(&s_arg, am);
+  __syncthreads();
+  if (tid < tp) {
+    __nv_bfloat16* dst = buf + ((size_t)tid * b_pad + row) * 4;
+    if (tid == rank) {
+      const int g = (s_arg == 0x7fffffff) ? 0 : (s_arg + v_offset);
+      // a shard with no valid column (padding past the real vocabulary) publishes the most negative finite bf16
+      const float val = (s_arg == 0x7fffffff) ? -3.3e38f : fmaxf(gmax, -3.3e38f);
+      dst[0] = __float2bfloat16(val);
+      dst[1] = __float2bfloat16((float)(g & 255));
+      dst[2] = __float2bfloat16((float)((g >> 8) & 255));
+      dst[3] = __float2bfloat16((float)((g >> 16) & 255));
+    } else {
+      dst[0] = dst[1] = dst[2] = dst[3] = __float2bfloat16(0.f);
+    }
+  }
+}
+
+__global__ void greedy_merge_kernel(const __nv_bfloat16* __restrict__ buf, int tp, int b_pad, int B, const int* __restrict__ out_slots,
+                                    int* __restrict__ next_token_buf, int* __restrict__ out_tokens) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  float best = -INFINITY; int tok = 0;
+  for (int r = 0; r < tp; ++r) {
+    const __nv_bfloat16* src = buf + ((size_t)r * b_pad + row) * 4;
+    const float v = __bfloat162float(src[0]);
+    if (v > best) {          // strict: equal maxima keep the lower rank = the lower global index
+      best = v;
+      tok = (int)__bfloat162float(src[1]) | ((int)__bfloat162float(src[2]) << 8) | ((int)__bfloat162float(src[3]) << 16);
+    }
+  }
+  out_tokens[row] = tok;
+  if (next_token_buf != nullptr && out_slots != nullptr) next_token_buf[out_slots[row]] = tok;
+}
+
+void greedy_shard(const void* logits, bool bf16, int B, int stride, int v_valid, int v_offset, int rank, int tp, int b_pad, void* buf,
+                  cudaStream_t stream) {
+  if (B <= 0) return;
+  if (tp > 32) throw std::runtime_error("sglb greedy_shard: tp <= 32");
+  if (bf16)
+    greedy_shard_kernel<__nv_bfloat16><<<B, SAMP_THREADS, 0, stream>>>((const __nv_bfloat16*)logits, stride, v_valid, v_offset, rank, tp, b_pad,
+                                                                       (__nv_bfloat16*)buf);
+  else
+    greedy_shard_kernel<float><<<B, SAMP_THREADS, 0, stream>>>((const float*)logits, stride, v_valid, v_offset, rank, tp, b_pad, (__nv_bfloat16*)buf);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void greedy_merge(const void* buf, int tp, int b_pad, int B, const int* out_slots, int* next_token_buf, int* out_tokens, cudaStream_t stream) {
+  if (B <= 0) return;
+  greedy_merge_kernel<<<(B + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16*)buf, tp, b_pad, B, out_slots, next_token_buf, out_tokens);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+}
+
 template <typename T>
 __global__ void apply_bitmask_kernel(T* __restrict__ logits, const int* __restrict__ bitmask, const int* __restrict__ row_idx,
                                      int V, int stride, int words) {

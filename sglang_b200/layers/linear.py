@@ -270,3 +270,22 @@ class ParallelLMHead(VocabParallelEmbedding):
         if self.tp.world_size > 1:
             y = self.tp.all_gather(y, dim=-1)
         return y[:, : self.vocab_size]
+
+
+def vocab_parallel_greedy(head: VocabParallelEmbedding, hidden: torch.Tensor, buf: torch.Tensor, out_slots, next_token_buf,
+                          out_tokens: torch.Tensor) -> torch.Tensor:
+    """Greedy next tokens WITHOUT gathering [B, V] logits: per-rank shard argmax -> 8 bytes per (rank, row) exchanged through the arena
+    all-reduce (sum with zeros = exact all-gather) -> merge.  ``buf`` is a zero-initialised bf16 [tp, Bpad, 4] scratch owned by the caller
+    (static inside a captured graph).  Replaces the NCCL all-gather of logits_processor.py:877-905 on the TP decode path."""
+    tp = head.tp
+    B = hidden.shape[0]
+    y = ops.linear(hidden, head.weight)                                        # [B, V / tp]
+    v_valid = max(0, min(head.local_vocab, head.vocab_size - head.vocab_start))
+    ops.greedy_shard(y, v_valid, head.vocab_start, tp.rank_in_group, tp.world_size, buf)
+    if tp.world_size == 1:
+        g = buf
+    elif buf.is_cuda:
+        g = tp.all_reduce(buf)
+    else:
+        g = tp.all_reduce(buf.float()).to(buf.dtype)       # Gloo (CPU tier): no bf16 reduction
+    return ops.greedy_merge(g, B, out_slots, next_token_buf, out_tokens)

@@ -157,6 +157,7 @@ class ModelRunner:
             self._res_ring = [(torch.zeros(self.max_running + 8, dtype=torch.int32).pin_memory(),
                                torch.zeros(self.max_running + 8, dtype=torch.float32).pin_memory()) for _ in range(8)]
         self.graphs: Dict[int, Any] = {}
+        self.graphs_greedy: Dict[int, Any] = {}      # TP > 1: all-greedy batches skip the [B, V] logits all-gather (vocab-parallel argmax)
         self.graph_bs: List[int] = []
         self.graph_launches = 0       # kernels replayed through CUDA graphs (for gpu_launches accounting)
         self.step_counter = 0
@@ -765,13 +766,34 @@ class ModelRunner:
         t0 = time.perf_counter()
         pool = None
         kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads
+        shard_greedy = self.greedy_head() is not None
         for bs in reversed(self.graph_bs):
             g = _DecodeGraph(self, bs)
             g.capture(pool)
             pool = g.graph.pool()
             self.graphs[bs] = g
+            if shard_greedy:
+                gg = _DecodeGraph(self, bs, greedy=True)
+                gg.capture(pool)
+                self.graphs_greedy[bs] = gg
         logger.info("captured %d decode graphs (bs %s..%s) in %.1fs", len(self.graphs), self.graph_bs[0], self.graph_bs[-1],
                     time.perf_counter() - t0)
+
+    def greedy_head(self):
+        """the vocab-sharded head when all-greedy decode batches may use the vocab-parallel argmax (TP > 1, plain LM head, no DP-attention
+        row exchange); None otherwise"""
+        from ..environ import envs
+        from ..layers.dp_attention import get_dp_ctx
+        from ..layers.linear import VocabParallelEmbedding
+        from ..models.llama import LlamaForCausalLM
+
+        if self.tp.world_size <= 1 or not envs.SGLB_TP_GREEDY_SHARD.get() or get_dp_ctx() is not None or not self.pp.is_last:
+            return None
+        m = self.model
+        if getattr(type(m), "compute_logits", None) is not LlamaForCausalLM.compute_logits:
+            return None
+        head = m.lm_head if getattr(m, "lm_head", None) is not None else getattr(getattr(m, "model", None), "embed_tokens", None)
+        return head if isinstance(head, VocabParallelEmbedding) else None
 
     def recapture_graphs(self) -> None:
         """components installed after construction that change what a decode step launches (the LoRA manager wraps every projection with
@@ -779,6 +801,7 @@ class ModelRunner:
         if not self.graphs:
             return
         self.graphs.clear()
+        self.graphs_greedy.clear()
         self.graph_bs = []
         with torch.cuda.stream(self.stream):
             self._capture_graphs()
@@ -789,10 +812,11 @@ class ModelRunner:
         import bisect
 
         bs = self.graph_bs[bisect.bisect_left(self.graph_bs, B)]
-        g = self.graphs[bs]
+        s4 = sampling_rows(sb.reqs)                  # [4, B] float32: temperature, top_p, min_p, top_k (cached per request)
+        g = self.graphs_greedy[bs] if (self.graphs_greedy and float(s4[3].max()) <= 1.0) else self.graphs[bs]
         # page-table deltas are applied eagerly (their count is unbounded), then one graph launch
         nd = 0 if sb.pt_rows is None else sb.pt_rows.size
-        g.load(sb, self.step_counter, self.args.random_seed)
+        g.load(sb, self.step_counter, self.args.random_seed, s4)
         if self.lora_manager is not None:
             self.lora_manager.prepare_batch(sb)          # refresh the static tile table the captured SGMV kernels read
         if nd:
@@ -829,9 +853,10 @@ def sampling_rows(reqs) -> np.ndarray:
 class _DecodeGraph:
     """One captured decode step for a fixed (padded) batch size."""
 
-    def __init__(self, runner: ModelRunner, bs: int):
+    def __init__(self, runner: ModelRunner, bs: int, greedy: bool = False):
         self.r = runner
         self.bs = bs
+        self.greedy = greedy
         dev = runner.device
         # static int region: positions | out_cache_loc | req_slots | seq_lens | step(2) | temperature | top_p | min_p | top_k
         self.n_int = 8 * bs + 2
@@ -845,6 +870,7 @@ class _DecodeGraph:
         self.min_p = s[o + 2 * bs:o + 3 * bs].view(torch.float32)
         self.top_k = s[o + 3 * bs:o + 4 * bs]
         self.out_tokens = torch.zeros(bs, dtype=torch.int32, device=dev)
+        self.greedy_buf = torch.zeros(runner.tp.world_size, (bs + 1) // 2 * 2, 4, dtype=torch.bfloat16, device=dev) if greedy else None
         self.graph = torch.cuda.CUDAGraph()
         self.num_kernels = 0
         self.num_splits = runner._pick_splits(bs, min(runner.max_context_len, 4096))
@@ -868,6 +894,11 @@ class _DecodeGraph:
         r = self.r
         fb = self._fb()
         hidden = r.model(fb)
+        if self.greedy:
+            from ..layers.linear import vocab_parallel_greedy
+
+            vocab_parallel_greedy(r.greedy_head(), hidden, self.greedy_buf, self.req_slots, r.next_token_buf, self.out_tokens)
+            return
         logits = r.model.compute_logits(hidden)
         torch.ops.sglb.sample(logits, self.temperature, self.top_k, self.top_p, self.min_p, None, self.req_slots,
                               r.next_token_buf, self.out_tokens, None, int(r.args.random_seed), self.step, 0)
@@ -899,7 +930,7 @@ class _DecodeGraph:
                 nvl.end_capture()
         self.num_kernels = ops.launch_count() - c0
 
-    def load(self, sb: ScheduleBatch, step: int, seed: int) -> None:
+    def load(self, sb: ScheduleBatch, step: int, seed: int, s4: Optional[np.ndarray] = None) -> None:
         B, bs = len(sb.reqs), self.bs
         r_ = self.r
         r_._ring_i += 1
@@ -911,7 +942,8 @@ class _DecodeGraph:
         h[3 * bs:3 * bs + B] = sb.seq_lens; h[3 * bs + B:4 * bs] = 1
         h[4 * bs:4 * bs + 2] = np.asarray([step], dtype=np.int64).view(np.int32)
         o = 4 * bs + 2
-        s4 = sampling_rows(sb.reqs)                  # [4, B] float32: temperature, top_p, min_p, top_k (cached per request)
+        if s4 is None:
+            s4 = sampling_rows(sb.reqs)
         h[o:o + B] = s4[0].view(np.int32)
         h[o + B:o + bs] = np.float32(1.0).view(np.int32)
         h[o + bs:o + bs + B] = s4[1].view(np.int32)

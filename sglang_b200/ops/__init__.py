@@ -333,6 +333,44 @@ def sample(logits, temperature, top_k, top_p, min_p, seeds=None, out_slots=None,
     return tok
 
 
+def greedy_shard(logits: torch.Tensor, v_valid: int, v_offset: int, rank: int, tp: int, buf: torch.Tensor) -> None:
+    """argmax of this rank's vocabulary shard -> buf[rank, row] = (max logit, idx byte 0, 1, 2) as bf16; the other ranks' planes are zeroed so
+    that an all-reduce (sum) of ``buf`` is an exact all-gather (sampling.cu greedy_shard_kernel)"""
+    B = logits.shape[0]
+    if _use_native(logits):
+        torch.ops.sglb.greedy_shard(logits, int(v_valid), int(v_offset), int(rank), int(tp), buf)
+        return
+    buf[:, :B].zero_()
+    if v_valid > 0:
+        val, idx = logits[:, :v_valid].float().max(dim=1)
+        g = idx + int(v_offset)
+    else:
+        val = torch.full((B,), -3.3e38, dtype=torch.float32, device=logits.device)
+        g = torch.zeros(B, dtype=torch.long, device=logits.device)
+    buf[rank, :B, 0] = val.clamp(min=-3.3e38).to(buf.dtype)
+    buf[rank, :B, 1] = (g & 255).to(buf.dtype)
+    buf[rank, :B, 2] = ((g >> 8) & 255).to(buf.dtype)
+    buf[rank, :B, 3] = ((g >> 16) & 255).to(buf.dtype)
+
+
+def greedy_merge(buf: torch.Tensor, B: int, out_slots=None, next_token_buf=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """winner over the gathered per-rank (max, index) pairs; equal maxima keep the lowest global index"""
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=buf.device)
+    if _use_native(buf):
+        torch.ops.sglb.greedy_merge(buf, int(B), out_slots, next_token_buf, out)
+        return out
+    v = buf[:, :B, 0].float()                              # [tp, B]
+    r = v.argmax(dim=0)                                    # first maximum = lowest rank
+    w = buf[:, :B, 1:].float().long()                      # [tp, B, 3]
+    sel = w.gather(0, r.view(1, B, 1).expand(1, B, 3)).squeeze(0)
+    tok = (sel[:, 0] | (sel[:, 1] << 8) | (sel[:, 2] << 16)).to(torch.int32)
+    out[:B] = tok
+    if next_token_buf is not None and out_slots is not None:
+        next_token_buf[out_slots[:B].long()] = tok
+    return out
+
+
 def apply_token_bitmask(logits: torch.Tensor, bitmask: torch.Tensor, row_idx: Optional[torch.Tensor] = None) -> None:
     if _use_native(logits):
         torch.ops.sglb.apply_token_bitmask(logits, bitmask, row_idx)

@@ -35,6 +35,23 @@ if int(os.environ.get("RANK", 0)) == 0:      # only the driver rank receives out
         res["dwdp"] = {"forwards": m.num_forwards, "prefetches": m.num_prefetches, "bytes": m.bytes_moved,
                        "a2a_calls": sum(getattr(l, "_a2a_calls", 0) for l in m.layers)}
     print("RESULT " + json.dumps(res), flush=True)
+if os.environ.get("SGLB_TEST_GREEDY_SHARD"):
+    import torch
+    from sglang_b200.layers.linear import vocab_parallel_greedy
+
+    r = eng.runner
+    head = r.greedy_head()
+    assert head is not None, "vocab-parallel greedy head expected at TP > 1"
+    g = torch.Generator().manual_seed(7)
+    hid = torch.randn(5, head.weight.shape[1], generator=g).to(head.weight.dtype)
+    head.weight.data[:, :] = torch.randn(head.weight.shape, generator=torch.Generator().manual_seed(11 + r.tp.rank)).to(head.weight.dtype) * 0.3
+    want = r.model.compute_logits(hid).float().argmax(dim=-1).to(torch.int32)
+    buf = torch.zeros(r.tp.world_size, 6, 4, dtype=torch.bfloat16)
+    nt = torch.zeros(16, dtype=torch.int32)
+    slots = torch.tensor([3, 1, 4, 9, 2], dtype=torch.int32)
+    got = vocab_parallel_greedy(head, hid, buf, slots, nt, torch.zeros(5, dtype=torch.int32))
+    assert torch.equal(got, want), (got, want)
+    assert torch.equal(nt[slots.long()], want)
 if os.environ.get("SGLB_TEST_EXPECT_A2A"):
     ex = eng.runner.model.model.layers[0].mlp.experts
     assert getattr(ex, "_a2a_calls", 0) > 0, "the all-to-all dispatcher was expected to run"

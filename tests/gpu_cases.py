@@ -580,6 +580,23 @@ def case_sampling():
     top1 = int(si[0])
     expect = float(sp[0] / sp[: len(nucleus)].sum())
     assert abs(cnt.get(top1, 0) / N - expect) < 0.12, (cnt.get(top1, 0) / N, expect)
+    # vocab-parallel greedy: shard argmax -> planes summed (what the arena all-reduce does) -> merge == argmax of the full row
+    tp, Bv, Vl, vocab = 4, 37, 8064, 32000              # 4 x 8064 = 32256 padded columns, the last 256 are padding
+    full = torch.randn(Bv, tp * Vl, device=DEV).to(torch.bfloat16)
+    full[3, 100] = full[3, 20000] = 50.0                # tie across shards: the lower index must win
+    full[5, vocab + 7] = 99.0                           # a padding column must never win
+    acc = torch.zeros(tp, 38, 4, dtype=torch.float32, device=DEV)
+    for r in range(tp):
+        b = torch.zeros(tp, 38, 4, dtype=torch.bfloat16, device=DEV)
+        ops.greedy_shard(full[:, r * Vl:(r + 1) * Vl], max(0, min(Vl, vocab - r * Vl)), r * Vl, r, tp, b)
+        acc += b.float()
+    nt = torch.zeros(64, dtype=torch.int32, device=DEV)
+    sl = torch.arange(1, Bv + 1, dtype=torch.int32, device=DEV)
+    got = ops.greedy_merge(acc.to(torch.bfloat16), Bv, sl, nt)
+    want = full[:, :vocab].float().argmax(-1)
+    want[3] = 100
+    assert torch.equal(got.long(), want), "vocab-parallel greedy mismatch"
+    assert torch.equal(nt[1:Bv + 1], got)
     # bitmask
     lg = torch.randn(4, 1000, device=DEV)
     bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (2, 32), dtype=torch.int32, device=DEV)

@@ -362,3 +362,8 @@ def test_lora_tp2_matches_single():
     ref = _run(kw, 1, gen)
     _check(_run({**kw, "tp_size": 2}, 2, gen), ref)
     assert ref["ids"] != _run(dict(model_path="dummy:tiny-llama", page_size=4), 1, LP)["ids"]
+
+
+def test_vocab_parallel_greedy_matches_gathered_argmax():
+    """TP decode: per-shard argmax + 8-byte exchange + merge == argmax over the all-gathered logits (layers/linear.py vocab_parallel_greedy)"""
+    _run({"model_path": "dummy:tiny-llama", "tp_size": 2, "page_size": 4}, 2, extra_env={"SGLB_TEST_GREEDY_SHARD": "1"})
