@@ -152,12 +152,15 @@ class ModelRunner:
         self._res_ring: List[Any] = []
         self._ring_i = 0
         if self.is_cuda:
-            n_stage = 8 * max(self.max_running, 512) + 2 + 3 * 8192
+            n_stage = max(8 * max(self.max_running, 512), 3 * 4096 + 10 * 128 + 8) + 2 + 3 * 8192
             self._stage_ring = [torch.zeros(n_stage, dtype=torch.int32).pin_memory() for _ in range(4)]
             self._res_ring = [(torch.zeros(self.max_running + 8, dtype=torch.int32).pin_memory(),
                                torch.zeros(self.max_running + 8, dtype=torch.float32).pin_memory()) for _ in range(8)]
         self.graphs: Dict[int, Any] = {}
         self.graphs_greedy: Dict[int, Any] = {}      # TP > 1: all-greedy batches skip the [B, V] logits all-gather (vocab-parallel argmax)
+        self.prefill_graphs: Dict[int, Any] = {}     # token-bucketed prefill graphs (small extends are launch-bound: ~10 kernels per layer)
+        self.prefill_graph_tokens: List[int] = []
+        self.prefill_graph_hits = 0
         self.graph_bs: List[int] = []
         self.graph_launches = 0       # kernels replayed through CUDA graphs (for gpu_launches accounting)
         self.step_counter = 0
@@ -452,6 +455,8 @@ class ModelRunner:
             B <= self.graph_bs[-1] and not sb.needs_host_state()
         if use_graph:
             return self._forward_graph(sb)
+        if self.prefill_graphs and not decode and self._prefill_graph_eligible(sb):
+            return self._forward_prefill_graph(sb)
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
         self.h2d_bytes += fb.h2d_bytes
         fb.num_splits = self._pick_splits(B, fb.max_kv_len) if decode else 1
@@ -778,6 +783,78 @@ class ModelRunner:
                 self.graphs_greedy[bs] = gg
         logger.info("captured %d decode graphs (bs %s..%s) in %.1fs", len(self.graphs), self.graph_bs[0], self.graph_bs[-1],
                     time.perf_counter() - t0)
+        self._capture_prefill_graphs(pool)
+
+    # ------------------------------------------------------------------ prefill graphs
+    def _capture_prefill_graphs(self, pool) -> None:
+        """Token-bucketed graphs of a whole ragged extend step (embed -> layers -> last-row gather -> LM head -> sampler).  Reference:
+        model_executor/runner/prefill_cuda_graph_runner.py (bucketed by token count, padded).  Every per-step quantity lives in ONE static
+        int32 buffer; padded requests have q_len 0 (their attention work items exit at once), padded tokens write their K/V to slot 0."""
+        a = self.args
+        cap_t = int(getattr(a, "prefill_cuda_graph_max_tokens", 0) or 0)
+        if cap_t <= 0 or a.disable_cuda_graph or not self.is_cuda:
+            return
+        if self.pp.world_size > 1 or self.cp is not None or a.enable_sp or a.enable_two_batch_overlap or getattr(self, "dcp", None) is not None:
+            return
+        from ..layers.dp_attention import get_dp_ctx
+
+        if get_dp_ctx() is not None or getattr(self.model, "is_embedding", False) or not hasattr(self.model, "compute_logits"):
+            return
+        buckets = [t for t in (64, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096) if t <= cap_t]
+        if not buckets:
+            return
+        t0 = time.perf_counter()
+        for T in reversed(buckets):
+            g = _PrefillGraph(self, T)
+            g.capture(pool)
+            pool = g.graph.pool()
+            self.prefill_graphs[T] = g
+        self.prefill_graph_tokens = sorted(self.prefill_graphs)
+        logger.info("captured %d prefill graphs (%d..%d tokens) in %.1fs", len(buckets), buckets[0], buckets[-1], time.perf_counter() - t0)
+
+    def _prefill_graph_eligible(self, sb: ScheduleBatch) -> bool:
+        if sb.return_logprob or sb.has_grammar or sb.spec_info is not None or sb.needs_host_state():
+            return False
+        if self.lora_manager is not None or self.hidden_tap is not None or self.aux_layer_ids is not None:
+            return False
+        T = int(sb.q_lens.sum())
+        if T > self.prefill_graph_tokens[-1]:
+            return False
+        import bisect
+
+        g = self.prefill_graphs[self.prefill_graph_tokens[bisect.bisect_left(self.prefill_graph_tokens, T)]]
+        if len(sb.reqs) > g.bcap:
+            return False
+        for r in sb.reqs:
+            if r.is_embedding or r.return_hidden_states or getattr(r, "mm_inputs", None) is not None:
+                return False
+        return True
+
+    def _forward_prefill_graph(self, sb: ScheduleBatch) -> BatchResult:
+        import bisect
+
+        B = len(sb.reqs)
+        T = int(sb.q_lens.sum())
+        g = self.prefill_graphs[self.prefill_graph_tokens[bisect.bisect_left(self.prefill_graph_tokens, T)]]
+        nd = g.load(sb, self.step_counter)
+        if nd:
+            d = g.delta_views(nd)
+            ops.apply_pt_delta(self.page_table, d[0], d[1], d[2])
+        g.graph.replay()
+        self.graph_launches += g.num_kernels
+        self.prefill_graph_hits += 1
+        res = BatchResult()
+        res.batch_size = B
+        samp = np.flatnonzero(sb.sample_mask)
+        res.sample_rows = samp
+        if samp.size == 0:
+            res.next_token_ids = np.full(B, -1, dtype=np.int64)
+            return res
+        toks = g.out_tokens[:B]
+        if samp.size != B:
+            toks = toks[torch.from_numpy(samp).to(self.device, non_blocking=True)]
+        self._finish_result(res, toks, None)
+        return res
 
     def greedy_head(self):
         """the vocab-sharded head when all-greedy decode batches may use the vocab-parallel argmax (TP > 1, plain LM head, no DP-attention
@@ -802,6 +879,8 @@ class ModelRunner:
             return
         self.graphs.clear()
         self.graphs_greedy.clear()
+        self.prefill_graphs.clear()
+        self.prefill_graph_tokens = []
         self.graph_bs = []
         with torch.cuda.stream(self.stream):
             self._capture_graphs()
@@ -848,6 +927,128 @@ def sampling_rows(reqs) -> np.ndarray:
             t = r.samp4 = (float(p.temperature), float(p.top_p), float(p.min_p), float(min(p.top_k, 1 << 30)))
         rows.append(t)
     return np.ascontiguousarray(np.asarray(rows, dtype=np.float32).reshape(-1, 4).T) if rows else np.zeros((4, 0), dtype=np.float32)
+
+
+class _PrefillGraph:
+    """One captured ragged-extend step for a token bucket: up to ``tcap`` new tokens spread over up to ``bcap`` requests."""
+
+    def __init__(self, runner: ModelRunner, tcap: int):
+        self.r = runner
+        self.tcap = tcap
+        self.bcap = bc = max(1, min(tcap // 4, 128))
+        dev = runner.device
+        # static int region: input_ids | positions | out_cache_loc (tcap each) | cu_q (bc + 1) | q_lens | req_slots | seq_lens | last_idx |
+        # sample_slots | temperature | top_p | min_p | top_k (bc each) | step (2)
+        self.n_int = 3 * tcap + (bc + 1) + 9 * bc + 2
+        self.static = torch.zeros(self.n_int + 3 * 8192, dtype=torch.int32, device=dev)
+        s = self.static
+        self.input_ids, self.positions, self.out_cache_loc = s[0:tcap], s[tcap:2 * tcap], s[2 * tcap:3 * tcap]
+        o = 3 * tcap
+        self.cu_q = s[o:o + bc + 1]
+        o += bc + 1
+        self.q_lens, self.req_slots, self.seq_lens = s[o:o + bc], s[o + bc:o + 2 * bc], s[o + 2 * bc:o + 3 * bc]
+        self.last_idx, self.sample_slots = s[o + 3 * bc:o + 4 * bc], s[o + 4 * bc:o + 5 * bc]
+        self.temperature = s[o + 5 * bc:o + 6 * bc].view(torch.float32)
+        self.top_p = s[o + 6 * bc:o + 7 * bc].view(torch.float32)
+        self.min_p = s[o + 7 * bc:o + 8 * bc].view(torch.float32)
+        self.top_k = s[o + 8 * bc:o + 9 * bc]
+        self.o_req = o
+        self.step = s[o + 9 * bc:o + 9 * bc + 2].view(torch.int64)
+        self.out_tokens = torch.zeros(bc, dtype=torch.int32, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.num_kernels = 0
+
+    def _run(self) -> None:
+        r = self.r
+        samp = SamplingTensors(self.temperature, self.top_k, self.top_p, self.min_p)
+        fb = ForwardBatch(mode=ForwardMode.EXTEND, batch_size=self.bcap, num_tokens=self.tcap, input_ids=self.input_ids,
+                          positions=self.positions, out_cache_loc=self.out_cache_loc, req_slots=self.req_slots, seq_lens=self.seq_lens,
+                          cu_q=self.cu_q, q_lens=self.q_lens, last_idx=self.last_idx, sample_slots=self.sample_slots,
+                          max_q_len=self.tcap, max_kv_len=r.max_context_len, page_table=r.page_table, page_size=r.page_size,
+                          kv_pool=r.kv_pool, sampling=samp, next_token_buf=r.next_token_buf)
+        hidden = r.model(fb)
+        h_last = ops.gather_rows(hidden, self.last_idx)
+        logits = r.model.compute_logits(h_last)
+        torch.ops.sglb.sample(logits, self.temperature, self.top_k, self.top_p, self.min_p, None, self.sample_slots, r.next_token_buf,
+                              self.out_tokens, None, int(r.args.random_seed), self.step, 0)
+
+    def _neutral(self) -> np.ndarray:
+        """host image of an empty step: one dummy request owning every token (so warm-up / capture exercise the real kernels)"""
+        bc, tcap = self.bcap, self.tcap
+        h = np.zeros(self.n_int, dtype=np.int32)
+        h[tcap:2 * tcap] = np.arange(tcap)                    # positions
+        o3 = 3 * tcap
+        h[o3 + 1:o3 + bc + 1] = tcap                          # cu_q: request 0 owns all tokens, the rest are empty
+        o = self.o_req
+        h[o] = tcap                                           # q_lens[0]
+        h[o + 2 * bc] = tcap                                  # seq_lens[0]
+        h[o + 5 * bc:o + 7 * bc] = np.float32(1.0).view(np.int32)   # temperature, top_p
+        h[o + 8 * bc:o + 9 * bc] = 1                          # top_k = 1
+        return h
+
+    def capture(self, pool) -> None:
+        self.static[:self.n_int].copy_(torch.from_numpy(self._neutral()))
+        stream = torch.cuda.current_stream()
+        for _ in range(2):
+            self._run()
+        stream.synchronize()
+        nvl = self.r.tp.nvl
+        if nvl is not None:
+            self.r.tp.barrier()
+            nvl.begin_capture()
+        c0 = ops.launch_count()
+        try:
+            with torch.cuda.graph(self.graph, pool=pool, stream=stream):
+                self._run()
+        finally:
+            if nvl is not None:
+                nvl.end_capture()
+        self.num_kernels = ops.launch_count() - c0
+
+    def load(self, sb: ScheduleBatch, step: int) -> int:
+        r_ = self.r
+        B, bc, tcap = len(sb.reqs), self.bcap, self.tcap
+        T = int(sb.q_lens.sum())
+        r_._ring_i += 1
+        host = r_._stage_ring[r_._ring_i % len(r_._stage_ring)]
+        if host.numel() < self.static.numel():
+            raise RuntimeError("prefill graph staging buffer too small")
+        h = host.numpy()
+        h[0:T] = sb.input_ids; h[T:tcap] = 0
+        h[tcap:tcap + T] = sb.positions; h[tcap + T:2 * tcap] = 0
+        h[2 * tcap:2 * tcap + T] = sb.out_cache_loc; h[2 * tcap + T:3 * tcap] = 0
+        o3 = 3 * tcap
+        h[o3] = 0
+        cu = np.cumsum(sb.q_lens)
+        h[o3 + 1:o3 + 1 + B] = cu; h[o3 + 1 + B:o3 + bc + 1] = T
+        o = self.o_req
+        h[o:o + B] = sb.q_lens; h[o + B:o + bc] = 0
+        h[o + bc:o + bc + B] = sb.req_slots; h[o + bc + B:o + 2 * bc] = 0
+        h[o + 2 * bc:o + 2 * bc + B] = sb.seq_lens; h[o + 2 * bc + B:o + 3 * bc] = 0
+        h[o + 3 * bc:o + 3 * bc + B] = cu - 1; h[o + 3 * bc + B:o + 4 * bc] = 0
+        # requests whose prompt is not finished by this chunk sample into the dummy slot 0
+        h[o + 4 * bc:o + 4 * bc + B] = np.where(sb.sample_mask, sb.req_slots, 0); h[o + 4 * bc + B:o + 5 * bc] = 0
+        s4 = sampling_rows(sb.reqs)
+        h[o + 5 * bc:o + 5 * bc + B] = s4[0].view(np.int32); h[o + 5 * bc + B:o + 6 * bc] = np.float32(1.0).view(np.int32)
+        h[o + 6 * bc:o + 6 * bc + B] = s4[1].view(np.int32); h[o + 6 * bc + B:o + 7 * bc] = np.float32(1.0).view(np.int32)
+        h[o + 7 * bc:o + 7 * bc + B] = s4[2].view(np.int32); h[o + 7 * bc + B:o + 8 * bc] = 0
+        h[o + 8 * bc:o + 8 * bc + B] = s4[3].astype(np.int32); h[o + 8 * bc + B:o + 9 * bc] = 1
+        h[o + 9 * bc:o + 9 * bc + 2] = np.asarray([step], dtype=np.int64).view(np.int32)
+        n = self.n_int
+        nd = 0 if sb.pt_rows is None else sb.pt_rows.size
+        if nd:
+            if n + 3 * nd > self.static.numel():
+                raise RuntimeError("page-table delta overflow in graph staging buffer")
+            h[n:n + nd] = sb.pt_rows; h[n + nd:n + 2 * nd] = sb.pt_cols; h[n + 2 * nd:n + 3 * nd] = sb.pt_vals
+        tot = n + 3 * nd
+        self.static[:tot].copy_(host[:tot], non_blocking=True)
+        r_.h2d_bytes += tot * 4
+        return nd
+
+    def delta_views(self, nd: int):
+        n = self.n_int
+        s = self.static
+        return s[n:n + nd], s[n + nd:n + 2 * nd], s[n + 2 * nd:n + 3 * nd]
 
 
 class _DecodeGraph:

@@ -91,6 +91,37 @@ print(json.dumps({{"ids": [o["output_ids"] for o in out],
 
 
 @pytest.mark.gpu
+def test_prefill_cuda_graphs_match_eager_prefill():
+    """token-bucketed prefill graphs (padded ragged extend + LM head + sampler in one replay) against the eager extend path"""
+    code = '''
+import json
+import sglang_b200 as sgl
+import numpy as np
+rng = np.random.default_rng(1)
+prompts = [rng.integers(3, 2000, size=int(n)).tolist() for n in rng.integers(5, 300, size=14)]
+eng = sgl.Engine(model_path="dummy:tiny-llama-gpu", page_size=32, chunked_prefill_size=256, cuda_graph_max_bs=16, mem_fraction_static=0.2,
+                 max_running_requests=16, prefill_cuda_graph_max_tokens=PGT)
+outs = []
+for p in prompts[:4]:                     # one request per step: small buckets
+    outs += eng.generate(input_ids=[p], sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True})
+outs += eng.generate(input_ids=prompts[4:], sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True})   # ragged multi-request chunks
+eng.scheduler.check_invariants()
+print(json.dumps({"ids": [o["output_ids"] for o in outs], "hits": eng.runner.prefill_graph_hits}))
+'''
+    res = {}
+    for tag, pgt in (("graph", "512"), ("eager", "0")):
+        p = subprocess.run([sys.executable, "-c", code.replace("PGT", pgt)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-4000:]
+        res[tag] = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["graph"]["hits"] >= 4 and res["eager"]["hits"] == 0
+    g, e = res["graph"]["ids"], res["eager"]["ids"]
+    first = sum(a[:1] == b[:1] for a, b in zip(g, e))
+    same = sum(a == b for a, b in zip(g, e))
+    assert first >= len(e) - 1 and same >= len(e) - 3, (first, same, g, e)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("model", ["tiny-mixtral-gpu"])
 def test_moe_engine_gpu_native_vs_torch_ops(model):
     """Mixtral-style engine on the GPU: native kernels (MoE block, tcgen05 attention, CUDA graphs) vs the same engine with every op forced
