@@ -364,6 +364,9 @@ def _free_port() -> int:
 def _peer_main(args: ServerArgs, rank: int, world: int, master_port: int, master_addr: str = "127.0.0.1", local_rank: Optional[int] = None) -> None:
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank if local_rank is None else local_rank), WORLD_SIZE=str(world), MASTER_ADDR=master_addr,
                       MASTER_PORT=str(master_port))
+    from ..utils.process_tree import die_with_parent
+
+    die_with_parent()          # a killed rank-0 server must not leave GPU-holding peers behind
     from .engine import Engine
 
     eng = Engine(server_args=args)
@@ -436,12 +439,22 @@ def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], pee
         if ready_event is not None:
             ready_event.set()
 
+    from ..utils.process_tree import SubprocessWatchdog, graceful_sigterm, kill_process_tree
+
+    graceful_sigterm()         # uvicorn re-raises the SIGTERM it captured once its loop stopped: make that run the clean-up below
+    children = list(peers) + [p for p in (getattr(engine, "_p_sched", None), getattr(engine, "_p_detok", None)) if p is not None]
+    dog = SubprocessWatchdog(children) if children else None
+    if dog is not None:
+        dog.start()
     try:
         uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5)
     finally:
-        engine.shutdown()
-        for p in peers:
-            p.terminate()
+        if dog is not None:
+            dog.stop()
+        try:
+            engine.shutdown()
+        finally:
+            kill_process_tree(children, grace_s=3.0)
 
 
 def main(argv=None) -> None:

@@ -27,6 +27,9 @@ logger = logging.getLogger(__name__)
 
 
 def _replica_main(args_dict: Dict[str, Any], dp_rank: int, inq: Any, outq: Any) -> None:
+    from ..utils.process_tree import die_with_parent
+
+    die_with_parent()
     args = ServerArgs(**args_dict)
     if args.device == "cuda":
         os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(args.base_gpu_id + dp_rank * args.tp_size + i) for i in range(args.tp_size))

@@ -48,6 +48,9 @@ def scheduler_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready: 
 
     from ..entrypoints.engine import Engine
 
+    from ..utils.process_tree import die_with_parent
+
+    die_with_parent()
     try:
         os.environ["SGLB_IN_SCHEDULER_PROCESS"] = "1"
         from ..entrypoints.http_server import spawn_peers
@@ -118,7 +121,9 @@ def detokenizer_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready
     from ..configs.model_config import load_model_config
     from ..utils.tokenizer import get_tokenizer
     from .detokenizer import Detokenizer
+    from ..utils.process_tree import die_with_parent
 
+    die_with_parent()
     try:
         cfg = load_model_config(server_args.model_path, None, server_args.context_length)
         tok = get_tokenizer(server_args.tokenizer_path, cfg.vocab_size, cfg.eos_token_id, cfg.bos_token_id, server_args.trust_remote_code)

@@ -48,3 +48,78 @@ def test_http_stream_and_control_over_processes(front):
         assert "sglang:" in c.get("/metrics").text
         assert c.get("/v1/models").json()["data"][0]["max_model_len"] > 0
     assert front.get_load()["num_running_reqs"] == 0
+
+
+def _children_of(pid: int):
+    import psutil
+
+    try:
+        return [c.pid for c in psutil.Process(pid).children(recursive=True)]
+    except psutil.NoSuchProcess:
+        return []
+
+
+@pytest.mark.parametrize("sig", ["TERM", "KILL"])
+def test_server_leaves_no_orphans(sig, tmp_path):
+    """SIGTERM runs the orderly shutdown (uvicorn re-raises the captured signal; utils/process_tree.graceful_sigterm turns it into the finally
+    path); SIGKILL of the front end still takes the scheduler / detokenizer down through PR_SET_PDEATHSIG (reference watchdog.py:166-223)"""
+    import os
+    import signal
+    import socket
+    import subprocess
+    import sys
+    import time
+    import urllib.request
+
+    import psutil
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
+                          "--host", "127.0.0.1", "--log-level", "error", "--enable-multi-process-frontend"], cwd=root,
+                         env=dict(os.environ, PYTHONPATH=root), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        for _ in range(120):
+            try:
+                if urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.5)
+        else:
+            pytest.fail("server did not come up")
+        kids = _children_of(p.pid)
+        assert len(kids) >= 2, kids
+        p.send_signal(signal.SIGTERM if sig == "TERM" else signal.SIGKILL)
+        p.wait(timeout=30)
+        t_end = time.time() + 15
+        while time.time() < t_end and any(psutil.pid_exists(k) and psutil.Process(k).status() != psutil.STATUS_ZOMBIE for k in kids):
+            time.sleep(0.25)
+        left = [k for k in kids if psutil.pid_exists(k) and psutil.Process(k).status() != psutil.STATUS_ZOMBIE]
+        assert not left, f"orphaned children after SIG{sig}: {left}"
+    finally:
+        if p.poll() is None:
+            p.kill()
+        for k in _children_of(p.pid):
+            try:
+                os.kill(k, signal.SIGKILL)
+            except OSError:
+                pass
+
+
+def test_subprocess_watchdog_reports_dead_child():
+    import subprocess
+    import sys
+    import time
+
+    from sglang_b200.utils.process_tree import SubprocessWatchdog
+
+    ok = subprocess.Popen([sys.executable, "-c", "import time; time.sleep(30)"])
+    bad = subprocess.Popen([sys.executable, "-c", "import sys; sys.exit(3)"])
+    seen = []
+    dog = SubprocessWatchdog([ok, bad], ["ok", "bad"], interval_s=0.05, on_death=lambda n, c: seen.append((n, c)))
+    dog.start()
+    t0 = time.time()
+    while not seen and time.time() - t0 < 10:
+        time.sleep(0.05)
+    dog.stop(); ok.kill(); ok.wait()
+    assert seen == [("bad", 3)]
