@@ -157,6 +157,13 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
   }
 }
 
+// bench tool: per-role cycle accounting of the decode attention kernel into buf [ctas * 30] (int64); an empty tensor turns it off
+void attn_decode_prof(const at::Tensor& buf) {
+  if (buf.numel() == 0) { sglb::attn_decode_set_prof(nullptr); return; }
+  CHECK_CUDA(buf); TORCH_CHECK(buf.scalar_type() == at::kLong && buf.is_contiguous() && buf.numel() >= 148 * 30);
+  sglb::attn_decode_set_prof((long long*)buf.data_ptr<int64_t>());
+}
+
 // out[M, N(/2 for silu_mul)] = a[M, K] @ w[N, K]^T (+bias | silu*mul)
 void gemm(const at::Tensor& a, const at::Tensor& w, at::Tensor out, c10::optional<at::Tensor> bias, int64_t epilogue,
           int64_t bn) {
@@ -519,6 +526,7 @@ TORCH_LIBRARY(sglb, m) {
         "Tensor(d!)? part_lse, Tensor page_table, Tensor req_slots, Tensor seq_lens, Tensor? cu_q, Tensor? tok2req, "
         "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
         "float k_scale, float v_scale, int impl) -> ()", &attn_fwd);
+  m.def("attn_decode_prof(Tensor buf) -> ()", &attn_decode_prof);
   m.def("gemm(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int bn) -> ()", &gemm);
   m.def("sample(Tensor logits, Tensor temperature, Tensor top_k, Tensor top_p, Tensor min_p, Tensor? seeds, "
         "Tensor? out_slots, Tensor(a!)? next_token_buf, Tensor(b!) out_tokens, Tensor(c!)? out_logprobs, int global_seed, "

@@ -53,9 +53,10 @@ struct DecodeParams {
   int window;
   int total_items;
   int* sched;             // [0] next item, [1] CTAs finished (the last one re-arms both)
+  long long* prof;        // PROF builds: [ctas][32] per-role cycle accounting (tools/attn_decode_bench.py prof)
 };
 
-template <int GMAX, bool HAS_CAP>
+template <int GMAX, bool HAS_CAP, bool PROF>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const DecodeParams p) {
@@ -86,6 +87,18 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 27); // [6] role state for the timeout dump
   float* red = reinterpret_cast<float*>(bars + 32);                         // [2][4 warps][GMAX] row-max exchange, then [4][GMAX] sums
 #define DA_WAIT(bar_, par_) mbar_wait((bar_), (par_), dbg, 6)
+
+  // PROF builds: the elected thread of each role charges the cycles of a statement to a slot of its local table
+  long long pacc[12];
+  if constexpr (PROF) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pacc[i] = 0;
+  }
+#define DA_T(slot, ...)                                                        \
+  do {                                                                         \
+    if constexpr (PROF) { const long long t0__ = clock64(); __VA_ARGS__; pacc[slot] += clock64() - t0__; } \
+    else { __VA_ARGS__; }                                                      \
+  } while (0)
 #define DA_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
 
   if (warp == 0 && lane == 0) {
@@ -136,7 +149,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int next_idx = atomicAdd(p.sched, 1);
     for (;;) {
       const int slot = n_it & 1;
-      DA_WAIT(&item_empty[slot], ((n_it >> 1) & 1) ^ 1);
+      DA_T(0, DA_WAIT(&item_empty[slot], ((n_it >> 1) & 1) ^ 1));
       // the queue atomic is a ~1 us L2 round trip: fetch the NEXT item's index now and consume it one iteration later, so the round trip
       // overlaps this item's TMA issue instead of stalling the only thread that feeds the ring
       const int idx = next_idx;
@@ -151,7 +164,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       {
         const int qs = n_q & 1;
         uint8_t* qdst = sQ + qs * DA_Q_BYTES;
-        DA_WAIT(&q_empty[qs], ((n_q >> 1) & 1) ^ 1);
+        DA_T(1, DA_WAIT(&q_empty[qs], ((n_q >> 1) & 1) ^ 1));
         mbar_expect_tx(&q_full[qs], 2 * G * 128);
         tma_load_4d(qdst, &tmQ, &q_full[qs], 0, 0, it.kvh, it.b);
         tma_load_4d(qdst + DA_NQ * 128, &tmQ, &q_full[qs], 64, 0, it.kvh, it.b);
@@ -165,7 +178,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);     // only pages that hold live keys
         const int pg0 = key0 / ps;
         const uint32_t bytes = (uint32_t)n_pages * ps * 256;
-        DA_WAIT(&k_empty[st], ph ^ 1);
+        DA_T(2, DA_WAIT(&k_empty[st], ph ^ 1));
+        if constexpr (PROF) pacc[4] += 1;
         mbar_expect_tx(&k_full[st], bytes);
         for (int i = 0; i < n_pages; ++i) {
           const int page = pt[pg0 + i];
@@ -173,7 +187,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, page * ps);
           tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, page * ps);
         }
-        DA_WAIT(&v_empty[st], ph ^ 1);
+        DA_T(3, DA_WAIT(&v_empty[st], ph ^ 1));
         mbar_expect_tx(&v_full[st], bytes);
         for (int i = 0; i < n_pages; ++i) {
           const int page = pt[pg0 + i];
@@ -190,7 +204,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
-      DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
+      DA_T(0, DA_WAIT(&item_full[slot], (n_it >> 1) & 1));
       const int idx = s_item[slot];
       mbar_arrive(&item_empty[slot]);
       ++n_it;
@@ -203,7 +217,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       DA_DBG(2, n_q, g);
       auto issue_S = [&](uint32_t gt, bool last) {
         const int st = gt % DA_STAGES;
-        DA_WAIT(&k_full[st], (gt / DA_STAGES) & 1);
+        DA_T(1, DA_WAIT(&k_full[st], (gt / DA_STAGES) & 1));
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * DA_TILE_BYTES);
 #pragma unroll
@@ -217,15 +231,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(&s_full[gt & 1]);
         if (last) umma_commit(&q_empty[qs]);
       };
-      DA_WAIT(&q_full[qs], (n_q >> 1) & 1);
+      DA_T(5, DA_WAIT(&q_full[qs], (n_q >> 1) & 1));
       issue_S(g, n_tiles == 1);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t gt = g + j;
         const int st = gt % DA_STAGES;
         if (j + 1 < n_tiles) issue_S(gt + 1, j + 2 == n_tiles);
-        DA_WAIT(&p_full[gt & 1], (gt >> 1) & 1);
-        DA_WAIT(&v_full[st], (gt / DA_STAGES) & 1);
-        if (j == 0) DA_WAIT(o_free, (n_q & 1) ^ 1);       // the previous item's epilogue has read O^T
+        DA_T(2, DA_WAIT(&p_full[gt & 1], (gt >> 1) & 1));
+        DA_T(3, DA_WAIT(&v_full[st], (gt / DA_STAGES) & 1));
+        if (j == 0) DA_T(4, DA_WAIT(o_free, (n_q & 1) ^ 1));       // the previous item's epilogue has read O^T
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * DA_TILE_BYTES);
         const uint32_t p_addr = smem_u32(sP + (gt & 1) * DA_P_BYTES);
@@ -251,7 +265,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t n_it = 0, n_q = 0, g = 0;
     for (;;) {
       const int slot = n_it & 1;
-      DA_WAIT(&item_full[slot], (n_it >> 1) & 1);
+      DA_T(0, DA_WAIT(&item_full[slot], (n_it >> 1) & 1));
       const int idx = s_item[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(&item_empty[slot]);
@@ -276,7 +290,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int i = 0; i < GMAX; ++i) { m_run[i] = -INFINITY; l_part[i] = 0.f; }
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t gt = g + j;
-        DA_WAIT(&s_full[gt & 1], (gt >> 1) & 1);
+        DA_T(1, DA_WAIT(&s_full[gt & 1], (gt >> 1) & 1));
+        if constexpr (PROF) pacc[8] += 1;
+        long long tp__ = 0;
+        if constexpr (PROF) tp__ = clock64();
         tc_fence_after();
         uint32_t sr[GMAX];
         {
@@ -293,6 +310,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tmem_ld_wait();
         }
+        if constexpr (PROF) { const long long t__ = clock64(); pacc[2] += t__ - tp__; tp__ = t__; }
         const int key = (it.tile_begin + j) * DA_KT + row;
         const bool live = key < it.kv_hi && key >= kv_first;
         float sv[GMAX], wmax[GMAX];
@@ -309,6 +327,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < GMAX; ++i) rbuf[q4 * GMAX + i] = wmax[i];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if constexpr (PROF) { const long long t__ = clock64(); pacc[3] += t__ - tp__; tp__ = t__; }
         bool need = false;
         float m_new[GMAX];
 #pragma unroll
@@ -340,6 +359,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_st_32x32b_x16(tmem_O + lane_addr, orow);
           tmem_st_wait();
         }
+        if constexpr (PROF) { const long long t__ = clock64(); pacc[4] += t__ - tp__; tp__ = t__; }
         // P^T[query row i][key] (bf16, K-major, 128-byte swizzle): rows >= G stay zero
         uint8_t* pbuf = sP + (gt & 1) * DA_P_BYTES + (row >> 6) * (DA_NQ * 128);
         const int c = row & 63;
@@ -355,11 +375,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's smem reads
         tc_fence_before();
+        if constexpr (PROF) { const long long t__ = clock64(); pacc[5] += t__ - tp__; tp__ = t__; }
         mbar_arrive(&p_full[gt & 1]);
+        if constexpr (PROF) pacc[6] += clock64() - tp__;
       }
       g += n_tiles;
 
       // ---- epilogue: row sums across the 128 key-threads, then O^T / l -> out (thread = output dim)
+      long long te__ = 0;
+      if constexpr (PROF) te__ = clock64();
       if (lane == 0) DA_DBG(4, n_q, g);
       float lsum[GMAX];
 #pragma unroll
@@ -400,10 +424,18 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");      // sbuf is reused by the next item's epilogue
+      if constexpr (PROF) pacc[7] += clock64() - te__;
     }
   }
 #undef DA_WAIT
 #undef DA_DBG
+#undef DA_T
+  if constexpr (PROF) {
+    if (p.prof != nullptr && lane == 0 && warp <= 2) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) p.prof[((size_t)blockIdx.x * 3 + warp) * 10 + i] = pacc[i];
+    }
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -424,6 +456,9 @@ bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size) {
   const int G = Hq / Hkv;
   return G >= 1 && G <= 16 && page_size >= 8 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
 }
+
+static long long* g_da_prof = nullptr;
+void attn_decode_set_prof(long long* buf) { g_da_prof = buf; }
 
 void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o, float* part_lse,
                     const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens, int B, int q_stride, int Hq, int Hkv,
@@ -447,18 +482,26 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
   p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens;
   p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.B = B;
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.window = window;
-  p.total_items = B * Hkv * num_splits; p.sched = sched;
+  p.total_items = B * Hkv * num_splits; p.sched = sched; p.prof = g_da_prof;
   const int ctas = std::min(p.total_items, num_sms);
   const bool capped = logit_cap > 0.f;
 #define SGLB_DA_LAUNCH(GM_, CAP_)                                                                                                    \
   do {                                                                                                                              \
     static bool configured = false;                                                                                                 \
     if (!configured) {                                                                                                              \
-      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<GM_, CAP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES)); \
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<GM_, CAP_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES)); \
       configured = true;                                                                                                            \
     }                                                                                                                               \
-    attn_decode_kernel<GM_, CAP_><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                                   \
+    attn_decode_kernel<GM_, CAP_, false><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                            \
   } while (0)
+  if (g_da_prof != nullptr && G <= 4 && !capped) {      // instrumented build (per-role cycle accounting), bench tool only
+    static bool configured = false;
+    if (!configured) {
+      SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
+      configured = true;
+    }
+    attn_decode_kernel<4, false, true><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  } else
   if (G <= 4) { if (capped) SGLB_DA_LAUNCH(4, true); else SGLB_DA_LAUNCH(4, false); }
   else if (G <= 8) { if (capped) SGLB_DA_LAUNCH(8, true); else SGLB_DA_LAUNCH(8, false); }
   else { if (capped) SGLB_DA_LAUNCH(16, true); else SGLB_DA_LAUNCH(16, false); }
