@@ -160,7 +160,7 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
 // bench tool: per-role cycle accounting of the decode attention kernel into buf [ctas * 30] (int64); an empty tensor turns it off
 void attn_decode_prof(const at::Tensor& buf) {
   if (buf.numel() == 0) { sglb::attn_decode_set_prof(nullptr); return; }
-  CHECK_CUDA(buf); TORCH_CHECK(buf.scalar_type() == at::kLong && buf.is_contiguous() && buf.numel() >= 148 * 30);
+  CHECK_CUDA(buf); TORCH_CHECK(buf.scalar_type() == at::kLong && buf.is_contiguous() && buf.numel() >= 148 * 40);
   sglb::attn_decode_set_prof((long long*)buf.data_ptr<int64_t>());
 }
 
@@ -270,6 +270,21 @@ void nvl_ar_add_rmsnorm(const at::Tensor& buf_ptrs, const at::Tensor& flag_ptrs,
                            residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), out.data_ptr(), (int)out.size(0),
                            (int)out.size(1), (float)eps, gemma, reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
                            reinterpret_cast<uint32_t*>(done.data_ptr<int>()), (int)channel, num_sms(), cur_stream());
+  count();
+}
+
+// large-T variant: reduce-scatter + residual add + RMSNorm + all-gather; the normalised rows land in the result region (slot_off + out_off)
+// of EVERY rank's arena, the residual stream stays row-sharded (row t belongs to rank t % world)
+void nvl_rs_add_rmsnorm_ag(const at::Tensor& buf_ptrs, const at::Tensor& flag_ptrs, int64_t mc_ptr, int64_t slot_off, int64_t out_off, int64_t rank,
+                           int64_t world, c10::optional<at::Tensor> residual, const at::Tensor& w, int64_t T, int64_t H, double eps, bool gemma,
+                           at::Tensor epoch, at::Tensor done, int64_t channel) {
+  CHECK_CUDA(w); CHECK_BF16(w);
+  if (residual.has_value()) TORCH_CHECK(residual->is_contiguous() && residual->scalar_type() == at::kBFloat16 && residual->numel() == T * H);
+  c10::cuda::CUDAGuard g(w.device());
+  sglb::nvl_rs_add_rmsnorm_ag(buf_ptrs.data_ptr<int64_t>(), flag_ptrs.data_ptr<int64_t>(), mc_ptr, slot_off, out_off, (int)rank, (int)world,
+                              residual.has_value() ? residual->data_ptr() : nullptr, w.data_ptr(), (int)T, (int)H, (float)eps, gemma,
+                              reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()), reinterpret_cast<uint32_t*>(done.data_ptr<int>()), (int)channel,
+                              num_sms(), cur_stream());
   count();
 }
 
@@ -512,6 +527,9 @@ TORCH_LIBRARY(sglb, m) {
         "Tensor(b!) epoch, Tensor(c!) done, int channel, int algo) -> ()", &nvl_allreduce);
   m.def("nvl_ar_add_rmsnorm(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int rank, int world, Tensor(a!)? residual, "
         "Tensor w, Tensor(b!) out, float eps, bool gemma, Tensor(c!) epoch, Tensor(d!) done, int channel) -> ()", &nvl_ar_add_rmsnorm);
+  m.def("nvl_rs_add_rmsnorm_ag(Tensor buf_ptrs, Tensor flag_ptrs, int mc_ptr, int slot_off, int out_off, int rank, int world, "
+        "Tensor(a!)? residual, Tensor w, int T, int H, float eps, bool gemma, Tensor(c!) epoch, Tensor(d!) done, int channel) -> ()",
+        &nvl_rs_add_rmsnorm_ag);
   m.def("launch_count() -> int", &launch_count);
   m.def("reset_launch_count() -> ()", &reset_launch_count);
   m.def("gemm_pick_bn(int M, int N, int K) -> int", &gemm_pick_bn);

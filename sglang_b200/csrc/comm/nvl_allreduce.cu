@@ -316,6 +316,107 @@ __global__ void __launch_bounds__(256) nvl_ar_add_rmsnorm_kernel(NvlPeers P, __n
   epoch_end(epoch_ptr, done_ctr, epoch);
 }
 
+// ---------------------------------------------------------------- fused reduce-scatter + residual add + RMSNorm + all-gather (large T)
+// The one-shot kernel above makes EVERY rank reduce EVERY row: per-rank NVLink traffic grows with world x bytes, which is what caps TP=4/8 at
+// decode batches of a few hundred tokens (8 MB of partials at bs 1024).  Here rank r owns rows r, r + world, ...:
+//   phase 1  (after flag round 2e-1)  reduced = multimem.ld_reduce(partials[row])  (or peer pulls without NVLS)
+//            residual[row] += reduced          -- the residual stream stays ROW-SHARDED across the whole layer stack: only its owner
+//                                                  ever reads or writes a row, and ownership depends on (row, world) only
+//            out[row] = rmsnorm(residual[row]) * w   -> ONE multimem.st per 16 bytes lands it in the result region of every rank's slot
+//   phase 2  grid-wide completion, flag round 2e: every rank's result region holds all T normalised rows; the next GEMM reads it in place.
+// Bytes per rank: T*H*2 in (reduce) + T*H*2 out (gather), independent of world.
+template <int MAXV>
+__global__ void __launch_bounds__(256) nvl_rs_add_rmsnorm_ag_kernel(NvlPeers P, __nv_bfloat16* __restrict__ residual,
+                                                                    const __nv_bfloat16* __restrict__ w, size_t out_off, int T, int H, float eps,
+                                                                    uint32_t* epoch_ptr, uint32_t* done_ctr, int channel, int gemma) {
+  const uint32_t epoch = epoch_begin(epoch_ptr);
+  nvl_barrier(P, channel, 2 * epoch - 1);
+  const int nvec = H >> 3;
+  __shared__ float red[8];
+  for (int row = blockIdx.x * P.world + P.rank; row < T; row += gridDim.x * P.world) {
+    float v[MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = threadIdx.x + i * 256;
+      if (vi < nvec) {
+        float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t off = (size_t)row * H + (size_t)vi * 8;
+        if (P.mc_buf) {
+          acc_bf16x8(a, mc_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(P.mc_buf) + off));
+        } else {
+#pragma unroll
+          for (int r = 0; r < NVL_MAX_RANKS; ++r)
+            if (r < P.world) acc_bf16x8(a, ld_peer128(reinterpret_cast<const __nv_bfloat16*>(P.buf[r]) + off));
+        }
+        if (residual) {
+          acc_bf16x8(a, ld128(residual + off));
+          const U4 s = pack8(a);
+          st128(residual + off, s);
+          a[0] = bf16_lo(s.x); a[1] = bf16_hi(s.x); a[2] = bf16_lo(s.y); a[3] = bf16_hi(s.y);
+          a[4] = bf16_lo(s.z); a[5] = bf16_hi(s.z); a[6] = bf16_lo(s.w); a[7] = bf16_hi(s.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[i][k] = a[k]; ss += a[k] * a[k]; }
+      }
+    }
+    ss = warp_sum(ss);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float rs = rsqrtf(tot / H + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = threadIdx.x + i * 256;
+      if (vi < nvec) {
+        const U4 ww = ldg128(w + (size_t)vi * 8);
+        const float g[8] = {bf16_lo(ww.x), bf16_hi(ww.x), bf16_lo(ww.y), bf16_hi(ww.y), bf16_lo(ww.z), bf16_hi(ww.z), bf16_lo(ww.w), bf16_hi(ww.w)};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = v[i][k] * rs * (gemma ? 1.f + g[k] : g[k]);
+        const U4 ov = pack8(o);
+        const size_t eoff = out_off + (size_t)row * H + (size_t)vi * 8;
+        if (P.mc_buf) {
+          mc_st_bf16x8(reinterpret_cast<__nv_bfloat16*>(P.mc_buf) + eoff, ov);
+        } else {
+#pragma unroll
+          for (int r = 0; r < NVL_MAX_RANKS; ++r)
+            if (r < P.world) st128(const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(P.buf[r])) + eoff, ov);
+        }
+      }
+    }
+  }
+  // every store of this grid must be on its way before block 0 publishes the second flag
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(done_ctr + 1, 1);
+    if (blockIdx.x == 0) {
+      uint32_t spins = 0;
+      unsigned long long t0 = 0;
+      while (*((volatile uint32_t*)(done_ctr + 1)) < gridDim.x) {
+        if (nvl_wait_expired(spins, t0)) { printf("sglb nvl: rs+norm+ag grid counter timeout rank=%d\n", P.rank); __trap(); }
+      }
+      __threadfence_system();
+    }
+  }
+  nvl_barrier(P, channel, 2 * epoch);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(done_ctr, 1);
+    if (t == gridDim.x - 1) {
+      *done_ctr = 0;
+      *(done_ctr + 1) = 0;
+      __threadfence();
+      *((volatile uint32_t*)epoch_ptr) = epoch;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- consumer of the push-GEMM (gemm_tc.cu EPI_PUSH)
 // All `world` partial copies of the [T,H] activation already sit in THIS rank's arena slot (layout [world][T][H]); wait
 // for every source rank's flag, then sum locally (+ residual) and normalise.  No NVLink traffic in this kernel.
@@ -451,6 +552,24 @@ void nvl_ar_add_rmsnorm(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64
   else if (nvec <= 512) nvl_ar_add_rmsnorm_kernel<2><<<grid, 256, 0, stream>>>(P, R, W, O, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
   else if (nvec <= 1024) nvl_ar_add_rmsnorm_kernel<4><<<grid, 256, 0, stream>>>(P, R, W, O, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
   else nvl_ar_add_rmsnorm_kernel<8><<<grid, 256, 0, stream>>>(P, R, W, O, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void nvl_rs_add_rmsnorm_ag(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc_ptr, int64_t slot_off, int64_t out_off_bytes, int rank,
+                           int world, void* residual, const void* w, int T, int H, float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr,
+                           int channel, int num_sms, cudaStream_t stream) {
+  if (H % 8 || H > 256 * 8 * 8) throw std::runtime_error("sglb nvl rs+norm+ag: H must be a multiple of 8 and <= 16384");
+  if (out_off_bytes % 16) throw std::runtime_error("sglb nvl rs+norm+ag: result region must be 16-byte aligned");
+  NvlPeers P = make_peers(buf_ptrs, flag_ptrs, mc_ptr, slot_off, rank, world);
+  const int own = (T + world - 1) / world;
+  const int grid = max(1, min(own, num_sms * 2));      // every block polls the second flag round: all of them must be resident
+  const int nvec = H / 8;
+  const size_t out_off = (size_t)out_off_bytes / 2;    // in bf16 elements, relative to the slot base the peers table already points at
+  auto R = (__nv_bfloat16*)residual; auto W = (const __nv_bfloat16*)w;
+  if (nvec <= 256) nvl_rs_add_rmsnorm_ag_kernel<1><<<grid, 256, 0, stream>>>(P, R, W, out_off, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
+  else if (nvec <= 512) nvl_rs_add_rmsnorm_ag_kernel<2><<<grid, 256, 0, stream>>>(P, R, W, out_off, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
+  else if (nvec <= 1024) nvl_rs_add_rmsnorm_ag_kernel<4><<<grid, 256, 0, stream>>>(P, R, W, out_off, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
+  else nvl_rs_add_rmsnorm_ag_kernel<8><<<grid, 256, 0, stream>>>(P, R, W, out_off, T, H, eps, epoch_ptr, done_ctr, channel, gemma);
   SGLB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -104,6 +104,9 @@ void bump_counts(int* counts, const int* tokens, int B, int V, cudaStream_t stre
 void nvl_allreduce(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc_ptr, int64_t slot_off, int rank, int world,
                    void* out, int n, uint32_t* epoch_ptr, uint32_t* done_ctr, int channel, int algo, int num_sms,
                    cudaStream_t stream);
+void nvl_rs_add_rmsnorm_ag(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc_ptr, int64_t slot_off, int64_t out_off_bytes, int rank,
+                           int world, void* residual, const void* w, int T, int H, float eps, bool gemma, uint32_t* epoch_ptr, uint32_t* done_ctr,
+                           int channel, int num_sms, cudaStream_t stream);
 void nvl_ar_add_rmsnorm(const int64_t* buf_ptrs, const int64_t* flag_ptrs, int64_t mc_ptr, int64_t slot_off, int rank, int world,
                         void* residual, const void* w, void* out, int T, int H, float eps, bool gemma, uint32_t* epoch_ptr,
                         uint32_t* done_ctr, int channel, int num_sms, cudaStream_t stream);

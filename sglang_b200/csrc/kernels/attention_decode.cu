@@ -31,7 +31,7 @@ namespace sglb {
 constexpr int DA_D = 128;                 // head dim
 constexpr int DA_KT = 128;                // keys per tile (UMMA M)
 constexpr int DA_NQ = 16;                 // padded query rows (UMMA N)
-constexpr int DA_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2-5 softmax (one key per thread)
+constexpr int DA_THREADS = 224;           // warp 0 scheduler + Q/K producer, warp 1 MMA, warps 2-5 softmax (one key per thread), warp 6 V producer
 constexpr int DA_STAGES = 3;
 constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile: two 64-wide d halves of [128 keys x 128 B])
 constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
@@ -81,7 +81,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* o_final = bars + 19;       // last PV of an item                         (phase = item ordinal)
   uint64_t* o_free = bars + 20;        // epilogue has read O^T (4 arrivals)         (phase = item ordinal)
   uint64_t* item_full = bars + 21;     // [2]
-  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps)
+  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps + V producer)
   volatile int* s_item = reinterpret_cast<volatile int*>(bars + 25);        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
   volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 27); // [6] role state for the timeout dump
@@ -105,7 +105,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 6); }
     mbar_init(o_done, 1); mbar_init(o_final, 1); mbar_init(o_free, 4);
     fence_barrier_init();
   }
@@ -178,23 +178,55 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);     // only pages that hold live keys
         const int pg0 = key0 / ps;
         const uint32_t bytes = (uint32_t)n_pages * ps * 256;
+        // page ids first (independent loads, one round trip), then the TMA issues: a single thread issues ~1 TMA per 200+ cycles, so the
+        // V tiles have their own producer warp (measured with tools/tma_gather_bench.cu: one issuing thread caps the gather below HBM speed)
+        int pg[DA_KT / 16];
+#pragma unroll
+        for (int i = 0; i < DA_KT / 16; ++i)
+          if (i < pages_per_tile) pg[i] = pt[min(pg0 + i, p.pt_stride - 1)];
         DA_T(2, DA_WAIT(&k_empty[st], ph ^ 1));
         if constexpr (PROF) pacc[4] += 1;
         mbar_expect_tx(&k_full[st], bytes);
-        for (int i = 0; i < n_pages; ++i) {
-          const int page = pt[pg0 + i];
-          uint8_t* dst = sK + st * DA_TILE_BYTES + i * ps * 128;
-          tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, page * ps);
-          tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, page * ps);
+#pragma unroll
+        for (int i = 0; i < DA_KT / 16; ++i) {
+          if (i < n_pages) {
+            uint8_t* dst = sK + st * DA_TILE_BYTES + i * ps * 128;
+            tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, pg[i] * ps);
+            tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, pg[i] * ps);
+          }
         }
+      }
+    }
+  } else if (warp == 6 && lane == 0) {
+    // ------------------------------------------------------------ V producer: one 5-D box per page (both d halves): smem [page][half][ps rows][128 B]
+    uint32_t n_it = 0, g = 0;
+    const int ps = p.page_size, pages_per_tile = DA_KT / ps;
+    for (;;) {
+      const int slot = n_it & 1;
+      DA_T(0, DA_WAIT(&item_full[slot], (n_it >> 1) & 1));
+      const int idx = s_item[slot];
+      mbar_arrive(&item_empty[slot]);
+      ++n_it;
+      if (idx >= p.total_items) break;
+      const Item it = decode_item(idx);
+      if (it.n_tiles == 0) continue;
+      const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
+      for (int j = 0; j < it.n_tiles; ++j, ++g) {
+        const int st = g % DA_STAGES;
+        const uint32_t ph = (g / DA_STAGES) & 1;
+        const int key0 = (it.tile_begin + j) * DA_KT;
+        const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);
+        const int pg0 = key0 / ps;
+        int pg[DA_KT / 16];
+#pragma unroll
+        for (int i = 0; i < DA_KT / 16; ++i)
+          if (i < pages_per_tile) pg[i] = pt[min(pg0 + i, p.pt_stride - 1)];
         DA_T(3, DA_WAIT(&v_empty[st], ph ^ 1));
-        mbar_expect_tx(&v_full[st], bytes);
-        for (int i = 0; i < n_pages; ++i) {
-          const int page = pt[pg0 + i];
-          uint8_t* dst = sV + st * DA_TILE_BYTES + i * ps * 128;
-          tma_load_3d(dst, &tmV, &v_full[st], 0, it.kvh, page * ps);
-          tma_load_3d(dst + DA_HALF_BYTES, &tmV, &v_full[st], 64, it.kvh, page * ps);
-        }
+        if constexpr (PROF) pacc[4] += 1;
+        mbar_expect_tx(&v_full[st], (uint32_t)n_pages * ps * 256);
+#pragma unroll
+        for (int i = 0; i < DA_KT / 16; ++i)
+          if (i < n_pages) tma_load_5d(sV + st * DA_TILE_BYTES + i * ps * 256, &tmV, &v_full[st], 0, 0, 0, it.kvh, pg[i]);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -242,10 +274,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (j == 0) DA_T(4, DA_WAIT(o_free, (n_q & 1) ^ 1));       // the previous item's epilogue has read O^T
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * DA_TILE_BYTES);
+        const int ps_ = p.page_size, lps_ = 31 - __clz(ps_);       // V tile layout [page][d half][ps keys][128 B]: a 16-key step stays inside one page (ps >= 16)
         const uint32_t p_addr = smem_u32(sP + (gt & 1) * DA_P_BYTES);
 #pragma unroll
         for (int k = 0; k < DA_KT / 16; ++k)      // 16 keys per step: A rows advance 16 x 128 B, B (P^T, K-major) advances 32 B inside a 64-key chunk
-          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + k * 2048, DA_HALF_BYTES, 1024),
+          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + (((k * 16) >> lps_) << (lps_ + 8)) + ((k * 16) & (ps_ - 1)) * 128, ps_ * 128, 1024),
                       make_smem_desc_sw128(p_addr + (k >> 2) * (DA_NQ * 128) + (k & 3) * 32, 0, 1024), idesc_o, (j | k) != 0);
         umma_commit(&v_empty[st]);
         umma_commit(o_done);
@@ -254,7 +287,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       g += n_tiles;
       ++n_q;
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 6) {
     // ------------------------------------------------------------ softmax (thread = key) + epilogue (thread = output dim)
     const int q4 = warp & 3;                              // TMEM lane quadrant of this warp
     const int row = (q4 << 5) + lane;                     // key index inside the tile / output dim in the epilogue
@@ -431,9 +464,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #undef DA_DBG
 #undef DA_T
   if constexpr (PROF) {
-    if (p.prof != nullptr && lane == 0 && warp <= 2) {
+    if (p.prof != nullptr && lane == 0 && (warp <= 2 || warp == 6)) {
+      const int role = warp == 6 ? 3 : warp;
 #pragma unroll
-      for (int i = 0; i < 10; ++i) p.prof[((size_t)blockIdx.x * 3 + warp) * 10 + i] = pacc[i];
+      for (int i = 0; i < 10; ++i) p.prof[((size_t)blockIdx.x * 4 + role) * 10 + i] = pacc[i];
     }
   }
 
@@ -454,7 +488,7 @@ __global__ void attn_merge_splits_kernel(const float* __restrict__ part_o, const
 bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size) {
   if (D != DA_D || Hkv <= 0 || Hq % Hkv) return false;
   const int G = Hq / Hkv;
-  return G >= 1 && G <= 16 && page_size >= 8 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
+  return G >= 1 && G <= 16 && page_size >= 16 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
 }
 
 static long long* g_da_prof = nullptr;
@@ -476,7 +510,11 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
   uint64_t sk[2] = {(uint64_t)D * 2, (uint64_t)Hkv * D * 2};
   uint32_t bk[3] = {64, 1, (uint32_t)page_size};
   CUtensorMap tmK = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
+  // V: (64 elems, key in page, d half, kv head, page) -> ONE box per page lands as [half][ps keys][128 B]
+  uint64_t dv[5] = {64, (uint64_t)page_size, 2, (uint64_t)Hkv, (uint64_t)(num_slots / page_size)};
+  uint64_t sv[4] = {(uint64_t)Hkv * D * 2, 128, (uint64_t)D * 2, (uint64_t)page_size * Hkv * D * 2};
+  uint32_t bv[5] = {64, (uint32_t)page_size, 2, 1, 1};
+  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
   p.out = (__nv_bfloat16*)out; p.part_o = part_o; p.part_lse = part_lse; p.lse = lse;
   p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens;

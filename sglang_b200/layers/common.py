@@ -17,6 +17,14 @@ from ..model_executor.forward_batch import ForwardBatch
 from ..ops import torch_ref
 
 
+def _rs_residual_active() -> bool:
+    from ..parallel.parallel_state import get_state
+
+    st = get_state()
+    nvl = getattr(st.tp, "nvl", None) if st is not None else None
+    return bool(nvl is not None and nvl.rs_active)
+
+
 class RMSNorm(nn.Module):
     def __init__(self, hidden_size: int, eps: float = 1e-6, dtype=torch.bfloat16, gemma: bool = False):
         super().__init__()
@@ -28,9 +36,10 @@ class RMSNorm(nn.Module):
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
         """residual given: (in place) residual += x; x = norm(residual); returns (x, residual)"""
         if hasattr(x, "consume_norm"):   # PendingAllReduce / PendingSlabs: (cross-rank | split-K) sum + residual add + norm in ONE kernel
-            out = torch.empty(x.T, x.H, dtype=self.weight.dtype, device=self.weight.device)
-            x.consume_norm(residual, self.weight, out, self.eps, self.gemma)
-            return out, residual
+            return x.consume_norm(residual, self.weight, self.eps, self.gemma), residual
+        if residual is not None and _rs_residual_active():
+            raise RuntimeError("row-sharded residual stream is active (NvlComm.rs_active) but a residual update bypassed the fused "
+                               "consume_norm path: this model family must not enable it")
         if residual is None:
             return ops.rmsnorm(x, self.weight, self.eps, gemma=self.gemma)
         ops.fused_add_rmsnorm(x, residual, self.weight, self.eps, gemma=self.gemma)

@@ -28,17 +28,21 @@ class PendingAllReduce:
     def __init__(self, nvl, off: int, T: int, H: int, mode: str = "pull", splits: int = 1):
         self.nvl, self.off, self.T, self.H, self.mode, self.splits = nvl, off, T, H, mode, splits
 
-    def consume_norm(self, residual, weight: torch.Tensor, out: torch.Tensor, eps: float, gemma: bool) -> None:
-        """cross-rank sum + residual add + RMSNorm in one kernel"""
+    def consume_norm(self, residual, weight: torch.Tensor, eps: float, gemma: bool) -> torch.Tensor:
+        """cross-rank sum + residual add + RMSNorm in one kernel; returns the normalised activations"""
+        if self.mode == "rs":       # large T: reduce-scatter + norm + all-gather, row-sharded residual; the result lives in the arena
+            return self.nvl.rs_add_rmsnorm_ag(self.off, self.T, self.H, residual, weight, eps, gemma)
+        out = torch.empty(self.T, self.H, dtype=weight.dtype, device=weight.device)
         if self.mode == "push":     # partials of all ranks were pushed into OUR arena by the peers' GEMM epilogues
             self.nvl.push_reduce_add_rmsnorm(self.off, self.T, self.H, residual, weight, out, eps, gemma, self.splits)
         else:                       # partials sit in each producer's arena: pull them over NVLink
             self.nvl.fused_allreduce_add_rmsnorm(self.off, residual, weight, out, eps, gemma)
+        return out
 
     def resolve(self) -> torch.Tensor:
         """plain all-reduce of the parked partials (used when the consumer is not an RMSNorm)"""
         out = torch.empty(self.T, self.H, dtype=torch.bfloat16, device=self.nvl.buf.device)
-        assert self.mode == "pull", "push-mode partials are always consumed by an RMSNorm (push is disabled under PP)"
+        assert self.mode == "pull", "push / reduce-scatter partials are always consumed by an RMSNorm"
         self.nvl.allreduce_from_slot(self.off, out)
         return out
 
@@ -51,8 +55,10 @@ class PendingSlabs:
     def __init__(self, slabs: torch.Tensor):
         self.slabs, self.T, self.H = slabs, slabs.shape[1], slabs.shape[2]
 
-    def consume_norm(self, residual, weight: torch.Tensor, out: torch.Tensor, eps: float, gemma: bool) -> None:
+    def consume_norm(self, residual, weight: torch.Tensor, eps: float, gemma: bool) -> torch.Tensor:
+        out = torch.empty(self.T, self.H, dtype=weight.dtype, device=weight.device)
         torch.ops.sglb.slab_reduce_add_rmsnorm(self.slabs, residual, weight, out, eps, gemma)
+        return out
 
     def resolve(self) -> torch.Tensor:
         return self.slabs[0] if self.slabs.shape[0] == 1 else self.slabs.float().sum(0).to(self.slabs.dtype)
@@ -223,6 +229,12 @@ class RowParallelLinear(LinearBase):
                     return PendingAllReduce(nvl, off, T, self.out_features, "push", splits)
                 off = nvl.gemm_push(x, self.weight)
                 return PendingAllReduce(nvl, off, T, self.out_features, "push")
+            if nvl.wants_rs(nbytes):      # large T: the consumer reduce-scatters (row-sharded residual), see nvl_comm.rs_add_rmsnorm_ag
+                from ..parallel.nvl_comm import CH_RS_AG
+
+                off, view = nvl.stage(CH_RS_AG, (T, self.out_features))
+                ops.linear(x, self.weight, None, out=view)
+                return PendingAllReduce(nvl, off, T, self.out_features, "rs")
             off, view = nvl.stage(CH_FUSED_NORM, (T, self.out_features))
             ops.linear(x, self.weight, None, out=view)
             return PendingAllReduce(nvl, off, T, self.out_features, "pull")

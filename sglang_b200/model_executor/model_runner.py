@@ -414,8 +414,8 @@ class ModelRunner:
         self.forward_ct += 1
         if self.is_cuda:
             with torch.cuda.stream(self.stream):
-                return self._forward(sb)
-        return self._forward(sb)
+                return self._forward_guarded(sb)
+        return self._forward_guarded(sb)
 
     @torch.no_grad()
     def forward_idle(self) -> None:
@@ -439,6 +439,12 @@ class ModelRunner:
         self.model.compute_logits(hidden[:0])        # the LM head gathers sampled rows across groups as well ...
         self.model.compute_logits(hidden[:0], key="logits_all")     # ... and the rows of a prompt-logprob pass
 
+    def _forward_guarded(self, sb: ScheduleBatch) -> BatchResult:
+        try:
+            return self._forward(sb)
+        finally:
+            self.set_rs(0)          # the row-sharded residual mode never outlives the forward that armed it
+
     @torch.no_grad()
     def _forward(self, sb: ScheduleBatch) -> BatchResult:
         from ..layers.dp_attention import get_dp_ctx
@@ -459,6 +465,7 @@ class ModelRunner:
             return self._forward_prefill_graph(sb)
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
         self.h2d_bytes += fb.h2d_bytes
+        self.set_rs(fb.num_tokens if sb.spec_info is None and not self.args.enable_two_batch_overlap else 0)
         fb.num_splits = self._pick_splits(B, fb.max_kv_len) if decode else 1
         self._attach_dcp(sb, fb)
         self._attach_mm(sb, fb)
@@ -856,6 +863,34 @@ class ModelRunner:
         self._finish_result(res, toks, None)
         return res
 
+    # ------------------------------------------------------------------ row-sharded residual (large-T tensor parallel steps)
+    def _rs_capable(self) -> bool:
+        """may this model run with a row-sharded residual stream (NvlComm.rs_add_rmsnorm_ag)?  Only when EVERY residual update is a fused
+        consume_norm of a row-parallel projection: the plain dense Llama-family stack, no PP / SP / DP-attention / aux-hidden capture."""
+        c = getattr(self, "_rs_capable_cached", None)
+        if c is None:
+            from ..layers.dp_attention import get_dp_ctx
+            from ..layers.quantization import UnquantizedMethod
+            from ..models.llama import LlamaDecoderLayer, LlamaForCausalLM, LlamaMLP
+
+            nvl = self.tp.nvl
+            c = bool(nvl is not None and self.tp.world_size > 2 and self.pp.world_size == 1 and not self.args.enable_sp
+                     and get_dp_ctx() is None and self.cp is None and getattr(self, "dcp", None) is None
+                     and type(self.model) is LlamaForCausalLM
+                     and all(type(l) is LlamaDecoderLayer and type(l.mlp) is LlamaMLP
+                             and isinstance(getattr(l.mlp.down_proj, "quant", None), UnquantizedMethod)
+                             and isinstance(getattr(l.self_attn.o_proj, "quant", None), UnquantizedMethod) for l in self.model.model.layers))
+            self._rs_capable_cached = c
+        return c
+
+    def set_rs(self, num_tokens: int) -> None:
+        """arm (or disarm, num_tokens = 0) the reduce-scatter path for the forward that follows"""
+        nvl = self.tp.nvl
+        if nvl is None:
+            return
+        nvl.rs_active = bool(num_tokens > 0 and self.aux_layer_ids is None and self.lora_manager is None and self._rs_capable()
+                             and nvl.wants_rs_bytes(num_tokens * self.cfg.hidden_size * 2))
+
     def greedy_head(self):
         """the vocab-sharded head when all-greedy decode batches may use the vocab-parallel argmax (TP > 1, plain LM head, no DP-attention
         row exchange); None otherwise"""
@@ -939,13 +974,13 @@ class _PrefillGraph:
         dev = runner.device
         # static int region: input_ids | positions | out_cache_loc (tcap each) | cu_q (bc + 1) | q_lens | req_slots | seq_lens | last_idx |
         # sample_slots | temperature | top_p | min_p | top_k (bc each) | step (2)
-        self.n_int = 3 * tcap + (bc + 1) + 9 * bc + 2
+        self.n_int = 3 * tcap + (bc + 2) + 9 * bc + 2          # cu_q padded to bc + 2 ints so that the int64 step word is 8-byte aligned
         self.static = torch.zeros(self.n_int + 3 * 8192, dtype=torch.int32, device=dev)
         s = self.static
         self.input_ids, self.positions, self.out_cache_loc = s[0:tcap], s[tcap:2 * tcap], s[2 * tcap:3 * tcap]
         o = 3 * tcap
         self.cu_q = s[o:o + bc + 1]
-        o += bc + 1
+        o += bc + 2
         self.q_lens, self.req_slots, self.seq_lens = s[o:o + bc], s[o + bc:o + 2 * bc], s[o + 2 * bc:o + 3 * bc]
         self.last_idx, self.sample_slots = s[o + 3 * bc:o + 4 * bc], s[o + 4 * bc:o + 5 * bc]
         self.temperature = s[o + 5 * bc:o + 6 * bc].view(torch.float32)
@@ -966,7 +1001,11 @@ class _PrefillGraph:
                           cu_q=self.cu_q, q_lens=self.q_lens, last_idx=self.last_idx, sample_slots=self.sample_slots,
                           max_q_len=self.tcap, max_kv_len=r.max_context_len, page_table=r.page_table, page_size=r.page_size,
                           kv_pool=r.kv_pool, sampling=samp, next_token_buf=r.next_token_buf)
-        hidden = r.model(fb)
+        r.set_rs(self.tcap)
+        try:
+            hidden = r.model(fb)
+        finally:
+            r.set_rs(0)
         h_last = ops.gather_rows(hidden, self.last_idx)
         logits = r.model.compute_logits(h_last)
         torch.ops.sglb.sample(logits, self.temperature, self.top_k, self.top_p, self.min_p, None, self.sample_slots, r.next_token_buf,
@@ -1094,7 +1133,11 @@ class _DecodeGraph:
     def _run(self) -> None:
         r = self.r
         fb = self._fb()
-        hidden = r.model(fb)
+        r.set_rs(self.bs)
+        try:
+            hidden = r.model(fb)
+        finally:
+            r.set_rs(0)
         if self.greedy:
             from ..layers.linear import vocab_parallel_greedy
 

@@ -22,7 +22,7 @@ from ..environ import envs
 
 logger = logging.getLogger(__name__)
 
-CH_ONESHOT, CH_TWOSHOT, CH_FUSED_NORM, CH_GEMM = 0, 1, 2, 3
+CH_ONESHOT, CH_TWOSHOT, CH_FUSED_NORM, CH_GEMM, CH_RS_AG = 0, 1, 2, 3, 4
 NUM_CHANNELS = 8
 MAX_RANKS = 8          # must match NVL_MAX_RANKS in csrc/comm/nvl_allreduce.cu
 FLAG_OFFSET = 1024
@@ -50,6 +50,12 @@ class NvlComm:
         self.max_oneshot_bytes = (1 << 40) if self.world == 2 else 512 * 1024
         self.calls = 0
         self.use_nvls = bool(self.mc_ptr) and envs.SGLB_NVLS.get()      # NVSwitch in-network reduction when a multicast alias exists
+        # large-T row-parallel outputs: reduce-scatter + norm + all-gather with a ROW-SHARDED residual stream (csrc/comm/nvl_allreduce.cu
+        # nvl_rs_add_rmsnorm_ag_kernel).  The model runner switches it on per forward (``rs_active``) for model families whose every residual
+        # update goes through a fused consume_norm; with two ranks the one-shot exchange moves the same bytes, so it stays off there.
+        self.rs_min_bytes = envs.SGLB_RS_AG_MIN_BYTES.get() if self.world > 2 else (1 << 60)
+        self.rs_active = False
+        self.rs_calls = 0
 
     @classmethod
     def create(cls, group: Any) -> "NvlComm":
@@ -87,7 +93,9 @@ class NvlComm:
         ctr = self.graph_epoch if self.capturing else self.host_epoch
         ctr[channel] += 1
         region = 1 if self.capturing else 0
-        return region * 2 * self.slot_bytes + (ctr[channel] & 1) * self.slot_bytes
+        # the reduce-scatter channel owns the upper half of every slot: its slots never alias the one-shot channels' slots
+        sub = self.slot_bytes // 2 if channel == CH_RS_AG else 0
+        return region * 2 * self.slot_bytes + (ctr[channel] & 1) * self.slot_bytes + sub
 
     def begin_capture(self) -> None:
         self.capturing = True
@@ -106,7 +114,7 @@ class NvlComm:
     def can_all_reduce(self, x: torch.Tensor) -> bool:
         nbytes = x.numel() * x.element_size()
         return (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
-                and 2 * nbytes <= self.slot_bytes)
+                and 4 * nbytes <= self.slot_bytes)
 
     # ------------------------------------------------------------------ collectives
     def all_reduce(self, x: torch.Tensor, algo: Optional[int] = None) -> torch.Tensor:
@@ -143,6 +151,26 @@ class NvlComm:
         torch.ops.sglb.nvl_ar_add_rmsnorm(self.buf_ptrs, self.flag_ptrs, self.mc_ptr if self.use_nvls else 0, off, self.rank, self.world, residual, weight, out,
                                           float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch], ch)
         self.calls += 1
+
+    def wants_rs_bytes(self, nbytes: int) -> bool:
+        return nbytes >= self.rs_min_bytes and 8 * nbytes <= self.slot_bytes
+
+    def wants_rs(self, nbytes: int) -> bool:
+        """row-parallel producers ask this when they stage their partial output: large enough and allowed for this forward?"""
+        return self.rs_active and nbytes >= self.rs_min_bytes and 8 * nbytes <= self.slot_bytes
+
+    def rs_add_rmsnorm_ag(self, off: int, T: int, H: int, residual: Optional[torch.Tensor], weight: torch.Tensor, eps: float,
+                          gemma: bool = False) -> torch.Tensor:
+        """consumer of partials staged with ``stage(CH_RS_AG, ...)``: returns the normalised [T, H] activations as a VIEW of this rank's arena
+        (result region of the same slot); ``residual`` is updated on this rank's rows (t % world == rank) only"""
+        nbytes = T * H * 2
+        out_off = (nbytes + 255) // 256 * 256
+        ch = CH_RS_AG
+        torch.ops.sglb.nvl_rs_add_rmsnorm_ag(self.buf_ptrs, self.flag_ptrs, self.mc_ptr if self.use_nvls else 0, off, out_off, self.rank, self.world,
+                                             residual, weight, T, H, float(eps), gemma, self.epochs[ch:ch + 1], self.done[ch], ch)
+        self.calls += 1
+        self.rs_calls += 1
+        return self.slot_view(off + out_off, (T, H))
 
     # ------------------------------------------------------------------ fused GEMM + all-reduce (push)
     def gemm_push(self, x: torch.Tensor, w: torch.Tensor, bn: int = 0) -> int:

@@ -175,6 +175,50 @@ else:
                                                   "fused_graph": 1000 * timed_graph(fused), "nccl_plus_norm_graph": 1000 * timed_graph(unfused)}
         log("fused ar+norm", json.dumps({k: v for k, v in res.items() if k.startswith("fused")}))
 
+    @section("rs_norm_ag")
+    def _rs():
+        """large-T variant: reduce-scatter + residual add + RMSNorm + all-gather with a row-sharded residual (nvl_rs_add_rmsnorm_ag_kernel)
+        against an fp32 reference; timed against the one-shot fused kernel and NCCL + local norm at decode batches of 128..1024 tokens"""
+        from sglang_b200.parallel.nvl_comm import CH_RS_AG
+        for T, H in ((3, 4096), (130, 4096), (256, 4096), (512, 4096), (1024, 4096), (1024, 8192)):
+            torch.manual_seed(300 + rank)
+            part = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16)
+            torch.manual_seed(9)
+            resid = (torch.randn(T, H, device=dev) * 0.3).to(torch.bfloat16); w = torch.randn(H, device=dev).to(torch.bfloat16)
+            full = part.float().clone(); dist.all_reduce(full)
+            r_ref = resid.clone(); x_ref = full.to(torch.bfloat16)
+            torch_ref.fused_add_rmsnorm(x_ref, r_ref, w, 1e-5)
+            for rep in range(3):        # several calls: slot alternation + epochs
+                off, view = nvl.stage(CH_RS_AG, (T, H)); view.copy_(part)
+                r2 = resid.clone()
+                out = nvl.rs_add_rmsnorm_ag(off, T, H, r2, w, 1e-5)
+                torch.cuda.synchronize()
+                own = torch.arange(rank, T, world, device=dev)
+                e1 = (out.float() - x_ref.float()).abs().max().item()
+                e2 = (r2[own].float() - r_ref[own].float()).abs().max().item() if own.numel() else 0.0
+                other = torch.ones(T, dtype=torch.bool, device=dev); other[own] = False
+                untouched = bool((r2[other] == resid[other]).all().item())
+                assert e1 < 0.15 and e2 < 0.1 and untouched, ("rs", T, H, rep, e1, e2, untouched)
+            log(f"  rs+norm+ag T={T} H={H} err_out={e1:.4f} err_resid(own rows)={e2:.4f}")
+            if T < 128:
+                continue
+            r3 = resid.clone(); o1 = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
+
+            def rs():
+                o, v = nvl.stage(CH_RS_AG, (T, H)); v.copy_(part)
+                nvl.rs_add_rmsnorm_ag(o, T, H, r3, w, 1e-5)
+
+            def oneshot():
+                o, v = nvl.stage(CH_FUSED_NORM, (T, H)); v.copy_(part)
+                nvl.fused_allreduce_add_rmsnorm(o, r3, w, o1, 1e-5)
+
+            def unfused():
+                y = part.clone(); dist.all_reduce(y); ops.fused_add_rmsnorm(y, r3, w, 1e-5)
+
+            res[f"rs_norm_ag_T{T}_H{H}_us"] = {"rs_graph": 1000 * timed_graph(rs), "oneshot_fused_graph": 1000 * timed_graph(oneshot),
+                                               "nccl_plus_norm_graph": 1000 * timed_graph(unfused)}
+        log("rs+norm+ag", json.dumps({k: v for k, v in res.items() if k.startswith("rs_norm")}))
+
     @section("gemm_push")
     def _push():
         for T, K, H in ((16, 4096 // world, 4096), (64, 14336 // world, 4096), (128, 4096 // world, 4096)):
