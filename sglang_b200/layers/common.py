@@ -84,6 +84,10 @@ class RadixAttention(nn.Module):
         kc, vc = pool.k(self.layer_id), pool.v(self.layer_id)
         dcp = getattr(fb, "dcp", None)
         out_loc = fb.out_cache_loc if dcp is None else dcp.local_loc
+        page_table = fb.page_table
+        if self.window > 0 and fb.out_cache_loc_swa is not None:      # sliding layer of a hybrid model: its own pool and page-table half
+            out_loc = fb.out_cache_loc_swa
+            page_table = fb.page_table[:, fb.swa_pt_offset:]
         if self.rope is not None:
             ov = fb.rope_override            # M-RoPE: a per-token cos/sin table indexed by row number instead of the position table
             ops.rope_kv_write(q3, k3, v3, fb.positions if ov is None else ov[1], self.rope.cos_sin if ov is None else ov[0], kc, vc, out_loc,
@@ -104,7 +108,7 @@ class RadixAttention(nn.Module):
         sinks = self.sinks
         lse = torch.empty(T, self.num_heads, dtype=torch.float32, device=q3.device) if sinks is not None else None
         mask = fb.custom_mask if not self.chunk else chunk_attention_mask(fb, self.chunk)
-        o = ops.paged_attention(q3, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
+        o = ops.paged_attention(q3, kc, vc, page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
                                 workspace=fb.attn_workspace, custom_mask=mask, lse=lse)

@@ -48,10 +48,20 @@ class Scheduler:
         self.max_context_len = info["max_context_len"]
         self.max_running = info["max_running"]
         self.allocator = PagedAllocator(info["num_pages"], self.page_size)
-        self.tree = create_radix_cache(self.allocator, self.page_size, server_args.radix_eviction_policy,
-                                       disable=server_args.disable_radix_cache, impl=server_args.radix_cache_impl,
-                                       enable_kv_events=server_args.enable_kv_events)
-        self.kv = KVManager(self.allocator, self.tree, self.page_size, self.max_running, self.max_context_len)
+        self.swa = info.get("swa")
+        if self.swa is None:
+            self.tree = create_radix_cache(self.allocator, self.page_size, server_args.radix_eviction_policy,
+                                           disable=server_args.disable_radix_cache, impl=server_args.radix_cache_impl,
+                                           enable_kv_events=server_args.enable_kv_events)
+            self.kv = KVManager(self.allocator, self.tree, self.page_size, self.max_running, self.max_context_len)
+        else:       # hybrid sliding-window model: second pool + page table, tombstoning prefix tree (mem_cache/swa.py)
+            from ..mem_cache.swa import SWAKVManager, SWARadixCache
+
+            self.swa_allocator = PagedAllocator(self.swa["num_pages"], self.page_size)
+            self.tree = SWARadixCache(self.allocator, self.swa_allocator, self.swa["window"], self.page_size, server_args.radix_eviction_policy,
+                                      disable=server_args.disable_radix_cache, enable_kv_events=server_args.enable_kv_events)
+            self.kv = SWAKVManager(self.allocator, self.swa_allocator, self.tree, self.page_size, self.max_running, self.max_context_len,
+                                   self.swa["window"], fetch_granularity=128 if getattr(worker, "is_cuda", False) else self.page_size)
         from .session_controller import SessionController
 
         self.sessions = SessionController(self.tree, self.page_size)
@@ -381,7 +391,10 @@ class Scheduler:
     def _prepare_for_extend(self, batch: ScheduleBatch) -> bool:
         """allocate pages, build token-level arrays (reference prepare_for_extend:2378)"""
         ids, pos, loc, qlens, plens, slots, seqlens, sample = [], [], [], [], [], [], [], []
+        loc_swa = [] if self.swa is not None else None
         for r in batch.reqs:
+            if self.swa is not None:
+                self.kv.slide(r)          # a long prompt's earlier chunks leave the window of the sliding layers
             if not self.kv.alloc_for_extend(r, r.fill_len):
                 return False
         for r in batch.reqs:
@@ -390,6 +403,8 @@ class Scheduler:
             ids.append(np.asarray(all_ids[s:e], dtype=np.int32))
             pos.append(np.arange(s, e, dtype=np.int32))
             loc.append(self.kv.slots_for(r, s, e))
+            if loc_swa is not None:
+                loc_swa.append(self.kv.slots_for_swa(r, s, e))
             qlens.append(e - s)
             plens.append(s)
             slots.append(r.req_slot)
@@ -403,6 +418,7 @@ class Scheduler:
         batch.input_ids = np.concatenate(ids)
         batch.positions = np.concatenate(pos)
         batch.out_cache_loc = np.concatenate(loc)
+        batch.out_cache_loc_swa = np.concatenate(loc_swa) if loc_swa is not None else None
         batch.q_lens = np.asarray(qlens, dtype=np.int32)
         batch.prefix_lens = np.asarray(plens, dtype=np.int32)
         batch.req_slots = np.asarray(slots, dtype=np.int32)
@@ -420,6 +436,9 @@ class Scheduler:
         rb.filter_batch(keep)
         if not rb.reqs:
             return None
+        if self.swa is not None:
+            for r in rb.reqs:
+                self.kv.slide(r)          # sliding layers: give back pages no future token of this request can see
         force_retract = envs.SGLB_TEST_RETRACT.get() and self.decode_ct > 0 and \
             self.decode_ct % envs.SGLB_TEST_RETRACT_INTERVAL.get() == 0 and len(rb.reqs) > 1
         positions = rb.seq_lens.copy()   # index of the token written this step
@@ -455,6 +474,7 @@ class Scheduler:
         rb.forward_mode = ForwardMode.DECODE
         rb.positions = positions.astype(np.int32)
         rb.out_cache_loc = loc
+        rb.out_cache_loc_swa = self.kv.decode_slots_swa(rb.req_slots, positions) if self.swa is not None else None
         rb.seq_lens = rb.seq_lens + 1
         rb.q_lens = None
         rb.input_ids = None
@@ -470,7 +490,7 @@ class Scheduler:
         # the worker gets a *snapshot* so later filter/merge of running_batch cannot race with it
         snap = ScheduleBatch(reqs=list(rb.reqs), forward_mode=ForwardMode.DECODE, seq_lens=rb.seq_lens.copy(),
                              req_slots=rb.req_slots.copy(), positions=rb.positions, out_cache_loc=rb.out_cache_loc,
-                             pt_rows=rb.pt_rows, pt_cols=rb.pt_cols, pt_vals=rb.pt_vals,
+                             out_cache_loc_swa=rb.out_cache_loc_swa, pt_rows=rb.pt_rows, pt_cols=rb.pt_cols, pt_vals=rb.pt_vals,
                              return_logprob=rb.return_logprob, has_grammar=rb.has_grammar)
         self.decode_ct += 1
         return snap

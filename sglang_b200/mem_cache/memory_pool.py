@@ -57,6 +57,40 @@ class KVPool:
         self.page_view().index_copy_(2, pages, data.to(self.buf.dtype))
 
 
+class HybridKVPool:
+    """Two KV planes for models that interleave full-attention and sliding-window layers (mem_cache/swa.py): ``full`` holds the
+    full-attention layers for the whole context, ``swa`` the sliding layers for a window per request.  Layer ids are the model's."""
+
+    def __init__(self, full: KVPool, swa: KVPool, sliding_layers):
+        self.full, self.swa = full, swa
+        self.sliding = sorted(int(i) for i in sliding_layers)
+        n = full.num_layers + swa.num_layers
+        self._loc = {}
+        fi = si = 0
+        sl = set(self.sliding)
+        for i in range(n):
+            if i in sl:
+                self._loc[i] = (swa, si); si += 1
+            else:
+                self._loc[i] = (full, fi); fi += 1
+        self.num_pages, self.page_size = full.num_pages, full.page_size
+        self.num_layers, self.num_kv_heads, self.head_dim = n, full.num_kv_heads, full.head_dim
+        self.dtype, self.device = full.dtype, full.device
+        self.k_scale, self.v_scale = full.k_scale, full.v_scale
+        self.mamba = None
+
+    def is_sliding(self, layer: int) -> bool:
+        return self._loc[layer][0] is self.swa
+
+    def k(self, layer: int) -> torch.Tensor:
+        p, i = self._loc[layer]
+        return p.buf[i, 0]
+
+    def v(self, layer: int) -> torch.Tensor:
+        p, i = self._loc[layer]
+        return p.buf[i, 1]
+
+
 class HostKVPool:
     """Pinned-host mirror used by the HiCache L2 tier (reference ``memory_pool_host.py``).
 

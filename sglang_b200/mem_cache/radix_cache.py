@@ -27,7 +27,7 @@ _EMPTY = np.empty(0, dtype=np.int32)
 
 class TreeNode:
     __slots__ = ("children", "parent", "key", "pages", "lock_ref", "last_access", "hit_count", "created",
-                 "priority", "host_pages", "id", "hashes")
+                 "priority", "host_pages", "id", "hashes", "swa_pages")
     _ctr = 0
 
     def __init__(self) -> None:
@@ -42,6 +42,7 @@ class TreeNode:
         self.hit_count = 0
         self.priority = 0
         self.hashes: Optional[np.ndarray] = None     # chained 64-bit page hashes (only when KV events are enabled)
+        self.swa_pages: Optional[np.ndarray] = None  # sliding-window pool pages of the same tokens (0 = tombstone: slid out / reclaimed)
         TreeNode._ctr += 1
         self.id = TreeNode._ctr
 
@@ -203,6 +204,8 @@ class RadixCache:
             new.host_pages, child.host_pages = child.host_pages[:m_pages], child.host_pages[m_pages:]
         if child.hashes is not None:
             new.hashes, child.hashes = child.hashes[:m_pages], child.hashes[m_pages:]
+        if child.swa_pages is not None:
+            new.swa_pages, child.swa_pages = child.swa_pages[:m_pages], child.swa_pages[m_pages:]
         child.parent.children[self._child_key(new.key)] = new
         child.key = child.key[m_pages * ps:]
         if child.pages is not None:

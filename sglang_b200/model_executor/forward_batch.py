@@ -70,6 +70,8 @@ class ForwardBatch:
     rope_override: Any = None        # (cos_sin rows [T, rot], row index [T]): per-token rotary table (M-RoPE)
     mrope_positions: Any = None      # i64 [3, T]
     cp: Any = None                   # layers/cp.py CpMeta inside a context-parallel prefill
+    out_cache_loc_swa: Optional[torch.Tensor] = None   # i32 [T] slots in the sliding-window pool (hybrid SWA models, mem_cache/swa.py)
+    swa_pt_offset: int = 0           # the sliding page table is columns [offset, 2 * offset) of ``page_table``
     dcp: Any = None                  # layers/dcp.py DcpMeta when decode context parallelism is on
 
 
@@ -112,6 +114,8 @@ class BatchPacker:
 
         add("positions", sb.positions)
         add("out_cache_loc", sb.out_cache_loc)
+        if sb.out_cache_loc_swa is not None:
+            add("out_cache_loc_swa", sb.out_cache_loc_swa)
         add("req_slots", sb.req_slots)
         add("seq_lens", sb.seq_lens)
         if not decode:
@@ -172,5 +176,5 @@ class BatchPacker:
             max_q_len=1 if decode else int(sb.q_lens.max()), max_kv_len=int(sb.seq_lens.max()) if B else 0,
             page_table=page_table, page_size=page_size, kv_pool=kv_pool, sampling=sampling, next_token_buf=next_token_buf,
             return_logprob=sb.return_logprob, h2d_bytes=int(packed.size * 4), seq_lens_cpu=sb.seq_lens,
-            q_lens_cpu=sb.q_lens, spec_info=sb.spec_info)
+            q_lens_cpu=sb.q_lens, spec_info=sb.spec_info, out_cache_loc_swa=v("out_cache_loc_swa"))
         return fb

@@ -201,7 +201,19 @@ class ModelRunner:
             q0 = self.model.model.layers[0].self_attn.qkv_proj if n_layers and hasattr(self.model.model.layers[0].self_attn, "qkv_proj") else None
             assert q0 is not None and getattr(q0, "kv_replicas", 1) % self.dcp.world_size == 0, \
                 "DCP: dcp_size must divide the KV-head replication factor tp_size / num_kv_heads (nothing to de-duplicate otherwise)"
+        # hybrid sliding-window models (--swa-full-tokens-ratio > 0): the sliding layers move to a second, smaller pool (mem_cache/swa.py)
+        sliding = [i for i, l in enumerate(self.model.model.layers) if getattr(getattr(getattr(l, "self_attn", None), "attn", None), "window", -1) > 0] \
+            if n_layers else []
+        self.swa = None
+        ratio = float(getattr(a, "swa_full_tokens_ratio", 0.0) or 0.0)
+        if ratio > 0 and sliding and len(sliding) < n_layers:
+            if self.dcp is not None or self.cp is not None or self.pp.world_size > 1 or a.enable_hierarchical_cache or a.speculative_algorithm:
+                raise ValueError("--swa-full-tokens-ratio: not combined with DCP / CP / PP / HiCache / speculative decoding yet")
+            self.swa = {"layers": sliding, "ratio": min(1.0, ratio), "window": max(self.model.model.layers[i].self_attn.attn.window for i in sliding)}
+        eff_layers = n_layers if self.swa is None else (n_layers - len(sliding)) + self.swa["ratio"] * len(sliding)
         per_page = KVPool.bytes_per_page(self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype)
+        if self.swa is not None:
+            per_page = int(per_page * eff_layers / n_layers)
         self.max_context_len = a.context_length or cfg.max_position_embeddings
         if self.is_cuda:
             free, total = torch.cuda.mem_get_info(self.device)
@@ -220,7 +232,17 @@ class ModelRunner:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.tp.device_group)
             num_pages = int(t.item())
         self.num_pages = int(num_pages)
-        self.kv_pool = KVPool(self.num_pages, self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
+        if self.swa is None:
+            self.kv_pool = KVPool(self.num_pages, self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
+        else:
+            from ..mem_cache.memory_pool import HybridKVPool
+
+            n_swa = max(8, int(self.num_pages * self.swa["ratio"]))
+            self.swa["num_pages"] = n_swa
+            self.kv_pool = HybridKVPool(KVPool(self.num_pages, self.local_page_size, n_layers - len(sliding), kv_heads, kv_dim, kv_dtype, str(self.device)),
+                                        KVPool(n_swa, self.local_page_size, len(sliding), kv_heads, kv_dim, kv_dtype, str(self.device)), sliding)
+            logger.info("sliding-window pool: %d of %d layers, %d pages (window %d) next to %d full pages", len(sliding), n_layers, n_swa,
+                        self.swa["window"], self.num_pages)
         tokens = (self.num_pages - 1) * self.page_size
         self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
@@ -234,13 +256,18 @@ class ModelRunner:
                     self.num_pages * per_page / 2 ** 30, self.max_running, self.weight_bytes / 2 ** 30)
 
     def get_memory_info(self) -> Dict[str, int]:
-        return {"num_pages": self.num_pages, "max_context_len": self.max_context_len, "max_running": self.max_running}
+        info = {"num_pages": self.num_pages, "max_context_len": self.max_context_len, "max_running": self.max_running}
+        if getattr(self, "swa", None) is not None:
+            info["swa"] = {"num_pages": self.swa["num_pages"], "window": self.swa["window"]}
+        return info
 
     def attach_kv_manager(self, kv: Any) -> None:
         self.kv_manager = kv
         assert kv.page_table.shape[1] <= self.page_table.shape[1] + 1
-        if kv.page_table.shape[1] != self.page_table.shape[1]:
-            self.page_table = torch.zeros(self.max_running + 1, kv.page_table.shape[1], dtype=torch.int32, device=self.device)
+        cols = kv.page_table.shape[1] * (2 if getattr(self, "swa", None) is not None else 1)     # [full | sliding] halves of one device table
+        self.swa_pt_offset = kv.page_table.shape[1] if getattr(self, "swa", None) is not None else 0
+        if cols != self.page_table.shape[1]:
+            self.page_table = torch.zeros(self.max_running + 1, cols, dtype=torch.int32, device=self.device)
 
     def get_eos_token_ids(self) -> List[int]:
         return self.cfg.eos_token_ids
@@ -458,12 +485,13 @@ class ModelRunner:
         # the captured sampler sees only the static tensors: anything that needs per-request host state (penalties, logit bias, active
         # min_new_tokens -> EOS mask, per-request seeds, hidden-state return) takes the eager path (ScheduleBatch.needs_host_state)
         use_graph = decode and self.graphs and not sb.return_logprob and not sb.has_grammar and sb.spec_info is None and \
-            B <= self.graph_bs[-1] and not sb.needs_host_state()
+            B <= self.graph_bs[-1] and not sb.needs_host_state() and (sb.out_cache_loc_swa is None or self.graphs[self.graph_bs[-1]].has_swa)
         if use_graph:
             return self._forward_graph(sb)
         if self.prefill_graphs and not decode and self._prefill_graph_eligible(sb):
             return self._forward_prefill_graph(sb)
         fb = self.packer.build(sb, self.page_table, self.page_size, self.kv_pool, self.next_token_buf, ops.apply_pt_delta)
+        fb.swa_pt_offset = getattr(self, "swa_pt_offset", 0)
         self.h2d_bytes += fb.h2d_bytes
         self.set_rs(fb.num_tokens if sb.spec_info is None and not self.args.enable_two_batch_overlap else 0)
         fb.num_splits = self._pick_splits(B, fb.max_kv_len) if decode else 1
@@ -820,7 +848,7 @@ class ModelRunner:
         logger.info("captured %d prefill graphs (%d..%d tokens) in %.1fs", len(buckets), buckets[0], buckets[-1], time.perf_counter() - t0)
 
     def _prefill_graph_eligible(self, sb: ScheduleBatch) -> bool:
-        if sb.return_logprob or sb.has_grammar or sb.spec_info is not None or sb.needs_host_state():
+        if sb.return_logprob or sb.has_grammar or sb.spec_info is not None or sb.needs_host_state() or sb.out_cache_loc_swa is not None:
             return False
         if self.lora_manager is not None or self.hidden_tap is not None or self.aux_layer_ids is not None:
             return False
@@ -1098,8 +1126,9 @@ class _DecodeGraph:
         self.bs = bs
         self.greedy = greedy
         dev = runner.device
-        # static int region: positions | out_cache_loc | req_slots | seq_lens | step(2) | temperature | top_p | min_p | top_k
-        self.n_int = 8 * bs + 2
+        # static int region: positions | out_cache_loc | req_slots | seq_lens | step(2) | temperature | top_p | min_p | top_k [| out_cache_loc_swa]
+        self.has_swa = getattr(runner, "swa", None) is not None
+        self.n_int = 8 * bs + 2 + (bs if self.has_swa else 0)
         self.static = torch.zeros(self.n_int + 3 * 8192, dtype=torch.int32, device=dev)
         s = self.static
         self.positions, self.out_cache_loc, self.req_slots, self.seq_lens = s[0:bs], s[bs:2 * bs], s[2 * bs:3 * bs], s[3 * bs:4 * bs]
@@ -1109,6 +1138,7 @@ class _DecodeGraph:
         self.top_p = s[o + bs:o + 2 * bs].view(torch.float32)
         self.min_p = s[o + 2 * bs:o + 3 * bs].view(torch.float32)
         self.top_k = s[o + 3 * bs:o + 4 * bs]
+        self.out_cache_loc_swa = s[8 * bs + 2:9 * bs + 2] if self.has_swa else None
         self.out_tokens = torch.zeros(bs, dtype=torch.int32, device=dev)
         self.greedy_buf = torch.zeros(runner.tp.world_size, (bs + 1) // 2 * 2, 4, dtype=torch.bfloat16, device=dev) if greedy else None
         self.graph = torch.cuda.CUDAGraph()
@@ -1128,7 +1158,8 @@ class _DecodeGraph:
                             seq_lens=self.seq_lens, cu_q=None, q_lens=None, last_idx=None, sample_slots=self.req_slots,
                             max_q_len=1, max_kv_len=r.max_context_len, page_table=r.page_table, page_size=r.page_size,
                             kv_pool=r.kv_pool, num_splits=self.num_splits, attn_workspace=self.workspace, sampling=samp,
-                            next_token_buf=r.next_token_buf)
+                            next_token_buf=r.next_token_buf, out_cache_loc_swa=self.out_cache_loc_swa,
+                            swa_pt_offset=getattr(r, "swa_pt_offset", 0))
 
     def _run(self) -> None:
         r = self.r
@@ -1196,6 +1227,8 @@ class _DecodeGraph:
         h[o + 2 * bs + B:o + 3 * bs] = 0
         h[o + 3 * bs:o + 3 * bs + B] = s4[3].astype(np.int32)
         h[o + 3 * bs + B:o + 4 * bs] = 1
+        if self.has_swa:
+            h[8 * bs + 2:8 * bs + 2 + B] = sb.out_cache_loc_swa; h[8 * bs + 2 + B:9 * bs + 2] = 0
         n = self.n_int
         nd = 0 if sb.pt_rows is None else sb.pt_rows.size
         if nd:
