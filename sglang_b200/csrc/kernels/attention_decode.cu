@@ -31,7 +31,7 @@ namespace sglb {
 constexpr int DA_D = 128;                 // head dim
 constexpr int DA_KT = 128;                // keys per tile (UMMA M)
 constexpr int DA_NQ = 16;                 // padded query rows (UMMA N)
-constexpr int DA_THREADS = 224;           // warp 0 scheduler + Q/K producer, warp 1 MMA, warps 2-5 softmax (one key per thread), warp 6 V producer
+constexpr int DA_THREADS = 256;           // warp 0 scheduler + Q/K producer, warp 1 MMA, warps 2-5 softmax (one key per thread), warp 6 V producer, warp 7 L2 prefetcher
 constexpr int DA_STAGES = 3;
 constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile: two 64-wide d halves of [128 keys x 128 B])
 constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
@@ -53,13 +53,14 @@ struct DecodeParams {
   int window;
   int total_items;
   int* sched;             // [0] next item, [1] CTAs finished (the last one re-arms both)
+  int prefetch_ahead;     // > 0: warp 7 prefetches the K/V pages of queue items up to this far ahead of the queue head into L2
   long long* prof;        // PROF builds: [ctas][32] per-role cycle accounting (tools/attn_decode_bench.py prof)
 };
 
 template <int GMAX, bool HAS_CAP, bool PROF>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const DecodeParams p) {
+                   const __grid_constant__ CUtensorMap tmK5, const DecodeParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.G;
   extern __shared__ uint8_t smem_raw[];
@@ -102,7 +103,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #define DA_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmK5);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 6); }
@@ -227,6 +228,33 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < DA_KT / 16; ++i)
           if (i < n_pages) tma_load_5d(sV + st * DA_TILE_BYTES + i * ps * 256, &tmV, &v_full[st], 0, 0, 0, it.kvh, pg[i]);
+      }
+    }
+  } else if (warp == 7 && lane == 0) {
+    // ------------------------------------------------------------ L2 prefetcher
+    // The smem rings hold at most 192 KB in flight per SM; at the ~5 us loaded DRAM latency of this gather that caps the kernel near 4.5 TB/s
+    // (Little's law; tools/tma_gather_bench.cu + the per-role cycle accounting).  This warp keeps MORE bytes in flight without smem: it walks the
+    // work queue in a static stride (item = blockIdx.x, + gridDim.x, ...), stays `prefetch_ahead` items in front of the queue head, and issues
+    // one L2 prefetch per page and tensor.  Whichever CTA later draws the item finds its pages in L2.
+    if (p.prefetch_ahead > 0) {
+      const int ps = p.page_size;
+      for (int pf = blockIdx.x; pf < p.total_items; pf += gridDim.x) {
+        uint32_t spins = 0;
+        while (pf > *((volatile int*)p.sched) + p.prefetch_ahead) {
+          __nanosleep(200);
+          if (++spins > (1u << 22)) break;          // never wedge the kernel on a heuristic
+        }
+        const Item it = decode_item(pf);
+        if (it.n_tiles == 0) continue;
+        const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
+        const int pg_lo = it.tile_begin * DA_KT / ps;
+        // bounded L2 footprint: the first four tiles of an item (ahead x 4 x 64 KB <= ~57 MB); longer items stream the rest through the ring
+        const int pg_hi = min((it.tile_begin + min(it.n_tiles, 4)) * DA_KT, it.kv_hi + ps - 1) / ps;
+        for (int pg = pg_lo; pg < pg_hi; ++pg) {
+          const int page = pt[min(pg, p.pt_stride - 1)];
+          tma_prefetch_5d(&tmK5, 0, 0, 0, it.kvh, page);
+          tma_prefetch_5d(&tmV, 0, 0, 0, it.kvh, page);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -521,6 +549,9 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
   p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.B = B;
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.window = window;
   p.total_items = B * Hkv * num_splits; p.sched = sched; p.prof = g_da_prof;
+  static const int prefetch_env = [] { const char* e = getenv("SGLB_ATTN_PREFETCH"); return e ? atoi(e) : 222; }();
+  p.prefetch_ahead = prefetch_env;
+  CUtensorMap tmK5 = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B);
   const int ctas = std::min(p.total_items, num_sms);
   const bool capped = logit_cap > 0.f;
 #define SGLB_DA_LAUNCH(GM_, CAP_)                                                                                                    \
@@ -530,7 +561,7 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
       SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<GM_, CAP_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES)); \
       configured = true;                                                                                                            \
     }                                                                                                                               \
-    attn_decode_kernel<GM_, CAP_, false><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                            \
+    attn_decode_kernel<GM_, CAP_, false><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmK5, p);                      \
   } while (0)
   if (g_da_prof != nullptr && G <= 4 && !capped) {      // instrumented build (per-role cycle accounting), bench tool only
     static bool configured = false;
@@ -538,7 +569,7 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
       SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
       configured = true;
     }
-    attn_decode_kernel<4, false, true><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    attn_decode_kernel<4, false, true><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmK5, p);
   } else
   if (G <= 4) { if (capped) SGLB_DA_LAUNCH(4, true); else SGLB_DA_LAUNCH(4, false); }
   else if (G <= 8) { if (capped) SGLB_DA_LAUNCH(8, true); else SGLB_DA_LAUNCH(8, false); }
