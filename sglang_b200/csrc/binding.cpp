@@ -106,7 +106,7 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
               const at::Tensor& page_table, const at::Tensor& req_slots, const at::Tensor& seq_lens,
               c10::optional<at::Tensor> cu_q, c10::optional<at::Tensor> tok2req, int64_t max_q_len, int64_t page_size,
               int64_t num_splits, double scale, bool causal, int64_t window, double logit_cap, double k_scale,
-              double v_scale, int64_t impl) {
+              double v_scale, int64_t impl, c10::optional<at::Tensor> tree_anc) {
   CHECK_CUDA(q); CHECK_BF16(q); CHECK_BF16(out); CHECK_I32(page_table); CHECK_I32(req_slots); CHECK_I32(seq_lens);
   TORCH_CHECK(q.dim() == 3 && q.stride(2) == 1 && q.stride(1) == q.size(2), "q must be [T, Hq, D] with packed heads");
   TORCH_CHECK(out.is_contiguous() && k_cache.is_contiguous() && v_cache.is_contiguous());
@@ -131,6 +131,9 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
     int* sched_ptr = sched[di].data_ptr<int>();
     // decode (one query token per request): keys-as-M kernel (attention_decode.cu) unless SGLB_ATTN_DECODE=v2 asks for the query-major one
     static const bool decode_v3 = [] { const char* e = getenv("SGLB_ATTN_DECODE"); return !(e && std::string(e) == "v2"); }();
+    if (tree_anc.has_value())
+      TORCH_CHECK(cu_q.has_value() && tree_anc->scalar_type() == at::kInt && tree_anc->is_contiguous() && tree_anc->numel() == T,
+                  "tree_anc must be int32 [T] (ancestor bits per query token)");
     if (!cu_q.has_value() && decode_v3 && sglb::attn_decode_tc_supported(Hq, Hkv, D, (int)page_size)) {
       TORCH_CHECK(T == B, "decode attention expects one query token per request");
       sglb::attn_decode_tc(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse), opt_mptr<float>(part_o),
@@ -145,9 +148,11 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
                       opt_mptr<float>(part_o), opt_mptr<float>(part_lse), page_table.data_ptr<int>(),
                       (int)page_table.stride(0), req_slots.data_ptr<int>(), seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), B, T,
                       (int)q.stride(0), (int)max_q_len, Hq, Hkv, D, (int)k_cache.size(0), (int)page_size, (int)num_splits,
-                      (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, sched_ptr, num_sms(), cur_stream());
+                      (float)scale, causal ? 1 : 0, (int)window, (float)logit_cap, sched_ptr, num_sms(), cur_stream(),
+                      tree_anc.has_value() ? reinterpret_cast<const unsigned*>(tree_anc->data_ptr<int>()) : nullptr);
     count(num_splits > 1 ? 2 : 1);
   } else {
+    TORCH_CHECK(!tree_anc.has_value(), "tree masks need the tcgen05 attention (impl 0 / 2)");
     sglb::attn_fwd_simt(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), opt_mptr<float>(lse),
                         page_table.data_ptr<int>(), (int)page_table.stride(0), req_slots.data_ptr<int>(),
                         seq_lens.data_ptr<int>(), opt_ptr<int>(cu_q), opt_ptr<int>(tok2req), T, (int)q.stride(0), Hq, Hkv, D,
@@ -543,7 +548,7 @@ TORCH_LIBRARY(sglb, m) {
   m.def("attn_fwd(Tensor q, Tensor k_cache, Tensor v_cache, Tensor(a!) out, Tensor(b!)? lse, Tensor(c!)? part_o, "
         "Tensor(d!)? part_lse, Tensor page_table, Tensor req_slots, Tensor seq_lens, Tensor? cu_q, Tensor? tok2req, "
         "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
-        "float k_scale, float v_scale, int impl) -> ()", &attn_fwd);
+        "float k_scale, float v_scale, int impl, Tensor? tree_anc=None) -> ()", &attn_fwd);
   m.def("attn_decode_prof(Tensor buf) -> ()", &attn_decode_prof);
   m.def("gemm(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int bn) -> ()", &gemm);
   m.def("sample(Tensor logits, Tensor temperature, Tensor top_k, Tensor top_p, Tensor min_p, Tensor? seeds, "

@@ -36,7 +36,7 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
                  float* part_lse, const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens,
                  const int* cu_q, int B, int T, int q_stride, int max_q_len, int Hq, int Hkv, int D, int num_slots,
                  int page_size, int num_splits, float scale, int causal, int window, float logit_cap, int* sched, int num_sms,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const unsigned* tree_anc = nullptr);
 
 // gemm_tc.cu
 void gemm_bf16_tc(const void* A, const void* W, void* C, const void* bias, int M, int N, int K, int lda, int ldw, int ldc,

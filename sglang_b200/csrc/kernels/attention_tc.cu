@@ -45,6 +45,7 @@ struct AttnParams {
   // persistent variant: work items = the (x, y, z) cells of the classic grid, handed out by an atomic counter
   int gx, gy, total_items;
   int* sched;         // [0] next item, [1] CTAs finished (the last one resets both: graph-replay safe)
+  const unsigned* tree_anc;   // speculative tree verify: [T] bit k of tree_anc[t] = query token t may see draft key `prefix + k` (classic launch)
   int legacy_epilogue_wait;   // FAULT INJECTION ONLY (SGLB_ATTN_LEGACY_EPILOGUE=1): re-creates the round-1 epilogue hand-off (wait on o_done by
                               // tile parity) so tools/attn_stress.py can reproduce the premature-pass race / the TP>=4 deadlock it caused
 };
@@ -267,6 +268,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int c = 0; c < NC; ++c) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(sr[c][i]));
+          }
+        }
+        if (p.tree_anc != nullptr && kv0 + KT > prefix) {
+          // token-tree verification: keys below `prefix` are the committed context (always visible); draft key prefix + k is visible to a
+          // query node iff k is one of its ancestors or itself.  Separate pass: the common path above stays untouched.
+          const unsigned anc = row_valid ? p.tree_anc[q_start + tok] : 0xffffffffu;
+          const int tree_lo = prefix - kv0;
+          mx_raw = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int rel = c * 32 + i - tree_lo;
+              const bool hidden = rel >= 0 && ((anc >> (rel & 31)) & 1u) == 0u;
+              const float v = hidden ? -INFINITY : __uint_as_float(sr[c][i]);
+              sr[c][i] = __float_as_uint(v);
+              mx_raw = fmaxf(mx_raw, v);
+            }
           }
         }
         const float mx = mx_raw * scale_log2;   // scale_log2 > 0: max commutes with the scaling
@@ -791,7 +810,7 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
                  float* part_lse, const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens,
                  const int* cu_q, int B, int T, int q_stride, int max_q_len, int Hq, int Hkv, int D, int num_slots, int page_size,
                  int num_splits, float scale, int causal, int window, float logit_cap, int* sched, int num_sms,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const unsigned* tree_anc) {
   if (D != ATT_D) throw std::runtime_error("sglb attn_tc: head_dim must be 128");
   const int G = Hq / Hkv;
   if (G < 1 || G > 128 || (128 % G) != 0) throw std::runtime_error("sglb attn_tc: GQA group must divide 128");
@@ -812,6 +831,11 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
   p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens; p.cu_q = cu_q;
   p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.T = T;
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.causal = causal; p.window = window;
+  p.tree_anc = tree_anc;
+  if (tree_anc != nullptr) {
+    if (max_q_len > 32 || num_splits != 1 || window > 0) throw std::runtime_error("sglb attn_tc: tree masks cover <= 32 draft nodes, no split-KV / window");
+    p.causal = 0;        // every draft key is a candidate; the ancestor bits decide
+  }
   dim3 grid((max_q_len + TQ - 1) / TQ, Hkv * num_splits, B);
   p.gx = (int)grid.x; p.gy = (int)grid.y; p.total_items = (int)(grid.x * grid.y * grid.z); p.sched = sched;
   static const int legacy = [] { const char* e = getenv("SGLB_ATTN_LEGACY_EPILOGUE"); return (e && e[0] == '1') ? 1 : 0; }();
@@ -841,7 +865,7 @@ void attn_fwd_tc(const void* q, const void* k_cache, const void* v_cache, void* 
     attn_fwd_tc_persist_kernel<KT_, CAP_><<<ctas, ATT_THREADS, att_smem_bytes<KT_>(), stream>>>(tmQ, tmK, tmV, p);        \
   } while (0)
   // persistent scheduling pays off once there are more items than resident CTAs (otherwise the classic launch is identical)
-  const bool persist = sched != nullptr && p.total_items > num_sms * (small ? 2 : 1);
+  const bool persist = sched != nullptr && tree_anc == nullptr && p.total_items > num_sms * (small ? 2 : 1);
   if (persist) {
     if (small) { if (capped) SGLB_ATT_LAUNCH_P(64, true); else SGLB_ATT_LAUNCH_P(64, false); }
     else { if (capped) SGLB_ATT_LAUNCH_P(128, true); else SGLB_ATT_LAUNCH_P(128, false); }

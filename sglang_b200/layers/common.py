@@ -111,7 +111,7 @@ class RadixAttention(nn.Module):
         o = ops.paged_attention(q3, kc, vc, page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,
-                                workspace=fb.attn_workspace, custom_mask=mask, lse=lse)
+                                workspace=fb.attn_workspace, custom_mask=mask, lse=lse, tree_anc=fb.tree_anc if not self.chunk else None)
         if sinks is not None:       # attention sinks (GPT-OSS): exp(sink_h) joins the soft-max denominator only -> o * sigmoid(lse - sink_h)
             o = (o.float() * torch.sigmoid(lse - sinks[None, :]).unsqueeze(-1)).to(o.dtype)
         return o.view(T, self.num_heads * self.head_dim)

@@ -60,6 +60,7 @@ class ForwardBatch:
     return_hidden: bool = False
     spec_info: Any = None
     custom_mask: Optional[torch.Tensor] = None
+    tree_anc: Optional[torch.Tensor] = None      # i32 [T] ancestor bits per query node (speculative tree verify on the tcgen05 kernel)
     h2d_bytes: int = 0
     # host mirrors (no sync needed)
     seq_lens_cpu: Optional[np.ndarray] = None

@@ -606,6 +606,10 @@ class ModelRunner:
             if cm is not None:       # token-tree verification: every node attends to the prefix and its own ancestors only
                 assert self.dcp is None, "tree drafts + DCP: not supported"
                 fb.custom_mask = torch.from_numpy(cm).to(self.device)
+            ta = (sb.spec_info or {}).get("tree_anc") if isinstance(sb.spec_info, dict) else None
+            if ta is not None and (cm is None or self.supports_tree_anc()):
+                assert self.dcp is None, "tree drafts + DCP: not supported"
+                fb.tree_anc = torch.from_numpy(ta).to(self.device)
             if self.aux_layer_ids is not None:
                 fb.capture_aux = self.aux_layer_ids
             hidden = self.model(fb)
@@ -918,6 +922,19 @@ class ModelRunner:
             return
         nvl.rs_active = bool(num_tokens > 0 and self.aux_layer_ids is None and self.lora_manager is None and self._rs_capable()
                              and nvl.wants_rs_bytes(num_tokens * self.cfg.hidden_size * 2))
+
+    def supports_tree_anc(self) -> bool:
+        """can token-tree verification run on the tcgen05 attention with per-node ancestor bits (attention_tc.cu ``tree_anc``) instead of a
+        dense custom mask on the reference path?"""
+        c = getattr(self, "_tree_anc_ok", None)
+        if c is None:
+            layers = getattr(getattr(self.model, "model", None), "layers", None) or []
+            attn = [getattr(getattr(l, "self_attn", None), "attn", None) for l in layers]
+            c = bool(self.is_cuda and ops.load_native() and ops.attn_impl() == 0 and attn and all(
+                a is not None and a.head_dim == 128 and 128 % (a.num_heads // a.num_kv_heads) == 0 and a.window <= 0 and not a.chunk
+                and a.sinks is None for a in attn) and self.kv_pool.dtype == torch.bfloat16 and self.dcp is None)
+            self._tree_anc_ok = c
+        return c
 
     def greedy_head(self):
         """the vocab-sharded head when all-greedy decode batches may use the vocab-parallel argmax (TP > 1, plain LM head, no DP-attention

@@ -125,9 +125,12 @@ def attn_impl() -> int:
 def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, q_lens, max_q_len: int, page_size: int,
                     scale: float, causal: bool = True, window: int = -1, logit_cap: float = 0.0, k_scale: float = 1.0,
                     v_scale: float = 1.0, num_splits: int = 1, workspace=None, tok2req=None, out=None, lse=None,
-                    impl: Optional[int] = None, custom_mask=None):
-    """q [T,Hq,D]; caches [slots,Hkv,D]; cu_q None => decode (q_len 1)."""
-    if _use_native(q) and q.dtype == torch.bfloat16 and custom_mask is None:
+                    impl: Optional[int] = None, custom_mask=None, tree_anc=None):
+    """q [T,Hq,D]; caches [slots,Hkv,D]; cu_q None => decode (q_len 1).  ``tree_anc`` int32 [T]: speculative token-tree verification on the
+    tcgen05 kernel (bit k = draft node k is an ancestor-or-self of this query node); ``custom_mask`` = the general (reference-path) form."""
+    tree_ok = (tree_anc is not None and _use_native(q) and q.dtype == torch.bfloat16 and attn_impl() == 0 and q.shape[-1] == 128
+               and k_cache.dtype == torch.bfloat16 and 128 % (q.shape[1] // k_cache.shape[1]) == 0 and int(max_q_len) <= 32 and window <= 0)
+    if _use_native(q) and q.dtype == torch.bfloat16 and (tree_ok or (custom_mask is None and tree_anc is None)):
         if out is None:
             out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
         impl = attn_impl() if impl is None else impl
@@ -149,12 +152,16 @@ def paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, cu_q, 
         if impl == 1 and cu_q is not None and tok2req is None:
             ql = cu_q[1:] - cu_q[:-1]
             tok2req = torch.repeat_interleave(torch.arange(ql.numel(), device=q.device, dtype=torch.int32), ql.long()).to(torch.int32)
+        if tree_ok:
+            impl, num_splits, part_o, part_lse = 0, 1, None, None
         if impl == 0 and envs.SGLB_ATTN_PERSIST.get():
             impl = 2        # same kernel family, persistent CTAs with an atomic work queue (falls back to the classic launch when small)
         torch.ops.sglb.attn_fwd(q, k_cache, v_cache, out, lse, part_o, part_lse, page_table, req_slots, seq_lens, cu_q, tok2req,
                                 int(max_q_len), int(page_size), int(num_splits), float(scale), bool(causal), int(window),
-                                float(logit_cap), float(k_scale), float(v_scale), int(impl))
+                                float(logit_cap), float(k_scale), float(v_scale), int(impl), tree_anc if tree_ok else None)
         return out
+    if custom_mask is None and tree_anc is not None:
+        custom_mask = torch_ref.tree_anc_to_mask(tree_anc, q_lens, seq_lens)
     r = torch_ref.paged_attention(q, k_cache, v_cache, page_table, req_slots, seq_lens, q_lens, page_size, scale, causal,
                                   window, logit_cap, k_scale, v_scale, custom_mask=custom_mask, return_lse=lse is not None)
     if lse is not None:

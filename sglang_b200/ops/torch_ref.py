@@ -313,3 +313,19 @@ def fp8_block_gemm(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: tor
     wsf = ws.repeat_interleave(block, 0)[:N].repeat_interleave(block, 1)[:, :K]
     w = wq.float() * wsf
     return (x.view(T, K) @ w.t()).to(out_dtype)
+
+
+def tree_anc_to_mask(tree_anc: torch.Tensor, q_lens: torch.Tensor, seq_lens: torch.Tensor) -> torch.Tensor:
+    """dense custom mask (flat, per request [q_len, seq_len] row-major) from per-node ancestor bits: keys below the prefix are visible to
+    every node, draft key ``prefix + k`` iff bit k of the node's word is set (speculative token-tree verification)"""
+    out = []
+    anc = tree_anc.to(torch.int64) & 0xFFFFFFFF
+    off = 0
+    for ql, L in zip(q_lens.tolist(), seq_lens.tolist()):
+        p = L - ql
+        m = torch.ones(ql, L, dtype=torch.bool, device=tree_anc.device)
+        bits = (anc[off:off + ql, None] >> torch.arange(ql, device=tree_anc.device)[None, :]) & 1
+        m[:, p:] = bits.bool()
+        out.append(m.reshape(-1))
+        off += ql
+    return torch.cat(out) if out else torch.zeros(0, dtype=torch.bool, device=tree_anc.device)

@@ -108,7 +108,20 @@ class BaseSpecWorker:
         d1 = kv.take_deltas()
         vb.pt_rows, vb.pt_cols, vb.pt_vals = (np.concatenate([a, b]) for a, b in zip(d0, d1))
         vb.spec_info = {"verify_all_positions": True}
-        if any_tree:
+        tree_anc = None
+        if any_tree and max(qlens) <= 32:
+            # compact form for the tcgen05 kernel: bit k of anc[node] = draft-region key k is an ancestor of the node (or the node itself)
+            anc_all = []
+            for i in range(B):
+                anc = [1] * qlens[i]
+                for j, pj in enumerate(trees[i]):
+                    anc[j + 1] = anc[pj + 1] | (1 << (j + 1))
+                anc_all.extend(anc)
+            tree_anc = np.asarray(anc_all, dtype=np.uint32).view(np.int32)
+            vb.spec_info["tree_anc"] = tree_anc
+        if any_tree and tree_anc is not None and getattr(runner, "supports_tree_anc", lambda: False)():
+            self.total_tree_verifies += 1        # masked tcgen05 verify: no O(q x context) host mask
+        elif any_tree:
             self.total_tree_verifies += 1
             masks = []
             for i in range(B):

@@ -135,6 +135,37 @@ def case_attn_tc_prefill():
     _attn_check(0, 1, [100], [400], Hq=16, Hkv=2, name="G=8")
 
 
+def case_attn_tree():
+    """token-tree verification on the tcgen05 kernel (per-node ancestor bits) against the reference path with the dense mask"""
+    import numpy as np
+
+    rng = np.random.default_rng(11)
+    for Hq, Hkv, ps in ((32, 8, 32), (16, 2, 16), (8, 8, 64)):
+        q_lens = [1, 9, 32, 17, 5]
+        prefixes = [0, 37, 500, 129, 1000]
+        seq_lens = [p + q for p, q in zip(prefixes, q_lens)]
+        s = _attn_setup(len(q_lens), q_lens, seq_lens, Hq, Hkv, 128, ps, seed=5)
+        anc = []
+        for ql in q_lens:                       # random topologically ordered trees: node j's parent is any earlier node
+            a = [1] * ql
+            for j in range(1, ql):
+                a[j] = a[int(rng.integers(0, j))] | (1 << j)
+            anc.extend(a)
+        ta = torch.from_numpy(np.asarray(anc, dtype=np.uint32).view(np.int32)).to(DEV)
+        scale = 128 ** -0.5
+        mask = torch_ref.tree_anc_to_mask(ta, s["ql"], s["seq"])
+        ref = torch_ref.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], s["ql"], ps, scale, True, -1, 0.0, custom_mask=mask)
+        out = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], s["cu"], s["ql"], max(q_lens), ps, scale, True, tree_anc=ta)
+        torch.cuda.synchronize()
+        _close(out.float(), ref.float(), 2e-2, 2e-2, f"tree verify Hq={Hq} Hkv={Hkv} ps={ps}")
+        # a chain tree must equal plain causal attention
+        chain = torch.from_numpy(np.concatenate([[(2 << j) - 1 for j in range(ql)] for ql in q_lens]).astype(np.uint32).view(np.int32)).to(DEV)
+        a = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], s["cu"], s["ql"], max(q_lens), ps, scale, True, tree_anc=chain)
+        b = ops.paged_attention(s["q"], s["kc"], s["vc"], s["pt"], s["slots"], s["seq"], s["cu"], s["ql"], max(q_lens), ps, scale, True, impl=0)
+        torch.cuda.synchronize()
+        _close(a.float(), b.float(), 2e-3, 2e-3, "chain tree == causal")
+
+
 def case_attn_tc_split():
     _attn_check(0, 2, [1, 1], [900, 130], decode=True, splits=4, name="decode split4")
     _attn_check(0, 1, [1], [40], decode=True, splits=8, name="decode split8 short (empty splits)")
