@@ -92,6 +92,9 @@ def main() -> None:
     kw = dict(model_path=model_dir, load_format="dummy", skip_tokenizer_init=True, tp_size=a.gpus, max_running_requests=a.max_running,
               random_seed=a.seed, log_level="error")
     kw.update(MODES[a.mode])
+    if a.gpus > 1:
+        # the reference's custom all-reduce lives in the sgl_kernel wheel (absent offline, see the header): its own switch falls back to NCCL
+        kw["disable_custom_all_reduce"] = True
     eng = sgl.Engine(**kw)
     sa = eng.server_args if hasattr(eng, "server_args") else None
     try:
@@ -117,7 +120,7 @@ def main() -> None:
                        "seq_len": f"sharegpt-shaped lognormal: mean in {total_in // a.num_prompts} / out {total_out // a.num_prompts}",
                        "parallelism": f"tp{a.gpus}", "step": "one full trace (request-rate inf, continuous batching)",
                        "l2": "inputs_larger_than_L2 (16 GB weights + KV streamed every decode step)",
-                       "reference_mode": a.mode, "reference_flags": MODES[a.mode],
+                       "reference_mode": a.mode, "reference_flags": dict(MODES[a.mode], **({"disable_custom_all_reduce": True} if a.gpus > 1 else {})),
                        "attention_backend": getattr(sa, "attention_backend", None), "sampling_backend": getattr(sa, "sampling_backend", None),
                        "page_size": getattr(sa, "page_size", None), "cuda_graph": not getattr(sa, "disable_cuda_graph", False),
                        "max_running": a.max_running, "input_tokens_per_step": total_in, "output_tokens_per_step": total_out,
