@@ -21,6 +21,11 @@
 // split-KV decode kernel (kernels/ops/attention/decode_attention.py:472).
 #include <math.h>
 
+// Round-2 experiments that did NOT pay and were removed again (numbers: profiles/attn_decode_r2.md, profiles/tma_gather_r2.md):
+//   * two softmax groups on alternating tiles (the consumer was not the limiter);
+//   * separate K / V producer warps + one 5-D TMA box per V page (fewer issues per thread; same speed, slower on ragged batches);
+//   * an L2 prefetcher warp running ahead of the work queue (extra TMA traffic cost more than the added bytes in flight gave).
+// The kernel sits on the loaded-latency curve of the paged gather: throughput ~ bytes in flight per SM, and 192 KB of smem rings is all there is.
 #include "common.cuh"
 #include "tma_host.h"
 
@@ -31,7 +36,7 @@ namespace sglb {
 constexpr int DA_D = 128;                 // head dim
 constexpr int DA_KT = 128;                // keys per tile (UMMA M)
 constexpr int DA_NQ = 16;                 // padded query rows (UMMA N)
-constexpr int DA_THREADS = 256;           // warp 0 scheduler + Q/K producer, warp 1 MMA, warps 2-5 softmax (one key per thread), warp 6 V producer, warp 7 L2 prefetcher
+constexpr int DA_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2-5 softmax (one key per thread)
 constexpr int DA_STAGES = 3;
 constexpr int DA_TILE_BYTES = DA_KT * DA_D * 2;          // 32 KB  (K or V tile: two 64-wide d halves of [128 keys x 128 B])
 constexpr int DA_HALF_BYTES = DA_TILE_BYTES / 2;
@@ -53,14 +58,13 @@ struct DecodeParams {
   int window;
   int total_items;
   int* sched;             // [0] next item, [1] CTAs finished (the last one re-arms both)
-  int prefetch_ahead;     // > 0: warp 7 prefetches the K/V pages of queue items up to this far ahead of the queue head into L2
   long long* prof;        // PROF builds: [ctas][32] per-role cycle accounting (tools/attn_decode_bench.py prof)
 };
 
 template <int GMAX, bool HAS_CAP, bool PROF>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmK5, const DecodeParams p) {
+                   const DecodeParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.G;
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +86,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* o_final = bars + 19;       // last PV of an item                         (phase = item ordinal)
   uint64_t* o_free = bars + 20;        // epilogue has read O^T (4 arrivals)         (phase = item ordinal)
   uint64_t* item_full = bars + 21;     // [2]
-  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps + V producer)
+  uint64_t* item_empty = bars + 23;    // [2]  (MMA thread + 4 softmax warps)
   volatile int* s_item = reinterpret_cast<volatile int*>(bars + 25);        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
   volatile uint32_t* dbg = reinterpret_cast<volatile uint32_t*>(bars + 27); // [6] role state for the timeout dump
@@ -103,10 +107,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #define DA_DBG(code_, a_, b_) dbg[warp] = ((uint32_t)(code_) << 28) | (((uint32_t)(a_) & 0x3fff) << 14) | ((uint32_t)(b_) & 0x3fff)
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmK5);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     for (int i = 0; i < DA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 6); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 5); }
     mbar_init(o_done, 1); mbar_init(o_final, 1); mbar_init(o_free, 4);
     fence_barrier_init();
   }
@@ -179,81 +183,22 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);     // only pages that hold live keys
         const int pg0 = key0 / ps;
         const uint32_t bytes = (uint32_t)n_pages * ps * 256;
-        // page ids first (independent loads, one round trip), then the TMA issues: a single thread issues ~1 TMA per 200+ cycles, so the
-        // V tiles have their own producer warp (measured with tools/tma_gather_bench.cu: one issuing thread caps the gather below HBM speed)
-        int pg[DA_KT / 16];
-#pragma unroll
-        for (int i = 0; i < DA_KT / 16; ++i)
-          if (i < pages_per_tile) pg[i] = pt[min(pg0 + i, p.pt_stride - 1)];
         DA_T(2, DA_WAIT(&k_empty[st], ph ^ 1));
         if constexpr (PROF) pacc[4] += 1;
         mbar_expect_tx(&k_full[st], bytes);
-#pragma unroll
-        for (int i = 0; i < DA_KT / 16; ++i) {
-          if (i < n_pages) {
-            uint8_t* dst = sK + st * DA_TILE_BYTES + i * ps * 128;
-            tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, pg[i] * ps);
-            tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, pg[i] * ps);
-          }
+        for (int i = 0; i < n_pages; ++i) {
+          const int page = pt[pg0 + i];
+          uint8_t* dst = sK + st * DA_TILE_BYTES + i * ps * 128;
+          tma_load_3d(dst, &tmK, &k_full[st], 0, it.kvh, page * ps);
+          tma_load_3d(dst + DA_HALF_BYTES, &tmK, &k_full[st], 64, it.kvh, page * ps);
         }
-      }
-    }
-  } else if (warp == 6 && lane == 0) {
-    // ------------------------------------------------------------ V producer: one 5-D box per page (both d halves): smem [page][half][ps rows][128 B]
-    uint32_t n_it = 0, g = 0;
-    const int ps = p.page_size, pages_per_tile = DA_KT / ps;
-    for (;;) {
-      const int slot = n_it & 1;
-      DA_T(0, DA_WAIT(&item_full[slot], (n_it >> 1) & 1));
-      const int idx = s_item[slot];
-      mbar_arrive(&item_empty[slot]);
-      ++n_it;
-      if (idx >= p.total_items) break;
-      const Item it = decode_item(idx);
-      if (it.n_tiles == 0) continue;
-      const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
-      for (int j = 0; j < it.n_tiles; ++j, ++g) {
-        const int st = g % DA_STAGES;
-        const uint32_t ph = (g / DA_STAGES) & 1;
-        const int key0 = (it.tile_begin + j) * DA_KT;
-        const int n_pages = min(pages_per_tile, (it.kv_hi - key0 + ps - 1) / ps);
-        const int pg0 = key0 / ps;
-        int pg[DA_KT / 16];
-#pragma unroll
-        for (int i = 0; i < DA_KT / 16; ++i)
-          if (i < pages_per_tile) pg[i] = pt[min(pg0 + i, p.pt_stride - 1)];
         DA_T(3, DA_WAIT(&v_empty[st], ph ^ 1));
-        if constexpr (PROF) pacc[4] += 1;
-        mbar_expect_tx(&v_full[st], (uint32_t)n_pages * ps * 256);
-#pragma unroll
-        for (int i = 0; i < DA_KT / 16; ++i)
-          if (i < n_pages) tma_load_5d(sV + st * DA_TILE_BYTES + i * ps * 256, &tmV, &v_full[st], 0, 0, 0, it.kvh, pg[i]);
-      }
-    }
-  } else if (warp == 7 && lane == 0) {
-    // ------------------------------------------------------------ L2 prefetcher
-    // The smem rings hold at most 192 KB in flight per SM; at the ~5 us loaded DRAM latency of this gather that caps the kernel near 4.5 TB/s
-    // (Little's law; tools/tma_gather_bench.cu + the per-role cycle accounting).  This warp keeps MORE bytes in flight without smem: it walks the
-    // work queue in a static stride (item = blockIdx.x, + gridDim.x, ...), stays `prefetch_ahead` items in front of the queue head, and issues
-    // one L2 prefetch per page and tensor.  Whichever CTA later draws the item finds its pages in L2.
-    if (p.prefetch_ahead > 0) {
-      const int ps = p.page_size;
-      for (int pf = blockIdx.x; pf < p.total_items; pf += gridDim.x) {
-        uint32_t spins = 0;
-        while (pf > *((volatile int*)p.sched) + p.prefetch_ahead) {
-          __nanosleep(200);
-          if (++spins > (1u << 22)) break;          // never wedge the kernel on a heuristic
-        }
-        const Item it = decode_item(pf);
-        if (it.n_tiles == 0) continue;
-        const int* pt = p.page_table + (size_t)p.req_slots[it.b] * p.pt_stride;
-        const int pg_lo = it.tile_begin * DA_KT / ps;
-        // bounded L2 footprint: the first four tiles of an item (ahead x 4 x 64 KB <= ~57 MB); longer items stream the rest through the ring
-        const int pg_hi = min((it.tile_begin + min(it.n_tiles, 4)) * DA_KT, it.kv_hi + ps - 1) / ps;
-        for (int pg = pg_lo; pg < pg_hi; ++pg) {
-          const int page = pt[min(pg, p.pt_stride - 1)];
-          tma_prefetch_5d(&tmK5, 0, 0, 0, it.kvh, page);
-          tma_prefetch_5d(&tmV, 0, 0, 0, it.kvh, page);
+        mbar_expect_tx(&v_full[st], bytes);
+        for (int i = 0; i < n_pages; ++i) {
+          const int page = pt[pg0 + i];
+          uint8_t* dst = sV + st * DA_TILE_BYTES + i * ps * 128;
+          tma_load_3d(dst, &tmV, &v_full[st], 0, it.kvh, page * ps);
+          tma_load_3d(dst + DA_HALF_BYTES, &tmV, &v_full[st], 64, it.kvh, page * ps);
         }
       }
     }
@@ -302,11 +247,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (j == 0) DA_T(4, DA_WAIT(o_free, (n_q & 1) ^ 1));       // the previous item's epilogue has read O^T
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * DA_TILE_BYTES);
-        const int ps_ = p.page_size, lps_ = 31 - __clz(ps_);       // V tile layout [page][d half][ps keys][128 B]: a 16-key step stays inside one page (ps >= 16)
         const uint32_t p_addr = smem_u32(sP + (gt & 1) * DA_P_BYTES);
 #pragma unroll
         for (int k = 0; k < DA_KT / 16; ++k)      // 16 keys per step: A rows advance 16 x 128 B, B (P^T, K-major) advances 32 B inside a 64-key chunk
-          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + (((k * 16) >> lps_) << (lps_ + 8)) + ((k * 16) & (ps_ - 1)) * 128, ps_ * 128, 1024),
+          umma_f16_ss(tmem_O, make_smem_desc_sw128(v_addr + k * 2048, DA_HALF_BYTES, 1024),
                       make_smem_desc_sw128(p_addr + (k >> 2) * (DA_NQ * 128) + (k & 3) * 32, 0, 1024), idesc_o, (j | k) != 0);
         umma_commit(&v_empty[st]);
         umma_commit(o_done);
@@ -315,7 +259,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       g += n_tiles;
       ++n_q;
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------ softmax (thread = key) + epilogue (thread = output dim)
     const int q4 = warp & 3;                              // TMEM lane quadrant of this warp
     const int row = (q4 << 5) + lane;                     // key index inside the tile / output dim in the epilogue
@@ -492,10 +436,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #undef DA_DBG
 #undef DA_T
   if constexpr (PROF) {
-    if (p.prof != nullptr && lane == 0 && (warp <= 2 || warp == 6)) {
-      const int role = warp == 6 ? 3 : warp;
+    if (p.prof != nullptr && lane == 0 && warp <= 2) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) p.prof[((size_t)blockIdx.x * 4 + role) * 10 + i] = pacc[i];
+      for (int i = 0; i < 10; ++i) p.prof[((size_t)blockIdx.x * 4 + warp) * 10 + i] = pacc[i];      // 4 slots per CTA (the tool's layout)
     }
   }
 
@@ -516,7 +459,7 @@ __global__ void attn_merge_splits_kernel(const float* __restrict__ part_o, const
 bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size) {
   if (D != DA_D || Hkv <= 0 || Hq % Hkv) return false;
   const int G = Hq / Hkv;
-  return G >= 1 && G <= 16 && page_size >= 16 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
+  return G >= 1 && G <= 16 && page_size >= 8 && page_size <= 128 && (page_size & (page_size - 1)) == 0;
 }
 
 static long long* g_da_prof = nullptr;
@@ -538,20 +481,13 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
   uint64_t sk[2] = {(uint64_t)D * 2, (uint64_t)Hkv * D * 2};
   uint32_t bk[3] = {64, 1, (uint32_t)page_size};
   CUtensorMap tmK = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
-  // V: (64 elems, key in page, d half, kv head, page) -> ONE box per page lands as [half][ps keys][128 B]
-  uint64_t dv[5] = {64, (uint64_t)page_size, 2, (uint64_t)Hkv, (uint64_t)(num_slots / page_size)};
-  uint64_t sv[4] = {(uint64_t)Hkv * D * 2, 128, (uint64_t)D * 2, (uint64_t)page_size * Hkv * D * 2};
-  uint32_t bv[5] = {64, (uint32_t)page_size, 2, 1, 1};
-  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmV = make_tmap(v_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
   p.out = (__nv_bfloat16*)out; p.part_o = part_o; p.part_lse = part_lse; p.lse = lse;
   p.page_table = page_table; p.req_slots = req_slots; p.seq_lens = seq_lens;
   p.pt_stride = pt_stride; p.Hq = Hq; p.Hkv = Hkv; p.G = G; p.page_size = page_size; p.num_splits = num_splits; p.B = B;
   p.scale_log2 = scale * 1.4426950408889634f; p.logit_cap = logit_cap; p.window = window;
   p.total_items = B * Hkv * num_splits; p.sched = sched; p.prof = g_da_prof;
-  static const int prefetch_env = [] { const char* e = getenv("SGLB_ATTN_PREFETCH"); return e ? atoi(e) : 222; }();
-  p.prefetch_ahead = prefetch_env;
-  CUtensorMap tmK5 = make_tmap(k_cache, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B);
   const int ctas = std::min(p.total_items, num_sms);
   const bool capped = logit_cap > 0.f;
 #define SGLB_DA_LAUNCH(GM_, CAP_)                                                                                                    \
@@ -561,7 +497,7 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
       SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<GM_, CAP_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES)); \
       configured = true;                                                                                                            \
     }                                                                                                                               \
-    attn_decode_kernel<GM_, CAP_, false><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmK5, p);                      \
+    attn_decode_kernel<GM_, CAP_, false><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                            \
   } while (0)
   if (g_da_prof != nullptr && G <= 4 && !capped) {      // instrumented build (per-role cycle accounting), bench tool only
     static bool configured = false;
@@ -569,7 +505,7 @@ void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, voi
       SGLB_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
       configured = true;
     }
-    attn_decode_kernel<4, false, true><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmK5, p);
+    attn_decode_kernel<4, false, true><<<ctas, DA_THREADS, DA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else
   if (G <= 4) { if (capped) SGLB_DA_LAUNCH(4, true); else SGLB_DA_LAUNCH(4, false); }
   else if (G <= 8) { if (capped) SGLB_DA_LAUNCH(8, true); else SGLB_DA_LAUNCH(8, false); }

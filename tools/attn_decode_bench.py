@@ -78,12 +78,12 @@ for name, (Hkv, lens, splits) in CASES.items():
         torch.ops.sglb.attn_decode_prof(torch.empty(0, dtype=torch.int64, device=dev))
         a = buf.view(148, 4, 10).double().cpu().numpy()
         tiles = a[:, 2, 8].sum()
-        names = [["item_empty", "q_empty", "k_empty", "-", "(tiles)"],
+        names = [["item_empty", "q_empty", "k_empty", "v_empty", "(tiles)"],
                  ["item_full", "k_full", "p_full", "v_full", "o_free", "q_full"],
                  ["item_full", "s_full", "tmem_ld", "max_exchange", "rescale", "p_store+fence", "arrive", "epilogue", "(tiles)"],
                  ["item_full", "-", "-", "v_empty", "(tiles)"]]
         print(f"  prof: {int(tiles)} tiles over 148 CTAs; cycles per tile, summed waits of each role's elected thread")
-        for r, role in enumerate(["K producer waits", "mma waits", "softmax", "V producer waits"]):
+        for r, role in enumerate(["producer waits", "mma waits", "softmax"]):
             print("   ", role + ":", ", ".join(f"{n} {a[:, r, i].sum() / tiles:.0f}" for i, n in enumerate(names[r]) if not n.startswith("(") and n != "-"))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 if not only:
