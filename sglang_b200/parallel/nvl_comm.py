@@ -53,7 +53,8 @@ class NvlComm:
         # large-T row-parallel outputs: reduce-scatter + norm + all-gather with a ROW-SHARDED residual stream (csrc/comm/nvl_allreduce.cu
         # nvl_rs_add_rmsnorm_ag_kernel).  The model runner switches it on per forward (``rs_active``) for model families whose every residual
         # update goes through a fused consume_norm; with two ranks the one-shot exchange moves the same bytes, so it stays off there.
-        self.rs_min_bytes = envs.SGLB_RS_AG_MIN_BYTES.get() if self.world > 2 else (1 << 60)
+        _rs = envs.SGLB_RS_AG_MIN_BYTES.get()
+        self.rs_min_bytes = _rs if (self.world > 2 and _rs > 0) else (1 << 60)
         self.rs_active = False
         self.rs_calls = 0
 
