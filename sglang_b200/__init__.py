@@ -11,6 +11,10 @@ _LAZY = {
     "Runtime": ("sglang_b200.lang.backend.runtime_endpoint", "Runtime"),
     "RuntimeEndpoint": ("sglang_b200.lang.backend.runtime_endpoint", "RuntimeEndpoint"),
     "launch_server": ("sglang_b200.entrypoints.http_server", "launch_server"),
+    "OpenAI": ("sglang_b200.lang.backend.openai", "OpenAI"),
+    "Anthropic": ("sglang_b200.lang.backend.openai", "Anthropic"),
+    "LiteLLM": ("sglang_b200.lang.backend.openai", "LiteLLM"),
+    "VertexAI": ("sglang_b200.lang.backend.openai", "VertexAI"),
 }
 _LANG = ["function", "gen", "gen_int", "gen_string", "select", "image", "video", "system", "user", "assistant",
          "system_begin", "system_end", "user_begin", "user_end", "assistant_begin", "assistant_end", "set_default_backend",
