@@ -863,7 +863,38 @@ class Scheduler:
             "cache_hit_rate": self.num_cached_tokens / max(1, self.num_cached_tokens + self.num_prefill_tokens),
             "max_running_requests": self.max_running, "max_context_len": self.max_context_len,
             "page_size": self.page_size, "overlap": self.enable_overlap,
+            **self._extra_state(),
         }
+
+    def _extra_state(self) -> Dict[str, Any]:
+        """everything else the metrics exporter publishes (cheap host counters only; never touches the device)"""
+        w = self.worker
+        out: Dict[str, Any] = {"decode_ct": self.decode_ct, "scheduler_iterations": self.step_calls, "scheduler_wall_s": self.step_wall_s,
+                               "grammar_queue": len(getattr(self, "grammar_queue", ()) or ()), "num_sessions": len(getattr(self.sessions, "sessions", {}) or {}),
+                               "chunked_req": int(self.chunked_req is not None), "pending_results": len(self.pending)}
+        for k in ("graph_launches", "h2d_bytes", "d2h_bytes", "prefill_graph_hits"):
+            v = getattr(w, k, None)
+            if isinstance(v, (int, float)):
+                out[k] = v
+        if self.swa is not None:
+            out.update(swa_total_pages=self.swa_allocator.total_pages, swa_available_pages=self.swa_allocator.available_pages(),
+                       swa_slid_pages=self.kv.swa_slid_pages, swa_tombstoned_pages=self.tree.swa_tombstoned)
+        sw = getattr(self, "spec_worker", None)
+        if sw is not None:
+            out.update(spec_accept_rate=sw.accept_rate(), spec_accept_length=sw.accept_length(), spec_verify_ct=sw.total_verify)
+        lm = getattr(w, "lora_manager", None)
+        if lm is not None and hasattr(lm, "pool"):
+            out.update(lora_slots_used=len(getattr(lm.pool, "slot_of", {}) or {}), lora_adapters_loaded=len(getattr(lm, "adapters", {}) or {}))
+        hc = getattr(self, "hicache", None)
+        if hc is not None:
+            for k in ("host_hits", "host_writes", "l3_hits", "l3_writes", "host_pages_used"):
+                v = getattr(hc, k, None)
+                if isinstance(v, (int, float)):
+                    out["hicache_" + k] = v
+        nvl = getattr(getattr(w, "tp", None), "nvl", None)
+        if nvl is not None:
+            out.update(nvl_collective_calls=nvl.calls, nvl_rs_calls=nvl.rs_calls)
+        return out
 
     def _log_decode_stats(self) -> None:
         now = time.perf_counter()
