@@ -93,7 +93,7 @@ class MetricsCollector:
         self.prompt_len.observe(meta.get("prompt_tokens", 0))
         self.gen_len.observe(meta.get("completion_tokens", 0))
         self.cached_len.observe(meta.get("cached_tokens", 0))
-        if "queue_time" in meta:
+        if meta.get("queue_time") is not None:
             self.queue_time.observe(meta["queue_time"])
         for dt in meta.get("itl", ()) or ():
             self.itl.observe(dt)
