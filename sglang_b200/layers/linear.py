@@ -47,6 +47,32 @@ class PendingAllReduce:
         return out
 
 
+class PendingLibraryAllReduce:
+    """Partial sums of a LARGE row-parallel output whose all-reduce goes to NCCL (NVLS algorithm inside the library): measured on 4 x B200
+    (profiles/mgpu_tp4_r2.md) the library beats both own kernels from ~2 MB up (8 MB: NCCL + local norm 57 us, own one-shot fused 75 us, own
+    reduce-scatter + norm + all-gather 77 us), while the own fused kernels win below ~1 MB.  Size-based dispatch, as the reference does
+    (custom all-reduce for small messages, NCCL for large ones: distributed/parallel_state.py:648-757)."""
+    __slots__ = ("y", "group", "T", "H")
+
+    def __init__(self, y: torch.Tensor, group):
+        self.y, self.group, self.T, self.H = y, group, y.shape[0], y.shape[1]
+
+    def consume_norm(self, residual, weight: torch.Tensor, eps: float, gemma: bool) -> torch.Tensor:
+        y = self.resolve()
+        if residual is None:
+            return ops.rmsnorm(y, weight, eps, gemma=gemma)
+        ops.fused_add_rmsnorm(y, residual, weight, eps, gemma=gemma)
+        return y
+
+    def resolve(self) -> torch.Tensor:
+        import torch.distributed as dist
+
+        self.group.comm_calls += 1
+        self.group.comm_bytes += self.y.numel() * self.y.element_size()
+        dist.all_reduce(self.y, group=self.group.device_group)
+        return self.y
+
+
 class PendingSlabs:
     """split-K partial products [splits, T, H] of a LOCAL decode-shape GEMM (ops.gemm_skinny_slabs); the next RMSNorm sums
     the slabs, adds the residual and normalises in one kernel."""
@@ -229,6 +255,8 @@ class RowParallelLinear(LinearBase):
                     return PendingAllReduce(nvl, off, T, self.out_features, "push", splits)
                 off = nvl.gemm_push(x, self.weight)
                 return PendingAllReduce(nvl, off, T, self.out_features, "push")
+            if nbytes >= nvl.library_ar_min_bytes and not nvl.wants_rs(nbytes):
+                return PendingLibraryAllReduce(ops.linear(x, self.weight), tp)
             if nvl.wants_rs(nbytes):      # large T: the consumer reduce-scatters (row-sharded residual), see nvl_comm.rs_add_rmsnorm_ag
                 from ..parallel.nvl_comm import CH_RS_AG
 

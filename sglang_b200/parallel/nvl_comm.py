@@ -56,6 +56,8 @@ class NvlComm:
         _rs = envs.SGLB_RS_AG_MIN_BYTES.get()
         self.rs_min_bytes = _rs if (self.world > 2 and _rs > 0) else (1 << 60)
         self.rs_active = False
+        _lib = envs.SGLB_TP_LIBRARY_AR_MIN_BYTES.get()
+        self.library_ar_min_bytes = _lib if (self.world > 2 and _lib > 0) else (1 << 60)
         self.rs_calls = 0
 
     @classmethod
