@@ -128,6 +128,12 @@ class Engine:
             self.scheduler.metrics = self.metrics
         self.weight_version = "default"
         self.start_time = time.time()
+        self.tracer = None
+        if a.enable_trace:
+            from ..observability.trace import get_tracer, init_tracing
+
+            ep = a.otlp_traces_endpoint if str(a.otlp_traces_endpoint or "").startswith("http") else None    # OTLP/HTTP JSON; a bare host:port is gRPC (no SDK here)
+            self.tracer = get_tracer() or init_tracing(level=int(getattr(a, "trace_level", 2) or 2), file=getattr(a, "trace_file", None), otlp_endpoint=ep)
 
     def _install_optional_components(self) -> None:
         a = self.server_args
@@ -320,6 +326,9 @@ class Engine:
                     m["ttft"] = st.first_token_time - st.created
                 if self.metrics is not None:
                     self.metrics.observe_request(m)
+                if self.tracer is not None:
+                    tc = getattr(st.obj, "trace_context", None) if st.obj is not None else None
+                    self.tracer.trace_request(rid, m, time.time() - m["e2e_latency"], tc)
             if st.out_q is not None:
                 st.out_q.put(st.result() if not st.finished else {**st.result(), "_done": True})
             if st.finished:

@@ -88,6 +88,7 @@ class _Envs:
     SGLB_STREAMK_MAX_M = EnvInt("SGLB_STREAMK_MAX_M", 0, "bf16 GEMMs with <= this many tokens run on the persistent stream-K tcgen05 kernel "
                                 "(gemm_streamk.cu); 0 = never (cuBLAS).  Default 0: measured in-graph it does not beat the library yet "
                                 "(profiles/gemm_streamk_r2.md)")
+    SGLB_NVTX = EnvBool("SGLB_NVTX", False, "bracket every model forward with an NVTX range (mode, batch size)")
     SGLB_TP_LIBRARY_AR_MIN_BYTES = EnvInt("SGLB_TP_LIBRARY_AR_MIN_BYTES", 3 << 19, "TP > 2: row-parallel outputs of at least this many bytes (default 1.5 MB) are all-reduced by NCCL (NVLS) + a local add+norm kernel; smaller ones by the own fused one-shot kernel (measured crossover, profiles/mgpu_tp4_r2.md); 0 = never")
     SGLB_RS_AG_MIN_BYTES = EnvInt("SGLB_RS_AG_MIN_BYTES", 0, "TP > 2: row-parallel outputs of at least this many bytes use reduce-scatter + norm + all-gather with a row-sharded residual (0 bytes per rank growth with world) instead of the one-shot fused all-reduce + norm; 0 = never (default: measured no faster than the one-shot kernel at 4 ranks, profiles/mgpu_tp4_r2.md)")
     SGLB_TP_GREEDY_SHARD = EnvBool("SGLB_TP_GREEDY_SHARD", True, "TP > 1: all-greedy decode batches take a vocab-parallel argmax (8 bytes per rank and row through the arena) instead of the [B, V] logits all-gather")

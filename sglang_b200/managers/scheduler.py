@@ -25,6 +25,7 @@ from ..environ import envs
 from ..mem_cache.allocator import PagedAllocator
 from ..mem_cache.kv_manager import KVManager
 from ..mem_cache.radix_cache import create_radix_cache
+from ..observability import trace as _trace
 from ..sampling.sampling_params import SamplingParams
 from ..server_args import ServerArgs
 from . import io_struct as ios
@@ -771,8 +772,15 @@ class Scheduler:
         try:
             return self._step()
         finally:
-            self.step_wall_s += time.perf_counter() - t0      # minus BatchResult.wait_s = pure host time (bench.py reports the split)
+            dt = time.perf_counter() - t0
+            self.step_wall_s += dt      # minus BatchResult.wait_s = pure host time (bench.py reports the split)
             self.step_calls += 1
+            if _trace.get_tracer() is not None and _trace.get_tracer().level >= 3:
+                lb = self.last_batch
+                now = time.time()
+                _trace.get_tracer().step_span("scheduler_step", now - dt, now, mode=str(getattr(lb, "forward_mode", None)) if lb is not None else "idle",
+                                              batch_size=len(lb.reqs) if lb is not None else 0, running=len(self.running_batch.reqs),
+                                              waiting=len(self.waiting_queue))
 
     def _step(self) -> bool:
         batch = self.get_next_batch_to_run()

@@ -467,10 +467,15 @@ class ModelRunner:
         self.model.compute_logits(hidden[:0], key="logits_all")     # ... and the rows of a prompt-logprob pass
 
     def _forward_guarded(self, sb: ScheduleBatch) -> BatchResult:
+        nvtx = self.is_cuda and envs.SGLB_NVTX.get()
+        if nvtx:     # nsys / ncu --nvtx timelines: one range per forward, named by mode and batch shape
+            torch.cuda.nvtx.range_push(f"{sb.forward_mode.name} bs={len(sb.reqs)}")
         try:
             return self._forward(sb)
         finally:
             self.set_rs(0)          # the row-sharded residual mode never outlives the forward that armed it
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
 
     @torch.no_grad()
     def _forward(self, sb: ScheduleBatch) -> BatchResult:

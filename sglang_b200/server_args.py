@@ -48,7 +48,9 @@ class ServerArgs:
     log_requests: bool = False
     enable_metrics: bool = False
     enable_trace: bool = False
-    otlp_traces_endpoint: str = "localhost:4317"
+    otlp_traces_endpoint: str = "localhost:4317"     # an http(s):// URL selects the OTLP/HTTP JSON exporter (observability/trace.py)
+    trace_level: int = 2                             # 1 request spans, 2 + queue / prefill / decode stages, 3 + one span per scheduler step
+    trace_file: Optional[str] = None                 # JSON-lines span log
     decode_log_interval: int = 40
     watchdog_timeout: float = 300.0
     soft_watchdog_timeout: Optional[float] = None

@@ -401,3 +401,55 @@ def test_expert_placement_planner_replicates_hot_experts_and_skips_dead_ranks():
 
     with pytest.raises(ValueError):
         plan(load, ep_size=4, slots=2, live=[0])                        # 2 slots cannot hold 8 experts
+
+
+def test_tracing_spans_and_otlp_http_export():
+    """request spans (root + queue / prefill / decode), scheduler-step spans at level 3, and the OTLP/HTTP JSON exporter posting well-formed
+    ExportTraceServiceRequest bodies to a collector (observability/trace.py; reference observability/trace.py:211,313)"""
+    import http.server
+    import json
+    import threading
+    import time
+
+    import sglang_b200 as sgl
+    from sglang_b200.observability import trace as T
+
+    got = []
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def do_POST(self):
+            body = self.rfile.read(int(self.headers["Content-Length"]))
+            got.append((self.path, self.headers.get("Content-Type"), json.loads(body)))
+            self.send_response(200); self.end_headers(); self.wfile.write(b"{}")
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    T._TRACER = None
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", log_level="error", enable_trace=True, trace_level=3,
+                     otlp_traces_endpoint=f"http://127.0.0.1:{srv.server_address[1]}")
+    try:
+        eng.generate(["hello there", "another prompt"], {"max_new_tokens": 4, "temperature": 0})
+        tr = T.get_tracer()
+        names = [d["name"] for d in tr.ring]
+        assert names.count("request") == 2 and {"queue", "prefill", "decode"} <= set(names) and "scheduler_step" in names
+        root = next(d for d in tr.ring if d["name"] == "request")
+        assert root["attrs"]["completion_tokens"] == 4 and root["end"] >= root["start"]
+        tr.otlp.flush()
+        t0 = time.time()
+        while not got and time.time() - t0 < 5:
+            time.sleep(0.05)
+        path, ctype, body = got[0]
+        assert path == "/v1/traces" and ctype == "application/json"
+        spans = body["resourceSpans"][0]["scopeSpans"][0]["spans"]
+        assert body["resourceSpans"][0]["resource"]["attributes"][0]["value"]["stringValue"] == "sglang_b200"
+        assert all(len(s["traceId"]) == 32 and len(s["spanId"]) == 16 and int(s["endTimeUnixNano"]) >= int(s["startTimeUnixNano"]) for s in spans)
+        assert tr.otlp.sent >= len(spans) and tr.otlp.failed == 0
+    finally:
+        eng.shutdown()
+        if T.get_tracer() is not None and T.get_tracer().otlp is not None:
+            T.get_tracer().otlp.shutdown()
+        T._TRACER = None
+        srv.shutdown()
