@@ -162,6 +162,46 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& 
   }
 }
 
+// Mamba: causal depthwise conv1d over a ragged batch with the rolling per-request state (decode when cu_q is None)
+void causal_conv1d(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, at::Tensor conv_state, c10::optional<at::Tensor> cu_q,
+                   const at::Tensor& req_slots, const at::Tensor& seq_lens, int64_t max_q_len, bool silu, at::Tensor u) {
+  CHECK_CUDA(x); CHECK_CUDA(conv_state); CHECK_I32(req_slots); CHECK_I32(seq_lens);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && w.dim() == 2 && w.is_contiguous() && conv_state.dim() == 3 && conv_state.is_contiguous());
+  const bool bf16 = x.scalar_type() == at::kBFloat16;
+  TORCH_CHECK((bf16 || x.scalar_type() == at::kFloat) && w.scalar_type() == x.scalar_type() && conv_state.scalar_type() == x.scalar_type(),
+              "causal_conv1d: x / weight / state must share bf16 or fp32");
+  const int C = (int)x.size(1), K = (int)w.size(1);
+  TORCH_CHECK(w.size(0) == C && conv_state.size(1) == C && conv_state.size(2) == K - 1 && u.scalar_type() == at::kFloat && u.stride(1) == 1 &&
+              u.size(0) == x.size(0) && u.size(1) == C);
+  if (bias.has_value()) TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->numel() == C);
+  c10::cuda::CUDAGuard g(x.device());
+  sglb::causal_conv1d(x.data_ptr(), (int)x.stride(0), w.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, conv_state.data_ptr(),
+                      opt_ptr<int>(cu_q), req_slots.data_ptr<int>(), seq_lens.data_ptr<int>(), (int)req_slots.size(0), (int)max_q_len, C, K, silu, bf16,
+                      u.data_ptr<float>(), (int)u.stride(0), cur_stream());
+  count(2);
+}
+
+// Mamba-2 decode: S = S * exp(dt A) + dt x B ; y = <S, C> + D x   (state fp32 [slots, H, P, N], one token per request)
+void selective_state_update(at::Tensor state, const at::Tensor& req_slots, const at::Tensor& x, const at::Tensor& dt, const at::Tensor& A,
+                            const at::Tensor& Bm, const at::Tensor& Cm, c10::optional<at::Tensor> D, at::Tensor y) {
+  CHECK_CUDA(state); CHECK_I32(req_slots);
+  TORCH_CHECK(state.dim() == 4 && state.is_contiguous() && state.scalar_type() == at::kFloat);
+  const int H = (int)state.size(1), P = (int)state.size(2), N = (int)state.size(3), B = (int)req_slots.size(0);
+  for (const at::Tensor* t : std::initializer_list<const at::Tensor*>{&x, &dt, &A, &Bm, &Cm, &y})
+    TORCH_CHECK(t->scalar_type() == at::kFloat && t->is_cuda(), "selective_state_update: fp32 CUDA tensors");
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(0) == B && x.size(1) == H * P && dt.is_contiguous() && dt.numel() == B * H && A.numel() == H);
+  TORCH_CHECK(Bm.dim() == 2 && Bm.stride(1) == 1 && Cm.dim() == 2 && Cm.stride(1) == 1 && Bm.stride(0) == Cm.stride(0) && Bm.size(1) % N == 0);
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(Bm.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(Cm.data_ptr()) & 15) == 0 && Bm.stride(0) % 4 == 0,
+              "selective_state_update: B / C rows must be 16-byte aligned");
+  const int G = (int)(Bm.size(1) / N);
+  TORCH_CHECK(y.is_contiguous() && y.numel() == (int64_t)B * H * P);
+  c10::cuda::CUDAGuard g(state.device());
+  sglb::selective_state_update(state.data_ptr<float>(), req_slots.data_ptr<int>(), x.data_ptr<float>(), (int)x.stride(0), dt.data_ptr<float>(),
+                               A.data_ptr<float>(), Bm.data_ptr<float>(), Cm.data_ptr<float>(), (int)Bm.stride(0),
+                               D.has_value() ? D->data_ptr<float>() : nullptr, B, H, P, N, G, y.data_ptr<float>(), cur_stream());
+  count();
+}
+
 // bench tool: per-role cycle accounting of the decode attention kernel into buf [ctas * 30] (int64); an empty tensor turns it off
 void attn_decode_prof(const at::Tensor& buf) {
   if (buf.numel() == 0) { sglb::attn_decode_set_prof(nullptr); return; }
@@ -550,6 +590,10 @@ TORCH_LIBRARY(sglb, m) {
         "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
         "float k_scale, float v_scale, int impl, Tensor? tree_anc=None) -> ()", &attn_fwd);
   m.def("attn_decode_prof(Tensor buf) -> ()", &attn_decode_prof);
+  m.def("causal_conv1d(Tensor x, Tensor w, Tensor? bias, Tensor(a!) conv_state, Tensor? cu_q, Tensor req_slots, Tensor seq_lens, int max_q_len, "
+        "bool silu, Tensor(b!) u) -> ()", &causal_conv1d);
+  m.def("selective_state_update(Tensor(a!) state, Tensor req_slots, Tensor x, Tensor dt, Tensor A, Tensor Bm, Tensor Cm, Tensor? D, Tensor(b!) y) -> ()",
+        &selective_state_update);
   m.def("gemm(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int epilogue, int bn) -> ()", &gemm);
   m.def("sample(Tensor logits, Tensor temperature, Tensor top_k, Tensor top_p, Tensor min_p, Tensor? seeds, "
         "Tensor? out_slots, Tensor(a!)? next_token_buf, Tensor(b!) out_tokens, Tensor(c!)? out_logprobs, int global_seed, "

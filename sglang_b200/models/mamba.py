@@ -181,20 +181,11 @@ class Mamba2Mixer(nn.Module):
         A = -torch.exp(self.A_log)
         rep = self.H // self.G
         slots = fb.req_slots.long()
-        if fb.cu_q is None:      # decode: one token per request, state rows gathered by request slot
-            cs = conv_s[slots]                                              # [B, conv_dim, k-1]
-            win = torch.cat([cs, xBC.unsqueeze(-1)], -1)                    # [B, conv_dim, k]
-            conv_s[slots] = win[..., 1:]
-            u = (win.float() * self.conv_weight.float()[None]).sum(-1)
-            if self.conv_bias is not None:
-                u = u + self.conv_bias.float()
-            u = F.silu(u)
-            x, Bm, Cm = u.split([di, gn, gn], dim=-1)
-            st = ssm_s[slots]
-            y = ssm_step(x.view(T, self.H, self.P), dt, A, Bm.view(T, self.G, self.N).repeat_interleave(rep, 1),
-                         Cm.view(T, self.G, self.N).repeat_interleave(rep, 1), st)
-            ssm_s[slots] = st
-            y = y + self.D[None, :, None] * x.view(T, self.H, self.P).float()
+        # causal conv + SiLU over the whole ragged batch, rolling per-request state updated in place (csrc/kernels/mamba.cu; fp32 out)
+        u_all = ops.causal_conv1d(xBC, self.conv_weight, self.conv_bias, conv_s, fb.cu_q, fb.req_slots, fb.seq_lens, fb.max_q_len, silu=True)
+        if fb.cu_q is None:      # decode: one token per request — ONE pass over the fp32 state (update + read-out + D skip)
+            x, Bm, Cm = u_all.split([di, gn, gn], dim=-1)
+            y = ops.selective_state_update(ssm_s, fb.req_slots, x, dt, A.float(), Bm, Cm, self.D.float())
         else:
             ys = []
             ql, sl = fb.q_lens_cpu, fb.seq_lens_cpu
@@ -202,14 +193,7 @@ class Mamba2Mixer(nn.Module):
             for b in range(len(ql)):
                 n, s = int(ql[b]), int(slots[b])
                 fresh = int(sl[b]) - n == 0
-                xb = xBC[off:off + n]                                       # [n, conv_dim]
-                prev = torch.zeros_like(conv_s[s]) if fresh else conv_s[s]
-                seq = torch.cat([prev.t(), xb], 0)                          # [k-1+n, conv_dim]
-                conv_s[s] = seq[-(self.k - 1):].t()
-                u = F.conv1d(seq.t().unsqueeze(0).float(), self.conv_weight.float().unsqueeze(1),
-                             self.conv_bias.float() if self.conv_bias is not None else None, groups=self.conv_dim)[0].t()      # [n, conv_dim]
-                u = F.silu(u)
-                x, Bm, Cm = u.split([di, gn, gn], dim=-1)
+                x, Bm, Cm = u_all[off:off + n].split([di, gn, gn], dim=-1)
                 st0 = torch.zeros_like(ssm_s[s]) if fresh else ssm_s[s]
                 xh = x.view(n, self.H, self.P)
                 yb, stN = ssd_chunk_scan(xh, dt[off:off + n], A, Bm.view(n, self.G, self.N).repeat_interleave(rep, 1),

@@ -340,6 +340,28 @@ def sample(logits, temperature, top_k, top_p, min_p, seeds=None, out_slots=None,
     return tok
 
 
+def causal_conv1d(x: torch.Tensor, w: torch.Tensor, bias, conv_state: torch.Tensor, cu_q, req_slots: torch.Tensor, seq_lens: torch.Tensor,
+                  max_q_len: int = 1, silu: bool = True) -> torch.Tensor:
+    """Mamba causal depthwise conv1d over a ragged batch, rolling state updated in place (csrc/kernels/mamba.cu); fp32 [T, C] out"""
+    if _use_native(x) and x.dtype in (torch.bfloat16, torch.float32) and x.stride(1) == 1 and 2 <= w.shape[1] <= 8:
+        u = torch.empty(x.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+        torch.ops.sglb.causal_conv1d(x, w.contiguous(), bias, conv_state, cu_q, req_slots, seq_lens, int(max_q_len), bool(silu), u)
+        return u
+    return torch_ref.causal_conv1d(x, w, bias, conv_state, cu_q, req_slots, seq_lens, silu)
+
+
+def selective_state_update(state: torch.Tensor, req_slots: torch.Tensor, x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor,
+                           Cm: torch.Tensor, D=None) -> torch.Tensor:
+    """Mamba-2 single-token state update + read-out, ONE pass over the fp32 state (csrc/kernels/mamba.cu); y fp32 [B, H, P]"""
+    if (_use_native(state) and state.dtype == torch.float32 and state.shape[3] % 4 == 0 and all(t.dtype == torch.float32 for t in (x, dt, A, Bm, Cm))
+            and Bm.stride(0) % 4 == 0 and Bm.stride(0) == Cm.stride(0) and Bm.data_ptr() % 16 == 0 and Cm.data_ptr() % 16 == 0 and x.stride(1) == 1):
+        B, (H, P) = req_slots.numel(), state.shape[1:3]
+        y = torch.empty(B, H, P, dtype=torch.float32, device=state.device)
+        torch.ops.sglb.selective_state_update(state, req_slots, x, dt.contiguous(), A.contiguous(), Bm, Cm, D, y)
+        return y
+    return torch_ref.selective_state_update(state, req_slots, x, dt, A, Bm, Cm, D)
+
+
 def greedy_shard(logits: torch.Tensor, v_valid: int, v_offset: int, rank: int, tp: int, buf: torch.Tensor) -> None:
     """argmax of this rank's vocabulary shard -> buf[rank, row] = (max logit, idx byte 0, 1, 2) as bf16; the other ranks' planes are zeroed so
     that an all-reduce (sum) of ``buf`` is an exact all-gather (sampling.cu greedy_shard_kernel)"""

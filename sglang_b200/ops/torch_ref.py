@@ -329,3 +329,50 @@ def tree_anc_to_mask(tree_anc: torch.Tensor, q_lens: torch.Tensor, seq_lens: tor
         out.append(m.reshape(-1))
         off += ql
     return torch.cat(out) if out else torch.zeros(0, dtype=torch.bool, device=tree_anc.device)
+
+
+def causal_conv1d(x: torch.Tensor, w: torch.Tensor, bias, conv_state: torch.Tensor, cu_q, req_slots: torch.Tensor, seq_lens: torch.Tensor,
+                  silu: bool = True) -> torch.Tensor:
+    """ragged causal depthwise conv with a rolling per-request state (in place): x [T, C], w [C, k], conv_state [slots, C, k-1] -> fp32 [T, C].
+    ``cu_q`` None = decode (one token per request)."""
+    import torch.nn.functional as F
+
+    T, C = x.shape
+    k = w.shape[1]
+    out = torch.empty(T, C, dtype=torch.float32, device=x.device)
+    B = req_slots.numel()
+    cu = cu_q.tolist() if cu_q is not None else list(range(B + 1))
+    sl = seq_lens.tolist()
+    slots = req_slots.tolist()
+    for b in range(B):
+        q0, n = cu[b], cu[b + 1] - cu[b]
+        if n <= 0:
+            continue
+        s = slots[b]
+        prev = torch.zeros_like(conv_state[s]) if sl[b] - n == 0 else conv_state[s]
+        seq = torch.cat([prev.t(), x[q0:q0 + n]], 0)                       # [k-1+n, C]
+        conv_state[s] = seq[-(k - 1):].t()
+        u = F.conv1d(seq.t().unsqueeze(0).float(), w.float().unsqueeze(1), bias.float() if bias is not None else None, groups=C)[0].t()
+        out[q0:q0 + n] = F.silu(u) if silu else u
+    return out
+
+
+def selective_state_update(state: torch.Tensor, req_slots: torch.Tensor, x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor,
+                           Cm: torch.Tensor, D) -> torch.Tensor:
+    """state fp32 [slots, H, P, N] (in place); x [B, H*P], dt [B, H], A [H], Bm / Cm [B, G*N], D [H] or None -> y fp32 [B, H, P]"""
+    Bn = req_slots.numel()
+    H, P, N = state.shape[1:]
+    G = Bm.shape[1] // N
+    rep = H // G
+    sl = req_slots.long()
+    st = state[sl]
+    xh = x.float().view(Bn, H, P)
+    dA = torch.exp(dt.float() * A.float()[None, :])
+    Bh = Bm.float().reshape(Bn, G, N).repeat_interleave(rep, 1)
+    Ch = Cm.float().reshape(Bn, G, N).repeat_interleave(rep, 1)
+    st = st * dA[..., None, None] + (dt.float()[..., None] * xh)[..., None] * Bh[:, :, None, :]
+    state[sl] = st
+    y = torch.einsum("bhpn,bhn->bhp", st, Ch)
+    if D is not None:
+        y = y + D.float()[None, :, None] * xh
+    return y

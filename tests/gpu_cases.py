@@ -135,6 +135,54 @@ def case_attn_tc_prefill():
     _attn_check(0, 1, [100], [400], Hq=16, Hkv=2, name="G=8")
 
 
+def case_mamba():
+    """causal conv1d (ragged extend with fresh / continued requests, decode) and the single-token selective state update against the
+    PyTorch formulations, states updated in place"""
+    torch.manual_seed(3)
+    for dtype in (torch.bfloat16, torch.float32):
+        C, K, slots_n = 640, 4, 9
+        w = (torch.randn(C, K, device=DEV) * 0.3).to(dtype)
+        bias = (torch.randn(C, device=DEV) * 0.1).to(dtype)
+        state0 = (torch.randn(slots_n, C, K - 1, device=DEV) * 0.5).to(dtype)
+        q_lens = [1, 2, 300, 3, 129]
+        prefix = [0, 7, 0, 50, 4]                      # 0 = fresh request (the slot's old state must be ignored)
+        seq = torch.tensor([p + q for p, q in zip(prefix, q_lens)], dtype=torch.int32, device=DEV)
+        cu = torch.tensor([0] + list(np.cumsum(q_lens)), dtype=torch.int32, device=DEV)
+        slots = torch.tensor([3, 1, 8, 2, 5], dtype=torch.int32, device=DEV)
+        x = (torch.randn(sum(q_lens), C + 16, device=DEV) * 0.5).to(dtype)[:, :C]          # row stride != C
+        s_ref, s_out = state0.clone(), state0.clone()
+        ref = torch_ref.causal_conv1d(x, w, bias, s_ref, cu, slots, seq, True)
+        out = ops.causal_conv1d(x, w, bias, s_out, cu, slots, seq, max(q_lens), True)
+        torch.cuda.synchronize()
+        tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+        _close(out, ref, tol, tol, f"causal_conv1d extend {dtype}")
+        assert torch.equal(s_out, s_ref), "conv state after extend"
+        # decode on top of the extended states
+        xd = (torch.randn(5, C, device=DEV) * 0.5).to(dtype)
+        seq_d = seq + 1
+        ref = torch_ref.causal_conv1d(xd, w, bias, s_ref, None, slots, seq_d, True)
+        out = ops.causal_conv1d(xd, w, bias, s_out, None, slots, seq_d, 1, True)
+        torch.cuda.synchronize()
+        _close(out, ref, tol, tol, f"causal_conv1d decode {dtype}")
+        assert torch.equal(s_out, s_ref), "conv state after decode"
+    # selective state update: H heads, G groups, P head dim, N state dim
+    for (H, G, P, N) in ((8, 2, 64, 128), (4, 1, 32, 16)):
+        B = 6
+        st0 = torch.randn(9, H, P, N, device=DEV)
+        sl = torch.tensor([4, 1, 8, 2, 6, 3], dtype=torch.int32, device=DEV)
+        u = torch.randn(B, H * P + 2 * G * N, device=DEV)
+        x, Bm, Cm = u.split([H * P, G * N, G * N], dim=-1)
+        dt = torch.rand(B, H, device=DEV) * 0.5 + 0.01
+        A = -torch.rand(H, device=DEV) - 0.1
+        D = torch.randn(H, device=DEV)
+        a, b = st0.clone(), st0.clone()
+        ref = torch_ref.selective_state_update(a, sl, x, dt, A, Bm, Cm, D)
+        out = ops.selective_state_update(b, sl, x, dt, A, Bm, Cm, D)
+        torch.cuda.synchronize()
+        _close(out, ref, 1e-4, 1e-4, f"selective_state_update y H={H} N={N}")
+        _close(b, a, 1e-5, 1e-5, "selective_state_update state")
+
+
 def case_attn_tree():
     """token-tree verification on the tcgen05 kernel (per-node ancestor bits) against the reference path with the dense mask"""
     import numpy as np
