@@ -615,23 +615,8 @@ class Mamba1Mixer(nn.Module):
         A = -torch.exp(self.A_log)
         slots = fb.req_slots.long()
         decode = fb.cu_q is None
-        if decode:
-            win = torch.cat([conv_s[slots], x.unsqueeze(-1)], -1)
-            conv_s[slots] = win[..., 1:]
-            u = (win.float() * self.conv_weight.float()[None]).sum(-1)
-        else:
-            outs, off = [], 0
-            for b in range(len(fb.q_lens_cpu)):
-                n, s = int(fb.q_lens_cpu[b]), int(slots[b])
-                fresh = int(fb.seq_lens_cpu[b]) - n == 0
-                seq = torch.cat([(torch.zeros_like(conv_s[s]) if fresh else conv_s[s]).t(), x[off:off + n]], 0)
-                conv_s[s] = seq[-(self.k - 1):].t()
-                outs.append(F.conv1d(seq.t().unsqueeze(0).float(), self.conv_weight.float().unsqueeze(1), None, groups=self.Dn)[0].t())
-                off += n
-            u = torch.cat(outs, 0) if outs else x.new_zeros(0, self.Dn).float()
-        if self.conv_bias is not None:
-            u = u + self.conv_bias.float()
-        u = F.silu(u).to(h.dtype)
+        # causal conv (+ bias) + SiLU over the ragged batch, rolling state in place (csrc/kernels/mamba.cu)
+        u = ops.causal_conv1d(x, self.conv_weight, self.conv_bias, conv_s, fb.cu_q, fb.req_slots, fb.seq_lens, fb.max_q_len, silu=True).to(h.dtype)
         dbc = self.x_proj(u)
         dbc = dbc.resolve() if hasattr(dbc, "resolve") else dbc
         dtr, Bm, Cm = dbc.split([self.R, self.N, self.N], dim=-1)
