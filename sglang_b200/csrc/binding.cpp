@@ -202,6 +202,24 @@ void selective_state_update(at::Tensor state, const at::Tensor& req_slots, const
   count();
 }
 
+// gated delta rule decode step (Qwen3-Next): u = conv output rows [q (Hk*Dk) | k (Hk*Dk) | v (Hv*Dv)], state fp32 [slots, Hv, Dk, Dv]
+void gated_delta_update(at::Tensor state, const at::Tensor& req_slots, const at::Tensor& u, const at::Tensor& g, const at::Tensor& beta, int64_t Hk,
+                        at::Tensor out) {
+  CHECK_CUDA(state); CHECK_I32(req_slots);
+  TORCH_CHECK(state.dim() == 4 && state.is_contiguous() && state.scalar_type() == at::kFloat && u.scalar_type() == at::kFloat && u.dim() == 2 &&
+              u.stride(1) == 1 && g.scalar_type() == at::kFloat && beta.scalar_type() == at::kFloat && g.is_contiguous() && beta.is_contiguous() &&
+              out.scalar_type() == at::kFloat && out.is_contiguous());
+  const int Hv = (int)state.size(1), Dk = (int)state.size(2), Dv = (int)state.size(3), B = (int)req_slots.size(0);
+  TORCH_CHECK(Hk > 0 && Hv % Hk == 0 && u.size(0) == B && u.size(1) == 2 * Hk * Dk + (int64_t)Hv * Dv && g.numel() == (int64_t)B * Hv &&
+              out.numel() == (int64_t)B * Hv * Dv);
+  c10::cuda::CUDAGuard guard(state.device());
+  const bool ok = sglb::gated_delta_update(state.data_ptr<float>(), req_slots.data_ptr<int>(), u.data_ptr<float>(), (int)u.stride(0), (int)(Hk * Dk),
+                                           (int)(2 * Hk * Dk), g.data_ptr<float>(), beta.data_ptr<float>(), B, Hv, (int)(Hv / Hk), Dk, Dv,
+                                           out.data_ptr<float>(), cur_stream());
+  TORCH_CHECK(ok, "gated_delta_update: key dim must be 64 or 128 and value dim <= 256");
+  count();
+}
+
 // bench tool: per-role cycle accounting of the decode attention kernel into buf [ctas * 30] (int64); an empty tensor turns it off
 void attn_decode_prof(const at::Tensor& buf) {
   if (buf.numel() == 0) { sglb::attn_decode_set_prof(nullptr); return; }
@@ -590,6 +608,7 @@ TORCH_LIBRARY(sglb, m) {
         "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
         "float k_scale, float v_scale, int impl, Tensor? tree_anc=None) -> ()", &attn_fwd);
   m.def("attn_decode_prof(Tensor buf) -> ()", &attn_decode_prof);
+  m.def("gated_delta_update(Tensor(a!) state, Tensor req_slots, Tensor u, Tensor g, Tensor beta, int Hk, Tensor(b!) out) -> ()", &gated_delta_update);
   m.def("causal_conv1d(Tensor x, Tensor w, Tensor? bias, Tensor(a!) conv_state, Tensor? cu_q, Tensor req_slots, Tensor seq_lens, int max_q_len, "
         "bool silu, Tensor(b!) u) -> ()", &causal_conv1d);
   m.def("selective_state_update(Tensor(a!) state, Tensor req_slots, Tensor x, Tensor dt, Tensor A, Tensor Bm, Tensor Cm, Tensor? D, Tensor(b!) y) -> ()",

@@ -96,6 +96,8 @@ void causal_conv1d(const void* x, int ldx, const void* w, const void* bias, void
                    const int* seq_lens, int B, int max_q_len, int C, int K, bool silu, bool bf16, float* u, int ldu, cudaStream_t stream);
 void selective_state_update(float* state, const int* req_slots, const float* x, int ldx, const float* dt, const float* A, const float* Bm,
                             const float* Cm, int ldbc, const float* Dv, int B, int H, int P, int N, int G, float* y, cudaStream_t stream);
+bool gated_delta_update(float* state, const int* req_slots, const float* u, int ldu, int k_off, int v_off, const float* g, const float* beta, int B,
+                        int Hv, int r, int Dk, int Dv, float* out, cudaStream_t stream);
 void greedy_shard(const void* logits, bool bf16, int B, int stride, int v_valid, int v_offset, int rank, int tp, int b_pad, void* buf,
                   cudaStream_t stream);
 void greedy_merge(const void* buf, int tp, int b_pad, int B, const int* out_slots, int* next_token_buf, int* out_tokens, cudaStream_t stream);

@@ -161,4 +161,63 @@ void selective_state_update(float* state, const int* req_slots, const float* x, 
   SGLB_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------- gated delta rule, one token per request (Qwen3-Next / GDN linear attention)
+//   S <- S * exp(g);  mem = S^T k;  delta = (v - mem) * beta;  S <- S + k delta^T;  o = S^T q        (S fp32 [Dk, Dv] per (request, value head))
+// q and k arrive un-normalised from the conv (+SiLU) output: l2-normalised here, q also scaled by Dk^-1/2; value head h uses key head h / r.
+// One block per (value head, request), thread = value column: the Dk-long column lives in registers between the two dependent passes,
+// so the 64 KB state is read once and written once (the PyTorch form makes five passes).  Reference: fla / sglang fused_recurrent_gated_delta_rule.
+template <int DK>
+__global__ void __launch_bounds__(256) gated_delta_update_kernel(float* __restrict__ state, const int* __restrict__ req_slots, const float* __restrict__ u,
+                                                                 int ldu, int k_off, int v_off, const float* __restrict__ g, const float* __restrict__ beta,
+                                                                 int Hv, int r, int Dv, float* __restrict__ out) {
+  __shared__ float sq[DK], sk[DK], red[16];
+  const int h = blockIdx.x, b = blockIdx.y, hk = h / r;
+  const float* row = u + (size_t)b * ldu;
+  float qs = 0.f, ks = 0.f;
+  for (int i = threadIdx.x; i < DK; i += blockDim.x) {
+    const float qv = row[hk * DK + i], kv = row[k_off + hk * DK + i];
+    sq[i] = qv; sk[i] = kv;
+    qs += qv * qv; ks += kv * kv;
+  }
+  qs = warp_sum(qs); ks = warp_sum(ks);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = qs; red[8 + w] = ks; }
+  __syncthreads();
+  float tq = 0.f, tk = 0.f;
+  for (int i = 0; i < nw; ++i) { tq += red[i]; tk += red[8 + i]; }
+  const float qn = rsqrtf(tq + 1e-6f) * rsqrtf((float)DK), kn = rsqrtf(tk + 1e-6f);
+  const int v = threadIdx.x;
+  if (v >= Dv) return;
+  const float decay = __expf(g[(size_t)b * Hv + h]);
+  float* S = state + (((size_t)req_slots[b] * Hv + h) * DK) * Dv + v;
+  float col[DK];
+  float mem = 0.f;
+#pragma unroll
+  for (int k = 0; k < DK; ++k) {
+    col[k] = S[(size_t)k * Dv] * decay;
+    mem += col[k] * (sk[k] * kn);
+  }
+  const float delta = (row[v_off + h * Dv + v] - mem) * beta[(size_t)b * Hv + h];
+  float o = 0.f;
+#pragma unroll
+  for (int k = 0; k < DK; ++k) {
+    const float s = col[k] + (sk[k] * kn) * delta;
+    S[(size_t)k * Dv] = s;
+    o += s * (sq[k] * qn);
+  }
+  out[((size_t)b * Hv + h) * Dv + v] = o;
+}
+
+bool gated_delta_update(float* state, const int* req_slots, const float* u, int ldu, int k_off, int v_off, const float* g, const float* beta, int B,
+                        int Hv, int r, int Dk, int Dv, float* out, cudaStream_t stream) {
+  if (B <= 0) return true;
+  if (Dv > 256 || (Dk != 64 && Dk != 128)) return false;
+  dim3 grid(Hv, B);
+  const int threads = ((Dv + 31) / 32) * 32;
+  if (Dk == 64) gated_delta_update_kernel<64><<<grid, threads, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, out);
+  else gated_delta_update_kernel<128><<<grid, threads, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, out);
+  SGLB_CUDA_CHECK(cudaGetLastError());
+  return true;
+}
+
 }  // namespace sglb

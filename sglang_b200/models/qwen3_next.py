@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from ..configs.model_config import ModelConfig
 from ..layers.common import RadixAttention, RMSNorm, RotaryEmbedding
 from ..layers.linear import ParallelLMHead, QKVParallelLinear, RowParallelLinear, VocabParallelEmbedding
@@ -148,25 +149,16 @@ class GatedDeltaNet(nn.Module):
         g = -self.A_log.exp() * F.softplus(a.float() + self.dt_bias)
         slots = fb.req_slots.long()
         decode = fb.cu_q is None
-        if decode:
-            win = torch.cat([conv_s[slots], mixed.unsqueeze(-1)], -1)
-            conv_s[slots] = win[..., 1:]
-            u = F.silu((win.float() * self.conv_weight.float()[None]).sum(-1))
-        else:
-            outs, off = [], 0
-            for i in range(len(fb.q_lens_cpu)):
-                n, s = int(fb.q_lens_cpu[i]), int(slots[i])
-                fresh = int(fb.seq_lens_cpu[i]) - n == 0
-                seq = torch.cat([(torch.zeros_like(conv_s[s]) if fresh else conv_s[s]).t(), mixed[off:off + n]], 0)
-                conv_s[s] = seq[-(self.k - 1):].t()
-                outs.append(F.silu(F.conv1d(seq.t().unsqueeze(0).float(), self.conv_weight.float().unsqueeze(1), None, groups=self.conv_dim)[0].t()))
-                off += n
-            u = torch.cat(outs, 0) if outs else mixed.new_zeros(0, self.conv_dim).float()
+        # causal conv + SiLU over the ragged batch, rolling state in place (csrc/kernels/mamba.cu)
+        u = ops.causal_conv1d(mixed, self.conv_weight, None, conv_s, fb.cu_q, fb.req_slots, fb.seq_lens, fb.max_q_len, silu=True)
+        o = ops.gated_delta_update(rec_s, fb.req_slots, u, g, beta, self.Hk) if decode else None      # one pass over the state (native kernel)
         qh, kh, vh = u.split([self.key_dim, self.key_dim, self.value_dim], dim=-1)
         qh = qh.view(T, self.Hk, self.Dk).repeat_interleave(self.r, 1)
         kh = kh.view(T, self.Hk, self.Dk).repeat_interleave(self.r, 1)
         vh = vh.view(T, self.Hv, self.Dv)
-        if decode:
+        if o is not None:
+            pass
+        elif decode:
             st = rec_s[slots]
             o = gated_delta_step(qh, kh, vh, g, beta, st)
             rec_s[slots] = st

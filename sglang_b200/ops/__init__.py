@@ -362,6 +362,18 @@ def selective_state_update(state: torch.Tensor, req_slots: torch.Tensor, x: torc
     return torch_ref.selective_state_update(state, req_slots, x, dt, A, Bm, Cm, D)
 
 
+def gated_delta_update(state: torch.Tensor, req_slots: torch.Tensor, u: torch.Tensor, g: torch.Tensor, beta: torch.Tensor, Hk: int) -> Optional[torch.Tensor]:
+    """gated delta rule, one token per request: u fp32 [B, 2*Hk*Dk + Hv*Dv] = conv output rows [q | k | v] (q, k un-normalised), state fp32
+    [slots, Hv, Dk, Dv] updated in place -> o fp32 [B, Hv, Dv]; None when the native kernel does not cover the shape (caller falls back)"""
+    if (_use_native(state) and state.dtype == torch.float32 and u.dtype == torch.float32 and u.stride(1) == 1 and state.shape[2] in (64, 128)
+            and state.shape[3] <= 256):
+        B, Hv, Dv = req_slots.numel(), state.shape[1], state.shape[3]
+        out = torch.empty(B, Hv, Dv, dtype=torch.float32, device=state.device)
+        torch.ops.sglb.gated_delta_update(state, req_slots, u, g.float().contiguous(), beta.float().contiguous(), int(Hk), out)
+        return out
+    return None
+
+
 def greedy_shard(logits: torch.Tensor, v_valid: int, v_offset: int, rank: int, tp: int, buf: torch.Tensor) -> None:
     """argmax of this rank's vocabulary shard -> buf[rank, row] = (max logit, idx byte 0, 1, 2) as bf16; the other ranks' planes are zeroed so
     that an all-reduce (sum) of ``buf`` is an exact all-gather (sampling.cu greedy_shard_kernel)"""

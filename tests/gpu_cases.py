@@ -183,6 +183,30 @@ def case_mamba():
         _close(b, a, 1e-5, 1e-5, "selective_state_update state")
 
 
+def case_gated_delta():
+    """gated delta rule decode step (Qwen3-Next linear attention): native one-pass kernel vs the PyTorch step"""
+    from sglang_b200.models.qwen3_next import gated_delta_step
+
+    torch.manual_seed(4)
+    for (Hk, r, Dk, Dv) in ((4, 2, 128, 128), (2, 1, 64, 96)):
+        Hv, B = Hk * r, 5
+        st0 = torch.randn(8, Hv, Dk, Dv, device=DEV) * 0.3
+        sl = torch.tensor([6, 1, 3, 7, 2], dtype=torch.int32, device=DEV)
+        u = torch.randn(B, 2 * Hk * Dk + Hv * Dv, device=DEV)
+        g = -torch.rand(B, Hv, device=DEV)
+        beta = torch.rand(B, Hv, device=DEV)
+        a, b = st0.clone(), st0.clone()
+        q, k, v = u.split([Hk * Dk, Hk * Dk, Hv * Dv], -1)
+        st = a[sl.long()]
+        ref = gated_delta_step(q.view(B, Hk, Dk).repeat_interleave(r, 1), k.view(B, Hk, Dk).repeat_interleave(r, 1), v.view(B, Hv, Dv), g, beta, st)
+        a[sl.long()] = st
+        out = ops.gated_delta_update(b, sl, u, g, beta, Hk)
+        assert out is not None
+        torch.cuda.synchronize()
+        _close(out, ref, 2e-4, 2e-4, f"gated delta o Dk={Dk} Dv={Dv}")
+        _close(b, a, 2e-5, 2e-5, "gated delta state")
+
+
 def case_attn_tree():
     """token-tree verification on the tcgen05 kernel (per-node ancestor bits) against the reference path with the dense mask"""
     import numpy as np
