@@ -166,11 +166,13 @@ void selective_state_update(float* state, const int* req_slots, const float* x, 
 // q and k arrive un-normalised from the conv (+SiLU) output: l2-normalised here, q also scaled by Dk^-1/2; value head h uses key head h / r.
 // One block per (value head, request), thread = value column: the Dk-long column lives in registers between the two dependent passes,
 // so the 64 KB state is read once and written once (the PyTorch form makes five passes).  Reference: fla / sglang fused_recurrent_gated_delta_rule.
+// Threads = (DK / 64) key slices x Dv value columns: a thread keeps 64 state values of one column in registers (128 would spill).
 template <int DK>
-__global__ void __launch_bounds__(256) gated_delta_update_kernel(float* __restrict__ state, const int* __restrict__ req_slots, const float* __restrict__ u,
+__global__ void __launch_bounds__(512) gated_delta_update_kernel(float* __restrict__ state, const int* __restrict__ req_slots, const float* __restrict__ u,
                                                                  int ldu, int k_off, int v_off, const float* __restrict__ g, const float* __restrict__ beta,
-                                                                 int Hv, int r, int Dv, float* __restrict__ out) {
-  __shared__ float sq[DK], sk[DK], red[16];
+                                                                 int Hv, int r, int Dv, int dv_pad, float* __restrict__ out) {
+  constexpr int NS = DK / 64;
+  __shared__ float sq[DK], sk[DK], red[32], part[NS][256];
   const int h = blockIdx.x, b = blockIdx.y, hk = h / r;
   const float* row = u + (size_t)b * ldu;
   float qs = 0.f, ks = 0.f;
@@ -181,31 +183,48 @@ __global__ void __launch_bounds__(256) gated_delta_update_kernel(float* __restri
   }
   qs = warp_sum(qs); ks = warp_sum(ks);
   const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[w] = qs; red[8 + w] = ks; }
+  if ((threadIdx.x & 31) == 0) { red[w] = qs; red[16 + w] = ks; }
   __syncthreads();
   float tq = 0.f, tk = 0.f;
-  for (int i = 0; i < nw; ++i) { tq += red[i]; tk += red[8 + i]; }
+  for (int i = 0; i < nw; ++i) { tq += red[i]; tk += red[16 + i]; }
   const float qn = rsqrtf(tq + 1e-6f) * rsqrtf((float)DK), kn = rsqrtf(tk + 1e-6f);
-  const int v = threadIdx.x;
-  if (v >= Dv) return;
+  const int slice = threadIdx.x / dv_pad, v = threadIdx.x - slice * dv_pad;
+  const bool live = v < Dv;
   const float decay = __expf(g[(size_t)b * Hv + h]);
-  float* S = state + (((size_t)req_slots[b] * Hv + h) * DK) * Dv + v;
-  float col[DK];
+  float* S = state + (((size_t)req_slots[b] * Hv + h) * DK + slice * 64) * Dv + v;
+  float col[64];
   float mem = 0.f;
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < DK; ++k) {
-    col[k] = S[(size_t)k * Dv] * decay;
-    mem += col[k] * (sk[k] * kn);
+    for (int k = 0; k < 64; ++k) {
+      col[k] = S[(size_t)k * Dv] * decay;
+      mem += col[k] * (sk[slice * 64 + k] * kn);
+    }
   }
-  const float delta = (row[v_off + h * Dv + v] - mem) * beta[(size_t)b * Hv + h];
+  part[slice][v] = mem;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) tot += part[i][v];
+  __syncthreads();
   float o = 0.f;
+  if (live) {
+    const float delta = (row[v_off + h * Dv + v] - tot) * beta[(size_t)b * Hv + h];
 #pragma unroll
-  for (int k = 0; k < DK; ++k) {
-    const float s = col[k] + (sk[k] * kn) * delta;
-    S[(size_t)k * Dv] = s;
-    o += s * (sq[k] * qn);
+    for (int k = 0; k < 64; ++k) {
+      const float s2 = col[k] + (sk[slice * 64 + k] * kn) * delta;
+      S[(size_t)k * Dv] = s2;
+      o += s2 * (sq[slice * 64 + k] * qn);
+    }
   }
-  out[((size_t)b * Hv + h) * Dv + v] = o;
+  part[slice][v] = o;
+  __syncthreads();
+  if (slice == 0 && live) {
+    float oo = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) oo += part[i][v];
+    out[((size_t)b * Hv + h) * Dv + v] = oo;
+  }
 }
 
 bool gated_delta_update(float* state, const int* req_slots, const float* u, int ldu, int k_off, int v_off, const float* g, const float* beta, int B,
@@ -213,9 +232,9 @@ bool gated_delta_update(float* state, const int* req_slots, const float* u, int 
   if (B <= 0) return true;
   if (Dv > 256 || (Dk != 64 && Dk != 128)) return false;
   dim3 grid(Hv, B);
-  const int threads = ((Dv + 31) / 32) * 32;
-  if (Dk == 64) gated_delta_update_kernel<64><<<grid, threads, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, out);
-  else gated_delta_update_kernel<128><<<grid, threads, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, out);
+  const int dv_pad = ((Dv + 31) / 32) * 32;
+  if (Dk == 64) gated_delta_update_kernel<64><<<grid, dv_pad, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, dv_pad, out);
+  else gated_delta_update_kernel<128><<<grid, 2 * dv_pad, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, dv_pad, out);
   SGLB_CUDA_CHECK(cudaGetLastError());
   return true;
 }
