@@ -168,7 +168,7 @@ void selective_state_update(float* state, const int* req_slots, const float* x, 
 // so the 64 KB state is read once and written once (the PyTorch form makes five passes).  Reference: fla / sglang fused_recurrent_gated_delta_rule.
 // Threads = (DK / 64) key slices x Dv value columns: a thread keeps 64 state values of one column in registers (128 would spill).
 template <int DK>
-__global__ void __launch_bounds__(512) gated_delta_update_kernel(float* __restrict__ state, const int* __restrict__ req_slots, const float* __restrict__ u,
+__global__ void __launch_bounds__(256) gated_delta_update_kernel(float* __restrict__ state, const int* __restrict__ req_slots, const float* __restrict__ u,
                                                                  int ldu, int k_off, int v_off, const float* __restrict__ g, const float* __restrict__ beta,
                                                                  int Hv, int r, int Dv, int dv_pad, float* __restrict__ out) {
   constexpr int NS = DK / 64;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(512) gated_delta_update_kernel(float* __restri
 bool gated_delta_update(float* state, const int* req_slots, const float* u, int ldu, int k_off, int v_off, const float* g, const float* beta, int B,
                         int Hv, int r, int Dk, int Dv, float* out, cudaStream_t stream) {
   if (B <= 0) return true;
-  if (Dv > 256 || (Dk != 64 && Dk != 128)) return false;
+  if ((Dk != 64 && Dk != 128) || Dv > (Dk == 64 ? 256 : 128)) return false;      // <= 256 threads per block
   dim3 grid(Hv, B);
   const int dv_pad = ((Dv + 31) / 32) * 32;
   if (Dk == 64) gated_delta_update_kernel<64><<<grid, dv_pad, 0, stream>>>(state, req_slots, u, ldu, k_off, v_off, g, beta, Hv, r, Dv, dv_pad, out);

@@ -366,7 +366,7 @@ def gated_delta_update(state: torch.Tensor, req_slots: torch.Tensor, u: torch.Te
     """gated delta rule, one token per request: u fp32 [B, 2*Hk*Dk + Hv*Dv] = conv output rows [q | k | v] (q, k un-normalised), state fp32
     [slots, Hv, Dk, Dv] updated in place -> o fp32 [B, Hv, Dv]; None when the native kernel does not cover the shape (caller falls back)"""
     if (_use_native(state) and state.dtype == torch.float32 and u.dtype == torch.float32 and u.stride(1) == 1 and state.shape[2] in (64, 128)
-            and state.shape[3] <= 256):
+            and state.shape[3] <= (256 if state.shape[2] == 64 else 128)):
         B, Hv, Dv = req_slots.numel(), state.shape[1], state.shape[3]
         out = torch.empty(B, Hv, Dv, dtype=torch.float32, device=state.device)
         torch.ops.sglb.gated_delta_update(state, req_slots, u, g.float().contiguous(), beta.float().contiguous(), int(Hk), out)
