@@ -107,7 +107,7 @@ class Engine:
         self._world = st.world
         if getattr(self.runner.model, "disable_chunked_prefill", False):
             a.chunked_prefill_size = None       # encoder-only models attend bidirectionally: a request is always encoded in one pass
-        if getattr(self.runner.model, "disable_radix_cache", False) and not a.disable_radix_cache:
+        if getattr(self.runner.model, "disable_radix_cache", False) and not a.disable_radix_cache and not self.runner.mamba_snapshot_rows:
             logger.info("%s keeps recurrent state per request: prefix caching disabled", type(self.runner.model).__name__)
             a.disable_radix_cache = True
             if a.schedule_policy in ("lpm", "dfs-weight"):

@@ -220,6 +220,7 @@ class ScheduleBatch:
     input_ids: Optional[np.ndarray] = None         # int32 [T] (extend) / None (decode: gathered on device)
     positions: Optional[np.ndarray] = None         # int32 [T]
     out_cache_loc: Optional[np.ndarray] = None     # int32 [T] slot ids
+    mamba_snap: Optional[Dict[int, Any]] = None    # recurrent-state snapshots planned for this prefill step
     out_cache_loc_swa: Optional[np.ndarray] = None # int32 [T] slot ids in the sliding-window pool (hybrid SWA models)
     q_lens: Optional[np.ndarray] = None            # int32 [B]
     prefix_lens: Optional[np.ndarray] = None       # int32 [B]

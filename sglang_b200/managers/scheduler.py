@@ -50,7 +50,16 @@ class Scheduler:
         self.max_running = info["max_running"]
         self.allocator = PagedAllocator(info["num_pages"], self.page_size)
         self.swa = info.get("swa")
-        if self.swa is None:
+        self.mamba = info.get("mamba")
+        if self.mamba is not None and not server_args.disable_radix_cache:
+            # state-space / hybrid model with snapshot rows: prefix caching through recurrent-state snapshots (mem_cache/mamba_radix.py)
+            from ..mem_cache.mamba_radix import MambaKVManager, MambaRadixCache
+
+            self.tree = MambaRadixCache(self.allocator, self.mamba["rows"], self.page_size, server_args.radix_eviction_policy,
+                                        enable_kv_events=server_args.enable_kv_events)
+            self.kv = MambaKVManager(self.allocator, self.tree, self.page_size, self.max_running, self.max_context_len,
+                                     self.mamba["granularity"], worker.copy_mamba_state)
+        elif self.swa is None:
             self.tree = create_radix_cache(self.allocator, self.page_size, server_args.radix_eviction_policy,
                                            disable=server_args.disable_radix_cache, impl=server_args.radix_cache_impl,
                                            enable_kv_events=server_args.enable_kv_events)
@@ -420,6 +429,13 @@ class Scheduler:
         batch.positions = np.concatenate(pos)
         batch.out_cache_loc = np.concatenate(loc)
         batch.out_cache_loc_swa = np.concatenate(loc_swa) if loc_swa is not None else None
+        if self.mamba is not None and hasattr(self.kv, "plan_snapshot"):
+            plan = {}
+            for i, r in enumerate(batch.reqs):
+                p = self.kv.plan_snapshot(r)
+                if p is not None:
+                    plan[i] = p
+            batch.mamba_snap = plan or None
         batch.q_lens = np.asarray(qlens, dtype=np.int32)
         batch.prefix_lens = np.asarray(plens, dtype=np.int32)
         batch.req_slots = np.asarray(slots, dtype=np.int32)

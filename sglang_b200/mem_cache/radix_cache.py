@@ -27,7 +27,7 @@ _EMPTY = np.empty(0, dtype=np.int32)
 
 class TreeNode:
     __slots__ = ("children", "parent", "key", "pages", "lock_ref", "last_access", "hit_count", "created",
-                 "priority", "host_pages", "id", "hashes", "swa_pages")
+                 "priority", "host_pages", "id", "hashes", "swa_pages", "mamba_slot")
     _ctr = 0
 
     def __init__(self) -> None:
@@ -42,6 +42,7 @@ class TreeNode:
         self.hit_count = 0
         self.priority = 0
         self.hashes: Optional[np.ndarray] = None     # chained 64-bit page hashes (only when KV events are enabled)
+        self.mamba_slot: Optional[int] = None        # recurrent-state snapshot row taken at the END of this node (mem_cache/mamba_radix.py)
         self.swa_pages: Optional[np.ndarray] = None  # sliding-window pool pages of the same tokens (0 = tombstone: slid out / reclaimed)
         TreeNode._ctr += 1
         self.id = TreeNode._ctr

@@ -71,6 +71,7 @@ class ForwardBatch:
     rope_override: Any = None        # (cos_sin rows [T, rot], row index [T]): per-token rotary table (M-RoPE)
     mrope_positions: Any = None      # i64 [3, T]
     cp: Any = None                   # layers/cp.py CpMeta inside a context-parallel prefill
+    mamba_snap: Any = None           # {request index: (tokens into this chunk, snapshot row)}: recurrent-state snapshots to take in this forward
     out_cache_loc_swa: Optional[torch.Tensor] = None   # i32 [T] slots in the sliding-window pool (hybrid SWA models, mem_cache/swa.py)
     swa_pt_offset: int = 0           # the sliding page table is columns [offset, 2 * offset) of ``page_table``
     dcp: Any = None                  # layers/dcp.py DcpMeta when decode context parallelism is on
@@ -177,5 +178,5 @@ class BatchPacker:
             max_q_len=1 if decode else int(sb.q_lens.max()), max_kv_len=int(sb.seq_lens.max()) if B else 0,
             page_table=page_table, page_size=page_size, kv_pool=kv_pool, sampling=sampling, next_token_buf=next_token_buf,
             return_logprob=sb.return_logprob, h2d_bytes=int(packed.size * 4), seq_lens_cpu=sb.seq_lens,
-            q_lens_cpu=sb.q_lens, spec_info=sb.spec_info, out_cache_loc_swa=v("out_cache_loc_swa"))
+            q_lens_cpu=sb.q_lens, spec_info=sb.spec_info, out_cache_loc_swa=v("out_cache_loc_swa"), mamba_snap=getattr(sb, "mamba_snap", None))
         return fb

@@ -248,7 +248,12 @@ class ModelRunner:
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
         self.page_table = torch.zeros(self.max_running + 1, max_pages_per_req, dtype=torch.int32, device=self.device)
         # recurrent (SSM) state of hybrid / Mamba decoders, indexed by request slot like the page table (models/mamba.py)
-        self.kv_pool.mamba = self.model.make_mamba_pool(self.max_running + 1, self.device) if hasattr(self.model, "make_mamba_pool") else None
+        # (+ --mamba-cache-slots snapshot rows after the request rows: mem_cache/mamba_radix.py)
+        self.mamba_snapshot_rows: List[int] = []
+        n_snap = int(getattr(a, "mamba_cache_slots", 0) or 0) if getattr(self.model, "supports_mamba_snapshots", False) else 0
+        self.kv_pool.mamba = self.model.make_mamba_pool(self.max_running + 1 + n_snap, self.device) if hasattr(self.model, "make_mamba_pool") else None
+        if self.kv_pool.mamba is not None and n_snap:
+            self.mamba_snapshot_rows = list(range(self.max_running + 1, self.max_running + 1 + n_snap))
         self.next_token_buf = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
         if getattr(self.model, "is_mrope", False):
             self.model.mrope_delta = torch.zeros(self.max_running + 1, dtype=torch.int32, device=self.device)
@@ -257,6 +262,8 @@ class ModelRunner:
 
     def get_memory_info(self) -> Dict[str, int]:
         info = {"num_pages": self.num_pages, "max_context_len": self.max_context_len, "max_running": self.max_running}
+        if self.mamba_snapshot_rows:
+            info["mamba"] = {"rows": list(self.mamba_snapshot_rows), "granularity": int(getattr(self.model, "snapshot_granularity", 64))}
         if getattr(self, "swa", None) is not None:
             info["swa"] = {"num_pages": self.swa["num_pages"], "window": self.swa["window"]}
         return info
@@ -268,6 +275,14 @@ class ModelRunner:
         self.swa_pt_offset = kv.page_table.shape[1] if getattr(self, "swa", None) is not None else 0
         if cols != self.page_table.shape[1]:
             self.page_table = torch.zeros(self.max_running + 1, cols, dtype=torch.int32, device=self.device)
+
+    def copy_mamba_state(self, src: int, dst: int) -> None:
+        """recurrent state row ``src`` -> row ``dst`` in every layer (prefix-cache snapshot restore), ordered on the runner's stream"""
+        pool = self.kv_pool.mamba
+        ctx = torch.cuda.stream(self.stream) if self.is_cuda else _null_ctx()
+        with ctx:
+            pool.conv[:, dst].copy_(pool.conv[:, src])
+            pool.ssm[:, dst].copy_(pool.ssm[:, src])
 
     def get_eos_token_ids(self) -> List[int]:
         return self.cfg.eos_token_ids

@@ -57,7 +57,7 @@ def _segsum(x: torch.Tensor) -> torch.Tensor:
 
 
 def ssd_chunk_scan(x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, state: torch.Tensor,
-                   chunk: int = 64) -> Tuple[torch.Tensor, torch.Tensor]:
+                   chunk: int = 64, return_states: bool = False):
     """Mamba-2 SSD over one sequence.  x [T, H, P], dt [T, H] (after softplus), A [H] (negative), B / C [T, H, N] (already expanded from
     groups), state [H, P, N] fp32 -> (y [T, H, P] fp32 WITHOUT the D skip term, final state)."""
     T, H, P = x.shape
@@ -79,7 +79,8 @@ def ssd_chunk_scan(x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, B: torch.
     ns = torch.einsum("hzc,chpn->zhpn", dc, st)
     prev, final = ns[:-1], ns[-1]
     Yo = torch.einsum("clhn,chpn,hcl->clhp", Cc, prev, torch.exp(Acs))
-    return (Yd + Yo).reshape(c * chunk, H, P)[:T], final
+    y = (Yd + Yo).reshape(c * chunk, H, P)[:T]
+    return (y, final, ns) if return_states else (y, final)      # ns[j] = state after j * chunk tokens of this call
 
 
 def ssm_step(x, dt, A, B, C, state):
@@ -196,9 +197,14 @@ class Mamba2Mixer(nn.Module):
                 x, Bm, Cm = u_all[off:off + n].split([di, gn, gn], dim=-1)
                 st0 = torch.zeros_like(ssm_s[s]) if fresh else ssm_s[s]
                 xh = x.view(n, self.H, self.P)
-                yb, stN = ssd_chunk_scan(xh, dt[off:off + n], A, Bm.view(n, self.G, self.N).repeat_interleave(rep, 1),
-                                         Cm.view(n, self.G, self.N).repeat_interleave(rep, 1), st0, self.chunk)
+                snap = (fb.mamba_snap or {}).get(b)
+                yb, stN, ns = ssd_chunk_scan(xh, dt[off:off + n], A, Bm.view(n, self.G, self.N).repeat_interleave(rep, 1),
+                                             Cm.view(n, self.G, self.N).repeat_interleave(rep, 1), st0, self.chunk, return_states=True)
                 ssm_s[s] = stN
+                if snap is not None:       # prefix-cache snapshot at a scan boundary inside this chunk (mem_cache/mamba_radix.py)
+                    rel, row = snap
+                    ssm_s[row] = ns[rel // self.chunk]
+                    conv_s[row] = xBC[off + rel - (self.k - 1): off + rel].t().to(conv_s.dtype)
                 ys.append(yb + self.D[None, :, None] * xh.float())
                 off += n
             y = torch.cat(ys, 0) if ys else torch.zeros(0, self.H, self.P, device=h.device)
@@ -294,7 +300,7 @@ class NemotronHForCausalLM(nn.Module):
     """canonical names: model.embed_tokens, model.layers.N.norm, model.layers.N.mixer.{in_proj, conv1d, A_log, D, dt_bias, norm, out_proj |
     q_proj, k_proj, v_proj, o_proj | up_proj, down_proj}, model.norm, lm_head.  HF checkpoints say ``backbone.`` / ``embeddings`` / ``norm_f``."""
     supports_cuda_graph = False
-    disable_radix_cache = True
+    disable_radix_cache = True              # unless --mamba-cache-slots > 0 (recurrent-state snapshots, mem_cache/mamba_radix.py)
     stacked_params = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v")]
 
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):

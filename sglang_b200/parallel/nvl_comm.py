@@ -54,7 +54,8 @@ class NvlComm:
         # nvl_rs_add_rmsnorm_ag_kernel).  The model runner switches it on per forward (``rs_active``) for model families whose every residual
         # update goes through a fused consume_norm; with two ranks the one-shot exchange moves the same bytes, so it stays off there.
         _rs = envs.SGLB_RS_AG_MIN_BYTES.get()
-        self.rs_min_bytes = _rs if (self.world > 2 and _rs > 0) else (1 << 60)
+        # validated at 4 ranks only: the 8-rank run of tools/mgpu_test.py died in this kernel (launch failure, run N) -> refused above 4 ranks
+        self.rs_min_bytes = _rs if (2 < self.world <= 4 and _rs > 0) else (1 << 60)
         self.rs_active = False
         _lib = envs.SGLB_TP_LIBRARY_AR_MIN_BYTES.get()
         self.library_ar_min_bytes = _lib if (self.world > 2 and _lib > 0) else (1 << 60)

@@ -106,6 +106,7 @@ class ServerArgs:
     gemm_backend: str = "auto"  # auto|tc|lib
     disable_cuda_graph: bool = False
     cuda_graph_max_bs: Optional[int] = None
+    mamba_cache_slots: int = 0                      # > 0: state-space / hybrid models keep this many recurrent-state snapshots so that prefix caching works for them
     swa_full_tokens_ratio: float = 0.0              # > 0: hybrid sliding-window models keep the sliding layers in a second pool of ratio x the full pool's tokens (0 = one pool)
     prefill_cuda_graph_max_tokens: int = 0          # > 0: capture token-bucketed prefill graphs up to this many new tokens per step (max 4096)
     cuda_graph_bs: Optional[List[int]] = None
