@@ -300,6 +300,8 @@ class NemotronHForCausalLM(nn.Module):
     """canonical names: model.embed_tokens, model.layers.N.norm, model.layers.N.mixer.{in_proj, conv1d, A_log, D, dt_bias, norm, out_proj |
     q_proj, k_proj, v_proj, o_proj | up_proj, down_proj}, model.norm, lm_head.  HF checkpoints say ``backbone.`` / ``embeddings`` / ``norm_f``."""
     supports_cuda_graph = False
+    supports_mamba_snapshots = True         # Mamba-2 mixers export the chunk-boundary state of the SSD scan (Mamba2Mixer.forward)
+    snapshot_granularity = 64
     disable_radix_cache = True              # unless --mamba-cache-slots > 0 (recurrent-state snapshots, mem_cache/mamba_radix.py)
     stacked_params = [(".qkv_proj", ".q_proj", "q"), (".qkv_proj", ".k_proj", "k"), (".qkv_proj", ".v_proj", "v")]
 
@@ -686,6 +688,7 @@ class _M1Block(nn.Module):
 
 class MambaForCausalLM(NemotronHForCausalLM):
     """Mamba-1 (state-spaces/mamba-*-hf) and FalconMamba (``cfg.mamba['bcdt_norm'] == 'plain'``)"""
+    supports_mamba_snapshots = False        # Mamba-1 selective scan: no boundary-state export yet -> prefix caching stays off
 
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
@@ -788,6 +791,7 @@ class _JambaBlock(nn.Module):
 
 
 class JambaForCausalLM(BambaForCausalLM):
+    supports_mamba_snapshots = False        # Mamba-1 selective scan: no boundary-state export yet -> prefix caching stays off
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
         self.cfg = cfg

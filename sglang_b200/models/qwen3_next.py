@@ -242,6 +242,7 @@ class _Block(nn.Module):
 
 
 class Qwen3NextForCausalLM(NemotronHForCausalLM):
+    supports_mamba_snapshots = False        # gated delta rule: no boundary-state export yet
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
         assert get_pp_group().world_size == 1
