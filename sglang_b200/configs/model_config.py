@@ -70,6 +70,7 @@ class ModelConfig:
     no_rope_layers: Optional[List[int]] = None  # SmolLM3: 0 = this layer applies no rotary embedding
     rope_local_base_freq: Optional[float] = None   # Gemma-3: rope base of the sliding-window layers
     logit_scale: Optional[float] = None         # Cohere
+    clip_qkv: Optional[float] = None            # OLMo: clamp the fused q/k/v projection
     norm_type: str = "rms"                      # rms | layernorm (Cohere: weight only) | layernorm1p (Nemotron: 1 + weight, bias)
     use_qk_norm: bool = False                   # Cohere-2 style flag in HF configs
     # Gemma-2 / Granite extras
@@ -305,7 +306,7 @@ _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_loca
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
                "activation_function": "hidden_act", "layer_norm_epsilon": "rms_norm_eps", "layer_norm_eps": "rms_norm_eps",
                "norm_epsilon": "rms_norm_eps", "ffn_dim": "intermediate_size", "rotary_pct": "partial_rotary_factor",
-               "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta", "experts_per_token": "num_experts_per_tok"}
+               "use_qkv_bias": "attention_bias", "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta", "experts_per_token": "num_experts_per_tok"}
 # per-architecture defaults for fields HF configs leave implicit
 _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
                   "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),

@@ -259,6 +259,79 @@ class NemotronForCausalLM(LlamaForCausalLM):
         self.model.norm = LayerNorm1P(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype)
 
 
+# ---------------------------------------------------------------- OLMo (v1) and StableLM: the Llama stack with LayerNorm
+class PlainLayerNorm(nn.Module):
+    """LayerNorm with optional affine parameters; OLMo-1 uses none at all (``elementwise_affine=False``), StableLM weight + bias"""
+
+    def __init__(self, n: int, eps: float, dtype, affine: bool):
+        super().__init__()
+        self.eps, self.n = eps, n
+        if affine:
+            self.weight = nn.Parameter(torch.ones(n, dtype=dtype), requires_grad=False)
+            self.bias = nn.Parameter(torch.zeros(n, dtype=dtype), requires_grad=False)
+        else:
+            self.weight = self.bias = None
+
+    def forward(self, x, residual=None):
+        if residual is not None:
+            x = x + residual
+            residual = x
+        y = F.layer_norm(x.float(), (self.n,), None if self.weight is None else self.weight.float(), None if self.bias is None else self.bias.float(),
+                         self.eps).to(x.dtype)
+        return y if residual is None else (y, residual)
+
+
+class _ClipAttention(LlamaAttention):
+    """OLMo ``clip_qkv``: the fused projection output is clamped before RoPE"""
+
+    def forward(self, x: torch.Tensor, fb: ForwardBatch):
+        qkv = self.qkv_proj(x)
+        if self.clip is not None:
+            qkv = qkv.clamp(-self.clip, self.clip)
+        q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        return self.o_proj(self.attn(q.contiguous(), k.contiguous(), v.contiguous(), fb))
+
+
+class _LNDecoderLayer(LlamaDecoderLayer):
+    affine = True
+
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
+        self.input_layernorm = PlainLayerNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, self.affine)
+        self.post_attention_layernorm = PlainLayerNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, self.affine)
+        if cfg.clip_qkv:
+            self.self_attn = _ClipAttention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
+            self.self_attn.clip = float(cfg.clip_qkv)
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        h = h + _resolve(self.self_attn(self.input_layernorm(h), fb))
+        return h + _resolve(self.mlp(self.post_attention_layernorm(h))), None
+
+
+class _OlmoLayer(_LNDecoderLayer):
+    affine = False
+
+
+class OlmoForCausalLM(LlamaForCausalLM):
+    """OLMo-1 (allenai/OLMo-*-hf): non-parametric LayerNorm, optional qkv clipping, otherwise Llama (reference models/olmo.py)"""
+    decoder_layer_cls = _OlmoLayer
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        self.model.norm = PlainLayerNorm(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype, False)
+
+
+class StableLmForCausalLM(LlamaForCausalLM):
+    """StableLM-2 / StableLM-3B-4E1T: LayerNorm with bias, partial rotary (25 %), optional qkv bias, gated SiLU MLP (reference models/stablelm.py)"""
+    decoder_layer_cls = _LNDecoderLayer
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        self.model.norm = PlainLayerNorm(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype, True)
+
+
 # ---------------------------------------------------------------- GLM-4.5 (Glm4Moe) and dots.llm1: DeepSeek-V3 style MoE + ordinary GQA attention
 def _ds():
     from . import deepseek

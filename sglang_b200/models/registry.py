@@ -74,7 +74,7 @@ def _register_builtins() -> None:
     from . import families2 as _f2
 
     for name in ("GlmForCausalLM", "Glm4ForCausalLM", "Gemma3ForCausalLM", "CohereForCausalLM", "OlmoeForCausalLM", "NemotronForCausalLM",
-                 "Glm4MoeForCausalLM", "Dots1ForCausalLM"):
+                 "Glm4MoeForCausalLM", "Dots1ForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM"):
         register_model(name, getattr(_f2, name))
     register_model("Gemma3ForConditionalGeneration", _f2.Gemma3ForCausalLM)      # text tower of the multimodal checkpoint
     from . import qwen2_vl as _qv

@@ -111,6 +111,8 @@ CASES = {
     "granite": ("GraniteConfig", "GraniteForCausalLM", dict(BASE, embedding_multiplier=3.0, residual_multiplier=0.5, attention_multiplier=0.2,
                                                             logits_scaling=2.0)),
     "olmo2": ("Olmo2Config", "Olmo2ForCausalLM", dict(BASE)),
+    "olmo": ("OlmoConfig", "OlmoForCausalLM", dict(BASE, clip_qkv=0.9)),
+    "stablelm": ("StableLmConfig", "StableLmForCausalLM", dict(BASE, partial_rotary_factor=0.25, use_qkv_bias=True, layer_norm_eps=1e-5)),
     "mixtral": ("MixtralConfig", "MixtralForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2)),
     "qwen2-moe": ("Qwen2MoeConfig", "Qwen2MoeForCausalLM", dict(BASE, num_experts=4, num_experts_per_tok=2, moe_intermediate_size=32,
                                                                 shared_expert_intermediate_size=64, decoder_sparse_step=1, mlp_only_layers=[])),
