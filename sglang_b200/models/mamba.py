@@ -550,13 +550,14 @@ class BambaForCausalLM(NemotronHForCausalLM):
 
 
 # ================================================================================================ Mamba-1 (selective scan per channel): Mamba, FalconMamba, Jamba
-def selective_scan_chunked(u, dt, A, B, C, state, chunk: int = 16):
+def selective_scan_chunked(u, dt, A, B, C, state, chunk: int = 16, snap_at: Optional[int] = None):
     """u, dt [T, Dn]; A [Dn, N] (negative); B, C [T, N]; state [Dn, N] fp32 -> (y [T, Dn] without the D skip, final state).
     h_t = exp(dt_t A) h_{t-1} + dt_t B_t u_t, y_t = h_t . C_t.  Inside a chunk the recurrence is solved in closed form with decay factors
     exp(sum_{s<k<=t} dt_k A) (all <= 1, so nothing overflows); chunks are chained through the carried state."""
     T, Dn = u.shape
     u, dt, B, C, A = u.float(), dt.float(), B.float(), C.float(), A.float()
     ys = []
+    snap = None
     for s in range(0, T, chunk):
         e = min(T, s + chunk)
         q = e - s
@@ -570,7 +571,10 @@ def selective_scan_chunked(u, dt, A, B, C, state, chunk: int = 16):
         h = torch.exp(cs) * state[None] + torch.einsum("tkdn,kdn->tdn", L, inp)
         ys.append(torch.einsum("tdn,tn->td", h, C[s:e]))
         state = h[-1]
-    return (torch.cat(ys, 0) if ys else u.new_zeros(0, Dn)), state
+        if snap_at is not None and e == snap_at:
+            snap = state.clone()          # prefix-cache snapshot at a chunk boundary (mem_cache/mamba_radix.py)
+    y = torch.cat(ys, 0) if ys else u.new_zeros(0, Dn)
+    return (y, state) if snap_at is None else (y, state, snap)
 
 
 class Mamba1Mixer(nn.Module):
@@ -642,7 +646,15 @@ class Mamba1Mixer(nn.Module):
                 n, s = int(fb.q_lens_cpu[b]), int(slots[b])
                 fresh = int(fb.seq_lens_cpu[b]) - n == 0
                 st0 = torch.zeros_like(ssm_s[s][:, 0]) if fresh else ssm_s[s][:, 0]
-                yb, stN = selective_scan_chunked(u[off:off + n], dt[off:off + n], A, Bm[off:off + n], Cm[off:off + n], st0, self.chunk)
+                snap = (fb.mamba_snap or {}).get(b)
+                if snap is None:
+                    yb, stN = selective_scan_chunked(u[off:off + n], dt[off:off + n], A, Bm[off:off + n], Cm[off:off + n], st0, self.chunk)
+                else:       # also export the state at a chunk boundary for the prefix cache
+                    rel, row = snap
+                    yb, stN, sn = selective_scan_chunked(u[off:off + n], dt[off:off + n], A, Bm[off:off + n], Cm[off:off + n], st0, self.chunk, snap_at=rel)
+                    if sn is not None:
+                        ssm_s[row] = sn.unsqueeze(1)
+                        conv_s[row] = x[off + rel - (self.k - 1): off + rel].t().to(conv_s.dtype)
                 ssm_s[s] = stN.unsqueeze(1)
                 ys.append(yb)
                 off += n
@@ -688,7 +700,6 @@ class _M1Block(nn.Module):
 
 class MambaForCausalLM(NemotronHForCausalLM):
     """Mamba-1 (state-spaces/mamba-*-hf) and FalconMamba (``cfg.mamba['bcdt_norm'] == 'plain'``)"""
-    supports_mamba_snapshots = False        # Mamba-1 selective scan: no boundary-state export yet -> prefix caching stays off
 
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
@@ -791,7 +802,6 @@ class _JambaBlock(nn.Module):
 
 
 class JambaForCausalLM(BambaForCausalLM):
-    supports_mamba_snapshots = False        # Mamba-1 selective scan: no boundary-state export yet -> prefix caching stays off
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
         self.cfg = cfg

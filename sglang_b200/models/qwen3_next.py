@@ -45,7 +45,7 @@ def gated_delta_step(q, k, v, g, beta, state):
     return torch.einsum("rhkv,rhk->rhv", state, q)
 
 
-def gated_delta_chunked(q, k, v, g, beta, state, chunk: int = 64):
+def gated_delta_chunked(q, k, v, g, beta, state, chunk: int = 64, snap_at: Optional[int] = None):
     """one sequence: q, k [T, H, Dk]; v [T, H, Dv]; g, beta [T, H]; state [H, Dk, Dv] fp32 -> (o [T, H, Dv] fp32, final state)"""
     T, H, Dk = q.shape
     Dv = v.shape[-1]
@@ -73,14 +73,17 @@ def gated_delta_chunked(q, k, v, g, beta, state, chunk: int = 64):
     w = Tm @ (kb * G.exp()[..., None])                                   # what the carried state contributes to them
     qk = (qc @ kc.transpose(-1, -2)) * D                                 # causal (diagonal included)
     S = state.float().clone()
+    snap = None
     outs = []
     for i in range(c):
         v_new = u[:, i] - w[:, i] @ S                                    # [H, Q, Dv]
         outs.append((qc[:, i] * G[:, i].exp()[..., None]) @ S + qk[:, i] @ v_new)
         last = G[:, i, -1]
         S = S * last.exp()[:, None, None] + (kc[:, i] * (last[:, None] - G[:, i]).exp()[..., None]).transpose(-1, -2) @ v_new
+        if snap_at is not None and (i + 1) * chunk == snap_at:
+            snap = S.clone()               # prefix-cache snapshot at a chunk boundary (mem_cache/mamba_radix.py)
     o = torch.stack(outs, 1).permute(1, 2, 0, 3).reshape(c * chunk, H, Dv)[:T]
-    return o, S
+    return (o, S) if snap_at is None else (o, S, snap)
 
 
 class GatedDeltaNet(nn.Module):
@@ -168,7 +171,15 @@ class GatedDeltaNet(nn.Module):
                 n, s = int(fb.q_lens_cpu[i]), int(slots[i])
                 fresh = int(fb.seq_lens_cpu[i]) - n == 0
                 st0 = torch.zeros_like(rec_s[s]) if fresh else rec_s[s]
-                oi, stN = gated_delta_chunked(qh[off:off + n], kh[off:off + n], vh[off:off + n], g[off:off + n], beta[off:off + n], st0)
+                snap = (fb.mamba_snap or {}).get(i)
+                if snap is None:
+                    oi, stN = gated_delta_chunked(qh[off:off + n], kh[off:off + n], vh[off:off + n], g[off:off + n], beta[off:off + n], st0)
+                else:
+                    rel, row = snap
+                    oi, stN, sn = gated_delta_chunked(qh[off:off + n], kh[off:off + n], vh[off:off + n], g[off:off + n], beta[off:off + n], st0, snap_at=rel)
+                    if sn is not None:
+                        rec_s[row] = sn
+                        conv_s[row] = mixed[off + rel - (self.k - 1): off + rel].t().to(conv_s.dtype)
                 rec_s[s] = stN
                 os_.append(oi)
                 off += n
@@ -242,7 +253,6 @@ class _Block(nn.Module):
 
 
 class Qwen3NextForCausalLM(NemotronHForCausalLM):
-    supports_mamba_snapshots = False        # gated delta rule: no boundary-state export yet
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         nn.Module.__init__(self)
         assert get_pp_group().world_size == 1

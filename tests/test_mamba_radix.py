@@ -47,3 +47,44 @@ def test_hybrid_engine_reuses_prefixes_through_snapshots(model):
     assert got1 == want[:1] and got2 == want
     assert tree.snapshots_taken >= 1 and tree.snapshot_hits >= 2 and eng.scheduler.num_cached_tokens >= 2 * 128
     eng.shutdown()
+
+
+@pytest.mark.parametrize("name", ["mamba1", "jamba", "qwen3-next"])
+def test_snapshot_prefix_cache_on_other_recurrent_families(name, tmp_path):
+    """Mamba-1 selective scan, Jamba (Mamba-1 + attention + MoE) and Qwen3-Next (gated delta rule) export boundary states too: a tiny random HF
+    checkpoint served with snapshot rows answers exactly like the uncached engine while later requests resume from a snapshot"""
+    import torch
+    import transformers as tf
+
+    from test_hf_parity import CASES
+
+    cfg_cls, model_cls, kw = CASES[name]
+    if not hasattr(tf, cfg_cls) or not hasattr(tf, model_cls):
+        pytest.skip(f"transformers has no {model_cls}")
+    torch.manual_seed(0)
+    try:
+        hf = getattr(tf, model_cls)(getattr(tf, cfg_cls)(**kw)).float().eval()
+    except Exception as e:
+        pytest.skip(f"HF {model_cls} unusable here: {e}")
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if p.dim() > 1:
+                p.normal_(0.0, 0.08)
+    d = str(tmp_path / name)
+    hf.save_pretrained(d, safe_serialization=True)
+    rng = np.random.default_rng(4)
+    shared = rng.integers(5, 500, size=140).tolist()
+    prompts = [shared + rng.integers(5, 500, size=int(n)).tolist() for n in (4, 25)] + [rng.integers(5, 500, size=70).tolist()]
+    sp = {"max_new_tokens": 8, "temperature": 0, "ignore_eos": True}
+    kw2 = dict(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error", max_running_requests=4)
+    ref = sgl.Engine(**kw2)
+    want = [o["output_ids"] for o in ref.generate(input_ids=prompts, sampling_params=sp)]
+    ref.shutdown()
+    eng = sgl.Engine(mamba_cache_slots=4, **kw2)
+    got1 = [o["output_ids"] for o in eng.generate(input_ids=prompts[:1], sampling_params=sp)]
+    got2 = [o["output_ids"] for o in eng.generate(input_ids=prompts, sampling_params=sp)]
+    eng.scheduler.check_invariants()
+    t = eng.scheduler.tree
+    assert got1 == want[:1] and got2 == want
+    assert t.snapshots_taken >= 1 and t.snapshot_hits >= 2 and eng.scheduler.num_cached_tokens >= 2 * 128
+    eng.shutdown()
