@@ -453,3 +453,45 @@ def test_tracing_spans_and_otlp_http_export():
             T.get_tracer().otlp.shutdown()
         T._TRACER = None
         srv.shutdown()
+
+
+def test_reasoning_parser_families_stream_equals_non_stream():
+    """every reasoning family: the streamed deltas (any chunking, markers split across chunks) concatenate to the non-streaming split"""
+    import random
+
+    from sglang_b200.parser.reasoning_parser import _FAMILIES, ReasoningParser
+
+    samples = {
+        "deepseek-r1": "let me think\nabout it</think>\nThe answer is 4.",
+        "qwen3": "<think>step 1\nstep 2</think>\n\nDone.",
+        "qwen3-thinking": "no opener here</think>Final.",
+        "kimi": "◁think▷hmm◁/think▷ok",
+        "kimi-k2": "<think>need a tool<|tool_calls_section_begin|>functions.f:0<|tool_call_argument_begin|>{}",
+        "glm45": "<think>plan</think>\n<tool_call>get_weather\n</tool_call>",
+        "mistral": "[THINK]chain[/THINK]Answer",
+        "hunyuan": "<think>t</think>\n<answer>42</answer>",
+        "seed-oss": "<seed:think>budget</seed:think>hi",
+        "minimax-append-think": "implicit start</think>text",
+        "gpt-oss": "<|channel|>analysis<|message|>User wants 2+2.<|end|><|start|>assistant<|channel|>final<|message|>4<|return|>",
+    }
+    rng = random.Random(0)
+    for fam in _FAMILIES:
+        text = samples.get(fam, "<think>x y z</think>answer")
+        want_r, want_c = ReasoningParser(fam).parse_non_stream(text)
+        for _ in range(20):
+            p = ReasoningParser(fam)
+            r, c, i = "", "", 0
+            while i < len(text):
+                n = rng.randint(1, 7)
+                dr, dc = p.parse_stream_chunk(text[i:i + n])
+                r, c, i = r + dr, c + dc, i + n
+            assert (r.strip() or None) == (want_r or None) and c.strip() == want_c.strip(), (fam, r, c, want_r, want_c)
+    r, c = ReasoningParser("gpt-oss").parse_non_stream(samples["gpt-oss"])
+    assert r == "User wants 2+2." and c == "4"
+    r, c = ReasoningParser("gpt-oss").parse_non_stream("<|channel|>analysis<|message|>call it<|end|><|start|>assistant<|channel|>commentary to=functions.f "
+                                                       '<|constrain|>json<|message|>{"a":1}<|call|>')
+    assert r == "call it" and "to=functions.f" in c and c.endswith("<|call|>")
+    r, c = ReasoningParser("hunyuan").parse_non_stream(samples["hunyuan"])
+    assert r == "t" and c.strip() == "42"
+    r, c = ReasoningParser("kimi-k2").parse_non_stream(samples["kimi-k2"])
+    assert r == "need a tool" and c.startswith("<|tool_calls_section_begin|>")
