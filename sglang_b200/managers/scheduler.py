@@ -76,6 +76,16 @@ class Scheduler:
 
         self.sessions = SessionController(self.tree, self.page_size)
         worker.attach_kv_manager(self.kv)
+        self.eplb = None
+        if getattr(server_args, "enable_eplb", False) and getattr(worker, "model", None) is not None:
+            from ..eplb.expert_distribution import EPLBManager, attach
+
+            rec = getattr(worker, "expert_recorder", None) or attach(worker)
+            if rec is not None:
+                if rec.mode == "stat":
+                    rec.mode = "window"
+                self.eplb = EPLBManager(worker, rec, getattr(getattr(worker, "ep", None), "world_size", 1) or 1,
+                                        server_args.eplb_rebalance_num_iterations, server_args.eplb_min_balancedness)
         self.policy = SchedulePolicy(server_args.schedule_policy, self.kv, server_args.enable_priority_scheduling,
                                      server_args.random_seed)
 
@@ -791,6 +801,8 @@ class Scheduler:
             dt = time.perf_counter() - t0
             self.step_wall_s += dt      # minus BatchResult.wait_s = pure host time (bench.py reports the split)
             self.step_calls += 1
+            if self.eplb is not None and self.last_batch is not None:
+                self.eplb.on_forward_pass()
             if _trace.get_tracer() is not None and _trace.get_tracer().level >= 3:
                 lb = self.last_batch
                 now = time.time()

@@ -106,6 +106,11 @@ class ServerArgs:
     gemm_backend: str = "auto"  # auto|tc|lib
     disable_cuda_graph: bool = False
     cuda_graph_max_bs: Optional[int] = None
+    enable_eplb: bool = False                       # automatic expert re-placement from the recorded load (eplb/expert_distribution.py EPLBManager)
+    eplb_rebalance_num_iterations: int = 1000       # forward passes between balance checks
+    eplb_min_balancedness: float = 0.8              # re-plan when mean / max rank load of the worst layer drops below this
+    eplb_window: int = 64                           # forward passes the windowed recorder modes look back
+    expert_distribution_recorder_mode: str = "stat"  # stat | window | per_pass
     mamba_cache_slots: int = 0                      # > 0: state-space / hybrid models keep this many recurrent-state snapshots so that prefix caching works for them
     swa_full_tokens_ratio: float = 0.0              # > 0: hybrid sliding-window models keep the sliding layers in a second pool of ratio x the full pool's tokens (0 = one pool)
     prefill_cuda_graph_max_tokens: int = 0          # > 0: capture token-bucketed prefill graphs up to this many new tokens per step (max 4096)

@@ -495,3 +495,44 @@ def test_reasoning_parser_families_stream_equals_non_stream():
     assert r == "t" and c.strip() == "42"
     r, c = ReasoningParser("kimi-k2").parse_non_stream(samples["kimi-k2"])
     assert r == "need a tool" and c.startswith("<|tool_calls_section_begin|>")
+
+
+def test_expert_recorder_modes_and_eplb_manager():
+    """device-side accumulation, windowed load, balancedness, and the automatic re-plan trigger (eplb/expert_distribution.py)"""
+    import numpy as np
+    import torch
+
+    from sglang_b200.eplb.expert_distribution import EPLBManager, ExpertDistributionRecorder
+
+    rec = ExpertDistributionRecorder(2, 8, mode="window", window=3)
+    rec.enabled = True
+    skew = torch.tensor([[0, 0], [0, 1], [0, 0], [0, 2]])                 # expert 0 is hot
+    for i in range(5):
+        rec.record(0, skew)
+        rec.record(1, torch.tensor([[i % 8, (i + 1) % 8]]))
+        rec.end_pass()
+    load = rec.load()
+    assert load.shape == (2, 8) and load[0, 0] == 3 * 6 and load[0].sum() == 3 * 8     # only the last 3 passes count
+    assert rec.dev_counts[0, 0].item() == 5 * 6                                          # the cumulative tensor keeps everything
+    bal = rec.balancedness(load, 4)
+    assert bal[0] < 0.5 and 0 < bal[1] <= 1.0
+    calls = []
+
+    class R:
+        expert_placement = None
+
+        def eplb_rebalance(self, redundant, load):
+            calls.append((redundant, load.copy()))
+
+    rec2 = ExpertDistributionRecorder(1, 8, mode="window", window=4)
+    mgr = EPLBManager(R(), rec2, ep_size=4, interval=4, threshold=0.8)
+    for i in range(8):
+        rec2.record(0, torch.tensor([[0, 0, 0, 1]]))
+        mgr.on_forward_pass()
+    assert mgr.rebalances == 2 and len(calls) == 2 and calls[0][1][0, 0] == 12 and mgr.last_balancedness < 0.8
+    even = ExpertDistributionRecorder(1, 8, mode="window", window=4)
+    mgr2 = EPLBManager(R(), even, ep_size=4, interval=4, threshold=0.8)
+    for i in range(8):
+        even.record(0, torch.arange(8).view(1, 8))
+        mgr2.on_forward_pass()
+    assert mgr2.rebalances == 0 and abs(mgr2.last_balancedness - 1.0) < 1e-9
