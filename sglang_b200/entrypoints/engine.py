@@ -326,7 +326,7 @@ class Engine:
                     m["ttft"] = st.first_token_time - st.created
                 if self.metrics is not None:
                     self.metrics.observe_request(m)
-                if self.tracer is not None:
+                if getattr(self, "tracer", None) is not None:
                     tc = getattr(st.obj, "trace_context", None) if st.obj is not None else None
                     self.tracer.trace_request(rid, m, time.time() - m["e2e_latency"], tc)
             if st.out_q is not None:

@@ -183,6 +183,12 @@ class FrontendEngine:
                 self._inbox = queue.Queue()
                 self._bg_stop, self._wake = threading.Event(), threading.Event()
                 self._bg_thread = _Sentinel()
+                self.tracer = None
+                if a.enable_trace:
+                    from ..observability.trace import get_tracer, init_tracing
+
+                    ep = a.otlp_traces_endpoint if str(a.otlp_traces_endpoint or "").startswith("http") else None
+                    self.tracer = get_tracer() or init_tracing(level=int(a.trace_level or 2), file=a.trace_file, otlp_endpoint=ep)
                 self.metrics = None
                 if a.enable_metrics:
                     from ..observability.metrics import MetricsCollector

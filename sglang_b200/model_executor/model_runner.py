@@ -246,7 +246,11 @@ class ModelRunner:
         tokens = (self.num_pages - 1) * self.page_size
         self.max_running = a.max_running_requests or max(1, min(4096 if self.is_cuda else 64, tokens // 64))
         max_pages_per_req = (self.max_context_len + self.page_size - 1) // self.page_size + 1
-        self.page_table = torch.zeros(self.max_running + 1, max_pages_per_req, dtype=torch.int32, device=self.device)
+        # hybrid sliding-window models: ONE device table, columns [0, P) full-attention pages, [P, 2P) sliding pages.  Sized HERE, before the
+        # decode graphs are captured: the graphs hold this tensor's address and the column offset
+        self.swa_pt_offset = max_pages_per_req if self.swa is not None else 0
+        self.page_table = torch.zeros(self.max_running + 1, max_pages_per_req * (2 if self.swa is not None else 1), dtype=torch.int32,
+                                      device=self.device)
         # recurrent (SSM) state of hybrid / Mamba decoders, indexed by request slot like the page table (models/mamba.py)
         # (+ --mamba-cache-slots snapshot rows after the request rows: mem_cache/mamba_radix.py)
         self.mamba_snapshot_rows: List[int] = []
@@ -270,11 +274,16 @@ class ModelRunner:
 
     def attach_kv_manager(self, kv: Any) -> None:
         self.kv_manager = kv
+        if getattr(self, "swa", None) is not None:
+            # captured graphs already point at the table and its sliding half: the manager's geometry has to match it exactly
+            assert kv.page_table.shape[1] == self.swa_pt_offset and self.page_table.shape[1] == 2 * self.swa_pt_offset, \
+                (kv.page_table.shape, self.page_table.shape, self.swa_pt_offset)
+            return
         assert kv.page_table.shape[1] <= self.page_table.shape[1] + 1
-        cols = kv.page_table.shape[1] * (2 if getattr(self, "swa", None) is not None else 1)     # [full | sliding] halves of one device table
-        self.swa_pt_offset = kv.page_table.shape[1] if getattr(self, "swa", None) is not None else 0
-        if cols != self.page_table.shape[1]:
-            self.page_table = torch.zeros(self.max_running + 1, cols, dtype=torch.int32, device=self.device)
+        if kv.page_table.shape[1] != self.page_table.shape[1]:
+            if self.graphs:
+                raise RuntimeError("page-table geometry changed after CUDA-graph capture")
+            self.page_table = torch.zeros(self.max_running + 1, kv.page_table.shape[1], dtype=torch.int32, device=self.device)
 
     def copy_mamba_state(self, src: int, dst: int) -> None:
         """recurrent state row ``src`` -> row ``dst`` in every layer (prefix-cache snapshot restore), ordered on the runner's stream"""

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(code: str, timeout: int = 600, env=None):
+def _run(code: str, timeout: int = 300, env=None):
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, cwd=ROOT,
                        env=dict(os.environ, PYTHONPATH=ROOT, **(env or {})))
     assert p.returncode == 0, p.stderr[-4000:]
@@ -58,9 +58,9 @@ shared = rng.integers(5, 500, size=150).tolist()
 prompts = [shared + rng.integers(5, 500, size=int(n)).tolist() for n in (3, 20, 70)] + [rng.integers(5, 500, size=90).tolist()]
 sp = {{"max_new_tokens": 12, "temperature": 0, "ignore_eos": True}}
 kw = dict(model_path="dummy:{model}", page_size=4, log_level="error", max_running_requests=8, mem_fraction_static=0.2)
-cpu = sgl.Engine(device="cpu", **kw)
-want = [o["output_ids"] for o in cpu.generate(input_ids=prompts, sampling_params=sp)]
-cpu.shutdown()
+ref = sgl.Engine(**kw)                                  # same device, same kernels, no snapshot rows: prefix caching off
+want = [o["output_ids"] for o in ref.generate(input_ids=prompts, sampling_params=sp)]
+ref.shutdown()
 eng = sgl.Engine(mamba_cache_slots=6, **kw)
 from sglang_b200 import ops
 c0 = ops.launch_count()
@@ -72,7 +72,7 @@ print(json.dumps({{"same": sum(a == b for a, b in zip(got2, want)) + int(got1 ==
                   "taken": t.snapshots_taken, "native_launches": ops.launch_count() - c0, "cached": eng.scheduler.num_cached_tokens}}))
 ''')
     assert r["native_launches"] > 0 and r["taken"] >= 1 and r["hits"] >= 2 and r["cached"] >= 256
-    assert r["same"] >= r["n"] - 1, r          # fp32 tiny models: GPU kernels vs the CPU reference ops
+    assert r["same"] >= r["n"] - 1, r          # resuming from a snapshot re-associates the scan's sums: allow one near-tie flip
 
 
 def test_sliding_window_pool_on_gpu():
