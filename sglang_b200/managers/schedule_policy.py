@@ -86,7 +86,10 @@ class PrefillAdder:
         return int(remain * self.new_token_ratio + self.ps - 1) // self.ps
 
     def rem_pages(self) -> int:
-        return self.kv.available_pages() - self.reserved_pages - self.used_pages
+        avail = self.kv.available_pages()
+        if hasattr(self.kv, "swa_available_pages"):        # hybrid sliding-window models: every new token needs a page in BOTH pools
+            avail = min(avail, self.kv.swa_available_pages())
+        return avail - self.reserved_pages - self.used_pages
 
     def _fits(self, new_pages: int, decode_reserve: int) -> bool:
         return new_pages + decode_reserve <= self.rem_pages()

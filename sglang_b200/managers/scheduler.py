@@ -405,6 +405,14 @@ class Scheduler:
                 r.is_chunked = 0
                 self.waiting_queue.insert(0, r)
             self.chunked_req = prev_chunked
+            if not self.running_batch.reqs and not self.pending and prev_chunked is None:
+                # nothing is running, nothing in flight, the tree had its chance to evict: this batch can never be placed.  Reject its largest
+                # request instead of retrying forever (seen with a KV pool of a handful of pages: the engine span at 20 k iterations / s)
+                victim = max((r for r in batch.reqs), key=lambda r: r.seqlen)
+                self.waiting_queue = [r for r in self.waiting_queue if r is not victim]
+                self._reject(victim, f"request ({victim.seqlen} tokens) does not fit in the KV cache "
+                                     f"({self.kv.total_pages() * self.page_size} tokens" + (f", sliding-window pool {self.swa_allocator.total_pages * self.page_size}"
+                                                                                              if self.swa is not None else "") + ")")
             return None
         return batch
 
@@ -810,6 +818,29 @@ class Scheduler:
                                               batch_size=len(lb.reqs) if lb is not None else 0, running=len(self.running_batch.reqs),
                                               waiting=len(self.waiting_queue))
 
+    _stall_iters = 0
+
+    def _check_starvation(self) -> None:
+        """Nothing runs, nothing is in flight, yet requests wait: the head of the queue passed validation but can not be placed (its decode
+        reserve or one of the pools is too small and there is nobody left to finish or be evicted).  After a few idle iterations reject it —
+        without this the engine spins forever (observed at 20 k iterations / s with a KV pool of a few pages)."""
+        if not self.waiting_queue or self.running_batch.reqs or self.chunked_req is not None or self.grammar_queue:
+            self._stall_iters = 0
+            return
+        if self.last_batch is not None and any(not r.finished() for r in self.last_batch.reqs):
+            self._stall_iters = 0
+            return
+        self._stall_iters += 1
+        if self._stall_iters < 64:
+            return
+        self._stall_iters = 0
+        victim = self.waiting_queue.pop(0)
+        if victim.req_slot is not None:
+            self.kv.release(victim, insert=False)
+        cap = f"{self.kv.total_pages() * self.page_size} tokens" + (f", sliding-window pool {self.swa_allocator.total_pages * self.page_size}" if self.swa is not None else "")
+        self._reject(victim, f"request ({victim.seqlen} prompt tokens + reserve for {victim.sampling_params.max_new_tokens} new tokens) can not be "
+                             f"scheduled in the KV cache ({cap})", 400)
+
     def _step(self) -> bool:
         batch = self.get_next_batch_to_run()
         if batch is None and self.args.enable_dp_attention:
@@ -821,8 +852,10 @@ class Scheduler:
             if self.pending:
                 self.drain()
                 return True
+            self._check_starvation()
             self._on_idle()
             return False
+        self._stall_iters = 0
         # grammar state, penalties, min_new_tokens and per-request seeds read host-side request state: it must not lag by a step
         host_state = batch.needs_host_state()
         need_sync = (not self.enable_overlap) or batch.has_grammar or host_state or \

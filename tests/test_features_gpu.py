@@ -77,8 +77,9 @@ print(json.dumps({{"same": sum(a == b for a, b in zip(got2, want)) + int(got1 ==
 
 def test_sliding_window_pool_on_gpu():
     """hybrid sliding / full model in bf16 with head_dim 128: tcgen05 attention with a window, decode CUDA graphs carrying the sliding slots,
-    sliding release at the kernels' 128-token fetch granularity"""
-    r = _run('''
+    sliding release at the kernels' 128-token fetch granularity.  The two engines run in separate processes (each sizes its pools from the
+    free device memory)."""
+    code = '''
 import json
 import numpy as np
 import sglang_b200 as sgl
@@ -86,23 +87,24 @@ rng = np.random.default_rng(3)
 shared = rng.integers(5, 2000, size=200).tolist()
 prompts = [shared + rng.integers(5, 2000, size=int(n)).tolist() for n in (3, 40, 300)] + [rng.integers(5, 2000, size=int(n)).tolist() for n in (5, 133, 700)]
 sp = {"max_new_tokens": 48, "temperature": 0, "ignore_eos": True}
-kw = dict(model_path="dummy:tiny-swa-gpu", page_size=32, chunked_prefill_size=256, log_level="error", max_running_requests=8, mem_fraction_static=0.2,
-          cuda_graph_max_bs=8)
-ref = sgl.Engine(**kw)
-want = [o["output_ids"] for o in ref.generate(input_ids=prompts, sampling_params=sp)]
-ref.shutdown()
-eng = sgl.Engine(swa_full_tokens_ratio=0.5, **kw)
+eng = sgl.Engine(model_path="dummy:tiny-swa-gpu", page_size=32, chunked_prefill_size=256, log_level="error", max_running_requests=8, mem_fraction_static=0.3,
+                 cuda_graph_max_bs=8, swa_full_tokens_ratio=RATIO)
 got = [o["output_ids"] for o in eng.generate(input_ids=prompts, sampling_params=sp)]
 eng.scheduler.check_invariants()
 got2 = [o["output_ids"] for o in eng.generate(input_ids=prompts[:3], sampling_params=sp)]
 eng.scheduler.check_invariants()
-print(json.dumps({"same": sum(a == b for a, b in zip(got, want)), "same2": sum(a == b for a, b in zip(got2, want[:3])), "n": len(prompts),
-                  "first": sum(a[:4] == b[:4] for a, b in zip(got, want)), "slid": eng.scheduler.kv.swa_slid_pages,
-                  "graphs": eng.runner.graph_launches > 0, "cached": eng.scheduler.num_cached_tokens}))
-''')
-    # same kernels and math; batch composition (hence split-KV / graph buckets) can differ between the two engines, so allow near-tie flips late
-    # in a sequence but require the first tokens of every request and the large majority of whole sequences to agree
-    assert r["first"] == r["n"] and r["same"] >= r["n"] - 1 and r["same2"] >= 2, r
+print(json.dumps({"ids": got, "ids2": got2, "slid": getattr(eng.scheduler.kv, "swa_slid_pages", 0), "graphs": eng.runner.graph_launches > 0,
+                  "cached": eng.scheduler.num_cached_tokens, "pool": eng.scheduler.swa is not None}))
+'''
+    ref = _run(code.replace("RATIO", "0.0"))
+    r = _run(code.replace("RATIO", "0.5"))
+    assert r["pool"] and not ref["pool"]
+    n = len(ref["ids"])
+    first = sum(a[:4] == b[:4] for a, b in zip(r["ids"], ref["ids"]))
+    same = sum(a == b for a, b in zip(r["ids"], ref["ids"]))
+    same2 = sum(a == b for a, b in zip(r["ids2"], ref["ids2"]))
+    # same kernels and math; batch composition (split-KV / graph buckets) may differ, so a late near-tie flip is tolerated
+    assert first == n and same >= n - 1 and same2 >= 2, (first, same, same2)
     assert r["slid"] > 0 and r["graphs"] and r["cached"] > 0, r
 
 

@@ -96,3 +96,21 @@ def test_engine_sliding_pool_under_memory_pressure():
         assert got == want
     assert eng.scheduler.tree.swa_tombstoned > 0 or eng.scheduler.kv.swa_slid_pages > 0
     eng.shutdown()
+
+
+def test_request_that_can_never_fit_is_rejected_not_retried_forever():
+    """a sliding pool of a handful of pages: prompts that fit the admission check but can never be placed must come back as aborted
+    (the scheduler used to spin at 20 k iterations / s without progress)"""
+    rng = np.random.default_rng(8)
+    prompts = [rng.integers(5, 500, size=int(n)).tolist() for n in (20, 24, 22)]
+    eng = sgl.Engine(model_path="dummy:tiny-gemma2", page_size=4, log_level="error", device="cpu", max_running_requests=4, swa_full_tokens_ratio=0.5,
+                     max_total_tokens=40)          # 10 full pages, 8 sliding pages
+    outs = eng.generate(input_ids=prompts, sampling_params={"max_new_tokens": 30, "temperature": 0, "ignore_eos": True})
+    kinds = [o["meta_info"]["finish_reason"]["type"] for o in outs]
+    assert len(outs) == 3 and all(k in ("length", "abort") for k in kinds) and "abort" in kinds
+    assert any("can not be scheduled" in (o["meta_info"]["finish_reason"].get("message") or "") for o in outs)
+    # the engine stays usable: a request that fits still runs
+    ok = eng.generate(input_ids=[prompts[0][:8]], sampling_params={"max_new_tokens": 4, "temperature": 0, "ignore_eos": True})
+    assert ok[0]["meta_info"]["finish_reason"]["type"] == "length"
+    eng.scheduler.check_invariants()
+    eng.shutdown()
