@@ -447,7 +447,9 @@ def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], pee
     if dog is not None:
         dog.start()
     try:
-        uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5)
+        # graceful drain: on SIGTERM uvicorn closes the listener and waits for the in-flight HTTP requests (= running generations) to complete
+        uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5,
+                    timeout_graceful_shutdown=max(1, int(server_args.graceful_shutdown_timeout)))
     finally:
         if dog is not None:
             dog.stop()

@@ -53,6 +53,7 @@ class ServerArgs:
     trace_file: Optional[str] = None                 # JSON-lines span log
     decode_log_interval: int = 40
     watchdog_timeout: float = 300.0
+    graceful_shutdown_timeout: float = 30.0         # SIGTERM / SIGINT: stop accepting connections, let in-flight requests finish for this long, then tear down
     soft_watchdog_timeout: Optional[float] = None
     crash_dump_folder: Optional[str] = None
     # --- memory / scheduling

@@ -123,3 +123,51 @@ def test_subprocess_watchdog_reports_dead_child():
         time.sleep(0.05)
     dog.stop(); ok.kill(); ok.wait()
     assert seen == [("bad", 3)]
+
+
+def test_sigterm_drains_in_flight_requests(tmp_path):
+    """graceful shutdown: a generation that is running when SIGTERM arrives still gets its full answer; new connections are refused"""
+    import os
+    import signal
+    import socket
+    import subprocess
+    import sys
+    import threading
+    import time
+    import urllib.request
+
+    import requests
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
+                          "--host", "127.0.0.1", "--log-level", "error", "--graceful-shutdown-timeout", "20"], cwd=root,
+                         env=dict(os.environ, PYTHONPATH=root), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        for _ in range(120):
+            try:
+                if urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.5)
+        else:
+            pytest.fail("server did not come up")
+        out = {}
+
+        def call():
+            r = requests.post(f"http://127.0.0.1:{port}/generate", json={"text": "drain me", "sampling_params": {"max_new_tokens": 200, "temperature": 0,
+                                                                                                              "ignore_eos": True}}, timeout=60)
+            out["status"], out["body"] = r.status_code, r.json()
+
+        t = threading.Thread(target=call)
+        t.start()
+        time.sleep(0.4)                              # the request is decoding now
+        p.send_signal(signal.SIGTERM)
+        t.join(timeout=40)
+        assert out.get("status") == 200 and out["body"]["meta_info"]["completion_tokens"] == 200, out
+        p.wait(timeout=30)
+        with pytest.raises(Exception):
+            requests.get(f"http://127.0.0.1:{port}/health", timeout=2)
+    finally:
+        if p.poll() is None:
+            p.kill()
