@@ -440,6 +440,12 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                                              for i in range(text["num_hidden_layers"])]
             kw["layer_types"] = lt
             kw["no_rope_layers"] = [int(t == "sliding_attention") for t in lt]
+        if arch == "Exaone4ForCausalLM":             # per-head q/k norm; hybrid checkpoints (32B): rotary on the sliding layers only, global layers NoPE
+            kw["qk_norm"] = True
+            if text.get("sliding_window"):
+                lt = text.get("layer_types") or ["sliding_attention"] * text["num_hidden_layers"]
+                kw["layer_types"] = lt
+                kw["no_rope_layers"] = [int(t == "sliding_attention") for t in lt]
         if arch == "GraniteMoeHybridForCausalLM":
             kw["shared_expert_intermediate_size"] = text.get("shared_intermediate_size")
             kw["pos_emb"] = "rope" if text.get("position_embedding_type", "rope") == "rope" else "none"

@@ -263,3 +263,26 @@ class Olmo2DecoderLayer(LlamaDecoderLayer):
 
 class Olmo2ForCausalLM(LlamaForCausalLM):
     decoder_layer_cls = Olmo2DecoderLayer
+
+
+# ---------------------------------------------------------------- EXAONE-4: post-norm blocks (like OLMo-2) around the ordinary attention with per-head q/k norm
+class Exaone4DecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)      # LlamaAttention: qk_norm per head, layer_types, NoPE layers
+        del self.input_layernorm
+        self.post_feedforward_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        a = self.self_attn(h, fb)
+        h = h + self.post_attention_layernorm(a.resolve() if hasattr(a, "resolve") else a)
+        m = self.mlp(h)
+        h = h + self.post_feedforward_layernorm(m.resolve() if hasattr(m, "resolve") else m)
+        return h, None
+
+
+class Exaone4ForCausalLM(LlamaForCausalLM):
+    """LG EXAONE-4.0 (reference models/exaone4.py): 1.2B is all-global with rotary everywhere; 32B interleaves sliding-window layers (rotary) with
+    global NoPE layers"""
+    decoder_layer_cls = Exaone4DecoderLayer

@@ -51,7 +51,7 @@ def _register_builtins() -> None:
     from . import families as _fam
 
     for name in ("Phi3ForCausalLM", "InternLM2ForCausalLM", "Qwen2MoeForCausalLM", "Qwen3MoeForCausalLM", "Gemma2ForCausalLM",
-                 "GraniteForCausalLM", "Olmo2ForCausalLM"):
+                 "GraniteForCausalLM", "Olmo2ForCausalLM", "Exaone4ForCausalLM"):
         register_model(name, getattr(_fam, name))
     from . import classic as _cl
 

@@ -112,6 +112,10 @@ CASES = {
                                                             logits_scaling=2.0)),
     "olmo2": ("Olmo2Config", "Olmo2ForCausalLM", dict(BASE)),
     "olmo": ("OlmoConfig", "OlmoForCausalLM", dict(BASE, clip_qkv=0.9)),
+    "exaone4": ("Exaone4Config", "Exaone4ForCausalLM", dict(BASE, head_dim=16, sliding_window=None, sliding_window_pattern=4,
+                                                            layer_types=["full_attention", "full_attention"])),
+    "exaone4-hybrid": ("Exaone4Config", "Exaone4ForCausalLM", dict(BASE, head_dim=16, num_hidden_layers=4, sliding_window=8, sliding_window_pattern=4,
+                                                                   layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"])),
     "stablelm": ("StableLmConfig", "StableLmForCausalLM", dict(BASE, partial_rotary_factor=0.25, use_qkv_bias=True, layer_norm_eps=1e-5)),
     "mixtral": ("MixtralConfig", "MixtralForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2)),
     "qwen2-moe": ("Qwen2MoeConfig", "Qwen2MoeForCausalLM", dict(BASE, num_experts=4, num_experts_per_tok=2, moe_intermediate_size=32,
