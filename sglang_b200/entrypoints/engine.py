@@ -694,6 +694,35 @@ class Engine:
         if self._bg_thread is not None:
             self._bg_thread.join(timeout=10)
             self._bg_thread = None
+        self._release_device_memory()
+
+    def _release_device_memory(self) -> None:
+        """give the device memory back (KV pools, captured graphs, weights): a second engine created in the same process sizes its pools from
+        the FREE memory and would otherwise end up with a pool of a handful of pages"""
+        r = getattr(self, "runner", None)
+        if r is None or not getattr(r, "is_cuda", False) or getattr(self, "_released", False):
+            return
+        self._released = True
+        try:
+            import gc
+
+            import torch
+
+            torch.cuda.synchronize(r.device)
+            for name in ("graphs", "graphs_greedy", "prefill_graphs"):
+                d = getattr(r, name, None)
+                if isinstance(d, dict):
+                    d.clear()
+            for name in ("kv_pool", "page_table", "next_token_buf", "model", "lora_manager", "_stage_ring", "_res_ring"):
+                if hasattr(r, name):
+                    setattr(r, name, None)
+            sch = getattr(self, "scheduler", None)
+            if sch is not None:
+                sch.worker = None
+            gc.collect()
+            torch.cuda.empty_cache()
+        except Exception:      # noqa: BLE001 — best effort: shutdown must not raise
+            pass
 
     def __enter__(self) -> "Engine":
         return self
