@@ -326,7 +326,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
                   "OlmoeForCausalLM": dict(norm_topk_prob=False),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
-                  "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"),
+                  "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"), "ApertusForCausalLM": dict(mlp_gated=False, qk_norm=True),
                   "GlmForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
                   "Glm4ForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
                   "NemotronForCausalLM": dict(mlp_gated=False, hidden_act="relu2", norm_type="layernorm1p", partial_rotary_factor=0.5),

@@ -176,6 +176,8 @@ def get_act(name: str):
 
     if name == "relu2":
         return lambda x: torch.relu(x).square()
+    if name == "xielu":          # learnable per layer: the owning block installs its own module (models/families2.py XIELU)
+        return None
     if name in ("gelu_pytorch_tanh", "gelu_tanh", "gelu_new", "gelu_fast"):
         return lambda x: F.gelu(x, approximate="tanh")
     return {"gelu": F.gelu, "relu": torch.relu, "silu": F.silu}[name]

@@ -43,7 +43,7 @@ def dummy_checkpoint_iterator(cfg: ModelConfig, device: torch.device, dtype: tor
 
     H, V, D = cfg.hidden_size, cfg.vocab_size, cfg.head_dim
     Hq, Hkv, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
-    gemma = cfg.architecture.startswith("Gemma")
+    gemma = "Gemma" in cfg.architecture
     norm = (lambda n: torch.zeros(n, dtype=dtype, device=device)) if gemma else (lambda n: torch.ones(n, dtype=dtype, device=device))
     yield "model.embed_tokens.weight", rnd("model.embed_tokens.weight", V, H)
     for i in range(cfg.num_hidden_layers):

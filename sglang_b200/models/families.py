@@ -192,6 +192,27 @@ class Gemma2ForCausalLM(LlamaForCausalLM):
     decoder_layer_cls = Gemma2DecoderLayer
 
 
+class VaultGemmaDecoderLayer(Gemma2DecoderLayer):
+    """VaultGemma (differentially private Gemma): the Gemma-2 block without the two post-norms"""
+
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, mlp_cls)
+        del self.post_attention_layernorm
+        del self.post_feedforward_layernorm
+
+    def forward(self, h, residual, fb: ForwardBatch):
+        if residual is not None:
+            h = h + residual
+        a = self.self_attn(self.input_layernorm(h), fb)
+        h = h + (a.resolve() if hasattr(a, "resolve") else a)
+        m = self.mlp(self.pre_feedforward_layernorm(h))
+        return h + (m.resolve() if hasattr(m, "resolve") else m), None
+
+
+class VaultGemmaForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = VaultGemmaDecoderLayer
+
+
 # ---------------------------------------------------------------- Granite (scalar multipliers)
 class GraniteForCausalLM(LlamaForCausalLM):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):

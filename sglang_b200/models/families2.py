@@ -332,6 +332,55 @@ class StableLmForCausalLM(LlamaForCausalLM):
         self.model.norm = PlainLayerNorm(cfg.hidden_size, cfg.rms_norm_eps, self.model.embed_tokens.weight.dtype, True)
 
 
+# ---------------------------------------------------------------- Apertus: non-gated MLP with the learnable xIELU activation, per-head q/k norm
+class XIELU(nn.Module):
+    """xIELU (arXiv 2411.13010): x > 0: a_p x^2 + b x ; x <= 0: a_n (expm1(min(x, eps)) - x) + b x, with a_p = softplus(alpha_p),
+    a_n = b + softplus(alpha_n) learned per layer"""
+
+    def __init__(self, dtype, beta: float = 0.5, eps: float = -1e-6):
+        super().__init__()
+        self.alpha_p = nn.Parameter(torch.zeros(1, dtype=dtype), requires_grad=False)
+        self.alpha_n = nn.Parameter(torch.zeros(1, dtype=dtype), requires_grad=False)
+        self.beta, self.eps = beta, eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        xf = x.float()
+        a_p = F.softplus(self.alpha_p.float())
+        a_n = self.beta + F.softplus(self.alpha_n.float())
+        y = torch.where(xf > 0, a_p * xf * xf + self.beta * xf, (torch.expm1(torch.clamp(xf, max=self.eps)) - xf) * a_n + self.beta * xf)
+        return y.to(x.dtype)
+
+
+class ApertusDecoderLayer(LlamaDecoderLayer):
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)      # cfg.mlp_gated = False -> up_proj / act / down_proj
+        if cfg.hidden_act == "xielu":
+            self.mlp.act = None
+            self.mlp.act_fn = XIELU(dtype)
+            self.mlp.forward = self._mlp_forward
+
+    def _mlp_forward(self, x):
+        m = self.mlp
+        return m.down_proj(m.act_fn(m.up_proj(x)), defer_reduce=True)
+
+
+class ApertusForCausalLM(LlamaForCausalLM):
+    """Swiss-AI Apertus (reference models/apertus.py): Llama skeleton, q/k RMSNorm per head, xIELU MLP; HF names its norms
+    attention_layernorm / feedforward_layernorm"""
+    decoder_layer_cls = ApertusDecoderLayer
+
+    def load_weights(self, weights):
+        ren = ((".attention_layernorm.", ".input_layernorm."), (".feedforward_layernorm.", ".post_attention_layernorm."))
+
+        def it():
+            for n, w in weights:
+                for a, b in ren:
+                    n = n.replace(a, b)
+                yield n, w
+
+        return super().load_weights(it())
+
+
 # ---------------------------------------------------------------- GLM-4.5 (Glm4Moe) and dots.llm1: DeepSeek-V3 style MoE + ordinary GQA attention
 def _ds():
     from . import deepseek

@@ -121,7 +121,7 @@ class LlamaAttention(nn.Module):
 class LlamaDecoderLayer(nn.Module):
     def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
         super().__init__()
-        gemma = cfg.architecture.startswith("Gemma")
+        gemma = ("Gemma" in cfg.architecture)
         self.self_attn = LlamaAttention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
         self.mlp = mlp_cls(cfg, dtype, quant, prefix + ".mlp") if mlp_cls is LlamaMLP else mlp_cls(cfg, layer_id, dtype, quant, prefix)
         self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype, gemma)
@@ -171,7 +171,7 @@ class LlamaModel(nn.Module):
         pp = get_pp_group()
         self.pp = pp
         self.start_layer, self.end_layer = pp_layer_range(cfg.num_hidden_layers, pp.rank, pp.world_size)
-        self.gemma = cfg.architecture.startswith("Gemma")
+        self.gemma = ("Gemma" in cfg.architecture)
         self.embed_tokens = VocabParallelEmbedding(cfg.vocab_size, cfg.hidden_size, dtype) if pp.is_first else None
         rope = RotaryEmbedding(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta, cfg.rope_scaling, cfg.rope_is_neox,
                                cfg.partial_rotary_factor, device)

@@ -51,7 +51,7 @@ def _register_builtins() -> None:
     from . import families as _fam
 
     for name in ("Phi3ForCausalLM", "InternLM2ForCausalLM", "Qwen2MoeForCausalLM", "Qwen3MoeForCausalLM", "Gemma2ForCausalLM",
-                 "GraniteForCausalLM", "Olmo2ForCausalLM", "Exaone4ForCausalLM"):
+                 "GraniteForCausalLM", "Olmo2ForCausalLM", "Exaone4ForCausalLM", "VaultGemmaForCausalLM"):
         register_model(name, getattr(_fam, name))
     from . import classic as _cl
 
@@ -74,7 +74,7 @@ def _register_builtins() -> None:
     from . import families2 as _f2
 
     for name in ("GlmForCausalLM", "Glm4ForCausalLM", "Gemma3ForCausalLM", "CohereForCausalLM", "OlmoeForCausalLM", "NemotronForCausalLM",
-                 "Glm4MoeForCausalLM", "Dots1ForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM"):
+                 "Glm4MoeForCausalLM", "Dots1ForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM", "ApertusForCausalLM"):
         register_model(name, getattr(_f2, name))
     register_model("Gemma3ForConditionalGeneration", _f2.Gemma3ForCausalLM)      # text tower of the multimodal checkpoint
     from . import qwen2_vl as _qv

@@ -107,6 +107,9 @@ CASES = {
     "qwen3": ("Qwen3Config", "Qwen3ForCausalLM", dict(BASE, head_dim=16)),
     "gemma": ("GemmaConfig", "GemmaForCausalLM", dict(BASE, head_dim=16, tie_word_embeddings=True)),
     "gemma2": ("Gemma2Config", "Gemma2ForCausalLM", dict(BASE, head_dim=16, sliding_window=8, query_pre_attn_scalar=16, tie_word_embeddings=True)),
+    "vaultgemma": ("VaultGemmaConfig", "VaultGemmaForCausalLM", dict(BASE, head_dim=16, sliding_window=8, query_pre_attn_scalar=16, tie_word_embeddings=True,
+                                                                    layer_types=["sliding_attention", "full_attention"])),
+    "apertus": ("ApertusConfig", "ApertusForCausalLM", dict(BASE, hidden_act="xielu", pad_token_id=0)),
     "phi3": ("Phi3Config", "Phi3ForCausalLM", dict(BASE, pad_token_id=0)),
     "granite": ("GraniteConfig", "GraniteForCausalLM", dict(BASE, embedding_multiplier=3.0, residual_multiplier=0.5, attention_multiplier=0.2,
                                                             logits_scaling=2.0)),
