@@ -407,6 +407,11 @@ def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) ->
 
     from .engine import Engine
 
+    if int(getattr(server_args, "tokenizer_worker_num", 1) or 1) > 1 and "RANK" not in os.environ and not os.environ.get("SGLB_IN_SCHEDULER_PROCESS"):
+        from ..managers.multiprocess import serve_multi_tokenizer
+
+        serve_multi_tokenizer(server_args)       # supervisor: N HTTP + tokenizer workers | scheduler | detokenizer
+        return
     if server_args.enable_multi_process_frontend and "RANK" not in os.environ and not os.environ.get("SGLB_IN_SCHEDULER_PROCESS"):
         # this process keeps HTTP + tokenizer + request states; the scheduler (and through it the TP x PP peers) and the detokenizer run in
         # their own processes (reference engine.py:905 _launch_subprocesses)

@@ -35,9 +35,45 @@ from ..server_args import ServerArgs
 logger = logging.getLogger(__name__)
 
 
-def _ipc_names() -> Dict[str, str]:
+def _ipc_names(num_workers: int = 1) -> Dict[str, str]:
     d = tempfile.mkdtemp(prefix="sglb-ipc-")
-    return {k: f"ipc://{d}/{k}" for k in ("req", "tok", "str", "ctl")}
+    names = {k: f"ipc://{d}/{k}" for k in ("req", "tok", "str", "ctl")}
+    for i in range(num_workers):          # one result socket per tokenizer worker (reference: MultiTokenizerRouter)
+        names[f"str{i}"] = f"ipc://{d}/str{i}"
+    return names
+
+
+WORKER_SEP = "~"        # request ids travel as "<worker>~<rid>" between a tokenizer worker and the scheduler; the detokenizer routes on the prefix
+
+
+def split_by_worker(out: "ios.BatchStrOutput", num_workers: int) -> Dict[int, "ios.BatchStrOutput"]:
+    """one BatchStrOutput per tokenizer worker: every per-request list is sliced by the worker prefix of its request id (prefix removed)"""
+    import dataclasses
+
+    groups: Dict[int, List[int]] = {}
+    clean: List[str] = []
+    for i, rid in enumerate(out.rids):
+        w, sep, rest = rid.partition(WORKER_SEP)
+        if sep and w.isdigit() and int(w) < num_workers:
+            groups.setdefault(int(w), []).append(i)
+            clean.append(rest)
+        else:
+            groups.setdefault(0, []).append(i)
+            clean.append(rid)
+    n = len(out.rids)
+    res = {}
+    for w, idx in groups.items():
+        kw = {}
+        for f in dataclasses.fields(out):
+            v = getattr(out, f.name)
+            if f.name == "rids":
+                kw[f.name] = [clean[i] for i in idx]
+            elif isinstance(v, list) and len(v) == n:
+                kw[f.name] = [v[i] for i in idx]
+            else:
+                kw[f.name] = v
+        res[w] = type(out)(**kw)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------------ scheduler process
@@ -130,7 +166,15 @@ def detokenizer_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready
         detok = Detokenizer(tok)
         ctx = zmq.Context(1)
         s_tok = ctx.socket(zmq.PULL); s_tok.bind(ipc["tok"])
-        s_str = ctx.socket(zmq.PUSH); s_str.connect(ipc["str"])
+        n_workers = max(1, int(getattr(server_args, "tokenizer_worker_num", 1) or 1))
+        if n_workers == 1:
+            outs = {0: ctx.socket(zmq.PUSH)}
+            outs[0].connect(ipc["str"])
+        else:
+            outs = {}
+            for i in range(n_workers):
+                outs[i] = ctx.socket(zmq.PUSH)
+                outs[i].connect(ipc[f"str{i}"])
         ready.put({"ok": True})
     except Exception as e:      # noqa: BLE001
         ready.put({"ok": False, "error": f"{type(e).__name__}: {e}"})
@@ -139,7 +183,12 @@ def detokenizer_process_main(server_args: ServerArgs, ipc: Dict[str, str], ready
         msg = ios.decode(s_tok.recv())
         if isinstance(msg, ios.ShutdownReq):
             return
-        s_str.send(ios.encode(detok.process(msg)))
+        out = detok.process(msg)
+        if n_workers == 1:
+            outs[0].send(ios.encode(out))
+        else:
+            for w, part in split_by_worker(out, n_workers).items():
+                outs[w].send(ios.encode(part))
 
 
 # ------------------------------------------------------------------------------------------------------------------ front end
@@ -156,7 +205,9 @@ class _Sentinel:
 class FrontendEngine:
     """Factory: builds an ``Engine`` subclass instance whose scheduler lives in another process"""
 
-    def __new__(cls, server_args: Optional[ServerArgs] = None, **kwargs: Any):
+    def __new__(cls, server_args: Optional[ServerArgs] = None, attach: Optional[Dict[str, Any]] = None, **kwargs: Any):
+        """``attach`` = {"ipc": names, "worker_id": i, "sched_info": {...}}: connect to a scheduler / detokenizer that a supervisor already started
+        (tokenizer worker i of ``--tokenizer-worker-num``) instead of spawning them"""
         from ..entrypoints.engine import Engine
 
         class _Frontend(Engine):
@@ -199,22 +250,28 @@ class FrontendEngine:
                 self.runner = _RunnerView(self)
                 self.scheduler = _SchedulerView(self)
                 # ---- processes and sockets
-                self._ipc = _ipc_names()
-                spawn = mp.get_context("spawn")
-                rq_s, rq_d = spawn.Queue(), spawn.Queue()
+                self._worker_id = None
                 self._ctx = zmq.Context(2)
-                self._s_str = self._ctx.socket(zmq.PULL); self._s_str.bind(self._ipc["str"])
-                self._p_detok = spawn.Process(target=detokenizer_process_main, args=(a, self._ipc, rq_d), daemon=True, name="sglb-detokenizer")
-                self._p_detok.start()
-                r = rq_d.get(timeout=600)
-                if not r.get("ok"):
-                    raise RuntimeError(f"detokenizer process failed: {r.get('error')}")
-                self._p_sched = spawn.Process(target=scheduler_process_main, args=(a, self._ipc, rq_s), daemon=False, name="sglb-scheduler")
-                self._p_sched.start()
-                r = rq_s.get(timeout=3600)
-                if not r.get("ok"):
-                    raise RuntimeError(f"scheduler process failed: {r.get('error')}")
-                self._sched_info = r
+                if attach is not None:          # tokenizer worker: the supervisor owns the scheduler and the detokenizer
+                    self._ipc, self._worker_id, self._sched_info = attach["ipc"], int(attach["worker_id"]), attach["sched_info"]
+                    self._s_str = self._ctx.socket(zmq.PULL); self._s_str.bind(self._ipc[f"str{self._worker_id}"])
+                    self._p_detok = self._p_sched = None
+                else:
+                    self._ipc = _ipc_names()
+                    spawn = mp.get_context("spawn")
+                    rq_s, rq_d = spawn.Queue(), spawn.Queue()
+                    self._s_str = self._ctx.socket(zmq.PULL); self._s_str.bind(self._ipc["str"])
+                    self._p_detok = spawn.Process(target=detokenizer_process_main, args=(a, self._ipc, rq_d), daemon=True, name="sglb-detokenizer")
+                    self._p_detok.start()
+                    r = rq_d.get(timeout=600)
+                    if not r.get("ok"):
+                        raise RuntimeError(f"detokenizer process failed: {r.get('error')}")
+                    self._p_sched = spawn.Process(target=scheduler_process_main, args=(a, self._ipc, rq_s), daemon=False, name="sglb-scheduler")
+                    self._p_sched.start()
+                    r = rq_s.get(timeout=3600)
+                    if not r.get("ok"):
+                        raise RuntimeError(f"scheduler process failed: {r.get('error')}")
+                    self._sched_info = r
                 self._s_req = self._ctx.socket(zmq.PUSH); self._s_req.connect(self._ipc["req"])
                 self._s_ctl = self._ctx.socket(zmq.DEALER); self._s_ctl.connect(self._ipc["ctl"])
                 self._req_lock, self._ctl_lock = threading.Lock(), threading.Lock()
@@ -225,11 +282,24 @@ class FrontendEngine:
                 threading.Thread(target=self._recv_ctl, daemon=True, name="sglb-front-ctl").start()
 
             # ---- seams
+            def _tag(self, rid: str) -> str:
+                return rid if self._worker_id is None or not rid else f"{self._worker_id}{WORKER_SEP}{rid}"
+
             def _dispatch(self, t: ios.TokenizedGenerateReqInput) -> None:
+                if self._worker_id is not None:          # the scheduler sees worker-qualified ids; results come back already stripped
+                    import dataclasses
+
+                    t = dataclasses.replace(t, rid=self._tag(t.rid))
                 with self._req_lock:
                     self._s_req.send(ios.encode(t))
 
             def _control(self, msg: Any) -> Any:
+                if self._worker_id is not None and isinstance(msg, ios.AbortReq) and msg.rid:
+                    import dataclasses
+
+                    msg = dataclasses.replace(msg, rid=self._tag(msg.rid))
+                if self._worker_id is not None and isinstance(msg, ios.ShutdownReq):
+                    return ios.GenericResp(True, "worker detached")      # only the supervisor stops the shared scheduler
                 cid = str(next(self._ctl_ids)).encode()
                 box: "queue.Queue[Any]" = queue.Queue()
                 self._ctl_wait[cid] = box
@@ -287,6 +357,8 @@ class FrontendEngine:
                     pass
                 self._closed = True
                 for p in (self._p_sched, self._p_detok):
+                    if p is None:
+                        continue
                     p.join(timeout=10)
                     if p.is_alive():
                         p.terminate()
@@ -341,3 +413,97 @@ class _SchedulerView:
     @property
     def tree(self) -> Any:
         raise AttributeError("the radix tree lives in the scheduler process (use /get_server_info or the KV-event stream)")
+
+
+# ------------------------------------------------------------------------------------------------------------------ multi-tokenizer serving
+def _http_worker_main(server_args: ServerArgs, attach: Dict[str, Any]) -> None:
+    """one HTTP + tokenizer worker: its own front end (request states, tokenizer, OpenAI layer) attached to the shared scheduler; all workers
+    listen on the SAME port with SO_REUSEPORT, the kernel spreads incoming connections"""
+    import socket
+
+    import uvicorn
+
+    from ..entrypoints.http_server import create_app
+    from ..utils.process_tree import die_with_parent, graceful_sigterm
+
+    die_with_parent()
+    graceful_sigterm()
+    engine = FrontendEngine(server_args, attach=attach)
+    app = create_app(engine)
+    wid = attach["worker_id"]
+
+    @app.middleware("http")
+    async def _tag(request, call_next):          # lets a client (and the tests) see which worker answered
+        resp = await call_next(request)
+        resp.headers["x-sglb-worker"] = str(wid)
+        return resp
+
+    sock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+    sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEPORT, 1)
+    sock.bind((server_args.host, server_args.port))
+    sock.listen(2048)
+    cfg = uvicorn.Config(app, log_level=server_args.log_level, timeout_keep_alive=5,
+                         timeout_graceful_shutdown=max(1, int(server_args.graceful_shutdown_timeout)))
+    try:
+        uvicorn.Server(cfg).run(sockets=[sock])
+    finally:
+        engine.shutdown()
+
+
+def serve_multi_tokenizer(server_args: ServerArgs) -> None:
+    """supervisor of ``--tokenizer-worker-num N`` (reference tokenizer_manager multi-worker mode + MultiTokenizerRouter): start the detokenizer
+    (which routes results by worker), the scheduler process, then N HTTP workers; watch all of them, tear everything down on SIGTERM or when
+    one dies"""
+    import signal
+    import zmq
+
+    from ..utils.process_tree import SubprocessWatchdog, graceful_sigterm, kill_process_tree
+
+    n = int(server_args.tokenizer_worker_num)
+    ipc = _ipc_names(n)
+    spawn = mp.get_context("spawn")
+    rq_s, rq_d = spawn.Queue(), spawn.Queue()
+    p_detok = spawn.Process(target=detokenizer_process_main, args=(server_args, ipc, rq_d), daemon=True, name="sglb-detokenizer")
+    p_detok.start()
+    r = rq_d.get(timeout=600)
+    if not r.get("ok"):
+        raise RuntimeError(f"detokenizer process failed: {r.get('error')}")
+    p_sched = spawn.Process(target=scheduler_process_main, args=(server_args, ipc, rq_s), daemon=False, name="sglb-scheduler")
+    p_sched.start()
+    info = rq_s.get(timeout=3600)
+    if not info.get("ok"):
+        kill_process_tree([p_detok])
+        raise RuntimeError(f"scheduler process failed: {info.get('error')}")
+    workers = []
+    for i in range(n):
+        p = spawn.Process(target=_http_worker_main, args=(server_args, {"ipc": ipc, "worker_id": i, "sched_info": info}), daemon=False,
+                          name=f"sglb-http-{i}")
+        p.start()
+        workers.append(p)
+    logger.info("multi-tokenizer serving: %d HTTP workers on %s:%d, one scheduler, one detokenizer", n, server_args.host, server_args.port)
+    graceful_sigterm()
+    stop = threading.Event()
+    dog = SubprocessWatchdog([p_sched, p_detok] + workers, on_death=lambda name, code: (logger.critical("%s died (exit code %s)", name, code), stop.set()))
+    dog.start()
+    try:
+        while not stop.wait(0.5):
+            pass
+    except (KeyboardInterrupt, SystemExit):
+        pass
+    finally:
+        dog.stop()
+        for p in workers:                 # workers first: they drain their in-flight HTTP requests on SIGTERM
+            if p.is_alive():
+                p.terminate()
+        for p in workers:
+            p.join(timeout=max(2.0, server_args.graceful_shutdown_timeout + 2))
+        try:                              # then the shared back end, through its own control socket
+            ctx = zmq.Context(1)
+            s = ctx.socket(zmq.DEALER); s.connect(ipc["ctl"])
+            s.send_multipart([b"0", ios.encode(ios.ShutdownReq())])
+            s.poll(5000)
+            ctx.destroy(linger=0)
+        except Exception:      # noqa: BLE001
+            pass
+        kill_process_tree([p_sched, p_detok] + workers, grace_s=5.0)

@@ -107,6 +107,7 @@ class ServerArgs:
     gemm_backend: str = "auto"  # auto|tc|lib
     disable_cuda_graph: bool = False
     cuda_graph_max_bs: Optional[int] = None
+    tokenizer_worker_num: int = 1                   # > 1: that many HTTP + tokenizer worker processes (SO_REUSEPORT) in front of ONE scheduler / detokenizer pair
     enable_eplb: bool = False                       # automatic expert re-placement from the recorded load (eplb/expert_distribution.py EPLBManager)
     eplb_rebalance_num_iterations: int = 1000       # forward passes between balance checks
     eplb_min_balancedness: float = 0.8              # re-plan when mean / max rank load of the worst layer drops below this

@@ -171,3 +171,69 @@ def test_sigterm_drains_in_flight_requests(tmp_path):
     finally:
         if p.poll() is None:
             p.kill()
+
+
+def test_multi_tokenizer_workers_share_one_scheduler(tmp_path):
+    """--tokenizer-worker-num 2: two HTTP + tokenizer processes on one port (SO_REUSEPORT), one scheduler, one detokenizer that routes results by
+    worker; answers equal the single-process engine, both workers serve traffic, aborts and streaming reach the right worker"""
+    import json
+    import os
+    import signal
+    import socket
+    import subprocess
+    import sys
+    import time
+    import urllib.request
+    from concurrent.futures import ThreadPoolExecutor
+
+    import requests
+
+    import sglang_b200 as sgl
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
+                          "--host", "127.0.0.1", "--log-level", "error", "--tokenizer-worker-num", "2", "--page-size", "4"], cwd=root,
+                         env=dict(os.environ, PYTHONPATH=root), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        for _ in range(160):
+            try:
+                if urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.5)
+        else:
+            pytest.fail("server did not come up")
+        time.sleep(1.0)                                   # let the second worker finish binding
+        ref = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, log_level="error")
+        prompts = [f"prompt number {i} about things" for i in range(24)]
+        sp = {"max_new_tokens": 6, "temperature": 0, "ignore_eos": True}
+        want = [o["output_ids"] for o in ref.generate(prompts, sp)]
+        ref.shutdown()
+
+        def call(i):
+            with requests.Session() as c:                 # a fresh connection per request: the kernel picks a worker each time
+                r = c.post(f"http://127.0.0.1:{port}/generate", json={"text": prompts[i], "sampling_params": sp, "rid": f"user-{i}"}, timeout=60)
+                return r.headers.get("x-sglb-worker"), r.json()
+
+        with ThreadPoolExecutor(8) as ex:
+            res = list(ex.map(call, range(len(prompts))))
+        assert [r[1]["output_ids"] for r in res] == want
+        assert all(r[1]["meta_info"]["id"] == f"user-{i}" for i, r in enumerate(res)), "the worker prefix must not leak into request ids"
+        assert {r[0] for r in res} == {"0", "1"}, "both workers must have answered"
+        # streaming through whichever worker takes the connection
+        r = requests.post(f"http://127.0.0.1:{port}/generate", json={"text": "stream me", "sampling_params": sp, "stream": True}, stream=True, timeout=60)
+        chunks = [json.loads(l[6:]) for l in r.iter_lines(decode_unicode=True) if l and l.startswith("data: {")]
+        assert chunks and chunks[-1]["meta_info"]["completion_tokens"] == 6
+        info = requests.get(f"http://127.0.0.1:{port}/get_server_info", timeout=10).json()
+        assert info["internal_states"][0]["num_generated_tokens"] >= 24 * 6
+        p.send_signal(signal.SIGTERM)
+        p.wait(timeout=40)
+    finally:
+        if p.poll() is None:
+            p.kill()
+        for k in _children_of(p.pid):
+            try:
+                os.kill(k, signal.SIGKILL)
+            except OSError:
+                pass
