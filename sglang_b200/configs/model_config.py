@@ -309,7 +309,7 @@ _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_loca
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
                "activation_function": "hidden_act", "layer_norm_epsilon": "rms_norm_eps", "layer_norm_eps": "rms_norm_eps",
                "norm_epsilon": "rms_norm_eps", "ffn_dim": "intermediate_size", "rotary_pct": "partial_rotary_factor",
-               "use_qkv_bias": "attention_bias", "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta", "experts_per_token": "num_experts_per_tok"}
+               "use_qkv_bias": "attention_bias", "qk_layernorm": "qk_norm", "use_parallel_residual": "parallel_residual", "rotary_emb_base": "rope_theta", "experts_per_token": "num_experts_per_tok"}
 # per-architecture defaults for fields HF configs leave implicit
 _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
                   "OPTForCausalLM": dict(pos_emb="learned", pos_offset=2, tie_word_embeddings=True, hidden_act="relu"),
@@ -318,6 +318,9 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "PhiForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", partial_rotary_factor=0.5),
                   "GPTJForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", rope_is_neox=False),
                   "GPTBigCodeForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_pytorch_tanh"),
+                  "CodeGenForCausalLM": dict(parallel_residual=True, norm_type="shared_layernorm", hidden_act="gelu_new", rope_is_neox=False),
+                  "GPTNeoForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
+                  "PersimmonForCausalLM": dict(hidden_act="relu2", partial_rotary_factor=0.5),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2ForSequenceClassification": dict(attention_bias=True),
                   "Qwen2Model": dict(attention_bias=True), "Qwen3ForSequenceClassification": dict(qk_norm=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True), "Qwen2_5_VLForConditionalGeneration": dict(attention_bias=True),
@@ -548,7 +551,14 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["attention_bias"] = kw["attention_out_bias"] = kw["mlp_bias"] = bool(text["use_bias"])
         if arch in ("NemotronForCausalLM",) and text.get("norm_eps") is not None:
             kw["rms_norm_eps"] = text["norm_eps"]
-        if arch == "GPTJForCausalLM" and text.get("rotary_dim"):
+        if arch == "GPTNeoForCausalLM":              # num_layers / num_heads / window_size / attention_layers; MLP width defaults to 4 x hidden
+            kw["num_hidden_layers"], kw["num_attention_heads"] = text["num_layers"], text["num_heads"]
+            kw["num_key_value_heads"] = text["num_heads"]
+            kw["intermediate_size"] = text.get("intermediate_size") or 4 * text["hidden_size"]
+            kw["sliding_window"] = text.get("window_size", 256)
+            al = text.get("attention_layers") or [t for types, n in text.get("attention_types", [[["global", "local"], text["num_layers"] // 2]]) for _ in range(n) for t in types]
+            kw["layer_types"] = ["sliding_attention" if t == "local" else "full_attention" for t in al]
+        if arch in ("GPTJForCausalLM", "CodeGenForCausalLM") and text.get("rotary_dim"):
             kw["partial_rotary_factor"] = text["rotary_dim"] / (kw["hidden_size"] // kw["num_attention_heads"])
         if arch == "GPTBigCodeForCausalLM":
             kw["num_key_value_heads"] = 1 if text.get("multi_query", True) else kw["num_attention_heads"]

@@ -29,7 +29,7 @@ from .llama import _DT, _load_stacked_bias
 
 _ACT = {"gelu": lambda x: torch.nn.functional.gelu(x), "gelu_new": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),
         "gelu_pytorch_tanh": lambda x: torch.nn.functional.gelu(x, approximate="tanh"), "gelu_fast": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),
-        "relu": torch.relu, "silu": torch.nn.functional.silu}
+        "relu": torch.relu, "silu": torch.nn.functional.silu, "relu2": lambda x: torch.relu(x).square()}
 
 
 class LayerNorm(nn.Module):
@@ -65,9 +65,17 @@ class ClassicAttention(nn.Module):
         self.q_size, self.kv_size = self.qkv_proj.q_size, self.qkv_proj.kv_size
         window = cfg.sliding_window if (cfg.sliding_window and cfg.sliding_window > 0) else -1
         self.attn = RadixAttention(self.qkv_proj.num_heads, cfg.head_dim, self.qkv_proj.num_kv_heads, layer_id, rope=rope, sliding_window=window)
+        self.q_layernorm = self.k_layernorm = None
+        if cfg.qk_norm:          # Persimmon: LayerNorm (weight + bias) over each head's q / k before the rotary embedding
+            self.q_layernorm = LayerNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
+            self.k_layernorm = LayerNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
 
     def forward(self, x, fb: ForwardBatch):
         q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        if self.q_layernorm is not None:
+            T, D = q.shape[0], self.attn.head_dim
+            q = self.q_layernorm(q.reshape(T * self.attn.num_heads, D)).view(T, self.q_size)
+            k = self.k_layernorm(k.reshape(T * self.attn.num_kv_heads, D)).view(T, self.kv_size)
         return self.o_proj(self.attn(q.contiguous(), k.contiguous(), v.contiguous(), fb))
 
 
@@ -286,6 +294,16 @@ class GPTNeoXForCausalLM(ClassicForCausalLM):
         yield name, w
 
 
+class PersimmonForCausalLM(GPTNeoXForCausalLM):
+    """Adept Persimmon / Fuyu text tower: NeoX-style fused ``query_key_value`` ([heads, 3, head_dim]), per-head q/k LayerNorm, partial rotary,
+    squared-ReLU MLP, sequential residual (reference models/persimmon.py)"""
+
+    def remap(self, name, w):
+        name = name.replace(".self_attn.query_key_value.", ".attention.query_key_value.").replace(".self_attn.dense.", ".attention.dense.")
+        name = name.replace("model.final_layernorm.", "model.norm.")
+        yield from super().remap(name, w)
+
+
 class PhiForCausalLM(ClassicForCausalLM):
     """phi-1 / phi-2: parallel block with one shared LayerNorm, partial rotary, biased lm_head"""
 
@@ -304,6 +322,67 @@ class GPTJForCausalLM(ClassicForCausalLM):
         if name.endswith((".self_attn.bias", ".masked_bias")):
             return
         yield name, w
+
+
+class CodeGenForCausalLM(GPTJForCausalLM):
+    """Salesforce CodeGen: the GPT-J block with a fused ``qkv_proj`` whose rows are grouped in ``mp_num = 4`` model-parallel blocks of
+    [q | v | k] (that order) — reference models/codegen-style checkpoints"""
+
+    def remap(self, name, w):
+        if ".attn.qkv_proj." in name:
+            mp, H = 4, self.cfg.hidden_size
+            w4 = w.view(mp, 3, H // mp, *w.shape[1:])                # [block][q, v, k][rows]
+            base = name.replace("transformer.h.", "model.layers.").replace(".attn.qkv_proj.", ".self_attn.{}.")
+            for j, nm in ((0, "q_proj"), (2, "k_proj"), (1, "v_proj")):
+                yield base.format(nm), w4[:, j].reshape(H, *w.shape[1:])
+            return
+        if name.endswith((".attn.causal_mask", ".attn.bias", ".masked_bias")):
+            return
+        yield from super().remap(name, w)
+
+
+class GPTNeoForCausalLM(ClassicForCausalLM):
+    """EleutherAI GPT-Neo: GPT-2 skeleton with nn.Linear weights, alternating global / local (window 256) attention and NO 1/sqrt(d) scaling
+    of the attention scores"""
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        lt = cfg.layer_types or []
+        for i, layer in enumerate(self.model.layers):
+            a = layer.self_attn.attn
+            a.scale = 1.0
+            a.window = cfg.sliding_window if (i < len(lt) and lt[i] == "sliding_attention" and cfg.sliding_window) else -1
+
+    def remap(self, name, w):
+        if name.startswith("model."):
+            yield name, w
+            return
+        name = name[len("transformer."):] if name.startswith("transformer.") else name
+        if name == "wte.weight":
+            yield "model.embed_tokens.weight", w
+        elif name == "wpe.weight":
+            yield "model.embed_positions.weight", w
+        elif name.startswith("ln_f."):
+            yield "model.norm." + name[5:], w
+        elif name.startswith("h."):
+            _, lid, rest = name.split(".", 2)
+            p, leaf = f"model.layers.{lid}.", rest.rsplit(".", 1)[1]
+            if rest.startswith("ln_1."):
+                yield p + "input_layernorm." + leaf, w
+            elif rest.startswith("ln_2."):
+                yield p + "post_attention_layernorm." + leaf, w
+            elif rest.startswith("attn.attention."):
+                sub = rest.split(".")[2]
+                if sub in ("q_proj", "k_proj", "v_proj"):
+                    yield p + f"self_attn.{sub}." + leaf, w
+                elif sub == "out_proj":
+                    yield p + "self_attn.o_proj." + leaf, w
+            elif rest.startswith("mlp.c_fc."):
+                yield p + "mlp.fc1." + leaf, w
+            elif rest.startswith("mlp.c_proj."):
+                yield p + "mlp.fc2." + leaf, w
+        elif name == "lm_head.weight":
+            yield name, w
 
 
 class GPTBigCodeForCausalLM(ClassicForCausalLM):

@@ -56,7 +56,7 @@ def _register_builtins() -> None:
     from . import classic as _cl
 
     for name in ("GPT2LMHeadModel", "OPTForCausalLM", "GPTNeoXForCausalLM", "Starcoder2ForCausalLM", "PhiForCausalLM", "GPTJForCausalLM",
-                 "GPTBigCodeForCausalLM"):
+                 "GPTBigCodeForCausalLM", "CodeGenForCausalLM", "GPTNeoForCausalLM", "PersimmonForCausalLM"):
         register_model(name, getattr(_cl, name))
     from . import llama4 as _l4
 

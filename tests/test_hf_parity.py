@@ -126,6 +126,11 @@ CASES = {
     "qwen3-moe": ("Qwen3MoeConfig", "Qwen3MoeForCausalLM", dict(BASE, head_dim=16, num_experts=4, num_experts_per_tok=2, moe_intermediate_size=32,
                                                                 decoder_sparse_step=1, mlp_only_layers=[], norm_topk_prob=True)),
     "gpt2": ("GPT2Config", "GPT2LMHeadModel", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512)),
+    "gpt-neo": ("GPTNeoConfig", "GPTNeoForCausalLM", dict(hidden_size=64, num_layers=4, num_heads=4, vocab_size=512, max_position_embeddings=512,
+                                                        window_size=8, attention_types=[[["global", "local"], 2]])),
+    "persimmon": ("PersimmonConfig", "PersimmonForCausalLM", dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                                                  vocab_size=512, max_position_embeddings=512, qk_layernorm=True, partial_rotary_factor=0.5)),
+    "codegen": ("CodeGenConfig", "CodeGenForCausalLM", dict(n_embd=64, n_layer=2, n_head=4, vocab_size=512, n_positions=512, rotary_dim=8)),
     "opt": ("OPTConfig", "OPTForCausalLM", dict(hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=512,
                                                 max_position_embeddings=512, word_embed_proj_dim=64)),
     "gpt-neox": ("GPTNeoXConfig", "GPTNeoXForCausalLM", dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
