@@ -87,6 +87,8 @@ class ModelConfig:
     linear_attn: Optional[Dict[str, Any]] = None
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
     mamba: Optional[Dict[str, Any]] = None
+    # architectures without a native class: {"path", "arch"} -> models/transformers_fallback.py runs the Hugging Face module tree
+    hf_fallback: Optional[Dict[str, Any]] = None
     num_labels: int = 1                              # classification / reward heads
     encoder: Optional[Dict[str, Any]] = None         # encoder-only models (BERT / RoBERTa): type_vocab_size, sep_token_id
     # speech encoder of encoder-decoder ASR models (models/whisper.py)
@@ -329,6 +331,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
                   "OlmoeForCausalLM": dict(norm_topk_prob=False),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
+                  "Ernie4_5_MoeForCausalLM": dict(rope_is_neox=False, scoring_func="softmax", topk_method="noaux_tc", norm_topk_prob=True),
                   "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"), "ApertusForCausalLM": dict(mlp_gated=False, qk_norm=True),
                   "GlmForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
                   "Glm4ForCausalLM": dict(rope_is_neox=False, partial_rotary_factor=0.5, attention_bias=True),
@@ -339,8 +342,32 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Qwen3ForCausalLM": dict(qk_norm=True), "Qwen3MoeForCausalLM": dict(qk_norm=True)}
 
 
+def _has_native_class(arch: str) -> bool:
+    from ..models.registry import supported_architectures
+
+    return arch in supported_architectures()
+
+
+def _transformers_fallback_config(model_path: str, arch: str, kw: Dict[str, Any]) -> Dict[str, Any]:
+    """geometry of an architecture served through ``models/transformers_fallback.py``: read through ``AutoConfig`` so that every family's
+    own key names (``n_embd``, ``num_heads`` ...) resolve to the standard attributes"""
+    import transformers as tf
+
+    t = tf.AutoConfig.from_pretrained(model_path).get_text_config()
+    nh = t.num_attention_heads
+    out = {k: v for k, v in kw.items() if k in ("rope_theta", "rope_scaling", "tie_word_embeddings", "sliding_window", "final_logit_softcapping",
+                                               "bos_token_id", "eos_token_id", "pad_token_id", "dtype", "name", "rms_norm_eps")}
+    out.update(architecture="TransformersForCausalLM", hf_fallback={"path": model_path, "arch": arch}, hidden_size=t.hidden_size,
+               num_hidden_layers=t.num_hidden_layers, num_attention_heads=nh, num_key_value_heads=getattr(t, "num_key_value_heads", None) or nh,
+               head_dim=getattr(t, "head_dim", None) or t.hidden_size // nh, vocab_size=t.vocab_size,
+               intermediate_size=getattr(t, "intermediate_size", None) or 4 * t.hidden_size,
+               max_position_embeddings=getattr(t, "max_position_embeddings", 8192))
+    return out
+
+
 def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = None, context_length: Optional[int] = None) -> ModelConfig:
     overrides = dict(overrides or {})
+    impl = overrides.pop("model_impl", "auto")
     if model_path.startswith("dummy:"):
         name = model_path.split(":", 1)[1]
         if name not in PRESETS:
@@ -547,8 +574,21 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))
         kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype") or hf.get("dtype") or text.get("dtype") or "bfloat16", "bfloat16")
-        if arch == "Ernie4_5ForCausalLM" and text.get("use_bias") is not None:
+        if arch in ("Ernie4_5ForCausalLM", "Ernie4_5_MoeForCausalLM") and text.get("use_bias") is not None:
             kw["attention_bias"] = kw["attention_out_bias"] = kw["mlp_bias"] = bool(text["use_bias"])
+        if arch == "Ernie4_5_MoeForCausalLM":
+            E = text.get("moe_num_experts") or 0
+            kw["num_local_experts"] = max(E) if isinstance(E, (list, tuple)) else E
+            kw["num_experts_per_tok"] = text.get("moe_k", 2)
+            kw["n_shared_experts"] = text.get("moe_num_shared_experts", 0)
+            mi = text.get("moe_intermediate_size")
+            kw["moe_intermediate_size"] = mi[0] if isinstance(mi, (list, tuple)) else mi
+            L = text["num_hidden_layers"]
+            lo, every = text.get("moe_layer_start_index", 0), max(1, text.get("moe_layer_interval", 1))
+            hi = text.get("moe_layer_end_index", -1)
+            hi = L - 1 if hi is None or hi < 0 else hi
+            lo = min(lo) if isinstance(lo, (list, tuple)) else lo
+            kw["mlp_only_layers"] = [i for i in range(L) if not (lo <= i <= hi and (i + 1) % every == 0)]
         if arch in ("NemotronForCausalLM",) and text.get("norm_eps") is not None:
             kw["rms_norm_eps"] = text["norm_eps"]
         if arch == "GPTNeoForCausalLM":              # num_layers / num_heads / window_size / attention_layers; MLP width defaults to 4 x hidden
@@ -567,6 +607,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         if text.get("hidden_activation"):          # Gemma-2 spells it differently
             kw["hidden_act"] = text["hidden_activation"]
         kw["name"] = os.path.basename(model_path.rstrip("/"))
+        if impl == "transformers" or (impl == "auto" and not model_path.endswith(".gguf") and not _has_native_class(kw["architecture"])):
+            kw = _transformers_fallback_config(model_path, arch, kw)
         kw.update(overrides)
     cfg = ModelConfig(**kw)
     if context_length is not None:

@@ -394,7 +394,8 @@ class _DsMoeLayer(LlamaDecoderLayer):
 
     def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
         super().__init__(cfg, layer_id, dtype, quant, rope, prefix, LlamaMLP)
-        if cfg.num_local_experts > 0 and _gid(prefix) >= (cfg.first_k_dense_replace or 0):
+        gid = _gid(prefix)
+        if cfg.num_local_experts > 0 and gid >= (cfg.first_k_dense_replace or 0) and gid not in (cfg.mlp_only_layers or []):
             self.mlp = _ds().DeepseekV2MoE(cfg, layer_id, dtype, quant, prefix + ".mlp")
         if cfg.use_qk_norm:
             sa = self.self_attn
@@ -414,3 +415,21 @@ class Glm4MoeForCausalLM(LlamaForCausalLM):
 
 class Dots1ForCausalLM(Glm4MoeForCausalLM):
     pass
+
+
+class Ernie4_5_MoeForCausalLM(Glm4MoeForCausalLM):
+    """ERNIE-4.5 MoE (reference ``python/sglang/srt/models/ernie4.py``): GPT-J style RoPE, soft-max router whose top-k choice adds the
+    ``moe_statics`` correction bias while the combine weights stay the unbiased probabilities (renormalised), shared experts of width
+    ``moe_intermediate_size * moe_num_shared_experts``; the sparse layers are ``start <= i <= end`` with ``(i + 1) % interval == 0`` (the config
+    loader turns that into ``mlp_only_layers``)."""
+
+    def load_weights(self, weights):
+        def rename():
+            for name, w in weights:
+                if name.endswith("mlp.moe_statics.e_score_correction_bias"):      # [1, E] under the block, [E] under the gate here
+                    yield name.replace("mlp.moe_statics.", "mlp.gate."), w.reshape(-1)
+                elif ".mtp_" in name or name.startswith("model.mtp_"):             # multi-token-prediction heads of the release checkpoints
+                    continue
+                else:
+                    yield name, w
+        return super().load_weights(rename())

@@ -74,7 +74,7 @@ def _register_builtins() -> None:
     from . import families2 as _f2
 
     for name in ("GlmForCausalLM", "Glm4ForCausalLM", "Gemma3ForCausalLM", "CohereForCausalLM", "OlmoeForCausalLM", "NemotronForCausalLM",
-                 "Glm4MoeForCausalLM", "Dots1ForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM", "ApertusForCausalLM"):
+                 "Glm4MoeForCausalLM", "Dots1ForCausalLM", "Ernie4_5_MoeForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM", "ApertusForCausalLM"):
         register_model(name, getattr(_f2, name))
     register_model("Gemma3ForConditionalGeneration", _f2.Gemma3ForCausalLM)      # text tower of the multimodal checkpoint
     from . import qwen2_vl as _qv
@@ -107,6 +107,10 @@ def _register_builtins() -> None:
     register_model("MistralForSequenceClassification", _emb.LlamaForSequenceClassification)
     register_model("MistralModel", _emb.LlamaEmbeddingModel)
     register_model("Qwen2Model", type("Qwen2EmbeddingModel", (_emb.LlamaEmbeddingModel,), {}))
+    from . import transformers_fallback as _tff
+
+    register_model("TransformersForCausalLM", _tff.TransformersForCausalLM)
+    register_model("TransformersMoEForCausalLM", _tff.TransformersForCausalLM)
     from . import bert as _bert
 
     for name in ("BertModel", "XLMRobertaModel", "BertForSequenceClassification", "XLMRobertaForSequenceClassification"):

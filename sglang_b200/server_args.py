@@ -24,6 +24,7 @@ class ServerArgs:
     model_path: str = "dummy:tiny-llama"
     tokenizer_path: Optional[str] = None
     load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf|remote_instance
+    model_impl: str = "auto"   # auto: native class, else the Transformers fallback | sglang: native only | transformers: always the fallback
     remote_instance_weight_loader_seed_instance_ip: Optional[str] = None
     remote_instance_weight_loader_seed_instance_service_port: Optional[int] = None
     remote_instance_weight_loader_send_weights_group_port: int = 31500
@@ -183,6 +184,14 @@ class ServerArgs:
                 self.device = "cpu"
         if self.load_format == "auto":
             self.load_format = "dummy" if self.model_path.startswith("dummy:") else ("gguf" if self.model_path.endswith(".gguf") else "safetensors")
+        if self.model_impl not in ("auto", "sglang", "transformers"):
+            raise ValueError("--model-impl must be auto, sglang or transformers")
+        if self.model_impl != "auto":          # travels with the other config overrides to every process that reads the model config
+            import json as _json
+
+            ov = _json.loads(self.json_model_override_args or "{}")
+            ov["model_impl"] = self.model_impl
+            self.json_model_override_args = _json.dumps(ov)
         if self.page_size < 1 or (self.page_size & (self.page_size - 1)):
             raise ValueError("--page-size must be a power of two")
         if self.chunked_prefill_size is None:

@@ -142,6 +142,8 @@ CASES = {
                                                                     qk_rope_head_dim=8, v_head_dim=16, n_routed_experts=8, num_experts_per_tok=2,
                                                                     moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1, n_group=2,
                                                                     topk_group=1, routed_scaling_factor=1.5, norm_topk_prob=True)),
+    "ernie4.5-moe": ("Ernie4_5_MoeConfig", "Ernie4_5_MoeForCausalLM", dict(BASE, moe_num_experts=4, moe_k=2, moe_intermediate_size=32,
+                                                                        moe_num_shared_experts=1, moe_layer_start_index=1, moe_layer_interval=1)),
     "mamba2": ("Mamba2Config", "Mamba2ForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, num_heads=8, head_dim=16, state_size=16,
                                                          n_groups=2, expand=2, conv_kernel=4, chunk_size=8, tie_word_embeddings=True)),
 }
