@@ -329,7 +329,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
-                  "OlmoeForCausalLM": dict(norm_topk_prob=False),
+                  "OlmoeForCausalLM": dict(norm_topk_prob=False), "MiniMaxM2ForCausalLM": dict(norm_topk_prob=True),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
                   "Ernie4_5_MoeForCausalLM": dict(rope_is_neox=False, scoring_func="softmax", topk_method="noaux_tc", norm_topk_prob=True),
                   "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"), "ApertusForCausalLM": dict(mlp_gated=False, qk_norm=True),
@@ -424,7 +424,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["layer_types"] = text.get("layer_types") or ["chunked_attention" if r else "full_attention" for r in nr]
             kw["rope_is_neox"] = False
             kw["architecture"] = "Llama4ForCausalLM"
-        if arch == "Qwen3NextForCausalLM":
+        if arch in ("Qwen3NextForCausalLM", "Qwen3_5ForCausalLM", "Qwen3_5MoeForCausalLM", "Qwen3_5ForConditionalGeneration",
+                    "Qwen3_5MoeForConditionalGeneration"):
             kw["linear_attn"] = {"num_k_heads": text.get("linear_num_key_heads", 16), "num_v_heads": text.get("linear_num_value_heads", 32),
                                  "k_head_dim": text.get("linear_key_head_dim", 128), "v_head_dim": text.get("linear_value_head_dim", 128),
                                  "conv_kernel": text.get("linear_conv_kernel_dim", 4)}
@@ -598,8 +599,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["sliding_window"] = text.get("window_size", 256)
             al = text.get("attention_layers") or [t for types, n in text.get("attention_types", [[["global", "local"], text["num_layers"] // 2]]) for _ in range(n) for t in types]
             kw["layer_types"] = ["sliding_attention" if t == "local" else "full_attention" for t in al]
-        if arch in ("GPTJForCausalLM", "CodeGenForCausalLM") and text.get("rotary_dim"):
-            kw["partial_rotary_factor"] = text["rotary_dim"] / (kw["hidden_size"] // kw["num_attention_heads"])
+        if arch in ("GPTJForCausalLM", "CodeGenForCausalLM", "MiniMaxM2ForCausalLM") and text.get("rotary_dim"):
+            kw["partial_rotary_factor"] = text["rotary_dim"] / (kw.get("head_dim") or kw["hidden_size"] // kw["num_attention_heads"])
         if arch == "GPTBigCodeForCausalLM":
             kw["num_key_value_heads"] = 1 if text.get("multi_query", True) else kw["num_attention_heads"]
         if text.get("use_sliding_window") is False:       # Qwen2 / SmolLM3 ship a window size next to a switch that disables it

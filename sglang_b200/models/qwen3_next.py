@@ -339,3 +339,46 @@ class Qwen3NextForCausalLM(NemotronHForCausalLM):
                 params[target].data.copy_(w)
             loaded.append(name)
         return loaded
+
+
+class Qwen3_5ForCausalLM(Qwen3NextForCausalLM):
+    """Qwen3.5 text decoder (reference ``python/sglang/srt/models/qwen3_5_text.py``): the Qwen3-Next hybrid with a dense (or MoE) MLP.  Its
+    checkpoints store the DeltaNet input projections separately and flat (``in_proj_qkv`` = [q | k | v], ``in_proj_z``, ``in_proj_b``,
+    ``in_proj_a``); they are regrouped per key head into this module's ``in_proj_qkvz`` / ``in_proj_ba`` layout while loading, so the forward
+    path (and its TP sharding by key head) is shared.  Text positions make the interleaved M-RoPE identical to plain rotary embedding; the
+    multimodal checkpoints' ``model.language_model.*`` names load as the text tower."""
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        la = self.cfg.linear_attn
+        Hk, Hv, Dk, Dv = la["num_k_heads"], la["num_v_heads"], la["k_head_dim"], la["v_head_dim"]
+        r = Hv // Hk
+        pend: dict = {}
+
+        def regroup():
+            for name, w in weights:
+                if name.startswith("model.language_model."):
+                    name = "model." + name[len("model.language_model."):]
+                elif name.startswith(("model.visual.", "visual.", "mtp.")):
+                    continue
+                leaf = name.rsplit(".linear_attn.", 1)[-1] if ".linear_attn." in name else ""
+                if leaf not in ("in_proj_qkv.weight", "in_proj_z.weight", "in_proj_b.weight", "in_proj_a.weight"):
+                    yield name, w
+                    continue
+                pre = name[: name.index(".linear_attn.") + len(".linear_attn.")]
+                d = pend.setdefault(pre, {})
+                d[leaf.split(".")[0]] = w
+                if "in_proj_qkv" in d and "in_proj_z" in d:
+                    qkv, z = d.pop("in_proj_qkv"), d.pop("in_proj_z")
+                    Hin = qkv.shape[1]
+                    q, k, v = qkv[: Hk * Dk].view(Hk, Dk, Hin), qkv[Hk * Dk: 2 * Hk * Dk].view(Hk, Dk, Hin), qkv[2 * Hk * Dk:].view(Hk, r * Dv, Hin)
+                    yield pre + "in_proj_qkvz.weight", torch.cat([q, k, v, z.view(Hk, r * Dv, Hin)], 1).reshape(-1, Hin)
+                if "in_proj_b" in d and "in_proj_a" in d:
+                    b, a = d.pop("in_proj_b"), d.pop("in_proj_a")
+                    Hin = b.shape[1]
+                    yield pre + "in_proj_ba.weight", torch.cat([b.view(Hk, r, Hin), a.view(Hk, r, Hin)], 1).reshape(-1, Hin)
+
+        return super().load_weights(regroup())
+
+
+class Qwen3_5MoeForCausalLM(Qwen3_5ForCausalLM):
+    pass

@@ -46,6 +46,7 @@ def _register_builtins() -> None:
     for name in ("LlamaForCausalLM", "MistralForCausalLM", "Qwen2ForCausalLM", "Qwen3ForCausalLM", "GemmaForCausalLM"):
         register_model(name, getattr(llama, name))
     register_model("MixtralForCausalLM", mixtral.MixtralForCausalLM)
+    register_model("MiniMaxM2ForCausalLM", mixtral.MiniMaxM2ForCausalLM)
     register_model("LlavaForConditionalGeneration", llava.LlavaForConditionalGeneration)
     register_model("LlavaLlamaForCausalLM", llava.LlavaForConditionalGeneration)
     from . import families as _fam
@@ -65,6 +66,10 @@ def _register_builtins() -> None:
     from . import qwen3_next as _qn
 
     register_model("Qwen3NextForCausalLM", _qn.Qwen3NextForCausalLM)
+    register_model("Qwen3_5ForCausalLM", _qn.Qwen3_5ForCausalLM)
+    register_model("Qwen3_5MoeForCausalLM", _qn.Qwen3_5MoeForCausalLM)
+    register_model("Qwen3_5ForConditionalGeneration", _qn.Qwen3_5ForCausalLM)            # text tower of the multimodal checkpoints
+    register_model("Qwen3_5MoeForConditionalGeneration", _qn.Qwen3_5MoeForCausalLM)
     from . import internvl as _iv
 
     register_model("InternVLForConditionalGeneration", _iv.InternVLForConditionalGeneration)

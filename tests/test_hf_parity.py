@@ -73,6 +73,14 @@ CASES = {
                                                                  moe_intermediate_size=32, shared_expert_intermediate_size=48, decoder_sparse_step=1,
                                                                  mlp_only_layers=[], norm_topk_prob=True,
                                                                  layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"])),
+    "qwen3.5": ("Qwen3_5TextConfig", "Qwen3_5ForCausalLM", dict(BASE, num_hidden_layers=4, head_dim=16, linear_num_key_heads=2, linear_num_value_heads=4,
+                                                              linear_key_head_dim=8, linear_value_head_dim=8, linear_conv_kernel_dim=4,
+                                                              layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"])),
+    "qwen3.5-moe": ("Qwen3_5MoeTextConfig", "Qwen3_5MoeForCausalLM", dict(BASE, num_hidden_layers=4, head_dim=16, linear_num_key_heads=2,
+                                                                         linear_num_value_heads=4, linear_key_head_dim=8, linear_value_head_dim=8,
+                                                                         linear_conv_kernel_dim=4, num_experts=4, num_experts_per_tok=2,
+                                                                         moe_intermediate_size=32, shared_expert_intermediate_size=48,
+                                                                         layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"])),
     "granite4-hybrid": ("GraniteMoeHybridConfig", "GraniteMoeHybridForCausalLM", dict(
         BASE, num_hidden_layers=3, layer_types=["mamba", "attention", "mamba"], mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=16,
         mamba_d_conv=4, mamba_expand=2, mamba_chunk_size=8, num_local_experts=4, num_experts_per_tok=2, shared_intermediate_size=48,
@@ -142,6 +150,7 @@ CASES = {
                                                                     qk_rope_head_dim=8, v_head_dim=16, n_routed_experts=8, num_experts_per_tok=2,
                                                                     moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1, n_group=2,
                                                                     topk_group=1, routed_scaling_factor=1.5, norm_topk_prob=True)),
+    "minimax-m2": ("MiniMaxM2Config", "MiniMaxM2ForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2, head_dim=16)),
     "ernie4.5-moe": ("Ernie4_5_MoeConfig", "Ernie4_5_MoeForCausalLM", dict(BASE, moe_num_experts=4, moe_k=2, moe_intermediate_size=32,
                                                                         moe_num_shared_experts=1, moe_layer_start_index=1, moe_layer_interval=1)),
     "mamba2": ("Mamba2Config", "Mamba2ForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, num_heads=8, head_dim=16, state_size=16,

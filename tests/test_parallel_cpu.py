@@ -367,3 +367,48 @@ def test_lora_tp2_matches_single():
 def test_vocab_parallel_greedy_matches_gathered_argmax():
     """TP decode: per-shard argmax + 8-byte exchange + merge == argmax over the all-gathered logits (layers/linear.py vocab_parallel_greedy)"""
     _run({"model_path": "dummy:tiny-llama", "tp_size": 2, "page_size": 4}, 2, extra_env={"SGLB_TEST_GREEDY_SHARD": "1"})
+
+
+def test_minimax_m2_full_width_qk_norm_tp(tmp_path):
+    """q/k RMSNorm over all heads of the layer: the mean square crosses TP ranks (one [T, 1] all-reduce); tp=4 > 2 KV heads exercises the
+    replicated-KV discount"""
+    import torch
+    import transformers as tf
+
+    torch.manual_seed(0)
+    cfg = tf.MiniMaxM2Config(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                             max_position_embeddings=512, head_dim=16, num_local_experts=4, num_experts_per_tok=2)
+    hf = tf.MiniMaxM2ForCausalLM(cfg).float()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.08)
+            elif "norm" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+    d = str(tmp_path / "mm2")
+    hf.save_pretrained(d, safe_serialization=True)
+    kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
+    ref = _run(kw, 1, LP)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), ref, atol=5e-3)
+    _check(_run({**kw, "tp_size": 4}, 4, LP), ref, atol=5e-3)
+
+
+def test_qwen3_5_tp2(tmp_path):
+    """Qwen3.5 checkpoints (flat in_proj_qkv / z / b / a) regrouped per key head at load, then sharded like Qwen3-Next"""
+    import torch
+    import transformers as tf
+
+    torch.manual_seed(0)
+    cfg = tf.Qwen3_5TextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                               max_position_embeddings=512, head_dim=16, linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=8,
+                               linear_value_head_dim=8, linear_conv_kernel_dim=4,
+                               layer_types=["linear_attention", "linear_attention", "linear_attention", "full_attention"], tie_word_embeddings=False)
+    hf = tf.Qwen3_5ForCausalLM(cfg).float()
+    with torch.no_grad():
+        for p in hf.parameters():
+            if p.dim() > 1:
+                p.normal_(0, 0.08)
+    d = str(tmp_path / "q35")
+    hf.save_pretrained(d, safe_serialization=True)
+    kw = dict(model_path=d, page_size=4, chunked_prefill_size=16, skip_tokenizer_init=True)
+    _check(_run({**kw, "tp_size": 2}, 2, LP), _run(kw, 1, LP), atol=5e-3)

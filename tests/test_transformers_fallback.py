@@ -10,7 +10,7 @@ import sglang_b200 as sgl
 BASE = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
             max_position_embeddings=512)
 CASES = {
-    "minimax-m2": ("MiniMaxM2Config", "MiniMaxM2ForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2, head_dim=16), "auto"),
+    "solar-open": ("SolarOpenConfig", "SolarOpenForCausalLM", dict(BASE), "auto"),
     "phimoe": ("PhimoeConfig", "PhimoeForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2), "auto"),
     "hunyuan-dense": ("HunYuanDenseV1Config", "HunYuanDenseV1ForCausalLM", dict(BASE, head_dim=16), "auto"),
     "llama-forced": ("LlamaConfig", "LlamaForCausalLM", dict(BASE), "transformers"),
