@@ -324,7 +324,8 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "GPTNeoForCausalLM": dict(pos_emb="learned", tie_word_embeddings=True, hidden_act="gelu_new"),
                   "PersimmonForCausalLM": dict(hidden_act="relu2", partial_rotary_factor=0.5),
                   "Qwen2ForCausalLM": dict(attention_bias=True), "Qwen2ForSequenceClassification": dict(attention_bias=True),
-                  "Qwen2Model": dict(attention_bias=True), "Qwen3ForSequenceClassification": dict(qk_norm=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
+                  "Qwen2Model": dict(attention_bias=True), "Qwen3ForSequenceClassification": dict(qk_norm=True),
+                  "Qwen2ForRewardModel": dict(attention_bias=True), "Qwen3ForRewardModel": dict(qk_norm=True), "Qwen3Model": dict(qk_norm=True), "Qwen2MoeForCausalLM": dict(attention_bias=True),
                   "Qwen2VLForConditionalGeneration": dict(attention_bias=True), "Qwen2_5_VLForConditionalGeneration": dict(attention_bias=True),
                   "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
@@ -562,6 +563,16 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "window_size": vc.get("window_size", 112), "fullatt_block_indexes": vc.get("fullatt_block_indexes", [7, 15, 23, 31])}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
+        if arch in ("Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration"):
+            vc = hf["vision_config"]
+            kw["vision"] = {"variant": "qwen3", "embed_dim": vc.get("hidden_size", 1152), "depth": vc.get("depth", 27), "num_heads": vc.get("num_heads", 16),
+                            "hidden_size": vc.get("out_hidden_size", kw["hidden_size"]), "intermediate_size": vc.get("intermediate_size", 4304),
+                            "patch_size": vc.get("patch_size", 16), "spatial_merge_size": vc.get("spatial_merge_size", 2),
+                            "temporal_patch_size": vc.get("temporal_patch_size", 2), "num_position_embeddings": vc.get("num_position_embeddings", 2304),
+                            "deepstack_visual_indexes": vc.get("deepstack_visual_indexes", [8, 16, 24]), "image_mean": [0.5, 0.5, 0.5],
+                            "image_std": [0.5, 0.5, 0.5], "min_pixels": 64 * 64, "max_pixels": 16 * 16 * 4 * 4096}
+            kw["image_token_id"] = hf.get("image_token_id", 151655)
+            kw["qk_norm"] = True
         if arch == "Qwen2VLForConditionalGeneration":
             vc = hf["vision_config"]
             kw["vision"] = {"embed_dim": vc.get("embed_dim", 1280), "depth": vc.get("depth", 32), "num_heads": vc.get("num_heads", 16),
@@ -570,7 +581,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration"):
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration",
+                                                 "Qwen3VLMoeForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))

@@ -207,11 +207,14 @@ class LlamaModel(nn.Module):
             h = sp.scatter(h)
         cap = fb.capture_aux
         aux = [] if cap is not None else None
+        hook = getattr(fb, "post_layer_hook", None)
         for i, layer in enumerate(self.layers):
             if cap is not None and (i + self.start_layer) in cap:       # EAGLE-3 auxiliary features: the residual stream entering this layer
                 h = h.resolve() if hasattr(h, "resolve") else h
                 aux.append(h if residual is None else h + residual)
             h, residual = layer(h, residual, fb)
+            if hook is not None:         # DeepStack (Qwen3-VL): visual features join the residual stream after the first few layers
+                h = hook(i + self.start_layer, h)
         if aux:
             fb.aux_hidden = torch.cat(aux, dim=-1)
         if not self.pp.is_last:

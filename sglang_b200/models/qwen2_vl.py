@@ -187,6 +187,96 @@ class Qwen25VisionTransformer(Qwen2VisionTransformer):
         return y[torch.argsort(oi)]
 
 
+class VisionBlock3(nn.Module):
+    """Qwen3-VL block: LayerNorm, biased qkv / proj, plain (non-gated) tanh-GELU MLP, full attention inside one image"""
+
+    def __init__(self, dim: int, heads: int, inter: int, dtype):
+        super().__init__()
+        self.heads = heads
+        self.norm1, self.norm2 = nn.LayerNorm(dim, eps=1e-6, dtype=dtype), nn.LayerNorm(dim, eps=1e-6, dtype=dtype)
+        self.qkv = nn.Linear(dim, 3 * dim, dtype=dtype)
+        self.proj = nn.Linear(dim, dim, dtype=dtype)
+        self.fc1 = nn.Linear(dim, inter, dtype=dtype)
+        self.fc2 = nn.Linear(inter, dim, dtype=dtype)
+
+    def forward(self, x, cos, sin, seg: List[int]):
+        N, D = x.shape
+        q, k, v = self.qkv(self.norm1(x)).view(N, 3, self.heads, D // self.heads).unbind(1)
+        q = (q.float() * cos[:, None] + _rot_half(q.float()) * sin[:, None]).to(x.dtype)
+        k = (k.float() * cos[:, None] + _rot_half(k.float()) * sin[:, None]).to(x.dtype)
+        outs, s = [], 0
+        for n in seg:
+            o = F.scaled_dot_product_attention(q[s:s + n].transpose(0, 1), k[s:s + n].transpose(0, 1), v[s:s + n].transpose(0, 1))
+            outs.append(o.transpose(0, 1).reshape(n, D))
+            s += n
+        x = x + self.proj(torch.cat(outs, 0))
+        return x + self.fc2(F.gelu(self.fc1(self.norm2(x)), approximate="tanh"))
+
+
+class _Merger3(nn.Module):
+    def __init__(self, dim: int, unit: int, out: int, postshuffle: bool, dtype):
+        super().__init__()
+        self.m, self.post = dim * unit, postshuffle
+        self.norm = nn.LayerNorm(self.m if postshuffle else dim, eps=1e-6, dtype=dtype)
+        self.fc1 = nn.Linear(self.m, self.m, dtype=dtype)
+        self.fc2 = nn.Linear(self.m, out, dtype=dtype)
+
+    def forward(self, x):
+        x = self.norm(x.view(-1, self.m) if self.post else x).view(-1, self.m)
+        return self.fc2(F.gelu(self.fc1(x)))
+
+
+class Qwen3VisionTransformer(Qwen2VisionTransformer):
+    """Qwen3-VL tower (reference ``python/sglang/srt/models/qwen3_vl.py``): biased patch embedding, a learned position grid that is bilinearly
+    resampled to each image's patch grid, 2-D rotary full attention, and DeepStack — the outputs of ``deepstack_visual_indexes`` blocks go
+    through their own mergers and are handed to the language model as extra feature columns (see ``Qwen3VLForConditionalGeneration``)."""
+
+    def __init__(self, v: Dict[str, Any], dtype):
+        nn.Module.__init__(self)
+        self.embed_dim, self.heads, self.patch, self.merge, self.tps = v["embed_dim"], v["num_heads"], v["patch_size"], v["spatial_merge_size"], \
+            v.get("temporal_patch_size", 2)
+        self.patch_embed = nn.Linear(3 * self.tps * self.patch * self.patch, self.embed_dim, bias=True, dtype=dtype)
+        self.pos_embed = nn.Embedding(v["num_position_embeddings"], self.embed_dim, dtype=dtype)
+        self.side = int(v["num_position_embeddings"] ** 0.5)
+        self.blocks = nn.ModuleList([VisionBlock3(self.embed_dim, self.heads, v["intermediate_size"], dtype) for _ in range(v["depth"])])
+        unit = self.merge ** 2
+        self.merger = _Merger3(self.embed_dim, unit, v["hidden_size"], False, dtype)
+        self.ds_index = list(v.get("deepstack_visual_indexes") or [])
+        self.deepstack_merger_list = nn.ModuleList([_Merger3(self.embed_dim, unit, v["hidden_size"], True, dtype) for _ in self.ds_index])
+        hd = self.embed_dim // self.heads
+        self.register_buffer("inv_freq", 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float32) / (hd // 2))), persistent=False)
+
+    def pos_interp(self, grid_thw: np.ndarray) -> torch.Tensor:
+        """the learned [side, side] position grid resampled (bilinear, align-corners) to each image's [h, w] patch grid, in merge-block order"""
+        W, m, n, dev = self.pos_embed.weight, self.merge, self.side, self.pos_embed.weight.device
+        out = []
+        for t, h, w in grid_thw.tolist():
+            hs, ws = torch.linspace(0, n - 1, h, device=dev), torch.linspace(0, n - 1, w, device=dev)
+            h0, w0 = hs.int(), ws.int()
+            h1, w1 = (h0 + 1).clamp(max=n - 1), (w0 + 1).clamp(max=n - 1)
+            dh, dw = (hs - h0)[:, None], (ws - w0)[None, :]
+            g = lambda a, b: W[(a[:, None] * n + b[None, :]).long()].float()               # [h, w, C]
+            e = g(h0, w0) * ((1 - dh) * (1 - dw))[..., None] + g(h0, w1) * ((1 - dh) * dw)[..., None] \
+                + g(h1, w0) * (dh * (1 - dw))[..., None] + g(h1, w1) * (dh * dw)[..., None]
+            e = e.view(h // m, m, w // m, m, -1).permute(0, 2, 1, 3, 4).reshape(h * w, -1)
+            out.append(e.repeat(t, 1))
+        return torch.cat(out).to(W.dtype)
+
+    def forward(self, patches: torch.Tensor, grid_thw: np.ndarray) -> torch.Tensor:
+        """-> [N / merge^2, hidden * (1 + len(deepstack))]: the merged features, then one column block per DeepStack level"""
+        x = self.patch_embed(patches) + self.pos_interp(grid_thw)
+        cos, sin = self.rot_pos_emb(grid_thw)
+        seg = []
+        for t, h, w in grid_thw.tolist():
+            seg += [h * w] * t
+        deep = []
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, cos, sin, seg)
+            if i in self.ds_index:
+                deep.append(self.deepstack_merger_list[self.ds_index.index(i)](x))
+        return torch.cat([self.merger(x)] + deep, -1)
+
+
 # ------------------------------------------------------------------------------------------------ M-RoPE helpers
 def mrope_index(ids: List[int], grids: List[Tuple[int, int, int]], image_token: int, merge: int) -> Tuple[np.ndarray, int]:
     """[3, len(ids)] rotary positions (temporal, height, width) and the delta ``next position - len(ids)`` for decode (reference
@@ -214,10 +304,15 @@ def mrope_index(ids: List[int], grids: List[Tuple[int, int, int]], image_token: 
     return pos, st - n
 
 
-def prepare_mrope(fb: ForwardBatch, cos_sin: torch.Tensor, pos3: torch.Tensor, sections: List[int]) -> None:
-    """assemble the per-token cos/sin rows: rotary dims [0, s0) follow the temporal position, [s0, s0+s1) height, the rest width"""
+def prepare_mrope(fb: ForwardBatch, cos_sin: torch.Tensor, pos3: torch.Tensor, sections: List[int], interleaved: bool = False) -> None:
+    """assemble the per-token cos/sin rows: rotary dims [0, s0) follow the temporal position, [s0, s0+s1) height, the rest width
+    (``interleaved``, Qwen3-VL: pair j follows height when j % 3 == 1 and j < 3 s1, width when j % 3 == 2 and j < 3 s2, else time)"""
     half = cos_sin.shape[1] // 2
-    sel = torch.repeat_interleave(torch.arange(3, device=cos_sin.device), torch.tensor(sections, device=cos_sin.device))[:half]      # [half] -> axis
+    if interleaved:
+        j = torch.arange(half, device=cos_sin.device)
+        sel = torch.where((j % 3 == 1) & (j < 3 * sections[1]), 1, torch.where((j % 3 == 2) & (j < 3 * sections[2]), 2, 0))
+    else:
+        sel = torch.repeat_interleave(torch.arange(3, device=cos_sin.device), torch.tensor(sections, device=cos_sin.device))[:half]  # [half] -> axis
     p = pos3.long()[sel, :].t()                                             # [T, half]: which position feeds each rotary pair
     d = torch.arange(half, device=cos_sin.device)[None, :]
     rows = torch.cat([cos_sin[p, d], cos_sin[p, d + half]], -1)             # [T, rot]
@@ -230,11 +325,12 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
     def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
         super().__init__(cfg, quant_name, device)
         v = cfg.vision
-        tower = Qwen25VisionTransformer if v.get("variant") == "qwen2.5" else Qwen2VisionTransformer
+        tower = {"qwen2.5": Qwen25VisionTransformer, "qwen3": Qwen3VisionTransformer}.get(v.get("variant"), Qwen2VisionTransformer)
         self.visual = None if v.get("skip_tower") else tower(v, _DT[cfg.dtype])
         self.vision_tower = self.visual            # name the shared multimodal plumbing looks for
         self.merge = v["spatial_merge_size"]
         self.sections = list((cfg.rope_scaling or {}).get("mrope_section", [cfg.head_dim // 2]))
+        self.interleaved = bool((cfg.rope_scaling or {}).get("mrope_interleaved", False))
         self.mrope_delta: Optional[torch.Tensor] = None       # [max_slots] i32, set per request at prefill (ModelRunner allocates)
 
     # ---- vision
@@ -251,7 +347,7 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
                 p = fb.positions.long() + self.mrope_delta[fb.req_slots.long()].long() if fb.cu_q is None else fb.positions.long()
                 pos3 = p[None, :].expand(3, -1)
             if pos3 is not None:
-                prepare_mrope(fb, cs, pos3.clamp(max=cs.shape[0] - 1), self.sections)
+                prepare_mrope(fb, cs, pos3.clamp(max=cs.shape[0] - 1), self.sections, self.interleaved)
         return self.model(fb, inputs_embeds)
 
     def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
@@ -278,3 +374,66 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
 
 class Qwen2_5_VLForConditionalGeneration(Qwen2VLForConditionalGeneration):
     """same language model and M-RoPE; windowed vision tower (``vision['variant'] == 'qwen2.5'`` is set by the config loader)"""
+
+
+class Qwen3VLForConditionalGeneration(Qwen2VLForConditionalGeneration):
+    """Qwen3-VL (reference ``python/sglang/srt/models/qwen3_vl.py``): Qwen3 decoder (per-head q/k norm) with *interleaved* M-RoPE and DeepStack.
+    The tower returns ``hidden * (1 + levels)`` columns per visual token; the first block replaces the placeholder embeddings as usual, level
+    ``l`` is added to the residual stream at the same rows after decoder layer ``l`` (``LlamaModel``'s ``post_layer_hook``).  Chunked prefill
+    and prefix-cache hits work unchanged because the shared splice path already hands over only the rows of the current chunk."""
+
+    def forward(self, fb: ForwardBatch, inputs_embeds=None):
+        H = self.cfg.hidden_size
+        if fb.mm_embeds is not None and fb.mm_embeds[1].shape[1] > H:
+            rows, emb = fb.mm_embeds
+            levels = emb[:, H:].split(H, dim=1)
+            fb.mm_embeds = (rows, emb[:, :H].contiguous())
+
+            def hook(layer: int, h):
+                if layer >= len(levels):
+                    return h
+                h = h.resolve() if hasattr(h, "resolve") else h
+                h.index_add_(0, rows, levels[layer].to(h.dtype))
+                return h
+
+            fb.post_layer_hook = hook
+        return super().forward(fb, inputs_embeds)
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        def rename():
+            for name, w in weights:
+                yield name.replace(".mlp.linear_fc1.", ".fc1.").replace(".mlp.linear_fc2.", ".fc2.").replace(".linear_fc1.", ".fc1.") \
+                    .replace(".linear_fc2.", ".fc2."), w
+        return super().load_weights(rename())
+
+
+def _make_qwen3_vl_moe():
+    from .families import Qwen3MoeForCausalLM
+
+    class Qwen3VLMoeForConditionalGeneration(Qwen3VLForConditionalGeneration, Qwen3MoeForCausalLM):
+        """Qwen3-VL with the Qwen3-MoE decoder (reference ``python/sglang/srt/models/qwen3_vl_moe.py``).  Release checkpoints store the experts
+        fused and transposed (``experts.gate_up_proj`` [E, H, 2I], ``experts.down_proj`` [E, I, H]); they are unpacked to per-expert tensors
+        on the way into the shared MoE loader."""
+
+        def load_weights(self, weights):
+            H = self.cfg.hidden_size
+
+            def unfuse():
+                for name, w in weights:
+                    if name.endswith(".mlp.experts.gate_up_proj") and w.dim() == 3:
+                        w = w.transpose(1, 2) if w.shape[1] == H and w.shape[2] != H else w          # -> [E, 2I, H]
+                        pre = name[: -len("gate_up_proj")]
+                        for e in range(w.shape[0]):
+                            g, u = w[e].chunk(2, 0)
+                            yield f"{pre}{e}.gate_proj.weight", g
+                            yield f"{pre}{e}.up_proj.weight", u
+                    elif name.endswith(".mlp.experts.down_proj") and w.dim() == 3:
+                        w = w.transpose(1, 2) if w.shape[2] == H and w.shape[1] != H else w          # -> [E, H, I]
+                        pre = name[: -len("down_proj")]
+                        for e in range(w.shape[0]):
+                            yield f"{pre}{e}.down_proj.weight", w[e]
+                    else:
+                        yield name, w
+            return super().load_weights(unfuse())
+
+    return Qwen3VLMoeForConditionalGeneration

@@ -86,6 +86,8 @@ def _register_builtins() -> None:
 
     register_model("Qwen2VLForConditionalGeneration", _qv.Qwen2VLForConditionalGeneration)
     register_model("Qwen2_5_VLForConditionalGeneration", _qv.Qwen2_5_VLForConditionalGeneration)
+    register_model("Qwen3VLForConditionalGeneration", _qv.Qwen3VLForConditionalGeneration)
+    register_model("Qwen3VLMoeForConditionalGeneration", _qv._make_qwen3_vl_moe())
     from . import gpt_oss as _go
 
     register_model("GptOssForCausalLM", _go.GptOssForCausalLM)
@@ -110,6 +112,11 @@ def _register_builtins() -> None:
         if fam + "ForCausalLM" in _REGISTRY:
             register_model(fam + "ForSequenceClassification", _emb.make_classifier(_REGISTRY[fam + "ForCausalLM"]))
     register_model("MistralForSequenceClassification", _emb.LlamaForSequenceClassification)
+    register_model("Qwen2ForRewardModel", _emb.make_reward_model(_REGISTRY["Qwen2ForCausalLM"], "Qwen2ForRewardModel"))
+    register_model("Qwen3ForRewardModel", _emb.make_reward_model(_REGISTRY["Qwen3ForCausalLM"], "Qwen3ForRewardModel"))
+    register_model("InternLM2ForRewardModel", _emb.make_v_head_reward(_REGISTRY["InternLM2ForCausalLM"], "InternLM2ForRewardModel"))
+    register_model("LlamaForSequenceClassificationWithNormal_Weights", _emb.LlamaForSequenceClassificationWithNormal_Weights)
+    register_model("Qwen3Model", type("Qwen3EmbeddingModel", (_emb.LlamaEmbeddingModel, _REGISTRY["Qwen3ForCausalLM"]), {}))
     register_model("MistralModel", _emb.LlamaEmbeddingModel)
     register_model("Qwen2Model", type("Qwen2EmbeddingModel", (_emb.LlamaEmbeddingModel,), {}))
     from . import transformers_fallback as _tff

@@ -118,7 +118,8 @@ def smart_resize(h: int, w: int, factor: int = 28, min_pixels: int = 56 * 56, ma
     return hb, wb
 
 
-def qwen_vl_patches(img: np.ndarray, patch: int, merge: int, temporal: int, min_pixels: int, max_pixels: int) -> Tuple[np.ndarray, Tuple[int, int, int]]:
+def qwen_vl_patches(img: np.ndarray, patch: int, merge: int, temporal: int, min_pixels: int, max_pixels: int, mean=None,
+                    std=None) -> Tuple[np.ndarray, Tuple[int, int, int]]:
     """uint8 HWC -> (flattened patches [gh*gw, 3*t*p*p] in merge-block order, (1, gh, gw))"""
     h, w = img.shape[:2]
     nh, nw = smart_resize(h, w, patch * merge, min_pixels, max_pixels)
@@ -129,7 +130,9 @@ def qwen_vl_patches(img: np.ndarray, patch: int, merge: int, temporal: int, min_
         from PIL import Image
 
         r = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
-    chw = ((r.astype(np.float32) / 255.0 - CLIP_MEAN) / CLIP_STD).transpose(2, 0, 1)
+    mean = CLIP_MEAN if mean is None else np.asarray(mean, np.float32)
+    std = CLIP_STD if std is None else np.asarray(std, np.float32)
+    chw = ((r.astype(np.float32) / 255.0 - mean) / std).transpose(2, 0, 1)
     return patchify(np.ascontiguousarray(chw), patch, merge, temporal), (1, nh // patch, nw // patch)
 
 
@@ -142,7 +145,8 @@ def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, toke
     patch, merge, tps = v["patch_size"], v["spatial_merge_size"], v.get("temporal_patch_size", 2)
     imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
     arrs = [load_image(x) for x in imgs]
-    pp = [qwen_vl_patches(a, patch, merge, tps, v.get("min_pixels", 56 * 56), v.get("max_pixels", 14 * 14 * 4 * 1280)) for a in arrs]
+    pp = [qwen_vl_patches(a, patch, merge, tps, v.get("min_pixels", 56 * 56), v.get("max_pixels", 14 * 14 * 4 * 1280), v.get("image_mean"),
+                          v.get("image_std")) for a in arrs]
     img_tok, V = cfg.image_token_id, cfg.vocab_size
     out, offsets, counts, pads, k = [], [], [], [], 0
     for t in input_ids:
@@ -242,7 +246,7 @@ def process_images_internvl(input_ids: List[int], image_data: Any, cfg: Any, tok
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
     if cfg.architecture.startswith("InternVL"):
         return process_images_internvl(input_ids, image_data, cfg, tokenizer, encoder)
-    if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL")):
+    if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL", "Qwen3VL")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
     return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)
 
