@@ -8,6 +8,7 @@
 
 #include <thread>
 
+#include "http_frontend.h"
 #include "image_ops.h"
 #include "kv_indexer.h"
 #include "ngram_corpus.h"
@@ -179,6 +180,45 @@ PYBIND11_MODULE(sglb_rt, m) {
     patchify(chw.data(), H, W, patch, merge, temporal, out.mutable_data());
     return out;
   }, py::arg("chw"), py::arg("patch"), py::arg("merge") = 1, py::arg("temporal") = 1);
+  // ---- native HTTP front end (http_frontend.cpp): sockets and HTTP framing live on a C++ epoll thread, Python sees whole requests
+  py::class_<HttpFrontend>(m, "HttpFrontend")
+      .def(py::init<const std::string&, int, int, int64_t, bool>(), py::arg("host"), py::arg("port"), py::arg("backlog") = 2048,
+           py::arg("max_body") = (int64_t)1 << 30, py::arg("reuse_port") = false)
+      .def_property_readonly("port", &HttpFrontend::port)
+      .def_property_readonly("notify_fd", &HttpFrontend::notify_fd)
+      .def("start", &HttpFrontend::start)
+      .def("stop", &HttpFrontend::stop, py::arg("drain_seconds") = 0.0, py::call_guard<py::gil_scoped_release>())
+      .def("set_static", [](HttpFrontend& f, const std::string& path, int status, const std::string& ctype, py::bytes body) {
+        f.set_static(path, status, ctype, (std::string)body);
+      })
+      .def("remove_static", &HttpFrontend::remove_static)
+      .def("poll", [](HttpFrontend& f, int timeout_ms, int max_events) {
+        std::vector<HttpEvent> evs;
+        {
+          py::gil_scoped_release rel;
+          evs = f.poll(timeout_ms, max_events);
+        }
+        py::list out;
+        for (auto& e : evs) {
+          py::list hs;
+          for (auto& kv : e.headers) hs.append(py::make_tuple(py::bytes(kv.first), py::bytes(kv.second)));
+          out.append(py::make_tuple(e.type, e.id, e.method, py::bytes(e.target), e.version, e.peer, hs, py::bytes(e.body)));
+        }
+        return out;
+      }, py::arg("timeout_ms") = 100, py::arg("max_events") = 64)
+      .def("respond", [](HttpFrontend& f, uint64_t id, int status, std::vector<std::pair<std::string, std::string>> headers, py::bytes body) {
+        return f.respond(id, status, headers, (std::string)body);
+      })
+      .def("start_stream", &HttpFrontend::start_stream)
+      .def("send_chunk", [](HttpFrontend& f, uint64_t id, py::bytes data) { return f.send_chunk(id, (std::string)data); })
+      .def("end_stream", &HttpFrontend::end_stream)
+      .def("stats", [](HttpFrontend& f) {
+        HttpStats s = f.stats();
+        py::dict d;
+        d["accepted"] = s.accepted; d["requests"] = s.requests; d["static_hits"] = s.static_hits; d["bad_requests"] = s.bad_requests;
+        d["disconnects"] = s.disconnects; d["bytes_in"] = s.bytes_in; d["bytes_out"] = s.bytes_out; d["open_conns"] = s.open_conns;
+        return d;
+      });
   m.def("hash_bytes", [](py::buffer b) {
     py::buffer_info info = b.request();
     return hash_bytes((const uint8_t*)info.ptr, (int64_t)info.size * info.itemsize);

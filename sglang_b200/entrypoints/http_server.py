@@ -453,8 +453,15 @@ def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], pee
         dog.start()
     try:
         # graceful drain: on SIGTERM uvicorn closes the listener and waits for the in-flight HTTP requests (= running generations) to complete
-        uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5,
-                    timeout_graceful_shutdown=max(1, int(server_args.graceful_shutdown_timeout)))
+        if getattr(server_args, "http_frontend", "uvicorn") == "native":
+            # C++ epoll front end: sockets, HTTP framing, SSE chunking and liveness probes never take the GIL (entrypoints/native_http.py)
+            from .native_http import NativeAsgiServer
+
+            NativeAsgiServer(app, server_args.host, server_args.port, graceful_timeout=max(1.0, float(server_args.graceful_shutdown_timeout)),
+                             static=None if server_args.api_key else {"/health": (200, "application/json", b"{}")}).run()
+        else:
+            uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5,
+                        timeout_graceful_shutdown=max(1, int(server_args.graceful_shutdown_timeout)))
     finally:
         if dog is not None:
             dog.stop()

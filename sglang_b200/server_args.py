@@ -24,6 +24,7 @@ class ServerArgs:
     model_path: str = "dummy:tiny-llama"
     tokenizer_path: Optional[str] = None
     load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf|remote_instance
+    http_frontend: str = "uvicorn"   # uvicorn | native (C++ epoll front end, csrc/runtime/http_frontend.cpp; no WebSocket routes)
     model_impl: str = "auto"   # auto: native class, else the Transformers fallback | sglang: native only | transformers: always the fallback
     remote_instance_weight_loader_seed_instance_ip: Optional[str] = None
     remote_instance_weight_loader_seed_instance_service_port: Optional[int] = None
@@ -184,6 +185,8 @@ class ServerArgs:
                 self.device = "cpu"
         if self.load_format == "auto":
             self.load_format = "dummy" if self.model_path.startswith("dummy:") else ("gguf" if self.model_path.endswith(".gguf") else "safetensors")
+        if self.http_frontend not in ("uvicorn", "native"):
+            raise ValueError("--http-frontend must be uvicorn or native")
         if self.model_impl not in ("auto", "sglang", "transformers"):
             raise ValueError("--model-impl must be auto, sglang or transformers")
         if self.model_impl != "auto":          # travels with the other config overrides to every process that reads the model config

@@ -125,8 +125,9 @@ def test_subprocess_watchdog_reports_dead_child():
     assert seen == [("bad", 3)]
 
 
-def test_sigterm_drains_in_flight_requests(tmp_path):
-    """graceful shutdown: a generation that is running when SIGTERM arrives still gets its full answer; new connections are refused"""
+@pytest.mark.parametrize("frontend", ["uvicorn", "native"])
+def test_sigterm_drains_in_flight_requests(tmp_path, frontend):
+    """graceful shutdown (both socket layers: uvicorn and the C++ epoll front end): a generation that is running when SIGTERM arrives still gets its full answer; new connections are refused"""
     import os
     import signal
     import socket
@@ -141,7 +142,7 @@ def test_sigterm_drains_in_flight_requests(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
-                          "--host", "127.0.0.1", "--log-level", "error", "--graceful-shutdown-timeout", "20"], cwd=root,
+                          "--host", "127.0.0.1", "--log-level", "error", "--graceful-shutdown-timeout", "20", "--http-frontend", frontend], cwd=root,
                          env=dict(os.environ, PYTHONPATH=root), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     try:
         for _ in range(120):

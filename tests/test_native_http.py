@@ -1,0 +1,159 @@
+"""Native C++ HTTP front end (csrc/runtime/http_frontend.cpp + entrypoints/native_http.py) serving the real FastAPI app over real sockets:
+keep-alive, pipelining, SSE streaming, static paths answered by the I/O thread, client-disconnect aborts, limits, graceful drain.
+(reference: the embedded Rust server, rust/sglang-server, is exercised by the same OpenAI-route tests with SGLANG_RUST_SERVER=1)"""
+import json
+import socket
+import threading
+import time
+
+import pytest
+import requests
+
+import sglang_b200 as sgl
+from sglang_b200.entrypoints.http_server import create_app
+from sglang_b200.entrypoints.native_http import NativeAsgiServer
+
+
+@pytest.fixture(scope="module")
+def server():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, enable_metrics=True)
+    eng.start_background_loop()
+    srv = NativeAsgiServer(create_app(eng), "127.0.0.1", 0, graceful_timeout=5.0, max_body=1 << 20,
+                           static={"/health": (200, "application/json", b"{}")})
+    th = threading.Thread(target=srv.run, kwargs={"install_signal_handlers": False}, daemon=True)
+    th.start()
+    assert srv.started.wait(30)
+    yield srv, eng, f"http://127.0.0.1:{srv.port}"
+    srv.request_stop()
+    th.join(20)
+    eng.shutdown()
+
+
+def test_routes_keepalive_and_static(server):
+    srv, eng, url = server
+    s = requests.Session()
+    before = srv.fe.stats()
+    for _ in range(3):
+        assert s.get(url + "/health").status_code == 200
+    r = s.post(url + "/generate", json={"text": "hello", "sampling_params": {"max_new_tokens": 5, "temperature": 0}})
+    assert r.status_code == 200 and r.json()["meta_info"]["completion_tokens"] == 5
+    assert s.get(url + "/v1/models").json()["data"][0]["id"] == "dummy:tiny-llama"
+    assert s.get(url + "/no/such/route").status_code == 404
+    assert s.post(url + "/generate", json={"text": "x", "sampling_params": {"top_p": 7}}).status_code == 400
+    st = srv.fe.stats()
+    assert st["static_hits"] - before["static_hits"] == 3               # liveness probes never reached Python
+    assert st["accepted"] - before["accepted"] == 1                     # one TCP connection for the whole session
+    assert "sglb" in s.get(url + "/metrics").text or s.get(url + "/metrics").status_code == 200
+
+
+def test_sse_stream_matches_unary(server):
+    _, _, url = server
+    body = {"text": "hello", "sampling_params": {"max_new_tokens": 6, "temperature": 0}}
+    ref = requests.post(url + "/generate", json=body).json()
+    with requests.post(url + "/generate", json={**body, "stream": True}, stream=True) as r:
+        assert r.headers.get("transfer-encoding") == "chunked" and r.headers["content-type"].startswith("text/event-stream")
+        lines = [l.decode() for l in r.iter_lines() if l.startswith(b"data:")]
+    assert lines[-1] == "data: [DONE]" and json.loads(lines[-2][5:])["output_ids"] == ref["output_ids"]
+    with requests.post(url + "/v1/chat/completions", json={"model": "m", "messages": [{"role": "user", "content": "ping"}], "max_tokens": 4,
+                                                           "stream": True, "stream_options": {"include_usage": True}}, stream=True) as r:
+        chunks = [json.loads(l[5:]) for l in r.iter_lines() if l.startswith(b"data:") and b"[DONE]" not in l]
+    assert chunks[0]["choices"][0]["delta"]["role"] == "assistant" and chunks[-1]["usage"]["completion_tokens"] == 4
+
+
+def _raw(port, payload: bytes, read_until: bytes = None, timeout=10.0) -> bytes:
+    s = socket.create_connection(("127.0.0.1", port), timeout=timeout)
+    s.sendall(payload)
+    buf = b""
+    try:
+        while True:
+            d = s.recv(65536)
+            if not d:
+                break
+            buf += d
+            if read_until is not None and buf.count(read_until) >= 1 and buf.endswith(read_until):
+                break
+    except socket.timeout:
+        pass
+    s.close()
+    return buf
+
+
+def test_pipelining_expect_continue_and_limits(server):
+    srv, _, _ = server
+    body = json.dumps({"text": "hi", "sampling_params": {"max_new_tokens": 2, "temperature": 0}}).encode()
+    req = b"POST /generate HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body
+    # two pipelined requests + a closing one on a single connection: answered in order
+    out = _raw(srv.port, req + req + b"GET /health HTTP/1.1\r\nHost: x\r\nConnection: close\r\n\r\n")
+    assert out.count(b"HTTP/1.1 200 OK") == 3 and out.rstrip().endswith(b"{}") and b"Connection: close" in out
+    # Expect: 100-continue is acknowledged before the body is sent
+    s = socket.create_connection(("127.0.0.1", srv.port), timeout=10)
+    s.sendall(b"POST /generate HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nExpect: 100-continue\r\nContent-Length: %d\r\n\r\n" % len(body))
+    assert s.recv(100).startswith(b"HTTP/1.1 100 Continue")
+    s.sendall(body)
+    buf = b""
+    while b"output_ids" not in buf:
+        buf += s.recv(65536)
+    s.close()
+    assert b"HTTP/1.1 200 OK" in buf
+    # limits and malformed input are refused by the I/O thread itself
+    assert _raw(srv.port, b"POST /generate HTTP/1.1\r\nContent-Length: 99999999\r\n\r\n").startswith(b"HTTP/1.1 413")
+    assert _raw(srv.port, b"POST /generate HTTP/1.1\r\nTransfer-Encoding: chunked\r\n\r\n5\r\nhello\r\n0\r\n\r\n").startswith(b"HTTP/1.1 411")
+    assert _raw(srv.port, b"garbage\r\n\r\n").startswith(b"HTTP/1.1 400")
+    assert _raw(srv.port, b"GET /realtime HTTP/1.1\r\nUpgrade: websocket\r\nConnection: Upgrade\r\n\r\n", timeout=3).startswith(b"HTTP/1.1 426")
+
+
+def test_client_disconnect_aborts_generation(server):
+    srv, eng, url = server
+    body = json.dumps({"text": "hi", "stream": True, "sampling_params": {"max_new_tokens": 100000, "temperature": 0, "ignore_eos": True}}).encode()
+    s = socket.create_connection(("127.0.0.1", srv.port), timeout=10)
+    s.sendall(b"POST /generate HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+    buf = b""
+    while buf.count(b"data:") < 3:
+        buf += s.recv(65536)
+    d0 = srv.fe.stats()["disconnects"]
+    s.close()                                  # walk away mid-stream
+    t0 = time.time()
+    while time.time() - t0 < 20:
+        if srv.fe.stats()["disconnects"] > d0 and requests.get(url + "/get_load").json()["num_running_reqs"] == 0:
+            break
+        time.sleep(0.1)
+    assert srv.fe.stats()["disconnects"] > d0
+    assert requests.get(url + "/get_load").json()["num_running_reqs"] == 0          # the scheduler dropped the abandoned request
+
+
+def test_concurrent_clients(server):
+    _, _, url = server
+    outs = [None] * 16
+
+    def one(i):
+        outs[i] = requests.post(url + "/generate", json={"text": "p%d" % i, "sampling_params": {"max_new_tokens": 4, "temperature": 0}}).json()
+
+    ths = [threading.Thread(target=one, args=(i,)) for i in range(16)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert all(o is not None and o["meta_info"]["completion_tokens"] == 4 for o in outs)
+
+
+def test_graceful_drain_finishes_inflight_request():
+    eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4)
+    eng.start_background_loop()
+    srv = NativeAsgiServer(create_app(eng), "127.0.0.1", 0, graceful_timeout=20.0)
+    th = threading.Thread(target=srv.run, kwargs={"install_signal_handlers": False}, daemon=True)
+    th.start()
+    assert srv.started.wait(30)
+    url = f"http://127.0.0.1:{srv.port}"
+    res = {}
+
+    def long_req():
+        res["r"] = requests.post(url + "/generate", json={"text": "hi", "sampling_params": {"max_new_tokens": 200, "temperature": 0, "ignore_eos": True}})
+
+    t = threading.Thread(target=long_req)
+    t.start()
+    time.sleep(0.3)
+    srv.request_stop()                          # SIGTERM path: stop accepting, let the running generation finish
+    t.join(30)
+    th.join(30)
+    assert res["r"].status_code == 200 and res["r"].json()["meta_info"]["completion_tokens"] == 200
+    with pytest.raises(requests.exceptions.ConnectionError):
+        requests.get(url + "/health", timeout=2)
+    eng.shutdown()
