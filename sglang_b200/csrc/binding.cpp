@@ -608,6 +608,11 @@ TORCH_LIBRARY(sglb, m) {
         "int max_q_len, int page_size, int num_splits, float scale, bool causal, int window, float logit_cap, "
         "float k_scale, float v_scale, int impl, Tensor? tree_anc=None) -> ()", &attn_fwd);
   m.def("attn_decode_prof(Tensor buf) -> ()", &attn_decode_prof);
+  m.def("green_ctx_streams(int device, int[] sm_counts) -> int[]", [](int64_t device, std::vector<int64_t> counts) {
+    std::vector<long long> c(counts.begin(), counts.end());
+    auto r = sglb::green_ctx_streams((int)device, c);
+    return std::vector<int64_t>(r.begin(), r.end());
+  });
   m.def("gated_delta_update(Tensor(a!) state, Tensor req_slots, Tensor u, Tensor g, Tensor beta, int Hk, Tensor(b!) out) -> ()", &gated_delta_update);
   m.def("causal_conv1d(Tensor x, Tensor w, Tensor? bias, Tensor(a!) conv_state, Tensor? cu_q, Tensor req_slots, Tensor seq_lens, int max_q_len, "
         "bool silu, Tensor(b!) u) -> ()", &causal_conv1d);

@@ -1,6 +1,7 @@
 // Host launch API of the sm_100a kernels (raw pointers + stream; no torch dependency so the .cu files
 // compile in seconds).  binding.cpp adapts these to torch.ops.sglb.*
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,6 +28,7 @@ void attn_fwd_simt(const void* q, const void* k_cache, const void* v_cache, void
 // attention_tc.cu
 // attention_decode.cu: decode attention with the keys as the UMMA M dimension (persistent, 3-deep 32 KB K/V ring, page-granular fetch)
 void attn_decode_set_prof(long long* buf);
+std::vector<long long> green_ctx_streams(int device, const std::vector<long long>& sm_counts);
 bool attn_decode_tc_supported(int Hq, int Hkv, int D, int page_size);
 void attn_decode_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, float* part_o, float* part_lse,
                     const int* page_table, int pt_stride, const int* req_slots, const int* seq_lens, int B, int q_stride, int Hq, int Hkv,

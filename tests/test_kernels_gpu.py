@@ -10,7 +10,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CASES = ["rmsnorm", "act", "rope", "misc", "sampling", "attn_simt", "gemm_tc", "gemm_split_silu", "gemm_skinny", "gemm_streamk", "lora", "kvio", "mamba", "gated_delta", "moe", "fp8", "attn_tc_decode", "attn_decode_v3", "attn_tree", "attn_tc_prefill",
-         "attn_tc_split", "attn_tc_persist", "attn_tc_window"]
+         "attn_tc_split", "attn_tc_persist", "attn_tc_window", "green_ctx"]
 
 
 def run_case(name: str, timeout: int = 300):
