@@ -824,8 +824,8 @@ class Scheduler:
         """Nothing runs, nothing is in flight, yet requests wait: the head of the queue passed validation but can not be placed (its decode
         reserve or one of the pools is too small and there is nobody left to finish or be evicted).  After a few idle iterations reject it —
         without this the engine spins forever (observed at 20 k iterations / s with a KV pool of a few pages)."""
-        if not self.waiting_queue or self.running_batch.reqs or self.chunked_req is not None or self.grammar_queue:
-            self._stall_iters = 0
+        if self.paused or not self.waiting_queue or self.running_batch.reqs or self.chunked_req is not None or self.grammar_queue:
+            self._stall_iters = 0          # (a paused scheduler is idle on purpose: its queue is not starving)
             return
         if self.last_batch is not None and any(not r.finished() for r in self.last_batch.reqs):
             self._stall_iters = 0
