@@ -563,6 +563,17 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "window_size": vc.get("window_size", 112), "fullatt_block_indexes": vc.get("fullatt_block_indexes", [7, 15, 23, 31])}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
+        if arch == "Mistral3ForConditionalGeneration":
+            vc = hf["vision_config"]
+            vrp = vc.get("rope_parameters") or {}
+            kw["vision"] = {"variant": "pixtral", "hidden_size": vc.get("hidden_size", 1024), "intermediate_size": vc.get("intermediate_size", 4096),
+                            "num_hidden_layers": vc.get("num_hidden_layers", 24), "num_attention_heads": vc.get("num_attention_heads", 16),
+                            "head_dim": vc.get("head_dim"), "patch_size": vc.get("patch_size", 14), "image_size": vc.get("image_size", 1540),
+                            "hidden_act": vc.get("hidden_act", "gelu"),
+                            "rope_theta": vrp.get("rope_theta", vc.get("rope_theta", 10000.0)), "spatial_merge_size": hf.get("spatial_merge_size", 2),
+                            "projector_hidden_act": hf.get("projector_hidden_act", "gelu"), "projector_bias": hf.get("multimodal_projector_bias", False),
+                            "image_break_token_id": hf.get("image_break_token_id", 12), "image_end_token_id": hf.get("image_end_token_id", 13)}
+            kw["image_token_id"] = hf.get("image_token_id", hf.get("image_token_index", 10))
         if arch in ("Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration"):
             vc = hf["vision_config"]
             kw["vision"] = {"variant": "qwen3", "embed_dim": vc.get("hidden_size", 1152), "depth": vc.get("depth", 27), "num_heads": vc.get("num_heads", 16),
@@ -581,7 +592,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration",
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration",
                                                  "Qwen3VLMoeForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

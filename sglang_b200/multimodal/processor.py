@@ -180,6 +180,65 @@ def process_images_qwen_vl(input_ids: List[int], image_data: Any, cfg: Any, toke
     return out, mm
 
 
+def pixtral_resize_shape(h: int, w: int, longest: int, unit: int) -> Tuple[int, int]:
+    """Pixtral / Mistral3 processor: shrink (never enlarge) so that both sides fit ``longest``, then round each side UP to a multiple of
+    ``unit`` (= patch * spatial merge)"""
+    import math
+
+    ratio = max(h / longest, w / longest)
+    if ratio > 1:
+        h, w = int(math.floor(h / ratio)), int(math.floor(w / ratio))
+    return ((h - 1) // unit + 1) * unit, ((w - 1) // unit + 1) * unit
+
+
+def process_images_pixtral(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None):
+    """Mistral3: the single ``[IMG]`` placeholder of each image expands to ``cols`` image tokens per merged row followed by ``[IMG_BREAK]``
+    (``[IMG_END]`` after the last row); only the image tokens receive vision features, so every row is its own splice run (reference
+    multimodal/processors/pixtral.py)"""
+    v = cfg.vision
+    patch, merge = v["patch_size"], v["spatial_merge_size"]
+    unit = patch * merge
+    imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
+    arrs = [load_image(x) for x in imgs]
+    rt = _native()
+    pp = []
+    for a in arrs:
+        nh, nw = pixtral_resize_shape(a.shape[0], a.shape[1], v.get("longest_edge", v["image_size"]), unit)
+        if rt is not None:
+            r = rt.image_resize(np.ascontiguousarray(a), nh, nw, 3)
+        else:
+            from PIL import Image
+
+            r = np.asarray(Image.fromarray(a).resize((nw, nh), Image.BICUBIC))
+        chw = ((r.astype(np.float32) / 255.0 - CLIP_MEAN) / CLIP_STD).transpose(2, 0, 1)
+        pp.append((patchify(np.ascontiguousarray(chw), patch, 1, 1), (1, nh // patch, nw // patch)))
+    img_tok, brk, end, V = cfg.image_token_id, v.get("image_break_token_id", 12), v.get("image_end_token_id", 13), cfg.vocab_size
+    out, offsets, counts, k = [], [], [], 0
+    for t in input_ids:
+        if t == img_tok and k < len(arrs):
+            _, gh, gw = pp[k][1]
+            rows, cols = gh // merge, gw // merge
+            h = image_hash(arrs[k])
+            pads = (int(h % max(1, V - 1)), int((h >> 17) % max(1, V - 1)))
+            for r_ in range(rows):
+                offsets.append(len(out))
+                counts.append(cols)
+                out.extend(pads[(r_ + j) & 1] for j in range(cols))       # hash-derived ids: different images never share a radix key
+                out.append(end if r_ == rows - 1 else brk)
+            k += 1
+        else:
+            out.append(t)
+    if k < len(arrs):
+        raise ValueError(f"{len(arrs)} images but only {k} image placeholder tokens in the prompt")
+    mm: Dict[str, Any] = {"image_offsets": offsets, "image_token_counts": counts, "num_image_tokens": 0, "grid_thw": [list(g) for _, g in pp]}
+    if encoder is not None:
+        embs = encoder.encode_items([{"hash": image_hash(a), "array": p_, "grid": list(g_)} for a, (p_, g_) in zip(arrs, pp)])
+        mm["image_embeds"] = np.concatenate(embs) if embs else np.zeros((0, cfg.hidden_size), np.float16)
+    else:
+        mm["pixel_patches"] = np.concatenate([p for p, _ in pp]) if pp else np.zeros((0, 3 * patch * patch), np.float32)
+    return out, mm
+
+
 IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], dtype=np.float32)
 IMAGENET_STD = np.array([0.229, 0.224, 0.225], dtype=np.float32)
 
@@ -246,6 +305,8 @@ def process_images_internvl(input_ids: List[int], image_data: Any, cfg: Any, tok
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
     if cfg.architecture.startswith("InternVL"):
         return process_images_internvl(input_ids, image_data, cfg, tokenizer, encoder)
+    if cfg.architecture.startswith("Mistral3"):
+        return process_images_pixtral(input_ids, image_data, cfg, tokenizer, encoder)
     if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL", "Qwen3VL")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
     return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)
