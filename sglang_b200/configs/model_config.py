@@ -563,6 +563,14 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "window_size": vc.get("window_size", 112), "fullatt_block_indexes": vc.get("fullatt_block_indexes", [7, 15, 23, 31])}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
+        if arch == "Gemma3ForConditionalGeneration" and hf.get("vision_config") is not None:
+            vc = hf["vision_config"]
+            kw["vision"] = {"variant": "siglip", "hidden_size": vc.get("hidden_size", 1152), "intermediate_size": vc.get("intermediate_size", 4304),
+                            "num_hidden_layers": vc.get("num_hidden_layers", 27), "num_attention_heads": vc.get("num_attention_heads", 16),
+                            "patch_size": vc.get("patch_size", 14), "image_size": vc.get("image_size", 896), "layer_norm_eps": vc.get("layer_norm_eps", 1e-6),
+                            "tokens_per_image": hf.get("mm_tokens_per_image", 256), "resize_mode": "squash", "resize_filter": 2,
+                            "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5]}
+            kw["image_token_id"] = hf.get("image_token_id", hf.get("image_token_index", 262144))
         if arch == "Mistral3ForConditionalGeneration":
             vc = hf["vision_config"]
             vrp = vc.get("rope_parameters") or {}
@@ -592,7 +600,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration",
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration", "Gemma3ForConditionalGeneration",
                                                  "Qwen3VLMoeForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

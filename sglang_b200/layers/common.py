@@ -108,6 +108,8 @@ class RadixAttention(nn.Module):
         sinks = self.sinks
         lse = torch.empty(T, self.num_heads, dtype=torch.float32, device=q3.device) if sinks is not None else None
         mask = fb.custom_mask if not self.chunk else chunk_attention_mask(fb, self.chunk)
+        if self.window > 0 and fb.custom_mask_sliding is not None:
+            mask = fb.custom_mask_sliding
         o = ops.paged_attention(q3, kc, vc, page_table, fb.req_slots, fb.seq_lens, fb.cu_q, fb.q_lens, fb.max_q_len,
                                 fb.page_size, self.scale, causal=True, window=self.window, logit_cap=self.logit_cap,
                                 k_scale=pool.k_scale, v_scale=pool.v_scale, num_splits=fb.num_splits,

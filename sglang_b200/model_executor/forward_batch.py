@@ -60,6 +60,7 @@ class ForwardBatch:
     return_hidden: bool = False
     spec_info: Any = None
     custom_mask: Optional[torch.Tensor] = None
+    custom_mask_sliding: Optional[torch.Tensor] = None      # the sliding-window layers' variant (Gemma-3 bidirectional image blocks)
     tree_anc: Optional[torch.Tensor] = None      # i32 [T] ancestor bits per query node (speculative tree verify on the tcgen05 kernel)
     h2d_bytes: int = 0
     # host mirrors (no sync needed)

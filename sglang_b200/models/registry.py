@@ -81,7 +81,9 @@ def _register_builtins() -> None:
     for name in ("GlmForCausalLM", "Glm4ForCausalLM", "Gemma3ForCausalLM", "CohereForCausalLM", "OlmoeForCausalLM", "NemotronForCausalLM",
                  "Glm4MoeForCausalLM", "Dots1ForCausalLM", "Ernie4_5_MoeForCausalLM", "OlmoForCausalLM", "StableLmForCausalLM", "ApertusForCausalLM"):
         register_model(name, getattr(_f2, name))
-    register_model("Gemma3ForConditionalGeneration", _f2.Gemma3ForCausalLM)      # text tower of the multimodal checkpoint
+    from . import gemma3_mm as _g3
+
+    register_model("Gemma3ForConditionalGeneration", _g3.Gemma3ForConditionalGeneration)
     from . import qwen2_vl as _qv
 
     register_model("Qwen2VLForConditionalGeneration", _qv.Qwen2VLForConditionalGeneration)

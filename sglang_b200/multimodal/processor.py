@@ -76,6 +76,22 @@ def _native():
         return None
 
 
+def squash_preprocess_batch(imgs: List[np.ndarray], size: int, mean, std, filt: int = 2) -> np.ndarray:
+    """[N, 3, size, size] float32: resize straight to size x size (filter 2 = bilinear, 3 = bicubic), rescale, normalise"""
+    rt = _native()
+    mean, std = np.asarray(mean, np.float32), np.asarray(std, np.float32)
+    out = []
+    for a in imgs:
+        if rt is not None:
+            r = rt.image_resize(np.ascontiguousarray(a), size, size, filt)
+        else:
+            from PIL import Image
+
+            r = np.asarray(Image.fromarray(a).resize((size, size), Image.BILINEAR if filt == 2 else Image.BICUBIC))
+        out.append(((r.astype(np.float32) / 255.0 - mean) / std).transpose(2, 0, 1))
+    return np.stack(out) if out else np.zeros((0, 3, size, size), np.float32)
+
+
 def clip_preprocess_batch(imgs: List[np.ndarray], size: int, threads: int = 4) -> np.ndarray:
     """[N, 3, size, size] float32; native thread pool when the runtime is built, Pillow otherwise (bit-identical resize)"""
     rt = _native()
@@ -317,10 +333,13 @@ def _process_images_clip(input_ids: List[int], image_data: Any, cfg: Any, tokeni
     image_offsets (start index of every image's pad run), pad_values, num_image_tokens."""
     v = cfg.vision
     size, patch = v["image_size"], v["patch_size"]
-    n_tok = (size // patch) ** 2
+    n_tok = int(v.get("tokens_per_image") or (size // patch) ** 2)
     imgs = image_data if isinstance(image_data, (list, tuple)) else [image_data]
     arrs = [load_image(x) for x in imgs]
-    pixels = clip_preprocess_batch(arrs, size)
+    if v.get("resize_mode") == "squash":          # SigLIP / Gemma-3: plain resize to the square input (aspect ratio not kept), own mean / std
+        pixels = squash_preprocess_batch(arrs, size, v.get("image_mean", CLIP_MEAN), v.get("image_std", CLIP_STD), int(v.get("resize_filter", 2)))
+    else:
+        pixels = clip_preprocess_batch(arrs, size)
     img_tok = cfg.image_token_id if cfg.image_token_id is not None else getattr(tokenizer, "image_token_id", None)
     if img_tok is None:
         raise ValueError("model config has no image_token_id")
