@@ -229,6 +229,7 @@ class ScheduleBatch:
     pt_cols: Optional[np.ndarray] = None
     pt_vals: Optional[np.ndarray] = None
     chunked_req: Optional[Req] = None
+    mixed_ids: Any = None                          # ids of running requests riding along as one-token extends (--enable-mixed-chunk)
     return_logprob: bool = False
     has_grammar: bool = False
     spec_info: Any = None

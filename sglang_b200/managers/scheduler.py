@@ -121,6 +121,11 @@ class Scheduler:
         self.num_retracted = 0
         self.num_generated_tokens = 0
         self.num_prefill_tokens = 0
+        self.num_mixed_decode_tokens = self.num_mixed_fallbacks = 0
+        a_ = server_args
+        self._mixed_chunk = bool(a_.enable_mixed_chunk and not a_.speculative_algorithm and not a_.enable_dp_attention
+                                 and getattr(a_, "disaggregation_mode", "null") in (None, "null") and not getattr(a_, "dllm_algorithm", None)
+                                 and self.swa is None and self.mamba is None and a_.pp_size == 1)
         self.num_cached_tokens = 0
         self.last_decode_log = time.perf_counter()
         self.last_decode_tokens = 0
@@ -395,8 +400,26 @@ class Scheduler:
             return None
         prev_chunked = self.chunked_req
         self.chunked_req = adder.new_chunked_req
-        batch = ScheduleBatch(reqs=adder.can_run, forward_mode=ForwardMode.EXTEND, chunked_req=self.chunked_req)
-        if not self._prepare_for_extend(batch):
+        mixed = self._mixable_running() if self._mixed_chunk else []
+        for r in mixed:          # a running request joins the extend step as a one-token extend over its own cached tokens
+            r.prefix_len, r.fill_len = r.kv_len, r.kv_len + 1
+        batch = ScheduleBatch(reqs=adder.can_run + mixed, forward_mode=ForwardMode.EXTEND, chunked_req=self.chunked_req)
+        batch.mixed_ids = {id(r) for r in mixed}
+        if mixed and not self._prepare_for_extend(batch):          # no room for the decode tokens on top of the prefill: plain prefill step
+            self.num_mixed_fallbacks += 1
+            for r in mixed:
+                self.kv.trim(r, r.kv_len)          # (a page taken for the extra token must not be allocated a second time by the decode path)
+            batch = ScheduleBatch(reqs=adder.can_run, forward_mode=ForwardMode.EXTEND, chunked_req=self.chunked_req)
+            batch.mixed_ids, mixed = set(), []
+            ok = self._prepare_for_extend(batch)
+        else:
+            ok = True if mixed else self._prepare_for_extend(batch)
+        if ok and mixed:
+            ids_ = batch.mixed_ids
+            rb = self.running_batch
+            rb.filter_batch([i for i, r in enumerate(rb.reqs) if id(r) not in ids_])      # they return through the last-batch merge
+            self.num_mixed_decode_tokens += len(mixed)
+        if not ok:
             # allocation failed despite the budget (fragmentation of reserves): put everything back
             for r in batch.reqs:
                 if r is prev_chunked:
@@ -415,6 +438,16 @@ class Scheduler:
                                                                                               if self.swa is not None else "") + ")")
             return None
         return batch
+
+    def _mixable_running(self) -> List[Req]:
+        """``--enable-mixed-chunk`` (reference ``ScheduleBatch.mix_with_running``): the running requests ride along with this prefill step
+        instead of stalling behind it.  The host must know their last token and finish state, so in-flight results are drained first;
+        requests whose decode step needs more than a sampled token (grammar, logprobs, hidden states) keep the plain decode path."""
+        if not self.running_batch.reqs:
+            return []
+        self.drain()
+        return [r for r in self.running_batch.reqs if r.finished_reason is None and not r.finished() and r.grammar is None
+                and not r.return_logprob and not getattr(r, "return_hidden_states", False) and r.to_abort is None]
 
     def _prepare_for_extend(self, batch: ScheduleBatch) -> bool:
         """allocate pages, build token-level arrays (reference prepare_for_extend:2378)"""
@@ -631,7 +664,7 @@ class Scheduler:
                 r.finished_time = now
                 r.kv_len = min(r.kv_len, r.seqlen - 1)
                 self.kv.release(r)
-            else:
+            elif not (batch.mixed_ids and id(r) in batch.mixed_ids):
                 self.kv.cache_unfinished(r)
             out.append(r)
         d = self.kv.take_deltas()
@@ -936,6 +969,7 @@ class Scheduler:
         }
 
     def _extra_state(self) -> Dict[str, Any]:
+
         """everything else the metrics exporter publishes (cheap host counters only; never touches the device)"""
         w = self.worker
         out: Dict[str, Any] = {"decode_ct": self.decode_ct, "scheduler_iterations": self.step_calls, "scheduler_wall_s": self.step_wall_s,
@@ -963,6 +997,8 @@ class Scheduler:
         nvl = getattr(getattr(w, "tp", None), "nvl", None)
         if nvl is not None:
             out.update(nvl_collective_calls=nvl.calls, nvl_rs_calls=nvl.rs_calls)
+        if self._mixed_chunk:
+            out.update(num_mixed_decode_tokens=self.num_mixed_decode_tokens, num_mixed_fallbacks=self.num_mixed_fallbacks)
         return out
 
     def _log_decode_stats(self) -> None:
