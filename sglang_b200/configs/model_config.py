@@ -540,6 +540,13 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                       rms_norm_eps=1e-5, pos_emb="learned", tie_word_embeddings=True, head_dim=hf["d_model"] // hf["decoder_attention_heads"])
             kw["audio"] = {k: hf[k] for k in ("d_model", "encoder_layers", "encoder_attention_heads", "encoder_ffn_dim", "num_mel_bins",
                                               "max_source_positions")}
+        if arch == "Qwen2AudioForConditionalGeneration":
+            ac = hf.get("audio_config") or {}
+            kw["audio"] = {"llm": True, "d_model": ac.get("d_model", 1280), "encoder_layers": ac.get("encoder_layers", 32),
+                           "encoder_attention_heads": ac.get("encoder_attention_heads", 20), "encoder_ffn_dim": ac.get("encoder_ffn_dim", 5120),
+                           "num_mel_bins": ac.get("num_mel_bins", 128), "max_source_positions": ac.get("max_source_positions", 1500),
+                           "audio_token_id": hf.get("audio_token_id", hf.get("audio_token_index", 151646))}
+            kw.setdefault("attention_bias", True)
         if arch == "InternVLForConditionalGeneration":
             vc = hf["vision_config"]
             size = vc.get("image_size", 448)

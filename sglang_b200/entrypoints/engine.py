@@ -183,7 +183,12 @@ class Engine:
         if g.audio_data is not None and self.model_config.audio is not None:
             from ..multimodal.audio import process_audio
 
-            mm = process_audio(g.audio_data, self.model_config)
+            if self.model_config.audio.get("llm"):          # audio clips spliced into a decoder-only prompt (Qwen2-Audio)
+                from ..multimodal.audio import process_audio_llm
+
+                ids, mm = process_audio_llm(ids, g.audio_data, self.model_config)
+            else:
+                mm = process_audio(g.audio_data, self.model_config)
         SamplingParams.from_dict(sp).verify(self.model_config.vocab_size)
         return ios.TokenizedGenerateReqInput(
             rid=g.rid or self._new_rid(), input_text=text, input_ids=ids, sampling_params=sp, return_logprob=bool(g.return_logprob),

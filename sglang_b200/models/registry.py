@@ -90,6 +90,9 @@ def _register_builtins() -> None:
     register_model("Qwen2_5_VLForConditionalGeneration", _qv.Qwen2_5_VLForConditionalGeneration)
     register_model("Qwen3VLForConditionalGeneration", _qv.Qwen3VLForConditionalGeneration)
     register_model("Qwen3VLMoeForConditionalGeneration", _qv._make_qwen3_vl_moe())
+    from . import qwen2_audio as _qa
+
+    register_model("Qwen2AudioForConditionalGeneration", _qa.Qwen2AudioForConditionalGeneration)
     from . import pixtral as _px
 
     register_model("Mistral3ForConditionalGeneration", _px.Mistral3ForConditionalGeneration)

@@ -40,11 +40,11 @@ class _EncLayer(nn.Module):
         self.final_layer_norm = nn.LayerNorm(H, dtype=dtype)
         self.fc1, self.fc2 = nn.Linear(H, ffn, dtype=dtype), nn.Linear(ffn, H, dtype=dtype)
 
-    def forward(self, x):                      # [B, S, H]
+    def forward(self, x, mask=None):           # [B, S, H]; mask: boolean key-padding mask broadcastable to [B, heads, S, S] (Qwen2-Audio)
         B, S, H = x.shape
         h = self.self_attn_layer_norm(x)
         sp = lambda t: t.view(B, S, self.heads, H // self.heads).transpose(1, 2)
-        a = F.scaled_dot_product_attention(sp(self.q_proj(h)), sp(self.k_proj(h)), sp(self.v_proj(h)))
+        a = F.scaled_dot_product_attention(sp(self.q_proj(h)), sp(self.k_proj(h)), sp(self.v_proj(h)), attn_mask=mask)
         x = x + self.out_proj(a.transpose(1, 2).reshape(B, S, H))
         return x + self.fc2(F.gelu(self.fc1(self.final_layer_norm(x))))
 

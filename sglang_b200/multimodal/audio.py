@@ -9,7 +9,7 @@ import base64
 import io
 import os
 import wave
-from typing import Any
+from typing import Any, List, Tuple
 
 import numpy as np
 import torch
@@ -106,3 +106,38 @@ def process_audio(audio_data: Any, cfg: Any) -> dict:
     a = cfg.audio
     feats = log_mel_spectrogram(load_audio(audio_data), a["num_mel_bins"], chunk_s=a.get("chunk_length", 30))
     return {"input_features": feats[:, : 2 * a["max_source_positions"]]}
+
+
+def process_audio_llm(input_ids: List[int], audio_data: Any, cfg: Any) -> Tuple[List[int], dict]:
+    """audio-understanding LLMs (Qwen2-Audio): every audio placeholder token expands to the encoder's output length for its clip; the clips'
+    padded log-mel windows and true frame counts travel in the request (reference multimodal/processors/qwen_audio.py)"""
+    import hashlib
+
+    a = cfg.audio
+    clips = audio_data if isinstance(audio_data, (list, tuple)) and not (len(audio_data) == 2 and isinstance(audio_data[1], (int, float))) else [audio_data]
+    tok, V = a["audio_token_id"], cfg.vocab_size
+    window = 2 * a["max_source_positions"]
+    feats, frames = [], []
+    for c in clips:
+        w = load_audio(c)
+        f = log_mel_spectrogram(w, a["num_mel_bins"], chunk_s=a.get("chunk_length", 30))[:, :window]
+        if f.shape[1] < window:
+            f = np.pad(f, ((0, 0), (0, window - f.shape[1])))
+        feats.append(f)
+        frames.append(max(2, min(window, w.shape[0] // 160)))
+    out, offsets, counts, k = [], [], [], 0
+    for t in input_ids:
+        if t == tok and k < len(clips):
+            l1 = (frames[k] - 1) // 2 + 1
+            n = (l1 - 2) // 2 + 1
+            h = int.from_bytes(hashlib.sha256(feats[k].tobytes()).digest()[:8], "little")
+            offsets.append(len(out))
+            counts.append(n)
+            out.extend(int(h % max(1, V - 1)) if (j & 1) == 0 else int((h >> 17) % max(1, V - 1)) for j in range(n))
+            k += 1
+        else:
+            out.append(t)
+    if k < len(clips):
+        raise ValueError(f"{len(clips)} audio clips but only {k} audio placeholder tokens in the prompt")
+    return out, {"image_offsets": offsets, "image_token_counts": counts, "num_image_tokens": 0,
+                 "audio_features": np.stack(feats) if feats else np.zeros((0, a["num_mel_bins"], window), np.float32), "audio_frames": frames}

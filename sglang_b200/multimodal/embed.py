@@ -20,9 +20,12 @@ def _encode(model: Any, mm: Dict[str, Any], device: torch.device, dtype: torch.d
         flat = torch.as_tensor(np.asarray(e), device=device).to(dtype)
         flat = flat.reshape(-1, flat.shape[-1])
     else:
-        if not hasattr(model, "encode_images") or getattr(model, "vision_tower", None) is None:
+        if not (hasattr(model, "encode_images") or hasattr(model, "encode_audio")) or getattr(model, "vision_tower", None) is None:
             raise RuntimeError("this server was started --language-only: images need --encoder-urls (no local vision tower)")
-        if mm.get("pixel_patches") is not None:     # dynamic-resolution towers (Qwen2-VL): flattened patches + grids
+        if mm.get("audio_features") is not None:    # audio-understanding LLMs: padded log-mel windows + true frame counts
+            px = torch.as_tensor(np.asarray(mm["audio_features"], dtype=np.float32), device=device)
+            flat = model.encode_audio(px.to(dtype), mm["audio_frames"])
+        elif mm.get("pixel_patches") is not None:     # dynamic-resolution towers (Qwen2-VL): flattened patches + grids
             px = torch.as_tensor(np.asarray(mm["pixel_patches"], dtype=np.float32), device=device)
             flat = model.encode_images(px.to(dtype), mm["grid_thw"])
         else:
