@@ -6,11 +6,15 @@ Parity: reference ``python/sglang/srt/configs/model_config.py`` (arch detection,
 """
 from __future__ import annotations
 
+import logging
+
 import dataclasses
 import json
 import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass
@@ -346,6 +350,9 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
 def _has_native_class(arch: str) -> bool:
     from ..models.registry import supported_architectures
 
+    # speculative draft heads are built by their workers (speculative/eagle.py), not through the registry
+    if arch.endswith(("Eagle", "Eagle3", "NextN", "MTP")) or "Eagle" in arch:
+        return True
     return arch in supported_architectures()
 
 
@@ -647,7 +654,12 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             kw["hidden_act"] = text["hidden_activation"]
         kw["name"] = os.path.basename(model_path.rstrip("/"))
         if impl == "transformers" or (impl == "auto" and not model_path.endswith(".gguf") and not _has_native_class(kw["architecture"])):
-            kw = _transformers_fallback_config(model_path, arch, kw)
+            try:
+                kw = _transformers_fallback_config(model_path, arch, kw)
+            except Exception as e:          # not a Hugging Face model directory either: the registry reports the unknown architecture later
+                if impl == "transformers":
+                    raise
+                logger.debug("no Transformers fallback for %s: %s", arch, e)
         kw.update(overrides)
     cfg = ModelConfig(**kw)
     if context_length is not None:

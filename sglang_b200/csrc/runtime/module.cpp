@@ -123,6 +123,18 @@ PYBIND11_MODULE(sglb_rt, m) {
         return py::make_tuple(to_np(toks), to_np(parents));
       }, py::arg("context"), py::arg("max_nodes"), py::arg("branch") = 2, py::arg("min_match") = 1)
       .def("num_nodes", &NgramCorpus::num_nodes);
+  py::class_<SuffixAutomaton>(m, "SuffixAutomaton")
+      .def(py::init<int64_t>(), py::arg("max_states") = (int64_t)1 << 23)
+      .def("reset", &SuffixAutomaton::reset)
+      .def("insert", [](SuffixAutomaton& c, i32arr toks, bool terminate) { py::gil_scoped_release r; c.insert(toks.data(), toks.size(), terminate); },
+           py::arg("tokens"), py::arg("terminate") = true)
+      .def("match_chain", [](SuffixAutomaton& c, i32arr ctx, int max_draft, int min_match) {
+        int matched = 0;
+        auto v = c.match_chain(ctx.data(), ctx.size(), max_draft, min_match, &matched);
+        return py::make_tuple(to_np(v), matched);
+      })
+      .def("num_states", &SuffixAutomaton::num_states)
+      .def("num_tokens", &SuffixAutomaton::num_tokens);
 
   py::class_<sglb::KvIndexer>(m, "KvIndexer")
       .def(py::init<>())

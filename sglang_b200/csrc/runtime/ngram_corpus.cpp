@@ -103,4 +103,100 @@ void NgramCorpus::match_tree(const int32_t* context, int64_t n, int max_nodes, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------ suffix automaton
+static const int32_t kSep = -1;
+
+void SuffixAutomaton::reset() {
+  std::lock_guard<std::mutex> g(mu_);
+  st_.clear();
+  st_.emplace_back();
+  text_.clear();
+  last_ = 0;
+}
+
+int32_t SuffixAutomaton::get(const State& s, int32_t tok) const {
+  auto it = std::lower_bound(s.next.begin(), s.next.end(), std::make_pair(tok, INT32_MIN));
+  return (it != s.next.end() && it->first == tok) ? it->second : -1;
+}
+
+void SuffixAutomaton::set(State& s, int32_t tok, int32_t to) {
+  auto it = std::lower_bound(s.next.begin(), s.next.end(), std::make_pair(tok, INT32_MIN));
+  if (it != s.next.end() && it->first == tok) it->second = to;
+  else s.next.insert(it, std::make_pair(tok, to));
+}
+
+void SuffixAutomaton::extend(int32_t tok) {
+  text_.push_back(tok);
+  int32_t cur = (int32_t)st_.size();
+  st_.emplace_back();
+  st_[cur].len = st_[last_].len + 1;
+  st_[cur].end = (int64_t)text_.size() - 1;
+  int32_t p = last_;
+  while (p != -1 && get(st_[p], tok) == -1) {
+    set(st_[p], tok, cur);
+    p = st_[p].link;
+  }
+  if (p == -1) {
+    st_[cur].link = 0;
+  } else {
+    int32_t q = get(st_[p], tok);
+    if (st_[p].len + 1 == st_[q].len) {
+      st_[cur].link = q;
+    } else {
+      int32_t cl = (int32_t)st_.size();
+      st_.push_back(st_[q]);                     // clone keeps q's transitions, link and first-occurrence end
+      st_[cl].len = st_[p].len + 1;
+      while (p != -1 && get(st_[p], tok) == q) {
+        set(st_[p], tok, cl);
+        p = st_[p].link;
+      }
+      st_[q].link = st_[cur].link = cl;
+    }
+  }
+  last_ = cur;
+}
+
+void SuffixAutomaton::insert(const int32_t* tokens, int64_t n, bool terminate) {
+  std::lock_guard<std::mutex> g(mu_);
+  if ((int64_t)st_.size() + 2 * (n + 1) > max_states_) {          // full: start over (the corpus is a cache, not a record)
+    st_.clear();
+    st_.emplace_back();
+    text_.clear();
+    last_ = 0;
+  }
+  for (int64_t i = 0; i < n; ++i) extend(tokens[i]);
+  if (terminate) extend(kSep);
+}
+
+std::vector<int32_t> SuffixAutomaton::match_chain(const int32_t* context, int64_t n, int max_draft, int min_match, int* matched_len) const {
+  std::lock_guard<std::mutex> g(mu_);
+  int32_t s = 0;
+  int l = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t t = context[i];
+    while (s != 0 && get(st_[s], t) == -1) {
+      s = st_[s].link;
+      l = st_[s].len;
+    }
+    int32_t to = get(st_[s], t);
+    if (to != -1) {
+      s = to;
+      ++l;
+    } else {
+      s = 0;
+      l = 0;
+    }
+  }
+  if (matched_len) *matched_len = l;
+  std::vector<int32_t> out;
+  if (l < min_match || s == 0) return out;
+  // prefer an occurrence that has something after it: walk up the suffix links while the first occurrence sits at the very end of the text
+  while (s != 0 && (st_[s].end + 1 >= (int64_t)text_.size() || text_[st_[s].end + 1] == kSep) && st_[st_[s].link].len >= min_match) s = st_[s].link;
+  for (int64_t p = st_[s].end + 1; p < (int64_t)text_.size() && (int)out.size() < max_draft; ++p) {
+    if (text_[p] == kSep) break;
+    out.push_back(text_[p]);
+  }
+  return out;
+}
+
 }  // namespace sglb_rt

@@ -242,7 +242,7 @@ def install_adapters(app: Any, engine: Any, serving: Any) -> None:
     async def anthropic_count(request: Request):
         body = await request.json()
         r = _anthropic_to_chat({**body, "max_tokens": 1})
-        prompt, _ = serving._render_chat(r)
+        prompt, _, _ = serving._render_chat(r)
         return {"input_tokens": len(engine.tokenizer.encode(prompt))}
 
     # ----- Ollama

@@ -131,15 +131,20 @@ class OpenAIServing:
         yield "data: [DONE]\n\n"
 
     # ------------------------------------------------------------------ chat
-    def _render_chat(self, r: P.ChatCompletionRequest) -> Tuple[str, Optional[List[Any]]]:
+    def _render_chat(self, r: P.ChatCompletionRequest) -> Tuple[str, Optional[List[Any]], Optional[List[Any]]]:
         msgs = [m.model_dump(exclude_none=True) for m in r.messages]
         images: List[Any] = []
+        audios: List[Any] = []
         for m in msgs:
             c = m.get("content")
             if isinstance(c, list):
                 for part in c:
                     if part.get("type") == "image_url":
                         images.append(part["image_url"]["url"] if isinstance(part["image_url"], dict) else part["image_url"])
+                    elif part.get("type") == "audio_url":          # URL / path / data-URL of a WAV clip
+                        audios.append(part["audio_url"]["url"] if isinstance(part["audio_url"], dict) else part["audio_url"])
+                    elif part.get("type") == "input_audio":        # OpenAI form: {"data": <base64>, "format": "wav"}
+                        audios.append(part["input_audio"]["data"] if isinstance(part["input_audio"], dict) else part["input_audio"])
         tools = [t.model_dump() for t in r.tools] if r.tools else None
         kw = dict(r.chat_template_kwargs or {})
         try:
@@ -147,7 +152,7 @@ class OpenAIServing:
                                                 tools=tools, **kw)
         except TypeError:
             text = self.tok.apply_chat_template(msgs, tokenize=False, add_generation_prompt=not r.continue_final_message)
-        return text, (images or None)
+        return text, (images or None), (audios or None)
 
     def _chat_sampling(self, r: P.ChatCompletionRequest) -> Dict[str, Any]:
         sp = r.base_sampling(r.max_completion_tokens or r.max_tokens)
@@ -165,11 +170,13 @@ class OpenAIServing:
         return sp
 
     async def chat_completions(self, r: P.ChatCompletionRequest):
-        prompt, images = self._render_chat(r)
+        prompt, images, audios = self._render_chat(r)
         sp = self._chat_sampling(r)
         rid = r.rid or P.new_id("chatcmpl")
         gen_kw = dict(sampling_params=sp, return_logprob=r.logprobs, top_logprobs_num=r.top_logprobs or 0,
                       lora_path=r.lora_path, priority=r.priority, image_data=images)
+        if audios:
+            gen_kw["audio_data"] = audios
         if r.stream:
             return self._stream_chat(r, prompt, gen_kw, rid)
         outs = await self.engine.async_generate(prompt, **gen_kw)

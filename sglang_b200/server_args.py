@@ -124,6 +124,7 @@ class ServerArgs:
     device: str = "auto"
     # --- speculative decoding
     speculative_algorithm: Optional[str] = None  # EAGLE|NGRAM|STANDALONE
+    speculative_ngram_index: str = "trie"        # NGRAM drafts from: trie (bounded n-gram depth, chain + tree) | suffix_automaton (unbounded matches)
     enable_dwdp: bool = False                    # DP-attention + EP prefill: prefetch peers' expert weights instead of dispatching tokens
     dwdp_min_tokens: int = 1024                  # DP-wide new-token count from which a forward uses DWDP
     dllm_algorithm: Optional[str] = None         # diffusion-LLM block decoding: LowConfidence | JointThreshold | a registered plug-in

@@ -198,37 +198,66 @@ class BaseSpecWorker:
 
 
 class NgramSpecWorker(BaseSpecWorker):
-    """drafts from an n-gram trie over everything this server has seen (prompts + generations)"""
+    """drafts from an n-gram index over everything this server has seen (prompts + generations).  ``--speculative-ngram-index trie``: the
+    bounded-depth counting trie (chain and tree drafts); ``suffix_automaton``: longest-suffix matches of unbounded length over the whole
+    token stream (chain drafts; reference ``ngram_corpus/suffix_automaton.cpp``)."""
 
     def __init__(self, args: Any, runner: Any, scheduler: Any, max_depth: int = 12):
         super().__init__(args, runner, scheduler)
         from .. import sglb_rt
 
-        self.corpus = sglb_rt.NgramCorpus(max_depth, 1 << 22)
-        self.max_depth = max_depth
+        self.index = getattr(args, "speculative_ngram_index", "trie") or "trie"
+        self.max_depth = max_depth if self.index == "trie" else 64
+        self.corpus = sglb_rt.NgramCorpus(max_depth, 1 << 22) if self.index == "trie" else sglb_rt.SuffixAutomaton(1 << 23)
         self._seen_prompt = set()
+        self._pending: dict = {}          # suffix automaton: generated tokens not yet in the index, per request
 
     def _ctx(self, req: Any) -> np.ndarray:
+        if self._pending:
+            self._flush_finished()
         if id(req) not in self._seen_prompt:
             self._seen_prompt.add(id(req))
             self.corpus.insert(np.asarray(req.origin_input_ids, dtype=np.int32))
         return np.asarray((req.origin_input_ids + req.output_ids)[-self.max_depth:], dtype=np.int32)
 
     def propose(self, req: Any, max_draft: int) -> List[int]:
+        if self.index != "trie":
+            return self.corpus.match_chain(self._ctx(req), max_draft, 2)[0].tolist()
         return self.corpus.match_chain(self._ctx(req), max_draft, 2).tolist()
 
     def propose_tree(self, req: Any, max_nodes: int):
         branch = int(self.args.speculative_eagle_topk or 1)
-        if branch <= 1:
+        if branch <= 1 or self.index != "trie":
             return super().propose_tree(req, max_nodes)
         toks, parents = self.corpus.match_tree(self._ctx(req), max_nodes, branch, 2)      # breadth-first over the trie's continuations
         return np.asarray(toks).tolist(), np.asarray(parents).tolist()
 
     def on_tokens_accepted(self, req: Any, new_tokens: List[int]) -> None:
-        tail = (req.origin_input_ids + req.output_ids)[-(self.max_depth - 1):] + list(new_tokens)
-        self.corpus.insert(np.asarray(tail, dtype=np.int32))
+        if self.index == "trie":
+            tail = (req.origin_input_ids + req.output_ids)[-(self.max_depth - 1):] + list(new_tokens)
+            self.corpus.insert(np.asarray(tail, dtype=np.int32))
+        else:
+            # the automaton indexes ONE token stream, so a request's generation enters it in closed pieces (with a little left context so
+            # that matches can run across the piece boundary), not token by token interleaved with other requests
+            n = self._pending.get(id(req), (req, 0))[1] + len(new_tokens)
+            if n >= 32:
+                allt = req.origin_input_ids + req.output_ids + list(new_tokens)          # (called before the tokens are appended to the request)
+                self.corpus.insert(np.asarray(allt[-(n + 16):], dtype=np.int32))
+                n = 0
+            self._pending[id(req)] = (req, n)
+            self._flush_finished()
         if req.finished():
             self._seen_prompt.discard(id(req))
+
+    def _flush_finished(self) -> None:
+        """index the unindexed tail of requests that have finished since the last call (the finish test runs after ``on_tokens_accepted``)"""
+        for k, (r, n) in list(self._pending.items()):
+            if r.finished():
+                if n > 0:
+                    allt = r.origin_input_ids + r.output_ids
+                    self.corpus.insert(np.asarray(allt[-(n + 16):], dtype=np.int32))
+                self._pending.pop(k, None)
+                self._seen_prompt.discard(k)
 
 
 class StandaloneSpecWorker(BaseSpecWorker):

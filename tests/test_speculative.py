@@ -253,3 +253,70 @@ def test_mtp_nextn_draft_from_target_checkpoint(tmp_path, preset):
     assert w.total_drafted > 0
     eng.scheduler.check_invariants()
     eng.shutdown()
+
+
+def test_suffix_automaton_matches_bruteforce_longest_suffix():
+    """C++ suffix automaton (csrc/runtime/ngram_corpus.cpp): the reported match length equals the brute-force longest suffix of the context
+    that occurs inside ONE inserted sequence, and the draft is what followed an occurrence of it"""
+    import numpy as np
+
+    from sglang_b200 import sglb_rt
+
+    rng = np.random.default_rng(0)
+    sa = sglb_rt.SuffixAutomaton(1 << 20)
+    seqs = [rng.integers(0, 6, size=int(n)).astype(np.int32) for n in rng.integers(5, 60, size=30)]
+    for s in seqs:
+        sa.insert(s, True)
+    assert sa.num_tokens() == sum(len(s) + 1 for s in seqs)
+
+    def occurs(sub, s):
+        n = len(sub)
+        return [i for i in range(len(s) - n + 1) if (s[i:i + n] == sub).all()]
+
+    for _ in range(200):
+        ctx = rng.integers(0, 6, size=int(rng.integers(1, 20))).astype(np.int32)
+        draft, matched = sa.match_chain(ctx, 8, 1)
+        best = 0
+        for l in range(len(ctx), 0, -1):
+            if any(occurs(ctx[-l:], s) for s in seqs):
+                best = l
+                break
+        assert matched == best
+        if best == 0:
+            assert len(draft) == 0
+            continue
+        # the draft continues SOME occurrence of a suffix of the context (a shorter suffix when the longest one only occurs at a sequence end)
+        ok = len(draft) == 0
+        for l in range(best, 0, -1):
+            for s in seqs:
+                for i in occurs(ctx[-l:], s):
+                    nxt = s[i + l:i + l + len(draft)]
+                    if len(draft) and len(nxt) == len(draft) and (nxt == draft).all():
+                        ok = True
+        assert ok
+    # no match crosses a sequence boundary
+    a, b = np.asarray([1, 2, 3, 4], np.int32) + 100, np.asarray([5, 6, 7], np.int32) + 100
+    sa.insert(a, True)
+    sa.insert(b, True)
+    assert sa.match_chain(np.asarray([103, 104, 105], np.int32), 4, 3)[1] < 3
+    d, m = sa.match_chain(np.asarray([101, 102], np.int32), 4, 2)
+    assert m == 2 and d.tolist() == [103, 104]
+
+
+def test_ngram_worker_with_suffix_automaton_index_is_lossless():
+    """--speculative-ngram-index suffix_automaton: same tokens as plain decoding, with accepted drafts on a repetitive prompt"""
+    ids = ([7, 8, 9, 10, 11, 12] * 12)[:70]
+    sp = {"max_new_tokens": 24, "temperature": 0, "ignore_eos": True}
+    ref = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error")
+    want = ref.generate(input_ids=ids, sampling_params=sp)["output_ids"]
+    ref.shutdown()
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error", speculative_algorithm="NGRAM",
+                     speculative_num_draft_tokens=4, speculative_ngram_index="suffix_automaton")
+    try:
+        got = eng.generate(input_ids=ids, sampling_params=sp)["output_ids"]
+        got2 = eng.generate(input_ids=ids, sampling_params=sp)["output_ids"]          # second pass: the first generation is in the index now
+        sw = eng.scheduler.spec_worker
+        assert got == want and got2 == want
+        assert sw.total_drafted > 0 and sw.corpus.num_tokens() > len(ids)
+    finally:
+        eng.shutdown()
