@@ -17,24 +17,31 @@ import torch
 
 class KVPool:
     def __init__(self, num_pages: int, page_size: int, num_layers: int, num_kv_heads: int, head_dim: int,
-                 dtype: torch.dtype, device: str):
+                 dtype: torch.dtype, device: str, latent_v_dim: int = 0):
+        """``latent_v_dim > 0``: MLA latent cache (reference ``MLATokenToKVPool``) — ONE plane of ``head_dim``-wide rows per token
+        (compressed KV | rope key); the "value" the absorbed attention reads is the first ``latent_v_dim`` columns of the same row, so
+        nothing is stored twice."""
         self.num_pages, self.page_size = num_pages, page_size
         self.num_layers, self.num_kv_heads, self.head_dim = num_layers, num_kv_heads, head_dim
         self.dtype, self.device = dtype, device
         self.num_slots = num_pages * page_size
-        self.buf = torch.zeros(num_layers, 2, self.num_slots, num_kv_heads, head_dim, dtype=dtype, device=device)
+        self.latent_v_dim = int(latent_v_dim)
+        self.planes = 1 if self.latent_v_dim > 0 else 2
+        self.buf = torch.zeros(num_layers, self.planes, self.num_slots, num_kv_heads, head_dim, dtype=dtype, device=device)
         # per-tensor scales for fp8 KV (1.0 for bf16)
         self.k_scale = 1.0
         self.v_scale = 1.0
 
     @staticmethod
-    def bytes_per_page(page_size: int, num_layers: int, num_kv_heads: int, head_dim: int, dtype: torch.dtype) -> int:
-        return 2 * num_layers * page_size * num_kv_heads * head_dim * torch.empty((), dtype=dtype).element_size()
+    def bytes_per_page(page_size: int, num_layers: int, num_kv_heads: int, head_dim: int, dtype: torch.dtype, planes: int = 2) -> int:
+        return planes * num_layers * page_size * num_kv_heads * head_dim * torch.empty((), dtype=dtype).element_size()
 
     def k(self, layer: int) -> torch.Tensor:
         return self.buf[layer, 0]
 
     def v(self, layer: int) -> torch.Tensor:
+        if self.planes == 1:          # MLA: a column view of the latent rows (writes go through k())
+            return self.buf[layer, 0][..., : self.latent_v_dim]
         return self.buf[layer, 1]
 
     def move_slots(self, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -47,8 +54,8 @@ class KVPool:
 
     # page-granular views for transfer engines (PD disaggregation / HiCache)
     def page_view(self) -> torch.Tensor:
-        """[layers, 2, num_pages, page_size, kv_heads, head_dim]"""
-        return self.buf.view(self.num_layers, 2, self.num_pages, self.page_size, self.num_kv_heads, self.head_dim)
+        """[layers, planes, num_pages, page_size, kv_heads, head_dim]"""
+        return self.buf.view(self.num_layers, self.planes, self.num_pages, self.page_size, self.num_kv_heads, self.head_dim)
 
     def gather_pages(self, pages: torch.Tensor) -> torch.Tensor:
         return self.page_view().index_select(2, pages)
@@ -103,11 +110,12 @@ class HostKVPool:
         assert layout in ("layer_first", "page_first"), layout
         self.num_pages, self.layout = num_pages, layout
         L, ps, H, D = like.num_layers, like.page_size, like.num_kv_heads, like.head_dim
-        shape = (L, 2, num_pages, ps, H, D) if layout == "layer_first" else (num_pages, L, 2, ps, H, D)
+        P = getattr(like, "planes", 2)            # 1 for the MLA latent pool
+        shape = (L, P, num_pages, ps, H, D) if layout == "layer_first" else (num_pages, L, P, ps, H, D)
         self.buf = torch.empty(shape, dtype=like.dtype, device="cpu")
         if pin and torch.cuda.is_available():
             self.buf = self.buf.pin_memory()
-        self.planes = L * 2
+        self.planes = L * P
         self.chunk_bytes = ps * H * D * self.buf.element_size()
         self._free = list(range(num_pages - 1, -1, -1))
         self.kernel_transfers = 0

@@ -211,7 +211,8 @@ class ModelRunner:
                 raise ValueError("--swa-full-tokens-ratio: not combined with DCP / CP / PP / HiCache / speculative decoding yet")
             self.swa = {"layers": sliding, "ratio": min(1.0, ratio), "window": max(self.model.model.layers[i].self_attn.attn.window for i in sliding)}
         eff_layers = n_layers if self.swa is None else (n_layers - len(sliding)) + self.swa["ratio"] * len(sliding)
-        per_page = KVPool.bytes_per_page(self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype)
+        latent_v = int(getattr(a0, "latent_v_dim", 0) or 0)       # MLA: one latent plane, the value is a column view of it
+        per_page = KVPool.bytes_per_page(self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, 1 if latent_v else 2)
         if self.swa is not None:
             per_page = int(per_page * eff_layers / n_layers)
         self.max_context_len = a.context_length or cfg.max_position_embeddings
@@ -234,7 +235,7 @@ class ModelRunner:
             num_pages = int(t.item())
         self.num_pages = int(num_pages)
         if self.swa is None:
-            self.kv_pool = KVPool(self.num_pages, self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device))
+            self.kv_pool = KVPool(self.num_pages, self.local_page_size, n_layers, kv_heads, kv_dim, kv_dtype, str(self.device), latent_v)
         else:
             from ..mem_cache.memory_pool import HybridKVPool
 

@@ -37,6 +37,7 @@ class _LatentAttn:
 
     def __init__(self, num_heads: int, kv_dim: int, layer_id: int, scale: float):
         self.num_heads, self.num_kv_heads, self.head_dim, self.kv_head_dim = num_heads, 1, kv_dim, kv_dim
+        self.latent_v_dim = 0          # set by the attention module: kv_lora_rank (the runner then builds a one-plane latent pool)
         self.layer_id, self.scale, self.window, self.logit_cap, self.rope = layer_id, scale, -1, 0.0, None
 
 
@@ -67,6 +68,7 @@ class DeepseekV2AttentionMLA(nn.Module):
             m = 0.1 * float(rs["mscale_all_dim"]) * math.log(float(rs.get("factor", 1.0))) + 1.0 if float(rs.get("factor", 1.0)) > 1 else 1.0
             scale *= m * m
         self.attn = _LatentAttn(self.nh, self.kv_rank + self.rope_dim, layer_id, scale)
+        self.attn.latent_v_dim = self.kv_rank
         self.layer_id = layer_id
         self.cos_sin = torch_ref.build_cos_sin_cache(self.rope_dim, cfg.max_position_embeddings, cfg.rope_theta, None, self.rope_dim)
 
@@ -93,9 +95,13 @@ class DeepseekV2AttentionMLA(nn.Module):
         kc, vc = pool.k(self.layer_id), pool.v(self.layer_id)
         loc = fb.out_cache_loc.long()
         kc[loc] = torch.cat([c_kv, k_pe.squeeze(1).to(c_kv.dtype)], dim=-1).unsqueeze(1).to(kc.dtype)
-        vc[loc] = torch.cat([c_kv, torch.zeros(T, self.rope_dim, dtype=c_kv.dtype, device=x.device)], dim=-1).unsqueeze(1).to(vc.dtype)
-        o_lat = torch_ref.paged_attention(q_abs, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.q_lens, fb.page_size, self.attn.scale,
-                                          True, -1, 0.0)[..., : self.kv_rank]
+        if getattr(pool, "planes", 2) == 1:       # latent pool: the value IS the first kv_rank columns of the row just written (vc = column view)
+            o_lat = torch_ref.paged_attention(q_abs, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.q_lens, fb.page_size, self.attn.scale,
+                                              True, -1, 0.0)
+        else:
+            vc[loc] = torch.cat([c_kv, torch.zeros(T, self.rope_dim, dtype=c_kv.dtype, device=x.device)], dim=-1).unsqueeze(1).to(vc.dtype)
+            o_lat = torch_ref.paged_attention(q_abs, kc, vc, fb.page_table, fb.req_slots, fb.seq_lens, fb.q_lens, fb.page_size, self.attn.scale,
+                                              True, -1, 0.0)[..., : self.kv_rank]
         o = torch.einsum("thk,hdk->thd", o_lat.float(), w_vc.float()).to(x.dtype).reshape(T, self.nh * self.vdim)
         return self.o_proj(o, defer_reduce=True)
 

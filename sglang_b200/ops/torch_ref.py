@@ -152,7 +152,7 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
     Hkv = k_cache.shape[1]
     g = Hq // Hkv
     B = req_slots.shape[0]
-    out = torch.empty_like(q)
+    out = q.new_empty(T, Hq, v_cache.shape[-1])          # (the value width may differ from the key width: MLA latent rows)
     lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
     qs = 0
     mask_off = 0

@@ -94,3 +94,31 @@ def test_write_policies():
     assert writes["write_through"][0] > 0
     assert writes["write_through_selective"][0] == 0 and writes["write_through_selective"][1] > 0
     assert writes["write_back"] == (0, 0)
+
+
+@pytest.mark.parametrize("layout", ["layer_first", "page_first"])
+def test_mla_latent_pool_is_one_plane_and_survives_the_host_tier(layout):
+    """DeepSeek MLA: the KV pool is ONE 576-wide latent plane (value = column view of the same rows); evicting to the host tier and loading
+    back (both host layouts) reproduces the generation"""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    A = rng.integers(3, 250, size=61).tolist()
+    fillers = [rng.integers(3, 250, size=70).tolist() for _ in range(4)]
+    sp = {"max_new_tokens": 6, "temperature": 0, "ignore_eos": True}
+    eng = sgl.Engine(model_path="dummy:tiny-deepseek-v3", device="cpu", page_size=4, max_total_tokens=200, enable_hierarchical_cache=True,
+                     hicache_ratio=4.0, radix_cache_impl="python", hicache_mem_layout=layout, log_level="error")
+    try:
+        pool = eng.runner.kv_pool
+        cfg = eng.model_config
+        assert pool.planes == 1 and pool.buf.shape[1] == 1 and pool.buf.shape[-1] == cfg.kv_lora_rank + cfg.qk_rope_head_dim
+        assert pool.v(0).shape[-1] == cfg.kv_lora_rank and pool.v(0).data_ptr() == pool.k(0).data_ptr()
+        ref = eng.generate(input_ids=A, sampling_params=sp)
+        for f in fillers:                       # push A's pages out of the device pool
+            eng.generate(input_ids=f, sampling_params=sp)
+        again = eng.generate(input_ids=A, sampling_params=sp)
+        tree = eng.scheduler.kv.tree
+        assert again["output_ids"] == ref["output_ids"]
+        assert tree.stats["host_writes"] > 0 and tree.stats["host_hits_pages"] > 0 and again["meta_info"]["cached_tokens"] > 0
+    finally:
+        eng.shutdown()
