@@ -15,6 +15,8 @@ scheduler share that process; two drive modes exist:
 """
 from __future__ import annotations
 
+import os
+
 import asyncio
 import dataclasses
 import logging
@@ -603,6 +605,30 @@ class Engine:
                 self._shm_bcast = None
         self._bg_thread = threading.Thread(target=self._bg_loop, name="sglb-scheduler", daemon=True)
         self._bg_thread.start()
+        a = self.server_args
+        if getattr(self, "_watchdog", None) is None and a.watchdog_timeout and a.watchdog_timeout > 0:
+            from ..utils.watchdog import SchedulerWatchdog
+
+            # reference utils/watchdog.py: forward_ct must advance while work is pending; soft timeout logs, hard timeout dumps and stops
+            self._watchdog = SchedulerWatchdog(self.scheduler, float(a.watchdog_timeout), a.soft_watchdog_timeout,
+                                               interval=min(1.0, max(0.05, float(a.watchdog_timeout) / 10)), on_hard=self._on_watchdog_timeout).start()
+
+    wedged = False
+    exit_on_watchdog = False          # servers set this: a wedged scheduler thread cannot be recovered, the process tree goes down
+
+    def _on_watchdog_timeout(self) -> None:
+        self.wedged = True
+        try:
+            path = self.dump_requests_before_crash()
+            logger.error("watchdog: in-flight requests dumped to %s", path)
+        except Exception as e:
+            logger.error("watchdog: crash dump failed: %s", e)
+        if self.exit_on_watchdog:
+            from ..utils.process_tree import kill_process_tree
+
+            kids = [p for p in (getattr(self, "_p_sched", None), getattr(self, "_p_detok", None)) if p is not None] + list(getattr(self, "_peers", []) or [])
+            kill_process_tree(kids, grace_s=1.0)
+            os._exit(1)
 
     def _bg_loop(self) -> None:
         sch = self.scheduler
@@ -694,6 +720,10 @@ class Engine:
             self.states.clear()
 
     def shutdown(self) -> None:
+        wd = getattr(self, "_watchdog", None)
+        if wd is not None:
+            wd.stop()
+            self._watchdog = None
         self._bg_stop.set()
         self._wake.set()
         if self._bg_thread is not None:

@@ -433,6 +433,7 @@ def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], pee
     import uvicorn
 
     app = create_app(engine)
+    engine.exit_on_watchdog = True          # a server whose scheduler stopped making progress dumps its requests and goes down
 
     @app.on_event("startup")
     async def _warm():

@@ -450,8 +450,8 @@ class ModelRunner:
 
     # ------------------------------------------------------------------ attention split heuristic
     def _pick_splits(self, bs: int, max_kv: int) -> int:
-        if not self.is_cuda:
-            return 1
+        if not self.is_cuda or getattr(self.args, "enable_deterministic_inference", False):
+            return 1          # (deterministic mode: a request's softmax reduction tree must not follow the batch size)
         if not len(self.model.model.layers):
             return 1
         kvh = self.model.model.layers[0].self_attn.attn.num_kv_heads

@@ -38,7 +38,6 @@ class ServerArgs:
     chat_template: Optional[str] = None
     is_embedding: bool = False
     skip_tokenizer_init: bool = False
-    revision: Optional[str] = None
     json_model_override_args: str = "{}"
     # --- server
     host: str = "127.0.0.1"
@@ -75,7 +74,6 @@ class ServerArgs:
     radix_cache_impl: str = "auto"  # auto|cpp|python
     disable_overlap_schedule: bool = False
     stream_interval: int = 1
-    num_continuous_decode_steps: int = 1
     enable_prefill_delayer: bool = False
     prefill_delayer_max_delay_passes: int = 30
     prefill_delayer_token_usage_low_watermark: Optional[float] = None
@@ -101,8 +99,6 @@ class ServerArgs:
     base_gpu_id: int = 0
     nccl_port: Optional[int] = None
     comm_backend: str = "auto"  # auto|nvl|nccl
-    enable_fused_gemm_allreduce: bool = True
-    launch_mode: str = "inproc"  # inproc (SPMD / single process) | subprocess (ZMQ)
     # --- kernels / runtime
     attention_backend: str = "auto"  # auto|tc|simt|torch_native
     sampling_backend: str = "auto"  # auto|native|pytorch|token_oracle
@@ -161,8 +157,6 @@ class ServerArgs:
     encoder_only: bool = False            # EPD: serve only the vision tower (disaggregation/encoder.py)
     language_only: bool = False           # EPD: do not load the vision tower; images require --encoder-urls
     encoder_urls: Optional[List[str]] = None
-    enable_multimodal: Optional[bool] = None
-    mm_attention_backend: Optional[str] = None
     # --- debugging
     kv_canary: str = "none"
     enable_kv_events: bool = False
@@ -188,6 +182,16 @@ class ServerArgs:
             self.load_format = "dummy" if self.model_path.startswith("dummy:") else ("gguf" if self.model_path.endswith(".gguf") else "safetensors")
         if self.http_frontend not in ("uvicorn", "native"):
             raise ValueError("--http-frontend must be uvicorn or native")
+        if self.enable_deterministic_inference:
+            # reduction orders must not depend on what else is in the batch: no split-K / stream-K GEMM variants (their split count follows
+            # the token count), one attention split per request (model_runner._pick_splits), the library all-reduce for every size (the
+            # size-based switch between the one-shot kernel and NCCL changes the summation order with the batch)
+            import os as _os
+
+            _os.environ["SGLB_SKINNY"] = "off"
+            _os.environ["SGLB_STREAMK_MAX_M"] = "0"
+            _os.environ["SGLB_TP_LIBRARY_AR_MIN_BYTES"] = "0"
+            _os.environ["SGLB_RS_AG_MIN_BYTES"] = "0"
         if self.model_impl not in ("auto", "sglang", "transformers"):
             raise ValueError("--model-impl must be auto, sglang or transformers")
         if self.model_impl != "auto":          # travels with the other config overrides to every process that reads the model config

@@ -137,3 +137,44 @@ def test_device_timer_cpu():
             torch.randn(64, 64) @ torch.randn(64, 64)
     s = t.summary()
     assert s["mm"]["calls"] == 3 and s["mm"]["ms"] > 0
+
+
+def test_engine_watchdog_fires_on_a_stuck_forward(tmp_path, monkeypatch):
+    """--watchdog-timeout is wired into the engine's background loop: a forward pass that hangs longer than the hard timeout produces the
+    soft warning first, then the crash dump of the in-flight requests, and marks the engine wedged (servers additionally exit)"""
+    import asyncio
+    import os
+
+    monkeypatch.setenv("SGLB_TEST_STUCK_SCHEDULER", "2.5")
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error", watchdog_timeout=1.0, soft_watchdog_timeout=0.3,
+                     crash_dump_folder=str(tmp_path / "dumps"))
+    try:
+        async def go():
+            return await eng.async_generate(input_ids=[5, 6, 7], sampling_params={"max_new_tokens": 2, "temperature": 0})
+
+        out = asyncio.run(go())                       # the stuck forward eventually completes (2.5 s per pass)
+        assert len(out["output_ids"]) == 2
+        wd = eng._watchdog
+        assert wd.fired_soft >= 1 and wd.fired_hard == 1 and eng.wedged
+        dumps = os.listdir(tmp_path / "dumps")
+        assert dumps and json.load(open(tmp_path / "dumps" / dumps[0]))["requests"][0]["input_ids"] == [5, 6, 7]
+    finally:
+        eng.shutdown()
+
+
+def test_deterministic_inference_flag_pins_reduction_orders(monkeypatch):
+    import os
+
+    for k in ("SGLB_SKINNY", "SGLB_STREAMK_MAX_M", "SGLB_TP_LIBRARY_AR_MIN_BYTES"):
+        monkeypatch.delenv(k, raising=False)
+    from sglang_b200.server_args import ServerArgs
+
+    ServerArgs(model_path="dummy:tiny-llama", enable_deterministic_inference=True)
+    assert os.environ["SGLB_SKINNY"] == "off" and os.environ["SGLB_STREAMK_MAX_M"] == "0" and os.environ["SGLB_TP_LIBRARY_AR_MIN_BYTES"] == "0"
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error", enable_deterministic_inference=True)
+    try:
+        eng.runner.is_cuda = True                     # the split heuristic is a pure function of its arguments
+        assert eng.runner._pick_splits(1, 1 << 16) == 1
+    finally:
+        eng.runner.is_cuda = False
+        eng.shutdown()
