@@ -94,16 +94,13 @@ class _Envs:
     SGLB_TP_GREEDY_SHARD = EnvBool("SGLB_TP_GREEDY_SHARD", True, "TP > 1: all-greedy decode batches take a vocab-parallel argmax (8 bytes per rank and row through the arena) instead of the [B, V] logits all-gather")
     SGLB_ATTN_DECODE = EnvStr("SGLB_ATTN_DECODE", "v3", "v3 = keys-as-M decode kernel (attention_decode.cu) | v2 = query-major kernel")
     SGLB_DISABLE_CUDA_GRAPH = EnvBool("SGLB_DISABLE_CUDA_GRAPH", False)
-    SGLB_KERNEL_LAUNCH_COUNT = EnvBool("SGLB_KERNEL_LAUNCH_COUNT", True, "count native kernel launches")
     # --- scheduler test hooks (reference: SGLANG_TEST_RETRACT etc., environ.py:384-393)
     SGLB_TEST_RETRACT = EnvBool("SGLB_TEST_RETRACT", False, "force a decode retraction every N steps")
     SGLB_TEST_RETRACT_INTERVAL = EnvInt("SGLB_TEST_RETRACT_INTERVAL", 3)
     SGLB_TEST_STUCK_SCHEDULER = EnvFloat("SGLB_TEST_STUCK_SCHEDULER", 0.0, "sleep seconds inside a forward (watchdog tests)")
     SGLB_TEST_DISAGG_FAILURE_PROB = EnvFloat("SGLB_TEST_DISAGG_FAILURE_PROB", 0.0)
     SGLB_STRICT_MEM_CHECK = EnvBool("SGLB_STRICT_MEM_CHECK", False, "run the pool invariant checker every busy step")
-    SGLB_SIMULATE_ACC_LEN = EnvFloat("SGLB_SIMULATE_ACC_LEN", -1.0, "simulated speculative accept length")
     # --- KV canary (reference: S/kv_canary)
-    SGLB_KV_CANARY = EnvStr("SGLB_KV_CANARY", "none", "none|log|raise")
     # --- distributed
     SGLB_COMM_IMPL = EnvStr("SGLB_COMM_IMPL", "auto", "auto|nvl (own P2P/multicast kernels)|nccl")
     SGLB_FUSED_AR = EnvStr("SGLB_FUSED_AR", "pull", "pull (GEMM writes its partial into the local arena slot, the next norm kernel reduces across "
@@ -117,7 +114,6 @@ class _Envs:
     SGLB_NVL_MAX_BYTES = EnvInt("SGLB_NVL_MAX_BYTES", 512 << 20, "symmetric arena bytes per rank")
     # --- observability
     SGLB_TORCH_PROFILER_DIR = EnvStr("SGLB_TORCH_PROFILER_DIR", "/tmp/sglb_profiles")
-    SGLB_LOG_LEVEL = EnvStr("SGLB_LOG_LEVEL", "info")
 
     def dump(self) -> Dict[str, Any]:
         return {k: v.get() for k, v in _REGISTRY.items()}

@@ -251,7 +251,9 @@ def init_distributed(tp_size: int = 1, pp_size: int = 1, ep_size: int = 1, devic
         assert a % dcp_size == 0, "dcp_size must divide the attention-TP size"
         attn_groups = [g[i:i + a] for g in tp_groups for i in range(0, tp_size, a)]
         _STATE.dcp = make([g[i:i + dcp_size] for g in attn_groups for i in range(0, a, dcp_size)], "dcp")
-    if use_cuda and enable_nvl and tp.world_size > 1:
+    from ..environ import envs as _envs
+
+    if use_cuda and enable_nvl and tp.world_size > 1 and _envs.SGLB_COMM_IMPL.get() != "nccl":      # "nccl": library collectives only (A/B runs)
         try:
             from .nvl_comm import NvlComm
 
