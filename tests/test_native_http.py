@@ -157,3 +157,15 @@ def test_graceful_drain_finishes_inflight_request():
     with pytest.raises(requests.exceptions.ConnectionError):
         requests.get(url + "/health", timeout=2)
     eng.shutdown()
+
+
+def test_bench_one_batch_server_against_a_live_server(server, tmp_path):
+    """the server-side static-batch benchmark (reference bench_one_batch_server.py) drives a real socket end to end"""
+    from sglang_b200 import bench_one_batch_server as B
+
+    _, _, url = server
+    out = tmp_path / "rows.jsonl"
+    rows = B.main(["--base-url", url, "--batch-size", "1", "3", "--input-len", "12", "--output-len", "5", "--result-file", str(out)])
+    assert [r["batch_size"] for r in rows] == [1, 3] and all(r["completed_tokens"] == r["batch_size"] * 5 for r in rows)
+    assert all(r["ttft_s"] > 0 and r["latency_s"] >= r["ttft_s"] and r["itl_ms"] > 0 for r in rows)
+    assert len(out.read_text().strip().splitlines()) == 2
