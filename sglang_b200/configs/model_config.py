@@ -585,6 +585,17 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "tokens_per_image": hf.get("mm_tokens_per_image", 256), "resize_mode": "squash", "resize_filter": 2,
                             "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5]}
             kw["image_token_id"] = hf.get("image_token_id", hf.get("image_token_index", 262144))
+        if arch in ("Glm4vForConditionalGeneration", "Glm4vMoeForConditionalGeneration"):
+            vc = hf["vision_config"]
+            kw["vision"] = {"variant": "glm4v", "embed_dim": vc.get("hidden_size", 1536), "depth": vc.get("depth", 24), "num_heads": vc.get("num_heads", 12),
+                            "hidden_size": vc.get("out_hidden_size", kw["hidden_size"]), "out_hidden_size": vc.get("out_hidden_size", kw["hidden_size"]),
+                            "intermediate_size": vc.get("intermediate_size", 13696), "patch_size": vc.get("patch_size", 14),
+                            "image_size": vc.get("image_size", 336), "spatial_merge_size": vc.get("spatial_merge_size", 2),
+                            "temporal_patch_size": vc.get("temporal_patch_size", 2), "rms_norm_eps": vc.get("rms_norm_eps", 1e-5),
+                            "attention_bias": vc.get("attention_bias", False), "min_pixels": 112 * 112, "max_pixels": 14 * 14 * 2 * 2 * 2 * 6144}
+            kw["image_token_id"] = hf.get("image_token_id", 151343)
+            for k_, v_ in _ARCH_DEFAULTS["Glm4MoeForCausalLM" if "Moe" in arch else "Glm4ForCausalLM"].items():
+                kw.setdefault(k_, v_)
         if arch == "Mistral3ForConditionalGeneration":
             vc = hf["vision_config"]
             vrp = vc.get("rope_parameters") or {}
@@ -614,7 +625,7 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration", "Gemma3ForConditionalGeneration",
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration", "Gemma3ForConditionalGeneration", "Glm4vForConditionalGeneration", "Glm4vMoeForConditionalGeneration",
                                                  "Qwen3VLMoeForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

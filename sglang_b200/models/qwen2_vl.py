@@ -326,6 +326,8 @@ class Qwen2VLForConditionalGeneration(LlamaForCausalLM):
         super().__init__(cfg, quant_name, device)
         v = cfg.vision
         tower = {"qwen2.5": Qwen25VisionTransformer, "qwen3": Qwen3VisionTransformer}.get(v.get("variant"), Qwen2VisionTransformer)
+        if v.get("variant") == "glm4v":
+            from .glm4v import Glm4vVisionTransformer as tower
         self.visual = None if v.get("skip_tower") else tower(v, _DT[cfg.dtype])
         self.vision_tower = self.visual            # name the shared multimodal plumbing looks for
         self.merge = v["spatial_merge_size"]

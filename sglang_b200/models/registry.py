@@ -90,6 +90,10 @@ def _register_builtins() -> None:
     register_model("Qwen2_5_VLForConditionalGeneration", _qv.Qwen2_5_VLForConditionalGeneration)
     register_model("Qwen3VLForConditionalGeneration", _qv.Qwen3VLForConditionalGeneration)
     register_model("Qwen3VLMoeForConditionalGeneration", _qv._make_qwen3_vl_moe())
+    from . import glm4v as _g4v
+
+    register_model("Glm4vForConditionalGeneration", _g4v.Glm4vForConditionalGeneration)
+    register_model("Glm4vMoeForConditionalGeneration", _g4v.Glm4vMoeForConditionalGeneration)
     from . import qwen2_audio as _qa
 
     register_model("Qwen2AudioForConditionalGeneration", _qa.Qwen2AudioForConditionalGeneration)

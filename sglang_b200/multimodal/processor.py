@@ -323,7 +323,7 @@ def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: A
         return process_images_internvl(input_ids, image_data, cfg, tokenizer, encoder)
     if cfg.architecture.startswith("Mistral3"):
         return process_images_pixtral(input_ids, image_data, cfg, tokenizer, encoder)
-    if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL", "Qwen3VL")):
+    if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL", "Qwen3VL", "Glm4v")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)
     return _process_images_clip(input_ids, image_data, cfg, tokenizer, encoder)
 

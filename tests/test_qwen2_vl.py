@@ -16,6 +16,25 @@ def _hf_model(tmp_path, v25=False):
     from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
 
     torch.manual_seed(0)
+    if v25 in ("glm4v", "glm4vmoe"):
+        from transformers import Glm4vConfig, Glm4vForConditionalGeneration, Glm4vMoeConfig, Glm4vMoeForConditionalGeneration
+
+        moe = dict(n_routed_experts=4, num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1, first_k_dense_replace=1, n_group=1, topk_group=1,
+                   norm_topk_prob=True, routed_scaling_factor=1.0) if v25 == "glm4vmoe" else {}
+        cfg = (Glm4vMoeConfig if moe else Glm4vConfig)(text_config=dict(**moe, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                           vocab_size=512, max_position_embeddings=2048,
+                                           rope_parameters={"rope_type": "default", "rope_theta": 10000.0, "mrope_section": [1, 1, 2],
+                                                            "partial_rotary_factor": 0.5}, tie_word_embeddings=False),
+                          vision_config=dict(hidden_size=32, out_hidden_size=64, intermediate_size=48, depth=2, num_heads=2, patch_size=14,
+                                             image_size=112, spatial_merge_size=2, temporal_patch_size=2),
+                          image_token_id=500, video_token_id=501, image_start_token_id=502, image_end_token_id=503, tie_word_embeddings=False)
+        m = (Glm4vMoeForConditionalGeneration if moe else Glm4vForConditionalGeneration)(cfg).float().eval()
+        for p in m.parameters():
+            if p.dim() > 1:
+                torch.nn.init.normal_(p, std=0.08)
+        d = tmp_path / v25
+        m.save_pretrained(str(d), safe_serialization=True)
+        return m, str(d)
     if v25 in ("v3", "v3moe"):
         from transformers import Qwen3VLConfig, Qwen3VLForConditionalGeneration, Qwen3VLMoeConfig, Qwen3VLMoeForConditionalGeneration
 
@@ -73,7 +92,7 @@ def test_smart_resize_and_patch_layout_match_hf():
         assert P.smart_resize(h, w, 28, 56 * 56, 28 * 28 * 100) == smart_resize(h, w, 28, 56 * 56, 28 * 28 * 100)
 
 
-@pytest.mark.parametrize("v25", [False, True, "v3", "v3moe"])
+@pytest.mark.parametrize("v25", [False, True, "v3", "v3moe", "glm4v", "glm4vmoe"])
 def test_engine_matches_hf(tmp_path, v25):
     hf, path = _hf_model(tmp_path, v25)
     rng = np.random.default_rng(0)
@@ -82,7 +101,7 @@ def test_engine_matches_hf(tmp_path, v25):
     ids = [5, 6, 502, 500, 7, 8, 9, 502, 500, 10, 11, 12, 13]
     eng = sgl.Engine(model_path=path, device="cpu", page_size=4, skip_tokenizer_init=True, chunked_prefill_size=16, disable_radix_cache=True)
     assert type(eng.runner.model).__name__ == {False: "Qwen2VLForConditionalGeneration", True: "Qwen2_5_VLForConditionalGeneration",
-                                               "v3": "Qwen3VLForConditionalGeneration", "v3moe": "Qwen3VLMoeForConditionalGeneration"}[v25]
+                                               "v3": "Qwen3VLForConditionalGeneration", "v3moe": "Qwen3VLMoeForConditionalGeneration", "glm4v": "Glm4vForConditionalGeneration", "glm4vmoe": "Glm4vMoeForConditionalGeneration"}[v25]
     o = eng.generate(input_ids=ids, image_data=imgs, sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True},
                      return_logprob=True, logprob_start_len=0)
     # the HF side: same patches / grids, placeholder runs expanded with the image token id
