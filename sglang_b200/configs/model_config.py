@@ -534,8 +534,9 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
         if hf.get("num_labels") is not None or hf.get("id2label"):
             kw["num_labels"] = int(hf.get("num_labels") or len(hf["id2label"]))
         if arch in ("BertModel", "XLMRobertaModel", "RobertaModel", "BertForSequenceClassification", "XLMRobertaForSequenceClassification",
-                    "RobertaForSequenceClassification"):
-            kw["encoder"] = {"type_vocab_size": hf.get("type_vocab_size", 2), "sep_token_id": hf.get("sep_token_id", 102 if arch.startswith("Bert") else 2)}
+                    "RobertaForSequenceClassification", "Contriever"):
+            kw["encoder"] = {"type_vocab_size": hf.get("type_vocab_size", 2),
+                             "sep_token_id": hf.get("sep_token_id", 102 if arch.startswith(("Bert", "Contriever")) else 2)}
             kw["rms_norm_eps"] = hf.get("layer_norm_eps", 1e-12)
             kw["num_key_value_heads"] = hf["num_attention_heads"]
             kw["pos_emb"] = "learned"

@@ -195,3 +195,18 @@ class XLMRobertaForSequenceClassification(XLMRobertaModel):
         if n.startswith("classifier."):
             return n.replace("classifier.dense.", "cls_dense.").replace("classifier.out_proj.", "cls_out.")
         return super()._map(n)
+
+
+class Contriever(BertModel):
+    """facebook/contriever (reference ``models/bert.py`` Contriever): BERT encoder, the sentence vector is the MEAN over the token rows,
+    not normalised"""
+
+    def pooled(self, h: torch.Tensor, lens: List[int]) -> torch.Tensor:
+        out, s = [], 0
+        for n in lens:
+            out.append(h[s:s + n].float().mean(0).to(h.dtype))
+            s += n
+        return torch.stack(out) if out else h[:0]
+
+    def pool(self, hidden_last: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        return hidden_last.float()

@@ -139,5 +139,6 @@ def _register_builtins() -> None:
 
     for name in ("BertModel", "XLMRobertaModel", "BertForSequenceClassification", "XLMRobertaForSequenceClassification"):
         register_model(name, getattr(_bert, name))
+    register_model("Contriever", _bert.Contriever)
     register_model("RobertaModel", _bert.XLMRobertaModel)
     register_model("RobertaForSequenceClassification", _bert.XLMRobertaForSequenceClassification)

@@ -173,3 +173,26 @@ def test_reward_heads(arch, tmp_path):
         with torch.no_grad():
             h = hf.model(input_ids=torch.tensor([ids])).last_hidden_state[0, -1]
         assert torch.allclose(torch.tensor(o["embedding"]), score(h), atol=2e-3), arch
+
+
+def test_contriever_mean_pooling_matches_hf(tmp_path):
+    """facebook/contriever layout: a BERT checkpoint whose architecture is ``Contriever``; the embedding is the un-normalised token mean"""
+    import json
+
+    torch.manual_seed(0)
+    hf = _randomise(tf.BertModel(tf.BertConfig(**ENC), add_pooling_layer=False))
+    d = str(tmp_path / "contriever")
+    hf.save_pretrained(d, safe_serialization=True)
+    c = json.load(open(d + "/config.json"))
+    c["architectures"] = ["Contriever"]
+    json.dump(c, open(d + "/config.json", "w"))
+    rng = np.random.default_rng(0)
+    seqs = [rng.integers(5, 500, size=n).tolist() for n in (9, 23, 4)]
+    e = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error")
+    assert type(e.runner.model).__name__ == "Contriever"
+    outs = e.encode(input_ids=seqs)
+    e.shutdown()
+    for ids, o in zip(seqs, outs):
+        with torch.no_grad():
+            ref = hf(input_ids=torch.tensor([ids])).last_hidden_state[0].mean(0)
+        assert torch.allclose(torch.tensor(o["embedding"]), ref, atol=2e-4)
