@@ -158,3 +158,28 @@ class Mistral3ForConditionalGeneration(LlamaForCausalLM):
                 continue
             rest.append((name, w))
         return loaded + super().load_weights(rest)
+
+
+class _LlavaProjector(nn.Module):
+    def __init__(self, vh: int, th: int, bias: bool, act: str, dtype):
+        super().__init__()
+        self.linear_1 = nn.Linear(vh, th, bias=bias, dtype=dtype)
+        self.linear_2 = nn.Linear(th, th, bias=bias, dtype=dtype)
+        self.act = act
+
+    def forward(self, x: torch.Tensor, grid_thw=None) -> torch.Tensor:
+        y = self.linear_1(x)
+        return self.linear_2(F.gelu(y) if self.act == "gelu" else F.silu(y))
+
+
+class PixtralForConditionalGeneration(Mistral3ForConditionalGeneration):
+    """Pixtral-12B in the Hugging Face LLaVA layout (``LlavaForConditionalGeneration`` whose ``vision_config.model_type`` is ``pixtral``; reference
+    ``python/sglang/srt/models/pixtral.py``): the same tower, no patch merging — every patch is one image token — and the two-layer LLaVA
+    projector.  The config loader routes such checkpoints here."""
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        super().__init__(cfg, quant_name, device)
+        if self.vision_tower is not None:
+            v = cfg.vision
+            self.projector = _LlavaProjector(v["hidden_size"], cfg.hidden_size, bool(v.get("projector_bias", True)), v.get("projector_hidden_act", "gelu"),
+                                             _DT[cfg.dtype])

@@ -100,6 +100,7 @@ def _register_builtins() -> None:
     from . import pixtral as _px
 
     register_model("Mistral3ForConditionalGeneration", _px.Mistral3ForConditionalGeneration)
+    register_model("PixtralForConditionalGeneration", _px.PixtralForConditionalGeneration)
     from . import gpt_oss as _go
 
     register_model("GptOssForCausalLM", _go.GptOssForCausalLM)

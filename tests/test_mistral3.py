@@ -18,27 +18,38 @@ def test_pixtral_resize_shape_matches_hf():
         assert P.pixtral_resize_shape(h, w, 1540, 28) == tuple(get_resize_output_image_size(img, size=(1540, 1540), patch_size=(28, 28)))
 
 
-def test_engine_matches_hf(tmp_path):
+@pytest.mark.parametrize("kind", ["mistral3", "pixtral-llava"])
+def test_engine_matches_hf(tmp_path, kind):
     if not hasattr(tf, "Mistral3ForConditionalGeneration"):
         pytest.skip("transformers has no Mistral3")
     torch.manual_seed(0)
-    cfg = tf.Mistral3Config(text_config=dict(model_type="mistral", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+    if kind == "pixtral-llava":          # pixtral-12b layout: LLaVA container, pixtral tower, one token per patch, biased two-layer projector
+        cfg = tf.LlavaConfig(text_config=dict(model_type="mistral", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                              num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=2048, rope_theta=10000.0,
+                                              sliding_window=None, tie_word_embeddings=False),
+                             vision_config=dict(model_type="pixtral", hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=2,
+                                                head_dim=16, patch_size=14, image_size=280),
+                             image_token_index=500, vision_feature_layer=-1, vision_feature_select_strategy="full", tie_word_embeddings=False)
+        hf = tf.LlavaForConditionalGeneration(cfg).float().eval()
+    else:
+        hf = None
+        cfg = tf.Mistral3Config(text_config=dict(model_type="mistral", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
                                              num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=2048, rope_theta=10000.0,
                                              sliding_window=None, tie_word_embeddings=False),
                             vision_config=dict(model_type="pixtral", hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=2,
                                                head_dim=16, patch_size=14, image_size=280),
                             spatial_merge_size=2, image_token_id=500, tie_word_embeddings=False)
-    hf = tf.Mistral3ForConditionalGeneration(cfg).float().eval()
+    hf = hf if hf is not None else tf.Mistral3ForConditionalGeneration(cfg).float().eval()
     for p in hf.parameters():
         if p.dim() > 1:
             torch.nn.init.normal_(p, std=0.08)
-    d = str(tmp_path / "mistral3")
+    d = str(tmp_path / kind)
     hf.save_pretrained(d, safe_serialization=True)
     rng = np.random.default_rng(0)
     imgs = [rng.integers(0, 255, size=(60, 90, 3), dtype=np.uint8), rng.integers(0, 255, size=(150, 56, 3), dtype=np.uint8)]
     ids = [5, 6, 500, 7, 8, 9, 500, 10, 11, 12, 13]
     eng = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, chunked_prefill_size=16, disable_radix_cache=True, log_level="error")
-    assert type(eng.runner.model).__name__ == "Mistral3ForConditionalGeneration"
+    assert type(eng.runner.model).__name__ == ("Mistral3ForConditionalGeneration" if kind == "mistral3" else "PixtralForConditionalGeneration")
     o = eng.generate(input_ids=ids, image_data=imgs, sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True},
                      return_logprob=True, logprob_start_len=0)
     exp_ids, mm = P.process_images(ids, imgs, eng.model_config, None)
@@ -47,8 +58,11 @@ def test_engine_matches_hf(tmp_path):
     for off, n in zip(mm["image_offsets"], mm["image_token_counts"]):
         hf_ids[off:off + n] = [500] * n
     grids, p = mm["grid_thw"], 14
-    assert grids == [[1, 6, 8], [1, 12, 4]] and len(mm["image_offsets"]) == 3 + 6                 # one splice run per merged row
-    assert [hf_ids[o_ + n] for o_, n in zip(mm["image_offsets"], mm["image_token_counts"])] == [12, 12, 13] + [12] * 5 + [13]
+    if kind == "mistral3":
+        assert grids == [[1, 6, 8], [1, 12, 4]] and len(mm["image_offsets"]) == 3 + 6                 # one splice run per merged row
+        assert [hf_ids[o_ + n] for o_, n in zip(mm["image_offsets"], mm["image_token_counts"])] == [12, 12, 13] + [12] * 5 + [13]
+    else:
+        assert len(mm["image_offsets"]) == sum(g[1] for g in grids) and mm["image_token_counts"][0] == grids[0][2]      # one run per patch row
     pats, s, pix = np.asarray(mm["pixel_patches"], np.float32), 0, []
     Hm, Wm = max(g[1] for g in grids) * p, max(g[2] for g in grids) * p
     for _, gh, gw in grids:                     # HF takes a padded image batch + the true sizes
