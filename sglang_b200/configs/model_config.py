@@ -555,6 +555,13 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                            "num_mel_bins": ac.get("num_mel_bins", 128), "max_source_positions": ac.get("max_source_positions", 1500),
                            "audio_token_id": hf.get("audio_token_id", hf.get("audio_token_index", 151646))}
             kw.setdefault("attention_bias", True)
+        if arch == "VoxtralForConditionalGeneration":
+            ac = hf.get("audio_config") or {}
+            d_, inter = ac.get("hidden_size", 1280), ac.get("intermediate_size", 5120)
+            kw["audio"] = {"llm": True, "d_model": d_, "encoder_layers": ac.get("num_hidden_layers", 32), "encoder_attention_heads": ac.get("num_attention_heads", 20),
+                           "encoder_ffn_dim": inter, "num_mel_bins": ac.get("num_mel_bins", 128), "max_source_positions": ac.get("max_source_positions", 1500),
+                           "audio_token_id": hf.get("audio_token_id", 24), "group": inter // d_,
+                           "tokens_per_window": ac.get("max_source_positions", 1500) // (inter // d_)}
         if arch == "InternVLForConditionalGeneration":
             vc = hf["vision_config"]
             size = vc.get("image_size", 448)

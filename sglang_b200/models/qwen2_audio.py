@@ -63,7 +63,8 @@ class Qwen2AudioForConditionalGeneration(LlamaForCausalLM):
             if n.startswith("language_model."):
                 n = n[len("language_model."):]
                 rest.append((n if n.startswith(("model.", "lm_head.")) else "model." + n, w))
-            elif n.startswith(("audio_tower.", "multi_modal_projector.")):
+            elif n.startswith(("audio_tower.", "multi_modal_projector.", "projector.", "model.projector.")):
+                n = n[len("model."):] if n.startswith("model.projector.") else n
                 n = n.replace(".self_attn.", ".").replace("audio_tower.ln_post.", "audio_tower.layer_norm.").replace("multi_modal_projector.linear.", "projector.")
                 if n in own:
                     own[n].data.copy_(w.reshape(own[n].shape))
@@ -71,3 +72,29 @@ class Qwen2AudioForConditionalGeneration(LlamaForCausalLM):
             else:
                 rest.append((name, w))
         return loaded + super().load_weights(rest)
+
+
+class VoxtralForConditionalGeneration(Qwen2AudioForConditionalGeneration):
+    """Voxtral (reference ``python/sglang/srt/models/voxtral.py``): the plain Whisper encoder over fixed windows (no length mask), groups of
+    ``intermediate_size / hidden_size`` consecutive frames concatenated into one soft token, bias-free two-layer projector, Llama / Mistral
+    decoder.  Audio longer than one window is cut into windows; every window contributes the same number of tokens."""
+
+    def __init__(self, cfg: ModelConfig, quant_name: Optional[str] = None, device="cpu"):
+        LlamaForCausalLM.__init__(self, cfg, quant_name, device)
+        a, dt = cfg.audio, _DT[cfg.dtype]
+        self.audio_tower = WhisperEncoder(a, dt)
+        self.group = int(a["group"])
+        self.projector = nn.Sequential(nn.Linear(a["d_model"] * self.group, cfg.hidden_size, bias=False, dtype=dt), nn.GELU(),
+                                       nn.Linear(cfg.hidden_size, cfg.hidden_size, bias=False, dtype=dt))
+        self.vision_tower = self.audio_tower
+
+    @torch.no_grad()
+    def encode_audio(self, feats: torch.Tensor, frames: Any) -> torch.Tensor:
+        h = self.audio_tower(feats)                                   # [windows, S, H]
+        return self.projector(h.reshape(-1, h.shape[-1] * self.group))
+
+    def load_weights(self, weights):
+        def rename():
+            for name, w in weights:
+                yield name.replace("multi_modal_projector.linear_1.", "projector.0.").replace("multi_modal_projector.linear_2.", "projector.2."), w
+        return super().load_weights(rename())

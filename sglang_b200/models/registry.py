@@ -97,6 +97,7 @@ def _register_builtins() -> None:
     from . import qwen2_audio as _qa
 
     register_model("Qwen2AudioForConditionalGeneration", _qa.Qwen2AudioForConditionalGeneration)
+    register_model("VoxtralForConditionalGeneration", _qa.VoxtralForConditionalGeneration)
     from . import pixtral as _px
 
     register_model("Mistral3ForConditionalGeneration", _px.Mistral3ForConditionalGeneration)

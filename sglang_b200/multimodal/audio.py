@@ -117,20 +117,29 @@ def process_audio_llm(input_ids: List[int], audio_data: Any, cfg: Any) -> Tuple[
     clips = audio_data if isinstance(audio_data, (list, tuple)) and not (len(audio_data) == 2 and isinstance(audio_data[1], (int, float))) else [audio_data]
     tok, V = a["audio_token_id"], cfg.vocab_size
     window = 2 * a["max_source_positions"]
-    feats, frames = [], []
+    feats, frames, per_clip = [], [], []
+    fixed = int(a.get("tokens_per_window") or 0)          # Voxtral: every window yields the same number of tokens, long audio = several windows
     for c in clips:
         w = load_audio(c)
-        f = log_mel_spectrogram(w, a["num_mel_bins"], chunk_s=a.get("chunk_length", 30))[:, :window]
-        if f.shape[1] < window:
-            f = np.pad(f, ((0, 0), (0, window - f.shape[1])))
-        feats.append(f)
-        frames.append(max(2, min(window, w.shape[0] // 160)))
+        pieces = [w] if not fixed else [w[i:i + window * 160] for i in range(0, max(1, w.shape[0]), window * 160)]
+        first = len(feats)
+        for piece in pieces:
+            f = log_mel_spectrogram(piece, a["num_mel_bins"], chunk_s=a.get("chunk_length", 30))[:, :window]
+            if f.shape[1] < window:
+                f = np.pad(f, ((0, 0), (0, window - f.shape[1])))
+            feats.append(f)
+            frames.append(max(2, min(window, piece.shape[0] // 160)))
+        per_clip.append((first, len(feats)))
     out, offsets, counts, k = [], [], [], 0
     for t in input_ids:
         if t == tok and k < len(clips):
-            l1 = (frames[k] - 1) // 2 + 1
-            n = (l1 - 2) // 2 + 1
-            h = int.from_bytes(hashlib.sha256(feats[k].tobytes()).digest()[:8], "little")
+            lo, hi = per_clip[k]
+            if fixed:
+                n = fixed * (hi - lo)
+            else:
+                l1 = (frames[lo] - 1) // 2 + 1
+                n = (l1 - 2) // 2 + 1
+            h = int.from_bytes(hashlib.sha256(np.stack(feats[lo:hi]).tobytes()).digest()[:8], "little")
             offsets.append(len(out))
             counts.append(n)
             out.extend(int(h % max(1, V - 1)) if (j & 1) == 0 else int((h >> 17) % max(1, V - 1)) for j in range(n))
