@@ -309,7 +309,8 @@ PRESETS: Dict[str, Dict[str, Any]] = {
 _HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM", "SeedOssForCausalLM": "LlamaForCausalLM", "HeliumForCausalLM": "LlamaForCausalLM",
                 "Ernie4_5ForCausalLM": "LlamaForCausalLM", "ArceeForCausalLM": "LlamaForCausalLM", "SmolLM3ForCausalLM": "LlamaForCausalLM",
                 "Ministral3ForCausalLM": "LlamaForCausalLM", "Olmo3ForCausalLM": "Olmo2ForCausalLM", "KimiK2ForCausalLM": "DeepseekV3ForCausalLM",
-                "CwmForCausalLM": "LlamaForCausalLM", "Cohere2ForCausalLM": "CohereForCausalLM"}
+                "CwmForCausalLM": "LlamaForCausalLM", "Cohere2ForCausalLM": "CohereForCausalLM",
+                "Glm4MoeLiteForCausalLM": "DeepseekV3ForCausalLM"}          # GLM-4.7-Flash: MLA + DeepSeek-V3 style MoE under GLM names
 # HF config keys that differ from our field names
 _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts", "n_embd": "hidden_size", "n_layer": "num_hidden_layers",
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",

@@ -153,6 +153,10 @@ CASES = {
     "minimax-m2": ("MiniMaxM2Config", "MiniMaxM2ForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2, head_dim=16)),
     "ernie4.5-moe": ("Ernie4_5_MoeConfig", "Ernie4_5_MoeForCausalLM", dict(BASE, moe_num_experts=4, moe_k=2, moe_intermediate_size=32,
                                                                         moe_num_shared_experts=1, moe_layer_start_index=1, moe_layer_interval=1)),
+    "glm4-moe-lite": ("Glm4MoeLiteConfig", "Glm4MoeLiteForCausalLM", dict(BASE, num_hidden_layers=3, num_key_value_heads=4, kv_lora_rank=32, q_lora_rank=24,
+                                                                            qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16, n_routed_experts=4,
+                                                                            num_experts_per_tok=2, moe_intermediate_size=32, n_shared_experts=1,
+                                                                            first_k_dense_replace=1, n_group=1, topk_group=1)),
     "mamba2": ("Mamba2Config", "Mamba2ForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, num_heads=8, head_dim=16, state_size=16,
                                                          n_groups=2, expand=2, conv_kernel=4, chunk_size=8, tie_word_embeddings=True)),
 }
