@@ -659,6 +659,18 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
             hi = L - 1 if hi is None or hi < 0 else hi
             lo = min(lo) if isinstance(lo, (list, tuple)) else lo
             kw["mlp_only_layers"] = [i for i in range(L) if not (lo <= i <= hi and (i + 1) % every == 0)]
+        if arch in ("HunYuanDenseV1ForCausalLM", "HunYuanMoEV1ForCausalLM"):
+            rp_ = text.get("rope_parameters") or text.get("rope_scaling") or {}
+            hd_ = kw.get("head_dim") or kw["hidden_size"] // kw["num_attention_heads"]
+            if rp_.get("alpha") and (rp_.get("rope_type") or rp_.get("type")) == "dynamic":       # NTK-alpha: a larger base, no position-dependent part
+                kw["rope_theta"] = float(rp_.get("rope_theta", kw.get("rope_theta", 10000.0))) * float(rp_["alpha"]) ** (hd_ / (hd_ - 2))
+                kw["rope_scaling"] = None
+            first = lambda v_: v_[0] if isinstance(v_, (list, tuple)) else v_
+            if arch.startswith("HunYuanMoE"):
+                kw["num_local_experts"] = first(text.get("num_local_experts", text.get("num_experts", 0)))          # (key already renamed by _HF_KEY_MAP)
+                kw["num_experts_per_tok"] = first(text.get("moe_topk", 1))
+                if text.get("moe_intermediate_size"):
+                    kw["moe_intermediate_size"] = first(text["moe_intermediate_size"])
         if arch in ("NemotronForCausalLM",) and text.get("norm_eps") is not None:
             kw["rms_norm_eps"] = text["norm_eps"]
         if arch == "GPTNeoForCausalLM":              # num_layers / num_heads / window_size / attention_layers; MLP width defaults to 4 x hidden

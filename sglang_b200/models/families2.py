@@ -433,3 +433,74 @@ class Ernie4_5_MoeForCausalLM(Glm4MoeForCausalLM):
                 else:
                     yield name, w
         return super().load_weights(rename())
+
+
+# ---------------------------------------------------------------- HunYuan (dense V1 / MoE V1): per-head q/k RMSNorm applied AFTER the rotary embedding
+class HunYuanDecoderLayer(LlamaDecoderLayer):
+    """reference ``python/sglang/srt/models/hunyuan.py``.  The norm sits between RoPE and the cache write, so the fused RoPE + KV-write kernel
+    cannot be used: rotate, normalise, then hand rotated keys to the attention layer with its own rotary step switched off."""
+
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+        super().__init__(cfg, layer_id, dtype, quant, rope, prefix, mlp_cls)
+        sa = self.self_attn
+        sa.query_layernorm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
+        sa.key_layernorm = RMSNorm(cfg.head_dim, cfg.rms_norm_eps, dtype)
+        sa._rope = sa.attn.rope
+        sa.attn.rope = None
+        sa.forward = _hunyuan_attn_forward.__get__(sa)
+
+
+def _hunyuan_attn_forward(self, x: torch.Tensor, fb: ForwardBatch):
+    from ..ops import torch_ref
+
+    T = x.shape[0]
+    q, k, v = self.qkv_proj(x).split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+    nh, nkv, hd = self.attn.num_heads, self.attn.num_kv_heads, self.head_dim
+    cs = self._rope.cos_sin
+    q = torch_ref.apply_rope(q.reshape(T, nh, hd), fb.positions, cs, True)
+    k = torch_ref.apply_rope(k.reshape(T, nkv, hd), fb.positions, cs, True)
+    q = self.query_layernorm(q.reshape(T * nh, hd).to(x.dtype)).view(T, nh * hd)
+    k = self.key_layernorm(k.reshape(T * nkv, hd).to(x.dtype)).view(T, nkv * hd)
+    return self.o_proj(self.attn(q.contiguous(), k.contiguous(), v.contiguous(), fb), defer_reduce=True)
+
+
+class HunYuanDenseV1ForCausalLM(LlamaForCausalLM):
+    decoder_layer_cls = HunYuanDecoderLayer
+
+
+class _HunYuanGate(nn.Module):
+    def __init__(self, cfg: ModelConfig, dtype, prefix: str):
+        super().__init__()
+        from ..layers.linear import ReplicatedLinear
+
+        self.wg = ReplicatedLinear(cfg.hidden_size, cfg.num_local_experts, False, dtype, None, prefix + ".wg")
+
+
+class HunYuanMoE(nn.Module):
+    """soft-max top-k experts (renormalised) plus an always-on shared MLP"""
+
+    def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, prefix: str):
+        super().__init__()
+        from ..layers.moe import FusedMoE
+        from .mixtral import _EP_SIZE
+
+        self.gate = _HunYuanGate(cfg, dtype, prefix + ".gate")
+        self.experts = FusedMoE(cfg.num_local_experts, cfg.num_experts_per_tok, cfg.hidden_size, cfg.moe_intermediate_size, dtype, True, _EP_SIZE["v"], quant,
+                                layer_id)
+        self.shared_mlp = LlamaMLP(cfg, dtype, quant, prefix + ".shared_mlp")
+
+    def forward(self, x: torch.Tensor):
+        y = _resolve(self.experts(x, self.gate.wg(x)))
+        return y + _resolve(self.shared_mlp(x))
+
+
+def _make_hunyuan_moe():
+    from .families import Qwen2MoeForCausalLM
+
+    class HunYuanMoEV1ForCausalLM(Qwen2MoeForCausalLM):          # (its loader already routes ``mlp.experts.<e>.{gate,up,down}_proj``)
+        decoder_layer_cls = HunYuanDecoderLayer
+
+        def _mlp_cls(self):
+            return lambda c, layer_id, dtype, quant, prefix: HunYuanMoE(c, layer_id, dtype, quant, prefix + ".mlp")
+
+    return HunYuanMoEV1ForCausalLM

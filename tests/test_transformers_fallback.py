@@ -12,7 +12,7 @@ BASE = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_atte
 CASES = {
     "solar-open": ("SolarOpenConfig", "SolarOpenForCausalLM", dict(BASE), "auto"),
     "phimoe": ("PhimoeConfig", "PhimoeForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2), "auto"),
-    "hunyuan-dense": ("HunYuanDenseV1Config", "HunYuanDenseV1ForCausalLM", dict(BASE, head_dim=16), "auto"),
+    "afmoe": ("AfmoeConfig", "AfmoeForCausalLM", dict(BASE), "auto"),
     "llama-forced": ("LlamaConfig", "LlamaForCausalLM", dict(BASE), "transformers"),
 }
 
@@ -57,13 +57,13 @@ def test_fallback_matches_hf(name, tmp_path):
 
 
 def test_model_impl_sglang_refuses_unknown_architecture(tmp_path):
-    _, d, _ = _save("hunyuan-dense", tmp_path)
+    _, d, _ = _save("solar-open", tmp_path)
     with pytest.raises(Exception, match="unsupported architecture"):
         sgl.Engine(model_path=d, device="cpu", skip_tokenizer_init=True, log_level="error", model_impl="sglang")
 
 
 def test_dummy_weights_through_fallback(tmp_path):
-    _, d, _ = _save("hunyuan-dense", tmp_path)
+    _, d, _ = _save("solar-open", tmp_path)
     eng = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, load_format="dummy", log_level="error")
     try:
         o = eng.generate(input_ids=[5, 6, 7, 8], sampling_params={"max_new_tokens": 4, "temperature": 0, "ignore_eos": True})

@@ -83,7 +83,7 @@ def text_case(name, cfg_cls, model_cls, extra, **ekw):
     run(name, f)
 
 
-text_case("transformers-fallback(hunyuan-dense)", "HunYuanDenseV1Config", "HunYuanDenseV1ForCausalLM", {})
+text_case("transformers-fallback(hunyuan-dense)", "HunYuanDenseV1Config", "HunYuanDenseV1ForCausalLM", {}, model_impl="transformers")
 text_case("minimax-m2", "MiniMaxM2Config", "MiniMaxM2ForCausalLM", dict(num_local_experts=4, num_experts_per_tok=2))
 text_case("ernie4.5-moe", "Ernie4_5_MoeConfig", "Ernie4_5_MoeForCausalLM", dict(moe_num_experts=4, moe_k=2, moe_intermediate_size=128, moe_num_shared_experts=1,
                                                                               moe_layer_start_index=1, moe_layer_interval=1))
