@@ -92,6 +92,7 @@ class ModelConfig:
     # state-space / hybrid decoders (models/mamba.py): num_heads, head_dim, d_state, d_conv, n_groups, norm_groups, chunk_size, pattern
     mamba: Optional[Dict[str, Any]] = None
     # architectures without a native class: {"path", "arch"} -> models/transformers_fallback.py runs the Hugging Face module tree
+    router_jitter_noise: Optional[float] = None      # Phi-3.5-MoE sparsemixer band
     hf_fallback: Optional[Dict[str, Any]] = None
     num_labels: int = 1                              # classification / reward heads
     encoder: Optional[Dict[str, Any]] = None         # encoder-only models (BERT / RoBERTa): type_vocab_size, sep_token_id
@@ -336,6 +337,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
                   "OlmoeForCausalLM": dict(norm_topk_prob=False), "MiniMaxM2ForCausalLM": dict(norm_topk_prob=True),
+                  "PhimoeForCausalLM": dict(attention_bias=True, attention_out_bias=True), "PhiMoEForCausalLM": dict(attention_bias=True, attention_out_bias=True),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
                   "Ernie4_5_MoeForCausalLM": dict(rope_is_neox=False, scoring_func="softmax", topk_method="noaux_tc", norm_topk_prob=True),
                   "ArceeForCausalLM": dict(mlp_gated=False, hidden_act="relu2"), "ApertusForCausalLM": dict(mlp_gated=False, qk_norm=True),

@@ -47,6 +47,10 @@ def _register_builtins() -> None:
         register_model(name, getattr(llama, name))
     register_model("MixtralForCausalLM", mixtral.MixtralForCausalLM)
     register_model("MiniMaxM2ForCausalLM", mixtral.MiniMaxM2ForCausalLM)
+    from . import phimoe as _pm
+
+    register_model("PhimoeForCausalLM", _pm.PhimoeForCausalLM)
+    register_model("PhiMoEForCausalLM", _pm.PhimoeForCausalLM)          # (the architecture string of the released checkpoints)
     register_model("LlavaForConditionalGeneration", llava.LlavaForConditionalGeneration)
     register_model("LlavaLlamaForCausalLM", llava.LlavaForConditionalGeneration)
     from . import families as _fam

@@ -11,7 +11,7 @@ BASE = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_atte
             max_position_embeddings=512)
 CASES = {
     "solar-open": ("SolarOpenConfig", "SolarOpenForCausalLM", dict(BASE), "auto"),
-    "phimoe": ("PhimoeConfig", "PhimoeForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2), "auto"),
+    "bitnet": ("BitNetConfig", "BitNetForCausalLM", dict(BASE), "auto"),
     "afmoe": ("AfmoeConfig", "AfmoeForCausalLM", dict(BASE), "auto"),
     "llama-forced": ("LlamaConfig", "LlamaForCausalLM", dict(BASE), "transformers"),
 }
