@@ -311,7 +311,10 @@ _HF_ARCH_MAP = {"MistralForCausalLM": "LlamaForCausalLM", "SeedOssForCausalLM": 
                 "Ernie4_5ForCausalLM": "LlamaForCausalLM", "ArceeForCausalLM": "LlamaForCausalLM", "SmolLM3ForCausalLM": "LlamaForCausalLM",
                 "Ministral3ForCausalLM": "LlamaForCausalLM", "Olmo3ForCausalLM": "Olmo2ForCausalLM", "KimiK2ForCausalLM": "DeepseekV3ForCausalLM",
                 "CwmForCausalLM": "LlamaForCausalLM", "Cohere2ForCausalLM": "CohereForCausalLM",
-                "Glm4MoeLiteForCausalLM": "DeepseekV3ForCausalLM"}          # GLM-4.7-Flash: MLA + DeepSeek-V3 style MoE under GLM names
+                "Glm4MoeLiteForCausalLM": "DeepseekV3ForCausalLM",
+                # Llama / Qwen2 bodies under other names (reference models/llama.py EntryClass list, models/mimo.py): extra heads in the
+                # checkpoint (MiMo's ``model.mtp_layers.*``) are not part of the served model and are skipped by the loader
+                "InternLM3ForCausalLM": "LlamaForCausalLM", "IQuestCoderForCausalLM": "LlamaForCausalLM", "MiMoForCausalLM": "Qwen2ForCausalLM"}          # GLM-4.7-Flash: MLA + DeepSeek-V3 style MoE under GLM names
 # HF config keys that differ from our field names
 _HF_KEY_MAP = {"num_experts": "num_local_experts", "n_routed_experts": "num_local_experts", "n_embd": "hidden_size", "n_layer": "num_hidden_layers",
                "n_head": "num_attention_heads", "n_positions": "max_position_embeddings", "n_inner": "intermediate_size",
@@ -646,6 +649,9 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}
             kw["image_token_id"] = hf.get("image_token_index", hf.get("image_token_id"))
         kw["dtype"] = {"float16": "float16", "float32": "float32"}.get(hf.get("torch_dtype") or hf.get("dtype") or text.get("dtype") or "bfloat16", "bfloat16")
+        if arch == "InternLM3ForCausalLM":           # ``qkv_bias`` for q/k/v, ``bias`` for o_proj and the MLP
+            kw["attention_bias"] = bool(text.get("qkv_bias", False))
+            kw["attention_out_bias"] = kw["mlp_bias"] = bool(text.get("bias", False))
         if arch in ("Ernie4_5ForCausalLM", "Ernie4_5_MoeForCausalLM") and text.get("use_bias") is not None:
             kw["attention_bias"] = kw["attention_out_bias"] = kw["mlp_bias"] = bool(text["use_bias"])
         if arch == "Ernie4_5_MoeForCausalLM":

@@ -253,3 +253,50 @@ def test_classic_checkpoint_dialects():
     m.load_weights(iter(ck))
     for (n1, p1), (n2, p2) in zip(ref.named_parameters(), m.named_parameters()):
         assert n1 == n2 and torch.equal(p1, p2), n1
+
+
+@pytest.mark.parametrize("arch", ["InternLM3ForCausalLM", "MiMoForCausalLM"])
+def test_renamed_llama_and_qwen2_bodies(arch, tmp_path):
+    """architectures that are a Llama / Qwen2 decoder under another name (their modelling code is remote): the checkpoint of the base family,
+    relabelled (plus InternLM3's bias switches / MiMo's extra MTP tensors), must serve identically to Hugging Face's base implementation"""
+    import json
+
+    import numpy as np
+    import torch
+    import transformers as tf
+    from safetensors.torch import load_file, save_file
+
+    torch.manual_seed(0)
+    base = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                max_position_embeddings=512)
+    if arch == "InternLM3ForCausalLM":
+        hf = tf.LlamaForCausalLM(tf.LlamaConfig(**base, attention_bias=True, mlp_bias=False)).float().eval()
+    else:
+        hf = tf.Qwen2ForCausalLM(tf.Qwen2Config(**base)).float().eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            p.normal_(0, 0.08) if p.dim() > 1 else (p.add_(torch.randn_like(p) * 0.05) if n.endswith("bias") else None)
+    d = str(tmp_path / arch)
+    hf.save_pretrained(d, safe_serialization=True)
+    c = json.load(open(d + "/config.json"))
+    c["architectures"] = [arch]
+    if arch == "InternLM3ForCausalLM":
+        c["qkv_bias"], c["bias"] = True, True
+        c.pop("attention_bias", None)
+    json.dump(c, open(d + "/config.json", "w"))
+    if arch == "MiMoForCausalLM":          # the release ships multi-token-prediction layers next to the decoder
+        sd = load_file(d + "/model.safetensors")
+        sd["model.mtp_layers.0.input_proj.weight"] = torch.randn(64, 128)
+        save_file(sd, d + "/model.safetensors")
+    ids = np.random.default_rng(1).integers(3, 500, size=21).tolist()
+    eng = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, log_level="error")
+    try:
+        o = eng.generate(input_ids=ids, sampling_params={"max_new_tokens": 5, "temperature": 0, "ignore_eos": True}, return_logprob=True, logprob_start_len=0)
+    finally:
+        eng.shutdown()
+    full = ids + o["output_ids"]
+    with torch.no_grad():
+        lp = torch.log_softmax(hf(input_ids=torch.tensor([full])).logits[0].float(), -1)
+    got = [v for v, _, _ in o["meta_info"]["input_token_logprobs"][1:]]
+    assert max(abs(float(lp[t, full[t + 1]]) - got[t]) for t in range(len(ids) - 1)) < 3e-3
+    assert all(int(lp[len(ids) - 1 + j].argmax()) == tok for j, tok in enumerate(o["output_ids"]))
