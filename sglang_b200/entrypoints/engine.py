@@ -411,6 +411,18 @@ class Engine:
         g = ios.GenerateReqInput(text=prompt, input_ids=input_ids, image_data=image_data, sampling_params=sampling_params,
                                  stream=stream, **kw)
         singles = g.normalize()
+        if self.server_args.enable_dynamic_batch_tokenizer and self.tokenizer is not None:
+            # text prompts are encoded off the event loop, batched with whatever else arrived in the same couple of milliseconds
+            dt = getattr(self, "_dyn_tok", None)
+            if dt is None:
+                from ..managers.async_batch_tokenizer import AsyncDynamicBatchTokenizer
+
+                dt = self._dyn_tok = AsyncDynamicBatchTokenizer(self.tokenizer, self.server_args.dynamic_batch_tokenizer_batch_size,
+                                                                self.server_args.dynamic_batch_tokenizer_batch_timeout)
+            todo = [s for s in singles if s.input_ids is None and isinstance(s.text, str) and s.image_data is None and s.audio_data is None]
+            if todo and type(self.tokenizer).__name__ != "ByteTokenizer":
+                for s_, ids_ in zip(todo, await asyncio.gather(*[dt.encode(s.text) for s in todo])):
+                    s_.input_ids = ids_
         aq: "asyncio.Queue[Dict[str, Any]]" = asyncio.Queue()
 
         class _Bridge:

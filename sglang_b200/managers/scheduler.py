@@ -122,6 +122,7 @@ class Scheduler:
         self.num_generated_tokens = 0
         self.num_prefill_tokens = 0
         self.num_mixed_decode_tokens = self.num_mixed_fallbacks = 0
+        self._has_timeouts = bool(server_args.request_waiting_timeout or server_args.request_running_timeout)
         a_ = server_args
         self._mixed_chunk = bool(a_.enable_mixed_chunk and not a_.speculative_algorithm and not a_.enable_dp_attention
                                  and getattr(a_, "disaggregation_mode", "null") in (None, "null") and not getattr(a_, "dllm_algorithm", None)
@@ -874,7 +875,30 @@ class Scheduler:
         self._reject(victim, f"request ({victim.seqlen} prompt tokens + reserve for {victim.sampling_params.max_new_tokens} new tokens) can not be "
                              f"scheduled in the KV cache ({cap})", 400)
 
+    def _expire_requests(self) -> None:
+        """``--request-waiting-timeout`` / ``--request-running-timeout`` (reference scheduler.py waiting / running timeouts): a queued request
+        that has waited too long is finished with an abort (HTTP 408); a running one is flagged and ends at its next result"""
+        now = time.perf_counter()
+        wt, rt = self.args.request_waiting_timeout, self.args.request_running_timeout
+        if wt and self.waiting_queue:
+            keep = []
+            for r in self.waiting_queue:
+                if r is not self.chunked_req and now - r.created_time > wt and not r.output_ids:
+                    if r.req_slot is not None:
+                        self.kv.release(r, insert=False)
+                    self._reject(r, f"request waited longer than {wt:g} s in the queue", 408)
+                else:
+                    keep.append(r)
+            self.waiting_queue = keep
+        if rt:
+            for r in self.live_reqs():
+                start = getattr(r, "queue_time_end", None) or r.created_time
+                if r.to_abort is None and not r.finished() and now - start > rt:
+                    r.to_abort = FINISH_ABORT(f"request ran longer than {rt:g} s", 408)
+
     def _step(self) -> bool:
+        if self._has_timeouts and (self.forward_ct & 7) == 0 or (self._has_timeouts and not self.running_batch.reqs):
+            self._expire_requests()
         batch = self.get_next_batch_to_run()
         if batch is None and self.args.enable_dp_attention:
             self.drain()

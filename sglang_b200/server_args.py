@@ -61,6 +61,11 @@ class ServerArgs:
     mem_fraction_static: Optional[float] = None
     max_running_requests: Optional[int] = None
     max_queued_requests: Optional[int] = None
+    enable_dynamic_batch_tokenizer: bool = False      # asyncio front half: batch-encode prompts that arrive within a short window, off the event loop
+    dynamic_batch_tokenizer_batch_size: int = 32
+    dynamic_batch_tokenizer_batch_timeout: float = 0.002
+    request_waiting_timeout: Optional[float] = None   # seconds a request may sit in the waiting queue before it is aborted (408)
+    request_running_timeout: Optional[float] = None   # seconds a request may run (from its first scheduling) before it is aborted (408)
     max_total_tokens: Optional[int] = None
     max_prefill_tokens: int = 16384
     chunked_prefill_size: Optional[int] = None

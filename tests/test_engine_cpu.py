@@ -175,3 +175,24 @@ def test_seeded_sampling_is_scheduling_independent_and_min_new_tokens_holds_unde
     ids = o["output_ids"]
     assert len(ids) >= 4 and first not in ids[:4], ids
     eng.shutdown()
+
+
+def test_request_waiting_and_running_timeouts():
+    """--request-waiting-timeout aborts what sat in the queue too long; --request-running-timeout ends a generation that runs too long"""
+    eng = sgl.Engine(model_path="dummy:tiny-llama", device="cpu", page_size=4, log_level="error", max_running_requests=1,
+                     request_waiting_timeout=0.4, request_running_timeout=1.2)
+    try:
+        eng.scheduler.forward_sleep_time = 0.03
+        sp = {"max_new_tokens": 400, "temperature": 0, "ignore_eos": True}
+        outs = eng.generate(input_ids=[[5, 6, 7], [8, 9, 10]], sampling_params=sp)
+        a, b = outs
+        assert a["meta_info"]["finish_reason"]["type"] == "abort" and "ran longer" in a["meta_info"]["finish_reason"]["message"]
+        assert 5 < a["meta_info"]["completion_tokens"] < 400                                  # it did run for a while
+        assert b["meta_info"]["finish_reason"]["type"] == "abort" and "waited longer" in b["meta_info"]["finish_reason"]["message"]
+        assert b["meta_info"]["completion_tokens"] == 0
+        eng.scheduler.forward_sleep_time = 0.0
+        ok = eng.generate(input_ids=[5, 6, 7], sampling_params={"max_new_tokens": 4, "temperature": 0, "ignore_eos": True})
+        assert ok["meta_info"]["finish_reason"]["type"] == "length"
+        eng.scheduler.check_invariants()
+    finally:
+        eng.shutdown()

@@ -536,3 +536,39 @@ def test_expert_recorder_modes_and_eplb_manager():
         even.record(0, torch.arange(8).view(1, 8))
         mgr2.on_forward_pass()
     assert mgr2.rebalances == 0 and abs(mgr2.last_balancedness - 1.0) < 1e-9
+
+
+def test_async_dynamic_batch_tokenizer_batches_concurrent_prompts():
+    """prompts arriving together are encoded by one batched call on a worker thread; results equal plain encode; failures reach every waiter"""
+    import asyncio
+    import threading
+
+    from sglang_b200.managers.async_batch_tokenizer import AsyncDynamicBatchTokenizer
+
+    class Tok:
+        def __init__(self):
+            self.calls, self.threads = [], set()
+
+        def encode(self, t):
+            return [ord(c) for c in t]
+
+        def __call__(self, texts):
+            self.calls.append(len(texts))
+            self.threads.add(threading.current_thread().name)
+            if any(t == "boom" for t in texts):
+                raise RuntimeError("bad batch")
+            return {"input_ids": [self.encode(t) for t in texts]}
+
+    tok = Tok()
+    dt = AsyncDynamicBatchTokenizer(tok, max_batch_size=8, batch_wait_timeout_s=0.02)
+
+    async def go():
+        texts = [f"prompt {i}" for i in range(20)]
+        out = await asyncio.gather(*[dt.encode(t) for t in texts])
+        assert out == [tok.encode(t) for t in texts]
+        assert max(tok.calls) == 8 and sum(tok.calls) >= 19 and dt.batches <= 4              # 20 prompts -> 3 batched calls, not 20
+        assert all(n.startswith("sglb-tokenize") for n in tok.threads)                       # never on the event loop thread
+        single = await dt.encode("solo")
+        assert single == tok.encode("solo")
+
+    asyncio.run(go())
