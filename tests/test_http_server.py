@@ -6,8 +6,45 @@ import pytest
 import sglang_b200 as sgl
 
 
-@pytest.fixture(scope="module")
-def client():
+class _SocketClient:
+    """the slice of the TestClient API these tests use, over real sockets (requests) — lets the same route tests run against the native C++ HTTP
+    front end (entrypoints/native_http.py)"""
+
+    def __init__(self, base):
+        import requests
+
+        self.base, self.s = base, requests.Session()
+
+    def get(self, path, **kw):
+        return self.s.get(self.base + path, **kw)
+
+    def post(self, path, **kw):
+        return self.s.post(self.base + path, **kw)
+
+    def stream(self, method, path, **kw):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            r = self.s.request(method, self.base + path, stream=True, **kw)
+
+            class _R:
+                status_code = r.status_code
+                headers = r.headers
+
+                @staticmethod
+                def iter_lines():
+                    for l in r.iter_lines():
+                        yield l.decode() if isinstance(l, bytes) else l
+            try:
+                yield _R
+            finally:
+                r.close()
+        return cm()
+
+
+@pytest.fixture(scope="module", params=["asgi", "native-socket"])
+def client(request):
     from fastapi.testclient import TestClient
 
     from sglang_b200.entrypoints.http_server import create_app
@@ -15,8 +52,21 @@ def client():
     eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, enable_metrics=True, tool_call_parser="qwen25",
                      reasoning_parser="qwen3", grammar_backend="regex_fsm")
     eng.start_background_loop()
-    with TestClient(create_app(eng)) as c:
-        yield c
+    if request.param == "asgi":
+        with TestClient(create_app(eng)) as c:
+            yield c
+    else:          # every route test again through the C++ epoll front end over a real TCP connection
+        import threading
+
+        from sglang_b200.entrypoints.native_http import NativeAsgiServer
+
+        srv = NativeAsgiServer(create_app(eng), "127.0.0.1", 0, graceful_timeout=3.0)
+        th = threading.Thread(target=srv.run, kwargs={"install_signal_handlers": False}, daemon=True)
+        th.start()
+        assert srv.started.wait(30)
+        yield _SocketClient(f"http://127.0.0.1:{srv.port}")
+        srv.request_stop()
+        th.join(20)
     eng.shutdown()
 
 
