@@ -69,6 +69,62 @@ static std::string head(int status, const std::vector<std::pair<std::string, std
   return h;
 }
 
+
+// ---- WebSocket helpers (RFC 6455): SHA-1 and base64 for the accept key, server-to-client frames are never masked
+static void sha1(const std::string& in, unsigned char out[20]) {
+  uint32_t h0 = 0x67452301, h1 = 0xEFCDAB89, h2 = 0x98BADCFE, h3 = 0x10325476, h4 = 0xC3D2E1F0;
+  std::string m = in;
+  uint64_t bits = (uint64_t)in.size() * 8;
+  m.push_back((char)0x80);
+  while (m.size() % 64 != 56) m.push_back((char)0);
+  for (int i = 7; i >= 0; --i) m.push_back((char)((bits >> (8 * i)) & 0xFF));
+  auto rol = [](uint32_t v, int s) { return (v << s) | (v >> (32 - s)); };
+  for (size_t off = 0; off < m.size(); off += 64) {
+    uint32_t w[80];
+    for (int i = 0; i < 16; ++i)
+      w[i] = ((uint32_t)(unsigned char)m[off + 4 * i] << 24) | ((uint32_t)(unsigned char)m[off + 4 * i + 1] << 16) |
+             ((uint32_t)(unsigned char)m[off + 4 * i + 2] << 8) | (uint32_t)(unsigned char)m[off + 4 * i + 3];
+    for (int i = 16; i < 80; ++i) w[i] = rol(w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16], 1);
+    uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
+    for (int i = 0; i < 80; ++i) {
+      uint32_t f, k;
+      if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999; }
+      else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1; }
+      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDC; }
+      else { f = b ^ c ^ d; k = 0xCA62C1D6; }
+      uint32_t t = rol(a, 5) + f + e + k + w[i];
+      e = d; d = c; c = rol(b, 30); b = a; a = t;
+    }
+    h0 += a; h1 += b; h2 += c; h3 += d; h4 += e;
+  }
+  uint32_t hs[5] = {h0, h1, h2, h3, h4};
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = (unsigned char)((hs[i] >> (24 - 8 * j)) & 0xFF);
+}
+
+static std::string b64(const unsigned char* p, size_t n) {
+  static const char* T = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  std::string o;
+  for (size_t i = 0; i < n; i += 3) {
+    uint32_t v = (uint32_t)p[i] << 16 | (i + 1 < n ? (uint32_t)p[i + 1] << 8 : 0) | (i + 2 < n ? (uint32_t)p[i + 2] : 0);
+    o.push_back(T[(v >> 18) & 63]);
+    o.push_back(T[(v >> 12) & 63]);
+    o.push_back(i + 1 < n ? T[(v >> 6) & 63] : '=');
+    o.push_back(i + 2 < n ? T[v & 63] : '=');
+  }
+  return o;
+}
+
+static std::string ws_frame(int opcode, const std::string& payload) {
+  std::string f;
+  f.push_back((char)(0x80 | (opcode & 0x0F)));
+  size_t n = payload.size();
+  if (n < 126) f.push_back((char)n);
+  else if (n < 65536) { f.push_back((char)126); f.push_back((char)(n >> 8)); f.push_back((char)(n & 0xFF)); }
+  else { f.push_back((char)127); for (int i = 7; i >= 0; --i) f.push_back((char)((n >> (8 * i)) & 0xFF)); }
+  return f + payload;
+}
+
 HttpFrontend::HttpFrontend(const std::string& host, int port, int backlog, int64_t max_body, bool reuse_port)
     : host_(host), port_(port), backlog_(backlog), max_body_(max_body), reuse_port_(reuse_port) {
   lfd_ = ::socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
@@ -229,6 +285,39 @@ bool HttpFrontend::end_stream(uint64_t id) {
   return true;
 }
 
+
+bool HttpFrontend::ws_accept(uint64_t id, const std::vector<std::pair<std::string, std::string>>& headers) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (live_.find(id) == live_.end()) return false;
+  }
+  std::string extra;
+  for (auto& kv : headers) extra += kv.first + ": " + kv.second + "\r\n";
+  push_cmd(Cmd{4, id, extra});          // the accept key is known to the I/O thread (it parsed the upgrade request)
+  return true;
+}
+
+bool HttpFrontend::ws_send(uint64_t id, bool binary, const std::string& payload) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (live_.find(id) == live_.end()) return false;
+  }
+  push_cmd(Cmd{5, id, ws_frame(binary ? 2 : 1, payload)});
+  return true;
+}
+
+bool HttpFrontend::ws_close(uint64_t id, int code) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (live_.find(id) == live_.end()) return false;
+  }
+  std::string p;
+  p.push_back((char)((code >> 8) & 0xFF));
+  p.push_back((char)(code & 0xFF));
+  push_cmd(Cmd{6, id, ws_frame(8, p)});
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ I/O thread
 void HttpFrontend::update_interest(Conn& c) {
   epoll_event ev{};
@@ -347,6 +436,7 @@ void HttpFrontend::try_parse(Conn& c) {
           if (vl.find("close") != std::string::npos) keep = false;
           else if (vl.find("keep-alive") != std::string::npos) keep = true;
         } else if (kl == "expect" && lower(v).find("100-continue") != std::string::npos) expect = true;
+        else if (kl == "sec-websocket-key") c.ws_key = v;
         e.headers.emplace_back(std::move(k), std::move(v));
       }
       p = q + 2;
@@ -431,7 +521,82 @@ void HttpFrontend::on_readable(Conn& c) {
     close_conn(c.fd, true);
     return;
   }
-  try_parse(c);
+  if (c.ws) parse_ws(c);
+  else try_parse(c);
+}
+
+void HttpFrontend::parse_ws(Conn& c) {
+  for (;;) {
+    if (c.in.size() < 2) return;
+    const unsigned char* b = (const unsigned char*)c.in.data();
+    bool fin = b[0] & 0x80, masked = b[1] & 0x80;
+    int op = b[0] & 0x0F;
+    uint64_t n = b[1] & 0x7F;
+    size_t hdr = 2;
+    if (n == 126) {
+      if (c.in.size() < 4) return;
+      n = ((uint64_t)b[2] << 8) | b[3];
+      hdr = 4;
+    } else if (n == 127) {
+      if (c.in.size() < 10) return;
+      n = 0;
+      for (int i = 0; i < 8; ++i) n = (n << 8) | b[2 + i];
+      hdr = 10;
+    }
+    if ((int64_t)n > max_body_ || !masked) {          // clients MUST mask; oversized messages are refused
+      close_conn(c.fd, true);
+      return;
+    }
+    if (c.in.size() < hdr + 4 + n) return;
+    const unsigned char* mask = b + hdr;
+    std::string payload((size_t)n, '\0');
+    for (uint64_t i = 0; i < n; ++i) payload[i] = (char)(b[hdr + 4 + i] ^ mask[i & 3]);
+    c.in.erase(0, hdr + 4 + (size_t)n);
+    if (op == 9) {          // ping -> pong, answered here
+      c.out.push_back(ws_frame(10, payload));
+      flush(c);
+      if (conns_.find(c.fd) == conns_.end()) return;
+      continue;
+    }
+    if (op == 10) continue;
+    if (op == 8) {          // close: echo it, tell Python, drop the connection once written
+      c.out.push_back(ws_frame(8, payload.substr(0, std::min<size_t>(2, payload.size()))));
+      uint64_t id = c.cur;
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        HttpEvent e;
+        e.type = 3;
+        e.id = id;
+        e.body = payload;
+        post_event(std::move(e));
+        live_.erase(id);
+        live_empty_ = live_.empty();
+      }
+      cv_.notify_one();
+      req_fd_.erase(id);
+      c.cur = 0;
+      c.close_after = true;
+      flush(c);
+      return;
+    }
+    if (op == 1 || op == 2) {
+      c.ws_opcode = op;
+      c.ws_msg = payload;
+    } else if (op == 0) {
+      c.ws_msg += payload;
+    }
+    if (fin) {
+      std::lock_guard<std::mutex> g(mu_);
+      HttpEvent e;
+      e.type = 2;
+      e.id = c.cur;
+      e.method = c.ws_opcode == 2 ? "binary" : "text";
+      e.body = std::move(c.ws_msg);
+      c.ws_msg.clear();
+      post_event(std::move(e));
+      cv_.notify_one();
+    }
+  }
 }
 
 void HttpFrontend::finish_response(Conn& c) {
@@ -493,6 +658,23 @@ void HttpFrontend::apply(Cmd& cmd) {
       size_t p = cmd.data.find("Connection: keep-alive\r\n");
       if (p != std::string::npos) cmd.data.replace(p, 24, "Connection: close\r\n");
     }
+  }
+  if (cmd.op == 4) {          // 101 Switching Protocols
+    unsigned char dg[20];
+    sha1(c.ws_key + "258EAFA5-E914-47DA-95CA-C5AB0DC85B11", dg);
+    c.out.push_back("HTTP/1.1 101 Switching Protocols\r\nUpgrade: websocket\r\nConnection: Upgrade\r\nSec-WebSocket-Accept: " + b64(dg, 20) + "\r\n" +
+                    cmd.data + "\r\n");
+    c.ws = true;
+    flush(c);
+    if (conns_.find(it->second) != conns_.end() && !c.in.empty()) parse_ws(c);
+    return;
+  }
+  if (cmd.op == 6) {          // our close: send it, forget the request, drop the connection once written
+    c.out.push_back(std::move(cmd.data));
+    finish_response(c);
+    c.close_after = true;
+    flush(c);
+    return;
   }
   c.out.push_back(std::move(cmd.data));
   if (cmd.op == 1) c.streaming = true;

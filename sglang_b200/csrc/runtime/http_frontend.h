@@ -17,7 +17,7 @@
 namespace sglb_rt {
 
 struct HttpEvent {
-  int type = 0;  // 0 = request, 1 = client went away before the response finished
+  int type = 0;  // 0 = request, 1 = client went away before the response finished, 2 = WebSocket message (method = "text" | "binary"), 3 = WebSocket closed
   uint64_t id = 0;
   std::string method, target, version, peer;
   std::vector<std::pair<std::string, std::string>> headers;
@@ -45,6 +45,11 @@ class HttpFrontend {
   bool start_stream(uint64_t id, int status, const std::vector<std::pair<std::string, std::string>>& headers);
   bool send_chunk(uint64_t id, const std::string& data);
   bool end_stream(uint64_t id);
+  // WebSocket (RFC 6455): accept answers the upgrade request `id` with 101 and switches the connection to frame mode; messages then arrive as
+  // events of type 2 (fragments reassembled, pings answered by the I/O thread) and the peer's close as type 3
+  bool ws_accept(uint64_t id, const std::vector<std::pair<std::string, std::string>>& headers);
+  bool ws_send(uint64_t id, bool binary, const std::string& payload);
+  bool ws_close(uint64_t id, int code);
   HttpStats stats() const;
 
  private:
@@ -55,9 +60,12 @@ class HttpFrontend {
     size_t out_off = 0;
     uint64_t cur = 0;          // request being answered (0 = idle, parsing allowed)
     bool streaming = false, keep_alive = true, close_after = false, want_write = false, sent_continue = false;
+    bool ws = false;            // upgraded: `in` holds WebSocket frames, `cur` stays the id of the upgrade request
+    std::string ws_key, ws_msg; // Sec-WebSocket-Key of the pending upgrade; fragments of the message being reassembled
+    int ws_opcode = 0;
   };
   struct Cmd {
-    int op;  // 0 respond, 1 start, 2 chunk, 3 end
+    int op;  // 0 respond, 1 start, 2 chunk, 3 end, 4 ws accept, 5 ws frame, 6 ws close
     uint64_t id;
     std::string data;          // fully formatted bytes to append to the connection's output
   };
@@ -65,6 +73,7 @@ class HttpFrontend {
   void on_accept();
   void on_readable(Conn& c);
   void try_parse(Conn& c);
+  void parse_ws(Conn& c);
   void flush(Conn& c);
   void close_conn(int fd, bool notify);
   void finish_response(Conn& c);

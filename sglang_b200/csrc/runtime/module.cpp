@@ -224,6 +224,9 @@ PYBIND11_MODULE(sglb_rt, m) {
       .def("start_stream", &HttpFrontend::start_stream)
       .def("send_chunk", [](HttpFrontend& f, uint64_t id, py::bytes data) { return f.send_chunk(id, (std::string)data); })
       .def("end_stream", &HttpFrontend::end_stream)
+      .def("ws_accept", &HttpFrontend::ws_accept)
+      .def("ws_send", [](HttpFrontend& f, uint64_t id, bool binary, py::bytes data) { return f.ws_send(id, binary, (std::string)data); })
+      .def("ws_close", &HttpFrontend::ws_close)
       .def("stats", [](HttpFrontend& f) {
         HttpStats s = f.stats();
         py::dict d;

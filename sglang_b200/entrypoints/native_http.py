@@ -7,7 +7,8 @@ itself, frames chunked / SSE output and notices disconnects; Python receives *co
 The existing FastAPI application (every route in ``docs/http_api.md``) runs unchanged on top through the ASGI protocol, so
 ``--http-frontend native`` swaps uvicorn's Python socket layer for the native one and nothing else.
 
-Not handled natively: WebSocket upgrades (the realtime routes answer 426 — use the uvicorn front end for them), TLS, HTTP/2.
+WebSocket routes (``/v1/realtime``) run on the same front end: handshake, masking, fragment reassembly, ping / pong and close are handled by
+the I/O thread, Python sees whole messages through the ASGI ``websocket`` scope.  Not handled natively: TLS, HTTP/2, permessage-deflate.
 """
 from __future__ import annotations
 
@@ -31,7 +32,7 @@ def _rt():
     return rt
 
 
-class NativeAsgiServer:
+class NativeAsgiServer(object):
     def __init__(self, app: Any, host: str = "127.0.0.1", port: int = 30000, *, reuse_port: bool = False, max_body: int = 1 << 30,
                  graceful_timeout: float = 30.0, static: Optional[Dict[str, Tuple[int, str, bytes]]] = None):
         self.app = app
@@ -41,6 +42,7 @@ class NativeAsgiServer:
         for path, (status, ctype, body) in (static or {}).items():
             self.fe.set_static(path, status, ctype, body)
         self._disc: Dict[int, asyncio.Event] = {}
+        self._wsq: Dict[int, "asyncio.Queue"] = {}
         self._tasks: set = set()
         self._stop: Optional[asyncio.Event] = None
         self._loop: Optional[asyncio.AbstractEventLoop] = None
@@ -91,10 +93,18 @@ class NativeAsgiServer:
 
     def _dispatch(self, evs: List[tuple]) -> None:
         for ev in evs:
+            if ev[0] in (2, 3):          # WebSocket message / peer close
+                q = self._wsq.get(ev[1])
+                if q is not None:
+                    q.put_nowait(ev)
+                continue
             if ev[0] == 1:
                 d = self._disc.get(ev[1])
                 if d is not None:
                     d.set()
+                q = self._wsq.get(ev[1])
+                if q is not None:
+                    q.put_nowait((3, ev[1], "", b"", "", "", [], b""))
                 continue
             t = asyncio.ensure_future(self._handle(ev))
             self._tasks.add(t)
@@ -105,11 +115,10 @@ class NativeAsgiServer:
         fe = self.fe
         path, _, qs = target.partition(b"?")
         hdrs = [(k.lower(), v) for k, v in headers]
-        if any(k == b"upgrade" and v.lower() == b"websocket" for k, v in hdrs):
-            fe.respond(rid, 426, [("Content-Type", "application/json")],
-                       b'{"error": "WebSocket routes are served by the uvicorn front end (--http-frontend uvicorn)"}')
-            return
         ip, _, port = peer.rpartition(":")
+        if any(k == b"upgrade" and v.lower() == b"websocket" for k, v in hdrs):
+            await self._handle_ws(rid, path, qs, hdrs, (ip, int(port or 0)), version)
+            return
         scope = {"type": "http", "asgi": {"version": "3.0", "spec_version": "2.3"}, "http_version": version.split("/")[-1], "method": method,
                  "scheme": "http", "path": unquote(path.decode("latin-1")), "raw_path": path, "query_string": qs, "root_path": "",
                  "headers": hdrs, "client": (ip, int(port or 0)), "server": (self.host, self.port)}
@@ -172,6 +181,65 @@ class NativeAsgiServer:
             self._disc.pop(rid, None)
 
 
+class _WsMixin:
+    async def _handle_ws(self, rid: int, path: bytes, qs: bytes, hdrs, client, version: str) -> None:
+        """ASGI ``websocket`` scope over the native frames: the C++ thread does the handshake hash, (un)masking, fragment reassembly, ping / pong
+        and close echo; here only whole messages move"""
+        fe = self.fe
+        q: asyncio.Queue = asyncio.Queue()
+        self._wsq[rid] = q
+        sub = [v.decode("latin-1") for k, v in hdrs if k == b"sec-websocket-protocol"]
+        scope = {"type": "websocket", "asgi": {"version": "3.0", "spec_version": "2.3"}, "http_version": version.split("/")[-1], "scheme": "ws",
+                 "path": unquote(path.decode("latin-1")), "raw_path": path, "query_string": qs, "root_path": "", "headers": hdrs, "client": client,
+                 "server": (self.host, self.port), "subprotocols": [p.strip() for s_ in sub for p in s_.split(",")]}
+        st = {"connected": False, "accepted": False, "closed": False}
+
+        async def receive():
+            if not st["connected"]:
+                st["connected"] = True
+                return {"type": "websocket.connect"}
+            ev = await q.get()
+            if ev[0] == 2:
+                return {"type": "websocket.receive", "text": ev[7].decode("utf-8")} if ev[2] == "text" else {"type": "websocket.receive", "bytes": ev[7]}
+            st["closed"] = True
+            code = int.from_bytes(ev[7][:2], "big") if len(ev[7]) >= 2 else 1005
+            return {"type": "websocket.disconnect", "code": code}
+
+        async def send(msg):
+            t = msg["type"]
+            if t == "websocket.accept":
+                hs = [(k.decode("latin-1"), v.decode("latin-1")) for k, v in msg.get("headers", [])]
+                if msg.get("subprotocol"):
+                    hs.append(("Sec-WebSocket-Protocol", msg["subprotocol"]))
+                st["accepted"] = fe.ws_accept(rid, hs)
+            elif t == "websocket.send":
+                if msg.get("text") is not None:
+                    fe.ws_send(rid, False, msg["text"].encode("utf-8"))
+                else:
+                    fe.ws_send(rid, True, bytes(msg.get("bytes") or b""))
+            elif t == "websocket.close":
+                if not st["accepted"]:
+                    fe.respond(rid, 403, [("Content-Type", "application/json")], b'{"error": "websocket rejected"}')
+                elif not st["closed"]:
+                    fe.ws_close(rid, int(msg.get("code", 1000)))
+                st["closed"] = True
+
+        try:
+            await self.app(scope, receive, send)
+            if st["accepted"] and not st["closed"]:
+                fe.ws_close(rid, 1000)
+            elif not st["accepted"] and not st["closed"]:
+                fe.respond(rid, 403, [("Content-Type", "application/json")], b'{"error": "websocket rejected"}')
+        except asyncio.CancelledError:
+            raise
+        except Exception:
+            logger.exception("unhandled error in websocket %s", path)
+            if st["accepted"] and not st["closed"]:
+                fe.ws_close(rid, 1011)
+        finally:
+            self._wsq.pop(rid, None)
+
+
 class _Lifespan:
     """ASGI lifespan protocol (startup / shutdown events of the FastAPI app)"""
 
@@ -205,3 +273,6 @@ class _Lifespan:
             await asyncio.wait_for(self.tx.get(), timeout=10)
         except asyncio.TimeoutError:
             self.task.cancel()
+
+
+NativeAsgiServer._handle_ws = _WsMixin._handle_ws

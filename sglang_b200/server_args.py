@@ -24,7 +24,7 @@ class ServerArgs:
     model_path: str = "dummy:tiny-llama"
     tokenizer_path: Optional[str] = None
     load_format: str = "auto"  # auto|dummy|safetensors|pt|sharded_state|gguf|remote_instance
-    http_frontend: str = "uvicorn"   # uvicorn | native (C++ epoll front end, csrc/runtime/http_frontend.cpp; no WebSocket routes)
+    http_frontend: str = "uvicorn"   # uvicorn | native (C++ epoll front end, csrc/runtime/http_frontend.cpp: HTTP/1.1 + SSE + WebSocket)
     model_impl: str = "auto"   # auto: native class, else the Transformers fallback | sglang: native only | transformers: always the fallback
     remote_instance_weight_loader_seed_instance_ip: Optional[str] = None
     remote_instance_weight_loader_seed_instance_service_port: Optional[int] = None

@@ -99,7 +99,6 @@ def test_pipelining_expect_continue_and_limits(server):
     assert _raw(srv.port, b"POST /generate HTTP/1.1\r\nContent-Length: 99999999\r\n\r\n").startswith(b"HTTP/1.1 413")
     assert _raw(srv.port, b"POST /generate HTTP/1.1\r\nTransfer-Encoding: chunked\r\n\r\n5\r\nhello\r\n0\r\n\r\n").startswith(b"HTTP/1.1 411")
     assert _raw(srv.port, b"garbage\r\n\r\n").startswith(b"HTTP/1.1 400")
-    assert _raw(srv.port, b"GET /realtime HTTP/1.1\r\nUpgrade: websocket\r\nConnection: Upgrade\r\n\r\n", timeout=3).startswith(b"HTTP/1.1 426")
 
 
 def test_client_disconnect_aborts_generation(server):
@@ -169,3 +168,56 @@ def test_bench_one_batch_server_against_a_live_server(server, tmp_path):
     assert [r["batch_size"] for r in rows] == [1, 3] and all(r["completed_tokens"] == r["batch_size"] * 5 for r in rows)
     assert all(r["ttft_s"] > 0 and r["latency_s"] >= r["ttft_s"] and r["itl_ms"] > 0 for r in rows)
     assert len(out.read_text().strip().splitlines()) == 2
+
+
+def test_websocket_echo_and_realtime_route_over_the_native_front_end(server):
+    """RFC 6455 on the C++ I/O thread (handshake hash, masking, fragments, ping/pong, close) + the ASGI websocket scope: a plain echo app,
+    then the engine's /v1/realtime text session"""
+    from websockets.sync.client import connect
+
+    async def echo(scope, receive, send):
+        assert scope["type"] == "websocket" and scope["path"] == "/echo"
+        assert (await receive())["type"] == "websocket.connect"
+        await send({"type": "websocket.accept"})
+        while True:
+            m = await receive()
+            if m["type"] == "websocket.disconnect":
+                return
+            if m.get("text") == "bye":
+                await send({"type": "websocket.close", "code": 1000})
+                return
+            await send({"type": "websocket.send", **({"text": m["text"].upper()} if m.get("text") is not None else {"bytes": m["bytes"][::-1]})})
+
+    srv2 = NativeAsgiServer(echo, "127.0.0.1", 0)
+    th = threading.Thread(target=srv2.run, kwargs={"install_signal_handlers": False}, daemon=True)
+    th.start()
+    assert srv2.started.wait(10)
+    try:
+        with connect(f"ws://127.0.0.1:{srv2.port}/echo") as ws:
+            ws.send("hello")
+            assert ws.recv() == "HELLO"
+            ws.send(b"\x01\x02\x03")
+            assert ws.recv() == b"\x03\x02\x01"
+            big = "x" * 200000                          # 64-bit length header, several TCP segments
+            ws.send(big)
+            assert ws.recv() == big.upper()
+            ws.ping().wait(5)                           # answered by the I/O thread
+            ws.send("bye")
+            with pytest.raises(Exception):
+                ws.recv()
+    finally:
+        srv2.request_stop()
+        th.join(10)
+    srv, eng, url = server
+    with connect(f"ws://127.0.0.1:{srv.port}/v1/realtime") as ws:
+        first = json.loads(ws.recv())
+        assert first["type"] == "session.created"
+        ws.send(json.dumps({"type": "conversation.item.create", "item": {"type": "message", "role": "user", "content": [{"type": "input_text", "text": "hi"}]}}))
+        ws.send(json.dumps({"type": "response.create", "response": {"max_output_tokens": 4}}))
+        kinds = []
+        for _ in range(50):
+            ev = json.loads(ws.recv())
+            kinds.append(ev["type"])
+            if ev["type"] in ("response.done", "error"):
+                break
+        assert "response.done" in kinds and any(k.endswith("delta") for k in kinds), kinds
