@@ -438,6 +438,16 @@ def _http_worker_main(server_args: ServerArgs, attach: Dict[str, Any]) -> None:
         resp.headers["x-sglb-worker"] = str(wid)
         return resp
 
+    if getattr(server_args, "http_frontend", "uvicorn") == "native":
+        # every worker runs its own C++ epoll front end on the shared port (SO_REUSEPORT: the kernel spreads new connections)
+        from ..entrypoints.native_http import NativeAsgiServer
+
+        try:
+            NativeAsgiServer(app, server_args.host, server_args.port, reuse_port=True,
+                             graceful_timeout=max(1.0, float(server_args.graceful_shutdown_timeout))).run()
+        finally:
+            engine.shutdown()
+        return
     sock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
     sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
     sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEPORT, 1)

@@ -174,8 +174,9 @@ def test_sigterm_drains_in_flight_requests(tmp_path, frontend):
             p.kill()
 
 
-def test_multi_tokenizer_workers_share_one_scheduler(tmp_path):
-    """--tokenizer-worker-num 2: two HTTP + tokenizer processes on one port (SO_REUSEPORT), one scheduler, one detokenizer that routes results by
+@pytest.mark.parametrize("frontend", ["uvicorn", "native"])
+def test_multi_tokenizer_workers_share_one_scheduler(tmp_path, frontend):
+    """--tokenizer-worker-num 2 (with either socket layer): two HTTP + tokenizer processes on one port (SO_REUSEPORT), one scheduler, one detokenizer that routes results by
     worker; answers equal the single-process engine, both workers serve traffic, aborts and streaming reach the right worker"""
     import json
     import os
@@ -194,7 +195,7 @@ def test_multi_tokenizer_workers_share_one_scheduler(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
-                          "--host", "127.0.0.1", "--log-level", "error", "--tokenizer-worker-num", "2", "--page-size", "4"], cwd=root,
+                          "--host", "127.0.0.1", "--log-level", "error", "--tokenizer-worker-num", "2", "--page-size", "4", "--http-frontend", frontend], cwd=root,
                          env=dict(os.environ, PYTHONPATH=root), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     try:
         for _ in range(160):
