@@ -339,7 +339,7 @@ _ARCH_DEFAULTS = {"GPT2LMHeadModel": dict(pos_emb="learned", tie_word_embeddings
                   "Glm4MoeForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", partial_rotary_factor=0.5, attention_bias=True),
                   "Dots1ForCausalLM": dict(scoring_func="sigmoid", topk_method="noaux_tc", use_qk_norm=True),
                   "Gemma3ForCausalLM": dict(hidden_act="gelu_pytorch_tanh", tie_word_embeddings=True),
-                  "OlmoeForCausalLM": dict(norm_topk_prob=False), "MiniMaxM2ForCausalLM": dict(norm_topk_prob=True),
+                  "OlmoeForCausalLM": dict(norm_topk_prob=False), "FlexOlmoForCausalLM": dict(norm_topk_prob=False), "MiniMaxM2ForCausalLM": dict(norm_topk_prob=True),
                   "PhimoeForCausalLM": dict(attention_bias=True, attention_out_bias=True), "PhiMoEForCausalLM": dict(attention_bias=True, attention_out_bias=True),
                   "HeliumForCausalLM": dict(rope_is_neox=False), "Ernie4_5ForCausalLM": dict(rope_is_neox=False),
                   "Ernie4_5_MoeForCausalLM": dict(rope_is_neox=False, scoring_func="softmax", topk_method="noaux_tc", norm_topk_prob=True),

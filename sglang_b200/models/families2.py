@@ -504,3 +504,21 @@ def _make_hunyuan_moe():
             return lambda c, layer_id, dtype, quant, prefix: HunYuanMoE(c, layer_id, dtype, quant, prefix + ".mlp")
 
     return HunYuanMoEV1ForCausalLM
+
+
+# ---------------------------------------------------------------- FlexOlmo: OLMo-2 post-norm blocks (q/k norm over the whole projection) around OLMoE experts
+def _make_flex_olmo():
+    from .families import Olmo2Attention, Olmo2DecoderLayer
+
+    class FlexOlmoDecoderLayer(Olmo2DecoderLayer):
+        def __init__(self, cfg: ModelConfig, layer_id: int, dtype, quant, rope, prefix: str, mlp_cls=LlamaMLP):
+            LlamaDecoderLayer.__init__(self, cfg, layer_id, dtype, quant, rope, prefix, OlmoeMoE)
+            self.self_attn = Olmo2Attention(cfg, layer_id, dtype, quant, rope, prefix + ".self_attn")
+            del self.input_layernorm
+            self.post_feedforward_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, dtype)
+
+    class FlexOlmoForCausalLM(OlmoeForCausalLM):
+        """reference ``python/sglang/srt/models/flex_olmo.py``"""
+        decoder_layer_cls = FlexOlmoDecoderLayer
+
+    return FlexOlmoForCausalLM

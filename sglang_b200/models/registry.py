@@ -87,6 +87,7 @@ def _register_builtins() -> None:
         register_model(name, getattr(_f2, name))
     from . import gemma3_mm as _g3
 
+    register_model("FlexOlmoForCausalLM", _f2._make_flex_olmo())
     register_model("HunYuanDenseV1ForCausalLM", _f2.HunYuanDenseV1ForCausalLM)
     register_model("HunYuanMoEV1ForCausalLM", _f2._make_hunyuan_moe())
     register_model("Gemma3ForConditionalGeneration", _g3.Gemma3ForConditionalGeneration)

@@ -162,6 +162,7 @@ CASES = {
         "rope_type": "dynamic", "rope_theta": 10000.0, "alpha": 50.0, "factor": 1.0})),
     "hunyuan-moe": ("HunYuanMoEV1Config", "HunYuanMoEV1ForCausalLM", dict(BASE, head_dim=16, num_experts=4, moe_topk=2, num_shared_expert=1)),
     "phimoe": ("PhimoeConfig", "PhimoeForCausalLM", dict(BASE, num_local_experts=4, num_experts_per_tok=2, router_jitter_noise=0.2)),
+    "flex-olmo": ("FlexOlmoConfig", "FlexOlmoForCausalLM", dict(BASE, num_experts=4, num_experts_per_tok=2, pad_token_id=0)),
     "mamba2": ("Mamba2Config", "Mamba2ForCausalLM", dict(hidden_size=64, num_hidden_layers=2, vocab_size=512, num_heads=8, head_dim=16, state_size=16,
                                                          n_groups=2, expand=2, conv_kernel=4, chunk_size=8, tie_word_embeddings=True)),
 }
