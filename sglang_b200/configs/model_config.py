@@ -612,7 +612,10 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                 kw.setdefault(k_, v_)
         if arch == "LlavaForConditionalGeneration" and (hf.get("vision_config") or {}).get("model_type") == "pixtral":
             arch = kw["architecture"] = "PixtralForConditionalGeneration"          # pixtral-12b ships in the LLaVA container
-        if arch in ("Mistral3ForConditionalGeneration", "PixtralForConditionalGeneration"):
+        if arch in ("LightOnOcrForConditionalGeneration", "LightOnOCRForConditionalGeneration"):
+            kw["qk_norm"] = True          # Qwen3 decoder
+        if arch in ("Mistral3ForConditionalGeneration", "PixtralForConditionalGeneration", "LightOnOcrForConditionalGeneration",
+                    "LightOnOCRForConditionalGeneration"):
             vc = hf["vision_config"]
             vrp = vc.get("rope_parameters") or {}
             kw["vision"] = {"variant": "pixtral", "hidden_size": vc.get("hidden_size", 1024), "intermediate_size": vc.get("intermediate_size", 4096),
@@ -620,9 +623,9 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "head_dim": vc.get("head_dim"), "patch_size": vc.get("patch_size", 14), "image_size": vc.get("image_size", 1540),
                             "hidden_act": vc.get("hidden_act", "gelu"),
                             "rope_theta": vrp.get("rope_theta", vc.get("rope_theta", 10000.0)),
-                            "spatial_merge_size": hf.get("spatial_merge_size", 2) if arch.startswith("Mistral3") else 1,
+                            "spatial_merge_size": 1 if arch.startswith("Pixtral") else hf.get("spatial_merge_size", 2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu"),
-                            "projector_bias": hf.get("multimodal_projector_bias", not arch.startswith("Mistral3")),
+                            "projector_bias": hf.get("multimodal_projector_bias", arch.startswith("Pixtral")),
                             "image_break_token_id": hf.get("image_break_token_id", 12), "image_end_token_id": hf.get("image_end_token_id", 13)}
             kw["image_token_id"] = hf.get("image_token_id", hf.get("image_token_index", 10))
         if arch in ("Qwen3VLForConditionalGeneration", "Qwen3VLMoeForConditionalGeneration"):
@@ -643,7 +646,8 @@ def load_model_config(model_path: str, overrides: Optional[Dict[str, Any]] = Non
                             "temporal_patch_size": vc.get("temporal_patch_size", 2)}
             kw["image_token_id"] = hf.get("image_token_id", 151655)
             kw.setdefault("attention_bias", True)
-        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration", "PixtralForConditionalGeneration", "Gemma3ForConditionalGeneration", "Glm4vForConditionalGeneration", "Glm4vMoeForConditionalGeneration",
+        elif "vision_config" in hf and arch not in ("Qwen2_5_VLForConditionalGeneration", "InternVLForConditionalGeneration", "Qwen3VLForConditionalGeneration", "Mistral3ForConditionalGeneration", "PixtralForConditionalGeneration", "LightOnOcrForConditionalGeneration", "LightOnOCRForConditionalGeneration",
+                                                 "Gemma3ForConditionalGeneration", "Glm4vForConditionalGeneration", "Glm4vMoeForConditionalGeneration",
                                                  "Qwen3VLMoeForConditionalGeneration"):
             kw["vision"] = {**_CLIP_L_336, **hf["vision_config"], "select_layer": hf.get("vision_feature_layer", -2),
                             "projector_hidden_act": hf.get("projector_hidden_act", "gelu")}

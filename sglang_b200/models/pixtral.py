@@ -183,3 +183,15 @@ class PixtralForConditionalGeneration(Mistral3ForConditionalGeneration):
             v = cfg.vision
             self.projector = _LlavaProjector(v["hidden_size"], cfg.hidden_size, bool(v.get("projector_bias", True)), v.get("projector_hidden_act", "gelu"),
                                              _DT[cfg.dtype])
+
+
+class LightOnOCRForConditionalGeneration(Mistral3ForConditionalGeneration):
+    """LightOnOCR (reference ``python/sglang/srt/models/lightonocr.py``): the Mistral3 recipe — Pixtral tower, RMSNorm + learned 2x2 merger, two
+    bias-free linears — in front of a Qwen3 decoder (per-head q/k norm comes from the config); the checkpoint calls the two vision parts
+    ``vision_encoder`` / ``vision_projection``."""
+
+    def load_weights(self, weights):
+        def rename():
+            for name, w in weights:
+                yield name.replace("vision_encoder.", "vision_tower.").replace("vision_projection.", "multi_modal_projector."), w
+        return super().load_weights(rename())

@@ -109,6 +109,8 @@ def _register_builtins() -> None:
 
     register_model("Mistral3ForConditionalGeneration", _px.Mistral3ForConditionalGeneration)
     register_model("PixtralForConditionalGeneration", _px.PixtralForConditionalGeneration)
+    register_model("LightOnOcrForConditionalGeneration", _px.LightOnOCRForConditionalGeneration)
+    register_model("LightOnOCRForConditionalGeneration", _px.LightOnOCRForConditionalGeneration)
     from . import gpt_oss as _go
 
     register_model("GptOssForCausalLM", _go.GptOssForCausalLM)

@@ -321,7 +321,7 @@ def process_images_internvl(input_ids: List[int], image_data: Any, cfg: Any, tok
 def process_images(input_ids: List[int], image_data: Any, cfg: Any, tokenizer: Any, encoder: Any = None) -> Tuple[List[int], Dict[str, Any]]:
     if cfg.architecture.startswith("InternVL"):
         return process_images_internvl(input_ids, image_data, cfg, tokenizer, encoder)
-    if cfg.architecture.startswith(("Mistral3", "Pixtral")):
+    if cfg.architecture.startswith(("Mistral3", "Pixtral", "LightOnO")):
         return process_images_pixtral(input_ids, image_data, cfg, tokenizer, encoder)
     if cfg.architecture.startswith(("Qwen2VL", "Qwen2_5_VL", "Qwen3VL", "Glm4v")):
         return process_images_qwen_vl(input_ids, image_data, cfg, tokenizer, encoder)

@@ -18,7 +18,7 @@ def test_pixtral_resize_shape_matches_hf():
         assert P.pixtral_resize_shape(h, w, 1540, 28) == tuple(get_resize_output_image_size(img, size=(1540, 1540), patch_size=(28, 28)))
 
 
-@pytest.mark.parametrize("kind", ["mistral3", "pixtral-llava"])
+@pytest.mark.parametrize("kind", ["mistral3", "pixtral-llava", "lightonocr"])
 def test_engine_matches_hf(tmp_path, kind):
     if not hasattr(tf, "Mistral3ForConditionalGeneration"):
         pytest.skip("transformers has no Mistral3")
@@ -31,6 +31,12 @@ def test_engine_matches_hf(tmp_path, kind):
                                                 head_dim=16, patch_size=14, image_size=280),
                              image_token_index=500, vision_feature_layer=-1, vision_feature_select_strategy="full", tie_word_embeddings=False)
         hf = tf.LlavaForConditionalGeneration(cfg).float().eval()
+    elif kind == "lightonocr":
+        cfg = tf.LightOnOcrConfig(text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                                   head_dim=16, vocab_size=512, max_position_embeddings=2048, tie_word_embeddings=False),
+                                  vision_config=dict(hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=2, head_dim=16, patch_size=14,
+                                                     image_size=280), image_token_id=500, tie_word_embeddings=False)
+        hf = tf.LightOnOcrForConditionalGeneration(cfg).float().eval()
     else:
         hf = None
         cfg = tf.Mistral3Config(text_config=dict(model_type="mistral", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
@@ -49,7 +55,8 @@ def test_engine_matches_hf(tmp_path, kind):
     imgs = [rng.integers(0, 255, size=(60, 90, 3), dtype=np.uint8), rng.integers(0, 255, size=(150, 56, 3), dtype=np.uint8)]
     ids = [5, 6, 500, 7, 8, 9, 500, 10, 11, 12, 13]
     eng = sgl.Engine(model_path=d, device="cpu", page_size=4, skip_tokenizer_init=True, chunked_prefill_size=16, disable_radix_cache=True, log_level="error")
-    assert type(eng.runner.model).__name__ == ("Mistral3ForConditionalGeneration" if kind == "mistral3" else "PixtralForConditionalGeneration")
+    assert type(eng.runner.model).__name__ == {"mistral3": "Mistral3ForConditionalGeneration", "pixtral-llava": "PixtralForConditionalGeneration",
+                                               "lightonocr": "LightOnOCRForConditionalGeneration"}[kind]
     o = eng.generate(input_ids=ids, image_data=imgs, sampling_params={"max_new_tokens": 6, "temperature": 0, "ignore_eos": True},
                      return_logprob=True, logprob_start_len=0)
     exp_ids, mm = P.process_images(ids, imgs, eng.model_config, None)
@@ -58,7 +65,7 @@ def test_engine_matches_hf(tmp_path, kind):
     for off, n in zip(mm["image_offsets"], mm["image_token_counts"]):
         hf_ids[off:off + n] = [500] * n
     grids, p = mm["grid_thw"], 14
-    if kind == "mistral3":
+    if kind in ("mistral3", "lightonocr"):
         assert grids == [[1, 6, 8], [1, 12, 4]] and len(mm["image_offsets"]) == 3 + 6                 # one splice run per merged row
         assert [hf_ids[o_ + n] for o_, n in zip(mm["image_offsets"], mm["image_token_counts"])] == [12, 12, 13] + [12] * 5 + [13]
     else:
