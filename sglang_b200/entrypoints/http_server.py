@@ -80,7 +80,11 @@ def create_app(engine: Any):
     async def metrics():
         if engine.metrics is None:
             return err("metrics are disabled (--enable-metrics)", 404)
-        return Response(engine.metrics.render(engine.scheduler.get_internal_state()), media_type="text/plain; version=0.0.4")
+        st = dict(engine.scheduler.get_internal_state())
+        fe = getattr(app.state, "native_frontend", None)
+        if fe is not None:          # the C++ socket layer's own counters (connections, requests, probes it answered itself, bytes)
+            st.update({"http_" + k: v for k, v in fe.stats().items()})
+        return Response(engine.metrics.render(st), media_type="text/plain; version=0.0.4")
 
     async def _ctl(fn, *a):
         return await asyncio.get_running_loop().run_in_executor(None, fn, *a)
@@ -458,8 +462,10 @@ def _serve(engine: Any, server_args: ServerArgs, ready_event: Optional[Any], pee
             # C++ epoll front end: sockets, HTTP framing, SSE chunking and liveness probes never take the GIL (entrypoints/native_http.py)
             from .native_http import NativeAsgiServer
 
-            NativeAsgiServer(app, server_args.host, server_args.port, graceful_timeout=max(1.0, float(server_args.graceful_shutdown_timeout)),
-                             static=None if server_args.api_key else {"/health": (200, "application/json", b"{}")}).run()
+            srv = NativeAsgiServer(app, server_args.host, server_args.port, graceful_timeout=max(1.0, float(server_args.graceful_shutdown_timeout)),
+                                   static=None if server_args.api_key else {"/health": (200, "application/json", b"{}")})
+            app.state.native_frontend = srv.fe
+            srv.run()
         else:
             uvicorn.run(app, host=server_args.host, port=server_args.port, log_level=server_args.log_level, timeout_keep_alive=5,
                         timeout_graceful_shutdown=max(1, int(server_args.graceful_shutdown_timeout)))

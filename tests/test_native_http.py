@@ -18,8 +18,10 @@ from sglang_b200.entrypoints.native_http import NativeAsgiServer
 def server():
     eng = sgl.Engine(model_path="dummy:tiny-llama", page_size=4, enable_metrics=True)
     eng.start_background_loop()
-    srv = NativeAsgiServer(create_app(eng), "127.0.0.1", 0, graceful_timeout=5.0, max_body=1 << 20,
+    app = create_app(eng)
+    srv = NativeAsgiServer(app, "127.0.0.1", 0, graceful_timeout=5.0, max_body=1 << 20,
                            static={"/health": (200, "application/json", b"{}")})
+    app.state.native_frontend = srv.fe
     th = threading.Thread(target=srv.run, kwargs={"install_signal_handlers": False}, daemon=True)
     th.start()
     assert srv.started.wait(30)
@@ -43,7 +45,8 @@ def test_routes_keepalive_and_static(server):
     st = srv.fe.stats()
     assert st["static_hits"] - before["static_hits"] == 3               # liveness probes never reached Python
     assert st["accepted"] - before["accepted"] == 1                     # one TCP connection for the whole session
-    assert "sglb" in s.get(url + "/metrics").text or s.get(url + "/metrics").status_code == 200
+    m = s.get(url + "/metrics").text
+    assert "http_static_hits" in m and "http_accepted" in m          # the socket layer's counters are exported next to the scheduler's
 
 
 def test_sse_stream_matches_unary(server):
