@@ -57,10 +57,40 @@ def sample_shared_prefix(groups: int, per_group: int, sys_len: int, q_len: int, 
     return [reqs[i] for i in order]
 
 
-async def _one(session: Any, url: str, ids: List[int], out_len: int, extra: Dict[str, Any], headers: Dict[str, str]) -> RequestOutput:
+def sample_random_image(n: int, in_len: int, out_len: int, vocab: int, seed: int, image_token_id: int, images: int, width: int, height: int):
+    """vision-language load (reference ``--dataset-name image``): random text around ``images`` placeholder tokens, each paired with a random-pixel
+    PNG of the given resolution (data URL) — exercises preprocessing, the vision tower and the embed splice under load"""
+    import base64
+    import io
+
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    reqs = []
+    for _ in range(n):
+        text = rng.integers(10, vocab - 10, size=in_len).tolist()
+        text = [t if t != image_token_id else t + 1 for t in text]
+        cut = sorted(rng.integers(0, in_len + 1, size=images).tolist())
+        ids, prev = [], 0
+        for c in cut:
+            ids += text[prev:c] + [image_token_id]
+            prev = c
+        ids += text[prev:]
+        pics = []
+        for _ in range(images):
+            buf = io.BytesIO()
+            Image.fromarray(rng.integers(0, 255, size=(height, width, 3), dtype=np.uint8)).save(buf, format="PNG")
+            pics.append("data:image/png;base64," + base64.b64encode(buf.getvalue()).decode())
+        reqs.append((ids, out_len, pics))
+    return reqs
+
+
+async def _one(session: Any, url: str, ids: List[int], out_len: int, extra: Dict[str, Any], headers: Dict[str, str], images: Any = None) -> RequestOutput:
     res = RequestOutput(prompt_len=len(ids))
     payload = {"input_ids": ids, "stream": True,
                "sampling_params": {"max_new_tokens": out_len, "temperature": 0.0, "ignore_eos": True, **extra}}
+    if images:
+        payload["image_data"] = images
     t0 = time.perf_counter()
     last = t0
     n_prev = 0
@@ -101,6 +131,10 @@ async def run(args: argparse.Namespace) -> Dict[str, Any]:
     elif args.dataset_name == "generated-shared-prefix":
         reqs = sample_shared_prefix(args.gsp_num_groups, args.gsp_prompts_per_group, args.gsp_system_prompt_len, args.gsp_question_len,
                                     args.gsp_output_len, vocab, args.seed)
+    elif args.dataset_name == "random-image":
+        w, h = (int(x) for x in args.image_resolution.lower().split("x"))
+        reqs = sample_random_image(args.num_prompts, args.random_input_len, args.random_output_len, vocab, args.seed, args.image_token_id,
+                                   args.image_count, w, h)
     else:
         raise ValueError(args.dataset_name)
     headers = {"Authorization": f"Bearer {args.api_key}"} if args.api_key else {}
@@ -111,16 +145,16 @@ async def run(args: argparse.Namespace) -> Dict[str, Any]:
         if args.flush_cache:
             await session.post(args.base_url + "/flush_cache")
 
-        async def guarded(ids, o):
+        async def guarded(ids, o, imgs=None):
             if sem is None:
-                return await _one(session, args.base_url, ids, o, {}, headers)
+                return await _one(session, args.base_url, ids, o, {}, headers, imgs)
             async with sem:
-                return await _one(session, args.base_url, ids, o, {}, headers)
+                return await _one(session, args.base_url, ids, o, {}, headers, imgs)
 
         t0 = time.perf_counter()
         tasks = []
-        for ids, o in reqs:
-            tasks.append(asyncio.create_task(guarded(ids, o)))
+        for r_ in reqs:
+            tasks.append(asyncio.create_task(guarded(*r_)))
             if args.request_rate != float("inf"):
                 await asyncio.sleep(rng.expovariate(args.request_rate))
         outs = await asyncio.gather(*tasks)
@@ -147,7 +181,10 @@ async def run(args: argparse.Namespace) -> Dict[str, Any]:
 def main(argv: Optional[List[str]] = None) -> Dict[str, Any]:
     ap = argparse.ArgumentParser("sglang_b200.bench_serving")
     ap.add_argument("--base-url", default="http://127.0.0.1:30000")
-    ap.add_argument("--dataset-name", default="sharegpt-shaped", choices=["random", "sharegpt", "sharegpt-shaped", "generated-shared-prefix"])
+    ap.add_argument("--dataset-name", default="sharegpt-shaped", choices=["random", "sharegpt", "sharegpt-shaped", "generated-shared-prefix", "random-image"])
+    ap.add_argument("--image-token-id", type=int, default=None, help="random-image: the model's image placeholder token id")
+    ap.add_argument("--image-count", type=int, default=1)
+    ap.add_argument("--image-resolution", default="448x448", help="random-image: WIDTHxHEIGHT of the generated pictures")
     ap.add_argument("--num-prompts", type=int, default=500)
     ap.add_argument("--request-rate", type=float, default=float("inf"))
     ap.add_argument("--max-concurrency", type=int, default=None)

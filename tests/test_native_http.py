@@ -224,3 +224,26 @@ def test_websocket_echo_and_realtime_route_over_the_native_front_end(server):
             if ev["type"] in ("response.done", "error"):
                 break
         assert "response.done" in kinds and any(k.endswith("delta") for k in kinds), kinds
+
+
+def test_bench_serving_random_image_dataset_against_a_vlm_server(tmp_path):
+    """bench_serving --dataset-name random-image: requests carry random PNGs as data URLs next to placeholder tokens; a tiny Qwen2-VL served by
+    the native front end answers all of them (preprocessing + tower + splice under concurrency)"""
+    from sglang_b200 import bench_serving as B
+
+    eng = sgl.Engine(model_path="dummy:tiny-qwen2-vl", device="cpu", page_size=4, log_level="error")
+    eng.start_background_loop()
+    srv = NativeAsgiServer(create_app(eng), "127.0.0.1", 0, graceful_timeout=3.0)
+    th = threading.Thread(target=srv.run, kwargs={"install_signal_handlers": False}, daemon=True)
+    th.start()
+    assert srv.started.wait(30)
+    try:
+        m = B.main(["--base-url", f"http://127.0.0.1:{srv.port}", "--dataset-name", "random-image", "--num-prompts", "5", "--random-input-len", "12",
+                    "--random-output-len", "4", "--image-token-id", str(eng.model_config.image_token_id), "--image-count", "2",
+                    "--image-resolution", "70x56", "--vocab-size", str(eng.model_config.vocab_size), "--request-rate", "inf"])
+        assert m["completed"] == 5 and m["total_output_tokens"] == 20, m
+        assert m["total_input_tokens"] == 5 * (12 + 2)                    # as sent: 12 text ids + 2 placeholders (the server expands them)
+    finally:
+        srv.request_stop()
+        th.join(20)
+        eng.shutdown()
