@@ -1,4 +1,4 @@
-"""``python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,version}`` (reference ``python/sglang/cli/main.py:12-45``)."""
+"""``python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,killall,version}`` (reference ``python/sglang/cli/main.py:12-45``)."""
 from __future__ import annotations
 
 import json
@@ -40,12 +40,26 @@ def main(argv=None) -> None:
         from .multimodal_gen.pipeline import main as dm
 
         dm(argv)
+    elif cmd == "killall":                  # reference `killall_sglang`: here by pid registry, never by command-line pattern
+        import argparse
+
+        from .utils.process_tree import killall_servers, list_servers
+
+        ap = argparse.ArgumentParser("sglang_b200 killall")
+        ap.add_argument("--port", type=int, default=None, help="only the server listening on this port")
+        ap.add_argument("--grace", type=float, default=10.0, help="seconds to wait for a graceful drain before SIGKILL")
+        ap.add_argument("--list", action="store_true", help="only list the registered servers")
+        ns = ap.parse_args(argv)
+        if ns.list:
+            print(json.dumps(list_servers(), indent=1))
+        else:
+            print(json.dumps({"stopped": killall_servers(ns.grace, ns.port)}))
     elif cmd == "version":
         from . import __version__
 
         print(__version__)
     else:
-        print("usage: python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,version} [args]")
+        print("usage: python -m sglang_b200.cli {serve,generate,diffusion,bench-serving,router,killall,version} [args]")
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ import json
 import logging
 import multiprocessing as mp
 import os
+import threading
 import socket
 import sys
 import time
@@ -410,6 +411,11 @@ def launch_server(server_args: ServerArgs, ready_event: Optional[Any] = None) ->
     import uvicorn
 
     from .engine import Engine
+
+    if "RANK" not in os.environ and not os.environ.get("SGLB_IN_SCHEDULER_PROCESS") and threading.current_thread() is threading.main_thread():
+        from ..utils.process_tree import register_server
+
+        register_server(server_args.port)          # `python -m sglang_b200.cli killall` stops registered servers by pid
 
     if int(getattr(server_args, "tokenizer_worker_num", 1) or 1) > 1 and "RANK" not in os.environ and not os.environ.get("SGLB_IN_SCHEDULER_PROCESS"):
         from ..managers.multiprocess import serve_multi_tokenizer

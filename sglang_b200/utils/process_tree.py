@@ -16,6 +16,7 @@ import ctypes
 import logging
 import os
 import signal
+import sys
 import threading
 import time
 from typing import Any, Callable, List, Optional, Sequence
@@ -114,3 +115,81 @@ def kill_process_tree(procs: Sequence[Any], grace_s: float = 5.0) -> None:
                     p.kill()
         except Exception:      # noqa: BLE001
             pass
+
+
+# ------------------------------------------------------------------------------------------------ pid registry (``cli killall``)
+def _pid_dir() -> str:
+    d = os.environ.get("SGLB_PID_DIR") or os.path.join(os.environ.get("XDG_RUNTIME_DIR") or "/tmp", "sglb-servers")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def register_server(port: int) -> str:
+    """top-level server processes record themselves (pid, port, start time) so that ``python -m sglang_b200.cli killall`` can stop exactly the
+    servers of this installation — by pid, never by matching command lines (reference ``sglang.cli.killall`` / ``kill_process_tree``)"""
+    import atexit
+    import json
+
+    path = os.path.join(_pid_dir(), f"{os.getpid()}.json")
+    with open(path, "w") as f:
+        json.dump({"pid": os.getpid(), "port": int(port), "started": time.time(), "cmd": " ".join(sys.argv[:6])}, f)
+
+    def _rm():
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    atexit.register(_rm)
+    return path
+
+
+def list_servers():
+    import json
+
+    out = []
+    for name in sorted(os.listdir(_pid_dir())):
+        if not name.endswith(".json"):
+            continue
+        path = os.path.join(_pid_dir(), name)
+        try:
+            rec = json.load(open(path))
+            os.kill(int(rec["pid"]), 0)          # still alive?
+            out.append(rec)
+        except (OSError, ValueError, KeyError):
+            try:
+                os.remove(path)                   # stale entry
+            except OSError:
+                pass
+    return out
+
+
+def killall_servers(grace_s: float = 10.0, port: Optional[int] = None) -> int:
+    """SIGTERM (graceful drain) every registered server (or the one on ``port``), SIGKILL what is still there after ``grace_s``"""
+    victims = [r for r in list_servers() if port is None or r["port"] == port]
+    for r in victims:
+        try:
+            os.kill(int(r["pid"]), signal.SIGTERM)
+        except OSError:
+            pass
+    deadline = time.time() + grace_s
+    while time.time() < deadline and any(_alive(int(r["pid"])) for r in victims):
+        time.sleep(0.1)
+    for r in victims:
+        if _alive(int(r["pid"])):
+            try:
+                os.kill(int(r["pid"]), signal.SIGKILL)
+            except OSError:
+                pass
+    return len(victims)
+
+
+def _alive(pid: int) -> bool:
+    try:
+        os.kill(pid, 0)
+    except OSError:
+        return False
+    try:          # a zombie child of ours still answers kill(0)
+        with open(f"/proc/{pid}/stat") as f:
+            return f.read().rsplit(")", 1)[1].split()[0] != "Z"
+    except OSError:
+        return True

@@ -239,3 +239,41 @@ def test_multi_tokenizer_workers_share_one_scheduler(tmp_path, frontend):
                 os.kill(k, signal.SIGKILL)
             except OSError:
                 pass
+
+
+def test_cli_killall_stops_registered_servers_by_pid(tmp_path):
+    """`cli killall`: servers register pid + port in a directory; killall sends SIGTERM to exactly those pids (graceful drain) — no pattern kills"""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    import time
+    import urllib.request
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root, SGLB_PID_DIR=str(tmp_path / "pids"))
+    p = subprocess.Popen([sys.executable, "-m", "sglang_b200.launch_server", "--model-path", "dummy:tiny-llama", "--device", "cpu", "--port", str(port),
+                          "--host", "127.0.0.1", "--log-level", "error"], cwd=root, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        for _ in range(120):
+            try:
+                if urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1).status == 200:
+                    break
+            except Exception:
+                time.sleep(0.5)
+        else:
+            pytest.fail("server did not come up")
+        ls = json.loads(subprocess.run([sys.executable, "-m", "sglang_b200.cli", "killall", "--list"], cwd=root, env=env, capture_output=True, text=True).stdout)
+        assert [r["pid"] for r in ls] == [p.pid] and ls[0]["port"] == port
+        other = subprocess.run([sys.executable, "-m", "sglang_b200.cli", "killall", "--port", str(port + 1)], cwd=root, env=env, capture_output=True, text=True)
+        assert json.loads(other.stdout) == {"stopped": 0} and p.poll() is None
+        out = subprocess.run([sys.executable, "-m", "sglang_b200.cli", "killall", "--grace", "20"], cwd=root, env=env, capture_output=True, text=True)
+        assert json.loads(out.stdout) == {"stopped": 1}
+        p.wait(timeout=30)
+        assert json.loads(subprocess.run([sys.executable, "-m", "sglang_b200.cli", "killall", "--list"], cwd=root, env=env, capture_output=True,
+                                         text=True).stdout) == []
+    finally:
+        if p.poll() is None:
+            p.kill()
