@@ -8,8 +8,11 @@ from typing import Any, Dict, Optional, Tuple
 import numpy as np
 import torch
 
+import itertools
+
 _ENC_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
 _ENC_CACHE_MAX = 64
+_ENC_SERIAL = itertools.count(1)
 
 
 def _encode(model: Any, mm: Dict[str, Any], device: torch.device, dtype: torch.dtype):
@@ -48,7 +51,11 @@ def build_mm_embeds(model: Any, sb: Any, device: torch.device, dtype: torch.dtyp
         need = [k for k, off in enumerate(mm["image_offsets"]) if off < e and off + counts[k] > s]
         if not need:
             continue
-        key = (id(mm), 0)
+        # a serial stamped on the request's own dict: ``id(mm)`` can be reused by a later request once this one is collected, which handed
+        # that request another image's rows (seen as a size mismatch in the EPD test)
+        if "_enc_serial" not in mm:
+            mm["_enc_serial"] = next(_ENC_SERIAL)
+        key = (mm["_enc_serial"], 0)
         emb = _ENC_CACHE.get(key)
         if emb is None:
             emb = _encode(model, mm, device, dtype)
